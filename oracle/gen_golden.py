@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference (/root/reference, imported through oracle/ref_shim/shim.py).
+
+TEST INFRASTRUCTURE ONLY (never imported by the product package).  Run in the build
+container (the GPU box has no /root/reference; it only reads the committed .npz):
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+What is pinned, and by which reference code:
+  focf_train_*.npz   recbole/model/fair_recommender/focf.py:75-169 (+autograd) and
+                     torch.optim.Adam as built by recbole/trainer/trainer.py:139
+  focf_eval_*.npz    focf.py:171-178, trainer.py:420-439 (_full_sort_batch_eval),
+                     evaluator/collector.py:131-205, evaluator/metrics.py (12 metrics)
+  ml100k_*.npz       the whole pipeline on the bundled ml-100k (quick_start.py:20-71):
+                     split tensors, the item draws of FOCFDataLoader, per-epoch loss and
+                     valid/test metric dicts.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "ref_shim"))
+import shim  # noqa: E402
+
+shim.install()
+import torch  # noqa: E402
+from recbole.data.interaction import Interaction  # noqa: E402
+from recbole.evaluator import Collector, Evaluator  # noqa: E402
+from recbole.model.fair_recommender.focf import FOCF  # noqa: E402
+from recbole.trainer import Trainer  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+METRICS12 = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
+             "ValueUnfairness", "AbsoluteUnfairness", "UnderUnfairness", "OverUnfairness", "NonParityUnfairness"]
+
+
+class Cfg(dict):
+    """dict that answers None for missing keys, like recbole Config.__getitem__ (configurator.py:405-409)."""
+
+    def __getitem__(self, k):
+        return self.get(k, None)
+
+
+class FakeDataset:
+    def __init__(self, n_users, n_items, max_rating):
+        self._n = {"user_id": n_users, "item_id": n_items}
+        self.inter_feat = {"rating": torch.tensor([1.0, float(max_rating)])}
+
+    def num(self, f):
+        return self._n[f]
+
+
+def base_cfg(**kw):
+    c = Cfg(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", RATING_FIELD="rating",
+            LABEL_FIELD="label", device=torch.device("cpu"), embedding_size=16, sst_attr_list=["gender"],
+            fair_weight=1.0, fair_objective="value", metric_decimal_place=12, topk=[10], metrics=METRICS12,
+            eval_args={"mode": "full"}, popularity_ratio=0.1)
+    c.update(kw)
+    return c
+
+
+def make_focf_batches(rng, n_users, n_items, n_steps, target_rows, single_group_step=None, shuffle=False,
+                      float_sst=False):
+    """Batches shaped like FOCFDataLoader's (focf_dataloader.py:37-50): whole items, item-contiguous,
+    unique (user,item) pairs."""
+    gender_of_user = rng.integers(1, 3, size=n_users)  # token ids 1/2 (row 0 = [PAD] unused)
+    batches = []
+    for s in range(n_steps):
+        items = rng.permutation(np.arange(1, n_items))
+        uid, iid = [], []
+        for it in items:
+            cnt = int(rng.integers(1, max(2, n_users // 3)))
+            us = rng.choice(np.arange(1, n_users), size=cnt, replace=False)
+            uid.append(us)
+            iid.append(np.full(cnt, it))
+            if sum(map(len, uid)) >= target_rows:
+                break
+        uid = np.concatenate(uid).astype(np.int64)
+        iid = np.concatenate(iid).astype(np.int64)
+        rating = rng.integers(1, 6, size=len(uid)).astype(np.float32)
+        g = gender_of_user[uid].astype(np.int64)
+        if single_group_step == s:
+            g[:] = 2
+        if shuffle:
+            p = rng.permutation(len(uid))
+            uid, iid, rating, g = uid[p], iid[p], rating[p], g[p]
+        if float_sst:
+            g = (g - 1).astype(np.float32)
+        batches.append((uid, iid, rating, g))
+    return batches
+
+
+def run_focf_train(name, objective, n_users=50, n_items=40, d=16, n_steps=3, target_rows=260, seed=0, scale=0.6,
+                   fair_weight=1.0, lr=1e-3, wd=1e-3, **bk):
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    cfg = base_cfg(embedding_size=d, fair_objective=objective, fair_weight=fair_weight)
+    model = FOCF(cfg, FakeDataset(n_users, n_items, 5.0))
+    with torch.no_grad():
+        model.user_embedding_layer.weight.copy_(torch.from_numpy(
+            (rng.standard_normal((n_users, d)) * scale).astype(np.float32)))
+        model.item_embedding_layer.weight.copy_(torch.from_numpy(
+            (rng.standard_normal((n_items, d)) * scale).astype(np.float32)))
+    U0 = model.user_embedding_layer.weight.detach().numpy().copy()
+    I0 = model.item_embedding_layer.weight.detach().numpy().copy()
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)  # trainer.py:139
+    batches = make_focf_batches(rng, n_users, n_items, n_steps, target_rows, **bk)
+    out = dict(U0=U0, I0=I0, n_steps=n_steps, objective=objective, fair_weight=fair_weight, lr=lr, wd=wd,
+               max_rating=5.0)
+    losses = []
+    for s, (uid, iid, rating, g) in enumerate(batches):
+        inter = Interaction({"user_id": torch.from_numpy(uid), "item_id": torch.from_numpy(iid),
+                             "rating": torch.from_numpy(rating), "gender": torch.from_numpy(g)})
+        opt.zero_grad()
+        loss = model.calculate_loss(inter)  # focf.py:152-169
+        loss.backward()
+        if s == 0:
+            pred, _, _ = model.forward(inter["user_id"], inter["item_id"])
+            out["pred0"] = pred.detach().numpy().copy()
+            out["dU0"] = model.user_embedding_layer.weight.grad.numpy().copy()
+            out["dI0"] = model.item_embedding_layer.weight.grad.numpy().copy()
+            out["predict0"] = model.predict(inter).detach().numpy().copy()  # focf.py:145-150
+        opt.step()
+        losses.append(loss.item())
+        out[f"uid{s}"], out[f"iid{s}"], out[f"rating{s}"], out[f"sst{s}"] = uid, iid, rating, g
+    out["losses"] = np.array(losses, dtype=np.float32)
+    out["U_final"] = model.user_embedding_layer.weight.detach().numpy().copy()
+    out["I_final"] = model.item_embedding_layer.weight.detach().numpy().copy()
+    st = opt.state[model.user_embedding_layer.weight]
+    out["mU_final"], out["vU_final"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    st = opt.state[model.item_embedding_layer.weight]
+    out["mI_final"], out["vI_final"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, f"focf_train_{name}.npz"), **out)
+    print(f"focf_train_{name}: losses={losses}")
+
+
+class FakeTrainer:
+    """Just the attributes Trainer._full_sort_batch_eval (trainer.py:420-439) touches."""
+
+    def __init__(self, model, n_items):
+        self.model, self.device, self.tot_item_num = model, torch.device("cpu"), n_items
+
+
+def run_focf_eval(name, n_users=60, n_items=97, d=16, K=10, topk=(5, 10), seed=1, scale=0.55, positive_only=False,
+                  users_per_batch=7, float_sst=False, n_groups=2):
+    """Full-sort eval of the reference: full_sort_predict -> mask -> Collector -> 12 metrics."""
+    rng = np.random.default_rng(seed)
+    cfg = base_cfg(embedding_size=d, topk=list(topk), metric_decimal_place=12)
+    model = FOCF(cfg, FakeDataset(n_users, n_items, 5.0))
+    U = (rng.standard_normal((n_users, d)) * scale).astype(np.float32)
+    It = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
+    if positive_only:  # tie-free variant: all dots strictly inside (0, max_rating)
+        U, It = np.abs(U) * 0.5 + 0.01, np.abs(It) * 0.5 + 0.01
+    with torch.no_grad():
+        model.user_embedding_layer.weight.copy_(torch.from_numpy(U))
+        model.item_embedding_layer.weight.copy_(torch.from_numpy(It))
+    model.eval()
+    sst_of_user = rng.integers(1, n_groups + 1, size=n_users)
+    if float_sst:
+        sst_of_user = (sst_of_user - 1).astype(np.float32)
+    # eval users: all but pad and a few users without positives
+    eval_users = np.array([u for u in range(1, n_users) if u % 9 != 0], dtype=np.int64)
+    hist, pos = {}, {}
+    for u in eval_users:
+        n_used = int(rng.integers(3, 30))
+        used = rng.choice(np.arange(1, n_items), size=n_used, replace=False)
+        n_pos = int(rng.integers(1, min(6, n_used)))
+        pos[u], hist[u] = used[:n_pos], used[n_pos:]
+    train_item_count = {int(i): int(c) for i, c in zip(np.arange(1, n_items), rng.integers(1, 50, n_items - 1))}
+
+    trainer = FakeTrainer(model, n_items)
+    collector = Collector(cfg)
+    collector.data_struct.set("data.num_items", n_items)  # collector.py:86-88
+    from collections import Counter
+    collector.data_struct.set("data.count_items", Counter(train_item_count))  # collector.py:91-93
+    with torch.no_grad():
+        for b0 in range(0, len(eval_users), users_per_batch):
+            bu = eval_users[b0:b0 + users_per_batch]
+            inter = Interaction({"user_id": torch.from_numpy(bu),
+                                 "gender": torch.from_numpy(sst_of_user[bu])})
+            hu = torch.cat([torch.full((len(hist[u]),), i, dtype=torch.int64) for i, u in enumerate(bu)])
+            hi = torch.cat([torch.from_numpy(hist[u]) for u in bu])
+            pu = torch.cat([torch.full((len(pos[u]),), i, dtype=torch.int64) for i, u in enumerate(bu)])
+            pi = torch.cat([torch.from_numpy(pos[u]) for u in bu])
+            inter, scores, pu, pi = Trainer._full_sort_batch_eval(trainer, (inter, (hu, hi), pu, pi))
+            collector.eval_batch_collect(scores, inter, pu, pi)
+    struct = collector.get_data_struct()
+    result = Evaluator(cfg).evaluate(struct)
+    out = dict(U=U, I=It, max_rating=5.0, K=K, topk=np.array(topk), eval_users=eval_users,
+               sst_of_user=sst_of_user,
+               hist_off=np.cumsum([0] + [len(hist[u]) for u in eval_users]),
+               hist_items=np.concatenate([hist[u] for u in eval_users]),
+               pos_off=np.cumsum([0] + [len(pos[u]) for u in eval_users]),
+               pos_items=np.concatenate([pos[u] for u in eval_users]),
+               train_count_items=np.array(sorted(train_item_count.items()), dtype=np.int64),
+               rec_items=struct.get("rec.items").numpy(), rec_topk=struct.get("rec.topk").numpy(),
+               rec_positive_score=struct.get("rec.positive_score").numpy(),
+               data_positive_i=struct.get("data.positive_i").numpy(),
+               data_sst=struct.get("data.gender").numpy(),
+               metric_names=np.array(list(result.keys())),
+               metric_values=np.array([float(v) for v in result.values()], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, f"focf_eval_{name}.npz"), **out)
+    print(f"focf_eval_{name}:", {k: float(v) for k, v in result.items()})
+
+
+def run_ml100k(epochs=2):
+    """End-to-end on the bundled ml-100k through run_recbole's own steps (quick_start.py:20-71); records
+    the split tensors, the FOCFDataLoader item draws, the per-epoch train loss and the metric dicts."""
+    import tempfile
+    import yaml
+    from recbole.config import Config
+    from recbole.data import create_dataset, data_preparation
+    from recbole.utils import init_seed, get_model, get_trainer
+    import recbole.data.dataloader.focf_dataloader as fdl
+
+    cfg_dict = dict(
+        data_path=os.path.join(shim.REFERENCE_ROOT, "recbole/dataset_example/"), RATING_FIELD="rating",
+        LABEL_FIELD="label", threshold={"rating": 3.0},
+        load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"], "item": ["item_id"]},
+        sst_attr_list=["gender"], fair_weight=1.0, neg_sampling=None, weight_decay=0.001,
+        embedding_size=64, epochs=epochs, topk=[10], valid_metric="NDCG@10", metrics=METRICS12, seed=2020,
+        use_gpu=False, state="WARNING", show_progress=False, metric_decimal_place=12,
+        eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"})
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+    try:
+        # fair_objective must come from a YAML file
+        with open("c.yaml", "w") as f:
+            yaml.safe_dump(dict(cfg_dict, fair_objective="value"), f)
+        sys.argv = sys.argv[:1]
+        config = Config(model="FOCF", dataset="ml-100k", config_file_list=["c.yaml"])
+        init_seed(config["seed"], config["reproducibility"])
+        dataset = create_dataset(config)
+        train_data, valid_data, test_data = data_preparation(config, dataset)
+        model = get_model("FOCF")(config, train_data.dataset).to(config["device"])
+        U0 = model.user_embedding_layer.weight.detach().numpy().copy()
+        I0 = model.item_embedding_layer.weight.detach().numpy().copy()
+        trainer = get_trainer(config["MODEL_TYPE"], config["model"])(config, model)
+
+        draws = []  # item ids drawn by FOCFDataLoader._next_batch_data, in order, -1 = batch end
+        orig_next = fdl.FOCFDataLoader._next_batch_data
+        orig_choice = np.random.choice
+
+        def rec_choice(*a, **k):
+            r = orig_choice(*a, **k)
+            draws.append(int(r[0]))
+            return r
+
+        def rec_next(self):
+            np.random.choice = rec_choice
+            try:
+                return orig_next(self)
+            finally:
+                np.random.choice = orig_choice
+                draws.append(-1)
+
+        fdl.FOCFDataLoader._next_batch_data = rec_next
+        trainer.eval_collector.data_collect(train_data)
+        losses, valids = [], []
+        for ep in range(epochs):
+            losses.append(trainer._train_epoch(train_data, ep))
+            valids.append(trainer.evaluate(valid_data, load_best_model=False))
+        test = trainer.evaluate(test_data, load_best_model=False)
+        fdl.FOCFDataLoader._next_batch_data = orig_next
+
+        def split(dl):
+            f = dl.dataset.inter_feat
+            return (f["user_id"].numpy().astype(np.int32), f["item_id"].numpy().astype(np.int32),
+                    f["rating"].numpy().astype(np.float32))
+
+        tr, va, te = split(train_data), split(valid_data), split(test_data)
+        gender = dataset.get_user_feature()["gender"].numpy().copy()
+        gender[0] = 0  # pad row (pandas-3 CoW leaves INT64_MIN there; never referenced)
+        out = dict(n_users=dataset.user_num, n_items=dataset.item_num,
+                   train_u=tr[0], train_i=tr[1], train_r=tr[2], valid_u=va[0], valid_i=va[1],
+                   test_u=te[0], test_i=te[1], gender=gender.astype(np.int8),
+                   draws=np.array(draws, dtype=np.int32), U0=U0, I0=I0,
+                   epoch_losses=np.array(losses, dtype=np.float64),
+                   metric_names=np.array(list(test.keys())),
+                   valid_metrics=np.array([[float(v) for v in r.values()] for r in valids]),
+                   test_metrics=np.array([float(v) for v in test.values()]),
+                   U_final=model.user_embedding_layer.weight.detach().numpy().copy(),
+                   I_final=model.item_embedding_layer.weight.detach().numpy().copy(),
+                   max_rating=float(model.max_rating), train_batch_size=config["train_batch_size"])
+        np.savez_compressed(os.path.join(OUT, "ml100k_focf_value.npz"), **out)
+        print("ml100k: losses", losses, "test", {k: float(v) for k, v in test.items()})
+    finally:
+        os.chdir(cwd)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for obj in ["none", "value", "absolute", "under", "over", "nonparity"]:
+        run_focf_train(obj, obj, seed=10 + len(obj))
+    run_focf_train("value_d64", "value", n_users=300, n_items=120, d=64, target_rows=900, seed=3, scale=0.3)
+    run_focf_train("value_single_group", "value", single_group_step=1, seed=4)
+    run_focf_train("value_shuffled", "value", shuffle=True, seed=5)
+    run_focf_train("value_float_sst", "value", float_sst=True, seed=6, fair_weight=0.5)
+    run_focf_eval("ties", seed=1)
+    run_focf_eval("tiefree", seed=2, positive_only=True)
+    run_focf_eval("float_sst", seed=3, positive_only=True, float_sst=True, d=64, n_users=130, n_items=300,
+                  users_per_batch=13)
+    run_ml100k()
+
+
+if __name__ == "__main__":
+    main()
