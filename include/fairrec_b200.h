@@ -1,0 +1,223 @@
+/* fairrec_b200.h -- C ABI of libfairrec_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for the hot path of RecBole-FairRec: the
+ * reference is pure Python/PyTorch, so the "FFI" a maintainer binds is ctypes;
+ * every entry point below names the reference code it replaces (paths relative to the reference
+ * root, file:line).
+ *
+ * Conventions
+ *  - Plain C: device pointers + sizes, no torch types.  All pointers are DEVICE pointers unless
+ *    the name ends in _host.  Every function enqueues work on `stream` (a cudaStream_t passed as
+ *    void*) and returns immediately; nothing here synchronises the device or allocates memory.
+ *  - Return value: FR_OK or an FR_ERR_* code; fr_last_error() gives the message of the last failure
+ *    on the calling thread.  Data-dependent faults the reference raises as Python exceptions (e.g.
+ *    more than two sensitive-attribute values in a FOCF batch -> IndexError at focf.py:86) are
+ *    recorded in a caller-owned device word `status_flags` (FR_FLAG_* bits) that the host reads at
+ *    its next natural synchronisation point.
+ *  - ids are int32 (the reference's int64 Interaction columns are narrowed by the host mirror),
+ *    embeddings/ratings/scores float32 row-major, exactly the reference's dtypes for arithmetic.
+ *  - Workspaces are caller-allocated; fr_*_workspace_bytes() tells the size.  They may be reused
+ *    between calls on the same stream.
+ */
+#ifndef FAIRREC_B200_H_
+#define FAIRREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_ABI_VERSION 1
+
+enum fr_status {
+  FR_OK = 0,
+  FR_ERR_INVALID = 1,   /* bad argument (null pointer, unsupported size) */
+  FR_ERR_CUDA = 2,      /* a CUDA runtime call failed */
+  FR_ERR_WORKSPACE = 3, /* workspace too small */
+  FR_ERR_UNSUPPORTED = 4
+};
+
+/* bits of the device-side status word */
+enum fr_flag {
+  FR_FLAG_TOO_MANY_GROUPS = 1, /* >2 distinct sensitive-attribute values in a FOCF batch (focf.py:81-86) */
+  FR_FLAG_SINGLE_GROUP = 2,    /* nonparity objective with <2 values (focf.py:129-130 IndexError) */
+  FR_FLAG_NAN_LOSS = 4         /* trainer.py:286-288 _check_nan */
+};
+
+/* focf.py:52-68 get_loss_fun */
+enum fr_objective {
+  FR_OBJ_NONE = 0, FR_OBJ_VALUE = 1, FR_OBJ_ABSOLUTE = 2, FR_OBJ_UNDER = 3, FR_OBJ_OVER = 4, FR_OBJ_NONPARITY = 5
+};
+
+/* score transform applied after the dot product */
+enum fr_transform {
+  FR_TRANSFORM_NONE = 0,      /* raw dot (focf.py:140) */
+  FR_TRANSFORM_CLAMP_DIV = 1, /* clamp(x,0,max_rating)/max_rating (focf.py:150,178) */
+  FR_TRANSFORM_SIGMOID = 2    /* pfcn_pmf.py:216 / nfcf.py:73 */
+};
+
+/* arithmetic of the full-sort scoring contraction */
+enum fr_score_mode {
+  FR_SCORE_EXACT_FP32 = 0, /* k-ascending fmaf chain on CUDA cores: bit-identical to oracle/c */
+  FR_SCORE_TC_3XTF32 = 1   /* tcgen05 tensor cores, 3xTF32 split (fp32-level accuracy, not bit-defined) */
+};
+
+int fr_abi_version(void);
+const char *fr_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t fr_launch_count(void);
+/* Measurement aid (bench.py roofline): while enabled, every kernel launch of this library is bracketed by two
+ * CUDA events on its stream; fr_profile_report synchronises, writes "kernel,count,total_ms" lines into buf and
+ * returns the number of distinct kernels.  Off by default (zero overhead). */
+void fr_profile_enable(int on);
+int fr_profile_report(char *buf, size_t buf_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sorting / segmentation primitives (replace torch.unique(return_inverse=True), focf.py:77-78, and the
+ * implicit sort inside nn.Embedding's dense backward; also used by the metric kernels).
+ * Stable LSD radix sort of (key, value) pairs; key_bits = number of significant key bits.
+ * ---------------------------------------------------------------------------------------------- */
+size_t fr_sort_pairs_workspace_bytes(int64_t n);
+int fr_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                      int64_t n, int key_bits, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FOCF training step.
+ *
+ * One struct describes the model state and one batch; the same struct drives
+ *   fr_focf_forward   -> focf.py:136-143 forward + 75-134 fairness objective + 152-169 calculate_loss
+ *   fr_focf_backward  -> autograd of the above + nn.Embedding dense backward (trainer.py:193)
+ *   fr_focf_adam      -> torch.optim.Adam dense step incl. L2 weight decay (trainer.py:139,196)
+ *   fr_focf_train_step = forward + backward + adam fused (the dense gradient is never materialised)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fr_focf_step {
+  /* model (focf.py:43-44): row-major float32 tables, row 0 is the [PAD] id */
+  float *U;            /* [n_users, d] */
+  float *I;            /* [n_items, d] */
+  int32_t n_users, n_items, d;
+  /* batch (data/interaction.py Interaction columns of focf_dataloader.py:49) */
+  const int32_t *uid;  /* [B] */
+  const int32_t *iid;  /* [B] */
+  const float *rating; /* [B] RATING_FIELD */
+  const float *sst;    /* [B] sensitive attribute VALUE (token id or 0/1 float), focf.py:77 */
+  int32_t B;
+  int32_t items_contiguous; /* 1: rows of one item are adjacent (FOCFDataLoader batches) -> no item sort */
+  /* objective */
+  int32_t objective;   /* enum fr_objective */
+  float fair_weight;   /* focf.py:166 */
+  /* outputs */
+  float *pred;         /* [B] forward scores */
+  float *loss;         /* [1] calculate_loss value (written at loss[0]) */
+  int32_t *status_flags; /* [1] OR-ed FR_FLAG_* */
+  /* Adam state (only read by fr_focf_adam / fr_focf_train_step) */
+  float *mU, *vU, *mI, *vI;
+  int32_t step;        /* 1-based optimizer step t */
+  float lr, beta1, beta2, eps, weight_decay;
+  /* dense gradients (only written by fr_focf_backward; may be NULL for fr_focf_train_step) */
+  float *dU, *dI;
+  /* scratch */
+  void *workspace;
+  size_t workspace_bytes;
+} fr_focf_step;
+
+size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch);
+/* zero the persistent part of a fresh workspace (row-stamp tables); call once after allocation */
+int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
+                           int32_t max_batch, void *stream);
+int fr_focf_forward(const fr_focf_step *s, void *stream);
+/* needs the workspace left by fr_focf_forward for the same batch; grad_scale = upstream dL (usually 1) */
+int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream);
+int fr_focf_adam(const fr_focf_step *s, void *stream);
+int fr_focf_train_step(const fr_focf_step *s, void *stream);
+
+/* focf_dataloader.py:37-50 (FOCFDataLoader._next_batch_data) + dataset join of the user feature: build the
+ * batch = all train rows of the drawn items.  The train split is device resident, sorted by item:
+ * item_off [n_items+1] offsets into train_uid / train_rating; sst_of_user [n_users].  draw_items [J] are the
+ * drawn item ids, draw_off [J+1] the exclusive prefix sum of their row counts (batch positions). */
+int fr_focf_gather_batch(const int32_t *item_off, const int32_t *train_uid, const float *train_rating,
+                         const float *sst_of_user, const int32_t *draw_items, const int32_t *draw_off, int32_t J,
+                         int32_t *uid, int32_t *iid, float *rating, float *sst, void *stream);
+
+/* focf.py:145-150 predict / pair scores with the EXACT (fmaf-chain) arithmetic of the scorer;
+ * also produces rec.positive_score (collector.py:179) */
+int fr_pair_scores(const float *U, const float *I, const int32_t *uid, const int32_t *iid, int64_t n, int32_t d,
+                   int32_t transform, float max_rating, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-sort evaluation: scoring contraction fused with the pad/history mask and a streaming top-K.
+ * Replaces focf.py:171-178 full_sort_predict + trainer.py:435-438 mask + collector.py:143-153 topk /
+ * pos-matrix / gather.  Scores are never materialised.
+ *
+ * Item sharding: the call scores items [item_base, item_base + n_items_local) held in I_shard; ids in
+ * hist/pos CSR and in the outputs are GLOBAL item ids.  Total order: (score desc, item id asc).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fr_fullsort {
+  const float *U;          /* [n_users_total, d] */
+  const float *I_shard;    /* [n_items_local, d] rows item_base.. */
+  int32_t d, n_items_local, item_base;
+  const int32_t *users;    /* [n] eval user ids (general_dataloader.py:188 uid_list) */
+  int32_t n;
+  const int64_t *hist_off; /* [n+1] CSR of history items per eval user, item ids ASCENDING per user */
+  const int32_t *hist_items;
+  int32_t K;               /* max(topk), 1..64 */
+  int32_t transform;       /* enum fr_transform */
+  float max_rating;
+  int32_t score_mode;      /* enum fr_score_mode */
+  int32_t *topk_id;        /* [n, K] out */
+  float *topk_score;       /* [n, K] out */
+  void *workspace;
+  size_t workspace_bytes;
+} fr_fullsort;
+
+size_t fr_fullsort_workspace_bytes(int32_t n, int32_t K, int32_t n_items_local, int32_t d);
+int fr_fullsort_topk(const fr_fullsort *a, void *stream);
+
+/* merge P per-shard top-K lists [P, n, K] (as gathered by NCCL all-gather) into the global top-K */
+int fr_topk_merge(const int32_t *ids_in, const float *scores_in, int32_t P, int32_t n, int32_t K,
+                  int32_t *ids_out, float *scores_out, void *stream);
+
+/* collector.py:147-153: hit bits of the top-K against the positives CSR (ascending item ids per user)
+ * -> rec.topk int32 [n, K+1] = [hit bits | pos_len] */
+int fr_hits(const int32_t *topk_id, int32_t n, int32_t K, const int64_t *pos_off, const int32_t *pos_items,
+            int32_t *rec_topk, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Metric accumulation (evaluator/metrics.py, the 12 metrics of properties/model/FOCF.yaml:29-30).
+ * ---------------------------------------------------------------------------------------------- */
+/* metrics.py:63-65,89-97,160-161,187-203 + base_metric.py:59-82: per-user Hit/MRR/Recall/NDCG@1..K summed
+ * over users in float64.  sums_out: [4, K] double (rows: ndcg, recall, hit, mrr) = SUM over users. */
+size_t fr_topk_metrics_workspace_bytes(int32_t n, int32_t K);
+int fr_topk_metrics(const int32_t *rec_topk, int32_t n, int32_t K, double *sums_out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* metrics.py:644-661 (GiniIndex) and 772-820 (PopularityPercentage):
+ * item_pos_count_out [K, n_items] int32: how often each item was recommended AT rank e (row e)
+ * pop_hits_out [K] int64: number of users whose rank-e recommendation is a popular item
+ * (PopularityPercentage@k = sum_{e<k} pop_hits[e] / (n * k); is_popular may be NULL) */
+int fr_rec_item_stats(const int32_t *topk_id, int32_t n, int32_t K, int32_t n_items, const uint8_t *is_popular,
+                      int32_t *item_pos_count_out, int64_t *pop_hits_out, void *stream);
+/* Gini@k from the first k rows of item_pos_count (sorts the summed counts; integer arithmetic until the
+ * final division): gini_out[0] double */
+size_t fr_gini_workspace_bytes(int32_t n_items);
+int fr_gini_at_k(const int32_t *item_pos_count, int32_t n_items, int32_t k_rows, int64_t n_users, double *gini_out,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* metrics.py:860-881, 935-1266, 1313-1341: per (positive item, group) sums over the eval positives.
+ * group[p] in [0,G).  Outputs (float64): stats [n_items, G, 2] = (sum score, count) per item x group.
+ * Deterministic (sorted-segment reduction, no float atomics). */
+size_t fr_item_group_stats_workspace_bytes(int64_t n_pos, int32_t n_items, int32_t G);
+int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const int32_t *group, int64_t n_pos,
+                        int32_t n_items, int32_t G, double *stats_out, void *workspace, size_t workspace_bytes,
+                        void *stream);
+/* reduce stats -> fairness metrics.  out[0..6] double: DifferentialFairness (metrics.py:1313-1341), Value,
+ * Absolute, Under, Over (935-1266; NaN unless G == 2), NonParity (860-881), n_distinct_positive_items */
+int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double *out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+size_t fr_fairness_metrics_workspace_bytes(int32_t n_items, int32_t G);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAIRREC_B200_H_ */

@@ -1,0 +1,22 @@
+"""recbole-fairrec_b200: B200-native (sm_100a) hot path of RecBole-FairRec behind the reference's plugin API.
+
+Only what the path needs lives here:
+  csrc/            hand-written CUDA kernels + the C ABI (include/fairrec_b200.h) -> libfairrec_b200.so
+  _lib.py          ctypes binding (fails loudly when the library is missing; no CPU fallback)
+  kernels.py       tensor-level wrappers of the C ABI
+  focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
+  dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
+  evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
+  trainer.py       FOCFTrainer (fit / evaluate)
+  synth.py         synthetic data of the benchmark shapes
+The directory name carries a hyphen; import it as `recbole_fairrec_b200` (shim at the repo root).
+"""
+from . import _lib, kernels  # noqa: F401
+from .config import Config  # noqa: F401
+from .dataloader import FOCFDataLoader, TrainData  # noqa: F401
+from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
+from .focf import FOCF  # noqa: F401
+from .interaction import Interaction  # noqa: F401
+from .trainer import FOCFTrainer  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,144 @@
+"""ctypes binding of libfairrec_b200.so (the C ABI declared in include/fairrec_b200.h).
+
+There is NO CPU fallback: if the shared library is missing the import of the product package fails with
+a build hint, and every wrapper refuses tensors that are not on a CUDA device.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfairrec_b200.so")
+
+FR_OK = 0
+FLAG_TOO_MANY_GROUPS, FLAG_SINGLE_GROUP, FLAG_NAN_LOSS = 1, 2, 4
+OBJECTIVES = {"none": 0, "value": 1, "absolute": 2, "under": 3, "over": 4, "nonparity": 5}
+TRANSFORM_NONE, TRANSFORM_CLAMP_DIV, TRANSFORM_SIGMOID = 0, 1, 2
+SCORE_EXACT_FP32, SCORE_TC_3XTF32 = 0, 1
+
+
+class FairRecLibraryError(RuntimeError):
+    pass
+
+
+class FocfStep(Structure):
+    """mirror of `struct fr_focf_step` (include/fairrec_b200.h)"""
+    _fields_ = [
+        ("U", c_void_p), ("I", c_void_p), ("n_users", c_int32), ("n_items", c_int32), ("d", c_int32),
+        ("uid", c_void_p), ("iid", c_void_p), ("rating", c_void_p), ("sst", c_void_p), ("B", c_int32),
+        ("items_contiguous", c_int32), ("objective", c_int32), ("fair_weight", c_float),
+        ("pred", c_void_p), ("loss", c_void_p), ("status_flags", c_void_p),
+        ("mU", c_void_p), ("vU", c_void_p), ("mI", c_void_p), ("vI", c_void_p),
+        ("step", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+        ("weight_decay", c_float), ("dU", c_void_p), ("dI", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+class FullSort(Structure):
+    """mirror of `struct fr_fullsort`"""
+    _fields_ = [
+        ("U", c_void_p), ("I_shard", c_void_p), ("d", c_int32), ("n_items_local", c_int32), ("item_base", c_int32),
+        ("users", c_void_p), ("n", c_int32), ("hist_off", c_void_p), ("hist_items", c_void_p), ("K", c_int32),
+        ("transform", c_int32), ("max_rating", c_float), ("score_mode", c_int32),
+        ("topk_id", c_void_p), ("topk_score", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+# name -> (restype, argtypes); also the list the ABI-surface test checks against the header
+SIGNATURES = {
+    "fr_abi_version": (c_int, []),
+    "fr_last_error": (c_char_p, []),
+    "fr_launch_count": (c_uint64, []),
+    "fr_profile_enable": (None, [c_int]),
+    "fr_profile_report": (c_int, [c_char_p, c_size_t]),
+    "fr_sort_pairs_workspace_bytes": (c_size_t, [c_int64]),
+    "fr_sort_pairs_u32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "fr_focf_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "fr_focf_workspace_init": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "fr_focf_forward": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_focf_backward": (c_int, [POINTER(FocfStep), c_float, c_void_p]),
+    "fr_focf_adam": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_focf_train_step": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_focf_gather_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "fr_pair_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
+                               c_void_p]),
+    "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
+    "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "fr_hits": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_topk_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "fr_topk_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fr_rec_item_stats": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_gini_workspace_bytes": (c_size_t, [c_int32]),
+    "fr_gini_at_k": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fr_item_group_stats_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "fr_item_group_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "fr_fairness_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "fr_fairness_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises FairRecLibraryError with a build hint when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FairRecLibraryError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (or `make -C recbole-fairrec_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = library/header mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.fr_abi_version() != 1:
+        raise FairRecLibraryError(f"ABI version mismatch: library {lib.fr_abi_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != FR_OK:
+        msg = load().fr_last_error().decode("utf-8", "replace")
+        raise FairRecLibraryError(f"{what} failed with status {rc}: {msg}")
+
+
+def ptr(t):
+    """device pointer of a CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FairRecLibraryError("fairrec_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise FairRecLibraryError("fairrec_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(load().fr_launch_count())
+
+
+def profile_enable(on):
+    load().fr_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """{kernel: (launches, total_ms)} of the launches recorded since profile_enable(True); synchronises"""
+    buf = ctypes.create_string_buffer(1 << 16)
+    load().fr_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(",", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -1,0 +1,711 @@
+// FOCF training step for sm_100a: embedding gather + score, item x group fairness regulariser,
+// deterministic sorted-segment embedding gradients, dense Adam fused with the gradient read-out.
+//
+// Reference being replaced (paths relative to the reference root):
+//   recbole/model/fair_recommender/focf.py:136-143  forward            -> k_forward
+//   focf.py:75-134 get_item_ratings + *_unfairness, 152-169 calculate_loss -> k_segment_loss
+//   autograd backward of the above + nn.Embedding dense backward (trainer.py:193) -> k_segment_grads
+//   torch.optim.Adam(lr, weight_decay) dense step (trainer.py:139,196)  -> k_apply<...>
+//
+// Data layout in HBM: U [n_users,d], I [n_items,d] and the Adam moments are row-major float32; a batch is
+// four SoA columns (uid, iid, rating, sst).  All of this is HBM/L2-bound gather/scatter + streaming work:
+// rows move as 128-bit lane loads (a warp covers 512 contiguous bytes of a row per request), the item x
+// group reduction is a warp-per-segment shuffle reduction, and gradients are reduced in sorted-segment
+// order with a fixed tree, so results are bit-stable run to run (no floating-point atomics anywhere).
+//
+// Algorithmic HBM bytes: per interaction 16*d+16 (gather 2 rows fwd, gather 2 rows bwd,
+// ids/rating/sst); per step 24*(n_users+n_items)*d for the dense Adam sweep (p,m,v read + write) --
+// the dense gradient is never materialised in fr_focf_train_step.
+#include "sort.cuh"
+
+namespace fr {
+
+constexpr int kMaxD = 512;            // embedding_size limit (multiple of 4)
+constexpr int kChunk = 32;            // sorted entries per gradient warp
+
+enum { CTRL_STAMP = 0, CTRL_MIN = 1, CTRL_MAX = 2, CTRL_TICKET = 3, CTRL_SAVED_MIN = 4, CTRL_SAVED_MAX = 5, CTRL_WORDS = 64 };
+
+struct FocfWs {
+  // persistent across steps
+  uint2 *row_tab_u, *row_tab_i;  // [n_users], [n_items]: {stamp, segment} of the last batch touching the row
+  uint32_t *ctrl;                // [CTRL_WORDS]
+  // per batch
+  uint32_t *skey_i, *ord_i, *skey_u, *ord_u;          // [B] sorted keys / entry order
+  int32_t *segid_i, *segoff_i, *J, *segid_u, *segoff_u, *Ju, *entry_seg;
+  float *cseg;      // [B,2] additive dL/dpred term of every (item segment, group)
+  float *seg_hx;    // [B]  smooth_l1(x_j)
+  float *seg_sq;    // [B]  sum (pred-r)^2 of the segment
+  float *seg_gs;    // [B,4] nonparity partials: sum pred g0,g1, count g0,g1
+  float *cglob;     // [2]  batch-global additive term per group (nonparity)
+  float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;  // gradient partials [B,d], [B/32+1,d] x2
+  SortScratch sort;
+  SegScratch seg;
+};
+
+static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
+  FocfWs w;
+  w.row_tab_u = c.take<uint2>(n_users);
+  w.row_tab_i = c.take<uint2>(n_items);
+  w.ctrl = c.take<uint32_t>(CTRL_WORDS);
+  const size_t b = (size_t)(B < 1 ? 1 : B), nch = b / kChunk + 2;
+  w.skey_i = c.take<uint32_t>(b);
+  w.ord_i = c.take<uint32_t>(b);
+  w.skey_u = c.take<uint32_t>(b);
+  w.ord_u = c.take<uint32_t>(b);
+  w.segid_i = c.take<int32_t>(b);
+  w.segoff_i = c.take<int32_t>(b + 1);
+  w.J = c.take<int32_t>(1);
+  w.segid_u = c.take<int32_t>(b);
+  w.segoff_u = c.take<int32_t>(b + 1);
+  w.Ju = c.take<int32_t>(1);
+  w.entry_seg = c.take<int32_t>(b);
+  w.cseg = c.take<float>(2 * b);
+  w.seg_hx = c.take<float>(b);
+  w.seg_sq = c.take<float>(b);
+  w.seg_gs = c.take<float>(4 * b);
+  w.cglob = c.take<float>(2);
+  w.gseg_i = c.take<float>(b * d);
+  w.head_i = c.take<float>(nch * d);
+  w.tail_i = c.take<float>(nch * d);
+  w.gseg_u = c.take<float>(b * d);
+  w.head_u = c.take<float>(nch * d);
+  w.tail_u = c.take<float>(nch * d);
+  w.sort = carve_sort_scratch(c, b);
+  w.seg = carve_seg_scratch(c, b);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+// One warp per entry: lanes cover the row with float4 loads (d floats = d/4 lanes per 128 columns).
+// Also folds the batch min/max of the sensitive attribute (the "rank among present values" of
+// torch.unique, focf.py:77) into two integer atomics.
+__global__ void __launch_bounds__(256)
+    k_forward(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
+              const int32_t *__restrict__ iid, const float *__restrict__ sst, int B, int d, float *__restrict__ pred,
+              uint32_t *__restrict__ ctrl) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int b0 = warp * 4; b0 < B; b0 += nwarps * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int b = b0 + e;
+      if (b < B) {
+        const float4 *pu = (const float4 *)(U + (size_t)uid[b] * d);
+        const float4 *pi = (const float4 *)(I + (size_t)iid[b] * d);
+        for (int k = lane; k * 4 < d; k += 32) {
+          const float4 x = __ldg(pu + k), y = __ldg(pi + k);
+          acc[e] = fmaf(x.x, y.x, acc[e]);
+          acc[e] = fmaf(x.y, y.y, acc[e]);
+          acc[e] = fmaf(x.z, y.z, acc[e]);
+          acc[e] = fmaf(x.w, y.w, acc[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float s = warp_sum(acc[e]);
+      const int b = b0 + e;
+      if (b < B && lane == 0) {
+        pred[b] = s;
+        const uint32_t o = f2ord(sst[b]);
+        lo = min(lo, o);
+        hi = max(hi, o);
+      }
+    }
+  }
+  if (lane == 0 && hi >= lo) {
+    atomicMin(&ctrl[CTRL_MIN], lo);
+    atomicMax(&ctrl[CTRL_MAX], hi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ segment loss
+// One warp per item segment (rows of one item are adjacent in item-sorted order): Sp/St/n per group,
+// D per objective, smooth-L1 of the group gap and the additive backward term of the segment (appendix
+// A.1/A.2 of SURVEY.md).  The last CTA to finish reduces the per-segment partials in a fixed order and
+// writes the loss.
+struct LossArgs {
+  const float *pred, *rating, *sst;
+  const uint32_t *ord_i;
+  const int32_t *segoff_i, *J;
+  int B;
+  int objective;
+  float fair_weight;
+  float *cseg, *seg_hx, *seg_sq, *seg_gs, *cglob, *loss;
+  uint32_t *ctrl;
+  int32_t *flags;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float *sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 8) t = sh[threadIdx.x];
+  if (threadIdx.x < 32) {
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+  }
+  if (threadIdx.x == 0) sh[8] = t;
+  __syncthreads();
+  t = sh[8];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
+  __shared__ float sh[9];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int J = *a.J;
+  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
+  int bad = 0;
+  for (int j = warp; j < J; j += nwarps) {
+    const int p0 = a.segoff_i[j], p1 = a.segoff_i[j + 1];
+    float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) {
+      const int b = a.ord_i ? (int)a.ord_i[p] : p;
+      const float pr = a.pred[b], r = a.rating[b], sv = a.sst[b];
+      const bool g = sv != vmin;
+      bad |= (g && sv != vmax);
+      const float df = pr - r;
+      sq = fmaf(df, df, sq);
+      if (g) {
+        sp1 += pr; st1 += r; c1 += 1.f;
+      } else {
+        sp0 += pr; st0 += r; c0 += 1.f;
+      }
+    }
+    sp0 = warp_sum(sp0); sp1 = warp_sum(sp1); st0 = warp_sum(st0); st1 = warp_sum(st1);
+    c0 = warp_sum(c0); c1 = warp_sum(c1); sq = warp_sum(sq);
+    if (lane == 0) {
+      a.seg_sq[j] = sq;
+      float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
+      if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+        const float n0 = c0 + 1e-5f, n1 = c1 + 1e-5f;                       // focf.py:89
+        const float P0 = sp0 / n0, P1 = sp1 / n1, T0 = st0 / n0, T1 = st1 / n1;  // focf.py:91
+        float D0, D1, dd0, dd1;
+        switch (a.objective) {
+          case FR_OBJ_VALUE:    D0 = P0 - T0; D1 = P1 - T1; dd0 = 1.f; dd1 = 1.f; break;
+          case FR_OBJ_ABSOLUTE: {
+            const float e0 = P0 - T0, e1 = P1 - T1;
+            D0 = fabsf(e0); D1 = fabsf(e1);
+            dd0 = (e0 > 0.f) - (e0 < 0.f); dd1 = (e1 > 0.f) - (e1 < 0.f);
+          } break;
+          case FR_OBJ_UNDER: {
+            const float e0 = T0 - P0, e1 = T1 - P1;
+            D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
+            dd0 = e0 > 0.f ? -1.f : 0.f; dd1 = e1 > 0.f ? -1.f : 0.f;
+          } break;
+          default: {
+            const float e0 = P0 - T0, e1 = P1 - T1;
+            D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
+            dd0 = e0 > 0.f ? 1.f : 0.f; dd1 = e1 > 0.f ? 1.f : 0.f;
+          }
+        }
+        const float z = D0 - D1, x = fabsf(z);
+        hx = x < 1.f ? 0.5f * x * x : x - 0.5f;                              // smooth_l1, beta = 1
+        const float hp = (x < 1.f ? x : 1.f) * (float)((z > 0.f) - (z < 0.f));
+        const float q = a.fair_weight * hp / (float)J;
+        cs0 = q * dd0 / n0;
+        cs1 = -q * dd1 / n1;
+      } else if (a.objective == FR_OBJ_NONPARITY) {
+        a.seg_gs[4 * j + 0] = sp0; a.seg_gs[4 * j + 1] = sp1;
+        a.seg_gs[4 * j + 2] = c0;  a.seg_gs[4 * j + 3] = c1;
+      }
+      a.seg_hx[j] = hx;
+      a.cseg[2 * j] = cs0;
+      a.cseg[2 * j + 1] = cs1;
+    }
+  }
+  // focf.py:81-86: a third attribute value indexes past the [J,2] tensors (IndexError in the reference).
+  // (nonparity in the reference silently keeps the two smallest values, focf.py:129-130; we flag instead.)
+  if (a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
+    atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+
+  // ---- last-CTA reduction (self-resetting ticket)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float sq = 0.f, hx = 0.f, g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
+  for (int j = threadIdx.x; j < J; j += 256) {
+    sq += a.seg_sq[j];
+    hx += a.seg_hx[j];
+    if (a.objective == FR_OBJ_NONPARITY) {
+      g0 += a.seg_gs[4 * j]; g1 += a.seg_gs[4 * j + 1]; n0 += a.seg_gs[4 * j + 2]; n1 += a.seg_gs[4 * j + 3];
+    }
+  }
+  sq = block_sum_256(sq, sh);
+  hx = block_sum_256(hx, sh);
+  if (a.objective == FR_OBJ_NONPARITY) {
+    g0 = block_sum_256(g0, sh); g1 = block_sum_256(g1, sh);
+    n0 = block_sum_256(n0, sh); n1 = block_sum_256(n1, sh);
+  }
+  if (threadIdx.x == 0) {
+    float loss = sq / (float)a.B;                                            // nn.MSELoss 'mean'
+    float cg0 = 0.f, cg1 = 0.f;
+    if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+      loss += a.fair_weight * (hx / (float)J);                               // focf.py:166
+    } else if (a.objective == FR_OBJ_NONPARITY) {
+      if (n1 == 0.f || n0 == 0.f) {
+        atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
+      } else {
+        const float z = g0 / n0 - g1 / n1, x = fabsf(z);                     // focf.py:131-134
+        loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
+        const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
+        cg0 = hp / n0;
+        cg1 = -hp / n1;
+      }
+    }
+    a.cglob[0] = cg0;
+    a.cglob[1] = cg1;
+    a.loss[0] = loss;
+    if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
+    // hand the group values to the backward kernels, re-arm the control block for the next batch
+    a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
+    a.ctrl[CTRL_SAVED_MAX] = a.ctrl[CTRL_MAX];
+    a.ctrl[CTRL_MIN] = 0xffffffffu;
+    a.ctrl[CTRL_MAX] = 0u;
+    a.ctrl[CTRL_TICKET] = 0u;
+    a.ctrl[CTRL_STAMP] += 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ gradients
+// Sorted-segment reduction of dL/dpred_b * other_row(b).  One warp owns 32 consecutive entries of the
+// (item- or user-) sorted order and walks them in order; a row whose segment lies inside the chunk is
+// written complete (gseg), a row continuing from / into a neighbouring chunk leaves a head / tail partial
+// that k_apply adds up in chunk order.  Uniform work per warp regardless of item popularity.
+struct GradArgs {
+  const float *U, *I;
+  const int32_t *uid, *iid;
+  const float *rating, *sst, *pred;
+  int B, d;
+  const uint32_t *ord_i, *ord_u;
+  const int32_t *segid_i, *segoff_i, *segid_u, *segoff_u, *entry_seg;
+  const float *cseg, *cglob;
+  const uint32_t *ctrl;
+  float grad_scale;
+  float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;
+};
+
+template <int kRowVecs>
+__global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
+  const int lane = threadIdx.x & 31;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const bool user_side = c >= nchunk;
+  if (user_side) c -= nchunk;
+  const int pbase = c * kChunk;
+  if (pbase >= a.B) return;
+  const uint32_t *ord = user_side ? a.ord_u : a.ord_i;
+  const int32_t *segid = user_side ? a.segid_u : a.segid_i;
+  const int32_t *segoff = user_side ? a.segoff_u : a.segoff_i;
+  const float *other = user_side ? a.I : a.U;
+  const int32_t *oid = user_side ? a.iid : a.uid;
+  float *gseg = user_side ? a.gseg_u : a.gseg_i;
+  float *head = user_side ? a.head_u : a.head_i;
+  float *tail = user_side ? a.tail_u : a.tail_i;
+  const int d = a.d;
+  const int nvalid = min(kChunk, a.B - pbase);
+  const float vmin = ord2f(a.ctrl[CTRL_SAVED_MIN]);
+
+  // lane l stages entry pbase + l
+  int my_seg = -1, my_oid = 0;
+  float my_coef = 0.f;
+  if (lane < nvalid) {
+    const int p = pbase + lane;
+    const int b = ord ? (int)ord[p] : p;
+    my_seg = segid[p];
+    my_oid = oid[b];
+    const int g = a.sst[b] != vmin;
+    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)a.B + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
+              a.grad_scale;
+  }
+  float4 acc[kRowVecs];
+#pragma unroll
+  for (int v = 0; v < kRowVecs; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = __shfl_sync(0xffffffffu, my_seg, 0);
+
+  auto flush = [&](int s) {
+    const int s0 = segoff[s], s1 = segoff[s + 1];
+    float *dst = (s0 >= pbase && s1 <= pbase + kChunk) ? gseg + (size_t)s * d
+                 : (s0 < pbase)                        ? head + (size_t)c * d
+                                                       : tail + (size_t)c * d;
+#pragma unroll
+    for (int v = 0; v < kRowVecs; ++v) {
+      const int k = lane * 4 + v * 128;
+      if (k < d) {
+        *(float4 *)(dst + k) = acc[v];
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+
+  for (int l0 = 0; l0 < nvalid; l0 += 4) {
+    float4 x[4][kRowVecs];
+    // issue the row loads of 4 entries before consuming them (memory-level parallelism)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int l = l0 + e;
+      const int o = __shfl_sync(0xffffffffu, my_oid, l & 31);
+      const float4 *row = (const float4 *)(other + (size_t)o * d);
+#pragma unroll
+      for (int v = 0; v < kRowVecs; ++v) {
+        const int k = lane * 4 + v * 128;
+        x[e][v] = (l < nvalid && k < d) ? __ldg(row + (k >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int l = l0 + e;
+      const int s = __shfl_sync(0xffffffffu, my_seg, l & 31);
+      const float cf = __shfl_sync(0xffffffffu, my_coef, l & 31);
+      if (l < nvalid) {
+        if (s != cur) {
+          flush(cur);
+          cur = s;
+        }
+#pragma unroll
+        for (int v = 0; v < kRowVecs; ++v) {
+          acc[v].x = fmaf(cf, x[e][v].x, acc[v].x);
+          acc[v].y = fmaf(cf, x[e][v].y, acc[v].y);
+          acc[v].z = fmaf(cf, x[e][v].z, acc[v].z);
+          acc[v].w = fmaf(cf, x[e][v].w, acc[v].w);
+        }
+      }
+    }
+  }
+  flush(cur);
+}
+
+// ------------------------------------------------------------------------------------------ apply
+// One thread per float4 of the concatenated [U ; I] parameter space.  The row's gradient is read from the
+// segment partials when the row was touched by this batch (row_tab stamp), else it is zero; then either
+//   kAdamFused : torch Adam with L2 weight decay, in place (p, m, v)
+//   kDenseOut  : write the dense gradient (compat path: autograd .grad of nn.Embedding)
+//   kAdamDense : Adam from a caller-provided dense gradient
+enum ApplyMode { kAdamFused = 0, kDenseOut = 1, kAdamDense = 2 };
+
+struct ApplyArgs {
+  float *U, *I, *mU, *vU, *mI, *vI, *dU, *dI;
+  int n_users, n_items, d;
+  const uint2 *row_tab_u, *row_tab_i;
+  const int32_t *segoff_u, *segoff_i;
+  const float *gseg_u, *head_u, *tail_u, *gseg_i, *head_i, *tail_i;
+  const uint32_t *ctrl;
+  int step;
+  float lr, beta1, beta2, eps, wd;
+};
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ float adam1(float &p, float &m, float &v, float g, float wd, float w1, float b2, float w2,
+                                       float bc2s, float eps, float neg_step) {
+  g = fmaf(wd, p, g);                       // grad.add(param, alpha=weight_decay)
+  m = fmaf(w1, g - m, m);                   // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(w2 * g, g, v * b2);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = sqrtf(v) / bc2s + eps;
+  p = fmaf(neg_step, m / denom, p);         // param.addcdiv_(exp_avg, denom, value=-step_size)
+  return p;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
+  __shared__ float sc[3];
+  if (kMode != kDenseOut) {
+    if (threadIdx.x == 0) {
+      const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
+      const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+      sc[0] = (float)(-(double)a.lr / bc1);
+      sc[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+  }
+  const float neg_step = sc[0], bc2s = sc[1];
+  const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+  const int dq = a.d >> 2;
+  const size_t nq_u = (size_t)a.n_users * dq, nq = nq_u + (size_t)a.n_items * dq;
+  const uint32_t stamp = a.ctrl[CTRL_STAMP] - 1u;  // k_segment_loss already advanced it
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+    const bool is_item = q >= nq_u;
+    const size_t ql = is_item ? q - nq_u : q;
+    const int row = (int)(ql / dq), k = (int)(ql % dq) * 4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kMode == kAdamDense) {
+      g = *(const float4 *)((is_item ? a.dI : a.dU) + ql * 4);
+    } else {
+      const uint2 t = (is_item ? a.row_tab_i : a.row_tab_u)[row];
+      if (t.x == stamp) {
+        const int32_t *segoff = is_item ? a.segoff_i : a.segoff_u;
+        const float *gseg = is_item ? a.gseg_i : a.gseg_u;
+        const float *head = is_item ? a.head_i : a.head_u;
+        const float *tail = is_item ? a.tail_i : a.tail_u;
+        const int s = (int)t.y, s0 = segoff[s], s1 = segoff[s + 1];
+        const int c0 = s0 / kChunk, c1 = (s1 - 1) / kChunk;
+        if (c0 == c1) {
+          g = *(const float4 *)(gseg + (size_t)s * a.d + k);
+        } else {
+          g = *(const float4 *)(tail + (size_t)c0 * a.d + k);
+          for (int c = c0 + 1; c <= c1; ++c) g = f4_add(g, *(const float4 *)(head + (size_t)c * a.d + k));
+        }
+      }
+    }
+    if (kMode == kDenseOut) {
+      *(float4 *)((is_item ? a.dI : a.dU) + ql * 4) = g;
+    } else {
+      float4 *pp = (float4 *)((is_item ? a.I : a.U) + ql * 4);
+      float4 *pm = (float4 *)((is_item ? a.mI : a.mU) + ql * 4);
+      float4 *pv = (float4 *)((is_item ? a.vI : a.vU) + ql * 4);
+      float4 p = *pp, m = ldg_stream(pm), v = ldg_stream(pv);
+      adam1(p.x, m.x, v.x, g.x, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
+      adam1(p.y, m.y, v.y, g.y, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
+      adam1(p.z, m.z, v.z, g.z, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
+      adam1(p.w, m.w, v.w, g.w, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
+      *pp = p;
+      stg_stream(pm, m);
+      stg_stream(pv, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pair scores
+// focf.py:145-150 predict / collector.py:179 rec.positive_score: k-ascending fmaf chain per pair, the
+// exact arithmetic of the scorer (bit-identical to oracle/c/fairrec_oracle.c).
+__device__ __forceinline__ float apply_transform(float x, int transform, float max_rating) {
+  if (transform == FR_TRANSFORM_CLAMP_DIV) {
+    x = fminf(fmaxf(x, 0.f), max_rating);
+    return __fdiv_rn(x, max_rating);
+  }
+  if (transform == FR_TRANSFORM_SIGMOID) return 1.f / (1.f + expf(-x));
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+    k_pair_scores(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
+                  const int32_t *__restrict__ iid, int64_t n, int d, int transform, float max_rating,
+                  float *__restrict__ out) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const float4 *pu = (const float4 *)(U + (size_t)uid[b] * d);
+    const float4 *pi = (const float4 *)(I + (size_t)iid[b] * d);
+    float acc = 0.f;
+    for (int k = 0; k < (d >> 2); ++k) {
+      const float4 x = __ldg(pu + k), y = __ldg(pi + k);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+      acc = fmaf(x.z, y.z, acc);
+      acc = fmaf(x.w, y.w, acc);
+    }
+    out[b] = apply_transform(acc, transform, max_rating);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ batch gather
+// focf_dataloader.py:37-50 + dataset.py __getitem__/join: a FOCF batch is the concatenation of ALL train rows
+// of the drawn items.  The train split lives on the device sorted by item (CSC: item_off); one warp copies
+// one drawn item's segment (coalesced) and joins the user's sensitive attribute.
+__global__ void __launch_bounds__(256)
+    k_gather_batch(const int32_t *__restrict__ item_off, const int32_t *__restrict__ train_uid,
+                   const float *__restrict__ train_rating, const float *__restrict__ sst_of_user,
+                   const int32_t *__restrict__ draw_items, const int32_t *__restrict__ draw_off, int J,
+                   int32_t *__restrict__ uid, int32_t *__restrict__ iid, float *__restrict__ rating,
+                   float *__restrict__ sst) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int j = warp; j < J; j += nwarps) {
+    const int it = draw_items[j], src = item_off[it], dst = draw_off[j], len = draw_off[j + 1] - dst;
+    for (int p = lane; p < len; p += 32) {
+      const int u = train_uid[src + p];
+      uid[dst + p] = u;
+      iid[dst + p] = it;
+      rating[dst + p] = train_rating[src + p];
+      sst[dst + p] = sst_of_user[u];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int check_step(const fr_focf_step *s, bool need_adam, const char *who) {
+  FR_REQUIRE(s, "%s: null step", who);
+  FR_REQUIRE(s->U && s->I && s->uid && s->iid && s->rating && s->sst && s->pred && s->loss && s->status_flags &&
+                 s->workspace,
+             "%s: null pointer in fr_focf_step", who);
+  FR_REQUIRE(s->d >= 4 && s->d % 4 == 0 && s->d <= kMaxD, "%s: embedding size %d must be a multiple of 4 in [4,%d]",
+             who, s->d, kMaxD);
+  FR_REQUIRE(s->B >= 1 && s->n_users >= 1 && s->n_items >= 1, "%s: empty batch or table", who);
+  FR_REQUIRE(s->objective >= FR_OBJ_NONE && s->objective <= FR_OBJ_NONPARITY, "%s: bad objective %d", who,
+             s->objective);
+  if (need_adam) {
+    FR_REQUIRE(s->mU && s->vU && s->mI && s->vI && s->step >= 1, "%s: Adam state missing", who);
+  }
+  return FR_OK;
+}
+
+static int carve_checked(const fr_focf_step *s, FocfWs *w, const char *who) {
+  Carver c(s->workspace, s->workspace_bytes);
+  *w = carve(c, s->n_users, s->n_items, s->d, s->B);
+  if (!c.ok()) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, s->workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  return FR_OK;
+}
+
+static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st) {
+  const int B = s->B;
+  // item side: segments of equal item id (sorted first unless the loader guarantees adjacency)
+  const uint32_t *skey_i = (const uint32_t *)s->iid, *ord_i = nullptr;
+  if (!s->items_contiguous) {
+    sort_pairs((const uint32_t *)s->iid, nullptr, w.skey_i, w.ord_i, B, nullptr, bits_for((uint32_t)s->n_items), w.sort,
+               st);
+    skey_i = w.skey_i;
+    ord_i = w.ord_i;
+  }
+  build_segments(skey_i, ord_i, B, nullptr, w.segid_i, w.segoff_i, w.J, w.row_tab_i, w.ctrl + CTRL_STAMP, w.entry_seg,
+                 w.seg, st);
+  // user side: always sorted (stable => batch order inside a user's segment, like index_add on CPU)
+  sort_pairs((const uint32_t *)s->uid, nullptr, w.skey_u, w.ord_u, B, nullptr, bits_for((uint32_t)s->n_users), w.sort,
+             st);
+  build_segments(w.skey_u, w.ord_u, B, nullptr, w.segid_u, w.segoff_u, w.Ju, w.row_tab_u, w.ctrl + CTRL_STAMP, nullptr,
+                 w.seg, st);
+  FR_LAUNCH(k_forward, grid_for((int64_t)B, 32), 256, 0, st, s->U, s->I, s->uid, s->iid, s->sst, B, s->d, s->pred,
+            w.ctrl);
+  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segoff_i, w.J, B, s->objective, s->fair_weight,
+              w.cseg, w.seg_hx, w.seg_sq, w.seg_gs, w.cglob, s->loss, w.ctrl, s->status_flags};
+  FR_LAUNCH(k_segment_loss, grid_for((int64_t)B, 8 * 16, kSMs * 2), 256, 0, st, la);
+  return FR_OK;
+}
+
+static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale, cudaStream_t st) {
+  const uint32_t *ord_i = s->items_contiguous ? nullptr : w.ord_i;
+  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, ord_i, w.ord_u,
+              w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
+              w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
+  const int nchunk = (s->B + kChunk - 1) / kChunk;
+  const int grid = (2 * nchunk + 7) / 8;
+  if (s->d <= 128) {
+    FR_LAUNCH(k_segment_grads<1>, grid, 256, 0, st, ga, nchunk);
+  } else if (s->d <= 256) {
+    FR_LAUNCH(k_segment_grads<2>, grid, 256, 0, st, ga, nchunk);
+  } else {
+    FR_LAUNCH(k_segment_grads<4>, grid, 256, 0, st, ga, nchunk);
+  }
+}
+
+static ApplyArgs apply_args(const fr_focf_step *s, const FocfWs &w) {
+  return ApplyArgs{s->U, s->I, s->mU, s->vU, s->mI, s->vI, s->dU, s->dI, s->n_users, s->n_items, s->d,
+                   w.row_tab_u, w.row_tab_i, w.segoff_u, w.segoff_i, w.gseg_u, w.head_u, w.tail_u,
+                   w.gseg_i, w.head_i, w.tail_i, w.ctrl, s->step, s->lr, s->beta1, s->beta2, s->eps, s->weight_decay};
+}
+
+static int apply_grid(const fr_focf_step *s) {
+  const int64_t nq = ((int64_t)s->n_users + s->n_items) * (s->d / 4);
+  return grid_for(nq, 256 * 4, kSMs * 8);
+}
+
+}  // namespace fr
+
+extern "C" {
+
+size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch) {
+  fr::Carver c(nullptr, 0);
+  fr::carve(c, n_users, n_items, d, max_batch);
+  return c.off;
+}
+
+int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
+                           int32_t max_batch, void *stream) {
+  FR_REQUIRE(workspace, "fr_focf_workspace_init: null workspace");
+  fr::Carver c(workspace, workspace_bytes);
+  fr::FocfWs w = fr::carve(c, n_users, n_items, d, max_batch);
+  if (!c.ok()) {
+    fr::set_error("fr_focf_workspace_init: workspace too small (%zu < %zu bytes)", workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FR_CUDA_OK(cudaMemsetAsync(w.row_tab_u, 0, sizeof(uint2) * (size_t)n_users, st));
+  FR_CUDA_OK(cudaMemsetAsync(w.row_tab_i, 0, sizeof(uint2) * (size_t)n_items, st));
+  uint32_t ctrl[fr::CTRL_WORDS] = {0};
+  ctrl[fr::CTRL_STAMP] = 1u;
+  ctrl[fr::CTRL_MIN] = 0xffffffffu;
+  FR_CUDA_OK(cudaMemcpyAsync(w.ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, st));
+  FR_CUDA_OK(cudaStreamSynchronize(st));  // ctrl[] is a stack buffer
+  return FR_OK;
+}
+
+int fr_focf_forward(const fr_focf_step *s, void *stream) {
+  int rc = fr::check_step(s, false, "fr_focf_forward");
+  if (rc) return rc;
+  fr::FocfWs w;
+  if ((rc = fr::carve_checked(s, &w, "fr_focf_forward"))) return rc;
+  fr::forward_impl(s, w, (cudaStream_t)stream);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream) {
+  int rc = fr::check_step(s, false, "fr_focf_backward");
+  if (rc) return rc;
+  FR_REQUIRE(s->dU && s->dI, "fr_focf_backward: dU/dI missing");
+  fr::FocfWs w;
+  if ((rc = fr::carve_checked(s, &w, "fr_focf_backward"))) return rc;
+  fr::grads_impl(s, w, grad_scale, (cudaStream_t)stream);
+  FR_LAUNCH(fr::k_apply<fr::kDenseOut>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_adam(const fr_focf_step *s, void *stream) {
+  FR_REQUIRE(s && s->U && s->I && s->mU && s->vU && s->mI && s->vI && s->dU && s->dI && s->workspace,
+             "fr_focf_adam: null pointer");
+  FR_REQUIRE(s->d >= 4 && s->d % 4 == 0 && s->step >= 1, "fr_focf_adam: bad d/step");
+  fr::Carver c(s->workspace, s->workspace_bytes);
+  fr::FocfWs w = fr::carve(c, s->n_users, s->n_items, s->d, 1);
+  FR_LAUNCH(fr::k_apply<fr::kAdamDense>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_train_step(const fr_focf_step *s, void *stream) {
+  int rc = fr::check_step(s, true, "fr_focf_train_step");
+  if (rc) return rc;
+  fr::FocfWs w;
+  if ((rc = fr::carve_checked(s, &w, "fr_focf_train_step"))) return rc;
+  fr::forward_impl(s, w, (cudaStream_t)stream);
+  fr::grads_impl(s, w, 1.0f, (cudaStream_t)stream);
+  FR_LAUNCH(fr::k_apply<fr::kAdamFused>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_pair_scores(const float *U, const float *I, const int32_t *uid, const int32_t *iid, int64_t n, int32_t d,
+                   int32_t transform, float max_rating, float *out, void *stream) {
+  if (n == 0) return FR_OK;
+  FR_REQUIRE(U && I && uid && iid && out && n > 0, "fr_pair_scores: null pointer");
+  FR_REQUIRE(d >= 4 && d % 4 == 0, "fr_pair_scores: d=%d must be a multiple of 4", d);
+  FR_LAUNCH(fr::k_pair_scores, fr::grid_for(n, 256), 256, 0, stream, U, I, uid, iid, n, d, transform, max_rating,
+            out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_gather_batch(const int32_t *item_off, const int32_t *train_uid, const float *train_rating,
+                         const float *sst_of_user, const int32_t *draw_items, const int32_t *draw_off, int32_t J,
+                         int32_t *uid, int32_t *iid, float *rating, float *sst, void *stream) {
+  FR_REQUIRE(item_off && train_uid && train_rating && sst_of_user && draw_items && draw_off && uid && iid && rating &&
+                 sst && J >= 1,
+             "fr_focf_gather_batch: bad argument");
+  FR_LAUNCH(fr::k_gather_batch, fr::grid_for(J, 8, fr::kSMs * 4), 256, 0, stream, item_off, train_uid, train_rating,
+            sst_of_user, draw_items, draw_off, J, uid, iid, rating, sst);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+// Metric accumulation on the device (sm_100a) for the 12 metrics of properties/model/FOCF.yaml:29-30.
+//
+// Reference being replaced (recbole/evaluator/metrics.py unless noted; numpy + Python loops, float64):
+//   Hit 63-65, MRR 89-97, Recall 160-161, NDCG 187-203, base_metric.py:59-82 (mean over users)
+//   GiniIndex 644-661, PopularityPercentage 772-820
+//   NonParity 860-881, Value/Absolute/Under/Over 935-1266 (full mode), DifferentialFairness 1313-1341
+//
+// Everything is either integer work (histograms, sorted counts: exact) or float64 sums reduced in a fixed
+// order (per-CTA partials -> one CTA), so results are bit-stable run to run.  HBM-bound streaming passes.
+#include "sort.cuh"
+
+namespace fr {
+
+constexpr int kMaxGroups = 64;
+
+__device__ __forceinline__ double block_sum_d(double v, double *sh) {  // 256 threads
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    sh[8] = t;
+  }
+  __syncthreads();
+  t = sh[8];
+  __syncthreads();
+  return t;
+}
+
+// ---------------------------------------------------------------- NDCG / Recall / Hit / MRR
+// rec_topk [n, K+1] = [hit bits | pos_len].  part[blk][4][K] per-CTA sums, then k_reduce_rows.
+__global__ void __launch_bounds__(256)
+    k_topk_metrics(const int32_t *__restrict__ rec_topk, int n, int K, double *__restrict__ part) {
+  __shared__ double sh[9];
+  __shared__ double disc[kMaxGroups];   // 1/log2(r+1), r = 1..K   (K <= 64)
+  __shared__ double idcg[kMaxGroups];   // cumulative
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int r = 1; r <= K; ++r) {
+      disc[r - 1] = 1.0 / log2((double)r + 1.0);
+      run += disc[r - 1];
+      idcg[r - 1] = run;
+    }
+  }
+  __syncthreads();
+  const int u = blockIdx.x * 256 + threadIdx.x;
+  const bool ok = u < n;
+  const int32_t *row = rec_topk + (size_t)(ok ? u : 0) * (K + 1);
+  const int pos_len = ok ? row[K] : 1;
+  int cum = 0, first = -1;
+  double dcg = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const int h = ok ? (row[k] != 0) : 0;
+    cum += h;
+    if (h && first < 0) first = k;
+    if (h) dcg += disc[k];
+    const int il = min(pos_len, k + 1);                               // metrics.py:188-196
+    const double v_ndcg = ok ? dcg / idcg[il - 1] : 0.0;
+    const double v_rec = ok ? (double)cum / (double)pos_len : 0.0;    // metrics.py:161
+    const double v_hit = (ok && cum > 0) ? 1.0 : 0.0;                  // metrics.py:64-65
+    const double v_mrr = (ok && first >= 0) ? 1.0 / (double)(first + 1) : 0.0;  // metrics.py:91-96
+    const double s0 = block_sum_d(v_ndcg, sh), s1 = block_sum_d(v_rec, sh), s2 = block_sum_d(v_hit, sh),
+                 s3 = block_sum_d(v_mrr, sh);
+    if (threadIdx.x == 0) {
+      double *o = part + (size_t)blockIdx.x * 4 * K;
+      o[0 * K + k] = s0; o[1 * K + k] = s1; o[2 * K + k] = s2; o[3 * K + k] = s3;
+    }
+  }
+}
+
+// out[v] = sum_{blk} part[blk][v] in block order (one thread per v)
+__global__ void k_reduce_rows(const double *__restrict__ part, int nblk, int V, double *__restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * V + v];
+  out[v] = s;
+}
+
+// ---------------------------------------------------------------- recommendation histograms
+// item_pos_count[e][item] += 1 for the item at rank e ; pop_hits[e] += is_popular[item]
+__global__ void __launch_bounds__(256)
+    k_rec_item_stats(const int32_t *__restrict__ topk_id, int n, int K, int n_items,
+                     const uint8_t *__restrict__ is_popular, int32_t *__restrict__ item_pos_count,
+                     unsigned long long *__restrict__ pop_hits) {
+  const int64_t tot = (int64_t)n * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % K);
+    const int id = topk_id[i];
+    if (id < 0 || id >= n_items) continue;  // sentinel of an under-full list
+    atomicAdd(&item_pos_count[(size_t)e * n_items + id], 1);
+    if (is_popular && is_popular[id]) atomicAdd(&pop_hits[e], 1ull);
+  }
+}
+
+__global__ void k_sum_count_rows(const int32_t *__restrict__ item_pos_count, int n_items, int k_rows,
+                                 uint32_t *__restrict__ keys, unsigned long long *__restrict__ acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) acc[0] = 0ull;
+  if (i >= n_items) return;
+  uint32_t c = 0;
+  for (int r = 0; r < k_rows; ++r) c += (uint32_t)item_pos_count[(size_t)r * n_items + i];
+  keys[i] = c;
+}
+
+// metrics.py:656-660: sum_p (2p - Ni - 1) * c_(p) over the ascending counts (zeros contribute nothing, and
+// the non-zero counts occupy exactly the positions Ni-m+1..Ni the reference assigns them)
+__global__ void __launch_bounds__(256) k_gini_sum(const uint32_t *__restrict__ sorted, int n_items, long long *acc) {
+  long long s = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x)
+    s += (2ll * (i + 1) - n_items - 1) * (long long)sorted[i];
+  // integer atomics: associative, so the result does not depend on arrival order
+  if (s != 0) atomicAdd((unsigned long long *)acc, (unsigned long long)s);
+}
+__global__ void k_gini_final(const long long *acc, long long total_recs, int n_items, double *out) {
+  out[0] = (double)acc[0] / (double)total_recs / (double)n_items;
+}
+
+// ---------------------------------------------------------------- item x group statistics of the positives
+// After a stable sort of the positives by item id, one warp per item segment accumulates (sum score, count)
+// per group in float64, lanes striding the segment and a fixed shuffle tree at the end.
+__global__ void __launch_bounds__(256)
+    k_item_group_stats(const uint32_t *__restrict__ sorted_items, const uint32_t *__restrict__ ord,
+                       const int32_t *__restrict__ seg_off, const int32_t *__restrict__ nseg,
+                       const float *__restrict__ score, const int32_t *__restrict__ group, int G,
+                       double *__restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int S = *nseg;
+  for (int s = warp; s < S; s += nwarps) {
+    const int p0 = seg_off[s], p1 = seg_off[s + 1];
+    const uint32_t item = sorted_items[p0];
+    for (int g = 0; g < G; ++g) {
+      double sum = 0.0, cnt = 0.0;
+      for (int p = p0 + lane; p < p1; p += 32) {
+        const uint32_t e = ord[p];
+        if (group[e] == g) {
+          sum += (double)score[e];
+          cnt += 1.0;
+        }
+      }
+      sum = warp_sum(sum);
+      cnt = warp_sum(cnt);
+      if (lane == 0) {
+        stats[((size_t)item * G + g) * 2 + 0] = sum;
+        stats[((size_t)item * G + g) * 2 + 1] = cnt;
+      }
+    }
+  }
+}
+
+// pass A: per-CTA partials [1 + 2G]: J (items with any positive), S_g, C_g
+__global__ void __launch_bounds__(256) k_fair_pass_a(const double *__restrict__ stats, int n_items, int G,
+                                                     double *__restrict__ part) {
+  __shared__ double sh[9];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double any = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const double s = i < n_items ? stats[((size_t)i * G + g) * 2] : 0.0;
+    const double c = i < n_items ? stats[((size_t)i * G + g) * 2 + 1] : 0.0;
+    if (c > 0.0) any = 1.0;
+    const double ss = block_sum_d(s, sh), cc = block_sum_d(c, sh);
+    if (threadIdx.x == 0) {
+      part[(size_t)blockIdx.x * (1 + 2 * G) + 1 + g] = ss;
+      part[(size_t)blockIdx.x * (1 + 2 * G) + 1 + G + g] = cc;
+    }
+  }
+  const double j = block_sum_d(any, sh);
+  if (threadIdx.x == 0) part[(size_t)blockIdx.x * (1 + 2 * G)] = j;
+}
+
+// single thread: totals -> out[5] NonParity (metrics.py:872-881), out[6] = J ; glob[0] = J
+__global__ void k_fair_mid(const double *__restrict__ tot, int G, double *__restrict__ out) {
+  const double J = tot[0];
+  out[6] = J;
+  double mean[kMaxGroups];
+  int ng = 0;
+  for (int g = 0; g < G; ++g)
+    if (tot[1 + G + g] > 0.0) mean[ng++] = tot[1 + g] / tot[1 + G + g];
+  double np = nan("");
+  if (ng == 2) {
+    np = fabs(mean[0] - mean[1]);
+  } else if (ng > 2) {
+    double mu = 0.0, var = 0.0;
+    for (int g = 0; g < ng; ++g) mu += mean[g];
+    mu /= ng;
+    for (int g = 0; g < ng; ++g) var += (mean[g] - mu) * (mean[g] - mu);
+    np = sqrt(var / ng);
+  }
+  out[5] = np;
+}
+
+// pass B: per-CTA partials [5]: sum eps_j (DifferentialFairness), sum |D0-D1| for value/absolute/under/over
+__global__ void __launch_bounds__(256) k_fair_pass_b(const double *__restrict__ stats, int n_items, int G,
+                                                     const double *__restrict__ Jp, double *__restrict__ part) {
+  __shared__ double sh[9];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const double J = Jp[0];
+  double eps = 0.0, vv = 0.0, va = 0.0, vu = 0.0, vo = 0.0;
+  bool any = false;
+  if (i < n_items) {
+    for (int g = 0; g < G; ++g) any |= stats[((size_t)i * G + g) * 2 + 1] > 0.0;
+  }
+  if (any) {
+    // metrics.py:1329-1339: M = (sum + 1/J) / (cnt + 1) stored as float32, eps = max_{g<g'} |ln M_g - ln M_g'|
+    const double alpha = 1.0 / J;
+    float lmin = INFINITY, lmax = -INFINITY;
+    for (int g = 0; g < G; ++g) {
+      const double s = stats[((size_t)i * G + g) * 2], c = stats[((size_t)i * G + g) * 2 + 1];
+      const float M = (float)((s + alpha) / (c + 1.0));
+      const float l = (float)log((double)M);
+      lmin = fminf(lmin, l);
+      lmax = fmaxf(lmax, l);
+    }
+    eps = (double)(lmax - lmin);
+    if (G == 2) {  // metrics.py:965-978 and the three siblings
+      const double s0 = stats[((size_t)i * 2 + 0) * 2], c0 = stats[((size_t)i * 2 + 0) * 2 + 1];
+      const double s1 = stats[((size_t)i * 2 + 1) * 2], c1 = stats[((size_t)i * 2 + 1) * 2 + 1];
+      const double n0 = c0 + 1e-5, n1 = c1 + 1e-5;
+      const double P0 = s0 / n0, P1 = s1 / n1, T0 = c0 / n0, T1 = c1 / n1;
+      vv = fabs((P0 - T0) - (P1 - T1));
+      va = fabs(fabs(P0 - T0) - fabs(P1 - T1));
+      vu = fabs(fmax(T0 - P0, 0.0) - fmax(T1 - P1, 0.0));
+      vo = fabs(fmax(P0 - T0, 0.0) - fmax(P1 - T1, 0.0));
+    }
+  }
+  const double r0 = block_sum_d(eps, sh), r1 = block_sum_d(vv, sh), r2 = block_sum_d(va, sh), r3 = block_sum_d(vu, sh),
+               r4 = block_sum_d(vo, sh);
+  if (threadIdx.x == 0) {
+    double *o = part + (size_t)blockIdx.x * 5;
+    o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
+  }
+}
+
+__global__ void k_fair_final(const double *__restrict__ tot, int G, double *__restrict__ out) {
+  const double J = out[6];
+  out[0] = tot[0] / J;
+  for (int m = 0; m < 4; ++m) out[1 + m] = (G == 2) ? tot[1 + m] / J : nan("");
+}
+
+}  // namespace fr
+
+extern "C" {
+
+size_t fr_topk_metrics_workspace_bytes(int32_t n, int32_t K) { return (size_t)((n + 255) / 256) * 4 * K * 8 + 256; }
+
+int fr_topk_metrics(const int32_t *rec_topk, int32_t n, int32_t K, double *sums_out, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(rec_topk && sums_out && workspace && n >= 1, "fr_topk_metrics: bad argument");
+  FR_REQUIRE(K >= 1 && K <= fr::kMaxGroups, "fr_topk_metrics: K=%d out of range", K);
+  const int nblk = (n + 255) / 256;
+  if (workspace_bytes < fr_topk_metrics_workspace_bytes(n, K)) {
+    fr::set_error("fr_topk_metrics: workspace too small");
+    return FR_ERR_WORKSPACE;
+  }
+  FR_LAUNCH(fr::k_topk_metrics, nblk, 256, 0, stream, rec_topk, n, K, (double *)workspace);
+  FR_LAUNCH(fr::k_reduce_rows, (4 * K + 127) / 128, 128, 0, stream, (const double *)workspace, nblk, 4 * K, sums_out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_rec_item_stats(const int32_t *topk_id, int32_t n, int32_t K, int32_t n_items, const uint8_t *is_popular,
+                      int32_t *item_count_out, int64_t *pop_hits_out, void *stream) {
+  FR_REQUIRE(topk_id && item_count_out && pop_hits_out && n >= 1 && K >= 1 && n_items >= 1,
+             "fr_rec_item_stats: bad argument");
+  FR_CUDA_OK(cudaMemsetAsync(item_count_out, 0, sizeof(int32_t) * (size_t)K * n_items, (cudaStream_t)stream));
+  FR_CUDA_OK(cudaMemsetAsync(pop_hits_out, 0, sizeof(int64_t) * (size_t)K, (cudaStream_t)stream));
+  FR_LAUNCH(fr::k_rec_item_stats, fr::grid_for((int64_t)n * K, 256), 256, 0, stream, topk_id, n, K, n_items,
+            is_popular, item_count_out, (unsigned long long *)pop_hits_out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_gini_workspace_bytes(int32_t n_items) {
+  fr::Carver c(nullptr, 0);
+  c.take<uint32_t>(n_items);  // keys
+  c.take<uint32_t>(n_items);  // sorted keys
+  c.take<uint32_t>(n_items);  // sorted vals (unused)
+  c.take<long long>(1);
+  fr::carve_sort_scratch(c, n_items);
+  return c.off;
+}
+
+int fr_gini_at_k(const int32_t *item_pos_count, int32_t n_items, int32_t k_rows, int64_t n_users, double *gini_out,
+                 void *workspace, size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(item_pos_count && gini_out && workspace && n_items >= 1 && k_rows >= 1 && n_users >= 1,
+             "fr_gini_at_k: bad argument");
+  fr::Carver c(workspace, workspace_bytes);
+  uint32_t *keys = c.take<uint32_t>(n_items);
+  uint32_t *skeys = c.take<uint32_t>(n_items);
+  uint32_t *svals = c.take<uint32_t>(n_items);
+  long long *acc = c.take<long long>(1);
+  fr::SortScratch ss = fr::carve_sort_scratch(c, n_items);
+  if (!c.ok()) {
+    fr::set_error("fr_gini_at_k: workspace too small (%zu < %zu)", workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FR_LAUNCH(fr::k_sum_count_rows, (n_items + 255) / 256, 256, 0, st, item_pos_count, n_items, k_rows, keys,
+            (unsigned long long *)acc);
+  const uint64_t maxc = (uint64_t)n_users + 1;
+  fr::sort_pairs(keys, nullptr, skeys, svals, n_items, nullptr, fr::bits_for((uint32_t)(maxc > 0xffffffffull ? 0xffffffffu : maxc)),
+                 ss, st);
+  FR_LAUNCH(fr::k_gini_sum, fr::grid_for(n_items, 256, fr::kSMs * 4), 256, 0, st, skeys, n_items, acc);
+  FR_LAUNCH(fr::k_gini_final, 1, 1, 0, st, acc, (long long)(n_users * k_rows), n_items, gini_out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_item_group_stats_workspace_bytes(int64_t n_pos, int32_t n_items, int32_t G) {
+  (void)n_items; (void)G;
+  fr::Carver c(nullptr, 0);
+  c.take<uint32_t>(n_pos);
+  c.take<uint32_t>(n_pos);
+  c.take<int32_t>(n_pos);
+  c.take<int32_t>(n_pos + 1);
+  c.take<int32_t>(1);
+  fr::carve_sort_scratch(c, n_pos);
+  fr::carve_seg_scratch(c, n_pos);
+  return c.off;
+}
+
+int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const int32_t *group, int64_t n_pos,
+                        int32_t n_items, int32_t G, double *stats_out, void *workspace, size_t workspace_bytes,
+                        void *stream) {
+  FR_REQUIRE(pos_items && pos_score && group && stats_out && workspace, "fr_item_group_stats: null pointer");
+  FR_REQUIRE(n_pos >= 1 && n_pos < (1ll << 31) && n_items >= 1 && G >= 1 && G <= fr::kMaxGroups,
+             "fr_item_group_stats: bad sizes n_pos=%lld G=%d", (long long)n_pos, G);
+  fr::Carver c(workspace, workspace_bytes);
+  uint32_t *skey = c.take<uint32_t>(n_pos);
+  uint32_t *ord = c.take<uint32_t>(n_pos);
+  int32_t *segid = c.take<int32_t>(n_pos);
+  int32_t *segoff = c.take<int32_t>(n_pos + 1);
+  int32_t *nseg = c.take<int32_t>(1);
+  fr::SortScratch ss = fr::carve_sort_scratch(c, n_pos);
+  fr::SegScratch sg = fr::carve_seg_scratch(c, n_pos);
+  if (!c.ok()) {
+    fr::set_error("fr_item_group_stats: workspace too small (%zu < %zu)", workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FR_CUDA_OK(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)n_items * G, st));
+  fr::sort_pairs((const uint32_t *)pos_items, nullptr, skey, ord, n_pos, nullptr, fr::bits_for((uint32_t)n_items), ss, st);
+  fr::build_segments(skey, ord, n_pos, nullptr, segid, segoff, nseg, nullptr, nullptr, nullptr, sg, st);
+  FR_LAUNCH(fr::k_item_group_stats, fr::grid_for(n_pos, 256, fr::kSMs * 8), 256, 0, st, skey, ord, segoff, nseg,
+            pos_score, group, G, stats_out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_fairness_metrics_workspace_bytes(int32_t n_items, int32_t G) {
+  const size_t nblk = (size_t)(n_items + 255) / 256;
+  return (nblk * (1 + 2 * (size_t)G) + nblk * 5 + (1 + 2 * (size_t)G) + 8) * 8 + 512;
+}
+
+int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double *out, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(stats && out && workspace && n_items >= 1 && G >= 1 && G <= fr::kMaxGroups,
+             "fr_fairness_metrics: bad argument");
+  if (workspace_bytes < fr_fairness_metrics_workspace_bytes(n_items, G)) {
+    fr::set_error("fr_fairness_metrics: workspace too small");
+    return FR_ERR_WORKSPACE;
+  }
+  const int nblk = (n_items + 255) / 256, VA = 1 + 2 * G;
+  fr::Carver c(workspace, workspace_bytes);
+  double *partA = c.take<double>((size_t)nblk * VA);
+  double *partB = c.take<double>((size_t)nblk * 5);
+  double *totA = c.take<double>(VA);
+  double *totB = c.take<double>(8);
+  FR_LAUNCH(fr::k_fair_pass_a, nblk, 256, 0, stream, stats, n_items, G, partA);
+  FR_LAUNCH(fr::k_reduce_rows, (VA + 127) / 128, 128, 0, stream, (const double *)partA, nblk, VA, totA);
+  FR_LAUNCH(fr::k_fair_mid, 1, 1, 0, stream, (const double *)totA, G, out);
+  FR_LAUNCH(fr::k_fair_pass_b, nblk, 256, 0, stream, stats, n_items, G, (const double *)totA, partB);
+  FR_LAUNCH(fr::k_reduce_rows, 1, 128, 0, stream, (const double *)partB, nblk, 5, totB);
+  FR_LAUNCH(fr::k_fair_final, 1, 1, 0, stream, (const double *)totB, G, out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+}  // extern "C"

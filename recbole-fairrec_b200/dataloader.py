@@ -1,0 +1,143 @@
+"""Device-side FOCF batch builder -- replaces FOCFDataLoader (recbole/data/dataloader/focf_dataloader.py:5-50)
+and the per-batch `Dataset.__getitem__` join (84 % of the reference's train epoch).
+
+The train split is sorted by item once (stable, like focf_dataloader.py:12 `dataset.sort(by=ITEM_ID)`) and kept
+on the device in CSC form; a batch is "all train rows of randomly drawn items until >= train_batch_size rows"
+(focf_dataloader.py:37-50).  The item draws of a whole epoch are made on the host in one go and uploaded with ONE
+copy; each batch is then materialised by the `fr_focf_gather_batch` kernel.
+
+Draw modes:
+  * "reference" -- calls `np.random.choice(candidates, 1, False)` exactly like focf_dataloader.py:43, so with the
+    same numpy global seed the batches are IDENTICAL to the reference's (parity tests; O(n_items) per draw).
+  * "fast"      -- one permutation of the candidate items per batch from a private Generator (same distribution:
+    uniform without replacement inside a batch, fresh for every batch).
+  * explicit `draws` (array, -1 terminates a batch) -- replay of recorded draws (golden fixtures).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, load, ptr, stream_ptr
+from .interaction import Interaction
+
+
+class TrainData:
+    """Item-sorted, device-resident train split + what the trainer needs from `train_data.dataset`."""
+
+    def __init__(self, uid, iid, rating, sst_of_user, n_users, n_items, device, uid_field="user_id",
+                 iid_field="item_id", rating_field="rating", sst_field="gender"):
+        uid, iid = np.asarray(uid), np.asarray(iid)
+        order = np.argsort(iid, kind="stable")                      # interaction.py:334
+        self.uid_h = np.ascontiguousarray(uid[order], dtype=np.int32)
+        self.iid_h = np.ascontiguousarray(iid[order], dtype=np.int32)
+        self.rating_h = np.ascontiguousarray(np.asarray(rating)[order], dtype=np.float32)
+        self.n_users, self.n_items, self.device = int(n_users), int(n_items), device
+        self.n_rows = len(self.uid_h)
+        self.item_count_h = np.bincount(self.iid_h, minlength=self.n_items).astype(np.int64)
+        self.item_off_h = np.zeros(self.n_items + 1, np.int32)
+        self.item_off_h[1:] = np.cumsum(self.item_count_h)
+        self.item_uniques = np.nonzero(self.item_count_h)[0]        # focf_dataloader.py:14
+        self.fields = (uid_field, iid_field, rating_field, sst_field)
+        self.max_rating = float(self.rating_h.max())
+        t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(device)
+        self.item_off = t(self.item_off_h, torch.int32)
+        self.train_uid = t(self.uid_h, torch.int32)
+        self.train_rating = t(self.rating_h, torch.float32)
+        self.sst_of_user = t(np.asarray(sst_of_user, dtype=np.float32), torch.float32)
+
+    # the two `dataset` members the reference trainer/model read (collector.py:91-93, focf.py:40)
+    @property
+    def item_counter(self):
+        return {int(i): int(self.item_count_h[i]) for i in self.item_uniques}
+
+
+class FOCFDataLoader:
+    def __init__(self, config, train, mode="fast", draws=None, seed=None):
+        self.config, self.train = config, train
+        self.dataset = train
+        self.step = int(config["train_batch_size"])
+        self.mode = mode
+        self._replay = None if draws is None else np.asarray(draws)
+        self._rng = np.random.default_rng(config["seed"] if seed is None else seed)
+        self.lib = load()
+        dev = train.device
+        # worst case: step-1 rows + the most popular item
+        self.max_batch = self.step + int(train.item_count_h.max())
+        self._cols = (torch.empty(self.max_batch, dtype=torch.int32, device=dev),
+                      torch.empty(self.max_batch, dtype=torch.int32, device=dev),
+                      torch.empty(self.max_batch, dtype=torch.float32, device=dev),
+                      torch.empty(self.max_batch, dtype=torch.float32, device=dev))
+        self._replay_pos = 0
+
+    def __len__(self):
+        return math.ceil(self.train.n_rows / self.step)              # abstract_dataloader.py:67-68
+
+    # ------------------------------------------------------------------ host-side draws
+    def _draw_batch(self):
+        tr = self.train
+        if self._replay is not None:
+            end = self._replay_pos
+            while self._replay[end] != -1:
+                end += 1
+            items = self._replay[self._replay_pos:end]
+            self._replay_pos = end + 1
+            return np.asarray(items, dtype=np.int64)
+        if self.mode == "reference":
+            # focf_dataloader.py:38-47 verbatim in effect: same calls on numpy's global RNG
+            select_item = np.arange(0, tr.n_items)
+            is_select = np.zeros(tr.n_items, dtype=bool)
+            is_select[tr.item_uniques] = True
+            cnt, items = 0, []
+            while cnt < self.step:
+                iid = np.random.choice(select_item[is_select], 1, False)[0]
+                cnt += int(tr.item_count_h[iid])
+                is_select[iid] = False
+                items.append(iid)
+            return np.asarray(items, dtype=np.int64)
+        perm = self._rng.permutation(tr.item_uniques)
+        csum = np.cumsum(tr.item_count_h[perm])
+        j = int(np.searchsorted(csum, self.step, side="left")) + 1
+        return perm[:j].astype(np.int64)
+
+    def plan_epoch(self):
+        """Draw every batch of the epoch; returns (draw_items, draw_off, batches) where batches is a list of
+        (first draw index, J, B) and draw_off holds, per batch, J+1 positions."""
+        items, offs, batches = [], [], []
+        pos_items = pos_offs = 0
+        for _ in range(len(self)):
+            it = self._draw_batch()
+            cnt = self.train.item_count_h[it]
+            off = np.zeros(len(it) + 1, np.int64)
+            off[1:] = np.cumsum(cnt)
+            batches.append((pos_items, pos_offs, len(it), int(off[-1])))
+            items.append(it)
+            offs.append(off)
+            pos_items += len(it)
+            pos_offs += len(it) + 1
+        return (np.concatenate(items).astype(np.int32), np.concatenate(offs).astype(np.int32), batches)
+
+    # ------------------------------------------------------------------ device-side materialisation
+    def gather(self, d_items, d_offs, batch):
+        """run fr_focf_gather_batch for one planned batch; returns the four columns (views of reused buffers)"""
+        pi, po, J, B = batch
+        tr = self.train
+        uid, iid, rating, sst = (c[:B] for c in self._cols)
+        check(self.lib.fr_focf_gather_batch(ptr(tr.item_off), ptr(tr.train_uid), ptr(tr.train_rating),
+                                            ptr(tr.sst_of_user), d_items[pi:pi + J].data_ptr(),
+                                            d_offs[po:po + J + 1].data_ptr(), J, ptr(uid), ptr(iid), ptr(rating),
+                                            ptr(sst), stream_ptr()), "fr_focf_gather_batch")
+        return uid, iid, rating, sst
+
+    def __iter__(self):
+        items, offs, batches = self.plan_epoch()
+        dev = self.train.device
+        d_items = torch.from_numpy(items).pin_memory().to(dev, non_blocking=True)
+        d_offs = torch.from_numpy(offs).pin_memory().to(dev, non_blocking=True)
+        uf, itf, rf, sf = self.train.fields
+        for b in batches:
+            uid, iid, rating, sst = self.gather(d_items, d_offs, b)
+            inter = Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
+            inter.items_contiguous = True
+            yield inter

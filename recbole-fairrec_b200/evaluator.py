@@ -1,0 +1,234 @@
+"""Fused full-sort fair evaluation -- replaces the per-batch loop of recbole/trainer/trainer.py:505-512
+(`full_sort_predict` -> mask -> `Collector.eval_batch_collect` -> `Evaluator.evaluate`) with one pass of
+device kernels over ALL eval users: scoring + mask + streaming top-K (never materialising scores), hit
+bits, positive scores, and the 12 metrics of properties/model/FOCF.yaml:29-30 accumulated on the device.
+
+`EvalData` is the device-resident form of what `FullSortEvalDataLoader` (general_dataloader.py:161-253)
+yields batch by batch: eval users, per-user history CSR (`used_ids - positives`, 201-207) and positives CSR.
+`FullSortEvaluator.evaluate()` returns the reference's metric dict (same keys, same rounding) and can emit
+the collector's `DataStruct` entries (collector.py:141-189) for cross-checking against metrics.py.
+
+Multi-GPU: the item table is row-sharded over the ranks of a torch.distributed group;
+each rank scores its shard, the per-shard top-K lists are all-gathered (NCCL) and merged under the total
+order (score desc, item id asc); per-item x group statistics are computed by the shard that owns the item
+and summed with one all-reduce.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib, kernels
+
+TOPK_ROWS = {"ndcg": 0, "recall": 1, "hit": 2, "mrr": 3}
+FAIR_SLOTS = {"differentialfairness": 0, "valueunfairness": 1, "absoluteunfairness": 2, "underunfairness": 3,
+              "overunfairness": 4, "nonparityunfairness": 5}
+FAIR_KEYS = {  # metrics.py:855, 924, 1021, 1117, 1213, 1308
+    "differentialfairness": "Differential Fairness of sensitive attribute {}",
+    "valueunfairness": "Value Unfairness of sensitive attribute {}",
+    "absoluteunfairness": "Absolute Unfairness of sensitive attribute {}",
+    "underunfairness": "Underestimation Unfairness of sensitive attribute {}",
+    "overunfairness": "Overestimation Unfairness of sensitive attribute {}",
+    "nonparityunfairness": "NonParity Unfairness of sensitive attribute {}",
+}
+SUPPORTED = set(TOPK_ROWS) | set(FAIR_SLOTS) | {"giniindex", "popularitypercentage"}
+
+
+class EvalData:
+    """Device-resident full-sort eval split.  All ids are int32, offsets int64."""
+
+    def __init__(self, users, hist_lists, pos_lists, sst_of_user, device):
+        """users: eval user ids (ascending, like general_dataloader.py:188); hist_lists / pos_lists: one
+        array of item ids per eval user; sst_of_user: {attr: array indexed by USER ID}."""
+        users = np.asarray(users, dtype=np.int64)
+        n = len(users)
+        self.n = n
+        self.device = device
+        hist_sorted = [np.sort(np.asarray(h, dtype=np.int64)) for h in hist_lists]
+        pos_orig = [np.asarray(p, dtype=np.int64) for p in pos_lists]
+        pos_sorted = [np.sort(p) for p in pos_orig]
+        hist_off = np.zeros(n + 1, np.int64)
+        pos_off = np.zeros(n + 1, np.int64)
+        hist_off[1:] = np.cumsum([len(h) for h in hist_sorted])
+        pos_off[1:] = np.cumsum([len(p) for p in pos_orig])
+        cat = lambda ls: np.concatenate(ls) if len(ls) and sum(map(len, ls)) else np.zeros(0, np.int64)
+        self.n_pos = int(pos_off[-1])
+        pos_row = np.repeat(np.arange(n), np.diff(pos_off))
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
+        self.users = t(users, torch.int32)
+        self.hist_off, self.hist_items = t(hist_off, torch.int64), t(cat(hist_sorted), torch.int32)
+        self.pos_off = t(pos_off, torch.int64)
+        self.pos_items_sorted = t(cat(pos_sorted), torch.int32)   # for the hit-bit binary search
+        self.pos_items = t(cat(pos_orig), torch.int32)            # emission order of data.positive_i
+        self.pos_row = t(pos_row, torch.int64)
+        self.pos_uid = t(users[pos_row], torch.int32)
+        if self.hist_items.numel() == 0:
+            self.hist_items = torch.zeros(1, dtype=torch.int32, device=device)
+        # sensitive attributes: value per eval user, group id = rank among the values present in the
+        # positives (np.unique(sst_value, return_inverse=True), metrics.py:941, 1327)
+        self.sst_value, self.group_of_pos, self.n_groups = {}, {}, {}
+        for attr, per_user in sst_of_user.items():
+            vals = np.asarray(per_user)[users]
+            uniq, inv = np.unique(vals[pos_row], return_inverse=True)
+            self.sst_value[attr] = torch.as_tensor(vals)
+            self.group_of_pos[attr] = t(inv, torch.int32)
+            self.n_groups[attr] = len(uniq)
+
+    @classmethod
+    def from_reference_loader(cls, loader, sst_attr_list, device):
+        """Adopt a reference FullSortEvalDataLoader (general_dataloader.py:173-199): uid_list,
+        uid2history_item, uid2positive_item, user_df."""
+        users = loader.uid_list.numpy()
+        hist = [loader.uid2history_item[u].numpy() for u in users]
+        pos = [loader.uid2positive_item[u].numpy() for u in users]
+        feat = loader.dataset.get_user_feature()
+        sst = {a: feat[a].numpy() for a in sst_attr_list}
+        return cls(users, hist, pos, sst, device)
+
+
+class FullSortEvaluator:
+    def __init__(self, config, n_items, train_item_count=None, group=None):
+        """train_item_count: {item id: #train interactions} (collector.py:91-93 data.count_items).
+        group: optional torch.distributed process group for item-sharded evaluation."""
+        self.config = config
+        self.metrics = [m.lower() for m in config["metrics"]]
+        bad = [m for m in self.metrics if m not in SUPPORTED]
+        if bad:
+            raise NotImplementedError(f"metrics {bad} are outside the fairness hot path (SURVEY.md section 2, row 10)")
+        self.topk = list(config["topk"]) if isinstance(config["topk"], (list, tuple)) else [config["topk"]]
+        self.K = max(self.topk)
+        self.decimal = config["metric_decimal_place"] if config["metric_decimal_place"] is not None else 4
+        self.sst_attr_list = list(config["sst_attr_list"])
+        self.n_items = int(n_items)
+        self.score_mode = {"exact": _lib.SCORE_EXACT_FP32, "tc": _lib.SCORE_TC_3XTF32}[config["score_mode"] or "exact"]
+        self.group = group
+        self._is_popular = None
+        self._pop_host = self._popular_items(train_item_count, config["popularity_ratio"])
+        self.last = None
+
+    @staticmethod
+    def _popular_items(count_items, ratio):
+        """metrics.py:786-794"""
+        if not count_items:
+            return None
+        if ratio is None or ratio <= 0:
+            ratio = 0.1
+        if ratio > 1:
+            return np.array([i for i, c in count_items.items() if c >= ratio], dtype=np.int64)
+        items = np.fromiter(count_items.keys(), dtype=np.int64, count=len(count_items))
+        cnts = np.fromiter(count_items.values(), dtype=np.int64, count=len(count_items))
+        order = np.lexsort((items, cnts))[::-1]          # (count, id) descending
+        cut = max(int(len(items) * ratio), 1)
+        return items[order[:cut]]
+
+    def _popular_mask(self, device):
+        if self._is_popular is None and self._pop_host is not None:
+            m = torch.zeros(self.n_items, dtype=torch.uint8)
+            m[torch.as_tensor(self._pop_host)] = 1
+            self._is_popular = m.to(device)
+        return self._is_popular
+
+    # ------------------------------------------------------------------ the fused pass
+    @torch.no_grad()
+    def collect(self, U, I, data, max_rating, transform=_lib.TRANSFORM_CLAMP_DIV):
+        """Runs the kernels; returns a dict of DEVICE tensors (no host sync)."""
+        K = self.K
+        if self.group is None:
+            ids, sc = kernels.fullsort_topk(U, I, data.users, data.hist_off, data.hist_items, K, transform, max_rating,
+                                            0, self.score_mode)
+        else:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            lo, hi = shard_bounds(self.n_items, world, rank)
+            ids_l, sc_l = kernels.fullsort_topk(U, I[lo:hi], data.users, data.hist_off, data.hist_items, K, transform,
+                                                max_rating, lo, self.score_mode)
+            ids_all = torch.empty((world,) + tuple(ids_l.shape), dtype=ids_l.dtype, device=ids_l.device)
+            sc_all = torch.empty((world,) + tuple(sc_l.shape), dtype=sc_l.dtype, device=sc_l.device)
+            dist.all_gather_into_tensor(ids_all, ids_l, group=self.group)
+            dist.all_gather_into_tensor(sc_all, sc_l, group=self.group)
+            ids, sc = kernels.topk_merge(ids_all, sc_all)
+        rec_topk = kernels.hits(ids, data.pos_off, data.pos_items_sorted)
+        pos_score = kernels.pair_scores(U, I, data.pos_uid, data.pos_items, transform, max_rating)
+        out = {"topk_id": ids, "topk_score": sc, "rec_topk": rec_topk, "pos_score": pos_score}
+        need = set(self.metrics)
+        if need & set(TOPK_ROWS):
+            out["topk_sums"] = kernels.topk_metric_sums(rec_topk)
+        if need & {"giniindex", "popularitypercentage"}:
+            cnt, pop = kernels.rec_item_stats(ids, self.n_items, self._popular_mask(U.device))
+            out["pop_hits"] = pop
+            if "giniindex" in need:
+                out["gini"] = {k: kernels.gini_at_k(cnt, k, data.n) for k in self.topk}
+        if need & set(FAIR_SLOTS):
+            out["fair"] = {}
+            attrs = self.sst_attr_list
+            for ai, attr in enumerate(attrs):
+                G = data.n_groups[attr]
+                if self.group is None:
+                    stats = kernels.item_group_stats(data.pos_items, pos_score, data.group_of_pos[attr], self.n_items, G)
+                else:
+                    import torch.distributed as dist
+                    world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+                    lo, hi = shard_bounds(self.n_items, world, rank)
+                    own = (data.pos_items >= lo) & (data.pos_items < hi)
+                    stats = torch.zeros((self.n_items, G, 2), dtype=torch.float64, device=U.device)
+                    if bool(own.any()):
+                        stats = kernels.item_group_stats(data.pos_items[own].contiguous(), pos_score[own].contiguous(),
+                                                         data.group_of_pos[attr][own].contiguous(), self.n_items, G)
+                    dist.all_reduce(stats, group=self.group)  # disjoint supports: x + 0, order-independent
+                out["fair"][attr] = kernels.fairness_metrics(stats)
+        self.last = out
+        return out
+
+    def evaluate(self, U, I, data, max_rating, transform=_lib.TRANSFORM_CLAMP_DIV):
+        """evaluator.py:28-42: OrderedDict metric -> value, keys and rounding as the reference."""
+        return self.finalize(self.collect(U, I, data, max_rating, transform), data)
+
+    def finalize(self, out, data, rounded=True):
+        n = data.n
+        rnd = (lambda v: round(v, self.decimal)) if rounded else (lambda v: v)
+        topk_sums = out["topk_sums"].cpu().numpy() if "topk_sums" in out else None
+        pop = out["pop_hits"].cpu().numpy() if "pop_hits" in out else None
+        fair = {a: v.cpu().numpy() for a, v in out.get("fair", {}).items()}
+        res = OrderedDict()
+        for m in self.metrics:
+            if m in TOPK_ROWS:
+                for k in self.topk:
+                    res[f"{m}@{k}"] = rnd(float(topk_sums[TOPK_ROWS[m], k - 1] / n))
+            elif m == "giniindex":
+                for k in self.topk:
+                    res[f"giniindex@{k}"] = rnd(float(out["gini"][k].item()))
+            elif m == "popularitypercentage":
+                for k in self.topk:
+                    res[f"popularitypercentage@{k}"] = rnd(float(pop[:k].sum() / (n * k)))
+            else:
+                # DifferentialFairness / NonParity report every attribute, the other four only the first
+                attrs = self.sst_attr_list if m in ("differentialfairness", "nonparityunfairness") \
+                    else self.sst_attr_list[:1]
+                for attr in attrs:
+                    v = float(fair[attr][FAIR_SLOTS[m]])
+                    if np.isnan(v):
+                        if m == "nonparityunfairness":
+                            raise ValueError(f"there is only one value for {attr} sensitive attribute")
+                        raise ValueError("sensitive attribute must be binary")   # metrics.py:951-952
+                    res[FAIR_KEYS[m].format(attr)] = rnd(v)
+        return res
+
+    def data_struct(self, data):
+        """The collector's DataStruct entries (collector.py:141-189) of the last collect(), on the host."""
+        out = self.last
+        st = {
+            "rec.items": out["topk_id"].cpu().to(torch.int64),
+            "rec.topk": out["rec_topk"].cpu(),
+            "rec.positive_score": out["pos_score"].cpu(),
+            "data.positive_i": data.pos_items.cpu().to(torch.int64),
+        }
+        for attr in self.sst_attr_list:
+            st["data." + attr] = data.sst_value[attr][data.pos_row.cpu()]
+        return st
+
+
+def shard_bounds(n_items, world, rank):
+    """contiguous item-id ranges so that the tie rule (lowest id) survives the merge"""
+    per = (n_items + world - 1) // world
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)

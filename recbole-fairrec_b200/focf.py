@@ -1,0 +1,172 @@
+"""FOCF (MF + fairness regulariser) -- drop-in for recbole/model/fair_recommender/focf.py:24-178.
+
+Same plugin surface (class name, `input_type`, ctor `(config, dataset)`, `calculate_loss / predict /
+full_sort_predict`, parameter names `user_embedding_layer.weight` / `item_embedding_layer.weight` so
+reference checkpoints load), but every computation runs in this package's sm_100a kernels through the
+C ABI.  Two ways to train:
+
+  * compat : `loss = model.calculate_loss(interaction); loss.backward(); optimizer.step()` -- what the
+    reference's own `Trainer` does (trainer.py:184-196).  `calculate_loss` is a torch.autograd.Function
+    whose backward materialises the dense embedding gradients exactly like nn.Embedding does.
+  * fused  : `model.train_step(interaction)` -- forward + backward + dense Adam (L2 form) in one kernel
+    chain; the dense gradient never exists.  Used by `FOCFTrainer` when `learner: adam`.
+
+There is no CPU path: the model must live on a CUDA device.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .kernels import FocfEngine, pair_scores
+
+POINTWISE = "POINTWISE"
+
+
+def _xavier_normal_initialization(module):
+    # recbole/model/init.py:15-31
+    if isinstance(module, nn.Embedding):
+        nn.init.xavier_normal_(module.weight.data)
+
+
+def batch_columns(interaction, uid_f, iid_f, rating_f, sst_f, device):
+    """Interaction -> the four int32/float32 device columns of include/fairrec_b200.h:fr_focf_step"""
+    def col(name, dtype):
+        t = interaction[name]
+        return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return (col(uid_f, torch.int32), col(iid_f, torch.int32), col(rating_f, torch.float32),
+            col(sst_f, torch.float32), bool(getattr(interaction, "items_contiguous", False)))
+
+
+class _FocfLoss(torch.autograd.Function):
+    """focf.py:152-169 calculate_loss with autograd semantics (dense grads for both embedding tables)."""
+
+    @staticmethod
+    def forward(ctx, U, I, model, batch):
+        eng = model._engine()
+        loss = torch.empty(1, dtype=torch.float32, device=U.device)
+        ctx.step = eng.forward(U.detach(), I.detach(), batch, model._objective, model.fair_weight, loss_out=loss)
+        ctx.model, ctx.batch, ctx.tables = model, batch, (U, I)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        U, I = ctx.tables
+        dU, dI = torch.empty_like(U), torch.empty_like(I)
+        ctx.model._engine().backward(ctx.step, dU, dI, float(grad_out))
+        return dU, dI, None, None
+
+
+class FOCF(nn.Module):
+    input_type = POINTWISE
+    type = "GENERAL"
+
+    def __init__(self, config, dataset):
+        super().__init__()
+        # abstract_recommender.py:92-104
+        self.USER_ID = config["USER_ID_FIELD"]
+        self.ITEM_ID = config["ITEM_ID_FIELD"]
+        self.NEG_ITEM_ID = config["NEG_PREFIX"] + self.ITEM_ID
+        self.n_users = dataset.num(self.USER_ID)
+        self.n_items = dataset.num(self.ITEM_ID)
+        self.device = config["device"]
+        # focf.py:35-48
+        self.embedding_size = config["embedding_size"]
+        self.RATING = config["RATING_FIELD"]
+        self.SST_FIELD = config["sst_attr_list"][0]
+        self.fair_weight = float(config["fair_weight"])
+        self.max_rating = float(dataset.inter_feat[self.RATING].max())
+        self.fair_objective = config["fair_objective"].strip().lower()
+        if self.fair_objective not in _lib.OBJECTIVES:
+            raise ValueError("you must set config['fair_objective'] be one of (none,"
+                             "value,absolute,under,over,nonparity)")
+        self._objective = _lib.OBJECTIVES[self.fair_objective]
+        if self.embedding_size % 4 != 0:
+            raise ValueError("fairrec_b200 FOCF needs embedding_size to be a multiple of 4")
+        self.user_embedding_layer = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding_layer = nn.Embedding(self.n_items, self.embedding_size)
+        self.apply(_xavier_normal_initialization)
+        self._eng = None
+        self._adam = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _engine(self):
+        U = self.user_embedding_layer.weight
+        if not U.is_cuda:
+            raise _lib.FairRecLibraryError("FOCF (fairrec_b200) runs on CUDA only: move the model to a cuda device")
+        if self._eng is None or self._eng.device != U.device:
+            self._eng = FocfEngine(self.n_users, self.n_items, self.embedding_size, 4096, U.device)
+        return self._eng
+
+    def _batch(self, interaction):
+        return batch_columns(interaction, self.USER_ID, self.ITEM_ID, self.RATING, self.SST_FIELD,
+                             self.user_embedding_layer.weight.device)
+
+    def other_parameter(self):
+        return dict()
+
+    def load_other_parameter(self, para):
+        if para:
+            for k, v in para.items():
+                setattr(self, k, v)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, user, item):
+        """focf.py:136-143; returns (pred, user_embedding, item_embedding)"""
+        U, I = self.user_embedding_layer.weight, self.item_embedding_layer.weight
+        pred = pair_scores(U.detach(), I.detach(), user.to(torch.int32).contiguous(),
+                           item.to(torch.int32).contiguous())
+        return pred, U[user.long()], I[item.long()]
+
+    def predict(self, interaction):
+        """focf.py:145-150"""
+        U, I = self.user_embedding_layer.weight, self.item_embedding_layer.weight
+        dev = U.device
+        user = interaction[self.USER_ID].to(device=dev, dtype=torch.int32).contiguous()
+        item = interaction[self.ITEM_ID].to(device=dev, dtype=torch.int32).contiguous()
+        return pair_scores(U.detach(), I.detach(), user, item, _lib.TRANSFORM_CLAMP_DIV, self.max_rating)
+
+    def calculate_loss(self, interaction):
+        """focf.py:152-169; 0-dim tensor connected to both embedding tables"""
+        return _FocfLoss.apply(self.user_embedding_layer.weight, self.item_embedding_layer.weight, self,
+                               self._batch(interaction))
+
+    def full_sort_predict(self, interaction):
+        """focf.py:171-178: dense [b * n_items] scores (compat API; the fused evaluator never calls this)"""
+        U, I = self.user_embedding_layer.weight, self.item_embedding_layer.weight
+        user = interaction[self.USER_ID].to(device=U.device, dtype=torch.int32)
+        uid = user.repeat_interleave(self.n_items).contiguous()
+        iid = torch.arange(self.n_items, dtype=torch.int32, device=U.device).repeat(user.numel()).contiguous()
+        return pair_scores(U.detach(), I.detach(), uid, iid, _lib.TRANSFORM_CLAMP_DIV, self.max_rating)
+
+    # ------------------------------------------------------------------ fused training step
+    def init_adam(self, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        """state of torch.optim.Adam(params, lr, weight_decay) as built by trainer.py:139"""
+        U, I = self.user_embedding_layer.weight, self.item_embedding_layer.weight
+        self._adam = dict(mU=torch.zeros_like(U), vU=torch.zeros_like(U), mI=torch.zeros_like(I),
+                          vI=torch.zeros_like(I), step=0, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                          weight_decay=weight_decay)
+        return self._adam
+
+    @torch.no_grad()
+    def train_step(self, interaction, loss_out=None):
+        """One fused optimisation step (trainer.py:183-196 for `learner: adam`).  Returns the device tensor
+        holding the loss; nothing synchronises."""
+        if self._adam is None:
+            raise RuntimeError("call init_adam() (FOCFTrainer does) before train_step()")
+        eng = self._engine()
+        self._adam["step"] += 1
+        out = eng.loss if loss_out is None else loss_out
+        eng.train_step(self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data, self._adam,
+                       self._batch(interaction), self._objective, self.fair_weight, loss_out=out)
+        return out
+
+    def check_flags(self):
+        """Raise what the reference would have raised for a faulty batch (synchronises the device)."""
+        f = self._engine().read_flags()
+        if f & _lib.FLAG_TOO_MANY_GROUPS:
+            raise IndexError("index 2 is out of bounds for dimension 1 with size 2 "
+                             "(more than two sensitive-attribute values in a batch, focf.py:86)")
+        if f & _lib.FLAG_SINGLE_GROUP:
+            raise IndexError("index 1 is out of bounds for dimension 0 with size 1 (focf.py:130)")
+        if f & _lib.FLAG_NAN_LOSS:
+            raise ValueError("Training loss is nan")  # trainer.py:286-288

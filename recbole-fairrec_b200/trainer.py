@@ -1,0 +1,208 @@
+"""FOCFTrainer -- the two hot loops of recbole/trainer/trainer.py (`_train_epoch` 155-204, `evaluate` 458-515)
+behind the reference's trainer interface (`fit` 332-418 / `evaluate`), running on this package's kernels.
+
+`get_trainer` in the reference resolves `<Model>Trainer` by name (utils/utils.py:86-94), so a class called
+FOCFTrainer placed in `recbole.trainer` is picked up automatically for `model: FOCF`.
+
+Differences from the reference loop that do not change results:
+  * the loss of every step stays on the device; the epoch total is formed on the host at the end of the epoch
+    as the same left-to-right Python-float sum of float32 step losses the reference builds with `.item()`
+    (trainer.py:191) -- no per-batch device->host sync;
+  * `learner: adam` runs the fused step (dense Adam with L2 weight decay, every row, exactly trainer.py:139);
+    other learners use `calculate_loss().backward()` + the torch optimizer, like the reference;
+  * evaluation is one fused pass over all eval users (evaluator.py) instead of 1-2 users per batch.
+"""
+import os
+import time
+from logging import getLogger
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from .evaluator import EvalData, FullSortEvaluator
+
+
+def early_stopping(value, best, cur_step, max_step, bigger=True):
+    """recbole/utils/utils.py:97-140"""
+    stop_flag = update_flag = False
+    if (value > best) if bigger else (value < best):
+        cur_step, best, update_flag = 0, value, True
+    else:
+        cur_step += 1
+        stop_flag = cur_step > max_step
+    return best, cur_step, stop_flag, update_flag
+
+
+class FOCFTrainer:
+    def __init__(self, config, model, group=None):
+        self.config, self.model = config, model
+        self.logger = getLogger()
+        self.learner = (config["learner"] or "adam").lower()
+        self.learning_rate = config["learning_rate"]
+        self.epochs = config["epochs"]
+        self.eval_step = min(config["eval_step"] or 1, self.epochs)
+        self.stopping_step = config["stopping_step"]
+        self.clip_grad_norm = config["clip_grad_norm"]
+        self.valid_metric = (config["valid_metric"] or "NDCG@5").lower()
+        self.valid_metric_bigger = config["valid_metric_bigger"] if config["valid_metric_bigger"] is not None else True
+        self.weight_decay = config["weight_decay"] or 0.0
+        self.device = config["device"]
+        self.checkpoint_dir = config["checkpoint_dir"] or "saved"
+        self.saved_model_file = os.path.join(self.checkpoint_dir, "{}-{}.pth".format(
+            config["model"] or "FOCF", time.strftime("%b-%d-%Y_%H-%M-%S")))
+        self.start_epoch, self.cur_step = 0, 0
+        self.best_valid_score = -np.inf if self.valid_metric_bigger else np.inf
+        self.best_valid_result = None
+        self.train_loss_dict = dict()
+        self.group = group
+        self.fused = self.learner == "adam" and not self.clip_grad_norm and (config["adam_mode"] or "dense_exact") == "dense_exact"
+        self.optimizer = None if self.fused else self._build_optimizer()
+        if self.fused:
+            model.init_adam(lr=self.learning_rate, weight_decay=self.weight_decay)
+        self.evaluator = None
+        self._train_item_count = None
+        self._eval_cache = {}
+        self._loss_buf = None
+
+    def _build_optimizer(self):
+        """trainer.py:114-153"""
+        p, lr, wd = self.model.parameters(), self.learning_rate, self.weight_decay
+        if self.learner == "adam":
+            return optim.Adam(p, lr=lr, weight_decay=wd)
+        if self.learner == "sgd":
+            return optim.SGD(p, lr=lr, weight_decay=wd)
+        if self.learner == "adagrad":
+            return optim.Adagrad(p, lr=lr, weight_decay=wd)
+        if self.learner == "rmsprop":
+            return optim.RMSprop(p, lr=lr, weight_decay=wd)
+        if self.learner == "sparse_adam":
+            return optim.SparseAdam(p, lr=lr)
+        self.logger.warning("Received unrecognized optimizer, set default Adam optimizer")
+        return optim.Adam(p, lr=lr)
+
+    # ------------------------------------------------------------------ hot loop 1
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False):
+        """trainer.py:155-204.  Returns the epoch's summed loss (Python float)."""
+        self.model.train()
+        n_steps = len(train_data)
+        if self._loss_buf is None or self._loss_buf.numel() < n_steps:
+            self._loss_buf = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=self.device)
+        k = 0
+        for interaction in train_data:
+            if k >= self._loss_buf.numel():
+                self._loss_buf = torch.cat([self._loss_buf, torch.zeros_like(self._loss_buf)])
+            slot = self._loss_buf[k:k + 1]
+            if self.fused:
+                self.model.train_step(interaction, loss_out=slot)
+            else:
+                self.optimizer.zero_grad()
+                loss = (loss_func or self.model.calculate_loss)(interaction.to(self.device))
+                slot.copy_(loss.detach().view(1))
+                loss.backward()
+                if self.clip_grad_norm:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+                self.optimizer.step()
+            k += 1
+        losses = self._loss_buf[:k].cpu().numpy()          # the epoch's single device->host sync
+        self.model.check_flags()
+        total = None
+        for v in losses:                                   # trainer.py:191: total_loss + losses.item()
+            total = float(v) if total is None else total + float(v)
+        if total is not None and np.isnan(total):
+            raise ValueError("Training loss is nan")        # trainer.py:286-288
+        return total
+
+    # ------------------------------------------------------------------ hot loop 2
+    def _eval_data(self, eval_data):
+        if isinstance(eval_data, EvalData):
+            return eval_data
+        key = id(eval_data)
+        if key not in self._eval_cache:  # a reference FullSortEvalDataLoader
+            self._eval_cache[key] = EvalData.from_reference_loader(eval_data, self.config["sst_attr_list"], self.device)
+        return self._eval_cache[key]
+
+    def data_collect(self, train_data):
+        """collector.py:80-95: what the metrics need from the training data"""
+        ds = train_data.dataset
+        self._train_item_count = dict(ds.item_counter)
+        self.evaluator = FullSortEvaluator(self.config, self.model.n_items, self._train_item_count, group=self.group)
+
+    @torch.no_grad()
+    def evaluate(self, eval_data, load_best_model=False, model_file=None, show_progress=False):
+        """trainer.py:458-515"""
+        if not eval_data:
+            return
+        if load_best_model:
+            checkpoint = torch.load(model_file or self.saved_model_file, weights_only=False)
+            self.model.load_state_dict(checkpoint["state_dict"])
+            self.model.load_other_parameter(checkpoint.get("other_parameter"))
+        self.model.eval()
+        if self.evaluator is None:
+            self.evaluator = FullSortEvaluator(self.config, self.model.n_items, self._train_item_count, group=self.group)
+        data = self._eval_data(eval_data)
+        return self.evaluator.evaluate(self.model.user_embedding_layer.weight.data,
+                                       self.model.item_embedding_layer.weight.data, data, self.model.max_rating)
+
+    # ------------------------------------------------------------------ bookkeeping (cold)
+    def _save_checkpoint(self, epoch):
+        """trainer.py:221-240"""
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        opt_state = self.optimizer.state_dict() if self.optimizer is not None else {
+            k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.model._adam.items()}
+        torch.save({"config": dict(self.config), "epoch": epoch, "cur_step": self.cur_step,
+                    "best_valid_score": self.best_valid_score, "state_dict": self.model.state_dict(),
+                    "other_parameter": self.model.other_parameter(), "optimizer": opt_state}, self.saved_model_file)
+
+    def resume_checkpoint(self, resume_file):
+        """trainer.py:258-284"""
+        ck = torch.load(str(resume_file), weights_only=False)
+        self.saved_model_file = str(resume_file)
+        self.start_epoch, self.cur_step = ck["epoch"] + 1, ck["cur_step"]
+        self.best_valid_score = ck["best_valid_score"]
+        self.model.load_state_dict(ck["state_dict"])
+        self.model.load_other_parameter(ck.get("other_parameter"))
+        if self.optimizer is not None:
+            self.optimizer.load_state_dict(ck["optimizer"])
+        else:
+            for k, v in ck["optimizer"].items():
+                self.model._adam[k] = v.to(self.device) if torch.is_tensor(v) else v
+
+    def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
+        """trainer.py:332-418"""
+        self.data_collect(train_data)
+        for epoch_idx in range(self.start_epoch, self.epochs):
+            t0 = time.time()
+            train_loss = self._train_epoch(train_data, epoch_idx, show_progress=show_progress)
+            self.train_loss_dict[epoch_idx] = train_loss
+            if verbose:
+                des = self.config["loss_decimal_place"] or 4
+                self.logger.info(("epoch %d training [time: %.2fs, train loss: %." + str(des) + "f]") %
+                                 (epoch_idx, time.time() - t0, train_loss))
+            if self.eval_step <= 0 or not valid_data:
+                if saved:
+                    self._save_checkpoint(epoch_idx)
+                continue
+            if (epoch_idx + 1) % self.eval_step == 0:
+                t1 = time.time()
+                valid_result = self.evaluate(valid_data, load_best_model=False)
+                valid_score = valid_result[self.valid_metric]
+                self.best_valid_score, self.cur_step, stop_flag, update_flag = early_stopping(
+                    valid_score, self.best_valid_score, self.cur_step, max_step=self.stopping_step,
+                    bigger=self.valid_metric_bigger)
+                if verbose:
+                    self.logger.info("epoch %d evaluating [time: %.2fs, valid_score: %f]" %
+                                     (epoch_idx, time.time() - t1, valid_score))
+                    self.logger.info("valid result: \n" + "    ".join(f"{k} : {v}" for k, v in valid_result.items()))
+                if update_flag:
+                    if saved:
+                        self._save_checkpoint(epoch_idx)
+                    self.best_valid_result = valid_result
+                if callback_fn:
+                    callback_fn(epoch_idx, valid_score)
+                if stop_flag:
+                    if verbose:
+                        self.logger.info("Finished training, best eval result in epoch %d" %
+                                         (epoch_idx - self.cur_step * self.eval_step))
+                    break
+        return self.best_valid_score, self.best_valid_result

@@ -1,0 +1,76 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header declares,
+the ctypes binding covers them all, and the product package never routes through oracle/."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fairrec_b200.h")
+PKG = os.path.join(ROOT, "recbole-fairrec_b200")
+LIB = os.path.join(PKG, "libfairrec_b200.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    names = declared_functions()
+    for must in ("fr_focf_forward", "fr_focf_backward", "fr_focf_train_step", "fr_fullsort_topk", "fr_topk_merge",
+                 "fr_item_group_stats", "fr_sort_pairs_u32"):
+        assert must in names
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="library not built (run __graft_entry__.build())")
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(LIB)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/fairrec_b200.h but not exported"
+    lib.fr_abi_version.restype = ctypes.c_int
+    assert lib.fr_abi_version() == 1
+
+
+def test_binding_covers_header():
+    import recbole_fairrec_b200 as pkg
+    assert sorted(pkg._lib.SIGNATURES) == declared_functions()
+    # struct mirrors: same field count/order as the header
+    src = open(HEADER).read()
+    for cname, pystruct in (("fr_focf_step", pkg._lib.FocfStep), ("fr_fullsort", pkg._lib.FullSort)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = re.sub(r"^(const\s+)?[a-z0-9_]+\s+", "", decl)
+            fields += [n.strip().lstrip("*").strip() for n in names.split(",")]
+        assert fields == [f[0] for f in pystruct._fields_], cname
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "libfairrec_oracle" not in txt and "oracle/_build" not in txt, f  # never dlopen/link the checker
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused instead of silently computed on the host."""
+    import torch
+    import recbole_fairrec_b200 as pkg
+    with pytest.raises(pkg._lib.FairRecLibraryError):
+        pkg._lib.ptr(torch.zeros(4))
+    cfg = pkg.Config(embedding_size=8, device=torch.device("cpu"))
+    from recbole_fairrec_b200.synth import SynthDataset
+    model = pkg.FOCF(cfg, SynthDataset(10, 12, 5.0))
+    inter = pkg.Interaction({"user_id": torch.tensor([1, 2]), "item_id": torch.tensor([1, 1]),
+                             "rating": torch.tensor([3.0, 4.0]), "gender": torch.tensor([1, 2])})
+    with pytest.raises(pkg._lib.FairRecLibraryError):
+        model.calculate_loss(inter)

@@ -1,0 +1,177 @@
+"""GPU parity of the fused full-sort evaluation against (1) the reference's golden fixtures and (2) the
+oracle (bit-exact: indices, hit bits, counts, and -- in exact scoring mode -- the scores themselves)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fullsort_oracle as fs
+from oracle import metrics_oracle as mo
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+HERE = os.path.dirname(__file__)
+EVAL = sorted(glob.glob(os.path.join(HERE, "golden", "focf_eval_*.npz")))
+
+
+def build(U, I, users, hist_off, hist_items, pos_off, pos_items, sst_of_user, topk, count_items=None, **cfg):
+    import recbole_fairrec_b200 as pkg
+    dev = torch.device("cuda")
+    hist = [hist_items[hist_off[r]:hist_off[r + 1]] for r in range(len(users))]
+    pos = [pos_items[pos_off[r]:pos_off[r + 1]] for r in range(len(users))]
+    data = pkg.EvalData(users, hist, pos, {"gender": sst_of_user}, dev)
+    conf = pkg.Config(topk=list(topk), metric_decimal_place=12, device=dev, **cfg)
+    ev = pkg.FullSortEvaluator(conf, I.shape[0], count_items)
+    return data, ev, torch.from_numpy(U).cuda(), torch.from_numpy(I).cuda()
+
+
+@pytest.mark.parametrize("path", EVAL, ids=[os.path.basename(p)[10:-4] for p in EVAL])
+def test_golden_fullsort_eval(path):
+    g = np.load(path)
+    K, users = int(g["K"]), g["eval_users"]
+    count_items = {int(i): int(c) for i, c in g["train_count_items"]}
+    data, ev, U, I = build(g["U"], g["I"], users, g["hist_off"], g["hist_items"], g["pos_off"], g["pos_items"],
+                           g["sst_of_user"], g["topk"], count_items)
+    res = ev.evaluate(U, I, data, float(g["max_rating"]))
+    st = ev.data_struct(data)
+    # ---- against the oracle: bit-exact everything (canonical tie order included)
+    scores = fs.mask_history(fs.full_sort_scores(g["U"], g["I"], users, float(g["max_rating"])),
+                             g["hist_off"], g["hist_items"])
+    ost = fs.collect(scores, K, g["pos_off"], g["pos_items"], g["sst_of_user"][users])
+    np.testing.assert_array_equal(st["rec.items"].numpy(), ost["rec.items"])
+    np.testing.assert_array_equal(st["rec.topk"].numpy(), ost["rec.topk"])
+    np.testing.assert_array_equal(st["rec.positive_score"].numpy(), ost["rec.positive_score"])
+    np.testing.assert_array_equal(st["data.positive_i"].numpy(), ost["data.positive_i"])
+    np.testing.assert_array_equal(ev.last["topk_score"].cpu().numpy(), fs.topk_canonical(scores, K)[1])
+    # ---- against the reference's own collector output where torch.topk is well defined (no near ties)
+    _, vals = fs.topk_canonical(scores, K + 1)
+    clean = np.all(np.abs(np.diff(vals, axis=1)) > 1e-6, axis=1)
+    np.testing.assert_array_equal(st["rec.items"].numpy()[clean], g["rec_items"][clean])
+    np.testing.assert_array_equal(st["rec.topk"].numpy()[clean], g["rec_topk"][clean])
+    np.testing.assert_allclose(st["rec.positive_score"].numpy(), g["rec_positive_score"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_array_equal(st["data.gender"].numpy(), g["data_sst"])
+    # ---- metrics: device accumulation vs the oracle on the same struct, and vs the reference when comparable
+    omet = mo.evaluate(ost, [int(k) for k in g["topk"]], g["I"].shape[0], count_items, 0.1)
+    assert list(res.keys()) == list(omet.keys()) == [str(k) for k in g["metric_names"]]
+    for k in res:
+        assert abs(res[k] - omet[k]) <= RTOL * max(abs(omet[k]), 1e-12) + 1e-12, (k, res[k], omet[k])
+    if clean.all():
+        for (k, v), ref in zip(res.items(), g["metric_values"]):
+            assert abs(v - ref) <= RTOL * max(abs(ref), 1e-12) + 1e-12, (k, v, ref)
+
+
+def random_eval_case(seed, n_users, n_items, d, n_eval, scale=0.3):
+    rng = np.random.default_rng(seed)
+    U = (rng.standard_normal((n_users, d)) * scale).astype(np.float32)
+    I = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
+    users = np.sort(rng.choice(np.arange(1, n_users), n_eval, replace=False))
+    hist, pos = [], []
+    for _ in users:
+        used = rng.choice(np.arange(1, n_items), int(rng.integers(2, min(200, n_items - 1))), replace=False)
+        npos = int(rng.integers(1, min(20, len(used))))
+        pos.append(used[:npos])
+        hist.append(used[npos:])
+    hist_off = np.r_[0, np.cumsum([len(h) for h in hist])]
+    pos_off = np.r_[0, np.cumsum([len(p) for p in pos])]
+    sst = rng.integers(1, 3, n_users)
+    return U, I, users, hist_off, np.concatenate(hist), pos_off, np.concatenate(pos), sst
+
+
+@pytest.mark.parametrize("n_users,n_items,d,n_eval,K", [(700, 1683, 64, 650, 10), (3000, 3707, 64, 2900, 10),
+                                                       (500, 9000, 128, 333, 20), (200, 130, 16, 150, 5),
+                                                       (300, 1000, 96, 257, 50)])
+def test_oracle_fullsort_random(n_users, n_items, d, n_eval, K):
+    U, I, users, ho, hi, po, pi, sst = random_eval_case(n_items + d, n_users, n_items, d, n_eval)
+    data, ev, Ud, Id = build(U, I, users, ho, hi, po, pi, sst, [K])
+    ev.collect(Ud, Id, data, 5.0)
+    st = ev.data_struct(data)
+    scores = fs.mask_history(fs.full_sort_scores(U, I, users, 5.0), ho, hi)
+    ost = fs.collect(scores, K, po, pi, sst[users])
+    np.testing.assert_array_equal(st["rec.items"].numpy(), ost["rec.items"])
+    np.testing.assert_array_equal(st["rec.topk"].numpy(), ost["rec.topk"])
+    np.testing.assert_array_equal(st["rec.positive_score"].numpy(), ost["rec.positive_score"])
+    np.testing.assert_array_equal(ev.last["topk_score"].cpu().numpy(), fs.topk_canonical(scores, K)[1])
+    res = ev.finalize(ev.last, data, rounded=False)
+    # metrics that do not need train counts
+    for name, fn in (("ndcg", mo.ndcg), ("recall", mo.recall)):
+        pos_index, pos_len = ost["rec.topk"][:, :K].astype(bool), ost["rec.topk"][:, K]
+        want = fn(pos_index, pos_len).mean(axis=0)[K - 1]
+        assert abs(res[f"{name}@{K}"] - want) <= RTOL * max(abs(want), 1e-12)
+    want = mo.gini(ost["rec.items"], n_items)
+    assert abs(res[f"giniindex@{K}"] - want) <= 1e-12 + RTOL * abs(want)
+    for key, fn in (("Value Unfairness", mo.value_unfairness), ("Absolute Unfairness", mo.absolute_unfairness),
+                    ("Underestimation Unfairness", mo.under_unfairness),
+                    ("Overestimation Unfairness", mo.over_unfairness),
+                    ("Differential Fairness", mo.differential_fairness)):
+        want = fn(ost["rec.positive_score"], ost["data.positive_i"], ost["data.sst"])
+        got = res[f"{key} of sensitive attribute gender"]
+        assert abs(got - want) <= RTOL * max(abs(want), 1e-12) + 1e-12, (key, got, want)
+    want = mo.nonparity(ost["rec.positive_score"], ost["data.sst"])
+    got = res["NonParity Unfairness of sensitive attribute gender"]
+    assert abs(got - want) <= 1e-5 * max(abs(want), 1e-3), (got, want)   # reference accumulates this one in fp32
+
+
+def test_item_sharded_merge_equals_unsharded():
+    """The multi-GPU protocol on one device: P contiguous item shards -> local top-K -> fr_topk_merge."""
+    from recbole_fairrec_b200 import _lib, kernels
+    from recbole_fairrec_b200.evaluator import shard_bounds
+    U, I, users, ho, hi, po, pi, sst = random_eval_case(3, 900, 2500, 64, 800)
+    data, ev, Ud, Id = build(U, I, users, ho, hi, po, pi, sst, [10])
+    full_ids, full_sc = kernels.fullsort_topk(Ud, Id, data.users, data.hist_off, data.hist_items, 10,
+                                              _lib.TRANSFORM_CLAMP_DIV, 5.0)
+    for P in (2, 3, 8):
+        ids, scs = [], []
+        for r in range(P):
+            lo, hi_ = shard_bounds(2500, P, r)
+            a, b = kernels.fullsort_topk(Ud, Id[lo:hi_].contiguous(), data.users, data.hist_off, data.hist_items, 10,
+                                         _lib.TRANSFORM_CLAMP_DIV, 5.0, item_base=lo)
+            ids.append(a)
+            scs.append(b)
+        mi, ms = kernels.topk_merge(torch.stack(ids).contiguous(), torch.stack(scs).contiguous())
+        assert torch.equal(mi, full_ids) and torch.equal(ms, full_sc)
+
+
+def test_clamp_ties_lowest_item_id_wins():
+    """clamp(0,max) creates exact ties at 0.0 and 1.0 (SURVEY.md hard part 3): canonical order is id ascending."""
+    from recbole_fairrec_b200 import _lib, kernels
+    rng = np.random.default_rng(0)
+    U = (rng.standard_normal((40, 16)) * 3).astype(np.float32)      # large dots: most scores clamp to 0 or 1
+    I = (rng.standard_normal((500, 16)) * 3).astype(np.float32)
+    users = np.arange(1, 40)
+    ho = np.zeros(40, np.int64)
+    ids, sc = kernels.fullsort_topk(torch.from_numpy(U).cuda(), torch.from_numpy(I).cuda(),
+                                    torch.from_numpy(users.astype(np.int32)).cuda(), torch.from_numpy(ho).cuda(),
+                                    torch.zeros(1, dtype=torch.int32, device="cuda"), 10, _lib.TRANSFORM_CLAMP_DIV, 5.0)
+    scores = fs.mask_history(fs.full_sort_scores(U, I, users, 5.0), ho, np.zeros(0, np.int64))
+    oi, os_ = fs.topk_canonical(scores, 10)
+    np.testing.assert_array_equal(ids.cpu().numpy(), oi)
+    np.testing.assert_array_equal(sc.cpu().numpy(), os_)
+    assert (os_ == 1.0).sum() > 100   # the case really is tie-heavy
+
+
+def test_kat2_metric_kernels():
+    """SURVEY.md section 4 KAT-2 through the metric kernels."""
+    from recbole_fairrec_b200 import kernels
+    rec_topk = torch.tensor([[1, 0, 1, 2], [0, 0, 0, 1], [0, 1, 0, 3]], dtype=torch.int32, device="cuda")
+    sums = kernels.topk_metric_sums(rec_topk).cpu().numpy() / 3
+    np.testing.assert_allclose(sums[0, 2], np.mean([0.91972079, 0, 0.29608191]), atol=1e-8)
+    np.testing.assert_allclose(sums[1, 2], np.mean([1, 0, 1 / 3]))
+    np.testing.assert_allclose(sums[2, 2], np.mean([1, 0, 1]))
+    np.testing.assert_allclose(sums[3, 2], np.mean([1, 0, 0.5]))
+    score = torch.tensor([0.9, 0.2, 0.4, 1.0, 0.0, 0.6, 0.7], device="cuda")
+    item = torch.tensor([1, 1, 2, 2, 2, 3, 3], dtype=torch.int32, device="cuda")
+    grp = torch.tensor([0, 1, 0, 1, 1, 0, 0], dtype=torch.int32, device="cuda")
+    out = kernels.fairness_metrics(kernels.item_group_stats(item, score, grp, 5, 2)).cpu().numpy()
+    np.testing.assert_allclose(out[0], 0.507108, rtol=1e-5)
+    np.testing.assert_allclose(out[1:4], 0.3833292371278623, rtol=1e-6)
+    assert out[4] == 0.0 and out[6] == 3
+    np.testing.assert_allclose(out[5], 0.25, rtol=1e-6)
+    items = torch.tensor([[1, 2, 3], [1, 2, 4], [1, 3, 2]], dtype=torch.int32, device="cuda")
+    pop = torch.zeros(5, dtype=torch.uint8, device="cuda")
+    pop[[1, 3]] = 1   # counts {1:10,2:5,3:5,4:1}, ratio .5 -> top 2 by (count,id) desc = items 1 and 3
+    cnt, hits = kernels.rec_item_stats(items, 5, pop)
+    np.testing.assert_allclose(kernels.gini_at_k(cnt, 3, 3).item(), 0.35555555555, rtol=1e-9)
+    h = hits.cpu().numpy()
+    np.testing.assert_allclose([h[:k].sum() / (3 * k) for k in (1, 2, 3)], [1, 2 / 3, 5 / 9])
