@@ -114,7 +114,7 @@ typedef struct fr_focf_step {
   /* Adam state (only read by fr_focf_adam / fr_focf_train_step) */
   float *mU, *vU, *mI, *vI;
   int32_t step;        /* 1-based optimizer step t */
-  float lr, beta1, beta2, eps, weight_decay;
+  double lr, beta1, beta2, eps, weight_decay; /* doubles: torch derives 1-beta, lr/(1-beta1^t) in double */
   /* dense gradients (only written by fr_focf_backward; may be NULL for fr_focf_train_step) */
   float *dU, *dI;
   /* scratch */

@@ -182,3 +182,17 @@ def train_steps(U, I, batches, objective, fair_weight=1.0, lr=1e-3, weight_decay
         adam_step(U, dU, mU, vU, t, lr, beta1, beta2, eps, weight_decay)
         adam_step(I, dI, mI, vI, t, lr, beta1, beta2, eps, weight_decay)
     return np.array(losses, F32), U, I, mU, vU, mI, vI
+
+
+def train_steps_f64(U, I, batches, objective, **kw):
+    """The same restatement evaluated in float64: the well-conditioned answer.  Tests use
+    err(fp32 oracle, fp64 oracle) as the conditioning yardstick of a case -- Adam divides by sqrt(v), so an
+    element whose gradient nearly cancels amplifies ordinary float32 rounding by orders of magnitude."""
+    global F32
+    keep = F32
+    F32 = np.float64
+    try:
+        b64 = [(u, i, np.asarray(r, np.float64), s) for u, i, r, s in batches]
+        return train_steps(np.asarray(U, np.float64), np.asarray(I, np.float64), b64, objective, **kw)
+    finally:
+        F32 = keep

@@ -5,7 +5,7 @@ a build hint, and every wrapper refuses tensors that are not on a CUDA device.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import torch
 
@@ -31,8 +31,8 @@ class FocfStep(Structure):
         ("items_contiguous", c_int32), ("objective", c_int32), ("fair_weight", c_float),
         ("pred", c_void_p), ("loss", c_void_p), ("status_flags", c_void_p),
         ("mU", c_void_p), ("vU", c_void_p), ("mI", c_void_p), ("vI", c_void_p),
-        ("step", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-        ("weight_decay", c_float), ("dU", c_void_p), ("dI", c_void_p),
+        ("step", c_int32), ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+        ("weight_decay", c_double), ("dU", c_void_p), ("dI", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 

