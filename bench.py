@@ -207,29 +207,34 @@ def run_ours(args, wname):
     uf, itf, rf, sf = tdata.fields
 
     n_plan = args.steps + args.warmup
-    loader_len = len(loader)
-    plans = []
-    while sum(len(p[2]) for p in plans) < 2 * n_plan + 8:
-        plans.append(loader.plan_epoch())
-    # flatten the planned batches: (device draw arrays, batch descriptor)
-    flat = []
-    for items, offs, batches in plans:
-        d_items = torch.from_numpy(items).to(dev)
-        d_offs = torch.from_numpy(offs).to(dev)
-        flat += [(d_items, d_offs, b) for b in batches]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    G = 8
+    use_graph = loader.max_batch <= 8192
+    losses = torch.zeros(max(len(loader), n_plan) * 2 + 16, device=dev)
+    if use_graph:
+        # planned epoch + CUDA-graph replay: one graph launch per step, zero per-step host work
+        runner = model.planned_runner(loader, losses, graph_steps=G)
+        dev_step = lambda: runner.run(1)
+    else:
+        plans, flat = [], []
+        while sum(len(p[2]) for p in plans) < 2 * n_plan + 8:
+            plans.append(loader.plan_epoch())
+        for items, offs, batches in plans:
+            d_items, d_offs = torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev)
+            flat += [(d_items, d_offs, b) for b in batches]
+        pos = [0]
 
-    def dev_step(k, loss_slot):
-        d_items, d_offs, b = flat[k]
-        uid, iid, rating, sst = loader.gather(d_items, d_offs, b)
-        inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
-        inter.items_contiguous = True
-        model.train_step(inter, loss_out=loss_slot)
-        return b[3]
+        def dev_step():
+            d_items, d_offs, b = flat[pos[0] % len(flat)]
+            pos[0] += 1
+            uid, iid, rating, sst = loader.gather(d_items, d_offs, b)
+            inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
+            inter.items_contiguous = True
+            model.train_step(inter, loss_out=losses[-1:])
+            return b[3]
 
-    losses = torch.zeros(n_plan * 2 + 16, device=dev)
     for k in range(args.warmup):
-        dev_step(k, losses[k:k + 1])
+        dev_step()
     barrier()
     model.check_flags()
 
@@ -242,28 +247,36 @@ def run_ours(args, wname):
         for s in range(args.steps):
             flush.zero_()
             evs[s][0].record()
-            rows += dev_step(args.warmup + s, losses[args.warmup + s:args.warmup + s + 1])
+            rows += dev_step()
             evs[s][1].record()
         barrier()
-        # a clock sample needs sustained load: keep stepping briefly (untimed) while nvidia-smi samples
-        t_end = time.time() + 0.6
-        k = 0
+        launches = _lib.launch_count() - launches0
+        # steady state (informational): back-to-back steps, no flush -- the regime an epoch really runs in at this
+        # shape (tables + Adam state + train split fit the 126 MB L2); also gives nvidia-smi a sustained load to sample
+        n_ss = 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rows_ss = 0
+        t_end = time.time() + 0.7
+        a.record()
         while time.time() < t_end:
-            dev_step(args.warmup + (k % args.steps), losses[-1:])
-            k += 1
+            rows_ss += runner.run(G) if use_graph else dev_step()
+            n_ss += G if use_graph else 1
+        b.record()
         torch.cuda.synchronize()
-    launches = _lib.launch_count() - launches0 - 0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
+        ss_ms = a.elapsed_time(b)
+    step_ms = [x.elapsed_time(y) for x, y in evs]
     t_dev = max_over_ranks(sum(step_ms) / 1e3)
     total_rows = sum_over_ranks(rows)
     value = total_rows / t_dev
-    kernels_per_step = None
-
+    steady = {"value": sum_over_ranks(rows_ss) / max_over_ranks(ss_ms / 1e3), "unit": "interactions/s",
+              "ms_per_step": ss_ms / n_ss, "steps": n_ss,
+              "note": "no L2 flush, back-to-back graph replays; informational (value above is the flushed number)"}
     # ---- timed region 2: end to end through the public API with host batches
     host_batches = []
+    e_items, e_offs, e_batches = loader.plan_epoch()
+    de_items, de_offs = torch.from_numpy(e_items).to(dev), torch.from_numpy(e_offs).to(dev)
     for s in range(args.steps):
-        d_items, d_offs, b = flat[args.warmup + args.steps + s]
-        cols = loader.gather(d_items, d_offs, b)
+        cols = loader.gather(de_items, de_offs, e_batches[s % len(e_batches)])
         host_batches.append(tuple(c.cpu().pin_memory() for c in cols))
     torch.cuda.synchronize()
     h2d = int(statistics.mean(sum(c.numel() * c.element_size() for c in hb) for hb in host_batches))
@@ -322,9 +335,18 @@ def run_ours(args, wname):
     _lib.profile_enable(True)
     nprof = min(args.steps, 50)
     rows_p = 0
-    for s in range(nprof):
-        flush.zero_()
-        rows_p += dev_step(args.warmup + s, losses[-1:])
+    if use_graph:   # graph replays bypass the library's launch macro: profile the same steps un-captured
+        st = model._graph_step
+        for s in range(nprof):
+            flush.zero_()
+            model._engine().run_planned(st)
+            rows_p += runner.plan["batch_rows"][(runner.cursor + s) % runner.plan["len"]]
+        runner.cursor += nprof
+        model._adam["step"] += nprof
+    else:
+        for s in range(nprof):
+            flush.zero_()
+            rows_p += dev_step()
     prof_train = _lib.profile_report()
     evaluator.collect(Uw, Iw, edata, 5.0)
     prof_eval = _lib.profile_report()
@@ -382,7 +404,9 @@ def run_ours(args, wname):
                    "NCCL all-gather top-K merge + all-reduce of item x group stats"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "kernels_per_step": kernels_per_step,
+        "gpu_launches": int(round(kernels_per_step * args.steps)), "kernels_per_step": kernels_per_step,
+        "launch_mode": "cuda graph replay (1 graph launch per step)" if use_graph else "stream launches",
+        "steady_state": steady,
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_roof, "unit": "GB/s",
                           "frac": step_roof / hbm},

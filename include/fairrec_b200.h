@@ -113,19 +113,39 @@ typedef struct fr_focf_step {
   int32_t *status_flags; /* [1] OR-ed FR_FLAG_* */
   /* Adam state (only read by fr_focf_adam / fr_focf_train_step) */
   float *mU, *vU, *mI, *vI;
-  int32_t step;        /* 1-based optimizer step t */
+  int32_t step;        /* 1-based optimizer step t; <= 0: use the workspace's device-resident counter
+                          (fr_focf_set_counters), advanced by every fr_focf_train_step -- CUDA-graph replay */
   double lr, beta1, beta2, eps, weight_decay; /* doubles: torch derives 1-beta, lr/(1-beta1^t) in double */
   /* dense gradients (only written by fr_focf_backward; may be NULL for fr_focf_train_step) */
   float *dU, *dI;
   /* scratch */
   void *workspace;
   size_t workspace_bytes;
+  /* --- optional: device-resident batch description, so that ONE captured CUDA graph of the step can be replayed on
+   * every batch of an epoch (batch sizes differ from step to step).  B above is then the CAPACITY of the columns. */
+  const int32_t *B_dev;       /* [1] actual number of rows of a caller-built batch (NULL: B is exact) */
+  /* planned epoch (focf_dataloader.py:37-50 for a whole epoch, drawn ahead): when plan_desc != NULL the step first
+   * materialises its batch itself (fr_focf_gather_batch semantics) into uid/iid/rating/sst (caller-owned scratch
+   * columns of capacity B) from descriptor row (cursor % plan_len) and writes its loss to loss[cursor]; the cursor
+   * lives in the workspace (fr_focf_set_counters) and advances by one per forward. */
+  const int32_t *plan_desc;   /* [plan_len, 4] = {first draw index, first offset index, J, B} */
+  const int32_t *plan_items;  /* concatenated drawn item ids */
+  const int32_t *plan_offs;   /* concatenated per-batch exclusive row offsets (J+1 each) */
+  int32_t plan_len;
+  const int32_t *item_off;    /* CSC of the item-sorted train split, as in fr_focf_gather_batch */
+  const int32_t *train_uid;
+  const float *train_rating;
+  const float *sst_of_user;
 } fr_focf_step;
 
 size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch);
 /* zero the persistent part of a fresh workspace (row-stamp tables); call once after allocation */
 int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
                            int32_t max_batch, void *stream);
+/* set the workspace's device-resident counters (-1 leaves one unchanged): the planned-batch cursor and the Adam
+ * step count used when fr_focf_step.step <= 0 */
+int fr_focf_set_counters(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
+                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, void *stream);
 int fr_focf_forward(const fr_focf_step *s, void *stream);
 /* needs the workspace left by fr_focf_forward for the same batch; grad_scale = upstream dL (usually 1) */
 int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream);

@@ -34,6 +34,9 @@ class FocfStep(Structure):
         ("step", c_int32), ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
         ("weight_decay", c_double), ("dU", c_void_p), ("dI", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("B_dev", c_void_p), ("plan_desc", c_void_p), ("plan_items", c_void_p), ("plan_offs", c_void_p),
+        ("plan_len", c_int32), ("item_off", c_void_p), ("train_uid", c_void_p), ("train_rating", c_void_p),
+        ("sst_of_user", c_void_p),
     ]
 
 
@@ -58,6 +61,7 @@ SIGNATURES = {
     "fr_sort_pairs_u32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "fr_focf_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "fr_focf_workspace_init": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "fr_focf_set_counters": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "fr_focf_forward": (c_int, [POINTER(FocfStep), c_void_p]),
     "fr_focf_backward": (c_int, [POINTER(FocfStep), c_float, c_void_p]),
     "fr_focf_adam": (c_int, [POINTER(FocfStep), c_void_p]),

@@ -23,7 +23,18 @@ namespace fr {
 constexpr int kMaxD = 512;            // embedding_size limit (multiple of 4)
 constexpr int kChunk = 32;            // sorted entries per gradient warp
 
-enum { CTRL_STAMP = 0, CTRL_MIN = 1, CTRL_MAX = 2, CTRL_TICKET = 3, CTRL_SAVED_MIN = 4, CTRL_SAVED_MAX = 5, CTRL_WORDS = 64 };
+enum {
+  CTRL_STAMP = 0,      // batch counter: tags row_tab entries, advanced by the last CTA of k_segment_loss
+  CTRL_MIN = 1, CTRL_MAX = 2,              // running min / max of the batch's attribute values (order-encoded)
+  CTRL_TICKET = 3,
+  CTRL_SAVED_MIN = 4, CTRL_SAVED_MAX = 5,  // the same, handed to the backward kernels
+  CTRL_CURSOR = 6,     // planned-batch cursor (fr_focf_plan): which batch of the epoch plan comes next
+  CTRL_ADAM_T = 7,     // device-resident Adam step count (used when fr_focf_step.step <= 0)
+  CTRL_B = 8,          // device-resident batch size (planned batches)
+  CTRL_WORDS = 64
+};
+// batch size: host value unless a device-resident one is given (CUDA-graph replay over batches of varying size)
+#define FR_B(host_B, dev_B) ((dev_B) ? *(dev_B) : (host_B))
 
 struct FocfWs {
   // persistent across steps
@@ -81,8 +92,9 @@ static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
 // torch.unique, focf.py:77) into two integer atomics.
 __global__ void __launch_bounds__(256)
     k_forward(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
-              const int32_t *__restrict__ iid, const float *__restrict__ sst, int B, int d, float *__restrict__ pred,
-              uint32_t *__restrict__ ctrl) {
+              const int32_t *__restrict__ iid, const float *__restrict__ sst, int B, const int32_t *__restrict__ B_dev,
+              int d, float *__restrict__ pred, uint32_t *__restrict__ ctrl) {
+  B = FR_B(B, B_dev);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t lo = 0xffffffffu, hi = 0u;
@@ -131,6 +143,9 @@ struct LossArgs {
   const uint32_t *ord_i;
   const int32_t *segoff_i, *J;
   int B;
+  const int32_t *B_dev;
+  int loss_by_cursor;   // planned batches: write loss[cursor] instead of loss[0]
+  int advance_adam;     // fused step with the device-resident Adam counter
   int objective;
   float fair_weight;
   float *cseg, *seg_hx, *seg_sq, *seg_gs, *cglob, *loss;
@@ -162,6 +177,7 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int J = *a.J;
+  const int B = FR_B(a.B, a.B_dev);
   const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
   int bad = 0;
   for (int j = warp; j < J; j += nwarps) {
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
     n0 = block_sum_256(n0, sh); n1 = block_sum_256(n1, sh);
   }
   if (threadIdx.x == 0) {
-    float loss = sq / (float)a.B;                                            // nn.MSELoss 'mean'
+    float loss = sq / (float)B;                                              // nn.MSELoss 'mean'
     float cg0 = 0.f, cg1 = 0.f;
     if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
       loss += a.fair_weight * (hx / (float)J);                               // focf.py:166
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
     }
     a.cglob[0] = cg0;
     a.cglob[1] = cg1;
-    a.loss[0] = loss;
+    a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] : 0u] = loss;
     if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
     // hand the group values to the backward kernels, re-arm the control block for the next batch
     a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
@@ -275,6 +291,8 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
     a.ctrl[CTRL_MAX] = 0u;
     a.ctrl[CTRL_TICKET] = 0u;
     a.ctrl[CTRL_STAMP] += 1u;
+    a.ctrl[CTRL_CURSOR] += 1u;
+    if (a.advance_adam) a.ctrl[CTRL_ADAM_T] += 1u;
   }
 }
 
@@ -288,6 +306,7 @@ struct GradArgs {
   const int32_t *uid, *iid;
   const float *rating, *sst, *pred;
   int B, d;
+  const int32_t *B_dev;
   const uint32_t *ord_i, *ord_u;
   const int32_t *segid_i, *segoff_i, *segid_u, *segoff_u, *entry_seg;
   const float *cseg, *cglob;
@@ -303,7 +322,8 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   const bool user_side = c >= nchunk;
   if (user_side) c -= nchunk;
   const int pbase = c * kChunk;
-  if (pbase >= a.B) return;
+  const int B = FR_B(a.B, a.B_dev);
+  if (pbase >= B) return;
   const uint32_t *ord = user_side ? a.ord_u : a.ord_i;
   const int32_t *segid = user_side ? a.segid_u : a.segid_i;
   const int32_t *segoff = user_side ? a.segoff_u : a.segoff_i;
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   float *head = user_side ? a.head_u : a.head_i;
   float *tail = user_side ? a.tail_u : a.tail_i;
   const int d = a.d;
-  const int nvalid = min(kChunk, a.B - pbase);
+  const int nvalid = min(kChunk, B - pbase);
   const float vmin = ord2f(a.ctrl[CTRL_SAVED_MIN]);
 
   // lane l stages entry pbase + l
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
     my_seg = segid[p];
     my_oid = oid[b];
     const int g = a.sst[b] != vmin;
-    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)a.B + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
+    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)B + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
               a.grad_scale;
   }
   float4 acc[kRowVecs];
@@ -421,8 +441,9 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
   __shared__ float sc[3];
   if (kMode != kDenseOut) {
     if (threadIdx.x == 0) {
-      const double bc1 = 1.0 - pow(a.beta1, (double)a.step);
-      const double bc2 = 1.0 - pow(a.beta2, (double)a.step);
+      const double t = a.step > 0 ? (double)a.step : (double)a.ctrl[CTRL_ADAM_T];
+      const double bc1 = 1.0 - pow(a.beta1, t);
+      const double bc2 = 1.0 - pow(a.beta2, t);
       sc[0] = (float)(-a.lr / bc1);
       sc[1] = (float)sqrt(bc2);
     }
@@ -513,12 +534,23 @@ __global__ void __launch_bounds__(256)
 // focf_dataloader.py:37-50 + dataset.py __getitem__/join: a FOCF batch is the concatenation of ALL train rows
 // of the drawn items.  The train split lives on the device sorted by item (CSC: item_off); one warp copies
 // one drawn item's segment (coalesced) and joins the user's sensitive attribute.
+// plan_desc == nullptr: (draw_items, draw_off, J) describe the batch directly.
+// plan_desc != nullptr: planned epoch -- descriptor row ctrl[CTRL_CURSOR] % plan_len = {item_pos, off_pos, J, B}
+// indexes into draw_items / draw_off; the kernel also publishes B in ctrl[CTRL_B] for the rest of the step.
 __global__ void __launch_bounds__(256)
     k_gather_batch(const int32_t *__restrict__ item_off, const int32_t *__restrict__ train_uid,
                    const float *__restrict__ train_rating, const float *__restrict__ sst_of_user,
                    const int32_t *__restrict__ draw_items, const int32_t *__restrict__ draw_off, int J,
+                   const int32_t *__restrict__ plan_desc, int plan_len, uint32_t *__restrict__ ctrl,
                    int32_t *__restrict__ uid, int32_t *__restrict__ iid, float *__restrict__ rating,
                    float *__restrict__ sst) {
+  if (plan_desc) {
+    const int32_t *dsc = plan_desc + 4 * (int)(ctrl[CTRL_CURSOR] % (uint32_t)plan_len);
+    draw_items += dsc[0];
+    draw_off += dsc[1];
+    J = dsc[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[CTRL_B] = (uint32_t)dsc[3];
+  }
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int j = warp; j < J; j += nwarps) {
@@ -533,7 +565,154 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused preparation
+// Batches of up to 8192 rows (every FOCFDataLoader batch at the ML-1M shape): ONE launch of two CTAs does what the
+// general path needs ~12 launches for -- CTA 0 the item side, CTA 1 the user side: load keys to shared memory,
+// stable LSD radix sort entirely in shared memory (ping-pong buffers, per-warp __match_any_sync ranking), segment
+// heads + block scan, and the write-out of sorted keys / order / segment ids / offsets / row stamps.
+constexpr int kPsThreads = 1024, kPsItems = 8, kPsMax = kPsThreads * kPsItems, kPsWarps = kPsThreads / 32;
+
+struct PrepSide {
+  const int32_t *keys_in;
+  uint32_t *skey, *ord;
+  int32_t *segid, *segoff, *count;
+  uint2 *row_tab;
+  int32_t *entry_seg;   // item side only
+  int key_bits, do_sort;
+};
+
+__global__ void __launch_bounds__(kPsThreads)
+    k_prepare_small(PrepSide item, PrepSide user, int B_host, const int32_t *__restrict__ B_dev,
+                    const uint32_t *__restrict__ ctrl) {
+  extern __shared__ __align__(16) uint32_t ps_smem[];
+  uint32_t *kA = ps_smem, *vA = kA + kPsMax, *kB = vA + kPsMax, *vB = kB + kPsMax;
+  uint16_t *cnt = (uint16_t *)(vB + kPsMax);           // [kPsWarps][256]
+  uint32_t *dbase = (uint32_t *)(cnt + kPsWarps * 256);  // [256]
+  uint32_t *wsum = dbase + 256;                          // [32]
+  const PrepSide sd = blockIdx.x == 0 ? item : user;
+  const int n = FR_B(B_host, B_dev);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t stamp = ctrl[CTRL_STAMP];
+
+  for (int p = tid; p < n; p += kPsThreads) {
+    kA[p] = (uint32_t)sd.keys_in[p];
+    vA[p] = (uint32_t)p;
+  }
+  __syncthreads();
+
+  if (sd.do_sort) {
+    const int passes = (sd.key_bits + 7) / 8;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int shift = 8 * pass;
+      for (int i = tid; i < kPsWarps * 256; i += kPsThreads) cnt[i] = 0;
+      __syncthreads();
+      uint32_t key[kPsItems], val[kPsItems], rnk[kPsItems];
+#pragma unroll
+      for (int r = 0; r < kPsItems; ++r) {
+        const int p = w * (kPsMax / kPsWarps) + r * 32 + lane;
+        const bool valid = p < n;
+        key[r] = valid ? kA[p] : 0u;
+        val[r] = valid ? vA[p] : 0u;
+        const uint32_t dig = valid ? ((key[r] >> shift) & 255u) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, dig);
+        const uint32_t before = valid ? cnt[w * 256 + dig] : 0u;
+        __syncwarp();
+        if (valid && lane == (__ffs(peers) - 1)) cnt[w * 256 + dig] = (uint16_t)(before + __popc(peers));
+        __syncwarp();
+        rnk[r] = before + __popc(peers & ((1u << lane) - 1u));
+      }
+      __syncthreads();
+      uint32_t tot = 0;
+      if (tid < 256) {  // digit tid: exclusive prefix over the warps
+#pragma unroll 8
+        for (int ww = 0; ww < kPsWarps; ++ww) {
+          const uint32_t t = cnt[ww * 256 + tid];
+          cnt[ww * 256 + tid] = (uint16_t)tot;
+          tot += t;
+        }
+        uint32_t inc = tot;  // exclusive scan of the 256 digit totals (8 warps)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        dbase[tid] = inc - tot;
+      }
+      __syncthreads();
+      if (tid < 256) {
+        uint32_t base = 0;
+        for (int ww = 0; ww < w; ++ww) base += wsum[ww];
+        dbase[tid] += base;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kPsItems; ++r) {
+        const int p = w * (kPsMax / kPsWarps) + r * 32 + lane;
+        if (p < n) {
+          const uint32_t dig = (key[r] >> shift) & 255u;
+          const uint32_t pos = dbase[dig] + cnt[w * 256 + dig] + rnk[r];
+          kB[pos] = key[r];
+          vB[pos] = val[r];
+        }
+      }
+      __syncthreads();
+      uint32_t *t0 = kA; kA = kB; kB = t0;
+      t0 = vA; vA = vB; vB = t0;
+    }
+  }
+
+  // ---- segments: thread tid owns the 8 consecutive sorted positions tid*8 .. tid*8+7
+  const int p0 = tid * kPsItems;
+  bool head[kPsItems];
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < kPsItems; ++i) {
+    const int p = p0 + i;
+    head[i] = p < n && (p == 0 || kA[p] != kA[p - 1]);
+    c += head[i];
+  }
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // wsum reuse
+  if (lane == 31) wsum[w] = (uint32_t)inc;
+  __syncthreads();
+  int run = inc - c;
+  for (int ww = 0; ww < w; ++ww) run += (int)wsum[ww];
+#pragma unroll
+  for (int i = 0; i < kPsItems; ++i) {
+    const int p = p0 + i;
+    if (p >= n) break;
+    const uint32_t k = kA[p];
+    if (head[i]) {
+      sd.segoff[run] = p;
+      sd.row_tab[k] = make_uint2(stamp, (uint32_t)run);
+      ++run;
+    }
+    const int sgm = run - 1;
+    sd.segid[p] = sgm;
+    sd.skey[p] = k;
+    sd.ord[p] = vA[p];
+    if (sd.entry_seg) sd.entry_seg[vA[p]] = sgm;
+    if (p == n - 1) {
+      sd.segoff[sgm + 1] = n;
+      sd.count[0] = sgm + 1;
+    }
+  }
+}
+
+__global__ void k_set_ctrl(uint32_t *ctrl, int cursor, int adam_t) {
+  if (cursor >= 0) ctrl[CTRL_CURSOR] = (uint32_t)cursor;
+  if (adam_t >= 0) ctrl[CTRL_ADAM_T] = (uint32_t)adam_t;
+}
+
 // ------------------------------------------------------------------------------------------ host side
+static bool planned(const fr_focf_step *s) { return s->plan_desc != nullptr; }
+
 static int check_step(const fr_focf_step *s, bool need_adam, const char *who) {
   FR_REQUIRE(s, "%s: null step", who);
   FR_REQUIRE(s->U && s->I && s->uid && s->iid && s->rating && s->sst && s->pred && s->loss && s->status_flags &&
@@ -544,8 +723,11 @@ static int check_step(const fr_focf_step *s, bool need_adam, const char *who) {
   FR_REQUIRE(s->B >= 1 && s->n_users >= 1 && s->n_items >= 1, "%s: empty batch or table", who);
   FR_REQUIRE(s->objective >= FR_OBJ_NONE && s->objective <= FR_OBJ_NONPARITY, "%s: bad objective %d", who,
              s->objective);
-  if (need_adam) {
-    FR_REQUIRE(s->mU && s->vU && s->mI && s->vI && s->step >= 1, "%s: Adam state missing", who);
+  if (need_adam) FR_REQUIRE(s->mU && s->vU && s->mI && s->vI, "%s: Adam state missing", who);
+  if (planned(s)) {
+    FR_REQUIRE(s->plan_items && s->plan_offs && s->plan_len >= 1 && s->item_off && s->train_uid && s->train_rating &&
+                   s->sst_of_user,
+               "%s: incomplete batch plan", who);
   }
   return FR_OK;
 }
@@ -560,34 +742,59 @@ static int carve_checked(const fr_focf_step *s, FocfWs *w, const char *who) {
   return FR_OK;
 }
 
-static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st) {
-  const int B = s->B;
-  // item side: segments of equal item id (sorted first unless the loader guarantees adjacency)
-  const uint32_t *skey_i = (const uint32_t *)s->iid, *ord_i = nullptr;
-  if (!s->items_contiguous) {
-    sort_pairs((const uint32_t *)s->iid, nullptr, w.skey_i, w.ord_i, B, nullptr, bits_for((uint32_t)s->n_items), w.sort,
-               st);
-    skey_i = w.skey_i;
-    ord_i = w.ord_i;
+// device-resident batch size: the caller's pointer, or ctrl[CTRL_B] published by the planned gather
+static const int32_t *dev_B(const fr_focf_step *s, const FocfWs &w) {
+  return planned(s) ? (const int32_t *)(w.ctrl + CTRL_B) : s->B_dev;
+}
+
+static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, bool advance_adam) {
+  const int B = s->B;  // upper bound when dev_B() is set
+  const int32_t *Bd = dev_B(s, w);
+  const bool contiguous = s->items_contiguous || planned(s);
+  if (planned(s)) {
+    FR_LAUNCH(k_gather_batch, grid_for(256, 8, kSMs * 2), 256, 0, st, s->item_off, s->train_uid, s->train_rating,
+              s->sst_of_user, s->plan_items, s->plan_offs, 0, s->plan_desc, s->plan_len, w.ctrl, (int32_t *)s->uid,
+              (int32_t *)s->iid, (float *)s->rating, (float *)s->sst);
   }
-  build_segments(skey_i, ord_i, B, nullptr, w.segid_i, w.segoff_i, w.J, w.row_tab_i, w.ctrl + CTRL_STAMP, w.entry_seg,
-                 w.seg, st);
-  // user side: always sorted (stable => batch order inside a user's segment, like index_add on CPU)
-  sort_pairs((const uint32_t *)s->uid, nullptr, w.skey_u, w.ord_u, B, nullptr, bits_for((uint32_t)s->n_users), w.sort,
-             st);
-  build_segments(w.skey_u, w.ord_u, B, nullptr, w.segid_u, w.segoff_u, w.Ju, w.row_tab_u, w.ctrl + CTRL_STAMP, nullptr,
-                 w.seg, st);
-  FR_LAUNCH(k_forward, grid_for((int64_t)B, 32), 256, 0, st, s->U, s->I, s->uid, s->iid, s->sst, B, s->d, s->pred,
+  const uint32_t *ord_i = contiguous ? nullptr : w.ord_i;
+  if (B <= kPsMax) {
+    PrepSide pi{s->iid, w.skey_i, w.ord_i, w.segid_i, w.segoff_i, w.J, w.row_tab_i, w.entry_seg,
+                bits_for((uint32_t)s->n_items), contiguous ? 0 : 1};
+    PrepSide pu{s->uid, w.skey_u, w.ord_u, w.segid_u, w.segoff_u, w.Ju, w.row_tab_u, nullptr,
+                bits_for((uint32_t)s->n_users), 1};
+    const size_t smem = (size_t)kPsMax * 16 + (size_t)kPsWarps * 256 * 2 + 256 * 4 + 32 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      FR_CUDA_OK(cudaFuncSetAttribute(k_prepare_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    FR_LAUNCH(k_prepare_small, 2, kPsThreads, smem, st, pi, pu, B, Bd, w.ctrl);
+  } else {
+    // item side: segments of equal item id (sorted first unless the loader guarantees adjacency)
+    const uint32_t *skey_i = (const uint32_t *)s->iid;
+    if (!contiguous) {
+      sort_pairs((const uint32_t *)s->iid, nullptr, w.skey_i, w.ord_i, B, Bd, bits_for((uint32_t)s->n_items), w.sort, st);
+      skey_i = w.skey_i;
+    }
+    build_segments(skey_i, ord_i, B, Bd, w.segid_i, w.segoff_i, w.J, w.row_tab_i, w.ctrl + CTRL_STAMP, w.entry_seg,
+                   w.seg, st);
+    // user side: always sorted (stable => batch order inside a user's segment, like index_add on CPU)
+    sort_pairs((const uint32_t *)s->uid, nullptr, w.skey_u, w.ord_u, B, Bd, bits_for((uint32_t)s->n_users), w.sort, st);
+    build_segments(w.skey_u, w.ord_u, B, Bd, w.segid_u, w.segoff_u, w.Ju, w.row_tab_u, w.ctrl + CTRL_STAMP, nullptr,
+                   w.seg, st);
+  }
+  FR_LAUNCH(k_forward, grid_for((int64_t)B, 32), 256, 0, st, s->U, s->I, s->uid, s->iid, s->sst, B, Bd, s->d, s->pred,
             w.ctrl);
-  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segoff_i, w.J, B, s->objective, s->fair_weight,
-              w.cseg, w.seg_hx, w.seg_sq, w.seg_gs, w.cglob, s->loss, w.ctrl, s->status_flags};
+  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segoff_i, w.J, B, Bd, planned(s) ? 1 : 0, advance_adam ? 1 : 0,
+              s->objective, s->fair_weight, w.cseg, w.seg_hx, w.seg_sq, w.seg_gs, w.cglob, s->loss, w.ctrl,
+              s->status_flags};
   FR_LAUNCH(k_segment_loss, grid_for((int64_t)B, 8 * 16, kSMs * 2), 256, 0, st, la);
   return FR_OK;
 }
 
 static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale, cudaStream_t st) {
-  const uint32_t *ord_i = s->items_contiguous ? nullptr : w.ord_i;
-  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, ord_i, w.ord_u,
+  const uint32_t *ord_i = (s->items_contiguous || planned(s)) ? nullptr : w.ord_i;
+  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), ord_i, w.ord_u,
               w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
               w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
   const int nchunk = (s->B + kChunk - 1) / kChunk;
@@ -609,7 +816,8 @@ static ApplyArgs apply_args(const fr_focf_step *s, const FocfWs &w) {
 
 static int apply_grid(const fr_focf_step *s) {
   const int64_t nq = ((int64_t)s->n_users + s->n_items) * (s->d / 4);
-  return grid_for(nq, 256 * 4, kSMs * 8);
+  // one float4 per thread while the table is small (latency-bound: maximise loads in flight), grid-stride beyond
+  return grid_for(nq, 256, kSMs * 16);
 }
 
 }  // namespace fr
@@ -642,12 +850,22 @@ int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_us
   return FR_OK;
 }
 
+int fr_focf_set_counters(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
+                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, void *stream) {
+  FR_REQUIRE(workspace, "fr_focf_set_counters: null workspace");
+  fr::Carver c(workspace, workspace_bytes);
+  fr::FocfWs w = fr::carve(c, n_users, n_items, d, max_batch);
+  FR_LAUNCH(fr::k_set_ctrl, 1, 1, 0, stream, w.ctrl, plan_cursor, adam_step);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
 int fr_focf_forward(const fr_focf_step *s, void *stream) {
   int rc = fr::check_step(s, false, "fr_focf_forward");
   if (rc) return rc;
   fr::FocfWs w;
   if ((rc = fr::carve_checked(s, &w, "fr_focf_forward"))) return rc;
-  fr::forward_impl(s, w, (cudaStream_t)stream);
+  if ((rc = fr::forward_impl(s, w, (cudaStream_t)stream, false))) return rc;
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
@@ -680,7 +898,7 @@ int fr_focf_train_step(const fr_focf_step *s, void *stream) {
   if (rc) return rc;
   fr::FocfWs w;
   if ((rc = fr::carve_checked(s, &w, "fr_focf_train_step"))) return rc;
-  fr::forward_impl(s, w, (cudaStream_t)stream);
+  if ((rc = fr::forward_impl(s, w, (cudaStream_t)stream, s->step <= 0))) return rc;
   fr::grads_impl(s, w, 1.0f, (cudaStream_t)stream);
   FR_LAUNCH(fr::k_apply<fr::kAdamFused>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
   FR_LAUNCH_CHECK();
@@ -705,7 +923,7 @@ int fr_focf_gather_batch(const int32_t *item_off, const int32_t *train_uid, cons
                  sst && J >= 1,
              "fr_focf_gather_batch: bad argument");
   FR_LAUNCH(fr::k_gather_batch, fr::grid_for(J, 8, fr::kSMs * 4), 256, 0, stream, item_off, train_uid, train_rating,
-            sst_of_user, draw_items, draw_off, J, uid, iid, rating, sst);
+            sst_of_user, draw_items, draw_off, J, nullptr, 0, nullptr, uid, iid, rating, sst);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

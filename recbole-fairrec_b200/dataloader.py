@@ -130,6 +130,27 @@ class FOCFDataLoader:
                                             ptr(sst), stream_ptr()), "fr_focf_gather_batch")
         return uid, iid, rating, sst
 
+    def plan_epoch_device(self):
+        """Draw the whole epoch on the host and place the plan in PERSISTENT device buffers (their addresses stay the
+        same from epoch to epoch, so a captured CUDA graph of the step keeps pointing at them).  Returns the plan dict
+        consumed by FocfEngine.planned_step; plan["rows"] is the host-side total number of interactions."""
+        items, offs, batches = self.plan_epoch()
+        desc = np.asarray(batches, dtype=np.int32).reshape(-1, 4)
+        dev = self.train.device
+        p = getattr(self, "_plan", None)
+        if p is None or p["items"].numel() < len(items) or p["offs"].numel() < len(offs) or p["desc"].shape[0] < len(desc):
+            grow = lambda n: int(n * 1.5) + 64
+            p = dict(items=torch.zeros(grow(len(items)), dtype=torch.int32, device=dev),
+                     offs=torch.zeros(grow(len(offs)), dtype=torch.int32, device=dev),
+                     desc=torch.zeros((grow(len(desc)), 4), dtype=torch.int32, device=dev),
+                     cols=self._cols, generation=(0 if p is None else p["generation"] + 1))
+            self._plan = p
+        p["items"][:len(items)].copy_(torch.from_numpy(items).pin_memory(), non_blocking=True)
+        p["offs"][:len(offs)].copy_(torch.from_numpy(offs).pin_memory(), non_blocking=True)
+        p["desc"][:len(desc)].copy_(torch.from_numpy(desc).pin_memory(), non_blocking=True)
+        p["len"], p["rows"], p["batch_rows"] = len(desc), int(desc[:, 3].sum()), desc[:, 3].tolist()
+        return p
+
     def __iter__(self):
         items, offs, batches = self.plan_epoch()
         dev = self.train.device

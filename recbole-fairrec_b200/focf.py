@@ -160,6 +160,47 @@ class FOCF(nn.Module):
                        self._batch(interaction), self._objective, self.fair_weight, loss_out=out)
         return out
 
+    @torch.no_grad()
+    def planned_runner(self, loader, loss_buf, graph_steps=8):
+        """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k fused steps
+        with NO per-step host work: the step's kernel sequence (gather -> prepare -> forward -> loss -> gradients ->
+        Adam) is captured once into CUDA graphs (1 step and `graph_steps` steps) and replayed; batch size, batch
+        cursor and Adam step count are device resident.  loss_buf[cursor] receives each step's loss."""
+        if self._adam is None:
+            raise RuntimeError("call init_adam() before planned_runner()")
+        eng = self._engine()
+        plan = loader.plan_epoch_device()
+        if loss_buf.numel() < plan["len"]:
+            raise ValueError("loss buffer shorter than the epoch")
+        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        key = (plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), graph_steps, plan["len"],
+               eng.ws.data_ptr())
+        eng.set_counters(plan_cursor=0, adam_step=self._adam["step"])
+        runner = _PlannedRunner(self, plan)
+        if getattr(self, "_graph_key", None) != key:
+            st = eng.planned_step(U, I, self._adam, plan, loader.train, self._objective, self.fair_weight, loss_buf)
+            eng.run_planned(st)          # eager first step: module loading, function attributes
+            runner.cursor = 1
+            self._adam["step"] += 1
+            torch.cuda.synchronize()
+            self._graphs = {}
+            for g_steps in sorted({graph_steps, 1}):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):   # capture does not execute
+                    for _ in range(g_steps):
+                        eng.run_planned(st)
+                self._graphs[g_steps] = g
+            self._graph_key, self._graph_step, self._graph_len = key, st, graph_steps
+        return runner
+
+    @torch.no_grad()
+    def train_epoch_planned(self, loader, loss_buf, graph_steps=8):
+        """One epoch through planned_runner.  Returns (number of steps, number of interactions)."""
+        runner = self.planned_runner(loader, loss_buf, graph_steps)
+        n = runner.plan["len"]
+        runner.run(n - runner.cursor)
+        return n, runner.plan["rows"]
+
     def check_flags(self):
         """Raise what the reference would have raised for a faulty batch (synchronises the device)."""
         f = self._engine().read_flags()
@@ -170,3 +211,22 @@ class FOCF(nn.Module):
             raise IndexError("index 1 is out of bounds for dimension 0 with size 1 (focf.py:130)")
         if f & _lib.FLAG_NAN_LOSS:
             raise ValueError("Training loss is nan")  # trainer.py:286-288
+
+
+class _PlannedRunner:
+    def __init__(self, model, plan):
+        self.model, self.plan, self.cursor = model, plan, 0
+
+    def run(self, k):
+        """execute the next k planned steps (graph replays only); returns the interactions they cover"""
+        m = self.model
+        big, one, G = m._graphs[m._graph_len], m._graphs[1], m._graph_len
+        for _ in range(k // G):
+            big.replay()
+        for _ in range(k % G):
+            one.replay()
+        n = self.plan["len"]
+        rows = sum(self.plan["batch_rows"][(self.cursor + i) % n] for i in range(k))
+        self.cursor += k
+        m._adam["step"] += k
+        return rows

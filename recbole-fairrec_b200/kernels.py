@@ -92,6 +92,40 @@ class FocfEngine:
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
         return s
 
+    def set_counters(self, plan_cursor=-1, adam_step=-1):
+        check(self.lib.fr_focf_set_counters(ptr(self.ws), self.ws.numel(), self.n_users, self.n_items, self.d,
+                                            self.max_batch, int(plan_cursor), int(adam_step), stream_ptr()),
+              "fr_focf_set_counters")
+
+    def planned_step(self, U, I, adam, plan, train, objective, fair_weight, loss_buf):
+        """fr_focf_step for planned batches (device-resident cursor / batch size / Adam step): the struct is the same
+        for every batch of the epoch, so the launch sequence can be captured once in a CUDA graph and replayed.
+        plan: dict(desc, items, offs, len, cols=(uid, iid, rating, sst) scratch columns); train: TrainData."""
+        uid, iid, rating, sst = plan["cols"]
+        cap = uid.numel()
+        if cap > self.max_batch:
+            self._ensure(cap)
+        s = FocfStep()
+        s.U, s.I = ptr(U), ptr(I)
+        s.n_users, s.n_items, s.d = self.n_users, self.n_items, self.d
+        s.uid, s.iid, s.rating, s.sst, s.B = ptr(uid), ptr(iid), ptr(rating), ptr(sst), cap
+        s.items_contiguous = 1
+        s.objective, s.fair_weight = objective, float(fair_weight)
+        s.pred, s.loss, s.status_flags = ptr(self.pred_buf), ptr(loss_buf), ptr(self.flags)
+        s.workspace, s.workspace_bytes = ptr(self.ws), self.ws.numel()
+        s.mU, s.vU, s.mI, s.vI = ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"])
+        s.step = 0   # device-resident counter
+        s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
+        s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
+        s.plan_desc, s.plan_items, s.plan_offs = ptr(plan["desc"]), ptr(plan["items"]), ptr(plan["offs"])
+        s.plan_len = int(plan["len"])
+        s.item_off, s.train_uid = ptr(train.item_off), ptr(train.train_uid)
+        s.train_rating, s.sst_of_user = ptr(train.train_rating), ptr(train.sst_of_user)
+        return s
+
+    def run_planned(self, s):
+        check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
+
     def adam_dense(self, U, I, dU, dI, adam):
         s = FocfStep()
         s.U, s.I, s.dU, s.dI = ptr(U), ptr(I), ptr(dU), ptr(dI)

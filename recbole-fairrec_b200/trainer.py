@@ -88,6 +88,11 @@ class FOCFTrainer:
         n_steps = len(train_data)
         if self._loss_buf is None or self._loss_buf.numel() < n_steps:
             self._loss_buf = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=self.device)
+        from .dataloader import FOCFDataLoader
+        if self.fused and isinstance(train_data, FOCFDataLoader) and train_data.max_batch <= 8192 \
+                and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
+            k, _ = self.model.train_epoch_planned(train_data, self._loss_buf)
+            return self._finish_epoch(k)
         k = 0
         for interaction in train_data:
             if k >= self._loss_buf.numel():
@@ -104,6 +109,9 @@ class FOCFTrainer:
                     torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
                 self.optimizer.step()
             k += 1
+        return self._finish_epoch(k)
+
+    def _finish_epoch(self, k):
         losses = self._loss_buf[:k].cpu().numpy()          # the epoch's single device->host sync
         self.model.check_flags()
         total = None

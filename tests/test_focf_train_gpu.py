@@ -220,3 +220,68 @@ def test_fault_flags():
     model.check_flags()
     np.testing.assert_allclose(loss.item(), fo.calculate_loss(U0, I0, uid, iid, r, np.ones_like(sst), "value", 1.0),
                                rtol=RTOL)
+
+
+def _ml_like_loader(seed, n_users=900, n_items=400, n_inter=60000, batch=2048, d=32):
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import synth
+    dev = torch.device("cuda")
+    uid, iid, rating, gender = synth.interactions(n_users, n_items, n_inter, seed, item_sigma=1.0)
+    cfg = pkg.Config(embedding_size=d, fair_objective="value", fair_weight=1.0, train_batch_size=batch, device=dev,
+                     learning_rate=1e-3, weight_decay=1e-3, seed=seed, epochs=2)
+    train = pkg.TrainData(uid, iid, rating, gender, n_users, n_items, dev)
+    rng = np.random.default_rng(seed)
+    U0 = (rng.standard_normal((n_users, d)) * 0.2).astype(np.float32)
+    I0 = (rng.standard_normal((n_items, d)) * 0.2).astype(np.float32)
+    return cfg, train, U0, I0
+
+
+def test_planned_graph_epoch_equals_stepwise_epoch():
+    """The CUDA-graph replay over a planned epoch (device-resident batch size / cursor / Adam step, fused single-CTA
+    preparation) is bit-identical to the same batches fed one fr_focf_train_step at a time."""
+    import recbole_fairrec_b200 as pkg
+    cfg, train, U0, I0 = _ml_like_loader(3)
+    results = []
+    for planned in (False, True):
+        loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=11)
+        model = make_model(U0, I0, "value", 1.0)
+        model.init_adam(lr=1e-3, weight_decay=1e-3)
+        n = len(loader)
+        losses = torch.zeros(2 * n, device="cuda")
+        for ep in range(2):
+            if planned:
+                k, rows = model.train_epoch_planned(loader, losses[ep * n:(ep + 1) * n], graph_steps=4)
+                assert k == n
+            else:
+                for k, inter in enumerate(loader):
+                    model.train_step(inter, loss_out=losses[ep * n + k:ep * n + k + 1])
+        model.check_flags()
+        results.append((losses.cpu().numpy().copy(), model.user_embedding_layer.weight.detach().cpu().numpy().copy(),
+                        model.item_embedding_layer.weight.detach().cpu().numpy().copy(), model._adam["step"]))
+    assert results[0][3] == results[1][3] == 2 * n
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_array_equal(results[0][1], results[1][1])
+    np.testing.assert_array_equal(results[0][2], results[1][2])
+
+
+def test_small_and_general_preparation_agree():
+    """B <= 8192 takes the fused single-CTA preparation, larger batches the multi-kernel path: same results"""
+    from recbole_fairrec_b200 import kernels
+    U0, I0, uid, iid, r, sst = random_case(21, 3000, 800, 64, 7000, shuffle=True)
+    outs = []
+    for pad in (0, 3000):   # padding rows from extra items push the batch over the 8192 limit
+        if pad:
+            rng = np.random.default_rng(0)
+            eu = rng.integers(1, 3000, pad)
+            ei = rng.integers(1, 800, pad)
+            u2, i2 = np.r_[uid, eu], np.r_[iid, ei]
+            r2, s2 = np.r_[r, rng.integers(1, 6, pad).astype(np.float32)], np.r_[sst, rng.integers(1, 3, pad)]
+        else:
+            u2, i2, r2, s2 = uid, iid, r, sst
+        model = make_model(U0, I0, "value", 1.0)
+        loss = model.calculate_loss(make_inter(u2, i2, r2, s2, False))
+        loss.backward()
+        o = fo.grads(U0, I0, u2, i2, r2, s2, "value", 1.0)
+        assert rel_err(model.user_embedding_layer.weight.grad.cpu().numpy(), o[2]) < RTOL
+        assert rel_err(model.item_embedding_layer.weight.grad.cpu().numpy(), o[3]) < RTOL
+        np.testing.assert_allclose(loss.item(), fo.calculate_loss(U0, I0, u2, i2, r2, s2, "value", 1.0), rtol=RTOL)
