@@ -358,6 +358,9 @@ def run_ours(args, wname):
         "k_apply<fr::kAdamFused>": 24.0 * n_rows_tab * d,
         "k_segment_grads": 8.0 * d * B_avg,
         "k_forward": 8.0 * d * B_avg + 16.0 * B_avg,
+        "k_gather_batch": 36.0 * B_avg,         # read uid, rating, sst(user) + item_off/draws; write 4 columns
+        "k_prepare_small": 8.0 * B_avg + 40.0 * B_avg,   # read both key columns; write keys/order/segment ids per side
+        "k_segment_loss": 16.0 * B_avg,          # read pred, rating, sst, segment id
     }
     tot_ms = sum(v[1] for v in prof_train.values()) or 1.0
     shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(prof_train.items(), key=lambda kv: -kv[1][1])}

@@ -126,7 +126,8 @@ typedef struct fr_focf_step {
   const int32_t *B_dev;       /* [1] actual number of rows of a caller-built batch (NULL: B is exact) */
   /* planned epoch (focf_dataloader.py:37-50 for a whole epoch, drawn ahead): when plan_desc != NULL the step first
    * materialises its batch itself (fr_focf_gather_batch semantics) into uid/iid/rating/sst (caller-owned scratch
-   * columns of capacity B) from descriptor row (cursor % plan_len) and writes its loss to loss[cursor]; the cursor
+   * columns of capacity B) from descriptor row (cursor % plan_len) and writes its loss to loss[cursor % plan_len]
+   * (loss must hold plan_len floats); the cursor
    * lives in the workspace (fr_focf_set_counters) and advances by one per forward. */
   const int32_t *plan_desc;   /* [plan_len, 4] = {first draw index, first offset index, J, B} */
   const int32_t *plan_items;  /* concatenated drawn item ids */

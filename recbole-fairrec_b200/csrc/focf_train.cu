@@ -21,7 +21,9 @@
 namespace fr {
 
 constexpr int kMaxD = 512;            // embedding_size limit (multiple of 4)
-constexpr int kChunk = 32;            // sorted entries per gradient warp
+constexpr int kChunk = 32;            // max sorted entries per gradient warp (runtime: 8 for small batches)
+constexpr int kChunkMin = 8;
+static inline int grad_chunk(int B) { return B <= 16384 ? kChunkMin : kChunk; }
 
 enum {
   CTRL_STAMP = 0,      // batch counter: tags row_tab entries, advanced by the last CTA of k_segment_loss
@@ -44,9 +46,9 @@ struct FocfWs {
   uint32_t *skey_i, *ord_i, *skey_u, *ord_u;          // [B] sorted keys / entry order
   int32_t *segid_i, *segoff_i, *J, *segid_u, *segoff_u, *Ju, *entry_seg;
   float *cseg;      // [B,2] additive dL/dpred term of every (item segment, group)
-  float *seg_hx;    // [B]  smooth_l1(x_j)
-  float *seg_sq;    // [B]  sum (pred-r)^2 of the segment
-  float *seg_gs;    // [B,4] nonparity partials: sum pred g0,g1, count g0,g1
+  float *rec_seg;   // [B,8]     loss-statistics record of a segment lying inside one 8-row thread chunk
+  float *rec_head;  // [B/8+2,8] record of the run continuing from the previous chunk
+  float *rec_tail;  // [B/8+2,8] record of the run continuing into the next chunk
   float *cglob;     // [2]  batch-global additive term per group (nonparity)
   float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;  // gradient partials [B,d], [B/32+1,d] x2
   SortScratch sort;
@@ -58,7 +60,7 @@ static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
   w.row_tab_u = c.take<uint2>(n_users);
   w.row_tab_i = c.take<uint2>(n_items);
   w.ctrl = c.take<uint32_t>(CTRL_WORDS);
-  const size_t b = (size_t)(B < 1 ? 1 : B), nch = b / kChunk + 2;
+  const size_t b = (size_t)(B < 1 ? 1 : B), nch = b / kChunkMin + 2;
   w.skey_i = c.take<uint32_t>(b);
   w.ord_i = c.take<uint32_t>(b);
   w.skey_u = c.take<uint32_t>(b);
@@ -71,9 +73,9 @@ static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
   w.Ju = c.take<int32_t>(1);
   w.entry_seg = c.take<int32_t>(b);
   w.cseg = c.take<float>(2 * b);
-  w.seg_hx = c.take<float>(b);
-  w.seg_sq = c.take<float>(b);
-  w.seg_gs = c.take<float>(4 * b);
+  w.rec_seg = c.take<float>(8 * b);
+  w.rec_head = c.take<float>(8 * (b / 8 + 2));
+  w.rec_tail = c.take<float>(8 * (b / 8 + 2));
   w.cglob = c.take<float>(2);
   w.gseg_i = c.take<float>(b * d);
   w.head_i = c.take<float>(nch * d);
@@ -134,72 +136,143 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------ segment loss
-// One warp per item segment (rows of one item are adjacent in item-sorted order): Sp/St/n per group,
-// D per objective, smooth-L1 of the group gap and the additive backward term of the segment (appendix
-// A.1/A.2 of SURVEY.md).  The last CTA to finish reduces the per-segment partials in a fixed order and
-// writes the loss.
+// Item x group statistics, fairness objective and loss (appendix A.1/A.2 of SURVEY.md) in one launch with an even
+// work split that does not depend on item popularity:
+//   phase 1 (all CTAs): thread t owns rows 8t..8t+7 of the item-sorted order and accumulates, per run of equal
+//            segment, (sum pred, sum rating, count) per group and sum (pred-r)^2.  A segment that lies inside the
+//            8 rows is written complete; a run continuing from / into a neighbouring thread leaves a head / tail record.
+//   phase 2 (the last CTA to finish, self-resetting ticket): warp per segment adds its records in a fixed order,
+//            derives D, smooth-L1 and the additive backward term cseg[j][g]; a fixed-order block reduction gives the loss.
+constexpr int kLossRows = 8;       // rows per thread in phase 1
+constexpr int kLossThreads = 1024;
+constexpr int kLossRec = 8;        // floats per record: sp0 sp1 st0 st1 c0 c1 sq (pad)
+
 struct LossArgs {
   const float *pred, *rating, *sst;
   const uint32_t *ord_i;
-  const int32_t *segoff_i, *J;
+  const int32_t *segid_i, *segoff_i, *J;
   int B;
   const int32_t *B_dev;
-  int loss_by_cursor;   // planned batches: write loss[cursor] instead of loss[0]
+  int loss_by_cursor;   // planned batches: plan length L > 0 -> write loss[cursor % L] instead of loss[0]
   int advance_adam;     // fused step with the device-resident Adam counter
   int objective;
   float fair_weight;
-  float *cseg, *seg_hx, *seg_sq, *seg_gs, *cglob, *loss;
+  float *cseg, *rec_seg, *rec_head, *rec_tail, *cglob, *loss;
   uint32_t *ctrl;
   int32_t *flags;
 };
 
-__device__ __forceinline__ float block_sum_256(float v, float *sh) {
+__device__ __forceinline__ float block_sum_1024(float v, float *sh) {  // sh: >= 33 floats
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = 0.f;
-  if (threadIdx.x < 8) t = sh[threadIdx.x];
+  float t = (threadIdx.x < 32) ? sh[threadIdx.x] : 0.f;
   if (threadIdx.x < 32) {
-    t += __shfl_xor_sync(0xffffffffu, t, 4);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sh[32] = t;
   }
-  if (threadIdx.x == 0) sh[8] = t;
   __syncthreads();
-  t = sh[8];
+  t = sh[32];
   __syncthreads();
   return t;
 }
 
-__global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
-  __shared__ float sh[9];
+__global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
+  __shared__ float sh[33];
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int J = *a.J;
   const int B = FR_B(a.B, a.B_dev);
   const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
-  int bad = 0;
-  for (int j = warp; j < J; j += nwarps) {
-    const int p0 = a.segoff_i[j], p1 = a.segoff_i[j + 1];
-    float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
-    for (int p = p0 + lane; p < p1; p += 32) {
-      const int b = a.ord_i ? (int)a.ord_i[p] : p;
-      const float pr = a.pred[b], r = a.rating[b], sv = a.sst[b];
-      const bool g = sv != vmin;
-      bad |= (g && sv != vmax);
-      const float df = pr - r;
-      sq = fmaf(df, df, sq);
-      if (g) {
-        sp1 += pr; st1 += r; c1 += 1.f;
-      } else {
-        sp0 += pr; st0 += r; c0 += 1.f;
+
+  // ---------------- phase 1
+  {
+    const int t = blockIdx.x * kLossThreads + threadIdx.x;
+    const int lo = t * kLossRows, hi = lo + kLossRows;
+    int bad = 0;
+    if (lo < B) {
+      float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int cur = a.segid_i[lo];
+      auto flush = [&](int sgm) {
+        const int s0 = a.segoff_i[sgm], s1 = a.segoff_i[sgm + 1];
+        float *dst = (s0 >= lo && s1 <= hi) ? a.rec_seg + (size_t)sgm * kLossRec
+                     : (s0 < lo)            ? a.rec_head + (size_t)t * kLossRec
+                                            : a.rec_tail + (size_t)t * kLossRec;
+        *(float4 *)dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *(float4 *)(dst + 4) = make_float4(acc[4], acc[5], acc[6], 0.f);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+      };
+      // issue every load of the 8 rows before consuming any (rows past B re-read row lo and are ignored)
+      int sg[kLossRows];
+      float prv[kLossRows], rv[kLossRows], svv[kLossRows];
+#pragma unroll
+      for (int i = 0; i < kLossRows; ++i) {
+        const int p = (lo + i < B) ? lo + i : lo;
+        const int b = a.ord_i ? (int)a.ord_i[p] : p;
+        sg[i] = a.segid_i[p];
+        prv[i] = a.pred[b];
+        rv[i] = a.rating[b];
+        svv[i] = a.sst[b];
       }
+#pragma unroll
+      for (int i = 0; i < kLossRows; ++i) {
+        if (lo + i < B) {
+          if (sg[i] != cur) {
+            flush(cur);
+            cur = sg[i];
+          }
+          const float pr = prv[i], r = rv[i], sv = svv[i];
+          const bool g = sv != vmin;
+          bad |= (g && sv != vmax);
+          const float df = pr - r;
+          acc[6] = fmaf(df, df, acc[6]);
+          if (g) {
+            acc[1] += pr; acc[3] += r; acc[5] += 1.f;
+          } else {
+            acc[0] += pr; acc[2] += r; acc[4] += 1.f;
+          }
+        }
+      }
+      flush(cur);
     }
-    sp0 = warp_sum(sp0); sp1 = warp_sum(sp1); st0 = warp_sum(st0); st1 = warp_sum(st1);
-    c0 = warp_sum(c0); c1 = warp_sum(c1); sq = warp_sum(sq);
+    // focf.py:81-86: a third attribute value indexes past the [J,2] tensors (IndexError in the reference).
+    // (nonparity in the reference silently keeps the two smallest values, focf.py:129-130; we flag instead.)
+    if (a.objective != FR_OBJ_NONE && bad) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+  }
+
+  // ---------------- last-CTA election (self-resetting ticket)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // ---------------- phase 2: warp per segment
+  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;  // lane 0 accumulates over its segments
+  for (int j = wib; j < J; j += kLossThreads / 32) {
+    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
+    const int t0 = s0 / kLossRows, t1 = (s1 - 1) / kLossRows;
+    float v[7];
+    if (t0 == t1) {
+      const float4 x = *(const float4 *)(a.rec_seg + (size_t)j * kLossRec);
+      const float4 y = *(const float4 *)(a.rec_seg + (size_t)j * kLossRec + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) v[k] = 0.f;
+      for (int t = t0 + lane; t <= t1; t += 32) {
+        const float *src = (t == t0) ? a.rec_tail + (size_t)t * kLossRec : a.rec_head + (size_t)t * kLossRec;
+        const float4 x = *(const float4 *)src, y = *(const float4 *)(src + 4);
+        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z;
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
+    }
     if (lane == 0) {
-      a.seg_sq[j] = sq;
+      const float sp0 = v[0], sp1 = v[1], st0 = v[2], st1 = v[3], c0 = v[4], c1 = v[5];
+      w_sq += v[6];
       float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
       if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
         const float n0 = c0 + 1e-5f, n1 = c1 + 1e-5f;                       // focf.py:89
@@ -230,39 +303,19 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
         cs0 = q * dd0 / n0;
         cs1 = -q * dd1 / n1;
       } else if (a.objective == FR_OBJ_NONPARITY) {
-        a.seg_gs[4 * j + 0] = sp0; a.seg_gs[4 * j + 1] = sp1;
-        a.seg_gs[4 * j + 2] = c0;  a.seg_gs[4 * j + 3] = c1;
+        w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
       }
-      a.seg_hx[j] = hx;
+      w_hx += hx;
       a.cseg[2 * j] = cs0;
       a.cseg[2 * j + 1] = cs1;
     }
   }
-  // focf.py:81-86: a third attribute value indexes past the [J,2] tensors (IndexError in the reference).
-  // (nonparity in the reference silently keeps the two smallest values, focf.py:129-130; we flag instead.)
-  if (a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
-    atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
-
-  // ---- last-CTA reduction (self-resetting ticket)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  float sq = 0.f, hx = 0.f, g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
-  for (int j = threadIdx.x; j < J; j += 256) {
-    sq += a.seg_sq[j];
-    hx += a.seg_hx[j];
-    if (a.objective == FR_OBJ_NONPARITY) {
-      g0 += a.seg_gs[4 * j]; g1 += a.seg_gs[4 * j + 1]; n0 += a.seg_gs[4 * j + 2]; n1 += a.seg_gs[4 * j + 3];
-    }
-  }
-  sq = block_sum_256(sq, sh);
-  hx = block_sum_256(hx, sh);
+  // fixed-order block reduction (only lane 0 of every warp carries a value)
+  const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
+  float g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
   if (a.objective == FR_OBJ_NONPARITY) {
-    g0 = block_sum_256(g0, sh); g1 = block_sum_256(g1, sh);
-    n0 = block_sum_256(n0, sh); n1 = block_sum_256(n1, sh);
+    g0 = block_sum_1024(w_g0, sh); g1 = block_sum_1024(w_g1, sh);
+    n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
   }
   if (threadIdx.x == 0) {
     float loss = sq / (float)B;                                              // nn.MSELoss 'mean'
@@ -282,7 +335,7 @@ __global__ void __launch_bounds__(256) k_segment_loss(LossArgs a) {
     }
     a.cglob[0] = cg0;
     a.cglob[1] = cg1;
-    a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] : 0u] = loss;
+    a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor : 0u] = loss;
     if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
     // hand the group values to the backward kernels, re-arm the control block for the next batch
     a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
@@ -312,6 +365,7 @@ struct GradArgs {
   const float *cseg, *cglob;
   const uint32_t *ctrl;
   float grad_scale;
+  int chunk;   // sorted entries per warp (8 or 32)
   float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;
 };
 
@@ -321,7 +375,8 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const bool user_side = c >= nchunk;
   if (user_side) c -= nchunk;
-  const int pbase = c * kChunk;
+  const int chunk = a.chunk;
+  const int pbase = c * chunk;
   const int B = FR_B(a.B, a.B_dev);
   if (pbase >= B) return;
   const uint32_t *ord = user_side ? a.ord_u : a.ord_i;
@@ -333,7 +388,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   float *head = user_side ? a.head_u : a.head_i;
   float *tail = user_side ? a.tail_u : a.tail_i;
   const int d = a.d;
-  const int nvalid = min(kChunk, B - pbase);
+  const int nvalid = min(chunk, B - pbase);
   const float vmin = ord2f(a.ctrl[CTRL_SAVED_MIN]);
 
   // lane l stages entry pbase + l
@@ -355,7 +410,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
 
   auto flush = [&](int s) {
     const int s0 = segoff[s], s1 = segoff[s + 1];
-    float *dst = (s0 >= pbase && s1 <= pbase + kChunk) ? gseg + (size_t)s * d
+    float *dst = (s0 >= pbase && s1 <= pbase + chunk) ? gseg + (size_t)s * d
                  : (s0 < pbase)                        ? head + (size_t)c * d
                                                        : tail + (size_t)c * d;
 #pragma unroll
@@ -422,6 +477,7 @@ struct ApplyArgs {
   const uint32_t *ctrl;
   int step;
   double lr, beta1, beta2, eps, wd;
+  int chunk;   // the gradient kernel's chunk size (head/tail partial indexing)
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -471,7 +527,7 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
         const float *head = is_item ? a.head_i : a.head_u;
         const float *tail = is_item ? a.tail_i : a.tail_u;
         const int s = (int)t.y, s0 = segoff[s], s1 = segoff[s + 1];
-        const int c0 = s0 / kChunk, c1 = (s1 - 1) / kChunk;
+        const int c0 = s0 / a.chunk, c1 = (s1 - 1) / a.chunk;
         if (c0 == c1) {
           g = *(const float4 *)(gseg + (size_t)s * a.d + k);
         } else {
@@ -551,17 +607,22 @@ __global__ void __launch_bounds__(256)
     J = dsc[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[CTRL_B] = (uint32_t)dsc[3];
   }
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int j = warp; j < J; j += nwarps) {
-    const int it = draw_items[j], src = item_off[it], dst = draw_off[j], len = draw_off[j + 1] - dst;
-    for (int p = lane; p < len; p += 32) {
-      const int u = train_uid[src + p];
-      uid[dst + p] = u;
-      iid[dst + p] = it;
-      rating[dst + p] = train_rating[src + p];
-      sst[dst + p] = sst_of_user[u];
+  // one thread per output row (work independent of item popularity): the row's drawn item is found by a binary
+  // search in the J+1 batch offsets (L1-resident), then the CSC row is copied and the user's attribute joined
+  const int B = draw_off[J];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < B; p += gridDim.x * blockDim.x) {
+    int lo = 0, hi = J;  // invariant: draw_off[lo] <= p < draw_off[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (draw_off[mid] <= p) lo = mid; else hi = mid;
     }
+    const int it = draw_items[lo];
+    const int src = item_off[it] + (p - draw_off[lo]);
+    const int u = train_uid[src];
+    uid[p] = u;
+    iid[p] = it;
+    rating[p] = train_rating[src];
+    sst[p] = sst_of_user[u];
   }
 }
 
@@ -593,6 +654,9 @@ __global__ void __launch_bounds__(kPsThreads)
   const int n = FR_B(B_host, B_dev);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t stamp = ctrl[CTRL_STAMP];
+  // radix ranking: warp w owns the contiguous keys [w*chunk, (w+1)*chunk), chunk a multiple of 32 chosen so that
+  // all 32 warps share the n keys evenly (rounds = chunk/32 <= 8)
+  const int rounds = (n + kPsThreads - 1) / kPsThreads, chunk = rounds * 32;
 
   for (int p = tid; p < n; p += kPsThreads) {
     kA[p] = (uint32_t)sd.keys_in[p];
@@ -609,7 +673,8 @@ __global__ void __launch_bounds__(kPsThreads)
       uint32_t key[kPsItems], val[kPsItems], rnk[kPsItems];
 #pragma unroll
       for (int r = 0; r < kPsItems; ++r) {
-        const int p = w * (kPsMax / kPsWarps) + r * 32 + lane;
+        if (r >= rounds) break;
+        const int p = w * chunk + r * 32 + lane;
         const bool valid = p < n;
         key[r] = valid ? kA[p] : 0u;
         val[r] = valid ? vA[p] : 0u;
@@ -648,7 +713,8 @@ __global__ void __launch_bounds__(kPsThreads)
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < kPsItems; ++r) {
-        const int p = w * (kPsMax / kPsWarps) + r * 32 + lane;
+        if (r >= rounds) break;
+        const int p = w * chunk + r * 32 + lane;
         if (p < n) {
           const uint32_t dig = (key[r] >> shift) & 255u;
           const uint32_t pos = dbase[dig] + cnt[w * 256 + dig] + rnk[r];
@@ -752,7 +818,7 @@ static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
   const int32_t *Bd = dev_B(s, w);
   const bool contiguous = s->items_contiguous || planned(s);
   if (planned(s)) {
-    FR_LAUNCH(k_gather_batch, grid_for(256, 8, kSMs * 2), 256, 0, st, s->item_off, s->train_uid, s->train_rating,
+    FR_LAUNCH(k_gather_batch, grid_for((int64_t)B, 256, kSMs * 8), 256, 0, st, s->item_off, s->train_uid, s->train_rating,
               s->sst_of_user, s->plan_items, s->plan_offs, 0, s->plan_desc, s->plan_len, w.ctrl, (int32_t *)s->uid,
               (int32_t *)s->iid, (float *)s->rating, (float *)s->sst);
   }
@@ -785,10 +851,11 @@ static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
   }
   FR_LAUNCH(k_forward, grid_for((int64_t)B, 32), 256, 0, st, s->U, s->I, s->uid, s->iid, s->sst, B, Bd, s->d, s->pred,
             w.ctrl);
-  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segoff_i, w.J, B, Bd, planned(s) ? 1 : 0, advance_adam ? 1 : 0,
-              s->objective, s->fair_weight, w.cseg, w.seg_hx, w.seg_sq, w.seg_gs, w.cglob, s->loss, w.ctrl,
+  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segid_i, w.segoff_i, w.J, B, Bd, planned(s) ? s->plan_len : 0,
+              advance_adam ? 1 : 0,
+              s->objective, s->fair_weight, w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl,
               s->status_flags};
-  FR_LAUNCH(k_segment_loss, grid_for((int64_t)B, 8 * 16, kSMs * 2), 256, 0, st, la);
+  FR_LAUNCH(k_segment_loss, (B + kLossThreads * kLossRows - 1) / (kLossThreads * kLossRows), kLossThreads, 0, st, la);
   return FR_OK;
 }
 
@@ -796,8 +863,8 @@ static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale,
   const uint32_t *ord_i = (s->items_contiguous || planned(s)) ? nullptr : w.ord_i;
   GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), ord_i, w.ord_u,
               w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
-              w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
-  const int nchunk = (s->B + kChunk - 1) / kChunk;
+              grad_chunk(s->B), w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
+  const int nchunk = (s->B + ga.chunk - 1) / ga.chunk;
   const int grid = (2 * nchunk + 7) / 8;
   if (s->d <= 128) {
     FR_LAUNCH(k_segment_grads<1>, grid, 256, 0, st, ga, nchunk);
@@ -811,7 +878,8 @@ static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale,
 static ApplyArgs apply_args(const fr_focf_step *s, const FocfWs &w) {
   return ApplyArgs{s->U, s->I, s->mU, s->vU, s->mI, s->vI, s->dU, s->dI, s->n_users, s->n_items, s->d,
                    w.row_tab_u, w.row_tab_i, w.segoff_u, w.segoff_i, w.gseg_u, w.head_u, w.tail_u,
-                   w.gseg_i, w.head_i, w.tail_i, w.ctrl, s->step, s->lr, s->beta1, s->beta2, s->eps, s->weight_decay};
+                   w.gseg_i, w.head_i, w.tail_i, w.ctrl, s->step, s->lr, s->beta1, s->beta2, s->eps, s->weight_decay,
+                   grad_chunk(s->B)};
 }
 
 static int apply_grid(const fr_focf_step *s) {
@@ -922,7 +990,7 @@ int fr_focf_gather_batch(const int32_t *item_off, const int32_t *train_uid, cons
   FR_REQUIRE(item_off && train_uid && train_rating && sst_of_user && draw_items && draw_off && uid && iid && rating &&
                  sst && J >= 1,
              "fr_focf_gather_batch: bad argument");
-  FR_LAUNCH(fr::k_gather_batch, fr::grid_for(J, 8, fr::kSMs * 4), 256, 0, stream, item_off, train_uid, train_rating,
+  FR_LAUNCH(fr::k_gather_batch, fr::grid_for((int64_t)J * 64, 256, fr::kSMs * 8), 256, 0, stream, item_off, train_uid, train_rating,
             sst_of_user, draw_items, draw_off, J, nullptr, 0, nullptr, uid, iid, rating, sst);
   FR_LAUNCH_CHECK();
   return FR_OK;
