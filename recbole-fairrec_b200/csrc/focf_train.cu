@@ -23,7 +23,9 @@ namespace fr {
 constexpr int kMaxD = 512;            // embedding_size limit (multiple of 4)
 constexpr int kChunk = 32;            // max sorted entries per gradient warp (runtime: 8 for small batches)
 constexpr int kChunkMin = 8;
-static inline int grad_chunk(int B) { return B <= 16384 ? kChunkMin : kChunk; }
+// 16 entries per warp for small batches (more warps, shorter dependent chains), 32 for large ones; rows spanning many
+// chunks cost k_apply one partial read per chunk, so the chunk must not get too small
+static inline int grad_chunk(int B) { return B <= 16384 ? 16 : kChunk; }
 
 enum {
   CTRL_STAMP = 0,      // batch counter: tags row_tab entries, advanced by the last CTA of k_segment_loss
@@ -423,11 +425,12 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
     }
   };
 
-  for (int l0 = 0; l0 < nvalid; l0 += 4) {
-    float4 x[4][kRowVecs];
-    // issue the row loads of 4 entries before consuming them (memory-level parallelism)
+  constexpr int kDepth = kRowVecs == 1 ? 8 : 4;
+  for (int l0 = 0; l0 < nvalid; l0 += kDepth) {
+    float4 x[kDepth][kRowVecs];
+    // issue the row loads of kDepth entries before consuming them (memory-level parallelism)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < kDepth; ++e) {
       const int l = l0 + e;
       const int o = __shfl_sync(0xffffffffu, my_oid, l & 31);
       const float4 *row = (const float4 *)(other + (size_t)o * d);
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
       }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < kDepth; ++e) {
       const int l = l0 + e;
       const int s = __shfl_sync(0xffffffffu, my_seg, l & 31);
       const float cf = __shfl_sync(0xffffffffu, my_coef, l & 31);
@@ -532,7 +535,8 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
           g = *(const float4 *)(gseg + (size_t)s * a.d + k);
         } else {
           g = *(const float4 *)(tail + (size_t)c0 * a.d + k);
-          for (int c = c0 + 1; c <= c1; ++c) g = f4_add(g, *(const float4 *)(head + (size_t)c * a.d + k));
+#pragma unroll 8
+          for (int c = c0 + 1; c <= c1; ++c) g = f4_add(g, __ldg((const float4 *)(head + (size_t)c * a.d + k)));
         }
       }
     }
