@@ -137,6 +137,11 @@ typedef struct fr_focf_step {
   const int32_t *train_uid;
   const float *train_rating;
   const float *sst_of_user;
+  /* --- optional: data-parallel step.  Every rank holds whole items (disjoint item partitions), so the item x group
+   * sums are rank-local; only the two means are global: norm_B / norm_J (> 0) replace this rank's B and J as the
+   * normalisers of MSE and of the fairness mean.  The loss written is this rank's share (sum over ranks = loss);
+   * gradients from fr_focf_backward are this rank's share (all-reduce, then fr_focf_adam on every replica). */
+  int32_t norm_B, norm_J;
 } fr_focf_step;
 
 size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch);

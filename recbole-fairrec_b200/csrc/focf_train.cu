@@ -158,6 +158,7 @@ struct LossArgs {
   int loss_by_cursor;   // planned batches: plan length L > 0 -> write loss[cursor % L] instead of loss[0]
   int advance_adam;     // fused step with the device-resident Adam counter
   int objective;
+  int norm_B, norm_J;   // > 0: global batch rows / item count of a data-parallel step (normalisers of the two means)
   float fair_weight;
   float *cseg, *rec_seg, *rec_head, *rec_tail, *cglob, *loss;
   uint32_t *ctrl;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int J = *a.J;
   const int B = FR_B(a.B, a.B_dev);
+  const float Bn = (float)(a.norm_B > 0 ? a.norm_B : B), Jn = (float)(a.norm_J > 0 ? a.norm_J : J);
   const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
 
   // ---------------- phase 1
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
         const float z = D0 - D1, x = fabsf(z);
         hx = x < 1.f ? 0.5f * x * x : x - 0.5f;                              // smooth_l1, beta = 1
         const float hp = (x < 1.f ? x : 1.f) * (float)((z > 0.f) - (z < 0.f));
-        const float q = a.fair_weight * hp / (float)J;
+        const float q = a.fair_weight * hp / Jn;
         cs0 = q * dd0 / n0;
         cs1 = -q * dd1 / n1;
       } else if (a.objective == FR_OBJ_NONPARITY) {
@@ -320,10 +322,10 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
     n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
   }
   if (threadIdx.x == 0) {
-    float loss = sq / (float)B;                                              // nn.MSELoss 'mean'
+    float loss = sq / Bn;                                                    // nn.MSELoss 'mean'
     float cg0 = 0.f, cg1 = 0.f;
     if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-      loss += a.fair_weight * (hx / (float)J);                               // focf.py:166
+      loss += a.fair_weight * (hx / Jn);                                     // focf.py:166
     } else if (a.objective == FR_OBJ_NONPARITY) {
       if (n1 == 0.f || n0 == 0.f) {
         atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
@@ -362,6 +364,7 @@ struct GradArgs {
   const float *rating, *sst, *pred;
   int B, d;
   const int32_t *B_dev;
+  int norm_B;
   const uint32_t *ord_i, *ord_u;
   const int32_t *segid_i, *segoff_i, *segid_u, *segoff_u, *entry_seg;
   const float *cseg, *cglob;
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
     my_seg = segid[p];
     my_oid = oid[b];
     const int g = a.sst[b] != vmin;
-    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)B + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
+    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)(a.norm_B > 0 ? a.norm_B : B) + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
               a.grad_scale;
   }
   float4 acc[kRowVecs];
@@ -794,6 +797,8 @@ static int check_step(const fr_focf_step *s, bool need_adam, const char *who) {
   FR_REQUIRE(s->objective >= FR_OBJ_NONE && s->objective <= FR_OBJ_NONPARITY, "%s: bad objective %d", who,
              s->objective);
   if (need_adam) FR_REQUIRE(s->mU && s->vU && s->mI && s->vI, "%s: Adam state missing", who);
+  FR_REQUIRE(!(s->objective == FR_OBJ_NONPARITY && (s->norm_B > 0 || s->norm_J > 0)),
+             "%s: the nonparity objective needs batch-global group means and is not available data-parallel", who);
   if (planned(s)) {
     FR_REQUIRE(s->plan_items && s->plan_offs && s->plan_len >= 1 && s->item_off && s->train_uid && s->train_rating &&
                    s->sst_of_user,
@@ -857,7 +862,7 @@ static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
             w.ctrl);
   LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segid_i, w.segoff_i, w.J, B, Bd, planned(s) ? s->plan_len : 0,
               advance_adam ? 1 : 0,
-              s->objective, s->fair_weight, w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl,
+              s->objective, s->norm_B, s->norm_J, s->fair_weight, w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl,
               s->status_flags};
   FR_LAUNCH(k_segment_loss, (B + kLossThreads * kLossRows - 1) / (kLossThreads * kLossRows), kLossThreads, 0, st, la);
   return FR_OK;
@@ -865,7 +870,7 @@ static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
 
 static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale, cudaStream_t st) {
   const uint32_t *ord_i = (s->items_contiguous || planned(s)) ? nullptr : w.ord_i;
-  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), ord_i, w.ord_u,
+  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), s->norm_B, ord_i, w.ord_u,
               w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
               grad_chunk(s->B), w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
   const int nchunk = (s->B + ga.chunk - 1) / ga.chunk;

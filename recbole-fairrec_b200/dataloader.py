@@ -54,8 +54,13 @@ class TrainData:
 
 
 class FOCFDataLoader:
-    def __init__(self, config, train, mode="fast", draws=None, seed=None):
+    def __init__(self, config, train, mode="fast", draws=None, seed=None, partition=None):
+        """partition=(rank, world): data-parallel training -- this rank draws only items of its slice
+        item_uniques[rank::world] (whole items stay on one rank, so item x group sums need no exchange) and an epoch
+        has ceil(N_train / (train_batch_size * world)) global steps of `world` local batches each."""
         self.config, self.train = config, train
+        self.partition = partition
+        self.candidates = train.item_uniques if partition is None else train.item_uniques[partition[0]::partition[1]]
         self.dataset = train
         self.step = int(config["train_batch_size"])
         self.mode = mode
@@ -72,7 +77,8 @@ class FOCFDataLoader:
         self._replay_pos = 0
 
     def __len__(self):
-        return math.ceil(self.train.n_rows / self.step)              # abstract_dataloader.py:67-68
+        world = 1 if self.partition is None else self.partition[1]
+        return math.ceil(self.train.n_rows / (self.step * world))    # abstract_dataloader.py:67-68
 
     # ------------------------------------------------------------------ host-side draws
     def _draw_batch(self):
@@ -88,7 +94,7 @@ class FOCFDataLoader:
             # focf_dataloader.py:38-47 verbatim in effect: same calls on numpy's global RNG
             select_item = np.arange(0, tr.n_items)
             is_select = np.zeros(tr.n_items, dtype=bool)
-            is_select[tr.item_uniques] = True
+            is_select[self.candidates] = True
             cnt, items = 0, []
             while cnt < self.step:
                 iid = np.random.choice(select_item[is_select], 1, False)[0]
@@ -96,7 +102,7 @@ class FOCFDataLoader:
                 is_select[iid] = False
                 items.append(iid)
             return np.asarray(items, dtype=np.int64)
-        perm = self._rng.permutation(tr.item_uniques)
+        perm = self._rng.permutation(self.candidates)
         csum = np.cumsum(tr.item_count_h[perm])
         j = int(np.searchsorted(csum, self.step, side="left")) + 1
         return perm[:j].astype(np.int64)

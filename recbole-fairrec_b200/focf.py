@@ -161,6 +161,28 @@ class FOCF(nn.Module):
         return out
 
     @torch.no_grad()
+    def dp_train_step(self, interaction, norm, group, loss_out=None):
+        """Data-parallel step: this rank's whole-item batch, global normalisers `norm = (B_total,
+        J_total)`, dense gradient shares summed with ONE NCCL all-reduce, then the same dense Adam on every replica.
+        Equals the fused single-GPU step on the union of the ranks' batches (up to summation order)."""
+        import torch.distributed as dist
+        if self._adam is None:
+            raise RuntimeError("call init_adam() before dp_train_step()")
+        eng = self._engine()
+        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        if getattr(self, "_dp_grad", None) is None:
+            self._dp_grad = torch.empty(U.numel() + I.numel(), dtype=torch.float32, device=U.device)
+        dU = self._dp_grad[:U.numel()].view_as(U)
+        dI = self._dp_grad[U.numel():].view_as(I)
+        out = eng.loss if loss_out is None else loss_out
+        st = eng.forward(U, I, self._batch(interaction), self._objective, self.fair_weight, loss_out=out, norm=norm)
+        eng.backward(st, dU, dI, 1.0)
+        dist.all_reduce(self._dp_grad, group=group)
+        self._adam["step"] += 1
+        eng.adam_dense(U, I, dU, dI, self._adam)
+        return out
+
+    @torch.no_grad()
     def planned_runner(self, loader, loss_buf, graph_steps=8):
         """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k fused steps
         with NO per-step host work: the step's kernel sequence (gather -> prepare -> forward -> loss -> gradients ->

@@ -56,7 +56,7 @@ class FocfEngine:
         self.max_batch = B
         self.pred_buf = torch.empty(B, dtype=torch.float32, device=self.device)
 
-    def _step(self, U, I, batch, objective, fair_weight, loss_out=None):
+    def _step(self, U, I, batch, objective, fair_weight, loss_out=None, norm=None):
         uid, iid, rating, sst, contiguous = batch
         B = uid.numel()
         self._ensure(B)
@@ -71,10 +71,12 @@ class FocfEngine:
         s.loss = ptr(self.loss if loss_out is None else loss_out)
         s.status_flags = ptr(self.flags)
         s.workspace, s.workspace_bytes = ptr(self.ws), self.ws.numel()
+        if norm is not None:
+            s.norm_B, s.norm_J = int(norm[0]), int(norm[1])
         return s
 
-    def forward(self, U, I, batch, objective, fair_weight, loss_out=None):
-        s = self._step(U, I, batch, objective, fair_weight, loss_out)
+    def forward(self, U, I, batch, objective, fair_weight, loss_out=None, norm=None):
+        s = self._step(U, I, batch, objective, fair_weight, loss_out, norm)
         check(self.lib.fr_focf_forward(ctypes.byref(s), stream_ptr()), "fr_focf_forward")
         return s
 

@@ -89,6 +89,8 @@ class FOCFTrainer:
         if self._loss_buf is None or self._loss_buf.numel() < n_steps:
             self._loss_buf = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=self.device)
         from .dataloader import FOCFDataLoader
+        if self.group is not None and isinstance(train_data, FOCFDataLoader) and train_data.partition is not None:
+            return self._train_epoch_dp(train_data)
         if self.fused and isinstance(train_data, FOCFDataLoader) and train_data.max_batch <= 8192 \
                 and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
             k, _ = self.model.train_epoch_planned(train_data, self._loss_buf)
@@ -110,6 +112,31 @@ class FOCFTrainer:
                 self.optimizer.step()
             k += 1
         return self._finish_epoch(k)
+
+    def _train_epoch_dp(self, train_data):
+        """Data-parallel epoch: every rank plans its own whole-item batches, the per-step (J, B) are summed over the
+        ranks once per epoch (they are host-known at planning time), each step all-reduces the gradient shares, and
+        the per-step loss shares are summed once at the end of the epoch."""
+        import torch.distributed as dist
+        if not self.fused:
+            raise NotImplementedError("data-parallel FOCF training uses the library's Adam (learner: adam)")
+        items, offs, batches = train_data.plan_epoch()
+        dev = self.device
+        sizes = torch.tensor([[b[2], b[3]] for b in batches], dtype=torch.int64, device=dev)
+        dist.all_reduce(sizes, group=self.group)
+        norms = sizes.cpu().numpy()
+        d_items = torch.from_numpy(items).to(dev)
+        d_offs = torch.from_numpy(offs).to(dev)
+        uf, itf, rf, sf = train_data.train.fields
+        from .interaction import Interaction
+        for k, b in enumerate(batches):
+            uid, iid, rating, sst = train_data.gather(d_items, d_offs, b)
+            inter = Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
+            inter.items_contiguous = True
+            self.model.dp_train_step(inter, (int(norms[k, 1]), int(norms[k, 0])), self.group,
+                                     loss_out=self._loss_buf[k:k + 1])
+        dist.all_reduce(self._loss_buf[:len(batches)], group=self.group)
+        return self._finish_epoch(len(batches))
 
     def _finish_epoch(self, k):
         losses = self._loss_buf[:k].cpu().numpy()          # the epoch's single device->host sync
