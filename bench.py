@@ -16,8 +16,8 @@ Prints ONE JSON line (rank 0).  A "step" is one FOCF optimisation step on one FO
   cpu_baseline  oracle/torch_port.py (the reference's op sequence on stock torch CPU kernels, all host threads) on a
              bounded sample of the same workload
 `--impl reference` prints the CPU line alone (the reference is Python and cannot travel: kind = "port").
-Multi-GPU (torchrun): training = independent replicas on different batches (weak scaling, no gradient exchange yet);
-evaluation = item table sharded over the ranks, NCCL all-gather of the per-shard top-K + merge, all-reduce of the
+Multi-GPU (torchrun): training = data-parallel (every rank draws whole items from its own item partition, one NCCL
+all-reduce of the gradient shares per step, weak scaling: global batch = N x train_batch_size); evaluation = item table sharded over the ranks, NCCL all-gather of the per-shard top-K + merge, all-reduce of the
 item x group statistics.
 """
 import argparse
@@ -196,7 +196,8 @@ def run_ours(args, wname):
     cfg = pkg.Config(embedding_size=d, fair_objective="value", fair_weight=1.0, topk=[K], valid_metric=f"NDCG@{K}",
                      train_batch_size=w["batch"], learning_rate=1e-3, weight_decay=1e-3, device=dev, seed=2020 + rank)
     tdata = pkg.TrainData(train[0], train[1], train[2], gender, w["n_users"], w["n_items"], dev)
-    loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020 + rank)
+    loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020 + rank,
+                                partition=(rank, world) if world > 1 else None)
     model = pkg.FOCF(cfg, synth.SynthDataset(w["n_users"], w["n_items"], 5.0))
     rng = np.random.default_rng(2020)
     with torch.no_grad():
@@ -209,7 +210,7 @@ def run_ours(args, wname):
     n_plan = args.steps + args.warmup
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     G = 8
-    use_graph = loader.max_batch <= 8192
+    use_graph = loader.max_batch <= 8192 and world == 1
     losses = torch.zeros(max(len(loader), n_plan) * 2 + 16, device=dev)
     if use_graph:
         # planned epoch + CUDA-graph replay: one graph launch per step, zero per-step host work
@@ -223,14 +224,27 @@ def run_ours(args, wname):
             d_items, d_offs = torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev)
             flat += [(d_items, d_offs, b) for b in batches]
         pos = [0]
+        norms = None
+        if world > 1:   # global normalisers of every planned step: sum of the ranks' (B, J), host-known at planning time
+            t = torch.tensor([[b[3], b[2]] for _, _, b in flat], dtype=torch.int64, device=dev)
+            nmin = torch.tensor([t.shape[0]], device=dev)
+            dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+            flat = flat[:int(nmin.item())]
+            t = t[:len(flat)].contiguous()
+            dist.all_reduce(t)
+            norms = t.cpu().numpy()
 
         def dev_step():
-            d_items, d_offs, b = flat[pos[0] % len(flat)]
+            k = pos[0] % len(flat)
+            d_items, d_offs, b = flat[k]
             pos[0] += 1
             uid, iid, rating, sst = loader.gather(d_items, d_offs, b)
             inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
             inter.items_contiguous = True
-            model.train_step(inter, loss_out=losses[-1:])
+            if world > 1:
+                model.dp_train_step(inter, (int(norms[k, 0]), int(norms[k, 1])), group, loss_out=losses[-1:])
+            else:
+                model.train_step(inter, loss_out=losses[-1:])
             return b[3]
 
     for k in range(args.warmup):
@@ -283,10 +297,18 @@ def run_ours(args, wname):
     barrier()
     t0 = time.perf_counter()
     rows_e = 0
-    for hb in host_batches:
+    if world > 1:
+        eb = torch.tensor([[hb[0].numel(), int(torch.unique_consecutive(hb[1]).numel())] for hb in host_batches],
+                          dtype=torch.int64, device=dev)
+        dist.all_reduce(eb)
+        eb = eb.cpu().numpy()
+    for k, hb in enumerate(host_batches):
         inter = pkg.Interaction({uf: hb[0], itf: hb[1], rf: hb[2], sf: hb[3]})
         inter.items_contiguous = True
-        loss = model.train_step(inter)          # .to(device) of the four columns happens inside
+        if world > 1:
+            loss = model.dp_train_step(inter, (int(eb[k, 0]), int(eb[k, 1])), group)
+        else:
+            loss = model.train_step(inter)      # .to(device) of the four columns happens inside
         _ = loss.item()                         # trainer.py:191 -- per-step D2H + sync
         rows_e += hb[0].numel()
     barrier()
@@ -356,6 +378,8 @@ def run_ours(args, wname):
     n_rows_tab = w["n_users"] + w["n_items"]
     alg = {  # algorithmic HBM bytes per launch
         "k_apply<fr::kAdamFused>": 24.0 * n_rows_tab * d,
+        "k_apply<fr::kAdamDense>": 28.0 * n_rows_tab * d,    # data-parallel: + read of the all-reduced dense gradient
+        "k_apply<fr::kDenseOut>": 4.0 * n_rows_tab * d,      # data-parallel: write the dense gradient share
         "k_segment_grads": 8.0 * d * B_avg,
         "k_forward": 8.0 * d * B_avg + 16.0 * B_avg,
         "k_gather_batch": 36.0 * B_avg,         # read uid, rating, sst(user) + item_off/draws; write 4 columns
@@ -364,10 +388,11 @@ def run_ours(args, wname):
     }
     tot_ms = sum(v[1] for v in prof_train.values()) or 1.0
     shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(prof_train.items(), key=lambda kv: -kv[1][1])}
-    dom = next((k for k in shares if any(k.startswith(a.split("<")[0]) for a in alg)), None)
+    match = lambda k: k if k in alg else next((a for a in alg if "<" not in a and k.startswith(a)), None)
+    dom = next((k for k in shares if match(k)), None)
     roofline = None
     if dom:
-        key = next(a for a in alg if dom.startswith(a.split("<")[0]))
+        key = match(dom)
         cnt, ms = prof_train[dom]
         ach = alg[key] / (ms / cnt * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -403,8 +428,9 @@ def run_ours(args, wname):
                    "fair_objective": "value", "optimizer": "adam(lr=1e-3, weight_decay=1e-3) dense-exact",
                    "l2": "flushed before every timed step (512 MB write outside the event bracket)",
                    "parallelism": "single GPU" if world == 1 else
-                   f"train: {world} independent replicas (no gradient exchange yet); eval: item table sharded x{world}, "
-                   "NCCL all-gather top-K merge + all-reduce of item x group stats"},
+                   f"train: data-parallel x{world} (disjoint item partitions, global normalisers, NCCL all-reduce of the dense "
+                   f"gradient shares, identical dense Adam on every replica; global batch = {world} x {w['batch']}); "
+                   f"eval: item table sharded x{world}, NCCL all-gather top-K merge + all-reduce of item x group stats"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(round(kernels_per_step * args.steps)), "kernels_per_step": kernels_per_step,

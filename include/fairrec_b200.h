@@ -197,7 +197,7 @@ typedef struct fr_fullsort {
   size_t workspace_bytes;
 } fr_fullsort;
 
-size_t fr_fullsort_workspace_bytes(int32_t n, int32_t K, int32_t n_items_local, int32_t d);
+size_t fr_fullsort_workspace_bytes(int32_t n, int32_t K, int32_t n_items_local, int32_t d, int32_t score_mode);
 int fr_fullsort_topk(const fr_fullsort *a, void *stream);
 
 /* merge P per-shard top-K lists [P, n, K] (as gathered by NCCL all-gather) into the global top-K */

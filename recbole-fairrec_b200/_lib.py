@@ -70,7 +70,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "fr_pair_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                c_void_p]),
-    "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
     "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_hits": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -329,12 +329,20 @@ static int pick_splits(int n, int n_items_local) {
   return s;
 }
 
+// fullsort_tc.cu
+size_t tc_plane_bytes(int n, int n_items_local, int d);
+int tc_pick_splits(int n, int n_items_local);
+int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, float *out_sc, cudaStream_t st);
+
 }  // namespace fr
 
 extern "C" {
 
-size_t fr_fullsort_workspace_bytes(int32_t n, int32_t K, int32_t n_items_local, int32_t d) {
-  (void)d;
+size_t fr_fullsort_workspace_bytes(int32_t n, int32_t K, int32_t n_items_local, int32_t d, int32_t score_mode) {
+  if (score_mode == FR_SCORE_TC_3XTF32) {
+    const int s = fr::tc_pick_splits(n, n_items_local);
+    return fr::tc_plane_bytes(n, n_items_local, d) + (s > 1 ? (size_t)s * n * K * 8 + 512 : 256);
+  }
   const int s = fr::pick_splits(n, n_items_local);
   return s > 1 ? (size_t)s * n * K * 8 + 512 : 256;
 }
@@ -345,9 +353,34 @@ int fr_fullsort_topk(const fr_fullsort *a, void *stream) {
   FR_REQUIRE(a->n >= 1 && a->n_items_local >= 1, "fr_fullsort_topk: empty input");
   FR_REQUIRE(a->K >= 1 && a->K <= fr::kMaxK, "fr_fullsort_topk: K=%d out of [1,%d]", a->K, fr::kMaxK);
   FR_REQUIRE(a->d >= 4 && a->d % 4 == 0, "fr_fullsort_topk: d=%d must be a multiple of 4", a->d);
+  if (a->score_mode == FR_SCORE_TC_3XTF32) {
+    FR_REQUIRE(a->d % 32 == 0 && a->d <= 128, "fr_fullsort_topk: tensor-core scorer needs d in {32,64,96,128} (d=%d)",
+               a->d);
+    const int splits = fr::tc_pick_splits(a->n, a->n_items_local);
+    const size_t planes = fr::tc_plane_bytes(a->n, a->n_items_local, a->d);
+    const size_t need = planes + (splits > 1 ? (size_t)splits * a->n * a->K * 8 + 512 : 256);
+    if (!a->workspace || a->workspace_bytes < need) {
+      fr::set_error("fr_fullsort_topk: workspace too small (%zu < %zu)", a->workspace_bytes, need);
+      return FR_ERR_WORKSPACE;
+    }
+    int32_t *pid = a->topk_id;
+    float *psc = a->topk_score;
+    if (splits > 1) {
+      pid = (int32_t *)((char *)a->workspace + planes);
+      psc = (float *)((char *)a->workspace + planes + (((size_t)splits * a->n * a->K * 4 + 255) & ~(size_t)255));
+    }
+    int rc = fr::tc_launch(a, a->workspace, splits, pid, psc, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (splits > 1) {
+      FR_LAUNCH(fr::k_topk_merge, (a->n + 127) / 128, 128, 0, stream, pid, psc, splits, a->n, a->K, a->topk_id,
+                a->topk_score);
+    }
+    FR_LAUNCH_CHECK();
+    return FR_OK;
+  }
   if (a->score_mode != FR_SCORE_EXACT_FP32) {
-    fr::set_error("fr_fullsort_topk: score_mode %d not built in this library version", a->score_mode);
-    return FR_ERR_UNSUPPORTED;
+    fr::set_error("fr_fullsort_topk: unknown score_mode %d", a->score_mode);
+    return FR_ERR_INVALID;
   }
   if (a->d > fr::kMaxDExact) {
     fr::set_error("fr_fullsort_topk: exact scorer supports d <= %d", fr::kMaxDExact);

@@ -1,0 +1,455 @@
+// Full-sort scoring on the 5th-generation tensor cores: tcgen05.mma kind::tf32 fed by TMA, accumulators in TMEM,
+// 3xTF32 split for fp32-level accuracy, fused with the pad/history mask and the streaming top-K.
+//
+// Reference being replaced: focf.py:171-178 (mm + clamp/max_rating), trainer.py:435-438 (masks),
+// collector.py:143-153 (topk).  This is FR_SCORE_TC_3XTF32; FR_SCORE_EXACT_FP32 (fullsort_eval.cu) is the
+// bit-defined mode the parity tests pin, this mode is checked against it with the near-tie protocol.
+//
+// 3xTF32: x = hi + lo with hi = x & ~0x1fff (exactly a TF32 number) and lo = x - hi (exact in fp32; the tensor core
+// keeps its top 10 mantissa bits).  U.I^T ~= Uh.Ih + Uh.Il + Ul.Ih, three MMAs per k-step into one fp32 TMEM
+// accumulator; the dropped lo.lo term is 2^-22 relative.  The planes are split ONCE per evaluation (k_split_planes),
+// not per tile.
+//
+// CTA = 128 eval users x a contiguous range of item tiles (128 items each); 6 warps:
+//   warp 0   TMA producer: one lane streams the item K-blocks (32 k-columns = one 128-byte swizzle atom row) of
+//            Ih and Il through a 4-stage shared-memory ring (cp.async.bulk.tensor, mbarrier complete_tx)
+//   warp 1   MMA issuer: one lane issues tcgen05.mma (M=128, N=128, K=8) x 4 k-steps x 3 products per K-block;
+//            tcgen05.commit releases the ring slot and, after the last K-block of a tile, publishes the accumulator
+//   warp 2-5 epilogue: TMEM lane == user row, so each thread OWNS one user: tcgen05.ld 32 columns at a time, mask
+//            bits from the thread's own walk of its sorted history, a one-compare filter on the raw dot against the
+//            raw value of the row's current K-th best, and (rarely) the exact transform + insertion into the row's
+//            K-list in shared memory.  No cross-thread synchronisation in the epilogue at all.
+// The user tile (both planes) is loaded once by TMA and stays resident; the TMEM accumulator is double buffered so
+// the MMAs of tile t+1 overlap the epilogue of tile t.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fr {
+
+constexpr int TCM = 128;          // users per CTA (UMMA M)
+constexpr int TCN = 128;          // items per tile (UMMA N)
+constexpr int TCKB = 32;          // k-columns per K-block: 32 fp32 = 128 bytes = one swizzle-128B row
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_KBLOCK_BYTES = TCN * TCKB * 4;   // 16 KB per plane per K-block (same for the user tile: TCM == TCN)
+constexpr int kTcMaxK = 64;
+constexpr int kTcMaxD = 128;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte offset = 1024 B between 8-row
+// groups in [32,46), version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6), a/b format TF32 = 2 @[7,10)/[10,13),
+// a/b K-major = 0 @15/16, n_dim = N>>3 @[17,23), m_dim = M>>4 @[24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- plane split (once per evaluation)
+// rows: gathered by `rows_idx` (eval users) or identity (items); hi = top 19 bits, lo = x - hi
+__global__ void __launch_bounds__(256)
+    k_split_planes(const float *__restrict__ src, const int32_t *__restrict__ rows_idx, int64_t n_rows, int d,
+                   float *__restrict__ hi, float *__restrict__ lo) {
+  const int dq = d >> 2;
+  const int64_t nq = n_rows * dq;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / dq;
+    const int c = (int)(q % dq);
+    const int64_t sr = rows_idx ? (int64_t)rows_idx[r] : r;
+    const float4 x = __ldg((const float4 *)(src + sr * d) + c);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+    *((float4 *)(hi + r * d) + c) = h;
+    *((float4 *)(lo + r * d) + c) = l;
+  }
+}
+
+// ---------------------------------------------------------------- the scorer
+struct TcArgs {
+  const int64_t *hist_off;
+  const int32_t *hist_items;
+  int n, d, n_items_local, item_base, K, transform;
+  float max_rating;
+  int tiles_per_split;
+  int stages;         // ring depth (2..4, what fits beside the resident user planes)
+  int32_t *out_id;    // [n_splits, n, K]
+  float *out_score;
+};
+
+__device__ __forceinline__ bool tc_better(float s, int id, float s2, int id2) { return s > s2 || (s == s2 && id < id2); }
+
+__device__ __forceinline__ float tc_transform(float x, int transform, float max_rating) {
+  if (transform == FR_TRANSFORM_CLAMP_DIV) return __fdiv_rn(fminf(fmaxf(x, 0.f), max_rating), max_rating);
+  if (transform == FR_TRANSFORM_SIGMOID) return 1.f / (1.f + expf(-x));
+  return x;
+}
+
+// A raw dot that certainly cannot beat a K-th best of transformed score thr_s (ids only grow while a CTA streams its
+// item range, so an equal score loses the tie): the transform is monotone, so raw <= bound  =>  s <= thr_s.
+__device__ __forceinline__ float tc_raw_bound(float thr_s, int transform, float max_rating) {
+  if (thr_s == -INFINITY) return -INFINITY;
+  if (transform == FR_TRANSFORM_NONE) return thr_s;
+  if (transform == FR_TRANSFORM_CLAMP_DIV) {
+    if (thr_s >= 1.f) return INFINITY;                    // saturated: clamp() cannot exceed 1
+    const float b = thr_s * max_rating;
+    return b - fabsf(b) * 4e-7f;                           // a few ulp below: the exact test decides inside the band
+  }
+  if (thr_s > 0.f && thr_s < 1.f) {                        // sigmoid
+    const float b = logf(thr_s / (1.f - thr_s));
+    return b - (fabsf(b) + 1.f) * 1e-4f;
+  }
+  return -INFINITY;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_fullsort_tc(const __grid_constant__ CUtensorMap map_uh, const __grid_constant__ CUtensorMap map_ul,
+                  const __grid_constant__ CUtensorMap map_ih, const __grid_constant__ CUtensorMap map_il, TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  const int nkb = a.d / TCKB;                                 // K-blocks per row (d = 32, 64, 96 or 128)
+  // carve: [A hi: nkb x 16 KB][A lo: nkb x 16 KB][ring: TC_STAGES x (B hi 16 KB + B lo 16 KB)][lists][barriers]
+  unsigned char *sA_hi = tc_smem;
+  unsigned char *sA_lo = sA_hi + nkb * TC_KBLOCK_BYTES;
+  unsigned char *sB = sA_lo + nkb * TC_KBLOCK_BYTES;
+  const int TC_STAGES = a.stages;
+  float *list_s = (float *)(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);   // [TCM][K]
+  int *list_i = (int *)(list_s + TCM * a.K);                         // [TCM][K]
+  uint64_t *bars = (uint64_t *)(((uintptr_t)(list_i + TCM * a.K) + 7) & ~(uintptr_t)7);
+  uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2,
+           *afull = tempty + 2;
+  uint32_t *tmem_slot = (uint32_t *)(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * TCM;
+  const int split = blockIdx.y;
+  const int n_tiles_total = (a.n_items_local + TCN - 1) / TCN;
+  const int tile_lo = split * a.tiles_per_split;
+  const int tile_hi = min(n_tiles_total, tile_lo + a.tiles_per_split);
+  const int ntile = max(0, tile_hi - tile_lo);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 128);   // every epilogue thread arrives
+    }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(afull, 2u * nkb * TC_KBLOCK_BYTES);
+      for (int kb = 0; kb < nkb; ++kb) {
+        tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &map_uh, kb * TCKB, u0, afull);
+        tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &map_ul, kb * TCKB, u0, afull);
+      }
+      int q = 0;
+      for (int tt = 0; tt < ntile; ++tt) {
+        const int row0 = (tile_lo + tt) * TCN;
+        for (int kb = 0; kb < nkb; ++kb, ++q) {
+          const int s = q % TC_STAGES;
+          const uint32_t ph = (q / TC_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], 2u * TC_KBLOCK_BYTES);
+          tma_load_2d(sB + (2 * s) * TC_KBLOCK_BYTES, &map_ih, kb * TCKB, row0, &full[s]);
+          tma_load_2d(sB + (2 * s + 1) * TC_KBLOCK_BYTES, &map_il, kb * TCKB, row0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TCM, TCN);
+      mbar_wait(afull, 0);
+      tc_fence_after();
+      int q = 0;
+      for (int tt = 0; tt < ntile; ++tt) {
+        const int buf = tt & 1;
+        const uint32_t tph = (tt >> 1) & 1;
+        mbar_wait(&tempty[buf], tph ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TCN);
+        for (int kb = 0; kb < nkb; ++kb, ++q) {
+          const int s = q % TC_STAGES;
+          const uint32_t ph = (q / TC_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA_hi + kb * TC_KBLOCK_BYTES), a_lo = smem_u32(sA_lo + kb * TC_KBLOCK_BYTES);
+          const uint32_t b_hi = smem_u32(sB + (2 * s) * TC_KBLOCK_BYTES), b_lo = b_hi + TC_KBLOCK_BYTES;
+#pragma unroll
+          for (int k = 0; k < TCKB / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes along the swizzled row
+            const uint32_t off = k * 32;
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, first);
+            umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1u);
+            umma_tf32(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1u);
+          }
+          umma_commit(&empty[s]);              // ring slot reusable once these MMAs have read it
+        }
+        umma_commit(&tfull[buf]);              // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================== epilogue: thread == user row
+    const int quarter = warp & 3;               // TMEM lanes [32*quarter, +32) are this warp's
+    const int row = quarter * 32 + lane;
+    const int r = u0 + row;
+    const bool live = r < a.n;
+    const int K = a.K;
+    float *ls = list_s + row * K;
+    int *li = list_i + row * K;
+    for (int e = 0; e < K; ++e) {
+      ls[e] = -INFINITY;
+      li[e] = 0x7fffffff;
+    }
+    float raw_thr = -INFINITY;                  // one-compare filter on the raw dot (tc_raw_bound), -inf while not full
+    float thr_s = -INFINITY;
+    int thr_i = 0x7fffffff;
+    long long hp = 0, hend = 0;
+    if (live) {
+      long long lo_ = a.hist_off[r], hi_ = a.hist_off[r + 1];
+      hend = hi_;
+      const int first = a.item_base + tile_lo * TCN;
+      while (lo_ < hi_) {
+        const long long mid = (lo_ + hi_) >> 1;
+        if (a.hist_items[mid] < first) lo_ = mid + 1; else hi_ = mid;
+      }
+      hp = lo_;
+    }
+    for (int tt = 0; tt < ntile; ++tt) {
+      const int buf = tt & 1;
+      const uint32_t tph = (tt >> 1) & 1;
+      const int tile_base = (tile_lo + tt) * TCN;
+      const int g0 = a.item_base + tile_base;
+      // mask words of this tile from the thread's own sorted history (+ the [PAD] item, global id 0)
+      uint32_t mask[TCN / 32];
+#pragma unroll
+      for (int w = 0; w < TCN / 32; ++w) mask[w] = 0u;
+      if (g0 == 0) mask[0] |= 1u;
+      while (hp < hend) {
+        const int it = a.hist_items[hp];
+        if (it >= g0 + TCN) break;
+        if (it >= g0) {
+          const int c = it - g0;
+#pragma unroll
+          for (int w = 0; w < TCN / 32; ++w)
+            if ((c >> 5) == w) mask[w] |= 1u << (c & 31);
+        }
+        ++hp;
+      }
+      mbar_wait(&tfull[buf], tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCN);
+#pragma unroll
+      for (int w = 0; w < TCN / 32; ++w) {
+        uint32_t v[32];
+        tmem_ld32(taddr + w * 32, v);
+        if (live) {
+          const int cols = min(32, a.n_items_local - (tile_base + w * 32));   // valid columns of this chunk
+          const uint32_t mw = mask[w];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float raw = __uint_as_float(v[c]);
+            if (c < cols && !((mw >> c) & 1u) && raw > raw_thr) {
+              const float s = tc_transform(raw, a.transform, a.max_rating);
+              const int gid = g0 + w * 32 + c;
+              if (tc_better(s, gid, thr_s, thr_i)) {
+                int p = K - 1;
+                while (p > 0 && tc_better(s, gid, ls[p - 1], li[p - 1])) {
+                  ls[p] = ls[p - 1];
+                  li[p] = li[p - 1];
+                  --p;
+                }
+                ls[p] = s;
+                li[p] = gid;
+                thr_s = ls[K - 1];
+                thr_i = li[K - 1];
+                if (thr_i != 0x7fffffff) raw_thr = tc_raw_bound(thr_s, a.transform, a.max_rating);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+    if (live) {
+      for (int e = 0; e < K; ++e) {
+        const size_t o = ((size_t)split * a.n + r) * K + e;
+        a.out_id[o] = li[e];
+        a.out_score[o] = ls[e];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp32 [rows, d] -> boxes of 128 rows x 32 columns (128 bytes), 128-byte swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int d) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TCKB, (cuuint32_t)TCN};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t tc_plane_bytes(int n, int n_items_local, int d) {
+  const size_t a = (((size_t)n * d * 4) + 255) & ~(size_t)255, b = (((size_t)n_items_local * d * 4) + 255) & ~(size_t)255;
+  return 2 * a + 2 * b;
+}
+
+int tc_pick_splits(int n, int n_items_local) {
+  const int utiles = (n + TCM - 1) / TCM, itiles = (n_items_local + TCN - 1) / TCN;
+  int s = (kSMs + utiles - 1) / utiles;
+  if (s > 32) s = 32;
+  if (s > itiles) s = itiles;
+  return s < 1 ? 1 : s;
+}
+
+// planes: workspace region of tc_plane_bytes(); part_id/part_sc: [splits, n, K] (or the outputs when splits == 1)
+int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, float *out_sc, cudaStream_t st) {
+  const int n = a->n, d = a->d, nl = a->n_items_local;
+  const size_t ab = (((size_t)n * d * 4) + 255) & ~(size_t)255, bb = (((size_t)nl * d * 4) + 255) & ~(size_t)255;
+  float *Uh = (float *)planes, *Ul = (float *)((char *)planes + ab);
+  float *Ih = (float *)((char *)planes + 2 * ab), *Il = (float *)((char *)planes + 2 * ab + bb);
+  FR_LAUNCH(k_split_planes, grid_for((int64_t)n * d / 4, 256, kSMs * 16), 256, 0, st, a->U, a->users, (int64_t)n, d, Uh, Ul);
+  FR_LAUNCH(k_split_planes, grid_for((int64_t)nl * d / 4, 256, kSMs * 16), 256, 0, st, a->I_shard, (const int32_t *)nullptr,
+            (int64_t)nl, d, Ih, Il);
+  CUtensorMap m_uh, m_ul, m_ih, m_il;
+  if (!make_map(&m_uh, Uh, n, d) || !make_map(&m_ul, Ul, n, d) || !make_map(&m_ih, Ih, nl, d) ||
+      !make_map(&m_il, Il, nl, d)) {
+    set_error("fr_fullsort_topk: cuTensorMapEncodeTiled failed");
+    return FR_ERR_CUDA;
+  }
+  const int nkb = d / TCKB;
+  const size_t fixed = (size_t)2 * nkb * TC_KBLOCK_BYTES + (size_t)TCM * a->K * 8 + 256;
+  int stages = (int)((232448 - 1024 - fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB alignment slack
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) {
+    set_error("fr_fullsort_topk: tensor-core scorer does not fit shared memory for d=%d K=%d", d, a->K);
+    return FR_ERR_UNSUPPORTED;
+  }
+  const size_t smem = fixed + (size_t)stages * 2 * TC_KBLOCK_BYTES + 1024;
+  const int itiles = (nl + TCN - 1) / TCN;
+  TcArgs t{a->hist_off, a->hist_items, n, d, nl, a->item_base, a->K, a->transform, a->max_rating,
+           (itiles + splits - 1) / splits, stages, out_id, out_sc};
+  FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n + TCM - 1) / TCM, splits);
+  FR_LAUNCH(k_fullsort_tc, grid, TC_THREADS, smem, st, m_uh, m_ul, m_ih, m_il, t);
+  return FR_OK;
+}
+
+}  // namespace fr

@@ -154,7 +154,7 @@ def fullsort_topk(U, I_shard, users, hist_off, hist_items, K, transform, max_rat
     n, d, nl = users.numel(), U.shape[1], I_shard.shape[0]
     ids = torch.empty((n, K), dtype=torch.int32, device=U.device)
     sc = torch.empty((n, K), dtype=torch.float32, device=U.device)
-    ws = _ws(lib.fr_fullsort_workspace_bytes(n, K, nl, d), U.device)
+    ws = _ws(lib.fr_fullsort_workspace_bytes(n, K, nl, d, int(score_mode)), U.device)
     a = FullSort()
     a.U, a.I_shard, a.d, a.n_items_local, a.item_base = ptr(U), ptr(I_shard), d, nl, int(item_base)
     a.users, a.n, a.hist_off, a.hist_items = ptr(users), n, ptr(hist_off), ptr(hist_items)

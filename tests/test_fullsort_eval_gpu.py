@@ -175,3 +175,45 @@ def test_kat2_metric_kernels():
     np.testing.assert_allclose(kernels.gini_at_k(cnt, 3, 3).item(), 0.35555555555, rtol=1e-9)
     h = hits.cpu().numpy()
     np.testing.assert_allclose([h[:k].sum() / (3 * k) for k in (1, 2, 3)], [1, 2 / 3, 5 / 9])
+
+
+@pytest.mark.parametrize("n_users,n_items,d,n_eval,K", [(700, 1683, 64, 650, 10), (3000, 3707, 64, 2900, 10),
+                                                       (500, 9000, 128, 333, 20), (400, 1000, 32, 257, 5),
+                                                       (300, 2100, 96, 129, 10)])
+def test_tc_scorer_matches_exact_scorer(n_users, n_items, d, n_eval, K):
+    """FR_SCORE_TC_3XTF32 (tcgen05 + TMA, 3xTF32) against the bit-defined exact scorer: scores within fp32-level
+    tolerance; ids identical wherever the exact top-(K+1) is separated by more than that tolerance (near-tie
+    protocol of SURVEY.md hard part 3), same score multiset elsewhere."""
+    from recbole_fairrec_b200 import _lib, kernels
+    U, I, users, ho, hi, po, pi, sst = random_eval_case(n_items + d + 1, n_users, n_items, d, n_eval)
+    data, ev, Ud, Id = build(U, I, users, ho, hi, po, pi, sst, [K])
+    args = (Ud, Id, data.users, data.hist_off, data.hist_items)
+    ids_e, sc_e = kernels.fullsort_topk(*args, K + 1, _lib.TRANSFORM_CLAMP_DIV, 5.0)
+    ids_t, sc_t = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_CLAMP_DIV, 5.0, 0, _lib.SCORE_TC_3XTF32)
+    torch.cuda.synchronize()
+    sc_e, sc_t, ids_e, ids_t = sc_e.cpu().numpy(), sc_t.cpu().numpy(), ids_e.cpu().numpy(), ids_t.cpu().numpy()
+    tol = 4e-6
+    np.testing.assert_allclose(sc_t, sc_e[:, :K], rtol=0, atol=tol)
+    clean = np.all(np.abs(np.diff(sc_e, axis=1)) > 2 * tol, axis=1)
+    assert clean.mean() > 0.5
+    np.testing.assert_array_equal(ids_t[clean], ids_e[clean, :K])
+    # raw-dot variant (no clamp): exercises the filter with negative scores
+    ids_e, sc_e = kernels.fullsort_topk(*args, K + 1, _lib.TRANSFORM_NONE, 1.0)
+    ids_t, sc_t = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_NONE, 1.0, 0, _lib.SCORE_TC_3XTF32)
+    sc_e, sc_t, ids_e, ids_t = sc_e.cpu().numpy(), sc_t.cpu().numpy(), ids_e.cpu().numpy(), ids_t.cpu().numpy()
+    np.testing.assert_allclose(sc_t, sc_e[:, :K], rtol=0, atol=2e-5)
+    clean = np.all(np.abs(np.diff(sc_e, axis=1)) > 4e-5, axis=1)
+    np.testing.assert_array_equal(ids_t[clean], ids_e[clean, :K])
+
+
+def test_tc_evaluator_metrics_close_to_exact():
+    """whole fused evaluation with score_mode: tc -- metrics within 1e-5 of the exact mode's on a tie-free case"""
+    U, I, users, ho, hi, po, pi, sst = random_eval_case(77, 1500, 2500, 64, 1400)
+    res = {}
+    for mode in ("exact", "tc"):
+        data, ev, Ud, Id = build(U, I, users, ho, hi, po, pi, sst, [10], score_mode=mode)
+        ev.collect(Ud, Id, data, 5.0)
+        res[mode] = ev.finalize(ev.last, data, rounded=False)
+    for k, v in res["exact"].items():
+        tol = 3.0 / 1400 if "@" in k else 1e-5 * max(abs(v), 1e-3)   # a near-tie flip moves a top-K metric by O(1/n)
+        assert abs(res["tc"][k] - v) <= tol, (k, res["tc"][k], v)
