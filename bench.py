@@ -223,7 +223,7 @@ def run_ours(args, wname):
         for items, offs, batches in plans:
             d_items, d_offs = torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev)
             flat += [(d_items, d_offs, b) for b in batches]
-        pos = [0]
+        step_pos = [0]
         norms = None
         if world > 1:   # global normalisers of every planned step: sum of the ranks' (B, J), host-known at planning time
             t = torch.tensor([[b[3], b[2]] for _, _, b in flat], dtype=torch.int64, device=dev)
@@ -235,9 +235,9 @@ def run_ours(args, wname):
             norms = t.cpu().numpy()
 
         def dev_step():
-            k = pos[0] % len(flat)
+            k = step_pos[0] % len(flat)
             d_items, d_offs, b = flat[k]
-            pos[0] += 1
+            step_pos[0] += 1
             uid, iid, rating, sst = loader.gather(d_items, d_offs, b)
             inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
             inter.items_contiguous = True
@@ -335,6 +335,28 @@ def run_ours(args, wname):
         torch.cuda.synchronize()
         ev_ms.append(a.elapsed_time(b))
     t_eval = max_over_ranks(statistics.mean(ev_ms) / 1e3)
+    # the tensor-core scorer (tcgen05 + TMA, 3xTF32) on the same pass, timed the same way
+    tc = None
+    try:
+        cfg_tc = pkg.Config(**{**dict(cfg), "score_mode": "tc"})
+        ev_tc = pkg.FullSortEvaluator(cfg_tc, w["n_items"], tdata.item_counter, group=group)
+        res_tc = ev_tc.evaluate(Uw, Iw, edata, 5.0)
+        barrier()
+        tc_ms = []
+        for _ in range(n_eval_pass):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ev_tc.collect(Uw, Iw, edata, 5.0)
+            b.record()
+            torch.cuda.synchronize()
+            tc_ms.append(a.elapsed_time(b))
+        t_tc = max_over_ranks(statistics.mean(tc_ms) / 1e3)
+        tc = {"value": edata.n / t_tc, "unit": "users/s", "ms_per_pass": 1e3 * t_tc, "score_mode": "tc_3xtf32",
+              "ndcg@10": res_tc.get(f"ndcg@{K}")}
+    except Exception as e:   # the exact scorer stays the reported default
+        tc = {"error": str(e)[:200]}
+
     # end to end: H2D of the eval lists (users, history CSR, positives CSR, groups) from pinned host memory, the fused
     # pass, and the D2H read of the metric accumulators, every pass
     import copy
@@ -372,6 +394,10 @@ def run_ours(args, wname):
     prof_train = _lib.profile_report()
     evaluator.collect(Uw, Iw, edata, 5.0)
     prof_eval = _lib.profile_report()
+    prof_tc = {}
+    if tc and "error" not in tc:
+        ev_tc.collect(Uw, Iw, edata, 5.0)
+        prof_tc = _lib.profile_report()
     _lib.profile_enable(False)
     hbm, bf16, peak_src = peaks()
     B_avg = rows_p / nprof
@@ -414,6 +440,16 @@ def run_ours(args, wname):
                      "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
                      "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}
 
+    if tc and "error" not in tc:
+        tc_kernel_ms = next((v[1] / v[0] for k, v in prof_tc.items() if k.startswith("k_fullsort_tc")), None)
+        if tc_kernel_ms:
+            ach = eval_flops / world / (tc_kernel_ms * 1e-3) / 1e12
+            tc["roofline"] = {"bound": "tensor", "kernel": "k_fullsort_tc (tcgen05.mma kind::tf32 x3, TMA, TMEM)",
+                              "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s (fp32-equivalent; 3 MMAs per product)",
+                              "frac": ach / tc_peak, "traffic": None, "avg_launch_us": 1e3 * tc_kernel_ms,
+                              "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}
+        tot = sum(v[1] for v in prof_tc.values()) or 1.0
+        tc["kernel_shares"] = {k: round(v[1] / tot, 4) for k, v in sorted(prof_tc.items(), key=lambda kv: -kv[1][1])[:6]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)
@@ -446,7 +482,8 @@ def run_ours(args, wname):
                  "e2e": {"value": n_eval / t_eval_e2e, "unit": "users/s", "h2d_bytes_per_pass": eval_h2d,
                          "d2h_bytes_per_pass": 8 * (4 * K + K + 7 + 2)},
                  "host_csr_build_s": t_build, "roofline": eval_roof, "kernel_shares": ev_shares,
-                 "ndcg@10": res.get(f"ndcg@{K}"), "metrics": {k: float(v) for k, v in res.items()}},
+                 "ndcg@10": res.get(f"ndcg@{K}"), "metrics": {k: float(v) for k, v in res.items()},
+                 "tensor_core": tc},
     }
     if world > 1:
         dist.destroy_process_group()

@@ -5,8 +5,7 @@
 // collector.py:143-153 (topk).  This is FR_SCORE_TC_3XTF32; FR_SCORE_EXACT_FP32 (fullsort_eval.cu) is the
 // bit-defined mode the parity tests pin, this mode is checked against it with the near-tie protocol.
 //
-// 3xTF32: x = hi + lo with hi = x & ~0x1fff (exactly a TF32 number) and lo = x - hi (exact in fp32; the tensor core
-// keeps its top 10 mantissa bits).  U.I^T ~= Uh.Ih + Uh.Il + Ul.Ih, three MMAs per k-step into one fp32 TMEM
+// 3xTF32: x = hi + lo with hi = tf32(x) (round to nearest) and lo = tf32(x - hi) (x - hi is exact in fp32).  U.I^T ~= Uh.Ih + Uh.Il + Ul.Ih, three MMAs per k-step into one fp32 TMEM
 // accumulator; the dropped lo.lo term is 2^-22 relative.  The planes are split ONCE per evaluation (k_split_planes),
 // not per tile.
 //
@@ -118,7 +117,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------- plane split (once per evaluation)
-// rows: gathered by `rows_idx` (eval users) or identity (items); hi = top 19 bits, lo = x - hi
+// rows: gathered by `rows_idx` (eval users) or identity (items); hi = x rounded to TF32 (nearest), lo = x - hi (exact
+// in fp32) rounded to TF32 as well, so that the tensor core's own truncation of the low 13 bits is a no-op
+__device__ __forceinline__ float rn_tf32(float x) {
+  const uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;   // inf / nan
+  return __uint_as_float((u + 0x1000u) & 0xffffe000u);
+}
 __global__ void __launch_bounds__(256)
     k_split_planes(const float *__restrict__ src, const int32_t *__restrict__ rows_idx, int64_t n_rows, int d,
                    float *__restrict__ hi, float *__restrict__ lo) {
@@ -130,10 +135,10 @@ __global__ void __launch_bounds__(256)
     const int64_t sr = rows_idx ? (int64_t)rows_idx[r] : r;
     const float4 x = __ldg((const float4 *)(src + sr * d) + c);
     float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+    h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
+    h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
+    h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
+    h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
     *((float4 *)(hi + r * d) + c) = h;
     *((float4 *)(lo + r * d) + c) = l;
   }
