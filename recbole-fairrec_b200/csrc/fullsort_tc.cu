@@ -152,6 +152,7 @@ struct TcArgs {
   float max_rating;
   int tiles_per_split;
   int stages;         // ring depth (2..4, what fits beside the resident user planes)
+  int use_scratch;    // 1: per-thread shared-memory scratch rows for the slow path (fast); 0: collective TMEM re-read
   int32_t *out_id;    // [n_splits, n, K]
   float *out_score;
 };
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int TC_STAGES = a.stages;
   float *list_s = (float *)(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);   // [TCM][K]
   int *list_i = (int *)(list_s + TCM * a.K);                         // [TCM][K]
-  uint64_t *bars = (uint64_t *)(((uintptr_t)(list_i + TCM * a.K) + 7) & ~(uintptr_t)7);
+  float *scr = (float *)(list_i + TCM * a.K);                        // [TCM][33] candidate scratch rows (optional)
+  uint64_t *bars = (uint64_t *)(((uintptr_t)(scr + (a.use_scratch ? TCM * 33 : 0)) + 7) & ~(uintptr_t)7);
   uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2,
            *afull = tempty + 2;
   uint32_t *tmem_slot = (uint32_t *)(afull + 1);
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int K = a.K;
     float *ls = list_s + row * K;
     int *li = list_i + row * K;
+    float *scratch = scr + row * 33;
     for (int e = 0; e < K; ++e) {
       ls[e] = -INFINITY;
       li[e] = 0x7fffffff;
@@ -298,6 +301,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     float raw_thr = -INFINITY;                  // one-compare filter on the raw dot (tc_raw_bound), -inf while not full
     float thr_s = -INFINITY;
     int thr_i = 0x7fffffff;
+    auto try_insert = [&](float raw, int gid) {   // exact transform + total-order insertion into the row's K-list
+      const float s = tc_transform(raw, a.transform, a.max_rating);
+      if (tc_better(s, gid, thr_s, thr_i)) {
+        int p = K - 1;
+        while (p > 0 && tc_better(s, gid, ls[p - 1], li[p - 1])) {
+          ls[p] = ls[p - 1];
+          li[p] = li[p - 1];
+          --p;
+        }
+        ls[p] = s;
+        li[p] = gid;
+        thr_s = ls[K - 1];
+        thr_i = li[K - 1];
+        if (thr_i != 0x7fffffff) raw_thr = tc_raw_bound(thr_s, a.transform, a.max_rating);
+      }
+    };
     long long hp = 0, hend = 0;
     if (live) {
       long long lo_ = a.hist_off[r], hi_ = a.hist_off[r + 1];
@@ -333,33 +352,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(&tfull[buf], tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCN);
-#pragma unroll
       for (int w = 0; w < TCN / 32; ++w) {
         uint32_t v[32];
         tmem_ld32(taddr + w * 32, v);
-        if (live) {
-          const int cols = min(32, a.n_items_local - (tile_base + w * 32));   // valid columns of this chunk
-          const uint32_t mw = mask[w];
+        // fast path: one compare per element -> candidate bit mask (branch free, ~2 instructions per score)
+        uint32_t cand = 0u;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float raw = __uint_as_float(v[c]);
-            if (c < cols && !((mw >> c) & 1u) && raw > raw_thr) {
-              const float s = tc_transform(raw, a.transform, a.max_rating);
-              const int gid = g0 + w * 32 + c;
-              if (tc_better(s, gid, thr_s, thr_i)) {
-                int p = K - 1;
-                while (p > 0 && tc_better(s, gid, ls[p - 1], li[p - 1])) {
-                  ls[p] = ls[p - 1];
-                  li[p] = li[p - 1];
-                  --p;
-                }
-                ls[p] = s;
-                li[p] = gid;
-                thr_s = ls[K - 1];
-                thr_i = li[K - 1];
-                if (thr_i != 0x7fffffff) raw_thr = tc_raw_bound(thr_s, a.transform, a.max_rating);
-              }
+        for (int c = 0; c < 32; ++c) cand |= (__uint_as_float(v[c]) > raw_thr ? 1u : 0u) << c;
+        const int cols = a.n_items_local - (tile_base + w * 32);             // valid columns of this chunk
+        const uint32_t colmask = cols >= 32 ? 0xffffffffu : (cols <= 0 ? 0u : ((1u << cols) - 1u));
+        const uint32_t mw = w == 0 ? mask[0] : (w == 1 ? mask[1] : (w == 2 ? mask[2] : mask[3]));
+        cand &= colmask & ~mw;
+        if (!live) cand = 0u;
+        // slow path: rare once the row's threshold has warmed up; ONE copy of the insertion code (instruction footprint)
+        if (a.use_scratch) {
+          if (cand) {   // park the 32 raw scores in this thread's scratch row and walk the candidate bits
+#pragma unroll
+            for (int c = 0; c < 32; ++c) scratch[c] = __uint_as_float(v[c]);
+            while (cand) {
+              const int c = __ffs(cand) - 1;
+              cand &= cand - 1u;
+              const float raw = scratch[c];
+              if (raw > raw_thr) try_insert(raw, g0 + w * 32 + c);
             }
+          }
+        } else {
+          // no room for scratch rows: warp-uniform walk over the union of the lanes' candidate columns, each column
+          // re-read for all 32 rows with a collective tcgen05.ld x1
+          uint32_t uni = cand;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) uni |= __shfl_xor_sync(0xffffffffu, uni, o);
+          while (uni) {
+            const int c = __ffs(uni) - 1;
+            uni &= uni - 1u;
+            uint32_t x;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr + w * 32 + c));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float raw = __uint_as_float(x);
+            if (((cand >> c) & 1u) && raw > raw_thr) try_insert(raw, g0 + w * 32 + c);
           }
         }
       }
@@ -440,8 +470,14 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
     return FR_ERR_CUDA;
   }
   const int nkb = d / TCKB;
-  const size_t fixed = (size_t)2 * nkb * TC_KBLOCK_BYTES + (size_t)TCM * a->K * 8 + 256;
-  int stages = (int)((232448 - 1024 - fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB alignment slack
+  size_t fixed = (size_t)2 * nkb * TC_KBLOCK_BYTES + (size_t)TCM * a->K * 8 + (size_t)TCM * 33 * 4 + 256;
+  int use_scratch = 1;
+  int stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB slack
+  if (stages < 2) {   // drop the scratch rows (slow path falls back to collective TMEM re-reads)
+    use_scratch = 0;
+    fixed -= (size_t)TCM * 33 * 4;
+    stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));
+  }
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) {
     set_error("fr_fullsort_topk: tensor-core scorer does not fit shared memory for d=%d K=%d", d, a->K);
@@ -450,7 +486,7 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   const size_t smem = fixed + (size_t)stages * 2 * TC_KBLOCK_BYTES + 1024;
   const int itiles = (nl + TCN - 1) / TCN;
   TcArgs t{a->hist_off, a->hist_items, n, d, nl, a->item_base, a->K, a->transform, a->max_rating,
-           (itiles + splits - 1) / splits, stages, out_id, out_sc};
+           (itiles + splits - 1) / splits, stages, use_scratch, out_id, out_sc};
   FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + TCM - 1) / TCM, splits);
   FR_LAUNCH(k_fullsort_tc, grid, TC_THREADS, smem, st, m_uh, m_ul, m_ih, m_il, t);
