@@ -292,8 +292,87 @@ def run_ml100k(epochs=2):
         os.chdir(cwd)
 
 
+def run_nfcf(name, fair, n_users=60, n_items=45, d=16, hidden=(32, 16), n_steps=3, B=96, seed=21, fair_weight=0.1,
+             lr=1e-3, wd=1e-6):
+    """NFCF (recbole/model/fair_recommender/nfcf.py): NCF tower + BCE (+ differential-fairness regulariser when a
+    pre-trained checkpoint was loaded: reset_params de-biases the user table and freezes it)."""
+    import tempfile
+    from recbole.model.fair_recommender.nfcf import NFCF
+
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    gender = rng.integers(1, 3, size=n_users)
+
+    class DS(FakeDataset):
+        def get_user_feature(self):
+            return Interaction({"user_id": torch.arange(n_users), "gender": torch.from_numpy(gender)})
+
+    cfg = base_cfg(embedding_size=d, mlp_hidden_size=list(hidden), dropout=0.0, fair_weight=fair_weight,
+                   load_pretrain_path=None, LABEL_FIELD="label")
+    pre = NFCF(cfg, DS(n_users, n_items, 5.0))
+    with torch.no_grad():   # make the scores spread out (default N(0,1) embeddings saturate ReLU towers less predictably)
+        pre.user_embedding.weight.mul_(0.5)
+        pre.item_embedding.weight.mul_(0.5)
+    if fair:
+        path = os.path.join(tempfile.mkdtemp(), "ncf.pth")
+        torch.save({"state_dict": pre.state_dict()}, path)
+        cfg = base_cfg(**{**cfg, "load_pretrain_path": path})
+        model = NFCF(cfg, DS(n_users, n_items, 5.0))
+        with torch.no_grad():
+            model.item_embedding.weight.mul_(0.5)
+    else:
+        model = pre
+    lin = [m for m in model.mlp_layers.mlp_layers if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():   # the tower ends in ReLU (layers.py:66-68): keep most logits alive so gradients are non-trivial
+        lin[-1].bias.fill_(0.3)
+    out = dict(U0=model.user_embedding.weight.detach().numpy().copy(),
+               I0=model.item_embedding.weight.detach().numpy().copy(), n_layers=len(lin), fair=int(fair),
+               fair_weight=fair_weight, lr=lr, wd=wd, n_steps=n_steps,
+               user_frozen=int(not model.user_embedding.weight.requires_grad))
+    for k, l in enumerate(lin):
+        out[f"W{k}_0"], out[f"b{k}_0"] = l.weight.detach().numpy().copy(), l.bias.detach().numpy().copy()
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, weight_decay=wd)
+    losses = []
+    for s in range(n_steps):
+        half = B // 2
+        u = rng.integers(1, n_users, half)
+        ipos = rng.integers(1, max(2, n_items // 3), half)   # few distinct positive items -> populated item x group cells
+        ineg = rng.integers(1, n_items, half)
+        uid = np.concatenate([u, u]).astype(np.int64)
+        iid = np.concatenate([ipos, ineg]).astype(np.int64)
+        label = np.concatenate([np.ones(half), np.zeros(half)]).astype(np.float32)
+        g = gender[uid].astype(np.int64)
+        inter = Interaction({"user_id": torch.from_numpy(uid), "item_id": torch.from_numpy(iid),
+                             "label": torch.from_numpy(label), "gender": torch.from_numpy(g)})
+        opt.zero_grad()
+        loss = model.calculate_loss(inter)
+        loss.backward()
+        if s == 0:
+            out["pred0"] = model.predict(inter).detach().numpy().copy()
+            out["dI0"] = model.item_embedding.weight.grad.numpy().copy()
+            if model.user_embedding.weight.grad is not None:
+                out["dU0"] = model.user_embedding.weight.grad.numpy().copy()
+            for k, l in enumerate(lin):
+                out[f"dW{k}_0"], out[f"db{k}_0"] = l.weight.grad.numpy().copy(), l.bias.grad.numpy().copy()
+        opt.step()
+        losses.append(loss.item())
+        out[f"uid{s}"], out[f"iid{s}"], out[f"label{s}"], out[f"sst{s}"] = uid, iid, label, g
+    out["losses"] = np.array(losses, np.float32)
+    out["U_final"] = model.user_embedding.weight.detach().numpy().copy()
+    out["I_final"] = model.item_embedding.weight.detach().numpy().copy()
+    for k, l in enumerate(lin):
+        out[f"W{k}_final"], out[f"b{k}_final"] = l.weight.detach().numpy().copy(), l.bias.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, f"nfcf_train_{name}.npz"), **out)
+    print(f"nfcf_train_{name}: losses={losses}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "nfcf":
+        run_nfcf("ncf", fair=False)
+        run_nfcf("fair", fair=True)
+        run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
+        return
     for obj in ["none", "value", "absolute", "under", "over", "nonparity"]:
         run_focf_train(obj, obj, seed=10 + len(obj))
     run_focf_train("value_d64", "value", n_users=300, n_items=120, d=64, target_rows=900, seed=3, scale=0.3)
@@ -305,6 +384,9 @@ def main():
     run_focf_eval("float_sst", seed=3, positive_only=True, float_sst=True, d=64, n_users=130, n_items=300,
                   users_per_batch=13)
     run_ml100k()
+    run_nfcf("ncf", fair=False)
+    run_nfcf("fair", fair=True)
+    run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
 
 
 if __name__ == "__main__":

@@ -185,3 +185,30 @@ def test_torch_port_eval_matches_reference():
     np.testing.assert_array_equal(st["rec.items"], g["rec_items"])
     for (k, v), ref in zip(res.items(), g["metric_values"]):
         assert abs(v - ref) <= 1e-6 * max(abs(ref), 1e-12) + 1e-12, (k, v, ref)
+
+
+NFCF = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "nfcf_train_*.npz")))
+
+
+@pytest.mark.parametrize("path", NFCF, ids=[os.path.basename(p)[11:-4] for p in NFCF])
+def test_nfcf_oracle_matches_reference(path):
+    from oracle import nfcf_oracle as no
+    g = np.load(path)
+    L = int(g["n_layers"])
+    Ws, bs = [g[f"W{k}_0"] for k in range(L)], [g[f"b{k}_0"] for k in range(L)]
+    batches = [(g[f"uid{s}"], g[f"iid{s}"], g[f"label{s}"], g[f"sst{s}"]) for s in range(int(g["n_steps"]))]
+    fair, fw = bool(g["fair"]), float(g["fair_weight"])
+    loss, p, dU, dI, dWs, dbs = no.loss_and_grads(g["U0"], g["I0"], Ws, bs, *batches[0], fair, fw)
+    assert rel_err(p, g["pred0"]) < RTOL
+    np.testing.assert_allclose(loss, g["losses"][0], rtol=RTOL)
+    assert rel_err(dI, g["dI0"]) < RTOL
+    if "dU0" in g:
+        assert rel_err(dU, g["dU0"]) < RTOL
+    for k in range(L):
+        assert rel_err(dWs[k], g[f"dW{k}_0"]) < RTOL and rel_err(dbs[k], g[f"db{k}_0"]) < RTOL, k
+    losses, U, I, Wf, bf = no.train_steps(g["U0"], g["I0"], Ws, bs, batches, fair, fw, float(g["lr"]), float(g["wd"]),
+                                          bool(g["user_frozen"]))
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+    assert rel_err(U, g["U_final"]) < RTOL and rel_err(I, g["I_final"]) < RTOL
+    for k in range(L):
+        assert rel_err(Wf[k], g[f"W{k}_final"]) < RTOL and rel_err(bf[k], g[f"b{k}_final"]) < RTOL, k
