@@ -366,12 +366,14 @@ def run_ours(args, wname):
     eval_h2d = sum(t.numel() * t.element_size() for t in list(pinned.values()) + list(pinned_grp.values()))
     barrier()
     t0 = time.perf_counter()
+    ev_main = ev_tc if tc and "error" not in tc else evaluator
     for _ in range(n_eval_pass):
-        ed = copy.copy(edata)
+        # the lists land in the SAME device buffers every pass (addresses fixed -> the captured graph is reused)
         for k in names:
-            setattr(ed, k, pinned[k].to(dev, non_blocking=True))
-        ed.group_of_pos = {a: g.to(dev, non_blocking=True) for a, g in pinned_grp.items()}
-        res = (ev_tc if tc and "error" not in tc else evaluator).evaluate(Uw, Iw, ed, 5.0)
+            getattr(edata, k).copy_(pinned[k], non_blocking=True)
+        for a_, g_ in pinned_grp.items():
+            edata.group_of_pos[a_].copy_(g_, non_blocking=True)
+        res = ev_main.evaluate(Uw, Iw, edata, 5.0)
     barrier()
     t_eval_e2e = max_over_ranks((time.perf_counter() - t0) / n_eval_pass)
 
@@ -450,6 +452,14 @@ def run_ours(args, wname):
                               "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}
         tot = sum(v[1] for v in prof_tc.values()) or 1.0
         tc["kernel_shares"] = {k: round(v[1] / tot, 4) for k, v in sorted(prof_tc.items(), key=lambda kv: -kv[1][1])[:6]}
+    probe = None
+    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_probe:
+        try:
+            del tdata, loader
+            torch.cuda.empty_cache()
+            probe = scaleout_probe(dev, flush)
+        except Exception as e:
+            probe = {"error": str(e)[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)
@@ -477,6 +487,7 @@ def run_ours(args, wname):
                           "frac": step_roof / hbm},
         "kernel_shares": shares,
         "cpu_baseline": cpu,
+        "scaleout_probe": probe,
         "eval": {"metric": "full-sort fair-eval users/s",
                  "value": tc["value"] if tc and "error" not in tc else n_eval / t_eval, "unit": "users/s",
                  "score_mode": "tc_3xtf32 (tcgen05+TMA; ids equal the exact mode's outside fp32-level near ties)"
@@ -495,6 +506,97 @@ def run_ours(args, wname):
     return out if rank == 0 else None
 
 
+def scaleout_probe(dev, flush):
+    """The HBM- and tensor-bound regime of BASELINE.json configs[4], reduced so that it runs in seconds: FOCF steps on
+    2M users x 262k items, d=128, 2^18-row batches (tables + Adam state 6.9 GB; random interactions drawn directly, no
+    uniqueness pass) and the tensor-core scorer on 37,888 users x 262,144 items.  Reported next to the ML-1M numbers
+    because at the ML-1M shape every kernel is latency-bound and a bandwidth fraction says little."""
+    import torch
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import _lib, kernels, synth
+    hbm, bf16, peak_src = peaks()
+    nu, ni, d, batch, n_inter = 2_000_001, 262_145, 128, 1 << 18, 6_000_000
+    rng = np.random.default_rng(0)
+    iid = (rng.lognormal(4.5, 1.4, n_inter) % (ni - 1)).astype(np.int32) + 1
+    uid = rng.integers(1, nu, n_inter).astype(np.int32)
+    rating = rng.integers(1, 6, n_inter).astype(np.float32)
+    gender = (rng.random(nu) < 0.28).astype(np.float32) + 1
+    cfg = pkg.Config(embedding_size=d, fair_objective="value", train_batch_size=batch, device=dev)
+    train = pkg.TrainData(uid, iid, rating, gender, nu, ni, dev)
+    loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=1)
+    model = pkg.FOCF(cfg, synth.SynthDataset(nu, ni, 5.0)).to(dev)
+    with torch.no_grad():
+        model.user_embedding_layer.weight.mul_(0.05)
+        model.item_embedding_layer.weight.mul_(0.05)
+    model.init_adam(lr=1e-3, weight_decay=1e-3)
+    it = iter(loader)
+    for _ in range(3):
+        model.train_step(next(it))
+    torch.cuda.synchronize()
+    n_t, rows, ms = 8, 0, []
+    for _ in range(n_t):
+        inter = next(it)
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        model.train_step(inter)
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+        rows += len(inter["user_id"])
+    _lib.profile_enable(True)
+    for _ in range(4):
+        flush.zero_()
+        model.train_step(next(it))
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    model.check_flags()
+    B_avg = rows / n_t
+    alg_apply = 24.0 * (nu + ni) * d
+    cnt, tot = prof["k_apply<fr::kAdamFused>"]
+    ach = alg_apply / (tot / cnt * 1e-3) / 1e9
+    step_bytes = (16.0 * d + 16.0) * B_avg + alg_apply
+    step_ach = step_bytes / (statistics.mean(ms) * 1e-3) / 1e9
+    out = {"workload": f"focf {nu - 1} users x {ni - 1} items, d={d}, batch 2^18 (reduced configs[4])",
+           "train": {"value": rows / (sum(ms) / 1e3), "unit": "interactions/s", "ms_per_step": statistics.mean(ms)},
+           "roofline": {"bound": "hbm", "kernel": "k_apply<fr::kAdamFused>", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                        "frac": ach / hbm, "algorithmic_bytes_per_launch": alg_apply, "avg_launch_us": 1e3 * tot / cnt,
+                        "traffic": 7.04e9, "traffic_source": "profiles/r01_ncu_summary.md (dram read 3.62 GB + write 3.42 GB)",
+                        "share_of_step": tot / (sum(v[1] for v in prof.values()) or 1.0), "peak_source": peak_src},
+           "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_ach, "unit": "GB/s",
+                             "frac": step_ach / hbm}}
+    del model, train, loader
+    torch.cuda.empty_cache()
+    # tensor-core scorer
+    n, nit, K = 37_888, 262_144, 10
+    g = torch.Generator(device=dev).manual_seed(0)
+    U = torch.randn(n + 1, d, device=dev, generator=g) * 0.3
+    I = torch.randn(nit, d, device=dev, generator=g) * 0.3
+    users = torch.arange(1, n + 1, dtype=torch.int32, device=dev)
+    hist_off = torch.arange(0, (n + 1) * 4, 4, dtype=torch.int64, device=dev)[:n + 1]
+    hist_items = torch.sort(torch.randint(1, nit, (n, 4), device=dev, generator=g), dim=1).values.to(torch.int32) \
+        .reshape(-1).contiguous()
+    run = lambda: kernels.fullsort_topk(U, I, users, hist_off, hist_items, K, _lib.TRANSFORM_CLAMP_DIV, 5.0, 0,
+                                        _lib.SCORE_TC_3XTF32)
+    for _ in range(2):
+        run()
+    _lib.profile_enable(True)
+    for _ in range(3):
+        run()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    cnt, tot = prof["k_fullsort_tc"]
+    tc_peak = bf16 / 2.0 / 3.0
+    ach = 2.0 * n * nit * d / (tot / cnt * 1e-3) / 1e12
+    out["eval"] = {"workload": f"{n} users x {nit} items, d={d}, K={K}", "value": n / (tot / cnt * 1e-3),
+                   "unit": "users/s (scoring + mask + top-K kernel)",
+                   "roofline": {"bound": "tensor", "kernel": "k_fullsort_tc", "achieved": ach, "peak": tc_peak,
+                                "unit": "TFLOP/s (fp32-equivalent; the kernel issues 3 TF32 MMAs per product)",
+                                "frac": ach / tc_peak, "avg_launch_us": 1e3 * tot / cnt, "traffic": None,
+                                "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -503,6 +605,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml1m", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probe", action="store_true", help="skip the scale-out roofline probe")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
