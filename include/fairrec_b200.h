@@ -172,6 +172,55 @@ int fr_pair_scores(const float *U, const float *I, const int32_t *uid, const int
                    int32_t transform, float max_rating, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Small-MLP towers (recbole/model/layers.py:30-85 MLPLayers) and the NFCF step built on them.
+ * ---------------------------------------------------------------------------------------------- */
+enum fr_activation { FR_ACT_NONE = 0, FR_ACT_RELU = 1, FR_ACT_LEAKYRELU = 2, FR_ACT_SIGMOID = 3, FR_ACT_TANH = 4 };
+
+/* MLPLayers(layers=dims[0..n_layers], dropout, activation): per layer Dropout -> Linear(W[l] [dims[l+1], dims[l]],
+ * b[l]) -> activation (also after the LAST layer, layers.py:66-68) */
+typedef struct fr_mlp_tower {
+  int32_t n_layers;
+  int32_t dims[9];
+  const float *W[8];
+  const float *b[8];
+  int32_t act;     /* enum fr_activation */
+  float dropout;   /* p of the Dropout in front of every Linear (training only) */
+} fr_mlp_tower;
+
+/* NFCF (recbole/model/fair_recommender/nfcf.py): p = sigmoid(tower(U[uid] || I[iid])) (69-74),
+ * loss = BCELoss(p, label) (+ fair_weight * differential fairness over the batch's positives, 76-110) */
+typedef struct fr_nfcf_step {
+  const float *U, *I;          /* [n_users, d], [n_items, d] */
+  int32_t n_users, n_items, d;
+  const int32_t *uid, *iid;    /* [M] */
+  const float *label;          /* [M] LABEL_FIELD (1 / 0) */
+  const float *sst;            /* [M] sensitive attribute value (use_df only) */
+  int64_t M;
+  fr_mlp_tower tower;          /* dims[0] == 2*d, dims[n_layers] == 1 */
+  int32_t use_df;              /* nfcf.py:106-110: regulariser active (a pre-trained model was loaded) */
+  float fair_weight;
+  int32_t training;            /* dropout active */
+  uint64_t seed;               /* dropout stream of this step */
+  float *pred;                 /* [M] out: p (nfcf.py:112-115 predict) */
+  float *loss;                 /* [1] out */
+  int32_t *status_flags;       /* FR_FLAG_TOO_MANY_GROUPS: the kernels implement the binary-attribute case */
+  /* backward outputs (fr_nfcf_backward): dense embedding grads (dU may be NULL: frozen table, nfcf.py:66) + tower */
+  float *dU, *dI;
+  float *dW[8];
+  float *db[8];
+  void *workspace;
+  size_t workspace_bytes;
+} fr_nfcf_step;
+
+size_t fr_nfcf_workspace_bytes(const fr_mlp_tower *t, int64_t M);
+int fr_nfcf_forward(const fr_nfcf_step *s, void *stream);
+/* needs the workspace left by fr_nfcf_forward of the same batch */
+int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream);
+/* torch.optim.Adam (L2 weight-decay form) on one flat parameter tensor (trainer.py:139 for the tower parameters) */
+int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32_t step, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Full-sort evaluation: scoring contraction fused with the pad/history mask and a streaming top-K.
  * Replaces focf.py:171-178 full_sort_predict + trainer.py:435-438 mask + collector.py:143-153 topk /
  * pos-matrix / gather.  Scores are never materialised.

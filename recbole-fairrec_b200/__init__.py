@@ -5,6 +5,7 @@ Only what the path needs lives here:
   _lib.py          ctypes binding (fails loudly when the library is missing; no CPU fallback)
   kernels.py       tensor-level wrappers of the C ABI
   focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
+  nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
   trainer.py       FOCFTrainer (fit / evaluate)
@@ -17,6 +18,7 @@ from .dataloader import FOCFDataLoader, TrainData  # noqa: F401
 from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
 from .focf import FOCF  # noqa: F401
 from .interaction import Interaction  # noqa: F401
+from .nfcf import NFCF  # noqa: F401
 from .trainer import FOCFTrainer  # noqa: F401
 
 __version__ = "0.1.0"

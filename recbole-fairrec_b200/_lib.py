@@ -40,6 +40,23 @@ class FocfStep(Structure):
     ]
 
 
+class MlpTower(Structure):
+    """mirror of `struct fr_mlp_tower`"""
+    _fields_ = [("n_layers", c_int32), ("dims", c_int32 * 9), ("W", c_void_p * 8), ("b", c_void_p * 8),
+                ("act", c_int32), ("dropout", c_float)]
+
+
+class NfcfStep(Structure):
+    """mirror of `struct fr_nfcf_step`"""
+    _fields_ = [
+        ("U", c_void_p), ("I", c_void_p), ("n_users", c_int32), ("n_items", c_int32), ("d", c_int32),
+        ("uid", c_void_p), ("iid", c_void_p), ("label", c_void_p), ("sst", c_void_p), ("M", c_int64),
+        ("tower", MlpTower), ("use_df", c_int32), ("fair_weight", c_float), ("training", c_int32), ("seed", c_uint64),
+        ("pred", c_void_p), ("loss", c_void_p), ("status_flags", c_void_p), ("dU", c_void_p), ("dI", c_void_p),
+        ("dW", c_void_p * 8), ("db", c_void_p * 8), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 class FullSort(Structure):
     """mirror of `struct fr_fullsort`"""
     _fields_ = [
@@ -70,6 +87,11 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "fr_pair_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                c_void_p]),
+    "fr_nfcf_workspace_bytes": (c_size_t, [POINTER(MlpTower), c_int64]),
+    "fr_nfcf_forward": (c_int, [POINTER(NfcfStep), c_void_p]),
+    "fr_nfcf_backward": (c_int, [POINTER(NfcfStep), c_float, c_void_p]),
+    "fr_adam_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double,
+                              c_double, c_double, c_void_p]),
     "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
     "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

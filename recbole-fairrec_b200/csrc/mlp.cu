@@ -1,0 +1,638 @@
+// Small-MLP building blocks for the NCF / PFCN towers (kernel K6) on sm_100a, plus the
+// NFCF differential-fairness regulariser.
+//
+// Reference being replaced (paths relative to the reference root):
+//   recbole/model/layers.py:58-70 MLPLayers (Dropout -> Linear -> activation per layer) and its autograd
+//   recbole/model/fair_recommender/nfcf.py:69-74 forward (emb || emb -> tower -> sigmoid), 99-110 BCE loss,
+//   nfcf.py:76-97 get_differential_fairness (item x group sums over the batch's positives via index_put_)
+//   nn.Embedding dense backward of the two towers' inputs; torch.optim.Adam for the tower parameters
+//
+// The towers are tiny (widths <= 256, M = batch rows): every layer is a 64x64x16 register-tiled fp32 GEMM on the CUDA
+// cores with the bias / activation / dropout fused into the epilogue or the operand loader.  fp32 FMA keeps the
+// 1e-5 parity bar against the reference's sgemm without a 3xTF32 split; at these sizes the step is launch-bound,
+// not math-bound.  Weight gradients reduce over the batch in fixed 2048-row chunks (partials + ordered sum), the
+// item x group statistics reuse the sorted-segment machinery of sort.cu: no floating-point atomics anywhere.
+#include "sort.cuh"
+
+namespace fr {
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3, ACT_TANH = 4 };
+
+// counter-based dropout mask: keep-scale of element idx of layer `layer` (1/(1-p) or 0); p == 0 -> 1
+__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t layer, uint32_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)layer << 32 | idx);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : 1.f / (1.f - p);
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_LEAKY: return x > 0.f ? x : 0.01f * x;
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    case ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+// derivative expressed through the activation OUTPUT y (what the forward pass keeps)
+__device__ __forceinline__ float act_bwd(float y, int act) {
+  switch (act) {
+    case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY: return y > 0.f ? 1.f : 0.01f;
+    case ACT_SIGMOID: return y * (1.f - y);
+    case ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+
+// ---------------------------------------------------------------- gather / concat of the two embedding rows
+__global__ void __launch_bounds__(256)
+    k_gather_concat(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
+                    const int32_t *__restrict__ iid, int64_t M, int d, float *__restrict__ X) {
+  const int dq = d >> 2;
+  const int64_t nq = M * 2 * dq;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / (2 * dq);
+    const int c = (int)(q % (2 * dq));
+    const float4 v = c < dq ? __ldg((const float4 *)(U + (size_t)uid[r] * d) + c)
+                            : __ldg((const float4 *)(I + (size_t)iid[r] * d) + (c - dq));
+    *((float4 *)(X + r * 2 * d) + c) = v;
+  }
+}
+
+// ---------------------------------------------------------------- tiled GEMM
+// C[M,N] = epilogue( sum_k A'[m,k] * B'[k,n] )
+//   A' = A[m*lda + k] scaled by the dropout mask of (layer, m*K + k) when drop_p > 0
+//   B' = kTB ? B[n*ldb + k] (weight [N,K], forward) : B[k*ldb + n] (weight [K,N] seen from dY.W, backward-data)
+//   epilogue: + bias[n], activation; or (backward-data) * dropout mask of the INPUT element and * act'(Yin) of the
+//   previous layer's output when `prev_out` is given.
+struct GemmArgs {
+  const float *A, *B, *bias;
+  float *C;
+  int M, N, K, lda, ldb, ldc;
+  int act;                      // forward epilogue activation
+  const float *prev_out;        // backward-data: multiply by act_bwd(prev_out[m,n], prev_act)
+  int prev_act;
+  float drop_p;                 // forward: mask on A ; backward-data: mask on C (same counter: layer, m*N + n)
+  unsigned long long seed;
+  int layer;
+  int drop_on_c;
+};
+
+template <bool kTB>
+__global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += 16) {
+    for (int f = threadIdx.x; f < 64 * 16; f += 256) {   // A tile: 64 rows x 16 k
+      const int r = f >> 4, kk = f & 15;
+      const int m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (m < a.M && k < a.K) {
+        v = a.A[(size_t)m * a.lda + k];
+        if (a.drop_p > 0.f && !a.drop_on_c) v *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.K + k), a.drop_p);
+      }
+      As[kk][r] = v;
+    }
+    for (int f = threadIdx.x; f < 64 * 16; f += 256) {   // B tile: 16 k x 64 n
+      int n, kk;
+      if (kTB) { n = f >> 4; kk = f & 15; } else { kk = f >> 6; n = f & 63; }
+      const int gn = n0 + n, k = k0 + kk;
+      float v = 0.f;
+      if (gn < a.N && k < a.K) v = kTB ? a.B[(size_t)gn * a.ldb + k] : a.B[(size_t)k * a.ldb + gn];
+      Bs[kk][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[n];
+      v = act_fwd(v, a.act);
+      if (a.prev_out) v *= act_bwd(a.prev_out[(size_t)m * a.ldc + n], a.prev_act);
+      if (a.drop_p > 0.f && a.drop_on_c) v *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.N + n), a.drop_p);
+      a.C[(size_t)m * a.ldc + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight / bias gradients
+// dW[n,k] = sum_m dY[m,n] * Xdrop[m,k] over one 2048-row chunk per blockIdx.z -> part[z][N][K]; db likewise.
+struct WgradArgs {
+  const float *dY, *X;
+  float *part_w, *part_b;       // [chunks, N, K], [chunks, N]
+  int M, N, K, ldy, ldx;
+  float drop_p;
+  unsigned long long seed;
+  int layer;
+};
+constexpr int kWgradChunk = 2048;
+
+__global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
+  __shared__ float Ys[16][64 + 4];
+  __shared__ float Xs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int mlo = blockIdx.z * kWgradChunk, mhi = min(a.M, mlo + kWgradChunk);
+  float acc[4][4], bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int mb = mlo; mb < mhi; mb += 16) {
+    for (int f = threadIdx.x; f < 16 * 64; f += 256) {
+      const int mm = f >> 6, c = f & 63;
+      const int m = mb + mm;
+      float y = 0.f, x = 0.f;
+      if (m < mhi) {
+        if (n0 + c < a.N) y = a.dY[(size_t)m * a.ldy + n0 + c];
+        if (k0 + c < a.K) {
+          x = a.X[(size_t)m * a.ldx + k0 + c];
+          if (a.drop_p > 0.f) x *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.K + k0 + c), a.drop_p);
+        }
+      }
+      Ys[mm][c] = y;
+      Xs[mm][c] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < 16; ++mm) {
+      float yv[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) yv[i] = Ys[mm][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = Xs[mm][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (tx == 0) bacc[i] += yv[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yv[i], xv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float *pw = a.part_w + (size_t)blockIdx.z * a.N * a.K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= a.N) continue;
+    if (tx == 0 && blockIdx.x == 0) a.part_b[(size_t)blockIdx.z * a.N + n] = bacc[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < a.K) pw[(size_t)n * a.K + k] = acc[i][j];
+    }
+  }
+}
+
+// out[i] = sum_c part[c][i] in chunk order
+__global__ void k_sum_chunks(const float *__restrict__ part, int chunks, int64_t n, float *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * n + i];
+    out[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------- NFCF head: sigmoid + BCE (+ DF regulariser)
+// p = sigmoid(z); per-CTA partial of the BCE sum -> part[blk]; dp_bce[b] = (-(y/p) + (1-y)/(1-p)) / B
+__global__ void __launch_bounds__(256)
+    k_sigmoid_bce(const float *__restrict__ z, const float *__restrict__ label, int M, float *__restrict__ p_out,
+                  float *__restrict__ dp, float *__restrict__ part) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  float l = 0.f;
+  if (b < M) {
+    const float p = 1.f / (1.f + expf(-z[b])), y = label[b];
+    p_out[b] = p;
+    l = -(y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(logf(1.f - p), -100.f));   // nn.BCELoss clamps the logs
+    dp[b] = (-(y / p) + (1.f - y) / (1.f - p)) / (float)M;
+  }
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    part[blockIdx.x] = t;
+  }
+}
+
+// compact the positives (label == 1): pos_idx[k] = b in batch order (stable), n_pos; single CTA (batches are small)
+__global__ void __launch_bounds__(1024) k_compact_pos(const float *__restrict__ label, int M, int32_t *__restrict__ pos_idx,
+                                                      int32_t *__restrict__ n_pos) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < M; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int f = (b < M && label[b] == 1.f) ? 1 : 0;
+    int inc = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int wb = 0, tot = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int t = wsum[i];
+      if (i < w) wb += t;
+      tot += t;
+    }
+    const int c = carry;
+    if (f) pos_idx[c + wb + inc - 1] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_pos[0] = carry;
+}
+
+__global__ void k_pos_keys(const int32_t *__restrict__ iid, const int32_t *__restrict__ pos_idx,
+                           const int32_t *__restrict__ n_pos, uint32_t *__restrict__ keys) {
+  const int n = *n_pos;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) keys[k] = (uint32_t)iid[pos_idx[k]];
+}
+
+// nfcf.py:76-97 for a binary attribute.  Warp per item segment of the (item-sorted) positives:
+//   M_g = (sum_g p + 1/J) / (cnt_g + 1) ; eps_j = |ln M_0 - ln M_1| ; d eps_j / d p_b = +-sgn / M_g / (cnt_g + 1)
+// seg_eps[j] = eps_j ; coef[j][g] = fair_weight * (1/J) * d eps_j / d(sum_g p).  The group of a row is the rank of
+// its attribute value among the values present IN THE POSITIVES (torch.unique), found via min/max.
+struct DfArgs {
+  const float *p, *sst;
+  const int32_t *pos_idx, *n_pos;
+  const uint32_t *ord;          // item-sorted order of the positives (values index pos_idx)
+  const int32_t *seg_off, *n_seg;
+  float fair_weight;
+  float *seg_eps, *coef;
+  uint32_t *mm;                 // [2] order-encoded min / max of sst over the positives
+  int32_t *flags;
+};
+
+__global__ void k_df_minmax(const float *__restrict__ sst, const int32_t *__restrict__ pos_idx,
+                            const int32_t *__restrict__ n_pos, uint32_t *__restrict__ mm) {
+  const int n = *n_pos;
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t o = f2ord(sst[pos_idx[k]]);
+    lo = min(lo, o);
+    hi = max(hi, o);
+  }
+  if (hi >= lo) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_df_segments(DfArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int J = *a.n_seg;
+  const float vmin = ord2f(a.mm[0]), vmax = ord2f(a.mm[1]);
+  const float alpha = 1.f / (float)J;
+  int bad = 0;
+  for (int j = warp; j < J; j += nwarps) {
+    const int p0 = a.seg_off[j], p1 = a.seg_off[j + 1];
+    float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+    for (int q = p0 + lane; q < p1; q += 32) {
+      const int b = a.pos_idx[a.ord[q]];
+      const float sv = a.sst[b], pv = a.p[b];
+      const bool g = sv != vmin;
+      bad |= (g && sv != vmax);
+      if (g) { s1 += pv; c1 += 1.f; } else { s0 += pv; c0 += 1.f; }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); c0 = warp_sum(c0); c1 = warp_sum(c1);
+    if (lane == 0) {
+      float eps = 0.f, k0 = 0.f, k1 = 0.f;
+      if (vmin != vmax) {   // a single attribute value among the positives: one column, no pair, eps = 0
+        const float M0 = (s0 + alpha) / (c0 + 1.f), M1 = (s1 + alpha) / (c1 + 1.f);
+        const float diff = logf(M0) - logf(M1);
+        eps = fabsf(diff);
+        const float sg = (float)((diff > 0.f) - (diff < 0.f));
+        if (eps > 0.f) {    // torch.where(epsilon > 0, ...) routes the gradient only when the pair took the max
+          k0 = a.fair_weight * alpha * sg / M0 / (c0 + 1.f);
+          k1 = -a.fair_weight * alpha * sg / M1 / (c1 + 1.f);
+        }
+      }
+      a.seg_eps[j] = eps;
+      a.coef[2 * j] = k0;
+      a.coef[2 * j + 1] = k1;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+}
+
+// loss = bce_sum / M + fair_weight * mean_j eps_j ; dz = (dp_bce + coef[seg(b)][g(b)]) * p (1 - p)
+__global__ void __launch_bounds__(256)
+    k_nfcf_finish(const float *__restrict__ bce_part, int n_part, int M, const float *__restrict__ seg_eps,
+                  const int32_t *__restrict__ n_seg, int use_df, float fair_weight, float *__restrict__ loss) {
+  __shared__ float sh[8];
+  float s = 0.f, e = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += 256) s += bce_part[i];
+  const int J = use_df ? *n_seg : 0;
+  for (int j = threadIdx.x; j < J; j += 256) e += seg_eps[j];
+  s = warp_sum(s);
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float st = 0.f;
+  if (threadIdx.x == 0) for (int i = 0; i < 8; ++i) st += sh[i];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float et = 0.f;
+    for (int i = 0; i < 8; ++i) et += sh[i];
+    loss[0] = st / (float)M + (use_df && J > 0 ? fair_weight * (et / (float)J) : 0.f);
+  }
+}
+
+__global__ void k_df_scatter_coef(DfArgs a, const int32_t *__restrict__ seg_id, float *__restrict__ dp) {
+  const int n = *a.n_pos;
+  const float vmin = ord2f(a.mm[0]);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const int b = a.pos_idx[a.ord[q]];
+    const int g = a.sst[b] != vmin;
+    dp[b] += a.coef[2 * seg_id[q] + g];
+  }
+}
+
+// dz[b] = dp[b] * p (1-p) * grad_scale   (sigmoid backward; the tower's last ReLU is handled by the GEMM epilogue)
+__global__ void k_sigmoid_bwd(const float *__restrict__ dp, const float *__restrict__ p, const float *__restrict__ last_out,
+                              int M, float grad_scale, float *__restrict__ dz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < M) dz[b] = dp[b] * p[b] * (1.f - p[b]) * grad_scale * (last_out[b] > 0.f ? 1.f : 0.f);
+}
+
+// ---------------------------------------------------------------- dense embedding gradient from row gradients
+// dTable[key] = sum of dX[b, col0 : col0+d] over the rows b with that key, in (stable) sorted order; one warp per
+// segment.  The dense gradient is zeroed first by the caller (cudaMemsetAsync).
+__global__ void __launch_bounds__(256)
+    k_segment_sum_rows(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ ord,
+                       const int32_t *__restrict__ seg_off, const int32_t *__restrict__ n_seg,
+                       const float *__restrict__ dX, int ldx, int col0, int d, float *__restrict__ dTable) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int S = *n_seg;
+  for (int s = warp; s < S; s += nwarps) {
+    const int p0 = seg_off[s], p1 = seg_off[s + 1];
+    const uint32_t key = skey[p0];
+    for (int c = lane; c < d; c += 32) {
+      float acc = 0.f;
+      for (int q = p0; q < p1; ++q) acc += dX[(size_t)ord[q] * ldx + col0 + c];
+      dTable[(size_t)key * d + c] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- generic dense Adam (torch.optim.Adam, L2 form)
+__global__ void __launch_bounds__(256)
+    k_adam_flat(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t n,
+                int step, double lr, double beta1, double beta2, double eps, double wd) {
+  __shared__ float sc[2];
+  if (threadIdx.x == 0) {
+    sc[0] = (float)(-lr / (1.0 - pow(beta1, (double)step)));
+    sc[1] = (float)sqrt(1.0 - pow(beta2, (double)step));
+  }
+  __syncthreads();
+  const float neg_step = sc[0], bc2s = sc[1], w1 = (float)(1.0 - beta1), w2 = (float)(1.0 - beta2), b2 = (float)beta2,
+              fwd = (float)wd, feps = (float)eps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = fmaf(fwd, p[i], g[i]);
+    float mi = fmaf(w1, gi - m[i], m[i]);
+    float vi = fmaf(w2 * gi, gi, v[i] * b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = fmaf(neg_step, mi / (sqrtf(vi) / bc2s + feps), p[i]);
+  }
+}
+
+static void launch_gemm(bool tb, const GemmArgs &g, cudaStream_t st) {
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  if (tb) {
+    FR_LAUNCH(k_gemm<true>, grid, 256, 0, st, g);
+  } else {
+    FR_LAUNCH(k_gemm<false>, grid, 256, 0, st, g);
+  }
+}
+
+struct MlpWs {
+  float *X;          // [M, dims[0]] gathered input
+  float *act[8];     // post-activation outputs of every layer [M, dims[l+1]]
+  float *dA, *dB;    // ping-pong row gradients [M, max width]
+  float *part_w, *part_b;
+  float *p, *dp, *dz, *bce_part, *seg_eps, *coef, *loss_tmp;
+  int32_t *pos_idx, *n_pos, *seg_id, *seg_off, *n_seg;
+  uint32_t *keys, *skey, *ord, *mm;
+  uint32_t *ukey, *uord, *ikey, *iord;
+  int32_t *useg_id, *useg_off, *un_seg, *iseg_id, *iseg_off, *in_seg;
+  SortScratch sort;
+  SegScratch seg;
+};
+
+static MlpWs carve_mlp(Carver &c, const fr_mlp_tower *t, int64_t M) {
+  MlpWs w;
+  int maxw = t->dims[0];
+  size_t maxwk = 0;
+  for (int l = 0; l < t->n_layers; ++l) {
+    maxw = max(maxw, t->dims[l + 1]);
+    maxwk = max(maxwk, (size_t)t->dims[l] * t->dims[l + 1]);
+  }
+  const size_t m = (size_t)(M < 1 ? 1 : M), chunks = (m + kWgradChunk - 1) / kWgradChunk;
+  w.X = c.take<float>(m * t->dims[0]);
+  for (int l = 0; l < 8; ++l) w.act[l] = l < t->n_layers ? c.take<float>(m * t->dims[l + 1]) : nullptr;
+  w.dA = c.take<float>(m * maxw);
+  w.dB = c.take<float>(m * maxw);
+  w.part_w = c.take<float>(chunks * maxwk);
+  w.part_b = c.take<float>(chunks * maxw);
+  w.p = c.take<float>(m);
+  w.dp = c.take<float>(m);
+  w.dz = c.take<float>(m);
+  w.bce_part = c.take<float>(m / 256 + 2);
+  w.seg_eps = c.take<float>(m);
+  w.coef = c.take<float>(2 * m);
+  w.loss_tmp = c.take<float>(4);
+  w.pos_idx = c.take<int32_t>(m);
+  w.n_pos = c.take<int32_t>(1);
+  w.seg_id = c.take<int32_t>(m);
+  w.seg_off = c.take<int32_t>(m + 1);
+  w.n_seg = c.take<int32_t>(1);
+  w.keys = c.take<uint32_t>(m);
+  w.skey = c.take<uint32_t>(m);
+  w.ord = c.take<uint32_t>(m);
+  w.mm = c.take<uint32_t>(2);
+  w.ukey = c.take<uint32_t>(m);
+  w.uord = c.take<uint32_t>(m);
+  w.ikey = c.take<uint32_t>(m);
+  w.iord = c.take<uint32_t>(m);
+  w.useg_id = c.take<int32_t>(m);
+  w.useg_off = c.take<int32_t>(m + 1);
+  w.un_seg = c.take<int32_t>(1);
+  w.iseg_id = c.take<int32_t>(m);
+  w.iseg_off = c.take<int32_t>(m + 1);
+  w.in_seg = c.take<int32_t>(1);
+  w.sort = carve_sort_scratch(c, m);
+  w.seg = carve_seg_scratch(c, m);
+  return w;
+}
+
+static int check_tower(const fr_mlp_tower *t, const char *who) {
+  FR_REQUIRE(t && t->n_layers >= 1 && t->n_layers <= 8, "%s: tower needs 1..8 layers", who);
+  for (int l = 0; l < t->n_layers; ++l) {
+    FR_REQUIRE(t->W[l] && t->b[l] && t->dims[l] >= 1 && t->dims[l + 1] >= 1, "%s: layer %d incomplete", who, l);
+  }
+  return FR_OK;
+}
+
+}  // namespace fr
+
+extern "C" {
+
+size_t fr_nfcf_workspace_bytes(const fr_mlp_tower *t, int64_t M) {
+  if (!t) return 0;
+  fr::Carver c(nullptr, 0);
+  fr::carve_mlp(c, t, M);
+  return c.off;
+}
+
+// forward: p = sigmoid(tower(U[uid] || I[iid])), loss = BCE(p, label) [+ fair_weight * DF over the positives]
+int fr_nfcf_forward(const fr_nfcf_step *s, void *stream) {
+  FR_REQUIRE(s && s->U && s->I && s->uid && s->iid && s->label && s->loss && s->pred && s->workspace && s->status_flags,
+             "fr_nfcf_forward: null pointer");
+  int rc = fr::check_tower(&s->tower, "fr_nfcf_forward");
+  if (rc) return rc;
+  const fr_mlp_tower *t = &s->tower;
+  FR_REQUIRE(s->d % 4 == 0 && t->dims[0] == 2 * s->d && t->dims[t->n_layers] == 1 && s->M >= 1,
+             "fr_nfcf_forward: tower must map 2*d -> 1");
+  FR_REQUIRE(!s->use_df || s->sst, "fr_nfcf_forward: sst missing");
+  fr::Carver c(s->workspace, s->workspace_bytes);
+  fr::MlpWs w = fr::carve_mlp(c, t, s->M);
+  if (!c.ok()) {
+    fr::set_error("fr_nfcf_forward: workspace too small (%zu < %zu)", s->workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = (int)s->M;
+  FR_LAUNCH(fr::k_gather_concat, fr::grid_for((int64_t)M * s->d / 2, 256), 256, 0, st, s->U, s->I, s->uid, s->iid, s->M,
+            s->d, w.X);
+  const float *in = w.X;
+  for (int l = 0; l < t->n_layers; ++l) {
+    fr::GemmArgs g{in, t->W[l], t->b[l], w.act[l], M, t->dims[l + 1], t->dims[l], t->dims[l], t->dims[l], t->dims[l + 1],
+                   t->act, nullptr, 0, s->training ? t->dropout : 0.f, s->seed, l, 0};
+    fr::launch_gemm(true, g, st);
+    in = w.act[l];
+  }
+  const int nblk = (M + 255) / 256;
+  FR_LAUNCH(fr::k_sigmoid_bce, nblk, 256, 0, st, w.act[t->n_layers - 1], s->label, M, w.p, w.dp, w.bce_part);
+  FR_CUDA_OK(cudaMemcpyAsync(s->pred, w.p, sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
+  if (s->use_df) {
+    FR_LAUNCH(fr::k_compact_pos, 1, 1024, 0, st, s->label, M, w.pos_idx, w.n_pos);
+    FR_LAUNCH(fr::k_pos_keys, fr::grid_for(M, 256), 256, 0, st, s->iid, w.pos_idx, w.n_pos, w.keys);
+    fr::sort_pairs(w.keys, nullptr, w.skey, w.ord, M, w.n_pos, fr::bits_for((uint32_t)s->n_items), w.sort, st);
+    fr::build_segments(w.skey, w.ord, M, w.n_pos, w.seg_id, w.seg_off, w.n_seg, nullptr, nullptr, nullptr, w.seg, st);
+    const uint32_t mm0[2] = {0xffffffffu, 0u};
+    FR_CUDA_OK(cudaMemcpyAsync(w.mm, mm0, sizeof(mm0), cudaMemcpyHostToDevice, st));
+    FR_LAUNCH(fr::k_df_minmax, fr::grid_for(M, 256), 256, 0, st, s->sst, w.pos_idx, w.n_pos, w.mm);
+    fr::DfArgs da{w.p, s->sst, w.pos_idx, w.n_pos, w.ord, w.seg_off, w.n_seg, s->fair_weight, w.seg_eps, w.coef, w.mm,
+                  s->status_flags};
+    FR_LAUNCH(fr::k_df_segments, fr::grid_for(M, 8 * 8, fr::kSMs * 2), 256, 0, st, da);
+    FR_LAUNCH(fr::k_df_scatter_coef, fr::grid_for(M, 256), 256, 0, st, da, w.seg_id, w.dp);
+  }
+  FR_LAUNCH(fr::k_nfcf_finish, 1, 256, 0, st, w.bce_part, nblk, M, w.seg_eps, w.n_seg, s->use_df, s->fair_weight, s->loss);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+// backward of fr_nfcf_forward (same workspace): dense dU (optional), dI, dW[l], db[l]; grad_scale = upstream dL
+int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream) {
+  FR_REQUIRE(s && s->workspace && s->dI, "fr_nfcf_backward: null pointer");
+  const fr_mlp_tower *t = &s->tower;
+  fr::Carver c(s->workspace, s->workspace_bytes);
+  fr::MlpWs w = fr::carve_mlp(c, t, s->M);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = (int)s->M, L = t->n_layers;
+  FR_LAUNCH(fr::k_sigmoid_bwd, (M + 255) / 256, 256, 0, st, w.dp, w.p, w.act[L - 1], M, grad_scale, w.dz);
+  const int chunks = (M + fr::kWgradChunk - 1) / fr::kWgradChunk;
+  float *dcur = w.dz;     // gradient w.r.t. the PRE-activation of layer l: [M, dims[l+1]]
+  float *bufs[2] = {w.dA, w.dB};
+  for (int l = L - 1; l >= 0; --l) {
+    const float *inp = l > 0 ? w.act[l - 1] : w.X;
+    const int N = t->dims[l + 1], K = t->dims[l];
+    fr::WgradArgs wa{dcur, inp, w.part_w, w.part_b, M, N, K, N, K, s->training ? t->dropout : 0.f, s->seed, l};
+    dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
+    FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
+    FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)w.part_w, chunks,
+              (int64_t)N * K, s->dW[l]);
+    FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)w.part_b, chunks, (int64_t)N, s->db[l]);
+    // dInput[M,K] = dcur[M,N] . W[N,K], then through the dropout mask of this layer's input and the previous
+    // layer's activation
+    float *dnext = bufs[l & 1];
+    fr::GemmArgs g{dcur, t->W[l], nullptr, dnext, M, K, N, N, K, K, fr::ACT_NONE, l > 0 ? w.act[l - 1] : nullptr, t->act,
+                   s->training ? t->dropout : 0.f, s->seed, l, 1};
+    fr::launch_gemm(false, g, st);
+    dcur = dnext;
+  }
+  // dcur = dX [M, 2d] -> dense embedding gradients (stable sort by id, ordered segment sums)
+  const int d = s->d;
+  if (s->dU) {
+    FR_CUDA_OK(cudaMemsetAsync(s->dU, 0, sizeof(float) * (size_t)s->n_users * d, st));
+    fr::sort_pairs((const uint32_t *)s->uid, nullptr, w.ukey, w.uord, M, nullptr, fr::bits_for((uint32_t)s->n_users),
+                   w.sort, st);
+    fr::build_segments(w.ukey, w.uord, M, nullptr, w.useg_id, w.useg_off, w.un_seg, nullptr, nullptr, nullptr, w.seg, st);
+    FR_LAUNCH(fr::k_segment_sum_rows, fr::grid_for(M, 8, fr::kSMs * 8), 256, 0, st, w.ukey, w.uord, w.useg_off, w.un_seg,
+              (const float *)dcur, 2 * d, 0, d, s->dU);
+  }
+  FR_CUDA_OK(cudaMemsetAsync(s->dI, 0, sizeof(float) * (size_t)s->n_items * d, st));
+  fr::sort_pairs((const uint32_t *)s->iid, nullptr, w.ikey, w.iord, M, nullptr, fr::bits_for((uint32_t)s->n_items), w.sort,
+                 st);
+  fr::build_segments(w.ikey, w.iord, M, nullptr, w.iseg_id, w.iseg_off, w.in_seg, nullptr, nullptr, nullptr, w.seg, st);
+  FR_LAUNCH(fr::k_segment_sum_rows, fr::grid_for(M, 8, fr::kSMs * 8), 256, 0, st, w.ikey, w.iord, w.iseg_off, w.in_seg,
+            (const float *)dcur, 2 * d, d, d, s->dI);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32_t step, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, void *stream) {
+  FR_REQUIRE(p && g && m && v && n >= 1 && step >= 1, "fr_adam_dense: bad argument");
+  FR_LAUNCH(fr::k_adam_flat, fr::grid_for(n, 256, fr::kSMs * 16), 256, 0, stream, p, g, m, v, n, step, lr, beta1, beta2,
+            eps, weight_decay);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+}  // extern "C"
