@@ -220,6 +220,36 @@ int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream);
 int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32_t step, double lr, double beta1,
                   double beta2, double eps, double weight_decay, void *stream);
 
+/* ---- generic layer ops: the pieces of MLPLayers (layers.py:58-70) for the PFCN / FairGo filter, discriminator and
+ * scorer MLPs.  Each is one layer's forward or backward; the host mirror chains them (torch.autograd.Functions). */
+/* Y = act(dropout(X) . W^T + b): nn.Dropout -> nn.Linear -> activation (layers.py:60-68 without BatchNorm) */
+int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
+                      float drop_p, uint64_t seed, int32_t layer, void *stream);
+size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N);
+/* dY is the gradient w.r.t. the layer OUTPUT Y (post-activation); dX may be NULL */
+int fr_linear_backward(const float *X, const float *W, const float *Y, const float *dY, int64_t M, int32_t K, int32_t N,
+                       int32_t act, float drop_p, uint64_t seed, int32_t layer, float *dX, float *dW, float *db,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* nn.BatchNorm1d (layers.py:64-65) fused with the following activation; training mode uses batch statistics and
+ * updates the running ones (momentum 0.1, unbiased variance), eval mode uses the running statistics */
+int fr_batchnorm_forward(const float *X, const float *gamma, const float *beta, float *running_mean, float *running_var,
+                         int64_t M, int32_t N, float momentum, float eps, int32_t training, int32_t act, float *Y,
+                         float *save_mean, float *save_invstd, void *stream);
+int fr_batchnorm_backward(const float *X, const float *Y, const float *dY, const float *gamma, const float *save_mean,
+                          const float *save_invstd, int64_t M, int32_t N, int32_t act, float *dX, float *dgamma,
+                          float *dbeta, void *stream);
+/* nn.Embedding lookup written into columns [col0, col0+d) of a wider row-major matrix (torch.cat for free) */
+int fr_gather_rows(const float *T, const int32_t *idx, int64_t M, int32_t d, float *out, int32_t ld_out, int32_t col0,
+                   void *stream);
+/* dense nn.Embedding backward from columns [col0, col0+d) of the row gradients (sorted-segment sums, batch order) */
+size_t fr_scatter_rows_workspace_bytes(int64_t M);
+int fr_scatter_rows_dense(const int32_t *idx, const float *dX, int32_t ldx, int32_t col0, int64_t M, int32_t d,
+                          int32_t n_rows, float *dT, void *workspace, size_t workspace_bytes, void *stream);
+/* recbole/model/loss.py:44-46 BPRLoss; pfcn_mlp.py:206-209 BCELoss(sigmoid(z), y) and CrossEntropyLoss */
+int fr_bpr_loss(const float *pos, const float *neg, int64_t M, float *loss, float *dpos, float *dneg, void *stream);
+int fr_sigmoid_bce_loss(const float *z, const float *y, int64_t M, float *loss, float *dz, void *stream);
+int fr_softmax_ce_loss(const float *Z, const int32_t *y, int64_t M, int32_t C, float *loss, float *dZ, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Full-sort evaluation: scoring contraction fused with the pad/history mask and a streaming top-K.
  * Replaces focf.py:171-178 full_sort_predict + trainer.py:435-438 mask + collector.py:143-153 topk /

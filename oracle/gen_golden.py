@@ -366,8 +366,101 @@ def run_nfcf(name, fair, n_users=60, n_items=45, d=16, hidden=(32, 16), n_steps=
     print(f"nfcf_train_{name}: losses={losses}")
 
 
+def _dump_mlp(prefix, mlp, out, tag):
+    for k, v in mlp.state_dict().items():
+        out[f"{prefix}.{k}@{tag}"] = v.detach().numpy().copy()
+
+
+def run_pfcn_mlp(name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, seed=31, n_rounds=2):
+    """PFCN_MLP (recbole/model/fair_recommender/pfcn_mlp.py) driven like PFCN_MLPTrainer (trainer.py:875-898,
+    1189-1198): alternating filter+scorer steps on `bpr - dis_weight*dis` and discriminator steps on `dis`;
+    dropout off (the reference's Philox masks cannot be reproduced), BatchNorm in training mode."""
+    from recbole.model.fair_recommender.pfcn_mlp import PFCN_MLP
+
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    gender = rng.integers(0, 2, n_users).astype(np.float32)
+    age = rng.integers(0, 4, n_users).astype(np.float32)
+
+    class DS(FakeDataset):
+        def get_user_feature(self):
+            return Interaction({"user_id": torch.arange(n_users), "gender": torch.from_numpy(gender),
+                                "age": torch.from_numpy(age)})
+
+    cfg = base_cfg(embedding_size=d, sst_attr_list=["gender", "age"], filter_mode=filter_mode, dis_dropout=0.0,
+                   dropout=0.0, dis_weight=10.0, dis_hidden_size_list=[32, 16], mlp_hidden_size_list=[16, 8],
+                   activation="leakyrelu")
+    model = PFCN_MLP(cfg, DS(n_users, n_items, 5.0))
+    with torch.no_grad():   # default inits (N(0,1) embeddings, N(0,0.01) filters) give vanishing signals: widen them
+        model.user_embedding.weight.mul_(0.5)
+        model.item_embedding.weight.mul_(0.5)
+        for m in list(model.filter_layer.values()) + list(model.dis_layer_dict.values()):
+            for p_ in m.parameters():
+                if p_.dim() == 2:
+                    p_.copy_(torch.randn_like(p_) * (1.0 / np.sqrt(p_.shape[1])))
+        for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
+            lin.bias.add_(0.2)
+    out = dict(filter_mode=filter_mode, d=d, gender=gender, age=age, n_users=n_users, n_items=n_items,
+               n_rounds=n_rounds)
+
+    def dump(tag):
+        out[f"user_embedding@{tag}"] = model.user_embedding.weight.detach().numpy().copy()
+        out[f"item_embedding@{tag}"] = model.item_embedding.weight.detach().numpy().copy()
+        _dump_mlp("mlp_layer", model.mlp_layer, out, tag)
+        for k, f in model.filter_layer.items():
+            _dump_mlp(f"filter_{k}", f, out, tag)
+        for k, f in model.dis_layer_dict.items():
+            _dump_mlp(f"dis_{k}", f, out, tag)
+
+    dump("init")
+    base = [model.user_embedding.weight, model.item_embedding.weight] + list(model.mlp_layer.parameters())
+    fparams = [p_ for f in model.filter_layer.values() for p_ in f.parameters()]
+    dparams = [p_ for f in model.dis_layer_dict.values() for p_ in f.parameters()]
+    opt_f = torch.optim.Adam(base + fparams, lr=1e-3, weight_decay=1e-4)
+    opt_d = torch.optim.Adam(dparams, lr=1e-3, weight_decay=1e-4)
+    model.train()
+    for m in list(model.filter_layer.values()) + list(model.dis_layer_dict.values()):
+        m.train()
+    sst_lists = [["gender", "age"], ["age"], ["gender"]]
+    losses = []
+    for r in range(n_rounds):
+        for phase, (fn, opt) in enumerate(((model.calculate_loss, opt_f), (model.calculate_dis_loss, opt_d))):
+            s = 2 * r + phase
+            u = rng.integers(1, n_users, B)
+            inter = Interaction({"user_id": torch.from_numpy(u.astype(np.int64)),
+                                 "item_id": torch.from_numpy(rng.integers(1, n_items, B).astype(np.int64)),
+                                 "neg_item_id": torch.from_numpy(rng.integers(1, n_items, B).astype(np.int64)),
+                                 "gender": torch.from_numpy(gender[u]), "age": torch.from_numpy(age[u])})
+            sst_list = sst_lists[r % len(sst_lists)]
+            opt.zero_grad()
+            loss = fn(inter, sst_list)
+            loss.backward()
+            if s == 0:
+                out["grad_user_embedding@0"] = model.user_embedding.weight.grad.numpy().copy()
+                out["grad_item_embedding@0"] = model.item_embedding.weight.grad.numpy().copy()
+                idx = sum(model.sst_dict[a] for a in sst_list) if filter_mode == "sm" else model.sst_dict[sst_list[0]]
+                for k_, p_ in model.filter_layer[idx].named_parameters():
+                    out[f"grad_filter_{idx}.{k_}@0"] = p_.grad.numpy().copy()
+                for k_, p_ in model.mlp_layer.named_parameters():
+                    out[f"grad_mlp_layer.{k_}@0"] = p_.grad.numpy().copy()
+                out["predict0"] = model.predict(inter, sst_list).detach().numpy().copy() if False else np.zeros(1)
+            opt.step()
+            losses.append(loss.item())
+            for k_ in ("user_id", "item_id", "neg_item_id"):
+                out[f"{k_}{s}"] = inter[k_].numpy()
+            out[f"sst_list{s}"] = np.array(sst_list)
+    out["losses"] = np.array(losses, np.float32)
+    dump("final")
+    np.savez_compressed(os.path.join(OUT, f"pfcn_mlp_{name}.npz"), **out)
+    print(f"pfcn_mlp_{name}: losses={losses}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "pfcn":
+        run_pfcn_mlp("sm", "sm")
+        run_pfcn_mlp("cm", "cm", seed=32)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "nfcf":
         run_nfcf("ncf", fair=False)
         run_nfcf("fair", fair=True)
@@ -387,6 +480,8 @@ def main():
     run_nfcf("ncf", fair=False)
     run_nfcf("fair", fair=True)
     run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
+    run_pfcn_mlp("sm", "sm")
+    run_pfcn_mlp("cm", "cm", seed=32)
 
 
 if __name__ == "__main__":

@@ -5,6 +5,8 @@ Only what the path needs lives here:
   _lib.py          ctypes binding (fails loudly when the library is missing; no CPU fallback)
   kernels.py       tensor-level wrappers of the C ABI
   focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
+  ops.py/layers.py autograd Functions over the generic layer kernels; MLPLayers mirror
+  pfcn_mlp.py      PFCN_MLP model + alternating trainer
   nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
@@ -19,6 +21,7 @@ from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
 from .focf import FOCF  # noqa: F401
 from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF  # noqa: F401
+from .pfcn_mlp import PFCN_MLP, PFCN_MLPTrainer  # noqa: F401
 from .trainer import FOCFTrainer  # noqa: F401
 
 __version__ = "0.1.0"

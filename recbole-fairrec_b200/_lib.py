@@ -92,6 +92,22 @@ SIGNATURES = {
     "fr_nfcf_backward": (c_int, [POINTER(NfcfStep), c_float, c_void_p]),
     "fr_adam_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double,
                               c_double, c_double, c_void_p]),
+    "fr_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
+                                  c_uint64, c_int32, c_void_p]),
+    "fr_linear_backward_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "fr_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
+                                   c_uint64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fr_batchnorm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float,
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_batchnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "fr_scatter_rows_workspace_bytes": (c_size_t, [c_int64]),
+    "fr_scatter_rows_dense": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
+    "fr_bpr_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_sigmoid_bce_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fr_softmax_ce_loss": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
     "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

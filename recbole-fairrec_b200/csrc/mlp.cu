@@ -441,6 +441,193 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---------------------------------------------------------------- generic layer ops (PFCN / FairGo building blocks)
+__global__ void k_act_bwd(const float *__restrict__ dY, const float *__restrict__ Y, int act, int64_t n,
+                          float *__restrict__ dpre) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dpre[i] = dY[i] * act_bwd(Y[i], act);
+}
+
+// BatchNorm1d over the batch dimension (nn.BatchNorm1d, layers.py:64-65), fused with the following activation.
+// One CTA owns 32 feature columns; warp w strides the rows w, w+8, ... (coalesced 128-byte row segments); two passes
+// (mean, then centred variance) with a fixed 8-way ordered combine -> deterministic.
+//   training: y = act((x - mean) * invstd * gamma + beta), running stats updated with the unbiased variance
+//   eval    : y = act((x - running_mean) / sqrt(running_var + eps) * gamma + beta)
+__global__ void __launch_bounds__(256)
+    k_bn_fwd(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
+             float *__restrict__ rmean, float *__restrict__ rvar, int M, int N, float momentum, float eps, int training,
+             int act, float *__restrict__ Y, float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < N;
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    for (int m = w; m < M; m += 8) s += ok ? X[(size_t)m * N + c] : 0.f;
+    red[w][lane] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    mean = s / (float)M;
+    __syncthreads();
+    float q = 0.f;
+    for (int m = w; m < M; m += 8) {
+      const float dlt = ok ? X[(size_t)m * N + c] - mean : 0.f;
+      q = fmaf(dlt, dlt, q);
+    }
+    red[w][lane] = q;
+    __syncthreads();
+    q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q += red[i][lane];
+    const float var = q / (float)M;
+    invstd = 1.f / sqrtf(var + eps);
+    if (w == 0 && ok) {
+      save_mean[c] = mean;
+      save_invstd[c] = invstd;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (M > 1 ? q / (float)(M - 1) : var);
+    }
+  } else {
+    mean = ok ? rmean[c] : 0.f;
+    invstd = ok ? 1.f / sqrtf(rvar[c] + eps) : 0.f;
+  }
+  const float g = ok ? gamma[c] : 0.f, b = ok ? beta[c] : 0.f;
+  for (int m = w; m < M; m += 8)
+    if (ok) Y[(size_t)m * N + c] = act_fwd(fmaf((X[(size_t)m * N + c] - mean) * invstd, g, b), act);
+}
+
+// backward of the above (training mode): dpre = dY * act'(Y); dbeta = sum dpre; dgamma = sum dpre * xhat;
+// dX = gamma * invstd / M * (M * dpre - dbeta - xhat * dgamma)
+__global__ void __launch_bounds__(256)
+    k_bn_bwd(const float *__restrict__ X, const float *__restrict__ Y, const float *__restrict__ dY,
+             const float *__restrict__ gamma, const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+             int M, int N, int act, float *__restrict__ dX, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < N;
+  const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f, g = ok ? gamma[c] : 0.f;
+  float sb = 0.f, sg = 0.f;
+  for (int m = w; m < M; m += 8) {
+    if (ok) {
+      const size_t i = (size_t)m * N + c;
+      const float dp = dY[i] * act_bwd(Y[i], act);
+      sb += dp;
+      sg = fmaf(dp, (X[i] - mean) * invstd, sg);
+    }
+  }
+  red[w][lane] = sb;
+  __syncthreads();
+  sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sb += red[i][lane];
+  __syncthreads();
+  red[w][lane] = sg;
+  __syncthreads();
+  sg = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sg += red[i][lane];
+  if (w == 0 && ok) {
+    dbeta[c] = sb;
+    dgamma[c] = sg;
+  }
+  const float k = g * invstd / (float)M;
+  for (int m = w; m < M; m += 8) {
+    if (ok) {
+      const size_t i = (size_t)m * N + c;
+      const float dp = dY[i] * act_bwd(Y[i], act), xh = (X[i] - mean) * invstd;
+      dX[i] = k * ((float)M * dp - sb - xh * sg);
+    }
+  }
+}
+
+// out[m, col0 : col0 + d] = T[idx[m], :]  (embedding lookup written straight into a slice of a wider row: concat for free)
+__global__ void __launch_bounds__(256)
+    k_gather_rows(const float *__restrict__ T, const int32_t *__restrict__ idx, int64_t M, int d, float *__restrict__ out,
+                  int ld_out, int col0) {
+  const int dq = d >> 2;
+  const int64_t nq = M * dq;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / dq;
+    const int c = (int)(q % dq);
+    const float4 v = __ldg((const float4 *)(T + (size_t)idx[r] * d) + c);
+    float *o = out + r * ld_out + col0 + c * 4;
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+}
+
+// single-CTA scalar losses with a fixed-order reduction (batches are a few thousand rows)
+__device__ __forceinline__ float block_total_1024(float v) {
+  __shared__ float sh[33];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < 32 ? sh[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sh[32] = t;
+  }
+  __syncthreads();
+  t = sh[32];
+  __syncthreads();
+  return t;
+}
+
+// loss.py:44-46 BPRLoss: -mean(log(1e-10 + sigmoid(pos - neg)))
+__global__ void __launch_bounds__(1024)
+    k_bpr(const float *__restrict__ pos, const float *__restrict__ neg, int M, float *__restrict__ loss,
+          float *__restrict__ dpos, float *__restrict__ dneg) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < M; i += 1024) {
+    const float sg = 1.f / (1.f + expf(-(pos[i] - neg[i])));
+    acc += -logf(1e-10f + sg);
+    const float g = -(sg * (1.f - sg)) / (1e-10f + sg) / (float)M;
+    dpos[i] = g;
+    dneg[i] = -g;
+  }
+  acc = block_total_1024(acc);
+  if (threadIdx.x == 0) loss[0] = acc / (float)M;
+}
+
+// nn.BCELoss(sigmoid(z), y) (pfcn_mlp.py:206-207): logs clamped at -100; dz through the sigmoid
+__global__ void __launch_bounds__(1024)
+    k_sigmoid_bce_loss(const float *__restrict__ z, const float *__restrict__ y, int M, float *__restrict__ loss,
+                       float *__restrict__ dz) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < M; i += 1024) {
+    const float p = 1.f / (1.f + expf(-z[i])), t = y[i];
+    acc += -(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(logf(1.f - p), -100.f));
+    const float den = fmaxf(p * (1.f - p), 1e-12f);
+    dz[i] = (p - t) / den * (p * (1.f - p)) / (float)M;
+  }
+  acc = block_total_1024(acc);
+  if (threadIdx.x == 0) loss[0] = acc / (float)M;
+}
+
+// nn.CrossEntropyLoss(Z, y) (pfcn_mlp.py:209): mean over rows of -log softmax(Z)[y]
+__global__ void __launch_bounds__(1024)
+    k_softmax_ce(const float *__restrict__ Z, const int32_t *__restrict__ y, int M, int C, float *__restrict__ loss,
+                 float *__restrict__ dZ) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < M; i += 1024) {
+    const float *zr = Z + (size_t)i * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, zr[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(zr[c] - mx);
+    const float lse = mx + logf(se);
+    const int t = y[i];
+    acc += lse - zr[t];
+    for (int c = 0; c < C; ++c) dZ[(size_t)i * C + c] = (expf(zr[c] - lse) - (c == t ? 1.f : 0.f)) / (float)M;
+  }
+  acc = block_total_1024(acc);
+  if (threadIdx.x == 0) loss[0] = acc / (float)M;
+}
+
 static void launch_gemm(bool tb, const GemmArgs &g, cudaStream_t st) {
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
   if (tb) {
@@ -631,6 +818,134 @@ int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32
   FR_REQUIRE(p && g && m && v && n >= 1 && step >= 1, "fr_adam_dense: bad argument");
   FR_LAUNCH(fr::k_adam_flat, fr::grid_for(n, 256, fr::kSMs * 16), 256, 0, stream, p, g, m, v, n, step, lr, beta1, beta2,
             eps, weight_decay);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+// ---------------------------------------------------------------- generic layer ops
+int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
+                      float drop_p, uint64_t seed, int32_t layer, void *stream) {
+  FR_REQUIRE(X && W && Y && M >= 1 && K >= 1 && N >= 1, "fr_linear_forward: bad argument");
+  fr::GemmArgs g{X, W, b, Y, (int)M, N, K, K, K, N, act, nullptr, 0, drop_p, seed, layer, 0};
+  fr::launch_gemm(true, g, (cudaStream_t)stream);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N) {
+  const size_t chunks = ((size_t)M + fr::kWgradChunk - 1) / fr::kWgradChunk;
+  return ((size_t)M * N + chunks * (size_t)N * K + chunks * (size_t)N) * 4 + 1024;
+}
+
+int fr_linear_backward(const float *X, const float *W, const float *Y, const float *dY, int64_t M, int32_t K, int32_t N,
+                       int32_t act, float drop_p, uint64_t seed, int32_t layer, float *dX, float *dW, float *db,
+                       void *workspace, size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(X && W && Y && dY && dW && workspace && M >= 1, "fr_linear_backward: bad argument");
+  if (workspace_bytes < fr_linear_backward_workspace_bytes(M, K, N)) {
+    fr::set_error("fr_linear_backward: workspace too small");
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = (int)((M + fr::kWgradChunk - 1) / fr::kWgradChunk);
+  fr::Carver c(workspace, workspace_bytes);
+  float *dpre = c.take<float>((size_t)M * N);
+  float *part_w = c.take<float>((size_t)chunks * N * K);
+  float *part_b = c.take<float>((size_t)chunks * N);
+  FR_LAUNCH(fr::k_act_bwd, fr::grid_for(M * N, 256), 256, 0, st, dY, Y, act, M * N, dpre);
+  fr::WgradArgs wa{dpre, X, part_w, part_b, (int)M, N, K, N, K, drop_p, seed, layer};
+  dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
+  FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
+  FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)part_w, chunks, (int64_t)N * K,
+            dW);
+  if (db) FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)part_b, chunks, (int64_t)N, db);
+  if (dX) {
+    fr::GemmArgs g{dpre, W, nullptr, dX, (int)M, K, N, N, K, K, fr::ACT_NONE, nullptr, 0, drop_p, seed, layer, 1};
+    fr::launch_gemm(false, g, st);
+  }
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_batchnorm_forward(const float *X, const float *gamma, const float *beta, float *running_mean, float *running_var,
+                         int64_t M, int32_t N, float momentum, float eps, int32_t training, int32_t act, float *Y,
+                         float *save_mean, float *save_invstd, void *stream) {
+  FR_REQUIRE(X && gamma && beta && running_mean && running_var && Y && save_mean && save_invstd && M >= 1 && N >= 1,
+             "fr_batchnorm_forward: bad argument");
+  FR_LAUNCH(fr::k_bn_fwd, (N + 31) / 32, 256, 0, stream, X, gamma, beta, running_mean, running_var, (int)M, N, momentum,
+            eps, training, act, Y, save_mean, save_invstd);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_batchnorm_backward(const float *X, const float *Y, const float *dY, const float *gamma, const float *save_mean,
+                          const float *save_invstd, int64_t M, int32_t N, int32_t act, float *dX, float *dgamma,
+                          float *dbeta, void *stream) {
+  FR_REQUIRE(X && Y && dY && gamma && save_mean && save_invstd && dX && dgamma && dbeta && M >= 1,
+             "fr_batchnorm_backward: bad argument");
+  FR_LAUNCH(fr::k_bn_bwd, (N + 31) / 32, 256, 0, stream, X, Y, dY, gamma, save_mean, save_invstd, (int)M, N, act, dX,
+            dgamma, dbeta);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_gather_rows(const float *T, const int32_t *idx, int64_t M, int32_t d, float *out, int32_t ld_out, int32_t col0,
+                   void *stream) {
+  FR_REQUIRE(T && idx && out && M >= 1 && d % 4 == 0, "fr_gather_rows: bad argument");
+  FR_LAUNCH(fr::k_gather_rows, fr::grid_for(M * d / 4, 256), 256, 0, stream, T, idx, M, d, out, ld_out, col0);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_scatter_rows_workspace_bytes(int64_t M) {
+  fr::Carver c(nullptr, 0);
+  const size_t m = (size_t)(M < 1 ? 1 : M);
+  c.take<uint32_t>(m); c.take<uint32_t>(m); c.take<int32_t>(m); c.take<int32_t>(m + 1); c.take<int32_t>(1);
+  fr::carve_sort_scratch(c, m);
+  fr::carve_seg_scratch(c, m);
+  return c.off;
+}
+
+// dense gradient of an embedding lookup: dT[idx[m], :] += dX[m, col0 : col0 + d], summed per row in batch order
+int fr_scatter_rows_dense(const int32_t *idx, const float *dX, int32_t ldx, int32_t col0, int64_t M, int32_t d,
+                          int32_t n_rows, float *dT, void *workspace, size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(idx && dX && dT && workspace && M >= 1, "fr_scatter_rows_dense: bad argument");
+  fr::Carver c(workspace, workspace_bytes);
+  const size_t m = (size_t)M;
+  uint32_t *skey = c.take<uint32_t>(m), *ord = c.take<uint32_t>(m);
+  int32_t *seg_id = c.take<int32_t>(m), *seg_off = c.take<int32_t>(m + 1), *n_seg = c.take<int32_t>(1);
+  fr::SortScratch ss = fr::carve_sort_scratch(c, m);
+  fr::SegScratch sg = fr::carve_seg_scratch(c, m);
+  if (!c.ok()) {
+    fr::set_error("fr_scatter_rows_dense: workspace too small");
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FR_CUDA_OK(cudaMemsetAsync(dT, 0, sizeof(float) * (size_t)n_rows * d, st));
+  fr::sort_pairs((const uint32_t *)idx, nullptr, skey, ord, M, nullptr, fr::bits_for((uint32_t)n_rows), ss, st);
+  fr::build_segments(skey, ord, M, nullptr, seg_id, seg_off, n_seg, nullptr, nullptr, nullptr, sg, st);
+  FR_LAUNCH(fr::k_segment_sum_rows, fr::grid_for(M, 8, fr::kSMs * 8), 256, 0, st, skey, ord, seg_off, n_seg, dX, ldx,
+            col0, d, dT);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_bpr_loss(const float *pos, const float *neg, int64_t M, float *loss, float *dpos, float *dneg, void *stream) {
+  FR_REQUIRE(pos && neg && loss && dpos && dneg && M >= 1, "fr_bpr_loss: bad argument");
+  FR_LAUNCH(fr::k_bpr, 1, 1024, 0, stream, pos, neg, (int)M, loss, dpos, dneg);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_sigmoid_bce_loss(const float *z, const float *y, int64_t M, float *loss, float *dz, void *stream) {
+  FR_REQUIRE(z && y && loss && dz && M >= 1, "fr_sigmoid_bce_loss: bad argument");
+  FR_LAUNCH(fr::k_sigmoid_bce_loss, 1, 1024, 0, stream, z, y, (int)M, loss, dz);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_softmax_ce_loss(const float *Z, const int32_t *y, int64_t M, int32_t C, float *loss, float *dZ, void *stream) {
+  FR_REQUIRE(Z && y && loss && dZ && M >= 1 && C >= 2, "fr_softmax_ce_loss: bad argument");
+  FR_LAUNCH(fr::k_softmax_ce, 1, 1024, 0, stream, Z, y, (int)M, C, loss, dZ);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
