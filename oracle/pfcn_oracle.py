@@ -69,7 +69,7 @@ def dis_loss(st, uid, labels, sst_list, sst_dict, sst_size, filter_mode, n_filte
     for s in sst_list:
         z = mlp_forward(ue, st, f"dis_{s}", n_layers_of(st, f"dis_{s}"), True, act)
         if sst_size[s] == 2:
-            loss = loss + F.binary_cross_entropy(torch.sigmoid(z), labels[s].float().view(-1, 1))
+            loss = loss + F.binary_cross_entropy(torch.sigmoid(z), labels[s].to(z.dtype).view(-1, 1))
         else:
             loss = loss + F.cross_entropy(z, labels[s].long())
     return loss

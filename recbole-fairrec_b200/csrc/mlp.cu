@@ -10,7 +10,7 @@
 // The towers are tiny (widths <= 256, M = batch rows): every layer is a 64x64x16 register-tiled fp32 GEMM on the CUDA
 // cores with the bias / activation / dropout fused into the epilogue or the operand loader.  fp32 FMA keeps the
 // 1e-5 parity bar against the reference's sgemm without a 3xTF32 split; at these sizes the step is launch-bound,
-// not math-bound.  Weight gradients reduce over the batch in fixed 2048-row chunks (partials + ordered sum), the
+// not math-bound.  Weight gradients reduce over the batch in fixed 256-row chunks (partials + ordered sum), the
 // item x group statistics reuse the sorted-segment machinery of sort.cu: no floating-point atomics anywhere.
 #include "sort.cuh"
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
 }
 
 // ---------------------------------------------------------------- weight / bias gradients
-// dW[n,k] = sum_m dY[m,n] * Xdrop[m,k] over one 2048-row chunk per blockIdx.z -> part[z][N][K]; db likewise.
+// dW[n,k] = sum_m dY[m,n] * Xdrop[m,k] over one 256-row chunk per blockIdx.z -> part[z][N][K]; db likewise.
 struct WgradArgs {
   const float *dY, *X;
   float *part_w, *part_b;       // [chunks, N, K], [chunks, N]
@@ -156,7 +156,7 @@ struct WgradArgs {
   unsigned long long seed;
   int layer;
 };
-constexpr int kWgradChunk = 2048;
+constexpr int kWgradChunk = 256;
 
 __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   __shared__ float Ys[16][64 + 4];

@@ -123,11 +123,12 @@ class BprLoss(_ScalarLoss):
     @staticmethod
     def forward(ctx, pos, neg):
         lib = load()
+        shape_p, shape_n = pos.shape, neg.shape
         pos, neg = pos.contiguous().view(-1), neg.contiguous().view(-1)
         loss = torch.empty(1, dtype=torch.float32, device=pos.device)
         dp, dn = torch.empty_like(pos), torch.empty_like(neg)
         check(lib.fr_bpr_loss(ptr(pos), ptr(neg), pos.numel(), ptr(loss), ptr(dp), ptr(dn), stream_ptr()), "fr_bpr_loss")
-        ctx.grads = (dp, dn)
+        ctx.grads = (dp.view(shape_p), dn.view(shape_n))
         return loss.view(())
 
 

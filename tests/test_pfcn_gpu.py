@@ -34,6 +34,11 @@ class UserFeatDataset:
         return self._feat
 
 
+def bias_before_bn(k, st):
+    """a Linear bias feeding BatchNorm: its gradient is zero mathematically and rounding noise numerically"""
+    return k.endswith(".bias") and not k.startswith("mlp_layer") and st[k[:-4] + "weight"].dim() == 2
+
+
 def owners(model):
     out = {"mlp_layer": model.mlp_layer}
     out.update({f"filter_{k}": m for k, m in model.filter_layer.items()})
@@ -95,7 +100,11 @@ def test_pfcn_mlp_matches_reference(path):
             n = 0
             for k in g.files:
                 if k.startswith("grad_") and k.endswith("@0"):
-                    assert rel_err(named[k[5:-2]].grad.cpu().numpy(), g[k]) < RTOL, k
+                    mine = named[k[5:-2]].grad.cpu().numpy()
+                    if bias_before_bn(k[5:-2], {q: p.detach() for q, p in named.items()}):
+                        assert np.abs(mine).max() < 1e-5 and np.abs(g[k]).max() < 1e-5, k
+                    else:
+                        assert rel_err(mine, g[k]) < RTOL, k
                     n += 1
             assert n >= 16
         opt.step()
@@ -106,6 +115,13 @@ def test_pfcn_mlp_matches_reference(path):
         if k.endswith("@final"):
             if "num_batches_tracked" in k:
                 assert int(final[k[:-6]]) == int(g[k]), k
+            elif bias_before_bn(k[:-6], {q: torch.from_numpy(v) for q, v in final.items()}):
+                # zero-gradient parameter: Adam turns rounding noise into +-lr steps whose sign is arbitrary; the value
+                # is cancelled by the BatchNorm that follows, so only its magnitude (<= n_steps * lr) is defined
+                assert np.abs(final[k[:-6]] - np.array(g[k[:-6] + "@init"])).max() <= 4 * 1e-3 * 1.01, k
+            elif k.endswith("running_mean@final") and not k.startswith("mlp_layer"):
+                # the running mean of a BatchNorm includes the (arbitrary, see above) bias of the Linear in front of it
+                assert np.abs(final[k[:-6]] - g[k]).max() <= 2 * 4 * 1e-3 * 1.01, k
             else:
                 assert rel_err(final[k[:-6]], g[k]) < RTOL, k
 
@@ -130,9 +146,11 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
         for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
             lin.bias.add_(0.2)
     st = {k: torch.from_numpy(v.copy()) for k, v in dump_state(model).items()}
+    st64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in st.items()}
     fkeys, dkeys = po.param_groups(st)
     for k in fkeys + dkeys:
         st[k].requires_grad_(True)
+        st64[k].requires_grad_(True)
     attrs = list(feats)
     if filter_mode == "sm":
         sst_dict, nf = {s: 2 ** i for i, s in enumerate(attrs)}, 7
@@ -150,9 +168,12 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
     model.train()
     loss = model.calculate_loss(inter, sst_list)
     loss.backward()
-    lo = po.calculate_loss(st, torch.from_numpy(u), torch.from_numpy(pos), torch.from_numpy(neg), labels, sst_list,
-                           sst_dict, sst_size, filter_mode, nf, "leakyrelu", 1.0)
+    args = (torch.from_numpy(u), torch.from_numpy(pos), torch.from_numpy(neg), labels, sst_list, sst_dict, sst_size,
+            filter_mode, nf, "leakyrelu", 1.0)
+    lo = po.calculate_loss(st, *args)
     lo.backward()
+    lo64 = po.calculate_loss(st64, *args)
+    lo64.backward()
     np.testing.assert_allclose(loss.item(), lo.item(), rtol=RTOL)
     named = {"user_embedding": model.user_embedding.weight, "item_embedding": model.item_embedding.weight}
     for name, mod in owners(model).items():
@@ -162,12 +183,17 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
         if st[k].grad is None:
             assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
             continue
-        ref = st[k].grad.numpy()
+        ref, ref64 = st[k].grad.numpy(), st64[k].grad.numpy()
         if np.abs(ref).max() == 0:
             continue
-        # deep BatchNorm stacks amplify fp32 summation-order noise; the bound is 1e-5 on the loss and 1e-4 on the
-        # gradients of this 8-layer case (torch-CPU fp32 vs fp64 differ by the same order)
-        assert rel_err(named[k].grad.cpu().numpy(), ref) < 1e-4, k
+        if bias_before_bn(k, st):
+            assert np.abs(named[k].grad.cpu().numpy()).max() < 1e-6 and np.abs(ref).max() < 1e-6, k
+            continue
+        # 1e-5 relative, widened only by how far the fp32 CPU oracle itself sits from the fp64 evaluation of the same
+        # graph (deep BatchNorm stacks amplify summation-order noise): the GPU result must be as close to the fp64
+        # truth as stock torch fp32 is, up to a factor 3
+        tol = max(RTOL, 3.0 * rel_err(ref, ref64))
+        assert rel_err(named[k].grad.cpu().numpy(), ref64) < tol, (k, tol)
         checked += 1
     assert checked > 30
 
