@@ -220,6 +220,18 @@ int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream);
 int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32_t step, double lr, double beta1,
                   double beta2, double eps, double weight_decay, void *stream);
 
+/* torch.optim.Adam (trainer.py:139, 1189-1235) over MANY small parameter tensors in one launch per 48 entries; every entry
+ * carries its own step count (torch keeps state['step'] per parameter and skips parameters without a gradient) */
+typedef struct fr_adam_entry {
+  float *p;
+  const float *g;
+  float *m, *v;
+  int64_t n;
+  int32_t step; /* 1-based step count of THIS parameter after the update */
+} fr_adam_entry;
+int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, void *stream);
+
 /* ---- generic layer ops: the pieces of MLPLayers (layers.py:58-70) for the PFCN / FairGo filter, discriminator and
  * scorer MLPs.  Each is one layer's forward or backward; the host mirror chains them (torch.autograd.Functions). */
 /* Y = act(dropout(X) . W^T + b): nn.Dropout -> nn.Linear -> activation (layers.py:60-68 without BatchNorm) */
@@ -249,6 +261,58 @@ int fr_scatter_rows_dense(const int32_t *idx, const float *dX, int32_t ldx, int3
 int fr_bpr_loss(const float *pos, const float *neg, int64_t M, float *loss, float *dpos, float *dneg, void *stream);
 int fr_sigmoid_bce_loss(const float *z, const float *y, int64_t M, float *loss, float *dz, void *stream);
 int fr_softmax_ce_loss(const float *Z, const int32_t *y, int64_t M, int32_t C, float *loss, float *dZ, void *stream);
+
+/* ---- row-wise scorers and glue ops of the PFCN / FairGo families (layer_ops.cu) */
+/* out[m] = sum_k A[m,k] * B[m,k]: torch.mul(u, i).sum(-1) (pfcn_pmf.py:172,183-184; fairgo_pmf.py:169) */
+int fr_rowdot_forward(const float *A, const float *B, int64_t M, int32_t d, float *out, void *stream);
+int fr_rowdot_backward(const float *A, const float *B, const float *dout, int64_t M, int32_t d, float *dA, float *dB,
+                       void *stream);
+/* nn.CosineSimilarity(dim=1, eps) (pfcn_dmf.py:176,190-191); norms = float[2*M] kept for the backward */
+int fr_cosine_forward(const float *A, const float *B, int64_t M, int32_t d, float eps, float *out, float *norms,
+                      void *stream);
+int fr_cosine_backward(const float *A, const float *B, const float *out, const float *norms, const float *dout, int64_t M,
+                       int32_t d, float eps, float *dA, float *dB, void *stream);
+/* pfcn_biasedmf.py:189-192: the [B] dots broadcast against [B,1] bias columns give [B,B] score matrices
+ *   pos[i,j] = dotp[j] + ub[i] + pib[i] + gb, neg[i,j] = dotn[j] + ub[i] + nib[i] + gb; loss = BPRLoss over all B*B pairs.
+ * Outputs the loss and the gradients of the four inputs that do not cancel; row_scratch = float[B]. */
+int fr_bpr_outer_loss(const float *dotp, const float *dotn, const float *ub, const float *pib, const float *nib,
+                      const float *gb, int32_t B, float *loss, float *d_dotp, float *d_dotn, float *d_pib, float *d_nib,
+                      float *row_scratch, void *stream);
+/* out = (x0 + x1 + ... ) * scale, or / scale when divide != 0; xs_host = HOST array of n_terms (<= 8) device pointers
+ * (cm-mode filter averaging pfcn_mlp.py:158-165, fairgo_pmf.py:163-168) */
+int fr_scaled_sum(const float *const *xs_host, int32_t n_terms, int64_t n, float scale, int32_t divide, float *out,
+                  void *stream);
+/* dst[m, col_dst : col_dst+ncols] = src[m, col_src : col_src+ncols] (torch.cat / torch.split along dim 1) */
+int fr_copy_cols(const float *src, int32_t ld_src, int32_t col_src, float *dst, int32_t ld_dst, int32_t col_dst, int64_t M,
+                 int32_t ncols, void *stream);
+/* nn.MSELoss() (fairgo_pmf.py:170-171): loss and d loss / d pred */
+int fr_mse_loss(const float *pred, const float *target, int64_t M, float *loss, float *dpred, void *stream);
+/* stand-alone activation (act codes of fr_linear_forward) and its backward through the OUTPUT y */
+int fr_act_forward(const float *x, int32_t act, int64_t n, float *y, void *stream);
+int fr_act_backward(const float *dY, const float *Y, int32_t act, int64_t n, float *dX, void *stream);
+/* out[m] = act(dot[m] + ub[m] + ib[m] + gb[0]) (pfcn_biasedmf.py:170-181 predict) */
+int fr_biased_score(const float *dot, const float *ub, const float *ib, const float *gb, int64_t M, int32_t act, float *out,
+                    void *stream);
+/* clamp(x, 0, hi) / hi (fairgo_pmf.py:248 predict) */
+int fr_clamp_div(const float *x, float hi, int64_t n, float *y, void *stream);
+
+/* ---- CSR SpMM for the FairGo ego-network aggregation (spmm.cu): Y = A . X, fairgo_pmf.py:199-202.
+ * The matrix is static: plan once on the host (rows cut into chunks of <= chunk nnz), copy the plan arrays to the
+ * device, then call fr_spmm_csr every step (backward = the same call on the CSR of A^T). */
+int fr_spmm_plan_sizes(const int64_t *row_off_host, int32_t n_rows, int32_t chunk, int64_t *n_chunks, int64_t *n_multi,
+                       int64_t *n_slots, int64_t *n_empty);
+int fr_spmm_plan_fill(const int64_t *row_off_host, int32_t n_rows, int32_t chunk, int32_t *chunk_row_host,
+                      int32_t *chunk_begin_host, int32_t *chunk_end_host, int32_t *chunk_slot_host, int32_t *multi_row_host,
+                      int32_t *multi_first_host /* n_multi + 1 */, int32_t *empty_row_host);
+typedef struct fr_spmm_plan {
+  const int32_t *chunk_row, *chunk_begin, *chunk_end, *chunk_slot; /* device, [n_chunks] */
+  const int32_t *multi_row, *multi_first;                          /* device, [n_multi], [n_multi + 1] */
+  const int32_t *empty_row;                                        /* device, [n_empty] */
+  int64_t n_chunks, n_multi, n_slots, n_empty;
+} fr_spmm_plan;
+/* partial = float[n_slots * d] scratch (may be NULL when n_slots == 0) */
+int fr_spmm_csr(const fr_spmm_plan *plan, const int32_t *col, const float *val, const float *X, int32_t d, float *Y,
+                float *partial, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Full-sort evaluation: scoring contraction fused with the pad/history mask and a streaming top-K.

@@ -371,11 +371,21 @@ def _dump_mlp(prefix, mlp, out, tag):
         out[f"{prefix}.{k}@{tag}"] = v.detach().numpy().copy()
 
 
-def run_pfcn_mlp(name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, seed=31, n_rounds=2):
-    """PFCN_MLP (recbole/model/fair_recommender/pfcn_mlp.py) driven like PFCN_MLPTrainer (trainer.py:875-898,
-    1189-1198): alternating filter+scorer steps on `bpr - dis_weight*dis` and discriminator steps on `dis`;
-    dropout off (the reference's Philox masks cannot be reproduced), BatchNorm in training mode."""
-    from recbole.model.fair_recommender.pfcn_mlp import PFCN_MLP
+PFCN_EXTRA = {
+    "PFCN_MLP": dict(dropout=0.0, mlp_hidden_size_list=[16, 8]),
+    "PFCN_PMF": dict(),
+    "PFCN_BiasedMF": dict(),
+    "PFCN_DMF": dict(num_layers=2, mlp_dropout=0.0, mlp_activation="leakyrelu", dis_activation="leakyrelu"),
+}
+
+
+def run_pfcn(model_name, name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, seed=31, n_rounds=2):
+    """PFCN_* (recbole/model/fair_recommender/pfcn_*.py) driven like PFCNTrainer (trainer.py:875-898, 1189-1235):
+    alternating filter+base steps on `bpr - dis_weight*dis` and discriminator steps on `dis`; dropout off (the
+    reference's Philox masks cannot be reproduced), BatchNorm in training mode.  State keys: `base.<state_dict key>` for
+    the registered modules, `filter_<idx>.…` / `dis_<attr>.…` for the dict-held MLPs."""
+    import importlib
+    cls = getattr(importlib.import_module(f"recbole.model.fair_recommender.{model_name.lower()}"), model_name)
 
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)
@@ -388,32 +398,36 @@ def run_pfcn_mlp(name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, se
                                 "age": torch.from_numpy(age)})
 
     cfg = base_cfg(embedding_size=d, sst_attr_list=["gender", "age"], filter_mode=filter_mode, dis_dropout=0.0,
-                   dropout=0.0, dis_weight=10.0, dis_hidden_size_list=[32, 16], mlp_hidden_size_list=[16, 8],
-                   activation="leakyrelu")
-    model = PFCN_MLP(cfg, DS(n_users, n_items, 5.0))
-    with torch.no_grad():   # default inits (N(0,1) embeddings, N(0,0.01) filters) give vanishing signals: widen them
-        model.user_embedding.weight.mul_(0.5)
-        model.item_embedding.weight.mul_(0.5)
-        for m in list(model.filter_layer.values()) + list(model.dis_layer_dict.values()):
+                   dis_weight=10.0, dis_hidden_size_list=[32, 16], activation="leakyrelu", **PFCN_EXTRA[model_name])
+    model = cls(cfg, DS(n_users, n_items, 5.0))
+    with torch.no_grad():   # default inits (N(0,1) embeddings, N(0,0.01) MLPs) give vanishing signals: widen them
+        for k_, p_ in model.named_parameters():
+            if "embedding" in k_:
+                p_.mul_(0.5)
+            elif "bias" in k_ and p_.dim() == 2:                    # nn.Embedding(n, 1) bias tables
+                p_.mul_(0.3)
+        mlps = list(model.filter_layer.values()) + list(model.dis_layer_dict.values())
+        mlps += [getattr(model, a_) for a_ in ("user_mlp", "item_mlp") if hasattr(model, a_)]
+        for m in mlps:
             for p_ in m.parameters():
                 if p_.dim() == 2:
                     p_.copy_(torch.randn_like(p_) * (1.0 / np.sqrt(p_.shape[1])))
-        for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
-            lin.bias.add_(0.2)
-    out = dict(filter_mode=filter_mode, d=d, gender=gender, age=age, n_users=n_users, n_items=n_items,
+        if hasattr(model, "mlp_layer"):
+            for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
+                lin.bias.add_(0.2)
+    out = dict(model=model_name, filter_mode=filter_mode, d=d, gender=gender, age=age, n_users=n_users, n_items=n_items,
                n_rounds=n_rounds)
 
     def dump(tag):
-        out[f"user_embedding@{tag}"] = model.user_embedding.weight.detach().numpy().copy()
-        out[f"item_embedding@{tag}"] = model.item_embedding.weight.detach().numpy().copy()
-        _dump_mlp("mlp_layer", model.mlp_layer, out, tag)
-        for k, f in model.filter_layer.items():
-            _dump_mlp(f"filter_{k}", f, out, tag)
-        for k, f in model.dis_layer_dict.items():
-            _dump_mlp(f"dis_{k}", f, out, tag)
+        for k_, v_ in model.state_dict().items():
+            out[f"base.{k_}@{tag}"] = v_.detach().numpy().copy()
+        for k_, f in model.filter_layer.items():
+            _dump_mlp(f"filter_{k_}", f, out, tag)
+        for k_, f in model.dis_layer_dict.items():
+            _dump_mlp(f"dis_{k_}", f, out, tag)
 
     dump("init")
-    base = [model.user_embedding.weight, model.item_embedding.weight] + list(model.mlp_layer.parameters())
+    base = list(model.parameters())
     fparams = [p_ for f in model.filter_layer.values() for p_ in f.parameters()]
     dparams = [p_ for f in model.dis_layer_dict.values() for p_ in f.parameters()]
     opt_f = torch.optim.Adam(base + fparams, lr=1e-3, weight_decay=1e-4)
@@ -436,14 +450,15 @@ def run_pfcn_mlp(name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, se
             loss = fn(inter, sst_list)
             loss.backward()
             if s == 0:
-                out["grad_user_embedding@0"] = model.user_embedding.weight.grad.numpy().copy()
-                out["grad_item_embedding@0"] = model.item_embedding.weight.grad.numpy().copy()
+                for k_, p_ in model.named_parameters():
+                    if p_.grad is not None:
+                        out[f"grad_base.{k_}@0"] = p_.grad.numpy().copy()
                 idx = sum(model.sst_dict[a] for a in sst_list) if filter_mode == "sm" else model.sst_dict[sst_list[0]]
                 for k_, p_ in model.filter_layer[idx].named_parameters():
                     out[f"grad_filter_{idx}.{k_}@0"] = p_.grad.numpy().copy()
-                for k_, p_ in model.mlp_layer.named_parameters():
-                    out[f"grad_mlp_layer.{k_}@0"] = p_.grad.numpy().copy()
-                out["predict0"] = model.predict(inter, sst_list).detach().numpy().copy() if False else np.zeros(1)
+                with torch.no_grad():
+                    out["predict0"] = model.predict(inter, sst_list).numpy().copy()   # train-mode batch statistics
+                    # NB: this extra train-mode forward also advances the BatchNorm running statistics; replays do the same
             opt.step()
             losses.append(loss.item())
             for k_ in ("user_id", "item_id", "neg_item_id"):
@@ -451,15 +466,26 @@ def run_pfcn_mlp(name, filter_mode="sm", n_users=80, n_items=50, d=16, B=128, se
             out[f"sst_list{s}"] = np.array(sst_list)
     out["losses"] = np.array(losses, np.float32)
     dump("final")
-    np.savez_compressed(os.path.join(OUT, f"pfcn_mlp_{name}.npz"), **out)
-    print(f"pfcn_mlp_{name}: losses={losses}")
+    np.savez_compressed(os.path.join(OUT, f"pfcn_{name}.npz"), **out)
+    print(f"pfcn_{name}: losses={losses}")
+
+
+def run_all_pfcn():
+    for old in ("pfcn_mlp_sm.npz", "pfcn_mlp_cm.npz"):
+        if os.path.exists(os.path.join(OUT, old)):
+            os.remove(os.path.join(OUT, old))
+    run_pfcn("PFCN_MLP", "mlp_sm", "sm")
+    run_pfcn("PFCN_MLP", "mlp_cm", "cm", seed=32)
+    run_pfcn("PFCN_PMF", "pmf_sm", "sm", seed=33)
+    run_pfcn("PFCN_PMF", "pmf_cm", "cm", seed=34)
+    run_pfcn("PFCN_BiasedMF", "biasedmf_sm", "sm", seed=35)
+    run_pfcn("PFCN_DMF", "dmf_cm", "cm", seed=36)
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "pfcn":
-        run_pfcn_mlp("sm", "sm")
-        run_pfcn_mlp("cm", "cm", seed=32)
+        run_all_pfcn()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "nfcf":
         run_nfcf("ncf", fair=False)
@@ -480,8 +506,7 @@ def main():
     run_nfcf("ncf", fair=False)
     run_nfcf("fair", fair=True)
     run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
-    run_pfcn_mlp("sm", "sm")
-    run_pfcn_mlp("cm", "cm", seed=32)
+    run_all_pfcn()
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ Only what the path needs lives here:
   kernels.py       tensor-level wrappers of the C ABI
   focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
   ops.py/layers.py autograd Functions over the generic layer kernels; MLPLayers mirror
-  pfcn_mlp.py      PFCN_MLP model + alternating trainer
+  pfcn.py          PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF models + alternating PFCNTrainer
   nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
@@ -21,7 +21,8 @@ from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
 from .focf import FOCF  # noqa: F401
 from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF  # noqa: F401
-from .pfcn_mlp import PFCN_MLP, PFCN_MLPTrainer  # noqa: F401
+from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFCN_MLPTrainer, PFCN_PMFTrainer,  # noqa: F401
+                   PFCN_BiasedMFTrainer, PFCN_DMFTrainer)
 from .trainer import FOCFTrainer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -67,6 +67,18 @@ class FullSort(Structure):
     ]
 
 
+class AdamEntry(Structure):
+    """mirror of `struct fr_adam_entry`"""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("step", c_int32)]
+
+
+class SpmmPlan(Structure):
+    """mirror of `struct fr_spmm_plan`"""
+    _fields_ = [("chunk_row", c_void_p), ("chunk_begin", c_void_p), ("chunk_end", c_void_p), ("chunk_slot", c_void_p),
+                ("multi_row", c_void_p), ("multi_first", c_void_p), ("empty_row", c_void_p),
+                ("n_chunks", c_int64), ("n_multi", c_int64), ("n_slots", c_int64), ("n_empty", c_int64)]
+
+
 # name -> (restype, argtypes); also the list the ABI-surface test checks against the header
 SIGNATURES = {
     "fr_abi_version": (c_int, []),
@@ -108,6 +120,26 @@ SIGNATURES = {
     "fr_bpr_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fr_sigmoid_bce_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "fr_softmax_ce_loss": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "fr_adam_multi": (c_int, [POINTER(AdamEntry), c_int32, c_double, c_double, c_double, c_double, c_double, c_void_p]),
+    "fr_biased_score": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "fr_rowdot_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "fr_rowdot_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "fr_cosine_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "fr_cosine_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p,
+                                   c_void_p, c_void_p]),
+    "fr_bpr_outer_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_scaled_sum": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_float, c_int32, c_void_p, c_void_p]),
+    "fr_copy_cols": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p]),
+    "fr_mse_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fr_act_forward": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "fr_act_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "fr_clamp_div": (c_int, [c_void_p, c_float, c_int64, c_void_p, c_void_p]),
+    "fr_spmm_plan_sizes": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                                   POINTER(c_int64)]),
+    "fr_spmm_plan_fill": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "fr_spmm_csr": (c_int, [POINTER(SpmmPlan), c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
     "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

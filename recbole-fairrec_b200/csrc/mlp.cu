@@ -12,42 +12,10 @@
 // 1e-5 parity bar against the reference's sgemm without a 3xTF32 split; at these sizes the step is launch-bound,
 // not math-bound.  Weight gradients reduce over the batch in fixed 256-row chunks (partials + ordered sum), the
 // item x group statistics reuse the sorted-segment machinery of sort.cu: no floating-point atomics anywhere.
+#include "act.cuh"
 #include "sort.cuh"
 
 namespace fr {
-
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3, ACT_TANH = 4 };
-
-// counter-based dropout mask: keep-scale of element idx of layer `layer` (1/(1-p) or 0); p == 0 -> 1
-__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t layer, uint32_t idx, float p) {
-  if (p <= 0.f) return 1.f;
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)layer << 32 | idx);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : 1.f / (1.f - p);
-}
-
-__device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
-    case ACT_RELU: return fmaxf(x, 0.f);
-    case ACT_LEAKY: return x > 0.f ? x : 0.01f * x;
-    case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
-    case ACT_TANH: return tanhf(x);
-    default: return x;
-  }
-}
-// derivative expressed through the activation OUTPUT y (what the forward pass keeps)
-__device__ __forceinline__ float act_bwd(float y, int act) {
-  switch (act) {
-    case ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case ACT_LEAKY: return y > 0.f ? 1.f : 0.01f;
-    case ACT_SIGMOID: return y * (1.f - y);
-    case ACT_TANH: return 1.f - y * y;
-    default: return 1.f;
-  }
-}
 
 // ---------------------------------------------------------------- gather / concat of the two embedding rows
 __global__ void __launch_bounds__(256)
@@ -442,6 +410,46 @@ __global__ void __launch_bounds__(256)
 }
 
 
+// Multi-tensor Adam: one launch updates up to kAdamMulti parameter tensors (the ~100 small weights / biases / BatchNorm
+// affine vectors of the PFCN / FairGo MLPs), each with its own step count (torch keeps `state['step']` per parameter and
+// skips parameters whose .grad is None).  CTA b serves 1024-element tile (b - first_tile[e]) of entry e.
+constexpr int kAdamMulti = 48;
+struct AdamMultiArgs {
+  float *p[kAdamMulti];
+  const float *g[kAdamMulti];
+  float *m[kAdamMulti], *v[kAdamMulti];
+  int n[kAdamMulti], step[kAdamMulti], first_tile[kAdamMulti + 1];
+  int n_entries;
+  double lr, beta1, beta2, eps, wd;
+};
+__global__ void __launch_bounds__(256) k_adam_multi(AdamMultiArgs a) {
+  __shared__ float sc[2];
+  __shared__ int se;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < a.n_entries && (int)blockIdx.x >= a.first_tile[e + 1]) ++e;
+    se = e;
+    sc[0] = (float)(-a.lr / (1.0 - pow(a.beta1, (double)a.step[e])));
+    sc[1] = (float)sqrt(1.0 - pow(a.beta2, (double)a.step[e]));
+  }
+  __syncthreads();
+  const int e = se;
+  const float neg_step = sc[0], bc2s = sc[1], w1 = (float)(1.0 - a.beta1), w2 = (float)(1.0 - a.beta2),
+              b2 = (float)a.beta2, fwd = (float)a.wd, feps = (float)a.eps;
+  float *p = a.p[e], *m = a.m[e], *v = a.v[e];
+  const float *g = a.g[e];
+  const int base = ((int)blockIdx.x - a.first_tile[e]) * 1024, hi = min(a.n[e], base + 1024);
+  for (int i = base + threadIdx.x; i < hi; i += 256) {
+    float gi = fmaf(fwd, p[i], g[i]);
+    float mi = fmaf(w1, gi - m[i], m[i]);
+    float vi = fmaf(w2 * gi, gi, v[i] * b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = fmaf(neg_step, mi / (sqrtf(vi) / bc2s + feps), p[i]);
+  }
+}
+
+
 // ---------------------------------------------------------------- generic layer ops (PFCN / FairGo building blocks)
 __global__ void k_act_bwd(const float *__restrict__ dY, const float *__restrict__ Y, int act, int64_t n,
                           float *__restrict__ dpre) {
@@ -557,6 +565,17 @@ __global__ void __launch_bounds__(256)
     const float4 v = __ldg((const float4 *)(T + (size_t)idx[r] * d) + c);
     float *o = out + r * ld_out + col0 + c * 4;
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_gather_rows_any(const float *__restrict__ T, const int32_t *__restrict__ idx, int64_t M, int d, float *__restrict__ out,
+                      int ld_out, int col0) {
+  const int64_t n = M * d;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / d;
+    const int c = (int)(q % d);
+    out[r * ld_out + col0 + c] = __ldg(T + (size_t)idx[r] * d + c);
   }
 }
 
@@ -822,6 +841,30 @@ int fr_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, int32
   return FR_OK;
 }
 
+int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, void *stream) {
+  FR_REQUIRE(entries_host && n_entries >= 1, "fr_adam_multi: bad argument");
+  for (int32_t e0 = 0; e0 < n_entries; e0 += fr::kAdamMulti) {
+    fr::AdamMultiArgs a;
+    const int cnt = n_entries - e0 < fr::kAdamMulti ? n_entries - e0 : fr::kAdamMulti;
+    int tiles = 0;
+    for (int e = 0; e < cnt; ++e) {
+      const fr_adam_entry &x = entries_host[e0 + e];
+      FR_REQUIRE(x.p && x.g && x.m && x.v && x.n >= 1 && x.n < (int64_t)INT32_MAX && x.step >= 1,
+                 "fr_adam_multi: bad entry");
+      a.p[e] = x.p; a.g[e] = x.g; a.m[e] = x.m; a.v[e] = x.v;
+      a.n[e] = (int)x.n; a.step[e] = x.step; a.first_tile[e] = tiles;
+      tiles += (int)((x.n + 1023) / 1024);
+    }
+    a.first_tile[cnt] = tiles;
+    a.n_entries = cnt;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    FR_LAUNCH(fr::k_adam_multi, tiles, 256, 0, stream, a);
+  }
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
 // ---------------------------------------------------------------- generic layer ops
 int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
                       float drop_p, uint64_t seed, int32_t layer, void *stream) {
@@ -890,8 +933,12 @@ int fr_batchnorm_backward(const float *X, const float *Y, const float *dY, const
 
 int fr_gather_rows(const float *T, const int32_t *idx, int64_t M, int32_t d, float *out, int32_t ld_out, int32_t col0,
                    void *stream) {
-  FR_REQUIRE(T && idx && out && M >= 1 && d % 4 == 0, "fr_gather_rows: bad argument");
-  FR_LAUNCH(fr::k_gather_rows, fr::grid_for(M * d / 4, 256), 256, 0, stream, T, idx, M, d, out, ld_out, col0);
+  FR_REQUIRE(T && idx && out && M >= 1 && d >= 1, "fr_gather_rows: bad argument");
+  if (d % 4 == 0) {
+    FR_LAUNCH(fr::k_gather_rows, fr::grid_for(M * d / 4, 256), 256, 0, stream, T, idx, M, d, out, ld_out, col0);
+  } else {   // bias tables ([n,1], pfcn_biasedmf.py:48-51) and other odd widths
+    FR_LAUNCH(fr::k_gather_rows_any, fr::grid_for(M * d, 256), 256, 0, stream, T, idx, M, d, out, ld_out, col0);
+  }
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

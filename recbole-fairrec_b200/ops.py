@@ -162,3 +162,320 @@ class SoftmaxCe(_ScalarLoss):
               "fr_softmax_ce_loss")
         ctx.grads = (dZ, None)
         return loss.view(())
+
+
+class RowDot(torch.autograd.Function):
+    """torch.mul(a, b).sum(-1)  (pfcn_pmf.py:172, fairgo_pmf.py:169)"""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        lib = load()
+        A, B = A.contiguous(), B.contiguous()
+        M, d = A.shape
+        out = torch.empty(M, dtype=torch.float32, device=A.device)
+        check(lib.fr_rowdot_forward(ptr(A), ptr(B), M, d, ptr(out), stream_ptr()), "fr_rowdot_forward")
+        ctx.save_for_backward(A, B)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load()
+        A, B = ctx.saved_tensors
+        M, d = A.shape
+        dA = torch.empty_like(A) if ctx.needs_input_grad[0] else None
+        dB = torch.empty_like(B) if ctx.needs_input_grad[1] else None
+        check(lib.fr_rowdot_backward(ptr(A), ptr(B), ptr(dout.contiguous()), M, d, ptr(dA), ptr(dB), stream_ptr()),
+              "fr_rowdot_backward")
+        return dA, dB
+
+
+class CosineSim(torch.autograd.Function):
+    """nn.CosineSimilarity()(a, b)  (pfcn_dmf.py:176,190-191)"""
+    EPS = 1e-8
+
+    @staticmethod
+    def forward(ctx, A, B):
+        lib = load()
+        A, B = A.contiguous(), B.contiguous()
+        M, d = A.shape
+        out = torch.empty(M, dtype=torch.float32, device=A.device)
+        norms = torch.empty(2 * M, dtype=torch.float32, device=A.device)
+        check(lib.fr_cosine_forward(ptr(A), ptr(B), M, d, CosineSim.EPS, ptr(out), ptr(norms), stream_ptr()),
+              "fr_cosine_forward")
+        ctx.save_for_backward(A, B, out, norms)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load()
+        A, B, out, norms = ctx.saved_tensors
+        M, d = A.shape
+        dA = torch.empty_like(A) if ctx.needs_input_grad[0] else None
+        dB = torch.empty_like(B) if ctx.needs_input_grad[1] else None
+        check(lib.fr_cosine_backward(ptr(A), ptr(B), ptr(out), ptr(norms), ptr(dout.contiguous()), M, d, CosineSim.EPS,
+                                     ptr(dA), ptr(dB), stream_ptr()), "fr_cosine_backward")
+        return dA, dB
+
+
+class BprOuter(torch.autograd.Function):
+    """BPRLoss over the [B,B] broadcast score matrices of PFCN_BiasedMF (pfcn_biasedmf.py:189-192).
+    Inputs: dotp[B], dotn[B], user_bias[B], pos_item_bias[B], neg_item_bias[B], global_bias[1]."""
+
+    @staticmethod
+    def forward(ctx, dotp, dotn, ub, pib, nib, gb):
+        lib = load()
+        B = dotp.numel()
+        args = [t.contiguous().view(-1) for t in (dotp, dotn, ub, pib, nib, gb)]
+        dev = dotp.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        g = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(5)]
+        check(lib.fr_bpr_outer_loss(*[ptr(t) for t in args], B, ptr(loss), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]),
+                                    ptr(g[4]), stream_ptr()), "fr_bpr_outer_loss")
+        ctx.shapes = (dotp.shape, dotn.shape, ub.shape, pib.shape, nib.shape, gb.shape)
+        ctx.save_for_backward(g[0], g[1], g[2], g[3])
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gl):
+        d_dotp, d_dotn, d_pib, d_nib = ctx.saved_tensors
+        s = ctx.shapes
+        zeros_ub = torch.zeros(s[2], dtype=torch.float32, device=gl.device)    # cancels between pos and neg
+        zeros_gb = torch.zeros(s[5], dtype=torch.float32, device=gl.device)
+        return ((d_dotp * gl).view(s[0]), (d_dotn * gl).view(s[1]), zeros_ub, (d_pib * gl).view(s[3]),
+                (d_nib * gl).view(s[4]), zeros_gb)
+
+
+def _scaled_sum(tensors, scale, divide):
+    import ctypes
+    lib = load()
+    arr = (ctypes.c_void_p * len(tensors))(*[ptr(t) for t in tensors])
+    out = torch.empty_like(tensors[0])
+    check(lib.fr_scaled_sum(arr, len(tensors), out.numel(), float(scale), 1 if divide else 0, ptr(out), stream_ptr()),
+          "fr_scaled_sum")
+    return out
+
+
+class SumDiv(torch.autograd.Function):
+    """(x0 + x1 + ...) / denom: cm-mode filter averaging (pfcn_mlp.py:158-165, fairgo_pmf.py:163-168)"""
+
+    @staticmethod
+    def forward(ctx, denom, *xs):
+        ctx.denom = float(denom)
+        ctx.n = len(xs)
+        return _scaled_sum([x.contiguous() for x in xs], denom, True)
+
+    @staticmethod
+    def backward(ctx, dY):
+        g = _scaled_sum([dY.contiguous()], ctx.denom, True)
+        return (None,) + (g,) * ctx.n
+
+
+class WeightedSum(torch.autograd.Function):
+    """(x0 + x1 + ...) * scale (WAP mean over the ego-network layers, fairgo_pmf.py:206-208)"""
+
+    @staticmethod
+    def forward(ctx, scale, *xs):
+        ctx.scale = float(scale)
+        ctx.n = len(xs)
+        return _scaled_sum([x.contiguous() for x in xs], scale, False)
+
+    @staticmethod
+    def backward(ctx, dY):
+        g = _scaled_sum([dY.contiguous()], ctx.scale, False)
+        return (None,) + (g,) * ctx.n
+
+
+class ConcatCols(torch.autograd.Function):
+    """torch.cat(xs, dim=1)"""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        lib = load()
+        M = xs[0].shape[0]
+        widths = [x.shape[1] for x in xs]
+        W = sum(widths)
+        out = torch.empty((M, W), dtype=torch.float32, device=xs[0].device)
+        c0 = 0
+        for x, w in zip(xs, widths):
+            x = x.contiguous()
+            check(lib.fr_copy_cols(ptr(x), w, 0, ptr(out), W, c0, M, w, stream_ptr()), "fr_copy_cols")
+            c0 += w
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, dY):
+        lib = load()
+        dY = dY.contiguous()
+        M, W = dY.shape
+        outs, c0 = [], 0
+        for i, w in enumerate(ctx.widths):
+            if ctx.needs_input_grad[i]:
+                g = torch.empty((M, w), dtype=torch.float32, device=dY.device)
+                check(lib.fr_copy_cols(ptr(dY), W, c0, ptr(g), w, 0, M, w, stream_ptr()), "fr_copy_cols")
+                outs.append(g)
+            else:
+                outs.append(None)
+            c0 += w
+        return tuple(outs)
+
+
+class MseLoss(_ScalarLoss):
+    """nn.MSELoss()(pred, target)  (fairgo_pmf.py:170-171)"""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        lib = load()
+        shape = pred.shape
+        p = pred.contiguous().view(-1)
+        loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        dp = torch.empty_like(p)
+        check(lib.fr_mse_loss(ptr(p), ptr(target.contiguous().view(-1)), p.numel(), ptr(loss), ptr(dp), stream_ptr()),
+              "fr_mse_loss")
+        ctx.grads = (dp.view(shape), None)
+        return loss.view(())
+
+
+class Act(torch.autograd.Function):
+    """a stand-alone activation module (nn.Sigmoid() etc. outside an MLPLayers)"""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        lib = load()
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.fr_act_forward(ptr(x), act, x.numel(), ptr(y), stream_ptr()), "fr_act_forward")
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dY):
+        lib = load()
+        (y,) = ctx.saved_tensors
+        dX = torch.empty_like(y)
+        check(lib.fr_act_backward(ptr(dY.contiguous()), ptr(y), ctx.act, y.numel(), ptr(dX), stream_ptr()),
+              "fr_act_backward")
+        return dX, None
+
+
+def clamp_div(x, hi):
+    """clamp(x, 0, hi) / hi (inference only: fairgo_pmf.py:248, focf.py:150)"""
+    lib = load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.fr_clamp_div(ptr(x), float(hi), x.numel(), ptr(y), stream_ptr()), "fr_clamp_div")
+    return y
+
+
+class SpmmMatrix:
+    """A static sparse matrix in CSR on the device together with the chunk plans of A and A^T (spmm.cu)."""
+
+    def __init__(self, csr, device, chunk=128):
+        import ctypes
+
+        import numpy as np
+        from ._lib import SpmmPlan
+        self.shape = csr.shape
+        self._keep = []
+        self.plans = []
+        lib = load()
+        for mat in (csr, csr.T.tocsr()):
+            mat.sort_indices()
+            row_off = np.ascontiguousarray(mat.indptr, dtype=np.int64)
+            n_rows = mat.shape[0]
+            sizes = [ctypes.c_int64() for _ in range(4)]
+            check(lib.fr_spmm_plan_sizes(row_off.ctypes.data, n_rows, chunk, *[ctypes.byref(s) for s in sizes]),
+                  "fr_spmm_plan_sizes")
+            nc, nm, ns, ne = [s.value for s in sizes]
+            host = [np.zeros(max(nc, 1), np.int32) for _ in range(4)] + [np.zeros(max(nm, 1), np.int32),
+                                                                         np.zeros(nm + 1, np.int32),
+                                                                         np.zeros(max(ne, 1), np.int32)]
+            check(lib.fr_spmm_plan_fill(row_off.ctypes.data, n_rows, chunk, *[h.ctypes.data for h in host]),
+                  "fr_spmm_plan_fill")
+            dev = [torch.from_numpy(h).to(device) for h in host]
+            col = torch.from_numpy(np.ascontiguousarray(mat.indices, dtype=np.int32)).to(device)
+            val = torch.from_numpy(np.ascontiguousarray(mat.data, dtype=np.float32)).to(device)
+            plan = SpmmPlan(*[t.data_ptr() for t in dev], nc, nm, ns, ne)
+            self._keep.append((dev, col, val))
+            self.plans.append((plan, col, val, ns))
+
+    def apply(self, X, transpose=False):
+        import ctypes
+        lib = load()
+        plan, col, val, ns = self.plans[1 if transpose else 0]
+        X = X.contiguous()
+        d = X.shape[1]
+        Y = torch.empty((self.shape[1] if transpose else self.shape[0], d), dtype=torch.float32, device=X.device)
+        partial = torch.empty(max(ns, 1) * d, dtype=torch.float32, device=X.device)
+        check(lib.fr_spmm_csr(ctypes.byref(plan), ptr(col), ptr(val), ptr(X), d, ptr(Y), ptr(partial), stream_ptr()),
+              "fr_spmm_csr")
+        return Y
+
+
+class Spmm(torch.autograd.Function):
+    """torch.sparse.mm(A, X) with a static A  (fairgo_pmf.py:201)"""
+
+    @staticmethod
+    def forward(ctx, X, mat):
+        ctx.mat = mat
+        return mat.apply(X, False)
+
+    @staticmethod
+    def backward(ctx, dY):
+        return ctx.mat.apply(dY, True), None
+
+
+def biased_score(dot, ub, ib, gb, act):
+    """act(dot + b_u + b_i + b_g) (inference: pfcn_biasedmf.py:170-181)"""
+    lib = load()
+    dot = dot.contiguous().view(-1)
+    out = torch.empty_like(dot)
+    check(lib.fr_biased_score(ptr(dot), ptr(ub.contiguous().view(-1)), ptr(ib.contiguous().view(-1)),
+                              ptr(gb.detach().contiguous().view(-1)), dot.numel(), act, ptr(out), stream_ptr()),
+          "fr_biased_score")
+    return out
+
+
+class AdamGroup:
+    """torch.optim.Adam(params, lr, weight_decay) semantics (betas 0.9/0.999, eps 1e-8, L2 form, per-parameter step
+    counts, parameters without a gradient skipped) on fr_adam_multi: one launch per 48 parameter tensors."""
+
+    def __init__(self, params, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.state = {}
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        from ._lib import AdamEntry
+        lib = load()
+        entries = []
+        for p in self.params:
+            if p.grad is None or not p.requires_grad:
+                continue
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
+            st["step"] += 1
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            st["_g"] = g                                    # keep alive until the kernel ran
+            entries.append(AdamEntry(p.data.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                     st["exp_avg_sq"].data_ptr(), p.numel(), st["step"]))
+        if not entries:
+            return
+        arr = (AdamEntry * len(entries))(*entries)
+        check(lib.fr_adam_multi(arr, len(entries), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                stream_ptr()), "fr_adam_multi")
+
+    def state_dict(self):
+        return {"state": {i: {k: v for k, v in self.state[p].items() if k != "_g"}
+                          for i, p in enumerate(self.params) if p in self.state},
+                "param_groups": [{"lr": self.lr, "weight_decay": self.weight_decay, "betas": self.betas, "eps": self.eps}]}
+
+    def load_state_dict(self, sd):
+        for i, st in sd["state"].items():
+            self.state[self.params[int(i)]] = dict(st)

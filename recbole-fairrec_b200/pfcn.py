@@ -1,0 +1,343 @@
+"""The PFCN family (personalised counterfactual-fairness filters + adversarial discriminators) -- drop-ins for
+recbole/model/fair_recommender/pfcn_{mlp,pmf,biasedmf,dmf}.py, computed by this package's kernels (layers.MLPLayers,
+ops.*).  One base class holds what the four reference files repeat verbatim (filter bookkeeping, discriminator loss,
+get_sst_embed); each subclass is its scorer.
+
+Kept from the reference, on purpose:
+  * filter / discriminator MLPs live in plain Python dicts (`filter_layer`, `dis_layer_dict`; pfcn_mlp.py:111-143), so
+    they are not part of `state_dict()`;
+  * `sm` mode owns one filter per non-empty attribute subset, index = sum of 2^attr (pfcn_mlp.py:74-78,152-157); `cm`
+    mode divides the sum of the selected single-attribute filters by the TOTAL number of filters (pfcn_mlp.py:158-165);
+  * binary attributes: one logit + BCE on float 0/1 labels; others: CrossEntropy on `.long()` labels (pfcn_mlp.py:203-209);
+  * PFCN_BiasedMF.calculate_loss adds [B] dot products to [B,1] bias columns, so its BPR runs over a [B,B] broadcast
+    matrix (pfcn_biasedmf.py:189-192) -- reproduced by ops.BprOuter;
+  * `full_sort_predict` is broken in all four reference files (the (user, item) tuple returned by forward is used as a
+    tensor, SURVEY.md section 7 hard part 7): here it raises NotImplementedError, the trainer's cue to fall back to
+    `predict` over all items (trainer.py:425-433).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import MLPLayers
+
+
+class _PFCNBase(nn.Module):
+    input_type = "PAIRWISE"
+    type = "GENERAL"
+    USER_EMB, ITEM_EMB = "user_embedding_layer", "item_embedding_layer"   # attribute names differ per reference file
+
+    def __init__(self, config, dataset):
+        super().__init__()
+        self.USER_ID, self.ITEM_ID = config["USER_ID_FIELD"], config["ITEM_ID_FIELD"]
+        self.POS_ITEM_ID = self.ITEM_ID
+        self.NEG_ITEM_ID = config["NEG_PREFIX"] + self.ITEM_ID
+        self.n_users, self.n_items = dataset.num(self.USER_ID), dataset.num(self.ITEM_ID)
+        self.device = config["device"]
+        self.filter_mode = config["filter_mode"].lower()
+        if self.filter_mode not in ("cm", "sm", "none"):
+            raise AssertionError("filter_mode must be cm, sm or none")
+        self.sst_attrs = list(config["sst_attr_list"])
+        self.embedding_size = config["embedding_size"]
+        if self.filter_mode != "none":
+            self.dis_drop_out = config["dis_dropout"]
+            self.dis_weight = config["dis_weight"]
+            self.dis_hidden_size_list = list(config["dis_hidden_size_list"])
+        self.activation = config["activation"]
+        self.filter_num, self.sst_dict = self._get_filter_info()
+        self.sst_size = self._get_sst_size(dataset.get_user_feature())
+        self._build_scorer(config)
+        if self.filter_mode != "none":
+            self.filter_layer = self.init_filter()
+            self.dis_layer_dict = self.init_dis_layer()
+
+    # ------------------------------------------------------------------ construction (pfcn_mlp.py:67-143)
+    def _get_filter_info(self):
+        if self.filter_mode == "cm":
+            return len(self.sst_attrs), {s: i + 1 for i, s in enumerate(self.sst_attrs)}
+        if self.filter_mode == "sm":
+            return 2 ** len(self.sst_attrs) - 1, {s: int(2 ** i) for i, s in enumerate(self.sst_attrs)}
+        return 0, {}
+
+    def _get_sst_size(self, user_feature):
+        size = {}
+        for sst in self.sst_attrs:
+            if sst not in user_feature.columns:
+                raise ValueError(f"{sst} sensitive attribute not in user feature")
+            size[sst] = len(user_feature[sst][1:].unique())
+        return size
+
+    def _filter_activation(self):
+        return self.activation
+
+    def _dis_activation(self):
+        return self.activation
+
+    def init_filter(self):
+        e = self.embedding_size
+        return {i + 1: MLPLayers([e, e * 2, e], activation=self._filter_activation(), bn=True,
+                                 init_method="norm").to(self.device) for i in range(self.filter_num)}
+
+    def init_dis_layer(self):
+        out = {}
+        for sst in self.sst_attrs:
+            c = self.sst_size[sst]
+            out[sst] = MLPLayers([self.embedding_size] + self.dis_hidden_size_list + [1 if c == 2 else c],
+                                 dropout=self.dis_drop_out, activation=self._dis_activation(), bn=True,
+                                 init_method="norm").to(self.device)
+        return out
+
+    def _dict_modules(self):
+        if self.filter_mode == "none":
+            return []
+        return list(self.filter_layer.values()) + list(self.dis_layer_dict.values())
+
+    def to(self, *a, **k):           # the dict-held sub-networks follow the model (the reference leaves them behind)
+        super().to(*a, **k)
+        for m in self._dict_modules():
+            m.to(*a, **k)
+        return self
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in self._dict_modules():
+            m.train(mode)
+        return self
+
+    def other_parameter(self):
+        return dict()
+
+    def load_other_parameter(self, para):
+        return
+
+    # ------------------------------------------------------------------ shared forward pieces
+    def _ids(self, t):
+        return t.to(device=getattr(self, self.USER_EMB).weight.device, dtype=torch.int32).contiguous()
+
+    def _user_base(self, user):
+        return ops.GatherRows.apply(getattr(self, self.USER_EMB).weight, self._ids(user))
+
+    def _item_base(self, item):
+        return ops.GatherRows.apply(getattr(self, self.ITEM_EMB).weight, self._ids(item))
+
+    def _apply_filters(self, user_embed, sst_list):
+        if self.filter_mode == "none":
+            return user_embed
+        if self.filter_mode == "sm":
+            return self.filter_layer[sum(self.sst_dict[s] for s in sst_list)](user_embed)
+        outs = [self.filter_layer[self.sst_dict[s]](user_embed) for s in sst_list]
+        return ops.SumDiv.apply(len(self.filter_layer), *outs)
+
+    def forward(self, user, item=None, sst_list=None):
+        """pfcn_mlp.py:145-167"""
+        user_embed = self._apply_filters(self._user_base(user), sst_list)
+        return user_embed, (None if item is None else self._item_base(item))
+
+    def calculate_dis_loss(self, interaction, sst_list=None):
+        """pfcn_mlp.py:195-211"""
+        user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
+        dev = user_embed.device
+        loss = 0.0
+        for sst in sst_list:
+            z = self.dis_layer_dict[sst](user_embed)
+            if self.sst_size[sst] == 2:
+                loss = loss + ops.SigmoidBce.apply(z, interaction[sst].to(device=dev, dtype=torch.float32))
+            else:
+                loss = loss + ops.SoftmaxCe.apply(z, interaction[sst].to(device=dev, dtype=torch.int32))
+        return loss
+
+    def _with_dis(self, bpr, interaction, sst_list):
+        if self.filter_mode != "none":
+            return bpr - self.dis_weight * self.calculate_dis_loss(interaction, sst_list)
+        return bpr
+
+    def full_sort_predict(self, interaction, sst_list=None):
+        raise NotImplementedError("PFCN full-sort scoring is undefined in the reference (forward() returns a tuple "
+                                  "that full_sort_predict uses as a tensor); use predict() over all items")
+
+    def get_sst_embed(self, user_data, sst_list=None):
+        """pfcn_mlp.py:224-232"""
+        ret = {}
+        user_indices = torch.arange(1, self.n_users)
+        sst_list = self.sst_attrs if self.filter_mode == "none" else sst_list
+        for sst in sst_list:
+            ret[sst] = user_data[sst][user_indices - 1]
+        ret["embedding"], _ = self.forward(user_indices.to(self.device), None, sst_list)
+        return ret
+
+
+class PFCN_MLP(_PFCNBase):
+    """pfcn_mlp.py:23-232: NCF-style tower over [filtered user || item]"""
+    USER_EMB, ITEM_EMB = "user_embedding", "item_embedding"
+
+    def _build_scorer(self, config):
+        self.dropout = config["dropout"]
+        self.mlp_hidden_size_list = list(config["mlp_hidden_size_list"])
+        self.user_embedding = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
+        self.mlp_layer = MLPLayers([self.embedding_size * 2] + self.mlp_hidden_size_list + [1], dropout=self.dropout)
+
+    def _score(self, user_embed, item_embed):
+        return self.mlp_layer(ops.ConcatCols.apply(user_embed, item_embed))
+
+    def predict(self, interaction, sst_list=None):
+        """pfcn_mlp.py:169-175"""
+        u, i = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID], sst_list)
+        return ops.Act.apply(self._score(u, i), ops.ACT["sigmoid"])
+
+    def calculate_loss(self, interaction, sst_list=None):
+        """pfcn_mlp.py:177-193: BPR(pos, neg) - dis_weight * discriminator loss"""
+        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
+        bpr = ops.BprLoss.apply(self._score(user_embed, pos_embed), self._score(user_embed, neg_embed))
+        return self._with_dis(bpr, interaction, sst_list)
+
+
+class PFCN_PMF(_PFCNBase):
+    """pfcn_pmf.py: dot-product scorer"""
+
+    def _build_scorer(self, config):
+        self.user_embedding_layer = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding_layer = nn.Embedding(self.n_items, self.embedding_size)
+
+    def predict(self, interaction, sst_list=None):
+        """pfcn_pmf.py:166-174 (keepdim=True: [B,1])"""
+        u, i = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID], sst_list)
+        return ops.Act.apply(ops.RowDot.apply(u, i), ops.ACT["sigmoid"]).view(-1, 1)
+
+    def calculate_loss(self, interaction, sst_list=None):
+        """pfcn_pmf.py:176-193"""
+        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
+        bpr = ops.BprLoss.apply(ops.RowDot.apply(user_embed, pos_embed), ops.RowDot.apply(user_embed, neg_embed))
+        return self._with_dis(bpr, interaction, sst_list)
+
+
+class PFCN_BiasedMF(_PFCNBase):
+    """pfcn_biasedmf.py: dot product + user / item / global biases"""
+
+    def _build_scorer(self, config):
+        self.user_embedding_layer = nn.Embedding(self.n_users, self.embedding_size)
+        self.user_bias = nn.Embedding(self.n_users, 1)
+        self.item_embedding_layer = nn.Embedding(self.n_items, self.embedding_size)
+        self.item_bias = nn.Embedding(self.n_items, 1)
+        self.global_bias = nn.Parameter(torch.tensor(0.1))
+
+    def _bias(self, table, ids):
+        return ops.GatherRows.apply(table.weight, self._ids(ids))          # [B,1]
+
+    def predict(self, interaction, sst_list=None):
+        """pfcn_biasedmf.py:170-181: sigmoid(dot + b_u + b_i + b_g), [B,1]"""
+        user, item = interaction[self.USER_ID], interaction[self.ITEM_ID]
+        with torch.no_grad():
+            u, i = self.forward(user, item, sst_list)
+            return ops.biased_score(ops.RowDot.apply(u, i), self._bias(self.user_bias, user),
+                                    self._bias(self.item_bias, item), self.global_bias, ops.ACT["sigmoid"]).view(-1, 1)
+
+    def calculate_loss(self, interaction, sst_list=None):
+        """pfcn_biasedmf.py:183-199 (the [B] + [B,1] broadcast makes the BPR run over B*B pairs)"""
+        user, pos, neg = interaction[self.USER_ID], interaction[self.POS_ITEM_ID], interaction[self.NEG_ITEM_ID]
+        user_embed, pos_embed = self.forward(user, pos, sst_list)
+        neg_embed = self._item_base(neg)
+        bpr = ops.BprOuter.apply(ops.RowDot.apply(user_embed, pos_embed), ops.RowDot.apply(user_embed, neg_embed),
+                                 self._bias(self.user_bias, user), self._bias(self.item_bias, pos),
+                                 self._bias(self.item_bias, neg), self.global_bias.view(1))
+        return self._with_dis(bpr, interaction, sst_list)
+
+
+class PFCN_DMF(_PFCNBase):
+    """pfcn_dmf.py: user / item MLPs + cosine similarity (x10 in the loss)"""
+
+    def __init__(self, config, dataset):
+        self.num_layers = config["num_layers"]
+        self.mlp_dropout = config["mlp_dropout"]
+        self.mlp_activation = config["mlp_activation"]
+        self.dis_activation = config["dis_activation"]
+        super().__init__(config, dataset)
+
+    def _filter_activation(self):
+        return self.mlp_activation          # pfcn_dmf.py:112
+
+    def _dis_activation(self):
+        return self.dis_activation          # pfcn_dmf.py:136
+
+    def _build_scorer(self, config):
+        e = self.embedding_size
+        self.user_embedding_layer = nn.Embedding(self.n_users, e)
+        self.item_embedding_layer = nn.Embedding(self.n_items, e)
+        self.user_mlp = MLPLayers([e] * (self.num_layers + 1), dropout=self.mlp_dropout, activation=self.mlp_activation,
+                                  init_method="norm")
+        self.item_mlp = MLPLayers([e] * (self.num_layers + 1), dropout=self.mlp_dropout, activation=self.mlp_activation,
+                                  init_method="norm")
+
+    def _user_base(self, user):
+        return self.user_mlp(super()._user_base(user))
+
+    def _item_base(self, item):
+        return self.item_mlp(super()._item_base(item))
+
+    def predict(self, interaction, sst_list=None):
+        """pfcn_dmf.py:170-178"""
+        u, i = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID], sst_list)
+        return ops.Act.apply(ops.CosineSim.apply(u, i), ops.ACT["sigmoid"])
+
+    def calculate_loss(self, interaction, sst_list=None):
+        """pfcn_dmf.py:180-199"""
+        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
+        pos = ops.WeightedSum.apply(10.0, ops.CosineSim.apply(user_embed, pos_embed))
+        neg = ops.WeightedSum.apply(10.0, ops.CosineSim.apply(user_embed, neg_embed))
+        return self._with_dis(ops.BprLoss.apply(pos, neg), interaction, sst_list)
+
+
+class PFCNTrainer:
+    """The alternating schedule of PFCNTrainer and its per-model subclasses (trainer.py:865-898, 1189-1235): per epoch
+    a random non-empty attribute subset; every `train_epoch_interval`-th epoch one pass on `bpr - dis_weight * dis` with
+    the filter optimizer (base model + filters), then always one pass on `dis` with the discriminator optimizer.
+    Optimizer steps run on this package's Adam kernel (ops.AdamGroup = torch.optim.Adam semantics, L2 form)."""
+
+    def __init__(self, config, model):
+        self.config, self.model = config, model
+        self.filter_mode = config["filter_mode"].lower()
+        self.train_epoch_interval = config["train_epoch_interval"] or 1
+        lr, wd = config["learning_rate"], config["weight_decay"] or 0.0
+        base = list(model.parameters())
+        if self.filter_mode != "none":
+            self.sst_attrs = list(config["sst_attr_list"])
+            fparams = [p for f in model.filter_layer.values() for p in f.parameters()]
+            dparams = [p for d in model.dis_layer_dict.values() for p in d.parameters()]
+            self.optimizer_filter = ops.AdamGroup(base + fparams, lr=lr, weight_decay=wd)
+            self.optimizer_dis = ops.AdamGroup(dparams, lr=lr, weight_decay=wd)
+        else:
+            self.optimizer_filter = ops.AdamGroup(base, lr=lr, weight_decay=wd)
+
+    def _pass(self, train_data, loss_func, optimizer, sst_list):
+        self.model.train()
+        total = None
+        for interaction in train_data:
+            optimizer.zero_grad()
+            loss = loss_func(interaction, sst_list)
+            v = loss.item()
+            if v != v:
+                raise ValueError("Training loss is nan")
+            total = v if total is None else total + v
+            loss.backward()
+            optimizer.step()
+        return total
+
+    def _train_epoch(self, train_data, epoch_idx):
+        if self.filter_mode == "none":
+            return self._pass(train_data, self.model.calculate_loss, self.optimizer_filter, None)
+        mask = np.zeros(len(self.sst_attrs))
+        while mask.sum() == 0:
+            mask = np.random.choice([0, 1], len(self.sst_attrs))
+        sst_list = [s for s, m in zip(self.sst_attrs, mask) if m != 0]
+        filter_loss = 0.0
+        if epoch_idx % self.train_epoch_interval == 0:
+            filter_loss = self._pass(train_data, self.model.calculate_loss, self.optimizer_filter, sst_list)
+        dis_loss = self._pass(train_data, self.model.calculate_dis_loss, self.optimizer_dis, sst_list)
+        return filter_loss, dis_loss
+
+
+PFCN_MLPTrainer = PFCN_PMFTrainer = PFCN_BiasedMFTrainer = PFCN_DMFTrainer = PFCNTrainer

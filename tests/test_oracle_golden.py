@@ -214,16 +214,17 @@ def test_nfcf_oracle_matches_reference(path):
         assert rel_err(Wf[k], g[f"W{k}_final"]) < RTOL and rel_err(bf[k], g[f"b{k}_final"]) < RTOL, k
 
 
-PFCN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pfcn_mlp_*.npz")))
+PFCN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pfcn_*.npz")))
 
 
-@pytest.mark.parametrize("path", PFCN, ids=[os.path.basename(p)[9:-4] for p in PFCN])
-def test_pfcn_mlp_oracle_matches_reference(path):
+@pytest.mark.parametrize("path", PFCN, ids=[os.path.basename(p)[5:-4] for p in PFCN])
+def test_pfcn_oracle_matches_reference(path):
     """oracle/pfcn_oracle.py replayed over the alternating filter / discriminator schedule of the fixture"""
     from oracle import pfcn_oracle as po
     g = np.load(path)
-    losses, grads0, final = po.replay(g)
+    losses, grads0, pred0, final = po.replay(g)
     np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+    assert rel_err(pred0, g["predict0"]) < RTOL
     n = 0
     for k in g.files:
         if k.startswith("grad_") and k.endswith("@0"):
