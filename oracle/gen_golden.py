@@ -482,8 +482,127 @@ def run_all_pfcn():
     run_pfcn("PFCN_DMF", "dmf_cm", "cm", seed=36)
 
 
+def run_fairgo(name, aggr, n_layers=2, n_users=70, n_items=45, d=16, B=96, n_inter=600, seed=41, n_rounds=2,
+               pretrain_steps=2):
+    """FairGo_PMF (recbole/model/fair_recommender/fairgo_pmf.py) driven like FairGo_PMFTrainer (trainer.py:534-704,
+    837-848): `pretrain_steps` pretrain steps on the rating loss (optimizer over the two embedding tables), then the
+    alternating fine-tune schedule (filter optimizer on `mse - fair_weight*dis`, discriminator (+aggr_layer for LBA)
+    optimizer on `dis`).  The model's MLPs have no dropout / BatchNorm, so the run is deterministic."""
+    import scipy.sparse as sp_
+    from recbole.model.fair_recommender.fairgo_pmf import FairGo_PMF
+
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    gender = rng.integers(0, 2, n_users).astype(np.float32)
+    age = rng.integers(0, 4, n_users).astype(np.float32)
+    pairs = rng.permutation((n_users - 1) * (n_items - 1))[:n_inter]
+    tu, ti = (pairs // (n_items - 1) + 1).astype(np.int64), (pairs % (n_items - 1) + 1).astype(np.int64)
+    tr = rng.integers(1, 6, n_inter).astype(np.float32)
+
+    class DS(FakeDataset):
+        def get_user_feature(self):
+            return Interaction({"user_id": torch.arange(n_users), "gender": torch.from_numpy(gender),
+                                "age": torch.from_numpy(age)})
+
+        def inter_matrix(self, form="coo", value_field=None):
+            return sp_.coo_matrix((tr, (tu, ti)), shape=(n_users, n_items))
+
+    cfg = base_cfg(embedding_size=d, sst_attr_list=["gender", "age"], n_layers=n_layers, activation="leakyrelu",
+                   dis_hidden_size_list=[16, 8], filter_hidden_size_list=[32, 16], fair_weight=0.5,
+                   load_pretrain_weight=False, aggr_method=aggr, vs_weights=[4, 1] if n_layers == 2 else [3, 2, 1])
+    model = FairGo_PMF(cfg, DS(n_users, n_items, 5.0))
+    with torch.no_grad():
+        model.user_embedding_layer.weight.mul_(0.6)
+        model.item_embedding_layer.weight.mul_(0.6)
+    out = dict(aggr=aggr, n_layers=n_layers, d=d, gender=gender, age=age, n_users=n_users, n_items=n_items,
+               n_rounds=n_rounds, pretrain_steps=pretrain_steps, train_u=tu, train_i=ti, train_r=tr,
+               vs_weights=np.array(cfg["vs_weights"], np.float32), fair_weight=0.5)
+    L = model.norm_rating_matrix.coalesce()
+    out["norm_row"], out["norm_col"] = L.indices()[0].numpy().copy(), L.indices()[1].numpy().copy()
+    out["norm_val"] = L.values().numpy().copy()
+
+    def dump(tag):
+        for k_, v_ in model.state_dict().items():
+            out[f"base.{k_}@{tag}"] = v_.detach().numpy().copy()
+        for k_, f in model.filter_layer_dict.items():
+            _dump_mlp(f"filter_{k_}", f, out, tag)
+        for k_, f in model.dis_layer_dict.items():
+            _dump_mlp(f"dis_{k_}", f, out, tag)
+
+    dump("init")
+    opt_p = torch.optim.Adam([model.user_embedding_layer.weight, model.item_embedding_layer.weight], lr=1e-3,
+                             weight_decay=1e-4)
+    dparams = [p_ for f in model.dis_layer_dict.values() for p_ in f.parameters()]
+    if aggr == "LBA":
+        dparams += list(model.aggr_layer.parameters())
+    opt_d = torch.optim.Adam(dparams, lr=1e-3, weight_decay=1e-4)
+    opt_f = torch.optim.Adam([p_ for f in model.filter_layer_dict.values() for p_ in f.parameters()], lr=1e-3,
+                             weight_decay=1e-4)
+    model.train()
+
+    def batch(s):
+        sel = rng.integers(0, n_inter, B)
+        u = tu[sel]
+        inter = Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(ti[sel]),
+                             "rating": torch.from_numpy(tr[sel]), "gender": torch.from_numpy(gender[u]),
+                             "age": torch.from_numpy(age[u])})
+        for k_ in ("user_id", "item_id", "rating"):
+            out[f"{k_}{s}"] = inter[k_].numpy()
+        return inter
+
+    losses = []
+    s = 0
+    model.train_stage = "pretrain"
+    for _ in range(pretrain_steps):
+        inter = batch(s)
+        opt_p.zero_grad()
+        loss = model.calculate_loss(inter, None)
+        loss.backward()
+        opt_p.step()
+        losses.append(loss.item())
+        out[f"sst_list{s}"] = np.array([], dtype="<U6")
+        s += 1
+    dump("pretrained")
+    model.train_stage = "finetune"
+    sst_lists = [["gender", "age"], ["age"], ["gender"]]
+    for r in range(n_rounds):
+        for phase, (fn, opt) in enumerate(((model.calculate_loss, opt_f), (model.calculate_dis_loss, opt_d))):
+            inter = batch(s)
+            sst_list = sst_lists[r % len(sst_lists)]
+            opt.zero_grad()
+            loss = fn(inter, sst_list)
+            loss.backward()
+            if r == 0 and phase == 0:
+                for k_, f in model.filter_layer_dict.items():
+                    for kk, p_ in f.named_parameters():
+                        if p_.grad is not None:
+                            out[f"grad_filter_{k_}.{kk}@ft0"] = p_.grad.numpy().copy()
+                with torch.no_grad():
+                    out["predict_ft0"] = model.predict(inter).numpy().copy()
+                    out["full_sort_ft0"] = model.full_sort_predict(
+                        Interaction({"user_id": torch.tensor([1, 2, 5])})).numpy().copy()
+            opt.step()
+            losses.append(loss.item())
+            out[f"sst_list{s}"] = np.array(sst_list)
+            s += 1
+    out["losses"] = np.array(losses, np.float32)
+    dump("final")
+    np.savez_compressed(os.path.join(OUT, f"fairgo_{name}.npz"), **out)
+    print(f"fairgo_{name}: losses={losses}")
+
+
+def run_all_fairgo():
+    run_fairgo("pmf_lba", "LBA")
+    run_fairgo("pmf_wap", "WAP", seed=42)
+    run_fairgo("pmf_lva", "LVA", seed=43)
+    run_fairgo("pmf_lba_3layers", "LBA", n_layers=3, seed=44)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "fairgo":
+        run_all_fairgo()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "pfcn":
         run_all_pfcn()
         return
@@ -507,6 +626,7 @@ def main():
     run_nfcf("fair", fair=True)
     run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
     run_all_pfcn()
+    run_all_fairgo()
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@ Only what the path needs lives here:
   focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
   ops.py/layers.py autograd Functions over the generic layer kernels; MLPLayers mirror
   pfcn.py          PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF models + alternating PFCNTrainer
+  fairgo.py        FairGo_PMF / FairGo_GCN (fine-tune stage) models + FairGoTrainer (SpMM + full-table filters)
   nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
@@ -18,6 +19,7 @@ from . import _lib, kernels  # noqa: F401
 from .config import Config  # noqa: F401
 from .dataloader import FOCFDataLoader, TrainData  # noqa: F401
 from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
+from .fairgo import FairGo_GCN, FairGo_GCNTrainer, FairGo_PMF, FairGo_PMFTrainer, FairGoTrainer  # noqa: F401
 from .focf import FOCF  # noqa: F401
 from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF  # noqa: F401

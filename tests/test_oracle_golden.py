@@ -234,3 +234,32 @@ def test_pfcn_oracle_matches_reference(path):
             assert rel_err(final[k[:-6]], g[k]) < RTOL, k
             n += 1
     assert n > 40
+
+
+FAIRGO = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fairgo_*.npz")))
+
+
+@pytest.mark.parametrize("path", FAIRGO, ids=[os.path.basename(p)[7:-4] for p in FAIRGO])
+def test_fairgo_oracle_matches_reference(path):
+    """oracle/fairgo_oracle.py replayed over the fixture's pretrain + alternating fine-tune schedule"""
+    from oracle import fairgo_oracle as go
+    g = np.load(path)
+    L = go.norm_matrix(g["train_u"], g["train_i"], g["train_r"], int(g["n_users"]), int(g["n_items"])).tocsr()
+    import scipy.sparse as sp
+    ref = sp.csr_matrix((g["norm_val"], (g["norm_row"], g["norm_col"])), shape=L.shape)
+    assert abs(L - ref).max() <= 1e-6 * abs(ref).max() and (L != 0).sum() == (ref != 0).sum()
+    losses, grads, extra, pretrained, final = go.replay(g)
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+    assert rel_err(extra["predict"], g["predict_ft0"]) < RTOL
+    assert rel_err(extra["full_sort"], g["full_sort_ft0"]) < RTOL
+    n = 0
+    for k in g.files:
+        if k.startswith("grad_") and k.endswith("@ft0"):
+            assert rel_err(grads[k[5:-4]], g[k]) < RTOL, k
+            n += 1
+        if k.endswith("@pretrained"):
+            assert rel_err(pretrained[k[:-11]], g[k]) < RTOL, k
+        if k.endswith("@final"):
+            assert rel_err(final[k[:-6]], g[k]) < RTOL, k
+            n += 1
+    assert n > 20
