@@ -460,6 +460,15 @@ def run_ours(args, wname):
             probe = scaleout_probe(dev, flush)
         except Exception as e:
             probe = {"error": str(e)[:300]}
+    families = None
+    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_families:
+        try:   # BASELINE.json configs[2] / configs[3]: PFCN_MLP and FairGo_PMF(LBA) training at the ML-1M shape
+            import bench_families as bf
+            torch.cuda.empty_cache()
+            families = {"pfcn_mlp": bf.bench_pfcn(dev, flush, cpu=not args.no_cpu_baseline),
+                        "fairgo_pmf": bf.bench_fairgo(dev, flush, cpu=not args.no_cpu_baseline)}
+        except Exception as e:
+            families = {"error": str(e)[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)
@@ -488,6 +497,7 @@ def run_ours(args, wname):
         "kernel_shares": shares,
         "cpu_baseline": cpu,
         "scaleout_probe": probe,
+        "families": families,
         "eval": {"metric": "full-sort fair-eval users/s",
                  "value": tc["value"] if tc and "error" not in tc else n_eval / t_eval, "unit": "users/s",
                  "score_mode": "tc_3xtf32 (tcgen05+TMA; ids equal the exact mode's outside fp32-level near ties)"
@@ -606,6 +616,7 @@ def main():
     ap.add_argument("--workload", default="ml1m", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true", help="skip the scale-out roofline probe")
+    ap.add_argument("--no-families", action="store_true", help="skip the PFCN / FairGo legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

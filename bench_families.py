@@ -1,0 +1,325 @@
+"""bench legs for the PFCN and FairGo families (BASELINE.json configs[2] and configs[3]) -- imported by bench.py.
+
+A "step" here is what one batch costs in an epoch where both phases run (trainer.py:875-898 / 687-704): one
+filter-phase step (calculate_loss -> backward -> Adam over base + filters) plus one discriminator-phase step
+(calculate_dis_loss -> backward -> Adam over the discriminators) on a 2048-row batch of the ML-1M shape.
+`value` = interactions/s over those two phases, device-timed with CUDA events, batches resident in HBM;
+`e2e`   = the same through the public model / trainer API with HOST (pinned) batches, H2D per step and the loss read
+          back every phase (trainer.py:191);
+`cpu_baseline` = oracle/pfcn_oracle.py / oracle/fairgo_oracle.py (the reference's op sequence on stock torch CPU kernels,
+          all host threads) on a bounded sample of the same steps.
+"""
+import os
+import statistics
+import time
+
+import numpy as np
+
+ML1M = dict(n_users=6041, n_items=3707, d=64, batch=2048)
+
+
+def _user_feats(rng, nu):
+    return {"gender": (rng.random(nu) < 0.28).astype(np.float32), "age": rng.integers(0, 7, nu).astype(np.float32),
+            "occupation": rng.integers(0, 21, nu).astype(np.float32)}
+
+
+class _DS:
+    def __init__(self, nu, ni, feats, coo=None):
+        import torch
+
+        import recbole_fairrec_b200 as pkg
+        self._n = {"user_id": nu, "item_id": ni}
+        self._feat = pkg.Interaction({"user_id": torch.arange(nu), **{k: torch.from_numpy(v) for k, v in feats.items()}})
+        self._coo = coo
+        self.inter_feat = {"rating": torch.tensor([1.0, 5.0])}
+
+    def num(self, f):
+        return self._n[f]
+
+    def get_user_feature(self):
+        return self._feat
+
+    def inter_matrix(self, form="coo", value_field=None):
+        return self._coo
+
+
+def _timed_steps(step_fn, batches_dev, n_warm, n_steps, flush):
+    import torch
+    for k in range(n_warm):
+        step_fn(batches_dev[k % len(batches_dev)])
+    torch.cuda.synchronize()
+    ms = []
+    for k in range(n_steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_fn(batches_dev[k % len(batches_dev)])
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return ms
+
+
+def _graphed_legs(pkg, dev, flush, hosts, devs, n_steps, phases, sst_list):
+    """(device-timed ms per step, e2e seconds per step) of the CUDA-graph-replayed step: both phases per batch.
+    e2e: pinned host batch -> H2D into the graph's static buffers -> replay -> loss D2H + sync, every phase."""
+    import torch
+    from recbole_fairrec_b200.graphed import GraphedStep
+    graphs = [GraphedStep(fn, opt, sst_list, devs[0], dev) for fn, opt in phases]
+
+    def step(inter):
+        return [g.run(inter) for g in graphs]
+
+    for k in range(3):
+        step(devs[k % len(devs)])
+    torch.cuda.synchronize()
+    ms = []
+    for k in range(n_steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(devs[k % len(devs)])
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        inter = pkg.Interaction(hosts[k % len(hosts)])
+        for g in graphs:
+            _ = g.run(inter).item()
+    torch.cuda.synchronize()
+    return ms, (time.perf_counter() - t0) / n_steps
+
+
+def _profile(step_fn, batch, n=5):
+    from recbole_fairrec_b200 import _lib
+    _lib.profile_enable(True)
+    for _ in range(n):
+        step_fn(batch)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    tot = sum(v[1] for v in prof.values()) or 1.0
+    shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    return shares, sum(v[0] for v in prof.values()) / n, tot / n
+
+
+def bench_pfcn(dev, flush, n_steps=30, cpu=True, seed=2020):
+    import torch
+
+    import recbole_fairrec_b200 as pkg
+    w = ML1M
+    rng = np.random.default_rng(seed)
+    feats = _user_feats(rng, w["n_users"])
+    attrs = list(feats)
+    cfg = pkg.Config(embedding_size=w["d"], sst_attr_list=attrs, filter_mode="sm", dropout=0.2, dis_dropout=0.3,
+                     dis_weight=10.0, dis_hidden_size_list=[128, 256, 128, 128, 64, 32], mlp_hidden_size_list=[64, 32, 16],
+                     activation="leakyrelu", device=dev, learning_rate=1e-3, weight_decay=1e-4, train_epoch_interval=1)
+    torch.manual_seed(seed)
+    model = pkg.PFCN_MLP(cfg, _DS(w["n_users"], w["n_items"], feats)).to(dev)
+    trainer = pkg.PFCNTrainer(cfg, model)
+    model.train()
+    sst_list = ["gender", "occupation"]
+    B = w["batch"]
+
+    def host_batch():
+        u = rng.integers(1, w["n_users"], B)
+        return {"user_id": torch.from_numpy(u).pin_memory(),
+                "item_id": torch.from_numpy(rng.integers(1, w["n_items"], B)).pin_memory(),
+                "neg_item_id": torch.from_numpy(rng.integers(1, w["n_items"], B)).pin_memory(),
+                **{a: torch.from_numpy(feats[a][u]).pin_memory() for a in attrs}}
+
+    hosts = [host_batch() for _ in range(8)]
+    devs = [pkg.Interaction({k: v.to(dev) for k, v in h.items()}) for h in hosts]
+
+    def step(inter, read_loss=False):
+        out = []
+        for fn, opt in ((model.calculate_loss, trainer.optimizer_filter), (model.calculate_dis_loss, trainer.optimizer_dis)):
+            opt.zero_grad()
+            loss = fn(inter, sst_list)
+            if read_loss:
+                out.append(loss.item())
+            loss.backward()
+            opt.step()
+        return out
+
+    eager_ms = _timed_steps(step, devs, 3, n_steps, flush)
+    shares, launches, kernel_ms = _profile(step, devs[0])
+    ms, t_e2e = _graphed_legs(pkg, dev, flush, hosts, devs, n_steps,
+                              [(model.calculate_loss, trainer.optimizer_filter), (model.calculate_dis_loss, trainer.optimizer_dis)],
+                              sst_list)
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
+    out = {"metric": "PFCN_MLP train interactions/s", "value": B / (statistics.mean(ms) * 1e-3), "unit": "interactions/s",
+           "ms_per_step": statistics.mean(ms), "steps": n_steps, "launch_mode": "cuda graph replay (one per phase)",
+           "eager_ms_per_step": statistics.mean(eager_ms),
+           "config": {"workload": "pfcn_mlp_ml1m", **w, "filter_mode": "sm (7 filters)", "sst_list": sst_list,
+                      "attrs": {a: int(len(np.unique(feats[a][1:]))) for a in attrs}, "dropout": [0.2, 0.3],
+                      "step": "filter-phase step + discriminator-phase step on one batch"},
+           "e2e": {"value": B / t_e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+           "gpu_launches_per_step": launches, "kernel_ms_per_step": kernel_ms, "kernel_shares": shares}
+    if cpu:
+        out["cpu_baseline"] = cpu_pfcn(model, feats, hosts, sst_list)
+    return out
+
+
+def cpu_pfcn(model, feats, hosts, sst_list, n=3):
+    """the reference's op sequence (oracle/pfcn_oracle.py) on stock torch CPU kernels, all host threads"""
+    import torch
+    from oracle import pfcn_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = {f"base.{k}": v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    for name, mods in (("filter", model.filter_layer), ("dis", model.dis_layer_dict)):
+        for k, m in mods.items():
+            st.update({f"{name}_{k}.{kk}": v.detach().cpu().clone() for kk, v in m.state_dict().items()})
+    fkeys, dkeys = po.param_groups(st)
+    for k in fkeys + dkeys:
+        st[k].requires_grad_(True)
+    opt_f = torch.optim.Adam([st[k] for k in fkeys], lr=1e-3, weight_decay=1e-4)
+    opt_d = torch.optim.Adam([st[k] for k in dkeys], lr=1e-3, weight_decay=1e-4)
+    attrs = list(feats)
+    sst_dict = {s: 2 ** i for i, s in enumerate(attrs)}
+    sst_size = {s: len(np.unique(feats[s][1:])) for s in attrs}
+
+    def step(h):
+        labels = {a: h[a] for a in attrs}
+        opt_f.zero_grad()
+        po.calculate_loss(st, "PFCN_MLP", h["user_id"], h["item_id"], h["neg_item_id"], labels, sst_list, sst_dict, sst_size,
+                          "sm", 7, "leakyrelu", 10.0).backward()
+        opt_f.step()
+        opt_d.zero_grad()
+        po.dis_loss(st, "PFCN_MLP", h["user_id"], labels, sst_list, sst_dict, sst_size, "sm", 7, "leakyrelu").backward()
+        opt_d.step()
+
+    step(hosts[0])
+    t0 = time.perf_counter()
+    for k in range(n):
+        step(hosts[(k + 1) % len(hosts)])
+    dt = (time.perf_counter() - t0) / n
+    B = hosts[0]["user_id"].numel()
+    return {"value": B / dt, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": f"{n} filter+discriminator steps of {B} rows (dropout off in the port)", "ms_per_step": 1e3 * dt}
+
+
+def bench_fairgo(dev, flush, n_steps=20, cpu=True, seed=2020):
+    import scipy.sparse as sp
+    import torch
+
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import synth
+    w = ML1M
+    rng = np.random.default_rng(seed)
+    feats = _user_feats(rng, w["n_users"])
+    attrs = ["gender", "age"]
+    feats = {a: feats[a] for a in attrs}
+    uid, iid, rating, _ = synth.interactions(w["n_users"], w["n_items"], 1_000_209, seed)
+    train = synth.split_by_user(uid, iid, rating, seed=seed)[0]
+    coo = sp.coo_matrix((train[2], (train[0].astype(np.int64), train[1].astype(np.int64))), shape=(w["n_users"], w["n_items"]))
+    cfg = pkg.Config(embedding_size=w["d"], sst_attr_list=attrs, n_layers=2, activation="leakyrelu",
+                     dis_hidden_size_list=[16, 8, 4], filter_hidden_size_list=[128, 64], fair_weight=0.1,
+                     load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1], device=dev, learning_rate=1e-3,
+                     weight_decay=1e-4, train_epoch_interval=1, pretrain_epochs=1)
+    torch.manual_seed(seed)
+    model = pkg.FairGo_PMF(cfg, _DS(w["n_users"], w["n_items"], feats, coo)).to(dev)
+    with torch.no_grad():
+        model.user_embedding_layer.weight.mul_(0.3)
+        model.item_embedding_layer.weight.mul_(0.3)
+    trainer = pkg.FairGoTrainer(cfg, model)
+    model.train_stage = "finetune"
+    model.train()
+    B = w["batch"]
+    n_train = len(train[0])
+
+    def host_batch():
+        sel = rng.integers(0, n_train, B)
+        u = train[0][sel].astype(np.int64)
+        return {"user_id": torch.from_numpy(u).pin_memory(), "item_id": torch.from_numpy(train[1][sel].astype(np.int64)).pin_memory(),
+                "rating": torch.from_numpy(train[2][sel]).pin_memory(),
+                **{a: torch.from_numpy(feats[a][u]).pin_memory() for a in attrs}}
+
+    hosts = [host_batch() for _ in range(8)]
+    devs = [pkg.Interaction({k: v.to(dev) for k, v in h.items()}) for h in hosts]
+
+    def step(inter, read_loss=False):
+        out = []
+        for fn, opt in ((model.calculate_loss, trainer.optimizer_filter), (model.calculate_dis_loss, trainer.optimizer_dis)):
+            opt.zero_grad()
+            loss = fn(inter, attrs)
+            if read_loss:
+                out.append(loss.item())
+            loss.backward()
+            opt.step()
+        return out
+
+    eager_ms = _timed_steps(step, devs, 3, n_steps, flush)
+    shares, launches, kernel_ms = _profile(step, devs[0])
+    model._matrix()
+    ms, t_e2e = _graphed_legs(pkg, dev, flush, hosts, devs, n_steps,
+                              [(model.calculate_loss, trainer.optimizer_filter), (model.calculate_dis_loss, trainer.optimizer_dis)],
+                              attrs)
+    N = w["n_users"] + w["n_items"]
+    nnz = model._norm_csr.nnz
+    out = {"metric": "FairGo_PMF (LBA) fine-tune interactions/s", "value": B / (statistics.mean(ms) * 1e-3),
+           "unit": "interactions/s", "ms_per_step": statistics.mean(ms), "steps": n_steps,
+           "launch_mode": "cuda graph replay (one per phase)", "eager_ms_per_step": statistics.mean(eager_ms),
+           "config": {"workload": "fairgo_pmf_lba_ml1m", **w, "n_layers": 2, "graph_rows": N, "graph_nnz": int(nnz),
+                      "filters": "[64,128,64,64] x 2 attributes over all graph rows", "discriminators": "[64,16,8,4,{1|7}]",
+                      "step": "filter-phase step + discriminator-phase step on one batch (each runs the full-table "
+                              "filters and 2 SpMM layers forward and backward)"},
+           "e2e": {"value": B / t_e2e, "unit": "interactions/s",
+                   "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in hosts[0].values()), "d2h_bytes_per_step": 8},
+           "gpu_launches_per_step": launches, "kernel_ms_per_step": kernel_ms, "kernel_shares": shares}
+    if cpu:
+        out["cpu_baseline"] = cpu_fairgo(model, feats, train, hosts, attrs)
+    return out
+
+
+def cpu_fairgo(model, feats, train, hosts, attrs, n=2):
+    import torch
+    from oracle import fairgo_oracle as go
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = {f"base.{k}": v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    for name, mods in (("filter", model.filter_layer_dict), ("dis", model.dis_layer_dict)):
+        for k, m in mods.items():
+            st.update({f"{name}_{k}.{kk}": v.detach().cpu().clone() for kk, v in m.state_dict().items()})
+    for v in st.values():
+        v.requires_grad_(True)
+    nu, ni = model.n_users, model.n_items
+    L = go.to_torch_sparse(go.norm_matrix(train[0].astype(np.int64), train[1].astype(np.int64), train[2], nu, ni))
+    dkeys = [k for k in st if k.startswith("dis_") or k.startswith("base.aggr_layer")]
+    fkeys = [k for k in st if k.startswith("filter_")]
+    opt_d = torch.optim.Adam([st[k] for k in dkeys], lr=1e-3, weight_decay=1e-4)
+    opt_f = torch.optim.Adam([st[k] for k in fkeys], lr=1e-3, weight_decay=1e-4)
+    sst_size = {s: len(np.unique(feats[s][1:])) for s in attrs}
+    assert attrs == go.ATTRS
+
+    def step(h):
+        labels = {a: h[a] for a in attrs}
+        opt_f.zero_grad()
+        go.calculate_loss(st, L, "finetune", h["user_id"], h["item_id"], h["rating"], labels, attrs, sst_size, nu, 2, "LBA",
+                          [0.8, 0.2], 0.1).backward()
+        opt_f.step()
+        opt_d.zero_grad()
+        go.dis_loss(st, L, h["user_id"], labels, attrs, sst_size, nu, 2, "LBA", [0.8, 0.2]).backward()
+        opt_d.step()
+
+    step(hosts[0])
+    t0 = time.perf_counter()
+    for k in range(n):
+        step(hosts[(k + 1) % len(hosts)])
+    dt = (time.perf_counter() - t0) / n
+    B = hosts[0]["user_id"].numel()
+    return {"value": B / dt, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": f"{n} filter+discriminator fine-tune steps of {B} rows", "ms_per_step": 1e3 * dt}
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    print(json.dumps({"pfcn_mlp": bench_pfcn(dev, flush), "fairgo_pmf": bench_fairgo(dev, flush)}))

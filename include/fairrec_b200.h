@@ -227,7 +227,9 @@ typedef struct fr_adam_entry {
   const float *g;
   float *m, *v;
   int64_t n;
-  int32_t step; /* 1-based step count of THIS parameter after the update */
+  int32_t step;      /* 1-based step count of THIS parameter after the update (used when step_dev is NULL) */
+  int32_t *step_dev; /* optional device-resident counter: incremented on the stream right before the update and used
+                        instead of `step`, so that a captured CUDA graph advances the bias correction on every replay */
 } fr_adam_entry;
 int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double lr, double beta1, double beta2, double eps,
                   double weight_decay, void *stream);
@@ -235,21 +237,27 @@ int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double l
 /* ---- generic layer ops: the pieces of MLPLayers (layers.py:58-70) for the PFCN / FairGo filter, discriminator and
  * scorer MLPs.  Each is one layer's forward or backward; the host mirror chains them (torch.autograd.Functions). */
 /* Y = act(dropout(X) . W^T + b): nn.Dropout -> nn.Linear -> activation (layers.py:60-68 without BatchNorm) */
+/* dropout masks are a counter-based hash of (seed + *seed_dev, layer, element); seed_dev (may be NULL) is a device-resident
+ * offset so that replays of a captured CUDA graph draw fresh masks (bump it with fr_bump_u64 inside the graph) */
 int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
-                      float drop_p, uint64_t seed, int32_t layer, void *stream);
+                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, void *stream);
+int fr_bump_u64(uint64_t *counter_dev, uint64_t inc, void *stream);
 size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N);
 /* dY is the gradient w.r.t. the layer OUTPUT Y (post-activation); dX may be NULL */
 int fr_linear_backward(const float *X, const float *W, const float *Y, const float *dY, int64_t M, int32_t K, int32_t N,
-                       int32_t act, float drop_p, uint64_t seed, int32_t layer, float *dX, float *dW, float *db,
-                       void *workspace, size_t workspace_bytes, void *stream);
+                       int32_t act, float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, float *dX, float *dW,
+                       float *db, int32_t *tickets, void *workspace, size_t workspace_bytes, void *stream);
+/* tickets (may be NULL): int32[1024] zero-initialised ONCE by the caller and then left alone (self-resetting); lets the
+ * weight-gradient kernel add its chunk partials itself instead of two extra reduction launches.  One buffer per stream. */
 /* nn.BatchNorm1d (layers.py:64-65) fused with the following activation; training mode uses batch statistics and
  * updates the running ones (momentum 0.1, unbiased variance), eval mode uses the running statistics */
+size_t fr_batchnorm_workspace_bytes(int32_t N);
 int fr_batchnorm_forward(const float *X, const float *gamma, const float *beta, float *running_mean, float *running_var,
                          int64_t M, int32_t N, float momentum, float eps, int32_t training, int32_t act, float *Y,
-                         float *save_mean, float *save_invstd, void *stream);
+                         float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes, void *stream);
 int fr_batchnorm_backward(const float *X, const float *Y, const float *dY, const float *gamma, const float *save_mean,
                           const float *save_invstd, int64_t M, int32_t N, int32_t act, float *dX, float *dgamma,
-                          float *dbeta, void *stream);
+                          float *dbeta, void *workspace, size_t workspace_bytes, void *stream);
 /* nn.Embedding lookup written into columns [col0, col0+d) of a wider row-major matrix (torch.cat for free) */
 int fr_gather_rows(const float *T, const int32_t *idx, int64_t M, int32_t d, float *out, int32_t ld_out, int32_t col0,
                    void *stream);

@@ -69,7 +69,8 @@ class FullSort(Structure):
 
 class AdamEntry(Structure):
     """mirror of `struct fr_adam_entry`"""
-    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("step", c_int32)]
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("step", c_int32),
+                ("step_dev", c_void_p)]
 
 
 class SpmmPlan(Structure):
@@ -105,14 +106,17 @@ SIGNATURES = {
     "fr_adam_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double,
                               c_double, c_double, c_void_p]),
     "fr_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
-                                  c_uint64, c_int32, c_void_p]),
+                                  c_uint64, c_void_p, c_int32, c_void_p]),
+    "fr_bump_u64": (c_int, [c_void_p, c_uint64, c_void_p]),
     "fr_linear_backward_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "fr_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
-                                   c_uint64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                   c_uint64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    "fr_batchnorm_workspace_bytes": (c_size_t, [c_int32]),
     "fr_batchnorm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float,
-                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fr_batchnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
-                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fr_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "fr_scatter_rows_workspace_bytes": (c_size_t, [c_int64]),
     "fr_scatter_rows_dense": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p,

@@ -49,46 +49,64 @@ struct GemmArgs {
   unsigned long long seed;
   int layer;
   int drop_on_c;
+  const float *a_out;           // backward-data: A' = A * act_bwd(a_out[m,k], a_act) (activation backward fused in the loader)
+  int a_act;
+  const unsigned long long *seed_dev;   // optional device-resident seed offset (CUDA-graph replays draw new masks)
 };
 
+// 64x64x32 tiles, 4x4 outputs per thread; the next k-slab is fetched into registers while the current one is
+// multiplied out of shared memory (these GEMMs are a handful of k-steps long: exposed load latency, not FLOPs, bounds them)
+constexpr int kGK = 32;   // k-depth of one slab
 template <bool kTB>
 __global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  __shared__ __align__(16) float As[kGK][64 + 4];
+  __shared__ __align__(16) float Bs[kGK][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const unsigned long long seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < a.K; k0 += 16) {
-    for (int f = threadIdx.x; f < 64 * 16; f += 256) {   // A tile: 64 rows x 16 k
-      const int r = f >> 4, kk = f & 15;
+  // raw operands of the next k-slab: every global load is issued before any is consumed (activation backward and
+  // dropout are applied when the registers are parked in shared memory, so no load waits behind a data-dependent op)
+  float ra[8], rao[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int f = threadIdx.x + t * 256;          // A tile: 64 rows x 32 k ; B tile: 32 k x 64 n
+      const int r = f >> 5, kk = f & 31;
       const int m = m0 + r, k = k0 + kk;
-      float v = 0.f;
-      if (m < a.M && k < a.K) {
-        v = a.A[(size_t)m * a.lda + k];
-        if (a.drop_p > 0.f && !a.drop_on_c) v *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.K + k), a.drop_p);
-      }
-      As[kk][r] = v;
+      const bool va = m < a.M && k < a.K;
+      ra[t] = va ? a.A[(size_t)m * a.lda + k] : 0.f;
+      rao[t] = (va && a.a_out) ? a.a_out[(size_t)m * a.lda + k] : 1.f;
+      int n, kb;
+      if (kTB) { n = f >> 5; kb = f & 31; } else { kb = f >> 6; n = f & 63; }
+      const int gn = n0 + n, k2 = k0 + kb;
+      const bool vb = gn < a.N && k2 < a.K;
+      rb[t] = vb ? (kTB ? a.B[(size_t)gn * a.ldb + k2] : a.B[(size_t)k2 * a.ldb + gn]) : 0.f;
     }
-    for (int f = threadIdx.x; f < 64 * 16; f += 256) {   // B tile: 16 k x 64 n
-      int n, kk;
-      if (kTB) { n = f >> 4; kk = f & 15; } else { kk = f >> 6; n = f & 63; }
-      const int gn = n0 + n, k = k0 + kk;
-      float v = 0.f;
-      if (gn < a.N && k < a.K) v = kTB ? a.B[(size_t)gn * a.ldb + k] : a.B[(size_t)k * a.ldb + gn];
-      Bs[kk][n] = v;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < a.K; k0 += kGK) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int f = threadIdx.x + t * 256;
+      float v = ra[t];
+      if (a.a_out) v *= act_bwd(rao[t], a.a_act);
+      if (a.drop_p > 0.f && !a.drop_on_c)
+        v *= drop_scale(seed, a.layer, (uint32_t)((m0 + (f >> 5)) * a.K + k0 + (f & 31)), a.drop_p);
+      As[f & 31][f >> 5] = v;
+      if (kTB) Bs[f & 31][f >> 5] = rb[t]; else Bs[f >> 6][f & 63] = rb[t];
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+    if (k0 + kGK < a.K) fetch(k0 + kGK);
+    const int kmax = min(kGK, a.K - k0);
+#pragma unroll 8
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float4 a4 = *(const float4 *)&As[kk][ty * 4], b4 = *(const float4 *)&Bs[kk][tx * 4];
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -108,14 +126,15 @@ __global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
       if (a.bias) v += a.bias[n];
       v = act_fwd(v, a.act);
       if (a.prev_out) v *= act_bwd(a.prev_out[(size_t)m * a.ldc + n], a.prev_act);
-      if (a.drop_p > 0.f && a.drop_on_c) v *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.N + n), a.drop_p);
+      if (a.drop_p > 0.f && a.drop_on_c) v *= drop_scale(seed, a.layer, (uint32_t)(m * a.N + n), a.drop_p);
       a.C[(size_t)m * a.ldc + n] = v;
     }
   }
 }
 
 // ---------------------------------------------------------------- weight / bias gradients
-// dW[n,k] = sum_m dY[m,n] * Xdrop[m,k] over one 256-row chunk per blockIdx.z -> part[z][N][K]; db likewise.
+// dW[n,k] = sum_m dY'[m,n] * Xdrop[m,k] over one row chunk per blockIdx.z -> part[z][N][K]; db likewise.
+// dY' = dY * act'(Yout) when y_out is given (the layer's activation backward fused into the loader).
 struct WgradArgs {
   const float *dY, *X;
   float *part_w, *part_b;       // [chunks, N, K], [chunks, N]
@@ -123,46 +142,63 @@ struct WgradArgs {
   float drop_p;
   unsigned long long seed;
   int layer;
+  const float *y_out;
+  int y_act;
+  const unsigned long long *seed_dev;
+  // optional fused chunk reduction: the LAST CTA of an (n,k) tile to finish (self-resetting ticket) adds the tile's chunk
+  // partials in chunk order into dW / db -- fixed order whichever CTA ends up last, so still bit-reproducible
+  int *tickets;
+  float *dW, *db;
+  int chunk;                    // rows per chunk (wgrad_chunk(M))
 };
-constexpr int kWgradChunk = 256;
+constexpr int kWgradChunk = 128;   // smallest chunk: workspace sizing
+// batches of a few thousand rows: 128-row chunks (more CTAs, 4 slabs each); full-table passes (FairGo): 256-row chunks
+static inline int wgrad_chunk(int64_t M) { return M <= 4096 ? 128 : 256; }
 
 __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
-  __shared__ float Ys[16][64 + 4];
-  __shared__ float Xs[16][64 + 4];
+  __shared__ __align__(16) float Ys[kGK][64 + 4];
+  __shared__ __align__(16) float Xs[kGK][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
-  const int mlo = blockIdx.z * kWgradChunk, mhi = min(a.M, mlo + kWgradChunk);
+  const int mlo = blockIdx.z * a.chunk, mhi = min(a.M, mlo + a.chunk);
+  const unsigned long long seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
   float acc[4][4], bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int mb = mlo; mb < mhi; mb += 16) {
-    for (int f = threadIdx.x; f < 16 * 64; f += 256) {
-      const int mm = f >> 6, c = f & 63;
-      const int m = mb + mm;
-      float y = 0.f, x = 0.f;
-      if (m < mhi) {
-        if (n0 + c < a.N) y = a.dY[(size_t)m * a.ldy + n0 + c];
-        if (k0 + c < a.K) {
-          x = a.X[(size_t)m * a.ldx + k0 + c];
-          if (a.drop_p > 0.f) x *= drop_scale(a.seed, a.layer, (uint32_t)(m * a.K + k0 + c), a.drop_p);
-        }
-      }
-      Ys[mm][c] = y;
-      Xs[mm][c] = x;
+  float ry[8], ryo[8], rx[8];
+  auto fetch = [&](int mb) {   // raw loads only (see k_gemm)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int f = threadIdx.x + t * 256;
+      const int m = mb + (f >> 6), c = f & 63;
+      const bool vy = m < mhi && n0 + c < a.N, vx = m < mhi && k0 + c < a.K;
+      ry[t] = vy ? a.dY[(size_t)m * a.ldy + n0 + c] : 0.f;
+      ryo[t] = (vy && a.y_out) ? a.y_out[(size_t)m * a.ldy + n0 + c] : 1.f;
+      rx[t] = vx ? a.X[(size_t)m * a.ldx + k0 + c] : 0.f;
+    }
+  };
+  fetch(mlo);
+  for (int mb = mlo; mb < mhi; mb += kGK) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int f = threadIdx.x + t * 256;
+      float y = ry[t], x = rx[t];
+      if (a.y_out) y *= act_bwd(ryo[t], a.y_act);
+      if (a.drop_p > 0.f) x *= drop_scale(seed, a.layer, (uint32_t)((mb + (f >> 6)) * a.K + k0 + (f & 63)), a.drop_p);
+      Ys[f >> 6][f & 63] = y;
+      Xs[f >> 6][f & 63] = x;
     }
     __syncthreads();
-#pragma unroll
-    for (int mm = 0; mm < 16; ++mm) {
-      float yv[4], xv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) yv[i] = Ys[mm][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) xv[j] = Xs[mm][tx * 4 + j];
+    if (mb + kGK < mhi) fetch(mb + kGK);
+#pragma unroll 8
+    for (int mm = 0; mm < kGK; ++mm) {     // rows past mhi were staged as zeros
+      const float4 y4 = *(const float4 *)&Ys[mm][ty * 4], x4 = *(const float4 *)&Xs[mm][tx * 4];
+      const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (tx == 0) bacc[i] += yv[i];
+        bacc[i] += yv[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yv[i], xv[j], acc[i][j]);
       }
@@ -181,6 +217,48 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
       if (k < a.K) pw[(size_t)n * a.K + k] = acc[i][j];
     }
   }
+  if (!a.tickets) return;
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) is_last = atomicAdd(&a.tickets[tile], 1) == (int)gridDim.z - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int chunks = gridDim.z;
+  const size_t cs = (size_t)a.N * a.K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= a.N) continue;
+    if (tx == 0 && blockIdx.x == 0 && a.db) {
+      float sb = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < chunks; ++c) sb += __ldcg(a.part_b + (size_t)c * a.N + n);
+      a.db[n] = sb;
+    }
+    const int k = k0 + tx * 4;
+    if ((a.K & 3) == 0 && k + 3 < a.K) {     // 128-bit reads, 8 chunks in flight, added in chunk order
+      const float *src = a.part_w + (size_t)n * a.K + k;
+      float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int c = 0; c < chunks; ++c) {
+        const float4 v = __ldcg((const float4 *)(src + c * cs));
+        sw.x += v.x; sw.y += v.y; sw.z += v.z; sw.w += v.w;
+      }
+      *(float4 *)(a.dW + (size_t)n * a.K + k) = sw;
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        if (k + j >= a.K) continue;
+        float sw = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < chunks; ++c) sw += __ldcg(a.part_w + c * cs + (size_t)n * a.K + k + j);
+        a.dW[(size_t)n * a.K + k + j] = sw;
+      }
+    }
+  }
+  if (threadIdx.x == 0) a.tickets[tile] = 0;
 }
 
 // out[i] = sum_c part[c][i] in chunk order
@@ -419,9 +497,16 @@ struct AdamMultiArgs {
   const float *g[kAdamMulti];
   float *m[kAdamMulti], *v[kAdamMulti];
   int n[kAdamMulti], step[kAdamMulti], first_tile[kAdamMulti + 1];
+  int *step_dev[kAdamMulti];     // optional device-resident step counters (bumped by k_adam_bump right before)
   int n_entries;
   double lr, beta1, beta2, eps, wd;
 };
+__global__ void k_adam_bump(AdamMultiArgs a) {
+  const int e = threadIdx.x;
+  if (e < a.n_entries && a.step_dev[e]) *a.step_dev[e] += 1;
+}
+__global__ void k_bump_u64(unsigned long long *c, unsigned long long inc) { *c += inc; }
+
 __global__ void __launch_bounds__(256) k_adam_multi(AdamMultiArgs a) {
   __shared__ float sc[2];
   __shared__ int se;
@@ -429,8 +514,9 @@ __global__ void __launch_bounds__(256) k_adam_multi(AdamMultiArgs a) {
     int e = 0;
     while (e + 1 < a.n_entries && (int)blockIdx.x >= a.first_tile[e + 1]) ++e;
     se = e;
-    sc[0] = (float)(-a.lr / (1.0 - pow(a.beta1, (double)a.step[e])));
-    sc[1] = (float)sqrt(1.0 - pow(a.beta2, (double)a.step[e]));
+    const double t = a.step_dev[e] ? (double)*a.step_dev[e] : (double)a.step[e];
+    sc[0] = (float)(-a.lr / (1.0 - pow(a.beta1, t)));
+    sc[1] = (float)sqrt(1.0 - pow(a.beta2, t));
   }
   __syncthreads();
   const int e = se;
@@ -458,69 +544,105 @@ __global__ void k_act_bwd(const float *__restrict__ dY, const float *__restrict_
 }
 
 // BatchNorm1d over the batch dimension (nn.BatchNorm1d, layers.py:64-65), fused with the following activation.
-// One CTA owns 32 feature columns; warp w strides the rows w, w+8, ... (coalesced 128-byte row segments); two passes
-// (mean, then centred variance) with a fixed 8-way ordered combine -> deterministic.
-//   training: y = act((x - mean) * invstd * gamma + beta), running stats updated with the unbiased variance
-//   eval    : y = act((x - running_mean) / sqrt(running_var + eps) * gamma + beta)
+// Two launches, both spread over (column groups of 32) x (row slices): the batch is a few thousand rows of <= 256
+// features, so a column-per-CTA sweep would leave most SMs idle.
+//   k_bn_fwd_stats : CTA (cg, sl) -> per column (count, mean, M2) of its row slice, two-pass inside the slice
+//   k_bn_fwd_apply : every CTA re-combines the slice statistics of its 32 columns in slice order (Chan's parallel
+//                    update: deterministic, no atomics), then normalises its own row slice:
+//                    y = act((x - mean) * invstd * gamma + beta); slice 0 also writes save_mean / save_invstd and the
+//                    running statistics (momentum update with the unbiased variance).
+//   eval mode      : k_bn_fwd_apply alone, with the running statistics.
+constexpr int kBnSlices = 32;
+__device__ __forceinline__ int bn_slice_rows(int M) { return (M + kBnSlices - 1) / kBnSlices; }
+
 __global__ void __launch_bounds__(256)
-    k_bn_fwd(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
-             float *__restrict__ rmean, float *__restrict__ rvar, int M, int N, float momentum, float eps, int training,
-             int act, float *__restrict__ Y, float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+    k_bn_fwd_stats(const float *__restrict__ X, int M, int N, float *__restrict__ part /* [slices][N][2]: mean, M2 */) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool ok = c < N;
-  float mean, invstd;
-  if (training) {
-    float s = 0.f;
-    for (int m = w; m < M; m += 8) s += ok ? X[(size_t)m * N + c] : 0.f;
-    red[w][lane] = s;
-    __syncthreads();
-    s = 0.f;
+  const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+  const int cnt = max(r1 - r0, 0);
+  float s = 0.f;
+  for (int m = r0 + w; m < r1; m += 8) s += ok ? X[(size_t)m * N + c] : 0.f;
+  red[w][lane] = s;
+  __syncthreads();
+  s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][lane];
-    mean = s / (float)M;
-    __syncthreads();
-    float q = 0.f;
-    for (int m = w; m < M; m += 8) {
-      const float dlt = ok ? X[(size_t)m * N + c] - mean : 0.f;
-      q = fmaf(dlt, dlt, q);
-    }
-    red[w][lane] = q;
-    __syncthreads();
+  for (int i = 0; i < 8; ++i) s += red[i][lane];
+  const float mean = cnt > 0 ? s / (float)cnt : 0.f;
+  __syncthreads();
+  float q = 0.f;
+  for (int m = r0 + w; m < r1; m += 8) {
+    const float dlt = ok ? X[(size_t)m * N + c] - mean : 0.f;
+    q = fmaf(dlt, dlt, q);
+  }
+  red[w][lane] = q;
+  __syncthreads();
+  if (w == 0 && ok) {
     q = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) q += red[i][lane];
-    const float var = q / (float)M;
-    invstd = 1.f / sqrtf(var + eps);
-    if (w == 0 && ok) {
-      save_mean[c] = mean;
-      save_invstd[c] = invstd;
-      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
-      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (M > 1 ? q / (float)(M - 1) : var);
+    part[((size_t)blockIdx.y * N + c) * 2] = mean;
+    part[((size_t)blockIdx.y * N + c) * 2 + 1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_bn_fwd_apply(const float *__restrict__ X, const float *__restrict__ gamma, const float *__restrict__ beta,
+                   float *__restrict__ rmean, float *__restrict__ rvar, int M, int N, float momentum, float eps,
+                   int training, int act, const float *__restrict__ part, float *__restrict__ Y,
+                   float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < N;
+  const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+  float mean = 0.f, invstd = 0.f;
+  if (ok) {
+    if (training) {
+      float n = 0.f, M2 = 0.f;
+      for (int sl = 0; sl < kBnSlices; ++sl) {       // Chan et al. pairwise update, slice order
+        const int cb = min(M, (sl + 1) * rows) - sl * rows;
+        if (cb <= 0) break;
+        const float mb = part[((size_t)sl * N + c) * 2], qb = part[((size_t)sl * N + c) * 2 + 1];
+        const float nb = (float)cb, nn = n + nb, dlt = mb - mean;
+        mean += dlt * (nb / nn);
+        M2 += qb + dlt * dlt * (n * nb / nn);
+        n = nn;
+      }
+      const float var = M2 / (float)M;
+      invstd = 1.f / sqrtf(var + eps);
+      if (blockIdx.y == 0 && w == 0) {
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (M > 1 ? M2 / (float)(M - 1) : var);
+      }
+    } else {
+      mean = rmean[c];
+      invstd = 1.f / sqrtf(rvar[c] + eps);
     }
-  } else {
-    mean = ok ? rmean[c] : 0.f;
-    invstd = ok ? 1.f / sqrtf(rvar[c] + eps) : 0.f;
   }
   const float g = ok ? gamma[c] : 0.f, b = ok ? beta[c] : 0.f;
-  for (int m = w; m < M; m += 8)
+  for (int m = r0 + w; m < r1; m += 8)
     if (ok) Y[(size_t)m * N + c] = act_fwd(fmaf((X[(size_t)m * N + c] - mean) * invstd, g, b), act);
 }
 
-// backward of the above (training mode): dpre = dY * act'(Y); dbeta = sum dpre; dgamma = sum dpre * xhat;
-// dX = gamma * invstd / M * (M * dpre - dbeta - xhat * dgamma)
+// backward (training mode): dpre = dY * act'(Y); dbeta = sum dpre; dgamma = sum dpre * xhat;
+// dX = gamma * invstd / M * (M * dpre - dbeta - xhat * dgamma).  Same slice decomposition: slice partials of the two
+// sums, then every CTA adds them in slice order and writes its rows of dX.
 __global__ void __launch_bounds__(256)
-    k_bn_bwd(const float *__restrict__ X, const float *__restrict__ Y, const float *__restrict__ dY,
-             const float *__restrict__ gamma, const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
-             int M, int N, int act, float *__restrict__ dX, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    k_bn_bwd_stats(const float *__restrict__ X, const float *__restrict__ Y, const float *__restrict__ dY,
+                   const float *__restrict__ save_mean, const float *__restrict__ save_invstd, int M, int N, int act,
+                   float *__restrict__ part /* [slices][N][2]: sum dpre, sum dpre*xhat */) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool ok = c < N;
-  const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f, g = ok ? gamma[c] : 0.f;
+  const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+  const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f;
   float sb = 0.f, sg = 0.f;
-  for (int m = w; m < M; m += 8) {
+  for (int m = r0 + w; m < r1; m += 8) {
     if (ok) {
       const size_t i = (size_t)m * N + c;
       const float dp = dY[i] * act_bwd(Y[i], act);
@@ -536,15 +658,38 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   red[w][lane] = sg;
   __syncthreads();
-  sg = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sg += red[i][lane];
   if (w == 0 && ok) {
-    dbeta[c] = sb;
-    dgamma[c] = sg;
+    sg = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sg += red[i][lane];
+    part[((size_t)blockIdx.y * N + c) * 2] = sb;
+    part[((size_t)blockIdx.y * N + c) * 2 + 1] = sg;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_apply(const float *__restrict__ X, const float *__restrict__ Y, const float *__restrict__ dY,
+                   const float *__restrict__ gamma, const float *__restrict__ save_mean,
+                   const float *__restrict__ save_invstd, int M, int N, int act, const float *__restrict__ part,
+                   float *__restrict__ dX, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool ok = c < N;
+  const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+  float sb = 0.f, sg = 0.f, mean = 0.f, invstd = 0.f, g = 0.f;
+  if (ok) {
+    for (int sl = 0; sl < kBnSlices && sl * rows < M; ++sl) {
+      sb += part[((size_t)sl * N + c) * 2];
+      sg += part[((size_t)sl * N + c) * 2 + 1];
+    }
+    mean = save_mean[c]; invstd = save_invstd[c]; g = gamma[c];
+    if (blockIdx.y == 0 && w == 0) {
+      dbeta[c] = sb;
+      dgamma[c] = sg;
+    }
   }
   const float k = g * invstd / (float)M;
-  for (int m = w; m < M; m += 8) {
+  for (int m = r0 + w; m < r1; m += 8) {
     if (ok) {
       const size_t i = (size_t)m * N + c;
       const float dp = dY[i] * act_bwd(Y[i], act), xh = (X[i] - mean) * invstd;
@@ -792,13 +937,14 @@ int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int M = (int)s->M, L = t->n_layers;
   FR_LAUNCH(fr::k_sigmoid_bwd, (M + 255) / 256, 256, 0, st, w.dp, w.p, w.act[L - 1], M, grad_scale, w.dz);
-  const int chunks = (M + fr::kWgradChunk - 1) / fr::kWgradChunk;
+  const int wchunk = fr::wgrad_chunk(M), chunks = (M + wchunk - 1) / wchunk;
   float *dcur = w.dz;     // gradient w.r.t. the PRE-activation of layer l: [M, dims[l+1]]
   float *bufs[2] = {w.dA, w.dB};
   for (int l = L - 1; l >= 0; --l) {
     const float *inp = l > 0 ? w.act[l - 1] : w.X;
     const int N = t->dims[l + 1], K = t->dims[l];
-    fr::WgradArgs wa{dcur, inp, w.part_w, w.part_b, M, N, K, N, K, s->training ? t->dropout : 0.f, s->seed, l};
+    fr::WgradArgs wa{dcur, inp, w.part_w, w.part_b, M, N, K, N, K, s->training ? t->dropout : 0.f, s->seed, l,
+                     nullptr, 0, nullptr, nullptr, nullptr, nullptr, wchunk};
     dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
     FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
     FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)w.part_w, chunks,
@@ -848,28 +994,39 @@ int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double l
     fr::AdamMultiArgs a;
     const int cnt = n_entries - e0 < fr::kAdamMulti ? n_entries - e0 : fr::kAdamMulti;
     int tiles = 0;
+    bool any_dev = false;
     for (int e = 0; e < cnt; ++e) {
       const fr_adam_entry &x = entries_host[e0 + e];
-      FR_REQUIRE(x.p && x.g && x.m && x.v && x.n >= 1 && x.n < (int64_t)INT32_MAX && x.step >= 1,
+      FR_REQUIRE(x.p && x.g && x.m && x.v && x.n >= 1 && x.n < (int64_t)INT32_MAX && (x.step >= 1 || x.step_dev),
                  "fr_adam_multi: bad entry");
       a.p[e] = x.p; a.g[e] = x.g; a.m[e] = x.m; a.v[e] = x.v;
-      a.n[e] = (int)x.n; a.step[e] = x.step; a.first_tile[e] = tiles;
+      a.n[e] = (int)x.n; a.step[e] = x.step; a.step_dev[e] = x.step_dev; a.first_tile[e] = tiles;
+      any_dev |= x.step_dev != nullptr;
       tiles += (int)((x.n + 1023) / 1024);
     }
     a.first_tile[cnt] = tiles;
     a.n_entries = cnt;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    if (any_dev) FR_LAUNCH(fr::k_adam_bump, 1, 64, 0, stream, a);
     FR_LAUNCH(fr::k_adam_multi, tiles, 256, 0, stream, a);
   }
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
 
+int fr_bump_u64(uint64_t *counter_dev, uint64_t inc, void *stream) {
+  FR_REQUIRE(counter_dev, "fr_bump_u64: null pointer");
+  FR_LAUNCH(fr::k_bump_u64, 1, 1, 0, stream, (unsigned long long *)counter_dev, (unsigned long long)inc);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
 // ---------------------------------------------------------------- generic layer ops
 int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
-                      float drop_p, uint64_t seed, int32_t layer, void *stream) {
+                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, void *stream) {
   FR_REQUIRE(X && W && Y && M >= 1 && K >= 1 && N >= 1, "fr_linear_forward: bad argument");
-  fr::GemmArgs g{X, W, b, Y, (int)M, N, K, K, K, N, act, nullptr, 0, drop_p, seed, layer, 0};
+  fr::GemmArgs g{X, W, b, Y, (int)M, N, K, K, K, N, act, nullptr, 0, drop_p, seed, layer, 0, nullptr, 0,
+                 (const unsigned long long *)seed_dev};
   fr::launch_gemm(true, g, (cudaStream_t)stream);
   FR_LAUNCH_CHECK();
   return FR_OK;
@@ -881,52 +1038,67 @@ size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N) {
 }
 
 int fr_linear_backward(const float *X, const float *W, const float *Y, const float *dY, int64_t M, int32_t K, int32_t N,
-                       int32_t act, float drop_p, uint64_t seed, int32_t layer, float *dX, float *dW, float *db,
-                       void *workspace, size_t workspace_bytes, void *stream) {
+                       int32_t act, float drop_p, uint64_t seed, const uint64_t *seed_dev_, int32_t layer, float *dX, float *dW,
+                       float *db, int32_t *tickets, void *workspace, size_t workspace_bytes, void *stream) {
+  const unsigned long long *seed_dev = (const unsigned long long *)seed_dev_;
   FR_REQUIRE(X && W && Y && dY && dW && workspace && M >= 1, "fr_linear_backward: bad argument");
   if (workspace_bytes < fr_linear_backward_workspace_bytes(M, K, N)) {
     fr::set_error("fr_linear_backward: workspace too small");
     return FR_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = (int)((M + fr::kWgradChunk - 1) / fr::kWgradChunk);
+  const int wchunk = fr::wgrad_chunk(M), chunks = (int)((M + wchunk - 1) / wchunk);
   fr::Carver c(workspace, workspace_bytes);
   float *dpre = c.take<float>((size_t)M * N);
   float *part_w = c.take<float>((size_t)chunks * N * K);
   float *part_b = c.take<float>((size_t)chunks * N);
-  FR_LAUNCH(fr::k_act_bwd, fr::grid_for(M * N, 256), 256, 0, st, dY, Y, act, M * N, dpre);
-  fr::WgradArgs wa{dpre, X, part_w, part_b, (int)M, N, K, N, K, drop_p, seed, layer};
+  (void)dpre;
   dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
+  const bool fused = tickets != nullptr && grid.x * grid.y <= 1024;
+  fr::WgradArgs wa{dY, X, part_w, part_b, (int)M, N, K, N, K, drop_p, seed, layer, act ? Y : nullptr, act, seed_dev,
+                   fused ? tickets : nullptr, dW, db, wchunk};
   FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
-  FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)part_w, chunks, (int64_t)N * K,
-            dW);
-  if (db) FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)part_b, chunks, (int64_t)N, db);
+  if (!fused) {
+    FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)part_w, chunks,
+              (int64_t)N * K, dW);
+    if (db) FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)part_b, chunks, (int64_t)N, db);
+  }
   if (dX) {
-    fr::GemmArgs g{dpre, W, nullptr, dX, (int)M, K, N, N, K, K, fr::ACT_NONE, nullptr, 0, drop_p, seed, layer, 1};
+    fr::GemmArgs g{dY, W, nullptr, dX, (int)M, K, N, N, K, K, fr::ACT_NONE, nullptr, 0, drop_p, seed, layer, 1,
+                   act ? Y : nullptr, act, seed_dev};
     fr::launch_gemm(false, g, st);
   }
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
 
+size_t fr_batchnorm_workspace_bytes(int32_t N) { return (size_t)fr::kBnSlices * (size_t)N * 2 * sizeof(float) + 256; }
+
 int fr_batchnorm_forward(const float *X, const float *gamma, const float *beta, float *running_mean, float *running_var,
                          int64_t M, int32_t N, float momentum, float eps, int32_t training, int32_t act, float *Y,
-                         float *save_mean, float *save_invstd, void *stream) {
+                         float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes, void *stream) {
   FR_REQUIRE(X && gamma && beta && running_mean && running_var && Y && save_mean && save_invstd && M >= 1 && N >= 1,
              "fr_batchnorm_forward: bad argument");
-  FR_LAUNCH(fr::k_bn_fwd, (N + 31) / 32, 256, 0, stream, X, gamma, beta, running_mean, running_var, (int)M, N, momentum,
-            eps, training, act, Y, save_mean, save_invstd);
+  FR_REQUIRE(!training || (workspace && workspace_bytes >= fr_batchnorm_workspace_bytes(N)),
+             "fr_batchnorm_forward: workspace too small");
+  dim3 grid((N + 31) / 32, fr::kBnSlices);
+  if (training) FR_LAUNCH(fr::k_bn_fwd_stats, grid, 256, 0, stream, X, (int)M, N, (float *)workspace);
+  FR_LAUNCH(fr::k_bn_fwd_apply, grid, 256, 0, stream, X, gamma, beta, running_mean, running_var, (int)M, N, momentum, eps,
+            training, act, (const float *)workspace, Y, save_mean, save_invstd);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
 
 int fr_batchnorm_backward(const float *X, const float *Y, const float *dY, const float *gamma, const float *save_mean,
                           const float *save_invstd, int64_t M, int32_t N, int32_t act, float *dX, float *dgamma,
-                          float *dbeta, void *stream) {
+                          float *dbeta, void *workspace, size_t workspace_bytes, void *stream) {
   FR_REQUIRE(X && Y && dY && gamma && save_mean && save_invstd && dX && dgamma && dbeta && M >= 1,
              "fr_batchnorm_backward: bad argument");
-  FR_LAUNCH(fr::k_bn_bwd, (N + 31) / 32, 256, 0, stream, X, Y, dY, gamma, save_mean, save_invstd, (int)M, N, act, dX,
-            dgamma, dbeta);
+  FR_REQUIRE(workspace && workspace_bytes >= fr_batchnorm_workspace_bytes(N), "fr_batchnorm_backward: workspace too small");
+  dim3 grid((N + 31) / 32, fr::kBnSlices);
+  FR_LAUNCH(fr::k_bn_bwd_stats, grid, 256, 0, stream, X, Y, dY, save_mean, save_invstd, (int)M, N, act, (float *)workspace);
+  FR_LAUNCH(fr::k_bn_bwd_apply, grid, 256, 0, stream, X, Y, dY, gamma, save_mean, save_invstd, (int)M, N, act,
+            (const float *)workspace, dX, dgamma, dbeta);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

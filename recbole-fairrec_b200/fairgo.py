@@ -193,9 +193,12 @@ class FairGo_PMF(nn.Module):
 
     def calculate_dis_loss(self, interaction, sst_list):
         """fairgo_pmf.py:190-236"""
-        table = self._forward_all(sst_list)
-        if table is None:
-            table = torch.cat([self.user_embedding_layer.weight, self.item_embedding_layer.weight], dim=0)
+        # the discriminator phase optimises the discriminators (+ aggr_layer) only: the filtered table enters as a
+        # constant (the reference also back-propagates into the filters here, but nothing ever uses those gradients)
+        with torch.no_grad():
+            table = self._forward_all(sst_list)
+            if table is None:
+                table = torch.cat([self.user_embedding_layer.weight, self.item_embedding_layer.weight], dim=0)
         return self._dis_loss(interaction, sst_list, table)
 
     def _dis_loss(self, interaction, sst_list, table):
@@ -318,6 +321,8 @@ class FairGoTrainer:
 
     def _pass(self, train_data, loss_func, optimizer, sst_list):
         self.model.train()
+        if self.config["use_cuda_graph"]:
+            return self._pass_graphed(train_data, loss_func, optimizer, sst_list)
         total = None
         for interaction in train_data:
             optimizer.zero_grad()
@@ -338,6 +343,23 @@ class FairGoTrainer:
         self.model.train_stage = "finetune"
         self.model._ego = None          # the tables moved under the cached [N, d] concatenation
         return losses
+
+    def _pass_graphed(self, train_data, loss_func, optimizer, sst_list):
+        """`use_cuda_graph: True`: one CUDA-graph replay per batch (graphed.py); the per-batch losses are summed on the
+        device and read back once per pass (the NaN check of trainer.py:192 moves to the end of the pass)"""
+        from .graphed import GraphedSteps
+        if getattr(self, "_graphs", None) is None:
+            self._graphs = GraphedSteps(next(self.model.parameters()).device)
+            self._graph_gen = 0
+        total = None
+        name = f"{loss_func.__name__}:{id(optimizer)}:{getattr(self.model, 'train_stage', '')}"
+        for interaction in train_data:
+            loss = self._graphs.run(name, loss_func, optimizer, sst_list, interaction)
+            total = loss.clone() if total is None else total + loss
+        v = float(total.item()) if total is not None else None
+        if v is not None and v != v:
+            raise ValueError("Training loss is nan")
+        return v
 
     def _train_epoch(self, train_data, epoch_idx):
         """trainer.py:687-704 -> (dis_loss, filter_loss)"""

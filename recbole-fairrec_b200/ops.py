@@ -9,10 +9,36 @@ from ._lib import check, load, ptr, stream_ptr
 
 ACT = {None: 0, "none": 0, "relu": 1, "leakyrelu": 2, "sigmoid": 3, "tanh": 4}
 _seed_counter = itertools.count(1)
+_seed_dev = {}
 
 
 def next_seed():
     return (torch.initial_seed() * 0x9E3779B1 + next(_seed_counter) * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+
+
+def seed_dev(device):
+    """device-resident dropout seed offset (added to every layer's host seed): graphed.GraphedStep bumps it inside the
+    captured graph so that replays draw fresh masks"""
+    key = (device.type, device.index)
+    if key not in _seed_dev:
+        _seed_dev[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _seed_dev[key]
+
+
+_tickets = {}
+
+
+def tickets(device):
+    """self-resetting ticket words of the fused weight-gradient reduction (one buffer per device: the layer kernels of
+    a step all run on one stream)"""
+    key = (device.type, device.index)
+    if key not in _tickets:
+        _tickets[key] = torch.zeros(1024, dtype=torch.int32, device=device)
+    return _tickets[key]
+
+
+def bump_seed(device, inc=0x9E3779B97F4A7C15):
+    check(load().fr_bump_u64(ptr(seed_dev(device)), inc & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "fr_bump_u64")
 
 
 def _ws(nbytes, device):
@@ -29,8 +55,9 @@ class LinearAct(torch.autograd.Function):
         M, K = X.shape
         N = W.shape[0]
         Y = torch.empty((M, N), dtype=torch.float32, device=X.device)
-        check(lib.fr_linear_forward(ptr(X), ptr(W), ptr(b), ptr(Y), M, K, N, act, float(drop_p), seed, 0, stream_ptr()),
-              "fr_linear_forward")
+        sd = seed_dev(X.device) if drop_p > 0 else None
+        check(lib.fr_linear_forward(ptr(X), ptr(W), ptr(b), ptr(Y), M, K, N, act, float(drop_p), seed, ptr(sd), 0,
+                                    stream_ptr()), "fr_linear_forward")
         ctx.save_for_backward(X, W, Y)
         ctx.cfg = (act, float(drop_p), seed, b is not None)
         return Y
@@ -47,8 +74,10 @@ class LinearAct(torch.autograd.Function):
         dW = torch.empty_like(W)
         db = torch.empty(N, dtype=torch.float32, device=X.device) if has_b else None
         ws = _ws(lib.fr_linear_backward_workspace_bytes(M, K, N), X.device)
-        check(lib.fr_linear_backward(ptr(X), ptr(W), ptr(Y), ptr(dY), M, K, N, act, drop_p, seed, 0, ptr(dX), ptr(dW),
-                                     ptr(db), ptr(ws), ws.numel(), stream_ptr()), "fr_linear_backward")
+        sd = seed_dev(X.device) if drop_p > 0 else None
+        check(lib.fr_linear_backward(ptr(X), ptr(W), ptr(Y), ptr(dY), M, K, N, act, drop_p, seed, ptr(sd), 0, ptr(dX),
+                                     ptr(dW), ptr(db), ptr(tickets(X.device)), ptr(ws), ws.numel(), stream_ptr()),
+              "fr_linear_backward")
         return dX, dW, db, None, None, None
 
 
@@ -63,9 +92,10 @@ class BatchNormAct(torch.autograd.Function):
         Y = torch.empty_like(X)
         sm = torch.empty(N, dtype=torch.float32, device=X.device)
         si = torch.empty(N, dtype=torch.float32, device=X.device)
+        ws = _ws(lib.fr_batchnorm_workspace_bytes(N), X.device)
         check(lib.fr_batchnorm_forward(ptr(X), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), M, N, float(momentum),
-                                       float(eps), 1 if training else 0, act, ptr(Y), ptr(sm), ptr(si), stream_ptr()),
-              "fr_batchnorm_forward")
+                                       float(eps), 1 if training else 0, act, ptr(Y), ptr(sm), ptr(si), ptr(ws),
+                                       ws.numel(), stream_ptr()), "fr_batchnorm_forward")
         ctx.save_for_backward(X, Y, gamma, sm, si)
         ctx.cfg = (act, training)
         return Y
@@ -79,8 +109,10 @@ class BatchNormAct(torch.autograd.Function):
             raise NotImplementedError("BatchNormAct backward is implemented for training mode (batch statistics)")
         M, N = X.shape
         dX, dg, db = torch.empty_like(X), torch.empty_like(gamma), torch.empty_like(gamma)
+        ws = _ws(lib.fr_batchnorm_workspace_bytes(N), X.device)
         check(lib.fr_batchnorm_backward(ptr(X), ptr(Y), ptr(dY.contiguous()), ptr(gamma), ptr(sm), ptr(si), M, N, act,
-                                        ptr(dX), ptr(dg), ptr(db), stream_ptr()), "fr_batchnorm_backward")
+                                        ptr(dX), ptr(dg), ptr(db), ptr(ws), ws.numel(), stream_ptr()),
+              "fr_batchnorm_backward")
         return dX, dg, db, None, None, None, None, None, None
 
 
@@ -439,16 +471,34 @@ def biased_score(dot, ub, ib, gb, act):
 
 class AdamGroup:
     """torch.optim.Adam(params, lr, weight_decay) semantics (betas 0.9/0.999, eps 1e-8, L2 form, per-parameter step
-    counts, parameters without a gradient skipped) on fr_adam_multi: one launch per 48 parameter tensors."""
+    counts, parameters without a gradient skipped) on fr_adam_multi: one launch per 48 parameter tensors.  The step
+    counts live on the device (bumped on the stream right before each update), so a step captured in a CUDA graph
+    keeps the right bias correction on every replay."""
 
     def __init__(self, params, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
         self.params = [p for p in params]
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.state = {}
+        self._steps = None          # int32 [n_params] on the device
+        self._index = {id(p): i for i, p in enumerate(self.params)}
 
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+
+    def _ensure(self, p):
+        st = self.state.get(p)
+        if st is None:
+            st = self.state[p] = {"exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
+        if self._steps is None:
+            self._steps = torch.zeros(len(self.params), dtype=torch.int32, device=p.device)
+        return st
+
+    def init_state(self):
+        """allocate every moment buffer up front (needed before capturing a step in a CUDA graph)"""
+        for p in self.params:
+            if p.requires_grad:
+                self._ensure(p)
 
     def step(self):
         from ._lib import AdamEntry
@@ -457,14 +507,12 @@ class AdamGroup:
         for p in self.params:
             if p.grad is None or not p.requires_grad:
                 continue
-            st = self.state.get(p)
-            if st is None:
-                st = self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
-            st["step"] += 1
+            st = self._ensure(p)
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             st["_g"] = g                                    # keep alive until the kernel ran
             entries.append(AdamEntry(p.data.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
-                                     st["exp_avg_sq"].data_ptr(), p.numel(), st["step"]))
+                                     st["exp_avg_sq"].data_ptr(), p.numel(), 0,
+                                     self._steps.data_ptr() + 4 * self._index[id(p)]))
         if not entries:
             return
         arr = (AdamEntry * len(entries))(*entries)
@@ -472,10 +520,15 @@ class AdamGroup:
                                 stream_ptr()), "fr_adam_multi")
 
     def state_dict(self):
-        return {"state": {i: {k: v for k, v in self.state[p].items() if k != "_g"}
+        steps = self._steps.cpu().tolist() if self._steps is not None else [0] * len(self.params)
+        return {"state": {i: {"step": steps[i], **{k: v for k, v in self.state[p].items() if k != "_g"}}
                           for i, p in enumerate(self.params) if p in self.state},
                 "param_groups": [{"lr": self.lr, "weight_decay": self.weight_decay, "betas": self.betas, "eps": self.eps}]}
 
     def load_state_dict(self, sd):
         for i, st in sd["state"].items():
-            self.state[self.params[int(i)]] = dict(st)
+            p = self.params[int(i)]
+            cur = self._ensure(p)
+            cur["exp_avg"].copy_(st["exp_avg"])
+            cur["exp_avg_sq"].copy_(st["exp_avg_sq"])
+            self._steps[int(i)] = int(st.get("step", 0))

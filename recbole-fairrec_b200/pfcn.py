@@ -135,8 +135,15 @@ class _PFCNBase(nn.Module):
         return user_embed, (None if item is None else self._item_base(item))
 
     def calculate_dis_loss(self, interaction, sst_list=None):
-        """pfcn_mlp.py:195-211"""
-        user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
+        """pfcn_mlp.py:195-211.  Called on its own (the discriminator phase, trainer.py:889-892) only the discriminators
+        are optimised, so the filtered embedding enters as a constant: the reference back-propagates into the filters
+        and embeddings here too, but no optimizer step ever uses those gradients (they are zeroed by the filter
+        optimizer before its own backward).  `calculate_loss` uses _dis_terms with the graph intact."""
+        with torch.no_grad():
+            user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
+        return self._dis_terms(user_embed, interaction, sst_list)
+
+    def _dis_terms(self, user_embed, interaction, sst_list):
         dev = user_embed.device
         loss = 0.0
         for sst in sst_list:
@@ -148,8 +155,11 @@ class _PFCNBase(nn.Module):
         return loss
 
     def _with_dis(self, bpr, interaction, sst_list):
+        """pfcn_mlp.py:188-191: the reference re-evaluates forward(user) inside calculate_dis_loss (a second pass through
+        the filter in training mode: BatchNorm running statistics advance twice per step) -- kept"""
         if self.filter_mode != "none":
-            return bpr - self.dis_weight * self.calculate_dis_loss(interaction, sst_list)
+            user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
+            return bpr - self.dis_weight * self._dis_terms(user_embed, interaction, sst_list)
         return bpr
 
     def full_sort_predict(self, interaction, sst_list=None):
@@ -314,6 +324,8 @@ class PFCNTrainer:
 
     def _pass(self, train_data, loss_func, optimizer, sst_list):
         self.model.train()
+        if self.config["use_cuda_graph"]:
+            return self._pass_graphed(train_data, loss_func, optimizer, sst_list)
         total = None
         for interaction in train_data:
             optimizer.zero_grad()
@@ -325,6 +337,23 @@ class PFCNTrainer:
             loss.backward()
             optimizer.step()
         return total
+
+    def _pass_graphed(self, train_data, loss_func, optimizer, sst_list):
+        """`use_cuda_graph: True`: one CUDA-graph replay per batch (graphed.py); the per-batch losses are summed on the
+        device and read back once per pass (the NaN check of trainer.py:192 moves to the end of the pass)"""
+        from .graphed import GraphedSteps
+        if getattr(self, "_graphs", None) is None:
+            self._graphs = GraphedSteps(next(self.model.parameters()).device)
+            self._graph_gen = 0
+        total = None
+        name = f"{loss_func.__name__}:{id(optimizer)}:{getattr(self.model, 'train_stage', '')}"
+        for interaction in train_data:
+            loss = self._graphs.run(name, loss_func, optimizer, sst_list, interaction)
+            total = loss.clone() if total is None else total + loss
+        v = float(total.item()) if total is not None else None
+        if v is not None and v != v:
+            raise ValueError("Training loss is nan")
+        return v
 
     def _train_epoch(self, train_data, epoch_idx):
         if self.filter_mode == "none":
