@@ -168,7 +168,9 @@ def run_ours(args, wname):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints there)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         group = dist.group.WORLD
 
     def barrier():
@@ -272,9 +274,14 @@ def run_ours(args, wname):
         rows_ss = 0
         t_end = time.time() + 0.7
         a.record()
-        while time.time() < t_end:
-            rows_ss += runner.run(G) if use_graph else dev_step()
-            n_ss += G if use_graph else 1
+        if world > 1:   # every rank must issue the SAME number of collectives: fixed step count, not a wall-clock window
+            for _ in range(args.steps):
+                rows_ss += dev_step()
+                n_ss += 1
+        else:
+            while time.time() < t_end:
+                rows_ss += runner.run(G) if use_graph else dev_step()
+                n_ss += G if use_graph else 1
         b.record()
         torch.cuda.synchronize()
         ss_ms = a.elapsed_time(b)
