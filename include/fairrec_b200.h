@@ -148,15 +148,21 @@ size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int3
 /* zero the persistent part of a fresh workspace (row-stamp tables); call once after allocation */
 int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
                            int32_t max_batch, void *stream);
-/* set the workspace's device-resident counters (-1 leaves one unchanged): the planned-batch cursor and the Adam
- * step count used when fr_focf_step.step <= 0 */
+/* set the workspace's device-resident counters: the planned-batch cursor (< 0: unchanged), the Adam step count used
+ * when fr_focf_step.step <= 0 (INT32_MIN: unchanged) and how far both advance per step (< 1: unchanged; 2 when two
+ * workspaces alternate the batches of one plan, see fr_focf_step_prepare / fr_focf_step_compute) */
 int fr_focf_set_counters(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
-                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, void *stream);
+                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, int32_t stride, void *stream);
 int fr_focf_forward(const fr_focf_step *s, void *stream);
 /* needs the workspace left by fr_focf_forward for the same batch; grad_scale = upstream dL (usually 1) */
 int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream);
 int fr_focf_adam(const fr_focf_step *s, void *stream);
 int fr_focf_train_step(const fr_focf_step *s, void *stream);
+/* fr_focf_train_step in two halves, for overlapping the preparation of batch t+1 (its own stream and workspace) with the
+ * compute of batch t: prepare = planned batch gather + sort / segments / row stamps (does not touch the embedding
+ * tables); compute = forward + loss + gradients + Adam (one cooperative launch for small batches) */
+int fr_focf_step_prepare(const fr_focf_step *s, void *stream);
+int fr_focf_step_compute(const fr_focf_step *s, void *stream);
 
 /* focf_dataloader.py:37-50 (FOCFDataLoader._next_batch_data) + dataset join of the user feature: build the
  * batch = all train rows of the drawn items.  The train split is device resident, sorted by item:

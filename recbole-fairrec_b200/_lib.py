@@ -91,7 +91,10 @@ SIGNATURES = {
     "fr_sort_pairs_u32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "fr_focf_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "fr_focf_workspace_init": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    "fr_focf_set_counters": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "fr_focf_set_counters": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_void_p]),
+    "fr_focf_step_prepare": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_focf_step_compute": (c_int, [POINTER(FocfStep), c_void_p]),
     "fr_focf_forward": (c_int, [POINTER(FocfStep), c_void_p]),
     "fr_focf_backward": (c_int, [POINTER(FocfStep), c_float, c_void_p]),
     "fr_focf_adam": (c_int, [POINTER(FocfStep), c_void_p]),

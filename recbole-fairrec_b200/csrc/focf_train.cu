@@ -16,6 +16,8 @@
 // Algorithmic HBM bytes: per interaction 16*d+16 (gather 2 rows fwd, gather 2 rows bwd,
 // ids/rating/sst); per step 24*(n_users+n_items)*d for the dense Adam sweep (p,m,v read + write) --
 // the dense gradient is never materialised in fr_focf_train_step.
+#include <stdlib.h>
+
 #include "sort.cuh"
 
 namespace fr {
@@ -35,6 +37,8 @@ enum {
   CTRL_CURSOR = 6,     // planned-batch cursor (fr_focf_plan): which batch of the epoch plan comes next
   CTRL_ADAM_T = 7,     // device-resident Adam step count (used when fr_focf_step.step <= 0)
   CTRL_B = 8,          // device-resident batch size (planned batches)
+  CTRL_GRID_BAR = 9,   // arrival counter of the fused step's grid barrier (monotonic)
+  CTRL_STRIDE = 10,    // how far CTRL_CURSOR / CTRL_ADAM_T advance per step (2 when two workspaces alternate batches)
   CTRL_WORDS = 64
 };
 // batch size: host value unless a device-resident one is given (CUDA-graph replay over batches of varying size)
@@ -94,11 +98,10 @@ static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
 // One warp per entry: lanes cover the row with float4 loads (d floats = d/4 lanes per 128 columns).
 // Also folds the batch min/max of the sensitive attribute (the "rank among present values" of
 // torch.unique, focf.py:77) into two integer atomics.
-__global__ void __launch_bounds__(256)
-    k_forward(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
-              const int32_t *__restrict__ iid, const float *__restrict__ sst, int B, const int32_t *__restrict__ B_dev,
-              int d, float *__restrict__ pred, uint32_t *__restrict__ ctrl) {
-  B = FR_B(B, B_dev);
+__device__ __forceinline__ void forward_body(const float *__restrict__ U, const float *__restrict__ I,
+                                             const int32_t *__restrict__ uid, const int32_t *__restrict__ iid,
+                                             const float *__restrict__ sst, int B, int d, float *__restrict__ pred,
+                                             uint32_t *__restrict__ ctrl) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t lo = 0xffffffffu, hi = 0u;
@@ -137,6 +140,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+__global__ void __launch_bounds__(256)
+    k_forward(const float *__restrict__ U, const float *__restrict__ I, const int32_t *__restrict__ uid,
+              const int32_t *__restrict__ iid, const float *__restrict__ sst, int B, const int32_t *__restrict__ B_dev,
+              int d, float *__restrict__ pred, uint32_t *__restrict__ ctrl) {
+  forward_body(U, I, uid, iid, sst, FR_B(B, B_dev), d, pred, ctrl);
+}
+
 // ------------------------------------------------------------------------------------------ segment loss
 // Item x group statistics, fairness objective and loss (appendix A.1/A.2 of SURVEY.md) in one launch with an even
 // work split that does not depend on item popularity:
@@ -169,7 +179,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float *sh) {  // sh: >=
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = (threadIdx.x < 32) ? sh[threadIdx.x] : 0.f;
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;   // any block size up to 1024 threads
   if (threadIdx.x < 32) {
     t = warp_sum(t);
     if (threadIdx.x == 0) sh[32] = t;
@@ -180,21 +190,45 @@ __device__ __forceinline__ float block_sum_1024(float v, float *sh) {  // sh: >=
   return t;
 }
 
-__global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
-  __shared__ float sh[33];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int J = *a.J;
-  const int B = FR_B(a.B, a.B_dev);
-  const float Bn = (float)(a.norm_B > 0 ? a.norm_B : B), Jn = (float)(a.norm_J > 0 ? a.norm_J : J);
-  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
+// fairness objective of ONE item segment (appendix A.1/A.2 of SURVEY.md): smooth-L1 term hx and the additive
+// dL/dpred terms cs0 / cs1 of the segment's two groups
+__device__ __forceinline__ void segment_terms(int objective, float fair_weight, float Jn, float sp0, float sp1, float st0,
+                                              float st1, float c0, float c1, float &hx, float &cs0, float &cs1) {
+  const float n0 = c0 + 1e-5f, n1 = c1 + 1e-5f;                       // focf.py:89
+  const float P0 = sp0 / n0, P1 = sp1 / n1, T0 = st0 / n0, T1 = st1 / n1;  // focf.py:91
+  float D0, D1, dd0, dd1;
+  switch (objective) {
+    case FR_OBJ_VALUE:    D0 = P0 - T0; D1 = P1 - T1; dd0 = 1.f; dd1 = 1.f; break;
+    case FR_OBJ_ABSOLUTE: {
+      const float e0 = P0 - T0, e1 = P1 - T1;
+      D0 = fabsf(e0); D1 = fabsf(e1);
+      dd0 = (e0 > 0.f) - (e0 < 0.f); dd1 = (e1 > 0.f) - (e1 < 0.f);
+    } break;
+    case FR_OBJ_UNDER: {
+      const float e0 = T0 - P0, e1 = T1 - P1;
+      D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
+      dd0 = e0 > 0.f ? -1.f : 0.f; dd1 = e1 > 0.f ? -1.f : 0.f;
+    } break;
+    default: {
+      const float e0 = P0 - T0, e1 = P1 - T1;
+      D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
+      dd0 = e0 > 0.f ? 1.f : 0.f; dd1 = e1 > 0.f ? 1.f : 0.f;
+    }
+  }
+  const float z = D0 - D1, x = fabsf(z);
+  hx = x < 1.f ? 0.5f * x * x : x - 0.5f;                              // smooth_l1, beta = 1
+  const float hp = (x < 1.f ? x : 1.f) * (float)((z > 0.f) - (z < 0.f));
+  const float q = fair_weight * hp / Jn;
+  cs0 = q * dd0 / n0;
+  cs1 = -q * dd1 / n1;
+}
 
-  // ---------------- phase 1
+__device__ __forceinline__ void loss_phase1(const LossArgs &a, int B) {
+  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
   {
-    const int t = blockIdx.x * kLossThreads + threadIdx.x;
-    const int lo = t * kLossRows, hi = lo + kLossRows;
     int bad = 0;
-    if (lo < B) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t * kLossRows < B; t += gridDim.x * blockDim.x) {
+      const int lo = t * kLossRows, hi = lo + kLossRows;
       float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int cur = a.segid_i[lo];
       auto flush = [&](int sgm) {
@@ -245,17 +279,15 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
     if (a.objective != FR_OBJ_NONE && bad) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
   }
 
-  // ---------------- last-CTA election (self-resetting ticket)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+}
 
-  // ---------------- phase 2: warp per segment
+// one CTA (any multiple of 32 threads up to 1024): warp per segment, then the loss and the control-block hand-over
+__device__ __forceinline__ void loss_phase2(const LossArgs &a, int B, float *sh) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int J = *a.J;
+  const float Bn = (float)(a.norm_B > 0 ? a.norm_B : B), Jn = (float)(a.norm_J > 0 ? a.norm_J : J);
   float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;  // lane 0 accumulates over its segments
-  for (int j = wib; j < J; j += kLossThreads / 32) {
+  for (int j = wib; j < J; j += (int)(blockDim.x >> 5)) {
     const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
     const int t0 = s0 / kLossRows, t1 = (s1 - 1) / kLossRows;
     float v[7];
@@ -279,33 +311,7 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
       w_sq += v[6];
       float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
       if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-        const float n0 = c0 + 1e-5f, n1 = c1 + 1e-5f;                       // focf.py:89
-        const float P0 = sp0 / n0, P1 = sp1 / n1, T0 = st0 / n0, T1 = st1 / n1;  // focf.py:91
-        float D0, D1, dd0, dd1;
-        switch (a.objective) {
-          case FR_OBJ_VALUE:    D0 = P0 - T0; D1 = P1 - T1; dd0 = 1.f; dd1 = 1.f; break;
-          case FR_OBJ_ABSOLUTE: {
-            const float e0 = P0 - T0, e1 = P1 - T1;
-            D0 = fabsf(e0); D1 = fabsf(e1);
-            dd0 = (e0 > 0.f) - (e0 < 0.f); dd1 = (e1 > 0.f) - (e1 < 0.f);
-          } break;
-          case FR_OBJ_UNDER: {
-            const float e0 = T0 - P0, e1 = T1 - P1;
-            D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
-            dd0 = e0 > 0.f ? -1.f : 0.f; dd1 = e1 > 0.f ? -1.f : 0.f;
-          } break;
-          default: {
-            const float e0 = P0 - T0, e1 = P1 - T1;
-            D0 = e0 > 0.f ? e0 : 0.f; D1 = e1 > 0.f ? e1 : 0.f;
-            dd0 = e0 > 0.f ? 1.f : 0.f; dd1 = e1 > 0.f ? 1.f : 0.f;
-          }
-        }
-        const float z = D0 - D1, x = fabsf(z);
-        hx = x < 1.f ? 0.5f * x * x : x - 0.5f;                              // smooth_l1, beta = 1
-        const float hp = (x < 1.f ? x : 1.f) * (float)((z > 0.f) - (z < 0.f));
-        const float q = a.fair_weight * hp / Jn;
-        cs0 = q * dd0 / n0;
-        cs1 = -q * dd1 / n1;
+        segment_terms(a.objective, a.fair_weight, Jn, sp0, sp1, st0, st1, c0, c1, hx, cs0, cs1);
       } else if (a.objective == FR_OBJ_NONPARITY) {
         w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
       }
@@ -348,9 +354,24 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
     a.ctrl[CTRL_MAX] = 0u;
     a.ctrl[CTRL_TICKET] = 0u;
     a.ctrl[CTRL_STAMP] += 1u;
-    a.ctrl[CTRL_CURSOR] += 1u;
-    if (a.advance_adam) a.ctrl[CTRL_ADAM_T] += 1u;
+    a.ctrl[CTRL_CURSOR] += a.ctrl[CTRL_STRIDE];
+    if (a.advance_adam) a.ctrl[CTRL_ADAM_T] += a.ctrl[CTRL_STRIDE];
   }
+}
+
+__global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
+  __shared__ float sh[33];
+  __shared__ bool is_last;
+  const int B = FR_B(a.B, a.B_dev);
+  loss_phase1(a, B);
+  // ---------------- last-CTA election (self-resetting ticket)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  loss_phase2(a, B, sh);
 }
 
 // ------------------------------------------------------------------------------------------ gradients
@@ -372,12 +393,12 @@ struct GradArgs {
   float grad_scale;
   int chunk;   // sorted entries per warp (8 or 32)
   float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;
+  int pre_handover;   // fused step: the control block has not been handed over yet -> read CTRL_MIN, not CTRL_SAVED_MIN
 };
 
 template <int kRowVecs>
-__global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
+__device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c) {   // c in [0, 2 * nchunk): one warp
   const int lane = threadIdx.x & 31;
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const bool user_side = c >= nchunk;
   if (user_side) c -= nchunk;
   const int chunk = a.chunk;
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   float *tail = user_side ? a.tail_u : a.tail_i;
   const int d = a.d;
   const int nvalid = min(chunk, B - pbase);
-  const float vmin = ord2f(a.ctrl[CTRL_SAVED_MIN]);
+  const float vmin = ord2f(a.ctrl[a.pre_handover ? CTRL_MIN : CTRL_SAVED_MIN]);
 
   // lane l stages entry pbase + l
   int my_seg = -1, my_oid = 0;
@@ -466,6 +487,11 @@ __global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
   flush(cur);
 }
 
+template <int kRowVecs>
+__global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
+  grads_chunk<kRowVecs>(a, nchunk, (blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+}
+
 // ------------------------------------------------------------------------------------------ apply
 // One thread per float4 of the concatenated [U ; I] parameter space.  The row's gradient is read from the
 // segment partials when the row was touched by this batch (row_tab stamp), else it is zero; then either
@@ -484,6 +510,7 @@ struct ApplyArgs {
   int step;
   double lr, beta1, beta2, eps, wd;
   int chunk;   // the gradient kernel's chunk size (head/tail partial indexing)
+  int pre_handover;   // fused step: CTRL_STAMP / CTRL_ADAM_T still hold the values from before this batch's hand-over
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -499,11 +526,11 @@ __device__ __forceinline__ float adam1(float &p, float &m, float &v, float g, fl
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
-  __shared__ float sc[3];
+__device__ __forceinline__ void apply_body(const ApplyArgs &a, float *sc) {
   if (kMode != kDenseOut) {
     if (threadIdx.x == 0) {
-      const double t = a.step > 0 ? (double)a.step : (double)a.ctrl[CTRL_ADAM_T];
+      const double t = a.step > 0 ? (double)a.step
+                                  : (double)(a.ctrl[CTRL_ADAM_T] + (a.pre_handover ? a.ctrl[CTRL_STRIDE] : 0u));
       const double bc1 = 1.0 - pow(a.beta1, t);
       const double bc2 = 1.0 - pow(a.beta2, t);
       sc[0] = (float)(-a.lr / bc1);
@@ -517,7 +544,7 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
               eps = (float)a.eps;
   const int dq = a.d >> 2;
   const size_t nq_u = (size_t)a.n_users * dq, nq = nq_u + (size_t)a.n_items * dq;
-  const uint32_t stamp = a.ctrl[CTRL_STAMP] - 1u;  // k_segment_loss already advanced it
+  const uint32_t stamp = a.ctrl[CTRL_STAMP] - (a.pre_handover ? 0u : 1u);  // k_segment_loss already advanced it
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
     const bool is_item = q >= nq_u;
     const size_t ql = is_item ? q - nq_u : q;
@@ -558,6 +585,164 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
       stg_stream(pm, m);
       stg_stream(pv, v);
     }
+  }
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
+  __shared__ float sc[3];
+  apply_body<kMode>(a, sc);
+}
+
+// ------------------------------------------------------------------------------------------ fused step
+// Batches at the ML-1M shape are a few thousand rows against ~15 MB of state: every kernel of the step is launch- /
+// latency-bound, so forward -> loss -> gradients -> Adam run as ONE cooperative launch (one CTA per SM) separated by
+// grid-wide barriers instead of four dependent launches.  The barrier is a monotonically increasing arrival counter in
+// the control block (cooperative launch guarantees that all CTAs are co-resident, so spinning cannot deadlock).
+__device__ __forceinline__ void grid_barrier(uint32_t *bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t n = gridDim.x;
+    const uint32_t target = (atomicAdd(bar, 1u) / n + 1u) * n;
+    while ((int32_t)(*(volatile uint32_t *)bar - target) < 0) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct FusedArgs {
+  const float *U, *I;
+  const int32_t *uid, *iid;
+  const float *sst;
+  int B, d;
+  const int32_t *B_dev;
+  float *pred;
+  LossArgs loss;
+  GradArgs grad;
+  ApplyArgs apply;
+  int cap;          // rows the shared-memory staging is sized for (>= any batch)
+  uint32_t *ctrl;
+};
+constexpr int kFusedThreads = 512;
+static size_t fused_smem_bytes(int cap) { return ((size_t)5 * cap + 8) * sizeof(float); }
+
+// Item x group statistics of the WHOLE batch, computed redundantly by every CTA out of shared memory: the batch is a
+// few thousand rows (36 KB of pred / rating / sst), so re-reading it per CTA is cheaper than a grid-wide hand-over --
+// it removes the single-CTA reduction phase and one grid barrier from the step.  Rows are staged with one coalesced
+// sweep, then a warp owns a segment (lanes stride its rows: popularity skew costs shared-memory, not DRAM, round
+// trips).  Every CTA runs the same code on the same data in the same order -> bit-identical cseg everywhere.
+// Returns (on thread 0 of CTA 0 only meaningful) the batch loss.
+__device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, float *sm, float *sh, float *s_cseg,
+                                             float *s_cglob) {
+  float *s_pred = sm, *s_rat = sm + cap, *s_sst = sm + 2 * cap;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int J = *a.J;
+  const float Bn = (float)B, Jn = (float)J;
+  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
+  for (int p = threadIdx.x; p < B; p += blockDim.x) {
+    const int b = a.ord_i ? (int)a.ord_i[p] : p;     // item-sorted order (identity for whole-item batches)
+    s_pred[p] = a.pred[b];
+    s_rat[p] = a.rating[b];
+    s_sst[p] = a.sst[b];
+  }
+  __syncthreads();
+  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;
+  int bad = 0;
+  for (int j = wib; j < J; j += nw) {
+    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
+    float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
+    for (int p = s0 + lane; p < s1; p += 32) {
+      const float pr = s_pred[p], r = s_rat[p], sv = s_sst[p];
+      const bool g = sv != vmin;
+      bad |= (g && sv != vmax);
+      const float df = pr - r;
+      sq = fmaf(df, df, sq);
+      if (g) { sp1 += pr; st1 += r; c1 += 1.f; } else { sp0 += pr; st0 += r; c0 += 1.f; }
+    }
+    sp0 = warp_sum(sp0); sp1 = warp_sum(sp1); st0 = warp_sum(st0); st1 = warp_sum(st1);
+    c0 = warp_sum(c0); c1 = warp_sum(c1); sq = warp_sum(sq);
+    if (lane == 0) {
+      float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
+      w_sq += sq;
+      if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+        segment_terms(a.objective, a.fair_weight, Jn, sp0, sp1, st0, st1, c0, c1, hx, cs0, cs1);
+      } else if (a.objective == FR_OBJ_NONPARITY) {
+        w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
+      }
+      w_hx += hx;
+      s_cseg[2 * j] = cs0;
+      s_cseg[2 * j + 1] = cs1;
+    }
+  }
+  if (blockIdx.x == 0 && a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
+    atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+  const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
+  float g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
+  if (a.objective == FR_OBJ_NONPARITY) {
+    g0 = block_sum_1024(w_g0, sh); g1 = block_sum_1024(w_g1, sh);
+    n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
+  }
+  float loss = sq / Bn;
+  if (threadIdx.x == 0) {
+    float cg0 = 0.f, cg1 = 0.f;
+    if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+      loss += a.fair_weight * (hx / Jn);
+    } else if (a.objective == FR_OBJ_NONPARITY) {
+      if (n1 == 0.f || n0 == 0.f) {
+        if (blockIdx.x == 0) atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
+      } else {
+        const float z = g0 / n0 - g1 / n1, x = fabsf(z);
+        loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
+        const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
+        cg0 = hp / n0;
+        cg1 = -hp / n1;
+      }
+    }
+    s_cglob[0] = cg0;
+    s_cglob[1] = cg1;
+  }
+  __syncthreads();
+  return loss;
+}
+
+// forward | barrier | batch statistics (per CTA, shared memory) + gradients | barrier | Adam | barrier | hand-over
+template <int kRowVecs>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_focf_fused_step(FusedArgs f) {
+  extern __shared__ __align__(16) float fused_sm[];
+  __shared__ float sh[33];
+  __shared__ float sc[3];
+  float *s_cseg = fused_sm + 3 * f.cap, *s_cglob = fused_sm + 5 * f.cap;
+  uint32_t *bar = f.ctrl + CTRL_GRID_BAR;
+  const int B = FR_B(f.B, f.B_dev);
+  forward_body(f.U, f.I, f.uid, f.iid, f.sst, B, f.d, f.pred, f.ctrl);
+  grid_barrier(bar);
+  const float loss = fused_stats(f.loss, B, f.cap, fused_sm, sh, s_cseg, s_cglob);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const LossArgs &a = f.loss;
+    a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor : 0u] = loss;
+    if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
+  }
+  {
+    GradArgs g = f.grad;
+    g.cseg = s_cseg;
+    g.cglob = s_cglob;
+    const int nchunk = (B + g.chunk - 1) / g.chunk;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = warp; c < 2 * nchunk; c += nwarps) grads_chunk<kRowVecs>(g, nchunk, c);
+  }
+  grid_barrier(bar);
+  apply_body<kAdamFused>(f.apply, sc);
+  grid_barrier(bar);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // hand the control block over to the next batch (cf. loss_phase2)
+    uint32_t *ctrl = f.ctrl;
+    ctrl[CTRL_SAVED_MIN] = ctrl[CTRL_MIN];
+    ctrl[CTRL_SAVED_MAX] = ctrl[CTRL_MAX];
+    ctrl[CTRL_MIN] = 0xffffffffu;
+    ctrl[CTRL_MAX] = 0u;
+    ctrl[CTRL_STAMP] += 1u;
+    ctrl[CTRL_CURSOR] += ctrl[CTRL_STRIDE];
+    if (f.loss.advance_adam) ctrl[CTRL_ADAM_T] += ctrl[CTRL_STRIDE];
   }
 }
 
@@ -778,9 +963,10 @@ __global__ void __launch_bounds__(kPsThreads)
   }
 }
 
-__global__ void k_set_ctrl(uint32_t *ctrl, int cursor, int adam_t) {
+__global__ void k_set_ctrl(uint32_t *ctrl, int cursor, int adam_t, int stride) {
   if (cursor >= 0) ctrl[CTRL_CURSOR] = (uint32_t)cursor;
-  if (adam_t >= 0) ctrl[CTRL_ADAM_T] = (uint32_t)adam_t;
+  if (adam_t != INT32_MIN) ctrl[CTRL_ADAM_T] = (uint32_t)adam_t;   // -1 is a legal start with stride 2 (becomes 1 on the first step)
+  if (stride >= 1) ctrl[CTRL_STRIDE] = (uint32_t)stride;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -822,7 +1008,8 @@ static const int32_t *dev_B(const fr_focf_step *s, const FocfWs &w) {
   return planned(s) ? (const int32_t *)(w.ctrl + CTRL_B) : s->B_dev;
 }
 
-static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, bool advance_adam) {
+// batch gather (planned) + sort / segment preparation of both sides
+static int prepare_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st) {
   const int B = s->B;  // upper bound when dev_B() is set
   const int32_t *Bd = dev_B(s, w);
   const bool contiguous = s->items_contiguous || planned(s);
@@ -858,21 +1045,42 @@ static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
     build_segments(w.skey_u, w.ord_u, B, Bd, w.segid_u, w.segoff_u, w.Ju, w.row_tab_u, w.ctrl + CTRL_STAMP, nullptr,
                    w.seg, st);
   }
+  return FR_OK;
+}
+
+static LossArgs loss_args(const fr_focf_step *s, const FocfWs &w, bool advance_adam) {
+  const bool contiguous = s->items_contiguous || planned(s);
+  return LossArgs{s->pred, s->rating, s->sst, contiguous ? nullptr : w.ord_i, w.segid_i, w.segoff_i, w.J, s->B, dev_B(s, w),
+                  planned(s) ? s->plan_len : 0, advance_adam ? 1 : 0, s->objective, s->norm_B, s->norm_J, s->fair_weight,
+                  w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl, s->status_flags};
+}
+
+static int forward_only_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, bool advance_adam);
+static int forward_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, bool advance_adam) {
+  int rc = prepare_impl(s, w, st);
+  if (rc) return rc;
+  return forward_only_impl(s, w, st, advance_adam);
+}
+
+static int forward_only_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, bool advance_adam) {
+  const int B = s->B;
+  const int32_t *Bd = dev_B(s, w);
   FR_LAUNCH(k_forward, grid_for((int64_t)B, 32), 256, 0, st, s->U, s->I, s->uid, s->iid, s->sst, B, Bd, s->d, s->pred,
             w.ctrl);
-  LossArgs la{s->pred, s->rating, s->sst, ord_i, w.segid_i, w.segoff_i, w.J, B, Bd, planned(s) ? s->plan_len : 0,
-              advance_adam ? 1 : 0,
-              s->objective, s->norm_B, s->norm_J, s->fair_weight, w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl,
-              s->status_flags};
+  LossArgs la = loss_args(s, w, advance_adam);
   FR_LAUNCH(k_segment_loss, (B + kLossThreads * kLossRows - 1) / (kLossThreads * kLossRows), kLossThreads, 0, st, la);
   return FR_OK;
 }
 
-static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale, cudaStream_t st) {
+static GradArgs grad_args(const fr_focf_step *s, const FocfWs &w, float grad_scale) {
   const uint32_t *ord_i = (s->items_contiguous || planned(s)) ? nullptr : w.ord_i;
-  GradArgs ga{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), s->norm_B, ord_i, w.ord_u,
-              w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
-              grad_chunk(s->B), w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
+  return GradArgs{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), s->norm_B, ord_i, w.ord_u,
+                  w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
+                  grad_chunk(s->B), w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
+}
+
+static void grads_impl(const fr_focf_step *s, const FocfWs &w, float grad_scale, cudaStream_t st) {
+  GradArgs ga = grad_args(s, w, grad_scale);
   const int nchunk = (s->B + ga.chunk - 1) / ga.chunk;
   const int grid = (2 * nchunk + 7) / 8;
   if (s->d <= 128) {
@@ -895,6 +1103,57 @@ static int apply_grid(const fr_focf_step *s) {
   const int64_t nq = ((int64_t)s->n_users + s->n_items) * (s->d / 4);
   // one float4 per thread while the table is small (latency-bound: maximise loads in flight), grid-stride beyond
   return grid_for(nq, 256, kSMs * 16);
+}
+
+// the fused cooperative step serves the latency-bound regime: small batches (the single-launch preparation path),
+// fused Adam, embedding rows of at most 128 floats
+static bool fused_eligible(const fr_focf_step *s) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char *e = getenv("FR_FOCF_NO_FUSED_STEP");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && s->B <= kPsMax && s->d <= 128 && s->norm_B == 0 && s->norm_J == 0 &&
+         fused_smem_bytes(s->B) <= 200 * 1024;
+}
+
+static int fused_step_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st) {
+  static int n_sm = 0, per_sm = -1;
+  if (per_sm < 0) {
+    int dev = 0;
+    FR_CUDA_OK(cudaGetDevice(&dev));
+    FR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    FR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_focf_fused_step<1>, kFusedThreads, 0));
+  }
+  if (per_sm < 1 || n_sm < 1) {
+    set_error("fr_focf_train_step: fused step kernel does not fit an SM");
+    return FR_ERR_UNSUPPORTED;
+  }
+  const size_t smem = fused_smem_bytes(s->B);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    FR_CUDA_OK(cudaFuncSetAttribute(k_focf_fused_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  GradArgs ga = grad_args(s, w, 1.0f);
+  ga.pre_handover = 1;
+  ApplyArgs aa = apply_args(s, w);
+  aa.pre_handover = 1;
+  FusedArgs f{s->U, s->I, s->uid, s->iid, s->sst, s->B, s->d, dev_B(s, w), s->pred, loss_args(s, w, s->step <= 0),
+              ga, aa, s->B, w.ctrl};
+  void *args[] = {&f};
+  const bool p = prof_on();
+  if (p) prof_begin("k_focf_fused_step", st);
+  // a few SMs are left to the preparation kernels of the NEXT batch (second stream, fr_focf_step_prepare)
+  const int grid = n_sm > 16 ? n_sm - 4 : n_sm;
+  cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_focf_fused_step<1>, dim3(grid), dim3(kFusedThreads), args, smem, st);
+  if (p) prof_end(st);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchCooperativeKernel(k_focf_fused_step) failed: %s", cudaGetErrorString(e));
+    return FR_ERR_CUDA;
+  }
+  return FR_OK;
 }
 
 }  // namespace fr
@@ -922,17 +1181,18 @@ int fr_focf_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_us
   uint32_t ctrl[fr::CTRL_WORDS] = {0};
   ctrl[fr::CTRL_STAMP] = 1u;
   ctrl[fr::CTRL_MIN] = 0xffffffffu;
+  ctrl[fr::CTRL_STRIDE] = 1u;
   FR_CUDA_OK(cudaMemcpyAsync(w.ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, st));
   FR_CUDA_OK(cudaStreamSynchronize(st));  // ctrl[] is a stack buffer
   return FR_OK;
 }
 
 int fr_focf_set_counters(void *workspace, size_t workspace_bytes, int32_t n_users, int32_t n_items, int32_t d,
-                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, void *stream) {
+                         int32_t max_batch, int32_t plan_cursor, int32_t adam_step, int32_t stride, void *stream) {
   FR_REQUIRE(workspace, "fr_focf_set_counters: null workspace");
   fr::Carver c(workspace, workspace_bytes);
   fr::FocfWs w = fr::carve(c, n_users, n_items, d, max_batch);
-  FR_LAUNCH(fr::k_set_ctrl, 1, 1, 0, stream, w.ctrl, plan_cursor, adam_step);
+  FR_LAUNCH(fr::k_set_ctrl, 1, 1, 0, stream, w.ctrl, plan_cursor, adam_step, stride);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
@@ -975,9 +1235,44 @@ int fr_focf_train_step(const fr_focf_step *s, void *stream) {
   if (rc) return rc;
   fr::FocfWs w;
   if ((rc = fr::carve_checked(s, &w, "fr_focf_train_step"))) return rc;
+  if (fr::fused_eligible(s)) {
+    if ((rc = fr::prepare_impl(s, w, (cudaStream_t)stream))) return rc;
+    if ((rc = fr::fused_step_impl(s, w, (cudaStream_t)stream))) return rc;
+    FR_LAUNCH_CHECK();
+    return FR_OK;
+  }
   if ((rc = fr::forward_impl(s, w, (cudaStream_t)stream, s->step <= 0))) return rc;
   fr::grads_impl(s, w, 1.0f, (cudaStream_t)stream);
   FR_LAUNCH(fr::k_apply<fr::kAdamFused>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+/* the two halves of fr_focf_train_step, for callers that overlap the preparation of batch t+1 (another stream, another
+ * workspace) with the compute of batch t: prepare = batch gather (planned) + sort / segments / row stamps (independent
+ * of the embedding tables); compute = forward + loss + gradients + Adam */
+int fr_focf_step_prepare(const fr_focf_step *s, void *stream) {
+  int rc = fr::check_step(s, true, "fr_focf_step_prepare");
+  if (rc) return rc;
+  fr::FocfWs w;
+  if ((rc = fr::carve_checked(s, &w, "fr_focf_step_prepare"))) return rc;
+  if ((rc = fr::prepare_impl(s, w, (cudaStream_t)stream))) return rc;
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_step_compute(const fr_focf_step *s, void *stream) {
+  int rc = fr::check_step(s, true, "fr_focf_step_compute");
+  if (rc) return rc;
+  fr::FocfWs w;
+  if ((rc = fr::carve_checked(s, &w, "fr_focf_step_compute"))) return rc;
+  if (fr::fused_eligible(s)) {
+    if ((rc = fr::fused_step_impl(s, w, (cudaStream_t)stream))) return rc;
+  } else {
+    if ((rc = fr::forward_only_impl(s, w, (cudaStream_t)stream, s->step <= 0))) return rc;
+    fr::grads_impl(s, w, 1.0f, (cudaStream_t)stream);
+    FR_LAUNCH(fr::k_apply<fr::kAdamFused>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));
+  }
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

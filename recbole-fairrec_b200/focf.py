@@ -185,34 +185,81 @@ class FOCF(nn.Module):
     @torch.no_grad()
     def planned_runner(self, loader, loss_buf, graph_steps=8):
         """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k fused steps
-        with NO per-step host work: the step's kernel sequence (gather -> prepare -> forward -> loss -> gradients ->
-        Adam) is captured once into CUDA graphs (1 step and `graph_steps` steps) and replayed; batch size, batch
-        cursor and Adam step count are device resident.  loss_buf[cursor] receives each step's loss."""
+        with NO per-step host work.  The step is captured once into CUDA graphs and replayed; batch size, batch cursor
+        and Adam step count are device resident.  loss_buf[cursor] receives each step's loss.
+
+        Two workspaces alternate the batches of the plan (even batches -> workspace 0, odd -> workspace 1): the
+        preparation of batch t+1 (gather + sort / segments / row stamps, independent of the tables) runs on a second
+        stream while batch t computes (forward + loss + gradients + Adam), so the captured graph of `graph_steps` steps
+        has a critical path of one compute per step instead of prepare + compute."""
         if self._adam is None:
             raise RuntimeError("call init_adam() before planned_runner()")
         eng = self._engine()
+        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        if getattr(self, "_eng2", None) is None or self._eng2.device != U.device:
+            self._eng2 = FocfEngine(self.n_users, self.n_items, self.embedding_size, 4096, U.device)
+            self._eng2.flags = eng.flags                      # one status word for both
+            self._cols2 = None
+        graph_steps = max(2, graph_steps + (graph_steps & 1))   # even: the pipelined graph starts on workspace 0
         plan = loader.plan_epoch_device()
         if loss_buf.numel() < plan["len"]:
             raise ValueError("loss buffer shorter than the epoch")
-        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        cap = plan["cols"][0].numel()
+        if self._cols2 is None or self._cols2[0].numel() != cap:
+            self._cols2 = tuple(torch.empty_like(c) for c in plan["cols"])
+        engines = (eng, self._eng2)
         key = (plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), graph_steps, plan["len"],
-               eng.ws.data_ptr())
-        eng.set_counters(plan_cursor=0, adam_step=self._adam["step"])
+               eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap)
         runner = _PlannedRunner(self, plan)
+        T = self._adam["step"]
         if getattr(self, "_graph_key", None) != key:
-            st = eng.planned_step(U, I, self._adam, plan, loader.train, self._objective, self.fair_weight, loss_buf)
-            eng.run_planned(st)          # eager first step: module loading, function attributes
-            runner.cursor = 1
-            self._adam["step"] += 1
+            plans = (plan, dict(plan, cols=self._cols2))
+            sts = [e.planned_step(U, I, self._adam, p, loader.train, self._objective, self.fair_weight, loss_buf)
+                   for e, p in zip(engines, plans)]
+            key = key[:6] + (eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap)     # planned_step may have grown a workspace
+            # eager first step on each workspace: module loading, function attributes
+            eng.set_counters(plan_cursor=0, adam_step=T, stride=1)
+            eng.run_planned(sts[0])
+            self._eng2.set_counters(plan_cursor=1, adam_step=T + 1, stride=1)
+            self._eng2.run_planned(sts[1])
+            runner.cursor = 2
+            T += 2
+            self._adam["step"] = T
             torch.cuda.synchronize()
             self._graphs = {}
-            for g_steps in sorted({graph_steps, 1}):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):   # capture does not execute
-                    for _ in range(g_steps):
-                        eng.run_planned(st)
-                self._graphs[g_steps] = g
-            self._graph_key, self._graph_step, self._graph_len = key, st, graph_steps
+            side = getattr(self, "_prep_stream", None) or torch.cuda.Stream(device=U.device)
+            self._prep_stream = side
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):   # capture does not execute
+                main = torch.cuda.current_stream()
+                done = [None, None]
+                side.wait_stream(main)
+                for t in range(graph_steps):
+                    k = t & 1
+                    with torch.cuda.stream(side):
+                        if done[k] is not None:
+                            side.wait_event(done[k])          # workspace k is free once its previous compute finished
+                        engines[k].run_prepare(sts[k])
+                        ready = torch.cuda.Event()
+                        ready.record(side)
+                    main.wait_event(ready)
+                    engines[k].run_compute(sts[k])
+                    done[k] = torch.cuda.Event()
+                    done[k].record(main)
+                main.wait_stream(side)
+            self._graphs[graph_steps] = g
+            for k in (0, 1):            # single steps (tail of an epoch): prepare + compute back to back
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    engines[k].run_planned(sts[k])
+                self._graphs[("one", k)] = g1
+            self._graph_key, self._graph_step, self._graph_len = key, sts[0], graph_steps
+        # workspace k serves the batches k, k+2, ...: cursor and Adam count advance by 2 per use
+        c = runner.cursor
+        k0 = c & 1                      # workspace of the next batch
+        for k, e in enumerate(engines):
+            first = c + ((k - k0) & 1)  # first batch this workspace will see
+            e.set_counters(plan_cursor=first, adam_step=T + (first - c) - 1, stride=2)
         return runner
 
     @torch.no_grad()
@@ -242,11 +289,18 @@ class _PlannedRunner:
     def run(self, k):
         """execute the next k planned steps (graph replays only); returns the interactions they cover"""
         m = self.model
-        big, one, G = m._graphs[m._graph_len], m._graphs[1], m._graph_len
-        for _ in range(k // G):
-            big.replay()
-        for _ in range(k % G):
-            one.replay()
+        G = m._graph_len
+        big = m._graphs[G]
+        left, c = k, self.cursor
+        while left > 0:
+            if (c & 1) == 0 and left >= G:
+                big.replay()
+                c += G
+                left -= G
+            else:
+                m._graphs[("one", c & 1)].replay()
+                c += 1
+                left -= 1
         n = self.plan["len"]
         rows = sum(self.plan["batch_rows"][(self.cursor + i) % n] for i in range(k))
         self.cursor += k

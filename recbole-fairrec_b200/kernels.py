@@ -94,10 +94,12 @@ class FocfEngine:
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
         return s
 
-    def set_counters(self, plan_cursor=-1, adam_step=-1):
+    def set_counters(self, plan_cursor=-1, adam_step=None, stride=0):
+        """device-resident counters of the workspace; None / negative cursor / stride 0 leave a counter unchanged"""
         check(self.lib.fr_focf_set_counters(ptr(self.ws), self.ws.numel(), self.n_users, self.n_items, self.d,
-                                            self.max_batch, int(plan_cursor), int(adam_step), stream_ptr()),
-              "fr_focf_set_counters")
+                                            self.max_batch, int(plan_cursor),
+                                            -2147483648 if adam_step is None else int(adam_step), int(stride),
+                                            stream_ptr()), "fr_focf_set_counters")
 
     def planned_step(self, U, I, adam, plan, train, objective, fair_weight, loss_buf):
         """fr_focf_step for planned batches (device-resident cursor / batch size / Adam step): the struct is the same
@@ -127,6 +129,12 @@ class FocfEngine:
 
     def run_planned(self, s):
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
+
+    def run_prepare(self, s):
+        check(self.lib.fr_focf_step_prepare(ctypes.byref(s), stream_ptr()), "fr_focf_step_prepare")
+
+    def run_compute(self, s):
+        check(self.lib.fr_focf_step_compute(ctypes.byref(s), stream_ptr()), "fr_focf_step_compute")
 
     def adam_dense(self, U, I, dU, dI, adam):
         s = FocfStep()
