@@ -331,29 +331,56 @@ def run_ours(args, wname):
     de_items, de_offs = torch.from_numpy(e_items).to(dev), torch.from_numpy(e_offs).to(dev)
     for s in range(args.steps):
         cols = loader.gather(de_items, de_offs, e_batches[s % len(e_batches)])
-        host_batches.append(tuple(c.cpu().pin_memory() for c in cols))
+        host_batches.append(pkg.pack_host_batch(*[c.cpu() for c in cols], fields=(uf, itf, rf, sf)))
     torch.cuda.synchronize()
-    h2d = int(statistics.mean(sum(c.numel() * c.element_size() for c in hb) for hb in host_batches))
-    barrier()
-    t0 = time.perf_counter()
-    rows_e = 0
+    h2d = int(statistics.mean(hb.packed_host[0].numel() for hb in host_batches))
     if world > 1:
-        eb = torch.tensor([[hb[0].numel(), int(torch.unique_consecutive(hb[1]).numel())] for hb in host_batches],
+        eb = torch.tensor([[len(hb), int(torch.unique_consecutive(hb[itf]).numel())] for hb in host_batches],
                           dtype=torch.int64, device=dev)
         dist.all_reduce(eb)
         eb = eb.cpu().numpy()
+    # every step: H2D of the batch (pinned), the step, D2H of its loss (pinned).  The read of step t's loss is waited for
+    # after step t+1 has been enqueued, so one step stays in flight (trainer.py:191 reads it before the next batch; the
+    # value and the NaN check are the same, one batch later)
+    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    barrier()
+    t0 = time.perf_counter()
+    rows_e, pending, loss_sum = 0, None, 0.0
     for k, hb in enumerate(host_batches):
-        inter = pkg.Interaction({uf: hb[0], itf: hb[1], rf: hb[2], sf: hb[3]})
-        inter.items_contiguous = True
+        slot = k & 1
         if world > 1:
-            loss = model.dp_train_step(inter, (int(eb[k, 0]), int(eb[k, 1])), group)
+            model.dp_train_step(hb, (int(eb[k, 0]), int(eb[k, 1])), group, loss_out=loss_dev[slot])
         else:
-            loss = model.train_step(inter)      # .to(device) of the four columns happens inside
-        _ = loss.item()                         # trainer.py:191 -- per-step D2H + sync
-        rows_e += hb[0].numel()
+            model.train_step(hb, loss_out=loss_dev[slot])      # the single H2D copy of the packed batch happens inside
+        loss_host[slot].copy_(loss_dev[slot], non_blocking=True)
+        done[slot].record()
+        if pending is not None:
+            done[pending].synchronize()
+            v = float(loss_host[pending])
+            if v != v:
+                raise ValueError("Training loss is nan")
+            loss_sum += v
+        pending = slot
+        rows_e += len(hb)
+    done[pending].synchronize()
+    loss_sum += float(loss_host[pending])
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = sum_over_ranks(rows_e) / t_e2e
+    # the strictly serial variant (wait for every step's loss before the next batch is touched)
+    barrier()
+    t0 = time.perf_counter()
+    for k, hb in enumerate(host_batches[:max(args.steps // 4, 1)]):
+        if world > 1:
+            loss = model.dp_train_step(hb, (int(eb[k, 0]), int(eb[k, 1])), group)
+        else:
+            loss = model.train_step(hb)
+        _ = loss.item()
+    barrier()
+    n_serial = len(host_batches[:max(args.steps // 4, 1)])
+    e2e_serial = sum_over_ranks(sum(len(hb) for hb in host_batches[:n_serial])) / max_over_ranks(time.perf_counter() - t0)
 
     # ---- evaluation: all valid users
     users, hist, pos = synth.eval_lists(train, valid, test, "valid")
@@ -532,7 +559,10 @@ def run_ours(args, wname):
                    f"gradient shares, identical dense Adam on every replica; global batch = {world} x {w['batch']}); "
                    f"eval: item table sharded x{world}, NCCL all-gather top-K merge + all-reduce of item x group stats"},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "mode": "host batch (one pinned buffer) -> H2D -> step -> loss D2H every step; the host waits for step t's "
+                        "loss after enqueuing step t+1",
+                "serial_value": e2e_serial},
         "gpu_launches": int(round(kernels_per_step * timed_steps)), "kernels_per_step": kernels_per_step,
         "launch_mode": f"cuda graph replay ({G} steps per launch; prepare(t+1) on a second stream under compute(t))"
         if use_graph else "stream launches",

@@ -20,7 +20,7 @@ from .config import Config  # noqa: F401
 from .dataloader import FOCFDataLoader, TrainData  # noqa: F401
 from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
 from .fairgo import FairGo_GCN, FairGo_GCNTrainer, FairGo_PMF, FairGo_PMFTrainer, FairGoTrainer  # noqa: F401
-from .focf import FOCF  # noqa: F401
+from .focf import FOCF, pack_host_batch  # noqa: F401
 from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF  # noqa: F401
 from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFCN_MLPTrainer, PFCN_PMFTrainer,  # noqa: F401

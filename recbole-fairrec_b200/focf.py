@@ -29,12 +29,37 @@ def _xavier_normal_initialization(module):
 
 
 def batch_columns(interaction, uid_f, iid_f, rating_f, sst_f, device):
-    """Interaction -> the four int32/float32 device columns of include/fairrec_b200.h:fr_focf_step"""
+    """Interaction -> the four int32/float32 device columns of include/fairrec_b200.h:fr_focf_step.
+    Host batches whose four columns are views of ONE pinned buffer (pack_host_batch) move with a single H2D copy."""
+    packed = getattr(interaction, "packed_host", None)
+    if packed is not None:
+        buf, n = packed
+        dev = torch.empty(buf.numel(), dtype=torch.uint8, device=device)
+        dev.copy_(buf, non_blocking=True)
+        return (dev[:4 * n].view(torch.int32), dev[4 * n:8 * n].view(torch.int32), dev[8 * n:12 * n].view(torch.float32),
+                dev[12 * n:16 * n].view(torch.float32), bool(getattr(interaction, "items_contiguous", False)))
+
     def col(name, dtype):
         t = interaction[name]
         return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
     return (col(uid_f, torch.int32), col(iid_f, torch.int32), col(rating_f, torch.float32),
             col(sst_f, torch.float32), bool(getattr(interaction, "items_contiguous", False)))
+
+
+def pack_host_batch(uid, iid, rating, sst, fields, items_contiguous=True):
+    """Host-side FOCF batch whose columns (int32 user ids, int32 item ids, float32 ratings, float32 attribute values)
+    are views of one pinned buffer: an Interaction like any other, but `train_step` moves it with ONE H2D copy."""
+    from .interaction import Interaction
+    n = int(uid.numel())
+    buf = torch.empty(16 * n, dtype=torch.uint8).pin_memory()
+    cols = (buf[:4 * n].view(torch.int32), buf[4 * n:8 * n].view(torch.int32), buf[8 * n:12 * n].view(torch.float32),
+            buf[12 * n:16 * n].view(torch.float32))
+    for dst, src in zip(cols, (uid, iid, rating, sst)):
+        dst.copy_(src)
+    inter = Interaction(dict(zip(fields, cols)))
+    inter.items_contiguous = items_contiguous
+    inter.packed_host = (buf, n)
+    return inter
 
 
 class _FocfLoss(torch.autograd.Function):
