@@ -47,6 +47,35 @@ class TrainData:
         self.train_rating = t(self.rating_h, torch.float32)
         self.sst_of_user = t(np.asarray(sst_of_user, dtype=np.float32), torch.float32)
 
+    @classmethod
+    def from_device(cls, uid, iid, rating, sst_of_user, n_users, n_items, uid_field="user_id", iid_field="item_id",
+                    rating_field="rating", sst_field="gender"):
+        """The same layout built ON THE DEVICE from device tensors (scale-out shapes: 10^9 rows never visit the host):
+        stable sort by item, CSC offsets from a bincount; only the per-item counts (n_items values) go to the host,
+        where the batch draws are planned."""
+        self = cls.__new__(cls)
+        dev = uid.device
+        order = torch.sort(iid, stable=True).indices
+        self.train_uid = uid[order].to(torch.int32).contiguous()
+        self.train_rating = rating[order].to(torch.float32).contiguous()
+        del order
+        counts = torch.bincount(iid, minlength=int(n_items))
+        self.item_count_h = counts.cpu().numpy().astype(np.int64)
+        self.item_off_h = np.zeros(int(n_items) + 1, np.int64)
+        self.item_off_h[1:] = np.cumsum(self.item_count_h)
+        if self.item_off_h[-1] >= 2 ** 31:
+            raise ValueError("the device-side batch builder indexes the train split with int32 offsets")
+        self.item_off_h = self.item_off_h.astype(np.int32)
+        self.item_uniques = np.nonzero(self.item_count_h)[0]
+        self.item_off = torch.from_numpy(self.item_off_h).to(dev)
+        self.sst_of_user = sst_of_user.to(device=dev, dtype=torch.float32).contiguous()
+        self.n_users, self.n_items, self.device = int(n_users), int(n_items), dev
+        self.n_rows = int(self.train_uid.numel())
+        self.fields = (uid_field, iid_field, rating_field, sst_field)
+        self.max_rating = float(self.train_rating.max())
+        self.uid_h = self.iid_h = self.rating_h = None
+        return self
+
     # the two `dataset` members the reference trainer/model read (collector.py:91-93, focf.py:40)
     @property
     def item_counter(self):
@@ -107,12 +136,12 @@ class FOCFDataLoader:
         j = int(np.searchsorted(csum, self.step, side="left")) + 1
         return perm[:j].astype(np.int64)
 
-    def plan_epoch(self):
-        """Draw every batch of the epoch; returns (draw_items, draw_off, batches) where batches is a list of
-        (first draw index, J, B) and draw_off holds, per batch, J+1 positions."""
+    def plan_epoch(self, n_batches=None):
+        """Draw every batch of the epoch (or only the first n_batches); returns (draw_items, draw_off, batches) where
+        batches is a list of (first draw index, first offset index, J, B) and draw_off holds, per batch, J+1 positions."""
         items, offs, batches = [], [], []
         pos_items = pos_offs = 0
-        for _ in range(len(self)):
+        for _ in range(len(self) if n_batches is None else int(n_batches)):
             it = self._draw_batch()
             cnt = self.train.item_count_h[it]
             off = np.zeros(len(it) + 1, np.int64)

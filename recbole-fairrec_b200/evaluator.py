@@ -75,6 +75,53 @@ class EvalData:
             self.n_groups[attr] = len(uniq)
 
     @classmethod
+    def from_device(cls, hist_uid, hist_iid, pos_uid, pos_iid, sst_of_user, n_users, n_items):
+        """The same CSR layout built ON THE DEVICE from interaction columns (scale-out shapes): hist_* = the interactions
+        already used in earlier phases (general_dataloader.py:201-207), pos_* = the phase's own interactions.  Eval users =
+        users with at least one positive, ascending; every per-user list ascending by item id.
+        sst_of_user: {attr: device tensor indexed by user id}."""
+        self = cls.__new__(cls)
+        dev = pos_uid.device
+        shift = max(int(n_items - 1).bit_length(), 1)
+        mask = (1 << shift) - 1
+
+        def grouped(u, i):
+            key = torch.sort((u.to(torch.int64) << shift) | i.to(torch.int64)).values
+            return (key >> shift), (key & mask).to(torch.int32)
+
+        pu, pi = grouped(pos_uid, pos_iid)
+        pcnt = torch.bincount(pu, minlength=int(n_users))
+        users = torch.nonzero(pcnt, as_tuple=False).view(-1)
+        n = int(users.numel())
+        self.n, self.device = n, dev
+        self.users = users.to(torch.int32)
+        self.pos_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        self.pos_off[1:] = torch.cumsum(pcnt[users], 0)
+        self.pos_items = pi.contiguous()
+        self.pos_items_sorted = self.pos_items
+        self.n_pos = int(pi.numel())
+        self.pos_row = torch.repeat_interleave(torch.arange(n, device=dev), pcnt[users])
+        self.pos_uid = pu.to(torch.int32).contiguous()
+        del pu
+        hu, hi = grouped(hist_uid, hist_iid)
+        keep = pcnt[hu] > 0
+        hcnt = torch.bincount(hu[keep], minlength=int(n_users))
+        self.hist_items = hi[keep].contiguous()
+        del hu, hi, keep
+        self.hist_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        self.hist_off[1:] = torch.cumsum(hcnt[users], 0)
+        if self.hist_items.numel() == 0:
+            self.hist_items = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sst_value, self.group_of_pos, self.n_groups = {}, {}, {}
+        for attr, per_user in sst_of_user.items():
+            vals = per_user.to(dev)[users]
+            uniq, inv = torch.unique(vals[self.pos_row], return_inverse=True)
+            self.sst_value[attr] = vals.cpu()
+            self.group_of_pos[attr] = inv.to(torch.int32).contiguous()
+            self.n_groups[attr] = int(uniq.numel())
+        return self
+
+    @classmethod
     def from_reference_loader(cls, loader, sst_attr_list, device):
         """Adopt a reference FullSortEvalDataLoader (general_dataloader.py:173-199): uid_list,
         uid2history_item, uid2positive_item, user_df."""
