@@ -14,11 +14,12 @@ KEYS = ['gpu__time_duration.sum','launch__grid_size','launch__block_size','launc
 lines = ['# Round 1 ncu summaries', '',
          'Captured with `ncu --set full --clock-control none --import-source on` under gpurun (one B200); the `.ncu-rep`',
          'files stay in gpurun_out/ (scratch).  Durations under ncu are cold-cache and serialised: use SHARES, not absolutes.', '']
-for title, rep in [('k_apply<kAdamFused> at the scale-out shape (2M users x 262k items, d=128; scratch/apply_prof.py)', 'gpurun_out/r01_apply_scaleout.ncu-rep'),
+for title, rep in [('k_focf_fused_step: the cooperative FOCF step (forward | barrier | per-CTA batch statistics + gradients | barrier | Adam) at the ML-1M shape (scratch/fused_prof.py)', 'gpurun_out/r01_fused_step.ncu-rep'),
+                   ('k_apply<kAdamFused> at the scale-out shape (2M users x 262k items, d=128; scratch/apply_prof.py)', 'gpurun_out/r01_apply_scaleout.ncu-rep'),
                    ('forward / loss / gradient kernels at the scale-out shape (B = 2^18)', 'gpurun_out/r01_step_scaleout.ncu-rep'),
                    ('k_fullsort_tc (tcgen05 3xTF32) 37,888 users x 262,144 items, d=128 (scratch/tc_prof.py)', 'gpurun_out/r01_fullsort_tc.ncu-rep'),
-                   ('k_fullsort_exact at the ML-1M shape (first version, before the graph/TC work)', 'gpurun_out/prof_fullsort_r1.ncu-rep'),
-                   ('FOCF step kernels at the ML-1M shape, warm L2 (scratch/step_prof.py)', 'gpurun_out/prof_step_r1.ncu-rep')]:
+                   ('layer kernels of the PFCN / FairGo MLPs: k_gemm<true> (forward), k_wgrad, k_gemm<false> (backward-data) at M=9748, K=64, N=128 (scratch/wgrad_one.py)', 'gpurun_out/r01_layer_gemms.ncu-rep'),
+                   ('k_fullsort_exact at the ML-1M shape (first version, before the graph/TC work)', 'gpurun_out/prof_fullsort_r1.ncu-rep')]:
     if not os.path.exists(rep): continue
     hdr, units, rows = raw(rep)
     lines += [f'## {title}', '', f'source: `{rep}`', '']
@@ -42,8 +43,8 @@ for r in rows[1:]:
     agg[re.sub(r'\(.*','',r[iK]).replace('void ','').replace('fr::','')].append(float(r[iV])/1e3)
 tot=sum(sum(v) for v in agg.values())
 with open(os.path.join(OUT,'r01_launches_summary.md'),'w') as f:
-    f.write('# Round 1 launch list -- `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 python bench.py --steps 20 --warmup 3 --no-cpu-baseline`\n\n')
-    f.write('First 3000 launches of the default bench command (ML-1M shape): warm-up steps, the timed FOCF steps (CUDA-graph kernel nodes are\nprofiled individually) and the evaluation passes.  Times are cold-cache and serialised by ncu: compare SHARES.\n\n')
+    f.write('# Round 1 launch list -- `ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 python bench.py --steps 24 --warmup 3 --no-cpu-baseline --no-probe`\n\n')
+    f.write('First 8000 launches of the default bench command (ML-1M shape): warm-up steps, the timed FOCF steps (CUDA-graph kernel nodes are\nprofiled individually: gather + prepare on the side stream, the cooperative fused step on the main one), the end-to-end steps,\nthe evaluation passes and the PFCN / FairGo legs.  Times are cold-cache and serialised by ncu: compare SHARES.\n\n')
     f.write('| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|\n')
     for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1])):
         f.write(f'| {k} | {len(v)} | {sum(v):.1f} | {100*sum(v)/tot:.1f}% | {sum(v)/len(v):.2f} |\n')
