@@ -374,4 +374,54 @@ class FairGoTrainer:
         return dis_loss, filter_loss
 
 
+    # ------------------------------------------------------------------ evaluation / fit (trainer.py:739-772, 332-418)
+    def data_collect(self, train_item_count):
+        """collector.py:80-95: {item id: #train interactions} for the popularity metric"""
+        self._train_item_count = dict(train_item_count) if train_item_count is not None else None
+        self.evaluator = None
+
+    @torch.no_grad()
+    def evaluate(self, eval_data):
+        """Full-sort fair evaluation of the CURRENT stage's tables (pretrain: the raw embeddings; fine-tune: the tables
+        filtered by all attributes, fairgo_pmf.py:250-257) with the fused evaluator: scoring + mask + top-K + the 12
+        metrics of FairGo_PMF.yaml.  eval_data: evaluator.EvalData or a reference FullSortEvalDataLoader."""
+        from .evaluator import EvalData, FullSortEvaluator
+        self.model.eval()
+        if getattr(self, "evaluator", None) is None:
+            self.evaluator = FullSortEvaluator(self.config, self.model.n_items, getattr(self, "_train_item_count", None))
+        if not isinstance(eval_data, EvalData):
+            cache = self.__dict__.setdefault("_eval_cache", {})
+            if id(eval_data) not in cache:
+                cache[id(eval_data)] = EvalData.from_reference_loader(eval_data, self.sst_attrs, self.model._dev())
+            eval_data = cache[id(eval_data)]
+        U, I = self.model.filtered_tables()
+        return self.evaluator.evaluate(U.detach(), I.detach(), eval_data, self.model.max_rating)
+
+    def fit(self, train_data, valid_data=None, epochs=None, train_item_count=None, verbose=False):
+        """pretrain (unless embeddings were given) + fine-tune with early stopping on `valid_metric`; train_data is any
+        re-iterable of Interactions (user_id, item_id, rating, <sst>...).  Returns (best valid score, best valid result)."""
+        from .trainer import early_stopping
+        if train_item_count is not None:
+            self.data_collect(train_item_count)
+        if self.model.train_stage == "pretrain":
+            self.pretrain(train_data)
+        metric = (self.config["valid_metric"] or "NDCG@5").lower()
+        bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
+        best, best_res, cur = (-np.inf if bigger else np.inf), None, 0
+        for epoch in range(epochs if epochs is not None else (self.config["epochs"] or 1)):
+            dis_loss, filter_loss = self._train_epoch(train_data, epoch)
+            if verbose:
+                print(f"epoch {epoch}: filter loss {filter_loss:.4f}, discriminator loss {dis_loss:.4f}")
+            if not valid_data:
+                continue
+            res = self.evaluate(valid_data)
+            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
+                                                     bigger=bigger)
+            if update:
+                best_res = res
+            if stop:
+                break
+        return best, best_res
+
+
 FairGo_PMFTrainer = FairGo_GCNTrainer = FairGoTrainer

@@ -207,3 +207,46 @@ def test_fairgo_trainer_runs_ml1m_widths():
         assert np.isfinite(dl) and np.isfinite(fl)
     U, I = model.filtered_tables()
     assert U.shape == (nu, d) and I.shape == (ni, d) and torch.isfinite(U).all() and torch.isfinite(I).all()
+
+
+def test_fairgo_trainer_fit_and_fused_full_sort_eval():
+    """FairGoTrainer.fit / evaluate: the fused full-sort evaluator on the filtered tables equals the oracle's canonical
+    top-K on the dense scores of full_sort_predict"""
+    import recbole_fairrec_b200 as pkg
+    from oracle import fullsort_oracle as fs
+    g = np.load(FAIRGO[0])
+    cfg, model, feats = build(g, topk=[5], valid_metric="NDCG@5", epochs=2, stopping_step=5)
+    load_state(model, go.load_state(g, "pretrained"))
+    trainer = pkg.FairGoTrainer(cfg, model)
+    model.train_stage = "finetune"
+    nu, ni = int(g["n_users"]), int(g["n_items"])
+    rng = np.random.default_rng(0)
+    tu, ti = g["train_u"], g["train_i"]
+    users = np.arange(1, nu)
+    hist = [np.unique(ti[tu == u]) for u in users]
+    pos = [np.setdiff1d(rng.choice(np.arange(1, ni), 4, replace=False), h)[:3] for h in hist]
+    pos = [p if len(p) else np.setdiff1d(np.arange(1, ni), h)[:1] for p, h in zip(pos, hist)]
+    data = pkg.EvalData(users, hist, pos, {"gender": feats["gender"], "age": feats["age"]}, torch.device("cuda"))
+
+    def batches():
+        for s in range(2, 6):
+            u = g[f"user_id{s}"]
+            yield pkg.Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(g[f"item_id{s}"]),
+                                   "rating": torch.from_numpy(g[f"rating{s}"]),
+                                   "gender": torch.from_numpy(feats["gender"][u]), "age": torch.from_numpy(feats["age"][u])})
+
+    np.random.seed(1)
+    cfg["sst_attr_list"] = ["gender", "age"]
+    best, res = trainer.fit(list(batches()), data, train_item_count={int(i): int(c) for i, c in
+                                                                       enumerate(np.bincount(ti, minlength=ni)) if c})
+    assert res is not None and 0.0 <= res["ndcg@5"] <= 1.0 and np.isfinite(best)
+    out = trainer.evaluate(data)
+    dense = model.full_sort_predict(pkg.Interaction({"user_id": torch.from_numpy(users)})).view(len(users), ni).cpu().numpy()
+    hist_off = np.r_[0, np.cumsum([len(h) for h in hist])]
+    ids, _ = fs.topk_canonical(fs.mask_history(dense, hist_off, np.concatenate(hist)), 5)
+    got = trainer.evaluator.last["topk_id"].cpu().numpy()
+    # the dense scores come from a different summation order than the scorer's fma chain: compare outside near-ties
+    srt = -np.sort(-fs.mask_history(dense, hist_off, np.concatenate(hist)), axis=1)[:, :6]
+    clear = (np.abs(np.diff(srt, axis=1)) > 1e-6).all(axis=1)
+    assert clear.sum() > len(users) // 2 and np.array_equal(got[clear], ids[clear])
+    assert set(out) >= {"ndcg@5", "giniindex@5", "Differential Fairness of sensitive attribute gender"}
