@@ -493,8 +493,12 @@ def run_ours(args, wname):
         key = match(dom)
         cnt, ms = prof_train[dom]
         ach = alg[key] / (ms / cnt * 1e-3) / 1e9
+        # DRAM bytes per launch from the committed ncu capture of the same kernel at this shape (profiles/r01_ncu_summary.md)
+        traffic = {"k_focf_fused_step": 7.71e6} if wname == "ml1m" else {}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[key],
+                    "traffic": traffic.get(key), "traffic_note": "ncu dram read 7.71 MB + write ~0 per launch: the tables and "
+                    "moments are read once; written lines stay in the 126 MB L2" if key in traffic else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[key],
                     "avg_launch_us": 1e3 * ms / cnt, "share_of_step": shares[dom]}
     kernels_per_step = sum(v[0] for v in prof_train.values()) / nprof
     step_bytes = (16.0 * d + 16.0) * B_avg + 24.0 * n_rows_tab * d
