@@ -212,9 +212,13 @@ def run_ours(args, wname):
     n_plan = args.steps + args.warmup
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     G = 8
-    use_graph = loader.max_batch <= 8192 and world == 1
+    use_graph = loader.max_batch <= 8192 and not args.no_graph and (world == 1 or args.dp_graph)
     losses = torch.zeros(max(len(loader), n_plan) * 2 + 16, device=dev)
-    if use_graph:
+    if use_graph and world > 1:
+        # data-parallel: forward -> backward -> NCCL all-reduce -> dense Adam of G planned steps in one CUDA graph
+        runner = model.dp_planned_runner(loader, losses, group, graph_steps=G)
+        dev_step = lambda: runner.run(1)
+    elif use_graph:
         # planned epoch + CUDA-graph replay: one graph launch per step, zero per-step host work
         runner = model.planned_runner(loader, losses, graph_steps=G)
         dev_step = lambda: runner.run(1)
@@ -261,7 +265,7 @@ def run_ours(args, wname):
     rows = 0
     launches0 = _lib.launch_count()
     with ClockSampler(local) as clocks:
-        if use_graph and (runner.cursor & 1):
+        if use_graph and world == 1 and (runner.cursor & 1):
             runner.run(1)              # align to workspace 0: every timed launch is the pipelined G-step graph
         barrier()
         if use_graph:
@@ -288,7 +292,7 @@ def run_ours(args, wname):
             single = {"value": rows_single / (sum(x.elapsed_time(y) for x, y in sevs) / 1e3), "unit": "interactions/s",
                       "ms_per_step": sum(x.elapsed_time(y) for x, y in sevs) / timed_steps,
                       "note": "one step per launch, L2 flushed before every step"}
-            if runner.cursor & 1:
+            if world == 1 and (runner.cursor & 1):
                 runner.run(1)
         else:
             single = None
@@ -308,9 +312,9 @@ def run_ours(args, wname):
         t_end = time.time() + 0.7
         a.record()
         if world > 1:   # every rank must issue the SAME number of collectives: fixed step count, not a wall-clock window
-            for _ in range(args.steps):
-                rows_ss += dev_step()
-                n_ss += 1
+            for _ in range(max(args.steps // G, 1) if use_graph else args.steps):
+                rows_ss += runner.run(G) if use_graph else dev_step()
+                n_ss += G if use_graph else 1
         else:
             while time.time() < t_end:
                 rows_ss += runner.run(G) if use_graph else dev_step()
@@ -449,14 +453,9 @@ def run_ours(args, wname):
     nprof = min(args.steps, 50)
     rows_p = 0
     if use_graph:   # graph replays bypass the library's launch macro: profile the same steps un-captured
-        st = model._graph_step
-        model._engine().set_counters(plan_cursor=runner.cursor, adam_step=model._adam["step"], stride=1)
         for s in range(nprof):
             flush.zero_()
-            model._engine().run_planned(st)
-            rows_p += runner.plan["batch_rows"][(runner.cursor + s) % runner.plan["len"]]
-        runner.cursor += nprof
-        model._adam["step"] += nprof
+            rows_p += runner.eager_steps(1)
     else:
         for s in range(nprof):
             flush.zero_()
@@ -568,7 +567,8 @@ def run_ours(args, wname):
                         "loss after enqueuing step t+1",
                 "serial_value": e2e_serial},
         "gpu_launches": int(round(kernels_per_step * timed_steps)), "kernels_per_step": kernels_per_step,
-        "launch_mode": f"cuda graph replay ({G} steps per launch; prepare(t+1) on a second stream under compute(t))"
+        "launch_mode": (f"cuda graph replay ({G} steps per launch; prepare(t+1) on a second stream under compute(t))"
+                        if world == 1 else f"cuda graph replay ({G} data-parallel steps per launch incl. the NCCL all-reduce)")
         if use_graph else "stream launches",
         "flushed_single_step": single,
         "steady_state": steady,
@@ -698,6 +698,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true", help="skip the scale-out roofline probe")
     ap.add_argument("--no-families", action="store_true", help="skip the PFCN / FairGo legs")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--dp-graph", action="store_true",
+                    help="multi-GPU: capture the data-parallel step incl. the NCCL all-reduce in a CUDA graph (experimental)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -706,9 +709,18 @@ def main():
         args.steps = min(args.steps, 40)     # bounded sample: the CPU loop runs ~0.03-0.3 s per step
         print(json.dumps(run_reference(args, args.workload)))
         return
-    out = run_ours(args, args.workload)
+    # libraries (NCCL's version banner, ...) may write to stdout: keep fd 1 for the ONE JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_ours(args, args.workload)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -142,6 +142,9 @@ typedef struct fr_focf_step {
    * normalisers of MSE and of the fairness mean.  The loss written is this rank's share (sum over ranks = loss);
    * gradients from fr_focf_backward are this rank's share (all-reduce, then fr_focf_adam on every replica). */
   int32_t norm_B, norm_J;
+  /* planned data-parallel steps (CUDA-graph replay): [plan_len, 2] = (B_total, J_total) of every planned batch, read at
+   * the device-resident cursor instead of norm_B / norm_J */
+  const int32_t *norm_dev;
 } fr_focf_step;
 
 size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch);

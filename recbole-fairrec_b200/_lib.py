@@ -36,7 +36,7 @@ class FocfStep(Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("B_dev", c_void_p), ("plan_desc", c_void_p), ("plan_items", c_void_p), ("plan_offs", c_void_p),
         ("plan_len", c_int32), ("item_off", c_void_p), ("train_uid", c_void_p), ("train_rating", c_void_p),
-        ("sst_of_user", c_void_p), ("norm_B", c_int32), ("norm_J", c_int32),
+        ("sst_of_user", c_void_p), ("norm_B", c_int32), ("norm_J", c_int32), ("norm_dev", c_void_p),
     ]
 
 

@@ -39,6 +39,7 @@ enum {
   CTRL_B = 8,          // device-resident batch size (planned batches)
   CTRL_GRID_BAR = 9,   // arrival counter of the fused step's grid barrier (monotonic)
   CTRL_STRIDE = 10,    // how far CTRL_CURSOR / CTRL_ADAM_T advance per step (2 when two workspaces alternate batches)
+  CTRL_NORM_B = 11, CTRL_NORM_J = 12,   // data-parallel planned steps: the current batch's global normalisers (from norm_dev)
   CTRL_WORDS = 64
 };
 // batch size: host value unless a device-resident one is given (CUDA-graph replay over batches of varying size)
@@ -169,6 +170,7 @@ struct LossArgs {
   int advance_adam;     // fused step with the device-resident Adam counter
   int objective;
   int norm_B, norm_J;   // > 0: global batch rows / item count of a data-parallel step (normalisers of the two means)
+  const int32_t *norm_dev;   // planned data-parallel steps: [plan_len, 2] = (B_total, J_total) of every planned batch
   float fair_weight;
   float *cseg, *rec_seg, *rec_head, *rec_tail, *cglob, *loss;
   uint32_t *ctrl;
@@ -285,7 +287,13 @@ __device__ __forceinline__ void loss_phase1(const LossArgs &a, int B) {
 __device__ __forceinline__ void loss_phase2(const LossArgs &a, int B, float *sh) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int J = *a.J;
-  const float Bn = (float)(a.norm_B > 0 ? a.norm_B : B), Jn = (float)(a.norm_J > 0 ? a.norm_J : J);
+  int nB = a.norm_B, nJ = a.norm_J;
+  if (a.norm_dev) {
+    const uint32_t k = a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor;
+    nB = a.norm_dev[2 * k];
+    nJ = a.norm_dev[2 * k + 1];
+  }
+  const float Bn = (float)(nB > 0 ? nB : B), Jn = (float)(nJ > 0 ? nJ : J);
   float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;  // lane 0 accumulates over its segments
   for (int j = wib; j < J; j += (int)(blockDim.x >> 5)) {
     const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
@@ -350,6 +358,8 @@ __device__ __forceinline__ void loss_phase2(const LossArgs &a, int B, float *sh)
     // hand the group values to the backward kernels, re-arm the control block for the next batch
     a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
     a.ctrl[CTRL_SAVED_MAX] = a.ctrl[CTRL_MAX];
+    a.ctrl[CTRL_NORM_B] = (uint32_t)(nB > 0 ? nB : 0);
+    a.ctrl[CTRL_NORM_J] = (uint32_t)(nJ > 0 ? nJ : 0);
     a.ctrl[CTRL_MIN] = 0xffffffffu;
     a.ctrl[CTRL_MAX] = 0u;
     a.ctrl[CTRL_TICKET] = 0u;
@@ -386,6 +396,7 @@ struct GradArgs {
   int B, d;
   const int32_t *B_dev;
   int norm_B;
+  int norm_from_ctrl;   // planned data-parallel steps: read the normaliser the loss kernel left in CTRL_NORM_B
   const uint32_t *ord_i, *ord_u;
   const int32_t *segid_i, *segoff_i, *segid_u, *segoff_u, *entry_seg;
   const float *cseg, *cglob;
@@ -416,6 +427,7 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
   const int d = a.d;
   const int nvalid = min(chunk, B - pbase);
   const float vmin = ord2f(a.ctrl[a.pre_handover ? CTRL_MIN : CTRL_SAVED_MIN]);
+  const int nB = a.norm_from_ctrl ? (int)a.ctrl[CTRL_NORM_B] : a.norm_B;
 
   // lane l stages entry pbase + l
   int my_seg = -1, my_oid = 0;
@@ -426,7 +438,7 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
     my_seg = segid[p];
     my_oid = oid[b];
     const int g = a.sst[b] != vmin;
-    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)(a.norm_B > 0 ? a.norm_B : B) + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
+    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)(nB > 0 ? nB : B) + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
               a.grad_scale;
   }
   float4 acc[kRowVecs];
@@ -983,7 +995,7 @@ static int check_step(const fr_focf_step *s, bool need_adam, const char *who) {
   FR_REQUIRE(s->objective >= FR_OBJ_NONE && s->objective <= FR_OBJ_NONPARITY, "%s: bad objective %d", who,
              s->objective);
   if (need_adam) FR_REQUIRE(s->mU && s->vU && s->mI && s->vI, "%s: Adam state missing", who);
-  FR_REQUIRE(!(s->objective == FR_OBJ_NONPARITY && (s->norm_B > 0 || s->norm_J > 0)),
+  FR_REQUIRE(!(s->objective == FR_OBJ_NONPARITY && (s->norm_B > 0 || s->norm_J > 0 || s->norm_dev)),
              "%s: the nonparity objective needs batch-global group means and is not available data-parallel", who);
   if (planned(s)) {
     FR_REQUIRE(s->plan_items && s->plan_offs && s->plan_len >= 1 && s->item_off && s->train_uid && s->train_rating &&
@@ -1051,7 +1063,8 @@ static int prepare_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st)
 static LossArgs loss_args(const fr_focf_step *s, const FocfWs &w, bool advance_adam) {
   const bool contiguous = s->items_contiguous || planned(s);
   return LossArgs{s->pred, s->rating, s->sst, contiguous ? nullptr : w.ord_i, w.segid_i, w.segoff_i, w.J, s->B, dev_B(s, w),
-                  planned(s) ? s->plan_len : 0, advance_adam ? 1 : 0, s->objective, s->norm_B, s->norm_J, s->fair_weight,
+                  planned(s) ? s->plan_len : 0, advance_adam ? 1 : 0, s->objective, s->norm_B, s->norm_J,
+                  planned(s) ? s->norm_dev : nullptr, s->fair_weight,
                   w.cseg, w.rec_seg, w.rec_head, w.rec_tail, w.cglob, s->loss, w.ctrl, s->status_flags};
 }
 
@@ -1074,7 +1087,8 @@ static int forward_only_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_
 
 static GradArgs grad_args(const fr_focf_step *s, const FocfWs &w, float grad_scale) {
   const uint32_t *ord_i = (s->items_contiguous || planned(s)) ? nullptr : w.ord_i;
-  return GradArgs{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), s->norm_B, ord_i, w.ord_u,
+  return GradArgs{s->U, s->I, s->uid, s->iid, s->rating, s->sst, s->pred, s->B, s->d, dev_B(s, w), s->norm_B,
+                  (planned(s) && s->norm_dev) ? 1 : 0, ord_i, w.ord_u,
                   w.segid_i, w.segoff_i, w.segid_u, w.segoff_u, w.entry_seg, w.cseg, w.cglob, w.ctrl, grad_scale,
                   grad_chunk(s->B), w.gseg_i, w.head_i, w.tail_i, w.gseg_u, w.head_u, w.tail_u};
 }
@@ -1113,7 +1127,7 @@ static bool fused_eligible(const fr_focf_step *s) {
     const char *e = getenv("FR_FOCF_NO_FUSED_STEP");
     disabled = (e && e[0] == '1') ? 1 : 0;
   }
-  return !disabled && s->B <= kPsMax && s->d <= 128 && s->norm_B == 0 && s->norm_J == 0 &&
+  return !disabled && s->B <= kPsMax && s->d <= 128 && s->norm_B == 0 && s->norm_J == 0 && !s->norm_dev &&
          fused_smem_bytes(s->B) <= 200 * 1024;
 }
 
@@ -1202,7 +1216,10 @@ int fr_focf_forward(const fr_focf_step *s, void *stream) {
   if (rc) return rc;
   fr::FocfWs w;
   if ((rc = fr::carve_checked(s, &w, "fr_focf_forward"))) return rc;
-  if ((rc = fr::forward_impl(s, w, (cudaStream_t)stream, false))) return rc;
+  // a planned training step driven by the device-resident counters (data-parallel graph replay: forward -> backward ->
+  // all-reduce -> fr_focf_adam): the loss kernel advances the Adam step count together with the batch cursor
+  const bool advance = fr::planned(s) && s->step <= 0 && s->mU != nullptr;
+  if ((rc = fr::forward_impl(s, w, (cudaStream_t)stream, advance))) return rc;
   FR_LAUNCH_CHECK();
   return FR_OK;
 }
@@ -1222,7 +1239,7 @@ int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream) {
 int fr_focf_adam(const fr_focf_step *s, void *stream) {
   FR_REQUIRE(s && s->U && s->I && s->mU && s->vU && s->mI && s->vI && s->dU && s->dI && s->workspace,
              "fr_focf_adam: null pointer");
-  FR_REQUIRE(s->d >= 4 && s->d % 4 == 0 && s->step >= 1, "fr_focf_adam: bad d/step");
+  FR_REQUIRE(s->d >= 4 && s->d % 4 == 0, "fr_focf_adam: bad d");   /* step <= 0: the workspace's device-resident count */
   fr::Carver c(s->workspace, s->workspace_bytes);
   fr::FocfWs w = fr::carve(c, s->n_users, s->n_items, s->d, 1);
   FR_LAUNCH(fr::k_apply<fr::kAdamDense>, fr::apply_grid(s), 256, 0, stream, fr::apply_args(s, w));

@@ -288,6 +288,55 @@ class FOCF(nn.Module):
         return runner
 
     @torch.no_grad()
+    def dp_planned_runner(self, loader, loss_buf, group, graph_steps=8):
+        """Data-parallel twin of planned_runner: this rank's planned whole-item batches, the global normalisers of
+        every planned batch in a device array (summed over the ranks once per epoch), and the step
+        forward -> backward (dense gradient shares) -> ONE NCCL all-reduce -> dense Adam captured into a CUDA graph of
+        `graph_steps` steps.  loss_buf[cursor] receives this rank's loss share of each step."""
+        import torch.distributed as dist
+        if self._adam is None:
+            raise RuntimeError("call init_adam() before dp_planned_runner()")
+        eng = self._engine()
+        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        dev = U.device
+        plan = loader.plan_epoch_device()
+        n = torch.tensor([plan["len"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(n, op=dist.ReduceOp.MIN, group=group)      # ranks may have planned different batch counts
+        L = int(n.item())
+        plan = dict(plan, len=L, rows=int(sum(plan["batch_rows"][:L])))
+        if loss_buf.numel() < L:
+            raise ValueError("loss buffer shorter than the epoch")
+        if getattr(self, "_dp_norm", None) is None or self._dp_norm.shape[0] < L:
+            self._dp_norm = torch.zeros((int(L * 1.5) + 64, 2), dtype=torch.int32, device=dev)
+        norms = plan["desc"][:L][:, [3, 2]].contiguous()            # (B, J) of this rank's batches
+        dist.all_reduce(norms, group=group)
+        self._dp_norm[:L].copy_(norms)
+        if getattr(self, "_dp_grad", None) is None:
+            self._dp_grad = torch.empty(U.numel() + I.numel(), dtype=torch.float32, device=dev)
+        dU, dI = self._dp_grad[:U.numel()].view_as(U), self._dp_grad[U.numel():].view_as(I)
+        key = ("dp", plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), graph_steps, L,
+               self._dp_norm.data_ptr())
+        runner = _DpPlannedRunner(self, plan, group)
+        if getattr(self, "_dp_graph_key", None) != key or eng.ws.data_ptr() != getattr(self, "_dp_graph_ws", None):
+            st = eng.planned_step(U, I, self._adam, plan, loader.train, self._objective, self.fair_weight, loss_buf)
+            st.norm_dev = self._dp_norm.data_ptr()
+            st.dU, st.dI = dU.data_ptr(), dI.data_ptr()
+            self._dp_step = st
+            eng.set_counters(plan_cursor=0, adam_step=self._adam["step"], stride=1)
+            runner.eager_steps(1)                                   # NCCL communicator, module loading
+            torch.cuda.synchronize()
+            self._dp_graphs = {}
+            for g_steps in sorted({graph_steps, 1}):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(g_steps):
+                        runner._enqueue()
+                self._dp_graphs[g_steps] = g
+            self._dp_graph_key, self._dp_graph_len, self._dp_graph_ws = key, graph_steps, eng.ws.data_ptr()
+        eng.set_counters(plan_cursor=runner.cursor, adam_step=self._adam["step"], stride=1)
+        return runner
+
+    @torch.no_grad()
     def train_epoch_planned(self, loader, loss_buf, graph_steps=8):
         """One epoch through planned_runner.  Returns (number of steps, number of interactions)."""
         runner = self.planned_runner(loader, loss_buf, graph_steps)
@@ -307,9 +356,59 @@ class FOCF(nn.Module):
             raise ValueError("Training loss is nan")  # trainer.py:286-288
 
 
+class _DpPlannedRunner:
+    def __init__(self, model, plan, group):
+        self.model, self.plan, self.group, self.cursor = model, plan, group, 0
+
+    def _enqueue(self):
+        import ctypes
+
+        import torch.distributed as dist
+        m = self.model
+        eng, st = m._engine(), m._dp_step
+        _lib.check(eng.lib.fr_focf_forward(ctypes.byref(st), _lib.stream_ptr()), "fr_focf_forward")
+        _lib.check(eng.lib.fr_focf_backward(ctypes.byref(st), 1.0, _lib.stream_ptr()), "fr_focf_backward")
+        dist.all_reduce(m._dp_grad, group=self.group)
+        _lib.check(eng.lib.fr_focf_adam(ctypes.byref(st), _lib.stream_ptr()), "fr_focf_adam")
+
+    def _account(self, k):
+        n = self.plan["len"]
+        rows = sum(self.plan["batch_rows"][(self.cursor + i) % n] for i in range(k))
+        self.cursor += k
+        self.model._adam["step"] += k
+        return rows
+
+    def eager_steps(self, k):
+        for _ in range(k):
+            self._enqueue()
+        return self._account(k)
+
+    def run(self, k):
+        m = self.model
+        G = m._dp_graph_len
+        for _ in range(k // G):
+            m._dp_graphs[G].replay()
+        for _ in range(k % G):
+            m._dp_graphs[1].replay()
+        return self._account(k)
+
+
 class _PlannedRunner:
     def __init__(self, model, plan):
         self.model, self.plan, self.cursor = model, plan, 0
+
+    def eager_steps(self, k):
+        """the next k steps launched one by one on workspace 0 (profiling: graph replays bypass the launch hooks)"""
+        m = self.model
+        eng = m._engine()
+        eng.set_counters(plan_cursor=self.cursor, adam_step=m._adam["step"], stride=1)
+        for _ in range(k):
+            eng.run_planned(m._graph_step)
+        n = self.plan["len"]
+        rows = sum(self.plan["batch_rows"][(self.cursor + i) % n] for i in range(k))
+        self.cursor += k
+        m._adam["step"] += k
+        return rows
 
     def run(self, k):
         """execute the next k planned steps (graph replays only); returns the interactions they cover"""

@@ -120,6 +120,14 @@ class FOCFTrainer:
         import torch.distributed as dist
         if not self.fused:
             raise NotImplementedError("data-parallel FOCF training uses the library's Adam (learner: adam)")
+        if self.config["dp_cuda_graph"]:
+            # opt-in: the captured data-parallel step (forward -> backward -> NCCL all-reduce -> Adam per graph node
+            # sequence) is bit-identical to the eager one on a 1-rank NCCL group; multi-rank replay is not validated yet
+            runner = self.model.dp_planned_runner(train_data, self._loss_buf, self.group)
+            k = runner.plan["len"]
+            runner.run(k - runner.cursor)
+            dist.all_reduce(self._loss_buf[:k], group=self.group)
+            return self._finish_epoch(k)
         items, offs, batches = train_data.plan_epoch()
         dev = self.device
         sizes = torch.tensor([[b[2], b[3]] for b in batches], dtype=torch.int64, device=dev)
