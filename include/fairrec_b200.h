@@ -248,8 +248,13 @@ int fr_adam_multi(const fr_adam_entry *entries_host, int32_t n_entries, double l
 /* Y = act(dropout(X) . W^T + b): nn.Dropout -> nn.Linear -> activation (layers.py:60-68 without BatchNorm) */
 /* dropout masks are a counter-based hash of (seed + *seed_dev, layer, element); seed_dev (may be NULL) is a device-resident
  * offset so that replays of a captured CUDA graph draw fresh masks (bump it with fr_bump_u64 inside the graph) */
+/* Shapes with K % 32 == 0 and N % 32 == 0 run on the tensor cores when allow_tensor_cores != 0 (tcgen05.mma kind::tf32
+ * fed by TMA, 3xTF32 split done in shared memory, accumulator in TMEM; linear_tc.cu): one launch, no workspace; results
+ * agree with the CUDA-core kernel to fp32 rounding.  Other shapes use the CUDA-core kernel. */
+int fr_linear_uses_tensor_cores(int64_t M, int32_t K, int32_t N);
 int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
-                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, void *stream);
+                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, int32_t allow_tensor_cores,
+                      void *stream);
 int fr_bump_u64(uint64_t *counter_dev, uint64_t inc, void *stream);
 size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N);
 /* dY is the gradient w.r.t. the layer OUTPUT Y (post-activation); dX may be NULL */

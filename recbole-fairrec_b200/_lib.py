@@ -108,8 +108,9 @@ SIGNATURES = {
     "fr_nfcf_backward": (c_int, [POINTER(NfcfStep), c_float, c_void_p]),
     "fr_adam_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double, c_double,
                               c_double, c_double, c_void_p]),
+    "fr_linear_uses_tensor_cores": (c_int, [c_int64, c_int32, c_int32]),
     "fr_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
-                                  c_uint64, c_void_p, c_int32, c_void_p]),
+                                  c_uint64, c_void_p, c_int32, c_int32, c_void_p]),
     "fr_bump_u64": (c_int, [c_void_p, c_uint64, c_void_p]),
     "fr_linear_backward_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "fr_linear_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,

@@ -792,6 +792,11 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) loss[0] = acc / (float)M;
 }
 
+// linear_tc.cu
+bool tc_linear_eligible(int64_t M, int K, int N);
+int tc_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int K, int N, int act,
+                      float drop_p, unsigned long long seed, const unsigned long long *seed_dev, int layer, cudaStream_t st);
+
 static void launch_gemm(bool tb, const GemmArgs &g, cudaStream_t st) {
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
   if (tb) {
@@ -1022,9 +1027,20 @@ int fr_bump_u64(uint64_t *counter_dev, uint64_t inc, void *stream) {
 }
 
 // ---------------------------------------------------------------- generic layer ops
+int fr_linear_uses_tensor_cores(int64_t M, int32_t K, int32_t N) { return fr::tc_linear_eligible(M, K, N) ? 1 : 0; }
+
 int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, int64_t M, int32_t K, int32_t N, int32_t act,
-                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, void *stream) {
+                      float drop_p, uint64_t seed, const uint64_t *seed_dev, int32_t layer, int32_t allow_tensor_cores,
+                      void *stream) {
   FR_REQUIRE(X && W && Y && M >= 1 && K >= 1 && N >= 1, "fr_linear_forward: bad argument");
+  if (allow_tensor_cores && fr::tc_linear_eligible(M, K, N)) {
+    // tensor-core path: tcgen05 3xTF32 (linear_tc.cu)
+    int rc = fr::tc_linear_forward(X, W, b, Y, M, K, N, act, drop_p, seed, (const unsigned long long *)seed_dev, layer,
+                                   (cudaStream_t)stream);
+    if (rc) return rc;
+    FR_LAUNCH_CHECK();
+    return FR_OK;
+  }
   fr::GemmArgs g{X, W, b, Y, (int)M, N, K, K, K, N, act, nullptr, 0, drop_p, seed, layer, 0, nullptr, 0,
                  (const unsigned long long *)seed_dev};
   fr::launch_gemm(true, g, (cudaStream_t)stream);

@@ -56,7 +56,7 @@ class LinearAct(torch.autograd.Function):
         N = W.shape[0]
         Y = torch.empty((M, N), dtype=torch.float32, device=X.device)
         sd = seed_dev(X.device) if drop_p > 0 else None
-        check(lib.fr_linear_forward(ptr(X), ptr(W), ptr(b), ptr(Y), M, K, N, act, float(drop_p), seed, ptr(sd), 0,
+        check(lib.fr_linear_forward(ptr(X), ptr(W), ptr(b), ptr(Y), M, K, N, act, float(drop_p), seed, ptr(sd), 0, 1,
                                     stream_ptr()), "fr_linear_forward")
         ctx.save_for_backward(X, W, Y)
         ctx.cfg = (act, float(drop_p), seed, b is not None)
