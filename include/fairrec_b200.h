@@ -395,6 +395,16 @@ size_t fr_gini_workspace_bytes(int32_t n_items);
 int fr_gini_at_k(const int32_t *item_pos_count, int32_t n_items, int32_t k_rows, int64_t n_users, double *gini_out,
                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* Sampled-negative ("uni100") ranking evaluation -- trainer.py:441-456 (_neg_sample_batch_eval: candidate scores
+ * scattered into a [users, n_items] matrix of -inf) + collector.py:141-153 (topk, hit bits, number of positives) without
+ * the dense matrix.  Candidates of user u = cand_items[cand_off[u] .. cand_off[u+1]) with their scores; the first
+ * n_pos_of_user[u] of them are the positives (general_dataloader.py:128-152 layout).  Canonical order (score desc, item
+ * id asc); duplicate candidates collapse; fewer than K distinct candidates -> lowest non-candidate ids as -inf filler.
+ * rec_topk [n, K+1] = hit bits | number of distinct positives. */
+int fr_sampled_topk(const int64_t *cand_off, const int32_t *cand_items, const float *cand_scores,
+                    const int32_t *n_pos_of_user, int32_t n, int32_t K, int32_t n_items, int32_t *topk_id,
+                    float *topk_score, int32_t *rec_topk, void *stream);
+
 /* metrics.py:860-881, 935-1266, 1313-1341: per (positive item, group) sums over the eval positives.
  * group[p] in [0,G).  Outputs (float64): stats [n_items, G, 2] = (sum score, count) per item x group.
  * Deterministic (sorted-segment reduction, no float atomics). */

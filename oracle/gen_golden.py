@@ -206,6 +206,71 @@ def run_focf_eval(name, n_users=60, n_items=97, d=16, K=10, topk=(5, 10), seed=1
     print(f"focf_eval_{name}:", {k: float(v) for k, v in result.items()})
 
 
+def run_uni_eval(name, n_users=50, n_items=400, d=16, topk=(5, 10), seed=51, neg_num=100, users_per_batch=1,
+                 transform="clamp"):
+    """Sampled-negative (uni100) ranking evaluation of the reference: NegSampleEvalDataLoader's batch layout
+    (general_dataloader.py:128-152: per user [positives ; neg_num negatives per positive], row index per interaction),
+    Trainer._neg_sample_batch_eval (trainer.py:441-456: predict + scatter into a -inf [users, n_items] matrix),
+    Collector.eval_batch_collect and the mode-independent metrics.  Negatives are drawn like
+    Sampler.sample_by_key_ids (uniform over the items not used by the user), recorded in the fixture."""
+    rng = np.random.default_rng(seed)
+    metrics = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
+               "NonParityUnfairness"]
+    cfg = base_cfg(embedding_size=d, topk=list(topk), metric_decimal_place=12, metrics=metrics,
+                   eval_args={"mode": f"uni{neg_num}"})
+    model = FOCF(cfg, FakeDataset(n_users, n_items, 5.0))
+    U = (np.abs(rng.standard_normal((n_users, d))) * 0.35 + 0.01).astype(np.float32)
+    It = (np.abs(rng.standard_normal((n_items, d))) * 0.35 + 0.01).astype(np.float32)
+    with torch.no_grad():
+        model.user_embedding_layer.weight.copy_(torch.from_numpy(U))
+        model.item_embedding_layer.weight.copy_(torch.from_numpy(It))
+    model.eval()
+    sst_of_user = rng.integers(1, 3, size=n_users)
+    eval_users = np.array([u for u in range(1, n_users) if u % 7 != 0], dtype=np.int64)
+    pos, neg = {}, {}
+    for u in eval_users:
+        n_used = int(rng.integers(4, 40))
+        used = rng.choice(np.arange(1, n_items), size=n_used, replace=False)
+        pos[u] = used[:int(rng.integers(1, min(6, n_used)))]
+        free = np.setdiff1d(np.arange(1, n_items), used)
+        neg[u] = rng.choice(free, size=neg_num * len(pos[u]), replace=True)     # [j * p + k] = j-th negative of positive k
+    train_item_count = {int(i): int(c) for i, c in zip(np.arange(1, n_items), rng.integers(1, 50, n_items - 1))}
+    trainer = FakeTrainer(model, n_items)
+    trainer.test_batch_size = 1 << 30
+    trainer.config = cfg
+    from recbole.utils import EvaluatorType
+    cfg["eval_type"] = EvaluatorType.RANKING
+    collector = Collector(cfg)
+    collector.data_struct.set("data.num_items", n_items)
+    from collections import Counter
+    collector.data_struct.set("data.count_items", Counter(train_item_count))
+    with torch.no_grad():
+        for b0 in range(0, len(eval_users), users_per_batch):
+            bu = eval_users[b0:b0 + users_per_batch]
+            uid = np.concatenate([np.full(len(pos[u]) * (neg_num + 1), u) for u in bu])
+            iid = np.concatenate([np.concatenate([pos[u], neg[u]]) for u in bu])
+            row = np.concatenate([np.full(len(pos[u]) * (neg_num + 1), i) for i, u in enumerate(bu)])
+            inter = Interaction({"user_id": torch.from_numpy(uid), "item_id": torch.from_numpy(iid),
+                                 "gender": torch.from_numpy(sst_of_user[uid])})
+            pu = torch.cat([torch.full((len(pos[u]),), i, dtype=torch.int64) for i, u in enumerate(bu)])
+            pi = torch.cat([torch.from_numpy(pos[u]) for u in bu])
+            inter, scores, pu, pi = Trainer._neg_sample_batch_eval(trainer, (inter, torch.from_numpy(row), pu, pi))
+            collector.eval_batch_collect(scores, inter, pu, pi)
+    struct = collector.get_data_struct()
+    result = Evaluator(cfg).evaluate(struct)
+    out = dict(U=U, I=It, max_rating=5.0, topk=np.array(topk), eval_users=eval_users, sst_of_user=sst_of_user,
+               neg_num=neg_num, pos_off=np.cumsum([0] + [len(pos[u]) for u in eval_users]),
+               pos_items=np.concatenate([pos[u] for u in eval_users]),
+               neg_items=np.concatenate([neg[u] for u in eval_users]),
+               train_count_items=np.array(sorted(train_item_count.items()), dtype=np.int64),
+               rec_items=struct.get("rec.items").numpy(), rec_topk=struct.get("rec.topk").numpy(),
+               rec_positive_score=struct.get("rec.positive_score").numpy(),
+               metric_names=np.array(list(result.keys())),
+               metric_values=np.array([float(v) for v in result.values()], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, f"uni_eval_{name}.npz"), **out)
+    print(f"uni_eval_{name}:", {k: float(v) for k, v in result.items()})
+
+
 def run_ml100k(epochs=2):
     """End-to-end on the bundled ml-100k through run_recbole's own steps (quick_start.py:20-71); records
     the split tensors, the FOCFDataLoader item draws, the per-epoch train loss and the metric dicts."""
@@ -600,6 +665,11 @@ def run_all_fairgo():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "uni":
+        run_uni_eval("uni100", users_per_batch=1)
+        run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
+        run_uni_eval("uni20_small_catalog", n_items=60, neg_num=20, users_per_batch=2, seed=53)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "fairgo":
         run_all_fairgo()
         return
@@ -627,6 +697,9 @@ def main():
     run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
     run_all_pfcn()
     run_all_fairgo()
+    run_uni_eval("uni100", users_per_batch=1)
+    run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
+    run_uni_eval("uni20_small_catalog", n_items=60, neg_num=20, users_per_batch=2, seed=53)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,7 @@ Only what the path needs lives here:
   nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
+  sampled_eval.py  sampled-negative (uni100) ranking evaluation (SampledEvalData, SampledEvaluator)
   trainer.py       FOCFTrainer (fit / evaluate)
   synth.py         synthetic data of the benchmark shapes
 The directory name carries a hyphen; import it as `recbole_fairrec_b200` (shim at the repo root).
@@ -25,6 +26,7 @@ from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF  # noqa: F401
 from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFCN_MLPTrainer, PFCN_PMFTrainer,  # noqa: F401
                    PFCN_BiasedMFTrainer, PFCN_DMFTrainer)
+from .sampled_eval import SampledEvalData, SampledEvaluator, sample_negatives  # noqa: F401
 from .trainer import FOCFTrainer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -150,6 +150,8 @@ SIGNATURES = {
     "fr_spmm_csr": (c_int, [POINTER(SpmmPlan), c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_fullsort_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fr_fullsort_topk": (c_int, [POINTER(FullSort), c_void_p]),
+    "fr_sampled_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
     "fr_topk_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_hits": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fr_topk_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),

@@ -434,3 +434,96 @@ int fr_hits(const int32_t *topk_id, int32_t n, int32_t K, const int64_t *pos_off
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Sampled-negative ("uni100") ranking evaluation: top-K over each user's CANDIDATE list.
+// Reference being replaced: trainer.py:441-456 (_neg_sample_batch_eval: scatter the candidate scores into a
+// [users, n_items] matrix of -inf) + collector.py:141-153 (topk, hit bits, number of positives).  The dense matrix is
+// never built: one warp owns a user and extracts the K best candidates in the canonical total order (score desc, item
+// id asc) by K rounds of "best entry strictly after the previous pick" -- duplicates of a candidate (same pair, same
+// score) collapse by construction, like the scatter.  A user with fewer than K distinct candidates gets the lowest
+// non-candidate item ids as filler (score -inf), which is what the canonical order gives on the dense -inf row.
+namespace fr {
+
+__device__ __forceinline__ bool cand_after(float s, int id, float ps, int pid) {   // (s,id) strictly after (ps,pid)
+  return s < ps || (s == ps && id > pid);
+}
+__device__ __forceinline__ bool cand_better(float s, int id, float s2, int id2) { return s > s2 || (s == s2 && id < id2); }
+
+__global__ void __launch_bounds__(256)
+    k_sampled_topk(const int64_t *__restrict__ cand_off, const int32_t *__restrict__ cand_items,
+                   const float *__restrict__ cand_scores, const int32_t *__restrict__ n_pos_of_user, int n, int K,
+                   int n_items, int32_t *__restrict__ topk_id, float *__restrict__ topk_score,
+                   int32_t *__restrict__ rec_topk) {
+  const int lane = threadIdx.x & 31;
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n) return;
+  const int64_t c0 = cand_off[u], c1 = cand_off[u + 1];
+  const int np = n_pos_of_user[u];
+  float ps = INFINITY;
+  int pid = -1;
+  bool exhausted = false;
+  int fill = 0;   // next filler id to try
+  for (int r = 0; r < K; ++r) {
+    float bs = -INFINITY;
+    int bid = 0x7fffffff;
+    if (!exhausted) {
+      for (int64_t c = c0 + lane; c < c1; c += 32) {
+        const float s = cand_scores[c];
+        const int id = cand_items[c];
+        if (s == s && cand_after(s, id, ps, pid) && cand_better(s, id, bs, bid)) { bs = s; bid = id; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int id2 = __shfl_xor_sync(0xffffffffu, bid, o);
+        if (cand_better(s2, id2, bs, bid)) { bs = s2; bid = id2; }
+      }
+      if (bid == 0x7fffffff) exhausted = true;
+    }
+    int hit = 0;
+    if (!exhausted) {
+      ps = bs; pid = bid;
+      for (int64_t c = c0 + lane; c < c0 + np; c += 32) hit |= cand_items[c] == bid;
+      hit = __any_sync(0xffffffffu, hit);
+    } else {   // filler: lowest item id that is not a candidate
+      while (true) {
+        int is_cand = 0;
+        for (int64_t c = c0 + lane; c < c1; c += 32) is_cand |= cand_items[c] == fill;
+        if (!__any_sync(0xffffffffu, is_cand) || fill >= n_items) break;
+        ++fill;
+      }
+      bid = fill++;
+      bs = -INFINITY;
+    }
+    if (lane == 0) {
+      topk_id[(size_t)u * K + r] = bid;
+      topk_score[(size_t)u * K + r] = bs;
+      rec_topk[(size_t)u * (K + 1) + r] = hit ? 1 : 0;
+    }
+  }
+  // number of DISTINCT positives (pos_matrix.sum(dim=1), collector.py:150)
+  int distinct = 0;
+  for (int a = lane; a < np; a += 32) {
+    const int id = cand_items[c0 + a];
+    bool first = true;
+    for (int b = 0; b < a; ++b) first &= cand_items[c0 + b] != id;
+    distinct += first;
+  }
+  distinct = warp_sum(distinct);
+  if (lane == 0) rec_topk[(size_t)u * (K + 1) + K] = distinct;
+}
+
+}  // namespace fr
+
+extern "C" int fr_sampled_topk(const int64_t *cand_off, const int32_t *cand_items, const float *cand_scores,
+                               const int32_t *n_pos_of_user, int32_t n, int32_t K, int32_t n_items, int32_t *topk_id,
+                               float *topk_score, int32_t *rec_topk, void *stream) {
+  FR_REQUIRE(cand_off && cand_items && cand_scores && n_pos_of_user && topk_id && topk_score && rec_topk && n >= 1 &&
+                 K >= 1 && n_items >= K,
+             "fr_sampled_topk: bad argument");
+  FR_LAUNCH(fr::k_sampled_topk, (n + 7) / 8, 256, 0, stream, cand_off, cand_items, cand_scores, n_pos_of_user, n, K,
+            n_items, topk_id, topk_score, rec_topk);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}

@@ -355,6 +355,24 @@ class PFCNTrainer:
             raise ValueError("Training loss is nan")
         return v
 
+    @torch.no_grad()
+    def evaluate(self, eval_data, sst_list=None, train_item_count=None):
+        """PFCNTrainer.pfcn_evaluate / evaluate (trainer.py:1010-1093) for one attribute subset: the sampled-negative
+        (`uni100`) evaluation -- the only one the reference defines for this family -- with `model.predict` as the scorer
+        and the fused candidate top-K + metrics (sampled_eval.SampledEvaluator).  eval_data: SampledEvalData."""
+        from .interaction import Interaction
+        from .sampled_eval import SampledEvaluator
+        self.model.eval()
+        if getattr(self, "sampled_evaluator", None) is None:
+            self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, train_item_count)
+        sst_list = (self.sst_attrs if self.filter_mode != "none" else None) if sst_list is None else sst_list
+        m = self.model
+
+        def score_fn(uid, iid):
+            return m.predict(Interaction({m.USER_ID: uid, m.ITEM_ID: iid}), sst_list).view(-1)
+
+        return self.sampled_evaluator.evaluate(score_fn, eval_data)
+
     def _train_epoch(self, train_data, epoch_idx):
         if self.filter_mode == "none":
             return self._pass(train_data, self.model.calculate_loss, self.optimizer_filter, None)

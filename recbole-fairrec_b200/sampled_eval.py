@@ -1,0 +1,140 @@
+"""Sampled-negative ("uni100") ranking evaluation -- replaces NegSampleEvalDataLoader batches
+(recbole/data/dataloader/general_dataloader.py:68-158) + Trainer._neg_sample_batch_eval (recbole/trainer/trainer.py:441-456)
++ Collector.eval_batch_collect (recbole/evaluator/collector.py:131-205) + the mode-independent metrics with one pass of
+device kernels over ALL eval users.  `uni100` is the default evaluation mode of all eight model YAMLs and the only
+evaluation the reference defines for the PFCN family.
+
+The reference scatters every user's candidate scores into a dense [users, n_items] row of -inf and runs torch.topk on
+it; here the dense rows never exist: candidates live in a CSR (positives first, then the sampled negatives, the
+dataloader's own order), their scores come from the model's `predict` (any model) or the pair-score kernel (dot-product
+models), and `fr_sampled_topk` extracts the K best per user in the canonical order (score desc, item id asc).
+
+Metrics: NDCG / Recall / Hit / MRR, GiniIndex, PopularityPercentage, DifferentialFairness, NonParityUnfairness -- the ones
+whose definition does not depend on the evaluation mode.  Two deliberate differences from the reference, both only
+visible when its dataloader packs SEVERAL users into one batch: (i) every positive carries its OWN user's sensitive
+attribute (the reference reads the attribute of the first P rows of the batch interaction, collector.py:203-205, which
+belong mostly to the batch's first user); (ii) Value / Absolute / Under / Over unfairness are not offered in sampled mode:
+the reference computes them from `interaction[item][P:2P]` scored in the positives' rows (collector.py:190-199), which
+for multi-user batches are -inf entries, i.e. its values are inf / NaN.  With one user per batch (i) coincides with the
+reference (tests/golden/uni_eval_uni100.npz)."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib, kernels
+from ._lib import check, load, ptr, stream_ptr
+from .evaluator import FAIR_KEYS, FAIR_SLOTS, TOPK_ROWS, FullSortEvaluator
+
+MODE_FREE = set(TOPK_ROWS) | {"giniindex", "popularitypercentage", "differentialfairness", "nonparityunfairness"}
+
+
+def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
+    """Sampler.sample_by_key_ids (recbole/sampler/sampler.py:145-197) in effect: for every positive `neg_num` items drawn
+    uniformly from the items the user has NOT used (ids 1..n_items-1), laid out like the dataloader does
+    (`[j * p + k]` = j-th negative of positive k, abstract_dataloader.py:190-198)."""
+    out = []
+    for pos, used in zip(pos_lists, used_lists):
+        banned = np.zeros(n_items, bool)
+        banned[0] = True
+        banned[np.asarray(used, np.int64)] = True
+        banned[np.asarray(pos, np.int64)] = True
+        need = neg_num * len(pos)
+        got = np.zeros(0, np.int64)
+        while len(got) < need:            # rejection sampling, like the reference
+            c = rng.integers(1, n_items, size=2 * (need - len(got)) + 8)
+            got = np.concatenate([got, c[~banned[c]]])
+        out.append(got[:need])
+    return out
+
+
+class SampledEvalData:
+    """Device-resident candidate lists: per eval user its positives followed by its sampled negatives."""
+
+    def __init__(self, users, pos_lists, neg_lists, sst_of_user, device):
+        users = np.asarray(users, np.int64)
+        n = len(users)
+        self.n, self.device = n, device
+        n_pos = np.array([len(p) for p in pos_lists], np.int64)
+        cand = [np.concatenate([np.asarray(p, np.int64), np.asarray(q, np.int64)]) for p, q in zip(pos_lists, neg_lists)]
+        cand_off = np.zeros(n + 1, np.int64)
+        cand_off[1:] = np.cumsum([len(c) for c in cand])
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
+        self.users = t(users, torch.int32)
+        self.cand_off = t(cand_off, torch.int64)
+        self.cand_items = t(np.concatenate(cand), torch.int32)
+        self.cand_uid = t(np.repeat(users, np.diff(cand_off)), torch.int32)
+        self.n_pos_of_user = t(n_pos, torch.int32)
+        # positions of the positives inside the candidate arrays (user-major, dataloader order)
+        pos_idx = np.concatenate([cand_off[k] + np.arange(n_pos[k]) for k in range(n)]) if n else np.zeros(0, np.int64)
+        self.pos_idx = t(pos_idx, torch.int64)
+        self.pos_items = t(np.concatenate([np.asarray(p, np.int64) for p in pos_lists]), torch.int32)
+        self.n_pos = int(n_pos.sum())
+        pos_row = np.repeat(np.arange(n), n_pos)
+        self.pos_row = t(pos_row, torch.int64)
+        self.sst_value, self.group_of_pos, self.n_groups = {}, {}, {}
+        for attr, per_user in sst_of_user.items():
+            vals = np.asarray(per_user)[users]
+            uniq, inv = np.unique(vals[pos_row], return_inverse=True)
+            self.sst_value[attr] = torch.as_tensor(vals)
+            self.group_of_pos[attr] = t(inv, torch.int32)
+            self.n_groups[attr] = len(uniq)
+
+
+def sampled_topk(data, scores, K, n_items):
+    """fr_sampled_topk -> (topk_id int32 [n,K], topk_score f32 [n,K], rec_topk int32 [n,K+1])"""
+    lib = load()
+    dev = scores.device
+    ids = torch.empty((data.n, K), dtype=torch.int32, device=dev)
+    sc = torch.empty((data.n, K), dtype=torch.float32, device=dev)
+    rec = torch.empty((data.n, K + 1), dtype=torch.int32, device=dev)
+    check(lib.fr_sampled_topk(ptr(data.cand_off), ptr(data.cand_items), ptr(scores.contiguous()), ptr(data.n_pos_of_user),
+                              data.n, int(K), int(n_items), ptr(ids), ptr(sc), ptr(rec), stream_ptr()), "fr_sampled_topk")
+    return ids, sc, rec
+
+
+class SampledEvaluator(FullSortEvaluator):
+    """evaluate(score_fn, data) -> the reference's metric dict (same keys, same rounding).  score_fn(uid int32 [C],
+    iid int32 [C]) -> float32 [C] scores of the candidate pairs; `dot_scorer` builds one for dot-product models."""
+
+    def __init__(self, config, n_items, train_item_count=None):
+        super().__init__(config, n_items, train_item_count)
+        bad = [m for m in self.metrics if m not in MODE_FREE]
+        if bad:
+            raise NotImplementedError(f"{bad}: in sampled mode the reference computes these from mis-indexed negative "
+                                      f"scores (collector.py:190-199); see recbole_fairrec_b200/sampled_eval.py")
+
+    @staticmethod
+    def dot_scorer(U, I, max_rating=None, transform=None):
+        if transform is None:
+            transform = _lib.TRANSFORM_CLAMP_DIV if max_rating is not None else _lib.TRANSFORM_NONE
+        return lambda uid, iid: kernels.pair_scores(U, I, uid, iid, transform, 1.0 if max_rating is None else max_rating)
+
+    @torch.no_grad()
+    def collect(self, score_fn, data):
+        scores = score_fn(data.cand_uid, data.cand_items).view(-1).to(torch.float32)
+        ids, sc, rec_topk = sampled_topk(data, scores, self.K, self.n_items)
+        pos_score = scores[data.pos_idx].contiguous()
+        out = {"topk_id": ids, "topk_score": sc, "rec_topk": rec_topk, "pos_score": pos_score}
+        need = set(self.metrics)
+        if need & set(TOPK_ROWS):
+            out["topk_sums"] = kernels.topk_metric_sums(rec_topk)
+        if need & {"giniindex", "popularitypercentage"}:
+            cnt, pop = kernels.rec_item_stats(ids, self.n_items, self._popular_mask(scores.device))
+            out["pop_hits"] = pop
+            if "giniindex" in need:
+                out["gini"] = {k: kernels.gini_at_k(cnt, k, data.n) for k in self.topk}
+        if need & set(FAIR_SLOTS):
+            out["fair"] = {}
+            for attr in self.sst_attr_list:
+                stats = kernels.item_group_stats(data.pos_items, pos_score, data.group_of_pos[attr], self.n_items,
+                                                 data.n_groups[attr])
+                out["fair"][attr] = kernels.fairness_metrics(stats)
+        self.last = out
+        return out
+
+    def evaluate(self, score_fn, data):
+        return self.finalize(self.collect(score_fn, data), data)
+
+
+__all__ = ["SampledEvalData", "SampledEvaluator", "sample_negatives", "sampled_topk", "OrderedDict", "FAIR_KEYS"]

@@ -181,6 +181,13 @@ class FOCFTrainer:
             self.model.load_state_dict(checkpoint["state_dict"])
             self.model.load_other_parameter(checkpoint.get("other_parameter"))
         self.model.eval()
+        from .sampled_eval import SampledEvalData, SampledEvaluator
+        if isinstance(eval_data, SampledEvalData):      # eval_args.mode uni<N>: sampled-negative ranking evaluation
+            if getattr(self, "sampled_evaluator", None) is None:
+                self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, self._train_item_count)
+            score_fn = SampledEvaluator.dot_scorer(self.model.user_embedding_layer.weight.data,
+                                                   self.model.item_embedding_layer.weight.data, self.model.max_rating)
+            return self.sampled_evaluator.evaluate(score_fn, eval_data)
         if self.evaluator is None:
             self.evaluator = FullSortEvaluator(self.config, self.model.n_items, self._train_item_count, group=self.group)
         data = self._eval_data(eval_data)
