@@ -212,7 +212,7 @@ def run_ours(args, wname):
     n_plan = args.steps + args.warmup
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     G = 8
-    use_graph = loader.max_batch <= 8192 and not args.no_graph and (world == 1 or args.dp_graph)
+    use_graph = loader.max_batch <= 8192 and not args.no_graph and (world == 1 or not args.no_dp_graph)
     losses = torch.zeros(max(len(loader), n_plan) * 2 + 16, device=dev)
     if use_graph and world > 1:
         # data-parallel: forward -> backward -> NCCL all-reduce -> dense Adam of G planned steps in one CUDA graph
@@ -593,6 +593,9 @@ def run_ours(args, wname):
                  "tensor_core": tc},
     }
     if world > 1:
+        runner = None
+        model.release_graphs()          # graphs holding captured NCCL kernels must go before the communicator does
+        dist.barrier()
         dist.destroy_process_group()
     return out if rank == 0 else None
 
@@ -699,8 +702,9 @@ def main():
     ap.add_argument("--no-probe", action="store_true", help="skip the scale-out roofline probe")
     ap.add_argument("--no-families", action="store_true", help="skip the PFCN / FairGo legs")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
-    ap.add_argument("--dp-graph", action="store_true",
-                    help="multi-GPU: capture the data-parallel step incl. the NCCL all-reduce in a CUDA graph (experimental)")
+    ap.add_argument("--no-dp-graph", action="store_true",
+                    help="multi-GPU: launch the data-parallel steps eagerly instead of replaying a CUDA graph that "
+                         "captured them together with their NCCL all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

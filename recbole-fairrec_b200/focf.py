@@ -336,6 +336,16 @@ class FOCF(nn.Module):
         eng.set_counters(plan_cursor=runner.cursor, adam_step=self._adam["step"], stride=1)
         return runner
 
+    def release_graphs(self):
+        """drop every captured CUDA graph (call before torch.distributed.destroy_process_group(): graphs that captured
+        NCCL kernels keep the communicator busy and make the teardown hang)"""
+        import gc
+        self._dp_graphs, self._dp_graph_key = {}, None
+        self._graphs, self._graph_key = {}, None
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     @torch.no_grad()
     def train_epoch_planned(self, loader, loss_buf, graph_steps=8):
         """One epoch through planned_runner.  Returns (number of steps, number of interactions)."""

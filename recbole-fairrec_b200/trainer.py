@@ -120,9 +120,10 @@ class FOCFTrainer:
         import torch.distributed as dist
         if not self.fused:
             raise NotImplementedError("data-parallel FOCF training uses the library's Adam (learner: adam)")
-        if self.config["dp_cuda_graph"]:
-            # opt-in: the captured data-parallel step (forward -> backward -> NCCL all-reduce -> Adam per graph node
-            # sequence) is bit-identical to the eager one on a 1-rank NCCL group; multi-rank replay is not validated yet
+        if (self.config["cuda_graph"] is None or self.config["cuda_graph"]) and self.config["dp_cuda_graph"] is not False:
+            # the data-parallel step (forward -> backward -> NCCL all-reduce -> Adam) of 8 planned batches per captured
+            # CUDA graph; call model.release_graphs() before destroying the process group (captured NCCL kernels keep
+            # the communicator busy)
             runner = self.model.dp_planned_runner(train_data, self._loss_buf, self.group)
             k = runner.plan["len"]
             runner.run(k - runner.cursor)

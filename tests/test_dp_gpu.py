@@ -71,6 +71,7 @@ def _worker(rank, world, port, out):
     r1 = ev1.evaluate(Uw, Iw, data, 5.0)
     rp = evp.evaluate(Uw, Iw, data, 5.0)
     ids_equal = bool(torch.equal(ev1.last["topk_id"], evp.last["topk_id"]))
+    model.release_graphs()      # captured NCCL kernels must go before the communicator
     if rank == 0:
         out.put(dict(loss_dp=loss_dp, loss_ref=loss_ref, U_dp=U_dp, U_ref=U_ref, I_dp=I_dp, I_ref=I_ref, r1=dict(r1),
                      rp=dict(rp), ids_equal=ids_equal))
