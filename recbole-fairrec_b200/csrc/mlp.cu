@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(256)
   const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
   const int cnt = max(r1 - r0, 0);
   float s = 0.f;
+#pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8) s += ok ? X[(size_t)m * N + c] : 0.f;
   red[w][lane] = s;
   __syncthreads();
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(256)
   const float mean = cnt > 0 ? s / (float)cnt : 0.f;
   __syncthreads();
   float q = 0.f;
+#pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8) {
     const float dlt = ok ? X[(size_t)m * N + c] - mean : 0.f;
     q = fmaf(dlt, dlt, q);
@@ -600,15 +602,21 @@ __global__ void __launch_bounds__(256)
   float mean = 0.f, invstd = 0.f;
   if (ok) {
     if (training) {
+      // all slice partials are fetched first (32 independent loads in flight), then combined in slice order with Chan
+      // et al.'s pairwise update; empty slices hold (0, 0) and are skipped by the predicate, not by a branch on loads
+      float2 pr[kBnSlices];
+#pragma unroll
+      for (int sl = 0; sl < kBnSlices; ++sl) pr[sl] = __ldg((const float2 *)(part + ((size_t)sl * N + c) * 2));
       float n = 0.f, M2 = 0.f;
-      for (int sl = 0; sl < kBnSlices; ++sl) {       // Chan et al. pairwise update, slice order
+#pragma unroll
+      for (int sl = 0; sl < kBnSlices; ++sl) {
         const int cb = min(M, (sl + 1) * rows) - sl * rows;
-        if (cb <= 0) break;
-        const float mb = part[((size_t)sl * N + c) * 2], qb = part[((size_t)sl * N + c) * 2 + 1];
-        const float nb = (float)cb, nn = n + nb, dlt = mb - mean;
-        mean += dlt * (nb / nn);
-        M2 += qb + dlt * dlt * (n * nb / nn);
-        n = nn;
+        if (cb > 0) {
+          const float nb = (float)cb, nn = n + nb, dlt = pr[sl].x - mean;
+          mean += dlt * (nb / nn);
+          M2 += pr[sl].y + dlt * dlt * (n * nb / nn);
+          n = nn;
+        }
       }
       const float var = M2 / (float)M;
       invstd = 1.f / sqrtf(var + eps);
@@ -624,6 +632,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   const float g = ok ? gamma[c] : 0.f, b = ok ? beta[c] : 0.f;
+#pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8)
     if (ok) Y[(size_t)m * N + c] = act_fwd(fmaf((X[(size_t)m * N + c] - mean) * invstd, g, b), act);
 }
@@ -642,6 +651,7 @@ __global__ void __launch_bounds__(256)
   const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
   const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f;
   float sb = 0.f, sg = 0.f;
+#pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8) {
     if (ok) {
       const size_t i = (size_t)m * N + c;
@@ -678,9 +688,15 @@ __global__ void __launch_bounds__(256)
   const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
   float sb = 0.f, sg = 0.f, mean = 0.f, invstd = 0.f, g = 0.f;
   if (ok) {
-    for (int sl = 0; sl < kBnSlices && sl * rows < M; ++sl) {
-      sb += part[((size_t)sl * N + c) * 2];
-      sg += part[((size_t)sl * N + c) * 2 + 1];
+    float2 pr[kBnSlices];
+#pragma unroll
+    for (int sl = 0; sl < kBnSlices; ++sl) pr[sl] = __ldg((const float2 *)(part + ((size_t)sl * N + c) * 2));
+#pragma unroll
+    for (int sl = 0; sl < kBnSlices; ++sl) {
+      if (sl * rows < M) {
+        sb += pr[sl].x;
+        sg += pr[sl].y;
+      }
     }
     mean = save_mean[c]; invstd = save_invstd[c]; g = gamma[c];
     if (blockIdx.y == 0 && w == 0) {
@@ -689,6 +705,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   const float k = g * invstd / (float)M;
+#pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8) {
     if (ok) {
       const size_t i = (size_t)m * N + c;
