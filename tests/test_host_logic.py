@@ -1,0 +1,93 @@
+"""CPU tests of the host-side logic around the kernels (no CUDA calls): the SpMM chunk planner of the C ABI, the
+normalised FairGo adjacency, negative sampling / candidate layout of the sampled evaluation, and the module trees
+(state_dict names) of the MLP families against the names recorded from the reference."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+HERE = os.path.dirname(__file__)
+
+
+def test_spmm_planner_covers_every_row_once():
+    from recbole_fairrec_b200._lib import load
+    lib = load()
+    rng = np.random.default_rng(0)
+    lens = np.minimum(rng.lognormal(3.0, 1.8, 500).astype(np.int64), 5000)
+    lens[:4] = [0, 1, 128, 129]
+    row_off = np.zeros(len(lens) + 1, np.int64)
+    row_off[1:] = np.cumsum(lens)
+    chunk = 128
+    sizes = [ctypes.c_int64() for _ in range(4)]
+    assert lib.fr_spmm_plan_sizes(row_off.ctypes.data, len(lens), chunk, *[ctypes.byref(s) for s in sizes]) == 0
+    nc, nm, ns, ne = [s.value for s in sizes]
+    assert nc == int(np.ceil(lens / chunk).sum()) and ne == int((lens == 0).sum())
+    assert nm == int((lens > chunk).sum()) and ns == int(np.ceil(lens[lens > chunk] / chunk).sum())
+    host = [np.zeros(max(nc, 1), np.int32) for _ in range(4)] + [np.zeros(max(nm, 1), np.int32), np.zeros(nm + 1, np.int32),
+                                                                np.zeros(max(ne, 1), np.int32)]
+    assert lib.fr_spmm_plan_fill(row_off.ctypes.data, len(lens), chunk, *[h.ctypes.data for h in host]) == 0
+    crow, cbeg, cend, cslot, mrow, mfirst, erow = host
+    covered = np.zeros(row_off[-1], np.int32)
+    for c in range(nc):
+        assert 0 < cend[c] - cbeg[c] <= chunk
+        assert row_off[crow[c]] <= cbeg[c] and cend[c] <= row_off[crow[c] + 1]
+        covered[cbeg[c]:cend[c]] += 1
+    assert (covered == 1).all()
+    # multi-chunk rows own consecutive slots, in chunk order; single-chunk rows write Y directly (slot -1)
+    for r in range(nm):
+        sl = [cslot[c] for c in range(nc) if crow[c] == mrow[r]]
+        assert sl == list(range(mfirst[r], mfirst[r + 1]))
+    single = lens[crow[:nc]] <= chunk
+    assert (cslot[:nc][single] == -1).all() and (cslot[:nc][~single] >= 0).all()
+    assert sorted(erow[:ne].tolist()) == np.nonzero(lens == 0)[0].tolist()
+
+
+def test_fairgo_normalised_adjacency_matches_the_oracle():
+    from oracle import fairgo_oracle as go
+    from recbole_fairrec_b200.fairgo import norm_rating_csr
+    rng = np.random.default_rng(1)
+    nu, ni, n = 40, 30, 300
+    pairs = rng.permutation((nu - 1) * (ni - 1))[:n]
+    tu, ti = pairs // (ni - 1) + 1, pairs % (ni - 1) + 1
+    tr = rng.integers(1, 6, n).astype(np.float32)
+    mine = norm_rating_csr(sp.coo_matrix((tr, (tu, ti)), shape=(nu, ni)), nu, ni)
+    ref = go.norm_matrix(tu, ti, tr, nu, ni).tocsr()
+    assert abs(mine - ref).max() <= 1e-7 and mine.nnz == ref.nnz == 2 * n
+    assert np.allclose(np.asarray(mine.sum(axis=1)).ravel()[np.asarray(mine.sum(axis=1)).ravel() > 0], 1.0, atol=1e-5)
+
+
+def test_sample_negatives_and_candidate_layout():
+    import recbole_fairrec_b200 as pkg
+    rng = np.random.default_rng(2)
+    n_items = 50
+    pos = [np.array([3, 7]), np.array([10])]
+    used = [np.array([1, 2, 3, 7, 8]), np.arange(1, 45)]
+    neg = pkg.sample_negatives(pos, used, n_items, 20, rng)
+    for p, u, q in zip(pos, used, neg):
+        assert len(q) == 20 * len(p) and q.min() >= 1 and q.max() < n_items
+        assert not np.isin(q, u).any() and not np.isin(q, p).any()
+    data = pkg.SampledEvalData([4, 9], pos, neg, {"gender": np.arange(12) % 2}, torch.device("cpu"))
+    off = data.cand_off.numpy()
+    assert off.tolist() == [0, 2 + 40, 2 + 40 + 1 + 20] and data.n_pos_of_user.tolist() == [2, 1]
+    assert data.cand_items[:2].tolist() == [3, 7] and data.cand_items[off[1]].item() == 10
+    assert data.cand_uid[:42].unique().tolist() == [4] and data.pos_idx.tolist() == [0, 1, 42]
+    assert data.group_of_pos["gender"].tolist() == [0, 0, 1] and data.n_groups["gender"] == 2
+
+
+@pytest.mark.parametrize("fixture,prefix,layers,kw", [
+    ("pfcn_mlp_sm.npz", "filter_1", [16, 32, 16], dict(activation="leakyrelu", bn=True, init_method="norm")),
+    ("pfcn_mlp_sm.npz", "dis_age", [16, 32, 16, 4], dict(activation="leakyrelu", bn=True, init_method="norm")),
+    ("pfcn_mlp_sm.npz", "base.mlp_layer", [32, 16, 8, 1], dict()),
+    ("fairgo_pmf_lba.npz", "filter_gender", [16, 32, 16, 16], dict(activation="leakyrelu")),
+])
+def test_mlp_module_tree_has_the_reference_state_dict_names(fixture, prefix, layers, kw):
+    """checkpoints are interchangeable: MLPLayers here exposes exactly the parameter / buffer names (and shapes) that the
+    reference's MLPLayers (recbole/model/layers.py:30-85) recorded in the golden fixtures"""
+    from recbole_fairrec_b200.layers import MLPLayers
+    g = np.load(os.path.join(HERE, "golden", fixture))
+    want = {k[len(prefix) + 1:-5]: g[k].shape for k in g.files if k.startswith(prefix + ".") and k.endswith("@init")}
+    got = {k: tuple(v.shape) for k, v in MLPLayers(layers, **kw).state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
