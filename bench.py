@@ -539,7 +539,8 @@ def run_ours(args, wname):
             import bench_families as bf
             torch.cuda.empty_cache()
             families = {"pfcn_mlp": bf.bench_pfcn(dev, flush, cpu=not args.no_cpu_baseline),
-                        "fairgo_pmf": bf.bench_fairgo(dev, flush, cpu=not args.no_cpu_baseline)}
+                        "fairgo_pmf": bf.bench_fairgo(dev, flush, cpu=not args.no_cpu_baseline),
+                        "sampled_eval": bf.bench_sampled_eval(dev, flush, cpu=not args.no_cpu_baseline)}
         except Exception as e:
             families = {"error": str(e)[:300]}
     cpu = None

@@ -314,6 +314,68 @@ def cpu_fairgo(model, feats, train, hosts, attrs, n=2):
             "sample": f"{n} filter+discriminator fine-tune steps of {B} rows", "ms_per_step": 1e3 * dt}
 
 
+def bench_sampled_eval(dev, flush, cpu=True, seed=2020, neg_num=100, K=10):
+    """Sampled-negative (uni100) fair ranking evaluation at the ML-1M shape: all valid users, 100
+    uniform negatives per positive, FOCF scorer; users/s of scoring + candidate top-K + metrics, device-timed."""
+    import torch
+
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import synth
+    w = ML1M
+    uid, iid, rating, gender = synth.interactions(w["n_users"], w["n_items"], 1_000_209, seed)
+    train, valid, test = synth.split_by_user(uid, iid, rating, seed=seed)
+    users, hist, pos = synth.eval_lists(train, valid, test, "valid")
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    neg = pkg.sample_negatives(pos, hist, w["n_items"], neg_num, rng)
+    t_sample = time.perf_counter() - t0
+    data = pkg.SampledEvalData(users, pos, neg, {"gender": gender.astype(np.int64)}, dev)
+    metrics = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
+               "NonParityUnfairness"]
+    cfg = pkg.Config(topk=[K], metrics=metrics, sst_attr_list=["gender"], device=dev, eval_args={"mode": f"uni{neg_num}"})
+    counts = np.bincount(train[1], minlength=w["n_items"])
+    ev = pkg.SampledEvaluator(cfg, w["n_items"], {int(i): int(c) for i, c in enumerate(counts) if c > 0})
+    g = torch.Generator(device=dev).manual_seed(seed)
+    U = torch.randn(w["n_users"], w["d"], device=dev, generator=g) * 0.2
+    I = torch.randn(w["n_items"], w["d"], device=dev, generator=g) * 0.2
+    score_fn = pkg.SampledEvaluator.dot_scorer(U, I, 5.0)
+    res = ev.evaluate(score_fn, data)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ev.collect(score_fn, data)
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    from recbole_fairrec_b200 import _lib
+    _lib.profile_enable(True)
+    ev.collect(score_fn, data)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    tot = sum(v[1] for v in prof.values()) or 1.0
+    n_cand = int(data.cand_items.numel())
+    out = {"metric": "sampled-negative (uni100) fair-eval users/s", "value": data.n / (statistics.mean(ms) * 1e-3),
+           "unit": "users/s", "ms_per_pass": statistics.mean(ms), "n_users": data.n, "candidates": n_cand,
+           "config": {"workload": "focf_ml1m_uni100", **w, "neg_per_positive": neg_num, "K": K},
+           "kernel_shares": {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:6]},
+           "host_negative_sampling_s": t_sample, "ndcg@10": float(res[f"ndcg@{K}"])}
+    if cpu:
+        from oracle import sampled_oracle as so
+        n_cpu = 300
+        Uc, Ic = U.cpu().numpy(), I.cpu().numpy()
+        cands = [(np.asarray(p), np.asarray(q)) for p, q in zip(pos[:n_cpu], neg[:n_cpu])]
+        t0 = time.perf_counter()
+        rows = so.dense_rows(Uc, Ic, users[:n_cpu], cands, w["n_items"], 5.0)
+        so.collect(rows, cands, K)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "users/s", "cores": 1, "kind": "port",
+                               "sample": f"{n_cpu} users: dense -inf rows + canonical top-K + hit bits (oracle/sampled_oracle.py)"}
+    return out
+
+
 if __name__ == "__main__":
     import json
     import sys
@@ -322,4 +384,5 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     dev = torch.device("cuda", 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    print(json.dumps({"pfcn_mlp": bench_pfcn(dev, flush), "fairgo_pmf": bench_fairgo(dev, flush)}))
+    print(json.dumps({"pfcn_mlp": bench_pfcn(dev, flush), "fairgo_pmf": bench_fairgo(dev, flush),
+                      "sampled_eval": bench_sampled_eval(dev, flush)}))

@@ -19,6 +19,7 @@ for title, rep in [('k_focf_fused_step: the cooperative FOCF step (forward | bar
                    ('forward / loss / gradient kernels at the scale-out shape (B = 2^18)', 'gpurun_out/r01_step_scaleout.ncu-rep'),
                    ('k_fullsort_tc (tcgen05 3xTF32) 37,888 users x 262,144 items, d=128 (scratch/tc_prof.py)', 'gpurun_out/r01_fullsort_tc.ncu-rep'),
                    ('layer kernels of the PFCN / FairGo MLPs: k_gemm<true> (forward), k_wgrad, k_gemm<false> (backward-data) at M=9748, K=64, N=128 (scratch/wgrad_one.py)', 'gpurun_out/r01_layer_gemms.ncu-rep'),
+                   ('k_linear_tc: MLP layer forward on tcgen05 (TMA raw K-blocks, in-smem TF32 split, 3xTF32 UMMA into TMEM) at M=2048,K=128,N=256 and M=9748,K=64,N=128 (scratch/linear_tc_prof.py)', 'gpurun_out/r01_linear_tc.ncu-rep'),
                    ('k_fullsort_exact at the ML-1M shape (first version, before the graph/TC work)', 'gpurun_out/prof_fullsort_r1.ncu-rep')]:
     if not os.path.exists(rep): continue
     hdr, units, rows = raw(rep)
