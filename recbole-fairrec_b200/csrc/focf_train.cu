@@ -37,7 +37,7 @@ enum {
   CTRL_CURSOR = 6,     // planned-batch cursor (fr_focf_plan): which batch of the epoch plan comes next
   CTRL_ADAM_T = 7,     // device-resident Adam step count (used when fr_focf_step.step <= 0)
   CTRL_B = 8,          // device-resident batch size (planned batches)
-  CTRL_GRID_BAR = 9,   // arrival counter of the fused step's grid barrier (monotonic)
+  CTRL_GRID_BAR = 14,  // arrival counter of the fused step's grid barrier: 64-bit (words 14-15, 8-byte aligned), monotonic
   CTRL_STRIDE = 10,    // how far CTRL_CURSOR / CTRL_ADAM_T advance per step (2 when two workspaces alternate batches)
   CTRL_NORM_B = 11, CTRL_NORM_J = 12,   // data-parallel planned steps: the current batch's global normalisers (from norm_dev)
   CTRL_WORDS = 64
@@ -611,13 +611,13 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
 // latency-bound, so forward -> loss -> gradients -> Adam run as ONE cooperative launch (one CTA per SM) separated by
 // grid-wide barriers instead of four dependent launches.  The barrier is a monotonically increasing arrival counter in
 // the control block (cooperative launch guarantees that all CTAs are co-resident, so spinning cannot deadlock).
-__device__ __forceinline__ void grid_barrier(uint32_t *bar) {
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const uint32_t n = gridDim.x;
-    const uint32_t target = (atomicAdd(bar, 1u) / n + 1u) * n;
-    while ((int32_t)(*(volatile uint32_t *)bar - target) < 0) {}
+    const unsigned long long n = gridDim.x;
+    const unsigned long long target = (atomicAdd(bar, 1ull) / n + 1ull) * n;   // 64-bit: never wraps
+    while (*(volatile unsigned long long *)bar < target) {}
     __threadfence();
   }
   __syncthreads();
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_focf_fused_step(FusedArgs 
   __shared__ float sh[33];
   __shared__ float sc[3];
   float *s_cseg = fused_sm + 3 * f.cap, *s_cglob = fused_sm + 5 * f.cap;
-  uint32_t *bar = f.ctrl + CTRL_GRID_BAR;
+  unsigned long long *bar = (unsigned long long *)(f.ctrl + CTRL_GRID_BAR);
   const int B = FR_B(f.B, f.B_dev);
   forward_body(f.U, f.I, f.uid, f.iid, f.sst, B, f.d, f.pred, f.ctrl);
   grid_barrier(bar);
