@@ -13,10 +13,13 @@ Only what the path needs lives here:
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
   sampled_eval.py  sampled-negative (uni100) ranking evaluation (SampledEvalData, SampledEvaluator)
   trainer.py       FOCFTrainer (fit / evaluate)
+  atomic.py        atomic-file datasets (.inter/.user/.item) -> ids, splits, history/positive lists (reference-identical)
+  quick_start.py   run_recbole(model, dataset, config_file_list, config_dict)
   synth.py         synthetic data of the benchmark shapes
 The directory name carries a hyphen; import it as `recbole_fairrec_b200` (shim at the repo root).
 """
 from . import _lib, kernels  # noqa: F401
+from .atomic import AtomicDataset  # noqa: F401
 from .config import Config  # noqa: F401
 from .dataloader import FOCFDataLoader, TrainData  # noqa: F401
 from .evaluator import EvalData, FullSortEvaluator  # noqa: F401

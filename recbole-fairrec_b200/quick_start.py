@@ -1,0 +1,163 @@
+"""run_recbole(model, dataset, config_file_list, config_dict) -- the reference's entry point
+(recbole/quick_start/quick_start.py:20-71, driven by run_recbole.py:16-26) over this package: YAML config ->
+init_seed -> atomic-file dataset -> split -> device-resident loaders -> model -> trainer.fit -> trainer.evaluate(test).
+
+Config precedence mirrors configurator.py:211-263 as far as the fairness configs need it: built-in defaults (config.py)
+< the YAML files of `config_file_list` (in order) < `config_dict`.  The reference's per-model / per-dataset property
+YAMLs are not shipped here; pass the keys you need in your own YAML (same key names).
+
+Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
+uniform negative per positive, `uni<N>` evaluation) and FairGo_PMF (pointwise batches, full-sort evaluation).  With the
+same seed the splits, the initial weights and FOCF's batch draws are identical to the reference's (tests/test_atomic.py,
+tests/test_run_recbole_gpu.py)."""
+import random
+from logging import getLogger
+
+import numpy as np
+import torch
+import yaml
+
+from .atomic import AtomicDataset, used_and_positive_lists
+from .config import Config
+from .interaction import Interaction
+
+
+def init_seed(seed, reproducibility=True):
+    """recbole/utils/utils.py:172-189"""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.benchmark = not reproducibility
+    torch.backends.cudnn.deterministic = bool(reproducibility)
+
+
+def build_config(model, dataset, config_file_list=None, config_dict=None):
+    merged = {}
+    for path in config_file_list or []:
+        with open(path, "r", encoding="utf-8") as f:
+            merged.update(yaml.safe_load(f) or {})
+    merged.update(config_dict or {})
+    merged["model"], merged["dataset"] = model, dataset
+    cfg = Config(**merged)
+    if "device" not in merged:
+        cfg["device"] = torch.device("cuda" if torch.cuda.is_available() and cfg["use_gpu"] is not False else "cpu")
+    return cfg
+
+
+class BatchLoader:
+    """TrainDataLoader (recbole/data/dataloader/general_dataloader.py:23-65) for the pointwise / pairwise families:
+    shuffled fixed-size batches of the train split with the users' sensitive attributes joined and, for pairwise models,
+    `neg_sampling: {uniform: n}` negatives (abstract_dataloader.py:182-188; uniform over the items the user has not
+    interacted with in the train split, by rejection like sampler.py:145-197)."""
+
+    def __init__(self, config, ds, split, pairwise, shuffle=True):
+        self.cfg, self.ds, self.split, self.pairwise, self.shuffle = config, ds, split, pairwise, shuffle
+        self.batch_size = int(config["train_batch_size"])
+        self.n = len(split[ds.uid_field])
+        self.attrs = [a for a in (config["sst_attr_list"] or []) if a in ds.user_feat]
+        self.neg_prefix = config["NEG_PREFIX"] or "neg_"
+        if pairwise:
+            key = split[ds.uid_field].astype(np.int64) * ds.item_num + split[ds.iid_field]
+            self._used = np.sort(key)
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
+
+    def _negatives(self, u):
+        neg = np.random.randint(1, self.ds.item_num, size=len(u))
+        while True:
+            key = u.astype(np.int64) * self.ds.item_num + neg
+            pos = np.searchsorted(self._used, key)
+            bad = (pos < len(self._used)) & (self._used[np.minimum(pos, len(self._used) - 1)] == key)
+            if not bad.any():
+                return neg
+            neg[bad] = np.random.randint(1, self.ds.item_num, size=int(bad.sum()))
+
+    def __iter__(self):
+        order = torch.randperm(self.n).numpy() if self.shuffle else np.arange(self.n)
+        uf, itf = self.ds.uid_field, self.ds.iid_field
+        for b0 in range(0, self.n, self.batch_size):
+            idx = order[b0:b0 + self.batch_size]
+            u = self.split[uf][idx]
+            cols = {k: torch.from_numpy(np.ascontiguousarray(v[idx])) for k, v in self.split.items()}
+            for a in self.attrs:
+                cols[a] = torch.from_numpy(self.ds.user_feat[a][u])
+            if self.pairwise:
+                cols[self.neg_prefix + itf] = torch.from_numpy(self._negatives(u))
+            yield Interaction(cols)
+
+
+def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=None, saved=False):
+    """quick_start.py:20-71 -> {'best_valid_score', 'valid_score_bigger', 'best_valid_result', 'test_result'}"""
+    import recbole_fairrec_b200 as pkg
+    from .sampled_eval import SampledEvalData, sample_negatives
+    cfg = build_config(model, dataset, config_file_list, config_dict)
+    init_seed(cfg["seed"], cfg["reproducibility"] if cfg["reproducibility"] is not None else True)
+    logger = getLogger()
+    ds = AtomicDataset(cfg)
+    splits = ds.build()
+    dev = cfg["device"]
+    uf, itf, rf = ds.uid_field, ds.iid_field, ds.rating_field
+    attrs = list(cfg["sst_attr_list"] or [])
+    train = splits[0]
+    counts = np.bincount(train[itf], minlength=ds.item_num)
+    item_counter = {int(i): int(c) for i, c in enumerate(counts) if c > 0}
+    mode = str((cfg["eval_args"] or {}).get("mode", "full"))
+
+    class TrainView:                         # what the models read from `train_data.dataset`
+        num = staticmethod(ds.num)
+        inter_feat = {k: torch.from_numpy(v) for k, v in train.items()}
+        get_user_feature = staticmethod(ds.get_user_feature)
+        inter_matrix = staticmethod(ds.inter_matrix)
+
+    sst_of_user = {a: ds.user_feat[a] for a in attrs}
+
+    def eval_data(phase):
+        users, hist, pos = used_and_positive_lists(splits, phase)
+        if mode == "full":
+            return pkg.EvalData(users, hist, pos, sst_of_user, dev)
+        neg_num = int(mode[3:])
+        neg = sample_negatives(pos, hist, ds.item_num, neg_num, np.random)
+        return SampledEvalData(users, pos, neg, sst_of_user, dev)
+
+    name = cfg["model"]
+    if name == "FOCF":
+        first = attrs[0]
+        tdata = pkg.TrainData(train[uf], train[itf], train[rf], ds.user_feat[first].astype(np.float32), ds.user_num,
+                              ds.item_num, dev, uf, itf, rf, first)
+        loader = pkg.FOCFDataLoader(cfg, tdata, mode=cfg["focf_draw_mode"] or "reference")
+        net = pkg.FOCF(cfg, TrainView).to(dev)
+        trainer = pkg.FOCFTrainer(cfg, net)
+        valid, test = eval_data("valid"), eval_data("test")      # negatives (uni<N>) drawn before training, like the
+        best, best_res = trainer.fit(loader, valid, saved=saved, verbose=cfg["verbose"] is not False)   # reference's samplers
+        test_res = trainer.evaluate(test)
+    elif name.startswith("PFCN_"):
+        net = getattr(pkg, name)(cfg, TrainView).to(dev)
+        trainer = pkg.PFCNTrainer(cfg, net)
+        loader = BatchLoader(cfg, ds, train, pairwise=True)
+        if mode == "full":
+            raise NotImplementedError("PFCN full-sort evaluation is undefined in the reference; use eval_args.mode uni100")
+        valid, test = eval_data("valid"), eval_data("test")
+        best, best_res = None, None
+        for epoch in range(cfg["epochs"] or 1):
+            losses = trainer._train_epoch(loader, epoch)
+            res = trainer.evaluate(valid, None, item_counter)
+            logger.info("epoch %d losses %s valid %s", epoch, losses, dict(res))
+            metric = (cfg["valid_metric"] or "NDCG@5").lower()
+            if best is None or res[metric] > best:
+                best, best_res = res[metric], res
+        test_res = trainer.evaluate(test, None, item_counter)
+    elif name in ("FairGo_PMF", "FairGo_GCN"):
+        net = getattr(pkg, name)(cfg, TrainView).to(dev)
+        trainer = pkg.FairGoTrainer(cfg, net)
+        loader = BatchLoader(cfg, ds, train, pairwise=False)
+        if mode != "full":
+            raise NotImplementedError("FairGo evaluation here is the fused full-sort one (eval_args.mode full)")
+        valid, test = eval_data("valid"), eval_data("test")
+        best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter)
+        test_res = trainer.evaluate(test)
+    else:
+        raise ValueError(f"unknown model {name}")
+    return {"best_valid_score": best, "valid_score_bigger": True, "best_valid_result": best_res, "test_result": test_res}

@@ -34,6 +34,7 @@ def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
     uniformly from the items the user has NOT used (ids 1..n_items-1), laid out like the dataloader does
     (`[j * p + k]` = j-th negative of positive k, abstract_dataloader.py:190-198)."""
     out = []
+    draw = getattr(rng, "integers", None) or rng.randint      # np.random.Generator, or the seeded np.random module
     for pos, used in zip(pos_lists, used_lists):
         banned = np.zeros(n_items, bool)
         banned[0] = True
@@ -42,7 +43,7 @@ def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
         need = neg_num * len(pos)
         got = np.zeros(0, np.int64)
         while len(got) < need:            # rejection sampling, like the reference
-            c = rng.integers(1, n_items, size=2 * (need - len(got)) + 8)
+            c = draw(1, n_items, size=2 * (need - len(got)) + 8)
             got = np.concatenate([got, c[~banned[c]]])
         out.append(got[:need])
     return out

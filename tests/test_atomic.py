@@ -1,0 +1,76 @@
+"""CPU: the atomic-file front end (atomic.py) reproduces the reference's data pipeline bit for bit -- id assignment,
+RO shuffle, 8:1:1 split grouped by user, token ids of the sensitive attribute, model initialisation and FOCF's batch
+draws -- against tensors exported from the UNMODIFIED reference's run on the bundled ml-100k
+(tests/golden/ml100k_focf_value.npz; the data files under tests/data/ml-100k are column-trimmed copies)."""
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(__file__)
+G = os.path.join(HERE, "golden", "ml100k_focf_value.npz")
+
+
+def make(device=torch.device("cpu")):
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.quick_start import init_seed
+    g = np.load(G)
+    cfg = pkg.Config(dataset="ml-100k", data_path=os.path.join(HERE, "data"), threshold={"rating": 3.0},
+                     load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"], "item": ["item_id"]},
+                     eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"},
+                     embedding_size=64, device=device, train_batch_size=int(g["train_batch_size"]), seed=2020)
+    init_seed(2020)
+    ds = pkg.AtomicDataset(cfg)
+    return g, cfg, ds, ds.build()
+
+
+def test_ids_split_and_attribute_match_the_reference():
+    g, cfg, ds, (tr, va, te) = make()
+    assert (ds.user_num, ds.item_num, len(ds)) == (int(g["n_users"]), int(g["n_items"]), 100000)
+    assert np.array_equal(ds.user_feat["gender"], g["gender"])            # token ids by first appearance: M=1, F=2
+    o = np.argsort(tr["item_id"], kind="stable")                          # FOCFDataLoader sorts the split by item
+    assert np.array_equal(tr["user_id"][o], g["train_u"]) and np.array_equal(tr["item_id"][o], g["train_i"])
+    assert np.array_equal(tr["rating"][o], g["train_r"])
+    for mine, (gu, gi) in ((va, ("valid_u", "valid_i")), (te, ("test_u", "test_i"))):
+        o = np.argsort(mine["user_id"], kind="stable")                    # the eval loader sorts by user
+        assert np.array_equal(mine["user_id"][o], g[gu]) and np.array_equal(mine["item_id"][o], g[gi])
+    assert np.array_equal(tr["label"], (tr["rating"] >= 3).astype(np.float32))
+
+
+def test_model_init_and_batch_draws_match_the_reference():
+    import recbole_fairrec_b200 as pkg
+    g, cfg, ds, (tr, va, te) = make()
+
+    class View:
+        num = staticmethod(ds.num)
+        inter_feat = {"rating": torch.from_numpy(tr["rating"])}
+
+    model = pkg.FOCF(cfg, View)
+    assert np.array_equal(model.user_embedding_layer.weight.detach().numpy(), g["U0"])
+    assert np.array_equal(model.item_embedding_layer.weight.detach().numpy(), g["I0"])
+    train = pkg.TrainData(tr["user_id"], tr["item_id"], tr["rating"], ds.user_feat["gender"].astype(np.float32),
+                          ds.user_num, ds.item_num, torch.device("cpu"))
+    loader = pkg.FOCFDataLoader(cfg, train, mode="reference")
+    draws = []
+    for _ in range(len(loader)):
+        draws += list(loader._draw_batch()) + [-1]
+    assert np.array_equal(np.array(draws), g["draws"][:len(draws)])
+
+
+def test_split_counts_rule():
+    from recbole_fairrec_b200.atomic import calcu_split_counts
+    # dataset.py:1339-1360: parts other than the first are rounded down, but a part that would be empty borrows one
+    got = calcu_split_counts(np.array([1, 2, 5, 9, 10, 20, 23]), [8, 1, 1])
+    want = []
+    for tot in [1, 2, 5, 9, 10, 20, 23]:
+        r = [0.8, 0.1, 0.1]
+        cnt = [int(r[i] * tot) for i in range(3)]
+        cnt[0] = tot - sum(cnt[1:])
+        for i in range(1, 3):
+            if cnt[0] <= 1:
+                break
+            if 0 < r[-i] * tot < 1:
+                cnt[-i] += 1
+                cnt[0] -= 1
+        want.append(cnt)
+    assert got.tolist() == want

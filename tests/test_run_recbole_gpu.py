@@ -1,0 +1,84 @@
+"""GPU end-to-end from RAW atomic files (BASELINE config #1): run_recbole('FOCF', 'ml-100k', yaml) -- ingestion, split,
+initialisation, the reference's batch draws, fused training, fused full-sort evaluation -- against the per-epoch losses
+and metric dicts the UNMODIFIED reference produced on the same files with the same seed
+(tests/golden/ml100k_focf_value.npz), plus smoke runs of the PFCN / FairGo families through the same entry point."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(__file__)
+G = os.path.join(HERE, "golden", "ml100k_focf_value.npz")
+METRICS12 = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
+             "ValueUnfairness", "AbsoluteUnfairness", "UnderUnfairness", "OverUnfairness", "NonParityUnfairness"]
+BASE = dict(data_path=os.path.join(HERE, "data"), RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0},
+            load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"], "item": ["item_id"]},
+            sst_attr_list=["gender"], embedding_size=64, seed=2020, metric_decimal_place=12, verbose=False,
+            eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"})
+
+
+def test_focf_ml100k_from_raw_files_matches_the_reference_run(tmp_path):
+    from recbole_fairrec_b200.quick_start import run_recbole
+    g = np.load(G)
+    cfg = dict(BASE, fair_objective="value", fair_weight=1.0, weight_decay=0.001, learning_rate=0.001, epochs=2,
+               topk=[10], valid_metric="NDCG@10", metrics=METRICS12, train_batch_size=int(g["train_batch_size"]))
+    path = tmp_path / "focf_ml100k.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    seen = {}
+    import recbole_fairrec_b200 as pkg
+    orig = pkg.FOCFTrainer._train_epoch
+
+    def spy(self, train_data, epoch_idx, *a, **k):
+        loss = orig(self, train_data, epoch_idx, *a, **k)
+        seen[epoch_idx] = loss
+        return loss
+
+    pkg.FOCFTrainer._train_epoch = spy
+    try:
+        out = run_recbole("FOCF", "ml-100k", [str(path)])
+    finally:
+        pkg.FOCFTrainer._train_epoch = orig
+    # identical splits, initial weights and batch draws (tests/test_atomic.py) -> the reference's epoch losses
+    np.testing.assert_allclose([seen[0], seen[1]], g["epoch_losses"], rtol=1e-5)
+    names = [str(k) for k in g["metric_names"]]
+    assert list(out["test_result"].keys()) == names
+    n_eval = 943
+    for k, ref in zip(names, g["test_metrics"]):
+        v = out["test_result"][k]
+        # weights differ from the reference's by float rounding: rank flips of near-tied items move a top-K metric by
+        # O(1/n_users); score-based fairness metrics stay within 1e-4
+        tol = 3.0 / n_eval if "@" in k else 1e-4 * max(abs(ref), 1e-3)
+        assert abs(v - ref) <= tol, (k, v, ref)
+    best = max(g["valid_metrics"][:, names.index("ndcg@10")])
+    assert abs(out["best_valid_score"] - best) <= 3.0 / n_eval
+
+
+def test_focf_uni100_and_other_families_run_from_raw_files(tmp_path):
+    from recbole_fairrec_b200.quick_start import run_recbole
+    # the PFCN / FairGo discriminators need 0/1 FLOAT attributes (pfcn_mlp.py:206-207): same data, gender as float
+    root = tmp_path / "data" / "ml-100k"
+    root.mkdir(parents=True)
+    for f in ("ml-100k.inter", "ml-100k.item"):
+        shutil.copy(os.path.join(HERE, "data", "ml-100k", f), root / f)
+    lines = open(os.path.join(HERE, "data", "ml-100k", "ml-100k.user")).read().splitlines()
+    (root / "ml-100k.user").write_text("\n".join(["user_id:token\tgender:float"] +
+                                                 [l.split("\t")[0] + "\t" + ("1" if l.split("\t")[1] == "F" else "0")
+                                                  for l in lines[1:]]) + "\n")
+    ranking = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage", "NonParityUnfairness"]
+    common = dict(BASE, data_path=str(tmp_path / "data"), epochs=2, topk=[5], valid_metric="NDCG@5", learning_rate=0.001)
+    out = run_recbole("FOCF", "ml-100k", None, dict(common, fair_objective="value", metrics=ranking, weight_decay=0.001,
+                                                    eval_args=dict(BASE["eval_args"], mode="uni100"), focf_draw_mode="fast"))
+    assert 0.0 < out["test_result"]["ndcg@5"] <= 1.0 and 0.0 < out["test_result"]["hit@5"] <= 1.0
+    out = run_recbole("PFCN_PMF", "ml-100k", None, dict(
+        common, metrics=ranking, filter_mode="sm", dis_dropout=0.0, dis_weight=1.0, dis_hidden_size_list=[32, 16],
+        activation="leakyrelu", weight_decay=0.0001, train_epoch_interval=1, use_cuda_graph=True,
+        eval_args=dict(BASE["eval_args"], mode="uni100")))
+    assert 0.0 <= out["test_result"]["ndcg@5"] <= 1.0 and np.isfinite(out["best_valid_score"])
+    out = run_recbole("FairGo_PMF", "ml-100k", None, dict(
+        common, metrics=METRICS12, n_layers=2, activation="leakyrelu", dis_hidden_size_list=[16, 8, 4],
+        filter_hidden_size_list=[128, 64], fair_weight=0.1, load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1],
+        weight_decay=0.0001, train_epoch_interval=1, pretrain_epochs=3, stopping_step=5))
+    assert 0.0 <= out["test_result"]["ndcg@5"] <= 1.0 and "Value Unfairness of sensitive attribute gender" in out["test_result"]
