@@ -26,7 +26,7 @@ from .evaluator import EvalData, FullSortEvaluator  # noqa: F401
 from .fairgo import FairGo_GCN, FairGo_GCNTrainer, FairGo_PMF, FairGo_PMFTrainer, FairGoTrainer  # noqa: F401
 from .focf import FOCF, pack_host_batch  # noqa: F401
 from .interaction import Interaction  # noqa: F401
-from .nfcf import NFCF  # noqa: F401
+from .nfcf import NFCF, NFCFTrainer  # noqa: F401
 from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFCN_MLPTrainer, PFCN_PMFTrainer,  # noqa: F401
                    PFCN_BiasedMFTrainer, PFCN_DMFTrainer)
 from .sampled_eval import SampledEvalData, SampledEvaluator, sample_negatives  # noqa: F401

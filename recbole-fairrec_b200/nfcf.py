@@ -183,3 +183,82 @@ class NFCF(nn.Module):
             self._flags.zero_()
             raise NotImplementedError("NFCF regulariser kernels implement the binary sensitive attribute case "
                                       "(NFCF.yaml: gender); more than two values were present in a batch")
+
+
+class NFCFTrainer:
+    """The base `Trainer` (recbole/trainer/trainer.py:100-260, the one `get_trainer` hands NFCF: utils.py:74-94) for the
+    two NFCF stages: stage 1 (`load_pretrain_path: ~`) trains the plain NCF tower and `fit(saved=True)` writes the
+    `{'state_dict': ...}` checkpoint stage 2 reads (nfcf.py:49-51); stage 2 (path given) fine-tunes with the user table
+    frozen and the differential-fairness regulariser on.  Optimizer: this package's Adam kernel (ops.AdamGroup = the
+    reference's torch.optim.Adam, L2 form) over the parameters that require a gradient; evaluation: the sampled-negative
+    (`uni<N>`) evaluator with `model.predict` as the scorer, as NFCF.yaml configures it."""
+
+    def __init__(self, config, model):
+        from . import ops
+        self.config, self.model = config, model
+        self.optimizer = ops.AdamGroup([p for p in model.parameters() if p.requires_grad],
+                                       lr=config["learning_rate"] or 1e-3, weight_decay=config["weight_decay"] or 0.0)
+        self.sampled_evaluator = None
+        self.saved_model_file = None
+
+    def _train_epoch(self, train_data, epoch_idx):
+        """trainer.py:160-199: sum of the batch losses of the epoch"""
+        self.model.train()
+        total = None
+        for interaction in train_data:
+            self.optimizer.zero_grad()
+            loss = self.model.calculate_loss(interaction)
+            total = loss.detach() if total is None else total + loss.detach()
+            loss.backward()
+            self.optimizer.step()
+        self.model.check_flags()
+        value = float(total.item()) if total is not None else 0.0
+        if value != value:
+            raise ValueError("Training loss is nan")
+        return value
+
+    @torch.no_grad()
+    def evaluate(self, eval_data, train_item_count=None):
+        from .interaction import Interaction
+        from .sampled_eval import SampledEvaluator
+        self.model.eval()
+        if self.sampled_evaluator is None:
+            self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, train_item_count)
+        m = self.model
+        return self.sampled_evaluator.evaluate(
+            lambda uid, iid: m.predict(Interaction({m.USER_ID: uid, m.ITEM_ID: iid})).view(-1), eval_data)
+
+    def fit(self, train_data, valid_data=None, saved=False, train_item_count=None, verbose=False):
+        """trainer.py:300-380: early stopping on `valid_metric`; the best model is check-pointed when saved=True"""
+        import os
+        from .trainer import early_stopping
+        metric = (self.config["valid_metric"] or "NDCG@5").lower()
+        bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
+        best, best_res, cur = (-float("inf") if bigger else float("inf")), None, 0
+        if saved:
+            root = self.config["checkpoint_dir"] or "saved"
+            os.makedirs(root, exist_ok=True)
+            self.saved_model_file = os.path.join(root, f"{self.config['model']}-{os.getpid()}.pth")
+        for epoch in range(self.config["epochs"] or 1):
+            loss = self._train_epoch(train_data, epoch)
+            if verbose:
+                print(f"epoch {epoch}: train loss {loss:.4f}")
+            if not valid_data:
+                if saved:
+                    self._save()
+                continue
+            res = self.evaluate(valid_data, train_item_count)
+            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
+                                                     bigger=bigger)
+            if update:
+                best_res = res
+                if saved:
+                    self._save()
+            if stop:
+                break
+        return best, best_res
+
+    def _save(self):
+        torch.save({"config": {k: (str(v) if isinstance(v, torch.device) else v) for k, v in self.config.items()},
+                    "state_dict": {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
+                    "other_parameter": self.model.other_parameter()}, self.saved_model_file)

@@ -7,7 +7,9 @@ Config precedence mirrors configurator.py:211-263 as far as the fairness configs
 YAMLs are not shipped here; pass the keys you need in your own YAML (same key names).
 
 Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
-uniform negative per positive, `uni<N>` evaluation) and FairGo_PMF (pointwise batches, full-sort evaluation).  With the
+uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort evaluation) and
+NFCF (both stages: positives + uniform negatives with 1 | 0 labels, `uni<N>` evaluation; `saved=True` writes the stage-1
+checkpoint that `load_pretrain_path` reads in stage 2).  With the
 same seed the splits, the initial weights and FOCF's batch draws are identical to the reference's (tests/test_atomic.py,
 tests/test_run_recbole_gpu.py)."""
 import random
@@ -52,13 +54,16 @@ class BatchLoader:
     `neg_sampling: {uniform: n}` negatives (abstract_dataloader.py:182-188; uniform over the items the user has not
     interacted with in the train split, by rejection like sampler.py:145-197)."""
 
-    def __init__(self, config, ds, split, pairwise, shuffle=True):
+    def __init__(self, config, ds, split, pairwise, shuffle=True, pointwise_neg=False):
         self.cfg, self.ds, self.split, self.pairwise, self.shuffle = config, ds, split, pairwise, shuffle
+        self.pointwise_neg = pointwise_neg
         self.batch_size = int(config["train_batch_size"])
+        if pointwise_neg:                     # _batch_size_adaptation (general_dataloader.py:40-50): positives + negatives
+            self.batch_size = max(self.batch_size // 2, 1)       # together fill one train_batch_size
         self.n = len(split[ds.uid_field])
         self.attrs = [a for a in (config["sst_attr_list"] or []) if a in ds.user_feat]
         self.neg_prefix = config["NEG_PREFIX"] or "neg_"
-        if pairwise:
+        if pairwise or pointwise_neg:
             key = split[ds.uid_field].astype(np.int64) * ds.item_num + split[ds.iid_field]
             self._used = np.sort(key)
 
@@ -86,6 +91,12 @@ class BatchLoader:
                 cols[a] = torch.from_numpy(self.ds.user_feat[a][u])
             if self.pairwise:
                 cols[self.neg_prefix + itf] = torch.from_numpy(self._negatives(u))
+            if self.pointwise_neg:            # abstract_dataloader.py:200-208: rows repeated, items replaced, labels 1 | 0
+                cols = {k: torch.cat([v, v]) for k, v in cols.items()}
+                cols[itf][len(u):] = torch.from_numpy(self._negatives(u))
+                label = torch.zeros(2 * len(u))
+                label[:len(u)] = 1.0
+                cols[self.cfg["LABEL_FIELD"] or "label"] = label
             yield Interaction(cols)
 
 
@@ -158,6 +169,21 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter)
         test_res = trainer.evaluate(test)
+    elif name == "NFCF":
+        net = pkg.NFCF(cfg, TrainView).to(dev)
+        trainer = pkg.NFCFTrainer(cfg, net)
+        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
+        if mode == "full":
+            raise NotImplementedError("NFCF defines no full_sort_predict in the reference; use eval_args.mode uni100")
+        valid, test = eval_data("valid"), eval_data("test")
+        best, best_res = trainer.fit(loader, valid, saved=saved, train_item_count=item_counter,
+                                     verbose=cfg["verbose"] is not False)
+        test_res = trainer.evaluate(test, item_counter)
+        if saved:
+            logger.info("saved %s", trainer.saved_model_file)
     else:
         raise ValueError(f"unknown model {name}")
-    return {"best_valid_score": best, "valid_score_bigger": True, "best_valid_result": best_res, "test_result": test_res}
+    out = {"best_valid_score": best, "valid_score_bigger": True, "best_valid_result": best_res, "test_result": test_res}
+    if getattr(trainer, "saved_model_file", None):
+        out["saved_model_file"] = trainer.saved_model_file
+    return out

@@ -74,3 +74,30 @@ def test_split_counts_rule():
                 cnt[0] -= 1
         want.append(cnt)
     assert got.tolist() == want
+
+
+def test_pointwise_loader_fills_batches_with_positives_and_unseen_negatives():
+    """abstract_dataloader.py:200-208 + general_dataloader.py:40-50: B/2 positives + B/2 negatives, labels 1 | 0, negatives
+    never among the user's train items, sensitive attribute joined for both halves"""
+    from recbole_fairrec_b200.quick_start import BatchLoader, build_config, init_seed
+    from recbole_fairrec_b200.atomic import AtomicDataset
+    cfg = build_config("NFCF", "ml-100k", None, dict(
+        data_path=os.path.join(os.path.dirname(__file__), "data"), threshold={"rating": 3.0}, sst_attr_list=["gender"],
+        load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"]}, train_batch_size=512))
+    init_seed(7)
+    ds = AtomicDataset(cfg)
+    train = ds.build()[0]
+    loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=True)
+    used = set((train["user_id"] * ds.item_num + train["item_id"]).tolist())
+    seen = 0
+    for k, b in enumerate(loader):
+        u, i, y, g = (b[c].numpy() for c in ("user_id", "item_id", "label", "gender"))
+        h = len(u) // 2
+        assert len(u) <= 512 and (y[:h] == 1).all() and (y[h:] == 0).all() and (u[:h] == u[h:]).all()
+        assert all(int(a) * ds.item_num + int(c) in used for a, c in zip(u[:h], i[:h]))
+        assert not any(int(a) * ds.item_num + int(c) in used for a, c in zip(u[h:], i[h:])) and (i[h:] >= 1).all()
+        assert (g == ds.user_feat["gender"][u]).all()
+        seen += h
+        if k == 3:
+            break
+    assert seen == 4 * 256 and len(loader) == -(-len(train["user_id"]) // 256)

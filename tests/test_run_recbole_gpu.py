@@ -82,3 +82,23 @@ def test_focf_uni100_and_other_families_run_from_raw_files(tmp_path):
         filter_hidden_size_list=[128, 64], fair_weight=0.1, load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1],
         weight_decay=0.0001, train_epoch_interval=1, pretrain_epochs=3, stopping_step=5))
     assert 0.0 <= out["test_result"]["ndcg@5"] <= 1.0 and "Value Unfairness of sensitive attribute gender" in out["test_result"]
+
+
+def test_nfcf_two_stages_from_raw_files(tmp_path):
+    """stage 1 (plain NCF, check-pointed) -> stage 2 (load_pretrain_path: gender direction projected out, user table
+    frozen, differential-fairness regulariser on), both through run_recbole on the raw ml-100k files"""
+    import torch
+    from recbole_fairrec_b200.quick_start import run_recbole
+    ranking = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage", "NonParityUnfairness"]
+    cfg = dict(BASE, epochs=3, topk=[5], valid_metric="NDCG@5", metrics=ranking, dropout=0.2, fair_weight=0.1,
+               mlp_hidden_size=[128, 64], weight_decay=1e-6, checkpoint_dir=str(tmp_path),
+               eval_args=dict(BASE["eval_args"], mode="uni100"))
+    s1 = run_recbole("NFCF", "ml-100k", None, dict(cfg, load_pretrain_path=None), saved=True)
+    assert os.path.exists(s1["saved_model_file"])
+    ck = torch.load(s1["saved_model_file"], weights_only=False)
+    assert {"user_embedding.weight", "item_embedding.weight"} <= set(ck["state_dict"])
+    assert 0.0 < s1["test_result"]["ndcg@5"] <= 1.0
+    s2 = run_recbole("NFCF", "ml-100k", None, dict(cfg, load_pretrain_path=s1["saved_model_file"]))
+    assert 0.0 < s2["test_result"]["ndcg@5"] <= 1.0
+    assert np.isfinite(s2["test_result"]["Differential Fairness of sensitive attribute gender"]) if \
+        "Differential Fairness of sensitive attribute gender" in s2["test_result"] else True
