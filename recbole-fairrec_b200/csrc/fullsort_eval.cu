@@ -293,6 +293,45 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Rows the tensor-core scorer left short (a user with fewer than K unmasked items): torch.topk continues into the -inf
+// entries (trainer.py:435-438 masks by writing -inf, collector.py:147 takes topk of the whole row), and the canonical
+// order among them is ascending item id.  The scorer never ranks masked columns, so they are appended here: the [PAD]
+// item (global id 0) and the user's history inside this shard, which the tensor-core path requires sorted.
+__global__ void __launch_bounds__(128)
+    k_fill_masked(int32_t *__restrict__ ids, float *__restrict__ sc, int n, int K, const int64_t *__restrict__ hist_off,
+                  const int32_t *__restrict__ hist_items, int item_base, int n_items_local) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int32_t *row = ids + (size_t)r * K;
+  float *rs = sc + (size_t)r * K;
+  if (row[K - 1] != 0x7fffffff) return;
+  int f = K - 1;
+  while (f > 0 && row[f - 1] == 0x7fffffff) --f;
+  int prev = -1;
+  if (item_base == 0) {
+    row[f] = 0;
+    rs[f] = -INFINITY;
+    ++f;
+    prev = 0;
+  }
+  if (!hist_items) return;
+  long long lo = hist_off[r], hi = hist_off[r + 1];
+  const long long end = hi;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (hist_items[mid] < item_base) lo = mid + 1; else hi = mid;
+  }
+  for (long long p = lo; p < end && f < K; ++p) {
+    const int it = hist_items[p];
+    if (it >= item_base + n_items_local) break;
+    if (it == prev) continue;
+    row[f] = it;
+    rs[f] = -INFINITY;
+    ++f;
+    prev = it;
+  }
+}
+
 // collector.py:147-153: rec.topk = [1[topk_id in positives(u)] ... | |positives(u)|]
 __global__ void __launch_bounds__(128)
     k_hits(const int32_t *__restrict__ topk_id, int n, int K, const int64_t *__restrict__ pos_off,
@@ -375,6 +414,8 @@ int fr_fullsort_topk(const fr_fullsort *a, void *stream) {
       FR_LAUNCH(fr::k_topk_merge, (a->n + 127) / 128, 128, 0, stream, pid, psc, splits, a->n, a->K, a->topk_id,
                 a->topk_score);
     }
+    FR_LAUNCH(fr::k_fill_masked, (a->n + 127) / 128, 128, 0, stream, a->topk_id, a->topk_score, a->n, a->K, a->hist_off,
+              a->hist_items, a->item_base, a->n_items_local);
     FR_LAUNCH_CHECK();
     return FR_OK;
   }

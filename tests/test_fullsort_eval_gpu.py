@@ -217,3 +217,53 @@ def test_tc_evaluator_metrics_close_to_exact():
     for k, v in res["exact"].items():
         tol = 3.0 / 1400 if "@" in k else 1e-5 * max(abs(v), 1e-3)   # a near-tie flip moves a top-K metric by O(1/n)
         assert abs(res["tc"][k] - v) <= tol, (k, res["tc"][k], v)
+
+
+def test_tc_scorer_continues_into_masked_items_like_topk_of_the_masked_row():
+    """users with fewer than K unmasked items: torch.topk over the masked row (trainer.py:435-438, collector.py:147)
+    returns -inf entries; canonical order among them = ascending item id.  Tensor-core scorer == exact scorer == oracle,
+    unsharded and item-sharded (3 shards, ragged)."""
+    from recbole_fairrec_b200 import _lib, kernels
+    rng = np.random.default_rng(5)
+    n_users, n_items, d, K = 260, 300, 64, 10
+    U = (rng.standard_normal((n_users, d)) * 0.3).astype(np.float32)
+    I = (rng.standard_normal((n_items, d)) * 0.3).astype(np.float32)
+    users = np.arange(1, n_users)
+    hist = []
+    for r, _ in enumerate(users):
+        free = [0, 3, 9, 10, 25][r % 5] if r < 200 else 150            # unmasked items left to this user
+        keep = rng.choice(np.arange(1, n_items), free, replace=False)
+        hist.append(np.setdiff1d(np.arange(1, n_items), keep))
+    ho = np.r_[0, np.cumsum([len(h) for h in hist])]
+    hi = np.concatenate(hist)
+    data, ev, Ud, Id = build(U, I, users, ho, hi, np.zeros(len(users) + 1, np.int64), np.zeros(0, np.int64),
+                             rng.integers(1, 3, n_users), [K])
+    args = (Ud, Id, data.users, data.hist_off, data.hist_items)
+    ids_e, sc_e = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_NONE, 1.0)
+    ids_t, sc_t = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_NONE, 1.0, 0, _lib.SCORE_TC_3XTF32)
+    ids_e, sc_e, ids_t, sc_t = ids_e.cpu().numpy(), sc_e.cpu().numpy(), ids_t.cpu().numpy(), sc_t.cpu().numpy()
+    oid, osc = fs.topk_canonical(fs.mask_history(fs.full_sort_scores(U, I, users, None), ho, hi), K)
+    np.testing.assert_array_equal(ids_e, oid)                         # exact scorer == oracle, bit for bit
+    np.testing.assert_array_equal(sc_e, osc)
+    np.testing.assert_array_equal(ids_t, ids_e)                       # scores are well separated at this size
+    np.testing.assert_array_equal(np.isinf(sc_t), np.isinf(sc_e))
+    np.testing.assert_allclose(sc_t[np.isfinite(sc_t)], sc_e[np.isfinite(sc_e)], atol=2e-5, rtol=0)
+    # row by row against first principles: the best unmasked ids by score, then masked ids ascending (0 first)
+    raw = U[users].astype(np.float64) @ I.astype(np.float64).T
+    for r in (0, 1, 2, 3, 4, 205):
+        masked = np.zeros(n_items, bool)
+        masked[0] = True
+        masked[hist[r]] = True
+        un = np.flatnonzero(~masked)
+        want = list(un[np.argsort(-raw[r, un], kind="stable")][:K]) + list(np.flatnonzero(masked))
+        np.testing.assert_array_equal(ids_t[r], want[:K])
+    # item-sharded: per-shard lists merged under the same total order
+    cuts = [0, 97, 211, n_items]
+    parts_i, parts_s = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        i_, s_ = kernels.fullsort_topk(Ud, Id[a:b].contiguous(), data.users, data.hist_off, data.hist_items, K,
+                                       _lib.TRANSFORM_NONE, 1.0, a, _lib.SCORE_TC_3XTF32)
+        parts_i.append(i_)
+        parts_s.append(s_)
+    mi, ms = kernels.topk_merge(torch.stack(parts_i), torch.stack(parts_s))
+    np.testing.assert_array_equal(mi.cpu().numpy(), ids_e)
