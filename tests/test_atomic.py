@@ -5,6 +5,7 @@ draws -- against tensors exported from the UNMODIFIED reference's run on the bun
 import os
 
 import numpy as np
+import pytest
 import torch
 
 HERE = os.path.dirname(__file__)
@@ -101,3 +102,19 @@ def test_pointwise_loader_fills_batches_with_positives_and_unseen_negatives():
         if k == 3:
             break
     assert seen == 4 * 256 and len(loader) == -(-len(train["user_id"]) // 256)
+
+
+def test_ingestion_identical_to_the_live_reference_on_synthetic_files(tmp_path):
+    """build container only (skipped where /root/reference is absent): the unmodified reference's create_dataset +
+    data_preparation on freshly written synthetic atomic files (3 float attributes, 60k rows) vs atomic.py -- splits,
+    user features and evaluation lists bit for bit (bench_ingest.py does the same at the ML-1M shape)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle", "ref_shim"))
+    import shim
+    if not shim.available():
+        pytest.skip("reference tree not present")
+    import bench_ingest as bi
+    name = bi.write_files(str(tmp_path), "tiny-synth", n_users=801, n_items=501, n_inter=60_000, seed=11)
+    _, ds, splits, lists = bi.ours(str(tmp_path), name)
+    _, rds, rloaders = bi.reference(str(tmp_path), name)
+    assert bi.compare(ds, splits, lists, rds, rloaders)
