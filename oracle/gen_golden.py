@@ -663,8 +663,50 @@ def run_all_fairgo():
     run_fairgo("pmf_lba_3layers", "LBA", n_layers=3, seed=44)
 
 
+def run_ingest():
+    """The reference's create_dataset + data_preparation on the `messy` atomic files (oracle/make_test_data.write_messy)
+    under each option set of make_test_data.INGEST_CASES -> tests/golden/ingest_<case>.npz (outputs only)."""
+    import tempfile
+    import yaml
+    from recbole.config import Config
+    from recbole.data import create_dataset, data_preparation
+    from recbole.utils import init_seed
+    import make_test_data as mtd
+    root = tempfile.mkdtemp()
+    name = mtd.write_messy(root)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        for case, opts in mtd.INGEST_CASES.items():
+            with open("c.yaml", "w") as f:
+                yaml.safe_dump(dict(mtd.INGEST_BASE, **opts, data_path=root, use_gpu=False, state="WARNING",
+                                    show_progress=False, neg_sampling=None, fair_objective="value"), f)
+            sys.argv = sys.argv[:1]
+            config = Config(model="FOCF", dataset=name, config_file_list=["c.yaml"])
+            init_seed(config["seed"], config["reproducibility"])
+            dataset = create_dataset(config)
+            built = dataset.build()                       # the split itself (data_preparation re-sorts train for FOCF)
+            out = dict(n_users=dataset.user_num, n_items=dataset.item_num,
+                       user_tokens=np.array([str(t) for t in dataset.field2id_token["user_id"]]),
+                       item_tokens=np.array([str(t) for t in dataset.field2id_token["item_id"]]))
+            for k, part in zip(("train", "valid", "test"), built):
+                f_ = part.inter_feat
+                for col in ("user_id", "item_id", "rating", "timestamp", "label"):
+                    out[f"{k}_{col}"] = f_[col].numpy() if len(f_) else np.zeros(0)
+            uf = dataset.get_user_feature()
+            for col in ("gender", "age", "occupation"):
+                out["user_" + col] = uf[col].numpy()[1:]
+            np.savez_compressed(os.path.join(OUT, f"ingest_{case}.npz"), **out)
+            print("ingest", case, dataset.user_num, dataset.item_num, [len(p.inter_feat) for p in built])
+    finally:
+        os.chdir(cwd)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "ingest":
+        run_ingest()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "uni":
         run_uni_eval("uni100", users_per_batch=1)
         run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
@@ -700,6 +742,7 @@ def main():
     run_uni_eval("uni100", users_per_batch=1)
     run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
     run_uni_eval("uni20_small_catalog", n_items=60, neg_num=20, users_per_batch=2, seed=53)
+    run_ingest()
 
 
 if __name__ == "__main__":

@@ -27,3 +27,56 @@ if __name__ == "__main__":
     trim("ml-100k.user", ("user_id", "gender"))
     trim("ml-100k.item", ("item_id",))
     print({n: os.path.getsize(os.path.join(DST, n)) for n in os.listdir(DST)})
+
+
+def write_messy(root, name="messy", seed=3, n_users=300, n_items=200, n_inter=6000):
+    """A small atomic dataset exercising every filtering branch of the reference's Dataset (dataset.py:160-181): duplicated
+    (user, item) pairs, tied timestamps, rows with a missing id, users / items absent from the feature files, feature rows
+    without interactions, float and token attributes.  Deterministic; used by gen_golden.py (`ingest`) and
+    tests/test_atomic.py so that the fixtures hold only the reference's OUTPUTS."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    d = os.path.join(root, name)
+    os.makedirs(d, exist_ok=True)
+    pu = rng.lognormal(0, 1.0, n_users)
+    pi = rng.lognormal(0, 1.2, n_items)
+    u = rng.choice(n_users, n_inter, p=pu / pu.sum())
+    i = rng.choice(n_items, n_inter, p=pi / pi.sum())
+    r = rng.integers(1, 6, n_inter)
+    t = rng.integers(1000, 1400, n_inter)                   # many ties
+    with open(os.path.join(d, name + ".inter"), "w") as f:
+        f.write("user_id:token\titem_id:token\trating:float\ttimestamp:float\n")
+        for k in range(n_inter):
+            us = "" if k % 997 == 5 else f"u{u[k]}"
+            it = "" if k in (1, 3) else f"i{i[k]}"      # before the first row without a user id: see atomic.data_filtering
+            f.write(f"{us}\t{it}\t{r[k]}\t{t[k]}\n")
+    in_file = np.sort(rng.choice(n_users, n_users - 20, replace=False))
+    with open(os.path.join(d, name + ".user"), "w") as f:
+        f.write("user_id:token\tgender:float\tage:float\toccupation:token\n")
+        for k in rng.permutation(np.r_[in_file, np.arange(n_users, n_users + 15)]):
+            f.write(f"u{k}\t{int(rng.integers(0, 2))}\t{int(rng.integers(0, 7))}\tocc{int(rng.integers(0, 9))}\n")
+    keep_items = np.sort(rng.choice(n_items, n_items - 10, replace=False))
+    with open(os.path.join(d, name + ".item"), "w") as f:
+        f.write("item_id:token\tgenre:token\n")
+        for k in rng.permutation(np.r_[keep_items, np.arange(n_items, n_items + 10)]):
+            f.write(f"i{k}\tg{int(rng.integers(0, 5))}\n")
+    return name
+
+
+INGEST_BASE = dict(RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0}, seed=2020, TIME_FIELD="timestamp",
+                   load_col={"inter": ["user_id", "item_id", "rating", "timestamp"],
+                             "user": ["user_id", "gender", "age", "occupation"], "item": ["item_id", "genre"]},
+                   sst_attr_list=["gender"])
+INGEST_CASES = {
+    "defaults": dict(eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"}),
+    "kcore_to_ls": dict(user_inter_num_interval="[5,inf)", item_inter_num_interval="[3,120]", rm_dup_inter="first",
+                        val_interval={"rating": "[2,5]"},
+                        eval_args={"split": {"LS": "valid_and_test"}, "group_by": "user", "order": "TO", "mode": "full"}),
+    "nogroup_keepall": dict(filter_inter_by_user_or_item=False, rm_dup_inter="last", user_inter_num_interval="[1,inf)",
+                            item_inter_num_interval="[1,inf)", val_interval={"occupation": ["occ1", "occ2", "occ3", "occ4", "occ5"]},
+                            eval_args={"split": {"RS": [7, 2, 1]}, "group_by": "none", "order": "RO", "mode": "full"}),
+    "ls_valid_only_to": dict(user_inter_num_interval="(2,60)",
+                             eval_args={"split": {"LS": "valid_only"}, "group_by": "user", "order": "TO", "mode": "full"}),
+    "ls_test_only_ro": dict(item_inter_num_interval="[2,inf)", val_interval={"timestamp": "[1000,1100);(1200,1399]"},
+                            eval_args={"split": {"LS": "test_only"}, "group_by": "user", "order": "RO", "mode": "full"}),
+}

@@ -9,6 +9,13 @@ id assignment, the same shuffle and the same per-user cut, so that the splits (a
 to the reference's for a given seed (tests/test_atomic.py pins this on ml-100k against tensors exported from the
 reference).  All of it is host-side numpy (vectorised; no per-row Python loops), done once per run.
 
+Also covered, with the reference's semantics and order of application (`_data_filtering`, dataset.py:160-181): rows with a
+missing user / item id dropped (624-642), `rm_dup_inter` (644-668), `val_interval` (803-821), `filter_inter_by_user_or_item`
+(847-863, on by default), `user_inter_num_interval` / `item_inter_num_interval` k-core filtering (670-728, vectorised:
+bincounts instead of Python Counters); `eval_args.order` RO | TO, `split` RS (grouped by user or not) | LS
+(`valid_and_test`, `valid_only`, `test_only`; 1398-1450).  tests/test_atomic.py pins them on golden splits exported from
+the reference (tests/golden/ingest_*.npz) and, in the build container, against the live reference.
+
 File format (RecBole atomic files): TSV with a `name:type` header, types token / float / token_seq / float_seq
 (sequences are not used by the fairness configs and are skipped)."""
 import os
@@ -56,6 +63,127 @@ def calcu_split_counts(tot, ratios):
     return cnt
 
 
+def parse_intervals(text):
+    """dataset.py:748-774 "(0,1];[3,inf)" -> [(left bracket, left, right, right bracket)] (None stays None)"""
+    if text is None:
+        return None
+    out = []
+    for part in str(text).split(";"):
+        part = part.strip()
+        lb, rb = part[0], part[-1]
+        ends = part[1:-1].split(",")
+        if len(ends) != 2 or lb not in "([" or rb not in ")]":
+            continue                                             # the reference warns and skips
+        out.append((lb, float(ends[0]), float(ends[1]), rb))
+    return out
+
+
+def within_intervals(x, intervals):
+    """dataset.py:776-786, elementwise over an array"""
+    x = np.asarray(x, np.float64)
+    res = np.ones(x.shape, bool)
+    for k, (lb, lo, hi, rb) in enumerate(intervals):
+        t = (x >= lo if lb == "[" else x > lo) & (x <= hi if rb == "]" else x < hi)
+        res = t if k == 0 else res | t
+    return res
+
+
+def _take(cols, keep):
+    return {k: v[keep] for k, v in cols.items()}
+
+
+def _isin(a, b):
+    import pandas as pd
+    return pd.Series(a).isin(b).to_numpy()
+
+
+def data_filtering(config, inter, user, item, types, uid_field, iid_field):
+    """dataset.py:160-181 on column dicts (user / item = None when the feature file is not loaded); returns the three
+    filtered dicts, row order preserved (after `rm_dup_inter`: the reference's time-sorted order)."""
+    import pandas as pd
+    # 1. missing ids (624-642).  Deliberate difference: the reference drops the item-less interactions by POSITION after the
+    # user-less ones were already removed (`inter_feat.index[labels]`, 638-642), i.e. once a user-less row precedes them
+    # it removes their neighbours instead and keeps the item-less rows (which then map to the [PAD] item); here the rows
+    # that actually miss an id are the ones dropped.
+    for field, name in ((uid_field, "user"), (iid_field, "item")):
+        feat = user if name == "user" else item
+        if feat is not None:
+            feat = _take(feat, ~pd.isna(feat[field]))
+        inter = _take(inter, ~pd.isna(inter[field]))
+        user, item = (feat, item) if name == "user" else (user, feat)
+    # 2. duplicated (user, item) pairs (644-668): pandas does it in the reference; the same two calls here, so that the
+    # order among equal timestamps (sort_values' default, unstable kind) is the reference's by construction
+    keep = config["rm_dup_inter"]
+    if keep is not None:
+        df = pd.DataFrame(inter)
+        tf = config["TIME_FIELD"] or "timestamp"
+        if tf in df:
+            df = df.sort_values(by=[tf], ascending=True)
+        df = df.drop_duplicates(subset=[uid_field, iid_field], keep=keep)
+        inter = {k: df[k].to_numpy() for k in inter}
+    # 3. value intervals (803-821), on every table that holds the field
+    for field, interval in (config["val_interval"] or {}).items():
+        if field not in types:
+            raise ValueError(f"Field [{field}] not defined in dataset.")
+        tabs = {"inter": inter, "user": user, "item": item}
+        for name, tab in tabs.items():
+            if tab is None or field not in tab:
+                continue
+            ok = within_intervals(tab[field], parse_intervals(interval)) if types[field] == "float" else \
+                _isin(tab[field], [str(v) for v in interval])
+            tabs[name] = _take(tab, ok)
+        inter, user, item = tabs["inter"], tabs["user"], tabs["item"]
+    # 4. interactions of users / items absent from a loaded feature file (847-863)
+    if config["filter_inter_by_user_or_item"] is True:
+        ok = np.ones(len(inter[uid_field]), bool)
+        if user is not None:
+            ok &= _isin(inter[uid_field], user[uid_field])
+        if item is not None:
+            ok &= _isin(inter[iid_field], item[iid_field])
+        inter = _take(inter, ok)
+    # 5. interaction-count intervals, iterated to the fixed point (670-746)
+    u_int, i_int = parse_intervals(config["user_inter_num_interval"]), parse_intervals(config["item_inter_num_interval"])
+    if u_int is not None or i_int is not None:
+        def codes(inter_col, feat, field):      # joint code space of the interaction column and the feature column
+            both = np.concatenate([inter_col] + ([feat[field]] if feat is not None else []))
+            c, _ = pd.factorize(both)
+            return c[:len(inter_col)], (c[len(inter_col):] if feat is not None else None), int(c.max()) + 1 if len(c) else 0
+
+        uc, ufc, nu = codes(inter[uid_field], user, uid_field)
+        ic, ifc, ni = codes(inter[iid_field], item, iid_field)
+        alive = np.ones(len(uc), bool)
+        ualive = np.ones(len(ufc), bool) if ufc is not None else None
+        ialive = np.ones(len(ifc), bool) if ifc is not None else None
+
+        def banned(code, fcode, falive, n, interval):
+            """ids present with a count outside the interval, plus feature rows whose count is below the first
+            interval's left end (_get_illegal_ids_by_inter_num; a Counter drops ids whose count reached 0)"""
+            cnt = np.bincount(code[alive], minlength=n) if interval else np.zeros(n, np.int64)
+            ban = (cnt > 0) & ~within_intervals(cnt, interval) if interval else np.zeros(n, bool)
+            if fcode is not None:
+                low = np.zeros(n, bool)
+                low[fcode[falive]] = True
+                ban |= low & (cnt < (interval[0][1] if interval else -1))
+            return ban
+
+        while True:
+            bu, bi = banned(uc, ufc, ualive, nu, u_int), banned(ic, ifc, ialive, ni, i_int)
+            if not bu.any() and not bi.any():
+                break
+            if ufc is not None:
+                ualive &= ~bu[ufc]
+            if ifc is not None:
+                ialive &= ~bi[ifc]
+            alive &= ~(bu[uc] | bi[ic])
+        inter = _take(inter, alive)
+        user = _take(user, ualive) if user is not None else None
+        item = _take(item, ialive) if item is not None else None
+    for name, tab in (("inter", inter), ("user", user), ("item", item)):
+        if tab is not None and len(next(iter(tab.values()))) == 0:
+            raise ValueError("Some feat is empty, please check the filtering settings.")
+    return inter, user, item
+
+
 class AtomicDataset:
     """The slice of recbole.data.dataset.Dataset the hot path reads: `num`, `inter_feat`, `get_user_feature`,
     `inter_matrix`, `field2id_token`, plus `build()` -> three column dicts (train / valid / test)."""
@@ -70,9 +198,13 @@ class AtomicDataset:
         inter, itypes = read_atomic(os.path.join(root, name + ".inter"), load_col.get("inter"))
         user_path, item_path = os.path.join(root, name + ".user"), os.path.join(root, name + ".item")
         user, utypes = read_atomic(user_path, load_col.get("user")) if os.path.exists(user_path) and \
-            (not load_col or "user" in load_col) else ({}, {})
-        item, _ = read_atomic(item_path, load_col.get("item")) if os.path.exists(item_path) and "item" in load_col \
-            else ({}, {})
+            (not load_col or "user" in load_col) else (None, {})
+        item, mtypes = read_atomic(item_path, load_col.get("item")) if os.path.exists(item_path) and "item" in load_col \
+            else (None, {})
+        self.time_field = config["TIME_FIELD"] or "timestamp"
+        inter, user, item = data_filtering(config, inter, user, item, {**mtypes, **utypes, **itypes}, self.uid_field,
+                                           self.iid_field)
+        user, item = user or {}, item or {}
         self.field2id_token = {}
         # ---- id remap: interactions first, then the feature file (dataset.py:894-918)
         chunks = [inter[self.uid_field]] + ([user[self.uid_field]] if self.uid_field in user else [])
@@ -105,8 +237,8 @@ class AtomicDataset:
                     vals, self.field2id_token[f] = factorize([user[f]])
                     col = np.zeros(self.user_num, np.int64)
                     col[feat_u] = vals[0]
-                else:
-                    col = np.zeros(self.user_num, np.float32)
+                else:     # users without a feature row (and the [PAD] row) get the column mean (_fill_nan, dataset.py:571-572)
+                    col = np.full(self.user_num, np.float32(np.nanmean(user[f])) if len(user[f]) else 0.0, np.float32)
                     col[feat_u] = user[f].astype(np.float32)
                 self.user_feat[f] = col
 
@@ -138,31 +270,63 @@ class AtomicDataset:
 
     # ------------------------------------------------------------------ ordering + splitting
     def build(self):
-        """eval_args {order: RO, split: {RS: [a, b, c]}, group_by: user} (the setting of all eight fairness YAMLs):
-        shuffle with torch.randperm (global torch RNG, as seeded by init_seed), then per user -- users in order of first
-        appearance in the shuffled data, rows in shuffled order -- the first a/(a+b+c) go to train, etc."""
+        """dataset.py:1467-1514.  eval_args.order: RO = shuffle with torch.randperm (global torch RNG, as seeded by
+        init_seed; interaction.py:293-297) | TO = stable sort by the time field.  eval_args.split: {RS: [a, b, c]} with
+        group_by user (per user -- users in order of first appearance in the ordered data, rows in that order -- the
+        first a/(a+b+c) go to train, etc.) or none (three contiguous ranges) | {LS: valid_and_test | valid_only |
+        test_only} (leave-one-out per user).  Returns three column dicts (a part may be empty)."""
         ea = self.config["eval_args"] or {}
-        if (ea.get("order") or "RO") != "RO" or "RS" not in (ea.get("split") or {"RS": [8, 1, 1]}) or \
-                (ea.get("group_by") or "user") != "user":
-            raise NotImplementedError("eval_args other than order RO / split RS / group_by user are outside the fairness configs")
-        ratios = (ea.get("split") or {"RS": [8, 1, 1]})["RS"]
+        order_mode = ea.get("order") or "RO"
+        split = ea.get("split") or {"RS": [8, 1, 1]}
+        group_by = ea.get("group_by", "user")
+        if not isinstance(split, dict) or len(split) != 1:
+            raise ValueError(f"The split_args [{split}] should be a dict with one key.")
         n = len(self)
-        perm = torch.randperm(n).numpy()                      # interaction.py:293-297
+        if order_mode == "RO":
+            perm = torch.randperm(n).numpy()
+        elif order_mode == "TO":
+            if self.time_field not in self.inter:
+                raise ValueError(f"[{self.time_field}] is not exist in interaction.")
+            perm = np.argsort(self.inter[self.time_field], kind="stable")       # interaction.py:333-337
+        else:
+            raise NotImplementedError(f"The ordering_method [{order_mode}] has not been implemented.")
         cols = {k: v[perm] for k, v in self.inter.items()}
+        mode = next(iter(split))
+        if mode == "RS" and (group_by is None or str(group_by).lower() == "none"):
+            cnt = calcu_split_counts([n], split["RS"])[0]
+            edges = np.r_[0, np.cumsum(cnt)]
+            splits = [{k: v[a:b] for k, v in cols.items()} for a, b in zip(edges[:-1], edges[1:])]
+            self._matrix_src = splits[0]
+            return splits
+        if mode not in ("RS", "LS") or (mode == "RS" and group_by != "user"):
+            raise NotImplementedError(f"The splitting_method [{split}] / grouping [{group_by}] has not been implemented.")
         u = cols[self.uid_field]
         first = np.full(self.user_num, n, np.int64)
         np.minimum.at(first, u, np.arange(n))
-        order = np.argsort(first[u], kind="stable")          # groups by first appearance, shuffled order inside
+        order = np.argsort(first[u], kind="stable")          # groups by first appearance, ordered rows inside
         us = u[order]
         starts = np.flatnonzero(np.r_[True, us[1:] != us[:-1]])
         lens = np.diff(np.r_[starts, n])
-        cnt = calcu_split_counts(lens, ratios)
         rank = np.arange(n) - np.repeat(starts, lens)
-        edges = np.cumsum(cnt, axis=1)
-        part = (rank[:, None] >= np.repeat(edges, lens, axis=0)).sum(axis=1)
+        if mode == "RS":
+            n_parts = len(split["RS"])
+            cnt = calcu_split_counts(lens, split["RS"])
+            edges = np.cumsum(cnt, axis=1)
+            part = (rank[:, None] >= np.repeat(edges, lens, axis=0)).sum(axis=1)
+            slot = list(range(n_parts))
+        else:
+            lom = split["LS"]
+            if lom not in ("valid_and_test", "valid_only", "test_only"):
+                raise NotImplementedError(f"The leave_one_mode [{lom}] has not been implemented.")
+            leave = 2 if lom == "valid_and_test" else 1      # dataset.py:1398-1418: the last min(leave, len - 1) rows
+            legal = np.minimum(leave, lens - 1)              # of a user go one each to the LAST `legal` parts
+            tot, leg = np.repeat(lens, lens), np.repeat(legal, lens)
+            part = np.where(rank < tot - leg, 0, leave + 1 - leg + (rank - (tot - leg)))
+            n_parts = 3
+            slot = [0, 1, 2] if lom == "valid_and_test" else ([0, 1, None] if lom == "valid_only" else [0, None, 1])
         splits = []
-        for p in range(len(ratios)):
-            idx = order[part == p]
+        for p in slot:
+            idx = order[part == p] if p is not None else np.zeros(0, np.int64)
             splits.append({k: v[idx] for k, v in cols.items()})
         self._matrix_src = splits[0]
         return splits

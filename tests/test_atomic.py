@@ -118,3 +118,43 @@ def test_ingestion_identical_to_the_live_reference_on_synthetic_files(tmp_path):
     _, ds, splits, lists = bi.ours(str(tmp_path), name)
     _, rds, rloaders = bi.reference(str(tmp_path), name)
     assert bi.compare(ds, splits, lists, rds, rloaders)
+
+
+def _ingest_case_names():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+    import make_test_data as mtd
+    return list(mtd.INGEST_CASES)
+
+
+@pytest.mark.parametrize("case", _ingest_case_names())
+def test_filtering_ordering_and_splitting_options_match_the_reference(case, tmp_path):
+    """every `_data_filtering` branch (missing ids, rm_dup_inter, val_interval on float and token fields,
+    filter_inter_by_user_or_item, k-core intervals), order RO | TO, split RS (grouped or not) | LS in its three modes:
+    ids, id->token maps, the three splits (row order included) and the user features, bit for bit against the outputs of
+    the unmodified reference on the same files (tests/golden/ingest_<case>.npz, oracle/gen_golden.py ingest)."""
+    import make_test_data as mtd
+    from recbole_fairrec_b200.atomic import AtomicDataset
+    from recbole_fairrec_b200.quick_start import build_config, init_seed
+    g = np.load(os.path.join(HERE, "golden", f"ingest_{case}.npz"))
+    name = mtd.write_messy(str(tmp_path))
+    cfg = build_config("FOCF", name, None, dict(mtd.INGEST_BASE, **mtd.INGEST_CASES[case], data_path=str(tmp_path),
+                                                device="cpu"))
+    init_seed(cfg["seed"])
+    ds = AtomicDataset(cfg)
+    assert (ds.user_num, ds.item_num) == (int(g["n_users"]), int(g["n_items"]))
+    np.testing.assert_array_equal(np.array([str(t) for t in ds.field2id_token["user_id"]]), g["user_tokens"])
+    np.testing.assert_array_equal(np.array([str(t) for t in ds.field2id_token["item_id"]]), g["item_tokens"])
+    splits = ds.build()
+    for k, part in zip(("train", "valid", "test"), splits):
+        for col in ("user_id", "item_id", "rating", "timestamp", "label"):
+            np.testing.assert_array_equal(part[col], g[f"{k}_{col}"], err_msg=f"{case} {k} {col}")
+    for col in ("gender", "age", "occupation"):
+        want = g["user_" + col].copy()
+        if want.dtype.kind == "f":
+            # users without a feature row: the reference fills the column mean (dataset.py:571-572); under pandas 3 that
+            # `fillna(inplace=True)` is a no-op and the fixture holds NaN there (SURVEY.md 8c caveat)
+            want[np.isnan(want)] = np.float32(np.nanmean(want.astype(np.float64)))
+        else:
+            want[want < 0] = 0                               # same no-op for token columns: INT64_MIN instead of [PAD]
+        np.testing.assert_array_equal(ds.user_feat[col][1:], want, err_msg=col)
