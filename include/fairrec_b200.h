@@ -312,6 +312,9 @@ int fr_mse_loss(const float *pred, const float *target, int64_t M, float *loss, 
 /* stand-alone activation (act codes of fr_linear_forward) and its backward through the OUTPUT y */
 int fr_act_forward(const float *x, int32_t act, int64_t n, float *y, void *stream);
 int fr_act_backward(const float *dY, const float *Y, int32_t act, int64_t n, float *dX, void *stream);
+/* stand-alone inverted dropout, y = x * mask(seed + *seed_dev, i) / (1 - p); applied to dY it is its own backward.
+   Replaces the F.dropout between the convolutions of torch_geometric.nn.GCN (fairgo_gcn.py:52-57, pretrain stage). */
+int fr_dropout(const float *x, float p, uint64_t seed, const uint64_t *seed_dev, int64_t n, float *y, void *stream);
 /* out[m] = act(dot[m] + ub[m] + ib[m] + gb[0]) (pfcn_biasedmf.py:170-181 predict) */
 int fr_biased_score(const float *dot, const float *ub, const float *ib, const float *gb, int64_t M, int32_t act, float *out,
                     void *stream);

@@ -185,3 +185,36 @@ def replay(g, lr=1e-3, wd=1e-4, dtype=torch.float32):
         opt.step()
         losses.append(loss.item())
     return np.array(losses, np.float32), grads, extra, pretrained, {k: v.detach().numpy() for k, v in st.items()}
+
+
+def gcn_edges(train_u, train_i, train_r, n_users, n_items):
+    """the edge list fairgo_gcn.py:60-66 hands to the GCN: (u -> n_users + i) and (n_users + i -> u), weight = rating"""
+    u = torch.as_tensor(np.asarray(train_u), dtype=torch.long)
+    i = torch.as_tensor(np.asarray(train_i), dtype=torch.long) + n_users
+    w = torch.as_tensor(np.asarray(train_r, np.float32))
+    return torch.stack([torch.cat([u, i]), torch.cat([i, u])]), torch.cat([w, w])
+
+
+def gcn_forward(x, edge_index, edge_weight, weights, biases, act=F.relu, dropout_masks=None):
+    """torch_geometric.nn.GCN (BasicGNN over GCNConv; third-party, absent here -- restated from its published algorithm,
+    Kipf & Welling 2017): per layer, self loops of weight 1 are added, deg_i = sum of the weights of the edges INTO i,
+    norm_e = deg^-1/2[src] * w_e * deg^-1/2[dst]; out_i = sum_{e: dst = i} norm_e * (x W^T)[src] + b; between layers act
+    then dropout (`dropout_masks[k]`, already scaled, multiplies the output of layer k), nothing after the last layer.
+    PARITY UNPINNED against torch_geometric itself."""
+    N = x.shape[0]
+    loops = torch.arange(N)
+    src = torch.cat([edge_index[0], loops])
+    dst = torch.cat([edge_index[1], loops])
+    w = torch.cat([edge_weight.to(x.dtype), torch.ones(N, dtype=x.dtype)])
+    deg = torch.zeros(N, dtype=x.dtype).index_add_(0, dst, w)
+    dinv = deg.pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    norm = dinv[src] * w * dinv[dst]
+    for k, (W, b) in enumerate(zip(weights, biases)):
+        h = x @ W.t()
+        x = torch.zeros(N, W.shape[0], dtype=x.dtype).index_add_(0, dst, norm[:, None] * h[src]) + b
+        if k + 1 < len(weights):
+            x = act(x)
+            if dropout_masks is not None:
+                x = x * dropout_masks[k]
+    return x

@@ -142,6 +142,7 @@ SIGNATURES = {
     "fr_mse_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "fr_act_forward": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "fr_act_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "fr_dropout": (c_int, [c_void_p, c_float, c_uint64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fr_clamp_div": (c_int, [c_void_p, c_float, c_int64, c_void_p, c_void_p]),
     "fr_spmm_plan_sizes": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
                                    POINTER(c_int64)]),

@@ -229,6 +229,15 @@ __global__ void __launch_bounds__(256)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dX[i] = dY[i] * act_bwd(Y[i], act);
 }
+// stand-alone inverted dropout (torch_geometric BasicGNN between its convolutions): y = x * mask / (1 - p); the mask is a
+// pure function of (seed, element index), so the backward pass is the same kernel applied to dY
+__global__ void __launch_bounds__(256)
+    k_dropout(const float *__restrict__ x, float p, unsigned long long seed, const unsigned long long *__restrict__ seed_dev,
+              int64_t n, float *__restrict__ y) {
+  const unsigned long long s = seed + (seed_dev ? *seed_dev : 0ull);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * drop_scale(s, 0x44524f50u, (uint32_t)i, p);
+}
 __global__ void __launch_bounds__(256)
     k_clamp_div(const float *__restrict__ x, float hi, int64_t n, float *__restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -341,6 +350,14 @@ int fr_act_forward(const float *x, int32_t act, int64_t n, float *y, void *strea
 int fr_act_backward(const float *dY, const float *Y, int32_t act, int64_t n, float *dX, void *stream) {
   FR_REQUIRE(dY && Y && dX && n >= 1, "fr_act_backward: bad argument");
   FR_LAUNCH(fr::k_act_bwd_out, fr::grid_for(n, 256), 256, 0, stream, dY, Y, act, n, dX);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_dropout(const float *x, float p, uint64_t seed, const uint64_t *seed_dev, int64_t n, float *y, void *stream) {
+  FR_REQUIRE(x && y && n >= 1 && n < (1ll << 32) && p >= 0.f && p < 1.f, "fr_dropout: bad argument");
+  FR_LAUNCH(fr::k_dropout, fr::grid_for(n, 256), 256, 0, stream, x, p, (unsigned long long)seed,
+            (const unsigned long long *)seed_dev, n, y);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

@@ -15,8 +15,9 @@ FairGo trainers contains them), so this implementation does not back-propagate i
 `forward(sst_list)` once and shares it between the rating term and the discriminator term (the reference evaluates the
 identical expression twice).
 FairGo_GCN: the fine-tune stage is identical to FairGo_PMF's.  Its pretrain stage calls torch_geometric.nn.GCN, a
-third-party dependency that is neither vendored nor pinned by the reference (parity unpinned) and is
-not rebuilt here: FairGo_GCN starts from given embeddings (`load_pretrain_weight` / checkpoint), as the survey prescribes.
+third-party dependency that is neither vendored nor pinned by the reference (parity unpinned); it
+is restated from the published algorithm on this package's SpMM / linear kernels (see FairGo_GCN), pinned on the oracle's
+restatement only.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -282,14 +283,83 @@ class FairGo_PMF(nn.Module):
         return ret
 
 
+def gcn_norm_csr(rating_matrix, n_users, n_items):
+    """Kipf & Welling's renormalised adjacency with edge weights, as torch_geometric's GCNConv builds it (gcn_norm with
+    add_self_loops, fill value 1): A_hat = D^-1/2 (A + I) D^-1/2 over the bipartite rating graph of fairgo_gcn.py:60-66
+    (user u <-> node n_users + i, weight = rating, both directions); deg_i = sum_j (A + I)_ij; isolated nodes keep their
+    self loop.  Host-side scipy, once per model."""
+    import scipy.sparse as sp
+    N = n_users + n_items
+    R = rating_matrix.tocoo()
+    A = sp.coo_matrix((np.r_[R.data, R.data].astype(np.float64),
+                       (np.r_[R.row, R.col + n_users], np.r_[R.col + n_users, R.row])), shape=(N, N)).tocsr()
+    A = A + sp.identity(N, dtype=np.float64, format="csr")
+    deg = np.asarray(A.sum(axis=1)).ravel()
+    with np.errstate(divide="ignore"):
+        dinv = np.where(deg > 0, deg ** -0.5, 0.0)
+    return sp.csr_matrix(sp.diags(dinv) @ A @ sp.diags(dinv), dtype=np.float32)
+
+
+class _GCNConv(nn.Module):
+    """parameters of one torch_geometric GCNConv (`lin.weight` glorot-uniform [out, in], `bias` zeros)"""
+
+    def __init__(self, n_in, n_out):
+        super().__init__()
+        self.lin = nn.Linear(n_in, n_out, bias=False)
+        nn.init.xavier_uniform_(self.lin.weight)
+        self.bias = nn.Parameter(torch.zeros(n_out))
+
+
+class _GCN(nn.Module):
+    """parameter tree of torch_geometric.nn.GCN(in, hidden, num_layers, out, dropout, act): `convs.<k>.lin.weight`,
+    `convs.<k>.bias`; widths in -> hidden x (num_layers - 1) -> out"""
+
+    def __init__(self, n_in, hidden, n_out, num_layers, dropout, act):
+        super().__init__()
+        dims = [n_in] + [hidden] * (num_layers - 1) + [n_out]
+        self.convs = nn.ModuleList(_GCNConv(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        self.dropout = float(dropout or 0.0)
+        self.act = (act or "relu").lower()
+
+
 class FairGo_GCN(FairGo_PMF):
-    """fairgo_gcn.py: fine-tune stage identical to FairGo_PMF; the torch_geometric GCN pretrain is not rebuilt (see the
-    module docstring) -- start from given embeddings."""
+    """fairgo_gcn.py.  Fine-tune stage: identical to FairGo_PMF (the reference applies its filters to the RAW embedding
+    tables there, fairgo_gcn.py:177-186; the GCN only shapes the pretrain stage).  Pretrain stage (fairgo_gcn.py:175-176):
+    rating MSE on `GCN(ego embeddings)`, the GCN being torch_geometric.nn.GCN in the reference -- a third-party module the
+    reference neither vendors nor pins.  It is restated here from the published algorithm (Kipf & Welling 2017 as
+    implemented by GCNConv / BasicGNN: x <- A_hat (x W^T) + b, then act and dropout between layers, none after the last)
+    and computed as LinearAct(Spmm(A_hat, dropout(x)), W, b, act) -- aggregation first, which is the same map by
+    linearity -- on this package's kernels.  Parity for this stage is pinned on the oracle's restatement only
+    (oracle/fairgo_oracle.gcn_forward), not on torch_geometric itself (absent from the build container)."""
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.gcn = _GCN(self.embedding_size, int(config["hidden_channels"] or 32), self.embedding_size,
+                        int(config["gcn_n_layers"] or 2), config["gcn_dropout"], config["gcn_act"])
+        self._gcn_csr = gcn_norm_csr(self.rating_matrix, self.n_users, self.n_items)
+        self._gcn_mat = None
+
+    def to(self, *a, **k):
+        super().to(*a, **k)
+        self._gcn_mat = None
+        return self
+
+    def _gcn_forward(self, x):
+        if self._gcn_mat is None:
+            self._gcn_mat = ops.SpmmMatrix(self._gcn_csr, self._dev())
+        g = self.gcn
+        act, last = ops.ACT[g.act], len(g.convs) - 1
+        for k, conv in enumerate(g.convs):
+            if k > 0 and self.training and g.dropout > 0:
+                x = ops.Dropout.apply(x, g.dropout, ops.next_seed())
+            x = ops.Spmm.apply(x, self._gcn_mat)
+            x = ops.LinearAct.apply(x, conv.lin.weight, conv.bias, act if k < last else 0, 0.0, 0)
+        return x
 
     def _forward_all(self, sst_list=None):
         if self.train_stage == "pretrain":
-            raise NotImplementedError("FairGo_GCN pretraining needs torch_geometric.nn.GCN (third-party, unpinned in the "
-                                      "reference); load pretrained embeddings and run the fine-tune stage")
+            ego = torch.cat([self.user_embedding_layer.weight, self.item_embedding_layer.weight], dim=0)
+            return self._gcn_forward(ego)
         return super()._forward_all(sst_list)
 
 
@@ -310,7 +380,9 @@ class FairGoTrainer:
         else:
             model.train_stage = "pretrain"
             self.pretrain_epochs = config["pretrain_epochs"]
-            self.optimizer_pretrain = ops.AdamGroup([model.user_embedding_layer.weight, model.item_embedding_layer.weight],
+            # the reference's pretrain optimizer holds model.parameters(); the ones that receive a gradient in this stage:
+            self.optimizer_pretrain = ops.AdamGroup([model.user_embedding_layer.weight, model.item_embedding_layer.weight] +
+                                                    (list(model.gcn.parameters()) if hasattr(model, "gcn") else []),
                                                     lr=lr, weight_decay=wd)
         dparams = [p for m in model.dis_layer_dict.values() for p in m.parameters()]
         if str(config["aggr_method"]).upper() == "LBA":

@@ -391,6 +391,29 @@ class Act(torch.autograd.Function):
         return dX, None
 
 
+class Dropout(torch.autograd.Function):
+    """inverted dropout with a counter-based mask (seed + device seed offset, element index): the backward pass applies the
+    same mask to the incoming gradient"""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(load().fr_dropout(ptr(x), float(p), seed, ptr(seed_dev(x.device)), x.numel(), ptr(y), stream_ptr()),
+              "fr_dropout")
+        ctx.cfg = (float(p), seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        check(load().fr_dropout(ptr(dy), p, seed, ptr(seed_dev(dy.device)), dy.numel(), ptr(dx), stream_ptr()),
+              "fr_dropout")
+        return dx, None, None
+
+
 def clamp_div(x, hi):
     """clamp(x, 0, hi) / hi (inference only: fairgo_pmf.py:248, focf.py:150)"""
     lib = load()

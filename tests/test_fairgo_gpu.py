@@ -155,23 +155,91 @@ def test_spmm_matches_scipy_on_skewed_rows():
             assert np.array_equal(got, mat.apply(Xg, tr).cpu().numpy())      # run-to-run bit stability
 
 
-def test_fairgo_gcn_finetune_equals_pmf_and_pretrain_is_refused():
+def test_fairgo_gcn_finetune_equals_pmf():
     import recbole_fairrec_b200 as pkg
     g = np.load(FAIRGO[0])
     _, pmf, feats = build(g)
-    _, gcn, _ = build(g, cls="FairGo_GCN")
+    _, gcn, _ = build(g, cls="FairGo_GCN", hidden_channels=32, gcn_n_layers=2, gcn_dropout=0.2, gcn_act="relu")
     st = go.load_state(g, "pretrained")
     load_state(pmf, st)
-    load_state(gcn, st)
+    gcn.load_state_dict({k[5:]: v for k, v in st.items() if k.startswith("base.")}, strict=False)   # + its own gcn.*
+    for name, mod in owners(gcn).items():
+        mod.load_state_dict({k[len(name) + 1:]: v for k, v in st.items() if k.startswith(name + ".")})
+    assert sorted(k for k in gcn.state_dict() if k.startswith("gcn.")) == \
+        ["gcn.convs.0.bias", "gcn.convs.0.lin.weight", "gcn.convs.1.bias", "gcn.convs.1.lin.weight"]
     u = g["user_id2"]
     inter = pkg.Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(g["item_id2"]),
                              "rating": torch.from_numpy(g["rating2"]), "gender": torch.from_numpy(feats["gender"][u]),
                              "age": torch.from_numpy(feats["age"][u])})
     pmf.train_stage = gcn.train_stage = "finetune"
     assert pmf.calculate_loss(inter, ["gender", "age"]).item() == gcn.calculate_loss(inter, ["gender", "age"]).item()
-    gcn.train_stage = "pretrain"
-    with pytest.raises(NotImplementedError):
-        gcn.calculate_loss(inter, None)
+
+
+@pytest.mark.parametrize("layers,hidden", [(2, 32), (3, 16), (1, 32)])
+def test_fairgo_gcn_pretrain_matches_the_restated_gcn(layers, hidden):
+    """pretrain stage of FairGo_GCN (fairgo_gcn.py:175-176, 190-199): rating MSE on GCN(ego embeddings) -- loss, gradients
+    of both tables and of every GCN parameter, and three Adam steps, against oracle/fairgo_oracle.gcn_forward (the
+    published GCNConv algorithm in its own order A_hat (x W^T) + b, torch CPU autograd + torch.optim.Adam)"""
+    import recbole_fairrec_b200 as pkg
+    g = np.load(FAIRGO[0])
+    cfg, model, feats = build(g, cls="FairGo_GCN", hidden_channels=hidden, gcn_n_layers=layers, gcn_dropout=0.0,
+                              gcn_act="relu")
+    trainer = pkg.FairGoTrainer(cfg, model)
+    assert model.train_stage == "pretrain"
+    nu, ni = int(g["n_users"]), int(g["n_items"])
+    with torch.no_grad():
+        for conv in model.gcn.convs:
+            conv.bias.copy_(torch.linspace(-0.1, 0.1, conv.bias.numel()))       # non-trivial biases
+    ref = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()
+           if k.startswith("gcn.") or k.endswith("embedding_layer.weight")}
+    ei, ew = go.gcn_edges(g["train_u"], g["train_i"], g["train_r"], nu, ni)
+    names = [f"gcn.convs.{k}" for k in range(layers)]
+    opt = torch.optim.Adam(list(ref.values()), lr=1e-3, weight_decay=1e-4)
+    u, i, r = (torch.from_numpy(np.asarray(g[k])) for k in ("user_id2", "item_id2", "rating2"))
+    inter = pkg.Interaction({"user_id": u, "item_id": i, "rating": r})
+    model.train()
+    for step in range(3):
+        x = torch.cat([ref["user_embedding_layer.weight"], ref["item_embedding_layer.weight"]])
+        out = go.gcn_forward(x, ei, ew, [ref[n + ".lin.weight"] for n in names], [ref[n + ".bias"] for n in names])
+        want = torch.nn.functional.mse_loss((out[u.long()] * out[nu + i.long()]).sum(-1), r.float())
+        opt.zero_grad()
+        want.backward()
+        trainer.optimizer_pretrain.zero_grad()
+        loss = model.calculate_loss(inter, None)
+        loss.backward()
+        assert abs(loss.item() - want.item()) <= RTOL * abs(want.item()), (step, loss.item(), want.item())
+        if step == 0:
+            for k, p in model.named_parameters():
+                if k in ref:
+                    assert rel_err(p.grad.cpu().numpy(), ref[k].grad.numpy()) < 2e-5, k
+        opt.step()
+        trainer.optimizer_pretrain.step()
+    for k, p in model.named_parameters():
+        if k in ref:
+            # Adam's first steps move every element by ~lr whatever the gradient's size: compare the UPDATE
+            assert np.abs(p.detach().cpu().numpy() - ref[k].detach().numpy()).max() < 1e-5, k
+    # evaluation of the stage scores with the GCN output (full_sort_predict -> forward, fairgo_gcn.py:264-271)
+    model.eval()
+    U, I = model.filtered_tables()
+    out = go.gcn_forward(torch.cat([ref["user_embedding_layer.weight"], ref["item_embedding_layer.weight"]]).detach(), ei, ew,
+                         [ref[n + ".lin.weight"].detach() for n in names], [ref[n + ".bias"].detach() for n in names])
+    assert rel_err(torch.cat([U, I]).cpu().numpy(), out.numpy()) < 1e-4
+
+
+def test_dropout_op_mask_statistics_and_backward():
+    from recbole_fairrec_b200 import ops
+    x = torch.randn(4000, 32, device="cuda", requires_grad=True)
+    y = ops.Dropout.apply(x, 0.2, 12345)
+    kept = (y != 0)
+    assert abs(kept.float().mean().item() - 0.8) < 0.01
+    torch.testing.assert_close(y[kept], (x.detach() / 0.8)[kept])
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    torch.testing.assert_close(x.grad, torch.where(kept, gy / 0.8, torch.zeros_like(gy)))
+    y2 = ops.Dropout.apply(x.detach(), 0.2, 12346)
+    assert ((y2 != 0) != kept).float().mean().item() > 0.2          # another seed, another mask
+    model_input = torch.ones(8, 4, device="cuda")
+    assert torch.equal(ops.Dropout.apply(model_input, 0.0, 1), model_input)
 
 
 def test_fairgo_trainer_runs_ml1m_widths():

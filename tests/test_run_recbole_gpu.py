@@ -82,6 +82,13 @@ def test_focf_uni100_and_other_families_run_from_raw_files(tmp_path):
         filter_hidden_size_list=[128, 64], fair_weight=0.1, load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1],
         weight_decay=0.0001, train_epoch_interval=1, pretrain_epochs=3, stopping_step=5))
     assert 0.0 <= out["test_result"]["ndcg@5"] <= 1.0 and "Value Unfairness of sensitive attribute gender" in out["test_result"]
+    # FairGo_GCN from scratch: GCN pretrain (dropout between the convolutions) -> fine-tune
+    out = run_recbole("FairGo_GCN", "ml-100k", None, dict(
+        common, metrics=METRICS12, n_layers=2, activation="leakyrelu", dis_hidden_size_list=[16, 8, 4],
+        filter_hidden_size_list=[128, 64], fair_weight=0.1, load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1],
+        weight_decay=0.0001, train_epoch_interval=1, pretrain_epochs=3, stopping_step=5, gcn_n_layers=2,
+        hidden_channels=32, gcn_dropout=0.2, gcn_act="relu"))
+    assert 0.0 <= out["test_result"]["ndcg@5"] <= 1.0 and np.isfinite(out["best_valid_score"])
 
 
 def test_nfcf_two_stages_from_raw_files(tmp_path):
