@@ -7,8 +7,8 @@ Only what the path needs lives here:
   focf.py          FOCF model (calculate_loss / predict / full_sort_predict + fused train_step)
   ops.py/layers.py autograd Functions over the generic layer kernels; MLPLayers mirror
   pfcn.py          PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF models + alternating PFCNTrainer
-  fairgo.py        FairGo_PMF / FairGo_GCN (fine-tune stage) models + FairGoTrainer (SpMM + full-table filters)
-  nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser)
+  fairgo.py        FairGo_PMF / FairGo_GCN models (GCN pretrain, filtered fine-tune) + FairGoTrainer (SpMM + full-table filters)
+  nfcf.py          NFCF model (NCF tower + BCE + differential-fairness regulariser) + NFCFTrainer (both stages)
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
   sampled_eval.py  sampled-negative (uni100) ranking evaluation (SampledEvalData, SampledEvaluator)

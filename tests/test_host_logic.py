@@ -91,3 +91,46 @@ def test_mlp_module_tree_has_the_reference_state_dict_names(fixture, prefix, lay
     want = {k[len(prefix) + 1:-5]: g[k].shape for k in g.files if k.startswith(prefix + ".") and k.endswith("@init")}
     got = {k: tuple(v.shape) for k, v in MLPLayers(layers, **kw).state_dict().items()}
     assert got == {k: tuple(v) for k, v in want.items()}
+
+
+def test_run_recbole_config_precedence_and_seeding(tmp_path):
+    """configurator.py:211-263 as far as the fairness configs need it: defaults < YAML files (in order) < config_dict;
+    init_seed seeds python / numpy / torch (utils.py:172-189)"""
+    import random
+    import yaml
+    from recbole_fairrec_b200.quick_start import build_config, init_seed
+    a, b = tmp_path / "a.yaml", tmp_path / "b.yaml"
+    a.write_text(yaml.safe_dump({"embedding_size": 32, "topk": [3], "fair_weight": 0.5}))
+    b.write_text(yaml.safe_dump({"topk": [7], "learning_rate": 0.01}))
+    cfg = build_config("FOCF", "ml-100k", [str(a), str(b)], {"learning_rate": 0.1, "device": "cpu"})
+    assert (cfg["embedding_size"], cfg["topk"], cfg["fair_weight"], cfg["learning_rate"]) == (32, [7], 0.5, 0.1)
+    assert cfg["model"] == "FOCF" and cfg["dataset"] == "ml-100k" and cfg["train_batch_size"] == 2048
+    assert cfg["no_such_key"] is None                       # configurator.py:405-409
+    init_seed(123)
+    x = (random.random(), np.random.rand(), torch.rand(1).item())
+    init_seed(123)
+    assert x == (random.random(), np.random.rand(), torch.rand(1).item())
+
+
+def test_pairwise_loader_negatives_are_unseen_items():
+    """abstract_dataloader.py:182-188 + sampler.py:145-197: one uniform negative per positive, never an item of the
+    user's train split, never the [PAD] item; every train row appears exactly once per epoch"""
+    import os
+    from recbole_fairrec_b200.atomic import AtomicDataset
+    from recbole_fairrec_b200.quick_start import BatchLoader, build_config, init_seed
+    cfg = build_config("PFCN_PMF", "ml-100k", None, dict(
+        data_path=os.path.join(os.path.dirname(__file__), "data"), sst_attr_list=["gender"], device="cpu",
+        load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"]}, train_batch_size=4096))
+    init_seed(5)
+    ds = AtomicDataset(cfg)
+    train = ds.build()[0]
+    used = set((train["user_id"] * ds.item_num + train["item_id"]).tolist())
+    seen = []
+    for b in BatchLoader(cfg, ds, train, pairwise=True):
+        u, i, n = b["user_id"].numpy(), b["item_id"].numpy(), b["neg_item_id"].numpy()
+        assert (n >= 1).all() and (n < ds.item_num).all()
+        assert not (set((u * ds.item_num + n).tolist()) & used)
+        assert (b["gender"].numpy() == ds.user_feat["gender"][u]).all()
+        seen.append(u * ds.item_num + i)
+    seen = np.concatenate(seen)
+    assert len(seen) == len(train["user_id"]) and set(seen.tolist()) == used
