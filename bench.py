@@ -548,6 +548,23 @@ def run_ours(args, wname):
         sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)
         cpu = run_reference(sub, wname)["cpu_baseline"]
 
+    ingest = None
+    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_cpu_baseline:
+        try:   # atomic files of this shape -> ids, labels, shuffle, split, eval lists (host side only)
+            import shutil
+            import tempfile
+            import bench_ingest as bi
+            root = tempfile.mkdtemp()
+            try:
+                t_ing, ds_ing, _, _ = bi.ours(root, bi.write_files(root))
+                ingest = {"value": t_ing["total_s"], "unit": "s", "rows": int(len(ds_ing)), "phases": t_ing,
+                          "reference_s": 12.5, "reference_source": "profiles/r01_ingest.json (unmodified reference on the same "
+                          "files, 8 cores of the build container; outputs bit-identical)"}
+            finally:
+                shutil.rmtree(root, ignore_errors=True)
+        except Exception as e:
+            ingest = {"error": str(e)[:300]}
+
     out = {
         "metric": "FOCF train interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
         "steps": timed_steps, "warmup": args.warmup, "ms_per_step": sum(step_ms) / timed_steps,
@@ -580,6 +597,7 @@ def run_ours(args, wname):
         "cpu_baseline": cpu,
         "scaleout_probe": probe,
         "families": families,
+        "ingest": ingest,
         "eval": {"metric": "full-sort fair-eval users/s",
                  "value": tc["value"] if tc and "error" not in tc else n_eval / t_eval, "unit": "users/s",
                  "score_mode": "tc_3xtf32 (tcgen05+TMA; ids equal the exact mode's outside fp32-level near ties)"
