@@ -696,6 +696,8 @@ def run_ingest():
             uf = dataset.get_user_feature()
             for col in ("gender", "age", "occupation"):
                 out["user_" + col] = uf[col].numpy()[1:]
+            for idf in (config["preload_weight"] or {}):
+                out["preload_" + idf] = dataset.get_preload_weight(idf)
             np.savez_compressed(os.path.join(OUT, f"ingest_{case}.npz"), **out)
             print("ingest", case, dataset.user_num, dataset.item_num, [len(p.inter_feat) for p in built])
     finally:

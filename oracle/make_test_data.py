@@ -60,6 +60,13 @@ def write_messy(root, name="messy", seed=3, n_users=300, n_items=200, n_inter=60
         f.write("item_id:token\tgenre:token\n")
         for k in rng.permutation(np.r_[keep_items, np.arange(n_items, n_items + 10)]):
             f.write(f"i{k}\tg{int(rng.integers(0, 5))}\n")
+    # pretrained-embedding files of FairGo's `load_pretrain_weight` route (FairGo_PMF.yaml:12-17): id alias + float_seq
+    for suf, idf, valf, prefix, ids in (("user_emb", "uid", "user_emb", "u", np.r_[rng.permutation(n_users)[:250], [900, 901, 902]]),
+                                        ("item_emb", "iid", "item_emb", "i", np.r_[rng.permutation(n_items)[:170], [700, 701]])):
+        with open(os.path.join(d, f"{name}.{suf}"), "w") as f:
+            f.write(f"{idf}:token\t{valf}:float_seq\n")
+            for k in ids:
+                f.write(f"{prefix}{k}\t" + " ".join(f"{v:.4f}" for v in rng.standard_normal(8)) + "\n")
     return name
 
 
@@ -67,7 +74,11 @@ INGEST_BASE = dict(RATING_FIELD="rating", LABEL_FIELD="label", threshold={"ratin
                    load_col={"inter": ["user_id", "item_id", "rating", "timestamp"],
                              "user": ["user_id", "gender", "age", "occupation"], "item": ["item_id", "genre"]},
                    sst_attr_list=["gender"])
+PRELOAD = dict(additional_feat_suffix=["user_emb", "item_emb"], alias_of_user_id=["uid"], alias_of_item_id=["iid"],
+               preload_weight={"uid": "user_emb", "iid": "item_emb"})
 INGEST_CASES = {
+    "preload": dict(PRELOAD, load_col=dict(INGEST_BASE["load_col"], user_emb=["uid", "user_emb"], item_emb=["iid", "item_emb"]),
+                    eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"}),
     "defaults": dict(eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"}),
     "kcore_to_ls": dict(user_inter_num_interval="[5,inf)", item_inter_num_interval="[3,120]", rm_dup_inter="first",
                         val_interval={"rating": "[2,5]"},

@@ -26,18 +26,33 @@ import torch
 from .interaction import Interaction
 
 
-def read_atomic(path, usecols=None, sep="\t"):
-    """-> (columns: {field: np.ndarray}, types: {field: 'token' | 'float'}).  Token columns come back as str arrays (ids are
-    assigned by first appearance, so the textual token is what matters), float columns as float64 like pandas gives."""
+def read_atomic(path, usecols=None, sep="\t", seq_sep=" ", with_seq=False):
+    """-> (columns: {field: np.ndarray}, types: {field: 'token' | 'float' | 'float_seq'}).  Token columns come back as str
+    arrays (ids are assigned by first appearance, so the textual token is what matters), float columns as float64 like
+    pandas gives, float_seq columns (only with `with_seq`: the pretrained-embedding files of `additional_feat_suffix`) as a
+    zero-padded float64 matrix [rows, longest sequence] (dataset.py:441-452)."""
     import pandas as pd
     with open(path, "r", encoding="utf-8") as f:
         header = f.readline().rstrip("\n").split(sep)
     names, types = zip(*[h.split(":") for h in header])
-    keep = [n for n, t in zip(names, types) if t in ("token", "float") and (usecols is None or n in usecols)]
-    dtype = {n: (str if t == "token" else np.float64) for n, t in zip(names, types) if n in keep}
+    ok = ("token", "float", "float_seq") if with_seq else ("token", "float")
+    keep = [n for n, t in zip(names, types) if t in ok and (usecols is None or n in usecols)]
+    dtype = {n: (np.float64 if t == "float" else str) for n, t in zip(names, types) if n in keep}
     df = pd.read_csv(path, sep=sep, header=0, names=list(names), usecols=keep, dtype=dtype, engine="c",
                      keep_default_na=False, na_values=[""])
-    return {n: df[n].to_numpy() for n in keep}, {n: t for n, t in zip(names, types) if n in keep}
+    kept = {n: t for n, t in zip(names, types) if n in keep}
+    cols = {}
+    for n in keep:
+        if kept[n] != "float_seq":
+            cols[n] = df[n].to_numpy()
+            continue
+        rows = [np.array([float(x) for x in (v.split(seq_sep) if isinstance(v, str) else []) if x], np.float64)
+                for v in df[n].to_numpy()]
+        mat = np.zeros((len(rows), max((len(r) for r in rows), default=0)), np.float64)
+        for k, r in enumerate(rows):
+            mat[k, :len(r)] = r
+        cols[n] = mat
+    return cols, kept
 
 
 def factorize(chunks):
@@ -205,15 +220,36 @@ class AtomicDataset:
         inter, user, item = data_filtering(config, inter, user, item, {**mtypes, **utypes, **itypes}, self.uid_field,
                                            self.iid_field)
         user, item = user or {}, item or {}
+        # ---- additional feature files (dataset.py:329-349), e.g. the pretrained embeddings FairGo preloads
+        self.extra, self.extra_ids = {}, {}
+        for suf in config["additional_feat_suffix"] or []:
+            path = os.path.join(root, f"{name}.{suf}")
+            if not os.path.isfile(path):
+                raise ValueError(f"Additional feature file [{path}] not found.")
+            self.extra[suf], _ = read_atomic(path, load_col.get(suf) if load_col else None, with_seq=True)
+
+        def alias_chunks(key):     # fields sharing the id space, in remap order (dataset.py:456-460, 894-927)
+            out = []
+            for field in dict.fromkeys(config[f"alias_of_{key}"] or []):
+                for suf, tab in self.extra.items():
+                    if field in tab:
+                        out.append((field, suf, tab[field]))
+            return out
+
         self.field2id_token = {}
-        # ---- id remap: interactions first, then the feature file (dataset.py:894-918)
+        # ---- id remap: interactions first, then the feature file, then the alias fields (dataset.py:894-927)
+        ua, ia = alias_chunks("user_id"), alias_chunks("item_id")
         chunks = [inter[self.uid_field]] + ([user[self.uid_field]] if self.uid_field in user else [])
-        ids, self.field2id_token[self.uid_field] = factorize(chunks)
+        ids, self.field2id_token[self.uid_field] = factorize(chunks + [c for _, _, c in ua])
         inter_u = ids[0]
-        feat_u = ids[1] if len(ids) > 1 else None
+        feat_u = ids[1] if self.uid_field in user else None
+        for (field, _, _), got in zip(ua, ids[len(chunks):]):
+            self.extra_ids[field], self.field2id_token[field] = got, self.field2id_token[self.uid_field]
         chunks = [inter[self.iid_field]] + ([item[self.iid_field]] if self.iid_field in item else [])
-        ids, self.field2id_token[self.iid_field] = factorize(chunks)
+        ids, self.field2id_token[self.iid_field] = factorize(chunks + [c for _, _, c in ia])
         inter_i = ids[0]
+        for (field, _, _), got in zip(ia, ids[len(chunks):]):
+            self.extra_ids[field], self.field2id_token[field] = got, self.field2id_token[self.iid_field]
         self.user_num, self.item_num = len(self.field2id_token[self.uid_field]), len(self.field2id_token[self.iid_field])
         cols = {self.uid_field: inter_u.astype(np.int64), self.iid_field: inter_i.astype(np.int64)}
         for f, t in itypes.items():
@@ -249,6 +285,22 @@ class AtomicDataset:
         if field == self.iid_field:
             return self.item_num
         return len(self.field2id_token[field])
+
+    def get_preload_weight(self, field):
+        """dataset.py:505-549, 1762-1775: `preload_weight: {id field: value field}` of one additional feature file ->
+        float64 [num(id field), width], row = id (row 0 and ids without a row in the file stay zero)"""
+        pw = self.config["preload_weight"] or {}
+        if field not in pw:
+            raise ValueError(f"Field [{field}] not in preload_weight")
+        value = pw[field]
+        tab = next((t for t in self.extra.values() if field in t and value in t), None)
+        if tab is None or field not in self.extra_ids:
+            raise ValueError(f"Preload id field [{field}] / value field [{value}] must come from one additional feature "
+                             f"file and the id field must be an alias of the user or item id")
+        vals = tab[value]
+        out = np.zeros(self.num(field)) if vals.ndim == 1 else np.zeros((self.num(field), vals.shape[1]))
+        out[self.extra_ids[field]] = vals
+        return out
 
     @property
     def inter_feat(self):

@@ -122,6 +122,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         inter_feat = {k: torch.from_numpy(v) for k, v in train.items()}
         get_user_feature = staticmethod(ds.get_user_feature)
         inter_matrix = staticmethod(ds.inter_matrix)
+        get_preload_weight = staticmethod(ds.get_preload_weight)
 
     sst_of_user = {a: ds.user_feat[a] for a in attrs}
 

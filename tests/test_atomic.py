@@ -149,6 +149,8 @@ def test_filtering_ordering_and_splitting_options_match_the_reference(case, tmp_
     for k, part in zip(("train", "valid", "test"), splits):
         for col in ("user_id", "item_id", "rating", "timestamp", "label"):
             np.testing.assert_array_equal(part[col], g[f"{k}_{col}"], err_msg=f"{case} {k} {col}")
+    for idf in (cfg["preload_weight"] or {}):              # pretrained-embedding matrices, row = remapped id
+        np.testing.assert_array_equal(ds.get_preload_weight(idf), g["preload_" + idf], err_msg=idf)
     for col in ("gender", "age", "occupation"):
         want = g["user_" + col].copy()
         if want.dtype.kind == "f":
