@@ -160,3 +160,54 @@ def test_filtering_ordering_and_splitting_options_match_the_reference(case, tmp_
         else:
             want[want < 0] = 0                               # same no-op for token columns: INT64_MIN instead of [PAD]
         np.testing.assert_array_equal(ds.user_feat[col][1:], want, err_msg=col)
+
+
+def test_split_counts_follow_the_scalar_rule_for_all_small_groups():
+    """dataset.py:1339-1360 restated scalar-wise (cnt = floor(ratio * tot), first part takes the rest, then every part
+    whose exact share lies in (0, 1) steals one row from the first while the first has more than one) vs the vectorised
+    calcu_split_counts, exhaustively for group sizes 0..400 and several ratio triples"""
+    from recbole_fairrec_b200.atomic import calcu_split_counts
+
+    def scalar(tot, ratios):
+        r = [x / sum(ratios) for x in ratios]
+        cnt = [int(x * tot) for x in r]
+        cnt[0] = tot - sum(cnt[1:])
+        for i in range(1, len(r)):
+            if cnt[0] <= 1:
+                break
+            if 0 < r[-i] * tot < 1:
+                cnt[-i] += 1
+                cnt[0] -= 1
+        return cnt
+
+    tots = np.arange(0, 401)
+    for ratios in ([8, 1, 1], [7, 2, 1], [0.6, 0.2, 0.2], [98, 1, 1], [1, 1, 1], [9, 1]):
+        got = calcu_split_counts(tots, ratios)
+        assert (got.sum(axis=1) == tots).all() and (got >= 0).all()
+        for t in tots:
+            assert got[t].tolist() == scalar(int(t), ratios), (t, ratios)
+
+
+def test_interval_parsing_and_kcore_fixed_point():
+    from recbole_fairrec_b200.atomic import data_filtering, parse_intervals, within_intervals
+    from recbole_fairrec_b200.config import Config
+    iv = parse_intervals("(0,1];[3,inf)")
+    assert iv == [("(", 0.0, 1.0, "]"), ("[", 3.0, float("inf"), ")")]
+    np.testing.assert_array_equal(within_intervals([0, 0.5, 1, 2, 3, 1e9], iv), [False, True, True, False, True, True])
+    assert parse_intervals(None) is None
+    rng = np.random.default_rng(0)
+    for trial in range(5):
+        n = 3000
+        inter = {"user_id": np.array([f"u{k}" for k in rng.zipf(1.6, n) % 200], dtype=object),
+                 "item_id": np.array([f"i{k}" for k in rng.zipf(1.4, n) % 150], dtype=object),
+                 "rating": rng.integers(1, 6, n).astype(np.float64)}
+        cfg = Config(user_inter_num_interval="[4,inf)", item_inter_num_interval="[3,200]", device="cpu")
+        out, _, _ = data_filtering(cfg, inter, None, None, {"rating": "float"}, "user_id", "item_id")
+        _, cu = np.unique(out["user_id"].astype(str), return_counts=True)
+        _, ci = np.unique(out["item_id"].astype(str), return_counts=True)
+        assert cu.min() >= 4 and ci.min() >= 3 and ci.max() <= 200      # a fixed point of both interval filters
+        # and the kept rows are a subsequence of the input (order preserved)
+        key_in = [a + "|" + b for a, b in zip(inter["user_id"], inter["item_id"])]
+        key_out = [a + "|" + b for a, b in zip(out["user_id"], out["item_id"])]
+        it = iter(key_in)
+        assert all(k in it for k in key_out)
