@@ -380,6 +380,9 @@ class FairGoTrainer:
         else:
             model.train_stage = "pretrain"
             self.pretrain_epochs = config["pretrain_epochs"]
+            if self.pretrain_epochs is None:
+                raise ValueError("pretrain_epochs must be set when neither load_pretrain_weight nor "
+                                 "pretrain_model_file_path is given (FairGo_*.yaml: 600)")
             # the reference's pretrain optimizer holds model.parameters(); the ones that receive a gradient in this stage:
             self.optimizer_pretrain = ops.AdamGroup([model.user_embedding_layer.weight, model.item_embedding_layer.weight] +
                                                     (list(model.gcn.parameters()) if hasattr(model, "gcn") else []),
