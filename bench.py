@@ -543,6 +543,10 @@ def run_ours(args, wname):
                         "sampled_eval": bf.bench_sampled_eval(dev, flush, cpu=not args.no_cpu_baseline)}
         except Exception as e:
             families = {"error": str(e)[:300]}
+        try:   # NFCF stage 2 (own guard: a failure here must not drop the legs above)
+            families["nfcf"] = bf.bench_nfcf(dev, flush, cpu=not args.no_cpu_baseline)
+        except Exception as e:
+            families["nfcf"] = {"error": str(e)[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)

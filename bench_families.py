@@ -386,3 +386,88 @@ if __name__ == "__main__":
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     print(json.dumps({"pfcn_mlp": bench_pfcn(dev, flush), "fairgo_pmf": bench_fairgo(dev, flush),
                       "sampled_eval": bench_sampled_eval(dev, flush)}))
+
+
+def bench_nfcf(dev, flush, n_steps=30, cpu=True, seed=2020):
+    """NFCF stage 2 (nfcf.py:99-110 with a pretrain loaded: BCE + fair_weight * differential fairness, user table
+    frozen) at the ML-1M shape, NFCF.yaml widths: batches of 1024 positives + 1024 uniform negatives (labels 1 | 0), one
+    step = calculate_loss -> backward -> Adam over the item table and the tower (NFCFTrainer's loop body)."""
+    import tempfile
+
+    import torch
+
+    import recbole_fairrec_b200 as pkg
+    w = ML1M
+    rng = np.random.default_rng(seed)
+    feats = {"gender": (rng.random(w["n_users"]) < 0.28).astype(np.float32)}
+    base = dict(embedding_size=w["d"], sst_attr_list=["gender"], mlp_hidden_size=[128, 64], dropout=0.2, fair_weight=0.1,
+                device=dev, learning_rate=1e-3, weight_decay=1e-6)
+    ds = _DS(w["n_users"], w["n_items"], feats)
+    torch.manual_seed(seed)
+    stage1 = pkg.NFCF(pkg.Config(load_pretrain_path=None, **base), ds)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ncf.pth")
+        torch.save({"state_dict": stage1.state_dict()}, path)
+        cfg = pkg.Config(load_pretrain_path=path, **base)
+        model = pkg.NFCF(cfg, ds).to(dev)
+    trainer = pkg.NFCFTrainer(cfg, model)
+    model.train()
+    B = w["batch"]
+
+    def host_batch():
+        u = rng.integers(1, w["n_users"], B // 2)
+        u = np.concatenate([u, u])
+        label = np.zeros(B, np.float32)
+        label[:B // 2] = 1.0
+        return {"user_id": torch.from_numpy(u).pin_memory(),
+                "item_id": torch.from_numpy(rng.integers(1, w["n_items"], B)).pin_memory(),
+                "label": torch.from_numpy(label).pin_memory(), "gender": torch.from_numpy(feats["gender"][u]).pin_memory()}
+
+    hosts = [host_batch() for _ in range(8)]
+    devs = [pkg.Interaction({k: v.to(dev) for k, v in h.items()}) for h in hosts]
+
+    def step(inter, read_loss=False):
+        trainer.optimizer.zero_grad()
+        loss = model.calculate_loss(inter)
+        out = loss.item() if read_loss else None
+        loss.backward()
+        trainer.optimizer.step()
+        return out
+
+    ms = _timed_steps(step, devs, 3, n_steps, flush)
+    shares, launches, kernel_ms = _profile(step, devs[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        step(pkg.Interaction(hosts[k % len(hosts)]), read_loss=True)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / n_steps
+    model.check_flags()
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
+    out = {"metric": "NFCF (stage 2) train interactions/s", "value": B / (statistics.mean(ms) * 1e-3), "unit": "interactions/s",
+           "ms_per_step": statistics.mean(ms), "steps": n_steps, "launch_mode": "stream launches",
+           "config": {"workload": "nfcf_ml1m", **w, "mlp_hidden_size": [128, 64], "dropout": 0.2, "fair_weight": 0.1,
+                      "step": "BCE + differential-fairness loss -> backward -> Adam (item table + tower; user table frozen)"},
+           "e2e": {"value": B / t_e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "gpu_launches_per_step": launches, "kernel_ms_per_step": kernel_ms, "kernel_shares": shares}
+    if cpu:
+        out["cpu_baseline"] = cpu_nfcf(model, hosts)
+    return out
+
+
+def cpu_nfcf(model, hosts, n=3):
+    """oracle/nfcf_oracle.py (numpy restatement of the reference step; BLAS threads) on a bounded sample of the same steps"""
+    from oracle import nfcf_oracle as no
+    f = lambda t: t.detach().cpu().numpy().copy()
+    U, I = f(model.user_embedding.weight), f(model.item_embedding.weight)
+    lin = list(model.mlp_layers.linears())
+    Ws, bs = [f(m.weight) for m in lin], [f(m.bias) for m in lin]
+    batches = [(h["user_id"].numpy(), h["item_id"].numpy(), h["label"].numpy(), h["gender"].numpy())
+               for h in hosts[:n + 1]]
+    no.train_steps(U, I, Ws, bs, batches[:1], True, 0.1, 1e-3, 1e-6, True)
+    t0 = time.perf_counter()
+    no.train_steps(U, I, Ws, bs, batches[1:], True, 0.1, 1e-3, 1e-6, True)
+    dt = (time.perf_counter() - t0) / n
+    B = hosts[0]["user_id"].numel()
+    return {"value": B / dt, "unit": "interactions/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n} steps of {B} rows (dropout off in the port)", "ms_per_step": 1e3 * dt}
