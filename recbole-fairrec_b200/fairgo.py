@@ -24,6 +24,7 @@ import scipy.sparse as sp
 import torch
 import torch.nn as nn
 
+from .checkpoint import CheckpointMixin
 from . import ops
 from .layers import _ACT_MODULES, MLPLayers
 
@@ -363,7 +364,7 @@ class FairGo_GCN(FairGo_PMF):
         return super()._forward_all(sst_list)
 
 
-class FairGoTrainer:
+class FairGoTrainer(CheckpointMixin):
     """FairGoTrainer / FairGo_PMFTrainer / FairGo_GCNTrainer (trainer.py:534-862): optional pretrain of the embedding
     tables on the rating loss, then the alternating fine-tune schedule -- per epoch a random non-empty attribute subset;
     every `train_epoch_interval`-th epoch one pass on `mse - fair_weight * dis` with the filter optimizer, then always one
@@ -472,18 +473,24 @@ class FairGoTrainer:
         U, I = self.model.filtered_tables()
         return self.evaluator.evaluate(U.detach(), I.detach(), eval_data, self.model.max_rating)
 
-    def fit(self, train_data, valid_data=None, epochs=None, train_item_count=None, verbose=False):
+    def fit(self, train_data, valid_data=None, epochs=None, train_item_count=None, verbose=False, saved=False):
         """pretrain (unless embeddings were given) + fine-tune with early stopping on `valid_metric`; train_data is any
-        re-iterable of Interactions (user_id, item_id, rating, <sst>...).  Returns (best valid score, best valid result)."""
+        re-iterable of Interactions (user_id, item_id, rating, <sst>...).  Returns (best valid score, best valid result).
+        saved=True check-points every improvement (checkpoint.py); after `resume_checkpoint` the loop continues at
+        `start_epoch` with the restored early-stopping state."""
         from .trainer import early_stopping
         if train_item_count is not None:
             self.data_collect(train_item_count)
-        if self.model.train_stage == "pretrain":
+        resumed = getattr(self, "start_epoch", 0) > 0
+        if self.model.train_stage == "pretrain" and not resumed:
             self.pretrain(train_data)
+        self.model.train_stage = "finetune"
         metric = (self.config["valid_metric"] or "NDCG@5").lower()
         bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
         best, best_res, cur = (-np.inf if bigger else np.inf), None, 0
-        for epoch in range(epochs if epochs is not None else (self.config["epochs"] or 1)):
+        if resumed:
+            best, cur = self.best_valid_score, self.cur_step
+        for epoch in range(getattr(self, "start_epoch", 0), epochs if epochs is not None else (self.config["epochs"] or 1)):
             dis_loss, filter_loss = self._train_epoch(train_data, epoch)
             if verbose:
                 print(f"epoch {epoch}: filter loss {filter_loss:.4f}, discriminator loss {dis_loss:.4f}")
@@ -492,8 +499,11 @@ class FairGoTrainer:
             res = self.evaluate(valid_data)
             best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
                                                      bigger=bigger)
+            self.best_valid_score, self.cur_step = best, cur
             if update:
                 best_res = res
+                if saved:
+                    self._save_checkpoint(epoch)
             if stop:
                 break
         return best, best_res

@@ -13,6 +13,7 @@ import ctypes
 import torch
 import torch.nn as nn
 
+from .checkpoint import CheckpointMixin
 from . import _lib
 from ._lib import MlpTower, NfcfStep, check, load, ptr, stream_ptr
 
@@ -185,7 +186,7 @@ class NFCF(nn.Module):
                                       "(NFCF.yaml: gender); more than two values were present in a batch")
 
 
-class NFCFTrainer:
+class NFCFTrainer(CheckpointMixin):
     """The base `Trainer` (recbole/trainer/trainer.py:100-260, the one `get_trainer` hands NFCF: utils.py:74-94) for the
     two NFCF stages: stage 1 (`load_pretrain_path: ~`) trains the plain NCF tower and `fit(saved=True)` writes the
     `{'state_dict': ...}` checkpoint stage 2 reads (nfcf.py:49-51); stage 2 (path given) fine-tunes with the user table
@@ -229,36 +230,32 @@ class NFCFTrainer:
             lambda uid, iid: m.predict(Interaction({m.USER_ID: uid, m.ITEM_ID: iid})).view(-1), eval_data)
 
     def fit(self, train_data, valid_data=None, saved=False, train_item_count=None, verbose=False):
-        """trainer.py:300-380: early stopping on `valid_metric`; the best model is check-pointed when saved=True"""
+        """trainer.py:300-380: early stopping on `valid_metric`; the best model is check-pointed when saved=True (the
+        reference's checkpoint layout, checkpoint.py: its 'state_dict' is what stage 2 loads, nfcf.py:49-51)"""
         import os
         from .trainer import early_stopping
         metric = (self.config["valid_metric"] or "NDCG@5").lower()
         bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
-        best, best_res, cur = (-float("inf") if bigger else float("inf")), None, 0
+        self.best_valid_score, best_res, self.cur_step = (-float("inf") if bigger else float("inf")), None, 0
         if saved:
             root = self.config["checkpoint_dir"] or "saved"
             os.makedirs(root, exist_ok=True)
             self.saved_model_file = os.path.join(root, f"{self.config['model']}-{os.getpid()}.pth")
-        for epoch in range(self.config["epochs"] or 1):
+        for epoch in range(getattr(self, "start_epoch", 0), self.config["epochs"] or 1):
             loss = self._train_epoch(train_data, epoch)
             if verbose:
                 print(f"epoch {epoch}: train loss {loss:.4f}")
             if not valid_data:
                 if saved:
-                    self._save()
+                    self._save_checkpoint(epoch)
                 continue
             res = self.evaluate(valid_data, train_item_count)
-            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
-                                                     bigger=bigger)
+            self.best_valid_score, self.cur_step, stop, update = early_stopping(
+                res[metric], self.best_valid_score, self.cur_step, max_step=self.config["stopping_step"] or 10, bigger=bigger)
             if update:
                 best_res = res
                 if saved:
-                    self._save()
+                    self._save_checkpoint(epoch)
             if stop:
                 break
-        return best, best_res
-
-    def _save(self):
-        torch.save({"config": {k: (str(v) if isinstance(v, torch.device) else v) for k, v in self.config.items()},
-                    "state_dict": {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
-                    "other_parameter": self.model.other_parameter()}, self.saved_model_file)
+        return self.best_valid_score, best_res

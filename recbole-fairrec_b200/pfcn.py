@@ -19,6 +19,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .checkpoint import CheckpointMixin
 from . import ops
 from .layers import MLPLayers
 
@@ -301,7 +302,7 @@ class PFCN_DMF(_PFCNBase):
         return self._with_dis(ops.BprLoss.apply(pos, neg), interaction, sst_list)
 
 
-class PFCNTrainer:
+class PFCNTrainer(CheckpointMixin):
     """The alternating schedule of PFCNTrainer and its per-model subclasses (trainer.py:865-898, 1189-1235): per epoch
     a random non-empty attribute subset; every `train_epoch_interval`-th epoch one pass on `bpr - dis_weight * dis` with
     the filter optimizer (base model + filters), then always one pass on `dis` with the discriminator optimizer.
@@ -385,6 +386,36 @@ class PFCNTrainer:
             filter_loss = self._pass(train_data, self.model.calculate_loss, self.optimizer_filter, sst_list)
         dis_loss = self._pass(train_data, self.model.calculate_dis_loss, self.optimizer_dis, sst_list)
         return filter_loss, dis_loss
+
+
+    def fit(self, train_data, valid_data=None, epochs=None, train_item_count=None, verbose=False, saved=False):
+        """trainer.py:300-380 around the alternating epochs: early stopping on `valid_metric` (all attributes filtered,
+        trainer.py:1010-1093), check-point on improvement when saved=True (checkpoint.py), continue at `start_epoch` after
+        `resume_checkpoint`.  Returns (best valid score, best valid result)."""
+        from .trainer import early_stopping
+        metric = (self.config["valid_metric"] or "NDCG@5").lower()
+        bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
+        start = getattr(self, "start_epoch", 0)
+        best, best_res, cur = (-np.inf if bigger else np.inf), None, 0
+        if start > 0:
+            best, cur = self.best_valid_score, self.cur_step
+        for epoch in range(start, epochs if epochs is not None else (self.config["epochs"] or 1)):
+            losses = self._train_epoch(train_data, epoch)
+            if verbose:
+                print(f"epoch {epoch}: losses {losses}")
+            if not valid_data:
+                continue
+            res = self.evaluate(valid_data, None, train_item_count)
+            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
+                                                     bigger=bigger)
+            self.best_valid_score, self.cur_step = best, cur
+            if update:
+                best_res = res
+                if saved:
+                    self._save_checkpoint(epoch)
+            if stop:
+                break
+        return best, best_res
 
 
 PFCN_MLPTrainer = PFCN_PMFTrainer = PFCN_BiasedMFTrainer = PFCN_DMFTrainer = PFCNTrainer

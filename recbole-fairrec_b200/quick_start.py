@@ -152,14 +152,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         if mode == "full":
             raise NotImplementedError("PFCN full-sort evaluation is undefined in the reference; use eval_args.mode uni100")
         valid, test = eval_data("valid"), eval_data("test")
-        best, best_res = None, None
-        for epoch in range(cfg["epochs"] or 1):
-            losses = trainer._train_epoch(loader, epoch)
-            res = trainer.evaluate(valid, None, item_counter)
-            logger.info("epoch %d losses %s valid %s", epoch, losses, dict(res))
-            metric = (cfg["valid_metric"] or "NDCG@5").lower()
-            if best is None or res[metric] > best:
-                best, best_res = res[metric], res
+        best, best_res = trainer.fit(loader, valid, train_item_count=item_counter, saved=saved,
+                                     verbose=cfg["verbose"] is not False)
         test_res = trainer.evaluate(test, None, item_counter)
     elif name in ("FairGo_PMF", "FairGo_GCN"):
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
@@ -168,7 +162,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         if mode != "full":
             raise NotImplementedError("FairGo evaluation here is the fused full-sort one (eval_args.mode full)")
         valid, test = eval_data("valid"), eval_data("test")
-        best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter)
+        best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter, saved=saved)
         test_res = trainer.evaluate(test)
     elif name == "NFCF":
         net = pkg.NFCF(cfg, TrainView).to(dev)

@@ -134,3 +134,132 @@ def test_pairwise_loader_negatives_are_unseen_items():
         seen.append(u * ds.item_num + i)
     seen = np.concatenate(seen)
     assert len(seen) == len(train["user_id"]) and set(seen.tolist()) == used
+
+
+class _StubDataset:
+    def __init__(self, nu, ni, feats, coo=None):
+        import recbole_fairrec_b200 as pkg
+        self._n = {"user_id": nu, "item_id": ni}
+        self._feat = pkg.Interaction({"user_id": torch.arange(nu), **{k: torch.from_numpy(v) for k, v in feats.items()}})
+        self._coo = coo
+        self.inter_feat = {"rating": torch.tensor([1.0, 5.0])}
+
+    def num(self, f):
+        return self._n[f]
+
+    def get_user_feature(self):
+        return self._feat
+
+    def inter_matrix(self, form="coo", value_field=None):
+        return self._coo
+
+
+def _family(name, seed):
+    """(config, model, trainer) of one MLP family on the CPU: construction, state and optimizer bookkeeping need no kernel"""
+    import recbole_fairrec_b200 as pkg
+    rng = np.random.default_rng(1)
+    nu, ni = 40, 30
+    feats = {"gender": (rng.random(nu) < 0.4).astype(np.float32), "age": rng.integers(0, 3, nu).astype(np.float32)}
+    coo = sp.coo_matrix((rng.integers(1, 6, 200).astype(np.float32), (rng.integers(1, nu, 200), rng.integers(1, ni, 200))),
+                        shape=(nu, ni))
+    common = dict(embedding_size=16, sst_attr_list=["gender", "age"], device=torch.device("cpu"), learning_rate=1e-3,
+                  weight_decay=1e-4, train_epoch_interval=1, activation="leakyrelu", model=name)
+    torch.manual_seed(seed)
+    if name == "PFCN_MLP":
+        cfg = pkg.Config(filter_mode="sm", dropout=0.0, dis_dropout=0.0, dis_weight=1.0, dis_hidden_size_list=[16, 8],
+                         mlp_hidden_size_list=[16, 8], **common)
+        model = pkg.PFCN_MLP(cfg, _StubDataset(nu, ni, feats))
+        return cfg, model, pkg.PFCNTrainer(cfg, model)
+    if name == "FairGo_GCN":
+        cfg = pkg.Config(n_layers=2, dis_hidden_size_list=[8, 4], filter_hidden_size_list=[16], fair_weight=0.1,
+                         load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1], pretrain_epochs=1,
+                         hidden_channels=8, gcn_n_layers=2, gcn_dropout=0.0, gcn_act="relu", **common)
+        model = pkg.FairGo_GCN(cfg, _StubDataset(nu, ni, feats, coo))
+        return cfg, model, pkg.FairGoTrainer(cfg, model)
+    cfg = pkg.Config(mlp_hidden_size=[16, 8], dropout=0.0, load_pretrain_path=None, **dict(common, sst_attr_list=["gender"]))
+    model = pkg.NFCF(cfg, _StubDataset(nu, ni, feats))
+    return cfg, model, pkg.NFCFTrainer(cfg, model)
+
+
+def _all_state(model, trainer):
+    out = {f"model.{k}": v for k, v in model.state_dict().items()}
+    for attr in ("filter_layer", "filter_layer_dict", "dis_layer_dict"):
+        for k, m in (getattr(model, attr, None) or {}).items():
+            out.update({f"{attr}.{k}.{kk}": v for kk, v in m.state_dict().items()})
+    for name in ("optimizer", "optimizer_filter", "optimizer_dis", "optimizer_pretrain"):
+        opt = getattr(trainer, name, None)
+        if opt is not None:
+            for i, st in opt.state_dict()["state"].items():
+                out.update({f"{name}.{i}.{kk}": torch.as_tensor(v) for kk, v in st.items()})
+    return out
+
+
+@pytest.mark.parametrize("name", ["PFCN_MLP", "FairGo_GCN", "NFCF"])
+def test_checkpoint_round_trip_of_the_mlp_family_trainers(name, tmp_path):
+    """trainer.py:221-284 / 784-830 / 1133-1184: the reference's checkpoint keys, plus the dict-held filter / discriminator
+    modules under 'dict_modules'; resume restores model, modules, every optimizer's moments and step counts, and the
+    early-stopping bookkeeping"""
+    cfg, model, trainer = _family(name, 1)
+    for opt_name in ("optimizer", "optimizer_filter", "optimizer_dis", "optimizer_pretrain"):
+        opt = getattr(trainer, opt_name, None)
+        if opt is not None:                                  # pretend some steps happened
+            opt.init_state()
+            for k, p in enumerate(opt.params):
+                if p in opt.state:
+                    opt.state[p]["exp_avg"].normal_()
+                    opt.state[p]["exp_avg_sq"].uniform_()
+                    opt._steps[k] = 3 + k
+    trainer.cur_step, trainer.best_valid_score = 2, 0.125
+    path = trainer._save_checkpoint(7, str(tmp_path / "ck.pth"))
+    ck = torch.load(path, weights_only=False)
+    assert {"config", "epoch", "cur_step", "best_valid_score", "state_dict", "other_parameter", "optimizer"} <= set(ck)
+    assert ck["epoch"] == 7 and ck["config"]["model"] == name
+    if name != "NFCF":
+        assert set(ck["dict_modules"]) and not any(k.startswith(("filter_layer", "dis_layer")) for k in ck["state_dict"])
+    want = _all_state(model, trainer)
+    cfg2, model2, trainer2 = _family(name, 2)                # other initial weights
+    assert any(not torch.equal(v, _all_state(model2, trainer2).get(k, v + 1)) for k, v in want.items() if k.startswith("model."))
+    trainer2.resume_checkpoint(path)
+    got = _all_state(model2, trainer2)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert torch.equal(torch.as_tensor(got[k]).cpu(), torch.as_tensor(v).cpu()), k
+    assert (trainer2.start_epoch, trainer2.cur_step, trainer2.best_valid_score) == (8, 2, 0.125)
+
+
+@pytest.mark.parametrize("name", ["PFCN_MLP", "FairGo_GCN"])
+def test_fit_loop_early_stopping_checkpoint_and_resume(name, tmp_path, monkeypatch):
+    """the epoch loop around the (faked) train / evaluate calls: best score tracking, stop after `stopping_step`
+    non-improving evaluations, check-point only on improvement, resume continues at the next epoch with the restored state"""
+    cfg, model, trainer = _family(name, 3)
+    cfg["stopping_step"], cfg["epochs"], cfg["valid_metric"] = 2, 20, "NDCG@5"
+    scores = [0.10, 0.30, 0.20, 0.25, 0.50, 0.1, 0.1, 0.1, 0.9]
+    calls = {"train": [], "saves": []}
+    model.train_stage = "finetune"
+
+    def fake_train(self, data, epoch):
+        calls["train"].append(epoch)
+        return (0.0, 0.0)
+
+    def fake_eval(self, *a, **k):
+        return {"ndcg@5": scores[len(calls["train"]) - 1]}
+
+    cls = type(trainer)
+    monkeypatch.setattr(cls, "_train_epoch", fake_train)
+    monkeypatch.setattr(cls, "evaluate", fake_eval)
+    orig_save = cls._save_checkpoint
+    monkeypatch.setattr(cls, "_save_checkpoint", lambda self, epoch, f=None: calls["saves"].append(epoch) or
+                        orig_save(self, epoch, str(tmp_path / "best.pth")))
+    best, res = trainer.fit([None], [None], saved=True)
+    # utils.py:97-140: stop once MORE than `stopping_step` evaluations in a row did not improve
+    assert calls["train"] == list(range(8)) and calls["saves"] == [0, 1, 4]
+    assert best == 0.50 and res == {"ndcg@5": 0.50} and trainer.cur_step == 3
+    # resume from the best checkpoint (epoch 4): continues at epoch 5 with best = 0.50 and the counter as saved (0)
+    cfg2, model2, trainer2 = _family(name, 4)
+    cfg2["stopping_step"], cfg2["epochs"], cfg2["valid_metric"] = 3, 9, "NDCG@5"
+    trainer2.resume_checkpoint(str(tmp_path / "best.pth"))
+    assert (trainer2.start_epoch, trainer2.best_valid_score, trainer2.cur_step) == (5, 0.50, 0)
+    calls["train"].clear()
+    scores[:] = [0.2, 0.2, 0.6, 0.1]
+    best, res = trainer2.fit([None], [None])
+    assert calls["train"] == [5, 6, 7, 8] and best == 0.6
