@@ -26,42 +26,136 @@ import torch
 from .interaction import Interaction
 
 
+# what pandas.read_csv treats as missing by default -- the reference reads with those defaults (dataset.py:433-435)
+NA_STRINGS = ["", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>", "N/A", "NA",
+              "NULL", "NaN", "None", "n/a", "nan", "null"]
+
+
+class TokenColumn:
+    """A token column as int64 codes into `vocab` (object array of str, in order of first appearance in the column);
+    code -1 = missing.  Tokens are identified by their TEXT ('01' != '1'); keeping codes instead of a Python string per
+    row is what lets the ingestion scale with the number of rows."""
+    __slots__ = ("codes", "vocab")
+
+    def __init__(self, codes, vocab):
+        self.codes, self.vocab = np.asarray(codes, np.int64), vocab
+
+    def __len__(self):
+        return len(self.codes)
+
+    def __getitem__(self, idx):
+        return TokenColumn(self.codes[idx], self.vocab)
+
+    def isna(self):
+        return self.codes < 0
+
+    def tokens(self):
+        """object array of str (NaN where missing)"""
+        out = np.empty(len(self.codes), object)
+        ok = self.codes >= 0
+        out[ok] = self.vocab[self.codes[ok]]
+        out[~ok] = np.nan
+        return out
+
+    @staticmethod
+    def of(values):
+        """from a TokenColumn (returned as is) or any array of str / NaN"""
+        if isinstance(values, TokenColumn):
+            return values
+        import pandas as pd
+        codes, vocab = pd.factorize(np.asarray(values, object))
+        return TokenColumn(codes, np.asarray(vocab, object))
+
+
+def _use_arrow():
+    if os.environ.get("FAIRREC_NO_PYARROW"):
+        return False
+    try:
+        import pyarrow.csv  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
 def read_atomic(path, usecols=None, sep="\t", seq_sep=" ", with_seq=False):
-    """-> (columns: {field: np.ndarray}, types: {field: 'token' | 'float' | 'float_seq'}).  Token columns come back as str
-    arrays (ids are assigned by first appearance, so the textual token is what matters), float columns as float64 like
-    pandas gives, float_seq columns (only with `with_seq`: the pretrained-embedding files of `additional_feat_suffix`) as a
-    zero-padded float64 matrix [rows, longest sequence] (dataset.py:441-452)."""
-    import pandas as pd
+    """-> (columns: {field: TokenColumn | np.ndarray}, types: {field: 'token' | 'float' | 'float_seq'}).  Token columns come
+    back as TokenColumn, float columns as float64 (NaN where missing), float_seq columns (only with `with_seq`: the
+    pretrained-embedding files of `additional_feat_suffix`) as a zero-padded float64 matrix [rows, longest sequence]
+    (dataset.py:385-454).  Parsed by pyarrow's multi-threaded CSV reader when it is importable (FAIRREC_NO_PYARROW=1
+    forces the pandas parser; both give the same columns, tests/test_atomic.py)."""
     with open(path, "r", encoding="utf-8") as f:
         header = f.readline().rstrip("\n").split(sep)
     names, types = zip(*[h.split(":") for h in header])
     ok = ("token", "float", "float_seq") if with_seq else ("token", "float")
     keep = [n for n, t in zip(names, types) if t in ok and (usecols is None or n in usecols)]
-    dtype = {n: (np.float64 if t == "float" else str) for n, t in zip(names, types) if n in keep}
-    df = pd.read_csv(path, sep=sep, header=0, names=list(names), usecols=keep, dtype=dtype, engine="c",
-                     keep_default_na=False, na_values=[""])
     kept = {n: t for n, t in zip(names, types) if n in keep}
-    cols = {}
+    raw = {}
+    if _use_arrow():
+        import pyarrow as pa
+        import pyarrow.csv as pc
+        tab = pc.read_csv(path, parse_options=pc.ParseOptions(delimiter=sep),
+                          read_options=pc.ReadOptions(skip_rows=1, column_names=list(names)),
+                          convert_options=pc.ConvertOptions(
+                              column_types={n: (pa.float64() if kept[n] == "float" else pa.string()) for n in keep},
+                              include_columns=keep, strings_can_be_null=True, null_values=NA_STRINGS))
+        def convert(n):
+            col = tab[n].combine_chunks()
+            if kept[n] == "float":
+                return col.to_numpy(zero_copy_only=False).astype(np.float64, copy=False)
+            if kept[n] == "token":
+                d = col.dictionary_encode()                   # dictionary in order of first appearance
+                return TokenColumn(d.indices.fill_null(-1).to_numpy(zero_copy_only=False),
+                                   np.array(d.dictionary.to_pylist(), dtype=object))
+            return col.to_pylist()
+
+        from concurrent.futures import ThreadPoolExecutor      # arrow's kernels release the GIL: columns in parallel
+        with ThreadPoolExecutor(max_workers=max(1, min(len(keep), os.cpu_count() or 1))) as pool:
+            raw = dict(zip(keep, pool.map(convert, keep)))
+    else:
+        import pandas as pd
+        df = pd.read_csv(path, sep=sep, header=0, names=list(names), usecols=keep, engine="c",
+                         dtype={n: (np.float64 if kept[n] == "float" else str) for n in keep})
+        for n in keep:
+            v = df[n].to_numpy()
+            raw[n] = v if kept[n] == "float" else (TokenColumn.of(v) if kept[n] == "token" else list(v))
     for n in keep:
         if kept[n] != "float_seq":
-            cols[n] = df[n].to_numpy()
             continue
         rows = [np.array([float(x) for x in (v.split(seq_sep) if isinstance(v, str) else []) if x], np.float64)
-                for v in df[n].to_numpy()]
+                for v in raw[n]]
         mat = np.zeros((len(rows), max((len(r) for r in rows), default=0)), np.float64)
         for k, r in enumerate(rows):
             mat[k, :len(r)] = r
-        cols[n] = mat
-    return cols, kept
+        raw[n] = mat
+    return raw, kept
+
+
+def unify(cols):
+    """codes of several token columns in ONE code space (string hashing only over the vocabularies, not the rows)
+    -> ([int64 codes per column, -1 = missing], joint vocabulary)"""
+    import pandas as pd
+    cols = [TokenColumn.of(c) for c in cols]
+    joint, vocab = pd.factorize(np.concatenate([c.vocab for c in cols]).astype(object)) if cols else (np.zeros(0, np.int64), [])
+    out, off = [], 0
+    for c in cols:
+        m = joint[off:off + len(c.vocab)]
+        off += len(c.vocab)
+        out.append(np.where(c.codes >= 0, m[np.maximum(c.codes, 0)], -1) if len(m) else np.full(len(c), -1, np.int64))
+    return out, np.asarray(vocab, object)
 
 
 def factorize(chunks):
-    """pd.factorize over the concatenation of `chunks`, ids + 1 (0 = '[PAD]'), split back (dataset.py:952-974)"""
+    """ids by first appearance over the concatenation of `chunks` (what pd.factorize gives the reference, dataset.py:952-974),
+    + 1 so that 0 = '[PAD]' (also the id of a missing token), split back -> ([ids per chunk], id -> token array)"""
     import pandas as pd
-    tokens = np.concatenate(chunks)
-    ids, mp = pd.factorize(tokens)
-    out = np.split(ids + 1, np.cumsum([len(c) for c in chunks])[:-1])
-    return out, np.array(["[PAD]"] + list(mp), dtype=object)
+    codes, vocab = unify(chunks)
+    flat = np.concatenate(codes) if codes else np.zeros(0, np.int64)
+    ids = np.zeros(len(flat), np.int64)
+    ok = flat >= 0
+    f, uniq = pd.factorize(flat[ok])
+    ids[ok] = f + 1
+    out = np.split(ids, np.cumsum([len(c) for c in codes])[:-1])
+    return out, np.array(["[PAD]"] + list(vocab[uniq]), dtype=object)
 
 
 def calcu_split_counts(tot, ratios):
@@ -107,35 +201,43 @@ def _take(cols, keep):
     return {k: v[keep] for k, v in cols.items()}
 
 
-def _isin(a, b):
-    import pandas as pd
-    return pd.Series(a).isin(b).to_numpy()
+def _rows(tab):
+    return len(next(iter(tab.values())))
 
 
 def data_filtering(config, inter, user, item, types, uid_field, iid_field):
-    """dataset.py:160-181 on column dicts (user / item = None when the feature file is not loaded); returns the three
-    filtered dicts, row order preserved (after `rm_dup_inter`: the reference's time-sorted order)."""
+    """dataset.py:160-181 on column dicts (user / item = None when the feature file is not loaded; token columns as
+    TokenColumn or arrays of str); returns the three filtered dicts, row order preserved (after `rm_dup_inter`: the
+    reference's time-sorted order).  All row-sized work runs on integer codes."""
     import pandas as pd
+    def tok(tab):       # token columns given as arrays of str (direct callers) become TokenColumns
+        if tab is None:
+            return None
+        is_token = lambda k, v: isinstance(v, TokenColumn) or types.get(k) == "token" or np.asarray(v).dtype == object
+        return {k: (TokenColumn.of(v) if is_token(k, v) else np.asarray(v)) for k, v in tab.items()}
+
+    inter, user, item = tok(inter), tok(user), tok(item)
     # 1. missing ids (624-642).  Deliberate difference: the reference drops the item-less interactions by POSITION after the
     # user-less ones were already removed (`inter_feat.index[labels]`, 638-642), i.e. once a user-less row precedes them
     # it removes their neighbours instead and keeps the item-less rows (which then map to the [PAD] item); here the rows
     # that actually miss an id are the ones dropped.
-    for field, name in ((uid_field, "user"), (iid_field, "item")):
-        feat = user if name == "user" else item
-        if feat is not None:
-            feat = _take(feat, ~pd.isna(feat[field]))
-        inter = _take(inter, ~pd.isna(inter[field]))
-        user, item = (feat, item) if name == "user" else (user, feat)
-    # 2. duplicated (user, item) pairs (644-668): pandas does it in the reference; the same two calls here, so that the
-    # order among equal timestamps (sort_values' default, unstable kind) is the reference's by construction
+    if user is not None:
+        user = _take(user, ~user[uid_field].isna())
+    inter = _take(inter, ~inter[uid_field].isna())
+    if item is not None:
+        item = _take(item, ~item[iid_field].isna())
+    inter = _take(inter, ~inter[iid_field].isna())
+    # 2. duplicated (user, item) pairs (644-668): pandas does it in the reference; the same two calls here (on codes), so
+    # that the order among equal timestamps (sort_values' default, unstable kind) is the reference's by construction
     keep = config["rm_dup_inter"]
     if keep is not None:
-        df = pd.DataFrame(inter)
+        df = pd.DataFrame({"u": inter[uid_field].codes, "i": inter[iid_field].codes, "row": np.arange(_rows(inter))})
         tf = config["TIME_FIELD"] or "timestamp"
-        if tf in df:
-            df = df.sort_values(by=[tf], ascending=True)
-        df = df.drop_duplicates(subset=[uid_field, iid_field], keep=keep)
-        inter = {k: df[k].to_numpy() for k in inter}
+        if tf in inter:
+            df["t"] = inter[tf]
+            df = df.sort_values(by=["t"], ascending=True)
+        df = df.drop_duplicates(subset=["u", "i"], keep=keep)
+        inter = _take(inter, df["row"].to_numpy())
     # 3. value intervals (803-821), on every table that holds the field
     for field, interval in (config["val_interval"] or {}).items():
         if field not in types:
@@ -144,32 +246,30 @@ def data_filtering(config, inter, user, item, types, uid_field, iid_field):
         for name, tab in tabs.items():
             if tab is None or field not in tab:
                 continue
-            ok = within_intervals(tab[field], parse_intervals(interval)) if types[field] == "float" else \
-                _isin(tab[field], [str(v) for v in interval])
+            if types[field] == "float":
+                ok = within_intervals(tab[field], parse_intervals(interval))
+            else:
+                col = tab[field]
+                allowed = np.isin(col.vocab.astype(str), [str(v) for v in interval]) if len(col.vocab) else np.zeros(0, bool)
+                ok = (col.codes >= 0) & allowed[np.maximum(col.codes, 0)] if len(allowed) else np.zeros(len(col), bool)
             tabs[name] = _take(tab, ok)
         inter, user, item = tabs["inter"], tabs["user"], tabs["item"]
+    # joint code spaces of the id columns of the interaction table and the feature tables
+    (uc, ufc), nu = _joint(inter[uid_field], user[uid_field] if user is not None else None)
+    (ic, ifc), ni = _joint(inter[iid_field], item[iid_field] if item is not None else None)
     # 4. interactions of users / items absent from a loaded feature file (847-863)
+    alive = np.ones(len(uc), bool)
     if config["filter_inter_by_user_or_item"] is True:
-        ok = np.ones(len(inter[uid_field]), bool)
-        if user is not None:
-            ok &= _isin(inter[uid_field], user[uid_field])
-        if item is not None:
-            ok &= _isin(inter[iid_field], item[iid_field])
-        inter = _take(inter, ok)
+        for code, fcode, n in ((uc, ufc, nu), (ic, ifc, ni)):
+            if fcode is not None:
+                present = np.zeros(n, bool)
+                present[fcode] = True
+                alive &= present[code]
     # 5. interaction-count intervals, iterated to the fixed point (670-746)
     u_int, i_int = parse_intervals(config["user_inter_num_interval"]), parse_intervals(config["item_inter_num_interval"])
+    ualive = np.ones(len(ufc), bool) if ufc is not None else None
+    ialive = np.ones(len(ifc), bool) if ifc is not None else None
     if u_int is not None or i_int is not None:
-        def codes(inter_col, feat, field):      # joint code space of the interaction column and the feature column
-            both = np.concatenate([inter_col] + ([feat[field]] if feat is not None else []))
-            c, _ = pd.factorize(both)
-            return c[:len(inter_col)], (c[len(inter_col):] if feat is not None else None), int(c.max()) + 1 if len(c) else 0
-
-        uc, ufc, nu = codes(inter[uid_field], user, uid_field)
-        ic, ifc, ni = codes(inter[iid_field], item, iid_field)
-        alive = np.ones(len(uc), bool)
-        ualive = np.ones(len(ufc), bool) if ufc is not None else None
-        ialive = np.ones(len(ifc), bool) if ifc is not None else None
-
         def banned(code, fcode, falive, n, interval):
             """ids present with a count outside the interval, plus feature rows whose count is below the first
             interval's left end (_get_illegal_ids_by_inter_num; a Counter drops ids whose count reached 0)"""
@@ -190,13 +290,33 @@ def data_filtering(config, inter, user, item, types, uid_field, iid_field):
             if ifc is not None:
                 ialive &= ~bi[ifc]
             alive &= ~(bu[uc] | bi[ic])
+    if not alive.all():
         inter = _take(inter, alive)
-        user = _take(user, ualive) if user is not None else None
-        item = _take(item, ialive) if item is not None else None
+    if ualive is not None and not ualive.all():
+        user = _take(user, ualive)
+    if ialive is not None and not ialive.all():
+        item = _take(item, ialive)
     for name, tab in (("inter", inter), ("user", user), ("item", item)):
-        if tab is not None and len(next(iter(tab.values()))) == 0:
+        if tab is not None and _rows(tab) == 0:
             raise ValueError("Some feat is empty, please check the filtering settings.")
     return inter, user, item
+
+
+def _joint(a, b):
+    """((codes of a, codes of b | None), size) in one code space"""
+    codes, vocab = unify([a] + ([b] if b is not None else []))
+    return (codes[0], codes[1] if b is not None else None), len(vocab)
+
+
+def _stable_group_order(keys, n_keys):
+    """np.argsort(keys, kind='stable') for int keys in [0, n_keys) as a counting sort (scipy's COO -> CSR conversion keeps
+    the input order inside a row): O(n) instead of a comparison sort"""
+    import scipy.sparse as sp
+    n = len(keys)
+    if n == 0:
+        return np.zeros(0, np.int64)
+    m = sp.coo_matrix((np.ones(n, np.int8), (keys, np.arange(n))), shape=(int(n_keys) + 1, n)).tocsr()
+    return m.indices.astype(np.int64)
 
 
 class AtomicDataset:
@@ -255,7 +375,7 @@ class AtomicDataset:
         for f, t in itypes.items():
             if f in (self.uid_field, self.iid_field):
                 continue
-            cols[f] = inter[f].astype(np.float32) if t == "float" else factorize([inter[f]])[0][0].astype(np.int64)
+            cols[f] = inter[f].astype(np.float32) if t == "float" else factorize([inter[f]])[0][0]
         # ---- label by threshold (dataset.py:865-892; the rating column is kept)
         thr = config["threshold"]
         if thr:
@@ -342,20 +462,20 @@ class AtomicDataset:
             perm = np.argsort(self.inter[self.time_field], kind="stable")       # interaction.py:333-337
         else:
             raise NotImplementedError(f"The ordering_method [{order_mode}] has not been implemented.")
-        cols = {k: v[perm] for k, v in self.inter.items()}
+        take = lambda idx: {k: v[idx] for k, v in self.inter.items()}      # one gather per column and split
         mode = next(iter(split))
         if mode == "RS" and (group_by is None or str(group_by).lower() == "none"):
             cnt = calcu_split_counts([n], split["RS"])[0]
             edges = np.r_[0, np.cumsum(cnt)]
-            splits = [{k: v[a:b] for k, v in cols.items()} for a, b in zip(edges[:-1], edges[1:])]
+            splits = [take(perm[a:b]) for a, b in zip(edges[:-1], edges[1:])]
             self._matrix_src = splits[0]
             return splits
         if mode not in ("RS", "LS") or (mode == "RS" and group_by != "user"):
             raise NotImplementedError(f"The splitting_method [{split}] / grouping [{group_by}] has not been implemented.")
-        u = cols[self.uid_field]
+        u = self.inter[self.uid_field][perm]
         first = np.full(self.user_num, n, np.int64)
         np.minimum.at(first, u, np.arange(n))
-        order = np.argsort(first[u], kind="stable")          # groups by first appearance, ordered rows inside
+        order = _stable_group_order(first[u], n)              # groups by first appearance, ordered rows inside
         us = u[order]
         starts = np.flatnonzero(np.r_[True, us[1:] != us[:-1]])
         lens = np.diff(np.r_[starts, n])
@@ -364,7 +484,9 @@ class AtomicDataset:
             n_parts = len(split["RS"])
             cnt = calcu_split_counts(lens, split["RS"])
             edges = np.cumsum(cnt, axis=1)
-            part = (rank[:, None] >= np.repeat(edges, lens, axis=0)).sum(axis=1)
+            part = np.zeros(n, np.int8)
+            for p in range(n_parts - 1):
+                part += rank >= np.repeat(edges[:, p], lens)
             slot = list(range(n_parts))
         else:
             lom = split["LS"]
@@ -376,21 +498,24 @@ class AtomicDataset:
             part = np.where(rank < tot - leg, 0, leave + 1 - leg + (rank - (tot - leg)))
             n_parts = 3
             slot = [0, 1, 2] if lom == "valid_and_test" else ([0, 1, None] if lom == "valid_only" else [0, None, 1])
-        splits = []
-        for p in slot:
-            idx = order[part == p] if p is not None else np.zeros(0, np.int64)
-            splits.append({k: v[idx] for k, v in cols.items()})
+        splits = [take(perm[order[part == p]] if p is not None else np.zeros(0, np.int64)) for p in slot]
         self._matrix_src = splits[0]
         return splits
 
 
 def used_and_positive_lists(splits, phase, uf="user_id", itf="item_id"):
     """sampler.py:243-264 + general_dataloader.py:173-207: eval users (ascending), their positives of the phase (in split
-    order) and history = items used in the EARLIER phases (valid: train; test: train + valid)."""
+    order) and history = the items used up to and including the phase minus the phase's positives (valid: train - valid;
+    test: (train + valid) - test; the subtraction only matters when a (user, item) pair occurs more than once)."""
     ev = splits[1] if phase == "valid" else splits[2]
     used = [splits[0]] + ([splits[1]] if phase == "test" else [])
     ku = np.concatenate([s[uf] for s in used])
     ki = np.concatenate([s[itf] for s in used])
+    n_items = int(max(ki.max(initial=0), ev[itf].max(initial=0))) + 1
+    import pandas as pd
+    dup = pd.Series(ku * n_items + ki).isin(ev[uf] * n_items + ev[itf]).to_numpy()     # hash set of the (small) eval side
+    if dup.any():
+        ku, ki = ku[~dup], ki[~dup]
 
     def group(u, i):
         o = np.argsort(u, kind="stable")

@@ -127,6 +127,15 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     sst_of_user = {a: ds.user_feat[a] for a in attrs}
 
     def eval_data(phase):
+        if mode == "full" and cfg["eval_lists"] == "device":
+            # large datasets: upload the split columns and group them on the device (EvalData.from_device: one sort per
+            # side instead of per-user host lists).  Assumes unique (user, item) pairs, i.e. history and positives disjoint.
+            t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+            ev = splits[1] if phase == "valid" else splits[2]
+            used = [splits[0]] + ([splits[1]] if phase == "test" else [])
+            return pkg.EvalData.from_device(t(np.concatenate([s[uf] for s in used])), t(np.concatenate([s[itf] for s in used])),
+                                            t(ev[uf]), t(ev[itf]), {a: t(v) for a, v in sst_of_user.items()},
+                                            ds.user_num, ds.item_num)
         users, hist, pos = used_and_positive_lists(splits, phase)
         if mode == "full":
             return pkg.EvalData(users, hist, pos, sst_of_user, dev)

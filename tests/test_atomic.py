@@ -120,6 +120,40 @@ def test_ingestion_identical_to_the_live_reference_on_synthetic_files(tmp_path):
     assert bi.compare(ds, splits, lists, rds, rloaders)
 
 
+def test_eval_lists_with_duplicated_pairs_match_the_live_reference(tmp_path):
+    """build container only: the `messy` files hold repeated (user, item) pairs, so an item can sit in a user's train
+    rows AND among the positives of the evaluated split -- the reference then keeps it out of the history
+    (general_dataloader.py:201-207); eval users, positives and histories of both phases vs the reference's loaders"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle", "ref_shim"))
+    import shim
+    if not shim.available():
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+    import bench_ingest as bi
+    import make_test_data as mtd
+    name = mtd.write_messy(str(tmp_path))
+    old = dict(bi.CFG)
+    try:
+        bi.CFG.update(mtd.INGEST_BASE, **mtd.INGEST_CASES["defaults"])
+        _, ds, splits, lists = bi.ours(str(tmp_path), name)
+        _, rds, rloaders = bi.reference(str(tmp_path), name)
+    finally:
+        bi.CFG.clear()
+        bi.CFG.update(old)
+    n_dup = 0
+    for ph, loader in (("valid", rloaders[1]), ("test", rloaders[2])):
+        users, hist, pos = lists[ph]
+        np.testing.assert_array_equal(users, np.asarray(loader.uid_list))
+        for r, u in enumerate(users.tolist()):
+            assert set(pos[r].tolist()) == set(loader.uid2positive_item[u].tolist())
+            assert set(hist[r].tolist()) == set(loader.uid2history_item[u].tolist()), (ph, u)
+        tr = set(zip(splits[0]["user_id"].tolist(), splits[0]["item_id"].tolist()))
+        ev = splits[1] if ph == "valid" else splits[2]
+        n_dup += len(tr & set(zip(ev["user_id"].tolist(), ev["item_id"].tolist())))
+    assert n_dup > 0                      # the case is actually exercised
+
+
 def _ingest_case_names():
     import sys
     sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
@@ -203,11 +237,12 @@ def test_interval_parsing_and_kcore_fixed_point():
                  "rating": rng.integers(1, 6, n).astype(np.float64)}
         cfg = Config(user_inter_num_interval="[4,inf)", item_inter_num_interval="[3,200]", device="cpu")
         out, _, _ = data_filtering(cfg, inter, None, None, {"rating": "float"}, "user_id", "item_id")
-        _, cu = np.unique(out["user_id"].astype(str), return_counts=True)
-        _, ci = np.unique(out["item_id"].astype(str), return_counts=True)
+        ku, ki = out["user_id"].tokens().astype(str), out["item_id"].tokens().astype(str)
+        _, cu = np.unique(ku, return_counts=True)
+        _, ci = np.unique(ki, return_counts=True)
         assert cu.min() >= 4 and ci.min() >= 3 and ci.max() <= 200      # a fixed point of both interval filters
         # and the kept rows are a subsequence of the input (order preserved)
         key_in = [a + "|" + b for a, b in zip(inter["user_id"], inter["item_id"])]
-        key_out = [a + "|" + b for a, b in zip(out["user_id"], out["item_id"])]
+        key_out = [a + "|" + b for a, b in zip(ku, ki)]
         it = iter(key_in)
         assert all(k in it for k in key_out)

@@ -263,3 +263,36 @@ def test_fit_loop_early_stopping_checkpoint_and_resume(name, tmp_path, monkeypat
     scores[:] = [0.2, 0.2, 0.6, 0.1]
     best, res = trainer2.fit([None], [None])
     assert calls["train"] == [5, 6, 7, 8] and best == 0.6
+
+
+def test_device_built_eval_lists_equal_the_host_built_ones():
+    """EvalData from per-user host lists (general_dataloader.py:173-207 order) vs EvalData.from_device from the raw split
+    columns (`eval_lists: device` in run_recbole; torch ops only, so it runs on CPU tensors too): same users, CSR offsets,
+    sorted histories / positives, groups; the positives' emission order differs (ascending item id on the device)"""
+    import os
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.atomic import AtomicDataset, used_and_positive_lists
+    from recbole_fairrec_b200.quick_start import build_config, init_seed
+    cfg = build_config("FOCF", "ml-100k", None, dict(
+        data_path=os.path.join(os.path.dirname(__file__), "data"), sst_attr_list=["gender"], device="cpu",
+        load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"]}))
+    init_seed(3)
+    ds = AtomicDataset(cfg)
+    splits = ds.build()
+    sst = {"gender": ds.user_feat["gender"]}
+    cpu = torch.device("cpu")
+    for phase in ("valid", "test"):
+        users, hist, pos = used_and_positive_lists(splits, phase)
+        a = pkg.EvalData(users, hist, pos, sst, cpu)
+        ev = splits[1] if phase == "valid" else splits[2]
+        used = [splits[0]] + ([splits[1]] if phase == "test" else [])
+        t = lambda x: torch.as_tensor(np.ascontiguousarray(x))
+        b = pkg.EvalData.from_device(t(np.concatenate([s["user_id"] for s in used])),
+                                     t(np.concatenate([s["item_id"] for s in used])), t(ev["user_id"]), t(ev["item_id"]),
+                                     {"gender": t(sst["gender"])}, ds.user_num, ds.item_num)
+        assert a.n == b.n and a.n_pos == b.n_pos and a.n_groups == b.n_groups
+        for f in ("users", "hist_off", "hist_items", "pos_off", "pos_items_sorted", "pos_row", "pos_uid"):
+            assert torch.equal(getattr(a, f).to(torch.int64), getattr(b, f).to(torch.int64)), f
+        assert torch.equal(b.pos_items, b.pos_items_sorted)
+        # group of a positive depends on its user only, and pos_row is identical
+        assert torch.equal(a.group_of_pos["gender"], b.group_of_pos["gender"])
