@@ -100,6 +100,14 @@ class BatchLoader:
             yield Interaction(cols)
 
 
+def _load_best(trainer, saved):
+    """quick_start.py:61 / trainer.py:476-482: the test split is evaluated with the best check-pointed model"""
+    import os
+    path = getattr(trainer, "saved_model_file", None)
+    if saved and path and os.path.exists(path):
+        trainer.resume_checkpoint(path)
+
+
 def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=None, saved=False):
     """quick_start.py:20-71 -> {'best_valid_score', 'valid_score_bigger', 'best_valid_result', 'test_result'}"""
     import recbole_fairrec_b200 as pkg
@@ -153,7 +161,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         trainer = pkg.FOCFTrainer(cfg, net)
         valid, test = eval_data("valid"), eval_data("test")      # negatives (uni<N>) drawn before training, like the
         best, best_res = trainer.fit(loader, valid, saved=saved, verbose=cfg["verbose"] is not False)   # reference's samplers
-        test_res = trainer.evaluate(test)
+        test_res = trainer.evaluate(test, load_best_model=bool(saved))      # quick_start.py:61: the best model when saved
     elif name.startswith("PFCN_"):
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
         trainer = pkg.PFCNTrainer(cfg, net)
@@ -163,6 +171,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(loader, valid, train_item_count=item_counter, saved=saved,
                                      verbose=cfg["verbose"] is not False)
+        _load_best(trainer, saved)
         test_res = trainer.evaluate(test, None, item_counter)
     elif name in ("FairGo_PMF", "FairGo_GCN"):
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
@@ -172,6 +181,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
             raise NotImplementedError("FairGo evaluation here is the fused full-sort one (eval_args.mode full)")
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter, saved=saved)
+        _load_best(trainer, saved)
         test_res = trainer.evaluate(test)
     elif name == "NFCF":
         net = pkg.NFCF(cfg, TrainView).to(dev)
@@ -182,6 +192,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(loader, valid, saved=saved, train_item_count=item_counter,
                                      verbose=cfg["verbose"] is not False)
+        _load_best(trainer, saved)
         test_res = trainer.evaluate(test, item_counter)
         if saved:
             logger.info("saved %s", trainer.saved_model_file)
