@@ -18,6 +18,34 @@ DEFAULTS = dict(
 )
 
 
+# Hyper-parameter defaults of the reference's per-model property files (recbole/properties/model/<Model>.yaml), the layer
+# configurator.py:211-257 puts between overall.yaml and the user's files.  Model / training keys only: the data keys of
+# those files (load_col, threshold, ...) are dead in the reference too (sample.yaml overrides them), and
+# eval_args stays with DEFAULTS (full-sort) because the sampled mode refuses four of the default metrics (sampled_eval.py).
+_DIS = [128, 256, 128, 128, 64, 32]
+MODEL_DEFAULTS = {
+    "FOCF": dict(embedding_size=64, fair_objective="none", fair_weight=1.0, neg_sampling=None, weight_decay=0.001),
+    "NFCF": dict(embedding_size=64, mlp_hidden_size=[128, 64], dropout=0.2, fair_weight=0.1, weight_decay=1e-6),
+    "PFCN_MLP": dict(embedding_size=64, mlp_hidden_size_list=[64, 32, 16], dis_hidden_size_list=_DIS, activation="leakyrelu",
+                     filter_mode="sm", dropout=0.2, dis_dropout=0.3, train_epoch_interval=5, weight_decay=0.0001,
+                     dis_weight=10.0),
+    "PFCN_PMF": dict(embedding_size=64, dis_hidden_size_list=_DIS, activation="leakyrelu", filter_mode="none",
+                     dis_dropout=0.3, train_epoch_interval=5, weight_decay=0.0001, dis_weight=10),
+    "PFCN_BiasedMF": dict(embedding_size=64, dis_hidden_size_list=_DIS, activation="leakyrelu", filter_mode="none",
+                          dis_dropout=0.3, train_epoch_interval=5, weight_decay=0.0001, dis_weight=10),
+    "PFCN_DMF": dict(embedding_size=64, num_layers=3, dis_hidden_size_list=_DIS, mlp_activation="relu",
+                     dis_activation="leakyrelu", filter_mode="sm", mlp_dropout=0.2, dis_dropout=0.3, train_epoch_interval=5,
+                     weight_decay=0.001, dis_weight=10),
+    "FairGo_PMF": dict(load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1], embedding_size=64,
+                       dis_hidden_size_list=[16, 8, 4], filter_hidden_size_list=[128, 64], activation="leakyrelu",
+                       fair_weight=0.1, pretrain_epochs=600, train_epoch_interval=5, weight_decay=0.0001),
+    "FairGo_GCN": dict(aggr_method="LBA", vs_weights=[4, 1], embedding_size=64, n_layers=2, dis_hidden_size_list=[16, 8, 4],
+                       filter_hidden_size_list=[128, 64], activation="leakyrelu", fair_weight=0.1, gcn_n_layers=2,
+                       hidden_channels=32, gcn_dropout=0.2, gcn_act="relu", pretrain_epochs=600, train_epoch_interval=5,
+                       weight_decay=0.0001),
+}
+
+
 class Config(dict):
     def __init__(self, **kw):
         super().__init__(DEFAULTS)

@@ -2,9 +2,10 @@
 (recbole/quick_start/quick_start.py:20-71, driven by run_recbole.py:16-26) over this package: YAML config ->
 init_seed -> atomic-file dataset -> split -> device-resident loaders -> model -> trainer.fit -> trainer.evaluate(test).
 
-Config precedence mirrors configurator.py:211-263 as far as the fairness configs need it: built-in defaults (config.py)
-< the YAML files of `config_file_list` (in order) < `config_dict`.  The reference's per-model / per-dataset property
-YAMLs are not shipped here; pass the keys you need in your own YAML (same key names).
+Config precedence mirrors configurator.py:211-263 as far as the fairness configs need it: built-in defaults (config.py
+DEFAULTS = overall.yaml / sample.yaml) < the model's hyper-parameter defaults (config.MODEL_DEFAULTS = the model / training
+keys of properties/model/<Model>.yaml) < the YAML files of `config_file_list` (in order) < `config_dict` < `--key=value`
+command-line overrides.
 
 Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
 uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort evaluation) and
@@ -35,12 +36,27 @@ def init_seed(seed, reproducibility=True):
     torch.backends.cudnn.deterministic = bool(reproducibility)
 
 
-def build_config(model, dataset, config_file_list=None, config_dict=None):
-    merged = {}
+def parse_argv_overrides(argv):
+    """`--key=value` command-line overrides (configurator.py:167-172): values are read as YAML scalars / lists / dicts
+    (the reference eval()s them, with the `value` pitfall of SURVEY.md section 5 (d); a YAML parse has the same results for
+    numbers, booleans, lists and dicts, and keeps plain words as strings)"""
+    out = {}
+    for arg in argv or []:
+        if not arg.startswith("--") or "=" not in arg:
+            continue
+        key, value = arg[2:].split("=", 1)
+        out[key] = yaml.safe_load(value)
+    return out
+
+
+def build_config(model, dataset, config_file_list=None, config_dict=None, argv=None):
+    from .config import MODEL_DEFAULTS
+    merged = dict(MODEL_DEFAULTS.get(model, {}))
     for path in config_file_list or []:
         with open(path, "r", encoding="utf-8") as f:
             merged.update(yaml.safe_load(f) or {})
     merged.update(config_dict or {})
+    merged.update(parse_argv_overrides(argv))
     merged["model"], merged["dataset"] = model, dataset
     cfg = Config(**merged)
     if "device" not in merged:
@@ -108,11 +124,11 @@ def _load_best(trainer, saved):
         trainer.resume_checkpoint(path)
 
 
-def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=None, saved=False):
+def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=None, saved=False, argv=None):
     """quick_start.py:20-71 -> {'best_valid_score', 'valid_score_bigger', 'best_valid_result', 'test_result'}"""
     import recbole_fairrec_b200 as pkg
     from .sampled_eval import SampledEvalData, sample_negatives
-    cfg = build_config(model, dataset, config_file_list, config_dict)
+    cfg = build_config(model, dataset, config_file_list, config_dict, argv)
     init_seed(cfg["seed"], cfg["reproducibility"] if cfg["reproducibility"] is not None else True)
     logger = getLogger()
     ds = AtomicDataset(cfg)

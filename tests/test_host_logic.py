@@ -106,6 +106,12 @@ def test_run_recbole_config_precedence_and_seeding(tmp_path):
     assert (cfg["embedding_size"], cfg["topk"], cfg["fair_weight"], cfg["learning_rate"]) == (32, [7], 0.5, 0.1)
     assert cfg["model"] == "FOCF" and cfg["dataset"] == "ml-100k" and cfg["train_batch_size"] == 2048
     assert cfg["no_such_key"] is None                       # configurator.py:405-409
+    # model property defaults sit between the built-ins and the files; --key=value overrides sit on top
+    cfg = build_config("NFCF", "ml-100k", [str(b)], {"dropout": 0.5, "device": "cpu"},
+                       argv=["--fair_weight=0.3", "--mlp_hidden_size=[32,16]", "--fair_objective=value", "--junk"])
+    assert (cfg["mlp_hidden_size"], cfg["dropout"], cfg["fair_weight"], cfg["weight_decay"]) == ([32, 16], 0.5, 0.3, 1e-6)
+    assert cfg["topk"] == [7] and cfg["fair_objective"] == "value"
+    assert build_config("FairGo_GCN", "x", None, {"device": "cpu"})["hidden_channels"] == 32
     init_seed(123)
     x = (random.random(), np.random.rand(), torch.rand(1).item())
     init_seed(123)
