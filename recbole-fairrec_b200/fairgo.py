@@ -454,7 +454,7 @@ class FairGoTrainer(CheckpointMixin):
     def data_collect(self, train_item_count):
         """collector.py:80-95: {item id: #train interactions} for the popularity metric"""
         self._train_item_count = dict(train_item_count) if train_item_count is not None else None
-        self.evaluator = None
+        self.evaluator = self.sampled_evaluator = None
 
     @torch.no_grad()
     def evaluate(self, eval_data):
@@ -462,7 +462,15 @@ class FairGoTrainer(CheckpointMixin):
         filtered by all attributes, fairgo_pmf.py:250-257) with the fused evaluator: scoring + mask + top-K + the 12
         metrics of FairGo_PMF.yaml.  eval_data: evaluator.EvalData or a reference FullSortEvalDataLoader."""
         from .evaluator import EvalData, FullSortEvaluator
+        from .sampled_eval import SampledEvalData, SampledEvaluator
         self.model.eval()
+        if isinstance(eval_data, SampledEvalData):      # eval_args.mode uni<N> (the FairGo YAMLs' default): the same
+            if getattr(self, "sampled_evaluator", None) is None:      # tables, scored on the candidate pairs only
+                self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items,
+                                                          getattr(self, "_train_item_count", None))
+            U, I = self.model.filtered_tables()
+            return self.sampled_evaluator.evaluate(
+                SampledEvaluator.dot_scorer(U.detach(), I.detach(), self.model.max_rating), eval_data)
         if getattr(self, "evaluator", None) is None:
             self.evaluator = FullSortEvaluator(self.config, self.model.n_items, getattr(self, "_train_item_count", None))
         if not isinstance(eval_data, EvalData):

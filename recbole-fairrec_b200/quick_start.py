@@ -8,7 +8,7 @@ keys of properties/model/<Model>.yaml) < the YAML files of `config_file_list` (i
 command-line overrides.
 
 Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
-uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort evaluation) and
+uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort or `uni<N>`) and
 NFCF (both stages: positives + uniform negatives with 1 | 0 labels, `uni<N>` evaluation; `saved=True` writes the stage-1
 checkpoint that `load_pretrain_path` reads in stage 2).  With the
 same seed the splits, the initial weights and FOCF's batch draws are identical to the reference's (tests/test_atomic.py,
@@ -193,8 +193,6 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
         trainer = pkg.FairGoTrainer(cfg, net)
         loader = BatchLoader(cfg, ds, train, pairwise=False)
-        if mode != "full":
-            raise NotImplementedError("FairGo evaluation here is the fused full-sort one (eval_args.mode full)")
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter, saved=saved)
         _load_best(trainer, saved)
