@@ -297,3 +297,42 @@ def test_sampled_eval_oracle_matches_reference(path):
                          g["I"].shape[0], count_items)
         for k, ref in zip(g["metric_names"], g["metric_values"]):
             assert abs(res[str(k)] - ref) <= 1e-5 * max(abs(ref), 1e-12) + 1e-9, (k, res[str(k)], ref)
+
+
+def test_gcn_restatement_equals_the_dense_formula_and_the_products_adjacency():
+    """oracle/fairgo_oracle.gcn_forward (edge-list form of GCNConv: self loops, symmetric normalisation by in-degree,
+    aggregate x W^T, + b, act between layers) == relu(A_hat (x W0^T) + b0) ... with the DENSE A_hat = D^-1/2 (A + I) D^-1/2,
+    and the adjacency the product builds on the host (fairgo.gcn_norm_csr) is that same matrix.  PARITY UNPINNED against
+    torch_geometric itself (absent from the build container): this pins the two restatements on each other only."""
+    import scipy.sparse as sp
+    import torch
+    from oracle import fairgo_oracle as go
+    from recbole_fairrec_b200.fairgo import gcn_norm_csr
+    rng = np.random.default_rng(0)
+    nu, ni, d = 30, 20, 8
+    tu, ti = rng.integers(1, nu, 200), rng.integers(1, ni, 200)          # repeated pairs included
+    tr = rng.integers(1, 6, 200).astype(np.float32)
+    N = nu + ni
+    A = np.zeros((N, N))
+    for u, i, r in zip(tu, ti, tr):
+        A[u, nu + i] += r
+        A[nu + i, u] += r
+    A += np.eye(N)
+    dinv = A.sum(1) ** -0.5
+    A_hat = dinv[:, None] * A * dinv[None, :]
+    got = gcn_norm_csr(sp.coo_matrix((tr, (tu, ti)), shape=(nu, ni)), nu, ni).toarray()
+    np.testing.assert_allclose(got, A_hat, rtol=2e-7, atol=1e-9)             # stored in float32
+    x = torch.randn(N, d, dtype=torch.float64)
+    W = [torch.randn(16, d, dtype=torch.float64), torch.randn(12, 16, dtype=torch.float64), torch.randn(d, 12, dtype=torch.float64)]
+    b = [torch.randn(16, dtype=torch.float64), torch.randn(12, dtype=torch.float64), torch.randn(d, dtype=torch.float64)]
+    ei, ew = go.gcn_edges(tu, ti, tr, nu, ni)
+    At = torch.from_numpy(A_hat)
+    h = x
+    for k in range(3):
+        h = At @ (h @ W[k].t()) + b[k]
+        if k < 2:
+            h = torch.relu(h)
+    out = go.gcn_forward(x, ei, ew.double(), W, b)
+    assert (out - h).abs().max().item() < 1e-12
+    # isolated nodes keep their self loop: user 0 ([PAD]) has no edges -> out row = W-chain of its own x
+    assert A_hat[0, 0] == 1.0 and np.count_nonzero(A_hat[0]) == 1
