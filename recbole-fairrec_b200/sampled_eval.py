@@ -15,7 +15,8 @@ visible when its dataloader packs SEVERAL users into one batch: (i) every positi
 attribute (the reference reads the attribute of the first P rows of the batch interaction, collector.py:203-205, which
 belong mostly to the batch's first user); (ii) Value / Absolute / Under / Over unfairness are not offered in sampled mode:
 the reference computes them from `interaction[item][P:2P]` scored in the positives' rows (collector.py:190-199), which
-for multi-user batches are -inf entries, i.e. its values are inf / NaN.  With one user per batch (i) coincides with the
+for multi-user batches are -inf entries, i.e. its values are inf / NaN (`sampled_undefined_metrics: nan` keeps their
+keys in the result with NaN values instead of refusing the metric list).  With one user per batch (i) coincides with the
 reference (tests/golden/uni_eval_uni100.npz)."""
 from collections import OrderedDict
 
@@ -101,9 +102,18 @@ class SampledEvaluator(FullSortEvaluator):
     def __init__(self, config, n_items, train_item_count=None):
         super().__init__(config, n_items, train_item_count)
         bad = [m for m in self.metrics if m not in MODE_FREE]
-        if bad:
+        self._undefined = set()
+        if bad and config["sampled_undefined_metrics"] == "nan":
+            # keep the reference's result keys (its model YAMLs list all 12 metrics with mode uni100) and report the four
+            # metrics that mode leaves undefined as NaN instead of refusing the configuration
+            import warnings
+            warnings.warn(f"{bad} are undefined in sampled mode (collector.py:190-199 scores mis-indexed negatives): "
+                          f"reported as NaN")
+            self._undefined = set(bad)
+        elif bad:
             raise NotImplementedError(f"{bad}: in sampled mode the reference computes these from mis-indexed negative "
-                                      f"scores (collector.py:190-199); see recbole_fairrec_b200/sampled_eval.py")
+                                      f"scores (collector.py:190-199); see recbole_fairrec_b200/sampled_eval.py "
+                                      f"(sampled_undefined_metrics: nan reports them as NaN instead)")
 
     @staticmethod
     def dot_scorer(U, I, max_rating=None, transform=None):
@@ -133,6 +143,21 @@ class SampledEvaluator(FullSortEvaluator):
                 out["fair"][attr] = kernels.fairness_metrics(stats)
         self.last = out
         return out
+
+    def finalize(self, out, data, rounded=True):
+        if not self._undefined:
+            return super().finalize(out, data, rounded)
+        res, every = OrderedDict(), self.metrics
+        try:
+            for m in every:                  # metric by metric, so that the keys keep the reference's order
+                if m in self._undefined:
+                    res[FAIR_KEYS[m].format(self.sst_attr_list[0])] = float("nan")
+                else:
+                    self.metrics = [m]
+                    res.update(super().finalize(out, data, rounded))
+        finally:
+            self.metrics = every
+        return res
 
     def evaluate(self, score_fn, data):
         return self.finalize(self.collect(score_fn, data), data)

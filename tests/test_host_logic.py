@@ -302,3 +302,37 @@ def test_device_built_eval_lists_equal_the_host_built_ones():
         assert torch.equal(b.pos_items, b.pos_items_sorted)
         # group of a positive depends on its user only, and pos_row is identical
         assert torch.equal(a.group_of_pos["gender"], b.group_of_pos["gender"])
+
+
+def test_sampled_mode_reports_its_undefined_metrics_as_nan_on_request():
+    """`sampled_undefined_metrics: nan`: the reference's 12-metric YAML list stays usable with mode uni<N>; the four
+    metrics that mode leaves undefined come back as NaN under the reference's keys, in the reference's key order"""
+    import warnings
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.evaluator import FAIR_KEYS
+    cfg = pkg.Config(topk=[2, 3], sst_attr_list=["gender"], device=torch.device("cpu"), metric_decimal_place=6)
+    with pytest.raises(NotImplementedError):
+        pkg.SampledEvaluator(cfg, 10)
+    cfg["sampled_undefined_metrics"] = "nan"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ev = pkg.SampledEvaluator(cfg, 10)
+    assert any("undefined in sampled mode" in str(x.message) for x in w)
+
+    class D:
+        n = 4
+    out = {"topk_sums": torch.tensor([[1.0, 2.0, 3.0]] * 4, dtype=torch.float64),
+           "pop_hits": torch.tensor([2.0, 1.0, 1.0], dtype=torch.float64),
+           "gini": {2: torch.tensor(0.25), 3: torch.tensor(0.5)},
+           "fair": {"gender": torch.tensor([0.5, 9.0, 9.0, 9.0, 9.0, 0.125], dtype=torch.float64)}}
+    res = ev.finalize(out, D())
+    keys = list(res)
+    want = []
+    for m in cfg["metrics"]:
+        m = m.lower()
+        want += [FAIR_KEYS[m].format("gender")] if m in FAIR_KEYS else [f"{m}@2", f"{m}@3"]
+    assert keys == want
+    for m in ("valueunfairness", "absoluteunfairness", "underunfairness", "overunfairness"):
+        assert np.isnan(res[FAIR_KEYS[m].format("gender")])
+    assert res[FAIR_KEYS["differentialfairness"].format("gender")] == 0.5 and res["ndcg@3"] == 0.75
+    assert ev.metrics == [m.lower() for m in cfg["metrics"]]
