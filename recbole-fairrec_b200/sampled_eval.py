@@ -123,7 +123,12 @@ class SampledEvaluator(FullSortEvaluator):
 
     @torch.no_grad()
     def collect(self, score_fn, data):
-        scores = score_fn(data.cand_uid, data.cand_items).view(-1).to(torch.float32)
+        C, chunk = data.cand_uid.numel(), int(self.config["sampled_chunk_rows"] or (1 << 21))
+        if C <= chunk:
+            scores = score_fn(data.cand_uid, data.cand_items).view(-1).to(torch.float32)
+        else:       # bound the activations of MLP scorers (PFCN predict over ~1e7 candidate rows); rows are independent
+            scores = torch.cat([score_fn(data.cand_uid[a:a + chunk], data.cand_items[a:a + chunk]).view(-1).to(torch.float32)
+                                for a in range(0, C, chunk)])
         ids, sc, rec_topk = sampled_topk(data, scores, self.K, self.n_items)
         pos_score = scores[data.pos_idx].contiguous()
         out = {"topk_id": ids, "topk_score": sc, "rec_topk": rec_topk, "pos_score": pos_score}
