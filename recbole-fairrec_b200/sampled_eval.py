@@ -123,7 +123,7 @@ class SampledEvaluator(FullSortEvaluator):
 
     @torch.no_grad()
     def collect(self, score_fn, data):
-        C, chunk = data.cand_uid.numel(), int(self.config["sampled_chunk_rows"] or (1 << 21))
+        C, chunk = data.cand_uid.numel(), int(self.config["sampled_chunk_rows"] or (1 << 24))
         if C <= chunk:
             scores = score_fn(data.cand_uid, data.cand_items).view(-1).to(torch.float32)
         else:       # bound the activations of MLP scorers (PFCN predict over ~1e7 candidate rows); rows are independent
