@@ -349,6 +349,38 @@ def run_ours(args, wname):
     loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
+    # self-check of the packed host path of train_step (persistent staging buffer + argument struct, kernels.py) against the
+    # generic one on the same batch and state: same launch arguments (tests/test_host_logic.py) => bit-equal loss and
+    # tables; anything else makes the bench fall back to the generic path and says so
+    host_path = None
+    if world == 1:
+        import recbole_fairrec_b200.focf as focf_mod
+        try:
+            adam = model._adam
+            state = [model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data,
+                     adam["mU"], adam["vU"], adam["mI"], adam["vI"]]
+            keep, step0 = [t.clone() for t in state], adam["step"]
+
+            def one(generic):
+                for dst, src in zip(state, keep):
+                    dst.copy_(src)
+                adam["step"] = step0
+                focf_mod._NO_FAST_HOST_STEP = generic
+                loss = model.train_step(host_batches[0]).clone()
+                return loss, state[0].clone(), state[1].clone()
+
+            fast, gen = one(False), one(True)
+            for dst, src in zip(state, keep):
+                dst.copy_(src)
+            adam["step"] = step0
+            torch.cuda.synchronize()
+            same = all(torch.equal(x, y) for x, y in zip(fast, gen))
+            focf_mod._NO_FAST_HOST_STEP = not same
+            host_path = "packed fast path (self-check: loss and tables bit-equal to the generic path)" if same else \
+                "generic path (the packed fast path differed in the self-check)"
+        except Exception as e:
+            focf_mod._NO_FAST_HOST_STEP = True
+            host_path = f"generic path (self-check failed: {str(e)[:160]})"
     barrier()
     t0 = time.perf_counter()
     rows_e, pending, loss_sum = 0, None, 0.0
@@ -587,7 +619,7 @@ def run_ours(args, wname):
         "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "mode": "host batch (one pinned buffer) -> H2D -> step -> loss D2H every step; the host waits for step t's "
                         "loss after enqueuing step t+1",
-                "serial_value": e2e_serial},
+                "serial_value": e2e_serial, "host_path": host_path},
         "gpu_launches": int(round(kernels_per_step * timed_steps)), "kernels_per_step": kernels_per_step,
         "launch_mode": (f"cuda graph replay ({G} steps per launch; prepare(t+1) on a second stream under compute(t))"
                         if world == 1 else f"cuda graph replay ({G} data-parallel steps per launch incl. the NCCL all-reduce)")

@@ -13,6 +13,8 @@ C ABI.  Two ways to train:
 
 There is no CPU path: the model must live on a CUDA device.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -26,6 +28,9 @@ def _xavier_normal_initialization(module):
     # recbole/model/init.py:15-31
     if isinstance(module, nn.Embedding):
         nn.init.xavier_normal_(module.weight.data)
+
+
+_NO_FAST_HOST_STEP = bool(os.environ.get("FR_FOCF_NO_FAST_HOST_STEP"))      # debugging switch: generic path for packed batches
 
 
 def batch_columns(interaction, uid_f, iid_f, rating_f, sst_f, device):
@@ -172,12 +177,28 @@ class FOCF(nn.Module):
                           weight_decay=weight_decay)
         return self._adam
 
-    @torch.no_grad()
     def train_step(self, interaction, loss_out=None):
         """One fused optimisation step (trainer.py:183-196 for `learner: adam`).  Returns the device tensor
         holding the loss; nothing synchronises."""
-        if self._adam is None:
+        adam = self._adam
+        if adam is None:
             raise RuntimeError("call init_adam() (FOCFTrainer does) before train_step()")
+        packed = getattr(interaction, "packed_host", None)
+        if packed is None or _NO_FAST_HOST_STEP:
+            return self._train_step_generic(interaction, loss_out)
+        # host batch in one pinned buffer: persistent staging buffer + persistent argument struct (kernels.py); nothing
+        # here is seen by autograd (`.data` tensors, one copy, one library call), so no grad-mode bookkeeping either
+        eng = self._engine()
+        adam["step"] += 1
+        out = eng.loss if loss_out is None else loss_out
+        mods = self._modules          # plain dict lookups instead of nn.Module.__getattr__
+        eng.train_step_packed(mods["user_embedding_layer"]._parameters["weight"].data,
+                              mods["item_embedding_layer"]._parameters["weight"].data, adam, packed,
+                              bool(getattr(interaction, "items_contiguous", False)), self._objective, self.fair_weight, out)
+        return out
+
+    @torch.no_grad()
+    def _train_step_generic(self, interaction, loss_out=None):
         eng = self._engine()
         self._adam["step"] += 1
         out = eng.loss if loss_out is None else loss_out

@@ -43,6 +43,8 @@ class FocfEngine:
         self.ws = None
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self._stage = None          # persistent device staging buffer of train_step_packed
+        self._fast = self._fast_key = None
         self._ensure(max_batch)
 
     def _ensure(self, B):
@@ -55,6 +57,7 @@ class FocfEngine:
                                               stream_ptr()), "fr_focf_workspace_init")
         self.max_batch = B
         self.pred_buf = torch.empty(B, dtype=torch.float32, device=self.device)
+        self._fast = None           # the persistent argument struct points into the buffers just replaced
 
     def _step(self, U, I, batch, objective, fair_weight, loss_out=None, norm=None):
         uid, iid, rating, sst, contiguous = batch
@@ -91,6 +94,45 @@ class FocfEngine:
         s.step = int(adam["step"])
         s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
         s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
+        check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
+        return s
+
+    def train_step_packed(self, U, I, adam, packed, contiguous, objective, fair_weight, loss_out):
+        """The eager fused step for a host batch packed into ONE pinned buffer (focf.pack_host_batch: int32 user ids |
+        int32 item ids | f32 ratings | f32 attribute values, n entries each).  The batch is staged into a persistent
+        device buffer with a single async H2D copy and the argument struct lives across steps: only the batch pointers /
+        size, the Adam step count and the loss pointer are rewritten, so the per-step host work is one copy, a handful of
+        integer stores and one library call (the generic path builds four tensor views and a fresh struct per step, which
+        costs more host time than the step takes on the device).  One staging buffer is enough: the copy of step t+1 is
+        enqueued behind the kernels of step t on the same stream."""
+        buf, n = packed
+        n = int(n)
+        self._ensure(n)
+        nbytes = 16 * n
+        if buf.numel() != nbytes:
+            raise ValueError("packed batch: the buffer must hold exactly 16 bytes per entry")
+        st = self._stage
+        if st is None or st.numel() < nbytes:
+            st = self._stage = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        key = (ptr(U), ptr(I), ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"]), objective,
+               float(fair_weight), adam["lr"], adam["beta1"], adam["beta2"], adam["eps"], adam["weight_decay"])
+        s = self._fast
+        if s is None or self._fast_key != key:
+            s = FocfStep()
+            s.U, s.I, s.mU, s.vU, s.mI, s.vI = key[:6]
+            s.n_users, s.n_items, s.d = self.n_users, self.n_items, self.d
+            s.objective, s.fair_weight = objective, float(fair_weight)
+            s.pred, s.status_flags = ptr(self.pred_buf), ptr(self.flags)
+            s.workspace, s.workspace_bytes = ptr(self.ws), self.ws.numel()
+            s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
+            s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
+            self._fast, self._fast_key = s, key
+        st[:nbytes].copy_(buf, non_blocking=True)
+        base = ptr(st)
+        s.uid, s.iid, s.rating, s.sst, s.B = base, base + 4 * n, base + 8 * n, base + 12 * n, n
+        s.items_contiguous = 1 if contiguous else 0
+        s.loss = ptr(loss_out)
+        s.step = int(adam["step"])
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
         return s
 

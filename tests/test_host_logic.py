@@ -336,3 +336,72 @@ def test_sampled_mode_reports_its_undefined_metrics_as_nan_on_request():
         assert np.isnan(res[FAIR_KEYS[m].format("gender")])
     assert res[FAIR_KEYS["differentialfairness"].format("gender")] == 0.5 and res["ndcg@3"] == 0.75
     assert ev.metrics == [m.lower() for m in cfg["metrics"]]
+
+
+def test_packed_fast_host_step_passes_the_same_arguments_as_the_generic_step(monkeypatch):
+    """FocfEngine.train_step_packed (persistent staging buffer + persistent argument struct) vs the generic
+    batch_columns + train_step path, with the library call intercepted: every field of `fr_focf_step` equal, the four
+    batch pointers at the same offsets of the staged copy, the staged bytes equal to the host buffer, and the persistent
+    struct refreshed when tables, moments, hyper-parameters or the workspace change.  (CPU tensors stand in for device
+    memory here: the launch itself is stubbed.)"""
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import _lib, focf as focf_mod, kernels, synth
+    from recbole_fairrec_b200.interaction import Interaction
+    real = _lib.load()
+    seen = []
+
+    class FakeLib:
+        fr_focf_workspace_bytes = staticmethod(real.fr_focf_workspace_bytes)
+
+        def fr_focf_workspace_init(self, *a):
+            return 0
+
+        def fr_focf_train_step(self, ref, stream):
+            s = ref._obj
+            seen.append({name: getattr(s, name) for name, _ in _lib.FocfStep._fields_})
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(kernels, "load", lambda: fake)
+    monkeypatch.setattr(kernels, "stream_ptr", lambda: 0)
+    monkeypatch.setattr(kernels, "ptr", lambda t: None if t is None else t.data_ptr())
+    cpu = torch.device("cpu")
+    cfg = pkg.Config(embedding_size=16, fair_objective="value", fair_weight=0.7, device=cpu)
+    m = pkg.FOCF(cfg, synth.SynthDataset(50, 40, 5.0))
+    eng = kernels.FocfEngine(50, 40, 16, 64, cpu)
+    monkeypatch.setattr(m, "_engine", lambda: eng)
+    m.init_adam(lr=2e-3, weight_decay=1e-3)
+    rng = np.random.default_rng(0)
+
+    def packed(n):
+        buf = torch.from_numpy(rng.integers(0, 255, 16 * n).astype(np.uint8))
+        it = Interaction({"user_id": buf[:4 * n].view(torch.int32), "item_id": buf[4 * n:8 * n].view(torch.int32),
+                          "rating": buf[8 * n:12 * n].view(torch.float32), "gender": buf[12 * n:].view(torch.float32)})
+        it.items_contiguous, it.packed_host = True, (buf, n)
+        return it, buf
+
+    loss = torch.zeros(1)
+    for n in (37, 37, 52, 300, 41):                     # 300 grows the workspace and the staging buffer
+        it, buf = packed(n)
+        monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", True)
+        m.train_step(it, loss_out=loss)
+        m._adam["step"] -= 1
+        monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", False)
+        m.train_step(it, loss_out=loss)
+        a, b = seen[-2], seen[-1]
+        batch_ptrs = ("uid", "iid", "rating", "sst")
+        for k in a:
+            if k not in batch_ptrs:
+                assert a[k] == b[k], (n, k, a[k], b[k])
+        base = eng._stage.data_ptr()
+        assert [b[k] - base for k in batch_ptrs] == [0, 4 * n, 8 * n, 12 * n]
+        assert [a[k] - a["uid"] for k in batch_ptrs] == [0, 4 * n, 8 * n, 12 * n]
+        assert torch.equal(eng._stage[:16 * n], buf) and b["B"] == n and b["step"] == m._adam["step"]
+    # the persistent struct follows a change of the Adam state, of the hyper-parameters and of the loss slot
+    m.init_adam(lr=5e-4, weight_decay=0.0)
+    other = torch.zeros(1)
+    it, _ = packed(20)
+    m.train_step(it, loss_out=other)
+    b = seen[-1]
+    assert b["lr"] == 5e-4 and b["weight_decay"] == 0.0 and b["mU"] == m._adam["mU"].data_ptr() and b["step"] == 1
+    assert b["loss"] == other.data_ptr() and b["objective"] == m._objective and abs(b["fair_weight"] - 0.7) < 1e-7
