@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Differential fuzz of the numpy oracle against the LIVE reference (build container only): random shapes, objectives,
+fairness weights, attribute encodings and batch layouts through the unmodified `FOCF.calculate_loss` + autograd +
+`torch.optim.Adam` (recbole/model/fair_recommender/focf.py, trainer.py:139) vs oracle/focf_oracle.py -- per-step losses,
+first-step gradients and the tables / Adam moments after the last step; and random full-sort evaluations through the
+reference's `_full_sort_batch_eval` + `Collector` + `Evaluator` vs oracle/fullsort_oracle.py + oracle/metrics_oracle.py.
+    python oracle/fuzz_oracle.py [seed] [trials]
+TEST INFRASTRUCTURE ONLY: widens the pinning of the oracle beyond the committed fixtures of tests/golden/."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.argv = sys.argv[:1] + sys.argv[1:]
+_args = sys.argv[1:]
+sys.argv = sys.argv[:1]
+import gen_golden as gg  # noqa: E402  (installs the shim, imports the reference)
+import torch  # noqa: E402
+from recbole.data.interaction import Interaction  # noqa: E402
+from recbole.model.fair_recommender.focf import FOCF  # noqa: E402
+
+from oracle import focf_oracle as fo  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def one_train_case(rng, trial):
+    objective = ["none", "value", "absolute", "under", "over", "nonparity"][trial % 6]
+    n_users, n_items = int(rng.integers(20, 200)), int(rng.integers(10, 120))
+    d = int(rng.choice([4, 8, 16, 32, 64]))
+    n_steps = int(rng.integers(1, 5))
+    fair_weight = float(rng.choice([0.1, 0.5, 1.0, 2.0]))
+    lr, wd = float(rng.choice([1e-3, 1e-2])), float(rng.choice([0.0, 1e-3, 1e-2]))
+    scale = float(rng.choice([0.2, 0.6, 1.0]))
+    bk = dict(shuffle=bool(rng.integers(0, 2)), float_sst=bool(rng.integers(0, 2)))
+    cfg = gg.base_cfg(embedding_size=d, fair_objective=objective, fair_weight=fair_weight)
+    model = FOCF(cfg, gg.FakeDataset(n_users, n_items, 5.0))
+    U0 = (rng.standard_normal((n_users, d)) * scale).astype(np.float32)
+    I0 = (rng.standard_normal((n_items, d)) * scale).astype(np.float32)
+    with torch.no_grad():
+        model.user_embedding_layer.weight.copy_(torch.from_numpy(U0))
+        model.item_embedding_layer.weight.copy_(torch.from_numpy(I0))
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    batches = gg.make_focf_batches(rng, n_users, n_items, n_steps, int(rng.integers(30, 600)), **bk)
+    losses, g0 = [], None
+    for s, (uid, iid, rating, g) in enumerate(batches):
+        inter = Interaction({"user_id": torch.from_numpy(uid), "item_id": torch.from_numpy(iid),
+                             "rating": torch.from_numpy(rating), "gender": torch.from_numpy(g)})
+        opt.zero_grad()
+        loss = model.calculate_loss(inter)
+        loss.backward()
+        if s == 0:
+            g0 = (model.user_embedding_layer.weight.grad.numpy().copy(), model.item_embedding_layer.weight.grad.numpy().copy())
+        opt.step()
+        losses.append(loss.item())
+    o_losses, U, I, mU, vU, mI, vI = fo.train_steps(U0, I0, batches, objective, fair_weight, lr, wd)
+    _, _, dU, dI = fo.grads(U0, I0, *batches[0], objective, fair_weight)
+    # conditioning yardstick: how far the float32 reference itself sits from the float64 evaluation of the same schedule
+    _, U64, I64, *_ = fo.train_steps_f64(U0, I0, batches, objective, fair_weight=fair_weight, lr=lr, weight_decay=wd)
+    Ur, Ir = model.user_embedding_layer.weight.detach().numpy(), model.item_embedding_layer.weight.detach().numpy()
+    cond = max(rel(Ur, U64), rel(Ir, I64))
+    errs = dict(loss=rel(o_losses, losses), dU=rel(dU, g0[0]), dI=rel(dI, g0[1]), U=rel(U, Ur), I=rel(I, Ir))
+    ok = errs["loss"] < 1e-5 and errs["dU"] < 2e-5 and errs["dI"] < 2e-5 and max(errs["U"], errs["I"]) < max(1e-5, 3 * cond)
+    return ok, dict(objective=objective, n_users=n_users, n_items=n_items, d=d, steps=n_steps, fw=fair_weight, lr=lr, wd=wd,
+                    **bk), errs, cond
+
+
+def main():
+    seed = int(_args[0]) if _args else 0
+    trials = int(_args[1]) if len(_args) > 1 else 24
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for t in range(trials):
+        try:
+            ok, case, errs, cond = one_train_case(rng, t)
+        except Exception as e:      # the reference raises on some batches (e.g. nonparity with one attribute value)
+            print(t, "reference/oracle raised:", type(e).__name__, str(e)[:80])
+            continue
+        bad += not ok
+        print(t, "ok " if ok else "BAD", {k: f"{v:.1e}" for k, v in errs.items()}, f"cond {cond:.1e}", case)
+    print("bad:", bad)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
