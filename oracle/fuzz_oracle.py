@@ -70,11 +70,57 @@ def one_train_case(rng, trial):
                     **bk), errs, cond
 
 
+def one_eval_case(rng, trial, tmp):
+    """the reference's full_sort_predict -> mask -> Collector -> Evaluator (gen_golden.run_focf_eval, fixture written to a
+    temp dir) vs fullsort_oracle + metrics_oracle, with the checks of tests/test_oracle_golden.py"""
+    from oracle import fullsort_oracle as fs
+    from oracle import metrics_oracle as mo
+    K = int(rng.choice([3, 5, 10]))
+    kw = dict(n_users=int(rng.integers(20, 120)), n_items=int(rng.integers(40, 300)), d=int(rng.choice([4, 16, 64])), K=K,
+              topk=(max(1, K // 2), K), seed=int(rng.integers(0, 1 << 30)), scale=float(rng.choice([0.3, 0.55, 0.9])),
+              positive_only=bool(trial % 2), users_per_batch=int(rng.integers(1, 12)), float_sst=bool(rng.integers(0, 2)))
+    keep, gg.OUT = gg.OUT, tmp
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            gg.run_focf_eval("fuzz", **kw)
+    finally:
+        gg.OUT = keep
+    g = np.load(os.path.join(tmp, "focf_eval_fuzz.npz"))
+    users = g["eval_users"]
+    scores = fs.mask_history(fs.full_sort_scores(g["U"], g["I"], users, float(g["max_rating"])), g["hist_off"], g["hist_items"])
+    st = fs.collect(scores, K, g["pos_off"], g["pos_items"], g["sst_of_user"][users])
+    ok = np.allclose(st["rec.positive_score"], g["rec_positive_score"], rtol=1e-5, atol=1e-7)
+    ok &= np.array_equal(st["data.positive_i"], g["data_positive_i"]) and np.array_equal(st["data.sst"], g["data_sst"])
+    _, vals = fs.topk_canonical(scores, K + 1)
+    clean = np.all(np.abs(np.diff(vals, axis=1)) > 1e-6, axis=1)
+    ok &= np.array_equal(st["rec.items"][clean], g["rec_items"][clean]) and np.array_equal(st["rec.topk"][clean], g["rec_topk"][clean])
+    worst = 0.0
+    # the metrics restated on the REFERENCE's own collector output (independent of tie handling) ...
+    ref_st = {"rec.items": g["rec_items"], "rec.topk": g["rec_topk"], "rec.positive_score": g["rec_positive_score"],
+              "data.positive_i": g["data_positive_i"], "data.sst": g["data_sst"]}
+    count_items = {int(i): int(c) for i, c in g["train_count_items"]}
+    res = mo.evaluate(ref_st, [int(k) for k in g["topk"]], g["I"].shape[0], count_items, 0.1)
+    ok &= list(res.keys()) == [str(k) for k in g["metric_names"]]
+    for (k, v), ref in zip(res.items(), g["metric_values"]):
+        e = abs(v - ref) / max(abs(ref), 1e-12) if abs(v - ref) > 1e-12 else 0.0
+        worst = max(worst, e)
+    ok &= worst <= 1e-5
+    return bool(ok), kw, worst, float(clean.mean())
+
+
 def main():
+    import tempfile
     seed = int(_args[0]) if _args else 0
     trials = int(_args[1]) if len(_args) > 1 else 24
     rng = np.random.default_rng(seed)
     bad = 0
+    tmp = tempfile.mkdtemp()
+    for t in range(max(trials // 3, 1)):
+        ok, case, worst, clean = one_eval_case(rng, t, tmp)
+        bad += not ok
+        print("eval", t, "ok " if ok else "BAD", f"metric err {worst:.1e}", f"tie-free rows {clean:.2f}", case)
     for t in range(trials):
         try:
             ok, case, errs, cond = one_train_case(rng, t)
