@@ -259,6 +259,7 @@ def run_uni_eval(name, n_users=50, n_items=400, d=16, topk=(5, 10), seed=51, neg
     struct = collector.get_data_struct()
     result = Evaluator(cfg).evaluate(struct)
     out = dict(U=U, I=It, max_rating=5.0, topk=np.array(topk), eval_users=eval_users, sst_of_user=sst_of_user,
+               users_per_batch=users_per_batch,
                neg_num=neg_num, pos_off=np.cumsum([0] + [len(pos[u]) for u in eval_users]),
                pos_items=np.concatenate([pos[u] for u in eval_users]),
                neg_items=np.concatenate([neg[u] for u in eval_users]),

@@ -289,7 +289,8 @@ def test_sampled_eval_oracle_matches_reference(path):
         count_items = {int(i): int(c) for i, c in g["train_count_items"]}
         # the reference attributes the sensitive attribute per BATCH ROW (collector.py:203-205): equal to the per-user
         # attribution only for single-user batches (fixture uni100); restated for the batched fixtures
-        upb = {"uni100": 1, "uni100_batched": 3, "uni20_small_catalog": 2}[os.path.basename(path)[9:-4]]
+        upb = int(g["users_per_batch"]) if "users_per_batch" in g else \
+            {"uni100": 1, "uni100_batched": 3, "uni20_small_catalog": 2}[os.path.basename(path)[9:-4]]
         sst_of_pos = so.reference_sst_of_pos(users, cands, g["sst_of_user"], upb)
         if upb == 1:
             np.testing.assert_array_equal(sst_of_pos, np.repeat(g["sst_of_user"][users], np.diff(g["pos_off"])))
