@@ -104,6 +104,7 @@ class FOCFDataLoader:
                       torch.empty(self.max_batch, dtype=torch.float32, device=dev),
                       torch.empty(self.max_batch, dtype=torch.float32, device=dev))
         self._replay_pos = 0
+        self._pool0 = np.sort(np.asarray(self.candidates, np.int64))     # items present in train (this rank's slice)
 
     def __len__(self):
         world = 1 if self.partition is None else self.partition[1]
@@ -120,16 +121,22 @@ class FOCFDataLoader:
             self._replay_pos = end + 1
             return np.asarray(items, dtype=np.int64)
         if self.mode == "reference":
-            # focf_dataloader.py:38-47 verbatim in effect: same calls on numpy's global RNG
-            select_item = np.arange(0, tr.n_items)
-            is_select = np.zeros(tr.n_items, dtype=bool)
-            is_select[self.candidates] = True
+            # focf_dataloader.py:38-47 in effect, on numpy's global RNG: `np.random.choice(pool, 1, False)` IS
+            # `pool[np.random.permutation(len(pool))[:1]]` (legacy RandomState.choice without replacement), so the same
+            # stream is consumed and the same items come out; the pool of still-selectable items (ascending, like
+            # `select_item[is_select]`) is kept as an array instead of being re-masked for every draw
+            pool = self._pool0
             cnt, items = 0, []
             while cnt < self.step:
-                iid = np.random.choice(select_item[is_select], 1, False)[0]
+                if len(pool) == 0:
+                    raise ValueError("a must be non-empty")          # what np.random.choice raises in the reference
+                j = int(np.random.permutation(len(pool))[0])
+                iid = int(pool[j])
                 cnt += int(tr.item_count_h[iid])
-                is_select[iid] = False
+                pool = np.delete(pool, j)
                 items.append(iid)
+            if len(pool) == 0:          # focf_dataloader.py:43 `or not any(is_select)`: a batch that uses up every item
+                raise ValueError("a must be non-empty")          # makes the reference draw from an empty pool
             return np.asarray(items, dtype=np.int64)
         perm = self._rng.permutation(self.candidates)
         csum = np.cumsum(tr.item_count_h[perm])
