@@ -28,6 +28,7 @@ class _PFCNBase(nn.Module):
     input_type = "PAIRWISE"
     type = "GENERAL"
     USER_EMB, ITEM_EMB = "user_embedding_layer", "item_embedding_layer"   # attribute names differ per reference file
+    SCORER_FIRST = True       # pfcn_pmf / pfcn_biasedmf / pfcn_dmf build the scorer before filters and discriminators
 
     def __init__(self, config, dataset):
         super().__init__()
@@ -48,10 +49,15 @@ class _PFCNBase(nn.Module):
         self.activation = config["activation"]
         self.filter_num, self.sst_dict = self._get_filter_info()
         self.sst_size = self._get_sst_size(dataset.get_user_feature())
-        self._build_scorer(config)
+        # module creation order = the reference file's, so that a seed gives the reference's initial weights
+        # (verified against the live reference for all four models: every tensor bit-identical)
+        if self.SCORER_FIRST:
+            self._build_scorer(config)
         if self.filter_mode != "none":
             self.filter_layer = self.init_filter()
             self.dis_layer_dict = self.init_dis_layer()
+        if not self.SCORER_FIRST:
+            self._build_scorer(config)
 
     # ------------------------------------------------------------------ construction (pfcn_mlp.py:67-143)
     def _get_filter_info(self):
@@ -181,6 +187,7 @@ class _PFCNBase(nn.Module):
 class PFCN_MLP(_PFCNBase):
     """pfcn_mlp.py:23-232: NCF-style tower over [filtered user || item]"""
     USER_EMB, ITEM_EMB = "user_embedding", "item_embedding"
+    SCORER_FIRST = False      # pfcn_mlp.py:55-63: filters and discriminators first, then embeddings and tower
 
     def _build_scorer(self, config):
         self.dropout = config["dropout"]

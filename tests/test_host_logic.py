@@ -405,3 +405,89 @@ def test_packed_fast_host_step_passes_the_same_arguments_as_the_generic_step(mon
     b = seen[-1]
     assert b["lr"] == 5e-4 and b["weight_decay"] == 0.0 and b["mU"] == m._adam["mU"].data_ptr() and b["step"] == 1
     assert b["loss"] == other.data_ptr() and b["objective"] == m._objective and abs(b["fair_weight"] - 0.7) < 1e-7
+
+
+def _live_reference():
+    import sys
+    here = os.path.dirname(__file__)
+    sys.path.insert(0, os.path.join(here, "..", "oracle", "ref_shim"))
+    import shim
+    if not shim.available():
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(here, "..", "oracle"))
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        import gen_golden as gg
+    finally:
+        sys.argv = argv
+    return gg
+
+
+def test_initial_weights_equal_the_live_references_for_a_seed():
+    """build container only: module creation order and initialisers consume torch's RNG exactly like the reference files,
+    so `init_seed(s)` + model construction gives the reference's initial weights -- every registered tensor and every
+    dict-held filter / discriminator MLP of PFCN_MLP / PMF / BiasedMF / DMF (sm, cm) and FairGo_PMF (LBA, WAP), and NFCF's
+    stage-2 construction (checkpoint load, gender-direction projection, frozen user table, re-initialised item table)"""
+    import importlib
+    import tempfile
+    gg = _live_reference()
+    import recbole_fairrec_b200 as pkg
+    from recbole.data.interaction import Interaction as RefInter
+    nu, ni, d = 80, 50, 16
+    rng = np.random.default_rng(0)
+    gender, age = rng.integers(0, 2, nu).astype(np.float32), rng.integers(0, 4, nu).astype(np.float32)
+    coo = sp.coo_matrix((rng.integers(1, 6, 400).astype(np.float32), (rng.integers(1, nu, 400), rng.integers(1, ni, 400))),
+                        shape=(nu, ni))
+
+    def dataset(inter_cls):
+        class DS:
+            inter_feat = {"rating": torch.tensor([1.0, 5.0])}
+
+            def num(self, f):
+                return {"user_id": nu, "item_id": ni}[f]
+
+            def inter_matrix(self, form="coo", value_field=None):
+                return coo
+
+            def get_user_feature(self):
+                return inter_cls({"user_id": torch.arange(nu), "gender": torch.from_numpy(gender), "age": torch.from_numpy(age)})
+        return DS()
+
+    def flat(model, attrs):
+        out = {f"base.{k}": v.detach().clone() for k, v in model.state_dict().items()}
+        for a in attrs:
+            for k, m in (getattr(model, a, None) or {}).items():
+                out.update({f"{a}.{k}.{kk}": v.detach().clone() for kk, v in m.state_dict().items()})
+        return out
+
+    cases = [(n, dict(filter_mode=m, dis_dropout=0.0, dis_weight=10.0, dis_hidden_size_list=[32, 16], activation="leakyrelu",
+                      **gg.PFCN_EXTRA[n]), ("filter_layer", "dis_layer_dict"))
+             for n in ("PFCN_MLP", "PFCN_PMF", "PFCN_BiasedMF", "PFCN_DMF") for m in ("sm", "cm")]
+    cases += [("FairGo_PMF", dict(n_layers=2, activation="leakyrelu", dis_hidden_size_list=[16, 8], filter_hidden_size_list=[32, 16],
+                                  fair_weight=0.1, load_pretrain_weight=False, aggr_method=a, vs_weights=[4, 1]),
+               ("filter_layer_dict", "dis_layer_dict")) for a in ("LBA", "WAP")]
+    for name, extra, attrs in cases:
+        ref_cls = getattr(importlib.import_module(f"recbole.model.fair_recommender.{name.lower()}"), name)
+        torch.manual_seed(7)
+        ref = ref_cls(gg.base_cfg(embedding_size=d, sst_attr_list=["gender", "age"], **extra), dataset(RefInter))
+        torch.manual_seed(7)
+        mine = getattr(pkg, name)(pkg.Config(embedding_size=d, sst_attr_list=["gender", "age"], device=torch.device("cpu"), **extra),
+                                  dataset(pkg.Interaction))
+        a, b = flat(ref, attrs), flat(mine, attrs)
+        assert set(a) == set(b), (name, set(a) ^ set(b))
+        for k in a:
+            assert torch.equal(a[k].float(), b[k].float()), (name, extra.get("filter_mode"), k)
+    # NFCF stage 2
+    from recbole.model.fair_recommender.nfcf import NFCF as RefNFCF
+    path = os.path.join(tempfile.mkdtemp(), "ncf.pth")
+    torch.save({"state_dict": {"user_embedding.weight": torch.randn(nu, d), "item_embedding.weight": torch.randn(ni, d)}}, path)
+    kw = dict(embedding_size=d, mlp_hidden_size=[32, 16], dropout=0.0, fair_weight=0.1, load_pretrain_path=path)
+    torch.manual_seed(3)
+    ref = RefNFCF(gg.base_cfg(**kw), dataset(RefInter))
+    torch.manual_seed(3)
+    mine = pkg.NFCF(pkg.Config(sst_attr_list=["gender"], device=torch.device("cpu"), **kw), dataset(pkg.Interaction))
+    assert torch.equal(ref.user_embedding.weight.data, mine.user_embedding.weight.data)
+    assert torch.equal(ref.item_embedding.weight.data, mine.item_embedding.weight.data)
+    assert not mine.user_embedding.weight.requires_grad and mine.item_embedding.weight.requires_grad
+    for r, m in zip([x for x in ref.mlp_layers.mlp_layers if isinstance(x, torch.nn.Linear)], mine.mlp_layers.linears()):
+        assert torch.equal(r.weight.data, m.weight.data) and torch.equal(r.bias.data, m.bias.data)
