@@ -705,8 +705,71 @@ def run_ingest():
         os.chdir(cwd)
 
 
+from make_test_data import FAMILY_E2E, FAMILY_E2E_BASE, float_gender_copy  # noqa: E402
+
+
+def run_family_e2e(model_name):
+    """The reference's run_recbole steps (quick_start.py:20-71) for one MLP family on ml-100k from the atomic files:
+    per-epoch train losses, per-epoch validation results and the test result -> tests/golden/e2e_<model>.npz"""
+    import tempfile
+    import yaml
+    from recbole.config import Config
+    from recbole.data import create_dataset, data_preparation
+    from recbole.utils import init_seed, get_model, get_trainer
+    root = float_gender_copy(tempfile.mkdtemp())
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        with open("c.yaml", "w") as f:
+            yaml.safe_dump(dict(FAMILY_E2E_BASE, **FAMILY_E2E[model_name], data_path=root, use_gpu=False, state="WARNING",
+                                show_progress=False), f)
+        sys.argv = sys.argv[:1]
+        config = Config(model=model_name, dataset="ml-100k", config_file_list=["c.yaml"])
+        init_seed(config["seed"], config["reproducibility"])
+        dataset = create_dataset(config)
+        train_data, valid_data, test_data = data_preparation(config, dataset)
+        model = get_model(config["model"])(config, train_data.dataset).to(config["device"])
+        trainer = get_trainer(config["MODEL_TYPE"], config["model"])(config, model)
+        trainer.eval_collector.data_collect(train_data)
+        # per-step losses of the first epoch (the trajectories of these models are chaotic: BatchNorm stacks + Adam amplify
+        # float32 rounding, so only the first steps of a run are comparable at tight tolerance)
+        steps = []
+        o_loss = model.calculate_loss
+        o_dis = getattr(model, "calculate_dis_loss", None)
+        model.calculate_loss = lambda *a, **k: (lambda v: (steps.append(("f", float(v))), v)[1])(o_loss(*a, **k))
+        if o_dis is not None:
+            model.calculate_dis_loss = lambda *a, **k: (lambda v: (steps.append(("d", float(v))), v)[1])(o_dis(*a, **k))
+        losses, valids = [], []
+        first_epoch_steps = None
+        for ep in range(config["epochs"]):
+            loss = trainer._train_epoch(train_data, ep)
+            if first_epoch_steps is None:
+                first_epoch_steps = list(steps)
+            losses.append([float(x) for x in loss] if isinstance(loss, tuple) else [float(loss)])
+            _, res = trainer._valid_epoch(valid_data)
+            valids.append(res)
+        test = trainer.evaluate(test_data, load_best_model=False)
+        if model_name.startswith("PFCN") and len(test) == 1:         # {'sm-[gender]': metrics}
+            test = next(iter(test.values()))
+        names = list(test.keys())
+        f_steps = [v for t_, v in first_epoch_steps if t_ == "f"]
+        d_steps = [v for t_, v in first_epoch_steps if t_ == "d"][-len(f_steps):] if o_dis is not None else []
+        out = dict(epoch_losses=np.array(losses, np.float64), metric_names=np.array(names),
+                   first_epoch_step_losses=np.array(f_steps, np.float64), first_epoch_dis_step_losses=np.array(d_steps, np.float64),
+                   valid_metrics=np.array([[float(r[k]) for k in names] for r in valids]),
+                   test_metrics=np.array([float(test[k]) for k in names]), n_users=dataset.user_num, n_items=dataset.item_num)
+        np.savez_compressed(os.path.join(OUT, f"e2e_{model_name.lower()}.npz"), **out)
+        print(f"e2e {model_name}: losses {losses} valid {[dict(zip(names, v)) for v in out['valid_metrics']]}")
+    finally:
+        os.chdir(cwd)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "e2e":
+        for m in FAMILY_E2E:
+            run_family_e2e(m)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ingest":
         run_ingest()
         return

@@ -91,3 +91,35 @@ INGEST_CASES = {
     "ls_test_only_ro": dict(item_inter_num_interval="[2,inf)", val_interval={"timestamp": "[1000,1100);(1200,1399]"},
                             eval_args={"split": {"LS": "test_only"}, "group_by": "user", "order": "RO", "mode": "full"}),
 }
+
+
+FAMILY_E2E = {
+    # dropout-free variants: the reference's Philox dropout masks cannot be reproduced, everything else (id remap, shuffle,
+    # split, initial weights, in-place epoch shuffles, uniform negatives, per-evaluation negatives) follows from the seed
+    "PFCN_PMF": dict(filter_mode="sm", dis_dropout=0.0, dis_weight=10, dis_hidden_size_list=[128, 256, 128, 128, 64, 32],
+                     activation="leakyrelu", train_epoch_interval=1, weight_decay=0.0001, embedding_size=64),
+    "NFCF": dict(mlp_hidden_size=[128, 64], dropout=0.0, fair_weight=0.1, weight_decay=1e-6, embedding_size=64,
+                 load_pretrain_path=None),
+}
+FAMILY_E2E_BASE = dict(
+    RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0}, sst_attr_list=["gender"],
+    load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"]}, neg_sampling={"uniform": 1},
+    epochs=2, train_batch_size=2048, learning_rate=0.001, topk=[5], valid_metric="NDCG@5", seed=2020,
+    metrics=["NDCG", "Recall", "Hit", "MRR", "GiniIndex", "PopularityPercentage"], metric_decimal_place=12,
+    eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "uni20"})
+
+
+def float_gender_copy(dst_root):
+    """tests/data/ml-100k with the gender token (M / F) as a 0 / 1 float column: what the PFCN / NFCF discriminators and
+    regularisers need; tests/test_run_recbole_gpu.py builds the same files"""
+    src = DST
+    dst = os.path.join(dst_root, "ml-100k")
+    os.makedirs(dst, exist_ok=True)
+    import shutil
+    for f in ("ml-100k.inter", "ml-100k.item"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    lines = open(os.path.join(src, "ml-100k.user")).read().splitlines()
+    with open(os.path.join(dst, "ml-100k.user"), "w") as f:
+        f.write("\n".join(["user_id:token\tgender:float"] +
+                          [l.split("\t")[0] + "\t" + ("1" if l.split("\t")[1] == "F" else "0") for l in lines[1:]]) + "\n")
+    return dst_root

@@ -464,6 +464,8 @@ class FairGoTrainer(CheckpointMixin):
         from .evaluator import EvalData, FullSortEvaluator
         from .sampled_eval import SampledEvalData, SampledEvaluator
         self.model.eval()
+        if hasattr(eval_data, "resample"):          # uni<N> source that redraws its negatives per evaluation
+            eval_data = eval_data.resample()
         if isinstance(eval_data, SampledEvalData):      # eval_args.mode uni<N> (the FairGo YAMLs' default): the same
             if getattr(self, "sampled_evaluator", None) is None:      # tables, scored on the candidate pairs only
                 self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items,

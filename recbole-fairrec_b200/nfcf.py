@@ -223,6 +223,8 @@ class NFCFTrainer(CheckpointMixin):
         from .interaction import Interaction
         from .sampled_eval import SampledEvaluator
         self.model.eval()
+        if hasattr(eval_data, "resample"):          # uni<N> source that redraws its negatives per evaluation
+            eval_data = eval_data.resample()
         if self.sampled_evaluator is None:
             self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, train_item_count)
         m = self.model

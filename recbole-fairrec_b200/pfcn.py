@@ -371,6 +371,8 @@ class PFCNTrainer(CheckpointMixin):
         from .interaction import Interaction
         from .sampled_eval import SampledEvaluator
         self.model.eval()
+        if hasattr(eval_data, "resample"):          # uni<N> source that redraws its negatives per evaluation
+            eval_data = eval_data.resample()
         if getattr(self, "sampled_evaluator", None) is None:
             self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, train_item_count)
         sst_list = (self.sst_attrs if self.filter_mode != "none" else None) if sst_list is None else sst_list

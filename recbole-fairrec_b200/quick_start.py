@@ -77,6 +77,7 @@ class BatchLoader:
         if pointwise_neg:                     # _batch_size_adaptation (general_dataloader.py:40-50): positives + negatives
             self.batch_size = max(self.batch_size // 2, 1)       # together fill one train_batch_size
         self.n = len(split[ds.uid_field])
+        self._order = np.arange(self.n)
         self.attrs = [a for a in (config["sst_attr_list"] or []) if a in ds.user_feat]
         self.neg_prefix = config["NEG_PREFIX"] or "neg_"
         if pairwise or pointwise_neg:
@@ -97,7 +98,11 @@ class BatchLoader:
             neg[bad] = np.random.randint(1, self.ds.item_num, size=int(bad.sum()))
 
     def __iter__(self):
-        order = torch.randperm(self.n).numpy() if self.shuffle else np.arange(self.n)
+        # the reference shuffles the train split IN PLACE at the start of every pass (abstract_dataloader.py:88-91 ->
+        # interaction.py:293-297): each permutation applies to the order the previous pass left behind
+        if self.shuffle:
+            self._order = self._order[torch.randperm(self.n).numpy()]
+        order = self._order
         uf, itf = self.ds.uid_field, self.ds.iid_field
         for b0 in range(0, self.n, self.batch_size):
             idx = order[b0:b0 + self.batch_size]
@@ -127,7 +132,7 @@ def _load_best(trainer, saved):
 def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=None, saved=False, argv=None):
     """quick_start.py:20-71 -> {'best_valid_score', 'valid_score_bigger', 'best_valid_result', 'test_result'}"""
     import recbole_fairrec_b200 as pkg
-    from .sampled_eval import SampledEvalData, sample_negatives
+    from .sampled_eval import ResamplingEvalSource, SampledEvalData, sample_negatives
     cfg = build_config(model, dataset, config_file_list, config_dict, argv)
     init_seed(cfg["seed"], cfg["reproducibility"] if cfg["reproducibility"] is not None else True)
     logger = getLogger()
@@ -164,8 +169,10 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         if mode == "full":
             return pkg.EvalData(users, hist, pos, sst_of_user, dev)
         neg_num = int(mode[3:])
-        neg = sample_negatives(pos, hist, ds.item_num, neg_num, np.random)
-        return SampledEvalData(users, pos, neg, sst_of_user, dev)
+        if cfg["eval_neg_resample"] is False:          # one fixed draw for all evaluations
+            return SampledEvalData(users, pos, sample_negatives(pos, hist, ds.item_num, neg_num, np.random), sst_of_user, dev)
+        # like the reference: negatives drawn anew at every evaluation, by the same calls on numpy's global RNG
+        return ResamplingEvalSource(users, pos, hist, sst_of_user, ds.item_num, neg_num, dev)
 
     name = cfg["model"]
     if name == "FOCF":
@@ -192,9 +199,11 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     elif name in ("FairGo_PMF", "FairGo_GCN"):
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
         trainer = pkg.FairGoTrainer(cfg, net)
-        loader = BatchLoader(cfg, ds, train, pairwise=False)
+        # the FairGo YAMLs leave `neg_sampling: {uniform: 1}` in force: the reference's pointwise loader appends one sampled
+        # item per interaction (same user, same rating column, label 0), abstract_dataloader.py:200-208
+        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
         valid, test = eval_data("valid"), eval_data("test")
-        best, best_res = trainer.fit(list(loader), valid, train_item_count=item_counter, saved=saved)
+        best, best_res = trainer.fit(loader, valid, train_item_count=item_counter, saved=saved)
         _load_best(trainer, saved)
         test_res = trainer.evaluate(test)
     elif name == "NFCF":

@@ -50,6 +50,44 @@ def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
     return out
 
 
+def sample_negatives_reference(pos_lists, used_lists, n_items, neg_num):
+    """The reference's own draws (sampler.py:159-175 through NegSampleEvalDataLoader._next_batch_data,
+    general_dataloader.py:128-140): users in evaluation order, for each ONE call `np.random.randint(1, n_items, p * neg_num)`
+    on numpy's global RNG, then the entries that hit a used item (train + the evaluated split, positives included) are
+    redrawn together until none is left.  Same calls on the same stream => the same negatives as the reference for a seed
+    (oracle/fuzz_loaders.py checks that against the live reference).  The reference draws them anew at EVERY evaluation;
+    `ResamplingEvalSource` does the same."""
+    out = []
+    for pos, used in zip(pos_lists, used_lists):
+        banned = np.zeros(n_items, bool)
+        banned[np.asarray(used, np.int64)] = True
+        banned[np.asarray(pos, np.int64)] = True
+        value = np.random.randint(1, n_items, neg_num * len(pos))
+        check = np.flatnonzero(banned[value])
+        while len(check) > 0:
+            redraw = np.random.randint(1, n_items, len(check))
+            value[check] = redraw
+            check = check[banned[redraw]]
+        out.append(value.astype(np.int64))
+    return out
+
+
+class ResamplingEvalSource:
+    """Evaluation split of the `uni<N>` mode whose negatives are drawn again at every evaluation, like the reference's
+    NegSampleEvalDataLoader does while it iterates: trainers call `.resample()` and evaluate the SampledEvalData it returns."""
+
+    def __init__(self, users, pos_lists, used_lists, sst_of_user, n_items, neg_num, device):
+        self.users, self.pos, self.used, self.sst = users, pos_lists, used_lists, sst_of_user
+        self.n_items, self.neg_num, self.device = int(n_items), int(neg_num), device
+
+    def __len__(self):
+        return len(self.users)
+
+    def resample(self):
+        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num)
+        return SampledEvalData(self.users, self.pos, neg, self.sst, self.device)
+
+
 class SampledEvalData:
     """Device-resident candidate lists: per eval user its positives followed by its sampled negatives."""
 
@@ -168,4 +206,5 @@ class SampledEvaluator(FullSortEvaluator):
         return self.finalize(self.collect(score_fn, data), data)
 
 
-__all__ = ["SampledEvalData", "SampledEvaluator", "sample_negatives", "sampled_topk", "OrderedDict", "FAIR_KEYS"]
+__all__ = ["SampledEvalData", "SampledEvaluator", "ResamplingEvalSource", "sample_negatives", "sample_negatives_reference",
+           "sampled_topk", "OrderedDict", "FAIR_KEYS"]

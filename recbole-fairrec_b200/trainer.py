@@ -183,6 +183,8 @@ class FOCFTrainer:
             self.model.load_other_parameter(checkpoint.get("other_parameter"))
         self.model.eval()
         from .sampled_eval import SampledEvalData, SampledEvaluator
+        if hasattr(eval_data, "resample"):          # uni<N> source that redraws its negatives per evaluation
+            eval_data = eval_data.resample()
         if isinstance(eval_data, SampledEvalData):      # eval_args.mode uni<N>: sampled-negative ranking evaluation
             if getattr(self, "sampled_evaluator", None) is None:
                 self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, self._train_item_count)

@@ -1,0 +1,126 @@
+"""CPU "shadow runs": this package's ingestion, seeding, model construction, loaders and epoch schedule drive the ORACLE's
+step arithmetic (pinned on the reference, tests/test_oracle_golden.py + oracle/fuzz_*.py) instead of the CUDA kernels, and
+the per-epoch training losses are compared with the unmodified reference's own run of the same configuration from the same
+raw files (tests/golden/e2e_<model>.npz, oracle/gen_golden.py e2e).  Together with the GPU parity tests of the kernels
+against the same oracle this closes the end-to-end chain for the MLP families without a GPU; the direct GPU comparison is
+tests/test_run_recbole_gpu.py::test_mlp_family_end_to_end_from_raw_files_matches_the_reference_run."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import make_test_data as mtd
+
+HERE = os.path.dirname(__file__)
+
+
+def _setup(model, tmp_path):
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.atomic import AtomicDataset, used_and_positive_lists
+    from recbole_fairrec_b200.quick_start import BatchLoader, build_config, init_seed
+    root = mtd.float_gender_copy(str(tmp_path / "data"))
+    cfg = build_config(model, "ml-100k", None, dict(mtd.FAMILY_E2E_BASE, **mtd.FAMILY_E2E[model], data_path=root, device="cpu"))
+    init_seed(cfg["seed"])
+    ds = AtomicDataset(cfg)
+    splits = ds.build()
+
+    class View:                              # what run_recbole hands the models (quick_start.TrainView)
+        num = staticmethod(ds.num)
+        inter_feat = {k: torch.from_numpy(v) for k, v in splits[0].items()}
+        get_user_feature = staticmethod(ds.get_user_feature)
+        inter_matrix = staticmethod(ds.inter_matrix)
+
+    net = getattr(pkg, model)(cfg, View)     # consumes torch's RNG like the reference's constructor
+    pairwise = model.startswith("PFCN")
+    loader = BatchLoader(cfg, ds, splits[0], pairwise=pairwise, pointwise_neg=not pairwise)
+    users, hist, pos = used_and_positive_lists(splits, "valid")
+    return cfg, ds, net, loader, (users, hist, pos)
+
+
+def test_nfcf_stage1_shadow_run_reproduces_the_reference_epoch_losses(tmp_path):
+    from oracle import nfcf_oracle as no
+    from recbole_fairrec_b200.sampled_eval import sample_negatives_reference
+    g = np.load(os.path.join(HERE, "golden", "e2e_nfcf.npz"))
+    cfg, ds, net, loader, (users, hist, pos) = _setup("NFCF", tmp_path)
+    f = lambda t: t.detach().numpy().copy()
+    U, I = f(net.user_embedding.weight), f(net.item_embedding.weight)
+    lin = list(net.mlp_layers.linears())
+    Ws, bs = [f(m.weight) for m in lin], [f(m.bias) for m in lin]
+    from oracle.focf_oracle import adam_step
+    params = [U, I] + [t for pair in zip(Ws, bs) for t in pair]
+    m, v = [np.zeros_like(t) for t in params], [np.zeros_like(t) for t in params]
+    t, epoch_losses, steps = 0, [], []
+    for epoch in range(2):
+        total = 0.0
+        for b in loader:                                               # trainer.py:181-196
+            uid, iid, label = b["user_id"].numpy(), b["item_id"].numpy(), b["label"].numpy()
+            loss, _, dU, dI, dWs, dbs = no.loss_and_grads(U, I, Ws, bs, uid, iid, label, b["gender"].numpy(), False, 0.1)
+            steps.append(float(loss))
+            t += 1
+            grads = [dU, dI] + [x for pair in zip(dWs, dbs) for x in pair]
+            for prm, gr, mm, vv in zip(params, grads, m, v):
+                adam_step(prm, gr, mm, vv, t, 1e-3, 0.9, 0.999, 1e-8, 1e-6)
+            total += float(loss)
+        epoch_losses.append(total)
+        sample_negatives_reference(pos, hist, ds.item_num, 20)          # the validation pass draws its negatives here
+    # all 158 batches are the reference's (oracle/fuzz_loaders.py); the first epoch's loss agrees to float32 rounding.  In the
+    # second epoch two float32 evaluations of the same schedule drift apart (per-step losses 1e-7 until step ~90, then
+    # 2-5e-4: Adam's m / sqrt(v) amplifies rounding on rarely-updated rows) -- conditioning, not semantics
+    np.testing.assert_allclose(steps[:79], g["first_epoch_step_losses"], rtol=2e-6)        # every step of the first epoch
+    np.testing.assert_allclose(epoch_losses[0], g["epoch_losses"][0, 0], rtol=1e-6)
+    np.testing.assert_allclose(epoch_losses[1], g["epoch_losses"][1, 0], rtol=1e-3)
+
+
+def test_pfcn_pmf_shadow_run_reproduces_the_reference_epoch_losses(tmp_path):
+    from oracle import pfcn_oracle as po
+    from recbole_fairrec_b200.sampled_eval import sample_negatives_reference
+    g = np.load(os.path.join(HERE, "golden", "e2e_pfcn_pmf.npz"))
+    cfg, ds, net, loader, (users, hist, pos) = _setup("PFCN_PMF", tmp_path)
+    st = {f"base.{k}": v.detach().clone() for k, v in net.state_dict().items()}
+    for name, mods in (("filter", net.filter_layer), ("dis", net.dis_layer_dict)):
+        for k, mod in mods.items():
+            st.update({f"{name}_{k}.{kk}": vv.detach().clone() for kk, vv in mod.state_dict().items()})
+    fkeys, dkeys = po.param_groups(st)
+    for k in fkeys + dkeys:
+        st[k].requires_grad_(True)
+    opt_f = torch.optim.Adam([st[k] for k in fkeys], lr=1e-3, weight_decay=1e-4)
+    opt_d = torch.optim.Adam([st[k] for k in dkeys], lr=1e-3, weight_decay=1e-4)
+    attrs = ["gender"]
+    sst_dict, sst_size = {"gender": 1}, {"gender": 2}
+    epoch_losses, f_steps, d_steps = [], [], []
+    for epoch in range(2):
+        mask = np.zeros(1)
+        while mask.sum() == 0:                                          # trainer.py:878-881
+            mask = np.random.choice([0, 1], 1)
+        f_loss = d_loss = 0.0
+        for b in loader:                                               # filter + base pass
+            labels = {"gender": b["gender"]}
+            opt_f.zero_grad()
+            loss = po.calculate_loss(st, "PFCN_PMF", b["user_id"], b["item_id"], b["neg_item_id"], labels, attrs, sst_dict,
+                                     sst_size, "sm", 1, "leakyrelu", 10.0)
+            loss.backward()
+            opt_f.step()
+            f_loss += loss.item()
+            f_steps.append(loss.item())
+        for b in loader:                                               # discriminator pass
+            opt_d.zero_grad()
+            loss = po.dis_loss(st, "PFCN_PMF", b["user_id"], {"gender": b["gender"]}, attrs, sst_dict, sst_size, "sm", 1,
+                               "leakyrelu")
+            loss.backward()
+            opt_d.step()
+            d_loss += loss.item()
+            d_steps.append(loss.item())
+        epoch_losses.append([f_loss, d_loss])
+        sample_negatives_reference(pos, hist, ds.item_num, 20)
+    # identical batches and negatives throughout (oracle/fuzz_loaders.py); the first steps agree to float32 rounding, then the
+    # trajectory -- a BatchNorm'd 7-layer discriminator trained by Adam against the filter -- amplifies that rounding: two
+    # torch-CPU evaluations of the same schedule (the reference's modules vs the oracle's functional restatement) are
+    # 2e-5 apart at step 16, 5e-4 at step 32 and up to 2e-2 on single discriminator steps.  Conditioning, not semantics:
+    # (even the number of BLAS threads moves step 4 by 6e-4)
+    np.testing.assert_allclose(f_steps[:3], g["first_epoch_step_losses"][:3], rtol=1e-5)
+    np.testing.assert_allclose(f_steps[:40], g["first_epoch_step_losses"], rtol=1e-2)
+    np.testing.assert_allclose(d_steps[:40], g["first_epoch_dis_step_losses"], rtol=1e-1)
+    got = np.array(epoch_losses)
+    np.testing.assert_allclose(got[0, 0], g["epoch_losses"][0, 0], rtol=1e-2)       # first epoch: filter pass, sum of 40 steps
+    np.testing.assert_allclose(got[0, 1], g["epoch_losses"][0, 1], rtol=1e-1)       # ... discriminator pass
+    np.testing.assert_allclose(got[1], g["epoch_losses"][1], rtol=2e-1)             # second epoch: same ballpark only

@@ -109,3 +109,51 @@ def test_nfcf_two_stages_from_raw_files(tmp_path):
     assert 0.0 < s2["test_result"]["ndcg@5"] <= 1.0
     assert np.isfinite(s2["test_result"]["Differential Fairness of sensitive attribute gender"]) if \
         "Differential Fairness of sensitive attribute gender" in s2["test_result"] else True
+
+
+@pytest.mark.skipif(os.environ.get("FAIRREC_E2E_FAMILIES") != "1",
+                    reason="written after the round's last GPU session; enable with FAIRREC_E2E_FAMILIES=1 (DESIGN.md section 7)")
+@pytest.mark.parametrize("model", ["PFCN_PMF", "NFCF"])
+def test_mlp_family_end_to_end_from_raw_files_matches_the_reference_run(model, tmp_path):
+    """run_recbole(model, 'ml-100k') from the RAW atomic files against the unmodified reference's own run of the same
+    configuration (tests/golden/e2e_<model>.npz, oracle/gen_golden.py e2e; dropout-free): ids, split, initial weights, the
+    in-place epoch shuffles, the uniform training negatives and the per-evaluation `uni20` negatives all follow from the
+    seed by the same RNG calls (oracle/fuzz_loaders.py, tests/test_host_logic.py), so the run follows the reference's as far as float32 conditioning lets two correct implementations agree."""
+    from oracle import make_test_data as mtd
+    from recbole_fairrec_b200.quick_start import run_recbole
+    import recbole_fairrec_b200 as pkg
+    g = np.load(os.path.join(HERE, "golden", f"e2e_{model.lower()}.npz"))
+    root = mtd.float_gender_copy(str(tmp_path / "data"))
+    cfg = dict(mtd.FAMILY_E2E_BASE, **mtd.FAMILY_E2E[model], data_path=root, verbose=False, stopping_step=100)
+    cls = pkg.PFCNTrainer if model.startswith("PFCN") else pkg.NFCFTrainer
+    seen, valids = [], []
+    orig_train, orig_eval = cls._train_epoch, cls.evaluate
+
+    def spy_train(self, *a, **k):
+        out = orig_train(self, *a, **k)
+        seen.append(list(out) if isinstance(out, tuple) else [out])
+        return out
+
+    def spy_eval(self, *a, **k):
+        out = orig_eval(self, *a, **k)
+        valids.append(out)
+        return out
+
+    cls._train_epoch, cls.evaluate = spy_train, spy_eval
+    try:
+        out = run_recbole(model, "ml-100k", None, cfg)
+    finally:
+        cls._train_epoch, cls.evaluate = orig_train, orig_eval
+    # the trajectories of these models amplify float32 rounding (tests/test_e2e_shadow.py measures it between two CPU
+    # evaluations of the same schedule): the first epoch's summed loss is tight for NFCF, everything later is loose
+    seen = np.array(seen, np.float64)
+    if model == "NFCF":
+        np.testing.assert_allclose(seen[0], g["epoch_losses"][0], rtol=1e-4)
+        np.testing.assert_allclose(seen[1], g["epoch_losses"][1], rtol=5e-3)
+    else:
+        np.testing.assert_allclose(seen[:, 0], g["epoch_losses"][:, 0], rtol=2e-2)
+        np.testing.assert_allclose(seen[:, 1], g["epoch_losses"][:, 1], rtol=2e-1)
+    names = [str(k) for k in g["metric_names"]]
+    for got, ref in zip(valids[:2] + [out["test_result"]], list(g["valid_metrics"]) + [g["test_metrics"]]):
+        for k, r in zip(names, ref):
+            assert abs(got[k] - r) <= 0.05, (k, got[k], r)
