@@ -411,11 +411,33 @@ class FairGoTrainer(CheckpointMixin):
             optimizer.step()
         return total
 
-    def pretrain(self, train_data, epochs=None):
-        """trainer.py:606-685 without the validation / checkpoint bookkeeping"""
+    def pretrain(self, train_data, epochs=None, valid_data=None):
+        """trainer.py:606-685: rating-loss epochs over the embedding tables (and the GCN of FairGo_GCN).  With `valid_data`
+        the reference's bookkeeping applies: evaluate after every epoch, early stopping on `valid_metric` after
+        `stopping_step` non-improving evaluations, and the BEST pretrained state -- not the last -- goes into the
+        fine-tune stage (the reference reloads its best pretrain checkpoint, trainer.py:677-679; kept in memory here)."""
+        from .trainer import early_stopping
         self.model.train_stage = "pretrain"
-        losses = [self._pass(train_data, self.model.calculate_loss, self.optimizer_pretrain, None)
-                  for _ in range(epochs if epochs is not None else self.pretrain_epochs)]
+        n = epochs if epochs is not None else self.pretrain_epochs
+        losses = []
+        if not valid_data:
+            losses = [self._pass(train_data, self.model.calculate_loss, self.optimizer_pretrain, None) for _ in range(n)]
+        else:
+            metric = (self.config["valid_metric"] or "NDCG@5").lower()
+            bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True
+            best, cur, best_state = (-np.inf if bigger else np.inf), 0, None
+            for _ in range(n):
+                losses.append(self._pass(train_data, self.model.calculate_loss, self.optimizer_pretrain, None))
+                res = self.evaluate(valid_data)            # pretrain stage: the raw tables (FairGo_GCN: the GCN output)
+                best, cur, stop, update = early_stopping(res[metric], best, cur,
+                                                         max_step=self.config["stopping_step"] or 10, bigger=bigger)
+                if update:
+                    best_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+                if stop:
+                    break
+            if best_state is not None:
+                self.model.load_state_dict(best_state)
+            self.pretrain_valid_score = best
         self.model.train_stage = "finetune"
         self.model._ego = None          # the tables moved under the cached [N, d] concatenation
         return losses
@@ -493,7 +515,7 @@ class FairGoTrainer(CheckpointMixin):
             self.data_collect(train_item_count)
         resumed = getattr(self, "start_epoch", 0) > 0
         if self.model.train_stage == "pretrain" and not resumed:
-            self.pretrain(train_data)
+            self.pretrain(train_data, valid_data=valid_data)
         self.model.train_stage = "finetune"
         metric = (self.config["valid_metric"] or "NDCG@5").lower()
         bigger = self.config["valid_metric_bigger"] if self.config["valid_metric_bigger"] is not None else True

@@ -491,3 +491,33 @@ def test_initial_weights_equal_the_live_references_for_a_seed():
     assert not mine.user_embedding.weight.requires_grad and mine.item_embedding.weight.requires_grad
     for r, m in zip([x for x in ref.mlp_layers.mlp_layers if isinstance(x, torch.nn.Linear)], mine.mlp_layers.linears()):
         assert torch.equal(r.weight.data, m.weight.data) and torch.equal(r.bias.data, m.bias.data)
+
+
+def test_fairgo_pretrain_keeps_the_best_validated_state(monkeypatch):
+    """trainer.py:606-685: validation after every pretrain epoch, early stopping, and the BEST pretrained tables go into the
+    fine-tune stage"""
+    cfg, model, trainer = _family("FairGo_GCN", 5)
+    cfg["stopping_step"], cfg["valid_metric"] = 1, "NDCG@5"
+    trainer.pretrain_epochs = 10
+    scores = iter([0.1, 0.4, 0.3, 0.2, 0.9])
+    calls = []
+
+    def fake_pass(self, data, loss_func, optimizer, sst_list):
+        with torch.no_grad():
+            self.model.user_embedding_layer.weight.add_(1.0)     # "training" moves the table by one per epoch
+        calls.append("train")
+        return 1.0
+
+    monkeypatch.setattr(type(trainer), "_pass", fake_pass)
+    monkeypatch.setattr(type(trainer), "evaluate", lambda self, data: {"ndcg@5": next(scores)})
+    u0 = model.user_embedding_layer.weight.detach().clone()
+    losses = trainer.pretrain([None], valid_data=[None])
+    # epochs 1..4 ran (0.4 stands for two evaluations with stopping_step 1); the state of epoch 2 is restored
+    assert len(losses) == 4 and model.train_stage == "finetune" and trainer.pretrain_valid_score == 0.4
+    torch.testing.assert_close(model.user_embedding_layer.weight.detach(), u0 + 2.0)
+    # without validation data: the plain loop, last state
+    cfg2, model2, trainer2 = _family("FairGo_GCN", 6)
+    monkeypatch.setattr(type(trainer2), "_pass", fake_pass)
+    u0 = model2.user_embedding_layer.weight.detach().clone()
+    trainer2.pretrain([None], epochs=3)
+    torch.testing.assert_close(model2.user_embedding_layer.weight.detach(), u0 + 3.0)
