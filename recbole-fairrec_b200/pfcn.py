@@ -397,6 +397,46 @@ class PFCNTrainer(CheckpointMixin):
         return filter_loss, dis_loss
 
 
+    def attribute_subsets(self):
+        """trainer.py:1012-1013, 1076-1077: the non-empty subsets of `sst_attr_list`, by size, in combination order"""
+        import itertools
+        return [list(c) for i in range(1, len(self.sst_attrs) + 1) for c in itertools.combinations(self.sst_attrs, i)]
+
+    @torch.no_grad()
+    def pfcn_evaluate(self, eval_data, train_item_count=None):
+        """The reference's VALIDATION pass (trainer.py:985-1030): every user batch is scored under each non-empty attribute
+        subset with the SAME negatives and all of it goes into one collector struct, so the validation metrics are taken
+        over (subset, user) pairs.  Here: one draw of negatives, the candidate lists tiled once per subset, each tile scored
+        with its subset, one pass of the evaluation kernels over the whole.  One subset (a single attribute, or
+        filter_mode none) is the plain `evaluate`."""
+        from .interaction import Interaction
+        from .sampled_eval import SampledEvaluator
+        subsets = self.attribute_subsets() if self.filter_mode != "none" else [None]
+        if len(subsets) == 1 or not hasattr(eval_data, "resample_tiled"):
+            return self.evaluate(eval_data, None, train_item_count)
+        self.model.eval()
+        if getattr(self, "sampled_evaluator", None) is None:
+            self.sampled_evaluator = SampledEvaluator(self.config, self.model.n_items, train_item_count)
+        data, per_copy = eval_data.resample_tiled(len(subsets))
+        m, chunk = self.model, int(self.config["sampled_chunk_rows"] or (1 << 24))
+        parts = []
+        for s, sst_list in enumerate(subsets):
+            for a in range(s * per_copy, (s + 1) * per_copy, chunk):
+                b = min(a + chunk, (s + 1) * per_copy)
+                inter = Interaction({m.USER_ID: data.cand_uid[a:b], m.ITEM_ID: data.cand_items[a:b]})
+                parts.append(m.predict(inter, sst_list).view(-1).to(torch.float32))
+        ev = self.sampled_evaluator
+        return ev.finalize(ev.collect_scores(torch.cat(parts), data), data)
+
+    @torch.no_grad()
+    def evaluate_subsets(self, eval_data, train_item_count=None):
+        """The reference's TEST evaluation (trainer.py:1072-1086): one full evaluation per attribute subset, each with its own
+        draw of negatives -> {'<filter_mode>-<subset>': metric dict}"""
+        if self.filter_mode == "none":
+            return {self.filter_mode: self.evaluate(eval_data, None, train_item_count)}
+        return {"{}-{}".format(self.filter_mode, sst_list): self.evaluate(eval_data, sst_list, train_item_count)
+                for sst_list in self.attribute_subsets()}
+
     def fit(self, train_data, valid_data=None, epochs=None, train_item_count=None, verbose=False, saved=False):
         """trainer.py:300-380 around the alternating epochs: early stopping on `valid_metric` (all attributes filtered,
         trainer.py:1010-1093), check-point on improvement when saved=True (checkpoint.py), continue at `start_epoch` after
@@ -414,7 +454,7 @@ class PFCNTrainer(CheckpointMixin):
                 print(f"epoch {epoch}: losses {losses}")
             if not valid_data:
                 continue
-            res = self.evaluate(valid_data, None, train_item_count)
+            res = self.pfcn_evaluate(valid_data, train_item_count)
             best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
                                                      bigger=bigger)
             self.best_valid_score, self.cur_step = best, cur

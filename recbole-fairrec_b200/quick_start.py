@@ -195,7 +195,10 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         best, best_res = trainer.fit(loader, valid, train_item_count=item_counter, saved=saved,
                                      verbose=cfg["verbose"] is not False)
         _load_best(trainer, saved)
-        test_res = trainer.evaluate(test, None, item_counter)
+        # several attributes: one evaluation per attribute subset, keyed like the reference's ('sm-[...]', trainer.py:1086);
+        # a single subset comes back flat
+        multi = net.filter_mode != "none" and len(trainer.attribute_subsets()) > 1
+        test_res = trainer.evaluate_subsets(test, item_counter) if multi else trainer.evaluate(test, None, item_counter)
     elif name in ("FairGo_PMF", "FairGo_GCN"):
         net = getattr(pkg, name)(cfg, TrainView).to(dev)
         trainer = pkg.FairGoTrainer(cfg, net)

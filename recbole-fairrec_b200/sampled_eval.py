@@ -87,6 +87,15 @@ class ResamplingEvalSource:
         neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num)
         return SampledEvalData(self.users, self.pos, neg, self.sst, self.device)
 
+    def resample_tiled(self, copies):
+        """ONE draw of negatives, the user list repeated `copies` times (copy-major): the layout in which the reference's
+        PFCN validation scores every batch under each attribute subset and collects everything into one struct
+        (trainer.py:1010-1023).  Returns (data, candidate rows per copy)."""
+        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num)
+        data = SampledEvalData(np.tile(np.asarray(self.users, np.int64), copies), list(self.pos) * copies, neg * copies,
+                               self.sst, self.device)
+        return data, int(data.cand_uid.numel()) // copies
+
 
 class SampledEvalData:
     """Device-resident candidate lists: per eval user its positives followed by its sampled negatives."""
@@ -167,6 +176,11 @@ class SampledEvaluator(FullSortEvaluator):
         else:       # bound the activations of MLP scorers (PFCN predict over ~1e7 candidate rows); rows are independent
             scores = torch.cat([score_fn(data.cand_uid[a:a + chunk], data.cand_items[a:a + chunk]).view(-1).to(torch.float32)
                                 for a in range(0, C, chunk)])
+        return self.collect_scores(scores, data)
+
+    @torch.no_grad()
+    def collect_scores(self, scores, data):
+        """the pass over given candidate scores (float32 [C], candidate order of `data`)"""
         ids, sc, rec_topk = sampled_topk(data, scores, self.K, self.n_items)
         pos_score = scores[data.pos_idx].contiguous()
         out = {"topk_id": ids, "topk_score": sc, "rec_topk": rec_topk, "pos_score": pos_score}

@@ -521,3 +521,43 @@ def test_fairgo_pretrain_keeps_the_best_validated_state(monkeypatch):
     u0 = model2.user_embedding_layer.weight.detach().clone()
     trainer2.pretrain([None], epochs=3)
     torch.testing.assert_close(model2.user_embedding_layer.weight.detach(), u0 + 3.0)
+
+
+def test_pfcn_validation_scores_every_attribute_subset_on_one_draw_of_negatives(monkeypatch):
+    """trainer.py:985-1030: the candidate lists are tiled once per non-empty attribute subset (same negatives), tile s is
+    scored with subset s, and ONE pass runs over the whole; trainer.py:1072-1086: the test evaluation is one pass per subset"""
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.sampled_eval import ResamplingEvalSource, SampledEvaluator
+    cfg, model, trainer = _family("PFCN_MLP", 8)                         # attributes gender, age
+    assert trainer.attribute_subsets() == [["gender"], ["age"], ["gender", "age"]]
+    rng = np.random.default_rng(0)
+    users = np.array([3, 5, 9, 11])
+    pos = [np.array([1, 2]), np.array([4]), np.array([7, 8, 9]), np.array([2])]
+    used = [np.array([5, 6]), np.array([1, 2, 3]), np.array([10]), np.array([20, 21])]
+    sst = {"gender": rng.integers(0, 2, 40).astype(np.float32), "age": rng.integers(0, 3, 40).astype(np.float32)}
+    src = ResamplingEvalSource(users, pos, used, sst, 30, 4, torch.device("cpu"))
+    np.random.seed(1)
+    data, per_copy = src.resample_tiled(3)
+    assert data.n == 12 and per_copy == sum(len(p) * 5 for p in pos) and data.cand_uid.numel() == 3 * per_copy
+    assert torch.equal(data.cand_items[:per_copy], data.cand_items[per_copy:2 * per_copy])          # same negatives per tile
+    assert torch.equal(data.users, torch.tensor(list(users) * 3, dtype=torch.int32))
+    calls, captured = [], {}
+
+    def fake_predict(inter, sst_list=None):
+        calls.append((list(sst_list), int(inter["user_id"].numel())))
+        return torch.full((inter["user_id"].numel(),), float(len(calls)))
+
+    monkeypatch.setattr(model, "predict", fake_predict)
+    monkeypatch.setattr(SampledEvaluator, "collect_scores", lambda self, scores, d: captured.update(scores=scores, data=d) or {})
+    monkeypatch.setattr(SampledEvaluator, "finalize", lambda self, out, d, rounded=True: {"ndcg@5": 0.5})
+    cfg["metrics"] = ["NDCG"]
+    np.random.seed(1)
+    res = trainer.pfcn_evaluate(src)
+    assert res == {"ndcg@5": 0.5} and calls == [(["gender"], per_copy), (["age"], per_copy), (["gender", "age"], per_copy)]
+    sc = captured["scores"]
+    assert sc.numel() == 3 * per_copy and torch.equal(sc, torch.repeat_interleave(torch.tensor([1.0, 2.0, 3.0]), per_copy))
+    assert torch.equal(captured["data"].cand_items, data.cand_items)                              # same RNG state, same draw
+    # test evaluation: one pass (and one draw) per subset, keyed like the reference
+    monkeypatch.setattr(type(trainer), "evaluate", lambda self, d, sst_list=None, c=None: {"subset": list(sst_list)})
+    out = trainer.evaluate_subsets(src)
+    assert list(out) == ["sm-['gender']", "sm-['age']", "sm-['gender', 'age']"] and out["sm-['age']"] == {"subset": ["age"]}
