@@ -764,11 +764,52 @@ def run_family_e2e(model_name):
         os.chdir(cwd)
 
 
+def run_focf_uni_e2e():
+    """FOCF on ml-100k through the reference's run_recbole steps with the evaluation mode of its own YAML (`uni<N>`,
+    FOCF.yaml:28): the numpy RNG stream interleaves FOCFDataLoader's item draws with the negatives the evaluation loader
+    draws at every validation -> tests/golden/e2e_focf_uni.npz (per-epoch losses, validation / test metrics)"""
+    import tempfile
+    import yaml
+    from recbole.config import Config
+    from recbole.data import create_dataset, data_preparation
+    from recbole.utils import init_seed, get_model, get_trainer
+    from make_test_data import FOCF_UNI_E2E
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        with open("c.yaml", "w") as f:
+            yaml.safe_dump(dict(FOCF_UNI_E2E, use_gpu=False, state="WARNING", show_progress=False), f)
+        sys.argv = sys.argv[:1]
+        config = Config(model="FOCF", dataset="ml-100k", config_file_list=["c.yaml"])
+        init_seed(config["seed"], config["reproducibility"])
+        dataset = create_dataset(config)
+        train_data, valid_data, test_data = data_preparation(config, dataset)
+        model = get_model("FOCF")(config, train_data.dataset).to(config["device"])
+        trainer = get_trainer(config["MODEL_TYPE"], config["model"])(config, model)
+        trainer.eval_collector.data_collect(train_data)
+        losses, valids = [], []
+        for ep in range(config["epochs"]):
+            losses.append(float(trainer._train_epoch(train_data, ep)))
+            valids.append(trainer.evaluate(valid_data, load_best_model=False))
+        test = trainer.evaluate(test_data, load_best_model=False)
+        names = list(test.keys())
+        np.savez_compressed(os.path.join(OUT, "e2e_focf_uni.npz"), epoch_losses=np.array(losses), metric_names=np.array(names),
+                            valid_metrics=np.array([[float(r[k]) for k in names] for r in valids]),
+                            test_metrics=np.array([float(test[k]) for k in names]))
+        print("e2e focf uni:", losses, {k: float(v) for k, v in test.items()})
+    finally:
+        os.chdir(cwd)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":
         for m in FAMILY_E2E:
             run_family_e2e(m)
+        run_focf_uni_e2e()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "e2e_focf":
+        run_focf_uni_e2e()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "ingest":
         run_ingest()

@@ -123,3 +123,12 @@ def float_gender_copy(dst_root):
         f.write("\n".join(["user_id:token\tgender:float"] +
                           [l.split("\t")[0] + "\t" + ("1" if l.split("\t")[1] == "F" else "0") for l in lines[1:]]) + "\n")
     return dst_root
+
+
+FOCF_UNI_E2E = dict(
+    data_path=os.path.dirname(DST), RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0},
+    load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"], "item": ["item_id"]},
+    sst_attr_list=["gender"], fair_objective="value", fair_weight=1.0, neg_sampling=None, weight_decay=0.001,
+    learning_rate=0.001, embedding_size=64, epochs=2, train_batch_size=2048, topk=[5], valid_metric="NDCG@5", seed=2020,
+    metrics=["NDCG", "Recall", "Hit", "MRR", "GiniIndex", "PopularityPercentage"], metric_decimal_place=12,
+    eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "uni20"})

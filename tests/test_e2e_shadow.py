@@ -124,3 +124,67 @@ def test_pfcn_pmf_shadow_run_reproduces_the_reference_epoch_losses(tmp_path):
     np.testing.assert_allclose(got[0, 0], g["epoch_losses"][0, 0], rtol=1e-2)       # first epoch: filter pass, sum of 40 steps
     np.testing.assert_allclose(got[0, 1], g["epoch_losses"][0, 1], rtol=1e-1)       # ... discriminator pass
     np.testing.assert_allclose(got[1], g["epoch_losses"][1], rtol=2e-1)             # second epoch: same ballpark only
+
+
+def test_focf_uni_mode_shadow_run_reproduces_the_reference_losses_and_metrics():
+    """FOCF with the evaluation mode of its own YAML (`uni<N>`): numpy's RNG interleaves the loader's item draws with the
+    negatives drawn at every validation.  This package's ingestion + construction + FOCFDataLoader(reference draws) +
+    per-evaluation negatives drive oracle/focf_oracle.py (loss, gradients, dense Adam) and oracle/sampled_oracle.py
+    (candidate rows, top-K, metrics) -> the reference's per-epoch losses and its validation / test metric dicts
+    (tests/golden/e2e_focf_uni.npz)."""
+    import recbole_fairrec_b200 as pkg
+    from oracle import focf_oracle as fo
+    from oracle import sampled_oracle as so
+    from recbole_fairrec_b200.atomic import AtomicDataset, used_and_positive_lists
+    from recbole_fairrec_b200.quick_start import build_config, init_seed
+    from recbole_fairrec_b200.sampled_eval import sample_negatives_reference
+    g = np.load(os.path.join(HERE, "golden", "e2e_focf_uni.npz"))
+    cfg = build_config("FOCF", "ml-100k", None, dict(mtd.FOCF_UNI_E2E, device="cpu"))
+    init_seed(cfg["seed"])
+    ds = AtomicDataset(cfg)
+    splits = ds.build()
+    tr = splits[0]
+
+    class View:
+        num = staticmethod(ds.num)
+        inter_feat = {"rating": torch.from_numpy(tr["rating"])}
+
+    net = pkg.FOCF(cfg, View)
+    U, I = net.user_embedding_layer.weight.detach().numpy().copy(), net.item_embedding_layer.weight.detach().numpy().copy()
+    gender = ds.user_feat["gender"].astype(np.float32)
+    train = pkg.TrainData(tr["user_id"], tr["item_id"], tr["rating"], gender, ds.user_num, ds.item_num, torch.device("cpu"))
+    loader = pkg.FOCFDataLoader(cfg, train, mode="reference")
+    counts = {int(i): int(c) for i, c in enumerate(np.bincount(tr["item_id"], minlength=ds.item_num)) if c}
+    names = [str(k) for k in g["metric_names"]]
+    mU, vU, mI, vI = np.zeros_like(U), np.zeros_like(U), np.zeros_like(I), np.zeros_like(I)
+
+    def evaluate(phase):
+        users, hist, pos = used_and_positive_lists(splits, phase)
+        neg = sample_negatives_reference(pos, hist, ds.item_num, 20)
+        cands = list(zip(pos, neg))
+        rows = so.dense_rows(U, I, users, cands, ds.item_num, 5.0)
+        ids, rec_topk, pos_score = so.collect(rows, cands, 5)
+        sst_of_pos = np.repeat(gender[users], [len(p) for p in pos])
+        return so.metrics(ids, rec_topk, pos_score, np.concatenate(pos), sst_of_pos, [5], ds.item_num, counts)
+
+    t, losses, valids = 0, [], []
+    for epoch in range(2):
+        total = 0.0
+        for _ in range(len(loader)):
+            items = loader._draw_batch()
+            rows = np.concatenate([np.arange(train.item_off_h[i], train.item_off_h[i + 1]) for i in items])
+            uid, iid, rating = train.uid_h[rows].astype(np.int64), train.iid_h[rows].astype(np.int64), train.rating_h[rows]
+            sst = gender[uid]
+            total += float(fo.calculate_loss(U, I, uid, iid, rating, sst, "value", 1.0))
+            _, _, dU, dI = fo.grads(U, I, uid, iid, rating, sst, "value", 1.0)
+            t += 1
+            fo.adam_step(U, dU, mU, vU, t, 1e-3, 0.9, 0.999, 1e-8, 1e-3)
+            fo.adam_step(I, dI, mI, vI, t, 1e-3, 0.9, 0.999, 1e-8, 1e-3)
+        losses.append(total)
+        valids.append(evaluate("valid"))
+    test = evaluate("test")
+    np.testing.assert_allclose(losses, g["epoch_losses"], rtol=1e-5)
+    for got, ref in zip(valids + [test], list(g["valid_metrics"]) + [g["test_metrics"]]):
+        for k, r in zip(names, ref):
+            # identical candidates; a near-tie flip inside a top-5 moves a ranking metric by O(1/943)
+            assert abs(got[k] - r) <= (2.0 / 943 if "@" in k else 1e-6), (k, got[k], r)
