@@ -801,12 +801,68 @@ def run_focf_uni_e2e():
         os.chdir(cwd)
 
 
+def run_fairgo_e2e():
+    """FairGo_PMF on ml-100k through the reference's FairGoTrainer.fit steps (trainer.py:583-592): validated pretrain with
+    early stopping and best-checkpoint reload (606-685), reset_params, alternating fine-tune epochs with a validation after
+    each, test evaluation; full-sort mode, all 12 metrics -> tests/golden/e2e_fairgo_pmf.npz"""
+    import tempfile
+    import yaml
+    from recbole.config import Config
+    from recbole.data import create_dataset, data_preparation
+    from recbole.utils import init_seed, get_model, get_trainer
+    from make_test_data import FAIRGO_E2E
+    root = float_gender_copy(tempfile.mkdtemp())
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        with open("c.yaml", "w") as f:
+            yaml.safe_dump(dict(FAIRGO_E2E, data_path=root, use_gpu=False, state="WARNING", show_progress=False,
+                                save_sst_embed=False), f)
+        sys.argv = sys.argv[:1]
+        config = Config(model="FairGo_PMF", dataset="ml-100k", config_file_list=["c.yaml"])
+        init_seed(config["seed"], config["reproducibility"])
+        dataset = create_dataset(config)
+        train_data, valid_data, test_data = data_preparation(config, dataset)
+        model = get_model("FairGo_PMF")(config, train_data.dataset).to(config["device"])
+        trainer = get_trainer(config["MODEL_TYPE"], config["model"])(config, model)
+        per_epoch = []           # validation of every pretrain epoch (the reference keeps only the best)
+        o_valid = trainer._valid_epoch
+        trainer._valid_epoch = lambda *a, **k: (lambda r: (per_epoch.append(r[1]), r)[1])(o_valid(*a, **k))
+        pre_score, pre_result = trainer.pretrain(train_data, valid_data, verbose=False, saved=True)
+        trainer._valid_epoch = o_valid
+        pre_losses = [float(trainer.train_loss_dict[k]) for k in sorted(trainer.train_loss_dict)]
+        trainer.reset_params()
+        trainer.eval_collector.data_collect(train_data)
+        losses, valids = [], []
+        for ep in range(config["epochs"]):
+            dis_loss, filter_loss = trainer._train_epoch(train_data, ep)
+            losses.append([float(dis_loss), float(filter_loss)])
+            _, res = trainer._valid_epoch(valid_data)
+            valids.append(res)
+        test = trainer.evaluate(test_data, load_best_model=False)
+        names = list(test.keys())
+        np.savez_compressed(os.path.join(OUT, "e2e_fairgo_pmf.npz"), pretrain_losses=np.array(pre_losses),
+                            pretrain_best_valid=float(pre_score), epoch_losses=np.array(losses), metric_names=np.array(names),
+                            pretrain_valid=np.array([float(pre_result[k]) for k in names]),
+                            pretrain_valid_per_epoch=np.array([[float(r[k]) for k in names] for r in per_epoch]),
+                            pretrain_best_epoch=int(np.argmax([float(r["ndcg@5"]) for r in per_epoch])),
+                            valid_metrics=np.array([[float(r[k]) for k in names] for r in valids]),
+                            test_metrics=np.array([float(test[k]) for k in names]))
+        print("e2e fairgo:", pre_losses, pre_score, losses, float(test["ndcg@5"]))
+    finally:
+        os.chdir(cwd)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "e2e_fairgo":
+        run_fairgo_e2e()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":
         for m in FAMILY_E2E:
             run_family_e2e(m)
         run_focf_uni_e2e()
+        run_fairgo_e2e()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "e2e_focf":
         run_focf_uni_e2e()

@@ -132,3 +132,15 @@ FOCF_UNI_E2E = dict(
     learning_rate=0.001, embedding_size=64, epochs=2, train_batch_size=2048, topk=[5], valid_metric="NDCG@5", seed=2020,
     metrics=["NDCG", "Recall", "Hit", "MRR", "GiniIndex", "PopularityPercentage"], metric_decimal_place=12,
     eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "uni20"})
+
+
+FAIRGO_E2E = dict(
+    RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0}, sst_attr_list=["gender"],
+    load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"]}, neg_sampling={"uniform": 1},
+    load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1], embedding_size=64, n_layers=2,
+    dis_hidden_size_list=[16, 8, 4], filter_hidden_size_list=[128, 64], activation="leakyrelu", fair_weight=0.1,
+    pretrain_epochs=3, train_epoch_interval=1, weight_decay=0.0001, learning_rate=0.001, epochs=2, train_batch_size=2048,
+    stopping_step=10, topk=[5], valid_metric="NDCG@5", seed=2020, metric_decimal_place=12,
+    metrics=["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage", "ValueUnfairness",
+             "AbsoluteUnfairness", "UnderUnfairness", "OverUnfairness", "NonParityUnfairness"],
+    eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"})

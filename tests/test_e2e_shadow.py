@@ -188,3 +188,112 @@ def test_focf_uni_mode_shadow_run_reproduces_the_reference_losses_and_metrics():
         for k, r in zip(names, ref):
             # identical candidates; a near-tie flip inside a top-5 moves a ranking metric by O(1/943)
             assert abs(got[k] - r) <= (2.0 / 943 if "@" in k else 1e-6), (k, got[k], r)
+
+
+def test_fairgo_pmf_shadow_run_reproduces_the_reference_run(tmp_path, monkeypatch):
+    """FairGo_PMF through the reference's FairGoTrainer.fit steps -- validated pretrain with best-state reload, then
+    alternating fine-tune epochs -- with this package's ingestion / construction / loaders (pointwise negatives like the
+    reference's default neg_sampling) / schedule and the oracle's arithmetic (fairgo_oracle, fullsort_oracle,
+    metrics_oracle): pretrain losses, the best pretrain validation score, fine-tune (discriminator, filter) losses and the
+    12 validation / test metrics of tests/golden/e2e_fairgo_pmf.npz."""
+    import recbole_fairrec_b200 as pkg
+    from oracle import fairgo_oracle as go
+    from oracle import fullsort_oracle as fs
+    from oracle import metrics_oracle as mo
+    from recbole_fairrec_b200.atomic import AtomicDataset, used_and_positive_lists
+    from recbole_fairrec_b200.quick_start import BatchLoader, build_config, init_seed
+    g = np.load(os.path.join(HERE, "golden", "e2e_fairgo_pmf.npz"))
+    root = mtd.float_gender_copy(str(tmp_path / "data"))
+    cfg = build_config("FairGo_PMF", "ml-100k", None, dict(mtd.FAIRGO_E2E, data_path=root, device="cpu"))
+    init_seed(cfg["seed"])
+    ds = AtomicDataset(cfg)
+    splits = ds.build()
+    tr = splits[0]
+
+    class View:
+        num = staticmethod(ds.num)
+        inter_feat = {k: torch.from_numpy(v) for k, v in tr.items()}
+        get_user_feature = staticmethod(ds.get_user_feature)
+        inter_matrix = staticmethod(ds.inter_matrix)
+
+    net = pkg.FairGo_PMF(cfg, View)
+    loader = BatchLoader(cfg, ds, tr, pairwise=False, pointwise_neg=True)
+    nu, ni = ds.user_num, ds.item_num
+    st = {f"base.{k}": v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    for name, mods in (("filter", net.filter_layer_dict), ("dis", net.dis_layer_dict)):
+        for k, m in mods.items():
+            st.update({f"{name}_{k}.{kk}": v.detach().clone().requires_grad_(True) for kk, v in m.state_dict().items()})
+    monkeypatch.setattr(go, "ATTRS", ["gender"])
+    L = go.to_torch_sparse(go.norm_matrix(tr["user_id"], tr["item_id"], tr["rating"], nu, ni))
+    emb = [st["base.user_embedding_layer.weight"], st["base.item_embedding_layer.weight"]]
+    opt_p = torch.optim.Adam(emb, lr=1e-3, weight_decay=1e-4)
+    opt_f = torch.optim.Adam([v for k, v in st.items() if k.startswith("filter_")], lr=1e-3, weight_decay=1e-4)
+    opt_d = torch.optim.Adam([v for k, v in st.items() if k.startswith("dis_") or k.startswith("base.aggr_layer")],
+                             lr=1e-3, weight_decay=1e-4)
+    gender = ds.user_feat["gender"]
+    counts = {int(i): int(c) for i, c in enumerate(np.bincount(tr["item_id"], minlength=ni)) if c}
+    names = [str(k) for k in g["metric_names"]]
+    lists = {ph: used_and_positive_lists(splits, ph) for ph in ("valid", "test")}
+
+    def evaluate(phase, stage):
+        users, hist, pos = lists[phase]
+        with torch.no_grad():
+            ua, ia = go.forward(st, stage, ["gender"], nu)
+        ho = np.r_[0, np.cumsum([len(h) for h in hist])]
+        po = np.r_[0, np.cumsum([len(p) for p in pos])]
+        struct = fs.full_sort_eval(ua.numpy(), ia.numpy(), users, 5.0, ho, np.concatenate(hist), po, np.concatenate(pos), gender, 5)
+        return mo.evaluate(struct, [5], ni, counts, 0.1)
+
+    def run_pass(stage, opt, which, sst_list):
+        total = 0.0
+        for b in loader:
+            labels = {"gender": b["gender"]}
+            opt.zero_grad()
+            if which == "loss":
+                loss = go.calculate_loss(st, L, stage, b["user_id"], b["item_id"], b["rating"], labels, sst_list, {"gender": 2},
+                                         nu, 2, "LBA", [0.8, 0.2], 0.1)
+            else:
+                loss = go.dis_loss(st, L, b["user_id"], labels, sst_list, {"gender": 2}, nu, 2, "LBA", [0.8, 0.2])
+            loss.backward()
+            opt.step()
+            total += loss.item()
+        return total
+
+    TIE_FREE = [k for k in names if "@" not in k]        # computed from the positives' scores: no top-K ties involved
+
+    def check(res, ref, rank_tol=2.0 / 943):
+        for k, r in zip(names, ref):
+            tol = rank_tol if k not in TIE_FREE else 2e-4 * max(abs(r), 1e-3) + 1e-7      # observed: 1.6e-5 / 5e-13
+            assert abs(res[k] - r) <= tol, (k, res[k], r)
+
+    # ---- pretrain (trainer.py:606-685): validation every epoch, the best state is reloaded
+    pre_losses, states = [], []
+    for epoch in range(3):
+        pre_losses.append(run_pass("pretrain", opt_p, "loss", None))
+        res = evaluate("valid", "pretrain")
+        # after three epochs from N(0,1) tables most scores sit on the clamp (exact ties at 0.0 and 1.0), where torch.topk's
+        # order is unspecified (DESIGN.md section 2): hits, value unfairness etc. agree to 1e-9, NDCG / MRR differ by the
+        # positions inside the ties (2e-2 relative) -- enough to pick another "best" epoch.  The metrics that do not depend
+        # on tie order are compared tightly, and the reference's choice of best epoch is followed.
+        for k, r in zip(names, g["pretrain_valid_per_epoch"][epoch]):
+            if k in TIE_FREE:
+                assert abs(res[k] - r) <= 1e-5 * max(abs(r), 1e-3) + 1e-7, (epoch, k, res[k], r)
+            else:
+                assert abs(res[k] - r) <= 5.0 / 943, (epoch, k, res[k], r)
+        states.append([e.detach().clone() for e in emb])
+    np.testing.assert_allclose(pre_losses, g["pretrain_losses"], rtol=1e-5)
+    with torch.no_grad():
+        for e, b in zip(emb, states[int(g["pretrain_best_epoch"])]):
+            e.copy_(b)
+    # ---- fine-tune (trainer.py:687-704): mask, filter pass, discriminator pass, validation
+    epoch_losses = []
+    for epoch in range(2):
+        mask = np.zeros(1)
+        while mask.sum() == 0:
+            mask = np.random.choice([0, 1], 1)
+        f = run_pass("finetune", opt_f, "loss", ["gender"])
+        d = run_pass("finetune", opt_d, "dis", ["gender"])
+        epoch_losses.append([d, f])
+        check(evaluate("valid", "finetune"), g["valid_metrics"][epoch])
+    check(evaluate("test", "finetune"), g["test_metrics"])
+    np.testing.assert_allclose(np.array(epoch_losses), g["epoch_losses"], rtol=1e-5)        # observed: 1e-8
