@@ -43,7 +43,25 @@ def rand_opts(rng):
     split = rng.choice([{"RS":[8,1,1]}, {"RS":[7,2,1]}, {"RS":[6,2,2]}, {"LS":"valid_and_test"}, {"LS":"valid_only"}, {"LS":"test_only"}])
     group = "user" if "LS" in split else rng.choice(["user", "none"])
     o["eval_args"] = {"split": split, "group_by": group, "order": order, "mode": "full"}
+    r = rng.random()
+    if r < 0.25: o["normalize_all"] = True
+    elif r < 0.55: o["normalize_field"] = rng.sample(["rating", "timestamp", "age", "gender", "occupation"], rng.choice([1, 2, 3]))
+    if rng.random() < 0.15: o["benchmark_filename"] = rng.choice([["train", "valid", "test"], ["test", "train"], ["valid"]])
     return o
+
+from recbole.data.dataset import Dataset
+from recbole.utils import FeatureType
+def _fill_nan(self):        # dataset.py:554-575 with assignments instead of `fillna(inplace=True)` (a no-op under pandas 3, which
+    for feat_name in self.feat_name_list:      # would turn every normalised user column into NaN through the [PAD] row)
+        feat = getattr(self, feat_name)
+        for field in feat:
+            ftype = self.field2type[field]
+            if ftype == FeatureType.TOKEN: feat[field] = feat[field].fillna(value=0)
+            elif ftype == FeatureType.FLOAT: feat[field] = feat[field].fillna(value=feat[field].mean())
+            else:
+                dtype = np.int64 if ftype == FeatureType.TOKEN_SEQ else float
+                feat[field] = feat[field].apply(lambda x: np.array([], dtype=dtype) if isinstance(x, float) else x)
+Dataset._fill_nan = _fill_nan
 
 root = tempfile.mkdtemp(); name = mtd.write_messy(root, seed=int(sys.argv[2]) if len(sys.argv)>2 else 3)
 os.chdir(tempfile.mkdtemp())
@@ -77,11 +95,16 @@ for trial in range(int(sys.argv[3]) if len(sys.argv)>3 else 25):
     if ok:
         for k, part in zip(range(3), built):
             f_ = part.inter_feat
-            for col in ("user_id","item_id","rating","timestamp"):
+            for col in ("user_id","item_id","rating","timestamp","label"):
                 a = splits[k][col]; b = f_[col].numpy() if len(f_) else np.zeros(0)
                 if len(a) != len(b) or not np.array_equal(a, b):
                     ok = False; why = f"split {k} col {col} len {len(a)} vs {len(b)}"; break
             if not ok: break
+    if ok:
+        uf = ds_r.get_user_feature()
+        for col in ("gender", "age", "occupation"):
+            if not np.array_equal(ds.user_feat[col], uf[col].numpy()):
+                ok = False; why = f"user feature {col}"; break
     if not ok:
         bad += 1
         print(trial, "MISMATCH", why, "|", opts)

@@ -355,6 +355,7 @@ def run_ml100k(epochs=2):
         np.savez_compressed(os.path.join(OUT, "ml100k_focf_value.npz"), **out)
         print("ml100k: losses", losses, "test", {k: float(v) for k, v in test.items()})
     finally:
+        Dataset._fill_nan = stock_fill_nan
         os.chdir(cwd)
 
 
@@ -677,8 +678,29 @@ def run_ingest():
     name = mtd.write_messy(root)
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())
+    from recbole.data.dataset import Dataset
+    from recbole.utils import FeatureType
+    stock_fill_nan = Dataset._fill_nan
+
+    def fill_nan(self):        # dataset.py:554-575 with assignments instead of `fillna(inplace=True)` (pandas 3 copy-on-write)
+        for feat_name in self.feat_name_list:
+            feat = getattr(self, feat_name)
+            for field in feat:
+                ftype = self.field2type[field]
+                if ftype == FeatureType.TOKEN:
+                    feat[field] = feat[field].fillna(value=0)
+                elif ftype == FeatureType.FLOAT:
+                    feat[field] = feat[field].fillna(value=feat[field].mean())
+                else:
+                    dtype = np.int64 if ftype == FeatureType.TOKEN_SEQ else float
+                    feat[field] = feat[field].apply(lambda x: np.array([], dtype=dtype) if isinstance(x, float) else x)
+
+    only = set(sys.argv[2:])
     try:
         for case, opts in mtd.INGEST_CASES.items():
+            if only and case not in only:
+                continue
+            Dataset._fill_nan = fill_nan if case in mtd.INGEST_PATCH_FILL_NAN else stock_fill_nan
             with open("c.yaml", "w") as f:
                 yaml.safe_dump(dict(mtd.INGEST_BASE, **opts, data_path=root, use_gpu=False, state="WARNING",
                                     show_progress=False, neg_sampling=None, fair_objective="value"), f)
@@ -702,6 +724,7 @@ def run_ingest():
             np.savez_compressed(os.path.join(OUT, f"ingest_{case}.npz"), **out)
             print("ingest", case, dataset.user_num, dataset.item_num, [len(p.inter_feat) for p in built])
     finally:
+        Dataset._fill_nan = stock_fill_nan
         os.chdir(cwd)
 
 

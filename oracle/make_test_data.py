@@ -67,6 +67,17 @@ def write_messy(root, name="messy", seed=3, n_users=300, n_items=200, n_inter=60
             f.write(f"{idf}:token\t{valf}:float_seq\n")
             for k in ids:
                 f.write(f"{prefix}{k}\t" + " ".join(f"{v:.4f}" for v in rng.standard_normal(8)) + "\n")
+    # pre-split interaction files of `benchmark_filename: [train, valid, test]` (dataset.py:265-285): the complete rows of
+    # the .inter file dealt out 8 : 1 : 1 by row index (no RNG draws: the files above stay what they were)
+    parts = {p: open(os.path.join(d, f"{name}.{p}.inter"), "w") for p in ("train", "valid", "test")}
+    for f in parts.values():
+        f.write("user_id:token\titem_id:token\trating:float\ttimestamp:float\n")
+    for k in range(n_inter):
+        if k % 997 == 5 or k in (1, 3):
+            continue
+        parts["train" if k % 10 < 8 else ("valid" if k % 10 == 8 else "test")].write(f"u{u[k]}\ti{i[k]}\t{r[k]}\t{t[k]}\n")
+    for f in parts.values():
+        f.close()
     return name
 
 
@@ -90,7 +101,21 @@ INGEST_CASES = {
                              eval_args={"split": {"LS": "valid_only"}, "group_by": "user", "order": "TO", "mode": "full"}),
     "ls_test_only_ro": dict(item_inter_num_interval="[2,inf)", val_interval={"timestamp": "[1000,1100);(1200,1399]"},
                             eval_args={"split": {"LS": "test_only"}, "group_by": "user", "order": "RO", "mode": "full"}),
+    # min-max normalisation of chosen float fields (interaction and user side; the label is taken before it)
+    "normalize_fields": dict(normalize_field=["rating", "age", "occupation"], rm_dup_inter="first",
+                             eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "TO", "mode": "full"}),
+    # ... of every float field of the inter / user / item files -- the preloaded float_seq matrices are NOT touched
+    "normalize_all": dict(PRELOAD, normalize_all=True,
+                          load_col=dict(INGEST_BASE["load_col"], user_emb=["uid", "user_emb"], item_emb=["iid", "item_emb"]),
+                          eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"}),
+    # pre-split files: no filtering, no shuffle, the parts come back as they are
+    "benchmark_files": dict(benchmark_filename=["train", "valid", "test"], normalize_field=["timestamp"],
+                            user_inter_num_interval="[50,inf)",        # ignored by the reference for benchmark files
+                            eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"}),
 }
+# cases generated with a copy-on-write-safe `_fill_nan` (SURVEY.md 8c caveat: under pandas 3 the reference's
+# `fillna(inplace=True)` is a no-op, the [PAD] row keeps NaN and a min-max over the column turns ALL of it into NaN)
+INGEST_PATCH_FILL_NAN = ("normalize_fields", "normalize_all")
 
 
 FAMILY_E2E = {

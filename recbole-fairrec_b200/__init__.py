@@ -15,6 +15,7 @@ Only what the path needs lives here:
   trainer.py       FOCFTrainer (fit / evaluate)
   atomic.py        atomic-file datasets (.inter/.user/.item) -> ids, splits, history/positive lists (reference-identical)
   quick_start.py   run_recbole(model, dataset, config_file_list, config_dict)
+  utils.py         get_model / get_trainer (plugin discovery by name, utils/utils.py:51-94)
   synth.py         synthetic data of the benchmark shapes
 The directory name carries a hyphen; import it as `recbole_fairrec_b200` (shim at the repo root).
 """
@@ -31,5 +32,6 @@ from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFC
                    PFCN_BiasedMFTrainer, PFCN_DMFTrainer)
 from .sampled_eval import SampledEvalData, SampledEvaluator, sample_negatives  # noqa: F401
 from .trainer import FOCFTrainer  # noqa: F401
+from .utils import get_model, get_trainer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,7 +13,8 @@ Also covered, with the reference's semantics and order of application (`_data_fi
 missing user / item id dropped (624-642), `rm_dup_inter` (644-668), `val_interval` (803-821), `filter_inter_by_user_or_item`
 (847-863, on by default), `user_inter_num_interval` / `item_inter_num_interval` k-core filtering (670-728, vectorised:
 bincounts instead of Python Counters); `eval_args.order` RO | TO, `split` RS (grouped by user or not) | LS
-(`valid_and_test`, `valid_only`, `test_only`; 1398-1450).  tests/test_atomic.py pins them on golden splits exported from
+(`valid_and_test`, `valid_only`, `test_only`; 1398-1450); `benchmark_filename` (pre-split `<name>.<part>.inter` files:
+265-285, 1476-1479) and `normalize_field` / `normalize_all` (min-max, 577-618).  tests/test_atomic.py pins them on golden splits exported from
 the reference (tests/golden/ingest_*.npz) and, in the build container, against the live reference.
 
 File format (RecBole atomic files): TSV with a `name:type` header, types token / float / token_seq / float_seq
@@ -29,6 +30,23 @@ from .interaction import Interaction
 # what pandas.read_csv treats as missing by default -- the reference reads with those defaults (dataset.py:433-435)
 NA_STRINGS = ["", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>", "N/A", "NA",
               "NULL", "NaN", "None", "n/a", "nan", "null"]
+
+
+SEQLEN_KEY = "__seqlen__"      # read_atomic(with_seq=True): {float_seq field: true sequence lengths} next to the columns
+
+
+def minmax(values, valid=None):
+    """`Dataset._normalize` (dataset.py:604-618) on float64 data: (x - min) / (max - min) over the `valid` entries, 1.0
+    everywhere when all of them are equal"""
+    x = np.asarray(values, np.float64)
+    sel = x if valid is None else x[valid]
+    if sel.size == 0:
+        return x
+    mx, mn = sel.max(), sel.min()
+    out = np.ones_like(x) if mx == mn else (x - mn) / (mx - mn)
+    if valid is not None:
+        out = np.where(valid, out, 0.0)
+    return out
 
 
 class TokenColumn:
@@ -127,6 +145,7 @@ def read_atomic(path, usecols=None, sep="\t", seq_sep=" ", with_seq=False):
         for k, r in enumerate(rows):
             mat[k, :len(r)] = r
         raw[n] = mat
+        raw.setdefault(SEQLEN_KEY, {})[n] = np.array([len(r) for r in rows], np.int64)     # the padding is not data
     return raw, kept
 
 
@@ -330,23 +349,46 @@ class AtomicDataset:
         self.uid_field, self.iid_field = config["USER_ID_FIELD"], config["ITEM_ID_FIELD"]
         self.rating_field = config["RATING_FIELD"]
         load_col = config["load_col"] or {}
-        inter, itypes = read_atomic(os.path.join(root, name + ".inter"), load_col.get("inter"))
+        bench = config["benchmark_filename"]
+        self.file_size_list = None
+        if bench:
+            # pre-split interaction files `<name>.<part>.inter` (dataset.py:265-285): concatenated for the id remap, handed
+            # back part by part by build(); the reference applies NO data filtering to them (dataset.py:150-151)
+            parts = []
+            for part in bench:
+                path = os.path.join(root, f"{name}.{part}.inter")
+                if not os.path.isfile(path):
+                    raise ValueError(f"File {path} not exist.")
+                tab, itypes = read_atomic(path, load_col.get("inter"))
+                parts.append(tab)
+            self.file_size_list = [_rows(t) for t in parts]
+            inter = {}
+            for f, t in itypes.items():
+                if t == "token":
+                    codes, vocab = unify([tab[f] for tab in parts])
+                    inter[f] = TokenColumn(np.concatenate(codes), vocab)
+                else:
+                    inter[f] = np.concatenate([tab[f] for tab in parts])
+        else:
+            inter, itypes = read_atomic(os.path.join(root, name + ".inter"), load_col.get("inter"))
         user_path, item_path = os.path.join(root, name + ".user"), os.path.join(root, name + ".item")
         user, utypes = read_atomic(user_path, load_col.get("user")) if os.path.exists(user_path) and \
             (not load_col or "user" in load_col) else (None, {})
         item, mtypes = read_atomic(item_path, load_col.get("item")) if os.path.exists(item_path) and "item" in load_col \
             else (None, {})
         self.time_field = config["TIME_FIELD"] or "timestamp"
-        inter, user, item = data_filtering(config, inter, user, item, {**mtypes, **utypes, **itypes}, self.uid_field,
-                                           self.iid_field)
+        if not bench:
+            inter, user, item = data_filtering(config, inter, user, item, {**mtypes, **utypes, **itypes}, self.uid_field,
+                                               self.iid_field)
         user, item = user or {}, item or {}
         # ---- additional feature files (dataset.py:329-349), e.g. the pretrained embeddings FairGo preloads
-        self.extra, self.extra_ids = {}, {}
+        self.extra, self.extra_ids, xtypes = {}, {}, {}
         for suf in config["additional_feat_suffix"] or []:
             path = os.path.join(root, f"{name}.{suf}")
             if not os.path.isfile(path):
                 raise ValueError(f"Additional feature file [{path}] not found.")
-            self.extra[suf], _ = read_atomic(path, load_col.get(suf) if load_col else None, with_seq=True)
+            self.extra[suf], xt = read_atomic(path, load_col.get(suf) if load_col else None, with_seq=True)
+            xtypes.update(xt)
 
         def alias_chunks(key):     # fields sharing the id space, in remap order (dataset.py:456-460, 894-927)
             out = []
@@ -381,6 +423,30 @@ class AtomicDataset:
         if thr:
             (field, value), = thr.items()
             cols[config["LABEL_FIELD"]] = (cols[field] >= value).astype(np.float32)
+        # ---- min-max normalisation (dataset.py:577-618; after the label, on the float64 file values, then float32)
+        all_types = {**mtypes, **utypes, **itypes, **xtypes}
+        if thr:
+            all_types[config["LABEL_FIELD"]] = "float"
+        if config["normalize_field"] is not None and config["normalize_all"] is True:
+            raise ValueError("Normalize_field and normalize_all can't be set at the same time.")
+        if config["normalize_field"]:
+            for f in config["normalize_field"]:
+                if f not in all_types:
+                    raise ValueError(f"Field [{f}] does not exist.")
+            norm = {f for f in config["normalize_field"] if all_types[f] in ("float", "float_seq")}
+        elif config["normalize_all"]:      # `float_like_fields` lists the inter / user / item sources only (dataset.py:1012-1020:
+            norm = {f for f, t in all_types.items() if t == "float" and f not in xtypes}      # additional files are not in FeatureSource)
+        else:
+            norm = set()
+        for f in norm:
+            if f in cols:
+                cols[f] = minmax(inter[f] if f in inter else cols[f]).astype(np.float32)
+            for tab in self.extra.values():
+                if f in tab and f in tab.get(SEQLEN_KEY, {}):
+                    width = tab[f].shape[1]
+                    tab[f] = minmax(tab[f], np.arange(width)[None, :] < tab[SEQLEN_KEY][f][:, None])
+                elif f in tab and xtypes.get(f) == "float":
+                    tab[f] = minmax(tab[f])
         self.inter = cols
         # ---- user features: row index == user id, row 0 = [PAD] (dataset.py:488-507); token attributes get ids by first
         # appearance in the FILE (dataset.py:927-929), float attributes stay as they are
@@ -394,8 +460,12 @@ class AtomicDataset:
                     col = np.zeros(self.user_num, np.int64)
                     col[feat_u] = vals[0]
                 else:     # users without a feature row (and the [PAD] row) get the column mean (_fill_nan, dataset.py:571-572)
-                    col = np.full(self.user_num, np.float32(np.nanmean(user[f])) if len(user[f]) else 0.0, np.float32)
-                    col[feat_u] = user[f].astype(np.float32)
+                    col = np.full(self.user_num, np.nanmean(user[f]) if len(user[f]) else 0.0, np.float64)
+                    col[feat_u] = user[f]
+                    col[np.isnan(col)] = np.nanmean(user[f]) if len(user[f]) else 0.0       # empty cells of the file, too
+                    if f in norm:
+                        col = minmax(col)
+                    col = col.astype(np.float32)
                 self.user_feat[f] = col
 
     # ------------------------------------------------------------------ the reference's Dataset surface
@@ -447,6 +517,11 @@ class AtomicDataset:
         group_by user (per user -- users in order of first appearance in the ordered data, rows in that order -- the
         first a/(a+b+c) go to train, etc.) or none (three contiguous ranges) | {LS: valid_and_test | valid_only |
         test_only} (leave-one-out per user).  Returns three column dicts (a part may be empty)."""
+        if self.file_size_list is not None:          # dataset.py:1476-1479: the benchmark files as they are, no shuffle
+            edges = np.r_[0, np.cumsum(self.file_size_list)]
+            splits = [{k: v[a:b] for k, v in self.inter.items()} for a, b in zip(edges[:-1], edges[1:])]
+            self._matrix_src = splits[0]
+            return splits
         ea = self.config["eval_args"] or {}
         order_mode = ea.get("order") or "RO"
         split = ea.get("split") or {"RS": [8, 1, 1]}

@@ -133,6 +133,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     """quick_start.py:20-71 -> {'best_valid_score', 'valid_score_bigger', 'best_valid_result', 'test_result'}"""
     import recbole_fairrec_b200 as pkg
     from .sampled_eval import ResamplingEvalSource, SampledEvalData, sample_negatives
+    from .utils import get_model, get_trainer
     cfg = build_config(model, dataset, config_file_list, config_dict, argv)
     init_seed(cfg["seed"], cfg["reproducibility"] if cfg["reproducibility"] is not None else True)
     logger = getLogger()
@@ -180,14 +181,14 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         tdata = pkg.TrainData(train[uf], train[itf], train[rf], ds.user_feat[first].astype(np.float32), ds.user_num,
                               ds.item_num, dev, uf, itf, rf, first)
         loader = pkg.FOCFDataLoader(cfg, tdata, mode=cfg["focf_draw_mode"] or "reference")
-        net = pkg.FOCF(cfg, TrainView).to(dev)
-        trainer = pkg.FOCFTrainer(cfg, net)
+        net = get_model(name)(cfg, TrainView).to(dev)
+        trainer = get_trainer(net.type, name)(cfg, net)
         valid, test = eval_data("valid"), eval_data("test")      # negatives (uni<N>) drawn before training, like the
         best, best_res = trainer.fit(loader, valid, saved=saved, verbose=cfg["verbose"] is not False)   # reference's samplers
         test_res = trainer.evaluate(test, load_best_model=bool(saved))      # quick_start.py:61: the best model when saved
     elif name.startswith("PFCN_"):
-        net = getattr(pkg, name)(cfg, TrainView).to(dev)
-        trainer = pkg.PFCNTrainer(cfg, net)
+        net = get_model(name)(cfg, TrainView).to(dev)
+        trainer = get_trainer(net.type, name)(cfg, net)
         loader = BatchLoader(cfg, ds, train, pairwise=True)
         if mode == "full":
             raise NotImplementedError("PFCN full-sort evaluation is undefined in the reference; use eval_args.mode uni100")
@@ -200,8 +201,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         multi = net.filter_mode != "none" and len(trainer.attribute_subsets()) > 1
         test_res = trainer.evaluate_subsets(test, item_counter) if multi else trainer.evaluate(test, None, item_counter)
     elif name in ("FairGo_PMF", "FairGo_GCN"):
-        net = getattr(pkg, name)(cfg, TrainView).to(dev)
-        trainer = pkg.FairGoTrainer(cfg, net)
+        net = get_model(name)(cfg, TrainView).to(dev)
+        trainer = get_trainer(net.type, name)(cfg, net)
         # the FairGo YAMLs leave `neg_sampling: {uniform: 1}` in force: the reference's pointwise loader appends one sampled
         # item per interaction (same user, same rating column, label 0), abstract_dataloader.py:200-208
         loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
@@ -210,8 +211,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         _load_best(trainer, saved)
         test_res = trainer.evaluate(test)
     elif name == "NFCF":
-        net = pkg.NFCF(cfg, TrainView).to(dev)
-        trainer = pkg.NFCFTrainer(cfg, net)
+        net = get_model(name)(cfg, TrainView).to(dev)
+        trainer = get_trainer(net.type, name)(cfg, net)
         loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
         if mode == "full":
             raise NotImplementedError("NFCF defines no full_sort_predict in the reference; use eval_args.mode uni100")

@@ -574,3 +574,20 @@ def test_loader_streams_equal_the_live_references(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(here, "..", "oracle", "fuzz_loaders.py"), "7", "3"], capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0 and "bad: 0" in r.stdout and r.stdout.count("IDENTICAL") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_plugin_discovery_by_name_like_the_reference():
+    """utils/utils.py:51-94: get_model finds the class called like the model, get_trainer `<name>Trainer` and otherwise the
+    base trainer; an unknown model name raises the reference's ValueError"""
+    import pytest
+    import recbole_fairrec_b200 as pkg
+    for name, trainer in (("FOCF", pkg.FOCFTrainer), ("PFCN_MLP", pkg.PFCNTrainer), ("PFCN_PMF", pkg.PFCNTrainer),
+                          ("PFCN_BiasedMF", pkg.PFCNTrainer), ("PFCN_DMF", pkg.PFCNTrainer), ("FairGo_PMF", pkg.FairGoTrainer),
+                          ("FairGo_GCN", pkg.FairGoTrainer), ("NFCF", pkg.NFCFTrainer)):
+        cls = pkg.get_model(name)
+        assert cls is getattr(pkg, name) and cls.__name__ == name and cls.type == "GENERAL"
+        assert pkg.get_trainer(cls.type, name) is trainer
+    assert pkg.get_trainer("GENERAL", "SomethingElse") is pkg.FOCFTrainer          # the base-trainer fall-through
+    for bad in ("BPR", "FOCFTrainer", "focf"):
+        with pytest.raises(ValueError, match="is not the name of an existing model"):
+            pkg.get_model(bad)
