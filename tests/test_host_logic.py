@@ -591,3 +591,66 @@ def test_plugin_discovery_by_name_like_the_reference():
     for bad in ("BPR", "FOCFTrainer", "focf"):
         with pytest.raises(ValueError, match="is not the name of an existing model"):
             pkg.get_model(bad)
+
+
+def test_run_recbole_wiring_of_every_family_with_faked_epochs(tmp_path, monkeypatch):
+    """run_recbole end to end on the raw ml-100k files for every branch of quick_start.run_recbole -- config, ingestion,
+    model and trainer discovery, model construction, loaders (a few batches are drawn), per-evaluation negatives, the fit
+    loops with check-pointing, best-model reload and the test evaluation -- with the kernel-calling methods (`_train_epoch`,
+    `_pass`, `evaluate`) replaced by fakes, so the host logic around the CUDA calls runs without a GPU.  The same
+    configurations run for real in tests/test_run_recbole_gpu.py."""
+    from oracle import make_test_data as mtd
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200.quick_start import run_recbole
+    base = dict(RATING_FIELD="rating", LABEL_FIELD="label", threshold={"rating": 3.0}, sst_attr_list=["gender"],
+                load_col={"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "gender"], "item": ["item_id"]},
+                embedding_size=64, seed=2020, verbose=False, device="cpu", epochs=2, topk=[5], valid_metric="NDCG@5",
+                data_path=mtd.float_gender_copy(str(tmp_path / "data")), checkpoint_dir=str(tmp_path),
+                eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"})
+    uni = dict(base["eval_args"], mode="uni100")
+    seen = []
+
+    def fake_train(self, data, epoch, *a, **k):
+        if isinstance(self, pkg.FOCFTrainer):
+            n = sum(len(data._draw_batch()) > 0 for _ in range(3))          # the host side of the FOCF loader
+        else:
+            n = sum(1 for _ in zip(range(3), data))
+        seen.append(("train", epoch, n))
+        return 0.3 if isinstance(self, (pkg.FOCFTrainer, pkg.NFCFTrainer)) else (0.1, 0.2)
+
+    def fake_pass(self, data, *a, **k):
+        return 0.5 * sum(1 for _ in zip(range(2), data))
+
+    def fake_eval(self, eval_data, *a, **k):
+        data = eval_data.resample() if hasattr(eval_data, "resample") else eval_data
+        seen.append(("eval", type(data).__name__, len(data.users) if hasattr(data, "users") else None))
+        return {"ndcg@5": 0.1 + 0.01 * len(seen)}
+
+    for cls in (pkg.FOCFTrainer, pkg.PFCNTrainer, pkg.FairGoTrainer, pkg.NFCFTrainer):
+        monkeypatch.setattr(cls, "_train_epoch", fake_train)
+        monkeypatch.setattr(cls, "evaluate", fake_eval)
+    monkeypatch.setattr(pkg.PFCNTrainer, "_pass", fake_pass)
+    monkeypatch.setattr(pkg.FairGoTrainer, "_pass", fake_pass)
+    dis = dict(dis_dropout=0.0, dis_weight=1.0, dis_hidden_size_list=[32, 16], activation="leakyrelu")
+    fairgo = dict(n_layers=2, activation="leakyrelu", dis_hidden_size_list=[16, 8, 4], filter_hidden_size_list=[128, 64],
+                  fair_weight=0.1, load_pretrain_weight=False, aggr_method="LBA", vs_weights=[4, 1], pretrain_epochs=3)
+    runs = [("FOCF", dict(fair_objective="value"), False, 3),
+            ("FOCF", dict(fair_objective="value", eval_args=uni, focf_draw_mode="fast"), False, 3),
+            ("PFCN_PMF", dict(dis, filter_mode="sm", eval_args=uni), False, 3),
+            ("PFCN_MLP", dict(dis, filter_mode="cm", mlp_hidden_size=[32, 16], dropout=0.0, eval_args=uni), True, 3),
+            ("FairGo_PMF", fairgo, False, 6),          # + one validation per pretrain epoch
+            ("FairGo_GCN", dict(fairgo, gcn_n_layers=2, hidden_channels=32, gcn_dropout=0.2, gcn_act="relu", eval_args=uni), True, 6),
+            ("NFCF", dict(dropout=0.2, fair_weight=0.1, mlp_hidden_size=[128, 64], eval_args=uni, load_pretrain_path=None), True, 3)]
+    for name, extra, saved, n_eval in runs:
+        seen.clear()
+        out = run_recbole(name, "ml-100k", None, dict(base, **extra), saved=saved)
+        evals = [s for s in seen if s[0] == "eval"]
+        assert len(evals) == n_eval, (name, seen)
+        assert all(s[2] > 0 for s in seen if s[0] == "train"), (name, seen)
+        assert out["best_valid_score"] == max(0.1 + 0.01 * (k + 1) for k, s in enumerate(seen[:-1]) if s[0] == "eval"), name
+        assert set(out) >= {"best_valid_score", "valid_score_bigger", "best_valid_result", "test_result"}
+        if saved:
+            assert os.path.exists(out["saved_model_file"]), name
+        if name == "NFCF":          # stage 2 reads the stage-1 checkpoint (nfcf.py:49-51)
+            out2 = run_recbole(name, "ml-100k", None, dict(dict(base, **extra), load_pretrain_path=out["saved_model_file"]))
+            assert out2["test_result"]["ndcg@5"] > 0
