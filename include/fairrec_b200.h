@@ -161,6 +161,17 @@ int fr_focf_forward(const fr_focf_step *s, void *stream);
 int fr_focf_backward(const fr_focf_step *s, float grad_scale, void *stream);
 int fr_focf_adam(const fr_focf_step *s, void *stream);
 int fr_focf_train_step(const fr_focf_step *s, void *stream);
+/* The training loop body of trainer.py:181-196 for batches that are still in HOST memory -- the entry a plugin calls
+ * with the reference's CPU-side Interaction columns: n_steps optimisation steps, batch k = batch_rows[k] rows packed at
+ * host_batches[k] (pinned memory for asynchronous copies) as int32 user ids | int32 item ids | float rating | float sst,
+ * 16 bytes per row.  Per step: ONE host->device copy into `stage` (device, stage_bytes >= 16 * largest batch),
+ * fr_focf_train_step on it with optimizer step tmpl->step + k, ONE device->host copy of the loss into loss_host[k]
+ * (loss_dev: 2 device floats).  The host waits for step k-1's loss after enqueuing step k and returns when the last one
+ * has arrived (so loss_host is complete on return).  tmpl: every field of the step except uid / iid / rating / sst / B /
+ * loss; tmpl->step = 1-based optimizer step of the first batch; no planned epoch (plan_desc, B_dev NULL). */
+int fr_focf_train_steps_host(const fr_focf_step *tmpl, int32_t n_steps, const void *const *host_batches,
+                             const int32_t *batch_rows, void *stage, size_t stage_bytes, float *loss_dev,
+                             float *loss_host, void *stream);
 /* fr_focf_train_step in two halves, for overlapping the preparation of batch t+1 (its own stream and workspace) with the
  * compute of batch t: prepare = planned batch gather + sort / segments / row stamps (does not touch the embedding
  * tables); compute = forward + loss + gradients + Adam (one cooperative launch for small batches) */

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfairrec_b200.so")
 
-FR_OK = 0
+FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_WORKSPACE, FR_ERR_UNSUPPORTED = 0, 1, 2, 3, 4      # include/fairrec_b200.h: enum fr_status
 FLAG_TOO_MANY_GROUPS, FLAG_SINGLE_GROUP, FLAG_NAN_LOSS = 1, 2, 4
 OBJECTIVES = {"none": 0, "value": 1, "absolute": 2, "under": 3, "over": 4, "nonparity": 5}
 TRANSFORM_NONE, TRANSFORM_CLAMP_DIV, TRANSFORM_SIGMOID = 0, 1, 2
@@ -99,6 +99,8 @@ SIGNATURES = {
     "fr_focf_backward": (c_int, [POINTER(FocfStep), c_float, c_void_p]),
     "fr_focf_adam": (c_int, [POINTER(FocfStep), c_void_p]),
     "fr_focf_train_step": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_focf_train_steps_host": (c_int, [POINTER(FocfStep), c_int32, POINTER(c_void_p), POINTER(c_int32), c_void_p, c_size_t,
+                                 c_void_p, c_void_p, c_void_p]),
     "fr_focf_gather_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "fr_pair_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,

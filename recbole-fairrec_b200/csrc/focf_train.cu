@@ -1265,6 +1265,63 @@ int fr_focf_train_step(const fr_focf_step *s, void *stream) {
   return FR_OK;
 }
 
+/* trainer.py:181-196 for batches that are still in HOST memory: per step one H2D copy of the packed batch into `stage`,
+ * fr_focf_train_step on it, one D2H copy of the loss; the host waits for the loss of step k-1 after it has enqueued step
+ * k and returns once the last loss has arrived.  Everything runs on `stream`, so the copy of batch k+1 into the single
+ * staging buffer is ordered behind the kernels that read batch k. */
+int fr_focf_train_steps_host(const fr_focf_step *tmpl, int32_t n_steps, const void *const *host_batches,
+                             const int32_t *batch_rows, void *stage, size_t stage_bytes, float *loss_dev,
+                             float *loss_host, void *stream) {
+  FR_REQUIRE(tmpl && n_steps >= 0, "fr_focf_train_steps_host: null step template or negative step count");
+  if (n_steps == 0) return FR_OK;
+  FR_REQUIRE(host_batches && batch_rows && stage && loss_dev && loss_host, "fr_focf_train_steps_host: null pointer");
+  FR_REQUIRE(tmpl->step >= 1, "fr_focf_train_steps_host: step must be the 1-based optimizer step of the first batch");
+  FR_REQUIRE(!tmpl->plan_desc && !tmpl->B_dev, "fr_focf_train_steps_host: takes host batches, not a planned epoch");
+  for (int32_t k = 0; k < n_steps; ++k) {
+    FR_REQUIRE(host_batches[k] && batch_rows[k] >= 1, "fr_focf_train_steps_host: batch %d is empty", k);
+    FR_REQUIRE((size_t)batch_rows[k] * 16 <= stage_bytes, "fr_focf_train_steps_host: batch %d (%d rows) exceeds the staging buffer (%zu bytes)",
+               k, batch_rows[k], stage_bytes);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      if (i == 1) cudaEventDestroy(ev[0]);
+      fr::set_error("fr_focf_train_steps_host: cudaEventCreate failed: %s", cudaGetErrorString(e));
+      return FR_ERR_CUDA;
+    }
+  }
+  fr_focf_step s = *tmpl;
+  int rc = FR_OK;
+  cudaError_t e = cudaSuccess;
+  for (int32_t k = 0; k < n_steps; ++k) {
+    const size_t n = (size_t)batch_rows[k];
+    if ((e = cudaMemcpyAsync(stage, host_batches[k], 16 * n, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    const char *base = (const char *)stage;
+    s.uid = (const int32_t *)base;
+    s.iid = (const int32_t *)(base + 4 * n);
+    s.rating = (const float *)(base + 8 * n);
+    s.sst = (const float *)(base + 12 * n);
+    s.B = (int32_t)n;
+    s.step = tmpl->step + k;
+    s.loss = loss_dev + (k & 1);
+    if ((rc = fr_focf_train_step(&s, stream))) break;
+    if ((e = cudaMemcpyAsync(loss_host + k, s.loss, sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    if ((e = cudaEventRecord(ev[k & 1], st)) != cudaSuccess) break;
+    if (k >= 1 && (e = cudaEventSynchronize(ev[(k - 1) & 1])) != cudaSuccess) break;   // loss of step k-1 is on the host
+  }
+  if (rc == FR_OK && e == cudaSuccess) e = cudaEventSynchronize(ev[(n_steps - 1) & 1]);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (rc) return rc;
+  if (e != cudaSuccess) {
+    fr::set_error("fr_focf_train_steps_host: %s", cudaGetErrorString(e));
+    return FR_ERR_CUDA;
+  }
+  return FR_OK;
+}
+
 /* the two halves of fr_focf_train_step, for callers that overlap the preparation of batch t+1 (another stream, another
  * workspace) with the compute of batch t: prepare = batch gather (planned) + sort / segments / row stamps (independent
  * of the embedding tables); compute = forward + loss + gradients + Adam */

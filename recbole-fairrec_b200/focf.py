@@ -197,6 +197,25 @@ class FOCF(nn.Module):
                               bool(getattr(interaction, "items_contiguous", False)), self._objective, self.fair_weight, out)
         return out
 
+    def train_steps_host(self, interactions):
+        """One fused optimisation step per HOST batch of `interactions` (pack_host_batch Interactions), driven by ONE call
+        into the library (include/fairrec_b200.h:fr_focf_train_steps_host): per step the batch is copied host -> device,
+        stepped, and its loss copied device -> host; the loop of trainer.py:181-196 runs in C instead of the interpreter.
+        Returns the per-step losses as a pinned host tensor, complete on return."""
+        adam = self._adam
+        if adam is None:
+            raise RuntimeError("call init_adam() (FOCFTrainer does) before train_steps_host()")
+        packed = [getattr(it, "packed_host", None) for it in interactions]
+        if any(p is None for p in packed):
+            raise ValueError("train_steps_host takes host batches built by pack_host_batch")
+        contiguous = all(bool(getattr(it, "items_contiguous", False)) for it in interactions)
+        mods = self._modules
+        losses = self._engine().train_steps_host(mods["user_embedding_layer"]._parameters["weight"].data,
+                                                 mods["item_embedding_layer"]._parameters["weight"].data, adam, packed,
+                                                 contiguous, self._objective, self.fair_weight)
+        adam["step"] += len(packed)
+        return losses
+
     @torch.no_grad()
     def _train_step_generic(self, interaction, loss_out=None):
         eng = self._engine()

@@ -136,6 +136,45 @@ class FocfEngine:
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
         return s
 
+    def train_steps_host(self, U, I, adam, packed_batches, contiguous, objective, fair_weight):
+        """fr_focf_train_steps_host: the optimisation steps of a LIST of host batches (each packed into one pinned buffer like
+        train_step_packed's) in ONE library call -- per step one H2D copy, the fused step, one D2H copy of its loss; the
+        host loop (copies, launches, waiting for the previous step's loss) runs in the library instead of the interpreter.
+        adam["step"] is the count BEFORE the first batch and is advanced by the caller.  Returns the pinned float32 tensor
+        of the per-step losses (complete on return)."""
+        k = len(packed_batches)
+        rows = [int(n) for _, n in packed_batches]
+        for (buf, _), n in zip(packed_batches, rows):
+            if buf.numel() != 16 * n or buf.is_cuda:
+                raise ValueError("packed batch: a host buffer of exactly 16 bytes per entry is expected")
+        if k == 0:
+            return torch.zeros(0, dtype=torch.float32)
+        self._ensure(max(rows))
+        nbytes = 16 * max(rows)
+        st = self._stage
+        if st is None or st.numel() < nbytes:
+            st = self._stage = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        if getattr(self, "_loss2", None) is None:
+            self._loss2 = torch.zeros(2, dtype=torch.float32, device=self.device)
+        host = getattr(self, "_loss_host", None)
+        if host is None or host.numel() < k:
+            host = self._loss_host = torch.zeros(max(k, 64), dtype=torch.float32).pin_memory()
+        s = FocfStep()
+        s.U, s.I, s.mU, s.vU, s.mI, s.vI = ptr(U), ptr(I), ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"])
+        s.n_users, s.n_items, s.d = self.n_users, self.n_items, self.d
+        s.objective, s.fair_weight = objective, float(fair_weight)
+        s.pred, s.status_flags = ptr(self.pred_buf), ptr(self.flags)
+        s.workspace, s.workspace_bytes = ptr(self.ws), self.ws.numel()
+        s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
+        s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
+        s.items_contiguous = 1 if contiguous else 0
+        s.step = int(adam["step"]) + 1
+        ptrs = (ctypes.c_void_p * k)(*[buf.data_ptr() for buf, _ in packed_batches])
+        nrow = (ctypes.c_int32 * k)(*rows)
+        check(self.lib.fr_focf_train_steps_host(ctypes.byref(s), k, ptrs, nrow, ptr(st), st.numel(), ptr(self._loss2),
+                                                host.data_ptr(), stream_ptr()), "fr_focf_train_steps_host")
+        return host[:k]
+
     def set_counters(self, plan_cursor=-1, adam_step=None, stride=0):
         """device-resident counters of the workspace; None / negative cursor / stride 0 leave a counter unchanged"""
         check(self.lib.fr_focf_set_counters(ptr(self.ws), self.ws.numel(), self.n_users, self.n_items, self.d,

