@@ -9,7 +9,8 @@ Prints ONE JSON line (rank 0).  A "step" is one FOCF optimisation step on one FO
   value      device-resident: train split, tables and Adam state live in HBM; each timed step is bracketed by CUDA
              events on the launching stream and preceded (outside the bracket) by an L2 flush (512 MB write)
   e2e        the same steps through the public API with HOST batches: pinned host columns -> H2D -> train_step ->
-             loss D2H + sync, every step, wall clock
+             loss D2H + sync, every step, wall clock; `value` is FOCF.train_steps_host (the loop inside the library,
+             one call for all batches) when its self-check passes, `python_loop_value` the per-batch Python loop
   eval       full-sort fair evaluation of all valid users (scoring + mask + top-K + 12 metrics): users/s, same two ways
   roofline   dominant training kernel: algorithmic bytes per launch / its CUDA-event duration (library profiler) vs
              the measured HBM copy bandwidth of MEASURED_PEAKS.json
