@@ -49,7 +49,9 @@ def host_batches(g):
 
 
 @pytest.mark.parametrize("path", TRAIN, ids=[os.path.basename(p)[11:-4] for p in TRAIN])
-def test_host_batch_loop_matches_the_reference_fixture_and_the_per_batch_path(path):
+def test_host_batch_loop_matches_the_reference_fixture_and_the_per_batch_path(path, monkeypatch):
+    import recbole_fairrec_b200.focf as focf_mod
+    monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", True)          # per-batch reference = the generic host path
     g = np.load(path)
     obj, fw = str(g["objective"]), float(g["fair_weight"])
     batches = host_batches(g)
@@ -72,10 +74,12 @@ def test_host_batch_loop_matches_the_reference_fixture_and_the_per_batch_path(pa
         assert torch.equal(a.detach(), b.detach())
 
 
-def test_host_batch_loop_on_ragged_batches_and_a_second_call():
+def test_host_batch_loop_on_ragged_batches_and_a_second_call(monkeypatch):
     """batch sizes that change from step to step (the staging buffer and the workspace grow), a second call continuing the
     optimizer step count, an empty list, and the library's refusal of a device buffer"""
     import recbole_fairrec_b200 as pkg
+    import recbole_fairrec_b200.focf as focf_mod
+    monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", True)
     rng = np.random.default_rng(7)
     nu, ni, d = 300, 200, 32
     U0 = (rng.standard_normal((nu, d)) * 0.3).astype(np.float32)
@@ -109,3 +113,23 @@ def test_host_batch_loop_on_ragged_batches_and_a_second_call():
     bad.packed_host = (bad.packed_host[0].cuda(), bad.packed_host[1])
     with pytest.raises(ValueError):
         loop.train_steps_host([bad])
+
+
+@pytest.mark.parametrize("path", TRAIN[:3], ids=[os.path.basename(p)[11:-4] for p in TRAIN[:3]])
+def test_packed_per_batch_path_equals_the_generic_one(path, monkeypatch):
+    """FocfEngine.train_step_packed (persistent staging buffer + argument struct, also written after the last GPU session)
+    against the generic per-batch path on the same host batches: the same bits"""
+    import recbole_fairrec_b200.focf as focf_mod
+    g = np.load(path)
+    obj, fw = str(g["objective"]), float(g["fair_weight"])
+    batches = host_batches(g)
+    out = []
+    for generic in (True, False):
+        monkeypatch.setattr(focf_mod, "_NO_FAST_HOST_STEP", generic)
+        m = make_model(g["U0"], g["I0"], obj, fw)
+        m.init_adam(lr=float(g["lr"]), weight_decay=float(g["wd"]))
+        losses = [float(m.train_step(b).item()) for b in batches]
+        m.check_flags()
+        out.append((losses, m.user_embedding_layer.weight.detach().clone(), m.item_embedding_layer.weight.detach().clone()))
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    np.testing.assert_allclose(out[1][0], g["losses"], rtol=RTOL)
