@@ -32,7 +32,7 @@ from recbole.utils import init_seed as ref_seed  # noqa: E402
 import make_test_data as mtd  # noqa: E402
 from recbole_fairrec_b200.atomic import AtomicDataset, used_and_positive_lists  # noqa: E402
 from recbole_fairrec_b200.quick_start import BatchLoader, build_config, init_seed  # noqa: E402
-from recbole_fairrec_b200.sampled_eval import sample_negatives_reference  # noqa: E402
+from recbole_fairrec_b200.sampled_eval import AliasSampler, sample_negatives_reference  # noqa: E402
 
 warnings.filterwarnings("ignore")
 logging.disable(logging.CRITICAL)
@@ -45,15 +45,17 @@ def main():
     name = mtd.write_messy(root)
     os.chdir(tempfile.mkdtemp())
     bad = 0
-    for model, pairwise, neg_num, bs in (("PFCN_PMF", True, 20, 512), ("NFCF", False, 50, 300)):
+    for model, pairwise, neg_num, bs, dist in (("PFCN_PMF", True, 20, 512, "uniform"), ("NFCF", False, 50, 300, "uniform"),
+                                               ("PFCN_PMF", True, 10, 700, "popularity"), ("NFCF", False, 30, 256, "popularity")):
+        pop = dist == "popularity"
         base = dict(mtd.INGEST_BASE, **mtd.INGEST_CASES["defaults"], seed=seed, train_batch_size=bs,
                     user_inter_num_interval="[3,inf)")
-        base["eval_args"] = dict(base["eval_args"], mode=f"uni{neg_num}")
+        base["eval_args"] = dict(base["eval_args"], mode=f"{'pop' if pop else 'uni'}{neg_num}")
         extra = dict(filter_mode="none", dis_hidden_size_list=[8], activation="leakyrelu", embedding_size=8) if pairwise else \
             dict(mlp_hidden_size=[8], dropout=0.0, embedding_size=8, fair_weight=0.1)
         with open("c.yaml", "w") as f:
             yaml.safe_dump(dict(base, **extra, data_path=root, use_gpu=False, state="CRITICAL", show_progress=False,
-                                neg_sampling={"uniform": 1}, eval_batch_size=4096), f)
+                                neg_sampling={dist: 1}, eval_batch_size=4096), f)
         config = Config(model=model, dataset=name, config_file_list=["c.yaml"])
         ref_seed(config["seed"], config["reproducibility"])
         train_r, valid_r, _ = data_preparation(config, create_dataset(config))
@@ -64,18 +66,19 @@ def main():
                                    (b["neg_item_id"] if pairwise else b["label"]).numpy().copy()))
             for cur, idx_list, pu, pi in valid_r:
                 ref_stream.append(("valid", cur["user_id"].numpy().copy(), cur["item_id"].numpy().copy(), None))
-        cfg = build_config(model, name, None, dict(base, **extra, data_path=root, device="cpu", neg_sampling={"uniform": 1}))
+        cfg = build_config(model, name, None, dict(base, **extra, data_path=root, device="cpu", neg_sampling={dist: 1}))
         init_seed(cfg["seed"])
         ds = AtomicDataset(cfg)
         splits = ds.build()
-        loader = BatchLoader(cfg, ds, splits[0], pairwise=pairwise, pointwise_neg=not pairwise)
+        sampling = AliasSampler(np.concatenate([sp["item_id"] for sp in splits])).sampling if pop else None
+        loader = BatchLoader(cfg, ds, splits[0], pairwise=pairwise, pointwise_neg=not pairwise, sampling=sampling)
         users, hist, pos = used_and_positive_lists(splits, "valid")
         mine = []
         for _ in range(passes):
             for b in loader:
                 mine.append(("train", b["user_id"].numpy(), b["item_id"].numpy(),
                              (b["neg_item_id"] if pairwise else b["label"]).numpy()))
-            neg = sample_negatives_reference(pos, hist, ds.item_num, neg_num)
+            neg = sample_negatives_reference(pos, hist, ds.item_num, neg_num, sampling)
             # the reference's evaluation batches: per user [positives ; negatives], several users per batch
             mine.append(("valid-all", np.concatenate([np.repeat(u, len(p) * (neg_num + 1)) for u, p in zip(users, pos)]),
                          np.concatenate([np.r_[p, q] for p, q in zip(pos, neg)]), None))
@@ -99,7 +102,7 @@ def main():
             if not ok and first is None:
                 first = (k, a[0], len(a[1]), len(b[1]))
             same &= ok
-        print(model, "records", len(ref2), len(mine), "IDENTICAL" if same else f"DIFFERENT at {first}")
+        print(model, dist, "records", len(ref2), len(mine), "IDENTICAL" if same else f"DIFFERENT at {first}")
         bad += not same
     print("bad:", bad)
     return bad

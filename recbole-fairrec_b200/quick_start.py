@@ -7,6 +7,8 @@ DEFAULTS = overall.yaml / sample.yaml) < the model's hyper-parameter defaults (c
 keys of properties/model/<Model>.yaml) < the YAML files of `config_file_list` (in order) < `config_dict` < `--key=value`
 command-line overrides.
 
+Negatives follow `neg_sampling: {uniform | popularity: 1}` in training and `eval_args.mode: uni<N> | pop<N>` in evaluation
+(popularity = the reference's alias table over the items of all interactions, sampler.py:72-120; same RNG calls, same draws).
 Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
 uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort or `uni<N>`) and
 NFCF (both stages: positives + uniform negatives with 1 | 0 labels, `uni<N>` evaluation; `saved=True` writes the stage-1
@@ -70,7 +72,7 @@ class BatchLoader:
     `neg_sampling: {uniform: n}` negatives (abstract_dataloader.py:182-188; uniform over the items the user has not
     interacted with in the train split, by rejection like sampler.py:145-197)."""
 
-    def __init__(self, config, ds, split, pairwise, shuffle=True, pointwise_neg=False):
+    def __init__(self, config, ds, split, pairwise, shuffle=True, pointwise_neg=False, sampling=None):
         self.cfg, self.ds, self.split, self.pairwise, self.shuffle = config, ds, split, pairwise, shuffle
         self.pointwise_neg = pointwise_neg
         self.batch_size = int(config["train_batch_size"])
@@ -80,6 +82,7 @@ class BatchLoader:
         self._order = np.arange(self.n)
         self.attrs = [a for a in (config["sst_attr_list"] or []) if a in ds.user_feat]
         self.neg_prefix = config["NEG_PREFIX"] or "neg_"
+        self.sampling = sampling or (lambda n: np.random.randint(1, self.ds.item_num, size=n))      # sampler.py:240-241
         if pairwise or pointwise_neg:
             key = split[ds.uid_field].astype(np.int64) * ds.item_num + split[ds.iid_field]
             self._used = np.sort(key)
@@ -88,14 +91,14 @@ class BatchLoader:
         return (self.n + self.batch_size - 1) // self.batch_size
 
     def _negatives(self, u):
-        neg = np.random.randint(1, self.ds.item_num, size=len(u))
+        neg = self.sampling(len(u))
         while True:
             key = u.astype(np.int64) * self.ds.item_num + neg
             pos = np.searchsorted(self._used, key)
             bad = (pos < len(self._used)) & (self._used[np.minimum(pos, len(self._used) - 1)] == key)
             if not bad.any():
                 return neg
-            neg[bad] = np.random.randint(1, self.ds.item_num, size=int(bad.sum()))
+            neg[bad] = self.sampling(int(bad.sum()))
 
     def __iter__(self):
         # the reference shuffles the train split IN PLACE at the start of every pass (abstract_dataloader.py:88-91 ->
@@ -155,6 +158,18 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         get_preload_weight = staticmethod(ds.get_preload_weight)
 
     sst_of_user = {a: ds.user_feat[a] for a in attrs}
+    _alias = []
+
+    def pop_sampling():        # one alias table over the items of all three splits (data/utils.py:244-265, sampler.py:234-238)
+        if not _alias:
+            from .sampled_eval import AliasSampler
+            _alias.append(AliasSampler(np.concatenate([s[itf] for s in splits])))
+        return _alias[0].sampling
+
+    ns = cfg["neg_sampling"] or {}
+    if ns and next(iter(ns)) not in ("uniform", "popularity"):
+        raise ValueError(f"The distribution [{next(iter(ns))}] of neg_sampling should in ['uniform', 'popularity']")
+    train_sampling = pop_sampling() if "popularity" in ns else None
 
     def eval_data(phase):
         if mode == "full" and cfg["eval_lists"] == "device":
@@ -169,11 +184,14 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         users, hist, pos = used_and_positive_lists(splits, phase)
         if mode == "full":
             return pkg.EvalData(users, hist, pos, sst_of_user, dev)
+        if mode[:3] not in ("uni", "pop") or not mode[3:].isdigit():
+            raise ValueError(f"the mode [{mode}] in eval_args is not supported.")       # configurator.py:380-390
         neg_num = int(mode[3:])
-        if cfg["eval_neg_resample"] is False:          # one fixed draw for all evaluations
+        if cfg["eval_neg_resample"] is False and mode[:3] == "uni":          # one fixed draw for all evaluations
             return SampledEvalData(users, pos, sample_negatives(pos, hist, ds.item_num, neg_num, np.random), sst_of_user, dev)
         # like the reference: negatives drawn anew at every evaluation, by the same calls on numpy's global RNG
-        return ResamplingEvalSource(users, pos, hist, sst_of_user, ds.item_num, neg_num, dev)
+        return ResamplingEvalSource(users, pos, hist, sst_of_user, ds.item_num, neg_num, dev,
+                                    sampling=pop_sampling() if mode[:3] == "pop" else None)
 
     name = cfg["model"]
     if name == "FOCF":
@@ -189,7 +207,7 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     elif name.startswith("PFCN_"):
         net = get_model(name)(cfg, TrainView).to(dev)
         trainer = get_trainer(net.type, name)(cfg, net)
-        loader = BatchLoader(cfg, ds, train, pairwise=True)
+        loader = BatchLoader(cfg, ds, train, pairwise=True, sampling=train_sampling)
         if mode == "full":
             raise NotImplementedError("PFCN full-sort evaluation is undefined in the reference; use eval_args.mode uni100")
         valid, test = eval_data("valid"), eval_data("test")
@@ -205,7 +223,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
         trainer = get_trainer(net.type, name)(cfg, net)
         # the FairGo YAMLs leave `neg_sampling: {uniform: 1}` in force: the reference's pointwise loader appends one sampled
         # item per interaction (same user, same rating column, label 0), abstract_dataloader.py:200-208
-        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
+        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None,
+                             sampling=train_sampling)
         valid, test = eval_data("valid"), eval_data("test")
         best, best_res = trainer.fit(loader, valid, train_item_count=item_counter, saved=saved)
         _load_best(trainer, saved)
@@ -213,7 +232,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     elif name == "NFCF":
         net = get_model(name)(cfg, TrainView).to(dev)
         trainer = get_trainer(net.type, name)(cfg, net)
-        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None)
+        loader = BatchLoader(cfg, ds, train, pairwise=False, pointwise_neg=cfg["neg_sampling"] is not None,
+                             sampling=train_sampling)
         if mode == "full":
             raise NotImplementedError("NFCF defines no full_sort_predict in the reference; use eval_args.mode uni100")
         valid, test = eval_data("valid"), eval_data("test")

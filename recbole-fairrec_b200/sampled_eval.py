@@ -50,7 +50,46 @@ def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
     return out
 
 
-def sample_negatives_reference(pos_lists, used_lists, n_items, neg_num):
+class AliasSampler:
+    """The reference's popularity-biased item sampler (sampler.py:72-120): Walker alias table over the item ids of ALL
+    interactions (train, valid, test rows in that order, sampler.py:234-238), keys in order of first appearance, the two
+    work queues first-in first-out -- and `sampling(n)` = ONE `np.random.randint(0, n_keys, n)` followed by ONE
+    `np.random.random(n)` on numpy's global RNG, so that a seed gives the reference's draws."""
+
+    def __init__(self, item_ids):
+        import pandas as pd
+        codes, keys = pd.factorize(np.asarray(item_ids, np.int64))
+        cnt = np.bincount(codes, minlength=len(keys))
+        prob = (cnt / len(codes) * len(keys)).tolist()
+        alias = [-1] * len(keys)
+        large = [i for i, p in enumerate(prob) if p > 1]
+        small = [i for i, p in enumerate(prob) if p < 1]
+        a = b = 0                                   # queue heads (the reference pops from the front of two lists)
+        while a < len(large) and b < len(small):
+            l, s_ = large[a], small[b]
+            a, b = a + 1, b + 1
+            alias[s_] = l
+            prob[l] = prob[l] - (1 - prob[s_])
+            if prob[l] < 1:
+                small.append(l)
+            elif prob[l] > 1:
+                large.append(l)
+        self.keys = np.asarray(keys, np.int64)
+        self.prob = np.asarray(prob, np.float64)
+        self.alias = np.where(np.asarray(alias) >= 0, self.keys[np.maximum(alias, 0)], -1)      # item ids (-1: never read)
+
+    def sampling(self, n):
+        idx = np.random.randint(0, len(self.keys), n)
+        p = np.random.random(n)
+        return np.where(self.prob[idx] > p, self.keys[idx], self.alias[idx]).astype(np.int64)
+
+
+def uniform_sampling(n_items):
+    """sampler.py:240-241"""
+    return lambda n: np.random.randint(1, n_items, n)
+
+
+def sample_negatives_reference(pos_lists, used_lists, n_items, neg_num, sampling=None):
     """The reference's own draws (sampler.py:159-175 through NegSampleEvalDataLoader._next_batch_data,
     general_dataloader.py:128-140): users in evaluation order, for each ONE call `np.random.randint(1, n_items, p * neg_num)`
     on numpy's global RNG, then the entries that hit a used item (train + the evaluated split, positives included) are
@@ -58,14 +97,15 @@ def sample_negatives_reference(pos_lists, used_lists, n_items, neg_num):
     (oracle/fuzz_loaders.py checks that against the live reference).  The reference draws them anew at EVERY evaluation;
     `ResamplingEvalSource` does the same."""
     out = []
+    sampling = sampling or uniform_sampling(n_items)          # `pop<N>` modes pass AliasSampler.sampling
     for pos, used in zip(pos_lists, used_lists):
         banned = np.zeros(n_items, bool)
         banned[np.asarray(used, np.int64)] = True
         banned[np.asarray(pos, np.int64)] = True
-        value = np.random.randint(1, n_items, neg_num * len(pos))
+        value = sampling(neg_num * len(pos))
         check = np.flatnonzero(banned[value])
         while len(check) > 0:
-            redraw = np.random.randint(1, n_items, len(check))
+            redraw = sampling(len(check))
             value[check] = redraw
             check = check[banned[redraw]]
         out.append(value.astype(np.int64))
@@ -76,22 +116,23 @@ class ResamplingEvalSource:
     """Evaluation split of the `uni<N>` mode whose negatives are drawn again at every evaluation, like the reference's
     NegSampleEvalDataLoader does while it iterates: trainers call `.resample()` and evaluate the SampledEvalData it returns."""
 
-    def __init__(self, users, pos_lists, used_lists, sst_of_user, n_items, neg_num, device):
+    def __init__(self, users, pos_lists, used_lists, sst_of_user, n_items, neg_num, device, sampling=None):
         self.users, self.pos, self.used, self.sst = users, pos_lists, used_lists, sst_of_user
         self.n_items, self.neg_num, self.device = int(n_items), int(neg_num), device
+        self.sampling = sampling                  # None: uniform (`uni<N>`); AliasSampler.sampling for `pop<N>`
 
     def __len__(self):
         return len(self.users)
 
     def resample(self):
-        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num)
+        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num, self.sampling)
         return SampledEvalData(self.users, self.pos, neg, self.sst, self.device)
 
     def resample_tiled(self, copies):
         """ONE draw of negatives, the user list repeated `copies` times (copy-major): the layout in which the reference's
         PFCN validation scores every batch under each attribute subset and collects everything into one struct
         (trainer.py:1010-1023).  Returns (data, candidate rows per copy)."""
-        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num)
+        neg = sample_negatives_reference(self.pos, self.used, self.n_items, self.neg_num, self.sampling)
         data = SampledEvalData(np.tile(np.asarray(self.users, np.int64), copies), list(self.pos) * copies, neg * copies,
                                self.sst, self.device)
         return data, int(data.cand_uid.numel()) // copies
@@ -220,5 +261,5 @@ class SampledEvaluator(FullSortEvaluator):
         return self.finalize(self.collect(score_fn, data), data)
 
 
-__all__ = ["SampledEvalData", "SampledEvaluator", "ResamplingEvalSource", "sample_negatives", "sample_negatives_reference",
+__all__ = ["SampledEvalData", "SampledEvaluator", "ResamplingEvalSource", "AliasSampler", "sample_negatives", "sample_negatives_reference",
            "sampled_topk", "OrderedDict", "FAIR_KEYS"]

@@ -565,15 +565,15 @@ def test_pfcn_validation_scores_every_attribute_subset_on_one_draw_of_negatives(
 
 def test_loader_streams_equal_the_live_references(tmp_path):
     """build container only (oracle/fuzz_loaders.py): pairwise and pointwise train batches over three passes (in-place
-    cumulative shuffles, negatives redrawn on collision) and the per-evaluation `uni<N>` negatives, identical to the
-    reference's TrainDataLoader / NegSampleEvalDataLoader for a seed"""
+    cumulative shuffles, negatives redrawn on collision) and the per-evaluation `uni<N>` / `pop<N>` negatives, with
+    `neg_sampling` uniform and popularity, identical to the reference's TrainDataLoader / NegSampleEvalDataLoader for a seed"""
     _live_reference()
     import subprocess
     import sys
     here = os.path.dirname(__file__)
     r = subprocess.run([sys.executable, os.path.join(here, "..", "oracle", "fuzz_loaders.py"), "7", "3"], capture_output=True,
                        text=True, timeout=900)
-    assert r.returncode == 0 and "bad: 0" in r.stdout and r.stdout.count("IDENTICAL") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "bad: 0" in r.stdout and r.stdout.count("IDENTICAL") == 4, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_plugin_discovery_by_name_like_the_reference():
@@ -638,6 +638,8 @@ def test_run_recbole_wiring_of_every_family_with_faked_epochs(tmp_path, monkeypa
             ("FOCF", dict(fair_objective="value", eval_args=uni, focf_draw_mode="fast"), False, 3),
             ("PFCN_PMF", dict(dis, filter_mode="sm", eval_args=uni), False, 3),
             ("PFCN_MLP", dict(dis, filter_mode="cm", mlp_hidden_size=[32, 16], dropout=0.0, eval_args=uni), True, 3),
+            ("PFCN_BiasedMF", dict(dis, filter_mode="sm", neg_sampling={"popularity": 1},          # popularity-biased negatives
+                                   eval_args=dict(uni, mode="pop50")), False, 3),                  # in training and evaluation
             ("FairGo_PMF", fairgo, False, 6),          # + one validation per pretrain epoch
             ("FairGo_GCN", dict(fairgo, gcn_n_layers=2, hidden_channels=32, gcn_dropout=0.2, gcn_act="relu", eval_args=uni), True, 6),
             ("NFCF", dict(dropout=0.2, fair_weight=0.1, mlp_hidden_size=[128, 64], eval_args=uni, load_pretrain_path=None), True, 3)]
@@ -747,3 +749,30 @@ def test_host_batch_step_loop_validates_its_arguments_before_touching_the_device
     rows[1] = 4
     s.step = 0                                              # device-resident step counts belong to the planned epoch
     assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
+
+
+def test_alias_sampler_follows_item_popularity_and_the_reference_call_pattern():
+    """sampler.py:72-120: keys in order of first appearance, a valid alias table (every column sums to 1 with its alias),
+    draws proportional to the interaction counts, and exactly one randint + one random call per `sampling(n)`"""
+    from recbole_fairrec_b200.sampled_eval import AliasSampler
+    rng = np.random.default_rng(3)
+    items = rng.choice(np.arange(1, 40), 5000, p=np.arange(1, 40) / np.arange(1, 40).sum())
+    a = AliasSampler(items)
+    _, first = np.unique(items, return_index=True)
+    assert a.keys.tolist() == items[np.sort(first)].tolist()
+    # mass conservation of the alias construction: P(key) = (prob[key] + sum of (1 - prob[j]) over j aliased to key) / n_keys
+    n = len(a.keys)
+    mass = a.prob.clip(max=1.0).copy()
+    for j in range(n):
+        if a.prob[j] < 1 and a.alias[j] >= 0:
+            mass[np.flatnonzero(a.keys == a.alias[j])[0]] += 1 - a.prob[j]
+    counts = np.array([np.sum(items == k) for k in a.keys])
+    np.testing.assert_allclose(mass / n, counts / len(items), atol=1e-12)
+    np.random.seed(5)
+    draw = a.sampling(200000)
+    freq = np.array([np.mean(draw == k) for k in a.keys])
+    assert np.abs(freq - counts / len(items)).max() < 4e-3 and set(draw.tolist()) <= set(items.tolist())
+    np.random.seed(5)
+    idx, p = np.random.randint(0, n, 17), np.random.random(17)
+    np.random.seed(5)
+    assert a.sampling(17).tolist() == np.where(a.prob[idx] > p, a.keys[idx], a.alias[idx]).tolist()
