@@ -45,8 +45,9 @@ def main():
     name = mtd.write_messy(root)
     os.chdir(tempfile.mkdtemp())
     bad = 0
-    for model, pairwise, neg_num, bs, dist in (("PFCN_PMF", True, 20, 512, "uniform"), ("NFCF", False, 50, 300, "uniform"),
-                                               ("PFCN_PMF", True, 10, 700, "popularity"), ("NFCF", False, 30, 256, "popularity")):
+    for model, pairwise, neg_num, bs, dist, by in (("PFCN_PMF", True, 20, 512, "uniform", 1), ("NFCF", False, 50, 300, "uniform", 1),
+                                                   ("PFCN_PMF", True, 10, 700, "popularity", 1), ("NFCF", False, 30, 256, "popularity", 1),
+                                                   ("PFCN_PMF", True, 5, 600, "uniform", 3), ("NFCF", False, 5, 500, "popularity", 4)):
         pop = dist == "popularity"
         base = dict(mtd.INGEST_BASE, **mtd.INGEST_CASES["defaults"], seed=seed, train_batch_size=bs,
                     user_inter_num_interval="[3,inf)")
@@ -55,7 +56,7 @@ def main():
             dict(mlp_hidden_size=[8], dropout=0.0, embedding_size=8, fair_weight=0.1)
         with open("c.yaml", "w") as f:
             yaml.safe_dump(dict(base, **extra, data_path=root, use_gpu=False, state="CRITICAL", show_progress=False,
-                                neg_sampling={dist: 1}, eval_batch_size=4096), f)
+                                neg_sampling={dist: by}, eval_batch_size=4096), f)
         config = Config(model=model, dataset=name, config_file_list=["c.yaml"])
         ref_seed(config["seed"], config["reproducibility"])
         train_r, valid_r, _ = data_preparation(config, create_dataset(config))
@@ -66,7 +67,7 @@ def main():
                                    (b["neg_item_id"] if pairwise else b["label"]).numpy().copy()))
             for cur, idx_list, pu, pi in valid_r:
                 ref_stream.append(("valid", cur["user_id"].numpy().copy(), cur["item_id"].numpy().copy(), None))
-        cfg = build_config(model, name, None, dict(base, **extra, data_path=root, device="cpu", neg_sampling={dist: 1}))
+        cfg = build_config(model, name, None, dict(base, **extra, data_path=root, device="cpu", neg_sampling={dist: by}))
         init_seed(cfg["seed"])
         ds = AtomicDataset(cfg)
         splits = ds.build()
@@ -102,7 +103,7 @@ def main():
             if not ok and first is None:
                 first = (k, a[0], len(a[1]), len(b[1]))
             same &= ok
-        print(model, dist, "records", len(ref2), len(mine), "IDENTICAL" if same else f"DIFFERENT at {first}")
+        print(model, dist, by, "records", len(ref2), len(mine), "IDENTICAL" if same else f"DIFFERENT at {first}")
         bad += not same
     print("bad:", bad)
     return bad

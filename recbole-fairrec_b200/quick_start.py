@@ -7,7 +7,7 @@ DEFAULTS = overall.yaml / sample.yaml) < the model's hyper-parameter defaults (c
 keys of properties/model/<Model>.yaml) < the YAML files of `config_file_list` (in order) < `config_dict` < `--key=value`
 command-line overrides.
 
-Negatives follow `neg_sampling: {uniform | popularity: 1}` in training and `eval_args.mode: uni<N> | pop<N>` in evaluation
+Negatives follow `neg_sampling: {uniform | popularity: n}` in training and `eval_args.mode: uni<N> | pop<N>` in evaluation
 (popularity = the reference's alias table over the items of all interactions, sampler.py:72-120; same RNG calls, same draws).
 Supported: FOCF (eval mode `full` or `uni<N>`), PFCN_MLP / PFCN_PMF / PFCN_BiasedMF / PFCN_DMF (pairwise batches with one
 uniform negative per positive, `uni<N>` evaluation), FairGo_PMF / FairGo_GCN (pointwise batches, full-sort or `uni<N>`) and
@@ -76,8 +76,11 @@ class BatchLoader:
         self.cfg, self.ds, self.split, self.pairwise, self.shuffle = config, ds, split, pairwise, shuffle
         self.pointwise_neg = pointwise_neg
         self.batch_size = int(config["train_batch_size"])
-        if pointwise_neg:                     # _batch_size_adaptation (general_dataloader.py:40-50): positives + negatives
-            self.batch_size = max(self.batch_size // 2, 1)       # together fill one train_batch_size
+        ns = config["neg_sampling"] or {}
+        self.neg_num = int(next(iter(ns.values()))) if ns and (pairwise or pointwise_neg) else 1      # `by` (configurator.py:355-366)
+        # general_dataloader.py:40-50: positives and their negatives together fill one train_batch_size
+        times = self.neg_num if pairwise else (1 + self.neg_num if pointwise_neg else 1)
+        self.batch_size = max(self.batch_size // times, 1)
         self.n = len(split[ds.uid_field])
         self._order = np.arange(self.n)
         self.attrs = [a for a in (config["sst_attr_list"] or []) if a in ds.user_feat]
@@ -91,6 +94,9 @@ class BatchLoader:
         return (self.n + self.batch_size - 1) // self.batch_size
 
     def _negatives(self, u):
+        """sampler.py:145-197 for the users of one batch: `neg_num` draws per row, laid out draw-major (all first draws,
+        then all second draws, ...), entries that hit an item of the user's train split redrawn together until none is left"""
+        u = np.tile(u, self.neg_num)
         neg = self.sampling(len(u))
         while True:
             key = u.astype(np.int64) * self.ds.item_num + neg
@@ -113,12 +119,14 @@ class BatchLoader:
             cols = {k: torch.from_numpy(np.ascontiguousarray(v[idx])) for k, v in self.split.items()}
             for a in self.attrs:
                 cols[a] = torch.from_numpy(self.ds.user_feat[a][u])
-            if self.pairwise:
+            if self.pairwise:                 # abstract_dataloader.py:190-198: rows repeated `neg_num` times + the negatives
+                if self.neg_num > 1:
+                    cols = {k: v.repeat(self.neg_num) for k, v in cols.items()}
                 cols[self.neg_prefix + itf] = torch.from_numpy(self._negatives(u))
             if self.pointwise_neg:            # abstract_dataloader.py:200-208: rows repeated, items replaced, labels 1 | 0
-                cols = {k: torch.cat([v, v]) for k, v in cols.items()}
+                cols = {k: v.repeat(1 + self.neg_num) for k, v in cols.items()}
                 cols[itf][len(u):] = torch.from_numpy(self._negatives(u))
-                label = torch.zeros(2 * len(u))
+                label = torch.zeros((1 + self.neg_num) * len(u))
                 label[:len(u)] = 1.0
                 cols[self.cfg["LABEL_FIELD"] or "label"] = label
             yield Interaction(cols)

@@ -566,14 +566,14 @@ def test_pfcn_validation_scores_every_attribute_subset_on_one_draw_of_negatives(
 def test_loader_streams_equal_the_live_references(tmp_path):
     """build container only (oracle/fuzz_loaders.py): pairwise and pointwise train batches over three passes (in-place
     cumulative shuffles, negatives redrawn on collision) and the per-evaluation `uni<N>` / `pop<N>` negatives, with
-    `neg_sampling` uniform and popularity, identical to the reference's TrainDataLoader / NegSampleEvalDataLoader for a seed"""
+    `neg_sampling` uniform and popularity with one and several negatives per positive, identical to the reference's TrainDataLoader / NegSampleEvalDataLoader for a seed"""
     _live_reference()
     import subprocess
     import sys
     here = os.path.dirname(__file__)
     r = subprocess.run([sys.executable, os.path.join(here, "..", "oracle", "fuzz_loaders.py"), "7", "3"], capture_output=True,
                        text=True, timeout=900)
-    assert r.returncode == 0 and "bad: 0" in r.stdout and r.stdout.count("IDENTICAL") == 4, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "bad: 0" in r.stdout and r.stdout.count("IDENTICAL") == 6, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_plugin_discovery_by_name_like_the_reference():
