@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
 // dY' = dY * act'(Yout) when y_out is given (the layer's activation backward fused into the loader).
 struct WgradArgs {
   const float *dY, *X;
-  float *part_w, *part_b;       // [chunks, N, K], [chunks, N]
+  float *part_w;                // [chunks, N, K]
+  double *part_b;               // [chunks, N]: bias-gradient column sums are carried in float64 (a column sum of +-O(1/B)
+                                // terms cancels ~1000x in the BPR tower; float64 makes its rounding negligible)
   int M, N, K, ldy, ldx;
   float drop_p;
   unsigned long long seed;
@@ -162,7 +164,8 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
   const int mlo = blockIdx.z * a.chunk, mhi = min(a.M, mlo + a.chunk);
   const unsigned long long seed = a.seed + (a.seed_dev ? *a.seed_dev : 0ull);
-  float acc[4][4], bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][4];
+  double bacc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
       const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        bacc[i] += yv[i];
+        if (tx == 0) bacc[i] += (double)yv[i];      // warp-uniform per half-warp; only column owners carry the sum
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yv[i], xv[j], acc[i][j]);
       }
@@ -233,10 +236,10 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
     const int n = n0 + ty * 4 + i;
     if (n >= a.N) continue;
     if (tx == 0 && blockIdx.x == 0 && a.db) {
-      float sb = 0.f;
+      double sb = 0.0;
 #pragma unroll 8
       for (int c = 0; c < chunks; ++c) sb += __ldcg(a.part_b + (size_t)c * a.N + n);
-      a.db[n] = sb;
+      a.db[n] = (float)sb;
     }
     const int k = k0 + tx * 4;
     if ((a.K & 3) == 0 && k + 3 < a.K) {     // 128-bit reads, 8 chunks in flight, added in chunk order
@@ -261,12 +264,13 @@ __global__ void __launch_bounds__(256) k_wgrad(WgradArgs a) {
   if (threadIdx.x == 0) a.tickets[tile] = 0;
 }
 
-// out[i] = sum_c part[c][i] in chunk order
-__global__ void k_sum_chunks(const float *__restrict__ part, int chunks, int64_t n, float *__restrict__ out) {
+// out[i] = sum_c part[c][i] in chunk order (float partials: weight gradients; double partials: bias gradients)
+template <typename T>
+__global__ void k_sum_chunks(const T *__restrict__ part, int chunks, int64_t n, float *__restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
+    T s = (T)0;
     for (int c = 0; c < chunks; ++c) s += part[(size_t)c * n + i];
-    out[i] = s;
+    out[i] = (float)s;
   }
 }
 
@@ -644,36 +648,38 @@ __global__ void __launch_bounds__(256)
     k_bn_bwd_stats(const float *__restrict__ X, const float *__restrict__ Y, const float *__restrict__ dY,
                    const float *__restrict__ save_mean, const float *__restrict__ save_invstd, int M, int N, int act,
                    float *__restrict__ part /* [slices][N][2]: sum dpre, sum dpre*xhat */) {
-  __shared__ float red[8][33];
+  // the two column sums cancel heavily under BPR (+g / -g per user): float64 accumulators inside the slice, float
+  // slice partials (a 1/32 slice of the batch), float64 again for the cross-slice combination in k_bn_bwd_apply
+  __shared__ double red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool ok = c < N;
   const int rows = bn_slice_rows(M), r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
   const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f;
-  float sb = 0.f, sg = 0.f;
+  double sb = 0.0, sg = 0.0;
 #pragma unroll 4
   for (int m = r0 + w; m < r1; m += 8) {
     if (ok) {
       const size_t i = (size_t)m * N + c;
       const float dp = dY[i] * act_bwd(Y[i], act);
-      sb += dp;
-      sg = fmaf(dp, (X[i] - mean) * invstd, sg);
+      sb += (double)dp;
+      sg += (double)(dp * ((X[i] - mean) * invstd));
     }
   }
   red[w][lane] = sb;
   __syncthreads();
-  sb = 0.f;
+  sb = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) sb += red[i][lane];
   __syncthreads();
   red[w][lane] = sg;
   __syncthreads();
   if (w == 0 && ok) {
-    sg = 0.f;
+    sg = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sg += red[i][lane];
-    part[((size_t)blockIdx.y * N + c) * 2] = sb;
-    part[((size_t)blockIdx.y * N + c) * 2 + 1] = sg;
+    part[((size_t)blockIdx.y * N + c) * 2] = (float)sb;
+    part[((size_t)blockIdx.y * N + c) * 2 + 1] = (float)sg;
   }
 }
 
@@ -691,13 +697,16 @@ __global__ void __launch_bounds__(256)
     float2 pr[kBnSlices];
 #pragma unroll
     for (int sl = 0; sl < kBnSlices; ++sl) pr[sl] = __ldg((const float2 *)(part + ((size_t)sl * N + c) * 2));
+    double sbd = 0.0, sgd = 0.0;
 #pragma unroll
     for (int sl = 0; sl < kBnSlices; ++sl) {
       if (sl * rows < M) {
-        sb += pr[sl].x;
-        sg += pr[sl].y;
+        sbd += (double)pr[sl].x;
+        sgd += (double)pr[sl].y;
       }
     }
+    sb = (float)sbd;
+    sg = (float)sgd;
     mean = save_mean[c]; invstd = save_invstd[c]; g = gamma[c];
     if (blockIdx.y == 0 && w == 0) {
       dbeta[c] = sb;
@@ -827,7 +836,8 @@ struct MlpWs {
   float *X;          // [M, dims[0]] gathered input
   float *act[8];     // post-activation outputs of every layer [M, dims[l+1]]
   float *dA, *dB;    // ping-pong row gradients [M, max width]
-  float *part_w, *part_b;
+  float *part_w;
+  double *part_b;
   float *p, *dp, *dz, *bce_part, *seg_eps, *coef, *loss_tmp;
   int32_t *pos_idx, *n_pos, *seg_id, *seg_off, *n_seg;
   uint32_t *keys, *skey, *ord, *mm;
@@ -851,7 +861,7 @@ static MlpWs carve_mlp(Carver &c, const fr_mlp_tower *t, int64_t M) {
   w.dA = c.take<float>(m * maxw);
   w.dB = c.take<float>(m * maxw);
   w.part_w = c.take<float>(chunks * maxwk);
-  w.part_b = c.take<float>(chunks * maxw);
+  w.part_b = c.take<double>(chunks * maxw);
   w.p = c.take<float>(m);
   w.dp = c.take<float>(m);
   w.dz = c.take<float>(m);
@@ -969,9 +979,9 @@ int fr_nfcf_backward(const fr_nfcf_step *s, float grad_scale, void *stream) {
                      nullptr, 0, nullptr, nullptr, nullptr, nullptr, wchunk};
     dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
     FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
-    FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)w.part_w, chunks,
+    FR_LAUNCH(fr::k_sum_chunks<float>, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)w.part_w, chunks,
               (int64_t)N * K, s->dW[l]);
-    FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)w.part_b, chunks, (int64_t)N, s->db[l]);
+    FR_LAUNCH(fr::k_sum_chunks<double>, 1, 256, 0, st, (const double *)w.part_b, chunks, (int64_t)N, s->db[l]);
     // dInput[M,K] = dcur[M,N] . W[N,K], then through the dropout mask of this layer's input and the previous
     // layer's activation
     float *dnext = bufs[l & 1];
@@ -1067,7 +1077,7 @@ int fr_linear_forward(const float *X, const float *W, const float *b, float *Y, 
 
 size_t fr_linear_backward_workspace_bytes(int64_t M, int32_t K, int32_t N) {
   const size_t chunks = ((size_t)M + fr::kWgradChunk - 1) / fr::kWgradChunk;
-  return ((size_t)M * N + chunks * (size_t)N * K + chunks * (size_t)N) * 4 + 1024;
+  return ((size_t)M * N + chunks * (size_t)N * K + 2 * chunks * (size_t)N) * 4 + 1024;
 }
 
 int fr_linear_backward(const float *X, const float *W, const float *Y, const float *dY, int64_t M, int32_t K, int32_t N,
@@ -1084,7 +1094,7 @@ int fr_linear_backward(const float *X, const float *W, const float *Y, const flo
   fr::Carver c(workspace, workspace_bytes);
   float *dpre = c.take<float>((size_t)M * N);
   float *part_w = c.take<float>((size_t)chunks * N * K);
-  float *part_b = c.take<float>((size_t)chunks * N);
+  double *part_b = c.take<double>((size_t)chunks * N);
   (void)dpre;
   dim3 grid((K + 63) / 64, (N + 63) / 64, chunks);
   const bool fused = tickets != nullptr && grid.x * grid.y <= 1024;
@@ -1092,9 +1102,9 @@ int fr_linear_backward(const float *X, const float *W, const float *Y, const flo
                    fused ? tickets : nullptr, dW, db, wchunk};
   FR_LAUNCH(fr::k_wgrad, grid, 256, 0, st, wa);
   if (!fused) {
-    FR_LAUNCH(fr::k_sum_chunks, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)part_w, chunks,
+    FR_LAUNCH(fr::k_sum_chunks<float>, fr::grid_for((int64_t)N * K, 256), 256, 0, st, (const float *)part_w, chunks,
               (int64_t)N * K, dW);
-    if (db) FR_LAUNCH(fr::k_sum_chunks, 1, 256, 0, st, (const float *)part_b, chunks, (int64_t)N, db);
+    if (db) FR_LAUNCH(fr::k_sum_chunks<double>, 1, 256, 0, st, (const double *)part_b, chunks, (int64_t)N, db);
   }
   if (dX) {
     fr::GemmArgs g{dY, W, nullptr, dX, (int)M, K, N, N, K, K, fr::ACT_NONE, nullptr, 0, drop_p, seed, layer, 1,

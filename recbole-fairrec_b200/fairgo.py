@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from .checkpoint import CheckpointMixin
+from .utils import stopping_step as _stopping_step
 from . import ops
 from .layers import _ACT_MODULES, MLPLayers
 
@@ -376,7 +377,15 @@ class FairGoTrainer(CheckpointMixin):
         self.sst_attrs = list(config["sst_attr_list"])
         lr, wd = config["learning_rate"], config["weight_decay"] or 0.0
         self.load_pretrain_weight = config["load_pretrain_weight"]
-        if self.load_pretrain_weight or config["pretrain_model_file_path"] is not None:
+        if config["pretrain_model_file_path"] is not None:
+            # trainer.py:541-549: the fine-tune stage starts from the checkpointed pretrain model
+            checkpoint = torch.load(config["pretrain_model_file_path"], map_location=model._dev(), weights_only=False)
+            model.load_state_dict(checkpoint["state_dict"])
+            model.load_other_parameter(checkpoint.get("other_parameter"))
+            model._ego = None           # the tables changed under the cached [N, d] concatenation
+            self.saved_pretrain_model_file = config["pretrain_model_file_path"]
+            model.train_stage = "finetune"
+        elif self.load_pretrain_weight:
             model.train_stage = "finetune"
         else:
             model.train_stage = "pretrain"
@@ -430,7 +439,7 @@ class FairGoTrainer(CheckpointMixin):
                 losses.append(self._pass(train_data, self.model.calculate_loss, self.optimizer_pretrain, None))
                 res = self.evaluate(valid_data)            # pretrain stage: the raw tables (FairGo_GCN: the GCN output)
                 best, cur, stop, update = early_stopping(res[metric], best, cur,
-                                                         max_step=self.config["stopping_step"] or 10, bigger=bigger)
+                                                         max_step=_stopping_step(self.config), bigger=bigger)
                 if update:
                     best_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
                 if stop:
@@ -529,7 +538,7 @@ class FairGoTrainer(CheckpointMixin):
             if not valid_data:
                 continue
             res = self.evaluate(valid_data)
-            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
+            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=_stopping_step(self.config),
                                                      bigger=bigger)
             self.best_valid_score, self.cur_step = best, cur
             if update:

@@ -283,12 +283,15 @@ class FOCF(nn.Module):
                    for e, p in zip(engines, plans)]
             key = key[:6] + (eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap)     # planned_step may have grown a workspace
             # eager first step on each workspace: module loading, function attributes
+            # (an epoch of ONE batch warms up workspace 0 only: cursor 1 would wrap to batch 0 and train it twice)
             eng.set_counters(plan_cursor=0, adam_step=T, stride=1)
             eng.run_planned(sts[0])
-            self._eng2.set_counters(plan_cursor=1, adam_step=T + 1, stride=1)
-            self._eng2.run_planned(sts[1])
-            runner.cursor = 2
-            T += 2
+            warm = min(2, plan["len"])
+            if warm == 2:
+                self._eng2.set_counters(plan_cursor=1, adam_step=T + 1, stride=1)
+                self._eng2.run_planned(sts[1])
+            runner.cursor = warm
+            T += warm
             self._adam["step"] = T
             torch.cuda.synchronize()
             self._graphs = {}
@@ -465,6 +468,7 @@ class _PlannedRunner:
         m = self.model
         G = m._graph_len
         big = m._graphs[G]
+        k = max(int(k), 0)
         left, c = k, self.cursor
         while left > 0:
             if (c & 1) == 0 and left >= G:

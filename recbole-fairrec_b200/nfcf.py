@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .checkpoint import CheckpointMixin
+from .utils import stopping_step as _stopping_step
 from . import _lib
 from ._lib import MlpTower, NfcfStep, check, load, ptr, stream_ptr
 
@@ -253,7 +254,7 @@ class NFCFTrainer(CheckpointMixin):
                 continue
             res = self.evaluate(valid_data, train_item_count)
             self.best_valid_score, self.cur_step, stop, update = early_stopping(
-                res[metric], self.best_valid_score, self.cur_step, max_step=self.config["stopping_step"] or 10, bigger=bigger)
+                res[metric], self.best_valid_score, self.cur_step, max_step=_stopping_step(self.config), bigger=bigger)
             if update:
                 best_res = res
                 if saved:

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .checkpoint import CheckpointMixin
+from .utils import stopping_step as _stopping_step
 from . import ops
 from .layers import MLPLayers
 
@@ -455,7 +456,7 @@ class PFCNTrainer(CheckpointMixin):
             if not valid_data:
                 continue
             res = self.pfcn_evaluate(valid_data, train_item_count)
-            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=self.config["stopping_step"] or 10,
+            best, cur, stop, update = early_stopping(res[metric], best, cur, max_step=_stopping_step(self.config),
                                                      bigger=bigger)
             self.best_valid_score, self.cur_step = best, cur
             if update:

@@ -253,7 +253,8 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
             logger.info("saved %s", trainer.saved_model_file)
     else:
         raise ValueError(f"unknown model {name}")
-    out = {"best_valid_score": best, "valid_score_bigger": True, "best_valid_result": best_res, "test_result": test_res}
+    bigger = cfg["valid_metric_bigger"]
+    out = {"best_valid_score": best, "valid_score_bigger": True if bigger is None else bool(bigger), "best_valid_result": best_res, "test_result": test_res}
     if getattr(trainer, "saved_model_file", None):
         out["saved_model_file"] = trainer.saved_model_file
     return out

@@ -28,3 +28,9 @@ def get_trainer(model_type, model_name):
     pkg = _package()
     cls = getattr(pkg, f"{model_name}Trainer", None)
     return cls if isinstance(cls, type) else pkg.FOCFTrainer
+
+
+def stopping_step(config, default=10):
+    """`stopping_step` of overall.yaml:13 (10); an explicit 0 stays 0 (stop at the first non-improving evaluation)"""
+    v = config["stopping_step"]
+    return default if v is None else int(v)

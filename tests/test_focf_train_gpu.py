@@ -264,6 +264,34 @@ def test_planned_graph_epoch_equals_stepwise_epoch():
     np.testing.assert_array_equal(results[0][2], results[1][2])
 
 
+def test_planned_epoch_of_a_single_batch_equals_train_step():
+    """train rows <= train_batch_size: the epoch plan holds ONE batch; the planned runner's warm-up must not run it twice
+    and the host's Adam step count must stay equal to the device's over several epochs"""
+    import recbole_fairrec_b200 as pkg
+    cfg, train, U0, I0 = _ml_like_loader(5, n_users=300, n_items=60, n_inter=1500, batch=4096)
+    results = []
+    for planned in (False, True):
+        loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=3)
+        assert len(loader) == 1
+        model = make_model(U0, I0, "value", 1.0)
+        model.init_adam(lr=1e-3, weight_decay=1e-3)
+        losses = torch.zeros(3, device="cuda")
+        for ep in range(3):
+            if planned:
+                k, _ = model.train_epoch_planned(loader, losses[ep:ep + 1], graph_steps=4)
+                assert k == 1
+            else:
+                for inter in loader:
+                    model.train_step(inter, loss_out=losses[ep:ep + 1])
+        model.check_flags()
+        results.append((losses.cpu().numpy().copy(), model.user_embedding_layer.weight.detach().cpu().numpy().copy(),
+                        model.item_embedding_layer.weight.detach().cpu().numpy().copy(), model._adam["step"]))
+    assert results[0][3] == results[1][3] == 3
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_array_equal(results[0][1], results[1][1])
+    np.testing.assert_array_equal(results[0][2], results[1][2])
+
+
 def test_small_and_general_preparation_agree():
     """B <= 8192 takes the fused single-CTA preparation, larger batches the multi-kernel path: same results"""
     from recbole_fairrec_b200 import kernels

@@ -192,18 +192,32 @@ def test_tc_scorer_matches_exact_scorer(n_users, n_items, d, n_eval, K):
     ids_t, sc_t = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_CLAMP_DIV, 5.0, 0, _lib.SCORE_TC_3XTF32)
     torch.cuda.synchronize()
     sc_e, sc_t, ids_e, ids_t = sc_e.cpu().numpy(), sc_t.cpu().numpy(), ids_e.cpu().numpy(), ids_t.cpu().numpy()
-    tol = 4e-6
-    np.testing.assert_allclose(sc_t, sc_e[:, :K], rtol=0, atol=tol)
-    clean = np.all(np.abs(np.diff(sc_e, axis=1)) > 2 * tol, axis=1)
-    assert clean.mean() > 0.5
-    np.testing.assert_array_equal(ids_t[clean], ids_e[clean, :K])
+    hist = [set(hi[ho[r]:ho[r + 1]].tolist()) for r in range(len(users))]
+
+    def check(ids_e, sc_e, ids_t, sc_t, transform, max_rating, tol):
+        """every row, clean or not: the K scores agree position by position (same multiset); each id the tensor-core scorer
+        returns is a legal candidate whose EXACT score is the one reported (within tol) and reaches the exact K-th score
+        (within tol), no id twice; rows whose exact top-(K+1) is separated by more than 2*tol must match id by id"""
+        np.testing.assert_allclose(sc_t, sc_e[:, :K], rtol=0, atol=tol)
+        n = ids_t.shape[0]
+        uid = torch.from_numpy(np.repeat(users.astype(np.int32), K)).cuda()
+        exact_of_picks = kernels.pair_scores(Ud, Id, uid, torch.from_numpy(ids_t.reshape(-1).astype(np.int32)).cuda(),
+                                             transform, max_rating).cpu().numpy().reshape(n, K)
+        np.testing.assert_allclose(exact_of_picks, sc_t, rtol=0, atol=tol)
+        assert np.all(exact_of_picks >= sc_e[:, K - 1:K] - tol)
+        for r in range(n):
+            row = ids_t[r].tolist()
+            assert len(set(row)) == K and 0 not in row and not (set(row) & hist[r]), r
+        clean = np.all(np.abs(np.diff(sc_e, axis=1)) > 2 * tol, axis=1)
+        assert clean.any()
+        np.testing.assert_array_equal(ids_t[clean], ids_e[clean, :K])
+
+    check(ids_e, sc_e, ids_t, sc_t, _lib.TRANSFORM_CLAMP_DIV, 5.0, 4e-6)
     # raw-dot variant (no clamp): exercises the filter with negative scores
     ids_e, sc_e = kernels.fullsort_topk(*args, K + 1, _lib.TRANSFORM_NONE, 1.0)
     ids_t, sc_t = kernels.fullsort_topk(*args, K, _lib.TRANSFORM_NONE, 1.0, 0, _lib.SCORE_TC_3XTF32)
     sc_e, sc_t, ids_e, ids_t = sc_e.cpu().numpy(), sc_t.cpu().numpy(), ids_e.cpu().numpy(), ids_t.cpu().numpy()
-    np.testing.assert_allclose(sc_t, sc_e[:, :K], rtol=0, atol=2e-5)
-    clean = np.all(np.abs(np.diff(sc_e, axis=1)) > 4e-5, axis=1)
-    np.testing.assert_array_equal(ids_t[clean], ids_e[clean, :K])
+    check(ids_e, sc_e, ids_t, sc_t, _lib.TRANSFORM_NONE, 1.0, 2e-5)
 
 
 def test_tc_evaluator_metrics_close_to_exact():

@@ -200,6 +200,26 @@ def _all_state(model, trainer):
     return out
 
 
+def test_fairgo_trainer_loads_the_pretrain_checkpoint(tmp_path):
+    """trainer.py:541-549: with `pretrain_model_file_path` the fine-tune stage starts from the checkpointed tables"""
+    import recbole_fairrec_b200 as pkg
+    cfg, model, _ = _family("FairGo_GCN", 1)
+    want = {k: torch.randn_like(v) if v.is_floating_point() else v.clone() for k, v in model.state_dict().items()}
+    path = str(tmp_path / "pretrain.pth")
+    torch.save({"state_dict": want, "other_parameter": None}, path)
+    cfg2, model2, _ = _family("FairGo_GCN", 2)
+    assert not torch.equal(model2.user_embedding_layer.weight, want["user_embedding_layer.weight"])
+    model2._ego = ("stale", None)
+    cfg2["pretrain_model_file_path"] = path
+    trainer = pkg.FairGoTrainer(cfg2, model2)
+    assert model2.train_stage == "finetune" and model2._ego is None and not hasattr(trainer, "optimizer_pretrain")
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    cfg2["pretrain_model_file_path"] = str(tmp_path / "missing.pth")
+    with pytest.raises(FileNotFoundError):
+        pkg.FairGoTrainer(cfg2, model2)
+
+
 @pytest.mark.parametrize("name", ["PFCN_MLP", "FairGo_GCN", "NFCF"])
 def test_checkpoint_round_trip_of_the_mlp_family_trainers(name, tmp_path):
     """trainer.py:221-284 / 784-830 / 1133-1184: the reference's checkpoint keys, plus the dict-held filter / discriminator

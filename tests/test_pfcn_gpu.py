@@ -148,6 +148,31 @@ def test_pfcn_matches_reference(path):
     assert n > 40
 
 
+def condition_away_from_kinks(model):
+    """Random weights for the wide-layer test, placed so that no pre-activation sits near a ReLU / LeakyReLU kink: with
+    ~3e6 activations per pass, float32 rounding otherwise flips the slope of a few of them, and ONE flipped term moves a
+    batch-summed weight gradient by ~1/sqrt(B) = 2 % -- in any float32 implementation, the reference's included.  (The
+    kinked regime is what the reference-generated fixtures above cover, at sizes where it is reproducible.)  BatchNorm'd
+    layers get beta = +6 (activations at 6 +- 1), except each discriminator's last layer, whose output feeds the
+    sigmoid / softmax and must stay O(1); the ReLU tower gets positive weights scaled 1/fan_in (activations stay O(1))."""
+    with torch.no_grad():
+        model.user_embedding.weight.mul_(0.5)
+        model.item_embedding.weight.mul_(0.5)
+        for m in list(model.filter_layer.values()) + list(model.dis_layer_dict.values()):
+            for p in m.parameters():
+                if p.dim() == 2:
+                    p.copy_(torch.randn_like(p) / np.sqrt(p.shape[1]))
+        for m in model.filter_layer.values():
+            for bn in [x for x in m.mlp_layers if isinstance(x, torch.nn.BatchNorm1d)]:
+                bn.bias.fill_(6.0)
+        for m in model.dis_layer_dict.values():
+            for bn in [x for x in m.mlp_layers if isinstance(x, torch.nn.BatchNorm1d)][:-1]:
+                bn.bias.fill_(6.0)
+        for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
+            lin.weight.copy_(torch.randn_like(lin.weight).abs() / lin.weight.shape[1])
+            lin.bias.add_(0.2)
+
+
 @pytest.mark.parametrize("filter_mode", ["sm", "cm"])
 def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
     """ML-1M configuration: d=64, filters [64,128,64], discriminators
@@ -159,21 +184,10 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
     torch.manual_seed(7)
     cfg, model = build("PFCN_MLP", filter_mode, nu, ni, d, feats, [128, 256, 128, 128, 64, 32], [64, 32, 16],
                        dis_weight=1.0)
-    with torch.no_grad():
-        model.user_embedding.weight.mul_(0.5)
-        model.item_embedding.weight.mul_(0.5)
-        for m in list(model.filter_layer.values()) + list(model.dis_layer_dict.values()):
-            for p in m.parameters():
-                if p.dim() == 2:
-                    p.copy_(torch.randn_like(p) / np.sqrt(p.shape[1]))
-        for lin in [m for m in model.mlp_layer.mlp_layers if isinstance(m, torch.nn.Linear)]:
-            lin.bias.add_(0.2)
+    condition_away_from_kinks(model)
     st = {k: torch.from_numpy(v.copy()) for k, v in dump_state(model).items()}
     st64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in st.items()}
     fkeys, dkeys = po.param_groups(st)
-    for k in fkeys + dkeys:
-        st[k].requires_grad_(True)
-        st64[k].requires_grad_(True)
     attrs = list(feats)
     if filter_mode == "sm":
         sst_dict, nf = {s: 2 ** i for i, s in enumerate(attrs)}, 7
@@ -193,30 +207,38 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
     loss.backward()
     args = ("PFCN_MLP", torch.from_numpy(u), torch.from_numpy(pos), torch.from_numpy(neg), labels, sst_list, sst_dict,
             sst_size, filter_mode, nf, "leakyrelu", 1.0)
-    lo = po.calculate_loss(st, *args)
-    lo.backward()
-    lo64 = po.calculate_loss(st64, *args)
-    lo64.backward()
-    np.testing.assert_allclose(loss.item(), lo.item(), rtol=RTOL)
+    # The yardstick is the float64 evaluation of the same graph and a tolerance derived from float64 quantities only
+    # (tests/abs_terms.py): 1e-5 relative to the value -- or, where a gradient is a cancelling sum over the batch (the BPR
+    # tower sees +g and -g for every user), to the sum of its terms' magnitudes -- widened only where the exact gradient
+    # itself moves by more than that under 1e-6 relative perturbations of its inputs (activations sitting on a
+    # ReLU / LeakyReLU kink, deep BatchNorm stacks).  Nothing depends on the host's float32 BLAS or thread count.
+    from abs_terms import gradient_tolerances
+    ref64, tol = gradient_tolerances(lambda s_: po.calculate_loss(s_, *args), st64, fkeys + dkeys, RTOL)
+    lo64 = float(po.calculate_loss(st64, *args))
+    np.testing.assert_allclose(loss.item(), lo64, rtol=RTOL)
     named = named_params(model)
-    checked = 0
+    checked, bad, rel_tols = 0, [], []
     for k in fkeys + dkeys:
-        if st[k].grad is None:
+        if ref64[k] is None:
             assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
             continue
-        ref, ref64 = st[k].grad.numpy(), st64[k].grad.numpy()
-        if np.abs(ref).max() == 0:
+        if np.abs(ref64[k]).max() == 0:
             continue
+        mine = named[k].grad.cpu().numpy()
         if bias_before_bn(k, st):
-            assert np.abs(named[k].grad.cpu().numpy()).max() < 1e-6 and np.abs(ref).max() < 1e-6, k
+            assert np.abs(mine).max() < 1e-6 and np.abs(ref64[k]).max() < 1e-6, k
             continue
-        # 1e-5 relative, widened only by how far the fp32 CPU oracle itself sits from the fp64 evaluation of the same
-        # graph (deep BatchNorm stacks amplify summation-order noise): the GPU result must be as close to the fp64
-        # truth as stock torch fp32 is, up to a factor 3
-        tol = max(RTOL, 3.0 * rel_err(ref, ref64))
-        assert rel_err(named[k].grad.cpu().numpy(), ref64) < tol, (k, tol)
+        err = float(np.abs(mine - ref64[k]).max())
+        scale = float(np.abs(ref64[k]).max())
+        rel_tols.append(tol[k] / scale)
+        if not err <= tol[k]:
+            bad.append((k, err / scale, tol[k] / scale))
         checked += 1
-    assert checked > 30
+    assert not bad, "gradients outside their tolerance (name, relative error, relative tolerance): %r" % (bad,)
+    # the yardstick must not have degenerated into a blanket loosening: the well-conditioned tensors (embedding tables,
+    # output layers) sit at 1e-5 of their value, the typical one within the ~10x cancellation that beta = 6 creates
+    # (a Linear behind such a BatchNorm sums dZ * (6 + x) with sum(dZ) = 0)
+    assert checked > 30 and min(rel_tols) <= 1.5 * RTOL and float(np.median(rel_tols)) < 5e-4, (min(rel_tols), np.median(rel_tols))
 
 
 def test_pfcn_mlp_trainer_epoch_runs_and_learns():
