@@ -43,7 +43,8 @@ enum fr_status {
 enum fr_flag {
   FR_FLAG_TOO_MANY_GROUPS = 1, /* >2 distinct sensitive-attribute values in a FOCF batch (focf.py:81-86) */
   FR_FLAG_SINGLE_GROUP = 2,    /* nonparity objective with <2 values (focf.py:129-130 IndexError) */
-  FR_FLAG_NAN_LOSS = 4         /* trainer.py:286-288 _check_nan */
+  FR_FLAG_NAN_LOSS = 4,        /* trainer.py:286-288 _check_nan */
+  FR_FLAG_XCHG_TIMEOUT = 8     /* a peer did not arrive at a cross-GPU barrier of the row-sharded step within 20 s */
 };
 
 /* focf.py:52-68 get_loss_fun */
@@ -145,6 +146,17 @@ typedef struct fr_focf_step {
   /* planned data-parallel steps (CUDA-graph replay): [plan_len, 2] = (B_total, J_total) of every planned batch, read at
    * the device-resident cursor instead of norm_B / norm_J */
   const int32_t *norm_dev;
+  /* --- optional: lazy_exact Adam (enum fr_adam_mode; 0 = dense_exact).  Needs step >= 1 (host-provided), the general
+   * (non-cooperative) step path, and three caller-owned buffers: last_step_u/i [n_users] / [n_items] uint32 zeroed at the
+   * start, adam_scalars [2 * scalars_cap] floats and the host counter scalars_filled (0 at the start). */
+  int32_t adam_mode;
+  uint32_t *last_step_u, *last_step_i;
+  float *adam_scalars;
+  int32_t scalars_cap;
+  int32_t *scalars_filled;
+  /* 1: never take the single-launch cooperative path for small batches.  Both paths are deterministic, but they add the
+   * item x group sums in different orders; set it to compare dense_exact with lazy_exact (always multi-launch) bit for bit. */
+  int32_t no_fused;
 } fr_focf_step;
 
 size_t fr_focf_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t max_batch);
@@ -431,6 +443,112 @@ int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const 
 int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double *out, void *workspace,
                         size_t workspace_bytes, void *stream);
 size_t fr_fairness_metrics_workspace_bytes(int32_t n_items, int32_t G);
+
+
+/* ----------------------------------------------------------------------------------------------
+ * Row-sharded FOCF training step over NVLink peer memory (SURVEY.md 8e "FOCF training", rows 1-2; the
+ * data-parallel form of trainer.py:181-196 for tables that do not belong on one GPU).
+ *
+ * World of P <= FR_MAX_RANKS processes, one GPU each.  Rank r OWNS rows r, r+P, r+2P, ... of the user table, the
+ * item table and their Adam moments (local row = global row / P) and holds the train interactions of ITS users,
+ * in CSC form by GLOBAL item id.  A batch is the reference's: all train rows of the drawn items
+ * (focf_dataloader.py:37-50); the draw list is the same on every rank, each rank materialises the rows of its own
+ * users.  Per step, user-side work (gather, gradient segments, Adam) is entirely local; what crosses NVLink is
+ *   (1) the current item rows of the J drawn items, pushed by their owners into every rank's staging table
+ *       [J, d] (the forward / backward kernels then index items by draw position),
+ *   (2) each rank's partial item x group sums [J, 8 floats] (all ranks reduce them in rank order -> identical
+ *       fairness terms and loss everywhere),
+ *   (3) each rank's partial item gradients [J, d], pushed to the item's owner, which adds them in rank order and
+ *       applies Adam to its rows.
+ * Nothing else is exchanged: J is ~10^3 rows when the batch is 10^6 interactions.  All transfers are plain stores
+ * into peer memory issued by the kernels themselves, separated by cross-GPU barriers (one flag word per peer,
+ * release/acquire at system scope; a barrier that does not complete within 20 s raises FR_FLAG_XCHG_TIMEOUT
+ * instead of hanging).  Every reduction has a fixed order: results are bit-stable run to run and equal to the
+ * single-GPU step on the same batch up to summation order.
+ *
+ * Exchange memory: ONE device allocation per rank (fr_xchg_alloc) laid out by fr_focf_shard_xchg_bytes, identical
+ * on all ranks; peers map it through CUDA IPC (fr_xchg_export / fr_xchg_open; the handles travel over whatever
+ * channel the host has -- torch.distributed here).  For single-process tests `xchg[k]` may simply be the
+ * allocations of P emulated ranks on one device; then the caller sequences the phases itself (no barrier:
+ * `barriers = 0`).
+ * ---------------------------------------------------------------------------------------------- */
+#define FR_MAX_RANKS 8
+
+int fr_xchg_alloc(size_t bytes, void **ptr_out);                 /* cudaMalloc + zero */
+int fr_xchg_free(void *ptr);
+int fr_xchg_export(void *ptr, void *handle64_out);               /* 64-byte CUDA IPC handle of a fr_xchg_alloc buffer */
+int fr_xchg_open(const void *handle64, void **peer_ptr_out);     /* map a peer's buffer into this process */
+int fr_xchg_close(void *peer_ptr);
+
+enum fr_shard_phase {
+  FR_SHARD_STAGE = 1, /* push the rows of stage_items that this rank owns into every rank's staging table (+ barrier) */
+  FR_SHARD_A = 2,     /* batch gather, sort / segments, forward, partial item x group sums pushed (+ barrier) */
+  FR_SHARD_B = 4,     /* reduce the sums -> loss + fairness terms; gradient segments; partial item gradients pushed (+ barrier) */
+  FR_SHARD_C = 8,     /* Adam: this rank's user rows, the item rows it owns */
+  FR_SHARD_FLUSH = 16 /* lazy_exact only: bring every local row up to optimizer step `step` (before the tables are read) */
+};
+
+enum fr_adam_mode {
+  FR_ADAM_DENSE_EXACT = 0, /* every row moves every step (torch.optim.Adam with weight_decay, trainer.py:139) */
+  FR_ADAM_LAZY_EXACT = 1   /* a row is brought up to date when a batch next touches it (or at FR_SHARD_FLUSH), by replaying the
+                              missed steps (gradient = weight_decay * p) with the same float32 operations: bit-identical to
+                              DENSE_EXACT, without the per-step sweep over all rows */
+};
+
+typedef struct fr_focf_shard_step {
+  /* this rank's rows of the tables and moments */
+  float *U, *I, *mU, *vU, *mI, *vI;
+  int32_t n_users_loc, n_items_loc, n_items, d; /* n_items: GLOBAL item count (CSC length) */
+  int32_t rank, world;
+  /* this rank's interactions, CSC by global item id; user ids are LOCAL rows */
+  const int32_t *item_off;     /* [n_items + 1] */
+  const int32_t *train_uid;
+  const float *train_rating;
+  const float *sst_of_user;    /* [n_users_loc] */
+  /* current batch */
+  const int32_t *draw_items;   /* [J] global ids of the drawn items, draw order (the same list on every rank) */
+  const int32_t *draw_off;     /* [J+1] exclusive prefix of THIS RANK's row counts of the drawn items */
+  const int32_t *draw_slot;    /* [J] position of item j among the batch items of its owner (owner = id % world) */
+  int32_t J, B_loc, B_glob;    /* drawn items; this rank's rows (= draw_off[J], may be 0); rows over all ranks */
+  int32_t parity;              /* step & 1: which half of the double-buffered exchange memory this step uses */
+  /* items whose rows FR_SHARD_STAGE pushes (the NEXT batch's draw list when combined with A|B|C; into parity ^ 1 then) */
+  const int32_t *stage_items;
+  int32_t stage_J, stage_parity;
+  /* objective (nonparity needs batch-global means: not available sharded) */
+  int32_t objective;
+  float fair_weight;
+  /* Adam */
+  int32_t adam_mode;           /* enum fr_adam_mode */
+  int32_t step;                /* 1-based optimizer step of this batch */
+  double lr, beta1, beta2, eps, weight_decay;
+  uint32_t *last_step_u, *last_step_i; /* lazy_exact: [n_users_loc], [n_items_loc] step each row is current for (zeroed at start) */
+  float *adam_scalars;         /* lazy_exact: [2 * scalars_cap] per-step (-lr / (1 - beta1^t), sqrt(1 - beta2^t)), filled on demand */
+  int32_t scalars_cap;
+  int32_t *scalars_filled;     /* lazy_exact: HOST int, number of steps already tabulated (updated by the call) */
+  /* columns of the materialised local batch (capacity >= B_loc) + outputs */
+  int32_t *uid, *iid;          /* iid holds DRAW POSITIONS j, not item ids */
+  float *rating, *sst, *pred;
+  float *loss;                 /* [1] the batch loss (identical on every rank) */
+  int32_t *status_flags;
+  void *workspace;             /* fr_focf_shard_workspace_bytes, zeroed once by fr_focf_shard_workspace_init */
+  size_t workspace_bytes;
+  /* exchange memory: xchg[k] = rank k's allocation as mapped in THIS process (xchg[rank] = own) */
+  void *xchg[FR_MAX_RANKS];
+  int32_t J_cap;               /* capacity the exchange layout was sized for (>= every batch's J) */
+  int32_t barriers;            /* 1: cross-GPU barriers after STAGE / A / B (real multi-process run); 0: caller sequences phases */
+} fr_focf_shard_step;
+
+size_t fr_focf_shard_xchg_bytes(int32_t world, int32_t J_cap, int32_t d);
+size_t fr_focf_shard_workspace_bytes(int32_t n_users_loc, int32_t n_items_loc, int32_t d, int32_t max_batch, int32_t J_cap);
+int fr_focf_shard_workspace_init(void *workspace, size_t workspace_bytes, int32_t n_users_loc, int32_t n_items_loc, int32_t d,
+                                 int32_t max_batch, int32_t J_cap, void *stream);
+/* run the phases in `phases` (OR of enum fr_shard_phase) in the order A, B, C, STAGE, FLUSH */
+int fr_focf_shard_step_run(const fr_focf_shard_step *s, int32_t phases, void *stream);
+
+/* lazy_exact for the single-GPU step: fr_focf_train_step with fr_focf_step.adam_mode = FR_ADAM_LAZY_EXACT updates only the
+ * rows the batch touches; fr_focf_adam_flush brings every row of both tables up to step `step` (call before anything
+ * reads the tables: evaluation, checkpoint, predict). */
+int fr_focf_adam_flush(const fr_focf_step *s, void *stream);
 
 #ifdef __cplusplus
 }

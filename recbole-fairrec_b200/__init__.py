@@ -12,6 +12,7 @@ Only what the path needs lives here:
   dataloader.py    device-side FOCF batch builder (FOCFDataLoader)
   evaluator.py     fused full-sort fair evaluation (EvalData, FullSortEvaluator)
   sampled_eval.py  sampled-negative (uni100) ranking evaluation (SampledEvalData, SampledEvaluator)
+  sharded.py       row-sharded FOCF training over NVLink peer memory (ShardedFOCF, ShardedGroupEmu)
   trainer.py       FOCFTrainer (fit / evaluate)
   atomic.py        atomic-file datasets (.inter/.user/.item) -> ids, splits, history/positive lists (reference-identical)
   quick_start.py   run_recbole(model, dataset, config_file_list, config_dict)
@@ -30,6 +31,7 @@ from .interaction import Interaction  # noqa: F401
 from .nfcf import NFCF, NFCFTrainer  # noqa: F401
 from .pfcn import (PFCN_MLP, PFCN_PMF, PFCN_BiasedMF, PFCN_DMF, PFCNTrainer, PFCN_MLPTrainer, PFCN_PMFTrainer,  # noqa: F401
                    PFCN_BiasedMFTrainer, PFCN_DMFTrainer)
+from .sharded import ShardedFOCF, ShardedFOCFLoader, ShardedGroupEmu, ShardedTrainData  # noqa: F401
 from .sampled_eval import SampledEvalData, SampledEvaluator, sample_negatives  # noqa: F401
 from .trainer import FOCFTrainer  # noqa: F401
 from .utils import get_model, get_trainer  # noqa: F401

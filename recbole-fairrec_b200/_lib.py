@@ -13,7 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfairrec_b200.so")
 
 FR_OK, FR_ERR_INVALID, FR_ERR_CUDA, FR_ERR_WORKSPACE, FR_ERR_UNSUPPORTED = 0, 1, 2, 3, 4      # include/fairrec_b200.h: enum fr_status
-FLAG_TOO_MANY_GROUPS, FLAG_SINGLE_GROUP, FLAG_NAN_LOSS = 1, 2, 4
+FLAG_TOO_MANY_GROUPS, FLAG_SINGLE_GROUP, FLAG_NAN_LOSS, FLAG_XCHG_TIMEOUT = 1, 2, 4, 8
+ADAM_DENSE_EXACT, ADAM_LAZY_EXACT = 0, 1                                   # enum fr_adam_mode
+SHARD_STAGE, SHARD_A, SHARD_B, SHARD_C, SHARD_FLUSH = 1, 2, 4, 8, 16      # enum fr_shard_phase
+MAX_RANKS = 8
 OBJECTIVES = {"none": 0, "value": 1, "absolute": 2, "under": 3, "over": 4, "nonparity": 5}
 TRANSFORM_NONE, TRANSFORM_CLAMP_DIV, TRANSFORM_SIGMOID = 0, 1, 2
 SCORE_EXACT_FP32, SCORE_TC_3XTF32 = 0, 1
@@ -37,6 +40,29 @@ class FocfStep(Structure):
         ("B_dev", c_void_p), ("plan_desc", c_void_p), ("plan_items", c_void_p), ("plan_offs", c_void_p),
         ("plan_len", c_int32), ("item_off", c_void_p), ("train_uid", c_void_p), ("train_rating", c_void_p),
         ("sst_of_user", c_void_p), ("norm_B", c_int32), ("norm_J", c_int32), ("norm_dev", c_void_p),
+        ("adam_mode", c_int32), ("last_step_u", c_void_p), ("last_step_i", c_void_p), ("adam_scalars", c_void_p),
+        ("scalars_cap", c_int32), ("scalars_filled", POINTER(c_int32)), ("no_fused", c_int32),
+    ]
+
+
+class FocfShardStep(Structure):
+    """mirror of `struct fr_focf_shard_step` (include/fairrec_b200.h)"""
+    _fields_ = [
+        ("U", c_void_p), ("I", c_void_p), ("mU", c_void_p), ("vU", c_void_p), ("mI", c_void_p), ("vI", c_void_p),
+        ("n_users_loc", c_int32), ("n_items_loc", c_int32), ("n_items", c_int32), ("d", c_int32),
+        ("rank", c_int32), ("world", c_int32),
+        ("item_off", c_void_p), ("train_uid", c_void_p), ("train_rating", c_void_p), ("sst_of_user", c_void_p),
+        ("draw_items", c_void_p), ("draw_off", c_void_p), ("draw_slot", c_void_p),
+        ("J", c_int32), ("B_loc", c_int32), ("B_glob", c_int32), ("parity", c_int32),
+        ("stage_items", c_void_p), ("stage_J", c_int32), ("stage_parity", c_int32),
+        ("objective", c_int32), ("fair_weight", c_float),
+        ("adam_mode", c_int32), ("step", c_int32),
+        ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double), ("weight_decay", c_double),
+        ("last_step_u", c_void_p), ("last_step_i", c_void_p), ("adam_scalars", c_void_p), ("scalars_cap", c_int32),
+        ("scalars_filled", POINTER(c_int32)),
+        ("uid", c_void_p), ("iid", c_void_p), ("rating", c_void_p), ("sst", c_void_p), ("pred", c_void_p),
+        ("loss", c_void_p), ("status_flags", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("xchg", c_void_p * 8), ("J_cap", c_int32), ("barriers", c_int32),
     ]
 
 
@@ -101,6 +127,16 @@ SIGNATURES = {
     "fr_focf_train_step": (c_int, [POINTER(FocfStep), c_void_p]),
     "fr_focf_train_steps_host": (c_int, [POINTER(FocfStep), c_int32, POINTER(c_void_p), POINTER(c_int32), c_void_p, c_size_t,
                                  c_void_p, c_void_p, c_void_p]),
+    "fr_focf_adam_flush": (c_int, [POINTER(FocfStep), c_void_p]),
+    "fr_xchg_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "fr_xchg_free": (c_int, [c_void_p]),
+    "fr_xchg_export": (c_int, [c_void_p, c_void_p]),
+    "fr_xchg_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "fr_xchg_close": (c_int, [c_void_p]),
+    "fr_focf_shard_xchg_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "fr_focf_shard_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "fr_focf_shard_workspace_init": (c_int, [c_void_p, c_size_t, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "fr_focf_shard_step_run": (c_int, [POINTER(FocfShardStep), c_int32, c_void_p]),
     "fr_focf_gather_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "fr_pair_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,

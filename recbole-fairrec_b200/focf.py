@@ -169,13 +169,34 @@ class FOCF(nn.Module):
         return pair_scores(U.detach(), I.detach(), uid, iid, _lib.TRANSFORM_CLAMP_DIV, self.max_rating)
 
     # ------------------------------------------------------------------ fused training step
-    def init_adam(self, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
-        """state of torch.optim.Adam(params, lr, weight_decay) as built by trainer.py:139"""
+    def init_adam(self, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, mode="dense_exact", max_steps=1 << 20):
+        """state of torch.optim.Adam(params, lr, weight_decay) as built by trainer.py:139.
+
+        mode "dense_exact": every row of both tables moves at every step, as in the reference (rows without a data gradient
+        still see weight_decay * p and the decay of their moments).  mode "lazy_exact": the same numbers bit for bit, but a
+        row is only brought up to date when a batch touches it or at `flush_adam()` -- by replaying the steps it missed in
+        registers -- so a step streams the touched rows instead of all of them (include/fairrec_b200.h: enum fr_adam_mode).
+        Everything that READS the tables outside train_step (predict, full_sort_predict, evaluation, state_dict) must see
+        flushed tables: the trainer calls flush_adam() before evaluating / checkpointing."""
+        if mode not in ("dense_exact", "lazy_exact"):
+            raise ValueError("adam mode must be dense_exact or lazy_exact")
         U, I = self.user_embedding_layer.weight, self.item_embedding_layer.weight
         self._adam = dict(mU=torch.zeros_like(U), vU=torch.zeros_like(U), mI=torch.zeros_like(I),
                           vI=torch.zeros_like(I), step=0, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
-                          weight_decay=weight_decay)
+                          weight_decay=weight_decay, mode=mode)
+        if mode == "lazy_exact":
+            import ctypes
+            self._adam.update(last_u=torch.zeros(U.shape[0], dtype=torch.int32, device=U.device),
+                              last_i=torch.zeros(I.shape[0], dtype=torch.int32, device=U.device),
+                              scalars=torch.zeros(2 * int(max_steps), dtype=torch.float32, device=U.device),
+                              filled=ctypes.c_int32(0))
         return self._adam
+
+    def flush_adam(self):
+        """lazy_exact: apply the pending updates of every row (no-op otherwise).  After it the tables, moments and step
+        count are exactly those of dense_exact training."""
+        if self._adam is not None:
+            self._engine().adam_flush(self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data, self._adam)
 
     def train_step(self, interaction, loss_out=None):
         """One fused optimisation step (trainer.py:183-196 for `learner: adam`).  Returns the device tensor
@@ -184,7 +205,7 @@ class FOCF(nn.Module):
         if adam is None:
             raise RuntimeError("call init_adam() (FOCFTrainer does) before train_step()")
         packed = getattr(interaction, "packed_host", None)
-        if packed is None or _NO_FAST_HOST_STEP:
+        if packed is None or _NO_FAST_HOST_STEP or adam.get("mode") == "lazy_exact":
             return self._train_step_generic(interaction, loss_out)
         # host batch in one pinned buffer: persistent staging buffer + persistent argument struct (kernels.py); nothing
         # here is seen by autograd (`.data` tensors, one copy, one library call), so no grad-mode bookkeeping either

@@ -31,6 +31,21 @@ def pair_scores(U, I, uid, iid, transform=_lib.TRANSFORM_NONE, max_rating=1.0):
     return out
 
 
+def fill_adam(s, adam):
+    """Adam hyper-parameters, moments and (lazy_exact) per-row state of `adam` (FOCF.init_adam) into a FocfStep"""
+    s.mU, s.vU, s.mI, s.vI = ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"])
+    s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
+    s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
+    if adam.get("mode", "dense_exact") == "lazy_exact":
+        s.adam_mode = _lib.ADAM_LAZY_EXACT
+        s.last_step_u, s.last_step_i, s.adam_scalars = ptr(adam["last_u"]), ptr(adam["last_i"]), ptr(adam["scalars"])
+        s.scalars_cap = adam["scalars"].numel() // 2
+        s.scalars_filled = ctypes.pointer(adam["filled"])
+    else:
+        s.adam_mode = _lib.ADAM_DENSE_EXACT
+    s.no_fused = 1 if adam.get("no_fused") else 0
+
+
 class FocfEngine:
     """Owns the workspace of the FOCF training kernels for one (U, I) pair and drives
     fr_focf_forward / backward / adam / train_step."""
@@ -90,12 +105,21 @@ class FocfEngine:
     def train_step(self, U, I, adam, batch, objective, fair_weight, loss_out=None):
         """adam: dict(mU, vU, mI, vI, step, lr, beta1, beta2, eps, weight_decay)"""
         s = self._step(U, I, batch, objective, fair_weight, loss_out)
-        s.mU, s.vU, s.mI, s.vI = ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"])
+        fill_adam(s, adam)
         s.step = int(adam["step"])
-        s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
-        s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
         check(self.lib.fr_focf_train_step(ctypes.byref(s), stream_ptr()), "fr_focf_train_step")
         return s
+
+    def adam_flush(self, U, I, adam):
+        """lazy_exact: replay the pending steps of every row (fr_focf_adam_flush); a no-op in dense_exact mode"""
+        if adam.get("mode", "dense_exact") != "lazy_exact" or int(adam["step"]) < 1:
+            return
+        s = FocfStep()
+        s.U, s.I = ptr(U), ptr(I)
+        s.n_users, s.n_items, s.d = self.n_users, self.n_items, self.d
+        fill_adam(s, adam)
+        s.step = int(adam["step"])
+        check(self.lib.fr_focf_adam_flush(ctypes.byref(s), stream_ptr()), "fr_focf_adam_flush")
 
     def train_step_packed(self, U, I, adam, packed, contiguous, objective, fair_weight, loss_out):
         """The eager fused step for a host batch packed into ONE pinned buffer (focf.pack_host_batch: int32 user ids |
@@ -160,13 +184,12 @@ class FocfEngine:
         if host is None or host.numel() < k:
             host = self._loss_host = torch.zeros(max(k, 64), dtype=torch.float32).pin_memory()
         s = FocfStep()
-        s.U, s.I, s.mU, s.vU, s.mI, s.vI = ptr(U), ptr(I), ptr(adam["mU"]), ptr(adam["vU"]), ptr(adam["mI"]), ptr(adam["vI"])
+        s.U, s.I = ptr(U), ptr(I)
+        fill_adam(s, adam)
         s.n_users, s.n_items, s.d = self.n_users, self.n_items, self.d
         s.objective, s.fair_weight = objective, float(fair_weight)
         s.pred, s.status_flags = ptr(self.pred_buf), ptr(self.flags)
         s.workspace, s.workspace_bytes = ptr(self.ws), self.ws.numel()
-        s.lr, s.beta1, s.beta2 = float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"])
-        s.eps, s.weight_decay = float(adam["eps"]), float(adam["weight_decay"])
         s.items_contiguous = 1 if contiguous else 0
         s.step = int(adam["step"]) + 1
         ptrs = (ctypes.c_void_p * k)(*[buf.data_ptr() for buf, _ in packed_batches])

@@ -56,10 +56,11 @@ class FOCFTrainer:
         self.best_valid_result = None
         self.train_loss_dict = dict()
         self.group = group
-        self.fused = self.learner == "adam" and not self.clip_grad_norm and (config["adam_mode"] or "dense_exact") == "dense_exact"
+        self.adam_mode = config["adam_mode"] or "dense_exact"
+        self.fused = self.learner == "adam" and not self.clip_grad_norm and self.adam_mode in ("dense_exact", "lazy_exact")
         self.optimizer = None if self.fused else self._build_optimizer()
         if self.fused:
-            model.init_adam(lr=self.learning_rate, weight_decay=self.weight_decay)
+            model.init_adam(lr=self.learning_rate, weight_decay=self.weight_decay, mode=self.adam_mode)
         self.evaluator = None
         self._train_item_count = None
         self._eval_cache = {}
@@ -91,8 +92,8 @@ class FOCFTrainer:
         from .dataloader import FOCFDataLoader
         if self.group is not None and isinstance(train_data, FOCFDataLoader) and train_data.partition is not None:
             return self._train_epoch_dp(train_data)
-        if self.fused and isinstance(train_data, FOCFDataLoader) and train_data.max_batch <= 8192 \
-                and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
+        if self.fused and self.adam_mode == "dense_exact" and isinstance(train_data, FOCFDataLoader) \
+                and train_data.max_batch <= 8192 and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
             k, _ = self.model.train_epoch_planned(train_data, self._loss_buf)
             return self._finish_epoch(k)
         k = 0
@@ -111,6 +112,8 @@ class FOCFTrainer:
                     torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
                 self.optimizer.step()
             k += 1
+        if self.fused:
+            self.model.flush_adam()     # lazy_exact: the tables are read next (evaluation, checkpoint); no-op otherwise
         return self._finish_epoch(k)
 
     def _train_epoch_dp(self, train_data):

@@ -39,7 +39,8 @@ def test_binding_covers_header():
     assert sorted(pkg._lib.SIGNATURES) == declared_functions()
     # struct mirrors: same field count/order as the header
     src = open(HEADER).read()
-    for cname, pystruct in (("fr_focf_step", pkg._lib.FocfStep), ("fr_fullsort", pkg._lib.FullSort)):
+    for cname, pystruct in (("fr_focf_step", pkg._lib.FocfStep), ("fr_fullsort", pkg._lib.FullSort),
+                            ("fr_focf_shard_step", pkg._lib.FocfShardStep)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
@@ -48,7 +49,7 @@ def test_binding_covers_header():
             if not decl:
                 continue
             names = re.sub(r"^(const\s+)?[a-z0-9_]+\s+", "", decl)
-            fields += [n.strip().lstrip("*").strip() for n in names.split(",")]
+            fields += [re.sub(r"\[.*\]$", "", n.strip().lstrip("*").strip()) for n in names.split(",")]
         assert fields == [f[0] for f in pystruct._fields_], cname
 
 
