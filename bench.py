@@ -1,30 +1,43 @@
 #!/usr/bin/env python
-"""bench.py -- FOCF train interactions/s and full-sort fair-eval users/s (BASELINE.json metric) on synthetic data
-of the ML-1M shape (BASELINE.json configs[1]; `--workload scaleout` runs a reduced configs[4] shape).
+"""bench.py -- FOCF train interactions/s and full-sort fair-eval users/s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ml1m|scaleout]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale F]
 
-Prints ONE JSON line (rank 0).  A "step" is one FOCF optimisation step on one FOCFDataLoader batch (whole items until
->= train_batch_size rows): batch gather + forward + fairness loss + sorted-segment gradients + dense Adam.
-  value      device-resident: train split, tables and Adam state live in HBM; each timed step is bracketed by CUDA
-             events on the launching stream and preceded (outside the bracket) by an L2 flush (512 MB write)
-  e2e        the same steps through the public API with HOST batches: pinned host columns -> H2D -> train_step ->
-             loss D2H + sync, every step, wall clock; `value` is FOCF.train_steps_host (the loop inside the library,
-             one call for all batches) when its self-check passes, `python_loop_value` the per-batch Python loop
-  eval       full-sort fair evaluation of all valid users (scoring + mask + top-K + 12 metrics): users/s, same two ways
-  roofline   dominant training kernel: algorithmic bytes per launch / its CUDA-event duration (library profiler) vs
-             the measured HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  oracle/torch_port.py (the reference's op sequence on stock torch CPU kernels, all host threads) on a
-             bounded sample of the same workload
-`--impl reference` prints the CPU line alone (the reference is Python and cannot travel: kind = "port").
-Multi-GPU (torchrun): training = data-parallel (every rank draws whole items from its own item partition, one NCCL
-all-reduce of the gradient shares per step, weak scaling: global batch = N x train_batch_size); evaluation = item table sharded over the ranks, NCCL all-gather of the per-shard top-K + merge, all-reduce of the
-item x group statistics.
+Headline workload = BASELINE.json configs[4], the configuration the metric is quoted on "at 1/2/4/8 B200" and the only one
+BASELINE.json shards: FOCF on 10M users x 1M items, d = 128, 1e9 synthetic interactions (generated on the device), value
+objective, Adam(lr 1e-3, weight_decay 1e-3), train_batch_size 2^20 rows PER GPU (weak scaling: global batch = N x 2^20, one
+optimizer step per global batch like the reference's loop).  It fits one GPU (74 GB), so N = 1 runs it whole; N > 1 runs the
+row-sharded step (recbole-fairrec_b200/sharded.py, csrc/focf_shard.cu: rank r owns rows r::N of both tables and moments,
+touched item rows / partial item x group sums / partial item gradients travel as stores into NVLink peer memory, no
+collective inside a step).  `--scale F` shrinks users / items / interactions / batch by F (smoke runs).
+
+ONE JSON line on stdout (rank 0):
+  value        dense_exact device-resident steps: exactly K steps between two CUDA events on the launching stream, barrier +
+               synchronize on both sides, max over ranks.  Every step streams >= 24 * rows * d bytes of tables + moments per
+               GPU (33.8 GB at N = 1), far beyond the 126 MB L2: no flush needed.
+  lazy_exact   the same K steps with adam_mode lazy_exact (bit-identical tables, untouched rows replayed on demand), the
+               closing flush INSIDE the timed region (it carries the deferred work of the K steps)
+  e2e          the same metric through the public API with HOST batches: pinned host batch -> H2D -> step -> loss D2H every
+               step (one step in flight), wall clock, max over ranks
+  roofline     dominant kernel of the timed steps: algorithmic bytes per launch / its mean CUDA-event duration (library
+               profiler, a second pass over K more batches in the same regime) vs MEASURED_PEAKS.json
+  eval         full-sort fair evaluation (tcgen05 3xTF32 scorer + history mask + top-K + the 12 metrics) of the first
+               --eval-users users with a valid interaction against all 1M items; item table sharded over the ranks for N > 1
+  ml1m         BASELINE.json configs[1] (6,040 x 3,706, d = 64, batch 2048) on one GPU: bench_ml1m.py (N = 1 only)
+  families     BASELINE.json configs[2] / [3] and the NFCF / sampled-evaluation legs: bench_families.py (N = 1 only)
+  dp_check     N > 1: the row-sharded step over CUDA-IPC peer memory vs the single-GPU step on the same batches, and the
+               item-sharded evaluation vs the unsharded one (ids bit-equal, metrics equal), on a reduced shape
+  cpu_baseline N = 1: the reference arm's figure (below) measured in the same run
+`--impl reference`: the UNMODIFIED reference (oracle/_ref = copy of its `recbole` package, imported through
+oracle/ref_shim) on the host cores: recbole.model.fair_recommender.focf.FOCF.calculate_loss + backward +
+torch.optim.Adam(weight_decay) + loss.item() on pre-built host Interactions -- the bracket of `e2e` -- on a 1/S-scale
+replica of the workload (users, items and batch divided by S, same d: the reference's step cost is linear in both, so
+interactions/s carries over), kind "reference".
 """
 import argparse
 import json
+import math
 import os
-import statistics
 import subprocess
 import sys
 import threading
@@ -35,132 +48,188 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # BASELINE.json configs[1]: ML-1M shape (ids include the [PAD] row 0)
-    "ml1m": dict(n_users=6041, n_items=3707, n_inter=1_000_209, d=64, batch=2048, K=10),
-    # reduced BASELINE.json configs[4] (10M x 1M x 128 needs ~45 s of host-side synthesis per 1e8 rows; this keeps the
-    # table shapes that make the kernels HBM-bound): 2M users x 262k items, d=128, 4e7 interactions, 2^18-row batches
-    "scaleout": dict(n_users=2_000_001, n_items=262_145, n_inter=40_000_000, d=128, batch=1 << 18, K=10),
-}
+SCALEOUT = dict(n_users=10_000_001, n_items=1_000_001, n_inter=1_000_000_000, d=128, batch=1 << 20, K=10)
+
+
+def scaled(scale):
+    w = dict(SCALEOUT)
+    if scale != 1.0:
+        w["n_users"] = max(int((w["n_users"] - 1) * scale), 1000) + 1
+        w["n_items"] = max(int((w["n_items"] - 1) * scale), 200) + 1
+        w["n_inter"] = max(int(w["n_inter"] * scale), 100_000)
+        w["batch"] = max(int(w["batch"] * scale), 4096)
+    return w
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source): MEASURED_PEAKS.json (driver-written) or the recipe's fallback"""
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            p = json.load(f)
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return 7700.0 * 0.85, 2250.0 * 0.75, "fallback (B200_PROFILING.md: 85 % of 7.7 TB/s, 75 % of 2.25 PFLOP/s)"
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi SM clock + throttle reasons sampled in a thread DURING the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.samples, self._stop = index, [], threading.Event()
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        def loop():
+            while not self._stop.is_set():
+                r = self._read()
+                if r:
+                    self.samples.append(r)
+                self._stop.wait(0.05)
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
         return self
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=2).stdout.strip().split(",")
+            return [x.strip() for x in out] if len(out) == 6 else None
+        except Exception:
+            return None
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        self._t.join(timeout=3)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.startswith("Active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
-
-
-def make_workload(name, seed=2020):
-    from recbole_fairrec_b200 import synth
-    w = WORKLOADS[name]
-    uid, iid, rating, gender = synth.interactions(w["n_users"], w["n_items"], w["n_inter"], seed)
-    train, valid, test = synth.split_by_user(uid, iid, rating, seed=seed)
-    return w, train, valid, test, gender
-
-
-def xavier(rng, rows, d):
-    return (rng.standard_normal((rows, d)) * np.sqrt(2.0 / (rows + d))).astype(np.float32)
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, wname):
-    """CPU port of the reference's loops (oracle/torch_port.py), all host threads, bounded sample."""
+def reference_arm(args, w, scale_div=8, quiet=False):
+    """The unmodified reference's FOCF step on the host cores (see the module docstring)."""
     import torch
-    from oracle import torch_port as tp
-    from recbole_fairrec_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shim"))
+    import shim
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    w, train, valid, test, gender = make_workload(wname)
+    kind = "reference"
+    try:
+        shim.install()
+        from recbole.data.interaction import Interaction
+        from recbole.model.fair_recommender.focf import FOCF as RefFOCF
+    except Exception as e:               # oracle/_ref missing (it is made by __graft_entry__.build()): the restated port
+        kind = "port"
+        why = str(e)[:120]
+    nu = (w["n_users"] - 1) // scale_div + 1
+    ni = (w["n_items"] - 1) // scale_div + 1
+    B = max(w["batch"] // scale_div, 256)
+    d = w["d"]
     rng = np.random.default_rng(2020)
-    model = tp.TorchFOCF(xavier(rng, w["n_users"], w["d"]), xavier(rng, w["n_items"], w["d"]), "value", 1.0, 5.0)
-    if wname != "ml1m":   # the reference's loader scans the whole split per drawn item: bound the split
-        keep = slice(0, 2_000_000)
-        train = tuple(a[keep] for a in train)
-    loader = tp.RefStyleLoader(train[0], train[1], train[2], gender.astype(np.int64), w["n_items"], w["batch"])
-    np.random.seed(2020)
-    tp.train_steps(model, loader, max(args.warmup, 1))
+    # batches shaped like FOCFDataLoader's: whole items (item-contiguous), log-normal popularity, ~B rows each
+    n_steps = args.steps + args.warmup
+    pop = rng.lognormal(4.5, 1.4, ni - 1)
+    mean_rows = w["n_inter"] * 0.8 / (w["n_items"] - 1)
+    cnt_of_item = np.maximum((pop / pop.mean() * mean_rows / 1.0).astype(np.int64), 1)
+    cnt_of_item = np.minimum(cnt_of_item, nu - 1)
+    ucdf = np.cumsum(rng.lognormal(4.5, 1.0, nu - 1))
+    ucdf /= ucdf[-1]
+    gender = (rng.random(nu) < 0.28).astype(np.int64) + 1
+    batches = []
+    for _ in range(n_steps):
+        perm = rng.permutation(ni - 1) + 1
+        csum = np.cumsum(cnt_of_item[perm - 1])
+        J = int(np.searchsorted(csum, B, side="left")) + 1
+        items = perm[:J]
+        iid = np.repeat(items, cnt_of_item[items - 1])
+        uid = np.searchsorted(ucdf, rng.random(len(iid))).clip(max=nu - 2) + 1
+        rating = rng.choice(np.arange(1, 6), size=len(iid), p=[.056, .107, .261, .349, .227]).astype(np.float32)
+        batches.append((uid.astype(np.int64), iid.astype(np.int64), rating, gender[uid]))
+    if kind == "reference":
+        class Cfg(dict):
+            def __getitem__(self, k):
+                return self.get(k, None)
+
+        class DS:
+            inter_feat = {"rating": torch.tensor([1.0, 5.0])}
+
+            def num(self, f):
+                return {"user_id": nu, "item_id": ni}[f]
+
+        cfg = Cfg(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", RATING_FIELD="rating",
+                  LABEL_FIELD="label", device=torch.device("cpu"), embedding_size=d, sst_attr_list=["gender"],
+                  fair_weight=1.0, fair_objective="value")
+        torch.manual_seed(2020)
+        model = RefFOCF(cfg, DS())
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)        # trainer.py:139
+        inters = [Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(i),
+                               "rating": torch.from_numpy(r), "gender": torch.from_numpy(g)}) for u, i, r, g in batches]
+
+        def step(it):
+            opt.zero_grad()
+            loss = model.calculate_loss(it)                                           # focf.py:152-169
+            loss.backward()
+            opt.step()
+            return loss.item()                                                        # trainer.py:191
+    else:
+        from oracle import torch_port as tp
+        model = tp.TorchFOCF((rng.standard_normal((nu, d)) * math.sqrt(2.0 / (nu + d))).astype(np.float32),
+                             (rng.standard_normal((ni, d)) * math.sqrt(2.0 / (ni + d))).astype(np.float32), "value", 1.0, 5.0)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+        inters = [tuple(torch.from_numpy(x) for x in b) for b in batches]
+
+        def step(it):
+            opt.zero_grad()
+            loss = model.loss(it[0], it[1], it[2], it[3])
+            loss.backward()
+            opt.step()
+            return loss.item()
+    for it in inters[:args.warmup]:
+        step(it)
     t0 = time.perf_counter()
-    rows, _ = tp.train_steps(model, loader, args.steps)
+    rows = 0
+    for it in inters[args.warmup:]:
+        v = step(it)
+        if v != v:
+            raise ValueError("Training loss is nan")
+        rows += len(it[0]) if kind == "port" else len(it)
     dt = time.perf_counter() - t0
-    # model-only variant (pre-built batches) so that the Python dataloader share is visible
-    pre = [loader.next_batch() for _ in range(min(args.steps, 10))]
-    t1 = time.perf_counter()
-    rows_m, _ = tp.train_steps(model, None, len(pre), prebuilt=pre)
-    dt_m = time.perf_counter() - t1
-    users, hist, pos = synth.eval_lists(train, valid, test, "valid")
-    n_eval = min(len(users), 2000 if wname == "ml1m" else 50)
-    upb = max(4096 // w["n_items"], 1)
-    t2 = time.perf_counter()
-    counts = np.bincount(train[1], minlength=w["n_items"])
-    count_items = {int(i): int(c) for i, c in enumerate(counts) if c > 0}
-    tp.evaluate(model, users[:n_eval], hist[:n_eval], pos[:n_eval], gender.astype(np.int64), w["n_items"], [w["K"]],
-                count_items, upb)
-    dt_e = time.perf_counter() - t2
     val = rows / dt
-    base = {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port",
-            "sample": f"{args.steps} FOCF steps ({rows} interactions) incl. the reference-style np.where dataloader; "
-                      f"model-only {rows_m / dt_m:.4g} interactions/s; eval {n_eval} users at {upb} users/batch",
-            "model_only_interactions_per_s": rows_m / dt_m, "eval_users_per_s": n_eval / dt_e}
+    sample = (f"{args.steps} steps of a 1/{scale_div}-scale replica of the workload ({nu - 1} users x {ni - 1} items, d {d}, "
+              f"~{B} rows per batch = whole items): the reference's step cost (dense autograd gradient + dense Adam over all "
+              f"rows, O(B) forward/backward) is linear in both table rows and batch rows, so interactions/s carries over; "
+              f"pre-built host Interactions -> calculate_loss -> backward -> Adam -> loss.item() (the bracket of e2e)")
+    base = {"value": val, "unit": "interactions/s", "cores": cores, "kind": kind, "sample": sample}
+    if kind == "port":
+        base["note"] = f"oracle/_ref not importable here ({why}); oracle/torch_port.py restates the same op sequence"
     return {"metric": "FOCF train interactions/s", "value": val, "unit": "interactions/s", "impl": "reference",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"focf_{wname}", **{k: w[k] for k in ("n_users", "n_items", "n_inter", "d", "batch")}},
-            "cpu_baseline": base,
-            "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "eval": {"metric": "full-sort fair-eval users/s", "value": n_eval / dt_e, "unit": "users/s"}}
+            "config": workload_config(w, args.gpus), "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(w, world):
+    return {"workload": "focf_scaleout (BASELINE.json configs[4])" if w["n_inter"] == SCALEOUT["n_inter"]
+            else "focf_scaleout REDUCED by --scale (not the BASELINE configuration)",
+            "n_users": w["n_users"], "n_items": w["n_items"], "n_inter": w["n_inter"], "d": w["d"],
+            "train_batch_size": w["batch"] * world, "fair_objective": "value",
+            "optimizer": "adam(lr=1e-3, weight_decay=1e-3)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args, wname):
+def run_ours(args, w):
     import torch
     import torch.distributed as dist
 
     import recbole_fairrec_b200 as pkg
-    from recbole_fairrec_b200 import _lib, synth
+    from recbole_fairrec_b200 import _lib, sharded, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -170,8 +239,8 @@ def run_ours(args, wname):
     group = None
     if world > 1:
         import datetime
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints there)
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
         group = dist.group.WORLD
 
     def barrier():
@@ -180,652 +249,459 @@ def run_ours(args, wname):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def note(msg):
+        if rank == 0:
+            print(f"[bench {time.perf_counter() - t_all:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
-    w, train, valid, test, gender = make_workload(wname)
-    d, K = w["d"], w["K"]
-    cfg = pkg.Config(embedding_size=d, fair_objective="value", fair_weight=1.0, topk=[K], valid_metric=f"NDCG@{K}",
-                     train_batch_size=w["batch"], learning_rate=1e-3, weight_decay=1e-3, device=dev, seed=2020 + rank)
-    tdata = pkg.TrainData(train[0], train[1], train[2], gender, w["n_users"], w["n_items"], dev)
-    loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020 + rank,
-                                partition=(rank, world) if world > 1 else None)
-    model = pkg.FOCF(cfg, synth.SynthDataset(w["n_users"], w["n_items"], 5.0))
-    rng = np.random.default_rng(2020)
-    with torch.no_grad():
-        model.user_embedding_layer.weight.copy_(torch.from_numpy(xavier(rng, w["n_users"], d)))
-        model.item_embedding_layer.weight.copy_(torch.from_numpy(xavier(rng, w["n_items"], d)))
-    model = model.to(dev)
-    model.init_adam(lr=1e-3, weight_decay=1e-3)
-    uf, itf, rf, sf = tdata.fields
-
-    n_plan = args.steps + args.warmup
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    G = 8
-    use_graph = loader.max_batch <= 8192 and not args.no_graph and (world == 1 or not args.no_dp_graph)
-    losses = torch.zeros(max(len(loader), n_plan) * 2 + 16, device=dev)
-    if use_graph and world > 1:
-        # data-parallel: forward -> backward -> NCCL all-reduce -> dense Adam of G planned steps in one CUDA graph
-        runner = model.dp_planned_runner(loader, losses, group, graph_steps=G)
-        dev_step = lambda: runner.run(1)
-    elif use_graph:
-        # planned epoch + CUDA-graph replay: one graph launch per step, zero per-step host work
-        runner = model.planned_runner(loader, losses, graph_steps=G)
-        dev_step = lambda: runner.run(1)
-        if runner.cursor & 1:          # align to workspace 0 so that timed launches are the pipelined G-step graph
-            runner.run(1)
-    else:
-        plans, flat = [], []
-        while sum(len(p[2]) for p in plans) < 2 * n_plan + 8:
-            plans.append(loader.plan_epoch())
-        for items, offs, batches in plans:
-            d_items, d_offs = torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev)
-            flat += [(d_items, d_offs, b) for b in batches]
-        step_pos = [0]
-        norms = None
-        if world > 1:   # global normalisers of every planned step: sum of the ranks' (B, J), host-known at planning time
-            t = torch.tensor([[b[3], b[2]] for _, _, b in flat], dtype=torch.int64, device=dev)
-            nmin = torch.tensor([t.shape[0]], device=dev)
-            dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
-            flat = flat[:int(nmin.item())]
-            t = t[:len(flat)].contiguous()
-            dist.all_reduce(t)
-            norms = t.cpu().numpy()
-
-        def dev_step():
-            k = step_pos[0] % len(flat)
-            d_items, d_offs, b = flat[k]
-            step_pos[0] += 1
-            uid, iid, rating, sst = loader.gather(d_items, d_offs, b)
-            inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
-            inter.items_contiguous = True
-            if world > 1:
-                model.dp_train_step(inter, (int(norms[k, 0]), int(norms[k, 1])), group, loss_out=losses[-1:])
-            else:
-                model.train_step(inter, loss_out=losses[-1:])
-            return b[3]
-
-    for k in range(args.warmup):
-        dev_step()
-    barrier()
-    model.check_flags()
-
-    # ---- timed region 1: device-resident steps, L2 flushed before each, CUDA events per step
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rows = 0
-    launches0 = _lib.launch_count()
-    with ClockSampler(local) as clocks:
-        if use_graph and world == 1 and (runner.cursor & 1):
-            runner.run(1)              # align to workspace 0: every timed launch is the pipelined G-step graph
-        barrier()
-        if use_graph:
-            # one timed iteration = one launch of the captured G-step graph (prepare of batch t+1 overlapped with the
-            # compute of batch t); L2 is flushed before every launch, so the first step of each group runs cold
-            n_groups = max(args.steps // G, 1)
-            evs = evs[:n_groups]
-            for s in range(n_groups):
-                flush.zero_()
-                evs[s][0].record()
-                rows += runner.run(G)
-                evs[s][1].record()
-            timed_steps = n_groups * G
-            barrier()
-            # the same K steps as single-step launches, L2 flushed before EVERY step (no overlap possible): reported too
-            sevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(timed_steps)]
-            rows_single = 0
-            for s in range(timed_steps):
-                flush.zero_()
-                sevs[s][0].record()
-                rows_single += runner.run(1)
-                sevs[s][1].record()
-            barrier()
-            single = {"value": rows_single / (sum(x.elapsed_time(y) for x, y in sevs) / 1e3), "unit": "interactions/s",
-                      "ms_per_step": sum(x.elapsed_time(y) for x, y in sevs) / timed_steps,
-                      "note": "one step per launch, L2 flushed before every step"}
-            if world == 1 and (runner.cursor & 1):
-                runner.run(1)
-        else:
-            single = None
-            timed_steps = args.steps
-            for s in range(args.steps):
-                flush.zero_()
-                evs[s][0].record()
-                rows += dev_step()
-                evs[s][1].record()
-        barrier()
-        launches = _lib.launch_count() - launches0
-        # steady state (informational): back-to-back steps, no flush -- the regime an epoch really runs in at this
-        # shape (tables + Adam state + train split fit the 126 MB L2); also gives nvidia-smi a sustained load to sample
-        n_ss = 0
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        rows_ss = 0
-        t_end = time.time() + 0.7
-        a.record()
-        if world > 1:   # every rank must issue the SAME number of collectives: fixed step count, not a wall-clock window
-            for _ in range(max(args.steps // G, 1) if use_graph else args.steps):
-                rows_ss += runner.run(G) if use_graph else dev_step()
-                n_ss += G if use_graph else 1
-        else:
-            while time.time() < t_end:
-                rows_ss += runner.run(G) if use_graph else dev_step()
-                n_ss += G if use_graph else 1
-        b.record()
-        torch.cuda.synchronize()
-        ss_ms = a.elapsed_time(b)
-    step_ms = [x.elapsed_time(y) for x, y in evs]
-    t_dev = max_over_ranks(sum(step_ms) / 1e3)
-    total_rows = sum_over_ranks(rows)
-    value = total_rows / t_dev
-    steady = {"value": sum_over_ranks(rows_ss) / max_over_ranks(ss_ms / 1e3), "unit": "interactions/s",
-              "ms_per_step": ss_ms / n_ss, "steps": n_ss,
-              "note": "no L2 flush, back-to-back graph replays; informational (value above is the flushed number)"}
-    # ---- timed region 2: end to end through the public API with host batches
-    host_batches = []
-    e_items, e_offs, e_batches = loader.plan_epoch()
-    de_items, de_offs = torch.from_numpy(e_items).to(dev), torch.from_numpy(e_offs).to(dev)
-    for s in range(args.steps):
-        cols = loader.gather(de_items, de_offs, e_batches[s % len(e_batches)])
-        host_batches.append(pkg.pack_host_batch(*[c.cpu() for c in cols], fields=(uf, itf, rf, sf)))
-    torch.cuda.synchronize()
-    h2d = int(statistics.mean(hb.packed_host[0].numel() for hb in host_batches))
-    if world > 1:
-        eb = torch.tensor([[len(hb), int(torch.unique_consecutive(hb[itf]).numel())] for hb in host_batches],
-                          dtype=torch.int64, device=dev)
-        dist.all_reduce(eb)
-        eb = eb.cpu().numpy()
-    # every step: H2D of the batch (pinned), the step, D2H of its loss (pinned).  The read of step t's loss is waited for
-    # after step t+1 has been enqueued, so one step stays in flight (trainer.py:191 reads it before the next batch; the
-    # value and the NaN check are the same, one batch later)
-    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
-    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    # self-check of the packed host path of train_step (persistent staging buffer + argument struct, kernels.py) against the
-    # generic one on the same batch and state: same launch arguments (tests/test_host_logic.py) => bit-equal loss and
-    # tables; anything else makes the bench fall back to the generic path and says so
-    host_path = None
-    if world == 1:
-        import recbole_fairrec_b200.focf as focf_mod
-        try:
-            adam = model._adam
-            state = [model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data,
-                     adam["mU"], adam["vU"], adam["mI"], adam["vI"]]
-            keep, step0 = [t.clone() for t in state], adam["step"]
-
-            def one(generic):
-                for dst, src in zip(state, keep):
-                    dst.copy_(src)
-                adam["step"] = step0
-                focf_mod._NO_FAST_HOST_STEP = generic
-                loss = model.train_step(host_batches[0]).clone()
-                return loss, state[0].clone(), state[1].clone()
-
-            fast, gen = one(False), one(True)
-            for dst, src in zip(state, keep):
-                dst.copy_(src)
-            adam["step"] = step0
-            torch.cuda.synchronize()
-            same = all(torch.equal(x, y) for x, y in zip(fast, gen))
-            focf_mod._NO_FAST_HOST_STEP = not same
-            host_path = "packed fast path (self-check: loss and tables bit-equal to the generic path)" if same else \
-                "generic path (the packed fast path differed in the self-check)"
-        except Exception as e:
-            focf_mod._NO_FAST_HOST_STEP = True
-            host_path = f"generic path (self-check failed: {str(e)[:160]})"
-    barrier()
-    t0 = time.perf_counter()
-    rows_e, pending, loss_sum = 0, None, 0.0
-    for k, hb in enumerate(host_batches):
-        slot = k & 1
-        if world > 1:
-            model.dp_train_step(hb, (int(eb[k, 0]), int(eb[k, 1])), group, loss_out=loss_dev[slot])
-        else:
-            model.train_step(hb, loss_out=loss_dev[slot])      # the single H2D copy of the packed batch happens inside
-        loss_host[slot].copy_(loss_dev[slot], non_blocking=True)
-        done[slot].record()
-        if pending is not None:
-            done[pending].synchronize()
-            v = float(loss_host[pending])
-            if v != v:
-                raise ValueError("Training loss is nan")
-            loss_sum += v
-        pending = slot
-        rows_e += len(hb)
-    done[pending].synchronize()
-    loss_sum += float(loss_host[pending])
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = sum_over_ranks(rows_e) / t_e2e
-    # the strictly serial variant (wait for every step's loss before the next batch is touched)
-    barrier()
-    t0 = time.perf_counter()
-    for k, hb in enumerate(host_batches[:max(args.steps // 4, 1)]):
-        if world > 1:
-            loss = model.dp_train_step(hb, (int(eb[k, 0]), int(eb[k, 1])), group)
-        else:
-            loss = model.train_step(hb)
-        _ = loss.item()
-    barrier()
-    n_serial = len(host_batches[:max(args.steps // 4, 1)])
-    e2e_serial = sum_over_ranks(sum(len(hb) for hb in host_batches[:n_serial])) / max_over_ranks(time.perf_counter() - t0)
-
-    # ---- the same steps through FOCF.train_steps_host: ONE library call (fr_focf_train_steps_host) runs the loop -- per
-    # step the H2D copy of the pinned batch, the fused step, the D2H copy of its loss, the host waiting for step t's loss
-    # after enqueuing step t+1 -- in C instead of the interpreter.  Used as the e2e figure only when its self-check (three
-    # batches from a saved state: losses and tables bit-equal to the per-batch path) passes; the Python-loop figure stays
-    # in the line either way.
-    e2e_loop = None
-    if world == 1:
-        try:
-            import recbole_fairrec_b200.focf as focf_mod
-            adam = model._adam
-            state = [model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data,
-                     adam["mU"], adam["vU"], adam["mI"], adam["vI"]]
-            keep, step0 = [t.clone() for t in state], adam["step"]
-            chk = host_batches[:3]
-
-            def restore():
-                for dst, src in zip(state, keep):
-                    dst.copy_(src)
-                adam["step"] = step0
-
-            restore()
-            was = focf_mod._NO_FAST_HOST_STEP
-            focf_mod._NO_FAST_HOST_STEP = True
-            ref_losses = [float(model.train_step(hb).item()) for hb in chk]
-            focf_mod._NO_FAST_HOST_STEP = was
-            ref_tables = [state[0].clone(), state[1].clone()]
-            restore()
-            got = model.train_steps_host(chk)
-            torch.cuda.synchronize()
-            same = [float(x) for x in got] == ref_losses and torch.equal(state[0], ref_tables[0]) and \
-                torch.equal(state[1], ref_tables[1]) and adam["step"] == step0 + len(chk)
-            restore()
-            if same:
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                losses = model.train_steps_host(host_batches)        # returns with every loss on the host
-                t_loop = time.perf_counter() - t0
-                if bool(torch.isnan(losses).any()):
-                    raise ValueError("Training loss is nan")
-                e2e_loop = {"value": sum(len(hb) for hb in host_batches) / t_loop, "steps": len(host_batches),
-                            "self_check": "losses and tables bit-equal to the per-batch path on 3 batches"}
-            else:
-                e2e_loop = {"error": "self-check differed from the per-batch path; figure not used"}
-        except Exception as e:
-            e2e_loop = {"error": str(e)[:200]}
-
-    # ---- evaluation: all valid users
-    users, hist, pos = synth.eval_lists(train, valid, test, "valid")
-    t_h = time.perf_counter()
-    edata = pkg.EvalData(users, hist, pos, {sf: gender.astype(np.int64)}, dev)
-    t_build = time.perf_counter() - t_h
-    evaluator = pkg.FullSortEvaluator(cfg, w["n_items"], tdata.item_counter, group=group)
-    Uw, Iw = model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data
-    evaluator.evaluate(Uw, Iw, edata, 5.0)      # warm-up pass (also builds the popularity mask)
-    n_eval_pass = 3
-    barrier()
-    ev_ms = []
-    for _ in range(n_eval_pass):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        evaluator.collect_graphed(Uw, Iw, edata, 5.0)
-        b.record()
-        torch.cuda.synchronize()
-        ev_ms.append(a.elapsed_time(b))
-    t_eval = max_over_ranks(statistics.mean(ev_ms) / 1e3)
-    # the tensor-core scorer (tcgen05 + TMA, 3xTF32) on the same pass, timed the same way
-    tc = None
-    try:
-        cfg_tc = pkg.Config(**{**dict(cfg), "score_mode": "tc"})
-        ev_tc = pkg.FullSortEvaluator(cfg_tc, w["n_items"], tdata.item_counter, group=group)
-        res_tc = ev_tc.evaluate(Uw, Iw, edata, 5.0)
-        barrier()
-        tc_ms = []
-        for _ in range(n_eval_pass):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            ev_tc.collect_graphed(Uw, Iw, edata, 5.0)
-            b.record()
-            torch.cuda.synchronize()
-            tc_ms.append(a.elapsed_time(b))
-        t_tc = max_over_ranks(statistics.mean(tc_ms) / 1e3)
-        tc = {"value": edata.n / t_tc, "unit": "users/s", "ms_per_pass": 1e3 * t_tc, "score_mode": "tc_3xtf32",
-              "ndcg@10": res_tc.get(f"ndcg@{K}")}
-    except Exception as e:   # the exact scorer stays the reported default
-        tc = {"error": str(e)[:200]}
-
-    # end to end: H2D of the eval lists (users, history CSR, positives CSR, groups) from pinned host memory, the fused
-    # pass, and the D2H read of the metric accumulators, every pass
-    import copy
-    names = ("users", "hist_off", "hist_items", "pos_off", "pos_items", "pos_items_sorted", "pos_uid", "pos_row")
-    pinned = {k: getattr(edata, k).cpu().pin_memory() for k in names}
-    pinned_grp = {a: g.cpu().pin_memory() for a, g in edata.group_of_pos.items()}
-    eval_h2d = sum(t.numel() * t.element_size() for t in list(pinned.values()) + list(pinned_grp.values()))
-    barrier()
-    t0 = time.perf_counter()
-    ev_main = ev_tc if tc and "error" not in tc else evaluator
-    for _ in range(n_eval_pass):
-        # the lists land in the SAME device buffers every pass (addresses fixed -> the captured graph is reused)
-        for k in names:
-            getattr(edata, k).copy_(pinned[k], non_blocking=True)
-        for a_, g_ in pinned_grp.items():
-            edata.group_of_pos[a_].copy_(g_, non_blocking=True)
-        res = ev_main.evaluate(Uw, Iw, edata, 5.0)
-    barrier()
-    t_eval_e2e = max_over_ranks((time.perf_counter() - t0) / n_eval_pass)
-
-    # ---- profile pass: per-kernel CUDA-event durations (library profiler) -> shares + roofline
-    _lib.profile_enable(True)
-    nprof = min(args.steps, 50)
-    rows_p = 0
-    if use_graph:   # graph replays bypass the library's launch macro: profile the same steps un-captured
-        for s in range(nprof):
-            flush.zero_()
-            rows_p += runner.eager_steps(1)
-    else:
-        for s in range(nprof):
-            flush.zero_()
-            rows_p += dev_step()
-    prof_train = _lib.profile_report()
-    evaluator.collect(Uw, Iw, edata, 5.0)
-    prof_eval = _lib.profile_report()
-    prof_tc = {}
-    if tc and "error" not in tc:
-        ev_tc.collect(Uw, Iw, edata, 5.0)
-        prof_tc = _lib.profile_report()
-    _lib.profile_enable(False)
+    vmax = lambda x: reduce_(x, dist.ReduceOp.MAX)
+    vsum = lambda x: reduce_(x, dist.ReduceOp.SUM)
     hbm, bf16, peak_src = peaks()
-    B_avg = rows_p / nprof
-    n_rows_tab = w["n_users"] + w["n_items"]
-    alg = {  # algorithmic HBM bytes per launch
-        "k_apply<fr::kAdamFused>": 24.0 * n_rows_tab * d,
-        "k_apply<fr::kAdamDense>": 28.0 * n_rows_tab * d,    # data-parallel: + read of the all-reduced dense gradient
-        "k_apply<fr::kDenseOut>": 4.0 * n_rows_tab * d,      # data-parallel: write the dense gradient share
-        "k_segment_grads": 8.0 * d * B_avg,
-        "k_forward": 8.0 * d * B_avg + 16.0 * B_avg,
-        "k_gather_batch": 36.0 * B_avg,         # read uid, rating, sst(user) + item_off/draws; write 4 columns
-        "k_prepare_small": 8.0 * B_avg + 40.0 * B_avg,   # read both key columns; write keys/order/segment ids per side
-        "k_segment_loss": 16.0 * B_avg,          # read pred, rating, sst, segment id
-        # forward + loss + gradients + dense Adam in one cooperative launch
-        "k_focf_fused_step": (16.0 * d + 32.0) * B_avg + 24.0 * n_rows_tab * d,
-    }
-    tot_ms = sum(v[1] for v in prof_train.values()) or 1.0
-    shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(prof_train.items(), key=lambda kv: -kv[1][1])}
-    match = lambda k: k if k in alg else next((a for a in alg if "<" not in a and k.startswith(a)), None)
-    dom = next((k for k in shares if match(k)), None)
-    roofline = None
-    if dom:
-        key = match(dom)
-        cnt, ms = prof_train[dom]
-        ach = alg[key] / (ms / cnt * 1e-3) / 1e9
-        # DRAM bytes per launch from the committed ncu capture of the same kernel at this shape (profiles/r01_ncu_summary.md)
-        traffic = {"k_focf_fused_step": 7.71e6} if wname == "ml1m" else {}
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": traffic.get(key), "traffic_note": "ncu dram read 7.71 MB + write ~0 per launch: the tables and "
-                    "moments are read once; written lines stay in the 126 MB L2" if key in traffic else None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[key],
-                    "avg_launch_us": 1e3 * ms / cnt, "share_of_step": shares[dom]}
-    kernels_per_step = sum(v[0] for v in prof_train.values()) / nprof
-    step_bytes = (16.0 * d + 16.0) * B_avg + 24.0 * n_rows_tab * d
-    step_roof = step_bytes / (sum(step_ms) / timed_steps * 1e-3) / 1e9
-    ev_tot = sum(v[1] for v in prof_eval.values()) or 1.0
-    ev_shares = {k: round(v[1] / ev_tot, 4) for k, v in sorted(prof_eval.items(), key=lambda kv: -kv[1][1])}
-    n_eval = edata.n
-    eval_flops = 2.0 * w["n_items"] * d * n_eval
-    fs_ms = next((v[1] / v[0] for k, v in prof_eval.items() if k.startswith("k_fullsort")), None)
-    tc_peak = bf16 / 2.0 / 3.0   # TF32 dense ~ bf16/2; 3xTF32 issues 3 MMAs per fp32-equivalent product
-    eval_roof = None
-    if fs_ms:
-        ach = eval_flops / world / (fs_ms * 1e-3) / 1e12
-        eval_roof = {"bound": "tensor", "kernel": "k_fullsort_exact (CUDA-core fp32 fma chain, bit-exact mode)",
-                     "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
-                     "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}
+    t_all = time.perf_counter()
+    nu, ni, d, K = w["n_users"], w["n_items"], w["d"], w["K"]
+    W_, K_ = args.warmup, args.steps
+    data = synth.device_interactions(nu, ni, w["n_inter"], 2020, dev)
+    tr_u, tr_i, tr_r = data["train"]
+    va_u, va_i = data["valid"]
+    gender = data["gender"]
+    torch.cuda.synchronize()
+    t_synth = time.perf_counter() - t_all
+    cfg = pkg.Config(embedding_size=d, fair_objective="value", fair_weight=1.0, topk=[K], valid_metric=f"NDCG@{K}",
+                     train_batch_size=w["batch"], learning_rate=1e-3, weight_decay=1e-3, device=dev, seed=2020,
+                     score_mode="tc", cuda_graph=False)
+    n_plan = W_ + 3 * K_ + 4
+    out_modes, prof_modes = {}, {}
+    uniq_users = None
 
-    if tc and "error" not in tc:
-        tc_kernel_ms = next((v[1] / v[0] for k, v in prof_tc.items() if k.startswith("k_fullsort_tc")), None)
-        if tc_kernel_ms:
-            ach = eval_flops / world / (tc_kernel_ms * 1e-3) / 1e12
-            tc["roofline"] = {"bound": "tensor", "kernel": "k_fullsort_tc (tcgen05.mma kind::tf32 x3, TMA, TMEM)",
-                              "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s (fp32-equivalent; 3 MMAs per product)",
-                              "frac": ach / tc_peak, "traffic": None, "avg_launch_us": 1e3 * tc_kernel_ms,
-                              "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}
-        tot = sum(v[1] for v in prof_tc.values()) or 1.0
-        tc["kernel_shares"] = {k: round(v[1] / tot, 4) for k, v in sorted(prof_tc.items(), key=lambda kv: -kv[1][1])[:6]}
-    probe = None
-    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_probe:
-        try:
-            del tdata, loader
-            torch.cuda.empty_cache()
-            probe = scaleout_probe(dev, flush)
-        except Exception as e:
-            probe = {"error": str(e)[:300]}
-    families = None
-    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_families:
-        try:   # BASELINE.json configs[2] / configs[3]: PFCN_MLP and FairGo_PMF(LBA) training at the ML-1M shape
-            import bench_families as bf
-            torch.cuda.empty_cache()
-            families = {"pfcn_mlp": bf.bench_pfcn(dev, flush, cpu=not args.no_cpu_baseline),
-                        "fairgo_pmf": bf.bench_fairgo(dev, flush, cpu=not args.no_cpu_baseline),
-                        "sampled_eval": bf.bench_sampled_eval(dev, flush, cpu=not args.no_cpu_baseline)}
-        except Exception as e:
-            families = {"error": str(e)[:300]}
-        try:   # NFCF stage 2 (own guard: a failure here must not drop the legs above)
-            families["nfcf"] = bf.bench_nfcf(dev, flush, cpu=not args.no_cpu_baseline)
-        except Exception as e:
-            families["nfcf"] = {"error": str(e)[:300]}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sub = argparse.Namespace(steps=20 if wname == "ml1m" else 3, warmup=1, gpus=1)
-        cpu = run_reference(sub, wname)["cpu_baseline"]
+    # ============================================================ training
+    if world == 1:
+        tdata = pkg.TrainData.from_device(tr_u, tr_i.long(), tr_r, gender, nu, ni)
+        n_train = tdata.n_rows
+        loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020)
+        with torch.device(dev):
+            model = pkg.FOCF(cfg, synth.SynthDataset(nu, ni, 5.0))
+        items, offs, batches = loader.plan_epoch(n_plan)
+        d_items, d_offs = torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev)
+        uf, itf, rf, sf = tdata.fields
+        losses = torch.zeros(n_plan, device=dev)
 
-    ingest = None
-    if rank == 0 and world == 1 and wname == "ml1m" and not args.no_cpu_baseline:
-        try:   # atomic files of this shape -> ids, labels, shuffle, split, eval lists (host side only)
-            import shutil
-            import tempfile
-            import bench_ingest as bi
-            root = tempfile.mkdtemp()
+        def make_step(model):
+            def step(k):
+                uid, iid, rating, sst = loader.gather(d_items, d_offs, batches[k])
+                inter = pkg.Interaction({uf: uid, itf: iid, rf: rating, sf: sst})
+                inter.items_contiguous = True
+                model.train_step(inter, loss_out=losses[k:k + 1])
+                return batches[k][3]
+            return step
+
+        def run_mode(mode):
+            model.init_adam(lr=1e-3, weight_decay=1e-3, mode=mode, max_steps=n_plan + 8)
+            step = make_step(model)
+            for k in range(W_):
+                step(k)
+            model.flush_adam()
+            barrier()
+            model.check_flags()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            launches0 = _lib.launch_count()
+            a.record()
+            rows = sum(step(W_ + k) for k in range(K_))
+            b.record()
+            model.flush_adam()
+            c.record()
+            barrier()
+            launches = _lib.launch_count() - launches0
+            ms_steps, ms_all = a.elapsed_time(b), a.elapsed_time(c)
+            _lib.profile_enable(True)
+            rows_p = sum(step(W_ + K_ + k) for k in range(K_))
+            model.flush_adam()
+            prof = _lib.profile_report()
+            _lib.profile_enable(False)
+            return dict(rows=rows, ms_steps=ms_steps, ms_all=ms_all, launches=launches, rows_p=rows_p), prof
+
+        u0 = loader.gather(d_items, d_offs, batches[0])[0]
+        uniq_users = int(torch.unique(u0).numel())
+        J_avg = float(np.mean([b[2] for b in batches]))
+        with ClockSampler(local) as clocks:
+            out_modes["dense_exact"], prof_modes["dense_exact"] = run_mode("dense_exact")
+        out_modes["lazy_exact"], prof_modes["lazy_exact"] = run_mode("lazy_exact")
+        rows_per_gpu_tab = nu + ni
+        parallelism = "single GPU"
+    else:
+        sd = sharded.ShardedTrainData(tr_u, tr_i, tr_r.float(), gender, nu, ni, rank, world, dev)
+        n_train = sd.n_rows
+        loader = sharded.ShardedFOCFLoader(w["batch"] * world, sd, 2020)
+        plan = loader.plan(n_plan)
+        losses = torch.zeros(n_plan, device=dev)
+        uf, itf, rf, sf = "user_id", "item_id", "rating", "gender"
+        model = None
+
+        def run_mode(mode):
+            m = sharded.ShardedFOCF(sd, d, objective="value", fair_weight=1.0, lr=1e-3, weight_decay=1e-3, adam_mode=mode,
+                                    J_cap=loader.J_cap, max_batch_loc=loader.max_batch_loc, max_steps=n_plan + 8)
             try:
-                t_ing, ds_ing, _, _ = bi.ours(root, bi.write_files(root))
-                ingest = {"value": t_ing["total_s"], "unit": "s", "rows": int(len(ds_ing)), "phases": t_ing,
-                          "reference_s": 10.3, "reference_source": "profiles/r01_ingest.json (unmodified reference on the same "
-                          "files, 8 cores of the build container, 10.3-12.5 s over runs; outputs bit-identical)"}
+                m.init_xavier(nu, ni, 2020)
+                m.connect(group)
+                m.stage(plan, 0)
+                step = lambda k: m.train_step(plan, k, next_k=k + 1, loss_out=losses[k:k + 1])
+                for k in range(W_):
+                    step(k)
+                m.flush()
+                barrier()
+                m.check_flags()
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                launches0 = _lib.launch_count()
+                a.record()
+                for k in range(K_):
+                    step(W_ + k)
+                b.record()
+                m.flush()
+                c.record()
+                barrier()
+                launches = _lib.launch_count() - launches0
+                rows = sum(plan["desc"][W_ + k]["B_glob"] for k in range(K_))
+                ms_steps, ms_all = a.elapsed_time(b), a.elapsed_time(c)
+                _lib.profile_enable(True)
+                for k in range(K_):
+                    step(W_ + K_ + k)
+                m.flush()
+                prof = _lib.profile_report()
+                _lib.profile_enable(False)
+                barrier()
+                m.check_flags()
+                # ---- end to end from host batches (this rank's rows of each batch in pinned host memory)
+                e2e = None
+                if mode == "dense_exact":
+                    base = W_ + 2 * K_
+                    hbs = [m.local_batch_to_host(plan, base + k) for k in range(K_)]
+                    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
+                    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+                    done = [torch.cuda.Event() for _ in range(2)]
+                    barrier()
+                    t0 = time.perf_counter()
+                    pending = None
+                    for k, hb in enumerate(hbs):
+                        slot = k & 1
+                        m.train_step_host(plan, base + k, hb, next_k=base + k + 1, loss_out=loss_dev[slot])
+                        loss_host[slot].copy_(loss_dev[slot], non_blocking=True)
+                        done[slot].record()
+                        if pending is not None:
+                            done[pending].synchronize()
+                            if float(loss_host[pending]) != float(loss_host[pending]):
+                                raise ValueError("Training loss is nan")
+                        pending = slot
+                    done[pending].synchronize()
+                    barrier()
+                    t_e = vmax(time.perf_counter() - t0)
+                    rows_e = sum(plan["desc"][base + k]["B_glob"] for k in range(K_))
+                    e2e = {"value": rows_e / t_e, "unit": "interactions/s",
+                           "h2d_bytes_per_step": int(np.mean([hb[0].numel() for hb in hbs])), "d2h_bytes_per_step": 4,
+                           "mode": "per rank: its rows of the batch in ONE pinned host buffer -> H2D -> row-sharded step -> loss "
+                                   "D2H every step; the host waits for step t's loss after enqueuing step t+1",
+                           "api": "ShardedFOCF.train_step_host(plan, k, host_batch)"}
+                    m.check_flags()
             finally:
-                shutil.rmtree(root, ignore_errors=True)
+                m.close()
+            return dict(rows=rows, ms_steps=ms_steps, ms_all=ms_all, launches=launches, rows_p=rows, e2e=e2e), prof
+
+        with ClockSampler(local) as clocks:
+            out_modes["dense_exact"], prof_modes["dense_exact"] = run_mode("dense_exact")
+        out_modes["lazy_exact"], prof_modes["lazy_exact"] = run_mode("lazy_exact")
+        rows_per_gpu_tab = sharded.local_rows(nu, rank, world) + sharded.local_rows(ni, rank, world)
+        J_avg = float(np.mean([b["J"] for b in plan["desc"]]))
+        parallelism = (f"row-sharded x{world}: rank r owns rows r::{world} of both tables and the Adam moments and the train rows "
+                       f"of its users; per step the drawn items' rows, the partial item x group sums and the partial item "
+                       f"gradients (O(J d), J ~ {J_avg:.0f}) cross NVLink as peer-memory stores of the step's kernels, 3 flag "
+                       f"barriers per step, no collective")
+
+    note("training modes done")
+    # ---- headline numbers (dense_exact) and the lazy block
+    dn, lz = out_modes["dense_exact"], out_modes["lazy_exact"]
+    t_dev = vmax(dn["ms_steps"] / 1e3)
+    value = dn["rows"] / t_dev
+    B_avg = dn["rows"] / K_ / world          # rows per GPU per step
+
+    def roofline_of(prof, n_steps, rows_tab, B_gpu, touched_users):
+        """dominant kernel + algorithmic bytes per launch"""
+        rows_touched = touched_users + J_avg
+        alg = {   # by kernel-name prefix; kernels launched once per table side report the mean over their two launches
+            "k_apply": 24.0 * rows_tab * d,
+            "k_shard_apply_users": 24.0 * (rows_tab - ni / world) * d, "k_shard_apply_items": 24.0 * (ni / world) * d,
+            "k_forward": (8.0 * d + 16.0) * B_gpu, "k_shard_forward": (8.0 * d + 16.0) * B_gpu,
+            "k_segment_grads": 8.0 * d * B_gpu + 4.0 * d * rows_touched,
+            "k_shard_grads": 8.0 * d * B_gpu + 4.0 * d * rows_touched,
+            "(k_adam_lazy<0, false>)": 24.0 * d * rows_touched / 2, "(k_adam_lazy<0, true>)": 28.0 * d * rows_touched / 2,
+            "(k_adam_lazy<2, false>)": 24.0 * rows_tab * d / 2,
+        }
+        tot = sum(v[1] for v in prof.values()) or 1.0
+        shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+        def key_of(k):
+            return next((a for a in alg if k.startswith(a)), None)
+
+        dom = next((k for k in shares if key_of(k)), None)
+        if dom is None:
+            return None, shares
+        cnt, ms = prof[dom]
+        ach = alg[key_of(dom)] / (ms / cnt * 1e-3) / 1e9
+        return ({"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                 "traffic": None, "algorithmic_bytes_per_launch": alg[key_of(dom)], "avg_launch_us": 1e3 * ms / cnt,
+                 "launches_profiled": cnt, "share_of_step": shares[dom], "peak_source": peak_src,
+                 "from": f"library CUDA-event profiler over {n_steps} further steps of the same loop (same batches regime, no "
+                         f"flush needed: every launch streams far more than the 126 MB L2)"}, shares)
+
+    touched = (uniq_users or B_avg * 0.5)
+    roof, shares = roofline_of(prof_modes["dense_exact"], K_, rows_per_gpu_tab, B_avg, touched)
+    if roof and world == 1:
+        roof["traffic_note"] = "ncu --set full capture of this kernel: profiles/ (dram bytes / algorithmic = 1.01 in round 1)"
+    roof_lz, shares_lz = roofline_of(prof_modes["lazy_exact"], K_, rows_per_gpu_tab, B_avg, touched)
+    t_lz = vmax(lz["ms_all"] / 1e3)
+    lazy = {"value": lz["rows"] / t_lz, "unit": "interactions/s", "ms_per_step": 1e3 * t_lz / K_,
+            "steps_only_ms_per_step": vmax(lz["ms_steps"]) / K_, "speedup_vs_dense_exact": (lz["rows"] / t_lz) / value,
+            "what": "adam_mode lazy_exact: tables, moments and losses BIT-IDENTICAL to dense_exact (tests/test_sharded_gpu.py); a "
+                    "row is replayed through the steps it missed when a batch next touches it, or at the flush.  The timed region "
+                    "is the K steps PLUS the closing flush, which carries the deferred updates of all rows for those K steps (the "
+                    "replay is float32 ALU work, ~35 instructions per parameter and step, instead of 24 bytes of HBM traffic).",
+            "roofline": roof_lz, "kernel_shares": dict(list(shares_lz.items())[:8])}
+
+    # ============================================================ e2e (N = 1): host batches through FOCF.train_step
+    if world == 1:
+        model.init_adam(lr=1e-3, weight_decay=1e-3, mode="dense_exact")
+        base = W_ + 2 * K_
+        hbs = []
+        for k in range(K_):
+            cols = loader.gather(d_items, d_offs, batches[base + k])
+            hbs.append(pkg.pack_host_batch(*[c.cpu() for c in cols], fields=(uf, itf, rf, sf)))
+        loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
+        loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        model.train_step(hbs[0], loss_out=loss_dev[0])          # staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        pending, rows_e = None, 0
+        for k, hb in enumerate(hbs):
+            slot = k & 1
+            model.train_step(hb, loss_out=loss_dev[slot])       # the single H2D copy of the packed batch happens inside
+            loss_host[slot].copy_(loss_dev[slot], non_blocking=True)
+            done[slot].record()
+            if pending is not None:
+                done[pending].synchronize()
+                if float(loss_host[pending]) != float(loss_host[pending]):
+                    raise ValueError("Training loss is nan")
+            pending = slot
+            rows_e += len(hb)
+        done[pending].synchronize()
+        barrier()
+        t_e = time.perf_counter() - t0
+        e2e = {"value": rows_e / t_e, "unit": "interactions/s",
+               "h2d_bytes_per_step": int(np.mean([hb.packed_host[0].numel() for hb in hbs])), "d2h_bytes_per_step": 4,
+               "mode": "host batch (one pinned buffer: int32 user | int32 item | f32 rating | f32 attribute) -> H2D -> step -> "
+                       "loss D2H every step; the host waits for step t's loss after enqueuing step t+1",
+               "api": "FOCF.train_step(interaction) with adam_mode dense_exact"}
+        model.check_flags()
+        del hbs
+    else:
+        e2e = dn["e2e"]
+
+    note("e2e done")
+    # ============================================================ evaluation
+    ev = None
+    try:
+        n_eval_cap = int(args.eval_users)
+        keep = va_u <= n_eval_cap
+        edata = pkg.EvalData.from_device(tr_u, tr_i, va_u[keep], va_i[keep], {sf: gender}, nu, ni)
+        del keep
+        counts = torch.bincount(tr_i.long(), minlength=ni).cpu().numpy()
+        del tr_u, tr_i, tr_r, va_u, va_i, data
+        if world == 1:
+            Uw, Iw = model.user_embedding_layer.weight.data, model.item_embedding_layer.weight.data
+        else:
+            g = torch.Generator(device=dev).manual_seed(77)
+            Uw = torch.randn((nu, d), generator=g, device=dev) * math.sqrt(2.0 / (nu + d))
+            Iw = torch.randn((ni, d), generator=g, device=dev) * math.sqrt(2.0 / (ni + d))
+        torch.cuda.empty_cache()
+        evaluator = pkg.FullSortEvaluator(cfg, ni, {int(i): int(c) for i, c in enumerate(counts) if c > 0}, group=group)
+        evaluator.evaluate(Uw, Iw, edata, 5.0)                   # warm-up pass (popularity mask, module load)
+        barrier()
+        n_pass = 2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(n_pass):
+            res = evaluator.evaluate(Uw, Iw, edata, 5.0)         # returns the metric dict on the host (D2H inside)
+        b.record()
+        barrier()
+        t_wall = vmax((time.perf_counter() - t0) / n_pass)
+        t_evd = vmax(a.elapsed_time(b) / 1e3 / n_pass)
+        _lib.profile_enable(True)
+        evaluator.collect(Uw, Iw, edata, 5.0)
+        prof_e = _lib.profile_report()
+        _lib.profile_enable(False)
+        tc_cnt, tc_ms = prof_e.get("k_fullsort_tc", (1, float("nan")))
+        tc_peak = bf16 / 2.0 / 3.0
+        flops = 2.0 * edata.n * (ni / world) * d
+        etot = sum(v[1] for v in prof_e.values()) or 1.0
+        ach = flops / (tc_ms / tc_cnt * 1e-3) / 1e12
+        ev = {"metric": "full-sort fair-eval users/s", "value": edata.n / t_evd, "unit": "users/s", "n_users": edata.n,
+              "n_items": ni, "n_pos": edata.n_pos, "history_entries": int(edata.hist_items.numel()),
+              "ms_per_pass": 1e3 * t_evd, "score_mode": "tc_3xtf32",
+              "e2e": {"value": edata.n / t_wall, "unit": "users/s",
+                      "what": "FullSortEvaluator.evaluate(U, I, data): wall clock incl. the read-back of the metric sums"},
+              "sharding": None if world == 1 else f"item table in {world} contiguous id ranges, NCCL all-gather of the per-shard "
+              f"top-{K} + merge, all-reduce of the item x group sums",
+              "roofline": {"bound": "tensor", "kernel": "k_fullsort_tc", "achieved": ach, "peak": tc_peak,
+                           "unit": "TFLOP/s (fp32-equivalent; 3 TF32 MMAs per product)", "frac": ach / tc_peak,
+                           "avg_launch_us": 1e3 * tc_ms / tc_cnt, "share_of_pass": round(tc_ms / etot, 4),
+                           "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"},
+              "kernel_shares": {k: round(v[1] / etot, 4) for k, v in sorted(prof_e.items(), key=lambda kv: -kv[1][1])[:6]},
+              "metrics": {k: float(v) for k, v in res.items()}}
+        del edata, evaluator
+    except Exception as e:
+        ev = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+    note("evaluation done")
+    # ============================================================ dp_check (N > 1)
+    dp_check = None
+    if world > 1:
+        try:
+            torch.cuda.empty_cache()
+            dp_check = {"train": sharded.selfcheck(rank, world, dev, group, adam_mode="dense_exact"),
+                        "train_lazy": sharded.selfcheck(rank, world, dev, group, adam_mode="lazy_exact"),
+                        "eval": eval_selfcheck(rank, world, dev, group)}
+            if rank == 0:
+                dp_check["pass"] = all(bool(v.get("pass")) for v in dp_check.values() if isinstance(v, dict))
         except Exception as e:
-            ingest = {"error": str(e)[:300]}
+            dp_check = {"pass": False, "error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+    # ============================================================ N = 1 only: configs[1], families, CPU baseline
+    ml1m = families = cpu = None
+    if world == 1 and rank == 0:
+        model = loader = tdata = make_step = run_mode = None       # (closures hold the tables)
+        Uw = Iw = d_items = d_offs = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        # the two side blocks run in their OWN processes after this one has released the GPU memory: a failure there cannot
+        # take the headline line down, and their CUDA-graph pools / side streams start from a clean context
+        def side_block(script, extra):
+            cmd = [sys.executable, os.path.join(ROOT, script), "--steps", str(max(K_, 20)), "--warmup", str(max(W_, 5))] + extra
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not lines:
+                return {"error": f"{script} exited with {r.returncode}: {r.stderr[-300:]}"}
+            return json.loads(lines[-1])
+
+        if not args.no_ml1m:
+            try:
+                note("ml1m block (bench_ml1m.py, own process)")
+                ml1m = side_block("bench_ml1m.py", ["--no-probe", "--no-families"] +
+                                  (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
+            except Exception as e:
+                ml1m = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if not args.no_families:
+            try:
+                note("families block (bench_families.py, own process)")
+                families = side_block("bench_families.py", ["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+            except Exception as e:
+                families = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if not args.no_cpu_baseline:
+            try:
+                note("cpu baseline (reference arm)")
+                sub = argparse.Namespace(steps=min(K_, 10), warmup=2, gpus=1)
+                cpu = reference_arm(sub, w)["cpu_baseline"]
+            except Exception as e:
+                cpu = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     out = {
-        "metric": "FOCF train interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world,
-        "steps": timed_steps, "warmup": args.warmup, "ms_per_step": sum(step_ms) / timed_steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"focf_{wname}", "n_users": w["n_users"], "n_items": w["n_items"], "n_inter": w["n_inter"],
-                   "d": d, "train_batch_size": w["batch"], "avg_batch_rows": rows / timed_steps,
-                   "fair_objective": "value", "optimizer": "adam(lr=1e-3, weight_decay=1e-3) dense-exact",
-                   "l2": (f"flushed before every timed launch = {G} pipelined steps (512 MB write outside the event bracket); "
-                          "flushed_single_step gives the per-step-flush number") if use_graph else
-                         "flushed before every timed step (512 MB write outside the event bracket)",
-                   "parallelism": "single GPU" if world == 1 else
-                   f"train: data-parallel x{world} (disjoint item partitions, global normalisers, NCCL all-reduce of the dense "
-                   f"gradient shares, identical dense Adam on every replica; global batch = {world} x {w['batch']}); "
-                   f"eval: item table sharded x{world}, NCCL all-gather top-K merge + all-reduce of item x group stats"},
+        "metric": "FOCF train interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K_,
+        "warmup": W_, "ms_per_step": 1e3 * t_dev / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (generated on the device, seed 2020)",
+        "gpu_launches": int(dn["launches"]),
+        "config": {**workload_config(w, world), "n_train": int(n_train), "avg_batch_rows_per_gpu": B_avg,
+                   "adam_mode": "dense_exact (every row moves every step, as torch.optim.Adam does in the reference)",
+                   "l2": f"no flush needed: every step streams 24 * rows * d = {24.0 * rows_per_gpu_tab * d / 1e9:.1f} GB of "
+                         f"tables + moments per GPU, far beyond the 126 MB L2",
+                   "parallelism": parallelism},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_loop["value"] if e2e_loop and "value" in e2e_loop else e2e_value,
-                "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "mode": "host batch (one pinned buffer) -> H2D -> step -> loss D2H every step; the host waits for step t's "
-                        "loss after enqueuing step t+1",
-                "api": ("FOCF.train_steps_host(batches): the loop over the batches runs inside the library "
-                        "(fr_focf_train_steps_host)") if e2e_loop and "value" in e2e_loop else
-                       "FOCF.train_step(batch) per batch from Python",
-                "python_loop_value": e2e_value, "library_loop": e2e_loop,
-                "serial_value": e2e_serial, "host_path": host_path},
-        "gpu_launches": int(round(kernels_per_step * timed_steps)), "kernels_per_step": kernels_per_step,
-        "launch_mode": (f"cuda graph replay ({G} steps per launch; prepare(t+1) on a second stream under compute(t))"
-                        if world == 1 else f"cuda graph replay ({G} data-parallel steps per launch incl. the NCCL all-reduce)")
-        if use_graph else "stream launches",
-        "flushed_single_step": single,
-        "steady_state": steady,
-        "roofline": roofline,
-        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_roof, "unit": "GB/s",
-                          "frac": step_roof / hbm},
-        "kernel_shares": shares,
+        "roofline": roof,
+        "kernel_shares": dict(list(shares.items())[:10]),
         "cpu_baseline": cpu,
-        "scaleout_probe": probe,
+        "e2e": e2e,
+        "lazy_exact": lazy,
+        "eval": ev,
+        "dp_check": dp_check,
+        "ml1m": ml1m,
         "families": families,
-        "ingest": ingest,
-        "eval": {"metric": "full-sort fair-eval users/s",
-                 "value": tc["value"] if tc and "error" not in tc else n_eval / t_eval, "unit": "users/s",
-                 "score_mode": "tc_3xtf32 (tcgen05+TMA; ids equal the exact mode's outside fp32-level near ties)"
-                 if tc and "error" not in tc else "exact_fp32",
-                 "exact_fp32": {"value": n_eval / t_eval, "unit": "users/s", "ms_per_pass": 1e3 * t_eval,
-                                "note": "bit-defined CUDA-core fma chain: top-K ids AND scores bit-equal to the oracle"},
-                 "n_users": n_eval, "ms_per_pass": tc["ms_per_pass"] if tc and "error" not in tc else 1e3 * t_eval,
-                 "e2e": {"value": n_eval / t_eval_e2e, "unit": "users/s", "h2d_bytes_per_pass": eval_h2d,
-                         "d2h_bytes_per_pass": 8 * (4 * K + K + 7 + 2)},
-                 "host_csr_build_s": t_build, "roofline": eval_roof, "kernel_shares": ev_shares,
-                 "ndcg@10": res.get(f"ndcg@{K}"), "metrics": {k: float(v) for k, v in res.items()},
-                 "tensor_core": tc},
+        "setup_s": {"synthesis": t_synth, "total_before_json": time.perf_counter() - t_all},
+        "hbm_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
     }
     if world > 1:
-        runner = None
-        model.release_graphs()          # graphs holding captured NCCL kernels must go before the communicator does
         dist.barrier()
         dist.destroy_process_group()
     return out if rank == 0 else None
 
 
-def scaleout_probe(dev, flush):
-    """The HBM- and tensor-bound regime of BASELINE.json configs[4], reduced so that it runs in seconds: FOCF steps on
-    2M users x 262k items, d=128, 2^18-row batches (tables + Adam state 6.9 GB; random interactions drawn directly, no
-    uniqueness pass) and the tensor-core scorer on 37,888 users x 262,144 items.  Reported next to the ML-1M numbers
-    because at the ML-1M shape every kernel is latency-bound and a bandwidth fraction says little."""
+def eval_selfcheck(rank, world, dev, group, n_users=3001, n_items=4099, d=64, K=10):
+    """item-sharded evaluation (NCCL all-gather + merge, all-reduce of the item x group sums) vs the unsharded pass on the
+    same tables: top-K ids bit-equal, the 12 metrics equal (SURVEY.md section 4 test plan iv)"""
     import torch
     import recbole_fairrec_b200 as pkg
-    from recbole_fairrec_b200 import _lib, kernels, synth
-    hbm, bf16, peak_src = peaks()
-    nu, ni, d, batch, n_inter = 2_000_001, 262_145, 128, 1 << 18, 6_000_000
-    rng = np.random.default_rng(0)
-    iid = (rng.lognormal(4.5, 1.4, n_inter) % (ni - 1)).astype(np.int32) + 1
-    uid = rng.integers(1, nu, n_inter).astype(np.int32)
-    rating = rng.integers(1, 6, n_inter).astype(np.float32)
-    gender = (rng.random(nu) < 0.28).astype(np.float32) + 1
-    cfg = pkg.Config(embedding_size=d, fair_objective="value", train_batch_size=batch, device=dev)
-    train = pkg.TrainData(uid, iid, rating, gender, nu, ni, dev)
-    loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=1)
-    model = pkg.FOCF(cfg, synth.SynthDataset(nu, ni, 5.0)).to(dev)
-    with torch.no_grad():
-        model.user_embedding_layer.weight.mul_(0.05)
-        model.item_embedding_layer.weight.mul_(0.05)
-    model.init_adam(lr=1e-3, weight_decay=1e-3)
-    it = iter(loader)
-    for _ in range(3):
-        model.train_step(next(it))
-    torch.cuda.synchronize()
-    n_t, rows, ms = 8, 0, []
-    for _ in range(n_t):
-        inter = next(it)
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        model.train_step(inter)
-        b.record()
-        torch.cuda.synchronize()
-        ms.append(a.elapsed_time(b))
-        rows += len(inter["user_id"])
-    _lib.profile_enable(True)
-    for _ in range(4):
-        flush.zero_()
-        model.train_step(next(it))
-    prof = _lib.profile_report()
-    _lib.profile_enable(False)
-    model.check_flags()
-    B_avg = rows / n_t
-    alg_apply = 24.0 * (nu + ni) * d
-    cnt, tot = prof["k_apply<fr::kAdamFused>"]
-    ach = alg_apply / (tot / cnt * 1e-3) / 1e9
-    step_bytes = (16.0 * d + 16.0) * B_avg + alg_apply
-    step_ach = step_bytes / (statistics.mean(ms) * 1e-3) / 1e9
-    out = {"workload": f"focf {nu - 1} users x {ni - 1} items, d={d}, batch 2^18 (reduced configs[4])",
-           "train": {"value": rows / (sum(ms) / 1e3), "unit": "interactions/s", "ms_per_step": statistics.mean(ms)},
-           "roofline": {"bound": "hbm", "kernel": "k_apply<fr::kAdamFused>", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                        "frac": ach / hbm, "algorithmic_bytes_per_launch": alg_apply, "avg_launch_us": 1e3 * tot / cnt,
-                        "traffic": 7.04e9, "traffic_source": "profiles/r01_ncu_summary.md (dram read 3.62 GB + write 3.42 GB)",
-                        "share_of_step": tot / (sum(v[1] for v in prof.values()) or 1.0), "peak_source": peak_src},
-           "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_ach, "unit": "GB/s",
-                             "frac": step_ach / hbm}}
-    del model, train, loader
-    torch.cuda.empty_cache()
-    # tensor-core scorer
-    n, nit, K = 37_888, 262_144, 10
-    g = torch.Generator(device=dev).manual_seed(0)
-    U = torch.randn(n + 1, d, device=dev, generator=g) * 0.3
-    I = torch.randn(nit, d, device=dev, generator=g) * 0.3
-    users = torch.arange(1, n + 1, dtype=torch.int32, device=dev)
-    hist_off = torch.arange(0, (n + 1) * 4, 4, dtype=torch.int64, device=dev)[:n + 1]
-    hist_items = torch.sort(torch.randint(1, nit, (n, 4), device=dev, generator=g), dim=1).values.to(torch.int32) \
-        .reshape(-1).contiguous()
-    run = lambda: kernels.fullsort_topk(U, I, users, hist_off, hist_items, K, _lib.TRANSFORM_CLAMP_DIV, 5.0, 0,
-                                        _lib.SCORE_TC_3XTF32)
-    for _ in range(2):
-        run()
-    _lib.profile_enable(True)
-    for _ in range(3):
-        run()
-    prof = _lib.profile_report()
-    _lib.profile_enable(False)
-    cnt, tot = prof["k_fullsort_tc"]
-    tc_peak = bf16 / 2.0 / 3.0
-    ach = 2.0 * n * nit * d / (tot / cnt * 1e-3) / 1e12
-    out["eval"] = {"workload": f"{n} users x {nit} items, d={d}, K={K}", "value": n / (tot / cnt * 1e-3),
-                   "unit": "users/s (scoring + mask + top-K kernel)",
-                   "roofline": {"bound": "tensor", "kernel": "k_fullsort_tc", "achieved": ach, "peak": tc_peak,
-                                "unit": "TFLOP/s (fp32-equivalent; the kernel issues 3 TF32 MMAs per product)",
-                                "frac": ach / tc_peak, "avg_launch_us": 1e3 * tot / cnt, "traffic": None,
-                                "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"}}
+    from recbole_fairrec_b200 import synth
+    uid, iid, rating, gender = synth.interactions(n_users, n_items, 60000, 3)
+    tr, va, te = synth.split_by_user(uid, iid, rating, seed=3)
+    users, hist, pos = synth.eval_lists(tr, va, te, "valid")
+    cfg = pkg.Config(embedding_size=d, topk=[K], device=dev, metric_decimal_place=12, score_mode="exact", cuda_graph=False)
+    edata = pkg.EvalData(users, hist, pos, {"gender": gender.astype(np.int64)}, dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    U = torch.randn((n_users, d), generator=g, device=dev) * 0.3
+    I = torch.randn((n_items, d), generator=g, device=dev) * 0.3
+    counts = np.bincount(tr[1], minlength=n_items)
+    ci = {int(i): int(c) for i, c in enumerate(counts) if c > 0}
+    sharded_ev = pkg.FullSortEvaluator(cfg, n_items, ci, group=group)
+    res_s = sharded_ev.evaluate(U, I, edata, 5.0)
+    ids_s = sharded_ev.last["topk_id"].clone()
+    out = {"world": world, "shape": [n_users, n_items, d, K]}
+    if rank == 0:
+        single = pkg.FullSortEvaluator(cfg, n_items, ci, group=None)
+        res_1 = single.evaluate(U, I, edata, 5.0)
+        out["ids_bit_equal"] = bool(torch.equal(ids_s, single.last["topk_id"]))
+        out["metrics_max_abs_diff"] = max(abs(float(res_s[k]) - float(res_1[k])) for k in res_1)
+        out["pass"] = out["ids_bit_equal"] and out["metrics_max_abs_diff"] <= 1e-9
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ml1m", choices=list(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (smoke runs; not the BASELINE config)")
+    ap.add_argument("--eval-users", type=float, default=1 << 19, help="evaluate users with id <= this")
+    ap.add_argument("--ref-scale-div", type=int, default=8, help="reference arm: 1/S-scale replica of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-probe", action="store_true", help="skip the scale-out roofline probe")
-    ap.add_argument("--no-families", action="store_true", help="skip the PFCN / FairGo legs")
-    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
-    ap.add_argument("--no-dp-graph", action="store_true",
-                    help="multi-GPU: launch the data-parallel steps eagerly instead of replaying a CUDA graph that "
-                         "captured them together with their NCCL all-reduce")
+    ap.add_argument("--no-ml1m", action="store_true")
+    ap.add_argument("--no-families", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = scaled(args.scale)
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        args.steps = min(args.steps, 40)     # bounded sample: the CPU loop runs ~0.03-0.3 s per step
-        print(json.dumps(run_reference(args, args.workload)))
+        print(json.dumps(reference_arm(args, w, args.ref_scale_div)), flush=True)
         return
+    args.warmup = max(args.warmup, 3)
     # libraries (NCCL's version banner, ...) may write to stdout: keep fd 1 for the ONE JSON line
     sys.stdout.flush()
     saved = os.dup(1)
     os.dup2(2, 1)
     try:
-        out = run_ours(args, args.workload)
+        out = run_ours(args, w)
     finally:
         sys.stdout.flush()
         os.dup2(saved, 1)

@@ -376,18 +376,6 @@ def bench_sampled_eval(dev, flush, cpu=True, seed=2020, neg_num=100, K=10):
     return out
 
 
-if __name__ == "__main__":
-    import json
-    import sys
-
-    import torch
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    dev = torch.device("cuda", 0)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    print(json.dumps({"pfcn_mlp": bench_pfcn(dev, flush), "fairgo_pmf": bench_fairgo(dev, flush),
-                      "sampled_eval": bench_sampled_eval(dev, flush)}))
-
-
 def bench_nfcf(dev, flush, n_steps=30, cpu=True, seed=2020):
     """NFCF stage 2 (nfcf.py:99-110 with a pretrain loaded: BCE + fair_weight * differential fairness, user table
     frozen) at the ML-1M shape, NFCF.yaml widths: batches of 1024 positives + 1024 uniform negatives (labels 1 | 0), one
@@ -471,3 +459,39 @@ def cpu_nfcf(model, hosts, n=3):
     B = hosts[0]["user_id"].numel()
     return {"value": B / dt, "unit": "interactions/s", "cores": os.cpu_count() or 1, "kind": "port",
             "sample": f"{n} steps of {B} rows (dropout off in the port)", "ms_per_step": 1e3 * dt}
+
+
+def main():
+    """stand-alone / as bench.py's `families` block (own process): ONE JSON line {leg: result}"""
+    import argparse
+    import json
+    import sys
+
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    saved = os.dup(1)
+    os.dup2(2, 1)          # keep stdout for the ONE JSON line
+    try:
+        for name, fn in (("pfcn_mlp", bench_pfcn), ("fairgo_pmf", bench_fairgo), ("nfcf", bench_nfcf),
+                         ("sampled_eval", bench_sampled_eval)):
+            try:
+                out[name] = fn(dev, flush, cpu=not args.no_cpu_baseline)
+            except Exception as e:
+                out[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

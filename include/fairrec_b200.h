@@ -536,6 +536,8 @@ typedef struct fr_focf_shard_step {
   void *xchg[FR_MAX_RANKS];
   int32_t J_cap;               /* capacity the exchange layout was sized for (>= every batch's J) */
   int32_t barriers;            /* 1: cross-GPU barriers after STAGE / A / B (real multi-process run); 0: caller sequences phases */
+  int32_t prebuilt;            /* 1: uid / iid (draw positions) / rating / sst already hold this rank's rows of the batch (a host
+                                  batch copied in by the caller, interaction.py:174-200 `.to(device)`): phase A skips its gather */
 } fr_focf_shard_step;
 
 size_t fr_focf_shard_xchg_bytes(int32_t world, int32_t J_cap, int32_t d);

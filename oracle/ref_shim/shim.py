@@ -2,13 +2,25 @@
 importable in this container.
 
 TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py (fixture generation, run
-in the build container where /root/reference exists) -- never by the product.
+in the build container where /root/reference exists), by `bench.py --impl reference`
+and by the drop-in tests (on the GPU box through the copy oracle/_ref that
+oracle/make_ref.py makes) -- never by the product.
 """
 import functools
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("FAIRREC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_COPY = os.path.join(os.path.dirname(_HERE), "_ref")        # oracle/_ref: made by oracle/make_ref.py, travels to the GPU box
+
+
+def _default_root():
+    if os.path.isdir("/root/reference/recbole"):
+        return "/root/reference"
+    return _REF_COPY
+
+
+REFERENCE_ROOT = os.environ.get("FAIRREC_REFERENCE_ROOT") or _default_root()
 
 
 def available() -> bool:

@@ -62,7 +62,7 @@ class FocfShardStep(Structure):
         ("scalars_filled", POINTER(c_int32)),
         ("uid", c_void_p), ("iid", c_void_p), ("rating", c_void_p), ("sst", c_void_p), ("pred", c_void_p),
         ("loss", c_void_p), ("status_flags", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
-        ("xchg", c_void_p * 8), ("J_cap", c_int32), ("barriers", c_int32),
+        ("xchg", c_void_p * 8), ("J_cap", c_int32), ("barriers", c_int32), ("prebuilt", c_int32),
     ]
 
 

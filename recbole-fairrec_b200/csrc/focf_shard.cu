@@ -465,8 +465,9 @@ static int phase_a(const fr_focf_shard_step *s, const ShardWs &w, const XchgLayo
   const float *xI = (const float *)((const char *)s->xchg[s->rank] + L.xI + (size_t)par * L.xI_par);
   FR_CUDA_OK(cudaMemsetAsync(w.seg_of_j, 0xff, sizeof(int32_t) * (size_t)s->J, st));
   if (B > 0) {
-    FR_LAUNCH(k_shard_gather, grid_for((int64_t)B, 256, kSMs * 8), 256, 0, st, s->item_off, s->train_uid, s->train_rating,
-              s->sst_of_user, s->draw_items, s->draw_off, s->J, s->uid, s->iid, s->rating, s->sst);
+    if (!s->prebuilt)
+      FR_LAUNCH(k_shard_gather, grid_for((int64_t)B, 256, kSMs * 8), 256, 0, st, s->item_off, s->train_uid, s->train_rating,
+                s->sst_of_user, s->draw_items, s->draw_off, s->J, s->uid, s->iid, s->rating, s->sst);
     // item side: rows of one draw position are adjacent and positions ascend -> segments without a sort
     build_segments((const uint32_t *)s->iid, nullptr, B, nullptr, w.f.segid_i, w.f.segoff_i, w.f.J, nullptr, nullptr,
                    w.f.entry_seg, w.f.seg, st);

@@ -279,6 +279,42 @@ class ShardedFOCF:
     def advance(self):
         self.adam["step"] += 1
 
+    def local_batch_to_host(self, plan, k):
+        """this rank's rows of batch k as ONE pinned host buffer (int32 local user rows | int32 draw positions | f32 ratings |
+        f32 attribute values) -- the host-side Interaction of the sharded step, for end-to-end runs that start from host
+        batches like the reference's loop does (trainer.py:181-184)"""
+        b = plan["desc"][k]
+        n = b["B_loc"]
+        s = self._struct()
+        self._set_batch(s, plan, k)
+        buf = torch.empty(16 * max(n, 1), dtype=torch.uint8).pin_memory()
+        if n:
+            d = self.data
+            uid, iid, rating, sst = (c[:n] for c in self.cols)
+            check(self.lib.fr_focf_gather_batch(ptr(d.item_off), ptr(d.train_uid), ptr(d.train_rating), ptr(d.sst_of_user),
+                                                s.draw_items, s.draw_off, b["J"], ptr(uid), ptr(iid), ptr(rating), ptr(sst),
+                                                stream_ptr()), "fr_focf_gather_batch")
+            # fr_focf_gather_batch writes item ids; the sharded step indexes the staged rows by draw position
+            off = plan["offs"][b["offs_pos"]:b["offs_pos"] + b["J"] + 1].long()
+            pos = torch.repeat_interleave(torch.arange(b["J"], device=off.device, dtype=torch.int32), off[1:] - off[:-1])
+            torch.cuda.synchronize()
+            for j, col in enumerate((uid, pos, rating, sst)):
+                buf[4 * n * j:4 * n * (j + 1)].copy_(col.contiguous().view(torch.uint8).cpu())
+        return buf, n
+
+    def train_step_host(self, plan, k, host_batch, next_k=None, loss_out=None):
+        """one whole step from a HOST batch of this rank's rows (local_batch_to_host layout): one H2D copy, then the step"""
+        buf, n = host_batch
+        if n:
+            for j, col in enumerate(self.cols):
+                col[:n].view(torch.uint8).copy_(buf[4 * n * j:4 * n * (j + 1)], non_blocking=True)
+        s = self._struct()
+        s.prebuilt = 1
+        try:
+            self.train_step(plan, k, next_k, loss_out)
+        finally:
+            s.prebuilt = 0
+
     def train_step(self, plan, k, next_k=None, loss_out=None):
         """one whole step (real multi-process run: the phases are separated by cross-GPU barriers inside the call)"""
         ph = _lib.SHARD_A | _lib.SHARD_B | _lib.SHARD_C | (_lib.SHARD_STAGE if next_k is not None else 0)
@@ -375,3 +411,76 @@ class ShardedGroupEmu:
     def close(self):
         for r in self.ranks:
             r.close()
+
+
+def selfcheck(rank, world, device, group=None, adam_mode="lazy_exact", n_users=20001, n_items=3001, d=128, n_inter=400_000,
+              batch=1 << 15, steps=4, seed=7, rtol=1e-5):
+    """Multi-process correctness check of the row-sharded step (run by bench.py's `dp_check` on the driver's multi-GPU
+    lines and by tests/test_dp_gpu.py): every rank trains `steps` batches through the real path (CUDA IPC exchange memory,
+    cross-GPU barriers); rank 0 then replays the same batches through the single-GPU fused step (FOCF.train_step, dense
+    Adam) and compares the losses and the gathered tables.  Returns a dict; `pass` is the verdict (valid on rank 0)."""
+    import torch.distributed as dist
+    from . import synth
+    from .config import Config
+    from .dataloader import FOCFDataLoader, TrainData
+    from .focf import FOCF
+    from .interaction import Interaction
+    data = synth.device_interactions(n_users, n_items, n_inter, seed, device)
+    tr_u, tr_i, tr_r = data["train"]
+    gender = data["gender"]
+    sd = ShardedTrainData(tr_u, tr_i, tr_r.float(), gender, n_users, n_items, rank, world, device)
+    loader = ShardedFOCFLoader(batch, sd, seed)
+    plan = loader.plan(steps)
+    model = ShardedFOCF(sd, d, objective="value", fair_weight=1.0, adam_mode=adam_mode, J_cap=loader.J_cap,
+                        max_batch_loc=max(loader.max_batch_loc, 1), max_steps=steps + 8)
+    g = torch.Generator(device=device).manual_seed(seed)
+    U0 = torch.randn((n_users, d), generator=g, device=device) * 0.1
+    I0 = torch.randn((n_items, d), generator=g, device=device) * 0.1
+    model.set_tables(U0, I0)
+    losses = torch.zeros(steps, device=device)
+    out = {"world": world, "steps": steps, "adam_mode": adam_mode, "shape": [n_users, n_items, d, batch]}
+    try:
+        model.connect(group)
+        model.stage(plan, 0)
+        for k in range(steps):
+            model.train_step(plan, k, next_k=k + 1 if k + 1 < steps else None, loss_out=losses[k:k + 1])
+        model.check_flags()
+        U, I = model.full_tables(group)
+        torch.cuda.synchronize()
+    finally:
+        model.close()
+    if rank == 0:
+        cfg = Config(embedding_size=d, fair_objective="value", fair_weight=1.0, device=device,
+                     train_batch_size=max(b["B_glob"] for b in plan["desc"]))
+        train = TrainData.from_device(tr_u, tr_i.long(), tr_r, gender, n_users, n_items)
+        items = plan["items"].cpu().numpy()
+        draws = np.concatenate([np.r_[items[b["items_pos"]:b["items_pos"] + b["J"]], -1] for b in plan["desc"]])
+        ld = FOCFDataLoader(cfg, train, draws=draws)
+        ref = FOCF(cfg, synth.SynthDataset(n_users, n_items, 5.0)).to(device)
+        with torch.no_grad():
+            ref.user_embedding_layer.weight.copy_(U0)
+            ref.item_embedding_layer.weight.copy_(I0)
+        ref.init_adam(lr=1e-3, weight_decay=1e-3)
+        ref_losses = torch.zeros(steps, device=device)
+        it, of, bs = ld.plan_epoch(steps)
+        d_it, d_of = torch.from_numpy(it).to(device), torch.from_numpy(of).to(device)
+        uf, itf, rf, sf = train.fields
+        for k, b in enumerate(bs):
+            u, i, r, s_ = ld.gather(d_it, d_of, b)
+            inter = Interaction({uf: u, itf: i, rf: r, sf: s_})
+            inter.items_contiguous = True
+            ref.train_step(inter, loss_out=ref_losses[k:k + 1])
+        ref.check_flags()
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+        out["loss_rel_err"] = float(((losses - ref_losses).abs() / ref_losses.abs()).max())
+        out["U_rel_err"] = rel(U, ref.user_embedding_layer.weight.data)
+        out["I_rel_err"] = rel(I, ref.item_embedding_layer.weight.data)
+        out["pass"] = bool(max(out["loss_rel_err"], out["U_rel_err"], out["I_rel_err"]) < rtol)
+        out["what"] = ("row-sharded step over CUDA-IPC peer memory vs the single-GPU fused step on the same batches: losses "
+                       "and updated tables within %g relative" % rtol)
+    if world > 1:
+        dist.barrier(group=group)
+    return out

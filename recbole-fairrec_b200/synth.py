@@ -76,3 +76,37 @@ def eval_lists(train, valid, test, phase="valid"):
     hmap = dict(zip(hu.tolist(), hl))
     hist = [hmap.get(int(u), np.zeros(0, np.int32)) for u in users]
     return users, hist, pos
+
+
+def device_interactions(n_users, n_items, n_inter, seed, device, chunk=100_000_000):
+    """BASELINE.json configs[4]-style data synthesised ON THE DEVICE (1e9 rows never visit the host):
+    user activity and item popularity log-normal (inverse-CDF sampling), ratings 1..5 with ML-1M's marginal, a binary
+    gender ~ Bernoulli(0.28) stored as 1/2 (row 0 = [PAD]); each interaction goes to train / valid / test with probability
+    .8 / .1 / .1 (the reference splits 8:1:1 per user; the per-interaction draw has the same shape).  (user, item) pairs
+    are not de-duplicated (collision probability ~1e-4 at the full shape).  The same seed gives the same tensors on every
+    rank.  Returns dict(train=(uid, iid, rating u8), valid=(uid, iid), gender f32[n_users])."""
+    import numpy as np
+    import torch
+    g = torch.Generator(device=device).manual_seed(int(seed))
+
+    def cdf(n, sigma):
+        w = torch.empty(n, device=device).log_normal_(4.5, sigma, generator=g).double()
+        return (torch.cumsum(w, 0) / w.sum()).float()
+
+    ucdf, icdf = cdf(n_users - 1, 1.0), cdf(n_items - 1, 1.4)
+    rcdf = torch.tensor(np.cumsum([.056, .107, .261, .349, .227]), dtype=torch.float32, device=device)
+    gender = (torch.rand(n_users, device=device, generator=g) < 0.28).float() + 1.0
+    gender[0] = 0.0
+    tr_u, tr_i, tr_r, va_u, va_i = [], [], [], [], []
+    for lo in range(0, n_inter, chunk):
+        m = min(chunk, n_inter - lo)
+        u = (torch.searchsorted(ucdf, torch.rand(m, device=device, generator=g)).clamp_(max=n_users - 2) + 1).to(torch.int32)
+        i = (torch.searchsorted(icdf, torch.rand(m, device=device, generator=g)).clamp_(max=n_items - 2) + 1).to(torch.int32)
+        r = (torch.searchsorted(rcdf, torch.rand(m, device=device, generator=g)).clamp_(max=4) + 1).to(torch.uint8)
+        part = torch.rand(m, device=device, generator=g)
+        tr = part < 0.8
+        va = (part >= 0.8) & (part < 0.9)
+        tr_u.append(u[tr]); tr_i.append(i[tr]); tr_r.append(r[tr]); va_u.append(u[va]); va_i.append(i[va])
+        del u, i, r, part, tr, va
+    return dict(train=(torch.cat(tr_u), torch.cat(tr_i), torch.cat(tr_r)), valid=(torch.cat(va_u), torch.cat(va_i)),
+                gender=gender)

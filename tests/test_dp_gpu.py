@@ -97,3 +97,30 @@ def test_dp_step_and_sharded_eval_match_single_gpu():
     assert res["ids_equal"]
     for k in res["r1"]:
         assert abs(res["r1"][k] - res["rp"][k]) <= 1e-9 * max(abs(res["r1"][k]), 1.0), k
+
+
+def _shard_worker(rank, world, port, out, adam_mode):
+    import torch.distributed as dist
+    from recbole_fairrec_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = sharded.selfcheck(rank, world, dev, dist.group.WORLD, adam_mode=adam_mode, n_users=5001, n_items=901, d=64,
+                            n_inter=120000, batch=1 << 13, steps=5)
+    if rank == 0:
+        out.update(res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("adam_mode", ["dense_exact", "lazy_exact"])
+def test_row_sharded_step_multi_process(adam_mode):
+    """the REAL exchange path: one process per GPU, CUDA IPC peer memory, cross-GPU flag barriers (csrc/focf_shard.cu)"""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_shard_worker, args=(world, 29541 + (adam_mode == "lazy_exact"), out, adam_mode), nprocs=world, join=True)
+    assert out["pass"], dict(out)
