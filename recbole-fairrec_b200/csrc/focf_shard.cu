@@ -99,7 +99,9 @@ struct ShardWs {
   int32_t *seg_of_j;    // [J_cap] local item segment of draw position j, -1 if this rank has no row of it
   uint2 *row_tab_i;     // [n_items_loc] {stamp, owner slot} of the batch that last touched the owned item row (dense mode)
   float *cseg_j;        // [J_cap, 2] fairness terms by draw position
+  float *red_part;      // [kRedMaxBlocks, 2] per-CTA partial sums of k_shard_stats_reduce
 };
+constexpr int kRedMaxBlocks = 128;
 
 static ShardWs carve_shard(Carver &c, int n_users_loc, int n_items_loc, int d, int B, int J_cap) {
   ShardWs w;
@@ -109,6 +111,7 @@ static ShardWs carve_shard(Carver &c, int n_users_loc, int n_items_loc, int d, i
   w.f = carve(c, n_users_loc, 1, d, B);   // item stamps of the single-GPU layout are not used here
   w.seg_of_j = c.take<int32_t>(J_cap);
   w.cseg_j = c.take<float>(2 * (size_t)J_cap);
+  w.red_part = c.take<float>(2 * kRedMaxBlocks);
   return w;
 }
 
@@ -200,15 +203,19 @@ __global__ void __launch_bounds__(256)
 }
 
 // every rank: add the P partial records of each draw position in rank order (groups re-based on the GLOBAL minimum of
-// the attribute), fairness terms per draw position and per local segment, the batch loss, control-block hand-over
-__global__ void __launch_bounds__(1024)
+// the attribute), fairness terms per draw position and per local segment; per-CTA partial sums of the squared errors and
+// the smooth-L1 terms, which the LAST CTA to finish (ticket) adds in CTA order -> the batch loss + control-block hand-over
+constexpr int kRedThreads = 256;
+__global__ void __launch_bounds__(kRedThreads)
     k_shard_stats_reduce(const char *__restrict__ xS, size_t xS_slot, const uint4 *__restrict__ hdr, int world, int J,
                          int B_loc, int B_glob, int objective, float fair_weight, const int32_t *__restrict__ seg_of_j,
                          float *__restrict__ cseg_j, float *__restrict__ cseg, float *__restrict__ cglob,
-                         float *__restrict__ loss, uint32_t *__restrict__ ctrl, int32_t *__restrict__ flags) {
+                         float *__restrict__ part /* [gridDim.x, 2] */, float *__restrict__ loss,
+                         uint32_t *__restrict__ ctrl, int32_t *__restrict__ flags) {
   __shared__ float sh[33];
   __shared__ uint32_t s_min, s_max;
   __shared__ int s_swap[FR_MAX_RANKS];
+  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (threadIdx.x == 0) {
     uint32_t lo = 0xffffffffu, hi = 0u;
@@ -226,14 +233,14 @@ __global__ void __launch_bounds__(1024)
       s_swap[k] = hdr[k].x != lo;
       bad |= (hdr[k].x != lo && hdr[k].x != hi) || (hdr[k].y != lo && hdr[k].y != hi);
     }
-    if (bad && objective != FR_OBJ_NONE) atomicOr(flags, FR_FLAG_TOO_MANY_GROUPS);   // focf.py:81-86
+    if (bad && objective != FR_OBJ_NONE && blockIdx.x == 0) atomicOr(flags, FR_FLAG_TOO_MANY_GROUPS);   // focf.py:81-86
     s_min = lo;
     s_max = hi;
   }
   __syncthreads();
   const float Bn = (float)B_glob, Jn = (float)J;
   float w_sq = 0.f, w_hx = 0.f;
-  for (int j = wib; j < J; j += nw) {
+  for (int j = blockIdx.x * nw + wib; j < J; j += gridDim.x * nw) {
     float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
     if (lane < world) {
@@ -268,18 +275,31 @@ __global__ void __launch_bounds__(1024)
   }
   const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
   if (threadIdx.x == 0) {
-    float l = sq / Bn;
-    if (objective >= FR_OBJ_VALUE && objective <= FR_OBJ_OVER) l += fair_weight * (hx / Jn);
-    loss[0] = l;
-    if (l != l) atomicOr(flags, FR_FLAG_NAN_LOSS);
-    cglob[0] = 0.f;
-    cglob[1] = 0.f;
-    ctrl[CTRL_SAVED_MIN] = s_min;   // the backward groups rows by the GLOBAL minimum
-    ctrl[CTRL_SAVED_MAX] = s_max;
-    ctrl[CTRL_MIN] = 0xffffffffu;
-    ctrl[CTRL_MAX] = 0u;
-    ctrl[CTRL_STAMP] += 1u;
+    part[2 * blockIdx.x] = sq;
+    part[2 * blockIdx.x + 1] = hx;
+    __threadfence();
+    is_last = atomicAdd(&ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  float tsq = 0.f, thx = 0.f;
+  for (unsigned b = 0; b < gridDim.x; ++b) {   // CTA order, whichever CTA ends up last
+    tsq += __ldcg(part + 2 * b);
+    thx += __ldcg(part + 2 * b + 1);
+  }
+  float l = tsq / Bn;
+  if (objective >= FR_OBJ_VALUE && objective <= FR_OBJ_OVER) l += fair_weight * (thx / Jn);
+  loss[0] = l;
+  if (l != l) atomicOr(flags, FR_FLAG_NAN_LOSS);
+  cglob[0] = 0.f;
+  cglob[1] = 0.f;
+  ctrl[CTRL_SAVED_MIN] = s_min;   // the backward groups rows by the GLOBAL minimum
+  ctrl[CTRL_SAVED_MAX] = s_max;
+  ctrl[CTRL_MIN] = 0xffffffffu;
+  ctrl[CTRL_MAX] = 0u;
+  ctrl[CTRL_TICKET] = 0u;
+  ctrl[CTRL_STAMP] += 1u;
 }
 
 template <int kRowVecs>
@@ -288,31 +308,47 @@ __global__ void __launch_bounds__(256) k_shard_grads(GradArgs a, int nchunk) {
 }
 
 // this rank's partial gradient row of every draw position (zero where it has no row) -> slot `rank` of the OWNER's xG,
-// at the item's owner slot
+// at the item's owner slot.  One CTA per draw position: a popular item's rows span thousands of gradient chunks, whose
+// partials the 8 warps add in a fixed two-level order (warp w takes chunks c0+1+w, c0+1+w+8, ... in increasing order,
+// then tail + the 8 warp sums in warp order) -- deterministic, and 8 dependent-load chains instead of one.
 __global__ void __launch_bounds__(256)
     k_shard_igrad_push(const int32_t *__restrict__ seg_of_j, const int32_t *__restrict__ segoff_i,
                        const float *__restrict__ gseg, const float *__restrict__ head, const float *__restrict__ tail,
                        int chunk, int d, const int32_t *__restrict__ draw_items, const int32_t *__restrict__ draw_slot,
                        int J, int B_loc, Peers px, size_t xG_off /* incl. parity and slot `rank` */, int world) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int j = warp; j < J; j += nwarps) {
-    const int s = B_loc > 0 ? seg_of_j[j] : -1;
-    float *dst = (float *)(px.base[draw_items[j] % world] + xG_off) + (size_t)draw_slot[j] * d;
+  __shared__ __align__(16) float part[8][kMaxD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x;
+  if (j >= J) return;
+  const int s = B_loc > 0 ? seg_of_j[j] : -1;
+  float *dst = (float *)(px.base[draw_items[j] % world] + xG_off) + (size_t)draw_slot[j] * d;
+  int c0 = 0, c1 = 0;
+  if (s >= 0) {
+    const int s0 = segoff_i[s], s1 = segoff_i[s + 1];
+    c0 = s0 / chunk;
+    c1 = (s1 - 1) / chunk;
+  }
+  const bool multi = s >= 0 && c1 > c0;
+  if (multi) {
     for (int k = lane * 4; k < d; k += 128) {
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (s >= 0) {
-        const int s0 = segoff_i[s], s1 = segoff_i[s + 1];
-        const int c0 = s0 / chunk, c1 = (s1 - 1) / chunk;
-        if (c0 == c1) {
-          g = *(const float4 *)(gseg + (size_t)s * d + k);
-        } else {
-          g = *(const float4 *)(tail + (size_t)c0 * d + k);
-          for (int c = c0 + 1; c <= c1; ++c) g = f4_add(g, __ldg((const float4 *)(head + (size_t)c * d + k)));
-        }
-      }
-      *(float4 *)(dst + k) = g;
+#pragma unroll 4
+      for (int c = c0 + 1 + w; c <= c1; c += 8) g = f4_add(g, __ldg((const float4 *)(head + (size_t)c * d + k)));
+      *(float4 *)&part[w][k] = g;
     }
+  }
+  __syncthreads();
+  if (w != 0) return;
+  for (int k = lane * 4; k < d; k += 128) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (multi) {
+      g = *(const float4 *)(tail + (size_t)c0 * d + k);
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) g = f4_add(g, *(const float4 *)&part[ww][k]);
+    } else if (s >= 0) {
+      g = *(const float4 *)(gseg + (size_t)s * d + k);
+    }
+    *(float4 *)(dst + k) = g;
   }
 }
 
@@ -503,9 +539,10 @@ static int phase_b(const fr_focf_shard_step *s, const ShardWs &w, const XchgLayo
   const int B = s->B_loc, par = s->parity & 1;
   const char *own = (const char *)s->xchg[s->rank];
   const float *xI = (const float *)(own + L.xI + (size_t)par * L.xI_par);
-  FR_LAUNCH(k_shard_stats_reduce, 1, 1024, 0, st, own + L.xS + (size_t)par * L.xS_par, L.xS_slot,
-            (const uint4 *)(own + L.hdr + (size_t)par * L.hdr_par), s->world, s->J, B, s->B_glob, s->objective,
-            s->fair_weight, w.seg_of_j, w.cseg_j, w.f.cseg, w.f.cglob, s->loss, w.f.ctrl, s->status_flags);
+  FR_LAUNCH(k_shard_stats_reduce, grid_for(s->J, kRedThreads / 32, kRedMaxBlocks), kRedThreads, 0, st,
+            own + L.xS + (size_t)par * L.xS_par, L.xS_slot, (const uint4 *)(own + L.hdr + (size_t)par * L.hdr_par), s->world,
+            s->J, B, s->B_glob, s->objective, s->fair_weight, w.seg_of_j, w.cseg_j, w.f.cseg, w.f.cglob, w.red_part, s->loss,
+            w.f.ctrl, s->status_flags);
   const int chunk = grad_chunk(B < 1 ? 1 : B);
   if (B > 0) {
     GradArgs ga{};
@@ -528,7 +565,7 @@ static int phase_b(const fr_focf_shard_step *s, const ShardWs &w, const XchgLayo
       FR_LAUNCH(k_shard_grads<4>, grid, 256, 0, st, ga, nchunk);
     }
   }
-  FR_LAUNCH(k_shard_igrad_push, grid_for((int64_t)s->J * 32, 256, kSMs * 8), 256, 0, st, w.seg_of_j, w.f.segoff_i,
+  FR_LAUNCH(k_shard_igrad_push, s->J, 256, 0, st, w.seg_of_j, w.f.segoff_i,
             w.f.gseg_i, w.f.head_i, w.f.tail_i, chunk, s->d, s->draw_items, s->draw_slot, s->J, B, peers_of(s),
             L.xG + (size_t)par * L.xG_par + (size_t)s->rank * L.xG_slot, s->world);
   xbar(s, L, st);
