@@ -41,6 +41,7 @@ struct FocfWs {
   float *rec_tail;  // [B/8+2,8] record of the run continuing into the next chunk
   float *cglob;     // [2]  batch-global additive term per group (nonparity)
   float *gseg_i, *head_i, *tail_i, *gseg_u, *head_u, *tail_u;  // gradient partials [B,d], [B/32+1,d] x2
+  float *red_part;  // [148 * 8, 8] per-CTA partial sums of k_segment_reduce
   SortScratch sort;
   SegScratch seg;
 };
@@ -73,6 +74,7 @@ static FocfWs carve(Carver &c, int n_users, int n_items, int d, int B) {
   w.gseg_u = c.take<float>(b * d);
   w.head_u = c.take<float>(nch * d);
   w.tail_u = c.take<float>(nch * d);
+  w.red_part = c.take<float>(8 * 148 * 8);
   w.sort = carve_sort_scratch(c, b);
   w.seg = carve_seg_scratch(c, b);
   return w;
@@ -257,6 +259,44 @@ __device__ __forceinline__ void loss_phase1(const LossArgs &a, int B) {
     if (a.objective != FR_OBJ_NONE && bad) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
   }
 
+}
+
+// Sum of the phase-1 records of ONE item segment by a whole CTA (kSegThreads threads): a popular item's rows span
+// thousands of 8-row thread chunks, so the records are strided over all threads (thread t takes records t, t + T, ... in
+// increasing order), then combined by the fixed shuffle tree of warp_sum and across warps in warp order -- deterministic.
+// Every thread returns with the 7 sums in v.  `sh` holds kSegThreads / 32 rows of 8 floats.
+constexpr int kSegThreads = 128;
+__device__ __forceinline__ void segment_record_sum(const LossArgs &a, int sgm, float v[7], float (*sh)[8]) {
+  const int s0 = a.segoff_i[sgm], s1 = a.segoff_i[sgm + 1];
+  const int t0 = s0 / kLossRows, t1 = (s1 - 1) / kLossRows;
+  if (t0 == t1) {   // the segment lies inside one thread chunk: one complete record
+    const float4 x = *(const float4 *)(a.rec_seg + (size_t)sgm * kLossRec);
+    const float4 y = *(const float4 *)(a.rec_seg + (size_t)sgm * kLossRec + 4);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z;
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[k] = 0.f;
+  for (int t = t0 + (int)threadIdx.x; t <= t1; t += kSegThreads) {
+    const float *src = (t == t0) ? a.rec_tail + (size_t)t * kLossRec : a.rec_head + (size_t)t * kLossRec;
+    const float4 x = *(const float4 *)src, y = *(const float4 *)(src + 4);
+    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();            // sh may still be read from the previous segment
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) sh[threadIdx.x >> 5][k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSegThreads / 32; ++w) t += sh[w][k];
+    v[k] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ gradients

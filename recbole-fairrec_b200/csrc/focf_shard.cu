@@ -164,38 +164,22 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(kLossThreads) k_shard_loss_records(LossArgs a) { loss_phase1(a, a.B); }
 
 // partial item x group sums of every draw position (zeros where this rank has no row) -> slot `rank` of every rank's xS;
-// header {local min, local max of the attribute (order-encoded), rows} -> slot `rank` of every rank's header block
-__global__ void __launch_bounds__(256)
+// header {local min, local max of the attribute (order-encoded), rows} -> slot `rank` of every rank's header block.
+// CTA b owns the draw positions b, b + G, ...: cooperative record sum (popular items span thousands of records).
+__global__ void __launch_bounds__(kSegThreads)
     k_shard_stats_push(LossArgs a, const int32_t *__restrict__ seg_of_j, int J, int B_loc, Peers px, size_t xS_off,
                        size_t hdr_off, int rank, int world) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  if (warp == 0 && lane < world) {
+  __shared__ float sh[kSegThreads / 32][8];
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     uint4 h = make_uint4(B_loc > 0 ? a.ctrl[CTRL_MIN] : 0xffffffffu, B_loc > 0 ? a.ctrl[CTRL_MAX] : 0u, (uint32_t)B_loc, 0u);
-    *((uint4 *)(px.base[lane] + hdr_off) + rank) = h;
+    *((uint4 *)(px.base[threadIdx.x] + hdr_off) + rank) = h;
   }
-  for (int j = warp; j < J; j += nwarps) {
-    const int s = B_loc > 0 ? seg_of_j[j] : -1;
+  for (int j = blockIdx.x; j < J; j += gridDim.x) {
+    const int s = B_loc > 0 ? seg_of_j[j] : -1;      // uniform over the CTA
     float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (s >= 0) {
-      const int s0 = a.segoff_i[s], s1 = a.segoff_i[s + 1];
-      const int t0 = s0 / kLossRows, t1 = (s1 - 1) / kLossRows;
-      if (t0 == t1) {
-        const float4 x = *(const float4 *)(a.rec_seg + (size_t)s * kLossRec);
-        const float4 y = *(const float4 *)(a.rec_seg + (size_t)s * kLossRec + 4);
-        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z;
-      } else {
-        for (int t = t0 + lane; t <= t1; t += 32) {
-          const float *src = (t == t0) ? a.rec_tail + (size_t)t * kLossRec : a.rec_head + (size_t)t * kLossRec;
-          const float4 x = *(const float4 *)src, y = *(const float4 *)(src + 4);
-          v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z;
-        }
-#pragma unroll
-        for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
-      }
-    }
-    if (lane < world) {   // xS_off already selects the parity half and slot `rank`
-      float *dst = (float *)(px.base[lane] + xS_off) + (size_t)j * 8;
+    if (s >= 0) segment_record_sum(a, s, v, sh);
+    if ((int)threadIdx.x < world) {   // xS_off already selects the parity half and slot `rank`
+      float *dst = (float *)(px.base[threadIdx.x] + xS_off) + (size_t)j * 8;
       *(float4 *)dst = make_float4(v[0], v[1], v[2], v[3]);
       *(float4 *)(dst + 4) = make_float4(v[4], v[5], v[6], 0.f);
     }
@@ -528,7 +512,7 @@ static int phase_a(const fr_focf_shard_step *s, const ShardWs &w, const XchgLayo
               w.f.ctrl);
     FR_LAUNCH(k_shard_loss_records, (B + kLossThreads * kLossRows - 1) / (kLossThreads * kLossRows), kLossThreads, 0, st, la);
   }
-  FR_LAUNCH(k_shard_stats_push, grid_for((int64_t)s->J * 32, 256, kSMs * 8), 256, 0, st, la, w.seg_of_j, s->J, B,
+  FR_LAUNCH(k_shard_stats_push, grid_for(s->J, 1, kSMs * 8), kSegThreads, 0, st, la, w.seg_of_j, s->J, B,
             peers_of(s), L.xS + (size_t)par * L.xS_par + (size_t)s->rank * L.xS_slot, L.hdr + (size_t)par * L.hdr_par,
             s->rank, s->world);
   xbar(s, L, st);

@@ -33,9 +33,15 @@ __global__ void __launch_bounds__(256)
 }
 
 
-// one CTA (any multiple of 32 threads up to 1024): warp per segment, then the loss and the control-block hand-over
-__device__ __forceinline__ void loss_phase2(const LossArgs &a, int B, float *sh) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+// Phase 2 of the loss: CTA b owns the item segments b, b + G, ...: cooperative record sum, fairness terms, additive
+// backward terms cseg[j][g]; per-CTA partial sums (squared error, smooth-L1, nonparity group sums) in segment order; the
+// LAST CTA to finish (self-resetting ticket) adds the partials in CTA order -> loss, flags, control-block hand-over.
+// (The segment -> CTA map depends only on J, so the result is bit-stable run to run.)
+constexpr int kSegMaxBlocks = 148 * 8;
+__global__ void __launch_bounds__(kSegThreads) k_segment_reduce(LossArgs a, float *__restrict__ part /* [grid, 8] */) {
+  __shared__ float sh[kSegThreads / 32][8];
+  __shared__ bool is_last;
+  const int B = FR_B(a.B, a.B_dev);
   const int J = *a.J;
   int nB = a.norm_B, nJ = a.norm_J;
   if (a.norm_dev) {
@@ -44,96 +50,71 @@ __device__ __forceinline__ void loss_phase2(const LossArgs &a, int B, float *sh)
     nJ = a.norm_dev[2 * k + 1];
   }
   const float Bn = (float)(nB > 0 ? nB : B), Jn = (float)(nJ > 0 ? nJ : J);
-  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;  // lane 0 accumulates over its segments
-  for (int j = wib; j < J; j += (int)(blockDim.x >> 5)) {
-    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
-    const int t0 = s0 / kLossRows, t1 = (s1 - 1) / kLossRows;
+  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;   // meaningful on thread 0
+  for (int j = blockIdx.x; j < J; j += gridDim.x) {
     float v[7];
-    if (t0 == t1) {
-      const float4 x = *(const float4 *)(a.rec_seg + (size_t)j * kLossRec);
-      const float4 y = *(const float4 *)(a.rec_seg + (size_t)j * kLossRec + 4);
-      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 7; ++k) v[k] = 0.f;
-      for (int t = t0 + lane; t <= t1; t += 32) {
-        const float *src = (t == t0) ? a.rec_tail + (size_t)t * kLossRec : a.rec_head + (size_t)t * kLossRec;
-        const float4 x = *(const float4 *)src, y = *(const float4 *)(src + 4);
-        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z;
-      }
-#pragma unroll
-      for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
-    }
-    if (lane == 0) {
-      const float sp0 = v[0], sp1 = v[1], st0 = v[2], st1 = v[3], c0 = v[4], c1 = v[5];
+    segment_record_sum(a, j, v, sh);
+    if (threadIdx.x == 0) {
       w_sq += v[6];
       float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
       if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-        segment_terms(a.objective, a.fair_weight, Jn, sp0, sp1, st0, st1, c0, c1, hx, cs0, cs1);
+        segment_terms(a.objective, a.fair_weight, Jn, v[0], v[1], v[2], v[3], v[4], v[5], hx, cs0, cs1);
       } else if (a.objective == FR_OBJ_NONPARITY) {
-        w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
+        w_g0 += v[0]; w_g1 += v[1]; w_n0 += v[4]; w_n1 += v[5];
       }
       w_hx += hx;
       a.cseg[2 * j] = cs0;
       a.cseg[2 * j + 1] = cs1;
     }
   }
-  // fixed-order block reduction (only lane 0 of every warp carries a value)
-  const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
-  float g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
-  if (a.objective == FR_OBJ_NONPARITY) {
-    g0 = block_sum_1024(w_g0, sh); g1 = block_sum_1024(w_g1, sh);
-    n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
-  }
   if (threadIdx.x == 0) {
-    float loss = sq / Bn;                                                    // nn.MSELoss 'mean'
-    float cg0 = 0.f, cg1 = 0.f;
-    if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-      loss += a.fair_weight * (hx / Jn);                                     // focf.py:166
-    } else if (a.objective == FR_OBJ_NONPARITY) {
-      if (n1 == 0.f || n0 == 0.f) {
-        atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
-      } else {
-        const float z = g0 / n0 - g1 / n1, x = fabsf(z);                     // focf.py:131-134
-        loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
-        const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
-        cg0 = hp / n0;
-        cg1 = -hp / n1;
-      }
-    }
-    a.cglob[0] = cg0;
-    a.cglob[1] = cg1;
-    a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor : 0u] = loss;
-    if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
-    // hand the group values to the backward kernels, re-arm the control block for the next batch
-    a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
-    a.ctrl[CTRL_SAVED_MAX] = a.ctrl[CTRL_MAX];
-    a.ctrl[CTRL_NORM_B] = (uint32_t)(nB > 0 ? nB : 0);
-    a.ctrl[CTRL_NORM_J] = (uint32_t)(nJ > 0 ? nJ : 0);
-    a.ctrl[CTRL_MIN] = 0xffffffffu;
-    a.ctrl[CTRL_MAX] = 0u;
-    a.ctrl[CTRL_TICKET] = 0u;
-    a.ctrl[CTRL_STAMP] += 1u;
-    a.ctrl[CTRL_CURSOR] += a.ctrl[CTRL_STRIDE];
-    if (a.advance_adam) a.ctrl[CTRL_ADAM_T] += a.ctrl[CTRL_STRIDE];
+    float *p = part + 8 * (size_t)blockIdx.x;
+    p[0] = w_sq; p[1] = w_hx; p[2] = w_g0; p[3] = w_g1; p[4] = w_n0; p[5] = w_n1;
+    __threadfence();
+    is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  float sq = 0.f, hx = 0.f, g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
+  for (unsigned b = 0; b < gridDim.x; ++b) {   // CTA order, whichever CTA ends up last
+    const float *p = part + 8 * (size_t)b;
+    sq += __ldcg(p); hx += __ldcg(p + 1); g0 += __ldcg(p + 2); g1 += __ldcg(p + 3); n0 += __ldcg(p + 4); n1 += __ldcg(p + 5);
+  }
+  float loss = sq / Bn;                                                    // nn.MSELoss 'mean'
+  float cg0 = 0.f, cg1 = 0.f;
+  if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+    loss += a.fair_weight * (hx / Jn);                                     // focf.py:166
+  } else if (a.objective == FR_OBJ_NONPARITY) {
+    if (n1 == 0.f || n0 == 0.f) {
+      atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
+    } else {
+      const float z = g0 / n0 - g1 / n1, x = fabsf(z);                     // focf.py:131-134
+      loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
+      const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
+      cg0 = hp / n0;
+      cg1 = -hp / n1;
+    }
+  }
+  a.cglob[0] = cg0;
+  a.cglob[1] = cg1;
+  a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor : 0u] = loss;
+  if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
+  // hand the group values to the backward kernels, re-arm the control block for the next batch
+  a.ctrl[CTRL_SAVED_MIN] = a.ctrl[CTRL_MIN];
+  a.ctrl[CTRL_SAVED_MAX] = a.ctrl[CTRL_MAX];
+  a.ctrl[CTRL_NORM_B] = (uint32_t)(nB > 0 ? nB : 0);
+  a.ctrl[CTRL_NORM_J] = (uint32_t)(nJ > 0 ? nJ : 0);
+  a.ctrl[CTRL_MIN] = 0xffffffffu;
+  a.ctrl[CTRL_MAX] = 0u;
+  a.ctrl[CTRL_TICKET] = 0u;
+  a.ctrl[CTRL_STAMP] += 1u;
+  a.ctrl[CTRL_CURSOR] += a.ctrl[CTRL_STRIDE];
+  if (a.advance_adam) a.ctrl[CTRL_ADAM_T] += a.ctrl[CTRL_STRIDE];
 }
 
-__global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) {
-  __shared__ float sh[33];
-  __shared__ bool is_last;
-  const int B = FR_B(a.B, a.B_dev);
-  loss_phase1(a, B);
-  // ---------------- last-CTA election (self-resetting ticket)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  loss_phase2(a, B, sh);
-}
-
+// phase 1 (all CTAs): per-thread records over 8 sorted rows each
+__global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) { loss_phase1(a, FR_B(a.B, a.B_dev)); }
 
 // ------------------------------------------------------------------------------------------ fused step
 // Batches at the ML-1M shape are a few thousand rows against ~15 MB of state: every kernel of the step is launch- /
@@ -611,6 +592,8 @@ static int forward_only_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_
             w.ctrl);
   LossArgs la = loss_args(s, w, advance_adam);
   FR_LAUNCH(k_segment_loss, (B + kLossThreads * kLossRows - 1) / (kLossThreads * kLossRows), kLossThreads, 0, st, la);
+  // J is device resident: the grid is sized for the batch (a segment holds >= 1 row), capped at 8 CTAs per SM
+  FR_LAUNCH(k_segment_reduce, grid_for(B, 64, kSegMaxBlocks), kSegThreads, 0, st, la, w.red_part);
   return FR_OK;
 }
 

@@ -434,8 +434,8 @@ def selfcheck(rank, world, device, group=None, adam_mode="lazy_exact", n_users=2
     model = ShardedFOCF(sd, d, objective="value", fair_weight=1.0, adam_mode=adam_mode, J_cap=loader.J_cap,
                         max_batch_loc=max(loader.max_batch_loc, 1), max_steps=steps + 8)
     g = torch.Generator(device=device).manual_seed(seed)
-    U0 = torch.randn((n_users, d), generator=g, device=device) * 0.1
-    I0 = torch.randn((n_items, d), generator=g, device=device) * 0.1
+    U0 = torch.randn((n_users, d), generator=g, device=device) * 0.2
+    I0 = torch.randn((n_items, d), generator=g, device=device) * 0.2
     model.set_tables(U0, I0)
     losses = torch.zeros(steps, device=device)
     out = {"world": world, "steps": steps, "adam_mode": adam_mode, "shape": [n_users, n_items, d, batch]}
