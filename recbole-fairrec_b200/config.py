@@ -12,7 +12,7 @@ DEFAULTS = dict(
     metrics=["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
              "ValueUnfairness", "AbsoluteUnfairness", "UnderUnfairness", "OverUnfairness", "NonParityUnfairness"],
     eval_args={"split": {"RS": [8, 1, 1]}, "group_by": "user", "order": "RO", "mode": "full"},
-    seed=2020, score_mode="exact", adam_mode="dense_exact", neg_sampling={"uniform": 1},
+    seed=2020, score_mode="auto", adam_mode="dense_exact", neg_sampling={"uniform": 1},
     TIME_FIELD="timestamp", filter_inter_by_user_or_item=True, user_inter_num_interval="[0,inf)",
     item_inter_num_interval="[0,inf)",
 )

@@ -147,7 +147,15 @@ class FullSortEvaluator:
         self.decimal = config["metric_decimal_place"] if config["metric_decimal_place"] is not None else 4
         self.sst_attr_list = list(config["sst_attr_list"])
         self.n_items = int(n_items)
-        self.score_mode = {"exact": _lib.SCORE_EXACT_FP32, "tc": _lib.SCORE_TC_3XTF32}[config["score_mode"] or "exact"]
+        # score_mode: "tc" = the tensor-core contraction (tcgen05 + TMA, 3xTF32: scores within ~2e-6 of float32, ids equal to
+        # the exact mode's outside float32-level near ties), "exact" = the bit-defined float32 FMA chain the oracle reproduces
+        # (the pinned parity mode), "auto" (default) = tc whenever the shape allows it (d in {32, 64, 96, 128}, K <= 64)
+        mode = config["score_mode"] or "auto"
+        if mode == "auto":
+            d = config["embedding_size"]
+            mode = "tc" if (d is not None and d % 32 == 0 and d <= 128 and self.K <= 64) else "exact"
+        self.score_mode = {"exact": _lib.SCORE_EXACT_FP32, "tc": _lib.SCORE_TC_3XTF32}[mode]
+        self.score_mode_name = mode
         self.group = group
         self._is_popular = None
         self._pop_host = self._popular_items(train_item_count, config["popularity_ratio"])
