@@ -116,7 +116,10 @@ class ShardedFOCFLoader:
             po += J + 1
             self.max_batch_loc = max(self.max_batch_loc, int(off[-1]))
         dev = d.device
-        up = lambda a: torch.from_numpy(np.concatenate(a).astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        def up(a):
+            t = torch.from_numpy(np.concatenate(a).astype(np.int32))
+            return t.pin_memory().to(dev, non_blocking=True) if torch.device(dev).type == "cuda" else t
+
         return dict(desc=desc, items=up(items), offs=up(offs), slots=up(slots),
                     rows_glob=sum(b["B_glob"] for b in desc))
 

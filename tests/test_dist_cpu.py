@@ -77,3 +77,107 @@ def test_dataloader_partitions_are_disjoint_and_cover():
     assert sorted(np.concatenate(parts).tolist()) == uniq.tolist()
     assert len(set(parts[0]) & set(parts[1])) == 0
     assert math.ceil(1000 / (128 * 3)) == 3
+
+
+# ------------------------------------------------------------------ row-sharded FOCF training: host-side protocol
+def _numpy_sharded_step(datas, plans, k, U, I, world, fair_weight=1.0):
+    """numpy restatement of one row-sharded step's EXCHANGE protocol (csrc/focf_shard.cu) from the ranks' plans: every rank's
+    partial item x group sums indexed by draw position, summed in rank order -> loss; checked against the single-process
+    oracle on the union batch.  Returns (loss_sharded, batch columns of the union in rank order)."""
+    J = plans[0]["desc"][k]["J"]
+    part = np.zeros((world, J, 7), np.float64)
+    cols = []
+    for r in range(world):
+        b = plans[r]["desc"][k]
+        items = plans[r]["items"][b["items_pos"]:b["items_pos"] + J].numpy()
+        off = plans[r]["offs"][b["offs_pos"]:b["offs_pos"] + J + 1].numpy()
+        d = datas[r]
+        item_off = d.item_off.numpy()
+        for j, it in enumerate(items):
+            lo = item_off[it]
+            n = off[j + 1] - off[j]
+            lu = d.train_uid.numpy()[lo:lo + n]
+            rt = d.train_rating.numpy()[lo:lo + n]
+            g = d.sst_of_user.numpy()[lu]
+            gu = lu.astype(np.int64) * world + r                       # back to global user ids
+            pred = (U[gu] * I[it]).sum(1)
+            for grp, val in ((0, 1.0), (1, 2.0)):
+                m = g == val
+                part[r, j, grp] = pred[m].sum()
+                part[r, j, 2 + grp] = rt[m].sum()
+                part[r, j, 4 + grp] = m.sum()
+            part[r, j, 6] = ((pred - rt) ** 2).sum()
+            cols.append((gu, np.full(n, it), rt, g))
+    tot = part.sum(0)                                                  # rank order
+    B = plans[0]["desc"][k]["B_glob"]
+    n = tot[:, 4:6] + 1e-5
+    D = tot[:, 0:2] / n - tot[:, 2:4] / n
+    x = np.abs(D[:, 0] - D[:, 1])
+    hx = np.where(x < 1, 0.5 * x * x, x - 0.5)
+    return tot[:, 6].sum() / B + fair_weight * hx.mean(), cols
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recbole_fairrec_b200 import synth
+    from recbole_fairrec_b200.sharded import ShardedFOCFLoader, ShardedTrainData, local_rows
+    nu, ni = 301, 83
+    uid, iid, rating, gender = synth.interactions(nu, ni, 4000, 9, item_sigma=1.0)
+    cpu = torch.device("cpu")
+    sd = ShardedTrainData(uid, iid, rating, gender, nu, ni, rank, world, cpu)
+    plan = ShardedFOCFLoader(500, sd, seed=3).plan(4)
+    # every rank draws the SAME items (same seed, GLOBAL item counts); local rows add up to the global batch
+    mine = [plan["items"].numpy().tolist(), [b["B_loc"] for b in plan["desc"]], [b["B_glob"] for b in plan["desc"]],
+            sd.n_rows_loc, sd.n_users_loc, sd.n_items_loc]
+    allp = [None] * world
+    dist.all_gather_object(allp, mine)
+    ok = all(p[0] == allp[0][0] and p[2] == allp[0][2] for p in allp)
+    ok &= all(sum(p[1][k] for p in allp) == allp[0][2][k] for k in range(4))
+    ok &= sum(p[3] for p in allp) == len(uid)
+    ok &= sum(p[4] for p in allp) == nu and sum(p[5] for p in allp) == ni
+    ok &= sd.n_users_loc == local_rows(nu, rank, world)
+    # owner slots: position of each drawn item among its owner's items, in draw order
+    b0 = plan["desc"][0]
+    items = plan["items"][:b0["J"]].numpy()
+    slots = plan["slots"][:b0["J"]].numpy()
+    for o in range(world):
+        ok &= slots[items % world == o].tolist() == list(range(int((items % world == o).sum())))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_row_sharded_plans_agree_across_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, 29546, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_row_sharded_exchange_protocol_equals_the_oracle_on_the_union_batch():
+    """one process, three emulated ranks, numpy only: partial item x group sums by draw position, summed in rank order, give
+    the loss the oracle computes for the union batch (what k_shard_stats_push / k_shard_stats_reduce implement)"""
+    from oracle import focf_oracle as fo
+    from recbole_fairrec_b200 import synth
+    from recbole_fairrec_b200.sharded import ShardedFOCFLoader, ShardedTrainData
+    nu, ni, d, world = 211, 61, 8, 3
+    uid, iid, rating, gender = synth.interactions(nu, ni, 3000, 4, item_sigma=1.0)
+    cpu = torch.device("cpu")
+    datas = [ShardedTrainData(uid, iid, rating, gender, nu, ni, r, world, cpu) for r in range(world)]
+    plans = [ShardedFOCFLoader(400, dt, seed=5).plan(2) for dt in datas]
+    rng = np.random.default_rng(0)
+    U = (rng.standard_normal((nu, d)) * 0.4).astype(np.float32)
+    I = (rng.standard_normal((ni, d)) * 0.4).astype(np.float32)
+    for k in range(2):
+        loss_s, cols = _numpy_sharded_step(datas, plans, k, U.astype(np.float64), I.astype(np.float64), world)
+        u = np.concatenate([c[0] for c in cols]); i = np.concatenate([c[1] for c in cols])
+        r = np.concatenate([c[2] for c in cols]); g = np.concatenate([c[3] for c in cols])
+        assert len(u) == plans[0]["desc"][k]["B_glob"]
+        want = fo.calculate_loss(U, I, u, i, r, g.astype(np.int64), "value", 1.0)
+        np.testing.assert_allclose(loss_s, want, rtol=2e-6)
