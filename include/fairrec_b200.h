@@ -443,6 +443,13 @@ int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const 
 int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double *out, void *workspace,
                         size_t workspace_bytes, void *stream);
 size_t fr_fairness_metrics_workspace_bytes(int32_t n_items, int32_t G);
+/* Value / Absolute / Under / Over unfairness in the sampled-negative (`uni<N>`) evaluation mode, metrics.py:935-978 and
+ * siblings with mode != 'full' (collector.py:190-205: each positive is paired with its FIRST sampled negative, scored for the
+ * positive's user): stats_all / stats_pos [n_items, 2, 2] = fr_item_group_stats over positives + paired negatives / over the
+ * positives only (binary attribute).  out[0..3] = the four metrics, out[4] = number of items in the union. */
+size_t fr_unfairness_sampled_workspace_bytes(int32_t n_items);
+int fr_unfairness_sampled(const double *stats_all, const double *stats_pos, int32_t n_items, double *out, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 
 /* ----------------------------------------------------------------------------------------------

@@ -207,7 +207,7 @@ def run_focf_eval(name, n_users=60, n_items=97, d=16, K=10, topk=(5, 10), seed=1
 
 
 def run_uni_eval(name, n_users=50, n_items=400, d=16, topk=(5, 10), seed=51, neg_num=100, users_per_batch=1,
-                 transform="clamp"):
+                 transform="clamp", all_metrics=False):
     """Sampled-negative (uni100) ranking evaluation of the reference: NegSampleEvalDataLoader's batch layout
     (general_dataloader.py:128-152: per user [positives ; neg_num negatives per positive], row index per interaction),
     Trainer._neg_sample_batch_eval (trainer.py:441-456: predict + scatter into a -inf [users, n_items] matrix),
@@ -216,6 +216,8 @@ def run_uni_eval(name, n_users=50, n_items=400, d=16, topk=(5, 10), seed=51, neg
     rng = np.random.default_rng(seed)
     metrics = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage",
                "NonParityUnfairness"]
+    if all_metrics:   # + the four unfairness metrics in their sampled mode (well defined with one user per batch)
+        metrics = METRICS12
     cfg = base_cfg(embedding_size=d, topk=list(topk), metric_decimal_place=12, metrics=metrics,
                    eval_args={"mode": f"uni{neg_num}"})
     model = FOCF(cfg, FakeDataset(n_users, n_items, 5.0))
@@ -359,7 +361,7 @@ def run_ml100k(epochs=2):
         os.chdir(cwd)
 
 
-def run_nfcf(name, fair, n_users=60, n_items=45, d=16, hidden=(32, 16), n_steps=3, B=96, seed=21, fair_weight=0.1,
+def run_nfcf(name, fair, n_users=60, n_items=45, d=16, hidden=(32, 16), n_steps=3, B=96, seed=21, fair_weight=0.1, n_groups=2,
              lr=1e-3, wd=1e-6):
     """NFCF (recbole/model/fair_recommender/nfcf.py): NCF tower + BCE (+ differential-fairness regulariser when a
     pre-trained checkpoint was loaded: reset_params de-biases the user table and freezes it)."""
@@ -368,7 +370,7 @@ def run_nfcf(name, fair, n_users=60, n_items=45, d=16, hidden=(32, 16), n_steps=
 
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)
-    gender = rng.integers(1, 3, size=n_users)
+    gender = rng.integers(1, 1 + n_groups, size=n_users)   # n_groups > 2: nfcf.py:91-95 takes the max over all pairs
 
     class DS(FakeDataset):
         def get_user_feature(self):
@@ -898,6 +900,10 @@ def main():
         run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
         run_uni_eval("uni20_small_catalog", n_items=60, neg_num=20, users_per_batch=2, seed=53)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "uni_unfair":
+        run_uni_eval("uni100_unfair", users_per_batch=1, seed=54, all_metrics=True)
+        run_uni_eval("uni10_unfair_small", n_items=90, neg_num=10, users_per_batch=1, seed=55, all_metrics=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "fairgo":
         run_all_fairgo()
         return
@@ -923,11 +929,15 @@ def main():
     run_nfcf("ncf", fair=False)
     run_nfcf("fair", fair=True)
     run_nfcf("fair_d64", fair=True, n_users=200, n_items=120, d=64, hidden=(128, 64), B=512, seed=22)
+    run_nfcf("fair_g3", fair=True, n_users=120, n_items=60, d=32, hidden=(64, 32), B=384, seed=23, n_groups=3, fair_weight=0.5)
+    run_nfcf("fair_g5", fair=True, n_users=150, n_items=40, d=16, hidden=(32, 16), B=512, seed=24, n_groups=5, fair_weight=1.0)
     run_all_pfcn()
     run_all_fairgo()
     run_uni_eval("uni100", users_per_batch=1)
     run_uni_eval("uni100_batched", users_per_batch=3, seed=52)
     run_uni_eval("uni20_small_catalog", n_items=60, neg_num=20, users_per_batch=2, seed=53)
+    run_uni_eval("uni100_unfair", users_per_batch=1, seed=54, all_metrics=True)
+    run_uni_eval("uni10_unfair_small", n_items=90, neg_num=10, users_per_batch=1, seed=55, all_metrics=True)
     run_ingest()
 
 

@@ -86,3 +86,30 @@ def metrics(ids, rec_topk, pos_score, pos_items, sst_of_pos, topk, num_items, co
         out[f"popularitypercentage@{k}"] = v
     out[f"NonParity Unfairness of sensitive attribute {sst_name}"] = mo.nonparity(pos_score, sst_of_pos)
     return out
+
+
+def unfairness_sampled(pos_score, pos_items, neg_score, neg_items, sst_of_pos):
+    """metrics.py:935-978, 1031-1074, 1127-1170, 1224-1266 with mode != 'full' (float64, like the reference's numpy loops):
+    item set = union of positive and paired-negative items; negatives add score + count under the positive's group, no
+    "true" mass.  Returns (value, absolute, under, over)."""
+    sst_unique, sst_idx = np.unique(sst_of_pos, return_inverse=True)
+    if len(sst_unique) != 2:
+        raise ValueError("sensitive attribute must be binary")
+    items, idx = np.unique(np.concatenate((pos_items, neg_items)), return_inverse=True)
+    P = len(pos_items)
+    pred = np.zeros((len(items), 2))
+    num = np.zeros((len(items), 2))
+    true = np.zeros((len(items), 2))
+    np.add.at(pred, (idx[:P], sst_idx), np.asarray(pos_score, np.float64))
+    np.add.at(num, (idx[:P], sst_idx), 1.0)
+    np.add.at(true, (idx[:P], sst_idx), 1.0)
+    np.add.at(pred, (idx[P:], sst_idx), np.asarray(neg_score, np.float64))
+    np.add.at(num, (idx[P:], sst_idx), 1.0)
+    num += 1e-5
+    pred /= num
+    true /= num
+    out = []
+    for D in (pred - true, np.abs(pred - true), np.where(true - pred > 0, true - pred, 0.0),
+              np.where(pred - true > 0, pred - true, 0.0)):
+        out.append(float(np.mean(np.abs(D[:, 0] - D[:, 1]))))
+    return tuple(out)

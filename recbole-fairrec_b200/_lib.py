@@ -202,6 +202,8 @@ SIGNATURES = {
     "fr_item_group_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
     "fr_fairness_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "fr_unfairness_sampled_workspace_bytes": (c_size_t, [c_int32]),
+    "fr_unfairness_sampled": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fr_fairness_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -239,6 +239,45 @@ __global__ void k_fair_final(const double *__restrict__ tot, int G, double *__re
   for (int m = 0; m < 4; ++m) out[1 + m] = (G == 2) ? tot[1 + m] / J : nan("");
 }
 
+
+// Sampled-negative ("uni<N>") mode of Value / Absolute / Under / Over unfairness (metrics.py:935-978 and its three siblings
+// with mode != 'full'): the item set is the union of the positives' and the paired negatives' items; a negative adds its
+// score and a count to (its item, the group of the positive's user) but nothing to the "true" sum.
+// all [n_items, 2, 2] = (sum score, count) over positives AND negatives; pos [n_items, 2, 2] over the positives only.
+// per-CTA partials [5]: J (items with any entry), sum |D0 - D1| for value / absolute / under / over.
+__global__ void __launch_bounds__(256) k_unfair_sampled_part(const double *__restrict__ all, const double *__restrict__ pos,
+                                                             int n_items, double *__restrict__ part) {
+  __shared__ double sh[9];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double any = 0.0, vv = 0.0, va = 0.0, vu = 0.0, vo = 0.0;
+  if (i < n_items) {
+    const double s0 = all[((size_t)i * 2 + 0) * 2], c0 = all[((size_t)i * 2 + 0) * 2 + 1];
+    const double s1 = all[((size_t)i * 2 + 1) * 2], c1 = all[((size_t)i * 2 + 1) * 2 + 1];
+    if (c0 + c1 > 0.0) {
+      any = 1.0;
+      const double t0 = pos[((size_t)i * 2 + 0) * 2 + 1], t1 = pos[((size_t)i * 2 + 1) * 2 + 1];
+      const double n0 = c0 + 1e-5, n1 = c1 + 1e-5;
+      const double P0 = s0 / n0, P1 = s1 / n1, T0 = t0 / n0, T1 = t1 / n1;
+      vv = fabs((P0 - T0) - (P1 - T1));
+      va = fabs(fabs(P0 - T0) - fabs(P1 - T1));
+      vu = fabs(fmax(T0 - P0, 0.0) - fmax(T1 - P1, 0.0));
+      vo = fabs(fmax(P0 - T0, 0.0) - fmax(P1 - T1, 0.0));
+    }
+  }
+  const double r0 = block_sum_d(any, sh), r1 = block_sum_d(vv, sh), r2 = block_sum_d(va, sh), r3 = block_sum_d(vu, sh),
+               r4 = block_sum_d(vo, sh);
+  if (threadIdx.x == 0) {
+    double *o = part + (size_t)blockIdx.x * 5;
+    o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
+  }
+}
+
+__global__ void k_unfair_sampled_final(const double *__restrict__ tot, double *__restrict__ out) {
+  const double J = tot[0];
+  for (int m = 0; m < 4; ++m) out[m] = tot[1 + m] / J;
+  out[4] = J;
+}
+
 }  // namespace fr
 
 extern "C" {
@@ -374,6 +413,28 @@ int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double 
   FR_LAUNCH(fr::k_fair_pass_b, nblk, 256, 0, stream, stats, n_items, G, (const double *)totA, partB);
   FR_LAUNCH(fr::k_reduce_rows, 1, 128, 0, stream, (const double *)partB, nblk, 5, totB);
   FR_LAUNCH(fr::k_fair_final, 1, 1, 0, stream, (const double *)totB, G, out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+size_t fr_unfairness_sampled_workspace_bytes(int32_t n_items) {
+  return ((size_t)(n_items + 255) / 256 * 5 + 8) * 8 + 512;
+}
+
+int fr_unfairness_sampled(const double *stats_all, const double *stats_pos, int32_t n_items, double *out, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(stats_all && stats_pos && out && workspace && n_items >= 1, "fr_unfairness_sampled: bad argument");
+  if (workspace_bytes < fr_unfairness_sampled_workspace_bytes(n_items)) {
+    fr::set_error("fr_unfairness_sampled: workspace too small");
+    return FR_ERR_WORKSPACE;
+  }
+  const int nblk = (n_items + 255) / 256;
+  fr::Carver c(workspace, workspace_bytes);
+  double *part = c.take<double>((size_t)nblk * 5);
+  double *tot = c.take<double>(8);
+  FR_LAUNCH(fr::k_unfair_sampled_part, nblk, 256, 0, stream, stats_all, stats_pos, n_items, part);
+  FR_LAUNCH(fr::k_reduce_rows, 1, 128, 0, stream, (const double *)part, nblk, 5, tot);
+  FR_LAUNCH(fr::k_unfair_sampled_final, 1, 1, 0, stream, (const double *)tot, out);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

@@ -348,62 +348,77 @@ struct DfArgs {
   const uint32_t *ord;          // item-sorted order of the positives (values index pos_idx)
   const int32_t *seg_off, *n_seg;
   float fair_weight;
-  float *seg_eps, *coef;
-  uint32_t *mm;                 // [2] order-encoded min / max of sst over the positives
+  float *seg_eps, *coef;        // [J], [J, G]
+  const int32_t *grp, *n_groups; // group (rank of the attribute value) of every positive, in pos_idx order; number of groups
   int32_t *flags;
 };
 
-__global__ void k_df_minmax(const float *__restrict__ sst, const int32_t *__restrict__ pos_idx,
-                            const int32_t *__restrict__ n_pos, uint32_t *__restrict__ mm) {
+// order-preserving integer keys of the positives' attribute values: sorted + segmented (sort.cu), they give
+// torch.unique(sst[pos], return_inverse=True) -- the group of every positive is the rank of its value (nfcf.py:79)
+__global__ void k_df_group_keys(const float *__restrict__ sst, const int32_t *__restrict__ pos_idx,
+                                const int32_t *__restrict__ n_pos, uint32_t *__restrict__ keys) {
   const int n = *n_pos;
-  uint32_t lo = 0xffffffffu, hi = 0u;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t o = f2ord(sst[pos_idx[k]]);
-    lo = min(lo, o);
-    hi = max(hi, o);
-  }
-  if (hi >= lo) {
-    atomicMin(&mm[0], lo);
-    atomicMax(&mm[1], hi);
-  }
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) keys[k] = f2ord(sst[pos_idx[k]]);
 }
 
+// nfcf.py:76-97 for any number of attribute values G <= kDfMaxG: per (positive item j, group g) M = (sum p + 1/J) /
+// (count + 1); eps_j = max over the pairs g < g' of |ln M_g - ln M_g'|, the gradient going to the FIRST pair (loop order
+// of nfcf.py:91-95) that attains it (torch.where(eps > running, ...) replaces only on a strict increase).
+// Warp per item segment; one pass over the segment's positives per group (segments are a few rows long).
+constexpr int kDfMaxG = 32;
 __global__ void __launch_bounds__(256) k_df_segments(DfArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int J = *a.n_seg;
-  const float vmin = ord2f(a.mm[0]), vmax = ord2f(a.mm[1]);
+  const int G = *a.n_groups;
+  if (G > kDfMaxG) {
+    if (warp == 0 && lane == 0) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+    return;
+  }
   const float alpha = 1.f / (float)J;
-  int bad = 0;
   for (int j = warp; j < J; j += nwarps) {
     const int p0 = a.seg_off[j], p1 = a.seg_off[j + 1];
-    float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
-    for (int q = p0 + lane; q < p1; q += 32) {
-      const int b = a.pos_idx[a.ord[q]];
-      const float sv = a.sst[b], pv = a.p[b];
-      const bool g = sv != vmin;
-      bad |= (g && sv != vmax);
-      if (g) { s1 += pv; c1 += 1.f; } else { s0 += pv; c0 += 1.f; }
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); c0 = warp_sum(c0); c1 = warp_sum(c1);
-    if (lane == 0) {
-      float eps = 0.f, k0 = 0.f, k1 = 0.f;
-      if (vmin != vmax) {   // a single attribute value among the positives: one column, no pair, eps = 0
-        const float M0 = (s0 + alpha) / (c0 + 1.f), M1 = (s1 + alpha) / (c1 + 1.f);
-        const float diff = logf(M0) - logf(M1);
-        eps = fabsf(diff);
-        const float sg = (float)((diff > 0.f) - (diff < 0.f));
-        if (eps > 0.f) {    // torch.where(epsilon > 0, ...) routes the gradient only when the pair took the max
-          k0 = a.fair_weight * alpha * sg / M0 / (c0 + 1.f);
-          k1 = -a.fair_weight * alpha * sg / M1 / (c1 + 1.f);
+    float M = 1.f, cnt = 0.f;       // lane g holds M[j][g] and the count of group g
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f, c = 0.f;
+      for (int q = p0 + lane; q < p1; q += 32) {
+        const int k = a.ord[q];
+        if (a.grp[k] == g) {
+          s += a.p[a.pos_idx[k]];
+          c += 1.f;
         }
       }
-      a.seg_eps[j] = eps;
-      a.coef[2 * j] = k0;
-      a.coef[2 * j + 1] = k1;
+      s = warp_sum(s);
+      c = warp_sum(c);
+      if (lane == g) {
+        M = (s + alpha) / (c + 1.f);
+        cnt = c;
+      }
+    }
+    const float lM = logf(M);
+    float eps = 0.f, sg = 0.f;
+    int bi = -1, bj = -1;
+    for (int x = 0; x < G; ++x) {
+      const float lx = __shfl_sync(0xffffffffu, lM, x);
+      for (int y = x + 1; y < G; ++y) {
+        const float diff = lx - __shfl_sync(0xffffffffu, lM, y);
+        const float e = fabsf(diff);
+        if (e > eps) {
+          eps = e;
+          sg = (float)((diff > 0.f) - (diff < 0.f));
+          bi = x;
+          bj = y;
+        }
+      }
+    }
+    if (lane == 0) a.seg_eps[j] = eps;
+    if (lane < G) {
+      float kf = 0.f;
+      if (lane == bi) kf = a.fair_weight * alpha * sg / M / (cnt + 1.f);
+      if (lane == bj) kf = -a.fair_weight * alpha * sg / M / (cnt + 1.f);
+      a.coef[(size_t)G * j + lane] = kf;
     }
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
 }
 
 // loss = bce_sum / M + fair_weight * mean_j eps_j ; dz = (dp_bce + coef[seg(b)][g(b)]) * p (1 - p)
@@ -433,11 +448,11 @@ __global__ void __launch_bounds__(256)
 
 __global__ void k_df_scatter_coef(DfArgs a, const int32_t *__restrict__ seg_id, float *__restrict__ dp) {
   const int n = *a.n_pos;
-  const float vmin = ord2f(a.mm[0]);
+  const int G = *a.n_groups;
+  if (G > kDfMaxG) return;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-    const int b = a.pos_idx[a.ord[q]];
-    const int g = a.sst[b] != vmin;
-    dp[b] += a.coef[2 * seg_id[q] + g];
+    const int k = a.ord[q];
+    dp[a.pos_idx[k]] += a.coef[(size_t)G * seg_id[q] + a.grp[k]];
   }
 }
 
@@ -840,7 +855,8 @@ struct MlpWs {
   double *part_b;
   float *p, *dp, *dz, *bce_part, *seg_eps, *coef, *loss_tmp;
   int32_t *pos_idx, *n_pos, *seg_id, *seg_off, *n_seg;
-  uint32_t *keys, *skey, *ord, *mm;
+  uint32_t *keys, *skey, *ord, *gkeys, *gskey, *gord;
+  int32_t *gseg_id, *gseg_off, *n_groups, *grp;
   uint32_t *ukey, *uord, *ikey, *iord;
   int32_t *useg_id, *useg_off, *un_seg, *iseg_id, *iseg_off, *in_seg;
   SortScratch sort;
@@ -867,7 +883,7 @@ static MlpWs carve_mlp(Carver &c, const fr_mlp_tower *t, int64_t M) {
   w.dz = c.take<float>(m);
   w.bce_part = c.take<float>(m / 256 + 2);
   w.seg_eps = c.take<float>(m);
-  w.coef = c.take<float>(2 * m);
+  w.coef = c.take<float>(32 * m);   // [J, G], G <= kDfMaxG
   w.loss_tmp = c.take<float>(4);
   w.pos_idx = c.take<int32_t>(m);
   w.n_pos = c.take<int32_t>(1);
@@ -877,7 +893,13 @@ static MlpWs carve_mlp(Carver &c, const fr_mlp_tower *t, int64_t M) {
   w.keys = c.take<uint32_t>(m);
   w.skey = c.take<uint32_t>(m);
   w.ord = c.take<uint32_t>(m);
-  w.mm = c.take<uint32_t>(2);
+  w.gkeys = c.take<uint32_t>(m);
+  w.gskey = c.take<uint32_t>(m);
+  w.gord = c.take<uint32_t>(m);
+  w.gseg_id = c.take<int32_t>(m);
+  w.gseg_off = c.take<int32_t>(m + 1);
+  w.n_groups = c.take<int32_t>(1);
+  w.grp = c.take<int32_t>(m);
   w.ukey = c.take<uint32_t>(m);
   w.uord = c.take<uint32_t>(m);
   w.ikey = c.take<uint32_t>(m);
@@ -947,11 +969,12 @@ int fr_nfcf_forward(const fr_nfcf_step *s, void *stream) {
     FR_LAUNCH(fr::k_pos_keys, fr::grid_for(M, 256), 256, 0, st, s->iid, w.pos_idx, w.n_pos, w.keys);
     fr::sort_pairs(w.keys, nullptr, w.skey, w.ord, M, w.n_pos, fr::bits_for((uint32_t)s->n_items), w.sort, st);
     fr::build_segments(w.skey, w.ord, M, w.n_pos, w.seg_id, w.seg_off, w.n_seg, nullptr, nullptr, nullptr, w.seg, st);
-    const uint32_t mm0[2] = {0xffffffffu, 0u};
-    FR_CUDA_OK(cudaMemcpyAsync(w.mm, mm0, sizeof(mm0), cudaMemcpyHostToDevice, st));
-    FR_LAUNCH(fr::k_df_minmax, fr::grid_for(M, 256), 256, 0, st, s->sst, w.pos_idx, w.n_pos, w.mm);
-    fr::DfArgs da{w.p, s->sst, w.pos_idx, w.n_pos, w.ord, w.seg_off, w.n_seg, s->fair_weight, w.seg_eps, w.coef, w.mm,
-                  s->status_flags};
+    // groups = torch.unique(sst[pos], return_inverse=True): sort the order-encoded values, segment, scatter the ranks back
+    FR_LAUNCH(fr::k_df_group_keys, fr::grid_for(M, 256), 256, 0, st, s->sst, w.pos_idx, w.n_pos, w.gkeys);
+    fr::sort_pairs(w.gkeys, nullptr, w.gskey, w.gord, M, w.n_pos, 32, w.sort, st);
+    fr::build_segments(w.gskey, w.gord, M, w.n_pos, w.gseg_id, w.gseg_off, w.n_groups, nullptr, nullptr, w.grp, w.seg, st);
+    fr::DfArgs da{w.p, s->sst, w.pos_idx, w.n_pos, w.ord, w.seg_off, w.n_seg, s->fair_weight, w.seg_eps, w.coef, w.grp,
+                  w.n_groups, s->status_flags};
     FR_LAUNCH(fr::k_df_segments, fr::grid_for(M, 8 * 8, fr::kSMs * 2), 256, 0, st, da);
     FR_LAUNCH(fr::k_df_scatter_coef, fr::grid_for(M, 256), 256, 0, st, da, w.seg_id, w.dp);
   }

@@ -344,3 +344,14 @@ def fairness_metrics(stats):
     check(lib.fr_fairness_metrics(ptr(stats), n_items, G, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
           "fr_fairness_metrics")
     return out
+
+
+def unfairness_sampled(stats_all, stats_pos):
+    """float64 [5]: value, absolute, under, over unfairness of the sampled-negative mode, number of items in the union"""
+    lib = load()
+    n_items = stats_all.shape[0]
+    out = torch.empty(5, dtype=torch.float64, device=stats_all.device)
+    ws = _ws(lib.fr_unfairness_sampled_workspace_bytes(n_items), stats_all.device)
+    check(lib.fr_unfairness_sampled(ptr(stats_all), ptr(stats_pos), n_items, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+          "fr_unfairness_sampled")
+    return out

@@ -183,8 +183,8 @@ class NFCF(nn.Module):
     def check_flags(self):
         if self._flags is not None and int(self._flags.item()) & _lib.FLAG_TOO_MANY_GROUPS:
             self._flags.zero_()
-            raise NotImplementedError("NFCF regulariser kernels implement the binary sensitive attribute case "
-                                      "(NFCF.yaml: gender); more than two values were present in a batch")
+            raise NotImplementedError("NFCF regulariser: more than 32 distinct sensitive-attribute values among the positives "
+                                      "of a batch (the kernel keeps one lane per group)")
 
 
 class NFCFTrainer(CheckpointMixin):

@@ -9,15 +9,18 @@ it; here the dense rows never exist: candidates live in a CSR (positives first, 
 dataloader's own order), their scores come from the model's `predict` (any model) or the pair-score kernel (dot-product
 models), and `fr_sampled_topk` extracts the K best per user in the canonical order (score desc, item id asc).
 
-Metrics: NDCG / Recall / Hit / MRR, GiniIndex, PopularityPercentage, DifferentialFairness, NonParityUnfairness -- the ones
-whose definition does not depend on the evaluation mode.  Two deliberate differences from the reference, both only
-visible when its dataloader packs SEVERAL users into one batch: (i) every positive carries its OWN user's sensitive
-attribute (the reference reads the attribute of the first P rows of the batch interaction, collector.py:203-205, which
-belong mostly to the batch's first user); (ii) Value / Absolute / Under / Over unfairness are not offered in sampled mode:
-the reference computes them from `interaction[item][P:2P]` scored in the positives' rows (collector.py:190-199), which
-for multi-user batches are -inf entries, i.e. its values are inf / NaN (`sampled_undefined_metrics: nan` keeps their
-keys in the result with NaN values instead of refusing the metric list).  With one user per batch (i) coincides with the
-reference (tests/golden/uni_eval_uni100.npz)."""
+Metrics: all 12 of the model YAMLs.  NDCG / Recall / Hit / MRR, GiniIndex, PopularityPercentage, DifferentialFairness and
+NonParityUnfairness are defined as in full mode.  Value / Absolute / Under / Over unfairness follow the sampled mode of
+metrics.py:935-978 (and siblings): the item set is the union of the positives' items and of the items of each positive's
+FIRST sampled negative (`interaction[item][P:2P]`, collector.py:190-199), a negative contributing its score (for the
+positive's user) and a count, but no "true" mass.
+
+One deliberate difference from the reference, only visible when its dataloader packs SEVERAL users into one batch (the
+default eval_batch_size does): its collector indexes the batch interaction as if it held one user -- `interaction[sst][:P]`
+is mostly the first user's attribute (collector.py:203-205) and `interaction[item][P:2P]` straddles the users' blocks, so
+the negative scores it reads are -inf entries of other users' rows and the four unfairness values come out inf / NaN.  Here
+every positive carries its OWN user's attribute and is paired with ITS first negative: with one user per batch this IS the
+reference (tests/golden/uni_eval_uni100.npz, uni_eval_uni100_unfair.npz), with several it is the value the reference means."""
 from collections import OrderedDict
 
 import numpy as np
@@ -27,7 +30,7 @@ from . import _lib, kernels
 from ._lib import check, load, ptr, stream_ptr
 from .evaluator import FAIR_KEYS, FAIR_SLOTS, TOPK_ROWS, FullSortEvaluator
 
-MODE_FREE = set(TOPK_ROWS) | {"giniindex", "popularitypercentage", "differentialfairness", "nonparityunfairness"}
+UNFAIR4 = ("valueunfairness", "absoluteunfairness", "underunfairness", "overunfairness")
 
 
 def sample_negatives(pos_lists, used_lists, n_items, neg_num, rng):
@@ -158,6 +161,11 @@ class SampledEvalData:
         # positions of the positives inside the candidate arrays (user-major, dataloader order)
         pos_idx = np.concatenate([cand_off[k] + np.arange(n_pos[k]) for k in range(n)]) if n else np.zeros(0, np.int64)
         self.pos_idx = t(pos_idx, torch.int64)
+        # ... and of each positive's FIRST sampled negative (negatives are laid out draw-major: [j * P + k] = j-th negative of
+        # positive k, general_dataloader.py / abstract_dataloader.py `times` layout), where a user has negatives at all
+        has_neg = np.array([len(q) >= len(p) > 0 for p, q in zip(pos_lists, neg_lists)], bool)
+        neg_idx = np.concatenate([cand_off[k] + n_pos[k] + np.arange(n_pos[k]) for k in range(n)]) if n else np.zeros(0, np.int64)
+        self.first_neg_idx = t(neg_idx, torch.int64) if bool(has_neg.all()) else None
         self.pos_items = t(np.concatenate([np.asarray(p, np.int64) for p in pos_lists]), torch.int32)
         self.n_pos = int(n_pos.sum())
         pos_row = np.repeat(np.arange(n), n_pos)
@@ -189,19 +197,6 @@ class SampledEvaluator(FullSortEvaluator):
 
     def __init__(self, config, n_items, train_item_count=None):
         super().__init__(config, n_items, train_item_count)
-        bad = [m for m in self.metrics if m not in MODE_FREE]
-        self._undefined = set()
-        if bad and config["sampled_undefined_metrics"] == "nan":
-            # keep the reference's result keys (its model YAMLs list all 12 metrics with mode uni100) and report the four
-            # metrics that mode leaves undefined as NaN instead of refusing the configuration
-            import warnings
-            warnings.warn(f"{bad} are undefined in sampled mode (collector.py:190-199 scores mis-indexed negatives): "
-                          f"reported as NaN")
-            self._undefined = set(bad)
-        elif bad:
-            raise NotImplementedError(f"{bad}: in sampled mode the reference computes these from mis-indexed negative "
-                                      f"scores (collector.py:190-199); see recbole_fairrec_b200/sampled_eval.py "
-                                      f"(sampled_undefined_metrics: nan reports them as NaN instead)")
 
     @staticmethod
     def dot_scorer(U, I, max_rating=None, transform=None):
@@ -235,27 +230,23 @@ class SampledEvaluator(FullSortEvaluator):
                 out["gini"] = {k: kernels.gini_at_k(cnt, k, data.n) for k in self.topk}
         if need & set(FAIR_SLOTS):
             out["fair"] = {}
-            for attr in self.sst_attr_list:
-                stats = kernels.item_group_stats(data.pos_items, pos_score, data.group_of_pos[attr], self.n_items,
-                                                 data.n_groups[attr])
-                out["fair"][attr] = kernels.fairness_metrics(stats)
+            for ai, attr in enumerate(self.sst_attr_list):
+                grp, G = data.group_of_pos[attr], data.n_groups[attr]
+                stats = kernels.item_group_stats(data.pos_items, pos_score, grp, self.n_items, G)
+                fair = kernels.fairness_metrics(stats)
+                if ai == 0 and need & set(UNFAIR4) and G == 2:
+                    # metrics.py:935-978 with mode != 'full': positives + each positive's first negative (see module docstring)
+                    if data.first_neg_idx is None:
+                        raise ValueError("the sampled-mode unfairness metrics need at least one negative per positive")
+                    neg_score = scores[data.first_neg_idx]
+                    neg_items = data.cand_items[data.first_neg_idx]
+                    both = kernels.item_group_stats(torch.cat([data.pos_items, neg_items]).contiguous(),
+                                                    torch.cat([pos_score, neg_score]).contiguous(),
+                                                    torch.cat([grp, grp]).contiguous(), self.n_items, 2)
+                    fair[1:5] = kernels.unfairness_sampled(both, stats)[:4]
+                out["fair"][attr] = fair
         self.last = out
         return out
-
-    def finalize(self, out, data, rounded=True):
-        if not self._undefined:
-            return super().finalize(out, data, rounded)
-        res, every = OrderedDict(), self.metrics
-        try:
-            for m in every:                  # metric by metric, so that the keys keep the reference's order
-                if m in self._undefined:
-                    res[FAIR_KEYS[m].format(self.sst_attr_list[0])] = float("nan")
-                else:
-                    self.metrics = [m]
-                    res.update(super().finalize(out, data, rounded))
-        finally:
-            self.metrics = every
-        return res
 
     def evaluate(self, score_fn, data):
         return self.finalize(self.collect(score_fn, data), data)

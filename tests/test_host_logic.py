@@ -324,38 +324,33 @@ def test_device_built_eval_lists_equal_the_host_built_ones():
         assert torch.equal(a.group_of_pos["gender"], b.group_of_pos["gender"])
 
 
-def test_sampled_mode_reports_its_undefined_metrics_as_nan_on_request():
-    """`sampled_undefined_metrics: nan`: the reference's 12-metric YAML list stays usable with mode uni<N>; the four
-    metrics that mode leaves undefined come back as NaN under the reference's keys, in the reference's key order"""
-    import warnings
+def test_sampled_mode_accepts_the_twelve_metric_list_and_keeps_the_reference_keys():
+    """the reference's 12-metric YAML list is usable with mode uni<N>: Value / Absolute / Under / Over unfairness take
+    their sampled-mode definition (metrics.py:935-978 with mode != 'full'); result keys in the reference's order"""
     import recbole_fairrec_b200 as pkg
     from recbole_fairrec_b200.evaluator import FAIR_KEYS
     cfg = pkg.Config(topk=[2, 3], sst_attr_list=["gender"], device=torch.device("cpu"), metric_decimal_place=6)
-    with pytest.raises(NotImplementedError):
-        pkg.SampledEvaluator(cfg, 10)
-    cfg["sampled_undefined_metrics"] = "nan"
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        ev = pkg.SampledEvaluator(cfg, 10)
-    assert any("undefined in sampled mode" in str(x.message) for x in w)
+    ev = pkg.SampledEvaluator(cfg, 10)
 
     class D:
         n = 4
     out = {"topk_sums": torch.tensor([[1.0, 2.0, 3.0]] * 4, dtype=torch.float64),
            "pop_hits": torch.tensor([2.0, 1.0, 1.0], dtype=torch.float64),
            "gini": {2: torch.tensor(0.25), 3: torch.tensor(0.5)},
-           "fair": {"gender": torch.tensor([0.5, 9.0, 9.0, 9.0, 9.0, 0.125], dtype=torch.float64)}}
+           "fair": {"gender": torch.tensor([0.5, 0.1, 0.2, 0.3, 0.4, 0.125], dtype=torch.float64)}}
     res = ev.finalize(out, D())
-    keys = list(res)
     want = []
     for m in cfg["metrics"]:
         m = m.lower()
         want += [FAIR_KEYS[m].format("gender")] if m in FAIR_KEYS else [f"{m}@2", f"{m}@3"]
-    assert keys == want
-    for m in ("valueunfairness", "absoluteunfairness", "underunfairness", "overunfairness"):
-        assert np.isnan(res[FAIR_KEYS[m].format("gender")])
+    assert list(res) == want
+    for m, v in (("valueunfairness", 0.1), ("absoluteunfairness", 0.2), ("underunfairness", 0.3), ("overunfairness", 0.4)):
+        assert res[FAIR_KEYS[m].format("gender")] == v
     assert res[FAIR_KEYS["differentialfairness"].format("gender")] == 0.5 and res["ndcg@3"] == 0.75
-    assert ev.metrics == [m.lower() for m in cfg["metrics"]]
+    # the pairing of each positive with its first negative (negatives are draw-major: [j * P + k])
+    data = pkg.SampledEvalData([3, 5], [[7, 8], [2]], [[11, 12, 13, 14], [4, 6, 9]], {"gender": np.array([0, 1, 2, 1, 2, 1])},
+                               torch.device("cpu"))
+    assert data.cand_items[data.first_neg_idx].tolist() == [11, 12, 4] and data.cand_items[data.pos_idx].tolist() == [7, 8, 2]
 
 
 def test_packed_fast_host_step_passes_the_same_arguments_as_the_generic_step(monkeypatch):

@@ -296,6 +296,14 @@ def test_sampled_eval_oracle_matches_reference(path):
             np.testing.assert_array_equal(sst_of_pos, np.repeat(g["sst_of_user"][users], np.diff(g["pos_off"])))
         res = so.metrics(ids, rec_topk, pos_score, g["pos_items"], sst_of_pos, [int(k) for k in g["topk"]],
                          g["I"].shape[0], count_items)
+        if any("Value Unfairness" in str(k) for k in g["metric_names"]):
+            # sampled mode of the four unfairness metrics: each positive paired with its FIRST negative (collector.py:190-199)
+            n_pos = np.diff(g["pos_off"])
+            neg_items = np.concatenate([np.asarray(c[1])[:p] for c, p in zip(cands, n_pos)])
+            neg_score = np.concatenate([rows[r, np.asarray(c[1])[:p]] for r, (c, p) in enumerate(zip(cands, n_pos))])
+            vals4 = so.unfairness_sampled(pos_score, g["pos_items"], neg_score, neg_items, sst_of_pos)
+            for name, v in zip(("Value", "Absolute", "Underestimation", "Overestimation"), vals4):
+                res[f"{name} Unfairness of sensitive attribute gender"] = v
         for k, ref in zip(g["metric_names"], g["metric_values"]):
             assert abs(res[str(k)] - ref) <= 1e-5 * max(abs(ref), 1e-12) + 1e-9, (k, res[str(k)], ref)
 

@@ -15,6 +15,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(__file__)
 UNI = sorted(glob.glob(os.path.join(HERE, "golden", "uni_eval_*.npz")))
 METRICS = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage", "NonParityUnfairness"]
+METRICS12 = ["NDCG", "Recall", "Hit", "MRR", "DifferentialFairness", "GiniIndex", "PopularityPercentage", "ValueUnfairness",
+             "AbsoluteUnfairness", "UnderUnfairness", "OverUnfairness", "NonParityUnfairness"]
 
 
 def setup(g):
@@ -23,8 +25,9 @@ def setup(g):
     cands = so.candidate_lists(g["pos_off"], g["pos_items"], g["neg_items"], int(g["neg_num"]))
     dev = torch.device("cuda")
     data = pkg.SampledEvalData(users, [c[0] for c in cands], [c[1] for c in cands], {"gender": g["sst_of_user"]}, dev)
-    cfg = pkg.Config(topk=[int(k) for k in g["topk"]], metrics=METRICS, metric_decimal_place=12, sst_attr_list=["gender"],
-                     device=dev, popularity_ratio=0.1, eval_args={"mode": "uni100"})
+    all12 = any("Value Unfairness" in str(k) for k in g["metric_names"])
+    cfg = pkg.Config(topk=[int(k) for k in g["topk"]], metrics=METRICS12 if all12 else METRICS, metric_decimal_place=12,
+                     sst_attr_list=["gender"], device=dev, popularity_ratio=0.1, eval_args={"mode": "uni100"})
     ev = pkg.SampledEvaluator(cfg, g["I"].shape[0], {int(i): int(c) for i, c in g["train_count_items"]})
     U, I = torch.from_numpy(g["U"]).to(dev), torch.from_numpy(g["I"]).to(dev)
     return users, cands, data, ev, U, I
@@ -49,7 +52,8 @@ def test_sampled_eval_matches_reference(path):
     assert clean.sum() >= len(users) // 2
     assert np.array_equal(ev.last["topk_id"].cpu().numpy()[clean], g["rec_items"][clean])
     assert np.array_equal(ev.last["rec_topk"].cpu().numpy()[clean], g["rec_topk"][clean])
-    single_user_batches = os.path.basename(path) == "uni_eval_uni100.npz"
+    single_user_batches = os.path.basename(path) in ("uni_eval_uni100.npz", "uni_eval_uni100_unfair.npz",
+                                                     "uni_eval_uni10_unfair_small.npz")
     for k, ref in zip(g["metric_names"], g["metric_values"]):
         k = str(k)
         if ("Differential" in k or "NonParity" in k) and not single_user_batches:
