@@ -111,8 +111,6 @@ def test_nfcf_two_stages_from_raw_files(tmp_path):
         "Differential Fairness of sensitive attribute gender" in s2["test_result"] else True
 
 
-@pytest.mark.skipif(os.environ.get("FAIRREC_E2E_FAMILIES") != "1",
-                    reason="written after the round's last GPU session; enable with FAIRREC_E2E_FAMILIES=1 (DESIGN.md section 7)")
 @pytest.mark.parametrize("model", ["PFCN_PMF", "NFCF"])
 def test_mlp_family_end_to_end_from_raw_files_matches_the_reference_run(model, tmp_path):
     """run_recbole(model, 'ml-100k') from the RAW atomic files against the unmodified reference's own run of the same
@@ -159,8 +157,6 @@ def test_mlp_family_end_to_end_from_raw_files_matches_the_reference_run(model, t
             assert abs(got[k] - r) <= 0.05, (k, got[k], r)
 
 
-@pytest.mark.skipif(os.environ.get("FAIRREC_E2E_FAMILIES") != "1",
-                    reason="written after the round's last GPU session; enable with FAIRREC_E2E_FAMILIES=1 (DESIGN.md section 7)")
 def test_focf_uni_mode_end_to_end_matches_the_reference_run():
     """FOCF with the evaluation mode of its own YAML (`uni<N>`; negatives drawn at every validation, interleaved with the
     loader's item draws on numpy's RNG) against the reference's run (tests/golden/e2e_focf_uni.npz).  The CPU shadow run
