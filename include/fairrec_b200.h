@@ -307,6 +307,58 @@ int fr_bpr_loss(const float *pos, const float *neg, int64_t M, float *loss, floa
 int fr_sigmoid_bce_loss(const float *z, const float *y, int64_t M, float *loss, float *dz, void *stream);
 int fr_softmax_ce_loss(const float *Z, const int32_t *y, int64_t M, int32_t C, float *loss, float *dZ, void *stream);
 
+/* ---- whole MLP chains in one launch (mlp_chain.cu): recbole/model/layers.py:30-85 MLPLayers -- [Dropout -> Linear ->
+ * BatchNorm1d? -> activation?] x L -- forward as ONE persistent cooperative kernel and backward as ONE, every GEMM (forward,
+ * data gradient, weight gradient) on tcgen05 (3xTF32, TMA-fed, TMEM accumulators); BatchNorm batch statistics and bias
+ * gradients are float64 column sums added in tile order.  Up to FR_CHAIN_MAX_CHAINS chains over the same M rows (the
+ * discriminators of one PFCN step, pfcn_mlp.py:195-211) share a launch.  Rules: every K % 4 == 0, widths <= 256,
+ * <= FR_CHAIN_MAX_LAYERS layers per chain, <= 24 layers per launch (fr_mlp_chain_eligible).
+ * Dropout masks are the ones of fr_linear_forward for the same (seed, seed_dev): hash of (seed, 0, row * K + k). */
+#define FR_CHAIN_MAX_LAYERS 8
+#define FR_CHAIN_MAX_CHAINS 4
+typedef struct fr_chain_layer {
+  int32_t K, N;              /* in / out features of the Linear */
+  int32_t act;               /* activation code of fr_linear_forward, applied after the Linear (or its BatchNorm) */
+  int32_t has_bn;
+  float drop_p;              /* dropout on the layer INPUT (training only) */
+  float bn_eps, bn_momentum;
+  uint64_t seed;             /* dropout seed of this layer */
+  const float *W, *b;        /* [N,K], [N] or NULL */
+  const float *gamma, *beta; /* BatchNorm affine */
+  float *running_mean, *running_var;
+  int64_t *num_batches_tracked; /* may be NULL; += 1 per training forward */
+  float *dW, *db, *dgamma, *dbeta; /* backward outputs (db / dgamma / dbeta may be NULL) */
+} fr_chain_layer;
+typedef struct fr_chain {
+  int32_t n_layers;
+  fr_chain_layer layer[FR_CHAIN_MAX_LAYERS];
+  const float *X;            /* [M, ldx] input (first layer's K columns used) */
+  int32_t ldx;               /* 0 = K of the first layer */
+  float *Y;                  /* [M, N_last] output (forward writes; backward reads it for the last activation) */
+  const float *dY;           /* backward: gradient w.r.t. Y */
+  float *dX;                 /* backward: [M, K_first] gradient w.r.t. X, or NULL */
+  void *fwd_ws;              /* forward workspace: written by the forward call, read by the backward call */
+  size_t fwd_ws_bytes;
+  void *bwd_ws;              /* backward scratch */
+  size_t bwd_ws_bytes;
+} fr_chain;
+/* bind the device's primary context to the calling thread: call once (outside any stream capture) on a thread that will
+ * call fr_mlp_chain_* without having used the CUDA runtime before (e.g. torch's autograd worker thread) */
+int fr_thread_init(void);
+int fr_mlp_chain_eligible(const fr_chain_layer *layers, int32_t n_layers, int64_t M);
+/* backward == 0: the forward workspace for (training, need_grad); backward != 0: the backward scratch */
+size_t fr_mlp_chain_workspace_bytes(const fr_chain_layer *layers, int32_t n_layers, int64_t M, int32_t training,
+                                    int32_t need_grad, int32_t backward);
+/* barrier_words: uint32[2] zero-initialised ONCE by the caller (self-resetting), one buffer per stream.
+ * training != 0: BatchNorm uses batch statistics and advances the running ones, dropout is on; need_grad != 0 keeps what
+ * fr_mlp_chain_backward needs in fwd_ws. */
+int fr_mlp_chain_forward(const fr_chain *chains, int32_t n_chains, int64_t M, int32_t training, int32_t need_grad,
+                         const uint64_t *seed_dev, uint32_t *barrier_words, void *stream);
+/* after fr_mlp_chain_forward(training = 1, need_grad = 1) with the same chains / workspaces; dX_sum (may be NULL): the
+ * fixed-order sum of the chains' dX (they then must all have a dX buffer and the same input width) */
+int fr_mlp_chain_backward(const fr_chain *chains, int32_t n_chains, int64_t M, const uint64_t *seed_dev, float *dX_sum,
+                          uint32_t *barrier_words, void *stream);
+
 /* ---- row-wise scorers and glue ops of the PFCN / FairGo families (layer_ops.cu) */
 /* out[m] = sum_k A[m,k] * B[m,k]: torch.mul(u, i).sum(-1) (pfcn_pmf.py:172,183-184; fairgo_pmf.py:169) */
 int fr_rowdot_forward(const float *A, const float *B, int64_t M, int32_t d, float *out, void *stream);

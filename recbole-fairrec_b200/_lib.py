@@ -106,6 +106,22 @@ class SpmmPlan(Structure):
                 ("n_chunks", c_int64), ("n_multi", c_int64), ("n_slots", c_int64), ("n_empty", c_int64)]
 
 
+class ChainLayer(Structure):
+    """mirror of `struct fr_chain_layer`"""
+    _fields_ = [("K", c_int32), ("N", c_int32), ("act", c_int32), ("has_bn", c_int32), ("drop_p", c_float),
+                ("bn_eps", c_float), ("bn_momentum", c_float), ("seed", c_uint64), ("W", c_void_p), ("b", c_void_p),
+                ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("num_batches_tracked", c_void_p), ("dW", c_void_p), ("db", c_void_p), ("dgamma", c_void_p),
+                ("dbeta", c_void_p)]
+
+
+class Chain(Structure):
+    """mirror of `struct fr_chain`"""
+    _fields_ = [("n_layers", c_int32), ("layer", ChainLayer * 8), ("X", c_void_p), ("ldx", c_int32), ("Y", c_void_p),
+                ("dY", c_void_p), ("dX", c_void_p), ("fwd_ws", c_void_p), ("fwd_ws_bytes", c_size_t),
+                ("bwd_ws", c_void_p), ("bwd_ws_bytes", c_size_t)]
+
+
 # name -> (restype, argtypes); also the list the ABI-surface test checks against the header
 SIGNATURES = {
     "fr_abi_version": (c_int, []),
@@ -204,6 +220,11 @@ SIGNATURES = {
     "fr_fairness_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "fr_unfairness_sampled_workspace_bytes": (c_size_t, [c_int32]),
     "fr_unfairness_sampled": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fr_thread_init": (c_int, []),
+    "fr_mlp_chain_eligible": (c_int, [POINTER(ChainLayer), c_int32, c_int64]),
+    "fr_mlp_chain_workspace_bytes": (c_size_t, [POINTER(ChainLayer), c_int32, c_int64, c_int32, c_int32, c_int32]),
+    "fr_mlp_chain_forward": (c_int, [POINTER(Chain), c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "fr_mlp_chain_backward": (c_int, [POINTER(Chain), c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fr_fairness_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -19,6 +19,7 @@ class GraphedStep:
             self.static[k].copy_(example[k])
         self.inter = Interaction(self.static)
         optimizer.init_state()
+        ops.init_autograd_thread(device)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         side = torch.cuda.Stream(device=device)

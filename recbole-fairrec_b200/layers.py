@@ -39,6 +39,9 @@ class MLPLayers(nn.Module):
                 module.bias.data.fill_(0.0)
 
     def forward(self, x):
+        fused = ops.mlp_chain([self], [x]) if x.dim() == 2 else None     # the whole chain in one launch (mlp_chain.cu)
+        if fused is not None:
+            return fused[0]
         act = ops.ACT[self.activation]
         mods = list(self.mlp_layers)
         k = 0

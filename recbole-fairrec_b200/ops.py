@@ -116,6 +116,244 @@ class BatchNormAct(torch.autograd.Function):
         return dX, dg, db, None, None, None, None, None, None
 
 
+_chain_bars = {}
+_chain_on = None
+CHAIN_MAX_TRAIN_ROWS = 32768
+CHAIN_EVAL_CHUNK = 65536
+
+
+def chain_enabled():
+    """the fused whole-chain kernels (mlp_chain.cu) are the default; FR_MLP_CHAIN=0 selects the per-layer kernels"""
+    global _chain_on
+    if _chain_on is None:
+        import os
+        _chain_on = os.environ.get("FR_MLP_CHAIN", "1") != "0"
+    return _chain_on
+
+
+def set_chain_enabled(on):
+    global _chain_on
+    _chain_on = bool(on)
+
+
+def chain_bars(device):
+    """the two self-resetting grid-barrier words of the chain kernels (one buffer per device: chains run on one stream)"""
+    key = (device.type, device.index)
+    if key not in _chain_bars:
+        _chain_bars[key] = torch.zeros(2, dtype=torch.int32, device=device)
+    return _chain_bars[key]
+
+
+_thread_state = __import__("threading").local()
+
+
+def _bind_thread():
+    """fr_thread_init once per Python thread, outside stream captures (see include/fairrec_b200.h)"""
+    if not getattr(_thread_state, "bound", False) and not torch.cuda.is_current_stream_capturing():
+        check(load().fr_thread_init(), "fr_thread_init")
+        _thread_state.bound = True
+
+
+class _TouchBackwardThread(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        _bind_thread()
+        return g
+
+
+def init_autograd_thread(device):
+    """run one trivial backward so that the autograd worker thread of `device` holds a CUDA context BEFORE a step is
+    captured into a CUDA graph (graphed.GraphedStep captures without an eager warm-up pass)"""
+    x = torch.zeros(1, device=device, requires_grad=True)
+    _TouchBackwardThread.apply(x).sum().backward()
+
+
+def _chain_layers(mod, training, seeds=None):
+    """[(Linear, BatchNorm1d | None)] of an MLPLayers module -> ctypes layer array (pointers filled, gradients not)"""
+    import torch.nn as nn
+    from ._lib import ChainLayer
+    mods = list(mod.mlp_layers)
+    pairs, k = [], 0
+    while k < len(mods):
+        lin = mods[k + 1]
+        k += 2
+        bn = None
+        if k < len(mods) and isinstance(mods[k], nn.BatchNorm1d):
+            bn = mods[k]
+            k += 1
+        if k < len(mods) and not isinstance(mods[k], nn.Dropout):
+            k += 1
+        pairs.append((lin, bn))
+    arr = (ChainLayer * 8)()
+    if len(pairs) > 8:
+        return None, pairs
+    act = ACT[mod.activation]
+    for i, (lin, bn) in enumerate(pairs):
+        L = arr[i]
+        L.K, L.N, L.act, L.has_bn = lin.in_features, lin.out_features, act, 1 if bn is not None else 0
+        L.drop_p = float(mod.dropout) if training else 0.0
+        L.seed = seeds[i] if seeds is not None else 0
+        L.W = lin.weight.data_ptr()
+        L.b = lin.bias.data_ptr() if lin.bias is not None else None
+        if bn is not None:
+            if bn.momentum is None or not bn.affine or not bn.track_running_stats:
+                return None, pairs
+            L.bn_eps, L.bn_momentum = float(bn.eps), float(bn.momentum)
+            L.gamma, L.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+            L.running_mean, L.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            L.num_batches_tracked = bn.num_batches_tracked.data_ptr()
+    return arr, pairs
+
+
+def _chain_params(pairs):
+    out = []
+    for lin, bn in pairs:
+        out.append(lin.weight)
+        if lin.bias is not None:
+            out.append(lin.bias)
+        if bn is not None:
+            out += [bn.weight, bn.bias]
+    return out
+
+
+class MLPChainGroup(torch.autograd.Function):
+    """Whole MLPLayers chains (layers.py:30-85) -- up to four over the same batch rows -- as ONE forward launch and ONE
+    backward launch of the tcgen05 chain kernels (fr_mlp_chain_forward / fr_mlp_chain_backward)."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        from ._lib import Chain
+        lib = load()
+        mods, n_x, training = spec["mods"], spec["n_x"], spec["training"]
+        xs = [t.contiguous() for t in tensors[:n_x]]
+        M = xs[0].shape[0]
+        dev = xs[0].device
+        need_grad = spec["grad"]        # (ctx.needs_input_grad ignores torch.no_grad())
+        chains = (Chain * len(mods))()
+        keep, ys, metas = [], [], []
+        for c, mod in enumerate(mods):
+            seeds = [next_seed() for _ in range(spec["n_layers"][c])]
+            arr, pairs = _chain_layers(mod, training, seeds)
+            C = chains[c]
+            C.n_layers = len(pairs)
+            for i in range(len(pairs)):
+                C.layer[i] = arr[i]
+            x = xs[c if n_x > 1 else 0]
+            y = torch.empty((M, pairs[-1][0].out_features), dtype=torch.float32, device=dev)
+            nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1 if training else 0, 1 if need_grad else 0, 0)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            C.X, C.ldx, C.Y = x.data_ptr(), x.shape[1], y.data_ptr()
+            C.fwd_ws, C.fwd_ws_bytes = ws.data_ptr(), nb
+            keep.append(ws)
+            ys.append(y)
+            metas.append((seeds, pairs))
+        sd = seed_dev(dev)
+        check(lib.fr_mlp_chain_forward(chains, len(mods), M, 1 if training else 0, 1 if need_grad else 0, ptr(sd),
+                                       ptr(chain_bars(dev)), stream_ptr()), "fr_mlp_chain_forward")
+        if need_grad:
+            if not training:
+                raise NotImplementedError("MLPChainGroup backward is implemented for training mode")
+            ctx.spec, ctx.metas, ctx.ws, ctx.xs_meta = spec, metas, keep, [(x.data_ptr(), x.shape[1]) for x in xs]
+            ctx.save_for_backward(*xs, *ys)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        from ._lib import Chain
+        lib = load()
+        _bind_thread()
+        spec = ctx.spec
+        mods, n_x = spec["mods"], spec["n_x"]
+        saved = ctx.saved_tensors
+        xs, ys = saved[:n_x], saved[n_x:]
+        M, dev = xs[0].shape[0], xs[0].device
+        chains = (Chain * len(mods))()
+        keep, grads_p, dxs = [], [], []
+        shared = n_x == 1 and len(mods) > 1
+        want_dx = [ctx.needs_input_grad[1 + (c if n_x > 1 else 0)] for c in range(len(mods))]
+        for c, mod in enumerate(mods):
+            seeds, pairs = ctx.metas[c]
+            arr, _ = _chain_layers(mod, True, seeds)
+            C = chains[c]
+            C.n_layers = len(pairs)
+            x = xs[c if n_x > 1 else 0]
+            dy = dys[c]
+            dy = torch.zeros_like(ys[c]) if dy is None else dy.contiguous()
+            for i, (lin, bn) in enumerate(pairs):
+                dW = torch.empty_like(lin.weight)
+                arr[i].dW = dW.data_ptr()
+                grads_p.append(dW)
+                if lin.bias is not None:
+                    db = torch.empty_like(lin.bias)
+                    arr[i].db = db.data_ptr()
+                    grads_p.append(db)
+                if bn is not None:
+                    dg, dbt = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+                    arr[i].dgamma, arr[i].dbeta = dg.data_ptr(), dbt.data_ptr()
+                    grads_p += [dg, dbt]
+                C.layer[i] = arr[i]
+            nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1, 1, 1)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            dx = torch.empty_like(x[:, :pairs[0][0].in_features].contiguous()) if want_dx[c] else None
+            C.X, C.ldx, C.Y, C.dY = x.data_ptr(), x.shape[1], ys[c].data_ptr(), dy.data_ptr()
+            C.dX = dx.data_ptr() if dx is not None else None
+            C.fwd_ws, C.fwd_ws_bytes = ctx.ws[c].data_ptr(), ctx.ws[c].numel()
+            C.bwd_ws, C.bwd_ws_bytes = ws.data_ptr(), nb
+            keep += [ws, dy]
+            dxs.append(dx)
+        dx_sum = None
+        if shared and want_dx[0]:
+            dx_sum = torch.empty_like(dxs[0])
+        check(lib.fr_mlp_chain_backward(chains, len(mods), M, ptr(seed_dev(dev)), ptr(dx_sum), ptr(chain_bars(dev)),
+                                        stream_ptr()), "fr_mlp_chain_backward")
+        gx = [dx_sum] if shared else (dxs if n_x > 1 else [dxs[0]])
+        return (None, *gx, *grads_p)
+
+
+def mlp_chain(mods, xs):
+    """Run MLPLayers modules `mods` over inputs `xs` (one shared input, or one per module; all [M, K]) with the fused chain
+    kernels.  Returns the list of outputs, or None when the configuration is outside the kernels' rules (the caller then
+    uses the per-layer path)."""
+    if not chain_enabled() or not xs[0].is_cuda or len(mods) > 4 or len(xs) not in (1, len(mods)):
+        return None
+    M = xs[0].shape[0]
+    training = mods[0].training
+    grad = torch.is_grad_enabled() and (any(x.requires_grad for x in xs) or
+                                        any(p.requires_grad for m in mods for p in m.parameters()))
+    if any(m.training != training for m in mods) or any(x.dim() != 2 or x.shape[0] != M for x in xs):
+        return None
+    if grad and (not training or M > CHAIN_MAX_TRAIN_ROWS):
+        return None
+    if training and M > CHAIN_MAX_TRAIN_ROWS:
+        return None
+    lib = load()
+    n_layers, total = [], 0
+    for c, m in enumerate(mods):
+        arr, pairs = _chain_layers(m, training)
+        if arr is None or not lib.fr_mlp_chain_eligible(arr, len(pairs), M):
+            return None
+        if pairs[0][0].in_features != xs[c if len(xs) > 1 else 0].shape[1]:
+            return None
+        n_layers.append(len(pairs))
+        total += len(pairs)
+    if total > 24:
+        return None
+    params = [p for m, nl in zip(mods, n_layers) for p in _chain_params(_chain_layers(m, training)[1])]
+    if not training and M > CHAIN_EVAL_CHUNK:
+        outs = [[] for _ in mods]
+        for a in range(0, M, CHAIN_EVAL_CHUNK):
+            part = mlp_chain(mods, [x[a:a + CHAIN_EVAL_CHUNK] for x in xs])
+            for o, p_ in zip(outs, part):
+                o.append(p_)
+        return [torch.cat(o) for o in outs]
+    spec = {"mods": list(mods), "n_x": len(xs), "training": training, "n_layers": n_layers, "grad": bool(grad)}
+    return list(MLPChainGroup.apply(spec, *xs, *params))
+
+
 class GatherRows(torch.autograd.Function):
     """nn.Embedding forward / dense backward"""
 

@@ -95,6 +95,7 @@ def test_pfcn_matches_reference(path):
     trainer = pkg.PFCNTrainer(cfg, model)
     model.train()
     losses = []
+    _, grads64, _, final64 = po.replay(g, dtype=torch.float64)     # the same schedule in float64: the conditioning yardstick
     for s in range(2 * int(g["n_rounds"])):
         u = g[f"user_id{s}"]
         inter = pkg.Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(g[f"item_id{s}"]),
@@ -117,7 +118,12 @@ def test_pfcn_matches_reference(path):
                     elif np.abs(g[k]).max() == 0:          # user_bias / global_bias of PFCN_BiasedMF cancel exactly
                         assert np.abs(mine).max() == 0, k
                     else:
-                        assert rel_err(mine, g[k]) < RTOL, k
+                        # 1e-5 relative to the reference's gradient; where the reference's own float32 gradient sits further
+                        # than that from the float64 evaluation of the same step (the BPR tower's batch sums cancel), the
+                        # bound is "as close to float64 as the reference, x3" -- the rule of the final-state check below
+                        ref64 = grads64[k[5:-2]]
+                        tol = max(RTOL, 3.0 * rel_err(g[k], ref64))
+                        assert rel_err(mine, g[k]) < RTOL or rel_err(mine, ref64) < tol, (k, tol)
                     n += 1
             assert n >= 10
             with torch.no_grad():     # the fixture's extra train-mode forward (moves the running statistics as well)
@@ -126,7 +132,6 @@ def test_pfcn_matches_reference(path):
         losses.append(loss.item())
     np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
     final = dump_state(model)
-    final64 = po.replay(g, dtype=torch.float64)[3]      # the same schedule evaluated in float64: the conditioning yardstick
     n = 0
     for k in g.files:
         if k.endswith("@final"):

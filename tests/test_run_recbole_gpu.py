@@ -149,8 +149,11 @@ def test_mlp_family_end_to_end_from_raw_files_matches_the_reference_run(model, t
         np.testing.assert_allclose(seen[0], g["epoch_losses"][0], rtol=1e-4)
         np.testing.assert_allclose(seen[1], g["epoch_losses"][1], rtol=5e-3)
     else:
-        np.testing.assert_allclose(seen[:, 0], g["epoch_losses"][:, 0], rtol=2e-2)
-        np.testing.assert_allclose(seen[:, 1], g["epoch_losses"][:, 1], rtol=2e-1)
+        # the bounds of the CPU shadow run (tests/test_e2e_shadow.py: two torch-CPU evaluations of this schedule are that
+        # far apart): first epoch 2e-2 on the filter pass, 1e-1 on the discriminator pass; second epoch same ballpark only
+        np.testing.assert_allclose(seen[0, 0], g["epoch_losses"][0, 0], rtol=2e-2)
+        np.testing.assert_allclose(seen[0, 1], g["epoch_losses"][0, 1], rtol=1e-1)
+        np.testing.assert_allclose(seen[1], g["epoch_losses"][1], rtol=2e-1)
     names = [str(k) for k in g["metric_names"]]
     for got, ref in zip(valids[:2] + [out["test_result"]], list(g["valid_metrics"]) + [g["test_metrics"]]):
         for k, r in zip(names, ref):
