@@ -35,13 +35,15 @@ constexpr int CH_MAX_LAYERS = FR_CHAIN_MAX_LAYERS;   // per chain
 constexpr int CH_MAX_CHAINS = FR_CHAIN_MAX_CHAINS;
 constexpr int CH_MAX_TOTAL = 24;                      // layers of all chains of one launch (kernel-parameter budget)
 constexpr int CH_MAXW = 256;                          // widest layer
-constexpr int CH_THREADS = 192;
+constexpr int CH_EPI_WARPS = 16;                      // 4 lane quarters x 4 column groups of 8
+constexpr int CH_EPI = CH_EPI_WARPS * 32;
+constexpr int CH_THREADS = 64 + CH_EPI;
 constexpr int CH_STAGES = 4;
 constexpr int CH_A_PLANE = TCM * TCKB * 4;            // 16 KB: 128 rows x one 128-byte swizzle row
-constexpr int CH_NT = 64;                             // widest B tile (rows of the B operand per item)
-constexpr int CH_B_PLANE = CH_NT * TCKB * 4;          // 8 KB
+constexpr int CH_NT = 32;                             // widest B tile (rows of the B operand per item)
+constexpr int CH_B_PLANE = CH_NT * TCKB * 4;          // 4 KB
 constexpr int CH_STAGE = 2 * CH_A_PLANE + 2 * CH_B_PLANE;
-constexpr int CH_TMEM_COLS = 64;
+constexpr int CH_TMEM_COLS = 32;
 constexpr int CH_WCHUNK = 256;                        // batch rows per weight-gradient partial
 constexpr int CH_EW = 1024;                           // elements per flat element-wise item
 
@@ -77,13 +79,19 @@ struct ChChain {
   float *dX;      // per-chain input gradient [M][K0] (NULL: not wanted)
 };
 
-struct ChParams {
+// everything but the tensor maps: copied into shared memory at kernel start (indexed reads of a 19 KB kernel-parameter block
+// thrash the constant cache: every field access in the row-wise loops became a ~200-cycle miss)
+struct ChHead {
   int n_chains, Lmax, M, Mpad, RB, training, need_grad, n_total;
   const unsigned long long *seed_dev;
   unsigned *bar;
   float *dX_sum;  // optional: fixed-order sum of the chains' dX
+  unsigned long long *trace;   // optional (FR_CHAIN_TRACE=1): %globaltimer stamps of CTA 0 at the phase boundaries
   ChChain chain[CH_MAX_CHAINS];
   ChLayer layer[CH_MAX_TOTAL];
+};
+struct ChParams {
+  ChHead h;
   CUtensorMap map[CH_MAX_TOTAL][4];   // forward: [0] Xin [1] Wp ; backward: [0] DZ [1] Wt [2] DZT [3] XinT
 };
 
@@ -95,7 +103,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI) : "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // grid barrier: arrival counter bar[0] (reset by the last CTA to leave the kernel, see chain_exit)
@@ -121,6 +129,40 @@ __device__ __forceinline__ void chain_exit(unsigned *bar) {
       bar[1] = 0;
       __threadfence();
     }
+  }
+}
+
+__device__ __forceinline__ void trace_stamp(const ChHead &P, int &slot) {
+  if (P.trace && blockIdx.x == 0 && threadIdx.x == 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[slot] = t;
+  }
+  ++slot;
+}
+
+// none / relu / leakyrelu as one branch-free expression (slope 1 / 0 / 0.01); sigmoid and tanh take the generic switch on a
+// warp-uniform branch OUTSIDE the per-element loops (a per-element switch on a run-time code cost ~250 ns per call here)
+__device__ __forceinline__ float act_slope(int act) { return act == ACT_NONE ? 1.f : (act == ACT_RELU ? 0.f : 0.01f); }
+__device__ __forceinline__ void act8_fwd(float (&y)[8], int act) {
+  if (act <= ACT_LEAKY) {
+    const float sl = act_slope(act);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : sl * y[j];
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) y[j] = act_fwd(y[j], act);
+  }
+}
+// g[j] *= act'(y[j]) with y the activation OUTPUT
+__device__ __forceinline__ void act8_bwd(float (&g)[8], const float (&y)[8], int act) {
+  if (act <= ACT_LEAKY) {
+    const float sl = act_slope(act);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= y[j] > 0.f ? 1.f : sl;
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) g[j] *= act_bwd(y[j], act);
   }
 }
 
@@ -179,92 +221,117 @@ __device__ __forceinline__ void gemm_mma(const GemmIt &g, const Pipe &p, uint32_
 
 // epilogue-side shared scratch
 struct Epi {
-  float (*scr)[33];      // [128][33]
+  float (*scr)[33];      // [128][33]  column-sum staging (first quantity)
+  float (*scr2)[33];     // [128][33]  (second quantity)
   double (*dscr)[4][32]; // [2][4][32]
-  float *colv;           // [5][CH_MAXW]
-  int er, et;            // tile row of this thread (TMEM lane), linear epilogue thread id
+  float *colv;           // [5][32]    per-column coefficients of the current BatchNorm item
+  int er, et, c8;        // tile row of this thread (TMEM lane), linear epilogue thread id, first of its 8 columns in a chunk
   unsigned long long seedoff;
 };
 
-// column sums over the tile rows of a[.] (and of a[.]^2 when kSq) for 32 columns; results land in threads et < 32
-template <bool kSq>
-__device__ __forceinline__ void colsum32(const Epi &e, const float (&a)[32], double &s_out, double &ss_out) {
-#pragma unroll
-  for (int c = 0; c < 32; ++c) e.scr[e.er][c] = a[c];
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// The row-wise bodies below handle EIGHT columns per iteration of a rolled loop (#pragma unroll 1): the epilogue code of
+// one item runs once, so its size -- not its instruction count -- is what the instruction cache sees; fully unrolled
+// 32-column bodies with inlined activations made these kernels 19k instructions long and instruction-fetch bound.
+
+// column sums over the 128 tile rows of what the row threads staged in scr (and scr2 when kTwo); with kSq the second sum
+// is the sum of squares of scr.  Results land in threads et < 32 (column et).
+template <bool kTwo, bool kSq>
+__device__ __forceinline__ void colsum_reduce(const Epi &e, double &s_out, double &ss_out) {
   bar_epi();
-  const int q = e.et >> 5, c = e.et & 31;
-  double s = 0.0, ss = 0.0;
+  const int q = (e.et >> 5) & 3, c = e.et & 31;
+  if (e.et < 128) {
+    double s = 0.0, ss = 0.0;
 #pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    const double v = (double)e.scr[q * 32 + r][c];
-    s += v;
-    if (kSq) ss += v * v;
+    for (int r = 0; r < 32; ++r) {
+      const double v = (double)e.scr[q * 32 + r][c];
+      s += v;
+      if (kSq) ss += v * v;
+      if (kTwo) ss += (double)e.scr2[q * 32 + r][c];
+    }
+    e.dscr[0][q][c] = s;
+    e.dscr[1][q][c] = ss;
   }
-  e.dscr[0][q][c] = s;
-  if (kSq) e.dscr[1][q][c] = ss;
   bar_epi();
   if (e.et < 32) {
     s_out = ((e.dscr[0][0][c] + e.dscr[0][1][c]) + e.dscr[0][2][c]) + e.dscr[0][3][c];
-    if (kSq) ss_out = ((e.dscr[1][0][c] + e.dscr[1][1][c]) + e.dscr[1][2][c]) + e.dscr[1][3][c];
+    ss_out = ((e.dscr[1][0][c] + e.dscr[1][1][c]) + e.dscr[1][2][c]) + e.dscr[1][3][c];
   }
   bar_epi();
 }
 
-// y[32] = outputs of layer `li` for row m, columns n0..n0+31 (already activated): hand them to the consumer
-__device__ __forceinline__ void emit_fwd(const ChParams &P, const Epi &e, int li, int m, bool mvalid, int n0,
-                                         const float (&y)[32]) {
-  const ChLayer &L = P.layer[li];
-  if (L.last_of_chain) {
-    if (!mvalid) return;
-    float *dst = P.chain[L.chain].Y + (size_t)m * L.N;
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (n0 + c < L.N) dst[n0 + c] = y[c];
-    return;
-  }
-  const ChLayer &T = P.layer[li + 1];
+// y[8] = input of layer T (before its dropout) for row m, columns n..n+7: dropout, TF32 hi/lo split, row-major planes
+// (A operand of T's forward GEMM) and, when a backward pass follows, transposed planes (B operand of T's weight gradient)
+__device__ __forceinline__ void emit8_into(const ChHead &P, const Epi &e, const ChLayer &T, int m, bool mvalid, int n,
+                                           const float (&y)[8]) {
   const int K = T.K;
+  if (n >= K) return;
   const float p = P.training ? T.drop_p : 0.f;
   const unsigned long long seed = T.seed + e.seedoff;
-  float hi[32], lo[32];
+  float hi[8], lo[8];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const int n = n0 + c;
-    float x = (n < K && mvalid) ? y[c] : 0.f;
-    if (p > 0.f && n < K) x *= drop_scale(seed, 0, (uint32_t)(m * K + n), p);
-    split_tf32(x, hi[c], lo[c]);
+  for (int j = 0; j < 8; ++j) {
+    float x = (n + j < K && mvalid) ? y[j] : 0.f;
+    if (p > 0.f && n + j < K) x *= drop_scale(seed, 0, (uint32_t)(m * K + n + j), p);
+    split_tf32(x, hi[j], lo[j]);
   }
   if (mvalid) {
-    float *r_hi = T.Xin + (size_t)m * K + n0, *r_lo = r_hi + (size_t)P.M * K;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4)
-      if (n0 + c < K) {
-        *(float4 *)(r_hi + c) = make_float4(hi[c], hi[c + 1], hi[c + 2], hi[c + 3]);
-        *(float4 *)(r_lo + c) = make_float4(lo[c], lo[c + 1], lo[c + 2], lo[c + 3]);
-      }
+    float *r_hi = T.Xin + (size_t)m * K + n, *r_lo = r_hi + (size_t)P.M * K;
+    *(float4 *)r_hi = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *(float4 *)r_lo = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    if (n + 4 < K) {
+      *(float4 *)(r_hi + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+      *(float4 *)(r_lo + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    }
   }
   if (P.need_grad) {
-    float *t_hi = T.XinT + (size_t)n0 * P.Mpad + m, *t_lo = t_hi + (size_t)K * P.Mpad;
+    float *t_hi = T.XinT + (size_t)n * P.Mpad + m, *t_lo = t_hi + (size_t)K * P.Mpad;
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (n0 + c < K) {
-        t_hi[(size_t)c * P.Mpad] = hi[c];
-        t_lo[(size_t)c * P.Mpad] = lo[c];
+    for (int j = 0; j < 8; ++j)
+      if (n + j < K) {
+        t_hi[(size_t)j * P.Mpad] = hi[j];
+        t_lo[(size_t)j * P.Mpad] = lo[j];
       }
   }
+}
+
+// y[8] = outputs of layer `li` for row m, columns n..n+7 (already activated): hand them to the consumer
+__device__ __forceinline__ void emit8_fwd(const ChHead &P, const Epi &e, int li, int m, bool mvalid, int n,
+                                          const float (&y)[8]) {
+  const ChLayer &L = P.layer[li];
+  if (L.last_of_chain) {
+    if (!mvalid || n >= L.N) return;
+    float *dst = P.chain[L.chain].Y + (size_t)m * L.N + n;
+    if ((L.N & 3) == 0) {
+      *(float4 *)dst = make_float4(y[0], y[1], y[2], y[3]);
+      if (n + 4 < L.N) *(float4 *)(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < L.N) dst[j] = y[j];
+    }
+    return;
+  }
+  emit8_into(P, e, P.layer[li + 1], m, mvalid, n, y);
 }
 
 // ---------------------------------------------------------------------------------------------- item enumeration
 __host__ __device__ inline int ch_tiles(int n, int t) { return (n + t - 1) / t; }
 
 // forward GEMM items of layer position l: per chain RB x ceil(N / NT)
-__host__ __device__ inline int fwd_gemm_items(const ChParams &P, int l) {
+__host__ __device__ inline int fwd_gemm_items(const ChHead &P, int l) {
   int n = 0;
   for (int c = 0; c < P.n_chains; ++c)
     if (l < P.chain[c].L) n += P.RB * ch_tiles(P.layer[P.chain[c].first + l].N, P.layer[P.chain[c].first + l].NT);
   return n;
 }
-__device__ inline bool fwd_gemm_decode(const ChParams &P, int l, int item, int &li, int &rb, int &nt) {
+__device__ inline bool fwd_gemm_decode(const ChHead &P, int l, int item, int &li, int &rb, int &nt) {
   for (int c = 0; c < P.n_chains; ++c) {
     if (l >= P.chain[c].L) continue;
     const int i = P.chain[c].first + l;
@@ -279,38 +346,62 @@ __device__ inline bool fwd_gemm_decode(const ChParams &P, int l, int item, int &
   }
   return false;
 }
-__host__ __device__ inline bool fwd_bn_phase(const ChParams &P, int l) {
+__host__ __device__ inline bool fwd_bn_phase(const ChHead &P, int l) {
   if (!P.training) return false;
   for (int c = 0; c < P.n_chains; ++c)
     if (l < P.chain[c].L && P.layer[P.chain[c].first + l].has_bn) return true;
   return false;
 }
-// BatchNorm items (forward: position l from the start; backward: step s from the end): one per (chain with BN there, row block)
-__device__ inline bool bn_decode(const ChParams &P, int pos, bool from_end, int item, int &li, int &rb) {
+// BatchNorm items (forward: position l from the start; backward: step s from the end): one per (chain with BN there, row
+// block, 32-column chunk)
+__device__ inline bool bn_decode(const ChHead &P, int pos, bool from_end, int item, int &li, int &rb, int &cc) {
   for (int c = 0; c < P.n_chains; ++c) {
     const int l = from_end ? P.chain[c].L - 1 - pos : pos;
     if (l < 0 || l >= P.chain[c].L) continue;
     const int i = P.chain[c].first + l;
     if (!P.layer[i].has_bn) continue;
-    if (item < P.RB) {
+    const int n = P.RB * ch_tiles(P.layer[i].N, 32);
+    if (item < n) {
       li = i;
-      rb = item;
+      rb = item % P.RB;
+      cc = item / P.RB;
       return true;
     }
-    item -= P.RB;
+    item -= n;
   }
   return false;
 }
-__host__ __device__ inline int bn_items(const ChParams &P, int pos, bool from_end) {
+__host__ __device__ inline int bn_items(const ChHead &P, int pos, bool from_end) {
   int n = 0;
   for (int c = 0; c < P.n_chains; ++c) {
     const int l = from_end ? P.chain[c].L - 1 - pos : pos;
-    if (l >= 0 && l < P.chain[c].L && P.layer[P.chain[c].first + l].has_bn) n += P.RB;
+    if (l >= 0 && l < P.chain[c].L && P.layer[P.chain[c].first + l].has_bn)
+      n += P.RB * ch_tiles(P.layer[P.chain[c].first + l].N, 32);
   }
   return n;
 }
+// import items (forward: X into the first layer; backward: dY through the last layer): (chain, row block, 32-column chunk)
+__host__ __device__ inline int import_width(const ChHead &P, int c, bool bwd) { return bwd ? P.chain[c].Nlast : P.chain[c].K0; }
+__host__ __device__ inline int import_items(const ChHead &P, bool bwd) {
+  int n = 0;
+  for (int c = 0; c < P.n_chains; ++c) n += P.RB * ch_tiles(import_width(P, c, bwd), 32);
+  return n;
+}
+__device__ inline bool import_decode(const ChHead &P, bool bwd, int item, int &c_out, int &rb, int &cc) {
+  for (int c = 0; c < P.n_chains; ++c) {
+    const int n = P.RB * ch_tiles(import_width(P, c, bwd), 32);
+    if (item < n) {
+      c_out = c;
+      rb = item % P.RB;
+      cc = item / P.RB;
+      return true;
+    }
+    item -= n;
+  }
+  return false;
+}
 // flat element-wise items over the layers: blocks of CH_EW elements of an N*K sized array per layer
-__host__ __device__ inline int flat_items(const ChParams &P, bool only_dgrad_layers) {
+__host__ __device__ inline int flat_items(const ChHead &P, bool only_dgrad_layers) {
   int n = 0;
   for (int i = 0; i < P.n_total; ++i) {
     if (only_dgrad_layers && P.layer[i].first_of_chain && !P.chain[P.layer[i].chain].dX) continue;
@@ -318,7 +409,7 @@ __host__ __device__ inline int flat_items(const ChParams &P, bool only_dgrad_lay
   }
   return n;
 }
-__device__ inline bool flat_decode(const ChParams &P, bool only_dgrad_layers, int item, int &li, int &blk) {
+__device__ inline bool flat_decode(const ChHead &P, bool only_dgrad_layers, int item, int &li, int &blk) {
   for (int i = 0; i < P.n_total; ++i) {
     if (only_dgrad_layers && P.layer[i].first_of_chain && !P.chain[P.layer[i].chain].dX) continue;
     const int n = ch_tiles(P.layer[i].N * P.layer[i].K, CH_EW);
@@ -331,11 +422,11 @@ __device__ inline bool flat_decode(const ChParams &P, bool only_dgrad_layers, in
   }
   return false;
 }
-__host__ __device__ inline bool needs_dgrad(const ChParams &P, int li) {
+__host__ __device__ inline bool needs_dgrad(const ChHead &P, int li) {
   return !P.layer[li].first_of_chain || P.chain[P.layer[li].chain].dX != nullptr;
 }
 // backward GEMM items at step s (layer L-1-s of each chain): weight-gradient tiles, then data-gradient tiles
-__host__ __device__ inline int bwd_gemm_items(const ChParams &P, int s) {
+__host__ __device__ inline int bwd_gemm_items(const ChHead &P, int s) {
   const int chunks = ch_tiles(P.M, CH_WCHUNK);
   int n = 0;
   for (int c = 0; c < P.n_chains; ++c) {
@@ -351,7 +442,7 @@ struct BwdIt {
   int li, kind;      // kind 0: weight gradient (nt128, kt, chunk) ; 1: data gradient (rb, kt)
   int a, b, c;
 };
-__device__ inline bool bwd_gemm_decode(const ChParams &P, int s, int item, BwdIt &o) {
+__device__ inline bool bwd_gemm_decode(const ChHead &P, int s, int item, BwdIt &o) {
   const int chunks = ch_tiles(P.M, CH_WCHUNK);
   for (int c = 0; c < P.n_chains; ++c) {
     const int l = P.chain[c].L - 1 - s;
@@ -384,141 +475,198 @@ __device__ inline bool bwd_gemm_decode(const ChParams &P, int s, int item, BwdIt
   return false;
 }
 
-// ---------------------------------------------------------------------------------------------- BatchNorm helpers
-// batch statistics of layer L from the per-row-block partial sums (tile order, float64) -> colv: [0] mean [1] gamma*invstd
-// [2] beta [3] invstd; the rb == 0 item also keeps them for the backward pass and advances the running statistics
-__device__ __forceinline__ void bn_fwd_finalize(const ChParams &P, const ChLayer &L, const Epi &e, bool owner) {
-  for (int n = e.et; n < L.N; n += 128) {
-    double s = 0.0, ss = 0.0;
-    for (int rb = 0; rb < P.RB; ++rb) {
-      s += __ldcg(L.stat + ((size_t)rb * L.N + n) * 2);
-      ss += __ldcg(L.stat + ((size_t)rb * L.N + n) * 2 + 1);
+// (s, ss) += the `count` double pairs at p, p + stride, ... in index order, eight loads in flight (the adds stay ordered)
+__device__ __forceinline__ void ordered_sum2(const double *p, size_t stride, int count, double &s, double &ss) {
+  int r = 0;
+  for (; r + 16 <= count; r += 16) {
+    double2 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldcg((const double2 *)(p + (size_t)(r + u) * stride));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      s += v[u].x;
+      ss += v[u].y;
     }
+  }
+  if (r < count) {          // tail: up to 15 loads in flight, padded with zeros (adding 0.0 does not change the ordered sum)
+    double2 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      v[u] = (r + u < count) ? __ldcg((const double2 *)(p + (size_t)(r + u) * stride)) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      s += v[u].x;
+      ss += v[u].y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BatchNorm helpers
+// batch statistics of columns [n0, n0+32) of layer L from the per-row-block partial sums (tile order, float64) -> colv:
+// [0] mean [1] gamma*invstd [2] beta [3] invstd, indexed by column - n0; the rb == 0 item also keeps them for the backward
+// pass and advances the running statistics
+__device__ __forceinline__ void bn_fwd_finalize(const ChHead &P, const ChLayer &L, const Epi &e, int n0, bool owner) {
+  const int n = n0 + e.et;
+  if (e.et < 32 && n < L.N) {
+    const float gam = __ldg(L.gamma + n), bet = __ldg(L.beta + n);       // in flight under the partial sums
+    const float rm0 = owner ? L.rmean[n] : 0.f, rv0 = owner ? L.rvar[n] : 0.f;
+    double s = 0.0, ss = 0.0;
+    ordered_sum2(L.stat + (size_t)n * 2, (size_t)L.N * 2, P.RB, s, ss);
     const double mean = s / (double)P.M;
     double var = ss / (double)P.M - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)L.bn_eps));
-    e.colv[n] = (float)mean;
-    e.colv[CH_MAXW + n] = __ldg(L.gamma + n) * invstd;
-    e.colv[2 * CH_MAXW + n] = __ldg(L.beta + n);
-    e.colv[3 * CH_MAXW + n] = invstd;
+    e.colv[e.et] = (float)mean;
+    e.colv[32 + e.et] = gam * invstd;
+    e.colv[64 + e.et] = bet;
+    e.colv[96 + e.et] = invstd;
     if (owner) {
       L.save_mean[n] = (float)mean;
       L.save_invstd[n] = invstd;
       const double unb = P.M > 1 ? var * (double)P.M / (double)(P.M - 1) : var;
-      L.rmean[n] = (1.f - L.bn_mom) * L.rmean[n] + L.bn_mom * (float)mean;
-      L.rvar[n] = (1.f - L.bn_mom) * L.rvar[n] + L.bn_mom * (float)unb;
+      L.rmean[n] = (1.f - L.bn_mom) * rm0 + L.bn_mom * (float)mean;
+      L.rvar[n] = (1.f - L.bn_mom) * rv0 + L.bn_mom * (float)unb;
+      if (n == 0 && L.nbt) *L.nbt += 1;
     }
   }
-  if (owner && e.et == 0 && L.nbt) *L.nbt += 1;
   bar_epi();
 }
 
-// ============================================================================================== forward kernel
-static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __grid_constant__ ChParams P) {
-  extern __shared__ __align__(1024) unsigned char ch_smem[];
-  unsigned char *base = (unsigned char *)(((uintptr_t)ch_smem + 1023) & ~(uintptr_t)1023);
+struct Ctx {     // per-thread kernel state shared by the two kernels
   Pipe pipe;
-  pipe.stages = base;
   Epi e;
-  e.scr = (float(*)[33])(base + CH_STAGES * CH_STAGE);
-  e.dscr = (double(*)[4][32])((unsigned char *)e.scr + 128 * 33 * 4);
-  e.colv = (float *)((unsigned char *)e.dscr + 2 * 4 * 32 * 8);
-  uint64_t *bars = (uint64_t *)(e.colv + 5 * CH_MAXW);
-  pipe.full = bars;
-  pipe.empty = bars + CH_STAGES;
-  pipe.tfull = bars + 2 * CH_STAGES;
-  pipe.tempty = pipe.tfull + 1;
-  uint32_t *tmem_slot = (uint32_t *)(pipe.tempty + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int warp, lane;
+  uint32_t taddr;
+  uint32_t *tmem_slot;
+  const ChHead *head;    // shared-memory copy
+};
+
+__device__ __forceinline__ void chain_setup(Ctx &c, unsigned char *smem, const ChHead &P) {
+  unsigned char *base = (unsigned char *)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  c.pipe.stages = base;
+  c.e.scr = (float(*)[33])(base + CH_STAGES * CH_STAGE);
+  c.e.scr2 = (float(*)[33])((unsigned char *)c.e.scr + 128 * 33 * 4);
+  c.e.dscr = (double(*)[4][32])((unsigned char *)c.e.scr2 + 128 * 33 * 4);
+  c.e.colv = (float *)((unsigned char *)c.e.dscr + 2 * 4 * 32 * 8);
+  uint64_t *bars = (uint64_t *)(c.e.colv + 5 * 32);
+  c.pipe.full = bars;
+  c.pipe.empty = bars + CH_STAGES;
+  c.pipe.tfull = bars + 2 * CH_STAGES;
+  c.pipe.tempty = c.pipe.tfull + 1;
+  c.tmem_slot = (uint32_t *)(c.pipe.tempty + 1);
+  {
+    uint32_t *dst = (uint32_t *)(((uintptr_t)(c.tmem_slot + 4) + 15) & ~(uintptr_t)15);
+    const uint32_t *src = (const uint32_t *)&P;
+    for (int i = threadIdx.x; i < (int)(sizeof(ChHead) / 4); i += CH_THREADS) dst[i] = src[i];
+    c.head = (const ChHead *)dst;
+  }
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < CH_STAGES; ++s) {
-      mbar_init(&pipe.full[s], 1);
-      mbar_init(&pipe.empty[s], 1);
+      mbar_init(&c.pipe.full[s], 1);
+      mbar_init(&c.pipe.empty[s], 1);
     }
-    mbar_init(pipe.tfull, 1);
-    mbar_init(pipe.tempty, 128);
+    mbar_init(c.pipe.tfull, 1);
+    mbar_init(c.pipe.tempty, CH_EPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+  if (c.warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(c.tmem_slot)),
                  "r"(CH_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pipe.tmem = *tmem_slot;
-  const int quarter = warp & 3;
-  e.er = quarter * 32 + lane;
-  e.et = (int)threadIdx.x - 64;
-  e.seedoff = P.seed_dev ? *P.seed_dev : 0ull;
-  const uint32_t taddr = pipe.tmem + ((uint32_t)(quarter * 32) << 16);
+  c.pipe.tmem = *c.tmem_slot;
+  const int quarter = c.warp & 3;
+  c.e.er = quarter * 32 + c.lane;
+  c.e.et = (int)threadIdx.x - 64;
+  c.e.c8 = ((c.warp - 2) >> 2) * 8;
+  c.e.seedoff = P.seed_dev ? *P.seed_dev : 0ull;
+  c.taddr = c.pipe.tmem + ((uint32_t)(quarter * 32) << 16);
+}
+
+__device__ __forceinline__ void chain_teardown(Ctx &c, const ChHead &P) {
+  tc_fence_before();
+  __syncthreads();
+  if (c.warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.pipe.tmem), "r"(CH_TMEM_COLS));
+  }
+  chain_exit(P.bar);
+}
+
+// TF32 planes of the weights: forward layout [2][N][K] (kT == false) or transposed [2][K][ldn] (kT == true)
+template <bool kT>
+__device__ __forceinline__ void weight_planes_item(const ChLayer &L, int blk, int et) {
+  const int n = L.N * L.K;
+#pragma unroll 1
+  for (int j = 0; j < CH_EW / CH_EPI; ++j) {
+    const int idx = blk * CH_EW + j * CH_EPI + et;
+    if (idx >= n) break;
+    float h, l;
+    if (!kT) {
+      split_tf32(__ldg(L.W + idx), h, l);
+      L.Wp[idx] = h;
+      L.Wp[n + idx] = l;
+    } else {
+      const int k = idx / L.N, nn = idx % L.N;      // idx = k * N + n: coalesced writes
+      split_tf32(__ldg(L.W + (size_t)nn * L.K + k), h, l);
+      L.Wt[(size_t)k * L.ldn + nn] = h;
+      L.Wt[(size_t)L.K * L.ldn + (size_t)k * L.ldn + nn] = l;
+    }
+  }
+}
+
+// ============================================================================================== forward kernel
+static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __grid_constant__ ChParams PP) {
+  extern __shared__ __align__(1024) unsigned char ch_smem[];
+  Ctx cx;
+  chain_setup(cx, ch_smem, PP.h);
+  const ChHead &P = *cx.head;
+  const Pipe &pipe = cx.pipe;
+  const Epi &e = cx.e;
+  const int warp = cx.warp, lane = cx.lane;
   uint32_t it = 0, gi = 0;
   unsigned target = 0;
+  int tslot = 0;
+  trace_stamp(P, tslot);
 
   // ------------------------------------------------------------------ phase 0: weight planes, import of X
   if (warp >= 2) {
-    const int n_flat = flat_items(P, false), n_imp = P.n_chains * P.RB;
+    const int n_flat = flat_items(P, false), n_imp = import_items(P, false);
     for (int item = blockIdx.x; item < n_flat + n_imp; item += gridDim.x) {
       if (item < n_flat) {
         int li, blk;
         flat_decode(P, false, item, li, blk);
-        const ChLayer &L = P.layer[li];
-        const int n = L.N * L.K;
-        for (int j = 0; j < CH_EW / 128; ++j) {
-          const int idx = blk * CH_EW + j * 128 + e.et;
-          if (idx < n) {
-            float h, l;
-            split_tf32(__ldg(L.W + idx), h, l);
-            L.Wp[idx] = h;
-            L.Wp[n + idx] = l;
-          }
-        }
+        weight_planes_item<false>(P.layer[li], blk, e.et);
       } else {
-        const int c = (item - n_flat) / P.RB, rb = (item - n_flat) % P.RB;
+        int c, rb, cc;
+        import_decode(P, false, item - n_flat, c, rb, cc);
         const ChChain &C = P.chain[c];
         const int m = rb * 128 + e.er;
         const bool mvalid = m < P.M;
-        for (int n0 = 0; n0 < C.K0; n0 += 32) {
-          float y[32];
+        const bool vec = (C.ldx & 3) == 0 && (((uintptr_t)C.X) & 15) == 0;
+        const int n = cc * 32 + e.c8;
+        if (n < C.K0) {
+          const float *src = C.X + (size_t)m * C.ldx + n;
+          float y[8];
+          if (mvalid && vec && n + 8 <= C.K0) {
+            const float4 a = __ldg((const float4 *)src), b = __ldg((const float4 *)(src + 4));
+            y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+          } else {
 #pragma unroll
-          for (int cc = 0; cc < 32; ++cc) y[cc] = (mvalid && n0 + cc < C.K0) ? __ldg(C.X + (size_t)m * C.ldx + n0 + cc) : 0.f;
-          // "layer -1": emit into the chain's first layer
-          const ChLayer &T = P.layer[C.first];
-          const float p = P.training ? T.drop_p : 0.f;
-          const unsigned long long seed = T.seed + e.seedoff;
-          float hi[32], lo[32];
-#pragma unroll
-          for (int cc = 0; cc < 32; ++cc) {
-            const int n = n0 + cc;
-            float x = y[cc];
-            if (p > 0.f && n < T.K && mvalid) x *= drop_scale(seed, 0, (uint32_t)(m * T.K + n), p);
-            split_tf32(x, hi[cc], lo[cc]);
+            for (int j = 0; j < 8; ++j) y[j] = (mvalid && n + j < C.K0) ? __ldg(src + j) : 0.f;
           }
-          if (mvalid) {
-            float *r_hi = T.Xin + (size_t)m * T.K + n0, *r_lo = r_hi + (size_t)P.M * T.K;
-#pragma unroll
-            for (int cc = 0; cc < 32; cc += 4)
-              if (n0 + cc < T.K) {
-                *(float4 *)(r_hi + cc) = make_float4(hi[cc], hi[cc + 1], hi[cc + 2], hi[cc + 3]);
-                *(float4 *)(r_lo + cc) = make_float4(lo[cc], lo[cc + 1], lo[cc + 2], lo[cc + 3]);
-              }
-          }
-          if (P.need_grad) {
-            float *t_hi = T.XinT + (size_t)n0 * P.Mpad + m, *t_lo = t_hi + (size_t)T.K * P.Mpad;
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc)
-              if (n0 + cc < T.K) {
-                t_hi[(size_t)cc * P.Mpad] = hi[cc];
-                t_lo[(size_t)cc * P.Mpad] = lo[cc];
-              }
-          }
+          emit8_into(P, e, P.layer[C.first], m, mvalid, n, y);
         }
       }
     }
   }
+  trace_stamp(P, tslot);
   chain_barrier(P.bar, target);
+  trace_stamp(P, tslot);
 
   for (int l = 0; l < P.Lmax; ++l) {
     // ---------------------------------------------------------------- GEMM items of layer position l
@@ -529,7 +677,7 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
       const ChLayer &L = P.layer[li];
       if (warp == 0) {
         if (lane == 0) {
-          GemmIt g{&P.map[li][0], &P.map[li][1], rb * 128, nt * L.NT, 0, ch_tiles(L.K, TCKB), L.NT};
+          GemmIt g{&PP.map[li][0], &PP.map[li][1], rb * 128, nt * L.NT, 0, ch_tiles(L.K, TCKB), L.NT};
           gemm_produce(g, pipe, it);
         }
       } else if (warp == 1) {
@@ -540,239 +688,219 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
       } else {
         mbar_wait(pipe.tfull, gi & 1);
         tc_fence_after();
+        trace_stamp(P, tslot);
         const int m = rb * 128 + e.er;
         const bool mvalid = m < P.M;
         const bool bn_batch = L.has_bn && P.training;
-        for (int w = 0; w < L.NT; w += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + w, v);
-          const int n0 = nt * L.NT + w;
-          float z[32];
+        const int n0 = nt * L.NT;
+        const int c8 = e.c8;
+        if (c8 < L.NT) {
+          uint32_t v[8];
+          tmem_ld8(cx.taddr + c8, v);
+          const int n = n0 + c8;
+          float z[8];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int n = n0 + c;
-            const bool ok = (w + c < L.NT) && n < L.N && mvalid;
-            z[c] = ok ? __uint_as_float(v[c]) + (L.b ? __ldg(L.b + n) : 0.f) : 0.f;
-          }
+          for (int j = 0; j < 8; ++j)
+            z[j] = (n + j < L.N && mvalid) ? __uint_as_float(v[j]) + (L.b ? __ldg(L.b + n + j) : 0.f) : 0.f;
           if (bn_batch) {
             if (mvalid) {
-              float *dst = L.Z + (size_t)m * L.ldn + n0;
+              float *dst = L.Z + (size_t)m * L.ldn + n;
+              if (n < L.ldn) *(float4 *)dst = make_float4(z[0], z[1], z[2], z[3]);
+              if (n + 4 < L.ldn) *(float4 *)(dst + 4) = make_float4(z[4], z[5], z[6], z[7]);
+            }
 #pragma unroll
-              for (int c = 0; c < 32; c += 4)
-                if (n0 + c < L.ldn && w + c < L.NT) *(float4 *)(dst + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
-            }
-            double s = 0.0, ss = 0.0;
-            colsum32<true>(e, z, s, ss);
-            if (e.et < 32 && w + e.et < L.NT && n0 + e.et < L.N) {
-              double *st = L.stat + ((size_t)rb * L.N + n0 + e.et) * 2;
-              st[0] = s;
-              st[1] = ss;
-            }
+            for (int j = 0; j < 8; ++j) e.scr[e.er][c8 + j] = z[j];
           } else {
-            float y[32];
+            float y[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int n = n0 + c;
-              float t = z[c];
-              if (L.has_bn && n < L.N)
-                t = (t - __ldg(L.rmean + n)) * (1.f / sqrtf(__ldg(L.rvar + n) + L.bn_eps)) * __ldg(L.gamma + n) +
-                    __ldg(L.beta + n);
-              y[c] = (w + c < L.NT) ? act_fwd(t, L.act) : 0.f;
+            for (int j = 0; j < 8; ++j) y[j] = z[j];
+            if (L.has_bn) {      // eval mode: running statistics
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < L.N)
+                  y[j] = (y[j] - __ldg(L.rmean + n + j)) * (1.f / sqrtf(__ldg(L.rvar + n + j) + L.bn_eps)) *
+                             __ldg(L.gamma + n + j) + __ldg(L.beta + n + j);
             }
-            emit_fwd(P, e, li, m, mvalid, n0, y);   // a 16-wide tile is the only tile of a layer with N <= 16
+            act8_fwd(y, L.act);
+            emit8_fwd(P, e, li, m, mvalid, n, y);
           }
         }
+        if (bn_batch) {
+          double s = 0.0, ss = 0.0;
+          colsum_reduce<false, true>(e, s, ss);
+          if (e.et < L.NT && n0 + e.et < L.N) {
+            double *st = L.stat + ((size_t)rb * L.N + n0 + e.et) * 2;
+            st[0] = s;
+            st[1] = ss;
+          }
+        }
+        trace_stamp(P, tslot);
         tc_fence_before();
         mbar_arrive(pipe.tempty);
         ++gi;
       }
     }
+    trace_stamp(P, tslot);
     chain_barrier(P.bar, target);
+    trace_stamp(P, tslot);
     // ---------------------------------------------------------------- BatchNorm items of layer position l
     if (fwd_bn_phase(P, l)) {
       if (warp >= 2) {
         const int nb = bn_items(P, l, false);
         for (int item = blockIdx.x; item < nb; item += gridDim.x) {
-          int li, rb;
-          bn_decode(P, l, false, item, li, rb);
+          int li, rb, cc;
+          bn_decode(P, l, false, item, li, rb, cc);
           const ChLayer &L = P.layer[li];
-          bn_fwd_finalize(P, L, e, rb == 0);
+          const int n0 = cc * 32;
           const int m = rb * 128 + e.er;
           const bool mvalid = m < P.M;
-          for (int n0 = 0; n0 < L.N; n0 += 32) {
-            float y[32];
+          const int c8 = e.c8, n = n0 + c8;
+          const float *zrow = L.Z + (size_t)m * L.ldn + n;
+          float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;      // the loads run under the statistics' finalisation
+          if (mvalid && n < L.ldn) za = __ldcg((const float4 *)zrow);
+          if (mvalid && n + 4 < L.ldn) zb = __ldcg((const float4 *)(zrow + 4));
+          bn_fwd_finalize(P, L, e, n0, rb == 0);
+          if (n < L.N) {
+            const float zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+            float y[8];
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (mvalid && n0 + c < L.ldn) z4 = __ldcg((const float4 *)(L.Z + (size_t)m * L.ldn + n0 + c));
-              const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = n0 + c + j;
-                y[c + j] = (n < L.N) ? act_fwd((zz[j] - e.colv[n]) * e.colv[CH_MAXW + n] + e.colv[2 * CH_MAXW + n], L.act) : 0.f;
-              }
-            }
-            emit_fwd(P, e, li, m, mvalid, n0, y);
+            for (int j = 0; j < 8; ++j)
+              y[j] = (n + j < L.N) ? (zz[j] - e.colv[c8 + j]) * e.colv[32 + c8 + j] + e.colv[64 + c8 + j] : 0.f;
+            act8_fwd(y, L.act);
+            emit8_fwd(P, e, li, m, mvalid, n, y);
           }
           bar_epi();   // colv is rewritten by the next item
         }
       }
+      trace_stamp(P, tslot);
       chain_barrier(P.bar, target);
+      trace_stamp(P, tslot);
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pipe.tmem), "r"(CH_TMEM_COLS));
-  }
-  chain_exit(P.bar);
+  trace_stamp(P, tslot);
+  chain_teardown(cx, P);
 }
 
 // ============================================================================================== backward kernel
-// g1[32] = gradient at the OUTPUT of layer li's BatchNorm (or Linear when it has none), i.e. already through the
-// activation, for row m and columns n0..: store what the layer's own backward GEMMs / BatchNorm item need + column sums
-__device__ __forceinline__ void bwd_tail(const ChParams &P, const Epi &e, int li, int rb, int m, bool mvalid, int n0,
-                                         float (&g1)[32]) {
-  const ChLayer &L = P.layer[li];
+// g1[8] = gradient at the OUTPUT of layer li's BatchNorm (or Linear when it has none), i.e. already through the activation,
+// for row m and columns n..n+7 of the 32-column chunk starting at n0: store what the layer's own backward GEMMs /
+// BatchNorm item need and stage the column sums (bwd_tail_finish reduces them once the chunk is complete)
+__device__ __forceinline__ void bwd_tail8(const ChHead &P, const Epi &e, const ChLayer &L, int m, bool mvalid, int n0, int n,
+                                          float (&g1)[8]) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c)
-    if (!mvalid || n0 + c >= L.N) g1[c] = 0.f;
-  double s0 = 0.0, s1 = 0.0, dummy = 0.0;
+  for (int j = 0; j < 8; ++j)
+    if (!mvalid || n + j >= L.N) g1[j] = 0.f;
   if (L.has_bn) {
-    float gx[32];
+    float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
     if (mvalid) {
-      float *dst = L.G1 + (size_t)m * L.ldn + n0;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        if (n0 + c < L.ldn) *(float4 *)(dst + c) = make_float4(g1[c], g1[c + 1], g1[c + 2], g1[c + 3]);
-    }
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mvalid && n0 + c < L.ldn) z4 = __ldg((const float4 *)(L.Z + (size_t)m * L.ldn + n0 + c));
-      const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + c + j;
-        gx[c + j] = (n < L.N) ? g1[c + j] * ((zz[j] - __ldg(L.save_mean + n)) * __ldg(L.save_invstd + n)) : 0.f;
+      float *dst = L.G1 + (size_t)m * L.ldn + n;
+      const float *zrow = L.Z + (size_t)m * L.ldn + n;
+      if (n < L.ldn) {
+        *(float4 *)dst = make_float4(g1[0], g1[1], g1[2], g1[3]);
+        za = __ldg((const float4 *)zrow);
+      }
+      if (n + 4 < L.ldn) {
+        *(float4 *)(dst + 4) = make_float4(g1[4], g1[5], g1[6], g1[7]);
+        zb = __ldg((const float4 *)(zrow + 4));
       }
     }
-    colsum32<false>(e, g1, s0, dummy);
-    colsum32<false>(e, gx, s1, dummy);
+    const float zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      e.scr[e.er][n - n0 + j] = g1[j];
+      e.scr2[e.er][n - n0 + j] =
+          (n + j < L.N) ? g1[j] * ((zz[j] - __ldg(L.save_mean + n + j)) * __ldg(L.save_invstd + n + j)) : 0.f;
+    }
   } else {
-    float hi[32], lo[32];
+    float hi[8], lo[8];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) split_tf32(g1[c], hi[c], lo[c]);
-    if (mvalid) {
-      float *r_hi = L.DZ + (size_t)m * L.ldn + n0, *r_lo = r_hi + (size_t)P.M * L.ldn;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        if (n0 + c < L.ldn) {
-          *(float4 *)(r_hi + c) = make_float4(hi[c], hi[c + 1], hi[c + 2], hi[c + 3]);
-          *(float4 *)(r_lo + c) = make_float4(lo[c], lo[c + 1], lo[c + 2], lo[c + 3]);
-        }
+    for (int j = 0; j < 8; ++j) {
+      split_tf32(g1[j], hi[j], lo[j]);
+      e.scr[e.er][n - n0 + j] = g1[j];
     }
-    float *t_hi = L.DZT + (size_t)n0 * P.Mpad + m, *t_lo = t_hi + (size_t)L.N * P.Mpad;
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (n0 + c < L.N) {
-        t_hi[(size_t)c * P.Mpad] = hi[c];
-        t_lo[(size_t)c * P.Mpad] = lo[c];
+    if (mvalid) {
+      float *r_hi = L.DZ + (size_t)m * L.ldn + n, *r_lo = r_hi + (size_t)P.M * L.ldn;
+      if (n < L.ldn) {
+        *(float4 *)r_hi = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *(float4 *)r_lo = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
-    colsum32<false>(e, g1, s0, dummy);
+      if (n + 4 < L.ldn) {
+        *(float4 *)(r_hi + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        *(float4 *)(r_lo + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    }
+    float *t_hi = L.DZT + (size_t)n * P.Mpad + m, *t_lo = t_hi + (size_t)L.N * P.Mpad;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n + j < L.N) {
+        t_hi[(size_t)j * P.Mpad] = hi[j];
+        t_lo[(size_t)j * P.Mpad] = lo[j];
+      }
   }
-  if (e.et < 32 && n0 + e.et < L.N) {
+}
+// `cols` = how many columns of the chunk the caller staged (the rest of scr is stale and ignored)
+__device__ __forceinline__ void bwd_tail_finish(const ChHead &P, const Epi &e, const ChLayer &L, int rb, int n0, int cols) {
+  double s0 = 0.0, s1 = 0.0;
+  if (L.has_bn)
+    colsum_reduce<true, false>(e, s0, s1);
+  else
+    colsum_reduce<false, false>(e, s0, s1);
+  if (e.et < cols && n0 + e.et < L.N) {
     double *st = L.bstat + ((size_t)rb * L.N + n0 + e.et) * 2;
     st[0] = s0;
-    st[1] = s1;
+    st[1] = L.has_bn ? s1 : 0.0;
   }
 }
 
-static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __grid_constant__ ChParams P) {
+static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __grid_constant__ ChParams PP) {
   extern __shared__ __align__(1024) unsigned char ch_smem[];
-  unsigned char *base = (unsigned char *)(((uintptr_t)ch_smem + 1023) & ~(uintptr_t)1023);
-  Pipe pipe;
-  pipe.stages = base;
-  Epi e;
-  e.scr = (float(*)[33])(base + CH_STAGES * CH_STAGE);
-  e.dscr = (double(*)[4][32])((unsigned char *)e.scr + 128 * 33 * 4);
-  e.colv = (float *)((unsigned char *)e.dscr + 2 * 4 * 32 * 8);
-  uint64_t *bars = (uint64_t *)(e.colv + 5 * CH_MAXW);
-  pipe.full = bars;
-  pipe.empty = bars + CH_STAGES;
-  pipe.tfull = bars + 2 * CH_STAGES;
-  pipe.tempty = pipe.tfull + 1;
-  uint32_t *tmem_slot = (uint32_t *)(pipe.tempty + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < CH_STAGES; ++s) {
-      mbar_init(&pipe.full[s], 1);
-      mbar_init(&pipe.empty[s], 1);
-    }
-    mbar_init(pipe.tfull, 1);
-    mbar_init(pipe.tempty, 128);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(CH_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pipe.tmem = *tmem_slot;
-  const int quarter = warp & 3;
-  e.er = quarter * 32 + lane;
-  e.et = (int)threadIdx.x - 64;
-  e.seedoff = P.seed_dev ? *P.seed_dev : 0ull;
-  const uint32_t taddr = pipe.tmem + ((uint32_t)(quarter * 32) << 16);
+  Ctx cx;
+  chain_setup(cx, ch_smem, PP.h);
+  const ChHead &P = *cx.head;
+  const Pipe &pipe = cx.pipe;
+  const Epi &e = cx.e;
+  const int warp = cx.warp, lane = cx.lane;
   uint32_t it = 0, gi = 0;
   unsigned target = 0;
   const int chunks = ch_tiles(P.M, CH_WCHUNK);
+  int tslot = 0;
+  trace_stamp(P, tslot);
 
   // ------------------------------------------------------------------ phase 0: transposed weight planes, import of dY
   if (warp >= 2) {
-    const int n_flat = flat_items(P, true), n_imp = P.n_chains * P.RB;
+    const int n_flat = flat_items(P, true), n_imp = import_items(P, true);
     for (int item = blockIdx.x; item < n_flat + n_imp; item += gridDim.x) {
       if (item < n_flat) {
         int li, blk;
         flat_decode(P, true, item, li, blk);
-        const ChLayer &L = P.layer[li];
-        const int n = L.N * L.K;
-        for (int j = 0; j < CH_EW / 128; ++j) {
-          const int idx = blk * CH_EW + j * 128 + e.et;   // idx = k * N + n: coalesced writes
-          if (idx < n) {
-            const int k = idx / L.N, nn = idx % L.N;
-            float h, l;
-            split_tf32(__ldg(L.W + (size_t)nn * L.K + k), h, l);
-            L.Wt[(size_t)k * L.ldn + nn] = h;
-            L.Wt[(size_t)L.K * L.ldn + (size_t)k * L.ldn + nn] = l;
-          }
-        }
+        weight_planes_item<true>(P.layer[li], blk, e.et);
       } else {
-        const int c = (item - n_flat) / P.RB, rb = (item - n_flat) % P.RB;
+        int c, rb, cc;
+        import_decode(P, true, item - n_flat, c, rb, cc);
         const ChChain &C = P.chain[c];
-        const int li = C.first + C.L - 1;
-        const ChLayer &L = P.layer[li];
-        const int m = rb * 128 + e.er;
+        const ChLayer &L = P.layer[C.first + C.L - 1];
+        const int m = rb * 128 + e.er, n0 = cc * 32;
         const bool mvalid = m < P.M;
-        for (int n0 = 0; n0 < L.N; n0 += 32) {
-          float g1[32];
+        const int cols = L.N - n0 < 32 ? L.N - n0 : 32;
+        const int n = n0 + e.c8;
+        if (n < L.N) {
+          float g1[8], yo[8];
 #pragma unroll
-          for (int cc = 0; cc < 32; ++cc) {
-            const int n = n0 + cc;
-            g1[cc] = (mvalid && n < L.N)
-                         ? __ldg(C.dY + (size_t)m * L.N + n) * act_bwd(__ldg(C.Y + (size_t)m * L.N + n), L.act)
-                         : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = mvalid && n + j < L.N;
+            g1[j] = ok ? __ldg(C.dY + (size_t)m * L.N + n + j) : 0.f;
+            yo[j] = ok ? __ldg(C.Y + (size_t)m * L.N + n + j) : 0.f;
           }
-          bwd_tail(P, e, li, rb, m, mvalid, n0, g1);
+          act8_bwd(g1, yo, L.act);
+          bwd_tail8(P, e, L, m, mvalid, n0, n, g1);
         }
+        bwd_tail_finish(P, e, L, rb, n0, cols);
       }
     }
   }
+  trace_stamp(P, tslot);
   chain_barrier(P.bar, target);
+  trace_stamp(P, tslot);
 
   for (int s = 0; s < P.Lmax; ++s) {
     // ---------------------------------------------------------------- BatchNorm backward items
@@ -780,72 +908,78 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
     if (nb > 0) {
       if (warp >= 2) {
         for (int item = blockIdx.x; item < nb; item += gridDim.x) {
-          int li, rb;
-          bn_decode(P, s, true, item, li, rb);
+          int li, rb, cc;
+          bn_decode(P, s, true, item, li, rb, cc);
           const ChLayer &L = P.layer[li];
-          for (int n = e.et; n < L.N; n += 128) {
+          const int n0 = cc * 32;
+          const int m = rb * 128 + e.er;
+          const bool mvalid = m < P.M;
+          const int c8 = e.c8, n = n0 + c8;
+          // this thread's row loads run under the finalisation of the column sums
+          float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za, ga = za, gb = za;
+          if (mvalid && n < L.N && n < L.ldn) {
+            za = __ldg((const float4 *)(L.Z + (size_t)m * L.ldn + n));
+            ga = __ldcg((const float4 *)(L.G1 + (size_t)m * L.ldn + n));
+          }
+          if (mvalid && n < L.N && n + 4 < L.ldn) {
+            zb = __ldg((const float4 *)(L.Z + (size_t)m * L.ldn + n + 4));
+            gb = __ldcg((const float4 *)(L.G1 + (size_t)m * L.ldn + n + 4));
+          }
+          if (e.et < 32 && n0 + e.et < L.N) {
+            const int nc = n0 + e.et;
+            const float invstd = __ldg(L.save_invstd + nc), mean = __ldg(L.save_mean + nc), gam = __ldg(L.gamma + nc);
             double s0 = 0.0, s1 = 0.0;
-            for (int r = 0; r < P.RB; ++r) {
-              s0 += __ldcg(L.bstat + ((size_t)r * L.N + n) * 2);
-              s1 += __ldcg(L.bstat + ((size_t)r * L.N + n) * 2 + 1);
-            }
-            const float invstd = __ldg(L.save_invstd + n);
-            e.colv[n] = __ldg(L.save_mean + n);
-            e.colv[CH_MAXW + n] = __ldg(L.gamma + n) * invstd;
-            e.colv[2 * CH_MAXW + n] = (float)(s0 / (double)P.M);
-            e.colv[3 * CH_MAXW + n] = invstd;
-            e.colv[4 * CH_MAXW + n] = (float)(s1 / (double)P.M);
+            ordered_sum2(L.bstat + (size_t)nc * 2, (size_t)L.N * 2, P.RB, s0, s1);
+            e.colv[e.et] = mean;
+            e.colv[32 + e.et] = gam * invstd;
+            e.colv[64 + e.et] = (float)(s0 / (double)P.M);
+            e.colv[96 + e.et] = invstd;
+            e.colv[128 + e.et] = (float)(s1 / (double)P.M);
             if (rb == 0) {
-              if (L.dbeta) L.dbeta[n] = (float)s0;
-              if (L.dgamma) L.dgamma[n] = (float)s1;
-              if (L.db) L.db[n] = 0.f;      // a bias in front of BatchNorm has a mathematically zero gradient
+              if (L.dbeta) L.dbeta[nc] = (float)s0;
+              if (L.dgamma) L.dgamma[nc] = (float)s1;
+              if (L.db) L.db[nc] = 0.f;      // a bias in front of BatchNorm has a mathematically zero gradient
             }
           }
           bar_epi();
-          const int m = rb * 128 + e.er;
-          const bool mvalid = m < P.M;
-          for (int n0 = 0; n0 < L.N; n0 += 32) {
-            float hi[32], lo[32];
+          if (n < L.N) {
+            const float zz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            float hi[8], lo[8];
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = z4;
-              if (mvalid && n0 + c < L.ldn) {
-                z4 = __ldg((const float4 *)(L.Z + (size_t)m * L.ldn + n0 + c));
-                g4 = __ldcg((const float4 *)(L.G1 + (size_t)m * L.ldn + n0 + c));
+            for (int j = 0; j < 8; ++j) {
+              float dz = 0.f;
+              if (n + j < L.N && mvalid) {
+                const float xh = (zz[j] - e.colv[c8 + j]) * e.colv[96 + c8 + j];
+                dz = e.colv[32 + c8 + j] * (gg[j] - e.colv[64 + c8 + j] - xh * e.colv[128 + c8 + j]);
               }
-              const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = n0 + c + j;
-                float dz = 0.f;
-                if (n < L.N && mvalid) {
-                  const float xh = (zz[j] - e.colv[n]) * e.colv[3 * CH_MAXW + n];
-                  dz = e.colv[CH_MAXW + n] * (gg[j] - e.colv[2 * CH_MAXW + n] - xh * e.colv[4 * CH_MAXW + n]);
-                }
-                split_tf32(dz, hi[c + j], lo[c + j]);
-              }
+              split_tf32(dz, hi[j], lo[j]);
             }
             if (mvalid) {
-              float *r_hi = L.DZ + (size_t)m * L.ldn + n0, *r_lo = r_hi + (size_t)P.M * L.ldn;
-#pragma unroll
-              for (int c = 0; c < 32; c += 4)
-                if (n0 + c < L.ldn) {
-                  *(float4 *)(r_hi + c) = make_float4(hi[c], hi[c + 1], hi[c + 2], hi[c + 3]);
-                  *(float4 *)(r_lo + c) = make_float4(lo[c], lo[c + 1], lo[c + 2], lo[c + 3]);
-                }
+              float *r_hi = L.DZ + (size_t)m * L.ldn + n, *r_lo = r_hi + (size_t)P.M * L.ldn;
+              if (n < L.ldn) {
+                *(float4 *)r_hi = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *(float4 *)r_lo = make_float4(lo[0], lo[1], lo[2], lo[3]);
+              }
+              if (n + 4 < L.ldn) {
+                *(float4 *)(r_hi + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *(float4 *)(r_lo + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+              }
             }
-            float *t_hi = L.DZT + (size_t)n0 * P.Mpad + m, *t_lo = t_hi + (size_t)L.N * P.Mpad;
+            float *t_hi = L.DZT + (size_t)n * P.Mpad + m, *t_lo = t_hi + (size_t)L.N * P.Mpad;
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (n0 + c < L.N) {
-                t_hi[(size_t)c * P.Mpad] = hi[c];
-                t_lo[(size_t)c * P.Mpad] = lo[c];
+            for (int j = 0; j < 8; ++j)
+              if (n + j < L.N) {
+                t_hi[(size_t)j * P.Mpad] = hi[j];
+                t_lo[(size_t)j * P.Mpad] = lo[j];
               }
           }
           bar_epi();
         }
       }
+      trace_stamp(P, tslot);
       chain_barrier(P.bar, target);
+      trace_stamp(P, tslot);
     }
     // ---------------------------------------------------------------- GEMM items: weight gradients + data gradients
     const int n_items = bwd_gemm_items(P, s);
@@ -858,9 +992,9 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
         const int kb0 = b.c * (CH_WCHUNK / TCKB);
         int nkb = ch_tiles(P.M, TCKB) - kb0;
         if (nkb > CH_WCHUNK / TCKB) nkb = CH_WCHUNK / TCKB;
-        g = GemmIt{&P.map[b.li][2], &P.map[b.li][3], b.a * TCM, b.b * L.KT, kb0, nkb, L.KT};
+        g = GemmIt{&PP.map[b.li][2], &PP.map[b.li][3], b.a * TCM, b.b * L.KT, kb0, nkb, L.KT};
       } else {
-        g = GemmIt{&P.map[b.li][0], &P.map[b.li][1], b.a * 128, b.b * L.KT, 0, ch_tiles(L.N, TCKB), L.KT};
+        g = GemmIt{&PP.map[b.li][0], &PP.map[b.li][1], b.a * 128, b.b * L.KT, 0, ch_tiles(L.N, TCKB), L.KT};
       }
       if (warp == 0) {
         if (lane == 0) gemm_produce(g, pipe, it);
@@ -869,73 +1003,75 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
       } else {
         mbar_wait(pipe.tfull, gi & 1);
         tc_fence_after();
+        const int k0 = b.b * L.KT;
         if (b.kind == 0) {
           // D[n (lane), k]: partial weight gradient of this 256-row chunk
           const int n = b.a * TCM + e.er;
-          float *dst = L.dWpart + ((size_t)b.c * L.N + n) * L.K;
-          for (int w = 0; w < L.KT; w += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + w, v);
-            const int k0 = b.b * L.KT + w;
+          float *dst = L.dWpart + ((size_t)b.c * L.N + n) * L.K + k0;
+          const int c8 = e.c8;
+          if (c8 < L.KT) {
+            uint32_t v[8];
+            tmem_ld8(cx.taddr + c8, v);
             if (n < L.N) {
-#pragma unroll
-              for (int c = 0; c < 32; c += 4)
-                if (k0 + c < L.K && w + c < L.KT)
-                  *(float4 *)(dst + k0 + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
-                                                          __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+              if (k0 + c8 < L.K)
+                *(float4 *)(dst + c8) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]),
+                                                    __uint_as_float(v[3]));
+              if (k0 + c8 + 4 < L.K)
+                *(float4 *)(dst + c8 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]),
+                                                        __uint_as_float(v[7]));
             }
           }
         } else {
           const int rb = b.a, m = rb * 128 + e.er;
           const bool mvalid = m < P.M;
           const float p = L.drop_p;     // backward runs in training mode only
+          const float keep = p > 0.f ? 1.f - p : 1.f;
           const unsigned long long seed = L.seed + e.seedoff;
-          for (int w = 0; w < L.KT; w += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + w, v);
-            const int k0 = b.b * L.KT + w;
-            float g1[32];
+          const int cols = L.K - k0 < L.KT ? L.K - k0 : L.KT;
+          const int c8 = e.c8, k = k0 + c8;
+          if (c8 < L.KT && k < L.K) {
+            uint32_t v[8];
+            tmem_ld8(cx.taddr + c8, v);
+            float g1[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int k = k0 + c;
-              float gq = ((w + c < L.KT) && k < L.K && mvalid) ? __uint_as_float(v[c]) : 0.f;
-              if (p > 0.f && k < L.K && mvalid) gq *= drop_scale(seed, 0, (uint32_t)(m * L.K + k), p);
-              g1[c] = gq;
+            for (int j = 0; j < 8; ++j) {
+              float gq = (k + j < L.K && mvalid) ? __uint_as_float(v[j]) : 0.f;
+              if (p > 0.f && k + j < L.K && mvalid) gq *= drop_scale(seed, 0, (uint32_t)(m * L.K + k + j), p);
+              g1[j] = gq;
             }
             if (L.first_of_chain) {
               if (mvalid) {
-                float *dst = P.chain[L.chain].dX + (size_t)m * L.K;
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (k0 + c < L.K && w + c < L.KT) dst[k0 + c] = g1[c];
+                float *dst = P.chain[L.chain].dX + (size_t)m * L.K + k;
+                *(float4 *)dst = make_float4(g1[0], g1[1], g1[2], g1[3]);
+                if (k + 4 < L.K) *(float4 *)(dst + 4) = make_float4(g1[4], g1[5], g1[6], g1[7]);
               }
             } else {
               const ChLayer &B = P.layer[b.li - 1];     // the layer below: its output (width L.K == B.N) fed this one
               if (mvalid) {
-                const float *x_hi = L.Xin + (size_t)m * L.K + k0, *x_lo = x_hi + (size_t)P.M * L.K;
-                const float keep = p > 0.f ? 1.f - p : 1.f;
-#pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                  if (k0 + c < L.K && w + c < L.KT) {
-                    const float4 h4 = __ldg((const float4 *)(x_hi + c)), l4 = __ldg((const float4 *)(x_lo + c));
-                    g1[c] *= act_bwd((h4.x + l4.x) * keep, B.act);
-                    g1[c + 1] *= act_bwd((h4.y + l4.y) * keep, B.act);
-                    g1[c + 2] *= act_bwd((h4.z + l4.z) * keep, B.act);
-                    g1[c + 3] *= act_bwd((h4.w + l4.w) * keep, B.act);
-                  }
+                const float *x_hi = L.Xin + (size_t)m * L.K + k, *x_lo = x_hi + (size_t)P.M * L.K;
+                const float4 h4 = __ldg((const float4 *)x_hi), l4 = __ldg((const float4 *)x_lo);
+                float4 h5 = make_float4(0.f, 0.f, 0.f, 0.f), l5 = h5;
+                if (k + 4 < L.K) {
+                  h5 = __ldg((const float4 *)(x_hi + 4));
+                  l5 = __ldg((const float4 *)(x_lo + 4));
+                }
+                const float yo[8] = {(h4.x + l4.x) * keep, (h4.y + l4.y) * keep, (h4.z + l4.z) * keep, (h4.w + l4.w) * keep,
+                                     (h5.x + l5.x) * keep, (h5.y + l5.y) * keep, (h5.z + l5.z) * keep, (h5.w + l5.w) * keep};
+                act8_bwd(g1, yo, B.act);
               }
-              // a 16-wide tile must not touch the columns of its neighbour: bwd_tail masks by B.N only, so tiles narrower
-              // than 32 columns are restricted to layers whose width is at most the tile (KT == 16 <=> K <= 16)
-              bwd_tail(P, e, b.li - 1, rb, m, mvalid, k0, g1);
+              bwd_tail8(P, e, B, m, mvalid, k0, k, g1);
             }
           }
+          if (!L.first_of_chain) bwd_tail_finish(P, e, P.layer[b.li - 1], rb, k0, cols);
         }
         tc_fence_before();
         mbar_arrive(pipe.tempty);
         ++gi;
       }
     }
+    trace_stamp(P, tslot);
     chain_barrier(P.bar, target);
+    trace_stamp(P, tslot);
   }
 
   // ------------------------------------------------------------------ reduce: dW, db, dX_sum
@@ -948,49 +1084,53 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
         flat_decode(P, false, item, li, blk);
         const ChLayer &L = P.layer[li];
         const int n = L.N * L.K;
-        for (int j = 0; j < CH_EW / 128; ++j) {
-          const int idx = blk * CH_EW + j * 128 + e.et;
-          if (idx < n) {
-            float sw = 0.f;
-            for (int c = 0; c < chunks; ++c) sw += __ldcg(L.dWpart + (size_t)c * n + idx);
-            L.dW[idx] = sw;
+#pragma unroll 1
+        for (int j = 0; j < CH_EW / CH_EPI; ++j) {
+          const int idx = blk * CH_EW + j * CH_EPI + e.et;
+          if (idx >= n) break;
+          float sw = 0.f;
+          int c = 0;
+          for (; c + 8 <= chunks; c += 8) {      // 8 loads in flight, added in chunk order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(L.dWpart + (size_t)(c + u) * n + idx);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sw += v[u];
           }
+          for (; c < chunks; ++c) sw += __ldcg(L.dWpart + (size_t)c * n + idx);
+          L.dW[idx] = sw;
         }
       } else if (item < n_flat + P.n_total) {
         const ChLayer &L = P.layer[item - n_flat];
         if (L.db && !L.has_bn)
-          for (int n = e.et; n < L.N; n += 128) {
-            double sb = 0.0;
-            for (int r = 0; r < P.RB; ++r) sb += __ldcg(L.bstat + ((size_t)r * L.N + n) * 2);
+          for (int n = e.et; n < L.N; n += CH_EPI) {
+            double sb = 0.0, unused = 0.0;
+            ordered_sum2(L.bstat + (size_t)n * 2, (size_t)L.N * 2, P.RB, sb, unused);
             L.db[n] = (float)sb;
           }
       } else {
         const int blk = item - n_flat - P.n_total, n = P.M * P.chain[0].K0;
-        for (int j = 0; j < CH_EW / 128; ++j) {
-          const int idx = blk * CH_EW + j * 128 + e.et;
-          if (idx < n) {
-            float sx = 0.f;
-            for (int c = 0; c < P.n_chains; ++c) sx += __ldcg(P.chain[c].dX + idx);
-            P.dX_sum[idx] = sx;
-          }
+#pragma unroll 1
+        for (int j = 0; j < CH_EW / CH_EPI; ++j) {
+          const int idx = blk * CH_EW + j * CH_EPI + e.et;
+          if (idx >= n) break;
+          float sx = 0.f;
+          for (int c = 0; c < P.n_chains; ++c) sx += __ldcg(P.chain[c].dX + idx);
+          P.dX_sum[idx] = sx;
         }
       }
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pipe.tmem), "r"(CH_TMEM_COLS));
-  }
-  chain_exit(P.bar);
+  trace_stamp(P, tslot);
+  chain_teardown(cx, P);
 }
 
 // ============================================================================================== host side
-constexpr size_t CH_SMEM = (size_t)CH_STAGES * CH_STAGE + 128 * 33 * 4 + 2 * 4 * 32 * 8 + 5 * CH_MAXW * 4 + 16 * 8 + 1024;
+constexpr size_t CH_SMEM = (size_t)CH_STAGES * CH_STAGE + 2 * 128 * 33 * 4 + 2 * 4 * 32 * 8 + 5 * 32 * 4 + 16 * 8 + sizeof(ChHead) + 64 + 1024;
 
 // planes [2][rows][ld] with `inner` valid columns -> boxes of box_rows x 32 columns of one plane
 static int g_map_err = 0;
+static unsigned long long *g_trace_buf = nullptr;
 static bool make_map3(CUtensorMap *m, const float *base, int inner, int rows, int ld, size_t plane_elems, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
@@ -1014,7 +1154,8 @@ static bool make_map3(CUtensorMap *m, const float *base, int inner, int rows, in
   return r == CUDA_SUCCESS;
 }
 
-static inline int tile_for(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : 64); }
+// B tiles are 16 or 32 rows wide: the work per item is the row-wise epilogue (thread == row), so narrow tiles = more CTAs busy
+static inline int tile_for(int n) { return n <= 16 ? 16 : 32; }
 static inline int pad4(int n) { return (n + 3) & ~3; }
 
 struct ChSizes {
@@ -1054,9 +1195,10 @@ static bool layer_ok(const fr_chain_layer &l) {
 }
 
 static int build_params(const fr_chain *chains, int n_chains, int64_t M, int training, int need_grad, bool backward,
-                        const uint64_t *seed_dev, uint32_t *bar, float *dX_sum, ChParams &P, const char *who) {
+                        const uint64_t *seed_dev, uint32_t *bar, float *dX_sum, ChParams &PP, const char *who) {
+  ChHead &P = PP.h;
   FR_REQUIRE(chains && n_chains >= 1 && n_chains <= CH_MAX_CHAINS && M >= 1 && M <= (1 << 22) && bar, "%s: bad argument", who);
-  memset(&P, 0, sizeof(P));
+  memset(&PP, 0, sizeof(PP));
   const ChSizes z = ch_sizes(M);
   P.n_chains = n_chains;
   P.M = (int)M;
@@ -1067,6 +1209,17 @@ static int build_params(const fr_chain *chains, int n_chains, int64_t M, int tra
   P.seed_dev = (const unsigned long long *)seed_dev;
   P.bar = bar;
   P.dX_sum = dX_sum;
+  {
+    static unsigned long long *trace_buf = nullptr;
+    static int trace_on = -1;
+    if (trace_on < 0) {
+      const char *e = getenv("FR_CHAIN_TRACE");
+      trace_on = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0);
+      if (trace_on) cudaMalloc(&trace_buf, 256 * sizeof(unsigned long long));
+    }
+    P.trace = (trace_on == 1 && !backward) || (trace_on == 2 && backward) ? trace_buf : nullptr;
+    g_trace_buf = trace_buf;
+  }
   int total = 0;
   for (int c = 0; c < n_chains; ++c) {
     const fr_chain &C = chains[c];
@@ -1135,13 +1288,13 @@ static int build_params(const fr_chain *chains, int n_chains, int64_t M, int tra
     ChLayer &L = P.layer[i];
     bool ok = true;
     if (!backward) {
-      ok = ok && make_map3(&P.map[i][0], L.Xin, L.K, P.M, L.K, (size_t)P.M * L.K, TCM);
-      ok = ok && make_map3(&P.map[i][1], L.Wp, L.K, L.N, L.K, (size_t)L.N * L.K, L.NT);
+      ok = ok && make_map3(&PP.map[i][0], L.Xin, L.K, P.M, L.K, (size_t)P.M * L.K, TCM);
+      ok = ok && make_map3(&PP.map[i][1], L.Wp, L.K, L.N, L.K, (size_t)L.N * L.K, L.NT);
     } else {
-      ok = ok && make_map3(&P.map[i][0], L.DZ, L.N, P.M, L.ldn, (size_t)P.M * L.ldn, TCM);
-      ok = ok && make_map3(&P.map[i][1], L.Wt, L.N, L.K, L.ldn, (size_t)L.K * L.ldn, L.KT);
-      ok = ok && make_map3(&P.map[i][2], L.DZT, P.M, L.N, P.Mpad, (size_t)L.N * P.Mpad, TCM);
-      ok = ok && make_map3(&P.map[i][3], L.XinT, P.M, L.K, P.Mpad, (size_t)L.K * P.Mpad, L.KT);
+      ok = ok && make_map3(&PP.map[i][0], L.DZ, L.N, P.M, L.ldn, (size_t)P.M * L.ldn, TCM);
+      ok = ok && make_map3(&PP.map[i][1], L.Wt, L.N, L.K, L.ldn, (size_t)L.K * L.ldn, L.KT);
+      ok = ok && make_map3(&PP.map[i][2], L.DZT, P.M, L.N, P.Mpad, (size_t)L.N * P.Mpad, TCM);
+      ok = ok && make_map3(&PP.map[i][3], L.XinT, P.M, L.K, P.Mpad, (size_t)L.K * P.Mpad, L.KT);
     }
     if (!ok) return FR_ERR_CUDA;
   }
@@ -1192,6 +1345,11 @@ static int launch_chain(const void *kernel, const char *name, ChParams &P, int w
 
 extern "C" {
 
+int fr_mlp_chain_trace(uint64_t *out_host, int32_t n) {
+  if (!fr::g_trace_buf || n > 256) return FR_ERR_INVALID;
+  return cudaMemcpy(out_host, fr::g_trace_buf, (size_t)n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? FR_OK : FR_ERR_CUDA;
+}
+
 int fr_thread_init(void) {
   // binds the device's primary context to the calling thread (a thread that never touched the CUDA runtime has none, and
   // the driver-API tensor-map encoder then fails with CUDA_ERROR_INVALID_CONTEXT).  Not legal inside a stream capture.
@@ -1232,12 +1390,11 @@ int fr_mlp_chain_forward(const fr_chain *chains, int32_t n_chains, int64_t M, in
   int rc = fr::build_params(chains, n_chains, M, training, need_grad, false, seed_dev, barrier_words, nullptr, P,
                             "fr_mlp_chain_forward");
   if (rc) return rc;
-  int want = P.n_chains * P.RB + fr::flat_items(P, false);
-  for (int l = 0; l < P.Lmax; ++l) {
-    const int g = fr::fwd_gemm_items(P, l);
+  int want = fr::import_items(P.h, false) + fr::flat_items(P.h, false);
+  for (int l = 0; l < P.h.Lmax; ++l) {
+    const int g = fr::fwd_gemm_items(P.h, l);
     if (g > want) want = g;
   }
-  if (want > P.n_chains * P.RB * 4) want = P.n_chains * P.RB * 4;   // barriers cost more with every extra CTA
   return fr::launch_chain((const void *)fr::k_mlp_chain_fwd, "k_mlp_chain_fwd", P, want, (cudaStream_t)stream);
 }
 
@@ -1246,9 +1403,9 @@ int fr_mlp_chain_backward(const fr_chain *chains, int32_t n_chains, int64_t M, c
   static fr::ChParams P;
   int rc = fr::build_params(chains, n_chains, M, 1, 1, true, seed_dev, barrier_words, dX_sum, P, "fr_mlp_chain_backward");
   if (rc) return rc;
-  int want = P.n_chains * P.RB;
-  for (int s = 0; s < P.Lmax; ++s) {
-    const int g = fr::bwd_gemm_items(P, s);
+  int want = fr::import_items(P.h, true) + fr::flat_items(P.h, true);
+  for (int s = 0; s < P.h.Lmax; ++s) {
+    const int g = fr::bwd_gemm_items(P.h, s);
     if (g > want) want = g;
   }
   return fr::launch_chain((const void *)fr::k_mlp_chain_bwd, "k_mlp_chain_bwd", P, want, (cudaStream_t)stream);

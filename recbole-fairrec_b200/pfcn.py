@@ -154,8 +154,10 @@ class _PFCNBase(nn.Module):
     def _dis_terms(self, user_embed, interaction, sst_list):
         dev = user_embed.device
         loss = 0.0
-        for sst in sst_list:
-            z = self.dis_layer_dict[sst](user_embed)
+        # the discriminators of the step share one forward and one backward launch (ops.mlp_chain); None = per-module path
+        zs = ops.mlp_chain([self.dis_layer_dict[s] for s in sst_list], [user_embed]) if len(sst_list) > 1 else None
+        for i, sst in enumerate(sst_list):
+            z = zs[i] if zs is not None else self.dis_layer_dict[sst](user_embed)
             if self.sst_size[sst] == 2:
                 loss = loss + ops.SigmoidBce.apply(z, interaction[sst].to(device=dev, dtype=torch.float32))
             else:
@@ -209,7 +211,14 @@ class PFCN_MLP(_PFCNBase):
         """pfcn_mlp.py:177-193: BPR(pos, neg) - dis_weight * discriminator loss"""
         user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
         neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
-        bpr = ops.BprLoss.apply(self._score(user_embed, pos_embed), self._score(user_embed, neg_embed))
+        # the positive and the negative pass of the tower share one forward and one backward launch (two chains of the same
+        # module: autograd adds their weight gradients); None = per-module path
+        both = ops.mlp_chain([self.mlp_layer, self.mlp_layer], [ops.ConcatCols.apply(user_embed, pos_embed),
+                                                                ops.ConcatCols.apply(user_embed, neg_embed)])
+        if both is not None:
+            bpr = ops.BprLoss.apply(both[0], both[1])
+        else:
+            bpr = ops.BprLoss.apply(self._score(user_embed, pos_embed), self._score(user_embed, neg_embed))
         return self._with_dis(bpr, interaction, sst_list)
 
 
