@@ -539,6 +539,32 @@ int fr_xchg_export(void *ptr, void *handle64_out);               /* 64-byte CUDA
 int fr_xchg_open(const void *handle64, void **peer_ptr_out);     /* map a peer's buffer into this process */
 int fr_xchg_close(void *peer_ptr);
 
+/* ---- data-parallel MLP chains: every rank runs fr_mlp_chain_*_dp on ITS rows [rank * M, (rank + 1) * M) of a global batch
+ * of world * M rows (recbole/trainer/trainer.py:865-898 sharded over the GPUs of one box).  BatchNorm keeps single-GPU
+ * batch semantics (recbole/model/layers.py:62-70): the per-row-block column sums (sum z, sum z^2; backward: sum g, sum g*xhat)
+ * are written by the GEMM epilogues straight into EVERY rank's exchange memory (NVLink peer stores), the launch is cut
+ * where they cross the ranks, a flag barrier (st.release.sys / ld.acquire.sys on peer memory) sits between the
+ * segments, and every rank then adds the world * ceil(M/128) partials in global row-block order: the statistics are
+ * bit-identical on all ranks and to the single-GPU run when M % 128 == 0.  Dropout masks use the global row index.
+ * Gradient outputs are this rank's share: the host sums them over the ranks (NCCL all-reduce).
+ * Exchange memory: one fr_xchg_alloc buffer per rank, mapped by the peers (fr_xchg_export / fr_xchg_open);
+ * 256 + 2 * sum over BatchNorm layers of world * ceil(M/128) * N * 16 bytes. */
+typedef struct fr_chain_dp {
+  int32_t rank, world;
+  void *xchg[FR_MAX_RANKS];
+  size_t xchg_bytes;
+  int32_t barriers;      /* 1: flag barriers between the segments (one process per GPU).  0: single-process emulation -- the
+                            caller runs segment after segment, rank after rank, and passes `segment` and `parity` */
+  int32_t segment;       /* barriers == 0: the segment to run (-1: all, for chains without BatchNorm) */
+  int32_t parity;        /* barriers == 0: exchange region written by this segment (reads use the other one) */
+  int32_t *status_flags; /* device word: FR_FLAG_XCHG_TIMEOUT when a peer never arrived (may be NULL) */
+} fr_chain_dp;
+int fr_mlp_chain_segments(const fr_chain *chains, int32_t n_chains, int32_t training, int32_t backward, int32_t world);
+int fr_mlp_chain_forward_dp(const fr_chain *chains, int32_t n_chains, int64_t M, int32_t training, int32_t need_grad,
+                            const uint64_t *seed_dev, uint32_t *barrier_words, const fr_chain_dp *dp, void *stream);
+int fr_mlp_chain_backward_dp(const fr_chain *chains, int32_t n_chains, int64_t M, const uint64_t *seed_dev, float *dX_sum,
+                             uint32_t *barrier_words, const fr_chain_dp *dp, void *stream);
+
 enum fr_shard_phase {
   FR_SHARD_STAGE = 1, /* push the rows of stage_items that this rank owns into every rank's staging table (+ barrier) */
   FR_SHARD_A = 2,     /* batch gather, sort / segments, forward, partial item x group sums pushed (+ barrier) */

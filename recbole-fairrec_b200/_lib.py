@@ -122,6 +122,12 @@ class Chain(Structure):
                 ("bwd_ws", c_void_p), ("bwd_ws_bytes", c_size_t)]
 
 
+class ChainDp(Structure):
+    """mirror of `struct fr_chain_dp`"""
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("xchg", c_void_p * 8), ("xchg_bytes", c_size_t),
+                ("barriers", c_int32), ("segment", c_int32), ("parity", c_int32), ("status_flags", c_void_p)]
+
+
 # name -> (restype, argtypes); also the list the ABI-surface test checks against the header
 SIGNATURES = {
     "fr_abi_version": (c_int, []),
@@ -225,6 +231,11 @@ SIGNATURES = {
     "fr_mlp_chain_workspace_bytes": (c_size_t, [POINTER(ChainLayer), c_int32, c_int64, c_int32, c_int32, c_int32]),
     "fr_mlp_chain_forward": (c_int, [POINTER(Chain), c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "fr_mlp_chain_backward": (c_int, [POINTER(Chain), c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fr_mlp_chain_segments": (c_int, [POINTER(Chain), c_int32, c_int32, c_int32, c_int32]),
+    "fr_mlp_chain_forward_dp": (c_int, [POINTER(Chain), c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                        POINTER(ChainDp), c_void_p]),
+    "fr_mlp_chain_backward_dp": (c_int, [POINTER(Chain), c_int32, c_int64, c_void_p, c_void_p, c_void_p, POINTER(ChainDp),
+                                         c_void_p]),
     "fr_fairness_metrics": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

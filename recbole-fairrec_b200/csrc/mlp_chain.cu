@@ -61,6 +61,7 @@ struct ChLayer {
   float *Z;       // [M][ldn]    pre-BatchNorm output (training, BatchNorm layers)
   double *stat;   // [RB][N][2]  per-row-block column sums (sum z, sum z^2)
   float *save_mean, *save_invstd;
+  size_t x_off;   // data-parallel: offset of this layer's [RBg][N][2] column sums inside a parity region
   // backward workspace
   float *Wt;      // [2][K][ldn] transposed planes
   float *G1;      // [M][ldn]    gradient at the BatchNorm output
@@ -87,6 +88,12 @@ struct ChHead {
   unsigned *bar;
   float *dX_sum;  // optional: fixed-order sum of the chains' dX
   unsigned long long *trace;   // optional (FR_CHAIN_TRACE=1): %globaltimer stamps of CTA 0 at the phase boundaries
+  // data-parallel BatchNorm (world > 1): this rank holds rows [row_base, row_base + M) of a global batch of Mg rows in
+  // RBg row blocks; the per-row-block column sums of the BatchNorm layers live in exchange memory (peer[k], written by
+  // every rank into every rank's copy) in two parity regions alternated per exchange
+  int rank, world, rb_base, RBg, Mg, row_base, phase_lo, phase_hi, x_parity;
+  char *peer[FR_MAX_RANKS];
+  size_t x_region, x_stride, x_epoch;     // byte offsets in exchange memory: parity-0 region, parity stride, epoch word
   ChChain chain[CH_MAX_CHAINS];
   ChLayer layer[CH_MAX_TOTAL];
 };
@@ -226,6 +233,7 @@ struct Epi {
   double (*dscr)[4][32]; // [2][4][32]
   float *colv;           // [5][32]    per-column coefficients of the current BatchNorm item
   int er, et, c8;        // tile row of this thread (TMEM lane), linear epilogue thread id, first of its 8 columns in a chunk
+  size_t xw, xr;         // data-parallel: byte offsets of the parity region written / read by this launch
   unsigned long long seedoff;
 };
 
@@ -278,7 +286,7 @@ __device__ __forceinline__ void emit8_into(const ChHead &P, const Epi &e, const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float x = (n + j < K && mvalid) ? y[j] : 0.f;
-    if (p > 0.f && n + j < K) x *= drop_scale(seed, 0, (uint32_t)(m * K + n + j), p);
+    if (p > 0.f && n + j < K) x *= drop_scale(seed, 0, (uint32_t)((P.row_base + m) * K + n + j), p);
     split_tf32(x, hi[j], lo[j]);
   }
   if (mvalid) {
@@ -501,6 +509,14 @@ __device__ __forceinline__ void ordered_sum2(const double *p, size_t stride, int
   }
 }
 
+// column-sum partials of a BatchNorm layer: private workspace, or (data-parallel) the exchange memory of rank k
+__device__ __forceinline__ double *bn_part_w(const ChHead &P, const Epi &e, const ChLayer &L, double *local, int k) {
+  return P.world > 1 ? (double *)(P.peer[k] + e.xw + L.x_off) : local;
+}
+__device__ __forceinline__ const double *bn_part_r(const ChHead &P, const Epi &e, const ChLayer &L, const double *local) {
+  return P.world > 1 ? (const double *)(P.peer[P.rank] + e.xr + L.x_off) : local;
+}
+
 // ---------------------------------------------------------------------------------------------- BatchNorm helpers
 // batch statistics of columns [n0, n0+32) of layer L from the per-row-block partial sums (tile order, float64) -> colv:
 // [0] mean [1] gamma*invstd [2] beta [3] invstd, indexed by column - n0; the rb == 0 item also keeps them for the backward
@@ -511,9 +527,9 @@ __device__ __forceinline__ void bn_fwd_finalize(const ChHead &P, const ChLayer &
     const float gam = __ldg(L.gamma + n), bet = __ldg(L.beta + n);       // in flight under the partial sums
     const float rm0 = owner ? L.rmean[n] : 0.f, rv0 = owner ? L.rvar[n] : 0.f;
     double s = 0.0, ss = 0.0;
-    ordered_sum2(L.stat + (size_t)n * 2, (size_t)L.N * 2, P.RB, s, ss);
-    const double mean = s / (double)P.M;
-    double var = ss / (double)P.M - mean * mean;
+    ordered_sum2(bn_part_r(P, e, L, L.stat) + (size_t)n * 2, (size_t)L.N * 2, P.RBg, s, ss);
+    const double mean = s / (double)P.Mg;
+    double var = ss / (double)P.Mg - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)L.bn_eps));
     e.colv[e.et] = (float)mean;
@@ -523,7 +539,7 @@ __device__ __forceinline__ void bn_fwd_finalize(const ChHead &P, const ChLayer &
     if (owner) {
       L.save_mean[n] = (float)mean;
       L.save_invstd[n] = invstd;
-      const double unb = P.M > 1 ? var * (double)P.M / (double)(P.M - 1) : var;
+      const double unb = P.Mg > 1 ? var * (double)P.Mg / (double)(P.Mg - 1) : var;
       L.rmean[n] = (1.f - L.bn_mom) * rm0 + L.bn_mom * (float)mean;
       L.rvar[n] = (1.f - L.bn_mom) * rv0 + L.bn_mom * (float)unb;
       if (n == 0 && L.nbt) *L.nbt += 1;
@@ -585,6 +601,13 @@ __device__ __forceinline__ void chain_setup(Ctx &c, unsigned char *smem, const C
   c.e.et = (int)threadIdx.x - 64;
   c.e.c8 = ((c.warp - 2) >> 2) * 8;
   c.e.seedoff = P.seed_dev ? *P.seed_dev : 0ull;
+  c.e.xw = c.e.xr = 0;
+  if (P.world > 1) {
+    const unsigned par = P.x_parity >= 0 ? (unsigned)P.x_parity
+                                         : (unsigned)(*(const unsigned long long *)(P.peer[P.rank] + P.x_epoch) & 1ull);
+    c.e.xw = P.x_region + (size_t)par * P.x_stride;
+    c.e.xr = P.x_region + (size_t)(par ^ 1u) * P.x_stride;
+  }
   c.taddr = c.pipe.tmem + ((uint32_t)(quarter * 32) << 16);
 }
 
@@ -633,8 +656,12 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
   int tslot = 0;
   trace_stamp(P, tslot);
 
+  // phases: 0 = weight planes + import of X ; 1 + 2l = GEMM items of layer position l ; 2 + 2l = its BatchNorm items.
+  // A launch runs the window [phase_lo, phase_hi) (the whole chain unless the data-parallel host cuts it where BatchNorm
+  // partials cross the ranks); grid barriers separate the phases inside the window.
+  const int plo = P.phase_lo, phi = P.phase_hi;
   // ------------------------------------------------------------------ phase 0: weight planes, import of X
-  if (warp >= 2) {
+  if (warp >= 2 && plo <= 0 && 0 < phi) {
     const int n_flat = flat_items(P, false), n_imp = import_items(P, false);
     for (int item = blockIdx.x; item < n_flat + n_imp; item += gridDim.x) {
       if (item < n_flat) {
@@ -665,12 +692,13 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
     }
   }
   trace_stamp(P, tslot);
-  chain_barrier(P.bar, target);
+  if (plo <= 0 && 1 < phi) chain_barrier(P.bar, target);
   trace_stamp(P, tslot);
 
   for (int l = 0; l < P.Lmax; ++l) {
     // ---------------------------------------------------------------- GEMM items of layer position l
-    const int n_items = fwd_gemm_items(P, l);
+    const int pg = 1 + 2 * l;
+    const int n_items = (plo <= pg && pg < phi) ? fwd_gemm_items(P, l) : 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int li, rb, nt;
       fwd_gemm_decode(P, l, item, li, rb, nt);
@@ -729,9 +757,11 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
           double s = 0.0, ss = 0.0;
           colsum_reduce<false, true>(e, s, ss);
           if (e.et < L.NT && n0 + e.et < L.N) {
-            double *st = L.stat + ((size_t)rb * L.N + n0 + e.et) * 2;
-            st[0] = s;
-            st[1] = ss;
+            for (int k = 0; k < P.world; ++k) {     // data-parallel: into every rank's copy (NVLink peer stores)
+              double *st = bn_part_w(P, e, L, L.stat, k) + ((size_t)(P.rb_base + rb) * L.N + n0 + e.et) * 2;
+              st[0] = s;
+              st[1] = ss;
+            }
           }
         }
         trace_stamp(P, tslot);
@@ -741,10 +771,10 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
       }
     }
     trace_stamp(P, tslot);
-    chain_barrier(P.bar, target);
+    if (plo <= pg && pg + 1 < phi) chain_barrier(P.bar, target);
     trace_stamp(P, tslot);
     // ---------------------------------------------------------------- BatchNorm items of layer position l
-    if (fwd_bn_phase(P, l)) {
+    if (fwd_bn_phase(P, l) && plo <= pg + 1 && pg + 1 < phi) {
       if (warp >= 2) {
         const int nb = bn_items(P, l, false);
         for (int item = blockIdx.x; item < nb; item += gridDim.x) {
@@ -773,7 +803,7 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
         }
       }
       trace_stamp(P, tslot);
-      chain_barrier(P.bar, target);
+      if (pg + 2 < phi) chain_barrier(P.bar, target);
       trace_stamp(P, tslot);
     }
   }
@@ -846,9 +876,17 @@ __device__ __forceinline__ void bwd_tail_finish(const ChHead &P, const Epi &e, c
   else
     colsum_reduce<false, false>(e, s0, s1);
   if (e.et < cols && n0 + e.et < L.N) {
-    double *st = L.bstat + ((size_t)rb * L.N + n0 + e.et) * 2;
-    st[0] = s0;
-    st[1] = L.has_bn ? s1 : 0.0;
+    if (L.has_bn) {
+      for (int k = 0; k < P.world; ++k) {
+        double *st = bn_part_w(P, e, L, L.bstat, k) + ((size_t)(P.rb_base + rb) * L.N + n0 + e.et) * 2;
+        st[0] = s0;
+        st[1] = s1;
+      }
+    } else {       // bias gradient partial of a layer without BatchNorm: stays local (the host all-reduces the gradients)
+      double *st = L.bstat + ((size_t)rb * L.N + n0 + e.et) * 2;
+      st[0] = s0;
+      st[1] = 0.0;
+    }
   }
 }
 
@@ -866,8 +904,11 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
   int tslot = 0;
   trace_stamp(P, tslot);
 
+  // phases: 0 = transposed weight planes + import of dY ; 1 + 2s = BatchNorm backward items of step s (layer L-1-s) ;
+  // 2 + 2s = its GEMM items ; 1 + 2 Lmax = reduce.  Window [phase_lo, phase_hi) as in the forward kernel.
+  const int plo = P.phase_lo, phi = P.phase_hi;
   // ------------------------------------------------------------------ phase 0: transposed weight planes, import of dY
-  if (warp >= 2) {
+  if (warp >= 2 && plo <= 0 && 0 < phi) {
     const int n_flat = flat_items(P, true), n_imp = import_items(P, true);
     for (int item = blockIdx.x; item < n_flat + n_imp; item += gridDim.x) {
       if (item < n_flat) {
@@ -899,12 +940,13 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
     }
   }
   trace_stamp(P, tslot);
-  chain_barrier(P.bar, target);
+  if (plo <= 0 && 1 < phi) chain_barrier(P.bar, target);
   trace_stamp(P, tslot);
 
   for (int s = 0; s < P.Lmax; ++s) {
     // ---------------------------------------------------------------- BatchNorm backward items
-    const int nb = bn_items(P, s, true);
+    const int pb = 1 + 2 * s;
+    const int nb = (plo <= pb && pb < phi) ? bn_items(P, s, true) : 0;
     if (nb > 0) {
       if (warp >= 2) {
         for (int item = blockIdx.x; item < nb; item += gridDim.x) {
@@ -929,13 +971,18 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
             const int nc = n0 + e.et;
             const float invstd = __ldg(L.save_invstd + nc), mean = __ldg(L.save_mean + nc), gam = __ldg(L.gamma + nc);
             double s0 = 0.0, s1 = 0.0;
-            ordered_sum2(L.bstat + (size_t)nc * 2, (size_t)L.N * 2, P.RB, s0, s1);
+            const double *bs = bn_part_r(P, e, L, L.bstat) + (size_t)nc * 2;
+            ordered_sum2(bs, (size_t)L.N * 2, P.RBg, s0, s1);
             e.colv[e.et] = mean;
             e.colv[32 + e.et] = gam * invstd;
-            e.colv[64 + e.et] = (float)(s0 / (double)P.M);
+            e.colv[64 + e.et] = (float)(s0 / (double)P.Mg);
             e.colv[96 + e.et] = invstd;
-            e.colv[128 + e.et] = (float)(s1 / (double)P.M);
+            e.colv[128 + e.et] = (float)(s1 / (double)P.Mg);
             if (rb == 0) {
+              if (P.world > 1) {      // gradient outputs are this rank's share (the host sums the ranks' gradients)
+                s0 = s1 = 0.0;
+                ordered_sum2(bs + (size_t)P.rb_base * L.N * 2, (size_t)L.N * 2, P.RB, s0, s1);
+              }
               if (L.dbeta) L.dbeta[nc] = (float)s0;
               if (L.dgamma) L.dgamma[nc] = (float)s1;
               if (L.db) L.db[nc] = 0.f;      // a bias in front of BatchNorm has a mathematically zero gradient
@@ -978,11 +1025,11 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
         }
       }
       trace_stamp(P, tslot);
-      chain_barrier(P.bar, target);
+      if (pb + 1 < phi) chain_barrier(P.bar, target);
       trace_stamp(P, tslot);
     }
     // ---------------------------------------------------------------- GEMM items: weight gradients + data gradients
-    const int n_items = bwd_gemm_items(P, s);
+    const int n_items = (plo <= pb + 1 && pb + 1 < phi) ? bwd_gemm_items(P, s) : 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       BwdIt b;
       bwd_gemm_decode(P, s, item, b);
@@ -1036,7 +1083,7 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float gq = (k + j < L.K && mvalid) ? __uint_as_float(v[j]) : 0.f;
-              if (p > 0.f && k + j < L.K && mvalid) gq *= drop_scale(seed, 0, (uint32_t)(m * L.K + k + j), p);
+              if (p > 0.f && k + j < L.K && mvalid) gq *= drop_scale(seed, 0, (uint32_t)((P.row_base + m) * L.K + k + j), p);
               g1[j] = gq;
             }
             if (L.first_of_chain) {
@@ -1070,12 +1117,12 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
       }
     }
     trace_stamp(P, tslot);
-    chain_barrier(P.bar, target);
+    if (plo <= pb + 1 && pb + 2 < phi) chain_barrier(P.bar, target);
     trace_stamp(P, tslot);
   }
 
   // ------------------------------------------------------------------ reduce: dW, db, dX_sum
-  if (warp >= 2) {
+  if (warp >= 2 && plo <= 1 + 2 * P.Lmax && 1 + 2 * P.Lmax < phi) {
     const int n_flat = flat_items(P, false);
     const int n_dx = P.dX_sum ? ch_tiles(P.M * P.chain[0].K0, CH_EW) : 0;
     for (int item = blockIdx.x; item < n_flat + P.n_total + n_dx; item += gridDim.x) {
@@ -1194,8 +1241,11 @@ static bool layer_ok(const fr_chain_layer &l) {
          (!l.has_bn || (l.gamma && l.beta && l.running_mean && l.running_var));
 }
 
+constexpr size_t X_FLAGS = 0, X_EPOCH = 64, X_REGION = 256;   // layout of the data-parallel exchange memory
+
 static int build_params(const fr_chain *chains, int n_chains, int64_t M, int training, int need_grad, bool backward,
-                        const uint64_t *seed_dev, uint32_t *bar, float *dX_sum, ChParams &PP, const char *who) {
+                        const uint64_t *seed_dev, uint32_t *bar, float *dX_sum, const fr_chain_dp *dp, ChParams &PP,
+                        const char *who) {
   ChHead &P = PP.h;
   FR_REQUIRE(chains && n_chains >= 1 && n_chains <= CH_MAX_CHAINS && M >= 1 && M <= (1 << 22) && bar, "%s: bad argument", who);
   memset(&PP, 0, sizeof(PP));
@@ -1204,6 +1254,26 @@ static int build_params(const fr_chain *chains, int n_chains, int64_t M, int tra
   P.M = (int)M;
   P.Mpad = (int)z.Mpad;
   P.RB = (int)z.RB;
+  P.world = 1;
+  P.RBg = P.RB;
+  P.Mg = P.M;
+  P.x_parity = -1;
+  P.phase_lo = 0;
+  P.phase_hi = 1 << 20;
+  if (dp && dp->world > 1) {
+    FR_REQUIRE(dp->world <= FR_MAX_RANKS && dp->rank >= 0 && dp->rank < dp->world, "%s: bad rank / world", who);
+    for (int k = 0; k < dp->world; ++k) FR_REQUIRE(dp->xchg[k], "%s: exchange memory of rank %d missing", who, k);
+    P.rank = dp->rank;
+    P.world = dp->world;
+    P.rb_base = dp->rank * P.RB;           // every rank holds the same number of rows
+    P.RBg = dp->world * P.RB;
+    P.Mg = dp->world * P.M;
+    P.row_base = dp->rank * P.M;
+    for (int k = 0; k < dp->world; ++k) P.peer[k] = (char *)dp->xchg[k];
+    P.x_epoch = X_EPOCH;
+    P.x_region = X_REGION;
+    P.x_parity = dp->barriers ? -1 : (dp->parity & 1);
+  }
   P.training = training ? 1 : 0;
   P.need_grad = (need_grad || backward) ? 1 : 0;
   P.seed_dev = (const unsigned long long *)seed_dev;
@@ -1283,6 +1353,18 @@ static int build_params(const fr_chain *chains, int n_chains, int64_t M, int tra
     for (int c = 0; c < n_chains; ++c)
       FR_REQUIRE(P.chain[c].dX && P.chain[c].K0 == P.chain[0].K0, "%s: dX_sum needs a dX buffer per chain and equal input widths", who);
   }
+  if (P.world > 1) {      // exchange-memory slots of the BatchNorm layers' column-sum partials
+    size_t off = 0;
+    for (int i = 0; i < total; ++i) {
+      P.layer[i].x_off = off;
+      if (P.layer[i].has_bn) off += (((size_t)P.RBg * P.layer[i].N * 2 * sizeof(double)) + 255) & ~(size_t)255;
+    }
+    P.x_stride = off;
+    if (X_REGION + 2 * off > dp->xchg_bytes) {
+      set_error("%s: exchange memory too small (%zu bytes needed)", who, X_REGION + 2 * off);
+      return FR_ERR_WORKSPACE;
+    }
+  }
   // tensor maps
   for (int i = 0; i < total; ++i) {
     ChLayer &L = P.layer[i];
@@ -1341,6 +1423,83 @@ static int launch_chain(const void *kernel, const char *name, ChParams &P, int w
   return FR_OK;
 }
 
+// ---------------------------------------------------------------- data-parallel: cross-GPU flag barrier between segments
+__device__ __forceinline__ unsigned long long chx_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void chx_st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+struct ChPeers {
+  char *base[FR_MAX_RANKS];
+};
+// thread k talks to rank k: publish "arrived at exchange #e" in slot `rank` of k's flag array, wait until k has published
+// e in mine.  The partial sums this rank stored into peer memory in the kernel before are ordered before the flag (kernel
+// boundary + system fence + release).  Also advances the epoch word whose parity selects the exchange region.
+static __global__ void k_chain_xbar(ChPeers px, int rank, int world, int32_t *status) {
+  __shared__ unsigned long long e;
+  unsigned long long *epoch = (unsigned long long *)(px.base[rank] + X_EPOCH);
+  if (threadIdx.x == 0) e = *epoch + 1ull;
+  __syncthreads();
+  const int k = threadIdx.x;
+  if (k < world) {
+    __threadfence_system();
+    chx_st_release_sys((unsigned long long *)(px.base[k] + X_FLAGS) + rank, e);
+    const unsigned long long *mine = (const unsigned long long *)(px.base[rank] + X_FLAGS) + k;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (chx_ld_acquire_sys(mine) < e) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 20000000000ull) {     // 20 s: a peer died; do not hang the GPU
+        if (status) atomicOr(status, FR_FLAG_XCHG_TIMEOUT);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = e;
+}
+
+// phase windows of a (data-parallel) launch sequence: a cut wherever BatchNorm partials have to cross the ranks, i.e.
+// forward: after the GEMM phase of every layer position with a BatchNorm layer; backward: before every BatchNorm phase
+static int chain_cuts(const ChHead &P, bool backward, int *cuts /* [2 * CH_MAX_LAYERS + 4] */) {
+  int n = 0;
+  cuts[n++] = 0;
+  if (P.world > 1) {
+    for (int l = 0; l < P.Lmax; ++l) {
+      if (!backward && fwd_bn_phase(P, l)) cuts[n++] = 2 + 2 * l;
+      if (backward && bn_items(P, l, true) > 0) cuts[n++] = 1 + 2 * l;
+    }
+  }
+  cuts[n] = 2 + 2 * P.Lmax;
+  return n;     // number of segments; segment i = [cuts[i], cuts[i+1])
+}
+
+static int run_chain(const void *kernel, const char *name, ChParams &P, bool backward, int want, const fr_chain_dp *dp,
+                     cudaStream_t st) {
+  int cuts[2 * CH_MAX_LAYERS + 4];
+  const int nseg = chain_cuts(P.h, backward, cuts);
+  const bool emu = dp && dp->world > 1 && !dp->barriers;
+  for (int i = 0; i < nseg; ++i) {
+    if (emu && dp->segment >= 0 && dp->segment != i) continue;
+    P.h.phase_lo = cuts[i];
+    P.h.phase_hi = cuts[i + 1];
+    int rc = launch_chain(kernel, name, P, want, st);
+    if (rc) return rc;
+    if (P.h.world > 1 && dp->barriers && i + 1 < nseg) {
+      ChPeers px;
+      for (int k = 0; k < FR_MAX_RANKS; ++k) px.base[k] = k < P.h.world ? P.h.peer[k] : nullptr;
+      FR_LAUNCH(k_chain_xbar, 1, 32, 0, st, px, P.h.rank, P.h.world, dp->status_flags);
+    }
+  }
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
 }  // namespace fr
 
 extern "C" {
@@ -1384,10 +1543,10 @@ size_t fr_mlp_chain_workspace_bytes(const fr_chain_layer *layers, int32_t n_laye
   return c.off + 256;
 }
 
-int fr_mlp_chain_forward(const fr_chain *chains, int32_t n_chains, int64_t M, int32_t training, int32_t need_grad,
-                         const uint64_t *seed_dev, uint32_t *barrier_words, void *stream) {
+int fr_mlp_chain_forward_dp(const fr_chain *chains, int32_t n_chains, int64_t M, int32_t training, int32_t need_grad,
+                            const uint64_t *seed_dev, uint32_t *barrier_words, const fr_chain_dp *dp, void *stream) {
   static fr::ChParams P;     // 19 KB: not on the stack of a ctypes caller thread
-  int rc = fr::build_params(chains, n_chains, M, training, need_grad, false, seed_dev, barrier_words, nullptr, P,
+  int rc = fr::build_params(chains, n_chains, M, training, need_grad, false, seed_dev, barrier_words, nullptr, dp, P,
                             "fr_mlp_chain_forward");
   if (rc) return rc;
   int want = fr::import_items(P.h, false) + fr::flat_items(P.h, false);
@@ -1395,20 +1554,48 @@ int fr_mlp_chain_forward(const fr_chain *chains, int32_t n_chains, int64_t M, in
     const int g = fr::fwd_gemm_items(P.h, l);
     if (g > want) want = g;
   }
-  return fr::launch_chain((const void *)fr::k_mlp_chain_fwd, "k_mlp_chain_fwd", P, want, (cudaStream_t)stream);
+  return fr::run_chain((const void *)fr::k_mlp_chain_fwd, "k_mlp_chain_fwd", P, false, want, dp, (cudaStream_t)stream);
 }
 
-int fr_mlp_chain_backward(const fr_chain *chains, int32_t n_chains, int64_t M, const uint64_t *seed_dev, float *dX_sum,
-                          uint32_t *barrier_words, void *stream) {
+int fr_mlp_chain_backward_dp(const fr_chain *chains, int32_t n_chains, int64_t M, const uint64_t *seed_dev, float *dX_sum,
+                             uint32_t *barrier_words, const fr_chain_dp *dp, void *stream) {
   static fr::ChParams P;
-  int rc = fr::build_params(chains, n_chains, M, 1, 1, true, seed_dev, barrier_words, dX_sum, P, "fr_mlp_chain_backward");
+  int rc = fr::build_params(chains, n_chains, M, 1, 1, true, seed_dev, barrier_words, dX_sum, dp, P, "fr_mlp_chain_backward");
   if (rc) return rc;
   int want = fr::import_items(P.h, true) + fr::flat_items(P.h, true);
   for (int s = 0; s < P.h.Lmax; ++s) {
     const int g = fr::bwd_gemm_items(P.h, s);
     if (g > want) want = g;
   }
-  return fr::launch_chain((const void *)fr::k_mlp_chain_bwd, "k_mlp_chain_bwd", P, want, (cudaStream_t)stream);
+  return fr::run_chain((const void *)fr::k_mlp_chain_bwd, "k_mlp_chain_bwd", P, true, want, dp, (cudaStream_t)stream);
+}
+
+int fr_mlp_chain_forward(const fr_chain *chains, int32_t n_chains, int64_t M, int32_t training, int32_t need_grad,
+                         const uint64_t *seed_dev, uint32_t *barrier_words, void *stream) {
+  return fr_mlp_chain_forward_dp(chains, n_chains, M, training, need_grad, seed_dev, barrier_words, nullptr, stream);
+}
+
+int fr_mlp_chain_backward(const fr_chain *chains, int32_t n_chains, int64_t M, const uint64_t *seed_dev, float *dX_sum,
+                          uint32_t *barrier_words, void *stream) {
+  return fr_mlp_chain_backward_dp(chains, n_chains, M, seed_dev, dX_sum, barrier_words, nullptr, stream);
+}
+
+int fr_mlp_chain_segments(const fr_chain *chains, int32_t n_chains, int32_t training, int32_t backward, int32_t world) {
+  // number of launch segments of a data-parallel chain call (cuts where BatchNorm partials cross the ranks)
+  if (!chains || n_chains < 1 || n_chains > fr::CH_MAX_CHAINS) return -1;
+  int n = 1;
+  if (world <= 1 || !(training || backward)) return n;
+  int Lmax = 0;
+  for (int c = 0; c < n_chains; ++c) Lmax = chains[c].n_layers > Lmax ? chains[c].n_layers : Lmax;
+  for (int pos = 0; pos < Lmax; ++pos) {
+    bool bn = false;
+    for (int c = 0; c < n_chains; ++c) {
+      const int l = backward ? chains[c].n_layers - 1 - pos : pos;
+      if (l >= 0 && l < chains[c].n_layers && chains[c].layer[l].has_bn) bn = true;
+    }
+    if (bn) ++n;
+  }
+  return n;
 }
 
 }  // extern "C"

@@ -153,6 +153,10 @@ class FairGo_PMF(nn.Module):
         """nn.Sequential(Linear, act, Linear, act, Linear) (fairgo_pmf.py:66-70) on the linear kernels"""
         act = ops.ACT[self.act.lower()]
         lins = [m for m in self.aggr_layer if isinstance(m, nn.Linear)]
+        fused = ops.mlp_chain([ops.SeqChain([(lin, None, act if k + 1 < len(lins) else 0, 0.0) for k, lin in enumerate(lins)],
+                                            self.training)], [x])
+        if fused is not None:       # the three layers in one forward / one backward launch (mlp_chain.cu)
+            return fused[0]
         for k, lin in enumerate(lins):
             x = ops.LinearAct.apply(x, lin.weight, lin.bias, act if k + 1 < len(lins) else 0, 0.0, 0)
         return x
@@ -230,22 +234,28 @@ class FairGo_PMF(nn.Module):
         sig = ops.ACT["sigmoid"]
         for sst in sst_list:
             dis = self.dis_layer_dict[sst]
+            # the discriminator's passes over the node rows and the ego-network rows share one forward and one backward
+            # launch (chains of the same module: autograd adds their weight gradients); None = per-module path
+            ins = [user_node] + (list(all_graph) if lva else [user_local])
+            zs = ops.mlp_chain([dis] * len(ins), ins) if len(ins) <= 4 else None
+            if zs is None:
+                zs = [dis(t) for t in ins]
             if self.sst_size[sst] == 2:
                 y = interaction[sst].to(device=dev, dtype=torch.float32)
-                node = node + ops.SigmoidBce.apply(dis(user_node), y)
+                node = node + ops.SigmoidBce.apply(zs[0], y)
                 if lva:
                     for k, w in enumerate(self.vs_weights):
-                        local = local + float(w) * ops.SigmoidBce.apply(dis(all_graph[k]), y)
+                        local = local + float(w) * ops.SigmoidBce.apply(zs[1 + k], y)
                 else:
-                    local = local + ops.SigmoidBce.apply(dis(user_local), y)
+                    local = local + ops.SigmoidBce.apply(zs[1], y)
             else:
                 y = interaction[sst].to(device=dev, dtype=torch.int32)
-                node = node + ops.SoftmaxCe.apply(dis(user_node), y)
+                node = node + ops.SoftmaxCe.apply(zs[0], y)
                 if lva:
                     for k, w in enumerate(self.vs_weights):
-                        local = local + float(w) * ops.SoftmaxCe.apply(ops.Act.apply(dis(all_graph[k]), sig), y)
+                        local = local + float(w) * ops.SoftmaxCe.apply(ops.Act.apply(zs[1 + k], sig), y)
                 else:
-                    local = local + ops.SoftmaxCe.apply(ops.Act.apply(dis(user_local), sig), y)
+                    local = local + ops.SoftmaxCe.apply(ops.Act.apply(zs[1], sig), y)
         return node + local
 
     def predict(self, interaction):

@@ -42,6 +42,8 @@ class MLPLayers(nn.Module):
         fused = ops.mlp_chain([self], [x]) if x.dim() == 2 else None     # the whole chain in one launch (mlp_chain.cu)
         if fused is not None:
             return fused[0]
+        if ops._chain_dp is not None and self.use_bn and self.training:
+            raise NotImplementedError("data-parallel BatchNorm needs the fused chain kernels (layer widths <= 256, K % 4 == 0)")
         act = ops.ACT[self.activation]
         mods = list(self.mlp_layers)
         k = 0

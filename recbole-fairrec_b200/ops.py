@@ -172,12 +172,31 @@ def init_autograd_thread(device):
     _TouchBackwardThread.apply(x).sum().backward()
 
 
-def _chain_layers(mod, training, seeds=None):
-    """[(Linear, BatchNorm1d | None)] of an MLPLayers module -> ctypes layer array (pointers filled, gradients not)"""
+class SeqChain:
+    """a chain that is not an MLPLayers module (e.g. FairGo's aggregation nn.Sequential(Linear, act, Linear, act, Linear)):
+    pairs = [(nn.Linear, nn.BatchNorm1d | None, activation code, dropout p)]"""
+
+    def __init__(self, pairs, training):
+        self._pairs, self.training = list(pairs), bool(training)
+
+    def chain_pairs(self):
+        return self._pairs
+
+    def parameters(self):
+        for lin, bn, _, _ in self._pairs:
+            yield from lin.parameters()
+            if bn is not None:
+                yield from bn.parameters()
+
+
+def _pairs_of(mod):
+    """[(Linear, BatchNorm1d | None, activation code, dropout p)] of an MLPLayers module or a SeqChain"""
     import torch.nn as nn
-    from ._lib import ChainLayer
+    if hasattr(mod, "chain_pairs"):
+        return mod.chain_pairs()
     mods = list(mod.mlp_layers)
     pairs, k = [], 0
+    act = ACT[mod.activation]
     while k < len(mods):
         lin = mods[k + 1]
         k += 2
@@ -187,15 +206,21 @@ def _chain_layers(mod, training, seeds=None):
             k += 1
         if k < len(mods) and not isinstance(mods[k], nn.Dropout):
             k += 1
-        pairs.append((lin, bn))
+        pairs.append((lin, bn, act, float(mod.dropout)))
+    return pairs
+
+
+def _chain_layers(mod, training, seeds=None):
+    """ctypes layer array of a chain (pointers filled, gradients not) + its pairs; (None, pairs) = outside the rules"""
+    from ._lib import ChainLayer
+    pairs = _pairs_of(mod)
     arr = (ChainLayer * 8)()
     if len(pairs) > 8:
         return None, pairs
-    act = ACT[mod.activation]
-    for i, (lin, bn) in enumerate(pairs):
+    for i, (lin, bn, act, p) in enumerate(pairs):
         L = arr[i]
         L.K, L.N, L.act, L.has_bn = lin.in_features, lin.out_features, act, 1 if bn is not None else 0
-        L.drop_p = float(mod.dropout) if training else 0.0
+        L.drop_p = float(p) if training else 0.0
         L.seed = seeds[i] if seeds is not None else 0
         L.W = lin.weight.data_ptr()
         L.b = lin.bias.data_ptr() if lin.bias is not None else None
@@ -211,7 +236,7 @@ def _chain_layers(mod, training, seeds=None):
 
 def _chain_params(pairs):
     out = []
-    for lin, bn in pairs:
+    for lin, bn, _, _ in pairs:
         out.append(lin.weight)
         if lin.bias is not None:
             out.append(lin.bias)
@@ -220,50 +245,177 @@ def _chain_params(pairs):
     return out
 
 
+class ChainDP:
+    """Data-parallel context of the chain kernels (fr_mlp_chain_*_dp): this process holds rows [rank * M, (rank + 1) * M)
+    of every batch; BatchNorm column sums cross the ranks through NVLink peer memory.  `group` = torch.distributed process
+    group (one process per GPU): the exchange buffers are CUDA-IPC mapped into the peers once, here."""
+
+    XCHG_BYTES = 32 << 20
+
+    def __init__(self, rank, world, group=None, device=None):
+        import ctypes
+
+        import torch.distributed as dist
+        self.rank, self.world, self.group = rank, world, group
+        self.lib = load()
+        own = ctypes.c_void_p()
+        check(self.lib.fr_xchg_alloc(self.XCHG_BYTES, ctypes.byref(own)), "fr_xchg_alloc")
+        self.own = own.value
+        self.peers = [None] * world
+        self.peers[rank] = self.own
+        self.opened = []
+        h = ctypes.create_string_buffer(64)
+        check(self.lib.fr_xchg_export(self.own, h), "fr_xchg_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        for k, raw in enumerate(handles):
+            if k == rank:
+                continue
+            pp = ctypes.c_void_p()
+            check(self.lib.fr_xchg_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(pp)), "fr_xchg_open")
+            self.peers[k] = pp.value
+            self.opened.append(pp.value)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def struct(self, segment=-1, parity=0):
+        from ._lib import ChainDp
+        d = ChainDp()
+        d.rank, d.world, d.xchg_bytes, d.barriers, d.segment, d.parity = self.rank, self.world, self.XCHG_BYTES, 1, -1, 0
+        for k in range(self.world):
+            d.xchg[k] = self.peers[k]
+        d.status_flags = self.status.data_ptr()
+        return d
+
+    def all_reduce_grads(self, params):
+        """sum the ranks' shares of the gradients (one NCCL all-reduce over a flat bucket)"""
+        import torch.distributed as dist
+        gs = [p.grad for p in params if p.grad is not None]
+        if not gs:
+            return
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        dist.all_reduce(flat, group=self.group)
+        off = 0
+        for g in gs:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def close(self):
+        for pp in self.opened:
+            self.lib.fr_xchg_close(pp)
+        self.opened = []
+        if self.own:
+            self.lib.fr_xchg_free(self.own)
+            self.own = None
+
+
+_chain_dp = None
+
+
+def set_chain_dp(ctx):
+    """install (or clear, with None) the data-parallel context used by every chain call of this process"""
+    global _chain_dp
+    _chain_dp = ctx
+
+
+def _chain_build_forward(mods, xs, training, need_grad, seeds_per_mod):
+    """ctypes chain array of a forward call: outputs and workspaces allocated -> (chains, ys, workspaces, metas)"""
+    from ._lib import Chain
+    lib = load()
+    M, dev = xs[0].shape[0], xs[0].device
+    chains = (Chain * len(mods))()
+    keep, ys, metas = [], [], []
+    for c, mod in enumerate(mods):
+        seeds = seeds_per_mod[c]
+        arr, pairs = _chain_layers(mod, training, seeds)
+        C = chains[c]
+        C.n_layers = len(pairs)
+        for i in range(len(pairs)):
+            C.layer[i] = arr[i]
+        x = xs[c if len(xs) > 1 else 0]
+        y = torch.empty((M, pairs[-1][0].out_features), dtype=torch.float32, device=dev)
+        nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1 if training else 0, 1 if need_grad else 0, 0)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        C.X, C.ldx, C.Y = x.data_ptr(), x.shape[1], y.data_ptr()
+        C.fwd_ws, C.fwd_ws_bytes = ws.data_ptr(), nb
+        keep.append(ws)
+        ys.append(y)
+        metas.append((seeds, pairs))
+    return chains, ys, keep, metas
+
+
+def _chain_build_backward(mods, xs, ys, dys, metas, fwd_ws, want_dx):
+    """ctypes chain array of a backward call: gradient outputs and scratch allocated
+    -> (chains, parameter gradients in _chain_params order, per-chain dX, dX_sum, tensors to keep alive)"""
+    from ._lib import Chain
+    lib = load()
+    M, dev = xs[0].shape[0], xs[0].device
+    chains = (Chain * len(mods))()
+    keep, grads_p, dxs = [], [], []
+    shared = len(xs) == 1 and len(mods) > 1
+    for c, mod in enumerate(mods):
+        seeds, pairs = metas[c]
+        arr, _ = _chain_layers(mod, True, seeds)
+        C = chains[c]
+        C.n_layers = len(pairs)
+        x = xs[c if len(xs) > 1 else 0]
+        dy = dys[c]
+        dy = torch.zeros_like(ys[c]) if dy is None else dy.contiguous()
+        for i, (lin, bn, _, _) in enumerate(pairs):
+            dW = torch.empty_like(lin.weight)
+            arr[i].dW = dW.data_ptr()
+            grads_p.append(dW)
+            if lin.bias is not None:
+                db = torch.empty_like(lin.bias)
+                arr[i].db = db.data_ptr()
+                grads_p.append(db)
+            if bn is not None:
+                dg, dbt = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+                arr[i].dgamma, arr[i].dbeta = dg.data_ptr(), dbt.data_ptr()
+                grads_p += [dg, dbt]
+            C.layer[i] = arr[i]
+        nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1, 1, 1)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        dx = torch.empty((M, pairs[0][0].in_features), dtype=torch.float32, device=dev) if want_dx[c] else None
+        C.X, C.ldx, C.Y, C.dY = x.data_ptr(), x.shape[1], ys[c].data_ptr(), dy.data_ptr()
+        C.dX = dx.data_ptr() if dx is not None else None
+        C.fwd_ws, C.fwd_ws_bytes = fwd_ws[c].data_ptr(), fwd_ws[c].numel()
+        C.bwd_ws, C.bwd_ws_bytes = ws.data_ptr(), nb
+        keep += [ws, dy]
+        dxs.append(dx)
+    dx_sum = torch.empty_like(dxs[0]) if (shared and want_dx[0]) else None
+    return chains, grads_p, dxs, dx_sum, keep
+
+
 class MLPChainGroup(torch.autograd.Function):
     """Whole MLPLayers chains (layers.py:30-85) -- up to four over the same batch rows -- as ONE forward launch and ONE
-    backward launch of the tcgen05 chain kernels (fr_mlp_chain_forward / fr_mlp_chain_backward)."""
+    backward launch of the tcgen05 chain kernels (fr_mlp_chain_forward / fr_mlp_chain_backward); with a data-parallel
+    context installed (set_chain_dp) the launches are cut where BatchNorm statistics cross the ranks."""
 
     @staticmethod
     def forward(ctx, spec, *tensors):
-        from ._lib import Chain
+        import ctypes
         lib = load()
         mods, n_x, training = spec["mods"], spec["n_x"], spec["training"]
         xs = [t.contiguous() for t in tensors[:n_x]]
-        M = xs[0].shape[0]
-        dev = xs[0].device
+        M, dev = xs[0].shape[0], xs[0].device
         need_grad = spec["grad"]        # (ctx.needs_input_grad ignores torch.no_grad())
-        chains = (Chain * len(mods))()
-        keep, ys, metas = [], [], []
-        for c, mod in enumerate(mods):
-            seeds = [next_seed() for _ in range(spec["n_layers"][c])]
-            arr, pairs = _chain_layers(mod, training, seeds)
-            C = chains[c]
-            C.n_layers = len(pairs)
-            for i in range(len(pairs)):
-                C.layer[i] = arr[i]
-            x = xs[c if n_x > 1 else 0]
-            y = torch.empty((M, pairs[-1][0].out_features), dtype=torch.float32, device=dev)
-            nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1 if training else 0, 1 if need_grad else 0, 0)
-            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-            C.X, C.ldx, C.Y = x.data_ptr(), x.shape[1], y.data_ptr()
-            C.fwd_ws, C.fwd_ws_bytes = ws.data_ptr(), nb
-            keep.append(ws)
-            ys.append(y)
-            metas.append((seeds, pairs))
-        sd = seed_dev(dev)
-        check(lib.fr_mlp_chain_forward(chains, len(mods), M, 1 if training else 0, 1 if need_grad else 0, ptr(sd),
-                                       ptr(chain_bars(dev)), stream_ptr()), "fr_mlp_chain_forward")
+        seeds = [[next_seed() for _ in range(n)] for n in spec["n_layers"]]
+        chains, ys, keep, metas = _chain_build_forward(mods, xs, training, need_grad, seeds)
+        dp = _chain_dp.struct() if _chain_dp is not None else None
+        check(lib.fr_mlp_chain_forward_dp(chains, len(mods), M, 1 if training else 0, 1 if need_grad else 0,
+                                          ptr(seed_dev(dev)), ptr(chain_bars(dev)),
+                                          ctypes.byref(dp) if dp is not None else None, stream_ptr()), "fr_mlp_chain_forward")
         if need_grad:
             if not training:
                 raise NotImplementedError("MLPChainGroup backward is implemented for training mode")
-            ctx.spec, ctx.metas, ctx.ws, ctx.xs_meta = spec, metas, keep, [(x.data_ptr(), x.shape[1]) for x in xs]
+            ctx.spec, ctx.metas, ctx.ws = spec, metas, keep
             ctx.save_for_backward(*xs, *ys)
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, *dys):
-        from ._lib import Chain
+        import ctypes
         lib = load()
         _bind_thread()
         spec = ctx.spec
@@ -271,47 +423,68 @@ class MLPChainGroup(torch.autograd.Function):
         saved = ctx.saved_tensors
         xs, ys = saved[:n_x], saved[n_x:]
         M, dev = xs[0].shape[0], xs[0].device
-        chains = (Chain * len(mods))()
-        keep, grads_p, dxs = [], [], []
         shared = n_x == 1 and len(mods) > 1
         want_dx = [ctx.needs_input_grad[1 + (c if n_x > 1 else 0)] for c in range(len(mods))]
-        for c, mod in enumerate(mods):
-            seeds, pairs = ctx.metas[c]
-            arr, _ = _chain_layers(mod, True, seeds)
-            C = chains[c]
-            C.n_layers = len(pairs)
-            x = xs[c if n_x > 1 else 0]
-            dy = dys[c]
-            dy = torch.zeros_like(ys[c]) if dy is None else dy.contiguous()
-            for i, (lin, bn) in enumerate(pairs):
-                dW = torch.empty_like(lin.weight)
-                arr[i].dW = dW.data_ptr()
-                grads_p.append(dW)
-                if lin.bias is not None:
-                    db = torch.empty_like(lin.bias)
-                    arr[i].db = db.data_ptr()
-                    grads_p.append(db)
-                if bn is not None:
-                    dg, dbt = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
-                    arr[i].dgamma, arr[i].dbeta = dg.data_ptr(), dbt.data_ptr()
-                    grads_p += [dg, dbt]
-                C.layer[i] = arr[i]
-            nb = lib.fr_mlp_chain_workspace_bytes(arr, len(pairs), M, 1, 1, 1)
-            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-            dx = torch.empty_like(x[:, :pairs[0][0].in_features].contiguous()) if want_dx[c] else None
-            C.X, C.ldx, C.Y, C.dY = x.data_ptr(), x.shape[1], ys[c].data_ptr(), dy.data_ptr()
-            C.dX = dx.data_ptr() if dx is not None else None
-            C.fwd_ws, C.fwd_ws_bytes = ctx.ws[c].data_ptr(), ctx.ws[c].numel()
-            C.bwd_ws, C.bwd_ws_bytes = ws.data_ptr(), nb
-            keep += [ws, dy]
-            dxs.append(dx)
-        dx_sum = None
-        if shared and want_dx[0]:
-            dx_sum = torch.empty_like(dxs[0])
-        check(lib.fr_mlp_chain_backward(chains, len(mods), M, ptr(seed_dev(dev)), ptr(dx_sum), ptr(chain_bars(dev)),
-                                        stream_ptr()), "fr_mlp_chain_backward")
+        chains, grads_p, dxs, dx_sum, keep = _chain_build_backward(mods, xs, ys, dys, ctx.metas, ctx.ws, want_dx)
+        dp = _chain_dp.struct() if _chain_dp is not None else None
+        check(lib.fr_mlp_chain_backward_dp(chains, len(mods), M, ptr(seed_dev(dev)), ptr(dx_sum), ptr(chain_bars(dev)),
+                                           ctypes.byref(dp) if dp is not None else None, stream_ptr()),
+              "fr_mlp_chain_backward")
         gx = [dx_sum] if shared else (dxs if n_x > 1 else [dxs[0]])
         return (None, *gx, *grads_p)
+
+
+def chain_dp_emulate(rank_mods, rank_xs, rank_dys):
+    """Single-process emulation of a data-parallel chain call (test / profiling harness): P emulated ranks on ONE device,
+    the host running segment after segment, rank after rank, instead of the flag barriers (fr_chain_dp.barriers = 0).
+    rank_mods[r]: chain modules of rank r (replicas); rank_xs[r] / rank_dys[r]: its inputs / output gradients.
+    -> (ys[r][c], dxs[r], grads[r]) with grads[r] in _chain_params order (this rank's share)."""
+    import ctypes
+
+    from ._lib import ChainDp
+    lib = load()
+    world = len(rank_mods)
+    dev = rank_xs[0][0].device
+    M = rank_xs[0][0].shape[0]
+    bufs = [torch.zeros(ChainDP.XCHG_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def dp_struct(r, seg, parity):
+        d = ChainDp()
+        d.rank, d.world, d.xchg_bytes, d.barriers, d.segment, d.parity = r, world, ChainDP.XCHG_BYTES, 0, seg, parity
+        for k in range(world):
+            d.xchg[k] = bufs[k].data_ptr()
+        d.status_flags = status.data_ptr()
+        return d
+
+    seeds = [[next_seed() for _ in _pairs_of(m)] for m in rank_mods[0]]      # the ranks share the dropout seeds
+    fw = [_chain_build_forward(rank_mods[r], rank_xs[r], True, True, seeds) for r in range(world)]
+    nseg = lib.fr_mlp_chain_segments(fw[0][0], len(rank_mods[0]), 1, 0, world)
+    exch = 0
+    for seg in range(nseg):
+        for r in range(world):
+            d = dp_struct(r, seg, (exch + seg) & 1)
+            check(lib.fr_mlp_chain_forward_dp(fw[r][0], len(rank_mods[r]), M, 1, 1, ptr(seed_dev(dev)), ptr(chain_bars(dev)),
+                                              ctypes.byref(d), stream_ptr()), "fr_mlp_chain_forward_dp")
+    exch += nseg - 1
+    outs = []
+    bw = []
+    for r in range(world):
+        chains, ys, keep, metas = fw[r]
+        want = [True] * len(rank_mods[r])
+        bw.append(_chain_build_backward(rank_mods[r], rank_xs[r], ys, rank_dys[r], metas, keep, want))
+    nseg_b = lib.fr_mlp_chain_segments(bw[0][0], len(rank_mods[0]), 1, 1, world)
+    for seg in range(nseg_b):
+        for r in range(world):
+            d = dp_struct(r, seg, (exch + seg) & 1)
+            check(lib.fr_mlp_chain_backward_dp(bw[r][0], len(rank_mods[r]), M, ptr(seed_dev(dev)), ptr(bw[r][3]),
+                                               ptr(chain_bars(dev)), ctypes.byref(d), stream_ptr()),
+                  "fr_mlp_chain_backward_dp")
+    torch.cuda.synchronize()
+    for r in range(world):
+        shared = len(rank_xs[r]) == 1 and len(rank_mods[r]) > 1
+        outs.append((fw[r][1], [bw[r][3]] if shared else bw[r][2], bw[r][1]))
+    return outs
 
 
 def mlp_chain(mods, xs):

@@ -319,14 +319,35 @@ class PFCN_DMF(_PFCNBase):
         return self._with_dis(ops.BprLoss.apply(pos, neg), interaction, sst_list)
 
 
+class _DpOptimizer:
+    """an AdamGroup whose step first sums the ranks' gradient shares (ops.ChainDP.all_reduce_grads: one NCCL all-reduce)"""
+
+    def __init__(self, opt, dp):
+        self.opt, self.dp = opt, dp
+
+    def __getattr__(self, k):
+        return getattr(self.opt, k)
+
+    def step(self):
+        self.dp.all_reduce_grads(self.opt.params)
+        self.opt.step()
+
+
 class PFCNTrainer(CheckpointMixin):
     """The alternating schedule of PFCNTrainer and its per-model subclasses (trainer.py:865-898, 1189-1235): per epoch
     a random non-empty attribute subset; every `train_epoch_interval`-th epoch one pass on `bpr - dis_weight * dis` with
     the filter optimizer (base model + filters), then always one pass on `dis` with the discriminator optimizer.
     Optimizer steps run on this package's Adam kernel (ops.AdamGroup = torch.optim.Adam semantics, L2 form)."""
 
-    def __init__(self, config, model):
-        self.config, self.model = config, model
+    def __init__(self, config, model, dp=None):
+        """dp: ops.ChainDP -- data-parallel training over the GPUs of one box (one process per GPU):
+        every rank takes rows [rank * B / world, (rank + 1) * B / world) of each batch (a tail of B % world rows is dropped),
+        BatchNorm keeps the statistics of the WHOLE batch (the chain kernels exchange their column sums through NVLink peer
+        memory, ops.set_chain_dp), the loss is the mean over the whole batch, and the ranks' gradient shares are summed by
+        one NCCL all-reduce before every Adam step: the replicas stay identical and follow the single-GPU trajectory."""
+        self.config, self.model, self.dp = config, model, dp
+        if dp is not None:
+            ops.set_chain_dp(dp)
         self.filter_mode = config["filter_mode"].lower()
         self.train_epoch_interval = config["train_epoch_interval"] or 1
         lr, wd = config["learning_rate"], config["weight_decay"] or 0.0
@@ -339,22 +360,55 @@ class PFCNTrainer(CheckpointMixin):
             self.optimizer_dis = ops.AdamGroup(dparams, lr=lr, weight_decay=wd)
         else:
             self.optimizer_filter = ops.AdamGroup(base, lr=lr, weight_decay=wd)
+        if dp is not None:
+            self.optimizer_filter = _DpOptimizer(self.optimizer_filter, dp)
+            if self.filter_mode != "none":
+                self.optimizer_dis = _DpOptimizer(self.optimizer_dis, dp)
+
+    def _shard(self, interaction):
+        """this rank's rows of a batch (data-parallel mode)"""
+        if self.dp is None:
+            return interaction
+        from .interaction import Interaction
+        n = len(interaction) // self.dp.world
+        lo = self.dp.rank * n
+        return Interaction({k: interaction[k][lo:lo + n] for k in interaction.columns})
+
+    def _dp_loss(self, loss_func):
+        if self.dp is None:
+            return loss_func
+        world = self.dp.world
+
+        def scaled(interaction, sst_list):        # the mean over the whole batch = the mean of the ranks' means
+            return ops.WeightedSum.apply(1.0 / world, loss_func(interaction, sst_list))
+        scaled.__name__ = loss_func.__name__
+        return scaled
 
     def _pass(self, train_data, loss_func, optimizer, sst_list):
         self.model.train()
         if self.config["use_cuda_graph"]:
             return self._pass_graphed(train_data, loss_func, optimizer, sst_list)
         total = None
+        loss_func = self._dp_loss(loss_func)
         for interaction in train_data:
             optimizer.zero_grad()
-            loss = loss_func(interaction, sst_list)
+            loss = loss_func(self._shard(interaction), sst_list)
             v = loss.item()
             if v != v:
                 raise ValueError("Training loss is nan")
             total = v if total is None else total + v
             loss.backward()
             optimizer.step()
-        return total
+        return self._dp_total(total)
+
+    def _dp_total(self, total):
+        """the pass's summed loss over all ranks (each rank summed its share of every batch mean)"""
+        if self.dp is None or total is None:
+            return total
+        import torch.distributed as dist
+        t = torch.tensor([total], dtype=torch.float64, device=next(self.model.parameters()).device)
+        dist.all_reduce(t, group=self.dp.group)
+        return float(t.item())
 
     def _pass_graphed(self, train_data, loss_func, optimizer, sst_list):
         """`use_cuda_graph: True`: one CUDA-graph replay per batch (graphed.py); the per-batch losses are summed on the
@@ -365,13 +419,14 @@ class PFCNTrainer(CheckpointMixin):
             self._graph_gen = 0
         total = None
         name = f"{loss_func.__name__}:{id(optimizer)}:{getattr(self.model, 'train_stage', '')}"
+        loss_func = self._dp_loss(loss_func)
         for interaction in train_data:
-            loss = self._graphs.run(name, loss_func, optimizer, sst_list, interaction)
+            loss = self._graphs.run(name, loss_func, optimizer, sst_list, self._shard(interaction))
             total = loss.clone() if total is None else total + loss
         v = float(total.item()) if total is not None else None
         if v is not None and v != v:
             raise ValueError("Training loss is nan")
-        return v
+        return self._dp_total(v)
 
     @torch.no_grad()
     def evaluate(self, eval_data, sst_list=None, train_item_count=None):

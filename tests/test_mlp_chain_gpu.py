@@ -228,3 +228,47 @@ def test_run_to_run_bit_stability():
         res.append([y.clone(), xx.grad.clone()] + [p.grad.clone() for p in m.parameters()])
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_data_parallel_chain_equals_the_single_gpu_chain(world):
+    """fr_mlp_chain_*_dp with the ranks emulated on one device (ops.chain_dp_emulate: the host sequences the launch segments
+    instead of the cross-GPU flag barriers; same kernels, same exchange layout): every rank holds M / world rows, the
+    BatchNorm column sums cross the ranks through the exchange buffers.  With M / world a multiple of 128 the global
+    row-block order equals the single-GPU one, so outputs, input gradients and running statistics are BIT-identical to the
+    single-GPU chain on the whole batch (dropout included: the masks hash the global row index); the parameter gradients
+    are the sum of the ranks' shares (another association of the same terms: 1e-6)."""
+    import itertools
+    from recbole_fairrec_b200 import ops
+    dev = torch.device("cuda", 0)
+    M = 2048
+    for layers, p, heads in (([64, 128, 64], 0.0, None), ([64, 128, 256, 128, 128, 64, 32], 0.3, (1, 7))):
+        torch.manual_seed(3)
+        x = torch.randn(M, layers[0], device=dev)
+        outs = heads or (layers[-1],)
+        base = layers if heads is None else layers
+        mods = [_make((base + [h]) if heads else base, p, "leakyrelu", True, 40 + h, dev).train() for h in outs]
+        gys = [torch.randn(M, (h if heads else layers[-1]), device=dev) / M for h in outs]
+        replicas = [[copy.deepcopy(m) for m in mods] for _ in range(world)]
+        # single GPU
+        ops._seed_counter = itertools.count(5000)
+        x1 = x.clone().requires_grad_(True)
+        ys = ops.mlp_chain(mods, [x1])
+        torch.autograd.backward(ys, gys)
+        # data parallel
+        ops._seed_counter = itertools.count(5000)
+        Ml = M // world
+        res = ops.chain_dp_emulate(replicas, [[x[r * Ml:(r + 1) * Ml].contiguous()] for r in range(world)],
+                                   [[g[r * Ml:(r + 1) * Ml].contiguous() for g in gys] for r in range(world)])
+        for c in range(len(mods)):
+            assert torch.equal(torch.cat([res[r][0][c] for r in range(world)]), ys[c]), "outputs"
+        assert torch.equal(torch.cat([res[r][1][0] for r in range(world)]), x1.grad), "input gradient"
+        params = [q for m in mods for q in ops._chain_params(ops._pairs_of(m))]
+        for i, q in enumerate(params):
+            total = sum(res[r][2][i] for r in range(world))
+            scale = max(float(q.grad.abs().max()), 1e-12)
+            assert float((total - q.grad).abs().max()) <= 2e-6 * scale + 1e-9, i
+        for m, reps in zip(mods, zip(*replicas)):
+            for rep in reps:
+                for (n, b), (_, b2) in zip(m.named_buffers(), rep.named_buffers()):
+                    assert torch.equal(b, b2), n
