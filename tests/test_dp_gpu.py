@@ -124,3 +124,96 @@ def test_row_sharded_step_multi_process(adam_mode):
     out = mgr.dict()
     mp.spawn(_shard_worker, args=(world, 29541 + (adam_mode == "lazy_exact"), out, adam_mode), nprocs=world, join=True)
     assert out["pass"], dict(out)
+
+
+def _pfcn_worker(rank, world, port, out):
+    """PFCN_MLP, data parallel over `world` GPUs (PFCNTrainer(dp=ops.ChainDP): rows of every batch split over the ranks,
+    BatchNorm column sums through NVLink peer memory, gradient shares summed by NCCL) against the single-GPU trainer on
+    the whole batches: first-step gradients, the losses of three alternating filter / discriminator steps, BatchNorm
+    running statistics."""
+    import copy
+
+    import torch.distributed as dist
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import ops
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from test_pfcn_gpu import UserFeatDataset
+    nu, ni, d, B = 600, 400, 64, 1024
+    rng = np.random.default_rng(7)
+    feats = {"gender": (rng.random(nu) < 0.3).astype(np.float32), "age": rng.integers(0, 7, nu).astype(np.float32)}
+    cfg = pkg.Config(embedding_size=d, sst_attr_list=list(feats), filter_mode="sm", dropout=0.0, dis_dropout=0.0,
+                     dis_weight=10.0, dis_hidden_size_list=[128, 256, 128, 128, 64, 32], mlp_hidden_size_list=[64, 32, 16],
+                     activation="leakyrelu", device=dev, learning_rate=1e-3, weight_decay=1e-4, train_epoch_interval=1)
+    torch.manual_seed(11)
+    model = pkg.PFCN_MLP(cfg, UserFeatDataset(nu, ni, feats)).to(dev)
+    ref = copy.deepcopy(model)
+    for src, dst in zip(model._dict_modules(), ref._dict_modules()):
+        dst.load_state_dict(src.state_dict())
+    batches = []
+    for _ in range(3):
+        u = rng.integers(1, nu, B)
+        batches.append(pkg.Interaction({"user_id": torch.from_numpy(u).to(dev),
+                                        "item_id": torch.from_numpy(rng.integers(1, ni, B)).to(dev),
+                                        "neg_item_id": torch.from_numpy(rng.integers(1, ni, B)).to(dev),
+                                        **{a: torch.from_numpy(feats[a][u]).to(dev) for a in feats}}))
+    sst = ["gender", "age"]
+
+    def run(m, trainer, shard):
+        losses, grads0 = [], None
+        for k, inter in enumerate(batches):
+            for fn, opt in ((m.calculate_loss, trainer.optimizer_filter), (m.calculate_dis_loss, trainer.optimizer_dis)):
+                opt.zero_grad()
+                loss = trainer._dp_loss(fn)(trainer._shard(inter), sst) if shard else fn(inter, sst)
+                loss.backward()
+                if shard:
+                    trainer.dp.all_reduce_grads(opt.opt.params)
+                if grads0 is None:
+                    ps = opt.opt.params if shard else opt.params
+                    grads0 = [None if p.grad is None else p.grad.detach().clone() for p in ps]
+                (opt.opt if shard else opt).step()
+                t = loss.detach().clone().double()
+                if shard:
+                    dist.all_reduce(t)
+                losses.append(float(t))
+        return losses, grads0
+
+    dp = ops.ChainDP(rank, world, dist.group.WORLD, dev)
+    model.train()
+    l_dp, g_dp = run(model, pkg.PFCNTrainer(cfg, model, dp=dp), True)
+    ops.set_chain_dp(None)
+    ref.train()
+    l_ref, g_ref = run(ref, pkg.PFCNTrainer(cfg, ref), False)
+    gerr = 0.0
+    for a, b in zip(g_dp, g_ref):
+        if a is None or float(b.abs().max()) < 1e-7:
+            continue
+        gerr = max(gerr, float((a - b).abs().max() / b.abs().max()))
+    berr = 0.0
+    for ma, mb in zip(model._dict_modules(), ref._dict_modules()):
+        for (n, x), (_, y) in zip(ma.named_buffers(), mb.named_buffers()):
+            if x.dtype == torch.float32 and "running_mean" not in n:     # running means carry the arbitrary pre-BN bias
+                berr = max(berr, float((x - y).abs().max() / y.abs().max().clamp_min(1e-12)))
+    if rank == 0:
+        out.update(dict(l_dp=l_dp, l_ref=l_ref, gerr=gerr, berr=berr, timeout=int(dp.status.item())))
+    dp.close()
+    dist.destroy_process_group()
+
+
+def test_pfcn_data_parallel_matches_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_pfcn_worker, args=(world, 29561, out), nprocs=world, join=True)
+    assert out["timeout"] == 0
+    # first batch (one filter step, one discriminator step): 1e-5; afterwards Adam has amplified the rounding of the
+    # all-reduce's other summation order (m / sqrt(v) on near-zero gradients), as between any two float32 runs: 1e-4
+    np.testing.assert_allclose(out["l_dp"][:2], out["l_ref"][:2], rtol=1e-5)
+    np.testing.assert_allclose(out["l_dp"], out["l_ref"], rtol=1e-4)
+    assert out["gerr"] < 2e-5, out["gerr"]
+    assert out["berr"] < 1e-5, out["berr"]
