@@ -579,6 +579,21 @@ def run_ours(args, w):
         except Exception as e:
             dp_check = {"pass": False, "error": f"{type(e).__name__}: {str(e)[:300]}"}
 
+    # ============================================================ N > 1: PFCN_MLP data parallel (configs[2] shape per rank)
+    families_dp = None
+    if world > 1 and not args.no_families:
+        try:
+            import bench_families
+            model = loader = tdata = make_step = run_mode = None
+            Uw = Iw = d_items = d_offs = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            note("families_dp block (PFCN_MLP data parallel)")
+            families_dp = {"pfcn_mlp": bench_families.bench_pfcn_dp(dev, rank, world, group)}
+        except Exception as e:
+            families_dp = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     # ============================================================ N = 1 only: configs[1], families, CPU baseline
     ml1m = families = cpu = None
     if world == 1 and rank == 0:
@@ -638,6 +653,7 @@ def run_ours(args, w):
         "dp_check": dp_check,
         "ml1m": ml1m,
         "families": families,
+        "families_dp": families_dp,
         "setup_s": {"synthesis": t_synth, "total_before_json": time.perf_counter() - t_all},
         "hbm_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
     }

@@ -461,6 +461,142 @@ def cpu_nfcf(model, hosts, n=3):
             "sample": f"{n} steps of {B} rows (dropout off in the port)", "ms_per_step": 1e3 * dt}
 
 
+def bench_pfcn_dp(dev, rank, world, group, n_steps=20, seed=2020):
+    """PFCN_MLP data parallel (bench.py --gpus N, all ranks call this): every rank trains on ITS 2048 rows of a global batch
+    of 2048 * world rows (weak scaling), BatchNorm column sums through NVLink peer memory (fr_mlp_chain_*_dp), one NCCL
+    all-reduce of the gradient shares per phase.  `value` = global interactions/s (eager launches, device-timed, max over
+    ranks); `dp_check` = first-step gradients and the losses of two steps against the single-GPU trainer on the whole
+    global batch (rank 0 computes the reference)."""
+    import copy
+
+    import torch
+    import torch.distributed as dist
+
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import ops
+    w = ML1M
+    rng = np.random.default_rng(seed)
+    feats = _user_feats(rng, w["n_users"])
+    attrs = list(feats)
+    cfg = pkg.Config(embedding_size=w["d"], sst_attr_list=attrs, filter_mode="sm", dropout=0.2, dis_dropout=0.3,
+                     dis_weight=10.0, dis_hidden_size_list=[128, 256, 128, 128, 64, 32], mlp_hidden_size_list=[64, 32, 16],
+                     activation="leakyrelu", device=dev, learning_rate=1e-3, weight_decay=1e-4, train_epoch_interval=1)
+    torch.manual_seed(seed)
+    model = pkg.PFCN_MLP(cfg, _DS(w["n_users"], w["n_items"], feats)).to(dev)
+    ref = copy.deepcopy(model)
+    for src, dst in zip(model._dict_modules(), ref._dict_modules()):
+        dst.load_state_dict(src.state_dict())
+    B = w["batch"] * world
+    sst_list = ["gender", "occupation"]
+
+    def batch():
+        u = rng.integers(1, w["n_users"], B)
+        return pkg.Interaction({"user_id": torch.from_numpy(u).to(dev),
+                                "item_id": torch.from_numpy(rng.integers(1, w["n_items"], B)).to(dev),
+                                "neg_item_id": torch.from_numpy(rng.integers(1, w["n_items"], B)).to(dev),
+                                **{a: torch.from_numpy(feats[a][u]).to(dev) for a in attrs}})
+
+    batches = [batch() for _ in range(4)]
+    dp = ops.ChainDP(rank, world, group, dev)
+    trainer = pkg.PFCNTrainer(cfg, model, dp=dp)
+    model.train()
+
+    def step(m, tr, inter, shard, keep=None):
+        out = []
+        for fn, opt in ((m.calculate_loss, tr.optimizer_filter), (m.calculate_dis_loss, tr.optimizer_dis)):
+            opt.zero_grad()
+            loss = tr._dp_loss(fn)(tr._shard(inter), sst_list) if shard else fn(inter, sst_list)
+            loss.backward()
+            if keep is not None and not keep:
+                if shard:
+                    dp.all_reduce_grads(opt.opt.params)
+                keep.extend(None if q.grad is None else q.grad.detach().clone() for q in (opt.opt.params if shard else opt.params))
+                (opt.opt if shard else opt).step()
+            else:
+                opt.step()
+            out.append(loss.detach())
+        return out
+
+    import itertools
+    ops._seed_counter = itertools.count(777)
+    g_dp = []
+    l_dp = []
+    for k in range(2):
+        for t in step(model, trainer, batches[k], True, g_dp):
+            t = t.clone().double()
+            dist.all_reduce(t, group=group)
+            l_dp.append(float(t))
+    check = None
+    ops.set_chain_dp(None)
+    if rank == 0:
+        ops._seed_counter = itertools.count(777)
+        ref.train()
+        rt = pkg.PFCNTrainer(cfg, ref)
+        g_ref, l_ref = [], []
+        for k in range(2):
+            l_ref += [float(t) for t in step(ref, rt, batches[k], False, g_ref)]
+        gerr = 0.0
+        for a, b in zip(g_dp, g_ref):
+            if a is not None and float(b.abs().max()) > 1e-7:
+                gerr = max(gerr, float((a - b).abs().max() / b.abs().max()))
+        lerr = max(abs(a - b) / max(abs(b), 1e-12) for a, b in zip(l_dp, l_ref))
+        check = {"world": world, "first_step_grad_rel_err": gerr, "loss_rel_err_2_steps": lerr,
+                 "pass": bool(gerr < 5e-5 and lerr < 1e-4),
+                 "what": "PFCNTrainer(dp) on 2048 rows per rank vs the single-GPU trainer on the whole global batch (dropout on: "
+                         "the masks hash the global row index, so both runs draw the same masks)"}
+    ops.set_chain_dp(dp)
+    dist.barrier(group=group)
+    for k in range(3):
+        step(model, trainer, batches[k % 4], True)
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for k in range(n_steps):
+        step(model, trainer, batches[k % 4], True)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / n_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms_eager = float(t)
+    # the same step as two CUDA-graph replays per batch (filter phase, discriminator phase): NCCL all-reduce and the flag
+    # barriers are captured with the kernels
+    ms, mode = ms_eager, "eager (host-paced)"
+    try:
+        from recbole_fairrec_b200.graphed import GraphedStep
+        shard0 = trainer._shard(batches[0])
+        graphs = [GraphedStep(trainer._dp_loss(fn), opt, sst_list, shard0, dev)
+                  for fn, opt in ((model.calculate_loss, trainer.optimizer_filter),
+                                  (model.calculate_dis_loss, trainer.optimizer_dis))]
+        shards = [trainer._shard(bt) for bt in batches]
+        for k in range(3):
+            for g in graphs:
+                g.run(shards[k % 4])
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        a.record()
+        for k in range(n_steps):
+            for g in graphs:
+                g.run(shards[k % 4])
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        ms, mode = float(t), "cuda graph replay (one per phase; NCCL + flag barriers captured)"
+        del graphs
+        torch.cuda.synchronize()
+    except Exception as e:
+        mode = f"eager (host-paced; graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+    dist.barrier(group=group)
+    timeout = int(dp.status.item())
+    ops.set_chain_dp(None)
+    dp.close()
+    return {"metric": "PFCN_MLP train interactions/s (data parallel)", "value": B / (ms * 1e-3), "unit": "interactions/s",
+            "ms_per_step": ms, "eager_ms_per_step": ms_eager, "steps": n_steps, "global_batch": B, "launch_mode": mode,
+            "exchange": "BatchNorm column sums: peer-memory stores + flag barriers inside the step; gradient shares: one NCCL "
+                        "all-reduce per phase", "xchg_timeout_flag": timeout, "dp_check": check}
+
+
 def main():
     """stand-alone / as bench.py's `families` block (own process): ONE JSON line {leg: result}"""
     import argparse
