@@ -346,6 +346,9 @@ typedef struct fr_chain {
  * call fr_mlp_chain_* without having used the CUDA runtime before (e.g. torch's autograd worker thread) */
 int fr_thread_init(void);
 int fr_mlp_chain_eligible(const fr_chain_layer *layers, int32_t n_layers, int64_t M);
+/* diagnostic: with FR_CHAIN_TRACE=1 (forward) / =2 (backward) in the environment, CTA 0 of every chain launch stamps
+ * %globaltimer at its phase boundaries; this copies the first n (<= 256) stamps of the LAST launch to the host */
+int fr_mlp_chain_trace(uint64_t *out_host, int32_t n);
 /* backward == 0: the forward workspace for (training, need_grad); backward != 0: the backward scratch */
 size_t fr_mlp_chain_workspace_bytes(const fr_chain_layer *layers, int32_t n_layers, int64_t M, int32_t training,
                                     int32_t need_grad, int32_t backward);
