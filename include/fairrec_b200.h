@@ -635,6 +635,11 @@ int fr_focf_shard_workspace_init(void *workspace, size_t workspace_bytes, int32_
 /* run the phases in `phases` (OR of enum fr_shard_phase) in the order A, B, C, STAGE, FLUSH */
 int fr_focf_shard_step_run(const fr_focf_shard_step *s, int32_t phases, void *stream);
 
+/* diagnostic: with FR_FOCF_TRACE=1 in the environment every CTA of the cooperative fused step stamps %globaltimer at its 8
+ * phase boundaries (start | forward done | barrier 1 passed | statistics done | gradients done | barrier 2 passed | Adam done |
+ * barrier 3 passed); this copies the first n (<= 2048) stamps ([CTA][8]) of the LAST launch to the host */
+int fr_focf_step_trace(uint64_t *out_host, int32_t n);
+
 /* lazy_exact for the single-GPU step: fr_focf_train_step with fr_focf_step.adam_mode = FR_ADAM_LAZY_EXACT updates only the
  * rows the batch touches; fr_focf_adam_flush brings every row of both tables up to step `step` (call before anything
  * reads the tables: evaluation, checkpoint, predict). */

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Phase trace of the cooperative FOCF fused step at the ML-1M shape (fr_focf_step_trace; FR_FOCF_TRACE=1): every CTA
+stamps %globaltimer at its 8 phase boundaries; printed per phase as (first CTA to get there, last CTA) in microseconds
+from the earliest start stamp of the launch, plus the per-phase duration of the slowest / median CTA.
+
+    FR_FOCF_TRACE=1 python profiles/tools/trace_fused.py
+"""
+import ctypes
+import os
+import sys
+
+os.environ.setdefault("FR_FOCF_TRACE", "1")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+import torch
+
+import recbole_fairrec_b200 as pkg
+from recbole_fairrec_b200 import _lib, synth
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import bench_ml1m as bm
+
+dev = torch.device("cuda", 0)
+w, train, valid, test, gender = bm.make_workload("ml1m")
+cfg = pkg.Config(embedding_size=w["d"], fair_objective="value", fair_weight=1.0, topk=[10], valid_metric="NDCG@10",
+                 train_batch_size=w["batch"], learning_rate=1e-3, weight_decay=1e-3, device=dev, seed=2020)
+tdata = pkg.TrainData(train[0], train[1], train[2], gender, w["n_users"], w["n_items"], dev)
+loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020)
+model = pkg.FOCF(cfg, synth.SynthDataset(w["n_users"], w["n_items"], 5.0)).to(dev)
+model.init_adam(lr=1e-3, weight_decay=1e-3)
+losses = torch.zeros(len(loader) * 2 + 16, device=dev)
+runner = model.planned_runner(loader, losses, graph_steps=8)
+runner.run(16)
+torch.cuda.synchronize()
+lib = _lib.load()
+names = ["forward", "barrier1", "stats", "grads", "barrier2", "adam", "barrier3"]
+acc = []
+for rep in range(6):
+    runner.eager_steps(1) if rep % 2 == 0 else runner.run(1)
+    torch.cuda.synchronize()
+    n_cta = 144
+    buf = (ctypes.c_uint64 * (8 * n_cta))()
+    _lib.check(lib.fr_focf_step_trace(buf, 8 * n_cta), "fr_focf_step_trace")
+    t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 8)
+    t0 = t[:, 0].min()
+    rel = (t - t0) / 1e3
+    dur = np.diff(rel, axis=1)
+    print(f"rep {rep} ({'eager' if rep % 2 == 0 else 'graph'}): step {rel[:, 7].max():.1f} us; boundaries (min..max over CTAs): "
+          + " ".join(f"{rel[:, k].min():.1f}..{rel[:, k].max():.1f}" for k in range(8)))
+    print("    per-phase duration median / max over CTAs: "
+          + " ".join(f"{n}={np.median(dur[:, k]):.1f}/{dur[:, k].max():.1f}" for k, n in enumerate(names)))

@@ -91,14 +91,32 @@ __device__ __forceinline__ void forward_body(const float *__restrict__ U, const 
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t lo = 0xffffffffu, hi = 0u;
-  for (int b0 = warp * 4; b0 < B; b0 += nwarps * 4) {
+  // lane e < 4 holds the ids and the attribute of entry b0 + e; those of the NEXT group of four are fetched before the
+  // row loads of the current one are issued, so the id -> row dependency is off the critical path after the first group
+  int nu = 0, ni = 0;
+  float ns = 0.f;
+  int b0 = warp * 4;
+  if (lane < 4 && b0 + lane < B) {
+    nu = uid[b0 + lane];
+    ni = iid[b0 + lane];
+    ns = sst[b0 + lane];
+  }
+  for (; b0 < B; b0 += nwarps * 4) {
+    const int cu = nu, ci = ni;
+    const float cs = ns;
+    const int nb = b0 + nwarps * 4 + lane;
+    if (lane < 4 && nb < B) {
+      nu = uid[nb];
+      ni = iid[nb];
+      ns = sst[nb];
+    }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int b = b0 + e;
-      if (b < B) {
-        const float4 *pu = (const float4 *)(U + (size_t)uid[b] * d);
-        const float4 *pi = (const float4 *)(I + (size_t)iid[b] * d);
+      const int u = __shfl_sync(0xffffffffu, cu, e), it = __shfl_sync(0xffffffffu, ci, e);
+      if (b0 + e < B) {
+        const float4 *pu = (const float4 *)(U + (size_t)u * d);
+        const float4 *pi = (const float4 *)(I + (size_t)it * d);
         for (int k = lane; k * 4 < d; k += 32) {
           const float4 x = __ldg(pu + k), y = __ldg(pi + k);
           acc[e] = fmaf(x.x, y.x, acc[e]);
@@ -108,18 +126,21 @@ __device__ __forceinline__ void forward_body(const float *__restrict__ U, const 
         }
       }
     }
+    float mine = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float s = warp_sum(acc[e]);
-      const int b = b0 + e;
-      if (b < B && lane == 0) {
-        pred[b] = s;
-        const uint32_t o = f2ord(sst[b]);
-        lo = min(lo, o);
-        hi = max(hi, o);
-      }
+      if (lane == e) mine = s;
+    }
+    if (lane < 4 && b0 + lane < B) {
+      pred[b0 + lane] = mine;
+      const uint32_t o = f2ord(cs);
+      lo = min(lo, o);
+      hi = max(hi, o);
     }
   }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
   if (lane == 0 && hi >= lo) {
     atomicMin(&ctrl[CTRL_MIN], lo);
     atomicMax(&ctrl[CTRL_MAX], hi);
@@ -299,6 +320,99 @@ __device__ __forceinline__ void segment_record_sum(const LossArgs &a, int sgm, f
   }
 }
 
+// Item x group statistics of the WHOLE batch, computed redundantly by every CTA out of shared memory: the batch is a
+// few thousand rows (36 KB of pred / rating / sst), so re-reading it per CTA is cheaper than a grid-wide hand-over --
+// it removes the single-CTA reduction phase and one grid barrier from the step.  Rows are staged with one coalesced
+// sweep, then a warp owns a segment (lanes stride its rows: popularity skew costs shared-memory, not DRAM, round
+// trips).  Every CTA runs the same code on the same data in the same order -> bit-identical cseg everywhere.
+// Returns (on thread 0 of CTA 0 only meaningful) the batch loss.
+// rest_staged: rating / attribute columns are already in shared memory (persistent epoch kernel: staged while it waits at
+// the grid barrier); need_sums == false: this CTA does not need the batch loss (only one CTA writes it), so the block-wide
+// sums are skipped unless the objective's backward term depends on them (nonparity).
+__device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, float *sm, float *sh, float *s_cseg,
+                                             float *s_cglob, bool rest_staged = false, bool need_sums = true) {
+  float *s_pred = sm, *s_rat = sm + cap, *s_sst = sm + 2 * cap;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int J = *a.J;
+  const float Bn = (float)B, Jn = (float)J;
+  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
+  for (int p = threadIdx.x; p < B; p += blockDim.x) {
+    const int b = a.ord_i ? (int)a.ord_i[p] : p;     // item-sorted order (identity for whole-item batches)
+    s_pred[p] = a.pred[b];
+    if (!rest_staged) {
+      s_rat[p] = a.rating[b];
+      s_sst[p] = a.sst[b];
+    }
+  }
+  __syncthreads();
+  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;
+  int bad = 0;
+  for (int j = wib; j < J; j += nw) {
+    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
+    float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
+#pragma unroll 4
+    for (int p = s0 + lane; p < s1; p += 32) {   // (unrolled: the shared-memory loads of a popular item's rows pipeline)
+      const float pr = s_pred[p], r = s_rat[p], sv = s_sst[p];
+      const bool g = sv != vmin;
+      bad |= (g && sv != vmax);
+      const float df = pr - r;
+      sq = fmaf(df, df, sq);
+      if (g) { sp1 += pr; st1 += r; c1 += 1.f; } else { sp0 += pr; st0 += r; c0 += 1.f; }
+    }
+    sp0 = warp_sum(sp0); sp1 = warp_sum(sp1); st0 = warp_sum(st0); st1 = warp_sum(st1);
+    c0 = warp_sum(c0); c1 = warp_sum(c1); sq = warp_sum(sq);
+    if (lane == 0) {
+      float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
+      w_sq += sq;
+      if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+        segment_terms(a.objective, a.fair_weight, Jn, sp0, sp1, st0, st1, c0, c1, hx, cs0, cs1);
+      } else if (a.objective == FR_OBJ_NONPARITY) {
+        w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
+      }
+      w_hx += hx;
+      s_cseg[2 * j] = cs0;
+      s_cseg[2 * j + 1] = cs1;
+    }
+  }
+  if (blockIdx.x == 0 && a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
+    atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
+  if (!need_sums && a.objective != FR_OBJ_NONPARITY) {
+    if (threadIdx.x == 0) {
+      s_cglob[0] = 0.f;
+      s_cglob[1] = 0.f;
+    }
+    __syncthreads();
+    return 0.f;
+  }
+  const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
+  float g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
+  if (a.objective == FR_OBJ_NONPARITY) {
+    g0 = block_sum_1024(w_g0, sh); g1 = block_sum_1024(w_g1, sh);
+    n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
+  }
+  float loss = sq / Bn;
+  if (threadIdx.x == 0) {
+    float cg0 = 0.f, cg1 = 0.f;
+    if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
+      loss += a.fair_weight * (hx / Jn);
+    } else if (a.objective == FR_OBJ_NONPARITY) {
+      if (n1 == 0.f || n0 == 0.f) {
+        if (blockIdx.x == 0) atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
+      } else {
+        const float z = g0 / n0 - g1 / n1, x = fabsf(z);
+        loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
+        const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
+        cg0 = hp / n0;
+        cg1 = -hp / n1;
+      }
+    }
+    s_cglob[0] = cg0;
+    s_cglob[1] = cg1;
+  }
+  __syncthreads();
+  return loss;
+}
+
 // ------------------------------------------------------------------------------------------ gradients
 // Sorted-segment reduction of dL/dpred_b * other_row(b).  One warp owns 32 consecutive entries of the
 // (item- or user-) sorted order and walks them in order; a row whose segment lies inside the chunk is
@@ -322,7 +436,9 @@ struct GradArgs {
   int pre_handover;   // fused step: the control block has not been handed over yet -> read CTRL_MIN, not CTRL_SAVED_MIN
 };
 
-template <int kRowVecs>
+// kNc: the other side's rows go through the read-only path (__ldg); false in the persistent epoch kernel, where the tables
+// change during the launch
+template <int kRowVecs, bool kNc = true>
 __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c) {   // c in [0, 2 * nchunk): one warp
   const int lane = threadIdx.x & 31;
   const bool user_side = c >= nchunk;
@@ -345,27 +461,28 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
   const int nB = a.norm_from_ctrl ? (int)a.ctrl[CTRL_NORM_B] : a.norm_B;
 
   // lane l stages entry pbase + l
-  int my_seg = -1, my_oid = 0;
-  float my_coef = 0.f;
+  int my_seg = -1, my_oid = 0, my_b = 0;
+  // the segments just outside the chunk (-1: none): a row whose segment equals one of them continues from / into a
+  // neighbouring chunk -- known without reading the segment offsets at every flush
+  int edge = -1;
+  if (lane == 0 && pbase > 0) edge = segid[pbase - 1];
+  if (lane == 1 && pbase + nvalid < B) edge = segid[pbase + nvalid];
   if (lane < nvalid) {
     const int p = pbase + lane;
-    const int b = ord ? (int)ord[p] : p;
+    my_b = ord ? (int)ord[p] : p;
     my_seg = segid[p];
-    my_oid = oid[b];
-    const int g = a.sst[b] != vmin;
-    my_coef = (2.f * (a.pred[b] - a.rating[b]) / (float)(nB > 0 ? nB : B) + a.cseg[2 * a.entry_seg[b] + g] + a.cglob[g]) *
-              a.grad_scale;
+    my_oid = oid[my_b];
   }
+  const int seg_before = __shfl_sync(0xffffffffu, edge, 0), seg_after = __shfl_sync(0xffffffffu, edge, 1);
   float4 acc[kRowVecs];
 #pragma unroll
   for (int v = 0; v < kRowVecs; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cur = __shfl_sync(0xffffffffu, my_seg, 0);
 
   auto flush = [&](int s) {
-    const int s0 = segoff[s], s1 = segoff[s + 1];
-    float *dst = (s0 >= pbase && s1 <= pbase + chunk) ? gseg + (size_t)s * d
-                 : (s0 < pbase)                        ? head + (size_t)c * d
-                                                       : tail + (size_t)c * d;
+    float *dst = (s != seg_before && s != seg_after) ? gseg + (size_t)s * d      // the segment lies inside the chunk
+                 : (s == seg_before)                  ? head + (size_t)c * d      // it started in an earlier chunk
+                                                      : tail + (size_t)c * d;     // it continues into the next one
 #pragma unroll
     for (int v = 0; v < kRowVecs; ++v) {
       const int k = lane * 4 + v * 128;
@@ -377,9 +494,9 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
   };
 
   constexpr int kDepth = kRowVecs == 1 ? 8 : 4;
-  for (int l0 = 0; l0 < nvalid; l0 += kDepth) {
-    float4 x[kDepth][kRowVecs];
-    // issue the row loads of kDepth entries before consuming them (memory-level parallelism)
+  float4 x[kDepth][kRowVecs];
+  // issue the row loads of kDepth entries before consuming them (memory-level parallelism)
+  auto issue = [&](int l0) {
 #pragma unroll
     for (int e = 0; e < kDepth; ++e) {
       const int l = l0 + e;
@@ -388,9 +505,22 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
 #pragma unroll
       for (int v = 0; v < kRowVecs; ++v) {
         const int k = lane * 4 + v * 128;
-        x[e][v] = (l < nvalid && k < d) ? __ldg(row + (k >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[e][v] = (l < nvalid && k < d) ? (kNc ? __ldg(row + (k >> 2)) : __ldcg(row + (k >> 2)))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  };
+  // the first rows need the other side's ids only: they are in flight while the entry's dL/dpred coefficient (two more
+  // dependent loads: the entry's columns, then its segment's fairness term) is formed
+  issue(0);
+  float my_coef = 0.f;
+  if (lane < nvalid) {
+    const int g = a.sst[my_b] != vmin;
+    my_coef = (2.f * (a.pred[my_b] - a.rating[my_b]) / (float)(nB > 0 ? nB : B) + a.cseg[2 * a.entry_seg[my_b] + g] +
+               a.cglob[g]) * a.grad_scale;
+  }
+  for (int l0 = 0; l0 < nvalid; l0 += kDepth) {
+    if (l0) issue(l0);
 #pragma unroll
     for (int e = 0; e < kDepth; ++e) {
       const int l = l0 + e;
@@ -415,7 +545,7 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
 }
 
 template <int kRowVecs>
-__global__ void __launch_bounds__(256) k_segment_grads(GradArgs a, int nchunk) {
+__global__ void __launch_bounds__(256, kRowVecs == 1 ? 4 : 2) k_segment_grads(GradArgs a, int nchunk) {
   grads_chunk<kRowVecs>(a, nchunk, (blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 }
 

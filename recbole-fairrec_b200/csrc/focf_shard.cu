@@ -265,13 +265,17 @@ __global__ void __launch_bounds__(kRedThreads)
     is_last = atomicAdd(&ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
+  if (!is_last || threadIdx.x >= 32) return;
   __threadfence();
   float tsq = 0.f, thx = 0.f;
-  for (unsigned b = 0; b < gridDim.x; ++b) {   // CTA order, whichever CTA ends up last
-    tsq += __ldcg(part + 2 * b);
-    thx += __ldcg(part + 2 * b + 1);
+  for (unsigned b = lane; b < gridDim.x; b += 32) {   // fixed order whichever CTA ends up last: lane-strided, then the shuffle tree
+    const float2 q = __ldcg((const float2 *)(part + 2 * b));
+    tsq += q.x;
+    thx += q.y;
   }
+  tsq = warp_sum(tsq);
+  thx = warp_sum(thx);
+  if (lane != 0) return;
   float l = tsq / Bn;
   if (objective >= FR_OBJ_VALUE && objective <= FR_OBJ_OVER) l += fair_weight * (thx / Jn);
   loss[0] = l;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kRedThreads)
 }
 
 template <int kRowVecs>
-__global__ void __launch_bounds__(256) k_shard_grads(GradArgs a, int nchunk) {
+__global__ void __launch_bounds__(256, kRowVecs == 1 ? 4 : 2) k_shard_grads(GradArgs a, int nchunk) {
   grads_chunk<kRowVecs>(a, nchunk, (blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 }
 

@@ -74,12 +74,30 @@ __global__ void __launch_bounds__(kSegThreads) k_segment_reduce(LossArgs a, floa
     is_last = atomicAdd(&a.ctrl[CTRL_TICKET], 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
+  if (!is_last) return;
   __threadfence();
+  // the per-CTA partials in a FIXED order, whichever CTA ends up last: thread t adds partials t, t + T, ... (independent
+  // loads: a serial walk by one thread costs one L2 round trip per partial -- 0.15 ms for 1184 CTAs), then the fixed
+  // shuffle tree of warp_sum, then the warps in warp order
+  float q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += kSegThreads) {
+    const float4 x = __ldcg((const float4 *)(part + 8 * (size_t)b));
+    const float2 y = __ldcg((const float2 *)(part + 8 * (size_t)b + 4));
+    q[0] += x.x; q[1] += x.y; q[2] += x.z; q[3] += x.w; q[4] += y.x; q[5] += y.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) q[k] = warp_sum(q[k]);
+  __syncthreads();   // sh may still be read by segment_record_sum's last combine
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sh[threadIdx.x >> 5][k] = q[k];
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   float sq = 0.f, hx = 0.f, g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
-  for (unsigned b = 0; b < gridDim.x; ++b) {   // CTA order, whichever CTA ends up last
-    const float *p = part + 8 * (size_t)b;
-    sq += __ldcg(p); hx += __ldcg(p + 1); g0 += __ldcg(p + 2); g1 += __ldcg(p + 3); n0 += __ldcg(p + 4); n1 += __ldcg(p + 5);
+#pragma unroll
+  for (int w = 0; w < kSegThreads / 32; ++w) {
+    sq += sh[w][0]; hx += sh[w][1]; g0 += sh[w][2]; g1 += sh[w][3]; n0 += sh[w][4]; n1 += sh[w][5];
   }
   float loss = sq / Bn;                                                    // nn.MSELoss 'mean'
   float cg0 = 0.f, cg1 = 0.f;
@@ -145,88 +163,17 @@ struct FusedArgs {
   ApplyArgs apply;
   int cap;          // rows the shared-memory staging is sized for (>= any batch)
   uint32_t *ctrl;
+  unsigned long long *trace;   // optional (FR_FOCF_TRACE=1): [gridDim.x][8] %globaltimer stamps at the phase boundaries
 };
+__device__ __forceinline__ void fused_stamp(unsigned long long *trace, int slot) {
+  if (trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 constexpr int kFusedThreads = 512;
 static size_t fused_smem_bytes(int cap) { return ((size_t)5 * cap + 8) * sizeof(float); }
-
-// Item x group statistics of the WHOLE batch, computed redundantly by every CTA out of shared memory: the batch is a
-// few thousand rows (36 KB of pred / rating / sst), so re-reading it per CTA is cheaper than a grid-wide hand-over --
-// it removes the single-CTA reduction phase and one grid barrier from the step.  Rows are staged with one coalesced
-// sweep, then a warp owns a segment (lanes stride its rows: popularity skew costs shared-memory, not DRAM, round
-// trips).  Every CTA runs the same code on the same data in the same order -> bit-identical cseg everywhere.
-// Returns (on thread 0 of CTA 0 only meaningful) the batch loss.
-__device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, float *sm, float *sh, float *s_cseg,
-                                             float *s_cglob) {
-  float *s_pred = sm, *s_rat = sm + cap, *s_sst = sm + 2 * cap;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int J = *a.J;
-  const float Bn = (float)B, Jn = (float)J;
-  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
-  for (int p = threadIdx.x; p < B; p += blockDim.x) {
-    const int b = a.ord_i ? (int)a.ord_i[p] : p;     // item-sorted order (identity for whole-item batches)
-    s_pred[p] = a.pred[b];
-    s_rat[p] = a.rating[b];
-    s_sst[p] = a.sst[b];
-  }
-  __syncthreads();
-  float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;
-  int bad = 0;
-  for (int j = wib; j < J; j += nw) {
-    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
-    float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
-    for (int p = s0 + lane; p < s1; p += 32) {
-      const float pr = s_pred[p], r = s_rat[p], sv = s_sst[p];
-      const bool g = sv != vmin;
-      bad |= (g && sv != vmax);
-      const float df = pr - r;
-      sq = fmaf(df, df, sq);
-      if (g) { sp1 += pr; st1 += r; c1 += 1.f; } else { sp0 += pr; st0 += r; c0 += 1.f; }
-    }
-    sp0 = warp_sum(sp0); sp1 = warp_sum(sp1); st0 = warp_sum(st0); st1 = warp_sum(st1);
-    c0 = warp_sum(c0); c1 = warp_sum(c1); sq = warp_sum(sq);
-    if (lane == 0) {
-      float hx = 0.f, cs0 = 0.f, cs1 = 0.f;
-      w_sq += sq;
-      if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-        segment_terms(a.objective, a.fair_weight, Jn, sp0, sp1, st0, st1, c0, c1, hx, cs0, cs1);
-      } else if (a.objective == FR_OBJ_NONPARITY) {
-        w_g0 += sp0; w_g1 += sp1; w_n0 += c0; w_n1 += c1;
-      }
-      w_hx += hx;
-      s_cseg[2 * j] = cs0;
-      s_cseg[2 * j + 1] = cs1;
-    }
-  }
-  if (blockIdx.x == 0 && a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
-    atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
-  const float sq = block_sum_1024(w_sq, sh), hx = block_sum_1024(w_hx, sh);
-  float g0 = 0.f, g1 = 0.f, n0 = 0.f, n1 = 0.f;
-  if (a.objective == FR_OBJ_NONPARITY) {
-    g0 = block_sum_1024(w_g0, sh); g1 = block_sum_1024(w_g1, sh);
-    n0 = block_sum_1024(w_n0, sh); n1 = block_sum_1024(w_n1, sh);
-  }
-  float loss = sq / Bn;
-  if (threadIdx.x == 0) {
-    float cg0 = 0.f, cg1 = 0.f;
-    if (a.objective >= FR_OBJ_VALUE && a.objective <= FR_OBJ_OVER) {
-      loss += a.fair_weight * (hx / Jn);
-    } else if (a.objective == FR_OBJ_NONPARITY) {
-      if (n1 == 0.f || n0 == 0.f) {
-        if (blockIdx.x == 0) atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
-      } else {
-        const float z = g0 / n0 - g1 / n1, x = fabsf(z);
-        loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
-        const float hp = a.fair_weight * (x < 1.f ? z : (float)((z > 0.f) - (z < 0.f)));
-        cg0 = hp / n0;
-        cg1 = -hp / n1;
-      }
-    }
-    s_cglob[0] = cg0;
-    s_cglob[1] = cg1;
-  }
-  __syncthreads();
-  return loss;
-}
 
 // forward | barrier | batch statistics (per CTA, shared memory) + gradients | barrier | Adam | barrier | hand-over
 template <int kRowVecs>
@@ -237,9 +184,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_focf_fused_step(FusedArgs 
   float *s_cseg = fused_sm + 3 * f.cap, *s_cglob = fused_sm + 5 * f.cap;
   unsigned long long *bar = (unsigned long long *)(f.ctrl + CTRL_GRID_BAR);
   const int B = FR_B(f.B, f.B_dev);
+  fused_stamp(f.trace, 0);
   forward_body(f.U, f.I, f.uid, f.iid, f.sst, B, f.d, f.pred, f.ctrl);
+  fused_stamp(f.trace, 1);
   grid_barrier(bar);
+  fused_stamp(f.trace, 2);
   const float loss = fused_stats(f.loss, B, f.cap, fused_sm, sh, s_cseg, s_cglob);
+  fused_stamp(f.trace, 3);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const LossArgs &a = f.loss;
     a.loss[a.loss_by_cursor ? a.ctrl[CTRL_CURSOR] % (uint32_t)a.loss_by_cursor : 0u] = loss;
@@ -253,9 +204,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_focf_fused_step(FusedArgs 
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int c = warp; c < 2 * nchunk; c += nwarps) grads_chunk<kRowVecs>(g, nchunk, c);
   }
+  fused_stamp(f.trace, 4);
   grid_barrier(bar);
+  fused_stamp(f.trace, 5);
   apply_body<kAdamFused>(f.apply, sc);
+  fused_stamp(f.trace, 6);
   grid_barrier(bar);
+  fused_stamp(f.trace, 7);
   if (blockIdx.x == 0 && threadIdx.x == 0) {   // hand the control block over to the next batch (cf. loss_phase2)
     uint32_t *ctrl = f.ctrl;
     ctrl[CTRL_SAVED_MIN] = ctrl[CTRL_MIN];
@@ -643,6 +598,7 @@ static bool fused_eligible(const fr_focf_step *s) {
          fused_smem_bytes(s->B) <= 200 * 1024;
 }
 
+static unsigned long long *g_fused_trace = nullptr;
 static int fused_step_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t st) {
   static int n_sm = 0, per_sm = -1;
   if (per_sm < 0) {
@@ -665,8 +621,14 @@ static int fused_step_impl(const fr_focf_step *s, const FocfWs &w, cudaStream_t 
   ga.pre_handover = 1;
   ApplyArgs aa = apply_args(s, w);
   aa.pre_handover = 1;
+  static int trace_on = -1;
+  if (trace_on < 0) {
+    const char *e = getenv("FR_FOCF_TRACE");
+    trace_on = (e && e[0] == '1') ? 1 : 0;
+    if (trace_on) FR_CUDA_OK(cudaMalloc(&g_fused_trace, sizeof(unsigned long long) * 8 * 256));
+  }
   FusedArgs f{s->U, s->I, s->uid, s->iid, s->sst, s->B, s->d, dev_B(s, w), s->pred, loss_args(s, w, s->step <= 0),
-              ga, aa, s->B, w.ctrl};
+              ga, aa, s->B, w.ctrl, trace_on ? g_fused_trace : nullptr};
   void *args[] = {&f};
   const bool p = prof_on();
   if (p) prof_begin("k_focf_fused_step", st);
@@ -824,6 +786,14 @@ int fr_focf_train_step(const fr_focf_step *s, void *stream) {
   fr::grads_impl(s, w, 1.0f, (cudaStream_t)stream);
   if ((rc = fr::adam_stage(s, w, (cudaStream_t)stream, "fr_focf_train_step"))) return rc;
   FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_focf_step_trace(uint64_t *out_host, int32_t n) {
+  FR_REQUIRE(out_host && n >= 0 && n <= 8 * 256, "fr_focf_step_trace: bad argument");
+  FR_REQUIRE(fr::g_fused_trace, "fr_focf_step_trace: set FR_FOCF_TRACE=1 before the first fused step");
+  FR_CUDA_OK(cudaDeviceSynchronize());
+  FR_CUDA_OK(cudaMemcpy(out_host, fr::g_fused_trace, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
   return FR_OK;
 }
 

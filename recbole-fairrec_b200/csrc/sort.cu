@@ -6,7 +6,7 @@
 //
 // Layout: one CTA owns a tile of 2048 consecutive keys.  A pass is
 //   hist    : per-CTA digit histogram (shared-memory integer atomics)
-//   scan    : one CTA turns [nblk][256] counts into global write offsets (digit-major exclusive scan)
+//   scan    : warp per digit: exclusive prefix of the digit-major [256][nblk] counts over the blocks + digit totals
 //   scatter : each warp ranks its 256 keys with __match_any_sync in 8 rounds of 32 consecutive keys
 //             (stable), then writes (key,value) to offset[digit] + rank.
 // When the whole input fits one tile the three kernels collapse into one (k_radix_single).
@@ -63,32 +63,40 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *__r
     if (p < n) atomicAdd(&h[(keys[p] >> shift) & (kRadix - 1)], 1u);
   }
   __syncthreads();
-  block_hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = h[threadIdx.x];
+  block_hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];   // digit-major: [256][nblk]
 }
 
-// single CTA, thread d owns digit d: offsets[blk][d] = sum_{d'<d} total[d'] + sum_{blk'<blk} hist[blk'][d]
-__global__ void __launch_bounds__(kRadix) k_radix_scan(uint32_t *__restrict__ block_hist, int64_t nblk) {
-  __shared__ uint32_t tot[kRadix];
-  const int dgt = threadIdx.x;
-  uint32_t sum = 0;
-  for (int64_t b = 0; b < nblk; ++b) sum += block_hist[b * kRadix + dgt];
-  tot[dgt] = sum;
-  __syncthreads();
-  if (dgt == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < kRadix; ++i) {
-      uint32_t t = tot[i];
-      tot[i] = run;
-      run += t;
+// Warp per digit (32 CTAs of 8 warps): the digit's counts hist[d][0..nblk) become their exclusive prefix over the blocks
+// and tot[d] their sum; the scatter kernel adds the exclusive scan of tot[] over the digits itself (256 values, per CTA).
+// 32 consecutive blocks per warp scan (coalesced), 16 scans' loads in flight.  (A single-CTA scan of the whole table
+// is bound by what ONE SM pulls from L2: 33-90 us per pass at 2^20 keys in three variants.)
+constexpr int kScanWarps = 8;
+__global__ void __launch_bounds__(kScanWarps * 32) k_radix_scan(uint32_t *__restrict__ hist, int64_t nblk,
+                                                               uint32_t *__restrict__ tot) {
+  const int lane = threadIdx.x & 31, dgt = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+  uint32_t *h = hist + (int64_t)dgt * nblk;
+  uint32_t carry = 0;
+  for (int64_t c0 = 0; c0 < nblk; c0 += 32 * 16) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int64_t b = c0 + 32 * i + lane;
+      v[i] = b < nblk ? h[b] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t inc = v[i];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int64_t b = c0 + 32 * i + lane;
+      if (b < nblk) h[b] = carry + inc - v[i];
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
-  __syncthreads();
-  uint32_t run = tot[dgt];
-  for (int64_t b = 0; b < nblk; ++b) {
-    uint32_t t = block_hist[b * kRadix + dgt];
-    block_hist[b * kRadix + dgt] = run;
-    run += t;
-  }
+  if (lane == 0) tot[dgt] = carry;
 }
 
 // Stable ranking + scatter of one 2048-key tile.  kSingle: the tile is the whole array, compute the digit
@@ -97,13 +105,31 @@ template <bool kSingle>
 __global__ void __launch_bounds__(kSortThreads)
     k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                    const int32_t *__restrict__ n_dev, int shift, const uint32_t *__restrict__ offsets) {
+                    const int32_t *__restrict__ n_dev, int shift, const uint32_t *__restrict__ offsets,
+                    const uint32_t *__restrict__ digit_tot) {
   if (n_dev) n = *n_dev;
   constexpr int kWarps = kSortThreads / 32;
   __shared__ uint32_t cnt[kWarps][kRadix];
   __shared__ uint32_t digit_base[kRadix];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  if (!kSingle) {   // exclusive scan of the 256 digit totals (thread d = digit d): the global base of every digit
+    __shared__ uint32_t wtot[kWarps];
+    const uint32_t t = digit_tot[threadIdx.x];
+    uint32_t inc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int ww = 0; ww < kWarps; ++ww)
+      if (ww < w) base += wtot[ww];
+    digit_base[threadIdx.x] = base + inc - t;
+  }
   __syncthreads();
 
   const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortTile / kWarps);
@@ -126,7 +152,7 @@ __global__ void __launch_bounds__(kSortThreads)
   {  // thread d: exclusive prefix over the warps of this CTA, on top of the CTA's global offset for digit d
     const int dgt = threadIdx.x;
     uint32_t run = 0;
-    if (!kSingle) run = offsets[(int64_t)blockIdx.x * kRadix + dgt];
+    if (!kSingle) run = offsets[(int64_t)dgt * gridDim.x + blockIdx.x] + digit_base[dgt];
     uint32_t tot = 0;
 #pragma unroll
     for (int ww = 0; ww < kWarps; ++ww) {
@@ -177,7 +203,7 @@ SortScratch carve_sort_scratch(Carver &c, int64_t n) {
   SortScratch s;
   s.tmp_keys = c.take<uint32_t>((size_t)n);
   s.tmp_vals = c.take<uint32_t>((size_t)n);
-  s.block_hist = c.take<uint32_t>((size_t)sort_num_blocks(n) * kRadix);
+  s.block_hist = c.take<uint32_t>((size_t)(sort_num_blocks(n) + 1) * kRadix);   // + the 256 digit totals
   return s;
 }
 
@@ -195,11 +221,13 @@ void sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys
     uint32_t *vo = to_out ? vals_out : s.tmp_vals;
     const int shift = 8 * p;
     if (nblk == 1) {
-      FR_LAUNCH(k_radix_scatter<true>, 1, kSortThreads, 0, stream, ki, vi, ko, vo, n, n_dev, shift, nullptr);
+      FR_LAUNCH(k_radix_scatter<true>, 1, kSortThreads, 0, stream, ki, vi, ko, vo, n, n_dev, shift, nullptr, nullptr);
     } else {
       FR_LAUNCH(k_radix_hist, (int)nblk, kSortThreads, 0, stream, ki, n, n_dev, shift, s.block_hist);
-      FR_LAUNCH(k_radix_scan, 1, kRadix, 0, stream, s.block_hist, nblk);
-      FR_LAUNCH(k_radix_scatter<false>, (int)nblk, kSortThreads, 0, stream, ki, vi, ko, vo, n, n_dev, shift, s.block_hist);
+      uint32_t *digit_tot = s.block_hist + nblk * kRadix;
+      FR_LAUNCH(k_radix_scan, kRadix / kScanWarps, kScanWarps * 32, 0, stream, s.block_hist, nblk, digit_tot);
+      FR_LAUNCH(k_radix_scatter<false>, (int)nblk, kSortThreads, 0, stream, ki, vi, ko, vo, n, n_dev, shift, s.block_hist,
+                digit_tot);
     }
     ki = ko;
     vi = vo;
