@@ -635,6 +635,28 @@ int fr_focf_shard_workspace_init(void *workspace, size_t workspace_bytes, int32_
 /* run the phases in `phases` (OR of enum fr_shard_phase) in the order A, B, C, STAGE, FLUSH */
 int fr_focf_shard_step_run(const fr_focf_shard_step *s, int32_t phases, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * A planned FOCF epoch (or any run of its steps) as ONE persistent cooperative launch (csrc/focf_epoch.cu): the body of
+ * Trainer._train_epoch (trainer.py:181-196) over the batches of FOCFDataLoader._next_batch_data
+ * (focf_dataloader.py:37-50).  For the latency-bound regime: batch capacity <= 8192 rows, d <= 128, dense_exact Adam,
+ * tables small enough for every compute CTA to keep its share of [U; I] and of both moments in shared memory
+ * (fr_focf_epoch_eligible).  Results (tables, moments, losses) are bit-identical to fr_focf_train_step over the same batches.
+ *
+ * slots[0..n_slots): n_slots (2..8; 4 is a good value) PLANNED fr_focf_step structs that differ only in their batch
+ * columns (uid / iid / rating / sst / pred, capacity B each) and workspace: producer CTAs fill slot (k mod n_slots) with
+ * batch first_batch + k of the plan while earlier steps compute.  The steps run are the plan rows
+ * (first_batch + k) mod plan_len, k = 0..n_steps-1; losses go to loss[(first_batch + k) mod plan_len]; adam_step is the
+ * 1-based optimizer step of the first of them.  The workspaces' device-resident cursor / Adam counters are neither read
+ * nor advanced.  sync_words: 64 bytes of device memory owned by the caller (zeroed by the call).
+ * ---------------------------------------------------------------------------------------------- */
+int fr_focf_epoch_eligible(const fr_focf_step *slots, int32_t n_slots);
+int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_batch, int32_t n_steps,
+                      int32_t adam_step, void *sync_words, void *stream);
+/* diagnostic (FR_FOCF_TRACE=1; FR_FOCF_TRACE_STEP selects the step, default 8): [CTA][8] %globaltimer stamps of the last
+ * epoch launch -- compute CTAs: step start | forward done | barrier 1 passed | statistics done | gradients done | barrier 2
+ * passed | Adam done | barrier 3 passed; producer CTAs: start | gathered | sorted | published */
+int fr_focf_epoch_trace(uint64_t *out_host, int32_t n);
+
 /* diagnostic: with FR_FOCF_TRACE=1 in the environment every CTA of the cooperative fused step stamps %globaltimer at its 8
  * phase boundaries (start | forward done | barrier 1 passed | statistics done | gradients done | barrier 2 passed | Adam done |
  * barrier 3 passed); this copies the first n (<= 2048) stamps ([CTA][8]) of the LAST launch to the host */

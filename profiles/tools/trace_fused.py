@@ -29,7 +29,7 @@ loader = pkg.FOCFDataLoader(cfg, tdata, mode="fast", seed=2020)
 model = pkg.FOCF(cfg, synth.SynthDataset(w["n_users"], w["n_items"], 5.0)).to(dev)
 model.init_adam(lr=1e-3, weight_decay=1e-3)
 losses = torch.zeros(len(loader) * 2 + 16, device=dev)
-runner = model.planned_runner(loader, losses, graph_steps=8)
+runner = model.planned_runner(loader, losses, graph_steps=8, persistent=False)
 runner.run(16)
 torch.cuda.synchronize()
 lib = _lib.load()
@@ -49,3 +49,34 @@ for rep in range(6):
           + " ".join(f"{rel[:, k].min():.1f}..{rel[:, k].max():.1f}" for k in range(8)))
     print("    per-phase duration median / max over CTAs: "
           + " ".join(f"{n}={np.median(dur[:, k]):.1f}/{dur[:, k].max():.1f}" for k, n in enumerate(names)))
+
+# ---- the persistent epoch kernel (fr_focf_epoch_run): timing of one launch of many steps + phase trace of one step
+runner = model.epoch_runner(loader, losses)
+if runner is None:
+    print("epoch kernel: shape not eligible")
+    sys.exit(0)
+for steps in (64, 256):
+    runner.run(8)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    runner.run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"epoch kernel: {steps} steps in one launch: {e0.elapsed_time(e1) * 1e3 / steps:.2f} us/step")
+n_cta, n_prod = 148, 8
+buf = (ctypes.c_uint64 * (8 * n_cta))()
+_lib.check(lib.fr_focf_epoch_trace(buf, 8 * n_cta), "fr_focf_epoch_trace")
+t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 8)
+c = t[n_prod:]
+t0 = c[:, 0].min()
+rel = (c - t0) / 1e3
+dur = np.diff(rel, axis=1)
+print(f"epoch kernel, traced step: {rel[:, 7].max():.1f} us; boundaries (min..max over compute CTAs): "
+      + " ".join(f"{rel[:, k].min():.1f}..{rel[:, k].max():.1f}" for k in range(8)))
+print("    per-phase duration median / max over CTAs: "
+      + " ".join(f"{n}={np.median(dur[:, k]):.1f}/{dur[:, k].max():.1f}" for k, n in enumerate(names)))
+for k in range(n_prod):
+    p = (t[k, :4] - t[k, 0]) / 1e3
+    print(f"    producer CTA {k} ({'user' if k & 1 else 'item'} side of slot {k >> 1}): gathered {p[1]:.1f}, sorted {p[2]:.1f}, "
+          f"published {p[3]:.1f} us after its start")

@@ -229,6 +229,9 @@ SIGNATURES = {
     "fr_thread_init": (c_int, []),
     "fr_mlp_chain_trace": (c_int, [c_void_p, c_int32]),
     "fr_focf_step_trace": (c_int, [c_void_p, c_int32]),
+    "fr_focf_epoch_eligible": (c_int, [c_void_p, c_int32]),
+    "fr_focf_epoch_run": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "fr_focf_epoch_trace": (c_int, [c_void_p, c_int32]),
     "fr_mlp_chain_eligible": (c_int, [POINTER(ChainLayer), c_int32, c_int64]),
     "fr_mlp_chain_workspace_bytes": (c_size_t, [POINTER(ChainLayer), c_int32, c_int64, c_int32, c_int32, c_int32]),
     "fr_mlp_chain_forward": (c_int, [POINTER(Chain), c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -330,7 +330,8 @@ __device__ __forceinline__ void segment_record_sum(const LossArgs &a, int sgm, f
 // the grid barrier); need_sums == false: this CTA does not need the batch loss (only one CTA writes it), so the block-wide
 // sums are skipped unless the objective's backward term depends on them (nonparity).
 __device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, float *sm, float *sh, float *s_cseg,
-                                             float *s_cglob, bool rest_staged = false, bool need_sums = true) {
+                                             float *s_cglob, bool rest_staged = false, bool need_sums = true,
+                                             int lead_cta = 0) {   // lead_cta: the CTA that raises the status flags
   float *s_pred = sm, *s_rat = sm + cap, *s_sst = sm + 2 * cap;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int J = *a.J;
@@ -374,7 +375,7 @@ __device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, 
       s_cseg[2 * j + 1] = cs1;
     }
   }
-  if (blockIdx.x == 0 && a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
+  if ((int)blockIdx.x == lead_cta && a.objective != FR_OBJ_NONE && __any_sync(0xffffffffu, bad) && lane == 0)
     atomicOr(a.flags, FR_FLAG_TOO_MANY_GROUPS);
   if (!need_sums && a.objective != FR_OBJ_NONPARITY) {
     if (threadIdx.x == 0) {
@@ -397,7 +398,7 @@ __device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, 
       loss += a.fair_weight * (hx / Jn);
     } else if (a.objective == FR_OBJ_NONPARITY) {
       if (n1 == 0.f || n0 == 0.f) {
-        if (blockIdx.x == 0) atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
+        if ((int)blockIdx.x == lead_cta) atomicOr(a.flags, FR_FLAG_SINGLE_GROUP);
       } else {
         const float z = g0 / n0 - g1 / n1, x = fabsf(z);
         loss += a.fair_weight * (x < 1.f ? 0.5f * x * x : x - 0.5f);
@@ -449,7 +450,6 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
   if (pbase >= B) return;
   const uint32_t *ord = user_side ? a.ord_u : a.ord_i;
   const int32_t *segid = user_side ? a.segid_u : a.segid_i;
-  const int32_t *segoff = user_side ? a.segoff_u : a.segoff_i;
   const float *other = user_side ? a.I : a.U;
   const int32_t *oid = user_side ? a.iid : a.uid;
   float *gseg = user_side ? a.gseg_u : a.gseg_i;

@@ -269,9 +269,51 @@ class FOCF(nn.Module):
         return out
 
     @torch.no_grad()
-    def planned_runner(self, loader, loss_buf, graph_steps=8):
+    def epoch_runner(self, loader, loss_buf, n_slots=4):
+        """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k steps as ONE
+        persistent cooperative launch (fr_focf_epoch_run: producer CTAs build the batches ahead, compute CTAs keep their
+        share of the tables and Adam moments in shared memory; bit-identical to the stepwise path), or None when the
+        shape is not eligible (tables too large for shared-memory residency, batches over 8192 rows, d > 128)."""
+        import ctypes
+        if self._adam is None:
+            raise RuntimeError("call init_adam() before epoch_runner()")
+        if self._adam.get("mode", "dense_exact") != "dense_exact":
+            return None
+        eng = self._engine()
+        U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
+        plan = loader.plan_epoch_device()
+        if loss_buf.numel() < plan["len"]:
+            raise ValueError("loss buffer shorter than the epoch")
+        cap = plan["cols"][0].numel()
+        if cap > 8192 or self.embedding_size > 128:
+            return None
+        st = getattr(self, "_ep_state", None)
+        if st is None or st["device"] != U.device or st["cap"] != cap or st["n_slots"] != n_slots:
+            engines = [FocfEngine(self.n_users, self.n_items, self.embedding_size, cap, U.device) for _ in range(n_slots)]
+            for e in engines:
+                e.flags = eng.flags                            # one status word for every slot
+            cols = [tuple(torch.empty_like(c) for c in plan["cols"]) for _ in range(n_slots)]
+            st = self._ep_state = dict(device=U.device, cap=cap, n_slots=n_slots, engines=engines, cols=cols,
+                                       sync=torch.zeros(16, dtype=torch.int32, device=U.device), key=None)
+        key = (plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), plan["len"], id(self._adam["mU"]))
+        if st["key"] != key:
+            steps = (_lib.FocfStep * n_slots)()
+            for k, (e, c) in enumerate(zip(st["engines"], st["cols"])):
+                s = e.planned_step(U, I, self._adam, dict(plan, cols=c), loader.train, self._objective, self.fair_weight,
+                                   loss_buf)
+                ctypes.memmove(ctypes.byref(steps[k]), ctypes.byref(s), ctypes.sizeof(s))
+            st["steps"], st["key"] = steps, key
+            st["eligible"] = bool(eng.lib.fr_focf_epoch_eligible(ctypes.cast(steps, ctypes.c_void_p), n_slots))
+        if not st["eligible"]:
+            return None
+        return _EpochRunner(self, plan, st)
+
+    @torch.no_grad()
+    def planned_runner(self, loader, loss_buf, graph_steps=8, persistent=None):
         """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k fused steps
-        with NO per-step host work.  The step is captured once into CUDA graphs and replayed; batch size, batch cursor
+        with NO per-step host work.  persistent (default: on unless FR_FOCF_NO_EPOCH_KERNEL=1): where the shape allows it
+        the runner is `epoch_runner`'s -- k steps = one persistent launch; otherwise (and below) the stepwise path:
+        the step is captured once into CUDA graphs and replayed; batch size, batch cursor
         and Adam step count are device resident.  loss_buf[cursor] receives each step's loss.
 
         Two workspaces alternate the batches of the plan (even batches -> workspace 0, odd -> workspace 1): the
@@ -280,6 +322,12 @@ class FOCF(nn.Module):
         has a critical path of one compute per step instead of prepare + compute."""
         if self._adam is None:
             raise RuntimeError("call init_adam() before planned_runner()")
+        if persistent is None:
+            persistent = os.environ.get("FR_FOCF_NO_EPOCH_KERNEL", "0") != "1"
+        if persistent:
+            runner = self.epoch_runner(loader, loss_buf)
+            if runner is not None:
+                return runner
         eng = self._engine()
         U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
         if getattr(self, "_eng2", None) is None or self._eng2.device != U.device:
@@ -411,9 +459,9 @@ class FOCF(nn.Module):
             torch.cuda.synchronize()
 
     @torch.no_grad()
-    def train_epoch_planned(self, loader, loss_buf, graph_steps=8):
+    def train_epoch_planned(self, loader, loss_buf, graph_steps=8, persistent=None):
         """One epoch through planned_runner.  Returns (number of steps, number of interactions)."""
-        runner = self.planned_runner(loader, loss_buf, graph_steps)
+        runner = self.planned_runner(loader, loss_buf, graph_steps, persistent)
         n = runner.plan["len"]
         runner.run(n - runner.cursor)
         return n, runner.plan["rows"]
@@ -465,6 +513,30 @@ class _DpPlannedRunner:
         for _ in range(k % G):
             m._dp_graphs[1].replay()
         return self._account(k)
+
+
+class _EpochRunner:
+    """k planned steps = ONE launch of the persistent epoch kernel (fr_focf_epoch_run)"""
+
+    def __init__(self, model, plan, state):
+        self.model, self.plan, self.state, self.cursor = model, plan, state, 0
+
+    def run(self, k):
+        import ctypes
+        m, st = self.model, self.state
+        k = max(int(k), 0)
+        if k == 0:
+            return 0
+        _lib.check(m._engine().lib.fr_focf_epoch_run(ctypes.cast(st["steps"], ctypes.c_void_p), st["n_slots"], self.cursor,
+                                                     k, m._adam["step"] + 1, _lib.ptr(st["sync"]), _lib.stream_ptr()),
+                   "fr_focf_epoch_run")
+        n = self.plan["len"]
+        rows = sum(self.plan["batch_rows"][(self.cursor + i) % n] for i in range(k))
+        self.cursor += k
+        m._adam["step"] += k
+        return rows
+
+    eager_steps = run
 
 
 class _PlannedRunner:
