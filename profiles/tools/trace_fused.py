@@ -65,10 +65,13 @@ for steps in (64, 256):
     torch.cuda.synchronize()
     print(f"epoch kernel: {steps} steps in one launch: {e0.elapsed_time(e1) * 1e3 / steps:.2f} us/step")
 n_cta, n_prod = 148, 8
-buf = (ctypes.c_uint64 * (8 * n_cta))()
-_lib.check(lib.fr_focf_epoch_trace(buf, 8 * n_cta), "fr_focf_epoch_trace")
-t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 8)
-c = t[n_prod:]
+buf = (ctypes.c_uint64 * (16 * n_cta))()
+_lib.check(lib.fr_focf_epoch_trace(buf, 16 * n_cta), "fr_focf_epoch_trace")
+t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 16)
+x = (t[n_prod:, 8:12] - t[n_prod:, 0].min()) / 1e3
+print("epoch kernel, barrier 3 in detail (min..max over compute CTAs): "
+      + " ".join(f"{n}={x[:, k].min():.1f}..{x[:, k].max():.1f}" for k, n in enumerate(["cta_done", "fenced", "arrived", "prefetched"])))
+c = t[n_prod:, :8]
 t0 = c[:, 0].min()
 rel = (c - t0) / 1e3
 dur = np.diff(rel, axis=1)

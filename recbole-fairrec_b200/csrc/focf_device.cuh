@@ -329,27 +329,57 @@ __device__ __forceinline__ void segment_record_sum(const LossArgs &a, int sgm, f
 // rest_staged: rating / attribute columns are already in shared memory (persistent epoch kernel: staged while it waits at
 // the grid barrier); need_sums == false: this CTA does not need the batch loss (only one CTA writes it), so the block-wide
 // sums are skipped unless the objective's backward term depends on them (nonparity).
+// pre: values the caller fetched ahead (persistent epoch kernel): segment count, batch min / max of the attribute, and the
+// bounds of the warp's first segment.
+struct StatsPre {
+  int J;
+  uint32_t vmin, vmax;   // order-encoded
+  int s0, s1;            // bounds of segment (threadIdx.x >> 5)
+};
 __device__ __forceinline__ float fused_stats(const LossArgs &a, int B, int cap, float *sm, float *sh, float *s_cseg,
                                              float *s_cglob, bool rest_staged = false, bool need_sums = true,
-                                             int lead_cta = 0) {   // lead_cta: the CTA that raises the status flags
+                                             int lead_cta = 0,   // lead_cta: the CTA that raises the status flags
+                                             const StatsPre *pre = nullptr) {
   float *s_pred = sm, *s_rat = sm + cap, *s_sst = sm + 2 * cap;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int J = *a.J;
+  const int J = pre ? pre->J : *a.J;
   const float Bn = (float)B, Jn = (float)J;
-  const float vmin = ord2f(a.ctrl[CTRL_MIN]), vmax = ord2f(a.ctrl[CTRL_MAX]);
-  for (int p = threadIdx.x; p < B; p += blockDim.x) {
-    const int b = a.ord_i ? (int)a.ord_i[p] : p;     // item-sorted order (identity for whole-item batches)
-    s_pred[p] = a.pred[b];
-    if (!rest_staged) {
-      s_rat[p] = a.rating[b];
-      s_sst[p] = a.sst[b];
+  const float vmin = ord2f(pre ? pre->vmin : a.ctrl[CTRL_MIN]), vmax = ord2f(pre ? pre->vmax : a.ctrl[CTRL_MAX]);
+  // (four rows per thread in flight: a rolled loop costs one L2 round trip per 512 rows)
+  for (int p0 = threadIdx.x; p0 < B; p0 += 4 * blockDim.x) {
+    int b[4];
+    float vp[4], vr[4], vs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + i * blockDim.x;
+      b[i] = p < B ? (a.ord_i ? (int)a.ord_i[p] : p) : 0;     // item-sorted order (identity for whole-item batches)
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      vp[i] = a.pred[b[i]];
+      if (!rest_staged) {
+        vr[i] = a.rating[b[i]];
+        vs[i] = a.sst[b[i]];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + i * blockDim.x;
+      if (p < B) {
+        s_pred[p] = vp[i];
+        if (!rest_staged) {
+          s_rat[p] = vr[i];
+          s_sst[p] = vs[i];
+        }
+      }
     }
   }
   __syncthreads();
   float w_sq = 0.f, w_hx = 0.f, w_g0 = 0.f, w_g1 = 0.f, w_n0 = 0.f, w_n1 = 0.f;
   int bad = 0;
   for (int j = wib; j < J; j += nw) {
-    const int s0 = a.segoff_i[j], s1 = a.segoff_i[j + 1];
+    const bool first = pre != nullptr && j == wib;
+    const int s0 = first ? pre->s0 : a.segoff_i[j], s1 = first ? pre->s1 : a.segoff_i[j + 1];
     float sp0 = 0.f, sp1 = 0.f, st0 = 0.f, st1 = 0.f, c0 = 0.f, c1 = 0.f, sq = 0.f;
 #pragma unroll 4
     for (int p = s0 + lane; p < s1; p += 32) {   // (unrolled: the shared-memory loads of a popular item's rows pipeline)
@@ -437,52 +467,75 @@ struct GradArgs {
   int pre_handover;   // fused step: the control block has not been handed over yet -> read CTRL_MIN, not CTRL_SAVED_MIN
 };
 
+// One warp's chunk of the sorted order in two steps: STAGE reads what the preparation left (sorted entry ids, segment ids,
+// the other side's row ids, the entry's item segment) -- nothing that depends on the forward, so the persistent epoch
+// kernel issues it ahead of the barrier; RUN forms the coefficients, gathers the rows and writes the partials.
+struct ChunkStage {
+  int c, pbase, nvalid;        // chunk index within its side, first sorted position, entries (0: nothing to do)
+  int my_seg, my_oid, my_b, my_es;   // lane l: segment, other-side row, entry index, item segment of entry pbase + l
+  int seg_before, seg_after;   // segments just outside the chunk (-1: none)
+  bool user_side;
+};
+
+__device__ __forceinline__ ChunkStage stage_chunk(const GradArgs &a, int nchunk, int c) {   // c in [0, 2 * nchunk)
+  const int lane = threadIdx.x & 31;
+  ChunkStage s;
+  s.user_side = c >= nchunk;
+  if (s.user_side) c -= nchunk;
+  s.c = c;
+  s.pbase = c * a.chunk;
+  const int B = FR_B(a.B, a.B_dev);
+  s.nvalid = s.pbase < B ? min(a.chunk, B - s.pbase) : 0;
+  s.my_seg = -1; s.my_oid = 0; s.my_b = 0; s.my_es = 0;
+  s.seg_before = s.seg_after = -1;
+  if (s.nvalid == 0) return s;
+  const uint32_t *ord = s.user_side ? a.ord_u : a.ord_i;
+  const int32_t *segid = s.user_side ? a.segid_u : a.segid_i;
+  const int32_t *oid = s.user_side ? a.iid : a.uid;
+  // the segments just outside the chunk: a row whose segment equals one of them continues from / into a neighbouring
+  // chunk -- known without reading the segment offsets at every flush
+  int edge = -1;
+  if (lane == 0 && s.pbase > 0) edge = segid[s.pbase - 1];
+  if (lane == 1 && s.pbase + s.nvalid < B) edge = segid[s.pbase + s.nvalid];
+  if (lane < s.nvalid) {   // lane l stages entry pbase + l
+    const int p = s.pbase + lane;
+    s.my_b = ord ? (int)ord[p] : p;
+    s.my_seg = segid[p];
+    s.my_oid = oid[s.my_b];
+    s.my_es = a.entry_seg[s.my_b];
+  }
+  s.seg_before = __shfl_sync(0xffffffffu, edge, 0);
+  s.seg_after = __shfl_sync(0xffffffffu, edge, 1);
+  return s;
+}
+
 // kNc: the other side's rows go through the read-only path (__ldg); false in the persistent epoch kernel, where the tables
 // change during the launch
 template <int kRowVecs, bool kNc = true>
-__device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c) {   // c in [0, 2 * nchunk): one warp
+__device__ __forceinline__ void run_chunk(const GradArgs &a, const ChunkStage &s) {
+  if (s.nvalid == 0) return;
   const int lane = threadIdx.x & 31;
-  const bool user_side = c >= nchunk;
-  if (user_side) c -= nchunk;
-  const int chunk = a.chunk;
-  const int pbase = c * chunk;
+  const bool user_side = s.user_side;
+  const int c = s.c, nvalid = s.nvalid;
   const int B = FR_B(a.B, a.B_dev);
-  if (pbase >= B) return;
-  const uint32_t *ord = user_side ? a.ord_u : a.ord_i;
-  const int32_t *segid = user_side ? a.segid_u : a.segid_i;
   const float *other = user_side ? a.I : a.U;
-  const int32_t *oid = user_side ? a.iid : a.uid;
   float *gseg = user_side ? a.gseg_u : a.gseg_i;
   float *head = user_side ? a.head_u : a.head_i;
   float *tail = user_side ? a.tail_u : a.tail_i;
   const int d = a.d;
-  const int nvalid = min(chunk, B - pbase);
   const float vmin = ord2f(a.ctrl[a.pre_handover ? CTRL_MIN : CTRL_SAVED_MIN]);
   const int nB = a.norm_from_ctrl ? (int)a.ctrl[CTRL_NORM_B] : a.norm_B;
-
-  // lane l stages entry pbase + l
-  int my_seg = -1, my_oid = 0, my_b = 0;
-  // the segments just outside the chunk (-1: none): a row whose segment equals one of them continues from / into a
-  // neighbouring chunk -- known without reading the segment offsets at every flush
-  int edge = -1;
-  if (lane == 0 && pbase > 0) edge = segid[pbase - 1];
-  if (lane == 1 && pbase + nvalid < B) edge = segid[pbase + nvalid];
-  if (lane < nvalid) {
-    const int p = pbase + lane;
-    my_b = ord ? (int)ord[p] : p;
-    my_seg = segid[p];
-    my_oid = oid[my_b];
-  }
-  const int seg_before = __shfl_sync(0xffffffffu, edge, 0), seg_after = __shfl_sync(0xffffffffu, edge, 1);
+  const int my_seg = s.my_seg, my_oid = s.my_oid, my_b = s.my_b;
+  const int seg_before = s.seg_before, seg_after = s.seg_after;
   float4 acc[kRowVecs];
 #pragma unroll
   for (int v = 0; v < kRowVecs; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   int cur = __shfl_sync(0xffffffffu, my_seg, 0);
 
-  auto flush = [&](int s) {
-    float *dst = (s != seg_before && s != seg_after) ? gseg + (size_t)s * d      // the segment lies inside the chunk
-                 : (s == seg_before)                  ? head + (size_t)c * d      // it started in an earlier chunk
-                                                      : tail + (size_t)c * d;     // it continues into the next one
+  auto flush = [&](int sg) {
+    float *dst = (sg != seg_before && sg != seg_after) ? gseg + (size_t)sg * d     // the segment lies inside the chunk
+                 : (sg == seg_before)                   ? head + (size_t)c * d      // it started in an earlier chunk
+                                                        : tail + (size_t)c * d;     // it continues into the next one
 #pragma unroll
     for (int v = 0; v < kRowVecs; ++v) {
       const int k = lane * 4 + v * 128;
@@ -510,13 +563,13 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
       }
     }
   };
-  // the first rows need the other side's ids only: they are in flight while the entry's dL/dpred coefficient (two more
-  // dependent loads: the entry's columns, then its segment's fairness term) is formed
+  // the first rows need the other side's ids only: they are in flight while the entry's dL/dpred coefficient (the
+  // entry's columns and its segment's fairness term) is formed
   issue(0);
   float my_coef = 0.f;
   if (lane < nvalid) {
     const int g = a.sst[my_b] != vmin;
-    my_coef = (2.f * (a.pred[my_b] - a.rating[my_b]) / (float)(nB > 0 ? nB : B) + a.cseg[2 * a.entry_seg[my_b] + g] +
+    my_coef = (2.f * (a.pred[my_b] - a.rating[my_b]) / (float)(nB > 0 ? nB : B) + a.cseg[2 * s.my_es + g] +
                a.cglob[g]) * a.grad_scale;
   }
   for (int l0 = 0; l0 < nvalid; l0 += kDepth) {
@@ -524,12 +577,12 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
 #pragma unroll
     for (int e = 0; e < kDepth; ++e) {
       const int l = l0 + e;
-      const int s = __shfl_sync(0xffffffffu, my_seg, l & 31);
+      const int sg = __shfl_sync(0xffffffffu, my_seg, l & 31);
       const float cf = __shfl_sync(0xffffffffu, my_coef, l & 31);
       if (l < nvalid) {
-        if (s != cur) {
+        if (sg != cur) {
           flush(cur);
-          cur = s;
+          cur = sg;
         }
 #pragma unroll
         for (int v = 0; v < kRowVecs; ++v) {
@@ -542,6 +595,11 @@ __device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c
     }
   }
   flush(cur);
+}
+
+template <int kRowVecs, bool kNc = true>
+__device__ __forceinline__ void grads_chunk(const GradArgs &a, int nchunk, int c) {   // c in [0, 2 * nchunk): one warp
+  run_chunk<kRowVecs, kNc>(a, stage_chunk(a, nchunk, c));
 }
 
 template <int kRowVecs>

@@ -31,6 +31,7 @@ namespace fr {
 constexpr int kEpThreads = 512, kEpWarps = kEpThreads / 32;
 constexpr int kEpMaxRows = 8192;      // batch rows (16 sorted keys per producer thread)
 constexpr int kEpMaxSlots = 8;
+constexpr int kEpMaxR = 4;           // resident float4 elements per compute thread (what shared memory holds at most)
 // mailbox of a slot inside its workspace's control block (words the stepwise path does not use)
 enum { EP_READY_U = 32, EP_READY_I = 33, EP_B = 34, EP_STAMP = 35, EP_SC0 = 36, EP_SC1 = 37 };
 
@@ -57,6 +58,7 @@ struct EpochArgs {
   unsigned long long *sync;    // [0] arrival counter of the compute CTAs' barrier, [1] steps completed
   unsigned long long *trace;   // optional: [gridDim.x][8] %globaltimer stamps of step `trace_step`
   int trace_step;
+  int dbg_skip;   // timing experiments only (FR_FOCF_EPOCH_SKIP bit mask: phases left out; results are then meaningless)
   EpSlot slot[kEpMaxSlots];
 };
 
@@ -66,8 +68,29 @@ __device__ __forceinline__ unsigned long long ep_now() {
   return t;
 }
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
-__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long *p) {
-  return *(const volatile unsigned long long *)p;
+// Release / acquire at GPU scope for the flags and the barrier counter.  NOT __threadfence(): that is fence.sc
+// (MEMBAR.SC.GPU), and ~140 CTAs issuing it in the same microsecond serialise -- 0.9 .. 6.3 us per fence in the phase
+// trace, the largest single item of a step.
+__device__ __forceinline__ uint32_t ld_acq(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acq(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_rel(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_rel(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_add_rel(unsigned long long *p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.add.release.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
 }
 
 // ------------------------------------------------------------------------------------------ producer
@@ -99,13 +122,12 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
   for (int i = k; i < a.n_steps; i += a.n_slots, ++uses) {
     if (i >= a.n_slots) {   // the slot is free once the step that used it last has finished
       if (tid == 0) {
-        while (ld_vol(a.sync + 1) < (unsigned long long)(i - a.n_slots + 1)) {}
-        __threadfence();
+        while (ld_acq(a.sync + 1) < (unsigned long long)(i - a.n_slots + 1)) {}
       }
       __syncthreads();
     }
     const bool tr = tr_cta && i >= a.trace_step && i < a.trace_step + a.n_slots;
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 0] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 0] = ep_now();
     const uint32_t stamp = stamp_base + (uint32_t)uses;
     const int32_t *dsc = a.plan_desc + 4 * (int)((unsigned)(a.first_batch + i) % (unsigned)a.plan_len);
     const int32_t *draw_items = a.plan_items + __ldg(dsc), *draw_off = a.plan_offs + __ldg(dsc + 1);
@@ -148,7 +170,7 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
       }
     }
     __syncthreads();
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 1] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 1] = ep_now();
 
     if (user_side) {   // stable LSD radix sort by user id (k_prepare_small's ranking, 16 warps)
       const int rounds = (n + kEpThreads - 1) / kEpThreads, chunk = rounds * 32;
@@ -207,7 +229,7 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
         t0 = vA; vA = vB; vB = t0;
       }
     }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 2] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 2] = ep_now();
 
     // segments: thread tid owns ipt consecutive sorted positions
     {
@@ -265,18 +287,14 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
       ctrl[EP_SC0] = __float_as_uint((float)(-a.lr / bc1));
       ctrl[EP_SC1] = __float_as_uint((float)sqrt(bc2));
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      *(volatile uint32_t *)(ctrl + (user_side ? EP_READY_U : EP_READY_I)) = (uint32_t)(i + 1);
-    }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 3] = ep_now();
+    if (tid == 0) st_rel(ctrl + (user_side ? EP_READY_U : EP_READY_I), (uint32_t)(i + 1));   // (cumulative over the CTA's writes)
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 3] = ep_now();
   }
   // leave the slot's workspace as the stepwise path expects it: stamp advanced past every use, hand-over words re-armed
   if (user_side && tid == 0) {
     // the last step must have read the words before they are re-armed
-    while (ld_vol(a.sync + 1) < (unsigned long long)a.n_steps) {}
+    while (ld_acq(a.sync + 1) < (unsigned long long)a.n_steps) {}
     ctrl[CTRL_STAMP] = stamp_base + (uint32_t)uses;
     ctrl[CTRL_MIN] = 0xffffffffu;
     ctrl[CTRL_MAX] = 0u;
@@ -290,15 +308,11 @@ struct EpBar {
 };
 __device__ __forceinline__ void ep_arrive(EpBar &b) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    b.target = (atomicAdd(b.ctr, 1ull) / b.n + 1ull) * b.n;
-  }
+  if (threadIdx.x == 0) b.target = (atom_add_rel(b.ctr, 1ull) / b.n + 1ull) * b.n;   // release: the CTA's writes first
 }
 __device__ __forceinline__ void ep_wait(EpBar &b) {
   if (threadIdx.x == 0) {
-    while (ld_vol(b.ctr) < b.target) {}
-    __threadfence();
+    while (ld_acq(b.ctr) < b.target) {}
   }
   __syncthreads();
 }
@@ -343,29 +357,79 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
     s_meta[r * kEpThreads + tid] = meta;
   }
 
+  // what a step needs from its slot, fetched AHEAD of the step (in the shadow of the previous step's last barrier):
+  // the mailbox, the ids of the warp's first forward group, the batch's segment count and attribute range, and for every
+  // resident element whether its row is touched by the batch and which gradient segment / chunks it reads then
+  int B = 0, pre_nu = 0, pre_ni = 0;
+  uint32_t stamp = 0;
+  float neg_step = 0.f, bc2s = 0.f;
+  StatsPre sp{0, 0u, 0u, 0, 0};
+  auto prefetch = [&](int i) {
+    const EpSlot &sl = a.slot[i % a.n_slots];
+    uint32_t *ctrl = sl.w.ctrl;
+    if (tid == 0) {
+      while (ld_acq(ctrl + EP_READY_U) < (uint32_t)(i + 1) || ld_acq(ctrl + EP_READY_I) < (uint32_t)(i + 1)) {}
+    }
+    __syncthreads();
+    B = (int)__ldcg(ctrl + EP_B);
+    stamp = __ldcg(ctrl + EP_STAMP);
+    neg_step = __uint_as_float(__ldcg(ctrl + EP_SC0));
+    bc2s = __uint_as_float(__ldcg(ctrl + EP_SC1));
+    sp.J = __ldcg(sl.w.J);
+    sp.vmin = __ldcg(ctrl + CTRL_MIN);
+    sp.vmax = __ldcg(ctrl + CTRL_MAX);
+    pre_nu = pre_ni = 0;
+    if (lane < 4) {   // (rows past the batch end hold stale ids of an earlier batch: never used)
+      const int b = min(gwarp * 4 + lane, cap - 1);
+      pre_nu = __ldcg(sl.uid + b);
+      pre_ni = __ldcg(sl.iid + b);
+    }
+    if (a.dbg_skip & 32) return;
+    // (all row-stamp loads first, then all segment-offset loads: two L2 round trips for the thread's R elements together)
+    int mx[kEpMaxR];
+    uint2 tab[kEpMaxR];
+#pragma unroll
+    for (int r = 0; r < kEpMaxR; ++r) {
+      mx[r] = r < R ? s_meta[r * kEpThreads + tid].x : -1;
+      tab[r] = make_uint2(0u, 0u);
+      if (mx[r] != -1) tab[r] = __ldcg((mx[r] < 0 ? sl.w.row_tab_i : sl.w.row_tab_u) + (mx[r] & 0x7fffffff));
+    }
+    int s0[kEpMaxR], s1[kEpMaxR];
+#pragma unroll
+    for (int r = 0; r < kEpMaxR; ++r) {
+      s0[r] = s1[r] = 0;
+      if (mx[r] != -1 && tab[r].x == stamp) {   // touched by this batch: its gradient segment ...
+        const int32_t *segoff = mx[r] < 0 ? sl.w.segoff_i : sl.w.segoff_u;
+        s0[r] = __ldcg(segoff + tab[r].y);
+        s1[r] = __ldcg(segoff + tab[r].y + 1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kEpMaxR; ++r) {
+      if (mx[r] == -1) continue;
+      int4 meta = make_int4(mx[r], -1, 0, 0);
+      if (tab[r].x == stamp) {                  // ... and the chunks the segment spans
+        meta.y = (int)tab[r].y;
+        meta.z = s0[r] / a.chunk;
+        meta.w = (s1[r] - 1) / a.chunk;
+      }
+      s_meta[r * kEpThreads + tid] = meta;
+    }
+  };
+  __shared__ int s_alloc;
+  prefetch(0);
+
   for (int i = 0; i < a.n_steps; ++i) {
     const EpSlot &sl = a.slot[i % a.n_slots];
     uint32_t *ctrl = sl.w.ctrl;
     const bool tr = tr_cta && i == a.trace_step;
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 0] = ep_now();
-    if (tid == 0) {
-      while (ld_vol(ctrl + EP_READY_U) < (uint32_t)(i + 1) || ld_vol(ctrl + EP_READY_I) < (uint32_t)(i + 1)) {}
-      __threadfence();
-    }
-    __syncthreads();
-    const int B = (int)__ldcg(ctrl + EP_B);
-    const uint32_t stamp = __ldcg(ctrl + EP_STAMP);
-    const float neg_step = __uint_as_float(__ldcg(ctrl + EP_SC0)), bc2s = __uint_as_float(__ldcg(ctrl + EP_SC1));
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 0] = ep_now();
+    if (tid == 0) s_alloc = 0;
 
     // ---- forward (focf.py:136-143): forward_body's arithmetic, rows through L2 (the tables change during the launch)
-    {
-      int nu = 0, ni = 0;
-      int b0 = gwarp * 4;
-      if (lane < 4 && b0 + lane < B) {
-        nu = __ldcg(sl.uid + b0 + lane);
-        ni = __ldcg(sl.iid + b0 + lane);
-      }
-      for (; b0 < B; b0 += nwarps * 4) {
+    if (!(a.dbg_skip & 1)) {
+      int nu = pre_nu, ni = pre_ni;
+      for (int b0 = gwarp * 4; b0 < B; b0 += nwarps * 4) {
         const int cu = nu, ci = ni;
         const int nb = b0 + nwarps * 4 + lane;
         if (lane < 4 && nb < B) {
@@ -391,112 +455,169 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
         float mine = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float s = warp_sum(acc[e]);
-          if (lane == e) mine = s;
+          const float sm = warp_sum(acc[e]);
+          if (lane == e) mine = sm;
         }
         if (lane < 4 && b0 + lane < B) sl.pred[b0 + lane] = mine;
       }
     }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 1] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 1] = ep_now();
     ep_arrive(bar);
 
-    // ---- in the shadow of barrier 1: everything that depends on the producer only
-    for (int p = tid; p < B; p += kEpThreads) {
-      s_rat[p] = __ldcg(sl.rating + p);
-      s_sst[p] = __ldcg(sl.sst + p);
-    }
-    for (int r = 0; r < R; ++r) {
-      int4 meta = s_meta[r * kEpThreads + tid];
-      if (meta.x == -1) continue;
-      const bool is_item = meta.x < 0;
-      const int row = meta.x & 0x7fffffff;
-      const uint2 t = __ldcg((is_item ? sl.w.row_tab_i : sl.w.row_tab_u) + row);
-      if (t.x == stamp) {   // touched by this batch: its gradient segment and the chunks the segment spans
-        const int32_t *segoff = is_item ? sl.w.segoff_i : sl.w.segoff_u;
-        const int s = (int)t.y, s0 = __ldcg(segoff + s), s1 = __ldcg(segoff + s + 1);
-        meta.y = s;
-        meta.z = s0 / a.chunk;
-        meta.w = (s1 - 1) / a.chunk;
-        s_meta[r * kEpThreads + tid] = meta;
-      } else {              // untouched: the step's update needs nothing from this batch (zero data gradient)
-        meta.y = -1;
-        s_meta[r * kEpThreads + tid] = meta;
-        float4 p = s_state[(r * 3 + 0) * kEpThreads + tid], m = s_state[(r * 3 + 1) * kEpThreads + tid],
-               v = s_state[(r * 3 + 2) * kEpThreads + tid];
-        adam1(p.x, m.x, v.x, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.y, m.y, v.y, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.z, m.z, v.z, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.w, m.w, v.w, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
-        s_state[(r * 3 + 0) * kEpThreads + tid] = p;
-        s_state[(r * 3 + 1) * kEpThreads + tid] = m;
-        s_state[(r * 3 + 2) * kEpThreads + tid] = v;
-        const long long q = (long long)g + (long long)r * NT;
-        const long long ql = is_item ? q - nq_u : q;
-        *(float4 *)((is_item ? a.I : a.U) + ql * 4) = p;
+    // ---- in the shadow of barrier 1: what the next two phases read from the producer, and the update of the resident
+    // rows this batch does not touch (zero data gradient: nothing of this step is needed; nobody reads them in this step)
+    GradArgs ga{a.U, a.I, sl.uid, sl.iid, s_rat, s_sst, fsm, B, d, nullptr, 0, 0, nullptr, sl.w.ord_u,
+                sl.w.segid_i, sl.w.segoff_i, sl.w.segid_u, sl.w.segoff_u, sl.w.entry_seg, s_cseg, s_cglob, ctrl, 1.0f,
+                a.chunk, sl.w.gseg_i, sl.w.head_i, sl.w.tail_i, sl.w.gseg_u, sl.w.head_u, sl.w.tail_u, 1};
+    const int nchunk = (B + a.chunk - 1) / a.chunk;
+    ChunkStage cs = stage_chunk(ga, nchunk, (gwarp < 2 * nchunk && !(a.dbg_skip & 4)) ? gwarp : 2 * nchunk);   // (2 * nchunk: an empty chunk)
+    {
+      const int wib = tid >> 5;
+      sp.s0 = sp.s1 = 0;
+      if (wib < sp.J) {
+        sp.s0 = __ldcg(sl.w.segoff_i + wib);
+        sp.s1 = __ldcg(sl.w.segoff_i + wib + 1);
       }
     }
+    for (int p0 = tid; p0 < B; p0 += 4 * kEpThreads) {
+      float vr[4], vs[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int p = min(p0 + q4 * kEpThreads, B - 1);
+        vr[q4] = __ldcg(sl.rating + p);
+        vs[q4] = __ldcg(sl.sst + p);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int p = p0 + q4 * kEpThreads;
+        if (p < B) {
+          s_rat[p] = vr[q4];
+          s_sst[p] = vs[q4];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kEpMaxR; ++r) {
+      if (r >= R || (a.dbg_skip & 16)) continue;
+      const int4 meta = s_meta[r * kEpThreads + tid];
+      if (meta.x == -1 || meta.y >= 0) continue;
+      const bool is_item = meta.x < 0;
+      float4 p = s_state[(r * 3 + 0) * kEpThreads + tid], m = s_state[(r * 3 + 1) * kEpThreads + tid],
+             v = s_state[(r * 3 + 2) * kEpThreads + tid];
+      adam1(p.x, m.x, v.x, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.y, m.y, v.y, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.z, m.z, v.z, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
+      adam1(p.w, m.w, v.w, 0.f, wd, w1, b2, w2, bc2s, eps, neg_step);
+      s_state[(r * 3 + 0) * kEpThreads + tid] = p;
+      s_state[(r * 3 + 1) * kEpThreads + tid] = m;
+      s_state[(r * 3 + 2) * kEpThreads + tid] = v;
+      const long long q = (long long)g + (long long)r * NT;
+      const long long ql = is_item ? q - nq_u : q;
+      *(float4 *)((is_item ? a.I : a.U) + ql * 4) = p;
+    }
     ep_wait(bar);
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 2] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 2] = ep_now();
 
     // ---- item x group statistics, fairness objective, loss (focf.py:75-134, 152-169): fused_stats, per CTA
     LossArgs la{sl.pred, s_rat, s_sst, nullptr, sl.w.segid_i, sl.w.segoff_i, sl.w.J, B, nullptr, a.plan_len, 0, a.objective,
                 0, 0, nullptr, a.fair_weight, nullptr, nullptr, nullptr, nullptr, nullptr, a.loss, ctrl, a.flags};
     const bool loss_cta = cta == n_comp - 1;
-    const float loss = fused_stats(la, B, cap, fsm, sh, s_cseg, s_cglob, true, loss_cta, (int)gridDim.x - 1);
+    const float loss = (a.dbg_skip & 2) ? 0.f : fused_stats(la, B, cap, fsm, sh, s_cseg, s_cglob, true, loss_cta, (int)gridDim.x - 1, &sp);
     if (loss_cta && tid == 0) {
       a.loss[(unsigned)(a.first_batch + i) % (unsigned)a.plan_len] = loss;
       if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
     }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 3] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 3] = ep_now();
 
-    // ---- gradients: grads_chunk over the item- and the user-sorted order, the batch columns from shared memory
-    {
-      GradArgs ga{a.U, a.I, sl.uid, sl.iid, s_rat, s_sst, fsm, B, d, nullptr, 0, 0, nullptr, sl.w.ord_u,
-                  sl.w.segid_i, sl.w.segoff_i, sl.w.segid_u, sl.w.segoff_u, sl.w.entry_seg, s_cseg, s_cglob, ctrl, 1.0f,
-                  a.chunk, sl.w.gseg_i, sl.w.head_i, sl.w.tail_i, sl.w.gseg_u, sl.w.head_u, sl.w.tail_u, 1};
-      const int nchunk = (B + a.chunk - 1) / a.chunk;
-      for (int c = gwarp; c < 2 * nchunk; c += nwarps) grads_chunk<1, false>(ga, nchunk, c);
+    // ---- gradients: the staged chunk (then any further ones) over the item- and the user-sorted order, the batch
+    // columns from shared memory
+    run_chunk<1, false>(ga, cs);
+    if (!(a.dbg_skip & 4))
+      for (int c = gwarp + nwarps; c < 2 * nchunk; c += nwarps) grads_chunk<1, false>(ga, nchunk, c);
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 4] = ep_now();
+    if (!(a.dbg_skip & 64)) {
+      ep_arrive(bar);
+      ep_wait(bar);
     }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 4] = ep_now();
-    ep_arrive(bar);
-    ep_wait(bar);
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 5] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 5] = ep_now();
 
-    // ---- Adam on the touched resident rows (apply_body's gradient assembly and update)
-    for (int r = 0; r < R; ++r) {
-      const int4 meta = s_meta[r * kEpThreads + tid];
-      if (meta.x == -1 || meta.y < 0) continue;
-      const bool is_item = meta.x < 0;
-      const long long q = (long long)g + (long long)r * NT;
-      const long long ql = is_item ? q - nq_u : q;
-      const int k = (int)(ql % dq) * 4;
-      const float *gseg = is_item ? sl.w.gseg_i : sl.w.gseg_u;
-      const float *head = is_item ? sl.w.head_i : sl.w.head_u;
-      const float *tail = is_item ? sl.w.tail_i : sl.w.tail_u;
-      float4 gr;
-      if (meta.z == meta.w) {
-        gr = __ldcg((const float4 *)(gseg + (size_t)meta.y * d + k));
-      } else {
-        gr = __ldcg((const float4 *)(tail + (size_t)meta.z * d + k));
-#pragma unroll 8
-        for (int c = meta.z + 1; c <= meta.w; ++c) gr = f4_add(gr, __ldcg((const float4 *)(head + (size_t)c * d + k)));
+    // ---- Adam on the touched resident rows (apply_body's gradient assembly and update).  A popular item's segment
+    // spans many chunks: its head partials are brought into shared memory with cp.async first (all in flight at once; the
+    // statistics staging area is free now) and then added in chunk order -- the stepwise path's order without one L2
+    // round trip per handful of partials.
+    if (!(a.dbg_skip & 8)) {
+      float4 *stage = (float4 *)fsm;
+      const int n_stage = (5 * cap) / 4;
+      int sbase[kEpMaxR];
+#pragma unroll
+      for (int r = 0; r < kEpMaxR; ++r) {
+        sbase[r] = -1;
+        if (r >= R) continue;
+        const int4 meta = s_meta[r * kEpThreads + tid];
+        if (meta.x == -1 || meta.y < 0 || meta.w - meta.z < 4) continue;
+        const int np = meta.w - meta.z;
+        const int base = atomicAdd(&s_alloc, np);
+        if (base + np > n_stage) continue;
+        sbase[r] = base;
+        const bool is_item = meta.x < 0;
+        const long long q = (long long)g + (long long)r * NT;
+        const int k = (int)((is_item ? q - nq_u : q) % dq) * 4;
+        const float *head = is_item ? sl.w.head_i : sl.w.head_u;
+        for (int c = 0; c < np; ++c) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + base + c);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(head + (size_t)(meta.z + 1 + c) * d + k)
+                       : "memory");
+        }
       }
-      float4 p = s_state[(r * 3 + 0) * kEpThreads + tid], m = s_state[(r * 3 + 1) * kEpThreads + tid],
-             v = s_state[(r * 3 + 2) * kEpThreads + tid];
-      adam1(p.x, m.x, v.x, gr.x, wd, w1, b2, w2, bc2s, eps, neg_step);
-      adam1(p.y, m.y, v.y, gr.y, wd, w1, b2, w2, bc2s, eps, neg_step);
-      adam1(p.z, m.z, v.z, gr.z, wd, w1, b2, w2, bc2s, eps, neg_step);
-      adam1(p.w, m.w, v.w, gr.w, wd, w1, b2, w2, bc2s, eps, neg_step);
-      s_state[(r * 3 + 0) * kEpThreads + tid] = p;
-      s_state[(r * 3 + 1) * kEpThreads + tid] = m;
-      s_state[(r * 3 + 2) * kEpThreads + tid] = v;
-      *(float4 *)((is_item ? a.I : a.U) + ql * 4) = p;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < kEpMaxR; ++r) {
+        if (r >= R) continue;
+        const int4 meta = s_meta[r * kEpThreads + tid];
+        if (meta.x == -1 || meta.y < 0) continue;
+        const bool is_item = meta.x < 0;
+        const long long q = (long long)g + (long long)r * NT;
+        const long long ql = is_item ? q - nq_u : q;
+        const int k = (int)(ql % dq) * 4;
+        const float *gseg = is_item ? sl.w.gseg_i : sl.w.gseg_u;
+        const float *head = is_item ? sl.w.head_i : sl.w.head_u;
+        const float *tail = is_item ? sl.w.tail_i : sl.w.tail_u;
+        float4 gr;
+        if (meta.z == meta.w) {
+          gr = __ldcg((const float4 *)(gseg + (size_t)meta.y * d + k));
+        } else {
+          gr = __ldcg((const float4 *)(tail + (size_t)meta.z * d + k));
+          if (sbase[r] >= 0) {
+            for (int c = 0; c < meta.w - meta.z; ++c) gr = f4_add(gr, stage[sbase[r] + c]);
+          } else {
+#pragma unroll 8
+            for (int c = meta.z + 1; c <= meta.w; ++c) gr = f4_add(gr, __ldcg((const float4 *)(head + (size_t)c * d + k)));
+          }
+        }
+        float4 p = s_state[(r * 3 + 0) * kEpThreads + tid], m = s_state[(r * 3 + 1) * kEpThreads + tid],
+               v = s_state[(r * 3 + 2) * kEpThreads + tid];
+        adam1(p.x, m.x, v.x, gr.x, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.y, m.y, v.y, gr.y, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.z, m.z, v.z, gr.z, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.w, m.w, v.w, gr.w, wd, w1, b2, w2, bc2s, eps, neg_step);
+        s_state[(r * 3 + 0) * kEpThreads + tid] = p;
+        s_state[(r * 3 + 1) * kEpThreads + tid] = m;
+        s_state[(r * 3 + 2) * kEpThreads + tid] = v;
+        *(float4 *)((is_item ? a.I : a.U) + ql * 4) = p;
+      }
     }
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 6] = ep_now();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 6] = ep_now();
+    __syncthreads();
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 8] = ep_now();    // the CTA's slowest thread is done
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 9] = ep_now();
     ep_arrive(bar);
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 10] = ep_now();   // arrived
+    if (i + 1 < a.n_steps) prefetch(i + 1);   // in the shadow of barrier 3
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 11] = ep_now();   // next step's prefetch done
     ep_wait(bar);
-    if (cta == 0 && tid == 0) *(volatile unsigned long long *)(a.sync + 1) = (unsigned long long)(i + 1);
-    if (tr && tid == 0) a.trace[blockIdx.x * 8 + 7] = ep_now();
+    if (cta == 0 && tid == 0) st_rel(a.sync + 1, (unsigned long long)(i + 1));
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 7] = ep_now();
   }
 
   // the moments go back to their tables (the parameters are current in global memory after every step)
@@ -542,7 +663,7 @@ static int ep_plan(const fr_focf_step *slots, int n_slots, EpPlan *out, const ch
   out->cap = s->B;
   const size_t sm_c = ep_comp_smem(s->B, out->R), sm_p = ep_prod_smem(s->B);
   out->smem = sm_c > sm_p ? sm_c : sm_p;
-  if (out->smem + 1024 > (size_t)smem_max) {
+  if (out->R > kEpMaxR || out->smem + 1024 > (size_t)smem_max) {
     set_error("%s: tables of %lld parameters and batches of up to %d rows need %zu bytes of shared memory per CTA (max %d)",
               who, nq * 4, s->B, out->smem, smem_max);
     return FR_ERR_UNSUPPORTED;
@@ -615,11 +736,17 @@ int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_
     const char *e = getenv("FR_FOCF_TRACE");
     trace_on = (e && e[0] == '1') ? 1 : 0;
     if (trace_on) {
-      FR_CUDA_OK(cudaMalloc(&g_epoch_trace, sizeof(unsigned long long) * 8 * 256));
+      FR_CUDA_OK(cudaMalloc(&g_epoch_trace, sizeof(unsigned long long) * 16 * 256));
       const char *ts = getenv("FR_FOCF_TRACE_STEP");
       g_epoch_trace_step = ts ? atoi(ts) : 8;
     }
   }
+  static int dbg_skip = -1;
+  if (dbg_skip < 0) {
+    const char *e = getenv("FR_FOCF_EPOCH_SKIP");
+    dbg_skip = e ? atoi(e) : 0;
+  }
+  a.dbg_skip = dbg_skip;
   a.trace = trace_on ? g_epoch_trace : nullptr;
   a.trace_step = g_epoch_trace_step < n_steps ? g_epoch_trace_step : n_steps - 1;
   for (int k = 0; k < n_slots; ++k) {
@@ -663,7 +790,7 @@ int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_
 }
 
 int fr_focf_epoch_trace(uint64_t *out_host, int32_t n) {
-  FR_REQUIRE(out_host && n >= 0 && n <= 8 * 256, "fr_focf_epoch_trace: bad argument");
+  FR_REQUIRE(out_host && n >= 0 && n <= 16 * 256, "fr_focf_epoch_trace: bad argument");
   FR_REQUIRE(fr::g_epoch_trace, "fr_focf_epoch_trace: set FR_FOCF_TRACE=1 before the first epoch launch");
   FR_CUDA_OK(cudaDeviceSynchronize());
   FR_CUDA_OK(cudaMemcpy(out_host, fr::g_epoch_trace, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
