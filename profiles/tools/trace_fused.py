@@ -64,7 +64,7 @@ for steps in (64, 256):
     e1.record()
     torch.cuda.synchronize()
     print(f"epoch kernel: {steps} steps in one launch: {e0.elapsed_time(e1) * 1e3 / steps:.2f} us/step")
-n_cta, n_prod = 148, 8
+n_cta, n_prod = 148, 2 * runner.state["n_slots"]
 buf = (ctypes.c_uint64 * (16 * n_cta))()
 _lib.check(lib.fr_focf_epoch_trace(buf, 16 * n_cta), "fr_focf_epoch_trace")
 t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 16)

@@ -33,7 +33,7 @@ constexpr int kEpMaxRows = 8192;      // batch rows (16 sorted keys per producer
 constexpr int kEpMaxSlots = 8;
 constexpr int kEpMaxR = 4;           // resident float4 elements per compute thread (what shared memory holds at most)
 // mailbox of a slot inside its workspace's control block (words the stepwise path does not use)
-enum { EP_READY_U = 32, EP_READY_I = 33, EP_B = 34, EP_STAMP = 35, EP_SC0 = 36, EP_SC1 = 37 };
+enum { EP_READY_U = 32, EP_READY_I = 33, EP_B = 34, EP_STAMP = 35 };
 
 struct EpSlot {
   int32_t *uid, *iid;
@@ -58,10 +58,30 @@ struct EpochArgs {
   unsigned long long *sync;    // [0] arrival counter of the compute CTAs' barrier, [1] steps completed
   unsigned long long *trace;   // optional: [gridDim.x][8] %globaltimer stamps of step `trace_step`
   int trace_step;
+  const float *sc_tab;   // [2 * n_steps] Adam scalars of the launch's steps (k_adam_scalars: apply_body's expressions)
   int dbg_skip;   // timing experiments only (FR_FOCF_EPOCH_SKIP bit mask: phases left out; results are then meaningless)
   EpSlot slot[kEpMaxSlots];
 };
 
+// spin until `cond` is false.  -DFR_EPOCH_WATCHDOG: give up after ~1 s, say where, and run on (debug builds only)
+#ifdef FR_EPOCH_WATCHDOG
+#define EP_SPIN(cond, id, info)                                                                     \
+  do {                                                                                              \
+    unsigned long long _n = 0;                                                                      \
+    while (cond) {                                                                                  \
+      if (++_n > (1ull << 20)) {                                                                    \
+        printf("EP WATCHDOG loop %d block %d info %d\n", (id), (int)blockIdx.x, (int)(info));       \
+        break;                                                                                      \
+      }                                                                                             \
+    }                                                                                               \
+  } while (0)
+#else
+#define EP_SPIN(cond, id, info) \
+  do {                          \
+    while (cond) {              \
+    }                           \
+  } while (0)
+#endif
 __device__ __forceinline__ unsigned long long ep_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -122,7 +142,7 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
   for (int i = k; i < a.n_steps; i += a.n_slots, ++uses) {
     if (i >= a.n_slots) {   // the slot is free once the step that used it last has finished
       if (tid == 0) {
-        while (ld_acq(a.sync + 1) < (unsigned long long)(i - a.n_slots + 1)) {}
+        EP_SPIN(ld_acq(a.sync + 1) < (unsigned long long)(i - a.n_slots + 1), 1, i);
       }
       __syncthreads();
     }
@@ -281,11 +301,6 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
       ctrl[CTRL_MAX] = hi;
       ctrl[EP_B] = (uint32_t)n;
       ctrl[EP_STAMP] = stamp;
-      // the step's Adam scalars, formed like apply_body's (double, rounded once)
-      const double t = (double)(a.adam_step0 + i);
-      const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
-      ctrl[EP_SC0] = __float_as_uint((float)(-a.lr / bc1));
-      ctrl[EP_SC1] = __float_as_uint((float)sqrt(bc2));
     }
     __syncthreads();
     if (tid == 0) st_rel(ctrl + (user_side ? EP_READY_U : EP_READY_I), (uint32_t)(i + 1));   // (cumulative over the CTA's writes)
@@ -294,7 +309,7 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
   // leave the slot's workspace as the stepwise path expects it: stamp advanced past every use, hand-over words re-armed
   if (user_side && tid == 0) {
     // the last step must have read the words before they are re-armed
-    while (ld_acq(a.sync + 1) < (unsigned long long)a.n_steps) {}
+    EP_SPIN(ld_acq(a.sync + 1) < (unsigned long long)a.n_steps, 2, a.n_steps);
     ctrl[CTRL_STAMP] = stamp_base + (uint32_t)uses;
     ctrl[CTRL_MIN] = 0xffffffffu;
     ctrl[CTRL_MAX] = 0u;
@@ -304,17 +319,96 @@ __device__ __forceinline__ void ep_produce(const EpochArgs &a, int k, bool user_
 // ------------------------------------------------------------------------------------------ compute
 struct EpBar {
   unsigned long long *ctr;
-  unsigned long long n, target;
+  unsigned long long n, target;   // the counter starts at zero at launch: the k-th barrier is complete at k * n arrivals
 };
 __device__ __forceinline__ void ep_arrive(EpBar &b) {
   __syncthreads();
-  if (threadIdx.x == 0) b.target = (atom_add_rel(b.ctr, 1ull) / b.n + 1ull) * b.n;   // release: the CTA's writes first
+  b.target += b.n;
+  if (threadIdx.x == 0)   // release (the CTA's writes first), no return value: nothing waits for the round trip
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(b.ctr), "l"(1ull) : "memory");
 }
 __device__ __forceinline__ void ep_wait(EpBar &b) {
   if (threadIdx.x == 0) {
-    while (ld_acq(b.ctr) < b.target) {}
+    EP_SPIN(ld_acq(b.ctr) < b.target, 3, (int)(b.target / b.n));
   }
   __syncthreads();
+}
+
+// The gradient chunk's rows in two steps, so that the loads can be issued ahead of the barrier that precedes their use
+// (run_chunk's arithmetic: entries in sorted order, acc = fmaf(coef, row, acc), partials flushed at segment ends).
+// kHalf (d <= 64): a warp request covers TWO rows -- lanes 0-15 row 2e, lanes 16-31 row 2e+1 -- so the 16 entries of a
+// chunk are one round of 8 requests; the odd rows are moved to the accumulating half by a shuffle.  Otherwise x holds the
+// first 8 rows and the second round is loaded when the first has been consumed.
+template <bool kHalf>
+__device__ __forceinline__ void ep_issue_rows(const GradArgs &a, const ChunkStage &s, int l0, float4 (&x)[8]) {
+  const int lane = threadIdx.x & 31;
+  const float *other = s.user_side ? a.I : a.U;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int l = kHalf ? l0 + 2 * e + (lane >> 4) : l0 + e;
+    const int k = kHalf ? (lane & 15) * 4 : lane * 4;
+    const int o = __shfl_sync(0xffffffffu, s.my_oid, l & 31);
+    x[e] = (l < s.nvalid && k < a.d) ? __ldcg((const float4 *)(other + (size_t)o * a.d) + (k >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool kHalf>
+__device__ __forceinline__ void ep_consume_rows(const GradArgs &a, const ChunkStage &s, float4 (&x)[8]) {
+  if (s.nvalid == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int c = s.c, nvalid = s.nvalid, d = a.d, B = a.B;
+  float *gseg = s.user_side ? a.gseg_u : a.gseg_i;
+  float *head = s.user_side ? a.head_u : a.head_i;
+  float *tail = s.user_side ? a.tail_u : a.tail_i;
+  const float vmin = ord2f(__ldcg(a.ctrl + CTRL_MIN));
+  float my_coef = 0.f;
+  if (lane < nvalid) {
+    const int gq = a.sst[s.my_b] != vmin;
+    my_coef = (2.f * (a.pred[s.my_b] - a.rating[s.my_b]) / (float)B + a.cseg[2 * s.my_es + gq] + a.cglob[gq]) * a.grad_scale;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = __shfl_sync(0xffffffffu, s.my_seg, 0);
+  const int kcol = kHalf ? (lane & 15) * 4 : lane * 4;
+  const bool writer = kHalf ? lane < 16 : true;
+  auto flush = [&](int sg) {
+    float *dst = (sg != s.seg_before && sg != s.seg_after) ? gseg + (size_t)sg * d
+                 : (sg == s.seg_before)                     ? head + (size_t)c * d
+                                                            : tail + (size_t)c * d;
+    if (writer && kcol < d) *(float4 *)(dst + kcol) = acc;
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto entry = [&](int l, const float4 &row) {   // l < nvalid is warp-uniform
+    const int sg = __shfl_sync(0xffffffffu, s.my_seg, l & 31);
+    const float cf = __shfl_sync(0xffffffffu, my_coef, l & 31);
+    if (l < nvalid) {
+      if (sg != cur) {
+        flush(cur);
+        cur = sg;
+      }
+      acc.x = fmaf(cf, row.x, acc.x);
+      acc.y = fmaf(cf, row.y, acc.y);
+      acc.z = fmaf(cf, row.z, acc.z);
+      acc.w = fmaf(cf, row.w, acc.w);
+    }
+  };
+  for (int l0 = 0; l0 < nvalid; l0 += (kHalf ? 16 : 8)) {
+    if (l0) ep_issue_rows<kHalf>(a, s, l0, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (kHalf) {
+        entry(l0 + 2 * e, x[e]);
+        float4 odd;   // row 2e+1 lives in the upper half-warp
+        odd.x = __shfl_xor_sync(0xffffffffu, x[e].x, 16);
+        odd.y = __shfl_xor_sync(0xffffffffu, x[e].y, 16);
+        odd.z = __shfl_xor_sync(0xffffffffu, x[e].z, 16);
+        odd.w = __shfl_xor_sync(0xffffffffu, x[e].w, 16);
+        entry(l0 + 2 * e + 1, odd);
+      } else {
+        entry(l0 + e, x[e]);
+      }
+    }
+  }
+  flush(cur);
 }
 
 __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_constant__ EpochArgs a) {
@@ -357,27 +451,39 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
     s_meta[r * kEpThreads + tid] = meta;
   }
 
-  // what a step needs from its slot, fetched AHEAD of the step (in the shadow of the previous step's last barrier):
-  // the mailbox, the ids of the warp's first forward group, the batch's segment count and attribute range, and for every
-  // resident element whether its row is touched by the batch and which gradient segment / chunks it reads then
-  int B = 0, pre_nu = 0, pre_ni = 0;
-  uint32_t stamp = 0;
-  float neg_step = 0.f, bc2s = 0.f;
-  StatsPre sp{0, 0u, 0u, 0, 0};
-  auto prefetch = [&](int i) {
+  // What a step needs from its slot is fetched AHEAD of the step.  Two steps ahead (in the shadow of barrier 3 of step
+  // i - 2): the slot's mailbox -- row count, stamp, Adam scalars, segment count, attribute range (`nx`).  One step ahead
+  // (shadow of barrier 3 of step i - 1): the ids of the warp's first forward group and, for every resident element,
+  // whether its row is touched by the batch and which gradient segment / chunks it reads then.
+  struct Mail {
+    int B, J;
+    uint32_t stamp, vmin, vmax;
+    float neg_step, bc2s;
+  };
+  auto poll_ready = [&](int i) {   // one thread polls; the CTA's other threads learn it at the next __syncthreads
+    uint32_t *ctrl = a.slot[i % a.n_slots].w.ctrl;
+    if (tid == 0) {
+      EP_SPIN(ld_acq(ctrl + EP_READY_U) < (uint32_t)(i + 1) || ld_acq(ctrl + EP_READY_I) < (uint32_t)(i + 1), 4, i);
+    }
+  };
+  auto wait_ready = [&](int i) {
+    poll_ready(i);
+    __syncthreads();
+  };
+  auto load_mail = [&](int i, Mail &m) {   // ends with the loads in flight; first use is the caller's
     const EpSlot &sl = a.slot[i % a.n_slots];
     uint32_t *ctrl = sl.w.ctrl;
-    if (tid == 0) {
-      while (ld_acq(ctrl + EP_READY_U) < (uint32_t)(i + 1) || ld_acq(ctrl + EP_READY_I) < (uint32_t)(i + 1)) {}
-    }
-    __syncthreads();
-    B = (int)__ldcg(ctrl + EP_B);
-    stamp = __ldcg(ctrl + EP_STAMP);
-    neg_step = __uint_as_float(__ldcg(ctrl + EP_SC0));
-    bc2s = __uint_as_float(__ldcg(ctrl + EP_SC1));
-    sp.J = __ldcg(sl.w.J);
-    sp.vmin = __ldcg(ctrl + CTRL_MIN);
-    sp.vmax = __ldcg(ctrl + CTRL_MAX);
+    m.B = (int)__ldcg(ctrl + EP_B);
+    m.stamp = __ldcg(ctrl + EP_STAMP);
+    m.neg_step = __ldg(a.sc_tab + 2 * i);       // (filled before the launch: double pow() on one thread of a producer
+    m.bc2s = __ldg(a.sc_tab + 2 * i + 1);       //  CTA cost 6-12 us per batch on this part's FP64 rate)
+    m.J = __ldcg(sl.w.J);
+    m.vmin = __ldcg(ctrl + CTRL_MIN);
+    m.vmax = __ldcg(ctrl + CTRL_MAX);
+  };
+  int pre_nu = 0, pre_ni = 0;
+  auto fetch_rows = [&](int i, uint32_t stamp) {   // ids of the first forward group + the resident elements' gradient sources
+    const EpSlot &sl = a.slot[i % a.n_slots];
     pre_nu = pre_ni = 0;
     if (lane < 4) {   // (rows past the batch end hold stale ids of an earlier batch: never used)
       const int b = min(gwarp * 4 + lane, cap - 1);
@@ -417,7 +523,28 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
     }
   };
   __shared__ int s_alloc;
-  prefetch(0);
+  // (with two slots the slot of step i + 2 is the one step i is using: its mailbox cannot be waited for inside step i)
+  const bool ahead2 = a.n_slots >= 3 && !(a.dbg_skip & 256);
+  auto grad_args = [&](const EpSlot &sl, int B) {
+    return GradArgs{a.U, a.I, sl.uid, sl.iid, s_rat, s_sst, fsm, B, d, nullptr, 0, 0, nullptr, sl.w.ord_u,
+                    sl.w.segid_i, sl.w.segoff_i, sl.w.segid_u, sl.w.segoff_u, sl.w.entry_seg, s_cseg, s_cglob, sl.w.ctrl, 1.0f,
+                    a.chunk, sl.w.gseg_i, sl.w.head_i, sl.w.tail_i, sl.w.gseg_u, sl.w.head_u, sl.w.tail_u, 1};
+  };
+  auto stage_first = [&](int i, int B) {   // the warp's first gradient chunk of step i: sorted entries, other-side row ids
+    const GradArgs ga = grad_args(a.slot[i % a.n_slots], B);
+    const int nchunk = (B + a.chunk - 1) / a.chunk;
+    return stage_chunk(ga, nchunk, (gwarp < 2 * nchunk && !(a.dbg_skip & 4)) ? gwarp : 2 * nchunk);   // (2 * nchunk: empty)
+  };
+  Mail cur{}, nx{};
+  wait_ready(0);
+  load_mail(0, cur);
+  fetch_rows(0, cur.stamp);
+  ChunkStage cs = stage_first(0, cur.B);
+  if (ahead2 && a.n_steps > 1) {
+    wait_ready(1);
+    load_mail(1, nx);
+  }
+  const bool half_rows = d <= 64;   // two rows per 512-byte warp request in the gradient gather
 
   for (int i = 0; i < a.n_steps; ++i) {
     const EpSlot &sl = a.slot[i % a.n_slots];
@@ -425,6 +552,8 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
     const bool tr = tr_cta && i == a.trace_step;
     if (tr && tid == 0) a.trace[blockIdx.x * 16 + 0] = ep_now();
     if (tid == 0) s_alloc = 0;
+    const int B = cur.B;
+    const float neg_step = cur.neg_step, bc2s = cur.bc2s;
 
     // ---- forward (focf.py:136-143): forward_body's arithmetic, rows through L2 (the tables change during the launch)
     if (!(a.dbg_skip & 1)) {
@@ -464,21 +593,21 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
     if (tr && tid == 0) a.trace[blockIdx.x * 16 + 1] = ep_now();
     ep_arrive(bar);
 
-    // ---- in the shadow of barrier 1: what the next two phases read from the producer, and the update of the resident
-    // rows this batch does not touch (zero data gradient: nothing of this step is needed; nobody reads them in this step)
-    GradArgs ga{a.U, a.I, sl.uid, sl.iid, s_rat, s_sst, fsm, B, d, nullptr, 0, 0, nullptr, sl.w.ord_u,
-                sl.w.segid_i, sl.w.segoff_i, sl.w.segid_u, sl.w.segoff_u, sl.w.entry_seg, s_cseg, s_cglob, ctrl, 1.0f,
-                a.chunk, sl.w.gseg_i, sl.w.head_i, sl.w.tail_i, sl.w.gseg_u, sl.w.head_u, sl.w.tail_u, 1};
+    // ---- in the shadow of barrier 1: what the next two phases read -- the rows of the warp's gradient chunk (its
+    // entries were staged a barrier earlier; the batch's rows do not change before the Adam phase), the bounds of the
+    // warp's first item segment, the rating / attribute columns
+    const GradArgs ga = grad_args(sl, B);
     const int nchunk = (B + a.chunk - 1) / a.chunk;
-    ChunkStage cs = stage_chunk(ga, nchunk, (gwarp < 2 * nchunk && !(a.dbg_skip & 4)) ? gwarp : 2 * nchunk);   // (2 * nchunk: an empty chunk)
+    StatsPre sp{cur.J, cur.vmin, cur.vmax, 0, 0};
     {
       const int wib = tid >> 5;
-      sp.s0 = sp.s1 = 0;
       if (wib < sp.J) {
         sp.s0 = __ldcg(sl.w.segoff_i + wib);
         sp.s1 = __ldcg(sl.w.segoff_i + wib + 1);
       }
     }
+    float4 x[8];
+    if (half_rows) ep_issue_rows<true>(ga, cs, 0, x); else ep_issue_rows<false>(ga, cs, 0, x);
     for (int p0 = tid; p0 < B; p0 += 4 * kEpThreads) {
       float vr[4], vs[4];
 #pragma unroll
@@ -496,6 +625,32 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
         }
       }
     }
+    ep_wait(bar);
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 2] = ep_now();
+
+    // ---- item x group statistics, fairness objective, loss (focf.py:75-134, 152-169): fused_stats, per CTA
+    LossArgs la{sl.pred, s_rat, s_sst, nullptr, sl.w.segid_i, sl.w.segoff_i, sl.w.J, B, nullptr, a.plan_len, 0, a.objective,
+                0, 0, nullptr, a.fair_weight, nullptr, nullptr, nullptr, nullptr, nullptr, a.loss, ctrl, a.flags};
+    const bool loss_cta = cta == n_comp - 1;
+    const float loss = (a.dbg_skip & 2) ? 0.f : fused_stats(la, B, cap, fsm, sh, s_cseg, s_cglob, true, loss_cta, (int)gridDim.x - 1, &sp);
+    if (loss_cta && tid == 0) {
+      a.loss[(unsigned)(a.first_batch + i) % (unsigned)a.plan_len] = loss;
+      if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
+    }
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 3] = ep_now();
+
+    // ---- gradients: the staged chunk (its rows are in registers), then any further ones, over the item- and the
+    // user-sorted order; the batch columns come from shared memory
+    if (half_rows) ep_consume_rows<true>(ga, cs, x); else ep_consume_rows<false>(ga, cs, x);
+    if (!(a.dbg_skip & 4))
+      for (int c = gwarp + nwarps; c < 2 * nchunk; c += nwarps) grads_chunk<1, false>(ga, nchunk, c);
+    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 4] = ep_now();
+    if (!(a.dbg_skip & 64)) ep_arrive(bar);
+
+    // ---- in the shadow of barrier 2: the slot of the step after next is polled for (the barrier's __syncthreads
+    // publishes it to the CTA), and Adam of the resident rows this batch does not touch (zero data gradient: nothing of
+    // this step is needed, and nobody reads those rows in this step)
+    if (ahead2 && i + 2 < a.n_steps) poll_ready(i + 2);
 #pragma unroll
     for (int r = 0; r < kEpMaxR; ++r) {
       if (r >= R || (a.dbg_skip & 16)) continue;
@@ -515,30 +670,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
       const long long ql = is_item ? q - nq_u : q;
       *(float4 *)((is_item ? a.I : a.U) + ql * 4) = p;
     }
-    ep_wait(bar);
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 2] = ep_now();
-
-    // ---- item x group statistics, fairness objective, loss (focf.py:75-134, 152-169): fused_stats, per CTA
-    LossArgs la{sl.pred, s_rat, s_sst, nullptr, sl.w.segid_i, sl.w.segoff_i, sl.w.J, B, nullptr, a.plan_len, 0, a.objective,
-                0, 0, nullptr, a.fair_weight, nullptr, nullptr, nullptr, nullptr, nullptr, a.loss, ctrl, a.flags};
-    const bool loss_cta = cta == n_comp - 1;
-    const float loss = (a.dbg_skip & 2) ? 0.f : fused_stats(la, B, cap, fsm, sh, s_cseg, s_cglob, true, loss_cta, (int)gridDim.x - 1, &sp);
-    if (loss_cta && tid == 0) {
-      a.loss[(unsigned)(a.first_batch + i) % (unsigned)a.plan_len] = loss;
-      if (loss != loss) atomicOr(a.flags, FR_FLAG_NAN_LOSS);
-    }
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 3] = ep_now();
-
-    // ---- gradients: the staged chunk (then any further ones) over the item- and the user-sorted order, the batch
-    // columns from shared memory
-    run_chunk<1, false>(ga, cs);
-    if (!(a.dbg_skip & 4))
-      for (int c = gwarp + nwarps; c < 2 * nchunk; c += nwarps) grads_chunk<1, false>(ga, nchunk, c);
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 4] = ep_now();
-    if (!(a.dbg_skip & 64)) {
-      ep_arrive(bar);
-      ep_wait(bar);
-    }
+    if (!(a.dbg_skip & 64)) ep_wait(bar);
     if (tr && tid == 0) a.trace[blockIdx.x * 16 + 5] = ep_now();
 
     // ---- Adam on the touched resident rows (apply_body's gradient assembly and update).  A popular item's segment
@@ -570,6 +702,20 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      // (the single-chunk gradients and the tails are loaded while the copies fly)
+      float4 gr[kEpMaxR];
+#pragma unroll
+      for (int r = 0; r < kEpMaxR; ++r) {
+        gr[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= R) continue;
+        const int4 meta = s_meta[r * kEpThreads + tid];
+        if (meta.x == -1 || meta.y < 0) continue;
+        const bool is_item = meta.x < 0;
+        const long long q = (long long)g + (long long)r * NT;
+        const int k = (int)((is_item ? q - nq_u : q) % dq) * 4;
+        gr[r] = meta.z == meta.w ? __ldcg((const float4 *)((is_item ? sl.w.gseg_i : sl.w.gseg_u) + (size_t)meta.y * d + k))
+                                 : __ldcg((const float4 *)((is_item ? sl.w.tail_i : sl.w.tail_u) + (size_t)meta.z * d + k));
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int r = 0; r < kEpMaxR; ++r) {
@@ -580,27 +726,22 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
         const long long q = (long long)g + (long long)r * NT;
         const long long ql = is_item ? q - nq_u : q;
         const int k = (int)(ql % dq) * 4;
-        const float *gseg = is_item ? sl.w.gseg_i : sl.w.gseg_u;
         const float *head = is_item ? sl.w.head_i : sl.w.head_u;
-        const float *tail = is_item ? sl.w.tail_i : sl.w.tail_u;
-        float4 gr;
-        if (meta.z == meta.w) {
-          gr = __ldcg((const float4 *)(gseg + (size_t)meta.y * d + k));
-        } else {
-          gr = __ldcg((const float4 *)(tail + (size_t)meta.z * d + k));
+        float4 gq = gr[r];
+        if (meta.z != meta.w) {
           if (sbase[r] >= 0) {
-            for (int c = 0; c < meta.w - meta.z; ++c) gr = f4_add(gr, stage[sbase[r] + c]);
+            for (int c = 0; c < meta.w - meta.z; ++c) gq = f4_add(gq, stage[sbase[r] + c]);
           } else {
 #pragma unroll 8
-            for (int c = meta.z + 1; c <= meta.w; ++c) gr = f4_add(gr, __ldcg((const float4 *)(head + (size_t)c * d + k)));
+            for (int c = meta.z + 1; c <= meta.w; ++c) gq = f4_add(gq, __ldcg((const float4 *)(head + (size_t)c * d + k)));
           }
         }
         float4 p = s_state[(r * 3 + 0) * kEpThreads + tid], m = s_state[(r * 3 + 1) * kEpThreads + tid],
                v = s_state[(r * 3 + 2) * kEpThreads + tid];
-        adam1(p.x, m.x, v.x, gr.x, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.y, m.y, v.y, gr.y, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.z, m.z, v.z, gr.z, wd, w1, b2, w2, bc2s, eps, neg_step);
-        adam1(p.w, m.w, v.w, gr.w, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.x, m.x, v.x, gq.x, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.y, m.y, v.y, gq.y, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.z, m.z, v.z, gq.z, wd, w1, b2, w2, bc2s, eps, neg_step);
+        adam1(p.w, m.w, v.w, gq.w, wd, w1, b2, w2, bc2s, eps, neg_step);
         s_state[(r * 3 + 0) * kEpThreads + tid] = p;
         s_state[(r * 3 + 1) * kEpThreads + tid] = m;
         s_state[(r * 3 + 2) * kEpThreads + tid] = v;
@@ -608,13 +749,22 @@ __global__ void __launch_bounds__(kEpThreads, 1) k_focf_epoch(const __grid_const
       }
     }
     if (tr && tid == 0) a.trace[blockIdx.x * 16 + 6] = ep_now();
-    __syncthreads();
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 8] = ep_now();    // the CTA's slowest thread is done
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 9] = ep_now();
     ep_arrive(bar);
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 10] = ep_now();   // arrived
-    if (i + 1 < a.n_steps) prefetch(i + 1);   // in the shadow of barrier 3
-    if (tr && tid == 0) a.trace[blockIdx.x * 16 + 11] = ep_now();   // next step's prefetch done
+    // ---- in the shadow of barrier 3: the mailbox of the step after next, the next step's row stamps / ids / gradient chunk
+    if (i + 1 < a.n_steps) {
+      if (ahead2) {
+        cur = nx;
+        if (i + 2 < a.n_steps) {
+          if (a.dbg_skip & 64) wait_ready(i + 2);   // (timing experiments without barrier 2: no poll happened there)
+          load_mail(i + 2, nx);
+        }
+      } else {
+        wait_ready(i + 1);
+        load_mail(i + 1, cur);
+      }
+      fetch_rows(i + 1, cur.stamp);
+      cs = stage_first(i + 1, cur.B);
+    }
     ep_wait(bar);
     if (cta == 0 && tid == 0) st_rel(a.sync + 1, (unsigned long long)(i + 1));
     if (tr && tid == 0) a.trace[blockIdx.x * 16 + 7] = ep_now();
@@ -720,6 +870,14 @@ int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_
   EpPlan pl;
   if ((rc = ep_plan(slots, n_slots, &pl, "fr_focf_epoch_run"))) return rc;
   const fr_focf_step *s = &slots[0];
+  const int max_steps = 4 * s->B;   // the scalars table lives in slot 0's record scratch (8 floats per row of capacity)
+  if (n_steps > max_steps) {        // (longer runs: one launch per max_steps steps)
+    for (int k = 0; k < n_steps; k += max_steps) {
+      const int n = n_steps - k < max_steps ? n_steps - k : max_steps;
+      if ((rc = fr_focf_epoch_run(slots, n_slots, first_batch + k, n, adam_step + k, sync_words, stream))) return rc;
+    }
+    return FR_OK;
+  }
   EpochArgs a{};
   a.U = s->U; a.I = s->I; a.mU = s->mU; a.vU = s->vU; a.mI = s->mI; a.vI = s->vI;
   a.n_users = s->n_users; a.n_items = s->n_items; a.d = s->d;
@@ -761,6 +919,12 @@ int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_
     a.slot[k].rating = (float *)sk->rating; a.slot[k].sst = (float *)sk->sst; a.slot[k].pred = sk->pred;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  {   // sc_tab[2k], [2k+1] = the scalars of optimizer step adam_step + k
+    float *tab = a.slot[0].w.rec_seg;
+    FR_LAUNCH(k_adam_scalars, grid_for(n_steps, 128, 64), 128, 0, st, tab - 2 * (ptrdiff_t)adam_step, adam_step,
+              adam_step + n_steps - 1, s->lr, s->beta1, s->beta2);
+    a.sc_tab = tab;
+  }
   static size_t smem_set = 0;
   if (pl.smem > smem_set) {
     FR_CUDA_OK(cudaFuncSetAttribute(k_focf_epoch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));

@@ -269,7 +269,7 @@ class FOCF(nn.Module):
         return out
 
     @torch.no_grad()
-    def epoch_runner(self, loader, loss_buf, n_slots=4):
+    def epoch_runner(self, loader, loss_buf, n_slots=6):
         """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k steps as ONE
         persistent cooperative launch (fr_focf_epoch_run: producer CTAs build the batches ahead, compute CTAs keep their
         share of the tables and Adam moments in shared memory; bit-identical to the stepwise path), or None when the
