@@ -654,8 +654,9 @@ int fr_focf_epoch_run(const fr_focf_step *slots, int32_t n_slots, int32_t first_
                       int32_t adam_step, void *sync_words, void *stream);
 /* diagnostic (FR_FOCF_TRACE=1; FR_FOCF_TRACE_STEP selects the step, default 8): [CTA][16] %globaltimer stamps of the last
  * epoch launch -- compute CTAs: step start | forward done | barrier 1 passed | statistics done | gradients done | barrier 2
- * passed | Adam done (thread 0) | barrier 3 passed | Adam done (whole CTA) | stores visible | arrived at barrier 3 | next
- * step's prefetch done; producer CTAs: start | gathered | sorted | published */
+ * passed | Adam done (thread 0) | barrier 3 passed; producer CTAs: start | gathered | sorted | published.
+ * (%globaltimer reads of ~140 CTAs in the same microsecond serialise: per-CTA phase durations are reliable, the cross-CTA
+ * alignment of simultaneous stamps is not.) */
 int fr_focf_epoch_trace(uint64_t *out_host, int32_t n);
 
 /* diagnostic: with FR_FOCF_TRACE=1 in the environment every CTA of the cooperative fused step stamps %globaltimer at its 8

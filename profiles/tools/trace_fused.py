@@ -68,9 +68,6 @@ n_cta, n_prod = 148, 2 * runner.state["n_slots"]
 buf = (ctypes.c_uint64 * (16 * n_cta))()
 _lib.check(lib.fr_focf_epoch_trace(buf, 16 * n_cta), "fr_focf_epoch_trace")
 t = np.array(list(buf), dtype=np.int64).reshape(n_cta, 16)
-x = (t[n_prod:, 8:12] - t[n_prod:, 0].min()) / 1e3
-print("epoch kernel, barrier 3 in detail (min..max over compute CTAs): "
-      + " ".join(f"{n}={x[:, k].min():.1f}..{x[:, k].max():.1f}" for k, n in enumerate(["cta_done", "fenced", "arrived", "prefetched"])))
 c = t[n_prod:, :8]
 t0 = c[:, 0].min()
 rel = (c - t0) / 1e3
