@@ -95,6 +95,9 @@ class FOCFDataLoader:
         self.mode = mode
         self._replay = None if draws is None else np.asarray(draws)
         self._rng = np.random.default_rng(config["seed"] if seed is None else seed)
+        # fast mode: items drawn per batch at first (3x what an average batch needs, at least 16)
+        mean_cnt = max(float(train.n_rows) / max(len(self.candidates), 1), 1.0)
+        self._prefix = max(16, int(3 * self.step / mean_cnt) + 8)
         self.lib = load()
         dev = train.device
         # worst case: step-1 rows + the most popular item
@@ -138,10 +141,21 @@ class FOCFDataLoader:
             if len(pool) == 0:          # focf_dataloader.py:43 `or not any(is_select)`: a batch that uses up every item
                 raise ValueError("a must be non-empty")          # makes the reference draw from an empty pool
             return np.asarray(items, dtype=np.int64)
-        perm = self._rng.permutation(self.candidates)
-        csum = np.cumsum(tr.item_count_h[perm])
+        # whole items in uniformly random order until the batch holds `step` rows = a prefix of a uniform permutation of
+        # the candidates.  Only a short prefix is ever used (step / mean item count items), so only a short prefix is
+        # drawn: k distinct positions in random order (Floyd's algorithm inside Generator.choice, O(k)); in the rare case
+        # that they do not suffice the permutation is continued over the remaining candidates.
+        cand = self.candidates
+        n = len(cand)
+        k = min(n, self._prefix)
+        idx = self._rng.choice(n, size=k, replace=False, shuffle=True)
+        csum = np.cumsum(tr.item_count_h[cand[idx]])
+        if csum[-1] < self.step and k < n:
+            rest = np.setdiff1d(np.arange(n), idx, assume_unique=True)
+            idx = np.concatenate([idx, self._rng.permutation(rest)])
+            csum = np.cumsum(tr.item_count_h[cand[idx]])
         j = int(np.searchsorted(csum, self.step, side="left")) + 1
-        return perm[:j].astype(np.int64)
+        return cand[idx[:j]].astype(np.int64)
 
     def plan_epoch(self, n_batches=None):
         """Draw every batch of the epoch (or only the first n_batches); returns (draw_items, draw_off, batches) where
@@ -187,9 +201,16 @@ class FOCFDataLoader:
                      desc=torch.zeros((grow(len(desc)), 4), dtype=torch.int32, device=dev),
                      cols=self._cols, generation=(0 if p is None else p["generation"] + 1))
             self._plan = p
-        p["items"][:len(items)].copy_(torch.from_numpy(items).pin_memory(), non_blocking=True)
-        p["offs"][:len(offs)].copy_(torch.from_numpy(offs).pin_memory(), non_blocking=True)
-        p["desc"][:len(desc)].copy_(torch.from_numpy(desc).pin_memory(), non_blocking=True)
+        if p.get("copied") is not None:
+            p["copied"].synchronize()          # the previous epoch's copies have read the pinned staging buffers
+        for name, arr in (("items", items), ("offs", offs), ("desc", desc)):
+            host = p.get("host_" + name)
+            if host is None or host.shape[0] < len(arr):   # pinned staging, allocated once (pin_memory() per epoch costs more than the copy)
+                host = p["host_" + name] = torch.empty((p[name].shape[0],) + tuple(arr.shape[1:]), dtype=torch.int32).pin_memory()
+            host[:len(arr)].copy_(torch.from_numpy(arr))
+            p[name][:len(arr)].copy_(host[:len(arr)], non_blocking=True)
+        p["copied"] = torch.cuda.Event()
+        p["copied"].record()
         p["len"], p["rows"], p["batch_rows"] = len(desc), int(desc[:, 3].sum()), desc[:, 3].tolist()
         return p
 
