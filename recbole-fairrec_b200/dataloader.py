@@ -186,21 +186,26 @@ class FOCFDataLoader:
                                             ptr(sst), stream_ptr()), "fr_focf_gather_batch")
         return uid, iid, rating, sst
 
-    def plan_epoch_device(self):
+    def plan_epoch_device(self, buf=0):
         """Draw the whole epoch on the host and place the plan in PERSISTENT device buffers (their addresses stay the
         same from epoch to epoch, so a captured CUDA graph of the step keeps pointing at them).  Returns the plan dict
-        consumed by FocfEngine.planned_step; plan["rows"] is the host-side total number of interactions."""
+        consumed by FocfEngine.planned_step; plan["rows"] is the host-side total number of interactions.
+        buf: which of the loader's plan buffer sets to fill -- a caller that plans epoch e + 1 on the host while epoch e
+        still runs on the device (FOCF.train_epochs_planned) alternates 0 / 1."""
         items, offs, batches = self.plan_epoch()
         desc = np.asarray(batches, dtype=np.int32).reshape(-1, 4)
         dev = self.train.device
-        p = getattr(self, "_plan", None)
+        if not hasattr(self, "_plans"):
+            self._plans = {}
+        p = self._plans.get(buf)
         if p is None or p["items"].numel() < len(items) or p["offs"].numel() < len(offs) or p["desc"].shape[0] < len(desc):
             grow = lambda n: int(n * 1.5) + 64
             p = dict(items=torch.zeros(grow(len(items)), dtype=torch.int32, device=dev),
                      offs=torch.zeros(grow(len(offs)), dtype=torch.int32, device=dev),
                      desc=torch.zeros((grow(len(desc)), 4), dtype=torch.int32, device=dev),
-                     cols=self._cols, generation=(0 if p is None else p["generation"] + 1))
-            self._plan = p
+                     cols=self._cols, generation=(0 if p is None else p["generation"] + 1), buf=buf)
+            self._plans[buf] = p
+        self._plan = p          # the plan drawn last
         if p.get("copied") is not None:
             p["copied"].synchronize()          # the previous epoch's copies have read the pinned staging buffers
         for name, arr in (("items", items), ("offs", offs), ("desc", desc)):

@@ -269,7 +269,7 @@ class FOCF(nn.Module):
         return out
 
     @torch.no_grad()
-    def epoch_runner(self, loader, loss_buf, n_slots=6):
+    def epoch_runner(self, loader, loss_buf, n_slots=6, plan_buf=0):
         """Plan an epoch of `loader` on the device and return a runner whose `.run(k)` executes the next k steps as ONE
         persistent cooperative launch (fr_focf_epoch_run: producer CTAs build the batches ahead, compute CTAs keep their
         share of the tables and Adam moments in shared memory; bit-identical to the stepwise path), or None when the
@@ -281,7 +281,7 @@ class FOCF(nn.Module):
             return None
         eng = self._engine()
         U, I = self.user_embedding_layer.weight.data, self.item_embedding_layer.weight.data
-        plan = loader.plan_epoch_device()
+        plan = loader.plan_epoch_device(plan_buf)
         if loss_buf.numel() < plan["len"]:
             raise ValueError("loss buffer shorter than the epoch")
         cap = plan["cols"][0].numel()
@@ -294,19 +294,65 @@ class FOCF(nn.Module):
                 e.flags = eng.flags                            # one status word for every slot
             cols = [tuple(torch.empty_like(c) for c in plan["cols"]) for _ in range(n_slots)]
             st = self._ep_state = dict(device=U.device, cap=cap, n_slots=n_slots, engines=engines, cols=cols,
-                                       sync=torch.zeros(16, dtype=torch.int32, device=U.device), key=None)
+                                       sync=torch.zeros(16, dtype=torch.int32, device=U.device), per_buf={})
+        # the argument structs point into the plan buffers and the loss buffer: one set per (plan buffer set)
+        pb = st["per_buf"].setdefault(plan_buf, dict(key=None))
         key = (plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), plan["len"], id(self._adam["mU"]))
-        if st["key"] != key:
+        if pb["key"] != key:
             steps = (_lib.FocfStep * n_slots)()
             for k, (e, c) in enumerate(zip(st["engines"], st["cols"])):
                 s = e.planned_step(U, I, self._adam, dict(plan, cols=c), loader.train, self._objective, self.fair_weight,
                                    loss_buf)
                 ctypes.memmove(ctypes.byref(steps[k]), ctypes.byref(s), ctypes.sizeof(s))
-            st["steps"], st["key"] = steps, key
-            st["eligible"] = bool(eng.lib.fr_focf_epoch_eligible(ctypes.cast(steps, ctypes.c_void_p), n_slots))
-        if not st["eligible"]:
+            pb["steps"], pb["key"] = steps, key
+            pb["eligible"] = bool(eng.lib.fr_focf_epoch_eligible(ctypes.cast(steps, ctypes.c_void_p), n_slots))
+        if not pb["eligible"]:
             return None
-        return _EpochRunner(self, plan, st)
+        return _EpochRunner(self, plan, st, pb["steps"])
+
+    @torch.no_grad()
+    def train_epochs_planned(self, loader, n_epochs):
+        """`n_epochs` epochs of trainer.py:181-196 with the host's share overlapped: while epoch e runs on the device (one
+        persistent launch) the host draws epoch e + 1 (two plan buffer sets and two loss buffers alternate) and reads the
+        losses of epoch e - 1.  Returns (list of per-epoch loss sums, total steps, total interactions); raises what the
+        reference raises for NaN losses.  Falls back to train_epoch_planned per epoch where the epoch kernel is not eligible."""
+        dev = self.user_embedding_layer.weight.device
+        n_max = len(loader) + 8
+        if getattr(self, "_ep_loss", None) is None or self._ep_loss[0].numel() < n_max:
+            self._ep_loss = [torch.zeros(n_max, device=dev) for _ in range(2)]
+            self._ep_loss_host = [torch.zeros(n_max).pin_memory() for _ in range(2)]
+            self._ep_done = [torch.cuda.Event() for _ in range(2)]
+        sums, steps, rows, pending = [], 0, 0, None
+
+        def consume(b, n):
+            self._ep_done[b].synchronize()
+            lh = self._ep_loss_host[b][:n]
+            if bool(torch.isnan(lh).any()):
+                raise ValueError("Training loss is nan")          # trainer.py:286-288
+            sums.append(float(lh.double().sum()))
+
+        for e in range(n_epochs):
+            b = e & 1
+            runner = self.epoch_runner(loader, self._ep_loss[b], plan_buf=b)
+            if runner is None:
+                if pending is not None:
+                    consume(*pending)
+                    pending = None
+                n, r = self.train_epoch_planned(loader, self._ep_loss[b], persistent=False)
+                sums.append(float(self._ep_loss[b][:n].double().sum()))
+            else:
+                n = runner.plan["len"]
+                r = runner.run(n)
+                self._ep_loss_host[b][:n].copy_(self._ep_loss[b][:n], non_blocking=True)
+                self._ep_done[b].record()
+                if pending is not None:
+                    consume(*pending)
+                pending = (b, n)
+            steps += n
+            rows += r
+        if pending is not None:
+            consume(*pending)
+        return sums, steps, rows
 
     @torch.no_grad()
     def planned_runner(self, loader, loss_buf, graph_steps=8, persistent=None):
@@ -518,8 +564,8 @@ class _DpPlannedRunner:
 class _EpochRunner:
     """k planned steps = ONE launch of the persistent epoch kernel (fr_focf_epoch_run)"""
 
-    def __init__(self, model, plan, state):
-        self.model, self.plan, self.state, self.cursor = model, plan, state, 0
+    def __init__(self, model, plan, state, steps):
+        self.model, self.plan, self.state, self.steps, self.cursor = model, plan, state, steps, 0
 
     def run(self, k):
         import ctypes
@@ -527,7 +573,7 @@ class _EpochRunner:
         k = max(int(k), 0)
         if k == 0:
             return 0
-        _lib.check(m._engine().lib.fr_focf_epoch_run(ctypes.cast(st["steps"], ctypes.c_void_p), st["n_slots"], self.cursor,
+        _lib.check(m._engine().lib.fr_focf_epoch_run(ctypes.cast(self.steps, ctypes.c_void_p), st["n_slots"], self.cursor,
                                                      k, m._adam["step"] + 1, _lib.ptr(st["sync"]), _lib.stream_ptr()),
                    "fr_focf_epoch_run")
         n = self.plan["len"]

@@ -130,3 +130,31 @@ def test_tables_too_large_for_residency_fall_back_to_the_stepwise_runner():
     assert type(runner).__name__ == "_PlannedRunner"
     runner.run(3)
     model.check_flags()
+
+
+def test_pipelined_epochs_equal_epoch_by_epoch_training():
+    """train_epochs_planned (host draws epoch e + 1 while epoch e runs; two plan / loss buffer sets) == one
+    train_epoch_planned call per epoch on a loader with the same seed"""
+    import recbole_fairrec_b200 as pkg
+    cfg, train, U0, I0 = _setup(13, 900, 400, 60000, 2048, 32, "value")
+    res = []
+    for pipelined in (False, True):
+        loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=5)
+        model = make_model(U0, I0, "value", 0.7)
+        model.init_adam(lr=1e-3, weight_decay=1e-3)
+        n = len(loader)
+        if pipelined:
+            sums, steps, rows = model.train_epochs_planned(loader, 3)
+            assert steps == 3 * n and len(sums) == 3
+        else:
+            losses = torch.zeros(n, device="cuda")
+            sums = []
+            for ep in range(3):
+                model.train_epoch_planned(loader, losses)
+                sums.append(float(losses[:n].double().sum()))
+        model.check_flags()
+        torch.cuda.synchronize()
+        res.append((sums, _state(model, torch.zeros(1, device="cuda"))[1:]))
+    assert res[0][0] == res[1][0]
+    for a, b, name in zip(res[0][1], res[1][1], ("U", "I", "mU", "vU", "mI", "vI")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
