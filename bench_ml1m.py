@@ -786,6 +786,17 @@ def run_ours(args, wname):
         out["config"]["l2"] = epoch["l2"]
         out["config"]["avg_batch_rows"] = epoch["avg_batch_rows"]
         out["gpu_launches"] = epoch["launches"]
+        pe = epoch.get("e2e_pipelined_epochs")
+        if pe:
+            # end to end the way the trainer feeds this path: the train split is device resident (uploaded once), the
+            # per-step host input is the step's draw (item ids + offsets), the per-step result read back is its loss;
+            # batch construction (draw -> gather from the split -> sort / segments) is INSIDE the bracket.  The figure for
+            # batches that arrive from host memory every step stays beside it.
+            out["e2e"] = dict(out["e2e"], host_batches_value=out["e2e"]["value"], host_batches_api=out["e2e"]["api"],
+                              host_batches_h2d_bytes_per_step=out["e2e"]["h2d_bytes_per_step"],
+                              value=pe["value"], h2d_bytes_per_step=pe["h2d_bytes_per_step"], d2h_bytes_per_step=4,
+                              mode=pe["what"], api="FOCF.train_epochs_planned(loader, n_epochs)",
+                              single_epoch_value=epoch["e2e_planned_epoch"]["value"])
     if world > 1:
         runner = None
         model.release_graphs()          # graphs holding captured NCCL kernels must go before the communicator does
