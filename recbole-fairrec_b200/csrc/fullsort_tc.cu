@@ -68,6 +68,12 @@ __device__ __forceinline__ float tc_raw_bound(float thr_s, int transform, float 
   return -INFINITY;
 }
 
+// kRegList (K <= 16): the row's K-list lives in registers and an insertion is a branch-free compare / select network
+// (16 compares, 32 selects, no memory round trips); otherwise it lives in shared memory and an insertion is a shift loop of
+// dependent LDS / STS pairs -- 40 % of the executed instructions and most of the latency at the ML-1M shape, where a
+// catalogue of 3,707 items never lets the threshold warm up.  Same total order, same lists.
+constexpr int TC_KREG = 16;
+template <bool kRegList>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_fullsort_tc(const __grid_constant__ CUtensorMap map_uh, const __grid_constant__ CUtensorMap map_ul,
                   const __grid_constant__ CUtensorMap map_ih, const __grid_constant__ CUtensorMap map_il, TcArgs a) {
@@ -180,16 +186,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     float *ls = list_s + row * K;
     int *li = list_i + row * K;
     float *scratch = scr + row * 33;
-    for (int e = 0; e < K; ++e) {
-      ls[e] = -INFINITY;
-      li[e] = 0x7fffffff;
+    float rs[TC_KREG];
+    int ri[TC_KREG];
+    // (right-aligned: slot TC_KREG - 1 is the K-th best, so the threshold is a fixed register; the unused leading slots
+    // hold an entry that everything loses against)
+#pragma unroll
+    for (int e = 0; e < TC_KREG; ++e) {
+      rs[e] = e < TC_KREG - K ? INFINITY : -INFINITY;
+      ri[e] = e < TC_KREG - K ? -1 : 0x7fffffff;
+    }
+    if (!kRegList) {
+      for (int e = 0; e < K; ++e) {
+        ls[e] = -INFINITY;
+        li[e] = 0x7fffffff;
+      }
     }
     float raw_thr = -INFINITY;                  // one-compare filter on the raw dot (tc_raw_bound), -inf while not full
     float thr_s = -INFINITY;
     int thr_i = 0x7fffffff;
     auto try_insert = [&](float raw, int gid) {   // exact transform + total-order insertion into the row's K-list
       const float s = tc_transform(raw, a.transform, a.max_rating);
-      if (tc_better(s, gid, thr_s, thr_i)) {
+      if (kRegList) {
+        if (tc_better(s, gid, thr_s, thr_i)) {
+          // b[e]: the new entry goes before entry e (monotone over the sorted list: false ... false true ... true);
+          // entry e becomes entry e-1 where b[e-1], the new entry where b[e] && !b[e-1], itself otherwise
+          bool b[TC_KREG];
+#pragma unroll
+          for (int e = 0; e < TC_KREG; ++e) b[e] = tc_better(s, gid, rs[e], ri[e]);
+#pragma unroll
+          for (int e = TC_KREG - 1; e >= 1; --e) {
+            rs[e] = b[e - 1] ? rs[e - 1] : (b[e] ? s : rs[e]);
+            ri[e] = b[e - 1] ? ri[e - 1] : (b[e] ? gid : ri[e]);
+          }
+          rs[0] = b[0] ? s : rs[0];
+          ri[0] = b[0] ? gid : ri[0];
+          thr_s = rs[TC_KREG - 1];
+          thr_i = ri[TC_KREG - 1];
+          if (thr_i != 0x7fffffff) raw_thr = tc_raw_bound(thr_s, a.transform, a.max_rating);
+        }
+      } else if (tc_better(s, gid, thr_s, thr_i)) {
         int p = K - 1;
         while (p > 0 && tc_better(s, gid, ls[p - 1], li[p - 1])) {
           ls[p] = ls[p - 1];
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
       for (int w = 0; w < TCN / 32; ++w) mask[w] = 0u;
       if (g0 == 0) mask[0] |= 1u;
-      while (hp < hend) {
+      while (hp < hend) {   // (the row's own sorted history: consecutive entries, L1-resident after the first of a line)
         const int it = a.hist_items[hp];
         if (it >= g0 + TCN) break;
         if (it >= g0) {
@@ -251,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         cand &= colmask & ~mw;
         if (!live) cand = 0u;
         // slow path: rare once the row's threshold has warmed up; ONE copy of the insertion code (instruction footprint)
-        if (a.use_scratch) {
+        if (kRegList || a.use_scratch) {   // (the register-list variant always has room for the scratch rows: one call site)
           if (cand) {   // park the 32 raw scores in this thread's scratch row and walk the candidate bits
 #pragma unroll
             for (int c = 0; c < 32; ++c) scratch[c] = __uint_as_float(v[c]);
@@ -283,10 +318,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_arrive(&tempty[buf]);
     }
     if (live) {
-      for (int e = 0; e < K; ++e) {
-        const size_t o = ((size_t)split * a.n + r) * K + e;
-        a.out_id[o] = li[e];
-        a.out_score[o] = ls[e];
+      if (kRegList) {
+#pragma unroll
+        for (int e = 0; e < TC_KREG; ++e) {
+          if (e >= TC_KREG - K) {
+            const size_t o = ((size_t)split * a.n + r) * K + (e - (TC_KREG - K));
+            a.out_id[o] = ri[e];
+            a.out_score[o] = rs[e];
+          }
+        }
+      } else {
+        for (int e = 0; e < K; ++e) {
+          const size_t o = ((size_t)split * a.n + r) * K + e;
+          a.out_id[o] = li[e];
+          a.out_score[o] = ls[e];
+        }
       }
     }
   }
@@ -303,12 +349,22 @@ size_t tc_plane_bytes(int n, int n_items_local, int d) {
   return 2 * a + 2 * b;
 }
 
+// Item splits per user tile: one CTA per SM (225 KB of shared memory), so the launch runs in waves of kSMs CTAs and a CTA
+// walks ceil(itiles / s) item tiles: minimise waves x tiles per CTA (the smallest s on ties: the merge grows with s).
+// (ceil(kSMs / utiles) made 188 CTAs = two waves of 8 tiles at the ML-1M shape; 3 splits are one wave of 10.)
 int tc_pick_splits(int n, int n_items_local) {
   const int utiles = (n + TCM - 1) / TCM, itiles = (n_items_local + TCN - 1) / TCN;
-  int s = (kSMs + utiles - 1) / utiles;
-  if (s > 32) s = 32;
-  if (s > itiles) s = itiles;
-  return s < 1 ? 1 : s;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 32 && s <= itiles; ++s) {
+    const long long waves = ((long long)utiles * s + kSMs - 1) / kSMs, per = (itiles + s - 1) / s;
+    const long long cost = waves * per;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
 }
 
 // planes: workspace region of tc_plane_bytes(); part_id/part_sc: [splits, n, K] (or the outputs when splits == 1)
@@ -330,7 +386,7 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   size_t fixed = (size_t)2 * nkb * TC_KBLOCK_BYTES + (size_t)TCM * a->K * 8 + (size_t)TCM * 33 * 4 + 256;
   int use_scratch = 1;
   int stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB slack
-  if (stages < 2) {   // drop the scratch rows (slow path falls back to collective TMEM re-reads)
+  if (stages < 2 && a->K > TC_KREG) {   // drop the scratch rows (slow path falls back to collective TMEM re-reads)
     use_scratch = 0;
     fixed -= (size_t)TCM * 33 * 4;
     stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));
@@ -344,9 +400,19 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   const int itiles = (nl + TCN - 1) / TCN;
   TcArgs t{a->hist_off, a->hist_items, n, d, nl, a->item_base, a->K, a->transform, a->max_rating,
            (itiles + splits - 1) / splits, stages, use_scratch, out_id, out_sc};
-  FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n + TCM - 1) / TCM, splits);
-  FR_LAUNCH(k_fullsort_tc, grid, TC_THREADS, smem, st, m_uh, m_ul, m_ih, m_il, t);
+  const bool prof = prof_on();   // (one profiler name for both instantiations)
+  if (a->K <= TC_KREG) {
+    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (prof) prof_begin("k_fullsort_tc", st);
+    k_fullsort_tc<true><<<grid, TC_THREADS, smem, st>>>(m_uh, m_ul, m_ih, m_il, t);
+  } else {
+    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (prof) prof_begin("k_fullsort_tc", st);
+    k_fullsort_tc<false><<<grid, TC_THREADS, smem, st>>>(m_uh, m_ul, m_ih, m_il, t);
+  }
+  if (prof) prof_end(st);
+  count_launch();
   return FR_OK;
 }
 
