@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       hp = lo_;
     }
+    int hw[8];
+    bool hw_valid = false;
     for (int tt = 0; tt < ntile; ++tt) {
       const int buf = tt & 1;
       const uint32_t tph = (tt >> 1) & 1;
@@ -259,16 +261,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
       for (int w = 0; w < TCN / 32; ++w) mask[w] = 0u;
       if (g0 == 0) mask[0] |= 1u;
-      while (hp < hend) {   // (the row's own sorted history: consecutive entries, L1-resident after the first of a line)
-        const int it = a.hist_items[hp];
-        if (it >= g0 + TCN) break;
-        if (it >= g0) {
-          const int c = it - g0;
+      // the row's own sorted history, eight entries per round trip (a one-entry walk is a chain of dependent loads: 21 % of
+      // the warp samples at the ML-1M shape, where a user has ~6 history items per tile)
+      // (the window is carried across tiles: a tile without history items -- nearly all of them for a large catalogue --
+      // costs eight register compares and no load)
+      while (true) {
+        if (!hw_valid) {
 #pragma unroll
-          for (int w = 0; w < TCN / 32; ++w)
-            if ((c >> 5) == w) mask[w] |= 1u << (c & 31);
+          for (int j = 0; j < 8; ++j) hw[j] = (hp + j < hend) ? a.hist_items[hp + j] : 0x7fffffff;
+          hw_valid = true;
         }
-        ++hp;
+        int used = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (hw[j] < g0 + TCN) {   // (ascending: the entries of this tile are a prefix of the window)
+            used = j + 1;
+            if (hw[j] >= g0) {
+              const int c = hw[j] - g0;
+#pragma unroll
+              for (int w = 0; w < TCN / 32; ++w)
+                if ((c >> 5) == w) mask[w] |= 1u << (c & 31);
+            }
+          }
+        }
+        hp += used;
+        if (used) hw_valid = false;
+        if (used < 8) break;
       }
       mbar_wait(&tfull[buf], tph);
       tc_fence_after();
