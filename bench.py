@@ -638,11 +638,14 @@ def run_ours(args, w):
         "warmup": W_, "ms_per_step": 1e3 * t_dev / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (generated on the device, seed 2020)",
         "gpu_launches": int(dn["launches"]),
-        "config": {**workload_config(w, world), "n_train": int(n_train), "avg_batch_rows_per_gpu": B_avg,
-                   "adam_mode": "dense_exact (every row moves every step, as torch.optim.Adam does in the reference)",
-                   "l2": f"no flush needed: every step streams 24 * rows * d = {24.0 * rows_per_gpu_tab * d / 1e9:.1f} GB of "
-                         f"tables + moments per GPU, far beyond the 126 MB L2",
-                   "parallelism": parallelism},
+        # `config` is the workload both arms run (identical dicts in this line and in --impl reference's); how THIS arm runs it
+        # is `config_detail`
+        "config": workload_config(w, world),
+        "config_detail": {"n_train": int(n_train), "avg_batch_rows_per_gpu": B_avg,
+                          "adam_mode": "dense_exact (every row moves every step, as torch.optim.Adam does in the reference)",
+                          "l2": f"no flush needed: every step streams 24 * rows * d = {24.0 * rows_per_gpu_tab * d / 1e9:.1f} GB "
+                                f"of tables + moments per GPU, far beyond the 126 MB L2",
+                          "parallelism": parallelism},
         "clocks": clocks.summary(),
         "roofline": roof,
         "kernel_shares": dict(list(shares.items())[:10]),
