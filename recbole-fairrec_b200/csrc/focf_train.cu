@@ -142,11 +142,14 @@ __global__ void __launch_bounds__(kLossThreads) k_segment_loss(LossArgs a) { los
 __device__ __forceinline__ void grid_barrier(unsigned long long *bar) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // release / acquire at GPU scope (not __threadfence() = fence.sc: ~140 CTAs issuing it at once serialise)
     const unsigned long long n = gridDim.x;
-    const unsigned long long target = (atomicAdd(bar, 1ull) / n + 1ull) * n;   // 64-bit: never wraps
-    while (*(volatile unsigned long long *)bar < target) {}
-    __threadfence();
+    unsigned long long old, v;
+    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(bar), "l"(1ull) : "memory");
+    const unsigned long long target = (old / n + 1ull) * n;   // 64-bit: never wraps
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }
