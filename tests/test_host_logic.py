@@ -768,6 +768,53 @@ def test_host_batch_step_loop_validates_its_arguments_before_touching_the_device
     assert lib.fr_focf_train_steps_host(ctypes.byref(s), 2, ptrs, rows, stage, 64, loss, loss, None) == _lib.FR_ERR_INVALID
 
 
+def test_epoch_kernel_entry_validates_its_slots_before_touching_the_device():
+    """fr_focf_epoch_run / fr_focf_epoch_eligible refuse malformed slot arrays with FR_ERR_INVALID and a message -- checked
+    before any CUDA call, so this runs without a GPU"""
+    from recbole_fairrec_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 256)()
+    p = ctypes.addressof(buf)
+
+    def slot(k, **kw):
+        s = _lib.FocfStep()
+        for f in ("U", "I", "mU", "vU", "mI", "vI", "loss", "status_flags", "plan_desc", "plan_items", "plan_offs", "item_off",
+                  "train_uid", "train_rating", "sst_of_user"):
+            setattr(s, f, p)
+        for f in ("uid", "iid", "rating", "sst", "pred", "workspace"):          # per-slot buffers must differ
+            setattr(s, f, p + 16 * (k + 1))
+        s.n_users, s.n_items, s.d, s.B, s.plan_len, s.objective, s.workspace_bytes = 10, 10, 32, 64, 3, 1, 1 << 20
+        for key, v in kw.items():
+            setattr(s, key, v)
+        return s
+
+    def arr(*slots):
+        a = (_lib.FocfStep * len(slots))()
+        for k, s in enumerate(slots):
+            ctypes.memmove(ctypes.byref(a[k]), ctypes.byref(s), ctypes.sizeof(s))
+        return ctypes.cast(a, ctypes.c_void_p), a
+
+    run = lambda a, n, first=0, steps=2, t=1, sync=p: lib.fr_focf_epoch_run(a, n, first, steps, t, sync, None)
+    good, keep = arr(slot(0), slot(1), slot(2))
+    assert run(good, 3, steps=0) == _lib.FR_OK                                   # nothing to do
+    assert run(None, 3) == _lib.FR_ERR_INVALID
+    assert run(good, 1) == _lib.FR_ERR_INVALID and b"slots" in lib.fr_last_error()
+    assert run(good, 9) == _lib.FR_ERR_INVALID
+    assert run(good, 3, t=0) == _lib.FR_ERR_INVALID                              # optimizer steps are 1-based
+    assert run(good, 3, sync=None) == _lib.FR_ERR_INVALID
+    bad, keep2 = arr(slot(0), slot(1, d=64))                                     # a slot with another shape
+    assert run(bad, 2) == _lib.FR_ERR_INVALID and b"differs from slot 0" in lib.fr_last_error()
+    bad, keep3 = arr(slot(0), slot(0))                                           # two slots on the same buffers
+    assert run(bad, 2) == _lib.FR_ERR_INVALID and b"share" in lib.fr_last_error()
+    bad, keep4 = arr(slot(0, plan_desc=None), slot(1, plan_desc=None))           # not a planned epoch
+    assert run(bad, 2) == _lib.FR_ERR_INVALID and b"planned epoch" in lib.fr_last_error()
+    bad, keep5 = arr(slot(0, B=9000), slot(1, B=9000))                           # batches beyond the producers' sort capacity
+    assert run(bad, 2) == _lib.FR_ERR_INVALID and b"batch capacity" in lib.fr_last_error()
+    bad, keep6 = arr(slot(0, adam_mode=1), slot(1, adam_mode=1))                 # lazy_exact belongs to the stepwise path
+    assert run(bad, 2) == _lib.FR_ERR_INVALID
+    assert lib.fr_focf_epoch_eligible(bad, 2) == 0
+
+
 def test_alias_sampler_follows_item_popularity_and_the_reference_call_pattern():
     """sampler.py:72-120: keys in order of first appearance, a valid alias table (every column sums to 1 with its alias),
     draws proportional to the interaction counts, and exactly one randint + one random call per `sampling(n)`"""
