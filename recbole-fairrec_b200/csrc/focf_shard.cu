@@ -366,13 +366,13 @@ __global__ void __launch_bounds__(256)
   const uint32_t stamp = ctrl[CTRL_STAMP] - 1u;   // k_shard_stats_reduce already advanced it
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(q / dq), k = (int)(q % dq) * 4;
+    float4 *pp = (float4 *)(I + q * 4), *pm = (float4 *)(mI + q * 4), *pv = (float4 *)(vI + q * 4);
+    float4 p = *pp, m = ldg_stream(pm), v = ldg_stream(pv);   // (requested before the stamp-dependent branch, see apply_body)
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint2 t = row_tab_i[row];
     if (t.x == stamp)
       for (int r = 0; r < world; ++r)
         g = f4_add(g, *(const float4 *)((const float *)(xG + (size_t)r * xG_slot) + (size_t)t.y * d + k));
-    float4 *pp = (float4 *)(I + q * 4), *pm = (float4 *)(mI + q * 4), *pv = (float4 *)(vI + q * 4);
-    float4 p = *pp, m = ldg_stream(pm), v = ldg_stream(pv);
     adam1(p.x, m.x, v.x, g.x, wd, w1, b2, w2, bc2s, eps, neg_step);
     adam1(p.y, m.y, v.y, g.y, wd, w1, b2, w2, bc2s, eps, neg_step);
     adam1(p.z, m.z, v.z, g.z, wd, w1, b2, w2, bc2s, eps, neg_step);

@@ -684,6 +684,7 @@ static int lazy_catchup(const fr_focf_step *s, const FocfWs &w, cudaStream_t st,
 // the Adam stage of the general (multi-launch) step: dense sweep, or lazy-exact update of the touched rows only
 static int adam_stage(const fr_focf_step *s, const FocfWs &w, cudaStream_t st, const char *who) {
   if (s->adam_mode == FR_ADAM_DENSE_EXACT) {
+    // (an L2 prefetch of the next grid-stride iteration's lines was tried: 0.856 of the copy peak against 0.878-0.892 without)
     FR_LAUNCH(k_apply<kAdamFused>, apply_grid(s), 256, 0, st, apply_args(s, w));
     return FR_OK;
   }
