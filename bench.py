@@ -458,8 +458,12 @@ def run_ours(args, w):
 
     touched = (uniq_users or B_avg * 0.5)
     roof, shares = roofline_of(prof_modes["dense_exact"], K_, rows_per_gpu_tab, B_avg, touched)
-    if roof and world == 1:
-        roof["traffic_note"] = "ncu --set full capture of this kernel: profiles/ (dram bytes / algorithmic = 1.01 in round 1)"
+    if roof and world == 1 and roof["kernel"].startswith("k_apply") and w["n_inter"] == SCALEOUT["n_inter"]:
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed `ncu --set full`
+        # capture (profiles/r02_ncu_summary.md, last section): 17.4823 GB + 16.8369 GB per launch
+        roof["traffic"] = 34.3192e9
+        roof["traffic_note"] = ("ncu --set full capture of this kernel at this shape (profiles/r02_ncu_summary.md): DRAM read "
+                                "17.48 GB + write 16.84 GB per launch = 1.016 x the algorithmic bytes")
     roof_lz, shares_lz = roofline_of(prof_modes["lazy_exact"], K_, rows_per_gpu_tab, B_avg, touched)
     t_lz = vmax(lz["ms_all"] / 1e3)
     lazy = {"value": lz["rows"] / t_lz, "unit": "interactions/s", "ms_per_step": 1e3 * t_lz / K_,
