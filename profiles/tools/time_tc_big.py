@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""The tensor-core full-sort scorer on a configs[4]-like slab (d = 128, K = 10, transform clamp/max_rating): `n` eval users
+(default 148 x 128 x 2: two waves of one CTA per SM) against `ni` items (default 262,144), a short random history per
+user.  Prints the kernel time from the library's CUDA-event profiler and the fp32-equivalent TFLOP/s against the 3xTF32
+peak, and checks the ids of a sample of rows against the exact scorer.
+    python profiles/tools/time_tc_big.py [n] [ni] [d]
+    ncu --set full --import-source on -k regex:k_fullsort_tc --launch-skip 1 -c 1 -o gpurun_out/x python profiles/tools/time_tc_big.py"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+
+import recbole_fairrec_b200 as pkg
+from recbole_fairrec_b200 import _lib, kernels
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 2
+ni = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+K = 10
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(7)
+U = torch.randn(n + 1, d, device=dev, generator=g) * 0.2
+I = torch.randn(ni, d, device=dev, generator=g) * 0.2
+users = torch.arange(1, n + 1, device=dev, dtype=torch.int32)
+H = 16
+hist = torch.randint(1, ni, (n, H), device=dev, generator=g, dtype=torch.int32).sort(dim=1).values
+hist_off = (torch.arange(n + 1, device=dev, dtype=torch.int64) * H)
+hist_items = hist.reshape(-1).contiguous()
+
+
+def run(mode):
+    return kernels.fullsort_topk(U, I, users, hist_off, hist_items, K, _lib.TRANSFORM_CLAMP_DIV if hasattr(_lib, "TRANSFORM_CLAMP_DIV") else 1,
+                                 5.0, 0, mode)
+
+
+for _ in range(2):
+    ids, sc = run(_lib.SCORE_TC_3XTF32)
+torch.cuda.synchronize()
+ts = []
+for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ids, sc = run(_lib.SCORE_TC_3XTF32)
+    b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ms = sorted(ts)[len(ts) // 2]
+tf = 2.0 * n * ni * d / (ms * 1e-3) / 1e12
+out = {"n": n, "ni": ni, "d": d, "ms_call": ms, "ms_all": [round(t, 3) for t in ts], "tflops_fp32_equiv": tf, "frac_of_272.95": tf / 272.95}
+# sample check against the exact scorer (ids equal outside near ties: count them)
+ns = min(n, 2048)
+sub = users[:ns].contiguous()
+ide, sce = kernels.fullsort_topk(U, I, sub, hist_off[: ns + 1].contiguous(), hist_items, K, 1, 5.0, 0, _lib.SCORE_EXACT_FP32)
+out["rows_ids_equal_exact"] = float((ide == ids[:ns]).all(dim=1).float().mean())
+out["max_score_diff"] = float((sce - sc[:ns]).abs().max())
+print(json.dumps(out))

@@ -10,34 +10,45 @@
 // not per tile.
 //
 // CTA = 128 eval users x a contiguous range of item tiles (128 items each); 6 warps:
-//   warp 0   TMA producer: one lane streams the item K-blocks (32 k-columns = one 128-byte swizzle atom row) of
-//            Ih and Il through a 4-stage shared-memory ring (cp.async.bulk.tensor, mbarrier complete_tx)
-//   warp 1   MMA issuer: one lane issues tcgen05.mma (M=128, N=128, K=8) x 4 k-steps x 3 products per K-block;
-//            tcgen05.commit releases the ring slot and, after the last K-block of a tile, publishes the accumulator
-//   warp 2-5 epilogue: TMEM lane == user row, so each thread OWNS one user: tcgen05.ld 32 columns at a time, mask
-//            bits from the thread's own walk of its sorted history, a one-compare filter on the raw dot against the
-//            raw value of the row's current K-th best, and (rarely) the exact transform + insertion into the row's
-//            K-list in shared memory.  No cross-thread synchronisation in the epilogue at all.
-// The user tile (both planes) is loaded once by TMA and stays resident; the TMEM accumulator is double buffered so
-// the MMAs of tile t+1 overlap the epilogue of tile t.
+//   warp 0   TMA producer: streams the item K-blocks (32 k-columns = one 128-byte swizzle atom row) of Ih and Il through a
+//            shared-memory ring of up to 6 stages (cp.async.bulk.tensor, mbarrier complete_tx)
+//   warp 1   MMA issuer: tcgen05.mma (M=128, N=128, K=8) x 4 k-steps x 3 products per K-block, A operand from TENSOR
+//            MEMORY, B from the ring; tcgen05.commit releases the ring slot and, after the last K-block of a tile,
+//            publishes the accumulator
+//   warp 2-5 epilogue: TMEM lane == user row, so each thread OWNS one user: it first stores its user's two planes into its
+//            TMEM lane (tcgen05.st: the A operand of every MMA of the CTA), then per tile tcgen05.ld 32 columns at a time,
+//            mask bits from the thread's own walk of its sorted history, a one-compare filter on the raw dot against the
+//            raw value of the row's current K-th best, and (rarely) the exact transform + insertion into the row's K-list.
+//            No cross-thread synchronisation in the epilogue at all.
+// TMEM (512 columns): two accumulators (2 x 128) so the MMAs of tile t+1 overlap the epilogue of tile t, then the user
+// tile's hi and lo planes (2 x d <= 256 columns).
+// Both issuing warps run their loops warp-uniformly and elect one lane per issue (elect_one(), tc_common.cuh): with the
+// loop under `if (lane == 0)` every UTCHMMA paid an ELECT / R2UR.BROADCAST waterfall and the kernel was ISSUE-bound at
+// ~106 cycles per 64-cycle MMA (74 % of the 3xTF32 peak; the same time with the item loads or the epilogue switched off,
+// FR_TC_DIAG).  Uniform issue: 98 %; A in tensor memory (an SS dispatch reads 8 KB of shared memory per 64 cycles = all
+// of the SM's 128 B/clk): 105-107 % of the figure derived from the measured bf16 peak, MMA-only floor 7.3 ms for the
+// 8.7 ms of profiles/tools/time_tc_big.py's slab (profiles/r02_tc_scorer.md).
 #include "tc_common.cuh"
 
 namespace fr {
 
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_THREADS = 192;
-constexpr int TC_KBLOCK_BYTES = TCN * TCKB * 4;   // 16 KB per plane per K-block (same for the user tile: TCM == TCN)
+constexpr int TC_KBLOCK_BYTES = TCN * TCKB * 4;   // 16 KB per plane per K-block
+constexpr int TC_ACC_COLS = 2 * TCN;               // TMEM: two accumulators, then the user tile's planes (2 x d columns)
 constexpr int kTcMaxK = 64;
 constexpr int kTcMaxD = 128;
 
 // ---------------------------------------------------------------- the scorer
 struct TcArgs {
+  const float *uh, *ul;   // the eval users' TF32 planes, row-major [n, d] (k_split_planes)
   const int64_t *hist_off;
   const int32_t *hist_items;
   int n, d, n_items_local, item_base, K, transform;
   float max_rating;
   int tiles_per_split;
   int stages;         // ring depth (2..4, what fits beside the resident user planes)
+  int diag;           // timing knob FR_TC_DIAG: bit 0 = no item loads (stale ring), bit 1 = no epilogue reads; results invalid
   int use_scratch;    // 1: per-thread shared-memory scratch rows for the slow path (fast); 0: collective TMEM re-read
   int32_t *out_id;    // [n_splits, n, K]
   float *out_score;
@@ -75,18 +86,16 @@ __device__ __forceinline__ float tc_raw_bound(float thr_s, int transform, float 
 constexpr int TC_KREG = 16;
 template <bool kRegList>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_fullsort_tc(const __grid_constant__ CUtensorMap map_uh, const __grid_constant__ CUtensorMap map_ul,
-                  const __grid_constant__ CUtensorMap map_ih, const __grid_constant__ CUtensorMap map_il, TcArgs a) {
+    k_fullsort_tc(const __grid_constant__ CUtensorMap map_ih, const __grid_constant__ CUtensorMap map_il, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int nkb = a.d / TCKB;                                 // K-blocks per row (d = 32, 64, 96 or 128)
-  // carve: [A hi: nkb x 16 KB][A lo: nkb x 16 KB][ring: TC_STAGES x (B hi 16 KB + B lo 16 KB)][lists][barriers]
-  unsigned char *sA_hi = tc_smem;
-  unsigned char *sA_lo = sA_hi + nkb * TC_KBLOCK_BYTES;
-  unsigned char *sB = sA_lo + nkb * TC_KBLOCK_BYTES;
+  // carve: [ring: TC_STAGES x (B hi 16 KB + B lo 16 KB)][lists][scratch][barriers]   (the user tile lives in TMEM)
+  unsigned char *sB = tc_smem;
   const int TC_STAGES = a.stages;
+  const int list_k = kRegList ? 0 : a.K;                             // (the register list needs no shared-memory rows)
   float *list_s = (float *)(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);   // [TCM][K]
-  int *list_i = (int *)(list_s + TCM * a.K);                         // [TCM][K]
-  float *scr = (float *)(list_i + TCM * a.K);                        // [TCM][33] candidate scratch rows (optional)
+  int *list_i = (int *)(list_s + TCM * list_k);                      // [TCM][K]
+  float *scr = (float *)(list_i + TCM * list_k);                     // [TCM][33] candidate scratch rows (optional)
   uint64_t *bars = (uint64_t *)(((uintptr_t)(scr + (a.use_scratch ? TCM * 33 : 0)) + 7) & ~(uintptr_t)7);
   uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2,
            *afull = tempty + 2;
@@ -109,12 +118,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 128);   // every epilogue thread arrives
     }
-    mbar_init(afull, 1);
+    mbar_init(afull, 128);          // every epilogue thread has stored its user row into TMEM
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
+  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns + the user tile's two planes (2 x d <= 256 columns): all 512
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(256));
+                 "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -123,57 +132,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(afull, 2u * nkb * TC_KBLOCK_BYTES);
+    // ===================================================== TMA producer (the whole warp walks the ring, one elected
+    // lane issues: see elect_one())
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tt = 0; tt < ntile; ++tt) {
+      const int row0 = (tile_lo + tt) * TCN;
       for (int kb = 0; kb < nkb; ++kb) {
-        tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &map_uh, kb * TCKB, u0, afull);
-        tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &map_ul, kb * TCKB, u0, afull);
-      }
-      int q = 0;
-      for (int tt = 0; tt < ntile; ++tt) {
-        const int row0 = (tile_lo + tt) * TCN;
-        for (int kb = 0; kb < nkb; ++kb, ++q) {
-          const int s = q % TC_STAGES;
-          const uint32_t ph = (q / TC_STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], 2u * TC_KBLOCK_BYTES);
-          tma_load_2d(sB + (2 * s) * TC_KBLOCK_BYTES, &map_ih, kb * TCKB, row0, &full[s]);
-          tma_load_2d(sB + (2 * s + 1) * TC_KBLOCK_BYTES, &map_il, kb * TCKB, row0, &full[s]);
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+          if (a.diag & 1) {
+            mbar_arrive(&full[s]);
+          } else {
+            mbar_expect_tx(&full[s], 2u * TC_KBLOCK_BYTES);
+            tma_load_2d(sB + (2 * s) * TC_KBLOCK_BYTES, &map_ih, kb * TCKB, row0, &full[s]);
+            tma_load_2d(sB + (2 * s + 1) * TC_KBLOCK_BYTES, &map_il, kb * TCKB, row0, &full[s]);
+          }
+        }
+        __syncwarp();
+        if (++s == TC_STAGES) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TCM, TCN);
-      mbar_wait(afull, 0);
+    // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc = umma_idesc_tf32(TCM, TCN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // (uniform for the compiler)
+    mbar_wait(afull, 0);
+    tc_fence_after();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tt = 0; tt < ntile; ++tt) {
+      const int buf = tt & 1;
+      const uint32_t tph = (tt >> 1) & 1;
+      mbar_wait(&tempty[buf], tph ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      int q = 0;
-      for (int tt = 0; tt < ntile; ++tt) {
-        const int buf = tt & 1;
-        const uint32_t tph = (tt >> 1) & 1;
-        mbar_wait(&tempty[buf], tph ^ 1);      // epilogue has drained this accumulator
+      const uint32_t tmem_d = tmem_u + (uint32_t)(buf * TCN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TCN);
-        for (int kb = 0; kb < nkb; ++kb, ++q) {
-          const int s = q % TC_STAGES;
-          const uint32_t ph = (q / TC_STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(sA_hi + kb * TC_KBLOCK_BYTES), a_lo = smem_u32(sA_lo + kb * TC_KBLOCK_BYTES);
-          const uint32_t b_hi = smem_u32(sB + (2 * s) * TC_KBLOCK_BYTES), b_lo = b_hi + TC_KBLOCK_BYTES;
+        if (elect_one()) {
+          const uint32_t a_hi = tmem_u + (uint32_t)(TC_ACC_COLS + kb * TCKB), a_lo = a_hi + (uint32_t)a.d;
+          const uint64_t b_hi = umma_desc_sw128(smem_u32(sB + (2 * s) * TC_KBLOCK_BYTES));
+          const uint64_t b_lo = umma_desc_sw128(smem_u32(sB + (2 * s + 1) * TC_KBLOCK_BYTES));
 #pragma unroll
-          for (int k = 0; k < TCKB / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes along the swizzled row
-            const uint32_t off = k * 32;
-            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-            umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, first);
-            umma_tf32(tmem_d, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1u);
-            umma_tf32(tmem_d, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1u);
+          for (int k = 0; k < TCKB / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes along the swizzled row = +2 in the descriptor's
+                                                 // 16-byte start-address units (no carry: the blocks are 1 KB aligned)
+            const uint64_t off = (uint64_t)(k * 2);
+            umma_tf32_ts(tmem_d, a_hi + k * 8, b_hi + off, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32_ts(tmem_d, a_lo + k * 8, b_hi + off, idesc, 1u);
+            umma_tf32_ts(tmem_d, a_hi + k * 8, b_lo + off, idesc, 1u);
           }
           umma_commit(&empty[s]);              // ring slot reusable once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(&tfull[buf]);   // accumulator complete
         }
-        umma_commit(&tfull[buf]);              // accumulator complete
+        __syncwarp();
+        if (++s == TC_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {
@@ -186,6 +205,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     float *ls = list_s + row * K;
     int *li = list_i + row * K;
     float *scratch = scr + row * 33;
+    {
+      // this thread's user row (both planes) into its TMEM lane: the A operand of every MMA of this CTA.  A in tensor
+      // memory halves the shared-memory operand traffic of an MMA (8 KB per 64-cycle M=128 N=128 K=8 dispatch is the whole
+      // 128 B/clk of the SM: 75-82 cycles per MMA measured, profiles/tools/mma_rate.cu) and frees 2 x d x 512 bytes of shared
+      // memory for ring stages.
+      const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)TC_ACC_COLS;
+      for (int pl = 0; pl < 2; ++pl) {
+        const float4 *src = (const float4 *)((pl ? a.ul : a.uh) + (size_t)(live ? r : 0) * a.d);
+        for (int c = 0; c < nkb; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = live ? __ldg(src + c * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j] = __float_as_uint(x.x);
+            v[4 * j + 1] = __float_as_uint(x.y);
+            v[4 * j + 2] = __float_as_uint(x.z);
+            v[4 * j + 3] = __float_as_uint(x.w);
+          }
+          tmem_st32(ta + (uint32_t)(pl * a.d + c * TCKB), v);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(afull);
+    }
     float rs[TC_KREG];
     int ri[TC_KREG];
     // (right-aligned: slot TC_KREG - 1 is the K-th best, so the threshold is a fixed register; the unused leading slots
@@ -291,7 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(&tfull[buf], tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TCN);
-      for (int w = 0; w < TCN / 32; ++w) {
+      for (int w = 0; w < ((a.diag & 2) ? 0 : TCN / 32); ++w) {
         uint32_t v[32];
         tmem_ld32(taddr + w * 32, v);
         // fast path: one compare per element -> candidate bit mask (branch free, ~2 instructions per score)
@@ -304,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         cand &= colmask & ~mw;
         if (!live) cand = 0u;
         // slow path: rare once the row's threshold has warmed up; ONE copy of the insertion code (instruction footprint)
-        if (kRegList || a.use_scratch) {   // (the register-list variant always has room for the scratch rows: one call site)
+        if (a.use_scratch) {
           if (cand) {   // park the 32 raw scores in this thread's scratch row and walk the candidate bits
 #pragma unroll
             for (int c = 0; c < 32; ++c) scratch[c] = __uint_as_float(v[c]);
@@ -314,6 +358,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               const float raw = scratch[c];
               if (raw > raw_thr) try_insert(raw, g0 + w * 32 + c);
             }
+          }
+        } else if (kRegList) {
+          // no scratch rows (their 17 KB buy one more ring stage at d = 128): the candidate's score is picked out of the
+          // registers by a select chain -- 32 selects per candidate, which a large catalogue makes rare
+          while (cand) {
+            const int c = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            uint32_t x = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) x = (j == c) ? v[j] : x;
+            const float raw = __uint_as_float(x);
+            if (raw > raw_thr) try_insert(raw, g0 + w * 32 + c);
           }
         } else {
           // no room for scratch rows: warp-uniform walk over the union of the lanes' candidate columns, each column
@@ -357,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -394,20 +450,25 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   FR_LAUNCH(k_split_planes, grid_for((int64_t)n * d / 4, 256, kSMs * 16), 256, 0, st, a->U, a->users, (int64_t)n, d, Uh, Ul);
   FR_LAUNCH(k_split_planes, grid_for((int64_t)nl * d / 4, 256, kSMs * 16), 256, 0, st, a->I_shard, (const int32_t *)nullptr,
             (int64_t)nl, d, Ih, Il);
-  CUtensorMap m_uh, m_ul, m_ih, m_il;
-  if (!make_map(&m_uh, Uh, n, d) || !make_map(&m_ul, Ul, n, d) || !make_map(&m_ih, Ih, nl, d) ||
-      !make_map(&m_il, Il, nl, d)) {
+  CUtensorMap m_ih, m_il;
+  if (!make_map(&m_ih, Ih, nl, d) || !make_map(&m_il, Il, nl, d)) {
     set_error("fr_fullsort_topk: cuTensorMapEncodeTiled failed");
     return FR_ERR_CUDA;
   }
-  const int nkb = d / TCKB;
-  size_t fixed = (size_t)2 * nkb * TC_KBLOCK_BYTES + (size_t)TCM * a->K * 8 + (size_t)TCM * 33 * 4 + 256;
+  const bool reg_list = a->K <= TC_KREG;
+  size_t fixed = (reg_list ? 0 : (size_t)TCM * a->K * 8) + (size_t)TCM * 33 * 4 + 256;
   int use_scratch = 1;
   int stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB slack
-  if (stages < 2 && a->K > TC_KREG) {   // drop the scratch rows (slow path falls back to collective TMEM re-reads)
+  // drop the scratch rows where that buys a ring stage below the full depth or where nothing fits otherwise
+  const int stages_ns = (int)((232448 - 1024 - (long long)(fixed - (size_t)TCM * 33 * 4)) / (2 * TC_KBLOCK_BYTES));
+  if (stages < TC_MAX_STAGES && stages_ns > stages && (reg_list || stages < 2)) {
     use_scratch = 0;
     fixed -= (size_t)TCM * 33 * 4;
-    stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));
+    stages = stages_ns;
+  }
+  if (const char *e = getenv("FR_TC_STAGES")) {   // (timing knob: profiles/tools/time_tc_big.py)
+    const int want = atoi(e);
+    if (want >= 2 && want <= stages) stages = want;
   }
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) {
@@ -416,18 +477,18 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   }
   const size_t smem = fixed + (size_t)stages * 2 * TC_KBLOCK_BYTES + 1024;
   const int itiles = (nl + TCN - 1) / TCN;
-  TcArgs t{a->hist_off, a->hist_items, n, d, nl, a->item_base, a->K, a->transform, a->max_rating,
-           (itiles + splits - 1) / splits, stages, use_scratch, out_id, out_sc};
+  TcArgs t{Uh, Ul, a->hist_off, a->hist_items, n, d, nl, a->item_base, a->K, a->transform, a->max_rating,
+           (itiles + splits - 1) / splits, stages, getenv("FR_TC_DIAG") ? atoi(getenv("FR_TC_DIAG")) : 0, use_scratch, out_id, out_sc};
   dim3 grid((n + TCM - 1) / TCM, splits);
   const bool prof = prof_on();   // (one profiler name for both instantiations)
-  if (a->K <= TC_KREG) {
+  if (reg_list) {
     FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (prof) prof_begin("k_fullsort_tc", st);
-    k_fullsort_tc<true><<<grid, TC_THREADS, smem, st>>>(m_uh, m_ul, m_ih, m_il, t);
+    k_fullsort_tc<true><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
   } else {
     FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (prof) prof_begin("k_fullsort_tc", st);
-    k_fullsort_tc<false><<<grid, TC_THREADS, smem, st>>>(m_uh, m_ul, m_ih, m_il, t);
+    k_fullsort_tc<false><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
   }
   if (prof) prof_end(st);
   count_launch();

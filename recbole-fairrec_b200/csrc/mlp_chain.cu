@@ -192,17 +192,23 @@ struct Pipe {
   uint32_t tmem;
 };
 
+// Both issuing loops are run by the WHOLE warp, one elected lane per issue (elect_one(), tc_common.cuh): under
+// `if (lane == 0)` the operands of UTMALDG / UTCHMMA live in vector registers and every instruction pays an ELECT /
+// R2UR.BROADCAST waterfall (110 of them in each chain kernel, ~100 cycles per 16-64-cycle MMA).
 __device__ __forceinline__ void gemm_produce(const GemmIt &g, const Pipe &p, uint32_t &it) {
   for (int kb = 0; kb < g.nkb; ++kb, ++it) {
     const int s = it % CH_STAGES;
     mbar_wait(&p.empty[s], ((it / CH_STAGES) & 1) ^ 1);
-    unsigned char *st = p.stages + (size_t)s * CH_STAGE;
-    mbar_expect_tx(&p.full[s], (uint32_t)(2 * CH_A_PLANE + 2 * g.nt * TCKB * 4));
-    const int x = (g.kb0 + kb) * TCKB;
-    tma_load_3d(st, g.ma, x, g.ay, 0, &p.full[s]);
-    tma_load_3d(st + CH_A_PLANE, g.ma, x, g.ay, 1, &p.full[s]);
-    tma_load_3d(st + 2 * CH_A_PLANE, g.mb, x, g.by, 0, &p.full[s]);
-    tma_load_3d(st + 2 * CH_A_PLANE + CH_B_PLANE, g.mb, x, g.by, 1, &p.full[s]);
+    if (elect_one()) {
+      unsigned char *st = p.stages + (size_t)s * CH_STAGE;
+      mbar_expect_tx(&p.full[s], (uint32_t)(2 * CH_A_PLANE + 2 * g.nt * TCKB * 4));
+      const int x = (g.kb0 + kb) * TCKB;
+      tma_load_3d(st, g.ma, x, g.ay, 0, &p.full[s]);
+      tma_load_3d(st + CH_A_PLANE, g.ma, x, g.ay, 1, &p.full[s]);
+      tma_load_3d(st + 2 * CH_A_PLANE, g.mb, x, g.by, 0, &p.full[s]);
+      tma_load_3d(st + 2 * CH_A_PLANE + CH_B_PLANE, g.mb, x, g.by, 1, &p.full[s]);
+    }
+    __syncwarp();
   }
 }
 
@@ -210,22 +216,31 @@ __device__ __forceinline__ void gemm_mma(const GemmIt &g, const Pipe &p, uint32_
   mbar_wait(p.tempty, (gi & 1) ^ 1);   // the epilogue of this CTA's previous GEMM item has drained the accumulator
   tc_fence_after();
   const uint32_t idesc = umma_idesc_tf32(TCM, g.nt);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, p.tmem, 0);   // (read from shared memory: make it uniform for ptxas)
   for (int kb = 0; kb < g.nkb; ++kb, ++it) {
     const int s = it % CH_STAGES;
     mbar_wait(&p.full[s], (it / CH_STAGES) & 1);
     tc_fence_after();
-    const uint32_t a_hi = smem_u32(p.stages + (size_t)s * CH_STAGE), a_lo = a_hi + CH_A_PLANE;
-    const uint32_t b_hi = a_hi + 2 * CH_A_PLANE, b_lo = b_hi + CH_B_PLANE;
+    if (elect_one()) {
+      const uint32_t a0 = smem_u32(p.stages + (size_t)s * CH_STAGE);
+      const uint64_t a_hi = umma_desc_sw128(a0), a_lo = umma_desc_sw128(a0 + CH_A_PLANE);
+      const uint64_t b_hi = umma_desc_sw128(a0 + 2 * CH_A_PLANE), b_lo = umma_desc_sw128(a0 + 2 * CH_A_PLANE + CH_B_PLANE);
 #pragma unroll
-    for (int k = 0; k < TCKB / 8; ++k) {
-      const uint32_t off = k * 32;
-      umma_tf32(p.tmem, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, (kb == 0 && k == 0) ? 0u : 1u);
-      umma_tf32(p.tmem, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1u);
-      umma_tf32(p.tmem, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1u);
+      for (int k = 0; k < TCKB / 8; ++k) {
+        const uint64_t off = (uint64_t)(k * 2);   // 32 bytes along the swizzled row, in the descriptor's 16-byte units
+        umma_tf32(tmem_u, a_hi + off, b_hi + off, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+        umma_tf32(tmem_u, a_hi + off, b_lo + off, idesc, 1u);
+        umma_tf32(tmem_u, a_lo + off, b_hi + off, idesc, 1u);
+      }
+      umma_commit(&p.empty[s]);
+      if (kb == g.nkb - 1) umma_commit(p.tfull);
     }
-    umma_commit(&p.empty[s]);
+    __syncwarp();
   }
-  umma_commit(p.tfull);
+  if (g.nkb <= 0) {   // (never for the shapes the chain rules admit; keeps the accumulator handshake whole)
+    if (elect_one()) umma_commit(p.tfull);
+    __syncwarp();
+  }
   ++gi;
 }
 
@@ -707,15 +722,11 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
       fwd_gemm_decode(P, l, item, li, rb, nt);
       const ChLayer &L = P.layer[li];
       if (warp == 0) {
-        if (lane == 0) {
-          GemmIt g{&PP.map[li][0], &PP.map[li][1], rb * 128, nt * L.NT, 0, ch_tiles(L.K, TCKB), L.NT};
-          gemm_produce(g, pipe, it);
-        }
+        GemmIt g{&PP.map[li][0], &PP.map[li][1], rb * 128, nt * L.NT, 0, ch_tiles(L.K, TCKB), L.NT};
+        gemm_produce(g, pipe, it);
       } else if (warp == 1) {
-        if (lane == 0) {
-          GemmIt g{nullptr, nullptr, 0, 0, 0, ch_tiles(L.K, TCKB), L.NT};
-          gemm_mma(g, pipe, it, gi);
-        }
+        GemmIt g{nullptr, nullptr, 0, 0, 0, ch_tiles(L.K, TCKB), L.NT};
+        gemm_mma(g, pipe, it, gi);
       } else {
         mbar_wait(pipe.tfull, gi & 1);
         tc_fence_after();
@@ -1047,9 +1058,9 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
         g = GemmIt{&PP.map[b.li][0], &PP.map[b.li][1], b.a * 128, b.b * L.KT, 0, ch_tiles(L.N, TCKB), L.KT};
       }
       if (warp == 0) {
-        if (lane == 0) gemm_produce(g, pipe, it);
+        gemm_produce(g, pipe, it);
       } else if (warp == 1) {
-        if (lane == 0) gemm_mma(g, pipe, it, gi);
+        gemm_mma(g, pipe, it, gi);
       } else {
         mbar_wait(pipe.tfull, gi & 1);
         tc_fence_after();
