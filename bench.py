@@ -562,7 +562,11 @@ def run_ours(args, w):
               "roofline": {"bound": "tensor", "kernel": "k_fullsort_tc", "achieved": ach, "peak": tc_peak,
                            "unit": "TFLOP/s (fp32-equivalent; 3 TF32 MMAs per product)", "frac": ach / tc_peak,
                            "avg_launch_us": 1e3 * tc_ms / tc_cnt, "share_of_pass": round(tc_ms / etot, 4),
-                           "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)"},
+                           "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)",
+                           "nominal_peak": 2250.0 / 2.0 / 3.0, "frac_of_nominal": ach / (2250.0 / 2.0 / 3.0),
+                           "note": "frac can exceed 1: the measured bf16 figure is cuBLAS at the 1000 W power cap (SM clock "
+                                   "~1.33 GHz under load in MEASURED_PEAKS.json), kind::tf32 at half the MAC rate stays near the "
+                                   "full clock; nominal_peak = 2.25 PFLOP/s bf16 / 2 / 3 (B200_PROFILING.md)"},
               "kernel_shares": {k: round(v[1] / etot, 4) for k, v in sorted(prof_e.items(), key=lambda kv: -kv[1][1])[:6]},
               "metrics": {k: float(v) for k, v in res.items()}}
         del edata, evaluator

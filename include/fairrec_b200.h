@@ -493,6 +493,15 @@ size_t fr_item_group_stats_workspace_bytes(int64_t n_pos, int32_t n_items, int32
 int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const int32_t *group, int64_t n_pos,
                         int32_t n_items, int32_t G, double *stats_out, void *workspace, size_t workspace_bytes,
                         void *stream);
+/* The same in two parts: the item-sorted view of the positive list (order, segments) depends on the evaluation data only,
+ * not on the scores, so it is built once (fr_item_group_plan into a caller-owned plan buffer of fr_item_group_plan_bytes)
+ * and every evaluation pass runs the segment reduction alone (fr_item_group_stats_planned; same sums, same order). */
+size_t fr_item_group_plan_bytes(int64_t n_pos);
+size_t fr_item_group_plan_workspace_bytes(int64_t n_pos);
+int fr_item_group_plan(const int32_t *pos_items, int64_t n_pos, int32_t n_items, void *plan, size_t plan_bytes,
+                       void *workspace, size_t workspace_bytes, void *stream);
+int fr_item_group_stats_planned(const void *plan, size_t plan_bytes, const float *pos_score, const int32_t *group,
+                                int64_t n_pos, int32_t n_items, int32_t G, double *stats_out, void *stream);
 /* reduce stats -> fairness metrics.  out[0..6] double: DifferentialFairness (metrics.py:1313-1341), Value,
  * Absolute, Under, Over (935-1266; NaN unless G == 2), NonParity (860-881), n_distinct_positive_items */
 int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double *out, void *workspace,

@@ -221,6 +221,11 @@ SIGNATURES = {
     "fr_gini_workspace_bytes": (c_size_t, [c_int32]),
     "fr_gini_at_k": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fr_item_group_stats_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "fr_item_group_plan_bytes": (c_size_t, [c_int64]),
+    "fr_item_group_plan_workspace_bytes": (c_size_t, [c_int64]),
+    "fr_item_group_plan": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "fr_item_group_stats_planned": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
+                                            c_void_p]),
     "fr_item_group_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
     "fr_fairness_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),

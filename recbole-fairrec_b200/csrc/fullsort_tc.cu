@@ -36,8 +36,6 @@ constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_THREADS = 192;
 constexpr int TC_KBLOCK_BYTES = TCN * TCKB * 4;   // 16 KB per plane per K-block
 constexpr int TC_ACC_COLS = 2 * TCN;               // TMEM: two accumulators, then the user tile's planes (2 x d columns)
-constexpr int kTcMaxK = 64;
-constexpr int kTcMaxD = 128;
 
 // ---------------------------------------------------------------- the scorer
 struct TcArgs {
@@ -83,8 +81,10 @@ __device__ __forceinline__ float tc_raw_bound(float thr_s, int transform, float 
 // (16 compares, 32 selects, no memory round trips); otherwise it lives in shared memory and an insertion is a shift loop of
 // dependent LDS / STS pairs -- 40 % of the executed instructions and most of the latency at the ML-1M shape, where a
 // catalogue of 3,707 items never lets the threshold warm up.  Same total order, same lists.
-constexpr int TC_KREG = 16;
-template <bool kRegList>
+// kKReg = register slots of the list (10 for the usual K <= 10, 16 for K <= 16: the network's cost is proportional to the
+// slot count), 0 = shared-memory list.
+constexpr int TC_KREG_MAX = 16;
+template <int kKReg>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_fullsort_tc(const __grid_constant__ CUtensorMap map_ih, const __grid_constant__ CUtensorMap map_il, TcArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // carve: [ring: TC_STAGES x (B hi 16 KB + B lo 16 KB)][lists][scratch][barriers]   (the user tile lives in TMEM)
   unsigned char *sB = tc_smem;
   const int TC_STAGES = a.stages;
+  constexpr bool kRegList = kKReg > 0;
+  constexpr int TC_KREG = kRegList ? kKReg : 1;
   const int list_k = kRegList ? 0 : a.K;                             // (the register list needs no shared-memory rows)
   float *list_s = (float *)(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);   // [TCM][K]
   int *list_i = (int *)(list_s + TCM * list_k);                      // [TCM][K]
@@ -447,15 +449,14 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
   const size_t ab = (((size_t)n * d * 4) + 255) & ~(size_t)255, bb = (((size_t)nl * d * 4) + 255) & ~(size_t)255;
   float *Uh = (float *)planes, *Ul = (float *)((char *)planes + ab);
   float *Ih = (float *)((char *)planes + 2 * ab), *Il = (float *)((char *)planes + 2 * ab + bb);
-  FR_LAUNCH(k_split_planes, grid_for((int64_t)n * d / 4, 256, kSMs * 16), 256, 0, st, a->U, a->users, (int64_t)n, d, Uh, Ul);
-  FR_LAUNCH(k_split_planes, grid_for((int64_t)nl * d / 4, 256, kSMs * 16), 256, 0, st, a->I_shard, (const int32_t *)nullptr,
-            (int64_t)nl, d, Ih, Il);
+  FR_LAUNCH(k_split_planes2, grid_for(((int64_t)n + nl) * d / 4, 256, kSMs * 16), 256, 0, st, a->U, a->users, (int64_t)n, Uh, Ul,
+            a->I_shard, (int64_t)nl, Ih, Il, d);
   CUtensorMap m_ih, m_il;
   if (!make_map(&m_ih, Ih, nl, d) || !make_map(&m_il, Il, nl, d)) {
     set_error("fr_fullsort_topk: cuTensorMapEncodeTiled failed");
     return FR_ERR_CUDA;
   }
-  const bool reg_list = a->K <= TC_KREG;
+  const bool reg_list = a->K <= TC_KREG_MAX;
   size_t fixed = (reg_list ? 0 : (size_t)TCM * a->K * 8) + (size_t)TCM * 33 * 4 + 256;
   int use_scratch = 1;
   int stages = (int)((232448 - 1024 - (long long)fixed) / (2 * TC_KBLOCK_BYTES));   // 227 KB dynamic smem, 1 KB slack
@@ -481,14 +482,16 @@ int tc_launch(const fr_fullsort *a, void *planes, int splits, int32_t *out_id, f
            (itiles + splits - 1) / splits, stages, getenv("FR_TC_DIAG") ? atoi(getenv("FR_TC_DIAG")) : 0, use_scratch, out_id, out_sc};
   dim3 grid((n + TCM - 1) / TCM, splits);
   const bool prof = prof_on();   // (one profiler name for both instantiations)
-  if (reg_list) {
-    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (prof) prof_begin("k_fullsort_tc", st);
-    k_fullsort_tc<true><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
+  if (prof) prof_begin("k_fullsort_tc", st);
+  if (a->K <= 10) {
+    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fullsort_tc<10><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
+  } else if (reg_list) {
+    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fullsort_tc<16><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
   } else {
-    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (prof) prof_begin("k_fullsort_tc", st);
-    k_fullsort_tc<false><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
+    FR_CUDA_OK(cudaFuncSetAttribute(k_fullsort_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fullsort_tc<0><<<grid, TC_THREADS, smem, st>>>(m_ih, m_il, t);
   }
   if (prof) prof_end(st);
   count_launch();

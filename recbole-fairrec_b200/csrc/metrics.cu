@@ -32,19 +32,22 @@ __device__ __forceinline__ double block_sum_d(double v, double *sh) {  // 256 th
 // rec_topk [n, K+1] = [hit bits | pos_len].  part[blk][4][K] per-CTA sums, then k_reduce_rows.
 __global__ void __launch_bounds__(256)
     k_topk_metrics(const int32_t *__restrict__ rec_topk, int n, int K, double *__restrict__ part) {
-  __shared__ double sh[9];
+  // (one __syncthreads for the whole kernel instead of two per (k, metric) block reduction: the sums of a warp go through
+  // shuffles into wpart[warp][metric * K + k], the eight warps are added in warp order at the end)
   __shared__ double disc[kMaxGroups];   // 1/log2(r+1), r = 1..K   (K <= 64)
   __shared__ double idcg[kMaxGroups];   // cumulative
+  __shared__ double wpart[8][4 * kMaxGroups];
+  if (threadIdx.x < K) disc[threadIdx.x] = 1.0 / log2((double)threadIdx.x + 2.0);
+  __syncthreads();
   if (threadIdx.x == 0) {
     double run = 0.0;
-    for (int r = 1; r <= K; ++r) {
-      disc[r - 1] = 1.0 / log2((double)r + 1.0);
-      run += disc[r - 1];
-      idcg[r - 1] = run;
+    for (int r = 0; r < K; ++r) {
+      run += disc[r];
+      idcg[r] = run;
     }
   }
   __syncthreads();
-  const int u = blockIdx.x * 256 + threadIdx.x;
+  const int u = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool ok = u < n;
   const int32_t *row = rec_topk + (size_t)(ok ? u : 0) * (K + 1);
   const int pos_len = ok ? row[K] : 1;
@@ -56,16 +59,30 @@ __global__ void __launch_bounds__(256)
     if (h && first < 0) first = k;
     if (h) dcg += disc[k];
     const int il = min(pos_len, k + 1);                               // metrics.py:188-196
-    const double v_ndcg = ok ? dcg / idcg[il - 1] : 0.0;
-    const double v_rec = ok ? (double)cum / (double)pos_len : 0.0;    // metrics.py:161
-    const double v_hit = (ok && cum > 0) ? 1.0 : 0.0;                  // metrics.py:64-65
-    const double v_mrr = (ok && first >= 0) ? 1.0 / (double)(first + 1) : 0.0;  // metrics.py:91-96
-    const double s0 = block_sum_d(v_ndcg, sh), s1 = block_sum_d(v_rec, sh), s2 = block_sum_d(v_hit, sh),
-                 s3 = block_sum_d(v_mrr, sh);
-    if (threadIdx.x == 0) {
-      double *o = part + (size_t)blockIdx.x * 4 * K;
-      o[0 * K + k] = s0; o[1 * K + k] = s1; o[2 * K + k] = s2; o[3 * K + k] = s3;
+    double v0 = ok ? dcg / idcg[il - 1] : 0.0;                         // ndcg
+    double v1 = ok ? (double)cum / (double)pos_len : 0.0;             // recall, metrics.py:161
+    double v2 = (ok && cum > 0) ? 1.0 : 0.0;                           // hit, metrics.py:64-65
+    double v3 = (ok && first >= 0) ? 1.0 / (double)(first + 1) : 0.0;  // mrr, metrics.py:91-96
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      v3 += __shfl_xor_sync(0xffffffffu, v3, o);
     }
+    if (lane == 0) {
+      wpart[warp][0 * K + k] = v0;
+      wpart[warp][1 * K + k] = v1;
+      wpart[warp][2 * K + k] = v2;
+      wpart[warp][3 * K + k] = v3;
+    }
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < 4 * K; v += 256) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wpart[w][v];
+    part[(size_t)blockIdx.x * 4 * K + v] = t;
   }
 }
 
@@ -117,6 +134,107 @@ __global__ void k_gini_final(const long long *acc, long long total_recs, int n_i
   out[0] = (double)acc[0] / (double)total_recs / (double)n_items;
 }
 
+// Small catalogue (n_items <= kGiniSmall): the row sum, the ascending sort and the weighted sum in ONE CTA (bitonic sort in
+// shared memory) instead of the nine launches of the radix path -- at the ML-1M shape (3,707 items) an evaluation pass is a
+// chain of small launches and those nine were ~12 % of it.  Integer arithmetic until the final division: same bits.
+constexpr int kGiniSmall = 8192;
+__global__ void __launch_bounds__(1024) k_gini_small(const int32_t *__restrict__ item_pos_count, int n_items, int k_rows,
+                                                     long long total_recs, double *__restrict__ out) {
+  __shared__ uint32_t key[kGiniSmall];
+  __shared__ long long wsum[32];
+  int np2 = 1;
+  while (np2 < n_items) np2 <<= 1;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    uint32_t c = 0xffffffffu;   // padding sorts to the end
+    if (i < n_items) {
+      c = 0;
+      for (int r = 0; r < k_rows; ++r) c += (uint32_t)item_pos_count[(size_t)r * n_items + i];
+    }
+    key[i] = c;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t a = key[i], b = key[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            key[i] = b;
+            key[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  long long s = 0;
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) s += (2ll * (i + 1) - n_items - 1) * (long long)key[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+    out[0] = (double)t / (double)total_recs / (double)n_items;
+  }
+}
+
+// Few users (n_users < kGiniBins): an item's summed count is at most n_users (a user recommends an item once), so the sort
+// is a histogram over count VALUES: the h items of value v occupy the ascending positions P+1 .. P+h (P = items of smaller
+// value) and contribute v * (2 * (h P + h (h + 1) / 2) - h (N + 1)).  One CTA: histogram, scan, sum -- a few microseconds
+// where the bitonic kernel above needs 78 synchronised stages.
+constexpr int kGiniBins = 8192;
+__global__ void __launch_bounds__(1024) k_gini_hist(const int32_t *__restrict__ item_pos_count, int n_items, int k_rows,
+                                                    long long total_recs, double *__restrict__ out) {
+  __shared__ uint32_t hist[kGiniBins];
+  __shared__ uint32_t wtot[32];
+  __shared__ long long wsum[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < kGiniBins; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  for (int i = t; i < n_items; i += blockDim.x) {
+    uint32_t c = 0;
+    for (int r = 0; r < k_rows; ++r) c += (uint32_t)item_pos_count[(size_t)r * n_items + i];
+    atomicAdd(&hist[c < (uint32_t)kGiniBins ? c : (uint32_t)kGiniBins - 1u], 1u);
+  }
+  __syncthreads();
+  uint32_t h[kGiniBins / 1024], local = 0;
+#pragma unroll
+  for (int j = 0; j < kGiniBins / 1024; ++j) {
+    h[j] = hist[t * (kGiniBins / 1024) + j];
+    local += h[j];
+  }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += x;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; ++w) base += wtot[w];
+  long long P = (long long)(base + incl - local), s = 0;
+#pragma unroll
+  for (int j = 0; j < kGiniBins / 1024; ++j) {
+    const long long v = t * (kGiniBins / 1024) + j, hj = h[j];
+    s += v * (2ll * (hj * P + hj * (hj + 1) / 2) - hj * (n_items + 1));
+    P += hj;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum[warp] = s;
+  __syncthreads();
+  if (t == 0) {
+    long long tot = 0;
+    for (int w = 0; w < 32; ++w) tot += wsum[w];
+    out[0] = (double)tot / (double)total_recs / (double)n_items;
+  }
+}
+
 // ---------------------------------------------------------------- item x group statistics of the positives
 // After a stable sort of the positives by item id, one warp per item segment accumulates (sum score, count)
 // per group in float64, lanes striding the segment and a fixed shuffle tree at the end.
@@ -152,7 +270,7 @@ __global__ void __launch_bounds__(256)
 
 // pass A: per-CTA partials [1 + 2G]: J (items with any positive), S_g, C_g
 __global__ void __launch_bounds__(256) k_fair_pass_a(const double *__restrict__ stats, int n_items, int G,
-                                                     double *__restrict__ part) {
+                                                     double *__restrict__ part, unsigned int *ticket) {
   __shared__ double sh[9];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double any = 0.0;
@@ -168,10 +286,11 @@ __global__ void __launch_bounds__(256) k_fair_pass_a(const double *__restrict__ 
   }
   const double j = block_sum_d(any, sh);
   if (threadIdx.x == 0) part[(size_t)blockIdx.x * (1 + 2 * G)] = j;
+  if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;   // (pass B's last-CTA ticket: this launch precedes it)
 }
 
 // single thread: totals -> out[5] NonParity (metrics.py:872-881), out[6] = J ; glob[0] = J
-__global__ void k_fair_mid(const double *__restrict__ tot, int G, double *__restrict__ out) {
+__device__ void fair_mid(const double *tot, int G, double *__restrict__ out) {
   const double J = tot[0];
   out[6] = J;
   double mean[kMaxGroups];
@@ -191,12 +310,27 @@ __global__ void k_fair_mid(const double *__restrict__ tot, int G, double *__rest
   out[5] = np;
 }
 
-// pass B: per-CTA partials [5]: sum eps_j (DifferentialFairness), sum |D0-D1| for value/absolute/under/over
+// pass B: per-CTA partials [5]: sum eps_j (DifferentialFairness), sum |D0-D1| for value/absolute/under/over.
+// The whole tail of the metric rides in this launch (it used to be four more: reduce, mid, reduce, final -- an evaluation
+// pass at the ML-1M shape is a chain of dependent small launches): every CTA adds pass A's partial J's itself (block
+// order, the sum k_reduce_rows made), CTA 0 also the group totals and the NonParity / J outputs, and the CTA that draws the
+// last ticket adds pass B's partials in block order and writes the five remaining outputs.
 __global__ void __launch_bounds__(256) k_fair_pass_b(const double *__restrict__ stats, int n_items, int G,
-                                                     const double *__restrict__ Jp, double *__restrict__ part) {
+                                                     const double *__restrict__ partA, int nblk, double *__restrict__ part,
+                                                     unsigned int *ticket, double *__restrict__ out) {
   __shared__ double sh[9];
+  __shared__ double totA[1 + 2 * kMaxGroups];
+  __shared__ bool last;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  const double J = Jp[0];
+  const int VA = 1 + 2 * G;
+  if (threadIdx.x < (blockIdx.x == 0 ? VA : 1)) {
+    double t = 0.0;
+    for (int b = 0; b < nblk; ++b) t += partA[(size_t)b * VA + threadIdx.x];
+    totA[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const double J = totA[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) fair_mid(totA, G, out);
   double eps = 0.0, vv = 0.0, va = 0.0, vu = 0.0, vo = 0.0;
   bool any = false;
   if (i < n_items) {
@@ -230,13 +364,17 @@ __global__ void __launch_bounds__(256) k_fair_pass_b(const double *__restrict__ 
   if (threadIdx.x == 0) {
     double *o = part + (size_t)blockIdx.x * 5;
     o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned int)(gridDim.x - 1);
   }
-}
-
-__global__ void k_fair_final(const double *__restrict__ tot, int G, double *__restrict__ out) {
-  const double J = out[6];
-  out[0] = tot[0] / J;
-  for (int m = 0; m < 4; ++m) out[1 + m] = (G == 2) ? tot[1 + m] / J : nan("");
+  __syncthreads();
+  if (last && threadIdx.x < 5) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = 0; b < nblk; ++b) t += __ldcg(part + (size_t)b * 5 + threadIdx.x);
+    if (threadIdx.x == 0) out[0] = t / J;
+    else out[threadIdx.x] = (G == 2) ? t / J : nan("");
+  }
 }
 
 
@@ -336,6 +474,16 @@ int fr_gini_at_k(const int32_t *item_pos_count, int32_t n_items, int32_t k_rows,
     return FR_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_users < fr::kGiniBins && n_items <= (1 << 18)) {
+    FR_LAUNCH(fr::k_gini_hist, 1, 1024, 0, st, item_pos_count, n_items, k_rows, (long long)(n_users * k_rows), gini_out);
+    FR_LAUNCH_CHECK();
+    return FR_OK;
+  }
+  if (n_items <= fr::kGiniSmall) {
+    FR_LAUNCH(fr::k_gini_small, 1, 1024, 0, st, item_pos_count, n_items, k_rows, (long long)(n_users * k_rows), gini_out);
+    FR_LAUNCH_CHECK();
+    return FR_OK;
+  }
   FR_LAUNCH(fr::k_sum_count_rows, (n_items + 255) / 256, 256, 0, st, item_pos_count, n_items, k_rows, keys,
             (unsigned long long *)acc);
   const uint64_t maxc = (uint64_t)n_users + 1;
@@ -388,6 +536,75 @@ int fr_item_group_stats(const int32_t *pos_items, const float *pos_score, const 
   return FR_OK;
 }
 
+namespace {
+struct IgPlan {
+  uint32_t *skey, *ord;
+  int32_t *segoff, *nseg;
+  bool ok;
+  size_t bytes;
+};
+IgPlan carve_ig_plan(void *plan, size_t plan_bytes, int64_t n_pos) {
+  fr::Carver c(plan, plan_bytes);
+  IgPlan p;
+  p.skey = c.take<uint32_t>(n_pos);
+  p.ord = c.take<uint32_t>(n_pos);
+  p.segoff = c.take<int32_t>(n_pos + 1);
+  p.nseg = c.take<int32_t>(1);
+  p.ok = c.ok();
+  p.bytes = c.off;
+  return p;
+}
+}  // namespace
+
+size_t fr_item_group_plan_bytes(int64_t n_pos) { return carve_ig_plan(nullptr, 0, n_pos).bytes; }
+
+size_t fr_item_group_plan_workspace_bytes(int64_t n_pos) {
+  fr::Carver c(nullptr, 0);
+  c.take<int32_t>(n_pos);
+  fr::carve_sort_scratch(c, n_pos);
+  fr::carve_seg_scratch(c, n_pos);
+  return c.off;
+}
+
+int fr_item_group_plan(const int32_t *pos_items, int64_t n_pos, int32_t n_items, void *plan, size_t plan_bytes,
+                       void *workspace, size_t workspace_bytes, void *stream) {
+  FR_REQUIRE(pos_items && plan && workspace, "fr_item_group_plan: null pointer");
+  FR_REQUIRE(n_pos >= 1 && n_pos < (1ll << 31) && n_items >= 1, "fr_item_group_plan: bad sizes n_pos=%lld", (long long)n_pos);
+  IgPlan p = carve_ig_plan(plan, plan_bytes, n_pos);
+  fr::Carver c(workspace, workspace_bytes);
+  int32_t *segid = c.take<int32_t>(n_pos);
+  fr::SortScratch ss = fr::carve_sort_scratch(c, n_pos);
+  fr::SegScratch sg = fr::carve_seg_scratch(c, n_pos);
+  if (!p.ok || !c.ok()) {
+    fr::set_error("fr_item_group_plan: plan or workspace too small (%zu < %zu or %zu < %zu)", plan_bytes, p.bytes,
+                  workspace_bytes, c.off);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  fr::sort_pairs((const uint32_t *)pos_items, nullptr, p.skey, p.ord, n_pos, nullptr, fr::bits_for((uint32_t)n_items), ss, st);
+  fr::build_segments(p.skey, p.ord, n_pos, nullptr, segid, p.segoff, p.nseg, nullptr, nullptr, nullptr, sg, st);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
+int fr_item_group_stats_planned(const void *plan, size_t plan_bytes, const float *pos_score, const int32_t *group,
+                                int64_t n_pos, int32_t n_items, int32_t G, double *stats_out, void *stream) {
+  FR_REQUIRE(plan && pos_score && group && stats_out, "fr_item_group_stats_planned: null pointer");
+  FR_REQUIRE(n_pos >= 1 && n_pos < (1ll << 31) && n_items >= 1 && G >= 1 && G <= fr::kMaxGroups,
+             "fr_item_group_stats_planned: bad sizes n_pos=%lld G=%d", (long long)n_pos, G);
+  IgPlan p = carve_ig_plan(const_cast<void *>(plan), plan_bytes, n_pos);
+  if (!p.ok) {
+    fr::set_error("fr_item_group_stats_planned: plan too small (%zu < %zu)", plan_bytes, p.bytes);
+    return FR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  FR_CUDA_OK(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)n_items * G, st));
+  FR_LAUNCH(fr::k_item_group_stats, fr::grid_for(n_pos, 256, fr::kSMs * 8), 256, 0, st, p.skey, p.ord, p.segoff, p.nseg,
+            pos_score, group, G, stats_out);
+  FR_LAUNCH_CHECK();
+  return FR_OK;
+}
+
 size_t fr_fairness_metrics_workspace_bytes(int32_t n_items, int32_t G) {
   const size_t nblk = (size_t)(n_items + 255) / 256;
   return (nblk * (1 + 2 * (size_t)G) + nblk * 5 + (1 + 2 * (size_t)G) + 8) * 8 + 512;
@@ -407,12 +624,10 @@ int fr_fairness_metrics(const double *stats, int32_t n_items, int32_t G, double 
   double *partB = c.take<double>((size_t)nblk * 5);
   double *totA = c.take<double>(VA);
   double *totB = c.take<double>(8);
-  FR_LAUNCH(fr::k_fair_pass_a, nblk, 256, 0, stream, stats, n_items, G, partA);
-  FR_LAUNCH(fr::k_reduce_rows, (VA + 127) / 128, 128, 0, stream, (const double *)partA, nblk, VA, totA);
-  FR_LAUNCH(fr::k_fair_mid, 1, 1, 0, stream, (const double *)totA, G, out);
-  FR_LAUNCH(fr::k_fair_pass_b, nblk, 256, 0, stream, stats, n_items, G, (const double *)totA, partB);
-  FR_LAUNCH(fr::k_reduce_rows, 1, 128, 0, stream, (const double *)partB, nblk, 5, totB);
-  FR_LAUNCH(fr::k_fair_final, 1, 1, 0, stream, (const double *)totB, G, out);
+  (void)totA;
+  unsigned int *ticket = (unsigned int *)totB;
+  FR_LAUNCH(fr::k_fair_pass_a, nblk, 256, 0, stream, stats, n_items, G, partA, ticket);
+  FR_LAUNCH(fr::k_fair_pass_b, nblk, 256, 0, stream, stats, n_items, G, (const double *)partA, nblk, partB, ticket, out);
   FR_LAUNCH_CHECK();
   return FR_OK;
 }

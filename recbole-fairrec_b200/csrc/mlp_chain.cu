@@ -668,7 +668,7 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_fwd(const __
   const ChHead &P = *cx.head;
   const Pipe &pipe = cx.pipe;
   const Epi &e = cx.e;
-  const int warp = cx.warp, lane = cx.lane;
+  const int warp = cx.warp;
   uint32_t it = 0, gi = 0;
   unsigned target = 0;
   int tslot = 0;
@@ -911,7 +911,7 @@ static __global__ void __launch_bounds__(CH_THREADS, 1) k_mlp_chain_bwd(const __
   const ChHead &P = *cx.head;
   const Pipe &pipe = cx.pipe;
   const Epi &e = cx.e;
-  const int warp = cx.warp, lane = cx.lane;
+  const int warp = cx.warp;
   uint32_t it = 0, gi = 0;
   unsigned target = 0;
   const int chunks = ch_tiles(P.M, CH_WCHUNK);

@@ -159,6 +159,30 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// two tables in one launch (the scorer's users and items: one launch less in an evaluation pass)
+static __global__ void __launch_bounds__(256)
+    k_split_planes2(const float *__restrict__ src0, const int32_t *__restrict__ idx0, int64_t n0, float *__restrict__ hi0,
+                    float *__restrict__ lo0, const float *__restrict__ src1, int64_t n1, float *__restrict__ hi1,
+                    float *__restrict__ lo1, int d) {
+  const int dq = d >> 2;
+  const int64_t nq0 = n0 * dq, nq = nq0 + n1 * dq;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const bool first = q < nq0;
+    const int64_t qq = first ? q : q - nq0;
+    const int64_t r = qq / dq;
+    const int c = (int)(qq % dq);
+    const int64_t sr = (first && idx0) ? (int64_t)idx0[r] : r;
+    const float4 x = __ldg((const float4 *)((first ? src0 : src1) + sr * d) + c);
+    float4 h, l;
+    h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
+    h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
+    h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
+    h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
+    *((float4 *)((first ? hi0 : hi1) + r * d) + c) = h;
+    *((float4 *)((first ? lo0 : lo1) + r * d) + c) = l;
+  }
+}
+
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

@@ -219,20 +219,39 @@ class FullSortEvaluator:
             for ai, attr in enumerate(attrs):
                 G = data.n_groups[attr]
                 if self.group is None:
-                    stats = kernels.item_group_stats(data.pos_items, pos_score, data.group_of_pos[attr], self.n_items, G)
+                    plan = self._ig_plan(data, None)
+                    stats = kernels.item_group_stats_planned(plan["plan"], pos_score, data.group_of_pos[attr], self.n_items, G)
                 else:
                     import torch.distributed as dist
                     world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-                    lo, hi = shard_bounds(self.n_items, world, rank)
-                    own = (data.pos_items >= lo) & (data.pos_items < hi)
-                    stats = torch.zeros((self.n_items, G, 2), dtype=torch.float64, device=U.device)
-                    if bool(own.any()):
-                        stats = kernels.item_group_stats(data.pos_items[own].contiguous(), pos_score[own].contiguous(),
-                                                         data.group_of_pos[attr][own].contiguous(), self.n_items, G)
+                    plan = self._ig_plan(data, shard_bounds(self.n_items, world, rank))
+                    if plan["n"] > 0:     # the positives whose item this rank owns (a host constant of the plan: no sync)
+                        if attr not in plan["group"]:
+                            plan["group"][attr] = data.group_of_pos[attr].index_select(0, plan["idx"]).contiguous()
+                        stats = kernels.item_group_stats_planned(plan["plan"], pos_score.index_select(0, plan["idx"]),
+                                                                 plan["group"][attr], self.n_items, G)
+                    else:
+                        stats = torch.zeros((self.n_items, G, 2), dtype=torch.float64, device=U.device)
                     dist.all_reduce(stats, group=self.group)  # disjoint supports: x + 0, order-independent
                 out["fair"][attr] = kernels.fairness_metrics(stats)
         self.last = out
         return out
+
+    def _ig_plan(self, data, bounds):
+        """The item-sorted view of the positive list (fr_item_group_plan) -- of the positives whose item lies in `bounds` for
+        an item-sharded pass -- depends on the evaluation data only: built once per EvalData and kept on it."""
+        cache = data.__dict__.setdefault("_ig_plans", {})
+        key = (self.n_items, bounds)
+        if key not in cache:
+            if bounds is None:
+                cache[key] = {"plan": kernels.item_group_plan(data.pos_items, self.n_items), "n": data.n_pos}
+            else:
+                lo, hi = bounds
+                idx = torch.nonzero((data.pos_items >= lo) & (data.pos_items < hi), as_tuple=False).view(-1)
+                n_own = int(idx.numel())
+                plan = kernels.item_group_plan(data.pos_items.index_select(0, idx).contiguous(), self.n_items) if n_own else None
+                cache[key] = {"plan": plan, "n": n_own, "idx": idx, "group": {}}
+        return cache[key]
 
     def collect_graphed(self, U, I, data, max_rating, transform=_lib.TRANSFORM_CLAMP_DIV):
         """collect() captured once into a CUDA graph and replayed: the pass is ~35 small launches, so at the ML-1M

@@ -335,6 +335,27 @@ def item_group_stats(pos_items, pos_score, group, n_items, G):
     return out
 
 
+def item_group_plan(pos_items, n_items):
+    """the item-sorted view of a positive list (uint8 plan buffer): depends on the evaluation data only, build it once"""
+    lib = load()
+    n_pos = pos_items.numel()
+    plan = torch.empty(max(int(lib.fr_item_group_plan_bytes(n_pos)), 256), dtype=torch.uint8, device=pos_items.device)
+    ws = _ws(lib.fr_item_group_plan_workspace_bytes(n_pos), pos_items.device)
+    check(lib.fr_item_group_plan(ptr(pos_items), n_pos, n_items, ptr(plan), plan.numel(), ptr(ws), ws.numel(), stream_ptr()),
+          "fr_item_group_plan")
+    return plan
+
+
+def item_group_stats_planned(plan, pos_score, group, n_items, G):
+    """item_group_stats() over a positive list whose plan exists: the segment reduction alone"""
+    lib = load()
+    n_pos = pos_score.numel()
+    out = torch.empty((n_items, G, 2), dtype=torch.float64, device=pos_score.device)
+    check(lib.fr_item_group_stats_planned(ptr(plan), plan.numel(), ptr(pos_score), ptr(group), n_pos, n_items, G, ptr(out),
+                                          stream_ptr()), "fr_item_group_stats_planned")
+    return out
+
+
 def fairness_metrics(stats):
     """float64 [7]: DF, value, absolute, under, over, nonparity, J"""
     lib = load()

@@ -177,9 +177,45 @@ def test_kat2_metric_kernels():
     np.testing.assert_allclose([h[:k].sum() / (3 * k) for k in (1, 2, 3)], [1, 2 / 3, 5 / 9])
 
 
+@pytest.mark.parametrize("n_users", [5000, 20000])
+@pytest.mark.parametrize("n_items", [1, 2, 777, 4096, 8192, 8193, 30000])
+def test_gini_small_and_radix_paths_vs_numpy(n_items, n_users):
+    """fr_gini_at_k: a one-CTA histogram over the count values when there are fewer than 8192 users, else a one-CTA
+    shared-memory sort up to 8192 items, else the radix sort -- the same integer sum every way (metrics.py:644-661 on the
+    summed rank rows)."""
+    from recbole_fairrec_b200 import kernels
+    rng = np.random.default_rng(n_items)
+    K = 3
+    cnt = rng.integers(0, 40, size=(K, n_items)).astype(np.int32)
+    cnt[:, : max(1, n_items // 50)] = n_users // K   # a few very popular items (the largest admissible count)
+    cnt[:, rng.random(n_items) < 0.3] = 0
+    for k in (1, 3):
+        c = np.sort(cnt[:k].sum(axis=0).astype(np.int64))
+        want = float(((2 * np.arange(1, n_items + 1) - n_items - 1) * c).sum()) / float(n_users * k) / float(n_items)
+        got = kernels.gini_at_k(torch.from_numpy(cnt).cuda(), k, n_users).item()
+        assert got == want, (n_items, k, got, want)
+
+
+def test_item_group_stats_planned_equals_unplanned():
+    """fr_item_group_plan + fr_item_group_stats_planned (the sort of the positives hoisted out of the pass) = fr_item_group_stats,
+    bit for bit, and the plan is reusable with new scores."""
+    from recbole_fairrec_b200 import kernels
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_pos, n_items, G = 50_000, 3707, 3
+    item = torch.randint(1, n_items, (n_pos,), device="cuda", generator=g, dtype=torch.int32)
+    grp = torch.randint(0, G, (n_pos,), device="cuda", generator=g, dtype=torch.int32)
+    plan = kernels.item_group_plan(item, n_items)
+    for _ in range(2):
+        score = torch.rand(n_pos, device="cuda", generator=g)
+        a = kernels.item_group_stats(item, score, grp, n_items, G)
+        b = kernels.item_group_stats_planned(plan, score, grp, n_items, G)
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("n_users,n_items,d,n_eval,K", [(700, 1683, 64, 650, 10), (3000, 3707, 64, 2900, 10),
                                                        (500, 9000, 128, 333, 20), (400, 1000, 32, 257, 5),
-                                                       (300, 2100, 96, 129, 10)])
+                                                       (300, 2100, 96, 129, 10), (350, 1500, 64, 300, 16),
+                                                       (350, 1500, 64, 300, 12)])
 def test_tc_scorer_matches_exact_scorer(n_users, n_items, d, n_eval, K):
     """FR_SCORE_TC_3XTF32 (tcgen05 + TMA, 3xTF32) against the bit-defined exact scorer: scores within fp32-level
     tolerance; ids identical wherever the exact top-(K+1) is separated by more than that tolerance (near-tie
