@@ -549,6 +549,10 @@ def run_ours(args, w):
         _lib.profile_enable(False)
         tc_cnt, tc_ms = prof_e.get("k_fullsort_tc", (1, float("nan")))
         tc_peak = bf16 / 2.0 / 3.0
+        try:
+            bf16_sus = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained") or 0.0)
+        except Exception:
+            bf16_sus = 0.0
         flops = 2.0 * edata.n * (ni / world) * d
         etot = sum(v[1] for v in prof_e.values()) or 1.0
         ach = flops / (tc_ms / tc_cnt * 1e-3) / 1e12
@@ -564,9 +568,12 @@ def run_ours(args, w):
                            "avg_launch_us": 1e3 * tc_ms / tc_cnt, "share_of_pass": round(tc_ms / etot, 4),
                            "peak_source": f"{peak_src}: bf16 {bf16} / 2 (tf32) / 3 (3xTF32)",
                            "nominal_peak": 2250.0 / 2.0 / 3.0, "frac_of_nominal": ach / (2250.0 / 2.0 / 3.0),
-                           "note": "frac can exceed 1: the measured bf16 figure is cuBLAS at the 1000 W power cap (SM clock "
-                                   "~1.33 GHz under load in MEASURED_PEAKS.json), kind::tf32 at half the MAC rate stays near the "
-                                   "full clock; nominal_peak = 2.25 PFLOP/s bf16 / 2 / 3 (B200_PROFILING.md)"},
+                           "peak_sustained": bf16_sus / 6.0 if bf16_sus else None,
+                           "frac_of_sustained": ach / (bf16_sus / 6.0) if bf16_sus else None,
+                           "note": "peak = the BURST bf16 figure / 6 although a pass is a 0.5-s kernel (the sustained figure / 6 "
+                                   "is peak_sustained); the same kernel timed alone with idle gaps reaches 297-300 TFLOP/s "
+                                   "(profiles/r02_tc_scorer.md), back to back the board's power management takes ~10 %; "
+                                   "nominal_peak = 2.25 PFLOP/s bf16 / 2 / 3 (B200_PROFILING.md)"},
               "kernel_shares": {k: round(v[1] / etot, 4) for k, v in sorted(prof_e.items(), key=lambda kv: -kv[1][1])[:6]},
               "metrics": {k: float(v) for k, v in res.items()}}
         del edata, evaluator

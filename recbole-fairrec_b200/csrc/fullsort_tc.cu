@@ -430,6 +430,10 @@ size_t tc_plane_bytes(int n, int n_items_local, int d) {
 // (ceil(kSMs / utiles) made 188 CTAs = two waves of 8 tiles at the ML-1M shape; 3 splits are one wave of 10.)
 int tc_pick_splits(int n, int n_items_local) {
   const int utiles = (n + TCM - 1) / TCM, itiles = (n_items_local + TCN - 1) / TCN;
+  if (const char *e = getenv("FR_TC_SPLITS")) {   // (timing knob)
+    const int want = atoi(e);
+    if (want >= 1 && want <= 32 && want <= itiles) return want;
+  }
   int best = 1;
   long long best_cost = -1;
   for (int s = 1; s <= 32 && s <= itiles; ++s) {
