@@ -322,6 +322,9 @@ typedef struct fr_chain_layer {
   int32_t has_bn;
   float drop_p;              /* dropout on the layer INPUT (training only) */
   float bn_eps, bn_momentum;
+  int32_t bn_repeat;         /* training forward: apply the running-statistics update this many times (0 or 1 = once).  2 = the
+                              * reference's PFCN loss, which evaluates the deterministic filter twice on the same batch
+                              * (pfcn_mlp.py:177-193): same output, the running statistics advance twice */
   uint64_t seed;             /* dropout seed of this layer */
   const float *W, *b;        /* [N,K], [N] or NULL */
   const float *gamma, *beta; /* BatchNorm affine */

@@ -109,7 +109,7 @@ class SpmmPlan(Structure):
 class ChainLayer(Structure):
     """mirror of `struct fr_chain_layer`"""
     _fields_ = [("K", c_int32), ("N", c_int32), ("act", c_int32), ("has_bn", c_int32), ("drop_p", c_float),
-                ("bn_eps", c_float), ("bn_momentum", c_float), ("seed", c_uint64), ("W", c_void_p), ("b", c_void_p),
+                ("bn_eps", c_float), ("bn_momentum", c_float), ("bn_repeat", c_int32), ("seed", c_uint64), ("W", c_void_p), ("b", c_void_p),
                 ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
                 ("num_batches_tracked", c_void_p), ("dW", c_void_p), ("db", c_void_p), ("dgamma", c_void_p),
                 ("dbeta", c_void_p)]

@@ -323,13 +323,20 @@ __global__ void __launch_bounds__(256) k_fair_pass_b(const double *__restrict__ 
   __shared__ bool last;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int VA = 1 + 2 * G;
-  if (threadIdx.x < (blockIdx.x == 0 ? VA : 1)) {
-    double t = 0.0;
-    for (int b = 0; b < nblk; ++b) t += partA[(size_t)b * VA + threadIdx.x];
-    totA[threadIdx.x] = t;
+  // J is a count (integer-valued: exact in any order), so every CTA adds the partial J's with all its threads -- a serial
+  // walk per CTA is O(nblk^2) in total: 0.7 ms at 1 M items; the group totals (order matters) only CTA 0 needs
+  double jl = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 256) jl += partA[(size_t)b * VA];
+  const double J = block_sum_d(jl, sh);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x >= 1 && threadIdx.x < VA) {
+      double t = 0.0;
+      for (int b = 0; b < nblk; ++b) t += partA[(size_t)b * VA + threadIdx.x];
+      totA[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) totA[0] = J;
+    __syncthreads();
   }
-  __syncthreads();
-  const double J = totA[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) fair_mid(totA, G, out);
   double eps = 0.0, vv = 0.0, va = 0.0, vu = 0.0, vo = 0.0;
   bool any = false;

@@ -50,6 +50,7 @@ constexpr int CH_EW = 1024;                           // elements per flat eleme
 struct ChLayer {
   int K, N, ldn, NT, KT, act, has_bn, first_of_chain, last_of_chain, chain;
   float drop_p, bn_eps, bn_mom;
+  int bn_repeat;
   unsigned long long seed;
   const float *W, *b, *gamma, *beta;
   float *rmean, *rvar;
@@ -558,9 +559,14 @@ __device__ __forceinline__ void bn_fwd_finalize(const ChHead &P, const ChLayer &
       L.save_mean[n] = (float)mean;
       L.save_invstd[n] = invstd;
       const double unb = P.Mg > 1 ? var * (double)P.Mg / (double)(P.Mg - 1) : var;
-      L.rmean[n] = (1.f - L.bn_mom) * rm0 + L.bn_mom * (float)mean;
-      L.rvar[n] = (1.f - L.bn_mom) * rv0 + L.bn_mom * (float)unb;
-      if (n == 0 && L.nbt) *L.nbt += 1;
+      float rm = rm0, rv = rv0;
+      for (int r = 0; r < L.bn_repeat; ++r) {   // (bn_repeat forward passes over the same batch: fr_chain_layer.bn_repeat)
+        rm = (1.f - L.bn_mom) * rm + L.bn_mom * (float)mean;
+        rv = (1.f - L.bn_mom) * rv + L.bn_mom * (float)unb;
+      }
+      L.rmean[n] = rm;
+      L.rvar[n] = rv;
+      if (n == 0 && L.nbt) *L.nbt += L.bn_repeat;
     }
   }
   bar_epi();
@@ -1340,6 +1346,7 @@ static int build_params(const fr_chain *chains, int n_chains, int64_t M, int tra
       L.drop_p = s.drop_p;
       L.bn_eps = s.bn_eps;
       L.bn_mom = s.bn_momentum;
+      L.bn_repeat = s.bn_repeat > 1 ? s.bn_repeat : 1;
       L.seed = s.seed;
       L.W = s.W;
       L.b = s.b;

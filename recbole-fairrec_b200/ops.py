@@ -210,6 +210,28 @@ def _pairs_of(mod):
     return pairs
 
 
+_bn_repeat = 1     # see bn_repeat()
+
+
+class bn_repeat:
+    """Context: the fused chain forwards launched inside apply their BatchNorm running-statistics update `n` times
+    (fr_chain_layer.bn_repeat).  For a DETERMINISTIC chain (no dropout) evaluated n times on the same batch in training
+    mode -- the reference's PFCN loss runs the filter twice per step (pfcn_mlp.py:177-193) -- one launch with n = 2 leaves
+    the same outputs and the same buffers as two launches."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        global _bn_repeat
+        self.prev, _bn_repeat = _bn_repeat, self.n
+        return self
+
+    def __exit__(self, *a):
+        global _bn_repeat
+        _bn_repeat = self.prev
+
+
 def _chain_layers(mod, training, seeds=None):
     """ctypes layer array of a chain (pointers filled, gradients not) + its pairs; (None, pairs) = outside the rules"""
     from ._lib import ChainLayer
@@ -231,6 +253,7 @@ def _chain_layers(mod, training, seeds=None):
             L.gamma, L.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
             L.running_mean, L.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
             L.num_batches_tracked = bn.num_batches_tracked.data_ptr()
+            L.bn_repeat = _bn_repeat
     return arr, pairs
 
 
@@ -487,10 +510,8 @@ def chain_dp_emulate(rank_mods, rank_xs, rank_dys):
     return outs
 
 
-def mlp_chain(mods, xs):
-    """Run MLPLayers modules `mods` over inputs `xs` (one shared input, or one per module; all [M, K]) with the fused chain
-    kernels.  Returns the list of outputs, or None when the configuration is outside the kernels' rules (the caller then
-    uses the per-layer path)."""
+def _chain_check(mods, xs):
+    """(training, grad, n_layers) when the fused chain kernels take `mods` over `xs`, else None (see mlp_chain)"""
     if not chain_enabled() or not xs[0].is_cuda or len(mods) > 4 or len(xs) not in (1, len(mods)):
         return None
     M = xs[0].shape[0]
@@ -515,6 +536,23 @@ def mlp_chain(mods, xs):
         total += len(pairs)
     if total > 24:
         return None
+    return training, grad, n_layers
+
+
+def mlp_chain_would_fuse(mods, xs):
+    """True when MLPLayers.forward / mlp_chain run these modules on the fused chain kernels (which honour bn_repeat)"""
+    return _chain_check(mods, xs) is not None
+
+
+def mlp_chain(mods, xs):
+    """Run MLPLayers modules `mods` over inputs `xs` (one shared input, or one per module; all [M, K]) with the fused chain
+    kernels.  Returns the list of outputs, or None when the configuration is outside the kernels' rules (the caller then
+    uses the per-layer path)."""
+    chk = _chain_check(mods, xs)
+    if chk is None:
+        return None
+    training, grad, n_layers = chk
+    M = xs[0].shape[0]
     params = [p for m, nl in zip(mods, n_layers) for p in _chain_params(_chain_layers(m, training)[1])]
     if not training and M > CHAIN_EVAL_CHUNK:
         outs = [[] for _ in mods]

@@ -142,6 +142,40 @@ class _PFCNBase(nn.Module):
         user_embed = self._apply_filters(self._user_base(user), sst_list)
         return user_embed, (None if item is None else self._item_base(item))
 
+    # The reference's loss evaluates forward(user) TWICE on the same batch (pfcn_mlp.py:177-193: once for the scorer, once more
+    # inside calculate_dis_loss).  Where the user path is deterministic in training mode (no dropout: the filters never have
+    # one) the two passes return the same tensor and differ only in that the BatchNorm buffers advance twice -- so one pass
+    # with ops.bn_repeat(2) and the tensor shared by both consumers is the same computation (autograd adds the two
+    # gradients at the shared output instead of after two backward passes: one filter forward, one filter backward, one
+    # embedding gather and one gradient scatter less per step).  Needs the fused chain kernels (they own the buffer
+    # update); anything else keeps the second evaluation.
+    SHARE_USER_FORWARD = True
+
+    def _user_path_dropout(self):
+        return 0.0
+
+    def _filters_of(self, sst_list):
+        if self.filter_mode == "none":
+            return []
+        if self.filter_mode == "sm":
+            return [self.filter_layer[sum(self.sst_dict[s] for s in sst_list)]]
+        return [self.filter_layer[self.sst_dict[s]] for s in sst_list]
+
+    def _forward_for_loss(self, user, item, sst_list):
+        """forward() for calculate_loss: -> (user_embed, item_embed, shared) with shared = the filtered embedding also
+        stands for the loss's second evaluation (the BatchNorm buffers have advanced twice already)"""
+        share = False
+        if self.SHARE_USER_FORWARD and self.filter_mode != "none" and self.training and self._user_path_dropout() == 0.0:
+            base = self._user_base(user)
+            mods = self._filters_of(sst_list)
+            if all(m.dropout == 0.0 and ops.mlp_chain_would_fuse([m], [base]) for m in mods):
+                with ops.bn_repeat(2):
+                    user_embed = self._apply_filters(base, sst_list)
+                return user_embed, (None if item is None else self._item_base(item)), True
+            return self._apply_filters(base, sst_list), (None if item is None else self._item_base(item)), False
+        user_embed, item_embed = self.forward(user, item, sst_list)
+        return user_embed, item_embed, share
+
     def calculate_dis_loss(self, interaction, sst_list=None):
         """pfcn_mlp.py:195-211.  Called on its own (the discriminator phase, trainer.py:889-892) only the discriminators
         are optimised, so the filtered embedding enters as a constant: the reference back-propagates into the filters
@@ -164,12 +198,14 @@ class _PFCNBase(nn.Module):
                 loss = loss + ops.SoftmaxCe.apply(z, interaction[sst].to(device=dev, dtype=torch.int32))
         return loss
 
-    def _with_dis(self, bpr, interaction, sst_list):
+    def _with_dis(self, bpr, interaction, sst_list, shared_user_embed=None):
         """pfcn_mlp.py:188-191: the reference re-evaluates forward(user) inside calculate_dis_loss (a second pass through
-        the filter in training mode: BatchNorm running statistics advance twice per step) -- kept"""
+        the filter in training mode: BatchNorm running statistics advance twice per step) -- kept, either literally or as
+        the shared pass of _forward_for_loss"""
         if self.filter_mode != "none":
-            user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
-            return bpr - self.dis_weight * self._dis_terms(user_embed, interaction, sst_list)
+            if shared_user_embed is None:
+                shared_user_embed, _ = self.forward(interaction[self.USER_ID], None, sst_list)
+            return bpr - self.dis_weight * self._dis_terms(shared_user_embed, interaction, sst_list)
         return bpr
 
     def full_sort_predict(self, interaction, sst_list=None):
@@ -209,7 +245,7 @@ class PFCN_MLP(_PFCNBase):
 
     def calculate_loss(self, interaction, sst_list=None):
         """pfcn_mlp.py:177-193: BPR(pos, neg) - dis_weight * discriminator loss"""
-        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        user_embed, pos_embed, shared = self._forward_for_loss(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
         neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
         # the positive and the negative pass of the tower share one forward and one backward launch (two chains of the same
         # module: autograd adds their weight gradients); None = per-module path
@@ -219,7 +255,7 @@ class PFCN_MLP(_PFCNBase):
             bpr = ops.BprLoss.apply(both[0], both[1])
         else:
             bpr = ops.BprLoss.apply(self._score(user_embed, pos_embed), self._score(user_embed, neg_embed))
-        return self._with_dis(bpr, interaction, sst_list)
+        return self._with_dis(bpr, interaction, sst_list, user_embed if shared else None)
 
 
 class PFCN_PMF(_PFCNBase):
@@ -236,10 +272,10 @@ class PFCN_PMF(_PFCNBase):
 
     def calculate_loss(self, interaction, sst_list=None):
         """pfcn_pmf.py:176-193"""
-        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        user_embed, pos_embed, shared = self._forward_for_loss(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
         neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
         bpr = ops.BprLoss.apply(ops.RowDot.apply(user_embed, pos_embed), ops.RowDot.apply(user_embed, neg_embed))
-        return self._with_dis(bpr, interaction, sst_list)
+        return self._with_dis(bpr, interaction, sst_list, user_embed if shared else None)
 
 
 class PFCN_BiasedMF(_PFCNBase):
@@ -266,12 +302,12 @@ class PFCN_BiasedMF(_PFCNBase):
     def calculate_loss(self, interaction, sst_list=None):
         """pfcn_biasedmf.py:183-199 (the [B] + [B,1] broadcast makes the BPR run over B*B pairs)"""
         user, pos, neg = interaction[self.USER_ID], interaction[self.POS_ITEM_ID], interaction[self.NEG_ITEM_ID]
-        user_embed, pos_embed = self.forward(user, pos, sst_list)
+        user_embed, pos_embed, shared = self._forward_for_loss(user, pos, sst_list)
         neg_embed = self._item_base(neg)
         bpr = ops.BprOuter.apply(ops.RowDot.apply(user_embed, pos_embed), ops.RowDot.apply(user_embed, neg_embed),
                                  self._bias(self.user_bias, user), self._bias(self.item_bias, pos),
                                  self._bias(self.item_bias, neg), self.global_bias.view(1))
-        return self._with_dis(bpr, interaction, sst_list)
+        return self._with_dis(bpr, interaction, sst_list, user_embed if shared else None)
 
 
 class PFCN_DMF(_PFCNBase):
@@ -299,6 +335,9 @@ class PFCN_DMF(_PFCNBase):
         self.item_mlp = MLPLayers([e] * (self.num_layers + 1), dropout=self.mlp_dropout, activation=self.mlp_activation,
                                   init_method="norm")
 
+    def _user_path_dropout(self):
+        return float(self.mlp_dropout)          # the user tower draws a new dropout mask per evaluation: no sharing unless 0
+
     def _user_base(self, user):
         return self.user_mlp(super()._user_base(user))
 
@@ -312,11 +351,11 @@ class PFCN_DMF(_PFCNBase):
 
     def calculate_loss(self, interaction, sst_list=None):
         """pfcn_dmf.py:180-199"""
-        user_embed, pos_embed = self.forward(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
+        user_embed, pos_embed, shared = self._forward_for_loss(interaction[self.USER_ID], interaction[self.POS_ITEM_ID], sst_list)
         neg_embed = self._item_base(interaction[self.NEG_ITEM_ID])
         pos = ops.WeightedSum.apply(10.0, ops.CosineSim.apply(user_embed, pos_embed))
         neg = ops.WeightedSum.apply(10.0, ops.CosineSim.apply(user_embed, neg_embed))
-        return self._with_dis(ops.BprLoss.apply(pos, neg), interaction, sst_list)
+        return self._with_dis(ops.BprLoss.apply(pos, neg), interaction, sst_list, user_embed if shared else None)
 
 
 class _DpOptimizer:

@@ -246,6 +246,58 @@ def test_pfcn_mlp_ml1m_widths_vs_oracle(filter_mode):
     assert checked > 30 and min(rel_tols) <= 1.5 * RTOL and float(np.median(rel_tols)) < 2e-3, (min(rel_tols), np.median(rel_tols))
 
 
+@pytest.mark.parametrize("model_name,filter_mode", [("PFCN_MLP", "sm"), ("PFCN_MLP", "cm"), ("PFCN_PMF", "sm"),
+                                                    ("PFCN_BiasedMF", "cm"), ("PFCN_DMF", "sm")])
+def test_shared_user_forward_equals_second_evaluation(model_name, filter_mode):
+    """calculate_loss with the filter evaluated once and its BatchNorm buffers advanced twice (ops.bn_repeat(2), the shared
+    pass of _forward_for_loss) against the literal second evaluation of the reference's loss (pfcn_mlp.py:177-193): buffers
+    bit-equal, loss equal, gradients equal up to the order in which the two consumers' gradients are added."""
+    rng = np.random.default_rng(11)
+    nu, ni, d, B = 900, 400, 64, 1024
+    feats = {"gender": rng.integers(0, 2, nu).astype(np.float32), "age": rng.integers(0, 7, nu).astype(np.float32)}
+    torch.manual_seed(3)
+    cfg, model = build(model_name, filter_mode, nu, ni, d, feats, [32, 16], [64, 32], dis_weight=2.0)
+    st0 = {k: torch.from_numpy(v.copy()) for k, v in dump_state(model).items()}
+    import recbole_fairrec_b200 as pkg
+    u = rng.integers(1, nu, B)
+    inter = pkg.Interaction({"user_id": torch.from_numpy(u), "item_id": torch.from_numpy(rng.integers(1, ni, B)),
+                             "neg_item_id": torch.from_numpy(rng.integers(1, ni, B)),
+                             **{a: torch.from_numpy(feats[a][u]) for a in feats}})
+    sst_list = ["gender", "age"]
+    runs = {}
+    for share in (True, False):
+        load_state(model, st0)
+        model.zero_grad(set_to_none=True)
+        for m in owners(model).values():
+            m.zero_grad(set_to_none=True)
+        model.SHARE_USER_FORWARD = share
+        model.train()
+        loss = model.calculate_loss(inter, sst_list)
+        loss.backward()
+        runs[share] = (loss.item(), dump_state(model), {k: (None if p.grad is None else p.grad.cpu().numpy().copy())
+                                                        for k, p in named_params(model).items()})
+    model.SHARE_USER_FORWARD = True
+    (la, sa, ga), (lb, sb, gb) = runs[True], runs[False]
+    np.testing.assert_allclose(la, lb, rtol=1e-6)
+    moved = 0
+    for k in sa:
+        if "running_" in k or "num_batches_tracked" in k:
+            np.testing.assert_array_equal(sa[k], sb[k], err_msg=k)
+            moved += int(not np.array_equal(sa[k], st0[k].numpy()))
+    assert moved > 0        # the used filters' buffers did advance (twice: the values equal the two-pass run's)
+    used = 0
+    for k in ga:
+        if ga[k] is None or gb[k] is None:
+            assert (ga[k] is None or not ga[k].any()) and (gb[k] is None or not gb[k].any()), k
+            continue
+        scale = max(float(np.abs(gb[k]).max()), 1e-12)
+        if bias_before_bn(k, st0):
+            continue
+        assert float(np.abs(ga[k] - gb[k]).max()) <= 2e-5 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()) / scale)
+        used += 1
+    assert used > 8
+
+
 def test_pfcn_mlp_trainer_epoch_runs_and_learns():
     """PFCN_MLPTrainer._train_epoch: alternating passes, finite losses, the discriminator loss goes down"""
     import recbole_fairrec_b200 as pkg
