@@ -101,7 +101,12 @@ def _profile(step_fn, batch, n=5):
     _lib.profile_enable(False)
     tot = sum(v[1] for v in prof.values()) or 1.0
     shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    global LAST_COUNTS     # launches per step and mean microseconds per launch of every library kernel of the step
+    LAST_COUNTS = {k: [round(v[0] / n, 2), round(1e3 * v[1] / max(v[0], 1), 1)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     return shares, sum(v[0] for v in prof.values()) / n, tot / n
+
+
+LAST_COUNTS = {}
 
 
 def bench_pfcn(dev, flush, n_steps=30, cpu=True, seed=2020):
@@ -156,7 +161,8 @@ def bench_pfcn(dev, flush, n_steps=30, cpu=True, seed=2020):
                       "attrs": {a: int(len(np.unique(feats[a][1:]))) for a in attrs}, "dropout": [0.2, 0.3],
                       "step": "filter-phase step + discriminator-phase step on one batch"},
            "e2e": {"value": B / t_e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
-           "gpu_launches_per_step": launches, "kernel_ms_per_step": kernel_ms, "kernel_shares": shares}
+           "gpu_launches_per_step": launches, "kernel_ms_per_step": kernel_ms, "kernel_shares": shares,
+           "kernel_launches_and_us": dict(LAST_COUNTS)}
     if cpu:
         out["cpu_baseline"] = cpu_pfcn(model, feats, hosts, sst_list)
     return out

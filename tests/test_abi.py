@@ -40,7 +40,8 @@ def test_binding_covers_header():
     # struct mirrors: same field count/order as the header
     src = open(HEADER).read()
     for cname, pystruct in (("fr_focf_step", pkg._lib.FocfStep), ("fr_fullsort", pkg._lib.FullSort),
-                            ("fr_focf_shard_step", pkg._lib.FocfShardStep)):
+                            ("fr_focf_shard_step", pkg._lib.FocfShardStep), ("fr_chain_layer", pkg._lib.ChainLayer),
+                            ("fr_chain", pkg._lib.Chain)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
