@@ -333,6 +333,33 @@ def run_ours(args, w):
         out_modes["lazy_exact"], prof_modes["lazy_exact"] = run_mode("lazy_exact")
         rows_per_gpu_tab = nu + ni
         parallelism = "single GPU"
+        # ---- the same dense_exact steps through the planned runner (FOCF.planned_runner, persistent=False): the whole epoch
+        # planned on the device, the step captured into CUDA graphs of 8 with the preparation of batch t + 1 (gather, sort,
+        # segments: independent of the tables) on a second stream under the Adam sweep of batch t
+        pipelined = None
+        if os.environ.get("FR_BENCH_PIPELINED", "1") != "0":
+            try:
+                model.init_adam(lr=1e-3, weight_decay=1e-3, mode="dense_exact", max_steps=n_plan + 4096)
+                lbuf = torch.zeros(8192, device=dev)
+                runner = model.planned_runner(loader, lbuf, graph_steps=8, persistent=False)
+                runner.run(W_ + ((W_ + runner.cursor) & 1))          # (an even cursor: the 8-step graphs start on workspace 0)
+                torch.cuda.synchronize()
+                c0 = runner.cursor
+                pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pa.record()
+                prow = runner.run(K_)
+                pb.record()
+                torch.cuda.synchronize()
+                model.check_flags()
+                pms = pa.elapsed_time(pb)
+                pl = lbuf[c0:c0 + K_].cpu().numpy()
+                pipelined = {"value": prow / (pms * 1e-3), "unit": "interactions/s", "ms_per_step": pms / K_, "steps": K_,
+                             "rows": int(prow), "losses_finite": bool(np.isfinite(pl).all()), "loss_first_last": [float(pl[0]), float(pl[-1])],
+                             "what": "FOCF.planned_runner(persistent=False): CUDA graphs of 8 steps, prepare(t + 1) on a second stream "
+                                     "under compute(t); same kernels and arithmetic as `value` (bit-identical steps: "
+                                     "tests/test_focf_train_gpu.py::test_planned_graph_epoch_equals_stepwise_epoch)"}
+            except Exception as e:
+                pipelined = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     else:
         sd = sharded.ShardedTrainData(tr_u, tr_i, tr_r.float(), gender, nu, ni, rank, world, dev)
         n_train = sd.n_rows
@@ -341,6 +368,7 @@ def run_ours(args, w):
         losses = torch.zeros(n_plan, device=dev)
         uf, itf, rf, sf = "user_id", "item_id", "rating", "gender"
         model = None
+        pipelined = None
 
         def run_mode(mode):
             m = sharded.ShardedFOCF(sd, d, objective="value", fair_weight=1.0, lr=1e-3, weight_decay=1e-3, adam_mode=mode,
@@ -667,6 +695,7 @@ def run_ours(args, w):
         "cpu_baseline": cpu,
         "e2e": e2e,
         "lazy_exact": lazy,
+        "pipelined": pipelined if world == 1 else None,
         "eval": ev,
         "dp_check": dp_check,
         "ml1m": ml1m,
