@@ -15,6 +15,8 @@ and summed with one all-reduce.
 """
 from collections import OrderedDict
 
+import os
+
 import numpy as np
 import torch
 
@@ -157,6 +159,9 @@ class FullSortEvaluator:
         self.score_mode = {"exact": _lib.SCORE_EXACT_FP32, "tc": _lib.SCORE_TC_3XTF32}[mode]
         self.score_mode_name = mode
         self.group = group
+        # the three metric chains behind the scorer on forked streams (FR_EVAL_STREAMS=0: one stream, as before)
+        self.branch_streams = os.environ.get("FR_EVAL_STREAMS", "1") != "0"
+        self._side = None
         self._is_popular = None
         self._pop_host = self._popular_items(train_item_count, config["popularity_ratio"])
         self.last = None
@@ -188,6 +193,14 @@ class FullSortEvaluator:
     def collect(self, U, I, data, max_rating, transform=_lib.TRANSFORM_CLAMP_DIV):
         """Runs the kernels; returns a dict of DEVICE tensors (no host sync)."""
         K = self.K
+        fork = None
+        if self.group is None and self.branch_streams:
+            self._popular_mask(U.device)            # (built on the current stream before anything forks)
+            cur = torch.cuda.current_stream(U.device)
+            if getattr(self, "_side", None) is None or self._side[0].device != U.device:
+                self._side = (torch.cuda.Stream(device=U.device), torch.cuda.Stream(device=U.device))
+            fork = (cur,) + self._side
+            self._side[0].wait_stream(cur)
         if self.group is None:
             ids, sc = kernels.fullsort_topk(U, I, data.users, data.hist_off, data.hist_items, K, transform, max_rating,
                                             0, self.score_mode)
@@ -202,38 +215,65 @@ class FullSortEvaluator:
             dist.all_gather_into_tensor(ids_all, ids_l, group=self.group)
             dist.all_gather_into_tensor(sc_all, sc_l, group=self.group)
             ids, sc = kernels.topk_merge(ids_all, sc_all)
-        rec_topk = kernels.hits(ids, data.pos_off, data.pos_items_sorted)
-        pos_score = kernels.pair_scores(U, I, data.pos_uid, data.pos_items, transform, max_rating)
-        out = {"topk_id": ids, "topk_score": sc, "rec_topk": rec_topk, "pos_score": pos_score}
+        # The pass behind the scorer is three independent chains of small launches: the positives' scores -> item x group
+        # sums -> fairness metrics (needs nothing from the scorer), the top-K ids -> hit bits -> NDCG / Recall / Hit / MRR
+        # sums, and the top-K ids -> recommendation histogram -> Gini / popularity.  Unsharded passes fork them onto side
+        # streams (captured as parallel branches by collect_graphed): at the ML-1M shape the pass is latency-bound and the
+        # fairness chain hides under the scorer.
         need = set(self.metrics)
-        if need & set(TOPK_ROWS):
-            out["topk_sums"] = kernels.topk_metric_sums(rec_topk)
-        if need & {"giniindex", "popularitypercentage"}:
-            cnt, pop = kernels.rec_item_stats(ids, self.n_items, self._popular_mask(U.device))
-            out["pop_hits"] = pop
-            if "giniindex" in need:
-                out["gini"] = {k: kernels.gini_at_k(cnt, k, data.n) for k in self.topk}
-        if need & set(FAIR_SLOTS):
-            out["fair"] = {}
-            attrs = self.sst_attr_list
-            for ai, attr in enumerate(attrs):
-                G = data.n_groups[attr]
-                if self.group is None:
-                    plan = self._ig_plan(data, None)
-                    stats = kernels.item_group_stats_planned(plan["plan"], pos_score, data.group_of_pos[attr], self.n_items, G)
-                else:
-                    import torch.distributed as dist
-                    world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-                    plan = self._ig_plan(data, shard_bounds(self.n_items, world, rank))
-                    if plan["n"] > 0:     # the positives whose item this rank owns (a host constant of the plan: no sync)
-                        if attr not in plan["group"]:
-                            plan["group"][attr] = data.group_of_pos[attr].index_select(0, plan["idx"]).contiguous()
-                        stats = kernels.item_group_stats_planned(plan["plan"], pos_score.index_select(0, plan["idx"]),
-                                                                 plan["group"][attr], self.n_items, G)
+        out = {"topk_id": ids, "topk_score": sc}
+
+        def fair_branch():
+            pos_score = kernels.pair_scores(U, I, data.pos_uid, data.pos_items, transform, max_rating)
+            out["pos_score"] = pos_score
+            if need & set(FAIR_SLOTS):
+                out["fair"] = {}
+                for ai, attr in enumerate(self.sst_attr_list):
+                    G = data.n_groups[attr]
+                    if self.group is None:
+                        plan = self._ig_plan(data, None)
+                        stats = kernels.item_group_stats_planned(plan["plan"], pos_score, data.group_of_pos[attr], self.n_items, G)
                     else:
-                        stats = torch.zeros((self.n_items, G, 2), dtype=torch.float64, device=U.device)
-                    dist.all_reduce(stats, group=self.group)  # disjoint supports: x + 0, order-independent
-                out["fair"][attr] = kernels.fairness_metrics(stats)
+                        import torch.distributed as dist
+                        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+                        plan = self._ig_plan(data, shard_bounds(self.n_items, world, rank))
+                        if plan["n"] > 0:     # the positives whose item this rank owns (a host constant of the plan: no sync)
+                            if attr not in plan["group"]:
+                                plan["group"][attr] = data.group_of_pos[attr].index_select(0, plan["idx"]).contiguous()
+                            stats = kernels.item_group_stats_planned(plan["plan"], pos_score.index_select(0, plan["idx"]),
+                                                                     plan["group"][attr], self.n_items, G)
+                        else:
+                            stats = torch.zeros((self.n_items, G, 2), dtype=torch.float64, device=U.device)
+                        dist.all_reduce(stats, group=self.group)  # disjoint supports: x + 0, order-independent
+                    out["fair"][attr] = kernels.fairness_metrics(stats)
+
+        def rec_branch():
+            if need & {"giniindex", "popularitypercentage"}:
+                cnt, pop = kernels.rec_item_stats(ids, self.n_items, self._popular_mask(U.device))
+                out["pop_hits"] = pop
+                if "giniindex" in need:
+                    out["gini"] = {k: kernels.gini_at_k(cnt, k, data.n) for k in self.topk}
+
+        def hit_branch():
+            rec_topk = kernels.hits(ids, data.pos_off, data.pos_items_sorted)
+            out["rec_topk"] = rec_topk
+            if need & set(TOPK_ROWS):
+                out["topk_sums"] = kernels.topk_metric_sums(rec_topk)
+
+        if fork is None:
+            hit_branch()
+            fair_branch()
+            rec_branch()
+        else:
+            cur, s_fair, s_rec = fork
+            with torch.cuda.stream(s_fair):         # (forked before the scorer was enqueued)
+                fair_branch()
+            s_rec.wait_stream(cur)                  # the ids exist on `cur` from here on
+            with torch.cuda.stream(s_rec):
+                rec_branch()
+            hit_branch()
+            cur.wait_stream(s_fair)
+            cur.wait_stream(s_rec)
         self.last = out
         return out
 
