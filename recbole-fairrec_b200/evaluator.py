@@ -194,7 +194,9 @@ class FullSortEvaluator:
         """Runs the kernels; returns a dict of DEVICE tensors (no host sync)."""
         K = self.K
         fork = None
-        if self.group is None and self.branch_streams:
+        # (only where the pass is a chain of short launches; behind a long scorer launch the side branches would just take
+        # SMs and bandwidth from it)
+        if self.group is None and self.branch_streams and data.n * self.n_items <= (1 << 27):
             self._popular_mask(U.device)            # (built on the current stream before anything forks)
             cur = torch.cuda.current_stream(U.device)
             if getattr(self, "_side", None) is None or self._side[0].device != U.device:
