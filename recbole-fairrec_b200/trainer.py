@@ -92,8 +92,12 @@ class FOCFTrainer:
         from .dataloader import FOCFDataLoader
         if self.group is not None and isinstance(train_data, FOCFDataLoader) and train_data.partition is not None:
             return self._train_epoch_dp(train_data)
+        # the planned runner: batches of up to 8192 rows as one persistent launch per epoch (fr_focf_epoch_run) or pipelined
+        # graphs of the fused step; larger batches as pipelined graphs of the multi-launch step (the preparation of batch
+        # t + 1 under the Adam sweep of batch t: bench.py's `pipelined` block at configs[4]) -- bit-identical to the loop
+        # below in every case (tests/test_focf_train_gpu.py, tests/test_focf_epoch_gpu.py)
         if self.fused and self.adam_mode == "dense_exact" and isinstance(train_data, FOCFDataLoader) \
-                and train_data.max_batch <= 8192 and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
+                and (self.config["cuda_graph"] is None or self.config["cuda_graph"]):
             k, _ = self.model.train_epoch_planned(train_data, self._loss_buf)
             return self._finish_epoch(k)
         k = 0

@@ -264,6 +264,37 @@ def test_planned_graph_epoch_equals_stepwise_epoch():
     np.testing.assert_array_equal(results[0][2], results[1][2])
 
 
+def test_planned_graph_epoch_with_large_batches_equals_stepwise_epoch():
+    """Batches beyond the fused single-CTA preparation (> 8192 rows: multi-kernel sort / segments, multi-launch compute):
+    the pipelined graphs of the planned runner -- preparation of batch t + 1 on a second stream under the compute of batch
+    t, the configs[4] regime of bench.py's `pipelined` block -- are bit-identical to one fr_focf_train_step per batch."""
+    import recbole_fairrec_b200 as pkg
+    cfg, train, U0, I0 = _ml_like_loader(9, n_users=4000, n_items=700, n_inter=260000, batch=30000, d=64)
+    results = []
+    for planned in (False, True):
+        loader = pkg.FOCFDataLoader(cfg, train, mode="fast", seed=5)
+        assert loader.max_batch > 8192
+        model = make_model(U0, I0, "value", 1.0)
+        model.init_adam(lr=1e-3, weight_decay=1e-3)
+        n = len(loader)
+        assert n >= 5
+        losses = torch.zeros(2 * n, device="cuda")
+        for ep in range(2):
+            if planned:
+                k, rows = model.train_epoch_planned(loader, losses[ep * n:(ep + 1) * n], graph_steps=4, persistent=False)
+                assert k == n
+            else:
+                for k, inter in enumerate(loader):
+                    model.train_step(inter, loss_out=losses[ep * n + k:ep * n + k + 1])
+        model.check_flags()
+        results.append((losses.cpu().numpy().copy(), model.user_embedding_layer.weight.detach().cpu().numpy().copy(),
+                        model.item_embedding_layer.weight.detach().cpu().numpy().copy(), model._adam["step"]))
+    assert results[0][3] == results[1][3] == 2 * n
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_array_equal(results[0][1], results[1][1])
+    np.testing.assert_array_equal(results[0][2], results[1][2])
+
+
 def test_planned_epoch_of_a_single_batch_equals_train_step():
     """train rows <= train_batch_size: the epoch plan holds ONE batch; the planned runner's warm-up must not run it twice
     and the host's Adam step count must stay equal to the device's over several epochs"""
