@@ -688,6 +688,10 @@ def run_ours(args, w):
                           "adam_mode": "dense_exact (every row moves every step, as torch.optim.Adam does in the reference)",
                           "l2": f"no flush needed: every step streams 24 * rows * d = {24.0 * rows_per_gpu_tab * d / 1e9:.1f} GB "
                                 f"of tables + moments per GPU, far beyond the 126 MB L2",
+                          "loop": ("value = one FOCF.train_step per batch on one stream (prepare -> forward -> loss -> gradients -> Adam "
+                                   "in series); FOCFTrainer._train_epoch itself runs the planned runner of the `pipelined` block "
+                                   "(same kernels, the next batch's preparation under the Adam sweep)") if world == 1 else
+                                  "row-sharded step, the next batch staged during phase C (next_k)",
                           "parallelism": parallelism},
         "clocks": clocks.summary(),
         "roofline": roof,
