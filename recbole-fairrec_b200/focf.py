@@ -192,6 +192,11 @@ class FOCF(nn.Module):
                               filled=ctypes.c_int32(0))
         return self._adam
 
+    def _moment_key(self):
+        """addresses of the Adam moments: part of every captured graph's key (init_adam() allocates new ones)"""
+        a = self._adam
+        return (a["mU"].data_ptr(), a["vU"].data_ptr(), a["mI"].data_ptr(), a["vI"].data_ptr())
+
     def flush_adam(self):
         """lazy_exact: apply the pending updates of every row (no-op otherwise).  After it the tables, moments and step
         count are exactly those of dense_exact training."""
@@ -389,14 +394,14 @@ class FOCF(nn.Module):
             self._cols2 = tuple(torch.empty_like(c) for c in plan["cols"])
         engines = (eng, self._eng2)
         key = (plan["generation"], loss_buf.data_ptr(), U.data_ptr(), I.data_ptr(), graph_steps, plan["len"],
-               eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap)
+               eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap) + self._moment_key()
         runner = _PlannedRunner(self, plan)
         T = self._adam["step"]
         if getattr(self, "_graph_key", None) != key:
             plans = (plan, dict(plan, cols=self._cols2))
             sts = [e.planned_step(U, I, self._adam, p, loader.train, self._objective, self.fair_weight, loss_buf)
                    for e, p in zip(engines, plans)]
-            key = key[:6] + (eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap)     # planned_step may have grown a workspace
+            key = key[:6] + (eng.ws.data_ptr(), self._eng2.ws.data_ptr(), cap) + self._moment_key()   # planned_step may have grown a workspace
             # eager first step on each workspace: module loading, function attributes
             # (an epoch of ONE batch warms up workspace 0 only: cursor 1 would wrap to batch 0 and train it twice)
             eng.set_counters(plan_cursor=0, adam_step=T, stride=1)

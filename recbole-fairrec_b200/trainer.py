@@ -205,11 +205,55 @@ class FOCFTrainer:
                                        self.model.item_embedding_layer.weight.data, data, self.model.max_rating)
 
     # ------------------------------------------------------------------ bookkeeping (cold)
+    def _adam_state_dict(self):
+        """The fused step's Adam state in torch.optim.Adam's own state_dict layout (parameter order = the reference model's:
+        user table, item table -- focf.py:43-44), so that the reference's resume_checkpoint (trainer.py:258-284) loads a
+        file written here and vice versa.  lazy_exact keeps nothing extra: the trainer flushes before it saves."""
+        a = self.model._adam
+        step = torch.tensor(float(a["step"]))
+        group = {"lr": a["lr"], "betas": (a["beta1"], a["beta2"]), "eps": a["eps"], "weight_decay": a["weight_decay"],
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": [0, 1]}
+        return {"state": {0: {"step": step.clone(), "exp_avg": a["mU"].detach().cpu().clone(),
+                              "exp_avg_sq": a["vU"].detach().cpu().clone()},
+                          1: {"step": step.clone(), "exp_avg": a["mI"].detach().cpu().clone(),
+                              "exp_avg_sq": a["vI"].detach().cpu().clone()}},
+                "param_groups": [group], "fairrec_b200": {"adam_mode": a.get("mode", "dense_exact")}}
+
+    def _load_adam_state_dict(self, sd):
+        """Into the EXISTING moment tensors (captured graphs and persistent argument structs hold their addresses).  Accepts
+        torch.optim.Adam's layout (ours and the reference's files) and the private dict earlier versions of this trainer wrote."""
+        a = self.model._adam
+        if "state" in sd and "param_groups" in sd:
+            st = sd["state"]
+            if len(st) == 0:                 # a checkpoint written before the first optimizer step
+                for k in ("mU", "vU", "mI", "vI"):
+                    a[k].zero_()
+                a["step"] = 0
+            else:
+                for idx, (m, v) in ((0, ("mU", "vU")), (1, ("mI", "vI"))):
+                    a[m].copy_(st[idx]["exp_avg"])
+                    a[v].copy_(st[idx]["exp_avg_sq"])
+                a["step"] = int(float(st[0]["step"]))
+            g = sd["param_groups"][0]
+            a["lr"], a["eps"], a["weight_decay"] = g["lr"], g["eps"], g["weight_decay"]
+            a["beta1"], a["beta2"] = g["betas"]
+        else:
+            for k in ("mU", "vU", "mI", "vI"):
+                a[k].copy_(sd[k])
+            for k in ("step", "lr", "beta1", "beta2", "eps", "weight_decay"):
+                if k in sd:
+                    a[k] = sd[k]
+        if a.get("mode") == "lazy_exact":    # the file holds flushed tables: every row is current for `step`
+            a["last_u"].fill_(int(a["step"]))
+            a["last_i"].fill_(int(a["step"]))
+
     def _save_checkpoint(self, epoch):
         """trainer.py:221-240"""
         os.makedirs(self.checkpoint_dir, exist_ok=True)
-        opt_state = self.optimizer.state_dict() if self.optimizer is not None else {
-            k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.model._adam.items()}
+        if self.optimizer is None and self.model._adam.get("mode") == "lazy_exact":
+            self.model.flush_adam()
+        opt_state = self.optimizer.state_dict() if self.optimizer is not None else self._adam_state_dict()
         torch.save({"config": dict(self.config), "epoch": epoch, "cur_step": self.cur_step,
                     "best_valid_score": self.best_valid_score, "state_dict": self.model.state_dict(),
                     "other_parameter": self.model.other_parameter(), "optimizer": opt_state}, self.saved_model_file)
@@ -225,8 +269,7 @@ class FOCFTrainer:
         if self.optimizer is not None:
             self.optimizer.load_state_dict(ck["optimizer"])
         else:
-            for k, v in ck["optimizer"].items():
-                self.model._adam[k] = v.to(self.device) if torch.is_tensor(v) else v
+            self._load_adam_state_dict(ck["optimizer"])
 
     def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
         """trainer.py:332-418"""

@@ -220,6 +220,53 @@ def test_fairgo_trainer_loads_the_pretrain_checkpoint(tmp_path):
         pkg.FairGoTrainer(cfg2, model2)
 
 
+def test_focf_fused_checkpoint_is_a_torch_adam_state_dict_and_resumes_in_place(tmp_path):
+    """FOCFTrainer in fused mode (trainer.py:221-284): the 'optimizer' entry has torch.optim.Adam's own layout -- a
+    torch.optim.Adam over the reference model's parameters loads it --, a resume copies INTO the existing moment tensors
+    (captured graphs hold their addresses), and a state_dict written by torch.optim.Adam (the reference's files) resumes too."""
+    import recbole_fairrec_b200 as pkg
+    from recbole_fairrec_b200 import synth
+
+    def make(seed):
+        torch.manual_seed(seed)
+        cfg = pkg.Config(embedding_size=8, fair_objective="value", device=torch.device("cpu"), learning_rate=2e-3,
+                         weight_decay=1e-3, checkpoint_dir=str(tmp_path), model="FOCF")
+        model = pkg.FOCF(cfg, synth.SynthDataset(30, 20, 5.0))
+        return cfg, model, pkg.FOCFTrainer(cfg, model)
+
+    cfg, model, trainer = make(1)
+    assert trainer.fused and trainer.optimizer is None
+    a = model._adam
+    for k in ("mU", "vU", "mI", "vI"):
+        a[k].uniform_()
+    a["step"] = 7
+    trainer.cur_step, trainer.best_valid_score = 1, 0.25
+    trainer._save_checkpoint(3)
+    ck = torch.load(trainer.saved_model_file, weights_only=False)
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(30, 8)), torch.nn.Parameter(torch.zeros(20, 8))], lr=1.0)
+    opt.load_state_dict(ck["optimizer"])                       # what the reference's resume_checkpoint does
+    assert opt.param_groups[0]["lr"] == 2e-3 and opt.param_groups[0]["weight_decay"] == 1e-3
+    st = [opt.state[p] for p in opt.param_groups[0]["params"]]
+    assert float(st[0]["step"]) == 7 and torch.equal(st[0]["exp_avg"], a["mU"]) and torch.equal(st[1]["exp_avg_sq"], a["vI"])
+    # resume: in place, every field
+    cfg2, model2, trainer2 = make(2)
+    ptrs = {k: model2._adam[k].data_ptr() for k in ("mU", "vU", "mI", "vI")}
+    trainer2.resume_checkpoint(trainer.saved_model_file)
+    for k in ("mU", "vU", "mI", "vI"):
+        assert model2._adam[k].data_ptr() == ptrs[k] and torch.equal(model2._adam[k], a[k]), k
+    assert model2._adam["step"] == 7 and (trainer2.start_epoch, trainer2.cur_step, trainer2.best_valid_score) == (4, 1, 0.25)
+    assert torch.equal(model2.user_embedding_layer.weight, model.user_embedding_layer.weight)
+    # a file whose optimizer entry torch.optim.Adam itself wrote
+    for p in opt.param_groups[0]["params"]:
+        opt.state[p]["exp_avg"].add_(1.0)
+    ck["optimizer"] = opt.state_dict()
+    path = str(tmp_path / "ref.pth")
+    torch.save(ck, path)
+    cfg3, model3, trainer3 = make(3)
+    trainer3.resume_checkpoint(path)
+    assert torch.equal(model3._adam["mU"], a["mU"] + 1.0) and torch.equal(model3._adam["vI"], a["vI"]) and model3._adam["step"] == 7
+
+
 @pytest.mark.parametrize("name", ["PFCN_MLP", "FairGo_GCN", "NFCF"])
 def test_checkpoint_round_trip_of_the_mlp_family_trainers(name, tmp_path):
     """trainer.py:221-284 / 784-830 / 1133-1184: the reference's checkpoint keys, plus the dict-held filter / discriminator
