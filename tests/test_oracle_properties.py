@@ -103,3 +103,23 @@ def test_gini_and_popularity_limits():
     assert sorted(top) == [1, 2, 3, 4] and len(top) == max(int(len(counts) * 0.1), 1)
     pp = mo.popularity_percentage(same, counts, 0.1)         # 4 of the 5 recommended items are popular
     assert pp.shape == same.shape and abs(pp.mean(axis=0)[-1] - 0.8) < 1e-12
+
+
+def test_gini_from_a_histogram_of_count_values_equals_the_sorted_definition():
+    """The identity `k_gini_hist` (csrc/metrics.cu) rests on: the h items whose count is v occupy the ascending positions
+    P + 1 .. P + h (P = items with a smaller count), so sum_p (2p - N - 1) c_(p) = sum_v v (2 (h P + h (h + 1) / 2) - h (N + 1))
+    -- integer arithmetic, no sort -- and the result is the oracle's Gini (metrics.py:644-661)."""
+    rng = np.random.default_rng(4)
+    for n_users, n_items, K in ((50, 40, 3), (300, 1000, 5), (2000, 257, 10)):
+        rec = np.stack([rng.choice(np.arange(1, n_items), size=K, replace=False, p=None) for _ in range(n_users)])
+        counts = np.bincount(rec.reshape(-1), minlength=n_items).astype(np.int64)      # <= n_users each
+        assert counts.max() <= n_users
+        c_sorted = np.sort(counts)
+        want_int = int(((2 * np.arange(1, n_items + 1) - n_items - 1) * c_sorted).sum())
+        hist = np.bincount(counts, minlength=n_users + 1).astype(np.int64)
+        P = np.concatenate([[0], np.cumsum(hist)[:-1]])
+        v = np.arange(hist.size, dtype=np.int64)
+        got_int = int((v * (2 * (hist * P + hist * (hist + 1) // 2) - hist * (n_items + 1))).sum())
+        assert got_int == want_int
+        got = got_int / float(n_users * K) / float(n_items)
+        np.testing.assert_allclose(got, mo.gini(rec, n_items), rtol=1e-12)
