@@ -76,3 +76,42 @@ def test_no_cpu_fallback():
                              "rating": torch.tensor([3.0, 4.0]), "gender": torch.tensor([1, 2])})
     with pytest.raises(pkg._lib.FairRecLibraryError):
         model.calculate_loss(inter)
+
+
+MIRRORS = (("fr_focf_step", "FocfStep"), ("fr_focf_shard_step", "FocfShardStep"), ("fr_mlp_tower", "MlpTower"),
+           ("fr_nfcf_step", "NfcfStep"), ("fr_fullsort", "FullSort"), ("fr_adam_entry", "AdamEntry"),
+           ("fr_spmm_plan", "SpmmPlan"), ("fr_chain_layer", "ChainLayer"), ("fr_chain", "Chain"), ("fr_chain_dp", "ChainDp"))
+
+
+def test_struct_mirrors_have_the_c_compilers_size_and_field_offsets(tmp_path):
+    """The header compiles as plain C (what a cgo / JNI / ctypes binding consumes) and every ctypes mirror of a `struct fr_*`
+    has the size and the per-field offsets gcc gives the C struct -- field names alone would not notice a padding mismatch."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    import recbole_fairrec_b200 as pkg
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fairrec_b200.h"', 'int main(void) {']
+    for cname, pyname in MIRRORS:
+        lines.append(f'  printf("{cname} . %zu\\n", sizeof({cname}));')
+        for field, _ in getattr(pkg._lib, pyname)._fields_:
+            lines.append(f'  printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    want = {}
+    for ln in out:
+        if ln.strip():
+            s, f, v = ln.split()
+            want[(s, f)] = int(v)
+    n = 0
+    for cname, pyname in MIRRORS:
+        cls = getattr(pkg._lib, pyname)
+        assert ctypes.sizeof(cls) == want[(cname, ".")], cname
+        for field, _ in cls._fields_:
+            assert getattr(cls, field).offset == want[(cname, field)], (cname, field)
+            n += 1
+    assert n > 150
