@@ -115,3 +115,25 @@ def test_struct_mirrors_have_the_c_compilers_size_and_field_offsets(tmp_path):
             assert getattr(cls, field).offset == want[(cname, field)], (cname, field)
             n += 1
     assert n > 150
+
+
+def test_ctypes_signatures_have_the_headers_parameter_counts():
+    """every `fr_*` prototype of the header against the ctypes table: same number of parameters, pointer parameters bound as
+    pointers, `size_t` returns bound as c_size_t"""
+    import recbole_fairrec_b200 as pkg
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = re.findall(r"\b(size_t|int|void|int64_t|uint64_t|const char \*)\s*(fr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    seen = 0
+    for ret, name, params in protos:
+        restype, argtypes = pkg._lib.SIGNATURES[name]
+        ps = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        assert len(ps) == len(argtypes), (name, len(ps), len(argtypes))
+        for p, t in zip(ps, argtypes):
+            is_ptr_c = "*" in p
+            is_ptr_py = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or hasattr(t, "_type_") and isinstance(
+                getattr(t, "_type_", None), type)
+            assert is_ptr_c == bool(is_ptr_py), (name, p, t)
+        if ret == "size_t":
+            assert restype is ctypes.c_size_t, name
+        seen += 1
+    assert seen == len(declared_functions())
